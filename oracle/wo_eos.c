@@ -1,0 +1,447 @@
+/*
+ * wo_eos.c -- oracle (TEST INFRASTRUCTURE): equations of state (we, w) and
+ * the local cell / face objects.  Restated from src/eos.F90:186-257,
+ * src/eos_we.F90:149-526, src/eos_w.F90, src/fluid.F90:197-370,
+ * src/rock.F90:142, src/cell.F90:114-142, src/face.F90:230-515.
+ *
+ * Fluid record layout (src/fluid.F90:232-267), nc components, nph phases:
+ *   0 pressure, 1 temperature, 2 region, 3 old_region, 4 phase_composition,
+ *   5 permeability_factor, 6..6+nc-1 partial_pressure, then per phase
+ *   (stride 8+nc-1): density, viscosity, saturation, relative_permeability,
+ *   capillary_pressure, specific_enthalpy, internal_energy, mass_fraction(nc).
+ * Rock record (src/rock.F90:97-112): permeability(3), wet_conductivity,
+ *   dry_conductivity, porosity, density, specific_heat.
+ */
+#include "oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct wo_eos {
+  wo_params prm;
+  wo_thermo *thermo;
+  int np, nc, nphase, nmobile, isothermal;
+  double primary_scale[WO_MAX_NP][5]; /* [var][region 1..4] */
+};
+
+enum { F_P = 0, F_T = 1, F_REGION = 2, F_OLD_REGION = 3, F_PHASES = 4, F_PERMFAC = 5, F_PARTIAL = 6 };
+enum { PH_RHO = 0, PH_MU = 1, PH_SAT = 2, PH_KR = 3, PH_PC = 4, PH_H = 5, PH_U = 6, PH_X = 7 };
+enum { R_PERM = 0, R_WET = 3, R_DRY = 4, R_POR = 5, R_RHO = 6, R_CP = 7 };
+
+static inline int bulk_dof(int nc) { return 7 + nc - 1; }
+static inline int phase_dof(int nc) { return 8 + nc - 1; }
+static inline double *phase_ptr(double *fluid, int nc, int p) { return fluid + bulk_dof(nc) + p * phase_dof(nc); }
+static inline const double *cphase_ptr(const double *fluid, int nc, int p) {
+  return fluid + bulk_dof(nc) + p * phase_dof(nc);
+}
+static inline int nint_(double x) { return (int)lround(x); }
+
+wo_eos *wo_eos_create(const wo_params *prm) {
+  wo_eos *e = (wo_eos *)calloc(1, sizeof(wo_eos));
+  e->prm = *prm;
+  e->thermo = wo_thermo_create(prm->thermo, prm->extrapolate);
+  double ps = prm->pressure_scale > 0 ? prm->pressure_scale : 1.e6;      /* eos_we.F90:75-76 */
+  double ts = prm->temperature_scale > 0 ? prm->temperature_scale : 1.e2;
+  switch (prm->eos) {
+    case WO_EOS_WE: /* eos_we.F90:78-109 */
+      e->np = 2; e->nc = 1; e->nphase = 2; e->nmobile = 2; e->isothermal = 0;
+      e->primary_scale[0][1] = ps; e->primary_scale[1][1] = ts;
+      e->primary_scale[0][2] = ps; e->primary_scale[1][2] = ts;
+      e->primary_scale[0][3] = 0.0; e->primary_scale[1][3] = 0.0;
+      e->primary_scale[0][4] = ps; e->primary_scale[1][4] = 1.0;
+      break;
+    case WO_EOS_W: /* eos_w.F90:67-96 */
+      e->np = 1; e->nc = 1; e->nphase = 1; e->nmobile = 1; e->isothermal = 1;
+      e->primary_scale[0][1] = ps; e->primary_scale[0][2] = ps;
+      break;
+    default:
+      wo_thermo_destroy(e->thermo);
+      free(e);
+      return NULL;
+  }
+  return e;
+}
+
+void wo_eos_destroy(wo_eos *e) {
+  if (!e) return;
+  wo_thermo_destroy(e->thermo);
+  free(e);
+}
+int wo_eos_num_primary(const wo_eos *e) { return e->np; }
+int wo_eos_num_components(const wo_eos *e) { return e->nc; }
+int wo_eos_num_phases(const wo_eos *e) { return e->nphase; }
+int wo_eos_fluid_dof(const wo_eos *e) { return bulk_dof(e->nc) + e->nphase * phase_dof(e->nc); }
+wo_thermo *wo_eos_thermo(wo_eos *e) { return e->thermo; }
+
+/* eos.F90:186-210 */
+void wo_eos_scale(const wo_eos *e, const double *primary, int region, double *scaled) {
+  for (int i = 0; i < e->np; i++) scaled[i] = primary[i] / e->primary_scale[i][region];
+}
+void wo_eos_unscale(const wo_eos *e, const double *scaled, int region, double *primary) {
+  for (int i = 0; i < e->np; i++) primary[i] = scaled[i] * e->primary_scale[i][region];
+}
+
+/* eos.F90:214-236 */
+static int eos_phase_composition(wo_eos *e, double *fluid) {
+  int region = nint_(fluid[F_REGION]);
+  int phases = wo_phase_composition(e->thermo, region, fluid[F_P], fluid[F_T]);
+  if (phases > 0) {
+    fluid[F_PHASES] = (double)phases;
+    return 0;
+  }
+  return 1;
+}
+
+/* eos_we.F90:327-390 ; eos_w.F90 bulk_properties */
+int wo_eos_bulk_properties(wo_eos *e, const double *primary, double *fluid) {
+  int err = 0;
+  int nc = e->nc;
+  if (e->prm.eos == WO_EOS_W) {
+    fluid[F_P] = primary[0];
+    fluid[F_T] = e->prm.eos_w_temperature;
+    phase_ptr(fluid, nc, 0)[PH_SAT] = 1.0;
+    err = eos_phase_composition(e, fluid);
+    fluid[F_PERMFAC] = 1.0;
+    fluid[F_PARTIAL] = fluid[F_P];
+    return err;
+  }
+  fluid[F_P] = primary[0];
+  int region = nint_(fluid[F_REGION]);
+  if (region == 4) err = wo_saturation_temperature(e->thermo, fluid[F_P], &fluid[F_T]);
+  else fluid[F_T] = primary[1];
+  if (err == 0) {
+    fluid[F_PERMFAC] = 1.0;
+    err = eos_phase_composition(e, fluid);
+    if (err == 0) {
+      /* phase_saturations: eos_we.F90:366-390 */
+      double *l = phase_ptr(fluid, nc, 0), *v = phase_ptr(fluid, nc, 1);
+      switch (region) {
+        case 1: l[PH_SAT] = 1.0; v[PH_SAT] = 0.0; break;
+        case 2: l[PH_SAT] = 0.0; v[PH_SAT] = 1.0; break;
+        case 4: l[PH_SAT] = 1.0 - primary[1]; v[PH_SAT] = primary[1]; break;
+        default: break;
+      }
+      fluid[F_PARTIAL] = fluid[F_P];
+    }
+  }
+  return err;
+}
+
+/* eos_we.F90:394-458 ; eos_w.F90 phase_properties */
+int wo_eos_phase_properties(wo_eos *e, const double *primary, const double *rock, double *fluid) {
+  (void)primary;
+  (void)rock;
+  int nc = e->nc, err = 0;
+  double properties[2];
+  if (e->prm.eos == WO_EOS_W) {
+    int p = nint_(fluid[F_REGION]);
+    double param[2] = {fluid[F_P], fluid[F_T]};
+    err = wo_region_properties(e->thermo, p, param, properties);
+    if (err == 0) {
+      double *ph = phase_ptr(fluid, nc, p - 1);
+      ph[PH_RHO] = properties[0];
+      ph[PH_U] = properties[1];
+      ph[PH_H] = ph[PH_U] + fluid[F_P] / ph[PH_RHO];
+      ph[PH_KR] = 1.0;
+      ph[PH_PC] = 0.0;
+      ph[PH_X] = 1.0;
+      ph[PH_MU] = wo_region_viscosity(e->thermo, p, fluid[F_T], fluid[F_P], ph[PH_RHO]);
+    }
+    return err;
+  }
+  int phases = nint_(fluid[F_PHASES]);
+  double sl = phase_ptr(fluid, nc, 0)[PH_SAT];
+  double relperm[2], cap[2];
+  wo_relperm_values(&e->prm.relperm, sl, relperm);
+  cap[0] = wo_cappress_value(&e->prm.cappress, sl, fluid[F_T]);
+  cap[1] = 0.0;
+  for (int p = 0; p < e->nphase; p++) {
+    double *ph = phase_ptr(fluid, nc, p);
+    if (phases & (1 << p)) {
+      double param[2] = {fluid[F_P], fluid[F_T]};
+      err = wo_region_properties(e->thermo, p + 1, param, properties);
+      if (err == 0) {
+        ph[PH_RHO] = properties[0];
+        ph[PH_U] = properties[1];
+        ph[PH_H] = ph[PH_U] + fluid[F_P] / ph[PH_RHO];
+        ph[PH_X] = 1.0;
+        ph[PH_KR] = relperm[p];
+        ph[PH_PC] = cap[p];
+        ph[PH_MU] = wo_region_viscosity(e->thermo, p + 1, fluid[F_T], fluid[F_P], ph[PH_RHO]);
+      } else
+        break;
+    } else {
+      ph[PH_RHO] = 0.0;
+      ph[PH_U] = 0.0;
+      ph[PH_H] = 0.0;
+      ph[PH_KR] = 0.0;
+      ph[PH_PC] = 0.0;
+      ph[PH_MU] = 0.0;
+      ph[PH_X] = 0.0;
+    }
+  }
+  return err;
+}
+
+/* ---- transitions: eos_we.F90:149-323 ---- */
+
+typedef struct {
+  const wo_thermo *thermo;
+  double v0[WO_MAX_NP], v1[WO_MAX_NP]; /* interpolator val(:,1), val(:,2) on coord [0,1] */
+} satline_ctx;
+
+/* interpolate_at_index with index fixed to 1 on the 2-point table x=[0,1]
+   (interpolation.F90:388-403,494-510; eos_we.F90:100-104,181-183) */
+static void pv_interp(const satline_ctx *c, int np, double x, double *y) {
+  double xi = (x - 0.0) / (1.0 - 0.0);
+  for (int i = 0; i < np; i++) y[i] = (1.0 - xi) * c->v0[i] + xi * c->v1[i];
+}
+
+/* eos_we.F90:530-553 */
+static double saturation_difference(double x, void *ctx) {
+  satline_ctx *c = (satline_ctx *)ctx;
+  double var[WO_MAX_NP], Ps = 0.0;
+  pv_interp(c, 2, x, var);
+  wo_saturation_pressure(c->thermo, var[1], &Ps);
+  return var[0] - Ps;
+}
+
+/* eos_we.F90:149-216 */
+static int we_transition_to_single_phase(wo_eos *e, const double *old_primary, const double *old_fluid,
+                                         int new_region, double *primary, double *fluid, int *transition) {
+  const double small = 1.e-6;
+  int err = 0;
+  *transition = 0;
+  double saturation_bound, pressure_factor;
+  if (new_region == 1) {
+    saturation_bound = 0.0;
+    pressure_factor = 1.0 + small;
+  } else {
+    saturation_bound = 1.0;
+    pressure_factor = 1.0 - small;
+  }
+  /* 2-point table on x = [0, 1], index set to 1; find xi where component 2 == bound */
+  double xs[2] = {0.0, 1.0};
+  double vals[2 * WO_MAX_NP];
+  for (int i = 0; i < 2; i++) {
+    vals[i] = old_primary[i];
+    vals[2 + i] = primary[i];
+  }
+  wo_table tbl;
+  wo_table_init(&tbl, xs, vals, 2, 2);
+  tbl.index = 1;
+  double xi = 0.0;
+  err = wo_table_find_component_at_index(&tbl, saturation_bound, 2, &xi);
+  if (err == 0) {
+    /* interpolate(xi): find + interpolate_at_index (interpolation.F90:533-545) */
+    double interpolated[WO_MAX_NP];
+    wo_table_interpolate(&tbl, xi, interpolated);
+    primary[0] = pressure_factor * interpolated[0];
+    err = wo_saturation_temperature(e->thermo, interpolated[0], &primary[1]);
+    if (err == 0) {
+      fluid[F_REGION] = (double)new_region;
+      *transition = 1;
+    }
+  } else {
+    double old_ps;
+    err = wo_saturation_pressure(e->thermo, old_fluid[F_T], &old_ps);
+    if (err == 0) {
+      primary[0] = pressure_factor * old_ps;
+      primary[1] = old_fluid[F_T];
+      fluid[F_REGION] = (double)new_region;
+      *transition = 1;
+    }
+  }
+  wo_table_destroy(&tbl);
+  return err;
+}
+
+/* eos_we.F90:220-268 */
+static int we_transition_to_two_phase(wo_eos *e, double saturation_pressure, const double *old_primary,
+                                      const double *old_fluid, double *primary, double *fluid,
+                                      int *transition) {
+  const double small = 1.e-6;
+  satline_ctx c;
+  c.thermo = e->thermo;
+  for (int i = 0; i < 2; i++) {
+    c.v0[i] = old_primary[i];
+    c.v1[i] = primary[i];
+  }
+  wo_root_finder rf;
+  wo_root_finder_init(&rf);
+  wo_root_finder_find(&rf, saturation_difference, &c);
+  if (rf.err == 0) {
+    /* interpolate(xi) = find + interpolate_at_index: clamps outside [0,1] */
+    double xs[2] = {0.0, 1.0}, vals[4] = {c.v0[0], c.v0[1], c.v1[0], c.v1[1]}, ip[2];
+    wo_table tbl;
+    wo_table_init(&tbl, xs, vals, 2, 2);
+    wo_table_interpolate(&tbl, rf.root, ip);
+    wo_table_destroy(&tbl);
+    primary[0] = ip[0];
+  } else {
+    primary[0] = saturation_pressure;
+  }
+  int old_region = nint_(old_fluid[F_REGION]);
+  primary[1] = (old_region == 1) ? small : 1.0 - small;
+  fluid[F_REGION] = 4.0;
+  *transition = 1;
+  return 0;
+}
+
+/* eos_we.F90:272-323 */
+int wo_eos_transition(wo_eos *e, const double *old_primary, double *primary, const double *old_fluid,
+                      double *fluid, int *transition) {
+  int err = 0;
+  *transition = 0;
+  if (e->prm.eos == WO_EOS_W) return 0;
+  int old_region = nint_(old_fluid[F_REGION]);
+  if (old_region == 4) {
+    double sv = primary[1];
+    if (sv < 0.0) err = we_transition_to_single_phase(e, old_primary, old_fluid, 1, primary, fluid, transition);
+    else if (sv > 1.0) err = we_transition_to_single_phase(e, old_primary, old_fluid, 2, primary, fluid, transition);
+  } else {
+    double ps;
+    err = wo_saturation_pressure(e->thermo, primary[1], &ps);
+    if (err == 0) {
+      if ((old_region == 1 && primary[0] < ps) || (old_region == 2 && primary[0] > ps))
+        err = we_transition_to_two_phase(e, ps, old_primary, old_fluid, primary, fluid, transition);
+    }
+  }
+  return err;
+}
+
+/* eos_we.F90:486-526 ; eos_w.F90 check_primary_variables */
+int wo_eos_check_primary_variables(const wo_eos *e, const double *fluid, double *primary, int *changed) {
+  *changed = 0;
+  double p = primary[0];
+  if (p < 0.0 || p > 100.e6) return 1;
+  if (e->prm.eos == WO_EOS_W) return 0;
+  int region = nint_(fluid[F_REGION]);
+  if (region == 4) {
+    double sv = primary[1];
+    if (sv < -1.0 || sv > 2.0) return 1;
+  } else {
+    double t = primary[1];
+    if (t < 0.0 || t > 800.0) return 1;
+  }
+  return 0;
+}
+
+/* eos.F90:240-257 */
+double wo_eos_conductivity(const double *rock, const double *fluid, int nc) {
+  double sl = cphase_ptr(fluid, nc, 0)[PH_SAT];
+  return rock[R_DRY] + sqrt(sl) * (rock[R_WET] - rock[R_DRY]);
+}
+
+/* ---- cell balance: cell.F90:114-142, fluid.F90:295-370, rock.F90:142 ---- */
+void wo_cell_balance(const double *rock, const double *fluid, int nc, int nphase, int np, double *balance) {
+  int isothermal = (np == nc);
+  double d[WO_MAX_NC];
+  for (int c = 0; c < nc; c++) d[c] = 0.0;
+  for (int p = 0; p < nphase; p++) {
+    const double *ph = cphase_ptr(fluid, nc, p);
+    double ds = ph[PH_RHO] * ph[PH_SAT];
+    for (int c = 0; c < nc; c++) d[c] = d[c] + ds * ph[PH_X + c];
+  }
+  for (int c = 0; c < nc; c++) balance[c] = rock[R_POR] * d[c];
+  if (!isothermal) {
+    double er = rock[R_RHO] * rock[R_CP] * fluid[F_T];
+    double ef = 0.0;
+    for (int p = 0; p < nphase; p++) {
+      const double *ph = cphase_ptr(fluid, nc, p);
+      double ds = ph[PH_RHO] * ph[PH_SAT];
+      ef = ef + ds * ph[PH_U];
+    }
+    balance[np - 1] = rock[R_POR] * ef + (1.0 - rock[R_POR]) * er;
+  }
+}
+
+/* ---- face: face.F90 ---- */
+enum { G_AREA = 0, G_DIST = 1, G_DIST12 = 3, G_NORMAL = 4, G_GRAVN = 7, G_CENTROID = 8, G_PERMDIR = 11 };
+
+/* face.F90:230-249 */
+void wo_face_calculate_distances(const double *c1, const double *c2, const double *fc, const double *normal,
+                                 double dist[2], double *dist12) {
+  double d1 = 0, d2 = 0, d12 = 0;
+  for (int i = 0; i < 3; i++) {
+    d1 += (fc[i] - c1[i]) * normal[i];
+    d2 += (c2[i] - fc[i]) * normal[i];
+    d12 += (c2[i] - c1[i]) * normal[i];
+  }
+  double correction = d12 / (d1 + d2);
+  dist[0] = d1 * correction;
+  dist[1] = d2 * correction;
+  *dist12 = d12;
+}
+
+/* face.F90:358-377 */
+double wo_face_harmonic_average(const double *g, const double x[2]) {
+  const double tol = 1.e-30;
+  double wx = (g[G_DIST] * x[1] + g[G_DIST + 1] * x[0]) / g[G_DIST12];
+  if (fabs(wx) > tol) return x[0] * x[1] / wx;
+  return 0.0;
+}
+
+/* face.F90:443-515 */
+void wo_face_flux(const double *g, const double *rock1, const double *rock2, const double *fluid1,
+                  const double *fluid2, int nc, int np, int nphase, int nmobile, int isothermal,
+                  double *flux) {
+  (void)nphase;
+  const double *rock[2] = {rock1, rock2};
+  const double *fluid[2] = {fluid1, fluid2};
+  int nf = np + nmobile;
+  for (int i = 0; i < nf; i++) flux[i] = 0.0;
+  /* permeability: face.F90:381-398 */
+  int direction = nint_(g[G_PERMDIR]);
+  double perm[2];
+  for (int i = 0; i < 2; i++) perm[i] = rock[i][R_PERM + direction - 1] * fluid[i][F_PERMFAC];
+  double k = wo_face_harmonic_average(g, perm);
+  if (!isothermal) {
+    double kcell[2], t[2];
+    for (int i = 0; i < 2; i++) {
+      kcell[i] = wo_eos_conductivity(rock[i], fluid[i], nc);
+      t[i] = fluid[i][F_T];
+    }
+    double cond = wo_face_harmonic_average(g, kcell);
+    double dtdn = (t[1] - t[0]) / g[G_DIST12];
+    flux[np - 1] = -cond * dtdn;
+  }
+  int phases[2];
+  for (int i = 0; i < 2; i++) phases[i] = nint_(fluid[i][F_PHASES]);
+  int phase_present = phases[0] | phases[1];
+  double *phase_flux = flux + np;
+  for (int p = 0; p < nmobile; p++) {
+    if (phase_present & (1 << p)) {
+      /* phase_density: face.F90:334-354 */
+      double rho = 0.0, weight = 0.0;
+      for (int i = 0; i < 2; i++) {
+        const double *ph = cphase_ptr(fluid[i], nc, p);
+        rho = rho + ph[PH_SAT] * ph[PH_RHO];
+        weight = weight + ph[PH_SAT];
+      }
+      rho = rho / weight;
+      /* pressure_gradient: face.F90:296-313 */
+      double pr[2];
+      for (int i = 0; i < 2; i++) pr[i] = fluid[i][F_P] + cphase_ptr(fluid[i], nc, p)[PH_PC];
+      double dpdn = (pr[1] - pr[0]) / g[G_DIST12];
+      double G = dpdn - rho * g[G_GRAVN];
+      int up = (G <= 0.0) ? 0 : 1; /* face.F90:426-439 */
+      if (phases[up] & (1 << p)) {
+        const double *ups = cphase_ptr(fluid[up], nc, p);
+        double mobility = ups[PH_KR] * ups[PH_RHO] / ups[PH_MU]; /* fluid.F90:197-207 */
+        double F = -k * mobility * G;
+        double sum = 0.0;
+        for (int c = 0; c < nc; c++) {
+          double pcf = F * ups[PH_X + c];
+          flux[c] = flux[c] + pcf;
+          sum += pcf;
+        }
+        if (!isothermal) {
+          double h = ups[PH_H];
+          flux[np - 1] = flux[np - 1] + h * F;
+        }
+        phase_flux[p] = sum;
+      }
+    }
+  }
+}

@@ -1,0 +1,278 @@
+/*
+ * wo_flow.c -- oracle (TEST INFRASTRUCTURE): the flow-simulation ODE loops.
+ * Restated from src/flow_simulation.F90:1102-1137 (update mask), :1242-1330
+ * (cell_balances), :1334-1485 (cell_inflows), :2022-2147 (pre_* hooks),
+ * :2171-2287 (fluid_init), :2291-2415 (fluid_properties), :2419-2576
+ * (fluid_transitions); src/timestepper.F90:345-374 (BE residual);
+ * src/dm_utils.F90:644-685 (max pointwise scaled abs).
+ *
+ * Local cell numbering: owned cells [0,nowned), partition ghost cells
+ * [nowned,ninterior), boundary (Dirichlet) ghost cells [ninterior,ncell).
+ * The reference loops visit owned cells in local index order; the face loop
+ * visits flux faces in flux_face order (here: face index order).
+ */
+#include "oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct wo_flow {
+  wo_params prm;
+  wo_mesh mesh;
+  wo_eos *eos;
+  int np, nc, nphase, nmobile, dof, nflux, isothermal;
+  double *fluid, *current_fluid, *last_iteration_fluid, *last_timestep_fluid;
+  double *balances; /* nowned*np: last unperturbed lhs */
+  double *flux;     /* nface*nflux */
+  double *update;   /* ncell: +1 / -1 */
+  double *rock;     /* private copy so boundary ghost rock can be set */
+  int unperturbed;
+};
+
+static inline int nint_(double x) { return (int)lround(x); }
+
+wo_flow *wo_flow_create(const wo_params *prm, const wo_mesh *mesh) {
+  wo_flow *f = (wo_flow *)calloc(1, sizeof(wo_flow));
+  f->prm = *prm;
+  f->mesh = *mesh;
+  f->eos = wo_eos_create(prm);
+  if (!f->eos) {
+    free(f);
+    return NULL;
+  }
+  f->np = wo_eos_num_primary(f->eos);
+  f->nc = wo_eos_num_components(f->eos);
+  f->nphase = wo_eos_num_phases(f->eos);
+  f->nmobile = f->nphase; /* we / w / wge: all phases mobile */
+  f->isothermal = (f->np == f->nc);
+  f->dof = wo_eos_fluid_dof(f->eos);
+  f->nflux = f->np + f->nmobile; /* flow_simulation.F90:174 */
+  size_t nfl = (size_t)mesh->ncell * f->dof;
+  f->fluid = (double *)calloc(nfl, sizeof(double));
+  f->current_fluid = (double *)calloc(nfl, sizeof(double));
+  f->last_iteration_fluid = (double *)calloc(nfl, sizeof(double));
+  f->last_timestep_fluid = (double *)calloc(nfl, sizeof(double));
+  f->balances = (double *)calloc((size_t)mesh->nowned * f->np, sizeof(double));
+  f->flux = (double *)calloc((size_t)mesh->nface * f->nflux, sizeof(double));
+  f->update = (double *)calloc(mesh->ncell, sizeof(double));
+  f->rock = (double *)malloc((size_t)mesh->ncell * 8 * sizeof(double));
+  memcpy(f->rock, mesh->rock, (size_t)mesh->ncell * 8 * sizeof(double));
+  f->mesh.rock = f->rock;
+  f->unperturbed = 1;
+  return f;
+}
+
+void wo_flow_destroy(wo_flow *f) {
+  if (!f) return;
+  wo_eos_destroy(f->eos);
+  free(f->fluid);
+  free(f->current_fluid);
+  free(f->last_iteration_fluid);
+  free(f->last_timestep_fluid);
+  free(f->balances);
+  free(f->flux);
+  free(f->update);
+  free(f->rock);
+  free(f);
+}
+
+wo_eos *wo_flow_eos(wo_flow *f) { return f->eos; }
+double *wo_flow_fluid(wo_flow *f) { return f->fluid; }
+double *wo_flow_current_fluid(wo_flow *f) { return f->current_fluid; }
+double *wo_flow_flux(wo_flow *f) { return f->flux; }
+
+void wo_flow_get_regions(wo_flow *f, int32_t *region) {
+  for (int c = 0; c < f->mesh.ncell; c++) region[c] = nint_(f->fluid[(size_t)c * f->dof + 2]);
+}
+
+/* boundary ghost cell: mesh.F90:1185-1202 (rock copied from interior cell, fluid from BC primary) */
+int wo_flow_set_boundary(wo_flow *f, int ghost_cell, int interior_cell, const double *primary, int region) {
+  double *rk = f->rock + (size_t)ghost_cell * 8;
+  memcpy(rk, f->rock + (size_t)interior_cell * 8, 8 * sizeof(double));
+  double *fl = f->fluid + (size_t)ghost_cell * f->dof;
+  fl[2] = (double)region;
+  int err = wo_eos_bulk_properties(f->eos, primary, fl);
+  if (err == 0) err = wo_eos_phase_properties(f->eos, primary, rk, fl);
+  memcpy(f->current_fluid + (size_t)ghost_cell * f->dof, fl, f->dof * sizeof(double));
+  return err;
+}
+
+/* fluid_init: flow_simulation.F90:2171-2287 (regions supplied with the initial conditions) */
+int wo_flow_fluid_init(wo_flow *f, const double *y, const int32_t *region) {
+  int err = 0;
+  double primary[WO_MAX_NP];
+  for (int c = 0; c < f->mesh.nowned; c++) {
+    double *fl = f->fluid + (size_t)c * f->dof;
+    fl[2] = (double)region[c];
+    wo_eos_unscale(f->eos, y + (size_t)c * f->np, region[c], primary);
+    err = wo_eos_bulk_properties(f->eos, primary, fl);
+    if (err == 0) err = wo_eos_phase_properties(f->eos, primary, f->rock + (size_t)c * 8, fl);
+    if (err) break;
+  }
+  memcpy(f->current_fluid, f->fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double));
+  return err;
+}
+
+/* identify_update_cells: flow_simulation.F90:1102-1137 */
+static void identify_update_cells(wo_flow *f, const int32_t *perturbed, int nperturbed) {
+  f->unperturbed = (nperturbed == 0);
+  if (f->unperturbed) {
+    for (int c = 0; c < f->mesh.ncell; c++) f->update[c] = 1.0;
+  } else {
+    for (int c = 0; c < f->mesh.ncell; c++) f->update[c] = -1.0;
+    for (int k = 0; k < nperturbed; k++) f->update[perturbed[k]] = 1.0;
+  }
+}
+
+/* fluid_properties: flow_simulation.F90:2291-2415 */
+static int fluid_properties(wo_flow *f, const double *y) {
+  int err = 0;
+  double primary[WO_MAX_NP];
+  memcpy(f->current_fluid, f->fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double)); /* :2331 */
+  for (int c = 0; c < f->mesh.nowned; c++) {
+    if (f->update[c] > 0) {
+      double *fl = f->current_fluid + (size_t)c * f->dof;
+      wo_eos_unscale(f->eos, y + (size_t)c * f->np, nint_(fl[2]), primary);
+      err = wo_eos_bulk_properties(f->eos, primary, fl);
+      if (err == 0) err = wo_eos_phase_properties(f->eos, primary, f->rock + (size_t)c * 8, fl);
+      if (err) break;
+    }
+  }
+  return err;
+}
+
+/* pre_eval: flow_simulation.F90:2126-2147 */
+int wo_flow_pre_eval(wo_flow *f, const double *y, const int32_t *perturbed, int nperturbed) {
+  identify_update_cells(f, perturbed, nperturbed);
+  int err = fluid_properties(f, y);
+  if (f->unperturbed) memcpy(f->fluid, f->current_fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double));
+  return err;
+}
+
+/* cell_balances: flow_simulation.F90:1242-1330 */
+int wo_flow_cell_balances(wo_flow *f, double *lhs) {
+  size_t n = (size_t)f->mesh.nowned * f->np;
+  memcpy(lhs, f->balances, n * sizeof(double)); /* :1273 */
+  for (int c = 0; c < f->mesh.nowned; c++) {
+    if (f->update[c] > 0)
+      wo_cell_balance(f->rock + (size_t)c * 8, f->current_fluid + (size_t)c * f->dof, f->nc, f->nphase, f->np,
+                      lhs + (size_t)c * f->np);
+  }
+  if (f->unperturbed) memcpy(f->balances, lhs, n * sizeof(double));
+  return 0;
+}
+
+/* cell_inflows: flow_simulation.F90:1334-1485 (no sources) */
+int wo_flow_cell_inflows(wo_flow *f, double *rhs) {
+  const wo_mesh *m = &f->mesh;
+  int np = f->np, nf = f->nflux;
+  const double flux_sign[2] = {-1.0, 1.0};
+  double face_flux[WO_MAX_NP + 3], flow[WO_MAX_NP];
+  for (size_t i = 0; i < (size_t)m->nowned * np; i++) rhs[i] = 0.0;
+  for (int iface = 0; iface < m->nface; iface++) {
+    const int32_t *cells = m->face_cells + 2 * (size_t)iface;
+    const double *g = m->face_geom + 12 * (size_t)iface;
+    int update_flux = 0;
+    for (int i = 0; i < 2; i++)
+      if (cells[i] < m->ninterior) update_flux = update_flux || (f->update[cells[i]] > 0);
+    double *stored = f->flux + (size_t)iface * nf;
+    if (update_flux) {
+      wo_face_flux(g, f->rock + 8 * (size_t)cells[0], f->rock + 8 * (size_t)cells[1],
+                   f->current_fluid + (size_t)cells[0] * f->dof, f->current_fluid + (size_t)cells[1] * f->dof,
+                   f->nc, np, f->nphase, f->nmobile, f->isothermal, face_flux);
+      if (f->unperturbed) memcpy(stored, face_flux, nf * sizeof(double));
+    } else {
+      memcpy(face_flux, stored, nf * sizeof(double));
+    }
+    for (int k = 0; k < np; k++) flow[k] = face_flux[k] * g[0];
+    for (int i = 0; i < 2; i++) {
+      int c = cells[i];
+      if (c < m->nowned) { /* ghost_cell(c) < 0 and c < end_interior_cell */
+        double vol = m->cell_geom[4 * (size_t)c + 3];
+        double *inflow = rhs + (size_t)c * np;
+        for (int k = 0; k < np; k++) inflow[k] = inflow[k] + flux_sign[i] * flow[k] / vol;
+      }
+    }
+  }
+  return 0;
+}
+
+void wo_flow_pre_iteration(wo_flow *f) { /* :2108-2122 */
+  memcpy(f->last_iteration_fluid, f->fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double));
+}
+void wo_flow_pre_timestep(wo_flow *f) { /* :2022-2035 */
+  memcpy(f->last_timestep_fluid, f->fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double));
+}
+void wo_flow_pre_retry_timestep(wo_flow *f) { /* :2093-2104 */
+  memcpy(f->fluid, f->last_timestep_fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double));
+}
+
+/* fluid_transitions: flow_simulation.F90:2419-2576.  changed_y keeps the reference's
+   semantics: it is overwritten per cell by check_primary_variables, so its final value
+   is the last visited cell's; changed_search is sticky. */
+int wo_flow_fluid_transitions(wo_flow *f, const double *y_old, double *search, double *y, int *changed_search,
+                              int *changed_y) {
+  int err = 0, np = f->np;
+  *changed_search = 0;
+  *changed_y = 0;
+  double primary[WO_MAX_NP], old_primary[WO_MAX_NP];
+  for (int c = 0; c < f->mesh.nowned; c++) {
+    double *fl = f->fluid + (size_t)c * f->dof;
+    const double *ofl = f->last_iteration_fluid + (size_t)c * f->dof;
+    double *yc = y + (size_t)c * np;
+    const double *yo = y_old + (size_t)c * np;
+    double *sc = search + (size_t)c * np;
+    int transition = 0;
+    wo_eos_unscale(f->eos, yc, nint_(fl[2]), primary);
+    wo_eos_unscale(f->eos, yo, nint_(ofl[2]), old_primary);
+    fl[3] = fl[2]; /* old_region = region :2502 */
+    err = wo_eos_transition(f->eos, old_primary, primary, ofl, fl, &transition);
+    if (err == 0) {
+      err = wo_eos_check_primary_variables(f->eos, fl, primary, changed_y);
+      if (err == 0) {
+        if (transition) *changed_y = 1;
+      } else
+        break;
+      if (*changed_y) {
+        *changed_search = 1;
+        wo_eos_scale(f->eos, primary, nint_(fl[2]), yc);
+        for (int k = 0; k < np; k++) sc[k] = yo[k] - yc[k];
+      }
+    } else
+      break;
+  }
+  return err;
+}
+
+/* SNES_residual + backwards_Euler_residual: timestepper.F90:345-374, 587-624 */
+int wo_residual_be(wo_flow *f, const double *y, const double *lhs_last, double dt, const int32_t *perturbed,
+                   int nperturbed, double *lhs, double *rhs, double *r) {
+  size_t n = (size_t)f->mesh.nowned * f->np;
+  int err = wo_flow_pre_eval(f, y, perturbed, nperturbed);
+  if (err) return err;
+  err = wo_flow_cell_balances(f, lhs);
+  if (err) return err;
+  for (size_t i = 0; i < n; i++) r[i] = lhs[i];                 /* VecCopy */
+  for (size_t i = 0; i < n; i++) r[i] = r[i] + (-1.0) * lhs_last[i]; /* VecAXPY */
+  err = wo_flow_cell_inflows(f, rhs);
+  if (err) return err;
+  for (size_t i = 0; i < n; i++) r[i] = r[i] + (-dt) * rhs[i];   /* VecAXPY */
+  return 0;
+}
+
+/* dm_utils.F90:644-685; VecMax returns the first location of the maximum */
+void wo_vec_max_pointwise_abs_scale(const double *v, const double *scale, double tol, int n, double *maxval,
+                                    int *maxloc) {
+  double best = -INFINITY;
+  int loc = -1;
+  for (int i = 0; i < n; i++) {
+    double s = fmax(fabs(scale[i]), tol);
+    double q = fabs(v[i]) / s;
+    if (q > best) {
+      best = q;
+      loc = i;
+    }
+  }
+  *maxval = best;
+  *maxloc = loc;
+}
