@@ -1,0 +1,317 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libwaiwera_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(waiwera_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libwaiwera_oracle.so")
+
+WO_MAX_TABLE = 16
+THERMO_IAPWS, THERMO_IFC67 = 0, 1
+EOS_WE, EOS_W, EOS_WCE, EOS_WAE = 0, 1, 2, 3
+RP_FULLY_MOBILE, RP_LINEAR, RP_PICKENS, RP_COREY, RP_GRANT, RP_VAN_GENUCHTEN, RP_TABLE = range(7)
+CP_ZERO, CP_LINEAR, CP_VAN_GENUCHTEN, CP_TABLE = range(4)
+PC_NONE, PC_PBJACOBI, PC_BJACOBI_ILU0 = 0, 1, 2
+KSP_GMRES, KSP_BCGS = 0, 1
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+class Relperm(C.Structure):
+    _fields_ = [("type", C.c_int), ("p", C.c_double * 8), ("nl", C.c_int), ("nv", C.c_int),
+                ("lx", C.c_double * WO_MAX_TABLE), ("ly", C.c_double * WO_MAX_TABLE),
+                ("vx", C.c_double * WO_MAX_TABLE), ("vy", C.c_double * WO_MAX_TABLE)]
+
+
+class Cappress(C.Structure):
+    _fields_ = [("type", C.c_int), ("p", C.c_double * 8), ("n", C.c_int),
+                ("x", C.c_double * WO_MAX_TABLE), ("y", C.c_double * WO_MAX_TABLE)]
+
+
+class Params(C.Structure):
+    _fields_ = [("eos", C.c_int), ("thermo", C.c_int), ("extrapolate", C.c_int),
+                ("pressure_scale", C.c_double), ("temperature_scale", C.c_double),
+                ("eos_w_temperature", C.c_double),
+                ("relperm", Relperm), ("cappress", Cappress), ("gravity", C.c_double * 3)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("ncell", C.c_int), ("ninterior", C.c_int), ("nowned", C.c_int), ("nface", C.c_int),
+                ("face_cells", c_ip), ("face_geom", c_dp), ("cell_geom", c_dp), ("rock", c_dp)]
+
+
+class Bsr(C.Structure):
+    _fields_ = [("nb", C.c_int), ("bs", C.c_int), ("nnzb", C.c_int),
+                ("rowptr", c_ip), ("colidx", c_ip), ("val", c_dp)]
+
+
+class KspOpts(C.Structure):
+    _fields_ = [("type", C.c_int), ("restart", C.c_int), ("maxit", C.c_int),
+                ("rtol", C.c_double), ("atol", C.c_double), ("dtol", C.c_double)]
+
+
+class NewtonOpts(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("min_iterations", C.c_int),
+                ("rel_tol", C.c_double), ("abs_tol", C.c_double),
+                ("update_rel_tol", C.c_double), ("update_abs_tol", C.c_double),
+                ("fd_err", C.c_double), ("fd_umin", C.c_double), ("pc_type", C.c_int), ("ksp", KspOpts)]
+
+
+class NewtonResult(C.Structure):
+    _fields_ = [("reason", C.c_int), ("iterations", C.c_int), ("linear_iterations", C.c_int),
+                ("max_residual", C.c_double * 32), ("lin_its", C.c_int * 32)]
+
+
+def build(force=False):
+    """Compile the oracle with gcc (oracle/Makefile)."""
+    if force:
+        subprocess.check_call(["make", "-C", _HERE, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        build()
+    L = C.CDLL(_LIB)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    sig = {
+        "wo_powertable_eval": (None, [c_ip, i, d, c_ip, i, c_dp]),
+        "wo_thermo_create": (vp, [i, i]),
+        "wo_thermo_destroy": (None, [vp]),
+        "wo_region_properties": (i, [vp, i, c_dp, c_dp]),
+        "wo_region_viscosity": (d, [vp, i, d, d, d]),
+        "wo_saturation_pressure": (i, [vp, d, c_dp]),
+        "wo_saturation_temperature": (i, [vp, d, c_dp]),
+        "wo_phase_composition": (i, [vp, i, d, d]),
+        "wo_boundary23_pressure": (d, [d]),
+        "wo_boundary23_temperature": (d, [d]),
+        "wo_relperm_values": (None, [C.POINTER(Relperm), d, c_dp]),
+        "wo_cappress_value": (d, [C.POINTER(Cappress), d, d]),
+        "wo_eos_create": (vp, [C.POINTER(Params)]),
+        "wo_eos_destroy": (None, [vp]),
+        "wo_eos_num_primary": (i, [vp]),
+        "wo_eos_fluid_dof": (i, [vp]),
+        "wo_eos_scale": (None, [vp, c_dp, i, c_dp]),
+        "wo_eos_unscale": (None, [vp, c_dp, i, c_dp]),
+        "wo_eos_bulk_properties": (i, [vp, c_dp, c_dp]),
+        "wo_eos_phase_properties": (i, [vp, c_dp, c_dp, c_dp]),
+        "wo_eos_transition": (i, [vp, c_dp, c_dp, c_dp, c_dp, C.POINTER(i)]),
+        "wo_eos_check_primary_variables": (i, [vp, c_dp, c_dp, C.POINTER(i)]),
+        "wo_eos_conductivity": (d, [c_dp, c_dp, i]),
+        "wo_cell_balance": (None, [c_dp, c_dp, i, i, i, c_dp]),
+        "wo_face_flux": (None, [c_dp, c_dp, c_dp, c_dp, c_dp, i, i, i, i, i, c_dp]),
+        "wo_face_calculate_distances": (None, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "wo_face_harmonic_average": (d, [c_dp, c_dp]),
+        "wo_flow_create": (vp, [C.POINTER(Params), C.POINTER(Mesh)]),
+        "wo_flow_destroy": (None, [vp]),
+        "wo_flow_eos": (vp, [vp]),
+        "wo_flow_fluid": (c_dp, [vp]),
+        "wo_flow_current_fluid": (c_dp, [vp]),
+        "wo_flow_flux": (c_dp, [vp]),
+        "wo_flow_fluid_init": (i, [vp, c_dp, c_ip]),
+        "wo_flow_set_boundary": (i, [vp, i, i, c_dp, i]),
+        "wo_flow_pre_eval": (i, [vp, c_dp, c_ip, i]),
+        "wo_flow_cell_balances": (i, [vp, c_dp]),
+        "wo_flow_cell_inflows": (i, [vp, c_dp]),
+        "wo_flow_pre_iteration": (None, [vp]),
+        "wo_flow_pre_timestep": (None, [vp]),
+        "wo_flow_pre_retry_timestep": (None, [vp]),
+        "wo_flow_fluid_transitions": (i, [vp, c_dp, c_dp, c_dp, C.POINTER(i), C.POINTER(i)]),
+        "wo_flow_get_regions": (None, [vp, c_ip]),
+        "wo_residual_be": (i, [vp, c_dp, c_dp, d, c_ip, i, c_dp, c_dp, c_dp]),
+        "wo_vec_max_pointwise_abs_scale": (None, [c_dp, c_dp, d, i, c_dp, C.POINTER(i)]),
+        "wo_bsr_from_mesh": (C.POINTER(Bsr), [C.POINTER(Mesh), i]),
+        "wo_bsr_destroy": (None, [C.POINTER(Bsr)]),
+        "wo_bsr_spmv": (None, [C.POINTER(Bsr), c_dp, c_dp]),
+        "wo_bsr_coloring": (i, [C.POINTER(Bsr), c_ip]),
+        "wo_fd_jacobian": (i, [vp, c_dp, c_dp, d, c_dp, c_ip, i, d, d, C.POINTER(Bsr)]),
+        "wo_pc_create": (vp, [C.POINTER(Bsr), i, c_ip]),
+        "wo_pc_apply": (None, [vp, c_dp, c_dp]),
+        "wo_pc_destroy": (None, [vp]),
+        "wo_ksp_solve": (i, [C.POINTER(Bsr), vp, C.POINTER(KspOpts), c_dp, c_dp, C.POINTER(i), c_dp]),
+        "wo_newton_solve_be": (i, [vp, C.POINTER(Bsr), c_ip, i, c_ip, C.POINTER(NewtonOpts), d, c_dp, c_dp,
+                                   C.POINTER(NewtonResult)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def dp(a):
+    """double* view of a contiguous float64 numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_dp)
+
+
+def ip(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_ip)
+
+
+def make_relperm(kind="linear", **kw):
+    r = Relperm()
+    if kind == "fully_mobile":
+        r.type = RP_FULLY_MOBILE
+    elif kind == "linear":
+        r.type = RP_LINEAR
+        liq = kw.get("liquid", (0.0, 1.0))
+        vap = kw.get("vapour", (0.0, 1.0))
+        r.p[0], r.p[1], r.p[2], r.p[3] = liq[0], liq[1], vap[0], vap[1]
+    elif kind == "pickens":
+        r.type = RP_PICKENS
+        r.p[0] = kw.get("power", 1.0)
+    elif kind in ("corey", "grant"):
+        r.type = RP_COREY if kind == "corey" else RP_GRANT
+        r.p[0], r.p[1] = kw.get("slr", 0.3), kw.get("ssr", 0.05 if kind == "corey" else 0.6)
+    elif kind == "van_genuchten":
+        r.type = RP_VAN_GENUCHTEN
+        r.p[0], r.p[1], r.p[2] = kw.get("lambda_", 0.45), kw.get("slr", 1e-3), kw.get("sls", 1.0)
+        r.p[3] = 0.0 if "ssr" in kw else 1.0
+        r.p[4] = kw.get("ssr", 0.0)
+    elif kind == "table":
+        r.type = RP_TABLE
+        liq, vap = kw["liquid"], kw["vapour"]
+        r.nl, r.nv = len(liq), len(vap)
+        for k, (x, y) in enumerate(liq):
+            r.lx[k], r.ly[k] = x, y
+        for k, (x, y) in enumerate(vap):
+            r.vx[k], r.vy[k] = x, y
+    else:
+        raise ValueError(kind)
+    return r
+
+
+def make_cappress(kind="zero", **kw):
+    c = Cappress()
+    if kind == "zero":
+        c.type = CP_ZERO
+    elif kind == "linear":
+        c.type = CP_LINEAR
+        lim = kw.get("saturation_limits", (0.0, 1.0))
+        c.p[0], c.p[1], c.p[2] = lim[0], lim[1], kw.get("pressure", 0.125e5)
+    elif kind == "van_genuchten":
+        c.type = CP_VAN_GENUCHTEN
+        c.p[0], c.p[1], c.p[2], c.p[3] = kw.get("P0", 0.125e5), kw.get("lambda_", 0.45), kw.get("slr", 1e-3), kw.get("sls", 1.0)
+        c.p[4] = kw.get("Pmax", 0.0)
+        c.p[5] = 1.0 if "Pmax" in kw else 0.0
+    elif kind == "table":
+        c.type = CP_TABLE
+        pts = kw["pressure"]
+        c.n = len(pts)
+        for k, (x, y) in enumerate(pts):
+            c.x[k], c.y[k] = x, y
+    else:
+        raise ValueError(kind)
+    return c
+
+
+def make_params(eos=EOS_WE, thermo=THERMO_IAPWS, relperm=None, cappress=None, gravity=(0.0, 0.0, -9.8),
+                extrapolate=0, eos_w_temperature=20.0):
+    p = Params()
+    p.eos, p.thermo, p.extrapolate = eos, thermo, extrapolate
+    p.pressure_scale, p.temperature_scale = 1.0e6, 1.0e2
+    p.eos_w_temperature = eos_w_temperature
+    p.relperm = relperm if relperm is not None else make_relperm("linear")
+    p.cappress = cappress if cappress is not None else make_cappress("zero")
+    for k in range(3):
+        p.gravity[k] = gravity[k]
+    return p
+
+
+class Flow:
+    """Thin OO wrapper over wo_flow for the tests and the CPU baseline."""
+
+    def __init__(self, params, ncell, ninterior, nowned, face_cells, face_geom, cell_geom, rock):
+        L = lib()
+        self.L = L
+        self.params = params
+        self._keep = (np.ascontiguousarray(face_cells, np.int32), np.ascontiguousarray(face_geom, np.float64),
+                      np.ascontiguousarray(cell_geom, np.float64), np.ascontiguousarray(rock, np.float64))
+        m = Mesh()
+        m.ncell, m.ninterior, m.nowned, m.nface = ncell, ninterior, nowned, len(self._keep[0]) // 2
+        m.face_cells, m.face_geom, m.cell_geom, m.rock = ip(self._keep[0]), dp(self._keep[1]), dp(self._keep[2]), dp(self._keep[3])
+        self.mesh = m
+        self.h = L.wo_flow_create(C.byref(params), C.byref(m))
+        assert self.h
+        self.eos = L.wo_flow_eos(self.h)
+        self.np = L.wo_eos_num_primary(self.eos)
+        self.dof = L.wo_eos_fluid_dof(self.eos)
+        self.ncell, self.nowned, self.ninterior = ncell, nowned, ninterior
+        self.n = nowned * self.np
+
+    def __del__(self):
+        try:
+            self.L.wo_flow_destroy(self.h)
+        except Exception:
+            pass
+
+    def fluid(self):
+        return np.ctypeslib.as_array(self.L.wo_flow_fluid(self.h), shape=(self.ncell, self.dof))
+
+    def current_fluid(self):
+        return np.ctypeslib.as_array(self.L.wo_flow_current_fluid(self.h), shape=(self.ncell, self.dof))
+
+    def fluid_init(self, y, region):
+        return self.L.wo_flow_fluid_init(self.h, dp(y), ip(region))
+
+    def set_boundary(self, ghost, interior, primary, region):
+        pr = np.ascontiguousarray(primary, np.float64)
+        return self.L.wo_flow_set_boundary(self.h, ghost, interior, dp(pr), region)
+
+    def regions(self):
+        r = np.zeros(self.ncell, np.int32)
+        self.L.wo_flow_get_regions(self.h, ip(r))
+        return r
+
+    def residual(self, y, lhs_last, dt, perturbed=None):
+        lhs, rhs, r = np.zeros(self.n), np.zeros(self.n), np.zeros(self.n)
+        npert = 0 if perturbed is None else len(perturbed)
+        err = self.L.wo_residual_be(self.h, dp(y), dp(lhs_last), dt, ip(perturbed), npert, dp(lhs), dp(rhs), dp(r))
+        return err, lhs, rhs, r
+
+    def lhs(self, y):
+        """pre_eval (unperturbed) + cell_balances."""
+        out = np.zeros(self.n)
+        err = self.L.wo_flow_pre_eval(self.h, dp(y), None, 0)
+        if err == 0:
+            err = self.L.wo_flow_cell_balances(self.h, dp(out))
+        return err, out
+
+    def bsr(self):
+        return self.L.wo_bsr_from_mesh(C.byref(self.mesh), self.np)
+
+
+def bsr_arrays(A):
+    a = A.contents
+    rowptr = np.ctypeslib.as_array(a.rowptr, shape=(a.nb + 1,))
+    colidx = np.ctypeslib.as_array(a.colidx, shape=(a.nnzb,))
+    val = np.ctypeslib.as_array(a.val, shape=(a.nnzb, a.bs * a.bs))
+    return rowptr, colidx, val
+
+
+def max_scaled(v, scale, tol):
+    mv, ml = C.c_double(), C.c_int()
+    lib().wo_vec_max_pointwise_abs_scale(dp(v), dp(scale), tol, len(v), C.byref(mv), C.byref(ml))
+    return mv.value, ml.value
