@@ -1,0 +1,254 @@
+/*
+ * waiwera_b200.h -- C ABI of the B200-native Newton-step engine for Waiwera.
+ *
+ * One opaque context per GPU (one process per GPU).  Every entry point takes
+ * plain pointers and sizes; array arguments may be HOST or DEVICE pointers
+ * (detected with cudaPointerGetAttributes; host arrays are staged through
+ * pinned buffers).  Array record layouts are the reference's own, so buffers
+ * obtained with VecGetArrayF90 on the Fortran side pass straight through:
+ *   fluid record   7+nc-1 + nph*(8+nc-1) doubles   (src/fluid.F90:232-267)
+ *   rock record    8 doubles                        (src/rock.F90:97-112)
+ *   cell geometry  4 doubles                        (src/cell.F90:54-57)
+ *   face geometry  12 doubles                       (src/face.F90:67-76)
+ *   primaries      np doubles per cell, SCALED      (src/eos.F90:186-210)
+ *   Jacobian       BAIJ: rowptr/colidx + bs*bs column-major blocks
+ *                                                   (src/ode.F90:266-287)
+ *
+ * Return value of every function: 0 ok; >0 recoverable physics / domain
+ * error (the reference's `err` argument, already reduced over all GPUs of the
+ * communicator -- src/mpi_utils.F90:46); <0 fatal (CUDA/NCCL/usage), message
+ * via wb_last_error().  Calls are stream-ordered on the context's stream and
+ * synchronous at return.  Not re-entrant per context.
+ *
+ * Each entry point cites the reference interface it stands in for.
+ */
+#ifndef WAIWERA_B200_H
+#define WAIWERA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB_VERSION 100
+
+/* thermodynamic formulation (src/thermodynamics_setup.F90:34-35) */
+#define WB_THERMO_IAPWS 0
+#define WB_THERMO_IFC67 1
+
+/* equation of state (src/eos_setup.F90) */
+#define WB_EOS_WE 0 /* water + energy, 2 primaries        (src/eos_we.F90)  */
+#define WB_EOS_W 1  /* isothermal water, 1 primary        (src/eos_w.F90)   */
+
+/* relative permeability curves (src/relative_permeability.F90:197-558) */
+#define WB_RP_FULLY_MOBILE 0
+#define WB_RP_LINEAR 1
+#define WB_RP_PICKENS 2
+#define WB_RP_COREY 3
+#define WB_RP_GRANT 4
+#define WB_RP_VAN_GENUCHTEN 5
+#define WB_RP_TABLE 6
+/* capillary pressure curves (src/capillary_pressure.F90:159-358) */
+#define WB_CP_ZERO 0
+#define WB_CP_LINEAR 1
+#define WB_CP_VAN_GENUCHTEN 2
+#define WB_CP_TABLE 3
+
+#define WB_MAX_TABLE 16
+#define WB_MAX_NP 3
+
+typedef struct {
+  int type;
+  /* linear: liquid limits p[0..1], vapour limits p[2..3]; pickens: p[0]=power;
+     corey/grant: p[0]=slr, p[1]=ssr;
+     van Genuchten: p[0]=lambda, p[1]=slr, p[2]=sls, p[3]=sum_unity(0/1), p[4]=ssr;
+     table: nl / nv points (saturation, value) sorted by saturation */
+  double p[8];
+  int nl, nv;
+  double lx[WB_MAX_TABLE], ly[WB_MAX_TABLE], vx[WB_MAX_TABLE], vy[WB_MAX_TABLE];
+} wb_relperm;
+
+typedef struct {
+  int type;
+  /* linear: p[0..1] saturation limits, p[2] pressure;
+     van Genuchten: p[0]=P0, p[1]=lambda, p[2]=slr, p[3]=sls, p[4]=Pmax, p[5]=apply_Pmax(0/1);
+     table: n points sorted by saturation */
+  double p[8];
+  int n;
+  double x[WB_MAX_TABLE], y[WB_MAX_TABLE];
+} wb_cappress;
+
+/* what flow_simulation_init reads from the JSON input for this path
+   (src/flow_simulation.F90:882-1045, src/eos_we.F90:75-109) */
+typedef struct {
+  int eos;         /* WB_EOS_* */
+  int thermo;      /* WB_THERMO_* */
+  int extrapolate; /* thermodynamics.extrapolate */
+  double pressure_scale, temperature_scale; /* eos.primary.scale.* (<=0: defaults 1e6, 1e2) */
+  double eos_w_temperature;                 /* eos.temperature for eos_w */
+  wb_relperm relperm;
+  wb_cappress cappress;
+  double gravity[3];
+} wb_params;
+
+typedef struct wb_ctx wb_ctx;
+
+const char *wb_last_error(void);
+int wb_version(void);
+
+/* ---- life cycle ------------------------------------------------------- */
+/* flow_simulation_init (src/flow_simulation.F90:882) / destroy (:1049) */
+int wb_create(const wb_params *prm, int device, wb_ctx **out);
+int wb_destroy(wb_ctx *ctx);
+int wb_num_primary(const wb_ctx *ctx);
+int wb_fluid_dof(const wb_ctx *ctx);
+
+/*
+ * Mesh arrays the path consumes.  Local cell numbering:
+ * owned cells [0,nowned), partition ghost cells [nowned,ninterior), boundary
+ * (Dirichlet) ghost cells [ninterior,ncell).  face_cells: 2 local cell indices
+ * per flux face in mesh%flux_face order (src/mesh.F90:769-802), normal from
+ * cell 1 to cell 2.  Also builds the BAIJ pattern of the Jacobian
+ * (src/dm_utils.F90:1041-1051: row i = {i} U face neighbours with dofs; columns
+ * in local numbering, ghost columns >= nowned).
+ */
+int wb_set_mesh(wb_ctx *ctx, int ncell, int ninterior, int nowned, int nface, const int32_t *face_cells,
+                const double *face_geom, const double *cell_geom, const double *rock);
+
+/* Jacobian pattern built by wb_set_mesh (DMCreateMatrix on interior_dm, src/ode.F90:275-283).
+   Pointers are DEVICE pointers owned by the context (vals: nnzb*bs*bs). */
+int wb_jacobian_pattern(wb_ctx *ctx, int *nb, int *bs, int *nnzb, const int32_t **rowptr, const int32_t **colidx,
+                        double **vals);
+/* copy pattern / values to host arrays (any may be NULL) */
+int wb_jacobian_get(wb_ctx *ctx, int32_t *rowptr, int32_t *colidx, double *vals);
+
+/* ---- multi-GPU -------------------------------------------------------- */
+/* NCCL communicator over the ranks of the partition (replaces PetscSF /
+   VecScatter, src/dm_utils.F90:480-498).  id: 128-byte ncclUniqueId made by
+   wb_comm_unique_id on rank 0 and broadcast by the host (torch.distributed / MPI). */
+int wb_comm_unique_id(void *id128);
+int wb_comm_init(wb_ctx *ctx, int rank, int nranks, const void *id128);
+/* halo plan: for each neighbour rank, the owned cells to send and the ghost cells
+   (local indices in [nowned,ninterior)) to receive, CSR style. */
+int wb_set_halo(wb_ctx *ctx, int nneigh, const int32_t *neigh_rank, const int32_t *send_ptr,
+                const int32_t *send_idx, const int32_t *recv_ptr, const int32_t *recv_idx);
+/* global offset of this rank's first owned cell (VecGetOwnershipRange / bs) */
+int wb_set_global_offset(wb_ctx *ctx, int64_t first_cell, int64_t ncell_global);
+
+/* ---- state ------------------------------------------------------------ */
+/* fluid_init (src/flow_simulation.F90:2171-2287): regions + fluid properties from
+   scaled primaries y[nowned*np] and region[nowned]. */
+int wb_fluid_init(wb_ctx *ctx, const double *y, const int32_t *region);
+/* Dirichlet boundary ghost cell (src/mesh.F90:1185-1202): rock copied from the interior
+   cell, fluid record from UNSCALED primary and region. */
+int wb_set_boundary(wb_ctx *ctx, int ghost_cell, int interior_cell, const double *primary, int region);
+/* current fluid records of all local cells, reference AoS layout [ncell*fluid_dof] */
+int wb_get_fluid(wb_ctx *ctx, double *fluid);
+int wb_get_regions(wb_ctx *ctx, int32_t *region);
+/* ode hooks pre_iteration / pre_timestep / pre_retry_timestep
+   (src/flow_simulation.F90:2108, :2022, :2093) */
+int wb_pre_iteration(wb_ctx *ctx);
+int wb_pre_timestep(wb_ctx *ctx);
+int wb_pre_retry_timestep(wb_ctx *ctx);
+
+/* ---- function evaluation (ode_type lhs / rhs, SNES_residual) ----------- */
+/* pre_eval (src/flow_simulation.F90:2126): fluid_properties for y.  perturbed /
+   nperturbed are the block columns MatFDColoring perturbed (src/dm_utils.F90:1544);
+   nperturbed == 0 is the "unperturbed" evaluation that also updates the stored fluid. */
+int wb_pre_eval(wb_ctx *ctx, const double *y, const int32_t *perturbed, int nperturbed);
+/* cell_balances (src/flow_simulation.F90:1242) and cell_inflows (:1334) for the state of the
+   last wb_pre_eval; out arrays nowned*np */
+int wb_cell_balances(wb_ctx *ctx, double *lhs);
+int wb_cell_inflows(wb_ctx *ctx, double *rhs);
+/* SNES_residual + backwards_Euler_residual (src/timestepper.F90:587, :345):
+   r = L(y) - lhs_last - dt*R(y); includes pre_eval.  lhs / rhs may be NULL. */
+int wb_residual_be(wb_ctx *ctx, const double *y, const double *lhs_last, double dt, const int32_t *perturbed,
+                   int nperturbed, double *lhs, double *rhs, double *r);
+/* vec_max_pointwise_abs_scale (src/dm_utils.F90:644-685): max_i |v_i| / max(|scale_i|, tol)
+   and its first (global) index, reduced over all ranks */
+int wb_max_scaled(wb_ctx *ctx, const double *v, const double *scale, double tol, double *maxval,
+                  int64_t *maxloc);
+
+/* ---- Jacobian (SNESComputeJacobianDefaultColor, src/timestepper.F90:1584-1611) -- */
+/* Local finite differences with the MATMFFD_DS step rule (err, umin): fills the
+   context's BAIJ matrix with J(:,j) = (F(y + h_j e_j) - F(y)) / h_j for the BE residual.
+   vals_out (host or device, may be NULL) receives nnzb*bs*bs values. */
+int wb_jacobian_be(wb_ctx *ctx, const double *y, const double *lhs_last, double dt, double fd_err,
+                   double fd_umin, double *vals_out);
+/* the same through the reference's colouring loop (one masked residual evaluation per colour
+   and per variable); slower, kept for parity checks against the local assembly */
+int wb_jacobian_be_colored(wb_ctx *ctx, const double *y, const double *lhs_last, double dt, double fd_err,
+                           double fd_umin, double *vals_out, int *ncolors);
+
+/* ---- transitions (post_linesearch, src/flow_simulation.F90:2419-2576) --- */
+int wb_fluid_transitions(wb_ctx *ctx, const double *y_old, double *search, double *y, int *changed_search,
+                         int *changed_y);
+
+/* ---- Mat / PC / KSP (PETSc plug-in seam, src/timestepper.F90:1645-1836) -- */
+typedef struct wb_mat wb_mat;
+typedef struct wb_pc wb_pc;
+
+/* MatCreateBAIJ + MatSetValuesBlocked: square block matrix, nb block rows, ncolb block
+   columns (>= nb; columns >= nb are ghost columns filled by the halo), column-major blocks. */
+int wb_mat_create(wb_ctx *ctx, int nb, int ncolb, int bs, int nnzb, const int32_t *rowptr,
+                  const int32_t *colidx, const double *vals, wb_mat **out);
+int wb_mat_set_values(wb_mat *A, const double *vals);
+int wb_mat_destroy(wb_mat *A);
+/* the context's own Jacobian as a wb_mat (borrowed; do not destroy) */
+int wb_jacobian_mat(wb_ctx *ctx, wb_mat **out);
+/* MatMult (MatMult_SeqBAIJ_2/3, MatMult_MPIBAIJ incl. ghost scatter): y = A x; x, y: nb*bs */
+int wb_mat_mult(wb_mat *A, const double *x, double *y);
+
+#define WB_PC_NONE 0
+#define WB_PC_PBJACOBI 1 /* point-block Jacobi */
+#define WB_PC_BJACOBI_ILU0 2 /* block Jacobi, ILU(0) natural ordering on each block */
+/* PCSetUp.  nblocks: number of block-Jacobi sub-domains on this GPU (PETSc
+   -pc_bjacobi_local_blocks; 1 = one ILU(0) over all owned rows, the PETSc default).
+   block_of_row[nb] (host, may be NULL => contiguous equal split) assigns rows to blocks. */
+int wb_pc_setup(wb_mat *A, int type, int nblocks, const int32_t *block_of_row, wb_pc **out);
+int wb_pc_apply(wb_pc *pc, const double *r, double *z);
+int wb_pc_destroy(wb_pc *pc);
+
+#define WB_KSP_GMRES 0
+#define WB_KSP_BCGS 1
+typedef struct {
+  int type, restart, maxit;
+  double rtol, atol, dtol;
+} wb_ksp_opts;
+/* KSPSolve with zero initial guess, left preconditioning; reason follows KSPConvergedReason */
+int wb_ksp_solve(wb_mat *A, wb_pc *pc, const wb_ksp_opts *opts, const double *b, double *x, int *its,
+                 int *reason, double *rnorm);
+
+/* ---- Newton (SNESSolve as configured by timestepper.F90:1552-1641) ------ */
+typedef struct {
+  int max_iterations, min_iterations;
+  double rel_tol, abs_tol, update_rel_tol, update_abs_tol;
+  double fd_err, fd_umin;
+  int pc_type, pc_nblocks;
+  wb_ksp_opts ksp;
+} wb_newton_opts;
+typedef struct {
+  int reason, iterations, linear_iterations;
+  double max_residual[32];
+  int lin_its[32];
+} wb_newton_result;
+/* one backward-Euler step solve: y in/out (scaled primaries of owned cells) */
+int wb_newton_solve_be(wb_ctx *ctx, const wb_newton_opts *opts, double dt, const double *lhs_last, double *y,
+                       wb_newton_result *res);
+
+/* ---- instrumentation (PetscLogEvent equivalents, src/profiling.F90:42-65) -- */
+/* accumulated device time (ms) and call count of a named phase:
+   "fluid_props", "cell_balances", "cell_inflows", "jacobian", "pc_setup", "ksp_solve", "mat_mult",
+   "pc_apply", "fluid_trans" */
+int wb_timer_get(wb_ctx *ctx, const char *name, double *ms, int64_t *count);
+int wb_timer_reset(wb_ctx *ctx);
+/* number of kernels launched by this context since creation */
+int64_t wb_launch_count(const wb_ctx *ctx);
+/* stream the context launches on (cudaStream_t) */
+void *wb_stream(wb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,258 @@
+"""The device physics headers, compiled for the host, against the CPU oracle.
+
+tests/hostcheck/hostcheck.cpp wraps waiwera_b200/csrc/wb_eos.cuh + wb_thermo.cuh +
+wb_iapws_gen.cuh (the exact source the CUDA kernels inline) behind a few C entry
+points and is compiled here with g++.  This is a CPU-side check of the source
+only -- the product never loads it and has no CPU path; the GPU parity tests
+proper are tests/test_gpu_*.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+LIB = os.path.join(HERE, "hostcheck", "_hostcheck.so")
+SEED = 20240917
+
+
+@pytest.fixture(scope="module")
+def hc(wo):
+    deps = [SRC] + [os.path.join(HERE, "..", "waiwera_b200", "csrc", f)
+                    for f in ("wb_eos.cuh", "wb_thermo.cuh", "wb_iapws_gen.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-o", LIB, SRC])
+    L = C.CDLL(LIB)
+    d, i, dp, ip = C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.hc_region_properties.argtypes = [i, i, i, d, d, dp]
+    L.hc_region_viscosity.restype = d
+    L.hc_region_viscosity.argtypes = [i, i, d, d, d]
+    L.hc_sat_pressure.argtypes = [i, d, dp]
+    L.hc_sat_temperature.argtypes = [i, d, dp]
+    L.hc_relperm.argtypes = [C.c_void_p, d, dp]
+    L.hc_cappress.restype = d
+    L.hc_cappress.argtypes = [C.c_void_p, d, d]
+    L.hc_we_fluid.argtypes = [C.c_void_p, dp, i, dp]
+    L.hc_we_flux.argtypes = [C.c_void_p, dp, dp, dp, dp, i, dp, i, dp, dp]
+    L.hc_we_transition.argtypes = [C.c_void_p, dp, dp, i, d, ip, ip]
+    return L
+
+
+def close(a, b, tol=1e-13):
+    return abs(a - b) <= tol * max(abs(a), abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_region_properties_match_oracle(wo, hc, thermo):
+    rng = np.random.default_rng(SEED)
+    th = wo.lib().wo_thermo_create(thermo, 0)
+    try:
+        cases = [(1, rng.uniform(1e5, 90e6, 200), rng.uniform(5, 340, 200)),
+                 (2, rng.uniform(1e3, 10e6, 200), rng.uniform(200, 780, 200))]
+        if thermo == 0:
+            cases.append((3, rng.uniform(200, 600, 100), rng.uniform(360, 500, 100)))  # (rho, t)
+        for region, ps, ts in cases:
+            for p, t in zip(ps, ts):
+                ref, got = np.zeros(2), np.zeros(2)
+                e0 = wo.lib().wo_region_properties(th, region, wo.dp(np.array([p, t])), wo.dp(ref))
+                e1 = hc.hc_region_properties(thermo, 0, region, p, t, wo.dp(got))
+                assert e0 == e1
+                if e0 == 0:
+                    # same operation order, FMA contraction off on both sides: bit-identical
+                    assert ref[0] == got[0] and ref[1] == got[1], (region, p, t, ref, got)
+                    if region != 3:
+                        v0 = wo.lib().wo_region_viscosity(th, region, t, p, ref[0])
+                        v1 = hc.hc_region_viscosity(thermo, region, t, p, ref[0])
+                        assert v0 == v1
+        # out-of-range error returns
+        for region, p, t in [(1, 20e6, 360.0), (1, 101e6, 60.0), (2, 1e5, 801.0)]:
+            ref, got = np.zeros(2), np.zeros(2)
+            assert wo.lib().wo_region_properties(th, region, wo.dp(np.array([p, t])), wo.dp(ref)) == \
+                hc.hc_region_properties(thermo, 0, region, p, t, wo.dp(got)) == 1
+    finally:
+        wo.lib().wo_thermo_destroy(th)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_saturation_matches_oracle(wo, hc, thermo):
+    rng = np.random.default_rng(SEED + 1)
+    th = wo.lib().wo_thermo_create(thermo, 0)
+    try:
+        for t in list(rng.uniform(1.0, 373.0, 200)) + [0.5, 374.1, 380.0]:
+            a, b = C.c_double(), C.c_double()
+            assert wo.lib().wo_saturation_pressure(th, t, C.byref(a)) == hc.hc_sat_pressure(thermo, t, C.byref(b))
+            assert a.value == b.value
+        for p in list(rng.uniform(700.0, 22.0e6, 200)) + [500.0, 23e6]:
+            a, b = C.c_double(), C.c_double()
+            assert wo.lib().wo_saturation_temperature(th, p, C.byref(a)) == hc.hc_sat_temperature(thermo, p, C.byref(b))
+            assert a.value == b.value
+    finally:
+        wo.lib().wo_thermo_destroy(th)
+
+
+def curve_cases(wo):
+    return [
+        (wo.make_relperm("linear"), wo.make_cappress("zero")),
+        (wo.make_relperm("linear", liquid=(0.1, 0.9), vapour=(0.2, 0.8)), wo.make_cappress("linear", saturation_limits=(0.1, 0.9), pressure=0.2e5)),
+        (wo.make_relperm("linear", liquid=(0.0, 0.0), vapour=(0.0, 0.0)), wo.make_cappress("zero")),
+        (wo.make_relperm("corey", slr=0.3, ssr=0.05), wo.make_cappress("van_genuchten", P0=0.125e5, lambda_=0.45, slr=1e-3, sls=1.0, Pmax=1e6)),
+        (wo.make_relperm("grant", slr=0.3, ssr=0.1), wo.make_cappress("van_genuchten")),
+        (wo.make_relperm("pickens", power=2.5), wo.make_cappress("zero")),
+        (wo.make_relperm("fully_mobile"), wo.make_cappress("zero")),
+        (wo.make_relperm("van_genuchten", lambda_=0.45, slr=0.1, sls=0.95), wo.make_cappress("zero")),
+        (wo.make_relperm("van_genuchten", lambda_=0.5, slr=0.1, sls=1.0, ssr=0.1), wo.make_cappress("zero")),
+        (wo.make_relperm("table", liquid=[(0, 0), (0.3, 0.1), (0.8, 0.7), (1, 1)], vapour=[(0, 0), (0.5, 0.6), (1, 1)]),
+         wo.make_cappress("table", pressure=[(0, -1e5), (0.4, -2e4), (1.0, 0.0)])),
+    ]
+
+
+def test_curves_match_oracle(wo, hc):
+    rng = np.random.default_rng(SEED + 2)
+    sls = list(rng.uniform(-0.1, 1.1, 100)) + [0.0, 1.0, 0.5, 0.9995, 0.3, 0.05]
+    for rp, cp in curve_cases(wo):
+        for sl in sls:
+            if rp.type == wo.RP_PICKENS and sl < 0:
+                continue
+            a, b = np.zeros(2), np.zeros(2)
+            wo.lib().wo_relperm_values(C.byref(rp), sl, wo.dp(a))
+            hc.hc_relperm(C.byref(rp), sl, wo.dp(b))
+            assert np.array_equal(a, b, equal_nan=True), (rp.type, sl, a, b)
+            assert wo.lib().wo_cappress_value(C.byref(cp), sl, 100.0) == hc.hc_cappress(C.byref(cp), sl, 100.0) or \
+                np.isnan(hc.hc_cappress(C.byref(cp), sl, 100.0))
+
+
+def we_cell(wo, thermo, rng, region):
+    """random valid (primary, region) for eos_we"""
+    th = wo.lib().wo_thermo_create(thermo, 0)
+    try:
+        if region == 1:
+            t = rng.uniform(10, 300)
+            ps = C.c_double()
+            wo.lib().wo_saturation_pressure(th, t, C.byref(ps))
+            return np.array([ps.value + rng.uniform(1e4, 2e7), t])
+        if region == 2:
+            t = rng.uniform(120, 340)
+            ps = C.c_double()
+            wo.lib().wo_saturation_pressure(th, t, C.byref(ps))
+            return np.array([ps.value * rng.uniform(0.05, 0.95), t])
+        return np.array([rng.uniform(1e5, 1.5e7), rng.uniform(0.01, 0.99)])
+    finally:
+        wo.lib().wo_thermo_destroy(th)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_we_fluid_record_matches_oracle(wo, hc, thermo):
+    rng = np.random.default_rng(SEED + 3)
+    rock = np.array([1e-13, 1e-13, 1e-14, 2.5, 1.5, 0.1, 2200.0, 1000.0])
+    for rp, cp in curve_cases(wo)[:5]:
+        prm = wo.make_params(eos=wo.EOS_WE, thermo=thermo, relperm=rp, cappress=cp)
+        eos = wo.lib().wo_eos_create(C.byref(prm))
+        try:
+            for region in (1, 2, 4):
+                for _ in range(40):
+                    primary = we_cell(wo, thermo, rng, region)
+                    ref = np.zeros(23)
+                    ref[2] = region
+                    e0 = wo.lib().wo_eos_bulk_properties(eos, wo.dp(primary), wo.dp(ref))
+                    if e0 == 0:
+                        e0 = wo.lib().wo_eos_phase_properties(eos, wo.dp(primary), wo.dp(rock), wo.dp(ref))
+                    got = np.zeros(23)
+                    e1 = hc.hc_we_fluid(C.byref(prm), wo.dp(primary), region, wo.dp(got))
+                    assert e0 == e1
+                    if e0 == 0:
+                        assert np.array_equal(ref, got), (region, primary, ref - got)
+        finally:
+            wo.lib().wo_eos_destroy(eos)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_we_flux_and_balance_match_oracle(wo, hc, thermo):
+    rng = np.random.default_rng(SEED + 4)
+    rp, cp = curve_cases(wo)[3]
+    prm = wo.make_params(eos=wo.EOS_WE, thermo=thermo, relperm=rp, cappress=cp)
+    eos = wo.lib().wo_eos_create(C.byref(prm))
+    try:
+        for trial in range(300):
+            r1, r2 = rng.choice([1, 2, 4], 2)
+            p1, p2 = we_cell(wo, thermo, rng, r1), we_cell(wo, thermo, rng, r2)
+            if trial % 3 == 0:  # nearly equal states: small gradients, either upstream direction
+                r2 = r1
+                p2 = p1 * (1 + rng.uniform(-1e-4, 1e-4, 2))
+            rock1 = np.array([1e-13, 2e-13, 1e-14, 2.5, 1.5, 0.1, 2200.0, 1000.0]) * rng.uniform(0.5, 1.5, 8)
+            rock2 = np.array([1e-13, 2e-13, 1e-14, 2.5, 1.5, 0.1, 2200.0, 1000.0]) * rng.uniform(0.5, 1.5, 8)
+            d1, d2 = rng.uniform(1, 20, 2)
+            g = np.zeros(12)
+            g[0], g[1], g[2], g[3] = rng.uniform(1, 100), d1, d2, d1 + d2
+            g[7] = rng.choice([0.0, -9.8, 9.8, 3.3])
+            g[11] = float(rng.integers(1, 4))
+            if trial % 10 == 1:  # Dirichlet boundary face: d2 = 0
+                g[2], g[3] = 0.0, d1
+            f1, f2 = np.zeros(23), np.zeros(23)
+            f1[2], f2[2] = r1, r2
+            ok = True
+            for pr, fl, rk in ((p1, f1, rock1), (p2, f2, rock2)):
+                e = wo.lib().wo_eos_bulk_properties(eos, wo.dp(pr), wo.dp(fl))
+                if e == 0:
+                    e = wo.lib().wo_eos_phase_properties(eos, wo.dp(pr), wo.dp(rk), wo.dp(fl))
+                ok = ok and e == 0
+            if not ok:
+                continue
+            ref = np.zeros(4)
+            wo.lib().wo_face_flux(wo.dp(g), wo.dp(rock1), wo.dp(rock2), wo.dp(f1), wo.dp(f2), 1, 2, 2, 2, 0, wo.dp(ref))
+            bref = np.zeros(2)
+            wo.lib().wo_cell_balance(wo.dp(rock1), wo.dp(f1), 1, 2, 2, wo.dp(bref))
+            got, bgot = np.zeros(4), np.zeros(2)
+            assert hc.hc_we_flux(C.byref(prm), wo.dp(g), wo.dp(rock1), wo.dp(rock2), wo.dp(p1), int(r1), wo.dp(p2), int(r2),
+                                 wo.dp(got), wo.dp(bgot)) == 0
+            assert np.array_equal(ref, got), (trial, ref, got)
+            assert np.array_equal(bref, bgot)
+    finally:
+        wo.lib().wo_eos_destroy(eos)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_we_transitions_match_oracle(wo, hc, thermo):
+    rng = np.random.default_rng(SEED + 5)
+    prm = wo.make_params(eos=wo.EOS_WE, thermo=thermo)
+    eos = wo.lib().wo_eos_create(C.byref(prm))
+    th = wo.lib().wo_thermo_create(thermo, 0)
+    ntrans = 0
+    try:
+        for trial in range(400):
+            old_region = int(rng.choice([1, 2, 4]))
+            oldp = we_cell(wo, thermo, rng, old_region)
+            if old_region == 4:
+                newp = oldp + np.array([rng.uniform(-2e5, 2e5), rng.uniform(-1.2, 1.2)])
+                if trial % 7 == 0:
+                    newp[1] = oldp[1]  # degenerate inverse interpolation -> fallback branch
+                    oldp[1] = newp[1] = rng.choice([-0.2, 1.3])
+            else:
+                ps = C.c_double()
+                wo.lib().wo_saturation_pressure(th, oldp[1], C.byref(ps))
+                newp = np.array([ps.value * rng.uniform(0.7, 1.3), oldp[1] + rng.uniform(-5, 5)])
+            old_fluid = np.zeros(23)
+            old_fluid[2] = old_region
+            assert wo.lib().wo_eos_bulk_properties(eos, wo.dp(oldp), wo.dp(old_fluid)) == 0
+            fluid = old_fluid.copy()
+            p_ref = newp.copy()
+            tr = C.c_int()
+            e0 = wo.lib().wo_eos_transition(eos, wo.dp(oldp), wo.dp(p_ref), wo.dp(old_fluid), wo.dp(fluid), C.byref(tr))
+            if e0 == 0:
+                ch = C.c_int()
+                e0 = wo.lib().wo_eos_check_primary_variables(eos, wo.dp(fluid), wo.dp(p_ref), C.byref(ch))
+            p_got = newp.copy()
+            reg, tr1 = C.c_int(old_region), C.c_int()
+            e1 = hc.hc_we_transition(C.byref(prm), wo.dp(oldp), wo.dp(p_got), old_region, old_fluid[1], C.byref(reg), C.byref(tr1))
+            assert (e0 != 0) == (e1 != 0), (trial, e0, e1)
+            if e0 == 0:
+                assert tr.value == tr1.value
+                assert int(round(fluid[2])) == reg.value
+                assert np.array_equal(p_ref, p_got), (trial, p_ref, p_got)
+                ntrans += tr.value
+        assert ntrans > 50
+    finally:
+        wo.lib().wo_eos_destroy(eos)
+        wo.lib().wo_thermo_destroy(th)

@@ -1,0 +1,194 @@
+// wb_common.cuh -- context, error handling, pointer staging, timers.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/waiwera_b200.h"
+#include "wb_eos.cuh"
+
+void wb_set_error(const char *fmt, ...);
+
+#define WB_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      wb_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return -1;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+#define WB_NCCL(call)                                                                      \
+  do {                                                                                     \
+    ncclResult_t r_ = (call);                                                              \
+    if (r_ != ncclSuccess) {                                                               \
+      wb_set_error("%s:%d NCCL error %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+      return -2;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+#define WB_CHECK(cond, ...)    \
+  do {                         \
+    if (!(cond)) {             \
+      wb_set_error(__VA_ARGS__); \
+      return -3;               \
+    }                          \
+  } while (0)
+
+#define WB_TRY(call)        \
+  do {                      \
+    int rc_ = (call);       \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+// number of SMs on a B200; grids of the persistent / grid-stride kernels are sized in multiples of it
+#define WB_NUM_SMS 148
+
+struct WbTimer {
+  double ms = 0.0;
+  int64_t count = 0;
+};
+
+struct WbHalo {
+  int nneigh = 0;
+  std::vector<int> rank;
+  std::vector<int> send_ptr, recv_ptr;  // host CSR
+  int32_t *d_send_idx = nullptr, *d_recv_idx = nullptr;
+  int nsend = 0, nrecv = 0;
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;  // (nsend|nrecv) * maxwidth
+  int maxwidth = 0;
+};
+
+struct wb_mat {
+  wb_ctx *ctx = nullptr;
+  int nb = 0, ncolb = 0, bs = 0, nnzb = 0;
+  int32_t *d_rowptr = nullptr, *d_colidx = nullptr;
+  double *d_val = nullptr;
+  double *d_xloc = nullptr;  // ncolb*bs: x with ghost entries (multi-GPU)
+  std::vector<int32_t> h_rowptr, h_colidx;
+  bool owns = true;
+};
+
+struct wb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  wb_params prm;
+  WbEosParams eos;
+  int np = 0, nc = 0, nph = 0, dof = 0, nf = 0;  // nf: SoA state fields per cell
+
+  // mesh
+  int ncell = 0, ninterior = 0, nowned = 0, nface = 0;
+  std::vector<int32_t> h_face_cells;
+  std::vector<double> h_rock, h_face_geom, h_cell_geom;
+  int32_t *d_face_cells = nullptr;
+  double *d_face = nullptr;   // SoA [6][nface]: area, d1, d2, d12, gravn, k
+  double *d_vol = nullptr;    // [ncell]
+  double *d_rockp = nullptr;  // SoA [5][ncell]: porosity, density, specific heat, wet, dry conductivity
+  // cell -> faces (owned cells), entries in ascending face order = the reference's scatter order
+  int32_t *d_cf_ptr = nullptr, *d_cf_face = nullptr, *d_cf_other = nullptr, *d_cf_bpos = nullptr;
+  int32_t *d_diagpos = nullptr;
+  int maxdeg = 0, ncf = 0;
+  std::vector<int32_t> h_cf_ptr, h_cf_face, h_cf_other;
+
+  // Jacobian
+  wb_mat J;
+  std::vector<int32_t> h_color;
+  int ncolor = 0;
+
+  // state
+  int32_t *d_region = nullptr, *d_region_iter = nullptr, *d_region_step = nullptr;  // [ncell]
+  double *d_T_iter = nullptr, *d_T_step = nullptr;                                   // [ncell]
+  double *d_sat_step = nullptr;  // [nph][ncell] saturations at the last time step (region 3 keeps them)
+  double *d_state = nullptr;     // [(np+1) variants][nf][ncell]
+  double *d_Lvar = nullptr;      // [(np+1)][np][nowned]
+  double *d_dx = nullptr;        // [np][ninterior] FD steps
+  double *d_yloc = nullptr;      // [ninterior*np] primaries incl. partition ghosts
+  double *d_balances = nullptr;  // [nowned*np] lhs of the last unperturbed evaluation
+  int eval_variant = 0;          // state slot of the last wb_pre_eval (0 unperturbed, 1 perturbed scratch)
+  int *d_flags = nullptr;        // [8] device flags (error, changed_y, changed_search, ...)
+  int *h_flags = nullptr;        // pinned mirror
+
+  // scratch pools
+  std::vector<void *> stage;  // device staging buffers (freed at destroy)
+  double *d_red = nullptr;    // reduction scratch
+  double *h_red = nullptr;    // pinned
+  size_t red_cap = 0;
+
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  int64_t first_cell = 0, ncell_global = 0;
+  WbHalo halo;
+
+  // instrumentation
+  std::map<std::string, WbTimer> timers;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ---- pointer staging: accept host or device arrays at the ABI ----------------
+bool wb_is_device_ptr(const void *p);
+
+// RAII-less helpers (ctx owns the temporaries until wb_stage_release)
+struct WbStage {
+  wb_ctx *ctx;
+  std::vector<void *> tmp;
+  struct Out { void *host; void *dev; size_t bytes; };
+  std::vector<Out> outs;
+  explicit WbStage(wb_ctx *c) : ctx(c) {}
+  ~WbStage();
+  // device view of an input array (copied if it lives on the host); nullptr stays nullptr
+  template <class T> const T *in(const T *p, size_t n, int *rc) { return (const T *)in_(p, n * sizeof(T), rc); }
+  // device view of an output (or in/out when `load`) array; copied back by finish()
+  template <class T> T *out(T *p, size_t n, int *rc, bool load = false) { return (T *)out_(p, n * sizeof(T), rc, load); }
+  int finish();  // copies outputs back and synchronises the stream
+  const void *in_(const void *p, size_t bytes, int *rc);
+  void *out_(void *p, size_t bytes, int *rc, bool load);
+};
+
+// ---- timers --------------------------------------------------------------------
+struct WbScopedTimer {
+  wb_ctx *ctx;
+  const char *name;
+  bool on;
+  WbScopedTimer(wb_ctx *c, const char *n);
+  ~WbScopedTimer();
+};
+extern bool g_wb_timers_enabled;
+
+#define WB_LAUNCH(ctx) ((ctx)->launches++)
+
+static inline int wb_grid(size_t n, int block) { return (int)((n + block - 1) / block); }
+
+// internal cross-file API
+int wb_halo_exchange(wb_ctx *ctx, double *vec, int width);  // vec[(ninterior)*width]: fills ghost entries
+int wb_allreduce_sum(wb_ctx *ctx, double *dbuf, int n);     // in-stream, device buffer
+int wb_allreduce_max_int(wb_ctx *ctx, int *dbuf, int n);
+int wb_reduce_flags(wb_ctx *ctx, int nflags);               // device flags -> host (max over ranks)
+
+int wb_spmv_launch(wb_mat *A, const double *d_x, double *d_y);  // device pointers, handles halo
+
+// device-pointer cores shared between the translation units (no staging, no flag check)
+int wb_pre_eval_dev(wb_ctx *c, const double *d_y, bool unperturbed);
+int wb_residual_be_dev(wb_ctx *c, const double *d_y, const double *d_lhs_last, double dt, bool unperturbed,
+                       double *d_lhs, double *d_rhs, double *d_r);
+int wb_jacobian_be_dev(wb_ctx *c, const double *d_y, const double *d_lhs_last, double dt, double fd_err,
+                       double fd_umin, bool base_valid);
+int wb_fluid_transitions_dev(wb_ctx *c, const double *d_y_old, double *d_search, double *d_y);
+int wb_max_scaled_core(wb_ctx *c, const double *d_v, const double *d_s, double tol, int n, double *maxval,
+                       int64_t *maxloc);
+int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z);
+int wb_ksp_solve_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b, double *d_x, int *its,
+                     int *reason, double *rnorm);
+int wb_vec_dot_host(wb_ctx *c, const double *d_a, const double *d_b, size_t n, double *out);
+int wb_vec_axpby_dev(wb_ctx *c, double *z, double a, const double *x, double b, const double *y, size_t n);
+extern "C" int wb_pc_refactor(wb_pc *pc);
+void wb_linalg_release(wb_ctx *c);
+void wb_flow_release(wb_ctx *c);
+void wb_newton_release(wb_ctx *c);

@@ -1,0 +1,331 @@
+// wb_core.cu -- context life cycle, error reporting, pointer staging, timers,
+// NCCL communicator and halo exchange.
+#include <stdarg.h>
+
+#include "wb_common.cuh"
+
+static thread_local char g_err[1024] = "";
+bool g_wb_timers_enabled = true;
+
+void wb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *wb_last_error(void) { return g_err; }
+extern "C" int wb_version(void) { return WB_VERSION; }
+
+bool wb_is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+const void *WbStage::in_(const void *p, size_t bytes, int *rc) {
+  if (!p || bytes == 0) return p;
+  if (wb_is_device_ptr(p)) return p;
+  void *d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) {
+    wb_set_error("staging cudaMalloc(%zu) failed", bytes);
+    *rc = -1;
+    return nullptr;
+  }
+  tmp.push_back(d);
+  if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+    wb_set_error("staging H2D copy failed");
+    *rc = -1;
+  }
+  return d;
+}
+
+void *WbStage::out_(void *p, size_t bytes, int *rc, bool load) {
+  if (!p || bytes == 0) return p;
+  if (wb_is_device_ptr(p)) return p;
+  void *d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) {
+    wb_set_error("staging cudaMalloc(%zu) failed", bytes);
+    *rc = -1;
+    return nullptr;
+  }
+  tmp.push_back(d);
+  if (load && cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+    wb_set_error("staging H2D copy failed");
+    *rc = -1;
+  }
+  outs.push_back({p, d, bytes});
+  return d;
+}
+
+int WbStage::finish() {
+  for (auto &o : outs) WB_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  outs.clear();
+  WB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+WbStage::~WbStage() {
+  if (!tmp.empty()) {
+    cudaStreamSynchronize(ctx->stream);
+    for (void *d : tmp) cudaFree(d);
+  }
+}
+
+WbScopedTimer::WbScopedTimer(wb_ctx *c, const char *n) : ctx(c), name(n), on(g_wb_timers_enabled) {
+  if (on) cudaEventRecord(ctx->ev0, ctx->stream);
+}
+WbScopedTimer::~WbScopedTimer() {
+  if (!on) return;
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  cudaEventSynchronize(ctx->ev1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  WbTimer &t = ctx->timers[name];
+  t.ms += ms;
+  t.count++;
+}
+
+extern "C" int wb_timer_get(wb_ctx *ctx, const char *name, double *ms, int64_t *count) {
+  auto it = ctx->timers.find(name);
+  if (it == ctx->timers.end()) {
+    if (ms) *ms = 0.0;
+    if (count) *count = 0;
+    return 0;
+  }
+  if (ms) *ms = it->second.ms;
+  if (count) *count = it->second.count;
+  return 0;
+}
+extern "C" int wb_timer_reset(wb_ctx *ctx) {
+  ctx->timers.clear();
+  return 0;
+}
+extern "C" int wb_timers_enable(int on) {
+  g_wb_timers_enabled = on != 0;
+  return 0;
+}
+extern "C" int64_t wb_launch_count(const wb_ctx *ctx) { return ctx->launches; }
+extern "C" void *wb_stream(wb_ctx *ctx) { return (void *)ctx->stream; }
+
+extern "C" int wb_create(const wb_params *prm, int device, wb_ctx **out) {
+  WB_CHECK(prm && out, "wb_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    // no CPU path exists: the engine is CUDA only
+    wb_set_error("wb_create: no CUDA device available (%s); waiwera_b200 has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    cudaGetLastError();
+    return -1;
+  }
+  WB_CHECK(device >= 0 && device < ndev, "wb_create: device %d out of range (%d devices)", device, ndev);
+  WB_CUDA(cudaSetDevice(device));
+  wb_ctx *c = new wb_ctx();
+  c->device = device;
+  c->prm = *prm;
+  if (wb_eos_params_make(*prm, c->eos)) {
+    delete c;
+    wb_set_error("wb_create: unsupported eos id %d", prm->eos);
+    return -3;
+  }
+  c->np = c->eos.np;
+  c->nc = c->eos.nc;
+  c->nph = c->eos.nphase;
+  c->dof = 7 + c->nc - 1 + c->nph * (8 + c->nc - 1);  // src/fluid.F90:223-226
+  c->nf = 4 + c->nph * (5 + (c->nc > 1 ? c->nc : 0));
+  WB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  WB_CUDA(cudaEventCreate(&c->ev0));
+  WB_CUDA(cudaEventCreate(&c->ev1));
+  WB_CUDA(cudaMalloc(&c->d_flags, 8 * sizeof(int)));
+  WB_CUDA(cudaMemset(c->d_flags, 0, 8 * sizeof(int)));
+  WB_CUDA(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
+  c->red_cap = 64 * 1024;
+  WB_CUDA(cudaMalloc(&c->d_red, c->red_cap * sizeof(double)));
+  WB_CUDA(cudaMallocHost(&c->h_red, 4096 * sizeof(double)));
+  c->J.ctx = c;
+  *out = c;
+  return 0;
+}
+
+static void free_mat(wb_mat &m) {
+  if (m.owns) {
+    cudaFree(m.d_rowptr);
+    cudaFree(m.d_colidx);
+    cudaFree(m.d_val);
+  }
+  cudaFree(m.d_xloc);
+  m.d_rowptr = m.d_colidx = nullptr;
+  m.d_val = m.d_xloc = nullptr;
+}
+
+void wb_free_mesh(wb_ctx *c) {
+  void *ptrs[] = {c->d_face_cells, c->d_face, c->d_vol, c->d_rockp, c->d_cf_ptr, c->d_cf_face, c->d_cf_other,
+                  c->d_cf_bpos, c->d_diagpos, c->d_region, c->d_region_iter, c->d_region_step, c->d_T_iter,
+                  c->d_T_step, c->d_sat_step, c->d_state, c->d_Lvar, c->d_dx, c->d_yloc, c->d_balances};
+  for (void *p : ptrs) cudaFree(p);
+  c->d_face_cells = c->d_cf_ptr = c->d_cf_face = c->d_cf_other = c->d_cf_bpos = c->d_diagpos = nullptr;
+  c->d_region = c->d_region_iter = c->d_region_step = nullptr;
+  c->d_face = c->d_vol = c->d_rockp = c->d_T_iter = c->d_T_step = c->d_sat_step = nullptr;
+  c->d_state = c->d_Lvar = c->d_dx = c->d_yloc = c->d_balances = nullptr;
+  free_mat(c->J);
+}
+
+extern "C" int wb_destroy(wb_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  wb_newton_release(c);
+  wb_linalg_release(c);
+  wb_flow_release(c);
+  wb_free_mesh(c);
+  for (void *p : c->stage) cudaFree(p);
+  cudaFree(c->halo.d_send_idx);
+  cudaFree(c->halo.d_recv_idx);
+  cudaFree(c->halo.d_sendbuf);
+  cudaFree(c->halo.d_recvbuf);
+  if (c->comm) ncclCommDestroy(c->comm);
+  cudaFree(c->d_flags);
+  cudaFreeHost(c->h_flags);
+  cudaFree(c->d_red);
+  cudaFreeHost(c->h_red);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int wb_num_primary(const wb_ctx *c) { return c->np; }
+extern "C" int wb_fluid_dof(const wb_ctx *c) { return c->dof; }
+
+// ---------------------------------------------------------------- comm
+
+extern "C" int wb_comm_unique_id(void *id128) {
+  ncclUniqueId id;
+  WB_NCCL(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+extern "C" int wb_comm_init(wb_ctx *c, int rank, int nranks, const void *id128) {
+  WB_CUDA(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  WB_NCCL(ncclCommInitRank(&c->comm, nranks, id, rank));
+  c->rank = rank;
+  c->nranks = nranks;
+  return 0;
+}
+
+extern "C" int wb_set_global_offset(wb_ctx *c, int64_t first_cell, int64_t ncell_global) {
+  c->first_cell = first_cell;
+  c->ncell_global = ncell_global;
+  return 0;
+}
+
+extern "C" int wb_set_halo(wb_ctx *c, int nneigh, const int32_t *neigh_rank, const int32_t *send_ptr,
+                           const int32_t *send_idx, const int32_t *recv_ptr, const int32_t *recv_idx) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WbHalo &h = c->halo;
+  cudaFree(h.d_send_idx);
+  cudaFree(h.d_recv_idx);
+  cudaFree(h.d_sendbuf);
+  cudaFree(h.d_recvbuf);
+  h = WbHalo();
+  h.nneigh = nneigh;
+  if (nneigh == 0) return 0;
+  h.rank.assign(neigh_rank, neigh_rank + nneigh);
+  h.send_ptr.assign(send_ptr, send_ptr + nneigh + 1);
+  h.recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1);
+  h.nsend = send_ptr[nneigh];
+  h.nrecv = recv_ptr[nneigh];
+  h.maxwidth = WB_MAX_NP + 1;
+  WB_CUDA(cudaMalloc(&h.d_send_idx, sizeof(int32_t) * (h.nsend + 1)));
+  WB_CUDA(cudaMalloc(&h.d_recv_idx, sizeof(int32_t) * (h.nrecv + 1)));
+  WB_CUDA(cudaMemcpy(h.d_send_idx, send_idx, sizeof(int32_t) * h.nsend, cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMemcpy(h.d_recv_idx, recv_idx, sizeof(int32_t) * h.nrecv, cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMalloc(&h.d_sendbuf, sizeof(double) * (size_t)(h.nsend + 1) * h.maxwidth));
+  WB_CUDA(cudaMalloc(&h.d_recvbuf, sizeof(double) * (size_t)(h.nrecv + 1) * h.maxwidth));
+  return 0;
+}
+
+__global__ void k_halo_pack(const double *__restrict__ vec, const int32_t *__restrict__ idx, int n, int width,
+                            double *__restrict__ buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * width) {
+    int c = i / width, k = i - c * width;
+    buf[i] = vec[(size_t)idx[c] * width + k];
+  }
+}
+__global__ void k_halo_unpack(double *__restrict__ vec, const int32_t *__restrict__ idx, int n, int width,
+                              const double *__restrict__ buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * width) {
+    int c = i / width, k = i - c * width;
+    vec[(size_t)idx[c] * width + k] = buf[i];
+  }
+}
+
+// Ghost exchange of a cell vector with `width` doubles per cell (replaces
+// DMGlobalToLocal / VecScatter, src/dm_utils.F90:480-498).  In-stream; no host sync.
+int wb_halo_exchange(wb_ctx *c, double *vec, int width) {
+  WbHalo &h = c->halo;
+  if (c->nranks <= 1 || h.nneigh == 0) return 0;
+  WB_CHECK(width <= h.maxwidth, "halo width %d too large", width);
+  WB_CHECK(c->comm, "halo exchange without communicator");
+  if (h.nsend > 0) {
+    k_halo_pack<<<wb_grid((size_t)h.nsend * width, 256), 256, 0, c->stream>>>(vec, h.d_send_idx, h.nsend, width,
+                                                                              h.d_sendbuf);
+    WB_LAUNCH(c);
+  }
+  WB_NCCL(ncclGroupStart());
+  for (int n = 0; n < h.nneigh; n++) {
+    int ns = h.send_ptr[n + 1] - h.send_ptr[n], nr = h.recv_ptr[n + 1] - h.recv_ptr[n];
+    if (ns > 0)
+      WB_NCCL(ncclSend(h.d_sendbuf + (size_t)h.send_ptr[n] * width, (size_t)ns * width, ncclDouble, h.rank[n],
+                       c->comm, c->stream));
+    if (nr > 0)
+      WB_NCCL(ncclRecv(h.d_recvbuf + (size_t)h.recv_ptr[n] * width, (size_t)nr * width, ncclDouble, h.rank[n],
+                       c->comm, c->stream));
+  }
+  WB_NCCL(ncclGroupEnd());
+  if (h.nrecv > 0) {
+    k_halo_unpack<<<wb_grid((size_t)h.nrecv * width, 256), 256, 0, c->stream>>>(vec, h.d_recv_idx, h.nrecv, width,
+                                                                                h.d_recvbuf);
+    WB_LAUNCH(c);
+  }
+  return 0;
+}
+
+int wb_allreduce_sum(wb_ctx *c, double *dbuf, int n) {
+  if (c->nranks <= 1) return 0;
+  WB_NCCL(ncclAllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, c->comm, c->stream));
+  return 0;
+}
+
+int wb_allreduce_max_int(wb_ctx *c, int *dbuf, int n) {
+  if (c->nranks <= 1) return 0;
+  WB_NCCL(ncclAllReduce(dbuf, dbuf, n, ncclInt, ncclMax, c->comm, c->stream));
+  return 0;
+}
+
+// device flags -> pinned host mirror, maximum over ranks (the reference's
+// mpi_broadcast_error_flag / Allreduce(LOR), src/mpi_utils.F90:46), then cleared on device.
+__global__ void k_clear_flags(int *f, int n) {
+  if (threadIdx.x < n) f[threadIdx.x] = 0;
+}
+int wb_reduce_flags(wb_ctx *c, int nflags) {
+  WB_TRY(wb_allreduce_max_int(c, c->d_flags, nflags));
+  WB_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, nflags * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  k_clear_flags<<<1, 32, 0, c->stream>>>(c->d_flags, nflags);
+  WB_LAUNCH(c);
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}

@@ -1,0 +1,545 @@
+// wb_eos.cuh -- per-cell equation of state, curves, cell balance, face flux
+// and phase transitions as stateless device functions.
+//
+// What is computed follows the reference (file:line cited per function); how
+// it is organised does not: the reference walks AoS fluid records through
+// class(eos_type) pointers, one cell at a time.  Here a cell's properties are
+// a register-resident struct (WbFluid) produced from (scaled primaries, region)
+// alone, and the face flux consumes a compact WbCellState -- only the ten or so
+// numbers a two-point flux needs -- so the hot kernels never touch the
+// 23-double record unless the caller asks for it.
+#pragma once
+#include "../../include/waiwera_b200.h"
+#include "wb_thermo.cuh"
+
+// ---------------------------------------------------------------- parameters
+
+struct WbEosParams {
+  int eos, np, nc, nphase;
+  WbThermo thermo;
+  double scale[WB_MAX_NP][5];  // primary_scale(var, region 1..4), src/eos_we.F90:104-109
+  double eos_w_temperature;
+  wb_relperm relperm;
+  wb_cappress cappress;
+};
+
+inline int wb_eos_params_make(const wb_params &prm, WbEosParams &e) {
+  e = WbEosParams();
+  e.eos = prm.eos;
+  e.thermo = wb_thermo_make(prm.thermo, prm.extrapolate);
+  e.eos_w_temperature = prm.eos_w_temperature;
+  e.relperm = prm.relperm;
+  e.cappress = prm.cappress;
+  const double ps = prm.pressure_scale > 0 ? prm.pressure_scale : 1.e6;  // src/eos_we.F90:75-76
+  const double ts = prm.temperature_scale > 0 ? prm.temperature_scale : 1.e2;
+  if (prm.eos == WB_EOS_WE) {  // src/eos_we.F90:78-109
+    e.np = 2; e.nc = 1; e.nphase = 2;
+    e.scale[0][1] = ps; e.scale[1][1] = ts;
+    e.scale[0][2] = ps; e.scale[1][2] = ts;
+    e.scale[0][4] = ps; e.scale[1][4] = 1.0;
+  } else if (prm.eos == WB_EOS_W) {  // src/eos_w.F90:67-96
+    e.np = 1; e.nc = 1; e.nphase = 1;
+    e.scale[0][1] = ps; e.scale[0][2] = ps;
+  } else {
+    return 1;
+  }
+  return 0;
+}
+
+template <int EOS> struct WbEosTraits;
+template <> struct WbEosTraits<WB_EOS_WE> { static constexpr int NP = 2, NC = 1, NPH = 2; };
+template <> struct WbEosTraits<WB_EOS_W> { static constexpr int NP = 1, NC = 1, NPH = 1; };
+
+// ---------------------------------------------------------------- curves
+
+// 2-point / n-point linear table with end clamping: find + interpolate_at_index
+// (src/interpolation.F90:202-306, 388-403, 494-510).  The reference's hunt cache
+// only changes how the bracket is found, not which bracket: a plain scan returns
+// the same interval.
+WB_HD double wb_table_interp(const double *xs, const double *ys, int n, double x) {
+  if (x <= xs[0]) return ys[0];
+  if (x >= xs[n - 1]) return ys[n - 1];
+  int i = 0;
+  while (i + 2 < n && x >= xs[i + 1]) i++;
+  const double xi = (x - xs[i]) / (xs[i + 1] - xs[i]);
+  return (1.0 - xi) * ys[i] + xi * ys[i + 1];
+}
+
+WB_HD double wb_table2(double x0, double x1, double y0, double y1, double x) {
+  if (x <= x0) return y0;
+  if (x >= x1) return y1;
+  const double xi = (x - x0) / (x1 - x0);
+  return (1.0 - xi) * y0 + xi * y1;
+}
+
+// src/relative_permeability.F90:197-558
+WB_HD void wb_relperm_values(const wb_relperm &rp, double sl, double &krl, double &krv) {
+  switch (rp.type) {
+    case WB_RP_FULLY_MOBILE:
+      krl = 1.0; krv = 1.0;
+      break;
+    case WB_RP_LINEAR:  // :213-259
+      krl = wb_table2(rp.p[0], rp.p[1], 0.0, 1.0, sl);
+      krv = wb_table2(rp.p[2], rp.p[3], 0.0, 1.0, 1.0 - sl);
+      break;
+    case WB_RP_PICKENS:  // :297-308
+      krl = pow(sl, rp.p[0]);
+      krv = 1.0;
+      break;
+    case WB_RP_COREY:
+    case WB_RP_GRANT: {  // :349-370, :399-420
+      const double slr = rp.p[0], ssr = rp.p[1];
+      const double sv = 1.0 - sl;
+      if (sv < ssr) {
+        krl = 1.0; krv = 0.0;
+      } else if (sv > 1.0 - slr) {
+        krl = 0.0; krv = 1.0;
+      } else {
+        const double sstar = (sl - slr) / (1.0 - slr - ssr);
+        const double sstar2 = sstar * sstar;
+        krl = sstar2 * sstar2;
+        krv = rp.type == WB_RP_COREY ? (1.0 - 2.0 * sstar + sstar2) * (1.0 - sstar2) : 1.0 - krl;
+      }
+      break;
+    }
+    case WB_RP_VAN_GENUCHTEN: {  // :461-491
+      const double lambda = rp.p[0], slr = rp.p[1], sls = rp.p[2], ssr = rp.p[4];
+      const double sstar = (sl - slr) / (sls - slr);
+      if (sstar < 0.0) krl = 0.0;
+      else if (sstar < 1.0) {
+        const double b = 1.0 - pow(1.0 - pow(sstar, 1.0 / lambda), lambda);
+        krl = sqrt(sstar) * (b * b);
+      } else
+        krl = 1.0;
+      if (rp.p[3] != 0.0) krv = 1.0 - krl;
+      else {
+        const double s_hat = (sl - slr) / (1.0 - slr - ssr);
+        const double s_hat2 = s_hat * s_hat;
+        krv = fmin(1.0, (1.0 - 2.0 * s_hat + s_hat2) * (1.0 - s_hat2));
+      }
+      break;
+    }
+    case WB_RP_TABLE:  // :547-558
+      krl = wb_table_interp(rp.lx, rp.ly, rp.nl, sl);
+      krv = wb_table_interp(rp.vx, rp.vy, rp.nv, 1.0 - sl);
+      break;
+    default:
+      krl = 0.0; krv = 0.0;
+  }
+}
+
+// src/capillary_pressure.F90:159-358
+WB_HD double wb_cappress_value(const wb_cappress &cp, double sl, double t) {
+  (void)t;
+  switch (cp.type) {
+    case WB_CP_LINEAR:  // :176-218
+      return wb_table2(cp.p[0], cp.p[1], -fabs(cp.p[2]), 0.0, sl);
+    case WB_CP_VAN_GENUCHTEN: {  // :273-305
+      const double eps = 1.e-3;
+      const double P0 = fabs(cp.p[0]), lambda = cp.p[1], slr = cp.p[2], sls = cp.p[3], Pmax = fabs(cp.p[4]);
+      double c;
+      if (sl < 1.0) {
+        const double sstar = (sl - slr) / (sls - slr);
+        if (sstar < 0.0) c = -Pmax;
+        else if (sstar < 1.0) c = -P0 * pow(pow(sstar, -1.0 / lambda) - 1.0, 1.0 - lambda);
+        else c = 0.0;
+        c = fmin(0.0, c);
+        if (cp.p[5] != 0.0) c = fmax(-Pmax, c);
+        if (sl > 1.0 - eps) c = c * (1.0 - sl) / eps;
+      } else
+        c = 0.0;
+      return c;
+    }
+    case WB_CP_TABLE:  // :349-358
+      return wb_table_interp(cp.x, cp.y, cp.n, sl);
+    default:  // zero :159
+      return 0.0;
+  }
+}
+
+// ---------------------------------------------------------------- fluid
+
+template <int NC, int NPH> struct WbFluid {
+  double P, T;
+  int region, phases;
+  double pp[NC];  // partial pressures
+  struct Phase { double rho, mu, sat, kr, pc, h, u, X[NC]; } ph[NPH];
+};
+
+// what a two-point flux and a cell balance need from a cell (WE: 14 numbers)
+template <int NC, int NPH> struct WbCellState {
+  double P, T, cond;
+  int phases;
+  double rho[NPH], sat[NPH], pc[NPH], mob[NPH], h[NPH];
+  double X[NPH][NC];
+};
+template <int NC, int NPH> struct WbStateLayout {
+  // SoA field count of WbCellState in global memory (phases stored as a double)
+  static constexpr int NF = 4 + NPH * (5 + (NC > 1 ? NC : 0));
+};
+
+WB_HD int wb_nint(double x) { return (int)(x < 0 ? x - 0.5 : x + 0.5); }
+
+// eos%unscale (src/eos.F90:200-210)
+template <int NP> WB_HD void wb_unscale(const WbEosParams &e, const double *y, int region, double *primary) {
+#pragma unroll
+  for (int i = 0; i < NP; i++) primary[i] = y[i] * e.scale[i][region];
+}
+// eos%scale (src/eos.F90:186-196)
+template <int NP> WB_HD void wb_scale(const WbEosParams &e, const double *primary, int region, double *y) {
+#pragma unroll
+  for (int i = 0; i < NP; i++) y[i] = primary[i] / e.scale[i][region];
+}
+
+// bulk_properties + phase_saturations + phase_properties for one cell:
+// eos_we: src/eos_we.F90:327-390, 394-458; eos_w: src/eos_w.F90.
+// `fl.region` must be set on entry.  Returns the reference's err (0 / 1).
+template <int EOS>
+WB_HD int wb_eos_properties(const WbEosParams &e, const double *primary,
+                            WbFluid<WbEosTraits<EOS>::NC, WbEosTraits<EOS>::NPH> &fl) {
+  const WbThermo &th = e.thermo;
+  int err = 0;
+  if (EOS == WB_EOS_W) {
+    fl.P = primary[0];
+    fl.T = e.eos_w_temperature;
+    fl.ph[0].sat = 1.0;
+    const int phases = wb_phase_composition(th, fl.region, fl.P, fl.T);
+    if (phases <= 0) return 1;
+    fl.phases = phases;
+    fl.pp[0] = fl.P;
+    const int p = fl.region;
+    double rho, u;
+    err = wb_region_properties(th, p, fl.P, fl.T, rho, u);
+    if (err) return err;
+    // eos_w has a single phase slot; region 2 (steam) would index phase 2 in the reference,
+    // which isothermal-water models never reach
+    fl.ph[0].rho = rho;
+    fl.ph[0].u = u;
+    fl.ph[0].h = u + fl.P / rho;
+    fl.ph[0].kr = 1.0;
+    fl.ph[0].pc = 0.0;
+    fl.ph[0].X[0] = 1.0;
+    fl.ph[0].mu = wb_region_viscosity(th, p, fl.T, fl.P, rho);
+    return 0;
+  } else {
+    constexpr int NPH = WbEosTraits<EOS>::NPH;
+    fl.P = primary[0];
+    const int region = fl.region;
+    if (region == 4) err = wb_saturation_temperature(th, fl.P, fl.T);
+    else fl.T = primary[1];
+    if (err) return err;
+    const int phases = wb_phase_composition(th, region, fl.P, fl.T);
+    if (phases <= 0) return 1;
+    fl.phases = phases;
+    // phase_saturations: src/eos_we.F90:366-390 (other regions leave saturations untouched)
+    double sl = fl.ph[0].sat, sv = fl.ph[1].sat;
+    if (region == 1) { sl = 1.0; sv = 0.0; }
+    else if (region == 2) { sl = 0.0; sv = 1.0; }
+    else if (region == 4) { sl = 1.0 - primary[1]; sv = primary[1]; }
+    fl.ph[0].sat = sl;
+    fl.ph[1].sat = sv;
+    fl.pp[0] = fl.P;
+    double kr[2], pc[2];
+    wb_relperm_values(e.relperm, sl, kr[0], kr[1]);
+    pc[0] = wb_cappress_value(e.cappress, sl, fl.T);
+    pc[1] = 0.0;
+#pragma unroll
+    for (int p = 0; p < NPH; p++) {
+      if (phases & (1 << p)) {
+        double rho, u;
+        err = wb_region_properties(th, p + 1, fl.P, fl.T, rho, u);
+        if (err) return err;
+        fl.ph[p].rho = rho;
+        fl.ph[p].u = u;
+        fl.ph[p].h = u + fl.P / rho;
+        fl.ph[p].X[0] = 1.0;
+        fl.ph[p].kr = kr[p];
+        fl.ph[p].pc = pc[p];
+        fl.ph[p].mu = wb_region_viscosity(th, p + 1, fl.T, fl.P, rho);
+      } else {
+        fl.ph[p].rho = 0.0; fl.ph[p].u = 0.0; fl.ph[p].h = 0.0; fl.ph[p].kr = 0.0;
+        fl.ph[p].pc = 0.0; fl.ph[p].mu = 0.0; fl.ph[p].X[0] = 0.0;
+      }
+    }
+    return 0;
+  }
+}
+
+// rock record offsets (src/rock.F90:97-112)
+enum { WB_R_PERM = 0, WB_R_WET = 3, WB_R_DRY = 4, WB_R_POR = 5, WB_R_RHO = 6, WB_R_CP = 7 };
+
+// cell%balance: src/cell.F90:114-142, src/fluid.F90:295-370, src/rock.F90:142
+template <int NP, int NC, int NPH>
+WB_HD void wb_cell_balance(const WbFluid<NC, NPH> &fl, double porosity, double rock_density, double rock_cp,
+                           double *balance) {
+  double d[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) d[c] = 0.0;
+#pragma unroll
+  for (int p = 0; p < NPH; p++) {
+    const double ds = fl.ph[p].rho * fl.ph[p].sat;
+#pragma unroll
+    for (int c = 0; c < NC; c++) d[c] = d[c] + ds * fl.ph[p].X[c];
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) balance[c] = porosity * d[c];
+  if (NP != NC) {
+    const double er = rock_density * rock_cp * fl.T;
+    double ef = 0.0;
+#pragma unroll
+    for (int p = 0; p < NPH; p++) {
+      const double ds = fl.ph[p].rho * fl.ph[p].sat;
+      ef = ef + ds * fl.ph[p].u;
+    }
+    balance[NP - 1] = porosity * ef + (1.0 - porosity) * er;
+  }
+}
+
+// compact state from the full property set; mobility = kr*rho/mu (src/fluid.F90:197-207),
+// conductivity = dry + sqrt(Sl)*(wet-dry) (src/eos.F90:240-257)
+template <int NC, int NPH>
+WB_HD void wb_state_from_fluid(const WbFluid<NC, NPH> &fl, double wet, double dry, WbCellState<NC, NPH> &s) {
+  s.P = fl.P;
+  s.T = fl.T;
+  s.phases = fl.phases;
+  s.cond = dry + sqrt(fl.ph[0].sat) * (wet - dry);
+#pragma unroll
+  for (int p = 0; p < NPH; p++) {
+    s.rho[p] = fl.ph[p].rho;
+    s.sat[p] = fl.ph[p].sat;
+    s.pc[p] = fl.ph[p].pc;
+    s.h[p] = fl.ph[p].h;
+    s.mob[p] = (fl.phases & (1 << p)) ? fl.ph[p].kr * fl.ph[p].rho / fl.ph[p].mu : 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) s.X[p][c] = fl.ph[p].X[c];
+  }
+}
+
+// face%harmonic_average: src/face.F90:358-377
+WB_HD double wb_harmonic(double d1, double d2, double d12, double x1, double x2) {
+  const double wx = (d1 * x2 + d2 * x1) / d12;
+  return (fabs(wx) > 1.e-30) ? x1 * x2 / wx : 0.0;
+}
+
+// face geometry as the flux needs it (subset of the 12-double record, src/face.F90:127-133)
+struct WbFaceGeom {
+  double area, d1, d2, d12, gravn, k;  // k: harmonic-averaged permeability along the face normal
+};
+
+// face%flux: src/face.F90:443-515.  flux[0..NC-1] component mass fluxes, flux[NP-1] energy
+// flux (if non-isothermal), accumulated in the reference's order: conduction, then phase 1, 2.
+template <int NP, int NC, int NPH>
+WB_HD void wb_face_flux(const WbFaceGeom &g, const WbCellState<NC, NPH> &s1, const WbCellState<NC, NPH> &s2,
+                        double *flux, double *phase_flux) {
+#pragma unroll
+  for (int i = 0; i < NP; i++) flux[i] = 0.0;
+  if (NP != NC) {
+    const double cond = wb_harmonic(g.d1, g.d2, g.d12, s1.cond, s2.cond);
+    const double dtdn = (s2.T - s1.T) / g.d12;
+    flux[NP - 1] = -cond * dtdn;
+  }
+  const int present = s1.phases | s2.phases;
+#pragma unroll
+  for (int p = 0; p < NPH; p++) {
+    double pf = 0.0;
+    if (present & (1 << p)) {
+      // phase_density: src/face.F90:334-354
+      double rho = 0.0, weight = 0.0;
+      rho = rho + s1.sat[p] * s1.rho[p];
+      weight = weight + s1.sat[p];
+      rho = rho + s2.sat[p] * s2.rho[p];
+      weight = weight + s2.sat[p];
+      rho = rho / weight;
+      // pressure_gradient: src/face.F90:296-313
+      const double dpdn = ((s2.P + s2.pc[p]) - (s1.P + s1.pc[p])) / g.d12;
+      const double G = dpdn - rho * g.gravn;
+      const bool up1 = (G <= 0.0);  // src/face.F90:426-439
+      const int up_phases = up1 ? s1.phases : s2.phases;
+      if (up_phases & (1 << p)) {
+        const double mob = up1 ? s1.mob[p] : s2.mob[p];
+        const double F = -g.k * mob * G;
+        double sum = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          const double pcf = F * (up1 ? s1.X[p][c] : s2.X[p][c]);
+          flux[c] = flux[c] + pcf;
+          sum += pcf;
+        }
+        if (NP != NC) {
+          const double h = up1 ? s1.h[p] : s2.h[p];
+          flux[NP - 1] = flux[NP - 1] + h * F;
+        }
+        pf = sum;
+      }
+    }
+    if (phase_flux) phase_flux[p] = pf;
+  }
+}
+
+// ---------------------------------------------------------------- transitions
+
+// Brent on f(x) = P(x) - Psat(T(x)) along the segment old -> new primaries
+// (src/root_finder.F90:127-248 with the defaults of :76-79; src/eos_we.F90:530-553)
+struct WbSatLine {
+  double p0, t0, p1, t1;
+};
+WB_HD double wb_satline_f(const WbThermo &th, const WbSatLine &c, double x) {
+  const double xi = (x - 0.0) / (1.0 - 0.0);
+  const double P = (1.0 - xi) * c.p0 + xi * c.p1;
+  const double T = (1.0 - xi) * c.t0 + xi * c.t1;
+  double Ps = 0.0;
+  wb_saturation_pressure(th, T, Ps);
+  return P - Ps;
+}
+
+WB_HD int wb_brent_satline(const WbThermo &th, const WbSatLine &ctx, double &root) {
+  const double rtol = 1.e-8, ftol = 1.e-8, small = 1.e-16;
+  const int max_iterations = 100;
+  double a = 0.0, b = 1.0, c, d = 0.0, e = 0.0, fa, fb, fc, dx, p, pc, q, r, s;
+  bool found = false;
+  root = 0.0;
+  fa = wb_satline_f(th, ctx, a);
+  fb = wb_satline_f(th, ctx, b);
+  if (fa * fb > 0.0) return 1;
+  c = b;
+  fc = fb;
+  for (int iter = 1; iter <= max_iterations; iter++) {
+    if (fb * fc > 0.0) {
+      c = a; fc = fa; d = b - a; e = d;
+    }
+    if (fabs(fc) < fabs(fb)) {
+      a = b; b = c; c = a;
+      fa = fb; fb = fc; fc = fa;
+    }
+    dx = 0.5 * (c - b);
+    if (fabs(dx) <= rtol || fabs(fb) <= ftol) {
+      found = true;
+      break;
+    }
+    if (fabs(e) >= rtol && fabs(fa) > fabs(fb)) {
+      s = fb / fa;
+      if (fabs(a - c) <= small) {
+        p = 2.0 * dx * s;
+        q = 1.0 - s;
+      } else {
+        q = fa / fc;
+        r = fb / fc;
+        p = s * (2.0 * dx * q * (q - r) - (b - a) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      else p = -p;
+      pc = fmin(3.0 * dx * q - fabs(rtol * q), fabs(e * q));
+      if (2.0 * p < pc) {
+        e = d;
+        d = p / q;
+      } else {
+        d = dx;
+        e = d;
+      }
+    } else {
+      d = dx;
+      e = d;
+    }
+    a = b;
+    fa = fb;
+    if (fabs(d) > rtol) b = b + d;
+    else b = b + copysign(rtol, dx);
+    fb = wb_satline_f(th, ctx, b);
+  }
+  root = b;
+  return found ? 0 : 2;
+}
+
+// eos_we%transition: src/eos_we.F90:149-323.  primary in/out (unscaled), region in/out.
+// old_region / old_T are the cell's values at the start of the Newton iteration
+// (last_iteration_fluid).  Returns err; transition set when the region changed.
+WB_HD int wb_we_transition(const WbThermo &th, const double *old_primary, double *primary, int old_region,
+                           double old_T, int &region, bool &transition) {
+  const double small = 1.e-6;
+  int err = 0;
+  transition = false;
+  if (old_region == 4) {
+    const double sv = primary[1];
+    int new_region = 0;
+    if (sv < 0.0) new_region = 1;
+    else if (sv > 1.0) new_region = 2;
+    if (new_region) {
+      // transition_to_single_phase: src/eos_we.F90:149-216
+      const double bound = (new_region == 1) ? 0.0 : 1.0;
+      const double pfac = (new_region == 1) ? 1.0 + small : 1.0 - small;
+      // inverse interpolation of the saturation component on x = [0,1]
+      // (src/interpolation.F90:407-438), tolerance 1e-8
+      const double v1 = old_primary[1], v2 = primary[1];
+      const double vmax = fmax(fabs(v1), fabs(v2));
+      if (fabs(v2 - v1) >= 1.e-8 * vmax) {
+        const double vs1 = v1 / vmax, vs2 = v2 / vmax, ys = bound / vmax;
+        const double xq = (ys - vs1) / (vs2 - vs1);
+        const double xi = (1.0 - xq) * 0.0 + xq * 1.0;
+        // interpolate(xi): find + interpolate_at_index, clamped outside [0,1]
+        double pint;
+        if (xi <= 0.0) pint = old_primary[0];
+        else if (xi >= 1.0) pint = primary[0];
+        else {
+          const double w = (xi - 0.0) / (1.0 - 0.0);
+          pint = (1.0 - w) * old_primary[0] + w * primary[0];
+        }
+        primary[0] = pfac * pint;
+        err = wb_saturation_temperature(th, pint, primary[1]);
+        if (err == 0) {
+          region = new_region;
+          transition = true;
+        }
+      } else {
+        double old_ps;
+        err = wb_saturation_pressure(th, old_T, old_ps);
+        if (err == 0) {
+          primary[0] = pfac * old_ps;
+          primary[1] = old_T;
+          region = new_region;
+          transition = true;
+        }
+      }
+    }
+  } else {
+    double ps;
+    err = wb_saturation_pressure(th, primary[1], ps);
+    if (err == 0) {
+      if ((old_region == 1 && primary[0] < ps) || (old_region == 2 && primary[0] > ps)) {
+        // transition_to_two_phase: src/eos_we.F90:220-268
+        WbSatLine c = {old_primary[0], old_primary[1], primary[0], primary[1]};
+        double root;
+        if (wb_brent_satline(th, c, root) == 0) {
+          double pint;
+          if (root <= 0.0) pint = c.p0;
+          else if (root >= 1.0) pint = c.p1;
+          else {
+            const double w = (root - 0.0) / (1.0 - 0.0);
+            pint = (1.0 - w) * c.p0 + w * c.p1;
+          }
+          primary[0] = pint;
+        } else {
+          primary[0] = ps;
+        }
+        primary[1] = (old_region == 1) ? small : 1.0 - small;
+        region = 4;
+        transition = true;
+      }
+    }
+  }
+  return err;
+}
+
+// eos_we%check_primary_variables: src/eos_we.F90:486-526
+WB_HD int wb_we_check_primary(const double *primary, int region) {
+  const double p = primary[0];
+  if (p < 0.0 || p > 100.e6) return 1;
+  if (region == 4) {
+    const double sv = primary[1];
+    if (sv < -1.0 || sv > 2.0) return 1;
+  } else {
+    const double t = primary[1];
+    if (t < 0.0 || t > 800.0) return 1;
+  }
+  return 0;
+}
