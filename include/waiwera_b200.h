@@ -143,6 +143,9 @@ int wb_fluid_init(wb_ctx *ctx, const double *y, const int32_t *region);
 /* Dirichlet boundary ghost cell (src/mesh.F90:1185-1202): rock copied from the interior
    cell, fluid record from UNSCALED primary and region. */
 int wb_set_boundary(wb_ctx *ctx, int ghost_cell, int interior_cell, const double *primary, int region);
+/* the same for n boundary cells at once: primary[n*np], region[n] */
+int wb_set_boundaries(wb_ctx *ctx, int n, const int32_t *ghost_cells, const int32_t *interior_cells,
+                      const double *primary, const int32_t *region);
 /* current fluid records of all local cells, reference AoS layout [ncell*fluid_dof] */
 int wb_get_fluid(wb_ctx *ctx, double *fluid);
 int wb_get_regions(wb_ctx *ctx, int32_t *region);
@@ -207,6 +210,8 @@ int wb_mat_mult(wb_mat *A, const double *x, double *y);
    -pc_bjacobi_local_blocks; 1 = one ILU(0) over all owned rows, the PETSc default).
    block_of_row[nb] (host, may be NULL => contiguous equal split) assigns rows to blocks. */
 int wb_pc_setup(wb_mat *A, int type, int nblocks, const int32_t *block_of_row, wb_pc **out);
+/* PCSetUp after the matrix values changed (same pattern): numeric part only */
+int wb_pc_refactor(wb_pc *pc);
 int wb_pc_apply(wb_pc *pc, const double *r, double *z);
 int wb_pc_destroy(wb_pc *pc);
 
@@ -219,6 +224,10 @@ typedef struct {
 /* KSPSolve with zero initial guess, left preconditioning; reason follows KSPConvergedReason */
 int wb_ksp_solve(wb_mat *A, wb_pc *pc, const wb_ksp_opts *opts, const double *b, double *x, int *its,
                  int *reason, double *rnorm);
+
+/* Krylov iterations enqueued between host-side convergence checks (the kernels skip their
+   work once the device-side flag says converged, so results do not depend on it); default 4 */
+int wb_ksp_set_check_every(int k);
 
 /* ---- Newton (SNESSolve as configured by timestepper.F90:1552-1641) ------ */
 typedef struct {
@@ -243,6 +252,8 @@ int wb_newton_solve_be(wb_ctx *ctx, const wb_newton_opts *opts, double dt, const
    "pc_apply", "fluid_trans" */
 int wb_timer_get(wb_ctx *ctx, const char *name, double *ms, int64_t *count);
 int wb_timer_reset(wb_ctx *ctx);
+/* phase timers synchronise the stream at every phase end; switch them off for throughput runs */
+int wb_timers_enable(int on);
 /* number of kernels launched by this context since creation */
 int64_t wb_launch_count(const wb_ctx *ctx);
 /* stream the context launches on (cudaStream_t) */

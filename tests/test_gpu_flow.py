@@ -1,0 +1,233 @@
+"""GPU parity: function evaluation, Jacobian and transitions through the C ABI vs the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import SEED, make_problem, oracle_flow, gpu_flow, relerr
+
+pytestmark = pytest.mark.gpu
+
+RESIDUAL_TOL = 1e-10  # north_star: nonlinear residual norm within 1e-10 relative
+
+
+@pytest.fixture(scope="module")
+def flow():
+    from waiwera_b200 import flow as _flow
+    return _flow
+
+
+CASES = [
+    dict(thermo=0, two_phase_layers=0, top_boundary=False),
+    dict(thermo=0, two_phase_layers=2, top_boundary=False),
+    dict(thermo=1, two_phase_layers=2, top_boundary=True),
+    dict(thermo=1, two_phase_layers=0, top_boundary=True),
+]
+
+
+def curves(wo, which):
+    if which == 0:
+        return None, None
+    return (wo.make_relperm("corey", slr=0.3, ssr=0.05),
+            wo.make_cappress("van_genuchten", P0=0.125e5, lambda_=0.45, slr=1e-3, sls=1.0, Pmax=1e6))
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_fluid_records_match_oracle(wo, flow, case):
+    """a2-a4: wb_fluid_init + wb_get_fluid vs fluid_init of the oracle, all 23 fields of every cell"""
+    rp, cp = curves(wo, case % 2)
+    m, y, region, prm = make_problem(wo, relperm=rp, cappress=cp, **CASES[case])
+    ref = oracle_flow(wo, m, prm, y, region)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    a, b = ref.fluid(), sim.fluid()
+    # integer-valued fields bit exact
+    for col in (2, 4):
+        assert np.array_equal(a[:, col], b[:, col])
+    scale = np.maximum(np.abs(a).max(axis=0), 1e-300)
+    assert (np.abs(a - b) / scale).max() < 1e-13
+    sim.destroy()
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_residual_matches_oracle(wo, flow, case):
+    """a8-a12: L, R, BE residual and the scaled max norm at identical states"""
+    rp, cp = curves(wo, case % 2)
+    m, y, region, prm = make_problem(wo, relperm=rp, cappress=cp, **CASES[case])
+    ref = oracle_flow(wo, m, prm, y, region)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    e0, L0 = ref.lhs(y)
+    e1, L1 = sim.lhs(y)
+    assert e0 == e1 == 0
+    assert relerr(L1, L0) < 1e-14
+    rng = np.random.default_rng(SEED + case)
+    y2 = y * (1 + 1e-4 * rng.uniform(-1, 1, len(y)))
+    dt = 1.0e6
+    e0, lhs0, rhs0, r0 = ref.residual(y2, L0, dt)
+    e1, lhs1, rhs1, r1 = sim.residual(y2, L0, dt)
+    assert e0 == e1 == 0
+    assert relerr(lhs1, lhs0) < 1e-14
+    assert relerr(rhs1, rhs0) < RESIDUAL_TOL
+    assert relerr(r1, r0) < RESIDUAL_TOL
+    assert abs(np.linalg.norm(r1) - np.linalg.norm(r0)) <= RESIDUAL_TOL * np.linalg.norm(r0)
+    mv0, ml0 = wo.max_scaled(r0, L0, 1.0)
+    mv1, ml1 = sim.max_scaled(r1, L0, 1.0)
+    assert ml0 == ml1
+    assert abs(mv0 - mv1) <= RESIDUAL_TOL * abs(mv0)
+    # masked (perturbed-column) evaluation: same result as the oracle's masked path, stored state untouched
+    cols = np.array([0, 5, 17], np.int32)
+    y3 = y2.copy()
+    y3[2 * cols] += 1e-8
+    e0, _, _, rp0 = ref.residual(y3, L0, dt, perturbed=cols)
+    e1, _, _, rp1 = sim.residual(y3, L0, dt, perturbed=cols)
+    assert relerr(rp1, rp0) < RESIDUAL_TOL
+    e1, _, _, r1b = sim.residual(y2, L0, dt)
+    assert np.array_equal(r1b, r1)
+    sim.destroy()
+
+
+def test_residual_domain_error(wo, flow):
+    """a2: out-of-range primaries give err > 0 on both sides (timestepper.F90:620 domain error)"""
+    m, y, region, prm = make_problem(wo)
+    ref = oracle_flow(wo, m, prm, y, region)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    _, L0 = ref.lhs(y)
+    ybad = y.copy()
+    ybad[2 * 11 + 1] = 5.0  # 500 degC in region 1
+    assert ref.residual(ybad, L0, 1e6)[0] != 0
+    assert sim.residual(ybad, L0, 1e6)[0] > 0
+    # and the context recovers
+    assert sim.residual(y, L0, 1e6)[0] == 0
+    sim.destroy()
+
+
+def oracle_jacobian(wo, ref, y, L0, dt):
+    e, _, _, F0 = ref.residual(y, L0, dt)
+    assert e == 0
+    A = ref.bsr()
+    nb = A.contents.nb
+    color = np.zeros(nb, np.int32)
+    nc = wo.lib().wo_bsr_coloring(A, wo.ip(color))
+    assert wo.lib().wo_fd_jacobian(ref.h, wo.dp(y), wo.dp(L0), dt, wo.dp(F0), wo.ip(color), nc, 1e-8, 1e-2, A) == 0
+    rowptr, colidx, val = wo.bsr_arrays(A)
+    return A, rowptr.copy(), colidx.copy(), val.copy(), F0
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_jacobian_matches_oracle(wo, flow, case):
+    """a13: local-FD BAIJ assembly vs the colour-by-colour FD Jacobian of the oracle"""
+    rp, cp = curves(wo, case % 2)
+    m, y, region, prm = make_problem(wo, relperm=rp, cappress=cp, **CASES[case])
+    ref = oracle_flow(wo, m, prm, y, region)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    _, L0 = ref.lhs(y)
+    rng = np.random.default_rng(SEED + 10 + case)
+    y2 = y * (1 + 1e-4 * rng.uniform(-1, 1, len(y)))
+    dt = 1.0e6
+    A, rowptr, colidx, val, F0 = oracle_jacobian(wo, ref, y2, L0, dt)
+    nb, bs, rp_g, ci_g = sim.jacobian_pattern()
+    # index / connectivity work is bit exact
+    assert nb == m.nowned and bs == 2
+    assert np.array_equal(rp_g, rowptr) and np.array_equal(ci_g, colidx)
+    assert sim.jacobian(y2, L0, dt) == 0
+    Jl = sim.jacobian_values()
+    # FD noise floor: eps*|F| / h; compare against the magnitude of each block row
+    rows = np.repeat(np.arange(nb), np.diff(rowptr))
+    rowmax = np.zeros((nb, 2))
+    for ii in range(2):
+        np.maximum.at(rowmax[:, ii], rows, np.abs(val[:, [ii, 2 + ii]]).max(axis=1))
+    scale = np.stack([rowmax[rows, 0], rowmax[rows, 1], rowmax[rows, 0], rowmax[rows, 1]], 1)
+    assert (np.abs(Jl - val) / np.maximum(scale, 1e-300)).max() < 2e-6
+    # the reference's colouring loop run on the GPU gives the same matrix as the local assembly
+    assert sim.jacobian(y2, L0, dt, colored=True) == 0
+    Jc = sim.jacobian_values()
+    assert (np.abs(Jc - Jl) / np.maximum(scale, 1e-300)).max() < 1e-12
+    wo.lib().wo_bsr_destroy(A)
+    sim.destroy()
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_transitions_match_oracle(wo, flow, thermo):
+    """a15: phase transitions after a line-search update: regions bit exact, primaries / search direction equal"""
+    m, y, region, prm = make_problem(wo, thermo=thermo, two_phase_layers=3)
+    ref = oracle_flow(wo, m, prm, y, region)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    ref.L.wo_flow_pre_eval(ref.h, wo.dp(y), None, 0)
+    assert sim.pre_eval(y) == 0
+    ref.L.wo_flow_pre_iteration(ref.h)
+    sim.pre_iteration()
+    rng = np.random.default_rng(SEED + 20 + thermo)
+    n = m.nowned
+    search = np.zeros(2 * n)
+    tp = region == 4
+    # push two-phase cells out of [0,1] in saturation, liquid cells across the saturation line
+    search[1::2] = np.where(tp, rng.choice([-0.7, 0.0, 0.9], n), -rng.choice([0.0, 0.0, 1.4], n))
+    search[0::2] = rng.uniform(-0.05, 0.05, n)
+    ynew = y - search
+    s0, y0 = search.copy(), ynew.copy()
+    s1, y1 = search.copy(), ynew.copy()
+    cs0, cy0 = C.c_int(), C.c_int()
+    e0 = ref.L.wo_flow_fluid_transitions(ref.h, wo.dp(y), wo.dp(s0), wo.dp(y0), C.byref(cs0), C.byref(cy0))
+    e1, cs1, cy1 = sim.fluid_transitions(y, s1, y1)
+    assert e0 == e1 == 0
+    assert cs0.value == cs1 and cy0.value == cy1
+    r0, r1 = ref.regions(), sim.regions()
+    assert np.array_equal(r0[:n], r1[:n])
+    assert (r0[:n] != region).sum() > 10
+    assert np.abs(y0 - y1).max() <= 1e-13 * np.abs(y0).max()
+    assert np.abs(s0 - s1).max() <= 1e-13 * max(np.abs(s0).max(), 1.0)
+    # a range violation is reported as a recoverable error on both sides
+    ybad = ynew.copy()
+    ybad[0] = -1.0
+    e0 = ref.L.wo_flow_fluid_transitions(ref.h, wo.dp(y), wo.dp(search.copy()), wo.dp(ybad.copy()), C.byref(cs0), C.byref(cy0))
+    e1, _, _ = sim.fluid_transitions(y, search.copy(), ybad.copy())
+    assert e0 != 0 and e1 > 0
+    sim.destroy()
+
+
+def test_device_pointer_arguments(wo, flow):
+    """the ABI takes device pointers as well as host pointers (torch tensors as device memory)"""
+    import torch
+    m, y, region, prm = make_problem(wo)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    _, L0 = sim.lhs(y)
+    _, _, _, r_host = sim.residual(y * 1.0001, L0, 1e6)
+    yd = torch.tensor(y * 1.0001, device="cuda")
+    Ld = torch.tensor(L0, device="cuda")
+    rd = torch.zeros_like(yd)
+    torch.cuda.synchronize()
+    err, _, _, _ = sim.residual(yd, Ld, 1e6, r=rd, want_parts=False)
+    assert err == 0
+    assert np.array_equal(rd.cpu().numpy(), r_host)
+    sim.destroy()
+
+
+def test_full_size_residual_properties(wo, flow):
+    """BASELINE config 2 size (100^3, eos_we, IAPWS): size-independent properties of the residual:
+    closed box => inflows conserve mass and energy (sum_i V_i R_i = 0 to rounding), L is a pure per-cell
+    function (a 1000-cell slab agrees with the oracle), and the evaluation is deterministic."""
+    m, y, region, prm = make_problem(wo, dims=(100, 100, 100))
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    e, L = sim.lhs(y)
+    assert e == 0
+    e, lhs, rhs, r = sim.residual(y, L, 1.0e6)
+    assert e == 0
+    vol = m.cell_geom[:m.nowned, 3]
+    for k in range(2):
+        tot = np.sum(vol * rhs[k::2])
+        assert abs(tot) <= 1e-9 * np.sum(vol * np.abs(rhs[k::2]))
+    e, _, _, r2 = sim.residual(y, L, 1.0e6)
+    assert np.array_equal(r, r2)
+    # oracle on a sub-slab: balances only need the cell itself
+    import ctypes as C2
+    eos = wo.lib().wo_eos_create(C2.byref(prm))
+    for c in range(0, 1000, 37):
+        fl = np.zeros(23)
+        fl[2] = region[c]
+        pr = np.array([y[2 * c] * 1e6, y[2 * c + 1] * 1e2])
+        assert wo.lib().wo_eos_bulk_properties(eos, wo.dp(pr), wo.dp(fl)) == 0
+        assert wo.lib().wo_eos_phase_properties(eos, wo.dp(pr), wo.dp(m.rock[c].copy()), wo.dp(fl)) == 0
+        bal = np.zeros(2)
+        wo.lib().wo_cell_balance(wo.dp(m.rock[c].copy()), wo.dp(fl), 1, 2, 2, wo.dp(bal))
+        assert np.allclose(bal, L[2 * c:2 * c + 2], rtol=1e-13, atol=0)
+    wo.lib().wo_eos_destroy(eos)
+    sim.destroy()

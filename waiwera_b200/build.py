@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -15,6 +15,23 @@
 
 void wb_set_error(const char *fmt, ...);
 
+// NCCL is bound at run time (dlopen of libnccl.so.2 on the first communicator call) so that the
+// library shares whichever NCCL the host process already carries (PyTorch's bundled one, or the
+// system's under an MPI/PETSc host) and single-GPU users need none at all.
+struct WbNccl {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(ncclResult_t);
+};
+const WbNccl *wb_nccl();  // nullptr (with wb_last_error set) if libnccl cannot be loaded
+
 #define WB_CUDA(call)                                                                      \
   do {                                                                                     \
     cudaError_t e_ = (call);                                                               \
@@ -28,7 +45,7 @@ void wb_set_error(const char *fmt, ...);
   do {                                                                                     \
     ncclResult_t r_ = (call);                                                              \
     if (r_ != ncclSuccess) {                                                               \
-      wb_set_error("%s:%d NCCL error %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+      wb_set_error("%s:%d NCCL error %s: %s", __FILE__, __LINE__, #call, wb_nccl()->GetErrorString(r_)); \
       return -2;                                                                           \
     }                                                                                      \
   } while (0)

@@ -1,5 +1,6 @@
 // wb_core.cu -- context life cycle, error reporting, pointer staging, timers,
 // NCCL communicator and halo exchange.
+#include <dlfcn.h>
 #include <stdarg.h>
 
 #include "wb_common.cuh"
@@ -12,6 +13,44 @@ void wb_set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+const WbNccl *wb_nccl() {
+  static WbNccl tbl;
+  static int state = 0;  // 0 untried, 1 ok, -1 failed
+  if (state == 1) return &tbl;
+  if (state == -1) return nullptr;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    wb_set_error("cannot load libnccl.so.2: %s", dlerror());
+    state = -1;
+    return nullptr;
+  }
+  bool ok = true;
+#define BIND(field, name)                                   \
+  do {                                                      \
+    *(void **)(&tbl.field) = dlsym(h, name);                \
+    if (!tbl.field) ok = false;                             \
+  } while (0)
+  BIND(GetUniqueId, "ncclGetUniqueId");
+  BIND(CommInitRank, "ncclCommInitRank");
+  BIND(CommDestroy, "ncclCommDestroy");
+  BIND(GroupStart, "ncclGroupStart");
+  BIND(GroupEnd, "ncclGroupEnd");
+  BIND(Send, "ncclSend");
+  BIND(Recv, "ncclRecv");
+  BIND(AllReduce, "ncclAllReduce");
+  BIND(AllGather, "ncclAllGather");
+  BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+  if (!ok) {
+    wb_set_error("libnccl.so.2 lacks a required symbol");
+    state = -1;
+    return nullptr;
+  }
+  state = 1;
+  return &tbl;
 }
 
 extern "C" const char *wb_last_error(void) { return g_err; }
@@ -189,7 +228,7 @@ extern "C" int wb_destroy(wb_ctx *c) {
   cudaFree(c->halo.d_recv_idx);
   cudaFree(c->halo.d_sendbuf);
   cudaFree(c->halo.d_recvbuf);
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm && wb_nccl()) wb_nccl()->CommDestroy(c->comm);
   cudaFree(c->d_flags);
   cudaFreeHost(c->h_flags);
   cudaFree(c->d_red);
@@ -208,7 +247,8 @@ extern "C" int wb_fluid_dof(const wb_ctx *c) { return c->dof; }
 
 extern "C" int wb_comm_unique_id(void *id128) {
   ncclUniqueId id;
-  WB_NCCL(ncclGetUniqueId(&id));
+  if (!wb_nccl()) return -2;
+  WB_NCCL(wb_nccl()->GetUniqueId(&id));
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   memcpy(id128, &id, 128);
   return 0;
@@ -218,7 +258,8 @@ extern "C" int wb_comm_init(wb_ctx *c, int rank, int nranks, const void *id128) 
   WB_CUDA(cudaSetDevice(c->device));
   ncclUniqueId id;
   memcpy(&id, id128, 128);
-  WB_NCCL(ncclCommInitRank(&c->comm, nranks, id, rank));
+  if (!wb_nccl()) return -2;
+  WB_NCCL(wb_nccl()->CommInitRank(&c->comm, nranks, id, rank));
   c->rank = rank;
   c->nranks = nranks;
   return 0;
@@ -285,17 +326,17 @@ int wb_halo_exchange(wb_ctx *c, double *vec, int width) {
                                                                               h.d_sendbuf);
     WB_LAUNCH(c);
   }
-  WB_NCCL(ncclGroupStart());
+  WB_NCCL(wb_nccl()->GroupStart());
   for (int n = 0; n < h.nneigh; n++) {
     int ns = h.send_ptr[n + 1] - h.send_ptr[n], nr = h.recv_ptr[n + 1] - h.recv_ptr[n];
     if (ns > 0)
-      WB_NCCL(ncclSend(h.d_sendbuf + (size_t)h.send_ptr[n] * width, (size_t)ns * width, ncclDouble, h.rank[n],
+      WB_NCCL(wb_nccl()->Send(h.d_sendbuf + (size_t)h.send_ptr[n] * width, (size_t)ns * width, ncclDouble, h.rank[n],
                        c->comm, c->stream));
     if (nr > 0)
-      WB_NCCL(ncclRecv(h.d_recvbuf + (size_t)h.recv_ptr[n] * width, (size_t)nr * width, ncclDouble, h.rank[n],
+      WB_NCCL(wb_nccl()->Recv(h.d_recvbuf + (size_t)h.recv_ptr[n] * width, (size_t)nr * width, ncclDouble, h.rank[n],
                        c->comm, c->stream));
   }
-  WB_NCCL(ncclGroupEnd());
+  WB_NCCL(wb_nccl()->GroupEnd());
   if (h.nrecv > 0) {
     k_halo_unpack<<<wb_grid((size_t)h.nrecv * width, 256), 256, 0, c->stream>>>(vec, h.d_recv_idx, h.nrecv, width,
                                                                                 h.d_recvbuf);
@@ -306,13 +347,13 @@ int wb_halo_exchange(wb_ctx *c, double *vec, int width) {
 
 int wb_allreduce_sum(wb_ctx *c, double *dbuf, int n) {
   if (c->nranks <= 1) return 0;
-  WB_NCCL(ncclAllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, c->comm, c->stream));
+  WB_NCCL(wb_nccl()->AllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, c->comm, c->stream));
   return 0;
 }
 
 int wb_allreduce_max_int(wb_ctx *c, int *dbuf, int n) {
   if (c->nranks <= 1) return 0;
-  WB_NCCL(ncclAllReduce(dbuf, dbuf, n, ncclInt, ncclMax, c->comm, c->stream));
+  WB_NCCL(wb_nccl()->AllReduce(dbuf, dbuf, n, ncclInt, ncclMax, c->comm, c->stream));
   return 0;
 }
 

@@ -1083,7 +1083,7 @@ int wb_max_scaled_core(wb_ctx *c, const double *d_v, const double *d_s, double t
   WB_CUDA(cudaGetLastError());
   int nslots = 1;
   if (c->nranks > 1) {
-    WB_NCCL(ncclAllGather(res + 2 * slot, res, 2, ncclDouble, c->comm, c->stream));
+    WB_NCCL(wb_nccl()->AllGather(res + 2 * slot, res, 2, ncclDouble, c->comm, c->stream));
     nslots = c->nranks;
   }
   WB_CUDA(cudaMemcpyAsync(c->h_red, res, sizeof(double) * 2 * nslots, cudaMemcpyDeviceToHost, c->stream));

@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference's interface for the Newton-step path.
+
+`FlowSimulation` exposes the `ode_type` hooks `flow_simulation_type` binds
+(src/flow_simulation.F90:103-128: lhs, rhs, pre_eval, pre_iteration, pre_timestep,
+pre_retry_timestep, post_linesearch, setup_jacobian) plus the Mat / PC / KSP / SNES calls
+`timestepper.F90` makes, each forwarding to the C ABI in include/waiwera_b200.h.  Arrays may be
+numpy arrays (host) or torch CUDA tensors (device, zero copy).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Params, Relperm, Cappress, KspOpts, NewtonOpts, NewtonResult, check
+
+THERMO_IAPWS, THERMO_IFC67 = 0, 1
+EOS_WE, EOS_W = 0, 1
+RP_FULLY_MOBILE, RP_LINEAR, RP_PICKENS, RP_COREY, RP_GRANT, RP_VAN_GENUCHTEN, RP_TABLE = range(7)
+CP_ZERO, CP_LINEAR, CP_VAN_GENUCHTEN, CP_TABLE = range(4)
+PC_NONE, PC_PBJACOBI, PC_BJACOBI_ILU0 = 0, 1, 2
+KSP_GMRES, KSP_BCGS = 0, 1
+
+
+def ptr(a, dtype=None):
+    """void* of a numpy array (host) or torch tensor (device); None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if dtype is not None:
+            assert a.dtype == dtype, (a.dtype, dtype)
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    # torch tensor
+    assert a.is_contiguous()
+    return a.data_ptr()
+
+
+def make_params(eos=EOS_WE, thermo=THERMO_IAPWS, relperm=None, cappress=None, gravity=(0.0, 0.0, -9.8),
+                extrapolate=0, eos_w_temperature=20.0):
+    """wb_params from any object with the same fields (e.g. the oracle's ctypes structs in the tests)."""
+    p = Params()
+    p.eos, p.thermo, p.extrapolate = eos, thermo, extrapolate
+    p.pressure_scale, p.temperature_scale = 1.0e6, 1.0e2
+    p.eos_w_temperature = eos_w_temperature
+    if relperm is None:
+        p.relperm.type = RP_LINEAR
+        p.relperm.p[0], p.relperm.p[1], p.relperm.p[2], p.relperm.p[3] = 0.0, 1.0, 0.0, 1.0
+    else:
+        C.memmove(C.byref(p.relperm), C.byref(relperm), C.sizeof(Relperm))
+    if cappress is None:
+        p.cappress.type = CP_ZERO
+    else:
+        C.memmove(C.byref(p.cappress), C.byref(cappress), C.sizeof(Cappress))
+    for k in range(3):
+        p.gravity[k] = gravity[k]
+    return p
+
+
+def ksp_opts(type=KSP_GMRES, restart=30, maxit=10000, rtol=1e-5, atol=1e-50, dtol=1e5):
+    """PETSc KSP defaults."""
+    o = KspOpts()
+    o.type, o.restart, o.maxit, o.rtol, o.atol, o.dtol = type, restart, maxit, rtol, atol, dtol
+    return o
+
+
+def newton_opts(max_iterations=8, min_iterations=0, rel_tol=1e-5, abs_tol=1.0, update_rel_tol=1e-10,
+                update_abs_tol=1.0, fd_err=1e-8, fd_umin=1e-2, pc_type=PC_BJACOBI_ILU0, pc_nblocks=1, ksp=None):
+    """defaults of src/timestepper.F90:1992-2020, 1572-1573"""
+    o = NewtonOpts()
+    o.max_iterations, o.min_iterations = max_iterations, min_iterations
+    o.rel_tol, o.abs_tol, o.update_rel_tol, o.update_abs_tol = rel_tol, abs_tol, update_rel_tol, update_abs_tol
+    o.fd_err, o.fd_umin, o.pc_type, o.pc_nblocks = fd_err, fd_umin, pc_type, pc_nblocks
+    o.ksp = ksp if ksp is not None else ksp_opts()
+    return o
+
+
+class Mat:
+    """BAIJ matrix on the GPU (MatCreateBAIJ / MatSetValuesBlocked / MatMult)."""
+
+    def __init__(self, sim, handle, nb, bs, owned=True):
+        self.sim, self.h, self.nb, self.bs, self.owned = sim, handle, nb, bs, owned
+        self.L = _lib.lib()
+
+    @classmethod
+    def create(cls, sim, nb, ncolb, bs, rowptr, colidx, vals=None):
+        L = _lib.lib()
+        h = C.c_void_p()
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        colidx = np.ascontiguousarray(colidx, np.int32)
+        check(L.wb_mat_create(sim.h, nb, ncolb, bs, len(colidx), ptr(rowptr), ptr(colidx), ptr(vals), C.byref(h)),
+              "wb_mat_create")
+        return cls(sim, h, nb, bs)
+
+    def set_values(self, vals):
+        check(self.L.wb_mat_set_values(self.h, ptr(vals)), "wb_mat_set_values")
+
+    def mult(self, x, y):
+        check(self.L.wb_mat_mult(self.h, ptr(x), ptr(y)), "wb_mat_mult")
+        return y
+
+    def destroy(self):
+        if self.owned and self.h:
+            self.L.wb_mat_destroy(self.h)
+            self.h = None
+
+
+class PC:
+    """PCSetUp / PCApply (pbjacobi, bjacobi + ILU(0))."""
+
+    def __init__(self, mat, type=PC_BJACOBI_ILU0, nblocks=1, block_of_row=None):
+        self.L = _lib.lib()
+        self.mat = mat
+        self.h = C.c_void_p()
+        bor = None if block_of_row is None else np.ascontiguousarray(block_of_row, np.int32)
+        self.rc = check(self.L.wb_pc_setup(mat.h, type, nblocks, ptr(bor), C.byref(self.h)), "wb_pc_setup")
+
+    def refactor(self):
+        return check(self.L.wb_pc_refactor(self.h), "wb_pc_refactor")
+
+    def apply(self, r, z):
+        check(self.L.wb_pc_apply(self.h, ptr(r), ptr(z)), "wb_pc_apply")
+        return z
+
+    def destroy(self):
+        if self.h:
+            self.L.wb_pc_destroy(self.h)
+            self.h = None
+
+
+def ksp_solve(mat, pc, b, x, opts=None):
+    """KSPSolve; returns (reason, iterations, residual norm)."""
+    L = _lib.lib()
+    o = opts if opts is not None else ksp_opts()
+    its, reason, rn = C.c_int(), C.c_int(), C.c_double()
+    check(L.wb_ksp_solve(mat.h, pc.h, C.byref(o), ptr(b), ptr(x), C.byref(its), C.byref(reason), C.byref(rn)),
+          "wb_ksp_solve")
+    return reason.value, its.value, rn.value
+
+
+class FlowSimulation:
+    """The flow-simulation ODE on one GPU (one instance per rank)."""
+
+    def __init__(self, params, mesh, device=0):
+        L = _lib.lib()
+        self.L = L
+        self.params = params
+        self.mesh = mesh
+        self.h = C.c_void_p()
+        check(L.wb_create(C.byref(params), device, C.byref(self.h)), "wb_create")
+        self.np = L.wb_num_primary(self.h)
+        self.dof = L.wb_fluid_dof(self.h)
+        self._keep = (np.ascontiguousarray(mesh.face_cells, np.int32), np.ascontiguousarray(mesh.face_geom, np.float64),
+                      np.ascontiguousarray(mesh.cell_geom, np.float64), np.ascontiguousarray(mesh.rock, np.float64))
+        check(L.wb_set_mesh(self.h, mesh.ncell, mesh.ninterior, mesh.nowned, len(self._keep[0]),
+                            ptr(self._keep[0]), ptr(self._keep[1]), ptr(self._keep[2]), ptr(self._keep[3])), "wb_set_mesh")
+        self.ncell, self.ninterior, self.nowned = mesh.ncell, mesh.ninterior, mesh.nowned
+        self.n = self.nowned * self.np
+        check(L.wb_set_global_offset(self.h, mesh.first_cell, mesh.ncell_global or mesh.nowned), "wb_set_global_offset")
+
+    # ---- multi-GPU plumbing: NCCL id is broadcast by the caller (torch.distributed)
+    def comm_init(self, rank, nranks, unique_id):
+        check(self.L.wb_comm_init(self.h, rank, nranks, ptr(unique_id)), "wb_comm_init")
+        m = self.mesh
+        if m.neigh_rank is not None and len(m.neigh_rank):
+            check(self.L.wb_set_halo(self.h, len(m.neigh_rank), ptr(m.neigh_rank), ptr(m.send_ptr), ptr(m.send_idx),
+                                     ptr(m.recv_ptr), ptr(m.recv_idx)), "wb_set_halo")
+
+    @staticmethod
+    def unique_id():
+        uid = np.zeros(128, np.uint8)
+        check(_lib.lib().wb_comm_unique_id(ptr(uid)), "wb_comm_unique_id")
+        return uid
+
+    def destroy(self):
+        if self.h:
+            self.L.wb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # ---- state
+    def fluid_init(self, y, region):
+        return check(self.L.wb_fluid_init(self.h, ptr(y), ptr(np.ascontiguousarray(region, np.int32))), "wb_fluid_init")
+
+    def set_boundaries(self, ghost_cells, interior_cells, primary, region):
+        g = np.ascontiguousarray(ghost_cells, np.int32)
+        ic = np.ascontiguousarray(interior_cells, np.int32)
+        pr = np.ascontiguousarray(primary, np.float64)
+        rg = np.ascontiguousarray(region, np.int32)
+        return check(self.L.wb_set_boundaries(self.h, len(g), ptr(g), ptr(ic), ptr(pr), ptr(rg)), "wb_set_boundaries")
+
+    def fluid(self):
+        out = np.zeros((self.ncell, self.dof))
+        check(self.L.wb_get_fluid(self.h, ptr(out)), "wb_get_fluid")
+        return out
+
+    def regions(self):
+        r = np.zeros(self.ncell, np.int32)
+        check(self.L.wb_get_regions(self.h, ptr(r)), "wb_get_regions")
+        return r
+
+    def pre_iteration(self):
+        check(self.L.wb_pre_iteration(self.h))
+
+    def pre_timestep(self):
+        check(self.L.wb_pre_timestep(self.h))
+
+    def pre_retry_timestep(self):
+        check(self.L.wb_pre_retry_timestep(self.h))
+
+    # ---- ode hooks
+    def pre_eval(self, y, perturbed_columns=None):
+        pc = None if perturbed_columns is None else np.ascontiguousarray(perturbed_columns, np.int32)
+        return check(self.L.wb_pre_eval(self.h, ptr(y), ptr(pc), 0 if pc is None else len(pc)), "wb_pre_eval")
+
+    def lhs(self, y, out=None):
+        """pre_eval + cell_balances, as timestepper's residual routines call them"""
+        out = np.zeros(self.n) if out is None else out
+        err = self.pre_eval(y)
+        if err == 0:
+            err = check(self.L.wb_cell_balances(self.h, ptr(out)), "wb_cell_balances")
+        return err, out
+
+    def rhs(self, out=None):
+        out = np.zeros(self.n) if out is None else out
+        err = check(self.L.wb_cell_inflows(self.h, ptr(out)), "wb_cell_inflows")
+        return err, out
+
+    def residual(self, y, lhs_last, dt, perturbed=None, lhs=None, rhs=None, r=None, want_parts=True):
+        if want_parts:
+            lhs = np.zeros(self.n) if lhs is None else lhs
+            rhs = np.zeros(self.n) if rhs is None else rhs
+        r = np.zeros(self.n) if r is None else r
+        pc = None if perturbed is None else np.ascontiguousarray(perturbed, np.int32)
+        err = check(self.L.wb_residual_be(self.h, ptr(y), ptr(lhs_last), dt, ptr(pc), 0 if pc is None else len(pc),
+                                          ptr(lhs), ptr(rhs), ptr(r)), "wb_residual_be")
+        return err, lhs, rhs, r
+
+    def max_scaled(self, v, scale, tol):
+        mv, ml = C.c_double(), C.c_int64()
+        check(self.L.wb_max_scaled(self.h, ptr(v), ptr(scale), tol, C.byref(mv), C.byref(ml)), "wb_max_scaled")
+        return mv.value, ml.value
+
+    # ---- Jacobian
+    def jacobian_pattern(self):
+        nb, bs, nnzb = C.c_int(), C.c_int(), C.c_int()
+        check(self.L.wb_jacobian_pattern(self.h, C.byref(nb), C.byref(bs), C.byref(nnzb), None, None, None))
+        rowptr, colidx = np.zeros(nb.value + 1, np.int32), np.zeros(nnzb.value, np.int32)
+        check(self.L.wb_jacobian_get(self.h, ptr(rowptr), ptr(colidx), None), "wb_jacobian_get")
+        return nb.value, bs.value, rowptr, colidx
+
+    def jacobian_values(self):
+        nb, bs, rowptr, colidx = self.jacobian_pattern()
+        vals = np.zeros((len(colidx), bs * bs))
+        check(self.L.wb_jacobian_get(self.h, None, None, ptr(vals)), "wb_jacobian_get")
+        return vals
+
+    def jacobian(self, y, lhs_last, dt, fd_err=1e-8, fd_umin=1e-2, colored=False, vals_out=None):
+        if colored:
+            nc = C.c_int()
+            err = check(self.L.wb_jacobian_be_colored(self.h, ptr(y), ptr(lhs_last), dt, fd_err, fd_umin, ptr(vals_out),
+                                                      C.byref(nc)), "wb_jacobian_be_colored")
+            self.ncolors = nc.value
+            return err
+        return check(self.L.wb_jacobian_be(self.h, ptr(y), ptr(lhs_last), dt, fd_err, fd_umin, ptr(vals_out)),
+                     "wb_jacobian_be")
+
+    def jacobian_mat(self):
+        h = C.c_void_p()
+        check(self.L.wb_jacobian_mat(self.h, C.byref(h)))
+        return Mat(self, h, self.nowned, self.np, owned=False)
+
+    # ---- transitions
+    def fluid_transitions(self, y_old, search, y):
+        cs, cy = C.c_int(), C.c_int()
+        err = check(self.L.wb_fluid_transitions(self.h, ptr(y_old), ptr(search), ptr(y), C.byref(cs), C.byref(cy)),
+                    "wb_fluid_transitions")
+        return err, cs.value, cy.value
+
+    # ---- Newton
+    def newton_solve(self, y, lhs_last, dt, opts=None):
+        o = opts if opts is not None else newton_opts()
+        res = NewtonResult()
+        check(self.L.wb_newton_solve_be(self.h, C.byref(o), dt, ptr(lhs_last), ptr(y), C.byref(res)), "wb_newton_solve_be")
+        return res
+
+    # ---- instrumentation
+    def timer(self, name):
+        ms, cnt = C.c_double(), C.c_int64()
+        self.L.wb_timer_get(self.h, name.encode(), C.byref(ms), C.byref(cnt))
+        return ms.value, cnt.value
+
+    def launches(self):
+        return self.L.wb_launch_count(self.h)
+
+    def stream(self):
+        return self.L.wb_stream(self.h)

@@ -1,0 +1,237 @@
+"""Synthetic mesh generator and partitioner producing the arrays the Newton-step path consumes.
+
+The reference builds these arrays with DMPlex (src/mesh.F90:438-664 geometry, :727-802 ghost /
+flux-face arrays, :143-171 distribution with overlap 1); that machinery is out of scope
+(SURVEY.md section 8), so structured grids are generated directly in the same layout:
+
+  face_cells [nf,2] int32   support cells of each flux face, normal from cell 1 to cell 2
+  face_geom  [nf,12]        area, distance(2), distance12, normal(3), gravity_normal,
+                            centroid(3), permeability_direction       (src/face.F90:127-133)
+  cell_geom  [nc,4]         centroid(3), volume                       (src/cell.F90:93-94)
+  rock       [nc,8]         permeability(3), wet/dry conductivity, porosity, density,
+                            specific heat                             (src/rock.F90:97-112)
+
+Local cell numbering: owned cells, then partition ghost cells (grouped by owner rank), then
+Dirichlet boundary ghost cells.  Setup-time host code (numpy); nothing here is on the hot path.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+SEED = 20240917
+
+
+@dataclass
+class Mesh:
+    ncell: int            # local cells incl. ghosts
+    ninterior: int        # owned + partition ghosts
+    nowned: int
+    face_cells: np.ndarray
+    face_geom: np.ndarray
+    cell_geom: np.ndarray
+    rock: np.ndarray
+    dims: tuple = (0, 0, 0)
+    natural: np.ndarray = None        # natural (global) index of each interior local cell
+    boundary: dict = field(default_factory=dict)  # ghost_cells, interior_cells (local indices)
+    # partition info (None on a serial mesh)
+    rank: int = 0
+    nranks: int = 1
+    first_cell: int = 0               # global (rank-contiguous) index of the first owned cell
+    ncell_global: int = 0
+    neigh_rank: np.ndarray = None
+    send_ptr: np.ndarray = None
+    send_idx: np.ndarray = None
+    recv_ptr: np.ndarray = None
+    recv_idx: np.ndarray = None
+
+    @property
+    def nface(self):
+        return len(self.face_cells)
+
+
+def default_rock(n, rng=None, heterogeneous=True):
+    """SURVEY 8(d) config 2 rock: k=(1e-13,1e-13,1e-14)*10^U(-0.5,0.5), defaults of src/rock.F90:69-76."""
+    rock = np.zeros((n, 8))
+    fac = 10.0 ** rng.uniform(-0.5, 0.5, n) if (heterogeneous and rng is not None) else np.ones(n)
+    rock[:, 0] = 1e-13 * fac
+    rock[:, 1] = 1e-13 * fac
+    rock[:, 2] = 1e-14 * fac
+    rock[:, 3] = 2.5
+    rock[:, 4] = 2.5
+    rock[:, 5] = 0.1
+    rock[:, 6] = 2200.0
+    rock[:, 7] = 1000.0
+    return rock
+
+
+def structured(nx, ny, nz, dx=10.0, dy=None, dz=None, gravity=(0.0, 0.0, -9.8), seed=SEED, heterogeneous=True,
+               top_boundary=False):
+    """nx*ny*nz box mesh; cell index i + nx*(j + ny*k); k = 0 is the top layer (z = -dz/2)."""
+    dy = dx if dy is None else dy
+    dz = dx if dz is None else dz
+    g = np.asarray(gravity, float)
+    rng = np.random.default_rng(seed)
+    n = nx * ny * nz
+    idx = np.arange(n, dtype=np.int64)
+    i, j, k = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+    cell_geom = np.zeros((n, 4))
+    cell_geom[:, 0] = (i + 0.5) * dx
+    cell_geom[:, 1] = (j + 0.5) * dy
+    cell_geom[:, 2] = -(k + 0.5) * dz
+    cell_geom[:, 3] = dx * dy * dz
+    fcs, fgs = [], []
+    for d, (cond, step, area, dist, normal) in enumerate([
+            (i < nx - 1, 1, dy * dz, dx, (1.0, 0.0, 0.0)),
+            (j < ny - 1, nx, dx * dz, dy, (0.0, 1.0, 0.0)),
+            (k < nz - 1, nx * ny, dx * dy, dz, (0.0, 0.0, -1.0))]):
+        c1 = idx[cond]
+        c2 = c1 + step
+        fg = np.zeros((len(c1), 12))
+        fg[:, 0] = area
+        fg[:, 1] = 0.5 * dist
+        fg[:, 2] = 0.5 * dist
+        fg[:, 3] = dist
+        fg[:, 4:7] = normal
+        fg[:, 7] = float(np.dot(g, normal))
+        fg[:, 8:11] = 0.5 * (cell_geom[c1, :3] + cell_geom[c2, :3])
+        fg[:, 11] = d + 1
+        fcs.append(np.stack([c1, c2], 1))
+        fgs.append(fg)
+    rock = default_rock(n, rng, heterogeneous)
+    ncell = n
+    boundary = {}
+    if top_boundary:
+        # Dirichlet ghost cell above every top-layer cell (src/mesh.F90:583-664, 1069-1264):
+        # cell 2 is the ghost, distance = (d1, 0), distance12 = d1, volume 0
+        top = idx[k == 0]
+        ghosts = n + np.arange(len(top))
+        fg = np.zeros((len(top), 12))
+        fg[:, 0] = dx * dy
+        fg[:, 1] = 0.5 * dz
+        fg[:, 2] = 0.0
+        fg[:, 3] = 0.5 * dz
+        fg[:, 4:7] = (0.0, 0.0, 1.0)
+        fg[:, 7] = float(np.dot(g, (0.0, 0.0, 1.0)))
+        fg[:, 8:11] = cell_geom[top, :3] + np.array([0.0, 0.0, 0.5 * dz])
+        fg[:, 11] = 3
+        fcs.append(np.stack([top, ghosts], 1))
+        fgs.append(fg)
+        gg = np.zeros((len(top), 4))
+        gg[:, :3] = fg[:, 8:11]
+        cell_geom = np.vstack([cell_geom, gg])
+        rock = np.vstack([rock, rock[top]])
+        ncell = n + len(top)
+        boundary = {"ghost_cells": ghosts.astype(np.int32), "interior_cells": top.astype(np.int32)}
+    return Mesh(ncell=ncell, ninterior=n, nowned=n,
+                face_cells=np.ascontiguousarray(np.vstack(fcs), dtype=np.int32),
+                face_geom=np.ascontiguousarray(np.vstack(fgs)),
+                cell_geom=np.ascontiguousarray(cell_geom), rock=np.ascontiguousarray(rock),
+                dims=(nx, ny, nz), natural=idx.copy(), boundary=boundary, ncell_global=n)
+
+
+def box_owner(mesh, parts):
+    """owner rank of each interior cell for a px*py*pz box decomposition (rank = a + px*(b + py*c))."""
+    nx, ny, nz = mesh.dims
+    px, py, pz = parts
+    idx = mesh.natural
+    i, j, k = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+    a = np.minimum(i * px // nx, px - 1)
+    b = np.minimum(j * py // ny, py - 1)
+    c = np.minimum(k * pz // nz, pz - 1)
+    return (a + px * (b + py * c)).astype(np.int32)
+
+
+def default_parts(nranks):
+    return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(nranks, (1, 1, nranks))
+
+
+def partition(mesh, owner, rank, nranks):
+    """Rank-local mesh with one layer of ghost cells (DMPlexDistribute overlap 1, src/mesh.F90:143-171).
+
+    Owned cells keep ascending natural order; ghost cells are grouped by owner rank, ascending
+    natural order inside a group (both sides of a halo pair therefore agree on the message order).
+    Faces: every face with at least one owned support cell, in global face order.
+    """
+    n = mesh.ninterior
+    fc = mesh.face_cells
+    mine = owner == rank
+    owned = np.flatnonzero(mine)
+    isb = fc[:, 1] >= n  # boundary faces (cell 2 is a Dirichlet ghost)
+    o1 = np.where(fc[:, 0] < n, owner[np.minimum(fc[:, 0], n - 1)], -1)
+    o2 = np.where(~isb, owner[np.minimum(fc[:, 1], n - 1)], -1)
+    keep = (o1 == rank) | (o2 == rank)
+    lf = np.flatnonzero(keep)
+    cells = fc[lf]
+    # partition ghosts: interior cells on kept faces that are not mine
+    cand = cells[cells < n]
+    gh = np.unique(cand[owner[cand] != rank])
+    gh = gh[np.lexsort((gh, owner[gh]))]
+    bnd = np.unique(cells[:, 1][cells[:, 1] >= n])
+    order = np.concatenate([owned, gh, bnd])
+    g2l = -np.ones(mesh.ncell, np.int64)
+    g2l[order] = np.arange(len(order))
+    local_fc = g2l[cells].astype(np.int32)
+    assert (local_fc >= 0).all()
+    counts = np.bincount(owner, minlength=nranks)
+    first = int(counts[:rank].sum())
+    # halo plan
+    neigh = np.unique(owner[gh]) if len(gh) else np.zeros(0, np.int32)
+    recv_ptr, recv_idx, send_ptr, send_idx = [0], [], [0], []
+    # cells I must send to rank r: my owned cells adjacent (through a face) to a cell owned by r
+    a, b = fc[~isb, 0], fc[~isb, 1]
+    oa, ob = owner[a], owner[b]
+    for r in neigh:
+        ridx = gh[owner[gh] == r]
+        recv_idx.extend(g2l[ridx])
+        recv_ptr.append(len(recv_idx))
+        s = np.unique(np.concatenate([a[(oa == rank) & (ob == r)], b[(ob == rank) & (oa == r)]]))
+        send_idx.extend(g2l[s])
+        send_ptr.append(len(send_idx))
+    boundary = {}
+    if len(bnd):
+        bfaces = cells[cells[:, 1] >= n]
+        boundary = {"ghost_cells": g2l[bfaces[:, 1]].astype(np.int32), "interior_cells": g2l[bfaces[:, 0]].astype(np.int32),
+                    "global_ghost": bfaces[:, 1].astype(np.int64)}
+    return Mesh(ncell=len(order), ninterior=len(owned) + len(gh), nowned=len(owned),
+                face_cells=np.ascontiguousarray(local_fc), face_geom=np.ascontiguousarray(mesh.face_geom[lf]),
+                cell_geom=np.ascontiguousarray(mesh.cell_geom[order]), rock=np.ascontiguousarray(mesh.rock[order]),
+                dims=mesh.dims, natural=order[:len(owned) + len(gh)].copy(), boundary=boundary,
+                rank=rank, nranks=nranks, first_cell=first, ncell_global=n,
+                neigh_rank=np.asarray(neigh, np.int32), send_ptr=np.asarray(send_ptr, np.int32),
+                send_idx=np.asarray(send_idx, np.int32), recv_ptr=np.asarray(recv_ptr, np.int32),
+                recv_idx=np.asarray(recv_idx, np.int32))
+
+
+def hydrostatic_state(mesh, seed=SEED, two_phase_layers=0, thermo_psat=None):
+    """SURVEY 8(d) config 2 initial state on the interior cells of a (serial) structured mesh.
+
+    Single-phase liquid: P = 1e5 + 9.8*997*depth (+U(-1e3,1e3)), T = 20 + 0.2*depth (+U(-0.5,0.5)), region 1.
+    With two_phase_layers > 0 the top layers are region 4 with P = Psat(T) (thermo_psat: callable T -> P)
+    and S_v = U(0.05, 0.4).  Returns unscaled primaries [n,2] and regions [n].
+    """
+    rng = np.random.default_rng(seed + 1)
+    n = mesh.ninterior
+    depth = -mesh.cell_geom[:n, 2]
+    P = 1.0e5 + 9.8 * 997.0 * depth + rng.uniform(-1e3, 1e3, n)
+    T = 20.0 + 0.2 * depth + rng.uniform(-0.5, 0.5, n)
+    sv = rng.uniform(0.05, 0.4, n)
+    primary = np.stack([P, T], 1)
+    region = np.ones(n, np.int32)
+    if two_phase_layers > 0:
+        nx, ny, nz = mesh.dims
+        k = mesh.natural[:n] // (nx * ny)
+        tp = k < two_phase_layers
+        # hot shallow zone so that Psat(T) is a sensible pressure
+        Ttp = 150.0 + 2.0 * depth[tp] / max(depth.max(), 1.0) + rng.uniform(-0.5, 0.5, tp.sum())
+        primary[tp, 0] = np.array([thermo_psat(t) for t in Ttp]) if tp.sum() < 50000 else thermo_psat(Ttp)
+        primary[tp, 1] = sv[tp]
+        region[tp] = 4
+    return primary, region
+
+
+def scale_primaries(primary, region, pressure_scale=1e6, temperature_scale=1e2):
+    """eos%scale for eos_we (src/eos.F90:186-196, src/eos_we.F90:104-109)."""
+    y = np.array(primary, float, copy=True)
+    y[:, 0] /= pressure_scale
+    y[:, 1] = np.where(region == 4, y[:, 1], y[:, 1] / temperature_scale)
+    return y
