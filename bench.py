@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dims", type=int, nargs=3, default=list(DIMS))
     ap.add_argument("--pc", default="ilu0", choices=["ilu0", "pbjacobi", "none"])
-    ap.add_argument("--pc-blocks", type=int, default=1, help="block-Jacobi sub-domains per GPU")
+    ap.add_argument("--pc-blocks", type=int, default=1, help="block-Jacobi sub-domains per GPU (contiguous row ranges)")
+    ap.add_argument("--pc-cube", type=int, default=10,
+                    help="block-Jacobi sub-domains = cubes of this many cells per side (0: use --pc-blocks)")
     ap.add_argument("--ksp", default="gmres", choices=["gmres", "bcgs"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-its", type=int, default=30)
@@ -48,7 +50,7 @@ def parse():
 
 
 def workload_name(dims):
-    return "eos_we IAPWS %dx%dx%d structured (%d cells), BAIJ bs=2, BE dt=1e6 s, GMRES(30)+bjacobi/ILU(0) rtol 1e-5" % (
+    return "eos_we IAPWS %dx%dx%d structured (%d cells), BAIJ bs=2, BE dt=1e6 s, Krylov+bjacobi/ILU(0) rtol 1e-5" % (
         dims[0], dims[1], dims[2], dims[0] * dims[1] * dims[2])
 
 
@@ -59,6 +61,10 @@ def build_problem(dims):
     primary, region = wmesh.hydrostatic_state(m, seed=wmesh.SEED)
     y = np.ascontiguousarray(wmesh.scale_primaries(primary, region)).reshape(-1)
     return m, y, region
+
+
+def hint_key(args):
+    return "%dx%dx%d/%s/%s/cube%d/blocks%d/gpus%d" % (tuple(args.dims) + (args.ksp, args.pc, args.pc_cube, args.pc_blocks, args.gpus))
 
 
 # ------------------------------------------------------------------ clocks sampler
@@ -103,7 +109,7 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------ CPU arm (oracle = port of the reference algorithm)
 
-def cpu_newton_sample(dims, pc_blocks, sample_its, total_its_hint=None):
+def cpu_newton_sample(dims, pc_blocks, sample_its, total_its_hint=None, pc_cube=0, ksp="gmres"):
     """Times the reference algorithm (oracle port: FD-coloured Jacobian, ILU(0), GMRES(30)) on the host cores
     on a bounded sample of the same workload: the full mesh, one residual, one FD Jacobian, one PC set-up
     and `sample_its` GMRES iterations; the Newton-step time is that with the Krylov part extrapolated
@@ -131,11 +137,15 @@ def cpu_newton_sample(dims, pc_blocks, sample_its, total_its_hint=None):
     t_jac = time.perf_counter() - t0
     nblk = max(pc_blocks, 1)
     bor = None if nblk == 1 else ((np.arange(nb, dtype=np.int64) * nblk) // nb).astype(np.int32)
+    if pc_cube > 0:
+        from waiwera_b200 import mesh as wmesh
+        bor = wmesh.cube_blocks(m, pc_cube)
     t0 = time.perf_counter()
     pc = L.wo_pc_create(A, wo.PC_BJACOBI_ILU0, wo.ip(bor))
     t_pc = time.perf_counter() - t0
     o = wo.KspOpts()
-    o.type, o.restart, o.maxit, o.rtol, o.atol, o.dtol = wo.KSP_GMRES, 30, sample_its, 1e-5, 1e-50, 1e5
+    o.type, o.restart, o.maxit = (wo.KSP_GMRES if ksp == "gmres" else wo.KSP_BCGS), 30, sample_its
+    o.rtol, o.atol, o.dtol = 1e-5, 1e-50, 1e5
     x = np.zeros(nb * 2)
     its, rn = C.c_int(), C.c_double()
     t0 = time.perf_counter()
@@ -157,7 +167,7 @@ def cpu_newton_sample(dims, pc_blocks, sample_its, total_its_hint=None):
     return {"value": 1.0 / t_step, "unit": UNIT, "cores": ncores, "kind": "port",
             "sample": "full %dx%dx%d mesh: 1 residual (%.2fs) + 1 FD-coloured Jacobian, %d colours (%.2fs) + ILU(0) factor "
                       "(%.2fs) + %d GMRES iterations (%.3fs each); Krylov part extrapolated to %d iterations; "
-                      "oracle port of the reference algorithm (not the PETSc binary), OpenMP in SpMV/dots only"
+                      "oracle port of the reference algorithm (not the PETSc binary), OpenMP over sub-domains / SpMV / dots"
                       % (dims[0], dims[1], dims[2], t_res, nc, t_jac, t_pc, its.value, per_it, total_its),
             "s_per_step": t_step, "spmv_gbs": spmv_bytes / t_spmv / 1e9, "ksp_iterations_assumed": total_its}
 
@@ -173,12 +183,12 @@ def run_reference(args):
     hint_file = os.path.join(ROOT, "profiles", "ksp_iterations_1m.json")
     if os.path.exists(hint_file):
         try:
-            hint = json.load(open(hint_file)).get("%dx%dx%d" % dims)
+            hint = json.load(open(hint_file)).get(hint_key(args))
         except Exception:
             hint = None
     nrep = max(1, min(args.steps, 2))
     for _ in range(nrep):
-        samples.append(cpu_newton_sample(dims, args.pc_blocks, args.cpu_sample_its, hint))
+        samples.append(cpu_newton_sample(dims, args.pc_blocks, args.cpu_sample_its, hint, args.pc_cube, args.ksp))
     best = max(samples, key=lambda s: s["value"])
     out = {"metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": nrep,
            "warmup": 0, "ms_per_step": 1e3 * best["s_per_step"], "higher_is_better": True, "scaling": "strong",
@@ -224,6 +234,8 @@ def run_b200(args):
     assert sim.fluid_init(y, region) == 0
     err, L0 = sim.lhs(y)
     assert err == 0
+    if args.pc_cube > 0 and args.pc == "ilu0":
+        sim.set_pc_blocks(wmesh.cube_blocks(m, args.pc_cube))
     pc_type = {"ilu0": flow.PC_BJACOBI_ILU0, "pbjacobi": flow.PC_PBJACOBI, "none": flow.PC_NONE}[args.pc]
     ksp_type = {"gmres": flow.KSP_GMRES, "bcgs": flow.KSP_BCGS}[args.ksp]
     opts = flow.newton_opts(max_iterations=1, pc_type=pc_type, pc_nblocks=args.pc_blocks, ksp=flow.ksp_opts(type=ksp_type))
@@ -335,7 +347,8 @@ def run_b200(args):
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name(dims), "parallelism": "domain decomposition %s, halo of x inside SpMV" % (wmesh.default_parts(world),),
-                      "pc": args.pc, "pc_blocks_per_gpu": args.pc_blocks, "ksp": args.ksp,
+                      "pc": args.pc, "pc_subdomains": ("cubes of %d^3 cells" % args.pc_cube) if args.pc_cube > 0 else ("%d contiguous ranges per GPU" % args.pc_blocks),
+                      "ksp": args.ksp,
                       "l2": "working set (Jacobian 222 MB + Krylov basis 496 MB) exceeds the 126 MB L2; no explicit flush",
                       "ksp_iterations_per_step": ksp_its, "newton_reason": int(res.reason),
                       "max_scaled_residual": [res.max_residual[0], res.max_residual[1]]},
@@ -348,13 +361,12 @@ def run_b200(args):
     try:
         hint_file = os.path.join(ROOT, "profiles", "ksp_iterations_1m.json")
         hints = json.load(open(hint_file)) if os.path.exists(hint_file) else {}
-        if world == 1 and args.pc == "ilu0" and args.pc_blocks == 1:
-            hints["%dx%dx%d" % dims] = ksp_its
-            json.dump(hints, open(hint_file, "w"))
+        hints[hint_key(args)] = ksp_its
+        json.dump(hints, open(hint_file, "w"), indent=1, sort_keys=True)
     except Exception:
         pass
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_newton_sample(dims, 1, args.cpu_sample_its, ksp_its)
+        out["cpu_baseline"] = cpu_newton_sample(dims, args.pc_blocks, args.cpu_sample_its, ksp_its, args.pc_cube, args.ksp)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -242,6 +242,10 @@ typedef struct {
   double max_residual[32];
   int lin_its[32];
 } wb_newton_result;
+/* sub-domain of every owned row for the block-Jacobi preconditioner the Newton solve sets up
+   (arbitrary index sets as with PCASMSetLocalSubdomains at overlap 0; NULL restores the default
+   contiguous split into opts->pc_nblocks ranges).  block_of_row: host array, nowned entries. */
+int wb_set_pc_blocks(wb_ctx *ctx, const int32_t *block_of_row);
 /* one backward-Euler step solve: y in/out (scaled primaries of owned cells) */
 int wb_newton_solve_be(wb_ctx *ctx, const wb_newton_opts *opts, double dt, const double *lhs_last, double *y,
                        wb_newton_result *res);

@@ -244,6 +244,11 @@ struct wo_pc {
   /* factor storage: same pattern as the (sub-domain restricted) matrix */
   int32_t *rowptr, *colidx, *diag;
   double *val; /* L (multipliers), inverted diagonal, U */
+  /* sub-domains (block Jacobi): rows of block b are blk_rows[blk_ptr[b]..blk_ptr[b+1]), ascending.
+     Sub-domains are independent, so they are factored / solved on separate host threads
+     (one MPI rank per block in the reference); per row the arithmetic is the sequential one. */
+  int nblocks;
+  int32_t *blk_ptr, *blk_rows;
 };
 
 wo_pc *wo_pc_create(const wo_bsr *A, int type, const int32_t *block_of_row) {
@@ -287,32 +292,59 @@ wo_pc *wo_pc_create(const wo_bsr *A, int type, const int32_t *block_of_row) {
         q++;
       }
   }
-  /* IKJ block ILU(0): MatILUFactorNumeric_SeqBAIJ_N_NaturalOrdering semantics */
-  int32_t *pos = (int32_t *)malloc(nb * sizeof(int32_t));
-  for (int i = 0; i < nb; i++) pos[i] = -1;
-  double mult[WO_MAX_NP * WO_MAX_NP], inv[WO_MAX_NP * WO_MAX_NP];
-  for (int i = 0; i < nb; i++) {
-    for (int k = pc->rowptr[i]; k < pc->rowptr[i + 1]; k++) pos[pc->colidx[k]] = k;
-    for (int k = pc->rowptr[i]; k < pc->diag[i]; k++) {
-      int kr = pc->colidx[k];
-      double *aik = pc->val + (size_t)k * bs2;
-      /* multiplier = A_ik * inv(A_kk) (diag of row kr already inverted) */
-      blk_mul(aik, pc->val + (size_t)pc->diag[kr] * bs2, mult, bs);
-      memcpy(aik, mult, bs2 * sizeof(double));
-      for (int q = pc->diag[kr] + 1; q < pc->rowptr[kr + 1]; q++) {
-        int p = pos[pc->colidx[q]];
-        if (p >= 0) blk_mulsub(mult, pc->val + (size_t)q * bs2, pc->val + (size_t)p * bs2, bs);
+  /* sub-domain row lists */
+  {
+    int nblk = 1;
+    if (block_of_row)
+      for (int i = 0; i < nb; i++)
+        if (block_of_row[i] + 1 > nblk) nblk = block_of_row[i] + 1;
+    pc->nblocks = nblk;
+    pc->blk_ptr = (int32_t *)calloc(nblk + 1, sizeof(int32_t));
+    pc->blk_rows = (int32_t *)malloc(nb * sizeof(int32_t));
+    for (int i = 0; i < nb; i++) pc->blk_ptr[(block_of_row ? block_of_row[i] : 0) + 1]++;
+    for (int b = 0; b < nblk; b++) pc->blk_ptr[b + 1] += pc->blk_ptr[b];
+    int32_t *fill = (int32_t *)malloc(nblk * sizeof(int32_t));
+    for (int b = 0; b < nblk; b++) fill[b] = pc->blk_ptr[b];
+    for (int i = 0; i < nb; i++) pc->blk_rows[fill[block_of_row ? block_of_row[i] : 0]++] = i;
+    free(fill);
+  }
+  /* IKJ block ILU(0): MatILUFactorNumeric_SeqBAIJ_N_NaturalOrdering semantics, sub-domain by sub-domain */
+  int failed = 0;
+#pragma omp parallel
+  {
+    int32_t *pos = (int32_t *)malloc(nb * sizeof(int32_t));
+    for (int i = 0; i < nb; i++) pos[i] = -1;
+    double mult[WO_MAX_NP * WO_MAX_NP], inv[WO_MAX_NP * WO_MAX_NP];
+#pragma omp for schedule(dynamic, 1)
+    for (int b = 0; b < pc->nblocks; b++) {
+      for (int q = pc->blk_ptr[b]; q < pc->blk_ptr[b + 1]; q++) {
+        int i = pc->blk_rows[q];
+        for (int k = pc->rowptr[i]; k < pc->rowptr[i + 1]; k++) pos[pc->colidx[k]] = k;
+        for (int k = pc->rowptr[i]; k < pc->diag[i]; k++) {
+          int kr = pc->colidx[k];
+          double *aik = pc->val + (size_t)k * bs2;
+          /* multiplier = A_ik * inv(A_kk) (diag of row kr already inverted) */
+          blk_mul(aik, pc->val + (size_t)pc->diag[kr] * bs2, mult, bs);
+          memcpy(aik, mult, bs2 * sizeof(double));
+          for (int qq = pc->diag[kr] + 1; qq < pc->rowptr[kr + 1]; qq++) {
+            int p = pos[pc->colidx[qq]];
+            if (p >= 0) blk_mulsub(mult, pc->val + (size_t)qq * bs2, pc->val + (size_t)p * bs2, bs);
+          }
+        }
+        if (blk_invert(pc->val + (size_t)pc->diag[i] * bs2, inv, bs)) {
+#pragma omp atomic write
+          failed = 1;
+        } else
+          memcpy(pc->val + (size_t)pc->diag[i] * bs2, inv, bs2 * sizeof(double));
+        for (int k = pc->rowptr[i]; k < pc->rowptr[i + 1]; k++) pos[pc->colidx[k]] = -1;
       }
     }
-    if (blk_invert(pc->val + (size_t)pc->diag[i] * bs2, inv, bs)) {
-      free(pos);
-      wo_pc_destroy(pc);
-      return NULL;
-    }
-    memcpy(pc->val + (size_t)pc->diag[i] * bs2, inv, bs2 * sizeof(double));
-    for (int k = pc->rowptr[i]; k < pc->rowptr[i + 1]; k++) pos[pc->colidx[k]] = -1;
+    free(pos);
   }
-  free(pos);
+  if (failed) {
+    wo_pc_destroy(pc);
+    return NULL;
+  }
   return pc;
 }
 
@@ -334,34 +366,40 @@ void wo_pc_apply(const wo_pc *pc, const double *r, double *z) {
     }
     return;
   }
-  /* MatSolve_SeqBAIJ_N_NaturalOrdering: forward (unit L), backward with inverted diagonal */
-  for (int i = 0; i < nb; i++) {
-    double s[WO_MAX_NP];
-    for (int ii = 0; ii < bs; ii++) s[ii] = r[(size_t)i * bs + ii];
-    for (int k = pc->rowptr[i]; k < pc->diag[i]; k++) {
-      const double *v = pc->val + (size_t)k * bs2;
-      const double *xb = z + (size_t)pc->colidx[k] * bs;
-      for (int jj = 0; jj < bs; jj++)
-        for (int ii = 0; ii < bs; ii++) s[ii] -= v[jj * bs + ii] * xb[jj];
+  /* MatSolve_SeqBAIJ_N_NaturalOrdering: forward (unit L), backward with inverted diagonal,
+     one sub-domain per host thread */
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < pc->nblocks; b++) {
+    for (int q = pc->blk_ptr[b]; q < pc->blk_ptr[b + 1]; q++) {
+      int i = pc->blk_rows[q];
+      double s[WO_MAX_NP];
+      for (int ii = 0; ii < bs; ii++) s[ii] = r[(size_t)i * bs + ii];
+      for (int k = pc->rowptr[i]; k < pc->diag[i]; k++) {
+        const double *v = pc->val + (size_t)k * bs2;
+        const double *xb = z + (size_t)pc->colidx[k] * bs;
+        for (int jj = 0; jj < bs; jj++)
+          for (int ii = 0; ii < bs; ii++) s[ii] -= v[jj * bs + ii] * xb[jj];
+      }
+      for (int ii = 0; ii < bs; ii++) z[(size_t)i * bs + ii] = s[ii];
     }
-    for (int ii = 0; ii < bs; ii++) z[(size_t)i * bs + ii] = s[ii];
-  }
-  for (int i = nb - 1; i >= 0; i--) {
-    double s[WO_MAX_NP], t[WO_MAX_NP];
-    for (int ii = 0; ii < bs; ii++) s[ii] = z[(size_t)i * bs + ii];
-    for (int k = pc->diag[i] + 1; k < pc->rowptr[i + 1]; k++) {
-      const double *v = pc->val + (size_t)k * bs2;
-      const double *xb = z + (size_t)pc->colidx[k] * bs;
-      for (int jj = 0; jj < bs; jj++)
-        for (int ii = 0; ii < bs; ii++) s[ii] -= v[jj * bs + ii] * xb[jj];
+    for (int q = pc->blk_ptr[b + 1] - 1; q >= pc->blk_ptr[b]; q--) {
+      int i = pc->blk_rows[q];
+      double s[WO_MAX_NP], t[WO_MAX_NP];
+      for (int ii = 0; ii < bs; ii++) s[ii] = z[(size_t)i * bs + ii];
+      for (int k = pc->diag[i] + 1; k < pc->rowptr[i + 1]; k++) {
+        const double *v = pc->val + (size_t)k * bs2;
+        const double *xb = z + (size_t)pc->colidx[k] * bs;
+        for (int jj = 0; jj < bs; jj++)
+          for (int ii = 0; ii < bs; ii++) s[ii] -= v[jj * bs + ii] * xb[jj];
+      }
+      const double *d = pc->val + (size_t)pc->diag[i] * bs2;
+      for (int ii = 0; ii < bs; ii++) {
+        double acc = 0.0;
+        for (int jj = 0; jj < bs; jj++) acc += d[jj * bs + ii] * s[jj];
+        t[ii] = acc;
+      }
+      for (int ii = 0; ii < bs; ii++) z[(size_t)i * bs + ii] = t[ii];
     }
-    const double *d = pc->val + (size_t)pc->diag[i] * bs2;
-    for (int ii = 0; ii < bs; ii++) {
-      double acc = 0.0;
-      for (int jj = 0; jj < bs; jj++) acc += d[jj * bs + ii] * s[jj];
-      t[ii] = acc;
-    }
-    for (int ii = 0; ii < bs; ii++) z[(size_t)i * bs + ii] = t[ii];
   }
 }
 
@@ -371,6 +409,8 @@ void wo_pc_destroy(wo_pc *pc) {
   free(pc->colidx);
   free(pc->diag);
   free(pc->val);
+  free(pc->blk_ptr);
+  free(pc->blk_rows);
   free(pc);
 }
 

@@ -44,7 +44,10 @@ def test_fluid_records_match_oracle(wo, flow, case):
     for col in (2, 4):
         assert np.array_equal(a[:, col], b[:, col])
     scale = np.maximum(np.abs(a).max(axis=0), 1e-300)
-    assert (np.abs(a - b) / scale).max() < 1e-13
+    # IFC-67 finds T_sat(P) by a Newton iteration stopped at |dT| <= 1e-10 (src/IFC67.F90:637-676), so
+    # two-phase cells only agree to that stopping tolerance; everything else agrees to rounding
+    tol = 1e-13 if CASES[case]["thermo"] == 0 else 5e-11
+    assert (np.abs(a - b) / scale).max() < tol
     sim.destroy()
 
 
@@ -58,14 +61,17 @@ def test_residual_matches_oracle(wo, flow, case):
     e0, L0 = ref.lhs(y)
     e1, L1 = sim.lhs(y)
     assert e0 == e1 == 0
-    assert relerr(L1, L0) < 1e-14
+    # IAPWS is pure +,*,/ and sqrt (correctly rounded on both sides, contraction off on both sides);
+    # IFC-67 goes through pow/exp/log whose CUDA and glibc versions differ by an ulp or two
+    ltol = 1e-14 if CASES[case]["thermo"] == 0 else 1e-12
+    assert relerr(L1, L0) < ltol
     rng = np.random.default_rng(SEED + case)
     y2 = y * (1 + 1e-4 * rng.uniform(-1, 1, len(y)))
     dt = 1.0e6
     e0, lhs0, rhs0, r0 = ref.residual(y2, L0, dt)
     e1, lhs1, rhs1, r1 = sim.residual(y2, L0, dt)
     assert e0 == e1 == 0
-    assert relerr(lhs1, lhs0) < 1e-14
+    assert relerr(lhs1, lhs0) < ltol
     assert relerr(rhs1, rhs0) < RESIDUAL_TOL
     assert relerr(r1, r0) < RESIDUAL_TOL
     assert abs(np.linalg.norm(r1) - np.linalg.norm(r0)) <= RESIDUAL_TOL * np.linalg.norm(r0)
@@ -92,7 +98,7 @@ def test_residual_domain_error(wo, flow):
     sim = gpu_flow(wo, flow, m, prm, y, region)
     _, L0 = ref.lhs(y)
     ybad = y.copy()
-    ybad[2 * 11 + 1] = 5.0  # 500 degC in region 1
+    ybad[2 * 11 + 1] = 9.0  # 900 degC: outside every region's range
     assert ref.residual(ybad, L0, 1e6)[0] != 0
     assert sim.residual(ybad, L0, 1e6)[0] > 0
     # and the context recovers
@@ -136,7 +142,10 @@ def test_jacobian_matches_oracle(wo, flow, case):
     for ii in range(2):
         np.maximum.at(rowmax[:, ii], rows, np.abs(val[:, [ii, 2 + ii]]).max(axis=1))
     scale = np.stack([rowmax[rows, 0], rowmax[rows, 1], rowmax[rows, 0], rowmax[rows, 1]], 1)
-    assert (np.abs(Jl - val) / np.maximum(scale, 1e-300)).max() < 2e-6
+    # IFC-67 two-phase cells carry the 1e-10 stopping tolerance of the T_sat(P) Newton iteration into F,
+    # which the difference quotient amplifies by 1/h: the reference's own FD Jacobian has that noise
+    jtol = 2e-6 if CASES[case]["thermo"] == 0 else 1e-3
+    assert (np.abs(Jl - val) / np.maximum(scale, 1e-300)).max() < jtol
     # the reference's colouring loop run on the GPU gives the same matrix as the local assembly
     assert sim.jacobian(y2, L0, dt, colored=True) == 0
     Jc = sim.jacobian_values()

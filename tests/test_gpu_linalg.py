@@ -100,11 +100,12 @@ def test_pc_apply_matches_oracle(wo, flow, bs, pctype, nblocks):
 def test_ilu0_exact_on_block_tridiagonal(wo, flow):
     """ILU(0) has no dropped fill on a 1-D chain: the PC apply is an exact solve (size-independent property),
     checked at 200 000 rows where the level schedule is one row per level ... the worst case for the sweep."""
-    dims = (1, 1, 2000)
+    dims = (1, 1, 200000)
     bs = 2
     m, A, rowptr, colidx, val = random_bsr(wo, dims, bs, SEED + 5)
-    _, y0, region, prm = make_problem(wo, dims=dims)
-    sim = gpu_flow(wo, flow, m, prm, y0, region)
+    from waiwera_b200 import mesh as wmesh
+    _, y0, region, prm = make_problem(wo, dims=(4, 4, 4))
+    sim = gpu_flow(wo, flow, wmesh.structured(4, 4, 4), prm, y0, region)
     nb = m.nowned
     M = flow.Mat.create(sim, nb, nb, bs, rowptr, colidx, val)
     pc = flow.PC(M, 2, 1)

@@ -95,6 +95,7 @@ SIGNATURES = {
     "wb_pc_destroy": (i, [vp]),
     "wb_ksp_solve": (i, [vp, vp, C.POINTER(KspOpts), vp, vp, C.POINTER(i), C.POINTER(i), C.POINTER(d)]),
     "wb_ksp_set_check_every": (i, [i]),
+    "wb_set_pc_blocks": (i, [vp, vp]),
     "wb_newton_solve_be": (i, [vp, C.POINTER(NewtonOpts), d, vp, vp, C.POINTER(NewtonResult)]),
     "wb_timer_get": (i, [vp, C.c_char_p, C.POINTER(d), C.POINTER(i64)]),
     "wb_timer_reset": (i, [vp]),

@@ -31,7 +31,11 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "_obj", src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        # the physics translation unit is compiled without FMA contraction so that every evaluation of
+        # F (residual kernel, Jacobian kernel, colouring loop) rounds identically, and identically to the
+        # reference arithmetic order; the bandwidth-bound linear algebra keeps FMA
+        extra = ["-fmad=false"] if src == "wb_flow.cu" else []
+        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

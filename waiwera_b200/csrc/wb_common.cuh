@@ -117,6 +117,7 @@ struct wb_ctx {
   wb_mat J;
   std::vector<int32_t> h_color;
   int ncolor = 0;
+  std::vector<int32_t> pc_blocks;  // optional sub-domain assignment for the Newton solve's block Jacobi
 
   // state
   int32_t *d_region = nullptr, *d_region_iter = nullptr, *d_region_step = nullptr;  // [ncell]

@@ -234,6 +234,18 @@ struct wb_pc {
   int *d_flag = nullptr;    // per-row completion epoch
   int *d_ticket = nullptr;  // CTA ticket counter
   int epoch = 0;
+  // sub-domain resident solve (one CTA per block-Jacobi sub-domain, solution kept in shared memory):
+  // level-ordered ELL streams of the L and U factors
+  bool blocked = false;
+  int nblk = 0, max_block_rows = 0, nent = 0, nlvlrow = 0;
+  int4 *d_blk = nullptr;        // per block: row0, nrows, lev0 (forward levels first, then backward), nlev_f | nlev_b << 16
+  int4 *d_lev = nullptr;        // per level: rbase, n, nk, ebase
+  int32_t *d_blk_rows = nullptr;  // global row of each block-local row
+  int32_t *d_lvl_row = nullptr;   // block-local row of each level slot
+  int32_t *d_ent_col = nullptr;   // block-local column of each entry (-1: padding)
+  int32_t *d_ent_src = nullptr;   // index into d_val of each entry (-1: padding)
+  int32_t *d_dinv_src = nullptr;  // index into d_val of the inverted diagonal of each backward level slot
+  double *d_ent_val = nullptr, *d_lvl_dinv = nullptr;
 };
 
 template <int BS>
@@ -413,6 +425,216 @@ __global__ void __launch_bounds__(128) k_ilu0_solve(const int32_t *__restrict__ 
   st_release(&flag[i], epoch);
 }
 
+
+template <class T> static int upload(T **p, const std::vector<T> &v) {
+  WB_CUDA(cudaMalloc((void **)p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) WB_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---- sub-domain resident ILU(0) solve ---------------------------------------------------
+// One CTA per block-Jacobi sub-domain.  The sub-domain's part of the solution lives in shared
+// memory for both sweeps, so the only HBM traffic is one streaming read of the factors (stored
+// level by level, ELL inside a level: thread r of a level reads consecutive 32-byte blocks) plus
+// r in and z out.  Levels are separated by __syncthreads; rows inside a level are independent.
+// Per row the blocks are applied in ascending column order, i.e. the arithmetic of the sequential
+// MatSolve_SeqBAIJ_N_NaturalOrdering restricted to the sub-domain.
+__global__ void k_ilu_repack(const double *__restrict__ fac, const int32_t *__restrict__ ent_src, int nent,
+                             const int32_t *__restrict__ dinv_src, int ndinv, int b2, double *__restrict__ ent_val,
+                             double *__restrict__ lvl_dinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nent * b2) {
+    const int e = i / b2, q = i - e * b2;
+    const int sidx = ent_src[e];
+    ent_val[i] = sidx >= 0 ? fac[(size_t)sidx * b2 + q] : 0.0;
+  }
+  if (i < ndinv * b2) {
+    const int e = i / b2, q = i - e * b2;
+    const int sidx = dinv_src[e];
+    lvl_dinv[i] = sidx >= 0 ? fac[(size_t)sidx * b2 + q] : 0.0;
+  }
+}
+
+#define WB_ILU_MAXLEV 384
+template <int BS>
+__global__ void __launch_bounds__(128) k_ilu0_block_solve(const int4 *__restrict__ blk, const int4 *__restrict__ lev,
+                                                          const int32_t *__restrict__ blk_rows,
+                                                          const int32_t *__restrict__ lvl_row,
+                                                          const int32_t *__restrict__ ent_col,
+                                                          const double *__restrict__ ent_val,
+                                                          const double *__restrict__ lvl_dinv,
+                                                          const double *__restrict__ r, double *__restrict__ z) {
+  constexpr int B2 = BS * BS;
+  extern __shared__ double zs[];
+  __shared__ int4 slev[WB_ILU_MAXLEV];
+  const int4 d = blk[blockIdx.x];
+  const int row0 = d.x, lev0 = d.z, nlf = d.w & 0xffff, nlb = (d.w >> 16) & 0xffff;
+  const int nl = nlf + nlb;
+  const bool cached = nl <= WB_ILU_MAXLEV;
+  if (cached)
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) slev[l] = lev[lev0 + l];
+  __syncthreads();
+  for (int l = 0; l < nl; l++) {
+    const int4 L = cached ? slev[l] : lev[lev0 + l];
+    const bool fwd = l < nlf;
+    for (int rr = threadIdx.x; rr < L.y; rr += blockDim.x) {
+      const int li = lvl_row[L.x + rr];
+      const int grow = blk_rows[row0 + li];
+      double s[BS];
+      if (fwd) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) s[i] = r[(size_t)grow * BS + i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < BS; i++) s[i] = zs[li * BS + i];
+      }
+      for (int k = 0; k < L.z; k++) {
+        const size_t e = (size_t)L.w + (size_t)k * L.y + rr;
+        const int col = ent_col[e];
+        if (col >= 0) {
+          double v[B2];
+          if (BS == 2) {
+            const double2 a = __ldcs(reinterpret_cast<const double2 *>(ent_val + e * 4));
+            const double2 b = __ldcs(reinterpret_cast<const double2 *>(ent_val + e * 4) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+          } else {
+#pragma unroll
+            for (int q = 0; q < B2; q++) v[q] = __ldcs(ent_val + e * B2 + q);
+          }
+#pragma unroll
+          for (int j = 0; j < BS; j++) {
+            const double xj = zs[col * BS + j];
+#pragma unroll
+            for (int i = 0; i < BS; i++) s[i] -= v[j * BS + i] * xj;
+          }
+        }
+      }
+      if (fwd) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) zs[li * BS + i] = s[i];
+      } else {
+        double t[BS];
+        const double *di = lvl_dinv + ((size_t)L.x + rr) * B2;
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < BS; j++) acc += di[j * BS + i] * s[j];
+          t[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          zs[li * BS + i] = t[i];
+          z[(size_t)grow * BS + i] = t[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// host: level-ordered ELL streams of every sub-domain (symbolic, once per pattern)
+static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, const std::vector<int32_t> &rowptr,
+                               const std::vector<int32_t> &colidx, const std::vector<int32_t> &diag) {
+  const int nb = pc->nb;
+  int nblk = 0;
+  for (int i = 0; i < nb; i++) nblk = std::max(nblk, blk_of[i] + 1);
+  std::vector<int32_t> bcount(nblk + 1, 0);
+  for (int i = 0; i < nb; i++) bcount[blk_of[i] + 1]++;
+  int maxrows = 0;
+  for (int b = 0; b < nblk; b++) {
+    maxrows = std::max(maxrows, bcount[b + 1]);
+    bcount[b + 1] += bcount[b];
+  }
+  std::vector<int32_t> blk_rows(nb), local(nb);
+  {
+    std::vector<int32_t> fill(bcount.begin(), bcount.end() - 1);
+    for (int i = 0; i < nb; i++) {
+      local[i] = fill[blk_of[i]] - bcount[blk_of[i]];
+      blk_rows[fill[blk_of[i]]++] = i;
+    }
+  }
+  // levels per row within its sub-domain
+  std::vector<int32_t> lf(nb, 0), lb(nb, 0);
+  for (int i = 0; i < nb; i++) {
+    int l = 0;
+    for (int k = rowptr[i]; k < diag[i]; k++) l = std::max(l, lf[colidx[k]] + 1);
+    lf[i] = l;
+  }
+  for (int i = nb - 1; i >= 0; i--) {
+    int l = 0;
+    for (int k = diag[i] + 1; k < rowptr[i + 1]; k++) l = std::max(l, lb[colidx[k]] + 1);
+    lb[i] = l;
+  }
+  std::vector<int4> blk(nblk), lev;
+  std::vector<int32_t> lvl_row, ent_col, ent_src, dinv_src;
+  std::vector<std::vector<int32_t>> rows_of_level;
+  for (int b = 0; b < nblk; b++) {
+    const int r0 = bcount[b], nr = bcount[b + 1] - bcount[b];
+    int nlev[2] = {0, 0};
+    const int lev0 = (int)lev.size();
+    for (int pass = 0; pass < 2; pass++) {
+      const std::vector<int32_t> &lv = pass == 0 ? lf : lb;
+      int nl = 0;
+      for (int q = 0; q < nr; q++) nl = std::max(nl, lv[blk_rows[r0 + q]] + 1);
+      rows_of_level.assign(nl, std::vector<int32_t>());
+      if (pass == 0)
+        for (int q = 0; q < nr; q++) rows_of_level[lv[blk_rows[r0 + q]]].push_back(blk_rows[r0 + q]);
+      else
+        for (int q = nr - 1; q >= 0; q--) rows_of_level[lv[blk_rows[r0 + q]]].push_back(blk_rows[r0 + q]);
+      for (int l = 0; l < nl; l++) {
+        const std::vector<int32_t> &rows = rows_of_level[l];
+        const int n = (int)rows.size();
+        int nk = 0;
+        for (int row : rows)
+          nk = std::max(nk, pass == 0 ? diag[row] - rowptr[row] : rowptr[row + 1] - diag[row] - 1);
+        int4 L;
+        L.x = (int)lvl_row.size();
+        L.y = n;
+        L.z = nk;
+        L.w = (int)ent_col.size();
+        lev.push_back(L);
+        for (int row : rows) {
+          lvl_row.push_back(local[row]);
+          dinv_src.push_back(pass == 1 ? diag[row] : -1);
+        }
+        const size_t e0 = ent_col.size();
+        ent_col.resize(e0 + (size_t)nk * n, -1);
+        ent_src.resize(e0 + (size_t)nk * n, -1);
+        for (int q = 0; q < n; q++) {
+          const int row = rows[q];
+          const int k0 = pass == 0 ? rowptr[row] : diag[row] + 1, k1 = pass == 0 ? diag[row] : rowptr[row + 1];
+          for (int k = k0; k < k1; k++) {
+            ent_col[e0 + (size_t)(k - k0) * n + q] = local[colidx[k]];
+            ent_src[e0 + (size_t)(k - k0) * n + q] = k;
+          }
+        }
+      }
+      nlev[pass] = nl;
+    }
+    WB_CHECK(nlev[0] < 65536 && nlev[1] < 65536, "wb_pc_setup: sub-domain with too many levels");
+    blk[b].x = r0;
+    blk[b].y = nr;
+    blk[b].z = lev0;
+    blk[b].w = nlev[0] | (nlev[1] << 16);
+  }
+  pc->nblk = nblk;
+  pc->max_block_rows = maxrows;
+  pc->nent = (int)ent_col.size();
+  pc->nlvlrow = (int)lvl_row.size();
+  const int b2 = pc->bs * pc->bs;
+  WB_TRY(upload(&pc->d_blk, blk));
+  WB_TRY(upload(&pc->d_lev, lev));
+  WB_TRY(upload(&pc->d_blk_rows, blk_rows));
+  WB_TRY(upload(&pc->d_lvl_row, lvl_row));
+  WB_TRY(upload(&pc->d_ent_col, ent_col));
+  WB_TRY(upload(&pc->d_ent_src, ent_src));
+  WB_TRY(upload(&pc->d_dinv_src, dinv_src));
+  WB_CUDA(cudaMalloc(&pc->d_ent_val, sizeof(double) * std::max<size_t>((size_t)pc->nent * b2, 1)));
+  WB_CUDA(cudaMalloc(&pc->d_lvl_dinv, sizeof(double) * std::max<size_t>((size_t)pc->nlvlrow * b2, 1)));
+  return 0;
+}
+
 static void level_schedule(int nb, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &colidx,
                            bool forward, std::vector<int32_t> &sched, int &nlev) {
   std::vector<int32_t> lev(nb, 0);
@@ -448,11 +670,6 @@ static void level_schedule(int nb, const std::vector<int32_t> &rowptr, const std
   }
 }
 
-template <class T> static int upload(T **p, const std::vector<T> &v) {
-  WB_CUDA(cudaMalloc((void **)p, std::max<size_t>(v.size(), 1) * sizeof(T)));
-  if (!v.empty()) WB_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return 0;
-}
 
 static int pc_numeric(wb_pc *pc) {
   wb_mat *A = pc->A;
@@ -480,6 +697,12 @@ static int pc_numeric(wb_pc *pc) {
       default: k_ilu0_factor<3><<<grid, 128, 0, c->stream>>>(pc->d_sched_f, pc->nsched_f, pc->d_rowptr, pc->d_colidx, pc->d_diag, pc->d_val, pc->d_flag, pc->epoch, pc->d_ticket, c->d_flags); break;
     }
     WB_LAUNCH(c);
+    if (pc->blocked) {
+      const size_t nthr = (size_t)std::max(pc->nent, pc->nlvlrow) * bs2;
+      k_ilu_repack<<<wb_grid(nthr, 256), 256, 0, c->stream>>>(pc->d_val, pc->d_ent_src, pc->nent, pc->d_dinv_src,
+                                                            pc->nlvlrow, bs2, pc->d_ent_val, pc->d_lvl_dinv);
+      WB_LAUNCH(c);
+    }
   }
   WB_CUDA(cudaGetLastError());
   return 0;
@@ -490,7 +713,8 @@ extern "C" int wb_pc_destroy(wb_pc *pc) {
   cudaSetDevice(pc->A->ctx->device);
   cudaStreamSynchronize(pc->A->ctx->stream);
   void *ptrs[] = {pc->d_dinv, pc->d_rowptr, pc->d_colidx, pc->d_diag, pc->d_src, pc->d_sched_f, pc->d_sched_b,
-                  pc->d_val, pc->d_flag, pc->d_ticket};
+                  pc->d_val, pc->d_flag, pc->d_ticket, pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_lvl_row,
+                  pc->d_ent_col, pc->d_ent_src, pc->d_dinv_src, pc->d_ent_val, pc->d_lvl_dinv};
   for (void *p : ptrs) cudaFree(p);
   delete pc;
   return 0;
@@ -544,6 +768,20 @@ extern "C" int wb_pc_setup(wb_mat *A, int type, int nblocks, const int32_t *bloc
     WB_CUDA(cudaMalloc(&pc->d_flag, sizeof(int) * nb));
     WB_CUDA(cudaMemset(pc->d_flag, 0, sizeof(int) * nb));
     WB_CUDA(cudaMalloc(&pc->d_ticket, sizeof(int)));
+    // sub-domains small enough for one CTA's shared memory use the resident solve
+    int nblk_used = 0, maxrows = 0;
+    {
+      std::vector<int32_t> cnt;
+      for (int i = 0; i < nb; i++) {
+        if ((int)cnt.size() <= blk[i]) cnt.resize(blk[i] + 1, 0);
+        maxrows = std::max(maxrows, ++cnt[blk[i]]);
+      }
+      nblk_used = (int)cnt.size();
+    }
+    if (nblk_used > 1 && (size_t)maxrows * A->bs * sizeof(double) <= 160 * 1024) {
+      WB_TRY(build_block_streams(pc, blk, rowptr, colidx, diag));
+      pc->blocked = true;
+    }
   }
   int rc;
   {
@@ -594,6 +832,25 @@ int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z) {
       case 2: k_pbjacobi_apply<2><<<grid, 256, 0, c->stream>>>(pc->d_dinv, d_r, d_z, nb); break;
       default: k_pbjacobi_apply<3><<<grid, 256, 0, c->stream>>>(pc->d_dinv, d_r, d_z, nb); break;
     }
+    WB_LAUNCH(c);
+    WB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (pc->blocked) {
+    const size_t smem = (size_t)pc->max_block_rows * pc->bs * sizeof(double);
+#define BSOLVE(BS)                                                                                                 \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      cudaFuncSetAttribute(k_ilu0_block_solve<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    k_ilu0_block_solve<BS><<<pc->nblk, 128, smem, c->stream>>>(pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_lvl_row, \
+                                                               pc->d_ent_col, pc->d_ent_val, pc->d_lvl_dinv, d_r, d_z); \
+  } while (0)
+    switch (pc->bs) {
+      case 1: BSOLVE(1); break;
+      case 2: BSOLVE(2); break;
+      default: BSOLVE(3); break;
+    }
+#undef BSOLVE
     WB_LAUNCH(c);
     WB_CUDA(cudaGetLastError());
     return 0;

@@ -62,6 +62,17 @@ void wb_newton_invalidate_pc(wb_ctx *c) {
   it->second.pc_type = -1;
 }
 
+extern "C" int wb_set_pc_blocks(wb_ctx *c, const int32_t *block_of_row) {
+  if (block_of_row) {
+    WB_CHECK(c->nowned > 0, "wb_set_pc_blocks: no mesh");
+    c->pc_blocks.assign(block_of_row, block_of_row + c->nowned);
+  } else {
+    c->pc_blocks.clear();
+  }
+  wb_newton_invalidate_pc(c);
+  return 0;
+}
+
 struct SnesState {
   double ttol, rnorm0;
 };
@@ -153,7 +164,7 @@ extern "C" int wb_newton_solve_be(wb_ctx *c, const wb_newton_opts *o, double dt,
     if (!w.pc || w.pc_type != o->pc_type || w.pc_nblocks != o->pc_nblocks) {
       if (w.pc) wb_pc_destroy(w.pc);
       w.pc = nullptr;
-      prc = wb_pc_setup(J, o->pc_type, o->pc_nblocks, nullptr, &w.pc);
+      prc = wb_pc_setup(J, o->pc_type, o->pc_nblocks, c->pc_blocks.empty() ? nullptr : c->pc_blocks.data(), &w.pc);
       w.pc_type = o->pc_type;
       w.pc_nblocks = o->pc_nblocks;
     } else {

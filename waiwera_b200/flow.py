@@ -282,6 +282,10 @@ class FlowSimulation:
         return err, cs.value, cy.value
 
     # ---- Newton
+    def set_pc_blocks(self, block_of_row):
+        bor = None if block_of_row is None else np.ascontiguousarray(block_of_row, np.int32)
+        check(self.L.wb_set_pc_blocks(self.h, ptr(bor)), "wb_set_pc_blocks")
+
     def newton_solve(self, y, lhs_last, dt, opts=None):
         o = opts if opts is not None else newton_opts()
         res = NewtonResult()

@@ -235,3 +235,14 @@ def scale_primaries(primary, region, pressure_scale=1e6, temperature_scale=1e2):
     y[:, 0] /= pressure_scale
     y[:, 1] = np.where(region == 4, y[:, 1], y[:, 1] / temperature_scale)
     return y
+
+
+def cube_blocks(mesh, size):
+    """block-Jacobi sub-domain of every owned cell: size^3 boxes of the structured grid (numbered per rank)"""
+    nx, ny, nz = mesh.dims
+    idx = mesh.natural[:mesh.nowned]
+    i, j, k = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+    bx, by = -(-nx // size), -(-ny // size)
+    key = (i // size) + bx * ((j // size) + by * (k // size))
+    _, inv = np.unique(key, return_inverse=True)
+    return inv.astype(np.int32)
