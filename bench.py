@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-its", type=int, default=30)
     ap.add_argument("--spmv-launches", type=int, default=50)
+    ap.add_argument("--ksp-maxit", type=int, default=10000,
+                    help="cap on Krylov iterations (profiling runs only: a capped solve is not a bench value)")
     return ap.parse_args()
 
 
@@ -238,7 +240,7 @@ def run_b200(args):
         sim.set_pc_blocks(wmesh.cube_blocks(m, args.pc_cube))
     pc_type = {"ilu0": flow.PC_BJACOBI_ILU0, "pbjacobi": flow.PC_PBJACOBI, "none": flow.PC_NONE}[args.pc]
     ksp_type = {"gmres": flow.KSP_GMRES, "bcgs": flow.KSP_BCGS}[args.ksp]
-    opts = flow.newton_opts(max_iterations=1, pc_type=pc_type, pc_nblocks=args.pc_blocks, ksp=flow.ksp_opts(type=ksp_type))
+    opts = flow.newton_opts(max_iterations=1, pc_type=pc_type, pc_nblocks=args.pc_blocks, ksp=flow.ksp_opts(type=ksp_type, maxit=args.ksp_maxit))
     n = sim.n
     stream = torch.cuda.ExternalStream(sim.stream())
     y0_d = torch.from_numpy(y).cuda()

@@ -74,3 +74,35 @@ def test_product_does_not_use_oracle():
                 if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                     txt = open(os.path.join(dp, fn)).read()
                     assert not pat.search(txt), os.path.join(dp, fn)
+
+
+def _header_prototypes():
+    src = open(os.path.join(ROOT, "include", "waiwera_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(wb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return protos
+
+
+def test_fortran_interface_matches_header():
+    """fortran/waiwera_b200.F90 (not compilable here: no Fortran compiler) binds every exported function with
+    the header's argument count, and its constants equal the header's #defines"""
+    f90 = open(os.path.join(ROOT, "fortran", "waiwera_b200.F90")).read()
+    f90 = re.sub(r"&\s*\n\s*", " ", f90)
+    bound = {}
+    for m in re.finditer(r"function\s+(wb_[a-z0-9_]+)\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(wb_[a-z0-9_]+)\"\)", f90):
+        assert m.group(1) == m.group(3)
+        args = m.group(2).strip()
+        bound[m.group(1)] = 0 if not args else len(args.split(","))
+    protos = _header_prototypes()
+    assert set(protos) == set(bound), set(protos) ^ set(bound)
+    for nm, n in protos.items():
+        assert bound[nm] == n, (nm, bound[nm], n)
+    hdr = open(os.path.join(ROOT, "include", "waiwera_b200.h")).read()
+    defines = dict(re.findall(r"#define\s+(WB_[A-Z0-9_]+)\s+(-?\d+)\b", hdr))
+    consts = dict(re.findall(r"\b(WB_[A-Z0-9_]+)\s*=\s*(-?\d+)", f90))
+    assert len(consts) >= 20
+    for k, v in consts.items():
+        assert defines.get(k) == v, (k, v, defines.get(k))

@@ -230,10 +230,11 @@ def hydrostatic_state(mesh, seed=SEED, two_phase_layers=0, thermo_psat=None):
 
 
 def scale_primaries(primary, region, pressure_scale=1e6, temperature_scale=1e2):
-    """eos%scale for eos_we (src/eos.F90:186-196, src/eos_we.F90:104-109)."""
+    """eos%scale for eos_we / eos_w (src/eos.F90:186-196, src/eos_we.F90:104-109, src/eos_w.F90: pressure only)."""
     y = np.array(primary, float, copy=True)
     y[:, 0] /= pressure_scale
-    y[:, 1] = np.where(region == 4, y[:, 1], y[:, 1] / temperature_scale)
+    if y.shape[1] > 1:
+        y[:, 1] = np.where(region == 4, y[:, 1], y[:, 1] / temperature_scale)
     return y
 
 
