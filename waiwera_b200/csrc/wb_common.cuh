@@ -80,6 +80,7 @@ struct WbHalo {
   int nsend = 0, nrecv = 0;
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;  // (nsend|nrecv) * maxwidth
   int maxwidth = 0;
+  bool recv_contiguous = false;  // ghost cell k of the receive list is local cell nowned + k
 };
 
 struct wb_mat {
@@ -87,7 +88,7 @@ struct wb_mat {
   int nb = 0, ncolb = 0, bs = 0, nnzb = 0;
   int32_t *d_rowptr = nullptr, *d_colidx = nullptr;
   double *d_val = nullptr;
-  double *d_xloc = nullptr;  // ncolb*bs: x with ghost entries (multi-GPU)
+  double *d_xloc = nullptr;  // (ncolb-nb)*bs: ghost entries of x (multi-GPU), filled by the halo exchange
   std::vector<int32_t> h_rowptr, h_colidx;
   bool owns = true;
 };
@@ -186,11 +187,15 @@ static inline int wb_grid(size_t n, int block) { return (int)((n + block - 1) / 
 
 // internal cross-file API
 int wb_halo_exchange(wb_ctx *ctx, double *vec, int width);  // vec[(ninterior)*width]: fills ghost entries
+// SpMV halo: owned[idx]*scale -> neighbours; ghost[(cell-nowned)*width+k] <- neighbours
+int wb_halo_exchange_ghost(wb_ctx *ctx, const double *owned, int width, const double *scale, double *ghost);
 int wb_allreduce_sum(wb_ctx *ctx, double *dbuf, int n);     // in-stream, device buffer
 int wb_allreduce_max_int(wb_ctx *ctx, int *dbuf, int n);
 int wb_reduce_flags(wb_ctx *ctx, int nflags);               // device flags -> host (max over ranks)
 
 int wb_spmv_launch(wb_mat *A, const double *d_x, double *d_y);  // device pointers, handles halo
+// y = A (x*scale); optionally stores the scaled owned entries to xn; skipped when *done
+int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d_xn, double *d_y, const int *done);
 
 // device-pointer cores shared between the translation units (no staging, no flag check)
 int wb_pre_eval_dev(wb_ctx *c, const double *d_y, bool unperturbed);
@@ -201,7 +206,7 @@ int wb_jacobian_be_dev(wb_ctx *c, const double *d_y, const double *d_lhs_last, d
 int wb_fluid_transitions_dev(wb_ctx *c, const double *d_y_old, double *d_search, double *d_y);
 int wb_max_scaled_core(wb_ctx *c, const double *d_v, const double *d_s, double tol, int n, double *maxval,
                        int64_t *maxloc);
-int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z);
+int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z, const int *done = nullptr);
 int wb_ksp_solve_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b, double *d_x, int *its,
                      int *reason, double *rnorm);
 int wb_vec_dot_host(wb_ctx *c, const double *d_a, const double *d_b, size_t n, double *out);

@@ -292,6 +292,11 @@ extern "C" int wb_set_halo(wb_ctx *c, int nneigh, const int32_t *neigh_rank, con
   WB_CUDA(cudaMalloc(&h.d_recv_idx, sizeof(int32_t) * (h.nrecv + 1)));
   WB_CUDA(cudaMemcpy(h.d_send_idx, send_idx, sizeof(int32_t) * h.nsend, cudaMemcpyHostToDevice));
   WB_CUDA(cudaMemcpy(h.d_recv_idx, recv_idx, sizeof(int32_t) * h.nrecv, cudaMemcpyHostToDevice));
+  // ghost cells are numbered owner by owner in the order they arrive: then the receive buffer is the ghost
+  // part of the vector itself and the SpMV halo needs no unpack kernel
+  h.recv_contiguous = true;
+  for (int k = 0; k < h.nrecv; k++)
+    if (recv_idx[k] != c->nowned + k) h.recv_contiguous = false;
   WB_CUDA(cudaMalloc(&h.d_sendbuf, sizeof(double) * (size_t)(h.nsend + 1) * h.maxwidth));
   WB_CUDA(cudaMalloc(&h.d_recvbuf, sizeof(double) * (size_t)(h.nrecv + 1) * h.maxwidth));
   return 0;
@@ -340,6 +345,56 @@ int wb_halo_exchange(wb_ctx *c, double *vec, int width) {
   if (h.nrecv > 0) {
     k_halo_unpack<<<wb_grid((size_t)h.nrecv * width, 256), 256, 0, c->stream>>>(vec, h.d_recv_idx, h.nrecv, width,
                                                                                 h.d_recvbuf);
+    WB_LAUNCH(c);
+  }
+  return 0;
+}
+
+__global__ void k_halo_pack_scaled(const double *__restrict__ vec, const int32_t *__restrict__ idx, int n, int width,
+                                   const double *scale, double *__restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * width) {
+    const int c = i / width, k = i - c * width;
+    buf[i] = vec[(size_t)idx[c] * width + k] * (scale ? *scale : 1.0);
+  }
+}
+__global__ void k_halo_unpack_ghost(double *__restrict__ ghost, const int32_t *__restrict__ idx, int n, int width,
+                                    int first_ghost, const double *__restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * width) {
+    const int c = i / width, k = i - c * width;
+    ghost[(size_t)(idx[c] - first_ghost) * width + k] = buf[i];
+  }
+}
+
+// Ghost exchange for the SpMV (MatMult_MPIBAIJ's VecScatter): owned entries of `owned` (times the device
+// scalar `scale`, if given) go to the neighbours; the entries of this rank's ghost cells arrive in
+// ghost[(cell - nowned)*width + k].  The owned part is never copied.
+int wb_halo_exchange_ghost(wb_ctx *c, const double *owned, int width, const double *scale, double *ghost) {
+  WbHalo &h = c->halo;
+  if (c->nranks <= 1 || h.nneigh == 0) return 0;
+  WB_CHECK(width <= h.maxwidth, "halo width %d too large", width);
+  WB_CHECK(c->comm, "halo exchange without communicator");
+  if (h.nsend > 0) {
+    k_halo_pack_scaled<<<wb_grid((size_t)h.nsend * width, 256), 256, 0, c->stream>>>(owned, h.d_send_idx, h.nsend,
+                                                                                     width, scale, h.d_sendbuf);
+    WB_LAUNCH(c);
+  }
+  double *rbuf = h.recv_contiguous ? ghost : h.d_recvbuf;
+  WB_NCCL(wb_nccl()->GroupStart());
+  for (int n = 0; n < h.nneigh; n++) {
+    int ns = h.send_ptr[n + 1] - h.send_ptr[n], nr = h.recv_ptr[n + 1] - h.recv_ptr[n];
+    if (ns > 0)
+      WB_NCCL(wb_nccl()->Send(h.d_sendbuf + (size_t)h.send_ptr[n] * width, (size_t)ns * width, ncclDouble, h.rank[n],
+                       c->comm, c->stream));
+    if (nr > 0)
+      WB_NCCL(wb_nccl()->Recv(rbuf + (size_t)h.recv_ptr[n] * width, (size_t)nr * width, ncclDouble, h.rank[n],
+                       c->comm, c->stream));
+  }
+  WB_NCCL(wb_nccl()->GroupEnd());
+  if (!h.recv_contiguous && h.nrecv > 0) {
+    k_halo_unpack_ghost<<<wb_grid((size_t)h.nrecv * width, 256), 256, 0, c->stream>>>(ghost, h.d_recv_idx, h.nrecv,
+                                                                                      width, c->nowned, h.d_recvbuf);
     WB_LAUNCH(c);
   }
   return 0;

@@ -719,8 +719,8 @@ extern "C" int wb_set_mesh(wb_ctx *c, int ncell, int ninterior, int nowned, int 
   WB_TRY(dev_upload(&J.d_colidx, J.h_colidx));
   WB_TRY(dev_alloc(&J.d_val, (size_t)J.nnzb * np * np));
   WB_CUDA(cudaMemset(J.d_val, 0, (size_t)J.nnzb * np * np * sizeof(double)));
-  WB_TRY(dev_alloc(&J.d_xloc, (size_t)ninterior * np));
-  WB_CUDA(cudaMemset(J.d_xloc, 0, (size_t)ninterior * np * sizeof(double)));
+  WB_TRY(dev_alloc(&J.d_xloc, (size_t)(ninterior - nowned + 1) * np));  // ghost entries of x for the SpMV
+  WB_CUDA(cudaMemset(J.d_xloc, 0, (size_t)(ninterior - nowned + 1) * np * sizeof(double)));
 
   // ---- state
   const size_t nslot = np + 1;

@@ -18,32 +18,50 @@
 // the algorithmic bytes) with every sector fully used; x is gathered through L2 (16 MB at
 // 1 M cells, resident in the 126 MB L2); a 3-step shuffle folds the eight partial block
 // products, in a fixed order.
+//
+// Fused Krylov form: with `scale` (device scalar) the operand is x*scale, rounded entry by entry
+// exactly as if the normalised vector had been stored first (VecScale then MatMult), and with `xn`
+// the row's own normalised entries are stored as a by-product -- this is how GMRES normalises the
+// new basis vector without a separate pass.  Ghost columns (col >= nb, multi-GPU) are read from
+// `xg`, which the halo exchange fills (MatMult_MPIBAIJ's off-diagonal part).
+struct SpmvArgs {
+  const int32_t *rowptr, *colidx;
+  const double *val, *x, *xg;
+  const double *scale;  // nullable
+  double *xn;           // nullable: xn[row] = x[row]*scale
+  double *y;
+  int nb;
+  const int *done;  // nullable: device-side "solver finished" flag
+};
+
 template <int BS>
-__global__ void __launch_bounds__(256) k_bsr_spmv(const int32_t *__restrict__ rowptr,
-                                                  const int32_t *__restrict__ colidx,
-                                                  const double *__restrict__ val, const double *__restrict__ x,
-                                                  double *__restrict__ y, int nb) {
+__global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
+  if (a.done && *a.done) return;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = gt >> 3, lane = gt & 7;
+  const double s = a.scale ? *a.scale : 1.0;
   double acc[BS];
 #pragma unroll
   for (int i = 0; i < BS; i++) acc[i] = 0.0;
-  if (row < nb) {
-    const int e1 = rowptr[row + 1];
-    for (int e = rowptr[row] + lane; e < e1; e += 8) {
-      const int col = colidx[e];
+  if (row < a.nb) {
+    const int e1 = a.rowptr[row + 1];
+    for (int e = a.rowptr[row] + lane; e < e1; e += 8) {
+      const int col = a.colidx[e];
+      const bool own = col < a.nb;
+      const double *xp = own ? a.x + (size_t)col * BS : a.xg + (size_t)(col - a.nb) * BS;
+      const double sc = own ? s : 1.0;  // ghost entries arrive already scaled by their owner
       double xb[BS], v[BS * BS];
       if (BS == 2) {
-        const double2 x2 = *reinterpret_cast<const double2 *>(x + (size_t)col * 2);
-        xb[0] = x2.x; xb[1] = x2.y;
-        const double2 a = __ldcs(reinterpret_cast<const double2 *>(val + (size_t)e * 4));
-        const double2 b = __ldcs(reinterpret_cast<const double2 *>(val + (size_t)e * 4) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        const double2 x2 = *reinterpret_cast<const double2 *>(xp);
+        xb[0] = x2.x * sc; xb[1] = x2.y * sc;
+        const double2 p = __ldcs(reinterpret_cast<const double2 *>(a.val + (size_t)e * 4));
+        const double2 q = __ldcs(reinterpret_cast<const double2 *>(a.val + (size_t)e * 4) + 1);
+        v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
       } else {
 #pragma unroll
-        for (int j = 0; j < BS; j++) xb[j] = x[(size_t)col * BS + j];
+        for (int j = 0; j < BS; j++) xb[j] = xp[j] * sc;
 #pragma unroll
-        for (int q = 0; q < BS * BS; q++) v[q] = __ldcs(val + (size_t)e * BS * BS + q);
+        for (int q = 0; q < BS * BS; q++) v[q] = __ldcs(a.val + (size_t)e * BS * BS + q);
       }
 #pragma unroll
       for (int j = 0; j < BS; j++)
@@ -55,37 +73,46 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(const int32_t *__restrict__ ro
   for (int off = 4; off > 0; off >>= 1)
 #pragma unroll
     for (int i = 0; i < BS; i++) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], off, 8);
-  if (row < nb && lane == 0) {
-    if (BS == 2) *reinterpret_cast<double2 *>(y + (size_t)row * 2) = make_double2(acc[0], acc[1]);
+  if (row < a.nb && lane == 0) {
+    if (BS == 2) *reinterpret_cast<double2 *>(a.y + (size_t)row * 2) = make_double2(acc[0], acc[1]);
     else {
 #pragma unroll
-      for (int i = 0; i < BS; i++) y[(size_t)row * BS + i] = acc[i];
+      for (int i = 0; i < BS; i++) a.y[(size_t)row * BS + i] = acc[i];
+    }
+    if (a.xn) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) a.xn[(size_t)row * BS + i] = a.x[(size_t)row * BS + i] * s;
     }
   }
 }
 
-// device pointers; x has nb*bs owned entries.  With ghost columns (multi-GPU) x is copied into
-// the matrix's local vector and the ghost entries are filled by the halo exchange
-// (MatMult_MPIBAIJ's VecScatter).
-int wb_spmv_launch(wb_mat *A, const double *d_x, double *d_y) {
+// y = A (x*scale) with device pointers; x holds the nb*bs owned entries.  With ghost columns
+// (multi-GPU) the ghost entries are gathered straight into the matrix's ghost buffer by the halo
+// exchange (MatMult_MPIBAIJ's VecScatter); the owned part is never copied.
+int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d_xn, double *d_y, const int *done) {
   wb_ctx *c = A->ctx;
-  const double *xin = d_x;
+  const double *xg = nullptr;
   if (A->ncolb > A->nb && c->nranks > 1) {
-    WB_CUDA(cudaMemcpyAsync(A->d_xloc, d_x, sizeof(double) * (size_t)A->nb * A->bs, cudaMemcpyDeviceToDevice,
-                            c->stream));
-    WB_TRY(wb_halo_exchange(c, A->d_xloc, A->bs));
-    xin = A->d_xloc;
+    WB_TRY(wb_halo_exchange_ghost(c, d_x, A->bs, d_scale, A->d_xloc));
+    xg = A->d_xloc;
+  } else if (A->ncolb > A->nb) {
+    xg = A->d_xloc;  // ghost columns without a communicator: zeros
   }
+  SpmvArgs a = {A->d_rowptr, A->d_colidx, A->d_val, d_x, xg, d_scale, d_xn, d_y, A->nb, done};
   const int grid = wb_grid((size_t)A->nb * 8, 256);
   switch (A->bs) {
-    case 1: k_bsr_spmv<1><<<grid, 256, 0, c->stream>>>(A->d_rowptr, A->d_colidx, A->d_val, xin, d_y, A->nb); break;
-    case 2: k_bsr_spmv<2><<<grid, 256, 0, c->stream>>>(A->d_rowptr, A->d_colidx, A->d_val, xin, d_y, A->nb); break;
-    case 3: k_bsr_spmv<3><<<grid, 256, 0, c->stream>>>(A->d_rowptr, A->d_colidx, A->d_val, xin, d_y, A->nb); break;
+    case 1: k_bsr_spmv<1><<<grid, 256, 0, c->stream>>>(a); break;
+    case 2: k_bsr_spmv<2><<<grid, 256, 0, c->stream>>>(a); break;
+    case 3: k_bsr_spmv<3><<<grid, 256, 0, c->stream>>>(a); break;
     default: WB_CHECK(false, "wb_mat_mult: block size %d not supported", A->bs);
   }
   WB_LAUNCH(c);
   WB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int wb_spmv_launch(wb_mat *A, const double *d_x, double *d_y) {
+  return wb_spmv_fused(A, d_x, nullptr, nullptr, d_y, nullptr);
 }
 
 extern "C" int wb_mat_create(wb_ctx *c, int nb, int ncolb, int bs, int nnzb, const int32_t *rowptr,
@@ -102,8 +129,8 @@ extern "C" int wb_mat_create(wb_ctx *c, int nb, int ncolb, int bs, int nnzb, con
   WB_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int32_t) * (nb + 1)));
   WB_CUDA(cudaMalloc(&A->d_colidx, sizeof(int32_t) * std::max(nnzb, 1)));
   WB_CUDA(cudaMalloc(&A->d_val, sizeof(double) * std::max<size_t>((size_t)nnzb * bs * bs, 1)));
-  WB_CUDA(cudaMalloc(&A->d_xloc, sizeof(double) * (size_t)ncolb * bs));
-  WB_CUDA(cudaMemset(A->d_xloc, 0, sizeof(double) * (size_t)ncolb * bs));
+  WB_CUDA(cudaMalloc(&A->d_xloc, sizeof(double) * (size_t)(ncolb - nb + 1) * bs));
+  WB_CUDA(cudaMemset(A->d_xloc, 0, sizeof(double) * (size_t)(ncolb - nb + 1) * bs));
   WB_CUDA(cudaMemcpy(A->d_rowptr, A->h_rowptr.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice));
   WB_CUDA(cudaMemcpy(A->d_colidx, A->h_colidx.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice));
   if (vals) WB_CUDA(cudaMemcpy(A->d_val, vals, sizeof(double) * (size_t)nnzb * bs * bs, cudaMemcpyDefault));
@@ -237,15 +264,14 @@ struct wb_pc {
   // sub-domain resident solve (one CTA per block-Jacobi sub-domain, solution kept in shared memory):
   // level-ordered ELL streams of the L and U factors
   bool blocked = false;
-  int nblk = 0, max_block_rows = 0, nent = 0, nlvlrow = 0;
-  int4 *d_blk = nullptr;        // per block: row0, nrows, lev0 (forward levels first, then backward), nlev_f | nlev_b << 16
-  int4 *d_lev = nullptr;        // per level: rbase, n, nk, ebase
+  int nblk = 0, max_block_rows = 0, nrepack = 0;
+  int4 *d_blk = nullptr;          // per block: row0, nrows, lev0 (forward levels first, then backward), number of levels
+  int4 *d_lev = nullptr;          // per level: word offset into d_stream, bytes, rows, unused
   int32_t *d_blk_rows = nullptr;  // global row of each block-local row
-  int32_t *d_lvl_row = nullptr;   // block-local row of each level slot
-  int32_t *d_ent_col = nullptr;   // block-local column of each entry (-1: padding)
-  int32_t *d_ent_src = nullptr;   // index into d_val of each entry (-1: padding)
-  int32_t *d_dinv_src = nullptr;  // index into d_val of the inverted diagonal of each backward level slot
-  double *d_ent_val = nullptr, *d_lvl_dinv = nullptr;
+  double *d_stream = nullptr;     // level-ordered factor stream (see "sub-domain resident ILU(0) solve")
+  size_t stream_words = 0;
+  int2 *d_repack = nullptr;       // (block index into d_val, word offset into d_stream) of every factor block
+  int stage_words = 0, nstage = 0, solve_threads = 128;  // TMA ring geometry (nstage 0: read the stream from global)
 };
 
 template <int BS>
@@ -434,109 +460,185 @@ template <class T> static int upload(T **p, const std::vector<T> &v) {
 
 // ---- sub-domain resident ILU(0) solve ---------------------------------------------------
 // One CTA per block-Jacobi sub-domain.  The sub-domain's part of the solution lives in shared
-// memory for both sweeps, so the only HBM traffic is one streaming read of the factors (stored
-// level by level, ELL inside a level: thread r of a level reads consecutive 32-byte blocks) plus
-// r in and z out.  Levels are separated by __syncthreads; rows inside a level are independent.
-// Per row the blocks are applied in ascending column order, i.e. the arithmetic of the sequential
-// MatSolve_SeqBAIJ_N_NaturalOrdering restricted to the sub-domain.
-__global__ void k_ilu_repack(const double *__restrict__ fac, const int32_t *__restrict__ ent_src, int nent,
-                             const int32_t *__restrict__ dinv_src, int ndinv, int b2, double *__restrict__ ent_val,
-                             double *__restrict__ lvl_dinv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nent * b2) {
-    const int e = i / b2, q = i - e * b2;
-    const int sidx = ent_src[e];
-    ent_val[i] = sidx >= 0 ? fac[(size_t)sidx * b2 + q] : 0.0;
-  }
-  if (i < ndinv * b2) {
-    const int e = i / b2, q = i - e * b2;
-    const int sidx = dinv_src[e];
-    lvl_dinv[i] = sidx >= 0 ? fac[(size_t)sidx * b2 + q] : 0.0;
-  }
+// memory for both sweeps, so the only HBM traffic is ONE streaming read of the factors plus r in
+// and z out.  The factors are stored as a level-ordered stream: for every dependency level of the
+// forward sweep, then of the backward sweep, one contiguous 16-byte-aligned record
+//     [n, nk, bwd, 0 : int32]  [row(n) : int32, padded to 16 B]  [col(nk*n) : int32, padded]
+//     [L or U blocks (nk*n, ELL: entry k of row r at k*n+r) : bs*bs doubles]  [inverted diagonal blocks (n), bwd only]
+// so a whole level is ONE TMA bulk copy (cp.async.bulk, mbarrier-completed) into a shared-memory
+// ring `nstage` levels deep: the copy of level l+nstage is in flight while level l is applied,
+// which takes the HBM latency off the level-to-level dependency chain.  Rows inside a level are
+// independent; levels are separated by __syncthreads.  Per row the blocks are applied in ascending
+// column order, i.e. the arithmetic of the sequential MatSolve_SeqBAIJ_N_NaturalOrdering
+// restricted to the sub-domain.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
-#define WB_ILU_MAXLEV 384
+__host__ __device__ __forceinline__ int ilu_pad_i32(int n) { return (n + 3) / 4 * 2; }  // int32 count -> 8-byte words, 16 B aligned
+__host__ __device__ __forceinline__ int ilu_pad_f64(int n) { return (n + 1) & ~1; }
+
+// apply one level record (in shared or global memory) to the sub-domain vector zs
 template <int BS>
-__global__ void __launch_bounds__(128) k_ilu0_block_solve(const int4 *__restrict__ blk, const int4 *__restrict__ lev,
-                                                          const int32_t *__restrict__ blk_rows,
-                                                          const int32_t *__restrict__ lvl_row,
-                                                          const int32_t *__restrict__ ent_col,
-                                                          const double *__restrict__ ent_val,
-                                                          const double *__restrict__ lvl_dinv,
-                                                          const double *__restrict__ r, double *__restrict__ z) {
+__device__ __forceinline__ void ilu_level(const double *lv, double *zs) {
   constexpr int B2 = BS * BS;
-  extern __shared__ double zs[];
-  __shared__ int4 slev[WB_ILU_MAXLEV];
-  const int4 d = blk[blockIdx.x];
-  const int row0 = d.x, lev0 = d.z, nlf = d.w & 0xffff, nlb = (d.w >> 16) & 0xffff;
-  const int nl = nlf + nlb;
-  const bool cached = nl <= WB_ILU_MAXLEV;
-  if (cached)
-    for (int l = threadIdx.x; l < nl; l += blockDim.x) slev[l] = lev[lev0 + l];
-  __syncthreads();
-  for (int l = 0; l < nl; l++) {
-    const int4 L = cached ? slev[l] : lev[lev0 + l];
-    const bool fwd = l < nlf;
-    for (int rr = threadIdx.x; rr < L.y; rr += blockDim.x) {
-      const int li = lvl_row[L.x + rr];
-      const int grow = blk_rows[row0 + li];
-      double s[BS];
-      if (fwd) {
+  const int4 hd = *reinterpret_cast<const int4 *>(lv);
+  const int n = hd.x, nk = hd.y;
+  const bool bwd = hd.z != 0;
+  const int *rows = reinterpret_cast<const int *>(lv + 2);
+  const int *cols = reinterpret_cast<const int *>(lv + 2 + ilu_pad_i32(n));
+  const double *vals = lv + 2 + ilu_pad_i32(n) + ilu_pad_i32(nk * n);
+  const double *dinv = vals + ilu_pad_f64(nk * n * B2);
+  for (int rr = threadIdx.x; rr < n; rr += blockDim.x) {
+    const int li = rows[rr];
+    double sv[BS];
 #pragma unroll
-        for (int i = 0; i < BS; i++) s[i] = r[(size_t)grow * BS + i];
-      } else {
+    for (int i = 0; i < BS; i++) sv[i] = zs[li * BS + i];
+    for (int k = 0; k < nk; k++) {
+      const int e = k * n + rr;
+      const int col = cols[e];
+      if (col >= 0) {
+        double v[B2];
+        if (BS == 2) {
+          const double2 p = *reinterpret_cast<const double2 *>(vals + (size_t)e * 4);
+          const double2 q = *reinterpret_cast<const double2 *>(vals + (size_t)e * 4 + 2);
+          v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
+        } else {
 #pragma unroll
-        for (int i = 0; i < BS; i++) s[i] = zs[li * BS + i];
-      }
-      for (int k = 0; k < L.z; k++) {
-        const size_t e = (size_t)L.w + (size_t)k * L.y + rr;
-        const int col = ent_col[e];
-        if (col >= 0) {
-          double v[B2];
-          if (BS == 2) {
-            const double2 a = __ldcs(reinterpret_cast<const double2 *>(ent_val + e * 4));
-            const double2 b = __ldcs(reinterpret_cast<const double2 *>(ent_val + e * 4) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-          } else {
-#pragma unroll
-            for (int q = 0; q < B2; q++) v[q] = __ldcs(ent_val + e * B2 + q);
-          }
-#pragma unroll
-          for (int j = 0; j < BS; j++) {
-            const double xj = zs[col * BS + j];
-#pragma unroll
-            for (int i = 0; i < BS; i++) s[i] -= v[j * BS + i] * xj;
-          }
-        }
-      }
-      if (fwd) {
-#pragma unroll
-        for (int i = 0; i < BS; i++) zs[li * BS + i] = s[i];
-      } else {
-        double t[BS];
-        const double *di = lvl_dinv + ((size_t)L.x + rr) * B2;
-#pragma unroll
-        for (int i = 0; i < BS; i++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < BS; j++) acc += di[j * BS + i] * s[j];
-          t[i] = acc;
+          for (int q = 0; q < B2; q++) v[q] = vals[(size_t)e * B2 + q];
         }
 #pragma unroll
-        for (int i = 0; i < BS; i++) {
-          zs[li * BS + i] = t[i];
-          z[(size_t)grow * BS + i] = t[i];
+        for (int j = 0; j < BS; j++) {
+          const double xj = zs[col * BS + j];
+#pragma unroll
+          for (int i = 0; i < BS; i++) sv[i] -= v[j * BS + i] * xj;
         }
       }
     }
-    __syncthreads();
+    if (!bwd) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) zs[li * BS + i] = sv[i];
+    } else {
+      const double *di = dinv + (size_t)rr * B2;
+      double t[BS];
+#pragma unroll
+      for (int i = 0; i < BS; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < BS; j++) acc += di[j * BS + i] * sv[j];
+        t[i] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < BS; i++) zs[li * BS + i] = t[i];
+    }
   }
 }
 
-// host: level-ordered ELL streams of every sub-domain (symbolic, once per pattern)
+struct IluSolveArgs {
+  const int4 *blk, *lev;
+  const int32_t *blk_rows;
+  const double *stream, *r;
+  double *z;
+  int stage_words, nstage;
+  const int *done;
+};
+
+template <int BS, bool TMA>
+__global__ void __launch_bounds__(256) k_ilu0_block_solve(const IluSolveArgs a) {
+  if (a.done && *a.done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+  double *ring = reinterpret_cast<double *>(smem_raw + 128);
+  double *zs = ring + (size_t)a.nstage * a.stage_words;
+  const int4 d = a.blk[blockIdx.x];
+  const int row0 = d.x, nrows = d.y, lev0 = d.z, nl = d.w;
+  const int tid = threadIdx.x;
+  if (TMA) {
+    if (tid == 0) {
+      for (int st = 0; st < a.nstage; st++) mbar_init(&bars[st], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int npre = nl < a.nstage ? nl : a.nstage;
+      for (int l = 0; l < npre; l++) {
+        const int4 L = a.lev[lev0 + l];
+        mbar_expect_tx(&bars[l], (uint32_t)L.y);
+        tma_load_1d(ring + (size_t)l * a.stage_words, a.stream + L.x, (uint32_t)L.y, &bars[l]);
+      }
+    }
+  }
+  // right-hand side of the sub-domain -> shared memory (overwritten in place by the sweeps)
+  for (int li = tid; li < nrows; li += blockDim.x) {
+    const int grow = a.blk_rows[row0 + li];
+#pragma unroll
+    for (int i = 0; i < BS; i++) zs[li * BS + i] = a.r[(size_t)grow * BS + i];
+  }
+  __syncthreads();
+  for (int l = 0; l < nl; l++) {
+    if (TMA) {
+      const int st = l % a.nstage;
+      int4 Lnext = make_int4(0, 0, 0, 0);
+      const bool refill = tid == 0 && l + a.nstage < nl;
+      if (refill) Lnext = a.lev[lev0 + l + a.nstage];  // in flight while this level is applied
+      mbar_wait(&bars[st], (uint32_t)((l / a.nstage) & 1));
+      ilu_level<BS>(ring + (size_t)st * a.stage_words, zs);
+      __syncthreads();  // level l applied by all threads: its ring slot is free and zs is consistent
+      if (refill) {
+        mbar_expect_tx(&bars[st], (uint32_t)Lnext.y);
+        tma_load_1d(ring + (size_t)st * a.stage_words, a.stream + Lnext.x, (uint32_t)Lnext.y, &bars[st]);
+      }
+    } else {
+      const int4 L = a.lev[lev0 + l];
+      ilu_level<BS>(a.stream + L.x, zs);
+      __syncthreads();
+    }
+  }
+  for (int li = tid; li < nrows; li += blockDim.x) {
+    const int grow = a.blk_rows[row0 + li];
+#pragma unroll
+    for (int i = 0; i < BS; i++) a.z[(size_t)grow * BS + i] = zs[li * BS + i];
+  }
+}
+
+// numeric part: scatter the factor blocks into the level stream
+__global__ void k_ilu_repack(const double *__restrict__ fac, const int2 *__restrict__ map, int nmap, int b2,
+                             double *__restrict__ stream) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nmap * b2) {
+    const int e = i / b2, q = i - e * b2;
+    const int2 m = map[e];
+    stream[(size_t)m.y + q] = fac[(size_t)m.x * b2 + q];
+  }
+}
+
+// host: level-ordered stream of every sub-domain (symbolic, once per pattern)
 static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, const std::vector<int32_t> &rowptr,
                                const std::vector<int32_t> &colidx, const std::vector<int32_t> &diag) {
-  const int nb = pc->nb;
+  const int nb = pc->nb, b2 = pc->bs * pc->bs;
   int nblk = 0;
   for (int i = 0; i < nb; i++) nblk = std::max(nblk, blk_of[i] + 1);
   std::vector<int32_t> bcount(nblk + 1, 0);
@@ -567,11 +669,14 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
     lb[i] = l;
   }
   std::vector<int4> blk(nblk), lev;
-  std::vector<int32_t> lvl_row, ent_col, ent_src, dinv_src;
+  std::vector<double> stream;  // 8-byte words
+  std::vector<int2> repack;
   std::vector<std::vector<int32_t>> rows_of_level;
+  stream.reserve((size_t)pc->nnzb * b2 + (size_t)pc->nnzb / 2 + 4 * (size_t)nb);
+  repack.reserve(pc->nnzb);
+  int max_level_words = 0, max_level_rows = 0;
   for (int b = 0; b < nblk; b++) {
     const int r0 = bcount[b], nr = bcount[b + 1] - bcount[b];
-    int nlev[2] = {0, 0};
     const int lev0 = (int)lev.size();
     for (int pass = 0; pass < 2; pass++) {
       const std::vector<int32_t> &lv = pass == 0 ? lf : lb;
@@ -588,50 +693,66 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
         int nk = 0;
         for (int row : rows)
           nk = std::max(nk, pass == 0 ? diag[row] - rowptr[row] : rowptr[row + 1] - diag[row] - 1);
-        int4 L;
-        L.x = (int)lvl_row.size();
-        L.y = n;
-        L.z = nk;
-        L.w = (int)ent_col.size();
-        lev.push_back(L);
-        for (int row : rows) {
-          lvl_row.push_back(local[row]);
-          dinv_src.push_back(pass == 1 ? diag[row] : -1);
-        }
-        const size_t e0 = ent_col.size();
-        ent_col.resize(e0 + (size_t)nk * n, -1);
-        ent_src.resize(e0 + (size_t)nk * n, -1);
+        const size_t w0 = stream.size();
+        const int w_rows = ilu_pad_i32(n), w_cols = ilu_pad_i32(nk * n), w_vals = ilu_pad_f64(nk * n * b2),
+                  w_dinv = pass == 1 ? ilu_pad_f64(n * b2) : 0;
+        const int words = 2 + w_rows + w_cols + w_vals + w_dinv;
+        WB_CHECK(w0 + words < ((size_t)1 << 31), "wb_pc_setup: factor stream too large for 32-bit word offsets");
+        stream.resize(w0 + words, 0.0);
+        int32_t *hd = reinterpret_cast<int32_t *>(&stream[w0]);
+        hd[0] = n; hd[1] = nk; hd[2] = pass; hd[3] = 0;
+        int32_t *prow = reinterpret_cast<int32_t *>(&stream[w0 + 2]);
+        int32_t *pcol = reinterpret_cast<int32_t *>(&stream[w0 + 2 + w_rows]);
+        for (int q = 0; q < nk * n; q++) pcol[q] = -1;
+        const size_t wv = w0 + 2 + w_rows + w_cols, wd = wv + w_vals;
         for (int q = 0; q < n; q++) {
           const int row = rows[q];
+          prow[q] = local[row];
           const int k0 = pass == 0 ? rowptr[row] : diag[row] + 1, k1 = pass == 0 ? diag[row] : rowptr[row + 1];
           for (int k = k0; k < k1; k++) {
-            ent_col[e0 + (size_t)(k - k0) * n + q] = local[colidx[k]];
-            ent_src[e0 + (size_t)(k - k0) * n + q] = k;
+            const int e = (k - k0) * n + q;
+            pcol[e] = local[colidx[k]];
+            repack.push_back(make_int2(k, (int)(wv + (size_t)e * b2)));
           }
+          if (pass == 1) repack.push_back(make_int2(diag[row], (int)(wd + (size_t)q * b2)));
         }
+        int4 L;
+        L.x = (int)w0; L.y = words * 8; L.z = n; L.w = 0;
+        lev.push_back(L);
+        max_level_words = std::max(max_level_words, words);
+        max_level_rows = std::max(max_level_rows, n);
       }
-      nlev[pass] = nl;
     }
-    WB_CHECK(nlev[0] < 65536 && nlev[1] < 65536, "wb_pc_setup: sub-domain with too many levels");
+    WB_CHECK((int)lev.size() - lev0 < (1 << 30), "wb_pc_setup: sub-domain with too many levels");
     blk[b].x = r0;
     blk[b].y = nr;
     blk[b].z = lev0;
-    blk[b].w = nlev[0] | (nlev[1] << 16);
+    blk[b].w = (int)lev.size() - lev0;
   }
   pc->nblk = nblk;
   pc->max_block_rows = maxrows;
-  pc->nent = (int)ent_col.size();
-  pc->nlvlrow = (int)lvl_row.size();
-  const int b2 = pc->bs * pc->bs;
+  pc->nrepack = (int)repack.size();
+  pc->stream_words = stream.size();
   WB_TRY(upload(&pc->d_blk, blk));
   WB_TRY(upload(&pc->d_lev, lev));
   WB_TRY(upload(&pc->d_blk_rows, blk_rows));
-  WB_TRY(upload(&pc->d_lvl_row, lvl_row));
-  WB_TRY(upload(&pc->d_ent_col, ent_col));
-  WB_TRY(upload(&pc->d_ent_src, ent_src));
-  WB_TRY(upload(&pc->d_dinv_src, dinv_src));
-  WB_CUDA(cudaMalloc(&pc->d_ent_val, sizeof(double) * std::max<size_t>((size_t)pc->nent * b2, 1)));
-  WB_CUDA(cudaMalloc(&pc->d_lvl_dinv, sizeof(double) * std::max<size_t>((size_t)pc->nlvlrow * b2, 1)));
+  WB_TRY(upload(&pc->d_stream, stream));
+  WB_TRY(upload(&pc->d_repack, repack));
+  // ring geometry: as many stages (<= 4) as keep >= 3 CTAs per SM when possible; a level record must fit
+  // the mbarrier transaction count (< 2^20 bytes); otherwise the stream is read from global memory
+  pc->solve_threads = max_level_rows > 128 ? 256 : 128;
+  pc->stage_words = max_level_words;
+  const size_t zs_bytes = (size_t)maxrows * pc->bs * sizeof(double), stage_bytes = (size_t)max_level_words * 8;
+  pc->nstage = 0;
+  if (stage_bytes < (1u << 20)) {
+    for (int ns = 4; ns >= 2; ns--) {
+      const size_t need = 128 + ns * stage_bytes + zs_bytes;
+      if (need <= (ns == 2 ? 200u * 1024 : 72u * 1024)) {
+        pc->nstage = ns;
+        break;
+      }
+    }
+  }
   return 0;
 }
 
@@ -698,9 +819,8 @@ static int pc_numeric(wb_pc *pc) {
     }
     WB_LAUNCH(c);
     if (pc->blocked) {
-      const size_t nthr = (size_t)std::max(pc->nent, pc->nlvlrow) * bs2;
-      k_ilu_repack<<<wb_grid(nthr, 256), 256, 0, c->stream>>>(pc->d_val, pc->d_ent_src, pc->nent, pc->d_dinv_src,
-                                                            pc->nlvlrow, bs2, pc->d_ent_val, pc->d_lvl_dinv);
+      k_ilu_repack<<<wb_grid((size_t)pc->nrepack * bs2, 256), 256, 0, c->stream>>>(pc->d_val, pc->d_repack, pc->nrepack,
+                                                                                  bs2, pc->d_stream);
       WB_LAUNCH(c);
     }
   }
@@ -713,8 +833,8 @@ extern "C" int wb_pc_destroy(wb_pc *pc) {
   cudaSetDevice(pc->A->ctx->device);
   cudaStreamSynchronize(pc->A->ctx->stream);
   void *ptrs[] = {pc->d_dinv, pc->d_rowptr, pc->d_colidx, pc->d_diag, pc->d_src, pc->d_sched_f, pc->d_sched_b,
-                  pc->d_val, pc->d_flag, pc->d_ticket, pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_lvl_row,
-                  pc->d_ent_col, pc->d_ent_src, pc->d_dinv_src, pc->d_ent_val, pc->d_lvl_dinv};
+                  pc->d_val, pc->d_flag, pc->d_ticket, pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_stream,
+                  pc->d_repack};
   for (void *p : ptrs) cudaFree(p);
   delete pc;
   return 0;
@@ -817,7 +937,7 @@ extern "C" int wb_pc_refactor(wb_pc *pc) {
   return 0;
 }
 
-int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z) {
+int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z, const int *done) {
   wb_ctx *c = pc->A->ctx;
   const int nb = pc->nb;
   if (pc->type == WB_PC_NONE) {
@@ -837,13 +957,17 @@ int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z) {
     return 0;
   }
   if (pc->blocked) {
-    const size_t smem = (size_t)pc->max_block_rows * pc->bs * sizeof(double);
-#define BSOLVE(BS)                                                                                                 \
-  do {                                                                                                             \
-    if (smem > 48 * 1024)                                                                                          \
-      cudaFuncSetAttribute(k_ilu0_block_solve<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    k_ilu0_block_solve<BS><<<pc->nblk, 128, smem, c->stream>>>(pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_lvl_row, \
-                                                               pc->d_ent_col, pc->d_ent_val, pc->d_lvl_dinv, d_r, d_z); \
+    const size_t smem = 128 + (size_t)pc->nstage * pc->stage_words * 8 + (size_t)pc->max_block_rows * pc->bs * sizeof(double);
+    IluSolveArgs a = {pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_stream, d_r, d_z, pc->stage_words, pc->nstage, done};
+#define BSOLVE(BS)                                                                                           \
+  do {                                                                                                       \
+    if (pc->nstage > 0) {                                                                                    \
+      cudaFuncSetAttribute(k_ilu0_block_solve<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      k_ilu0_block_solve<BS, true><<<pc->nblk, pc->solve_threads, smem, c->stream>>>(a);                     \
+    } else {                                                                                                 \
+      cudaFuncSetAttribute(k_ilu0_block_solve<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      k_ilu0_block_solve<BS, false><<<pc->nblk, pc->solve_threads, smem, c->stream>>>(a);                    \
+    }                                                                                                        \
   } while (0)
     switch (pc->bs) {
       case 1: BSOLVE(1); break;
@@ -896,84 +1020,277 @@ extern "C" int wb_pc_apply(wb_pc *pc, const double *r, double *z) {
   if (rc) return rc;
   {
     WbScopedTimer tm(c, "pc_apply");
-    WB_TRY(wb_pc_apply_dev(pc, dr, dz));
+    WB_TRY(wb_pc_apply_dev(pc, dr, dz, nullptr));
   }
   return st.finish();
 }
 
 // ================================================================ vector kernels (K7)
 
+// Persistent-style grid for the streaming vector kernels: 4 CTAs of 256 threads per SM.
 #define RED_BLOCKS (4 * WB_NUM_SMS)
+#define KRY_MAXV 32  // vectors per fused multi-dot / multi-axpy launch (>= restart + 1 is not needed: one cycle
+                     // of GMRES(30) dots against at most 30 vectors; longer restarts go in chunks)
+
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
+__device__ __forceinline__ double4 ld256(const double *p) {
+  double4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double4 ld256_stream(const double *p) {  // evict-first: the Krylov basis is read once per pass
+  double4 r;
+  asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256(double *p, const double4 &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
+}
 
 __device__ __forceinline__ double block_sum(double v) {
   __shared__ double sh[32];
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __syncthreads();
   if (l == 0) sh[w] = v;
   __syncthreads();
   if (w == 0) {
     v = l < (blockDim.x >> 5) ? sh[l] : 0.0;
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    v = warp_sum(v);
   }
   return v;  // valid in thread 0
 }
 
+// true in every thread of the LAST CTA of the grid to get here (its view of the other CTAs' global
+// writes is complete); resets the counter for the next launch
+__device__ __forceinline__ bool last_block(unsigned *counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+struct KspState {
+  double res, rnorm0;
+  int its, reason, it_inner, pad;
+};
+
+// Arnoldi column `it_inner` is complete (hcol = dots, scal[0] = |w|^2): update the Givens QR and the
+// convergence state (KSPGMRESUpdateHessenberg + KSPConvergedDefault).  One thread.
+struct GmresUpd {
+  double *hcol, *H, *cs, *sn, *rs, *scal;
+  KspState *st;
+  int *done;
+  double rtol, atol, dtol;
+  int m, maxit;
+};
+__device__ void gmres_update(const GmresUpd &u) {
+  if (*u.done) return;
+  KspState *st = u.st;
+  const int it = st->it_inner, m = u.m;
+  const double tt = sqrt(u.scal[0]);
+  u.hcol[it + 1] = tt;
+  const bool happy = (tt < 1.e-30 * fmax(st->res, 1e-300)) || tt == 0.0;
+  u.scal[1] = happy ? 1.0 : 1.0 / tt;
+  double *Hc = u.H + (size_t)(m + 1) * it;
+  for (int j = 0; j <= it + 1; j++) Hc[j] = u.hcol[j];
+  for (int j = 0; j < it; j++) {
+    const double t1 = Hc[j], t2 = Hc[j + 1];
+    Hc[j] = u.cs[j] * t1 + u.sn[j] * t2;
+    Hc[j + 1] = -u.sn[j] * t1 + u.cs[j] * t2;
+  }
+  const double hh = Hc[it], hp = Hc[it + 1];
+  const double den = sqrt(hh * hh + hp * hp);
+  if (den == 0.0) {
+    st->reason = -5;  // KSP_DIVERGED_BREAKDOWN
+    *u.done = 1;
+    return;
+  }
+  u.cs[it] = hh / den;
+  u.sn[it] = hp / den;
+  u.rs[it + 1] = -u.sn[it] * u.rs[it];
+  u.rs[it] = u.cs[it] * u.rs[it];
+  Hc[it] = u.cs[it] * hh + u.sn[it] * hp;
+  Hc[it + 1] = 0.0;
+  const double res = fabs(u.rs[it + 1]);
+  st->res = res;
+  st->it_inner = it + 1;
+  st->its += 1;
+  int reason = 0;
+  const double ttol = fmax(u.rtol * st->rnorm0, u.atol);
+  if (res != res) reason = -9;
+  else if (res <= ttol) reason = (res < u.atol) ? 3 : 2;
+  else if (res >= u.dtol * st->rnorm0) reason = -4;
+  if (!reason && happy) reason = 5;
+  if (!reason && st->its >= u.maxit) reason = -3;
+  if (reason) {
+    st->reason = reason;
+    *u.done = 1;
+  }
+}
+__global__ void k_gmres_update(const GmresUpd u) { gmres_update(u); }
+
 // Krylov kernels all take the solver's device-side `done` flag and return at once when it is
-// set, so the host can enqueue several iterations between convergence checks.
+// set, so the host can enqueue a whole restart cycle between convergence checks.
 
-// part[j*RED_BLOCKS + blk] = partial (w . V_j) for up to 8 vectors per launch
-template <int NV>
-__global__ void __launch_bounds__(256) k_mdot(const double *__restrict__ w, const double *__restrict__ V, size_t ldv,
-                                              int n, double *__restrict__ part, const int *done) {
-  if (done && *done) return;
-  double acc[NV];
+// out[j] = w . V_j, j < nv <= NVT, in ONE pass over w and the nv basis vectors (VecMDot): every thread
+// keeps nv partial sums; 32-byte vector loads; partials are folded warp -> CTA -> last CTA in a fixed
+// order, so the result does not depend on scheduling.
+struct MdotArgs {
+  const double *w, *V;
+  size_t ldv;
+  int n, nv;
+  double *part, *out;
+  unsigned *counter;
+  const int *done;
+};
+template <int NVT, bool VEC>
+__global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
+  if (a.done && *a.done) return;
+  double acc[NVT];
 #pragma unroll
-  for (int j = 0; j < NV; j++) acc[j] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double wi = w[i];
+  for (int j = 0; j < NVT; j++) acc[j] = 0.0;
+  if (VEC) {
+    const int n4 = a.n >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const double4 wi = ld256(a.w + 4 * (size_t)i);
 #pragma unroll
-    for (int j = 0; j < NV; j++) acc[j] += wi * V[(size_t)j * ldv + i];
+      for (int j = 0; j < NVT; j++) {
+        if (j < a.nv) {
+          const double4 v = ld256_stream(a.V + (size_t)j * a.ldv + 4 * (size_t)i);
+          acc[j] += wi.x * v.x;
+          acc[j] += wi.y * v.y;
+          acc[j] += wi.z * v.z;
+          acc[j] += wi.w * v.w;
+        }
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {  // tail
+      const int i = (n4 << 2) + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < NVT; j++)
+        if (j < a.nv) acc[j] += a.w[i] * a.V[(size_t)j * a.ldv + i];
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+      const double wi = a.w[i];
+#pragma unroll
+      for (int j = 0; j < NVT; j++)
+        if (j < a.nv) acc[j] += wi * a.V[(size_t)j * a.ldv + i];
+    }
   }
+  __shared__ double sh[8][NVT];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < NV; j++) {
-    const double s = block_sum(acc[j]);
-    if (threadIdx.x == 0) part[(size_t)j * RED_BLOCKS + blockIdx.x] = s;
+  for (int j = 0; j < NVT; j++) {
+    if (j < a.nv) {
+      const double v = warp_sum(acc[j]);
+      if (lane == 0) sh[wid][j] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < a.nv) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += sh[q][threadIdx.x];
+    a.part[(size_t)threadIdx.x * RED_BLOCKS + blockIdx.x] = s;
+  }
+  if (last_block(a.counter)) {
+    for (int j = wid; j < a.nv; j += 8) {
+      double s = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&a.part[(size_t)j * RED_BLOCKS + b]);
+      s = warp_sum(s);
+      if (lane == 0) a.out[j] = s;
+    }
   }
 }
 
-// out[j] = sum of the partials of dot j, fixed order; one warp per dot
-__global__ void k_reduce_final(const double *__restrict__ part, int nblk, int nd, double *__restrict__ out,
-                               const int *done) {
-  if (done && *done) return;
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
-  if (j >= nd) return;
-  double s = 0.0;
-  for (int b = l; b < nblk; b += 32) s += part[(size_t)j * RED_BLOCKS + b];
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-  if (l == 0) out[j] = s;
-}
-
-// w += sign * sum_j coef[j] V_j (sequential in j, as repeated VecAXPY); optional partial |w|^2
-template <int NV>
-__global__ void __launch_bounds__(256) k_maxpy(double *__restrict__ w, const double *__restrict__ V, size_t ldv,
-                                               const double *__restrict__ coef, double sign, int n,
-                                               double *__restrict__ part, const int *done) {
-  if (done && *done) return;
-  double cf[NV];
+// w += sign * sum_j coef[j] V_j, j < nv <= NVT (VecMAXPY; sequential in j per entry), in one pass; with
+// `part` also |w|^2 of the result (VecNorm), and with `upd` the last CTA finishes the Arnoldi step
+// (single-GPU: no collective is needed between the norm and the Hessenberg update).
+struct MaxpyArgs {
+  double *w;
+  const double *V;
+  size_t ldv;
+  const double *coef;
+  double sign;
+  int n, nv;
+  double *part, *out;  // nullable
+  unsigned *counter;
+  const int *done;
+  int with_upd;
+  GmresUpd upd;
+};
+template <int NVT, bool VEC>
+__global__ void __launch_bounds__(256) k_maxpy_all(const MaxpyArgs a) {
+  if (a.done && *a.done) return;
+  double cf[NVT];
 #pragma unroll
-  for (int j = 0; j < NV; j++) cf[j] = sign * coef[j];
+  for (int j = 0; j < NVT; j++) cf[j] = j < a.nv ? a.sign * a.coef[j] : 0.0;
   double nrm = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    double wi = w[i];
+  if (VEC) {
+    const int n4 = a.n >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      double4 wi = ld256(a.w + 4 * (size_t)i);
 #pragma unroll
-    for (int j = 0; j < NV; j++) wi += cf[j] * V[(size_t)j * ldv + i];
-    w[i] = wi;
-    nrm += wi * wi;
+      for (int j = 0; j < NVT; j++) {
+        if (j < a.nv) {
+          const double4 v = ld256_stream(a.V + (size_t)j * a.ldv + 4 * (size_t)i);
+          wi.x += cf[j] * v.x;
+          wi.y += cf[j] * v.y;
+          wi.z += cf[j] * v.z;
+          wi.w += cf[j] * v.w;
+        }
+      }
+      st256(a.w + 4 * (size_t)i, wi);
+      nrm += wi.x * wi.x;
+      nrm += wi.y * wi.y;
+      nrm += wi.z * wi.z;
+      nrm += wi.w * wi.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {  // tail
+      const int i = (n4 << 2) + threadIdx.x;
+      double wi = a.w[i];
+      for (int j = 0; j < a.nv; j++) wi += a.sign * a.coef[j] * a.V[(size_t)j * a.ldv + i];
+      a.w[i] = wi;
+      nrm += wi * wi;
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+      double wi = a.w[i];
+#pragma unroll
+      for (int j = 0; j < NVT; j++)
+        if (j < a.nv) wi += cf[j] * a.V[(size_t)j * a.ldv + i];
+      a.w[i] = wi;
+      nrm += wi * wi;
+    }
   }
-  if (part) {
-    const double s = block_sum(nrm);
-    if (threadIdx.x == 0) part[blockIdx.x] = s;
+  if (!a.part) return;
+  const double s = block_sum(nrm);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = s;
+  if (last_block(a.counter)) {
+    if (threadIdx.x < 32) {
+      double t = 0.0;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += __ldcg(&a.part[b]);
+      t = warp_sum(t);
+      if (threadIdx.x == 0) {
+        a.out[0] = t;
+        if (a.with_upd) gmres_update(a.upd);
+      }
+    }
   }
 }
 
@@ -1002,65 +1319,19 @@ __global__ void __launch_bounds__(256) k_lin3(double *__restrict__ z, Lin3 q, in
   }
 }
 
-// ================================================================ GMRES (K7)
-
-struct GmresDev {
-  // layout of the small device state block (doubles)
-  // [0..m]   hcol (dots of the current column, then rotated)
-  // then H (m+1)*m, cs m+1, sn m+1, rs m+2, yv m+1, scal[8]: 0 tt2, 1 scale, 2 res, 3 rnorm0, 4 res0sq
-};
-
-struct KspState {
-  double res, rnorm0;
-  int its, reason, it_inner, pad;
-};
-
-// one thread: finish Arnoldi column `it`, update the Givens QR and the convergence state
-// (KSPGMRESUpdateHessenberg + KSPConvergedDefault)
-__global__ void k_gmres_update(double *hcol, double *H, double *cs, double *sn, double *rs, double *scal, int m,
-                               KspState *st, int *done, double rtol, double atol, double dtol, int maxit) {
-  if (*done) return;
-  const int it = st->it_inner;
-  const double tt = sqrt(scal[0]);
-  hcol[it + 1] = tt;
-  const bool happy = (tt < 1.e-30 * fmax(st->res, 1e-300)) || tt == 0.0;
-  scal[1] = happy ? 1.0 : 1.0 / tt;
-  double *Hc = H + (size_t)(m + 1) * it;
-  for (int j = 0; j <= it + 1; j++) Hc[j] = hcol[j];
-  for (int j = 0; j < it; j++) {
-    const double t1 = Hc[j], t2 = Hc[j + 1];
-    Hc[j] = cs[j] * t1 + sn[j] * t2;
-    Hc[j + 1] = -sn[j] * t1 + cs[j] * t2;
-  }
-  const double hh = Hc[it], hp = Hc[it + 1];
-  const double den = sqrt(hh * hh + hp * hp);
-  if (den == 0.0) {
-    st->reason = -5;  // KSP_DIVERGED_BREAKDOWN
-    *done = 1;
-    return;
-  }
-  cs[it] = hh / den;
-  sn[it] = hp / den;
-  rs[it + 1] = -sn[it] * rs[it];
-  rs[it] = cs[it] * rs[it];
-  Hc[it] = cs[it] * hh + sn[it] * hp;
-  Hc[it + 1] = 0.0;
-  const double res = fabs(rs[it + 1]);
-  st->res = res;
-  st->it_inner = it + 1;
-  st->its += 1;
-  int reason = 0;
-  const double ttol = fmax(rtol * st->rnorm0, atol);
-  if (res != res) reason = -9;
-  else if (res <= ttol) reason = (res < atol) ? 3 : 2;
-  else if (res >= dtol * st->rnorm0) reason = -4;
-  if (!reason && happy) reason = 5;
-  if (!reason && st->its >= maxit) reason = -3;
-  if (reason) {
-    st->reason = reason;
-    *done = 1;
-  }
+// out[j] = sum of the partials of dot j, fixed order; one warp per dot
+__global__ void k_reduce_final(const double *__restrict__ part, int nblk, int nd, double *__restrict__ out,
+                               const int *done) {
+  if (done && *done) return;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
+  if (j >= nd) return;
+  double s = 0.0;
+  for (int b = l; b < nblk; b += 32) s += part[(size_t)j * RED_BLOCKS + b];
+  s = warp_sum(s);
+  if (l == 0) out[j] = s;
 }
+
+// ================================================================ GMRES (K7)
 
 // start of a restart cycle: res = sqrt(rr); first cycle fixes rnorm0 and tests convergence
 __global__ void k_gmres_begin(double *rs, double *scal, KspState *st, int *done, int first, double rtol,
@@ -1099,29 +1370,38 @@ __global__ void k_gmres_solve_y(const double *H, const double *rs, double *yv, i
 
 struct KspWork {
   wb_ctx *ctx = nullptr;
-  size_t n = 0;
+  size_t n = 0, ld = 0;  // ld: n rounded up to 32 doubles so every basis vector is 256-byte aligned
   int m = 0;
-  double *V = nullptr, *tmp = nullptr, *small = nullptr, *part = nullptr;
+  double *V = nullptr, *tmp = nullptr, *wbuf = nullptr, *small = nullptr, *part = nullptr;
   KspState *d_st = nullptr, *h_st = nullptr;
   int *d_done = nullptr;
-  double *bc[8] = {nullptr};  // BCGS vectors
+  unsigned *d_counter = nullptr;
 };
 static std::map<wb_ctx *, KspWork> g_work;
+
+static void free_work(KspWork &w) {
+  cudaFree(w.V); cudaFree(w.tmp); cudaFree(w.small); cudaFree(w.part); cudaFree(w.d_st); cudaFree(w.d_done);
+  cudaFree(w.d_counter);
+  if (w.h_st) cudaFreeHost(w.h_st);
+}
 
 static int ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
   KspWork &w = g_work[c];
   if (w.n != n || w.m < m) {
-    cudaFree(w.V); cudaFree(w.tmp); cudaFree(w.small); cudaFree(w.part); cudaFree(w.d_st); cudaFree(w.d_done);
-    if (w.h_st) cudaFreeHost(w.h_st);
+    free_work(w);
     w = KspWork();
     w.ctx = c; w.n = n; w.m = m;
-    WB_CUDA(cudaMalloc(&w.V, sizeof(double) * n * (m + 1)));
-    WB_CUDA(cudaMalloc(&w.tmp, sizeof(double) * n * 2));
+    w.ld = (n + 31) / 32 * 32;
+    WB_CUDA(cudaMalloc(&w.V, sizeof(double) * w.ld * (m + 1)));
+    WB_CUDA(cudaMalloc(&w.tmp, sizeof(double) * w.ld * 3));
+    w.wbuf = w.tmp + 2 * w.ld;
     WB_CUDA(cudaMalloc(&w.small, sizeof(double) * ((size_t)(m + 1) * m + 6 * (m + 2) + 16)));
-    WB_CUDA(cudaMalloc(&w.part, sizeof(double) * RED_BLOCKS * 8));
+    WB_CUDA(cudaMalloc(&w.part, sizeof(double) * RED_BLOCKS * KRY_MAXV));
     WB_CUDA(cudaMalloc(&w.d_st, sizeof(KspState)));
     WB_CUDA(cudaMallocHost(&w.h_st, sizeof(KspState)));
     WB_CUDA(cudaMalloc(&w.d_done, sizeof(int)));
+    WB_CUDA(cudaMalloc(&w.d_counter, sizeof(unsigned)));
+    WB_CUDA(cudaMemset(w.d_counter, 0, sizeof(unsigned)));
   }
   *out = &w;
   return 0;
@@ -1130,33 +1410,40 @@ static int ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
 void wb_linalg_release(wb_ctx *c) {
   auto it = g_work.find(c);
   if (it == g_work.end()) return;
-  KspWork &w = it->second;
-  cudaFree(w.V); cudaFree(w.tmp); cudaFree(w.small); cudaFree(w.part); cudaFree(w.d_st); cudaFree(w.d_done);
-  if (w.h_st) cudaFreeHost(w.h_st);
+  free_work(it->second);
   g_work.erase(it);
 }
 
-static int red_blocks(size_t n) { return (int)std::min<size_t>(RED_BLOCKS, (n + 255) / 256); }
+static int red_blocks(size_t n) { return (int)std::min<size_t>(RED_BLOCKS, (n / 4 + 255) / 256 + 1); }
 
-// dots[j] = w . V_j for j in [0, nd), summed over ranks
-static int multi_dot(KspWork &w, const double *d_w, const double *V, int nd, double *d_out, const int *done) {
+static bool aligned32(const void *p) { return ((uintptr_t)p & 31) == 0; }
+template <int NVT> static void launch_mdot(const MdotArgs &a, int nblk, cudaStream_t s) {
+  if (aligned32(a.w) && aligned32(a.V) && (a.ldv & 3) == 0) k_mdot_all<NVT, true><<<nblk, 256, 0, s>>>(a);
+  else k_mdot_all<NVT, false><<<nblk, 256, 0, s>>>(a);
+}
+template <int NVT> static void launch_maxpy(const MaxpyArgs &a, int nblk, cudaStream_t s) {
+  if (aligned32(a.w) && aligned32(a.V) && (a.ldv & 3) == 0) k_maxpy_all<NVT, true><<<nblk, 256, 0, s>>>(a);
+  else k_maxpy_all<NVT, false><<<nblk, 256, 0, s>>>(a);
+}
+
+// dots[j] = w . V_j for j in [0, nd), summed over ranks.  V_j = V + j*ldv (16-byte aligned vectors).
+static int multi_dot(KspWork &w, const double *d_w, const double *V, size_t ldv, int nd, double *d_out,
+                     const int *done) {
   wb_ctx *c = w.ctx;
-  const int n = (int)w.n, nblk = red_blocks(w.n);
-  for (int j0 = 0; j0 < nd; j0 += 8) {
-    const int nv = std::min(8, nd - j0);
-    const double *Vj = V + (size_t)j0 * w.n;
-    switch (nv) {
-      case 1: k_mdot<1><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-      case 2: k_mdot<2><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-      case 3: k_mdot<3><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-      case 4: k_mdot<4><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-      case 5: k_mdot<5><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-      case 6: k_mdot<6><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-      case 7: k_mdot<7><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-      default: k_mdot<8><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, n, w.part, done); break;
-    }
-    WB_LAUNCH(c);
-    k_reduce_final<<<1, 256, 0, c->stream>>>(w.part, nblk, nv, d_out + j0, done);
+  const int nblk = red_blocks(w.n);
+  for (int j0 = 0; j0 < nd; j0 += KRY_MAXV) {
+    const int nv = std::min(KRY_MAXV, nd - j0);
+    MdotArgs a = {d_w, V + (size_t)j0 * ldv, ldv, (int)w.n, nv, w.part, d_out + j0, w.d_counter, done};
+    if (nv <= 1) launch_mdot<1>(a, nblk, c->stream);
+    else if (nv <= 2) launch_mdot<2>(a, nblk, c->stream);
+    else if (nv <= 4) launch_mdot<4>(a, nblk, c->stream);
+    else if (nv <= 8) launch_mdot<8>(a, nblk, c->stream);
+    else if (nv <= 12) launch_mdot<12>(a, nblk, c->stream);
+    else if (nv <= 16) launch_mdot<16>(a, nblk, c->stream);
+    else if (nv <= 20) launch_mdot<20>(a, nblk, c->stream);
+    else if (nv <= 24) launch_mdot<24>(a, nblk, c->stream);
+    else if (nv <= 28) launch_mdot<28>(a, nblk, c->stream);
+    else launch_mdot<32>(a, nblk, c->stream);
     WB_LAUNCH(c);
   }
   WB_CUDA(cudaGetLastError());
@@ -1164,41 +1451,48 @@ static int multi_dot(KspWork &w, const double *d_w, const double *V, int nd, dou
   return 0;
 }
 
-// w += sign * sum_j coef[j] V_j ; if d_nrm2: also |w|^2 (summed over ranks)
-static int multi_axpy(KspWork &w, double *d_w, const double *V, int nd, const double *d_coef, double sign,
-                      double *d_nrm2, const int *done) {
+// w += sign * sum_j coef[j] V_j ; if d_nrm2: also |w|^2 (summed over ranks); if upd (and one rank): the
+// Arnoldi-step update runs in the same launch
+static int multi_axpy(KspWork &w, double *d_w, const double *V, size_t ldv, int nd, const double *d_coef, double sign,
+                      double *d_nrm2, const int *done, const GmresUpd *upd) {
   wb_ctx *c = w.ctx;
-  const int n = (int)w.n, nblk = red_blocks(w.n);
-  for (int j0 = 0; j0 < nd; j0 += 8) {
-    const int nv = std::min(8, nd - j0);
+  const int nblk = red_blocks(w.n);
+  const bool fuse_upd = upd && c->nranks <= 1;
+  for (int j0 = 0; j0 < nd; j0 += KRY_MAXV) {
+    const int nv = std::min(KRY_MAXV, nd - j0);
     const bool last = j0 + nv >= nd;
-    double *part = (last && d_nrm2) ? w.part : nullptr;
-    const double *Vj = V + (size_t)j0 * w.n;
-    switch (nv) {
-      case 1: k_maxpy<1><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-      case 2: k_maxpy<2><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-      case 3: k_maxpy<3><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-      case 4: k_maxpy<4><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-      case 5: k_maxpy<5><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-      case 6: k_maxpy<6><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-      case 7: k_maxpy<7><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-      default: k_maxpy<8><<<nblk, 256, 0, c->stream>>>(d_w, Vj, w.n, d_coef + j0, sign, n, part, done); break;
-    }
+    MaxpyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w = d_w; a.V = V + (size_t)j0 * ldv; a.ldv = ldv; a.coef = d_coef + j0; a.sign = sign; a.n = (int)w.n; a.nv = nv;
+    a.part = (last && d_nrm2) ? w.part : nullptr;
+    a.out = d_nrm2; a.counter = w.d_counter; a.done = done;
+    a.with_upd = (last && fuse_upd) ? 1 : 0;
+    if (a.with_upd) a.upd = *upd;
+    if (nv <= 1) launch_maxpy<1>(a, nblk, c->stream);
+    else if (nv <= 2) launch_maxpy<2>(a, nblk, c->stream);
+    else if (nv <= 4) launch_maxpy<4>(a, nblk, c->stream);
+    else if (nv <= 8) launch_maxpy<8>(a, nblk, c->stream);
+    else if (nv <= 12) launch_maxpy<12>(a, nblk, c->stream);
+    else if (nv <= 16) launch_maxpy<16>(a, nblk, c->stream);
+    else if (nv <= 20) launch_maxpy<20>(a, nblk, c->stream);
+    else if (nv <= 24) launch_maxpy<24>(a, nblk, c->stream);
+    else if (nv <= 28) launch_maxpy<28>(a, nblk, c->stream);
+    else launch_maxpy<32>(a, nblk, c->stream);
     WB_LAUNCH(c);
-  }
-  if (d_nrm2) {
-    k_reduce_final<<<1, 32, 0, c->stream>>>(w.part, nblk, 1, d_nrm2, done);
-    WB_LAUNCH(c);
-    WB_TRY(wb_allreduce_sum(c, d_nrm2, 1));
   }
   WB_CUDA(cudaGetLastError());
+  if (d_nrm2) WB_TRY(wb_allreduce_sum(c, d_nrm2, 1));
+  if (upd && !fuse_upd) {
+    k_gmres_update<<<1, 1, 0, c->stream>>>(*upd);
+    WB_LAUNCH(c);
+  }
   return 0;
 }
 
 static int lin3(KspWork &w, double *z, const double *x, double a, const double *sa, const double *y, double b,
                 const double *sb, const double *v3, double cc, const double *sc, double *d_nrm2, const int *done) {
   wb_ctx *c = w.ctx;
-  const int nblk = red_blocks(w.n);
+  const int nblk = std::min<int>(RED_BLOCKS, (int)((w.n + 255) / 256));
   Lin3 q = {x, y, v3, sa, sb, sc, a, b, cc};
   k_lin3<<<nblk, 256, 0, c->stream>>>(z, q, (int)w.n, d_nrm2 ? w.part : nullptr, done);
   WB_LAUNCH(c);
@@ -1211,7 +1505,6 @@ static int lin3(KspWork &w, double *z, const double *x, double a, const double *
   return 0;
 }
 
-int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z);
 
 static int fetch_state(KspWork &w) {
   wb_ctx *c = w.ctx;
@@ -1220,7 +1513,8 @@ static int fetch_state(KspWork &w) {
   return 0;
 }
 
-// how many Krylov iterations are enqueued between host convergence checks
+// how many Krylov iterations are enqueued between host convergence checks in the first restart cycle
+// (later cycles are enqueued whole: a solve that needs a second cycle is a long one)
 static int g_check_every = 4;
 extern "C" int wb_ksp_set_check_every(int k) {
   g_check_every = std::max(1, k);
@@ -1228,7 +1522,9 @@ extern "C" int wb_ksp_set_check_every(int k) {
 }
 
 // KSPSolve_GMRES: restarted, classical Gram-Schmidt (no refinement), left preconditioning,
-// convergence on the preconditioned residual norm
+// convergence on the preconditioned residual norm.  Four launches per iteration on one GPU:
+//   SpMV (normalises the new basis vector on the fly and stores it), PC apply, fused multi-dot,
+//   fused multi-axpy + norm + Hessenberg/Givens update.
 static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b, double *d_x, int *its,
                      int *reason, double *rnorm) {
   wb_ctx *c = A->ctx;
@@ -1237,56 +1533,53 @@ static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
   KspWork *wp;
   WB_TRY(ensure_work(c, n, m, &wp));
   KspWork &w = *wp;
+  const size_t ld = w.ld;
   double *hcol = w.small, *H = hcol + (m + 2), *cs = H + (size_t)(m + 1) * m, *sn = cs + (m + 1),
          *rs = sn + (m + 1), *yv = rs + (m + 2), *scal = yv + (m + 1);
-  double *tmp = w.tmp;
+  double *tmp = w.tmp, *wbuf = w.wbuf;
+  const GmresUpd upd = {hcol, H, cs, sn, rs, scal, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, m, o->maxit};
   WB_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * n, c->stream));
   WB_CUDA(cudaMemsetAsync(w.d_done, 0, sizeof(int), c->stream));
   WB_CUDA(cudaMemsetAsync(w.d_st, 0, sizeof(KspState), c->stream));
   bool first = true;
   while (true) {
-    // r = M^-1 (b - A x) -> V_0
+    // r = M^-1 (b - A x) -> wbuf (unnormalised start vector of the cycle)
     if (first) {
-      WB_TRY(wb_pc_apply_dev(pc, d_b, w.V));
+      WB_TRY(wb_pc_apply_dev(pc, d_b, wbuf));
     } else {
       WB_TRY(wb_spmv_launch(A, d_x, tmp));
       WB_TRY(lin3(w, tmp, d_b, 1.0, nullptr, tmp, -1.0, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr));
-      WB_TRY(wb_pc_apply_dev(pc, tmp, w.V));
+      WB_TRY(wb_pc_apply_dev(pc, tmp, wbuf));
     }
-    WB_TRY(multi_dot(w, w.V, w.V, 1, scal, nullptr));
+    WB_TRY(multi_dot(w, wbuf, wbuf, ld, 1, scal, nullptr));
     k_gmres_begin<<<1, 1, 0, c->stream>>>(rs, scal, w.d_st, w.d_done, first ? 1 : 0, o->rtol, o->atol, o->dtol);
     WB_LAUNCH(c);
     if (first) {
       WB_TRY(fetch_state(w));
       if (w.h_st->reason != 0) break;
     }
-    first = false;
-    WB_TRY(lin3(w, w.V, w.V, 1.0, scal + 1, nullptr, 0.0, nullptr, nullptr, 0.0, nullptr, nullptr, w.d_done));
     int it = 0;
     bool stop = false;
     while (it < m && !stop) {
-      const int chunk = std::min(g_check_every, m - it);
+      const int chunk = first ? std::min(g_check_every, m - it) : m - it;
       for (int q = 0; q < chunk; q++, it++) {
-        double *vn = w.V + (size_t)(it + 1) * n;
         // the kernels below are no-ops once the device-side done flag is up
-        WB_TRY(wb_spmv_launch(A, w.V + (size_t)it * n, tmp));
-        WB_TRY(wb_pc_apply_dev(pc, tmp, vn));
-        WB_TRY(multi_dot(w, vn, w.V, it + 1, hcol, w.d_done));
-        WB_TRY(multi_axpy(w, vn, w.V, it + 1, hcol, -1.0, scal, w.d_done));
-        k_gmres_update<<<1, 1, 0, c->stream>>>(hcol, H, cs, sn, rs, scal, m, w.d_st, w.d_done, o->rtol, o->atol,
-                                               o->dtol, o->maxit);
-        WB_LAUNCH(c);
-        WB_TRY(lin3(w, vn, vn, 1.0, scal + 1, nullptr, 0.0, nullptr, nullptr, 0.0, nullptr, nullptr, w.d_done));
+        // V_it = wbuf * (1/|wbuf|) stored by the SpMV that also forms tmp = A V_it
+        WB_TRY(wb_spmv_fused(A, wbuf, scal + 1, w.V + (size_t)it * ld, tmp, w.d_done));
+        WB_TRY(wb_pc_apply_dev(pc, tmp, wbuf, w.d_done));
+        WB_TRY(multi_dot(w, wbuf, w.V, ld, it + 1, hcol, w.d_done));
+        WB_TRY(multi_axpy(w, wbuf, w.V, ld, it + 1, hcol, -1.0, scal, w.d_done, &upd));
       }
       WB_TRY(fetch_state(w));
       if (w.h_st->reason != 0) stop = true;
     }
+    first = false;
     // x += sum_j y_j V_j over the columns actually built (the host copy of the state is current)
     const int ncol = w.h_st->it_inner;
     if (ncol > 0) {
       k_gmres_solve_y<<<1, 1, 0, c->stream>>>(H, rs, yv, m, w.d_st);
       WB_LAUNCH(c);
-      WB_TRY(multi_axpy(w, d_x, w.V, ncol, yv, 1.0, nullptr, nullptr));
+      WB_TRY(multi_axpy(w, d_x, w.V, ld, ncol, yv, 1.0, nullptr, nullptr, nullptr));
     }
     if (w.h_st->reason != 0) break;
   }
@@ -1402,7 +1695,8 @@ static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_
   WB_TRY(ensure_work(c, n, 30, &wp));
   KspWork &w = *wp;
   // carve the BCGS vectors out of the Krylov basis storage
-  double *R = w.V, *RP = R + n, *P = RP + n, *V = P + n, *S = V + n, *T = S + n, *tmp = w.tmp;
+  const size_t ld = w.ld;
+  double *R = w.V, *RP = R + ld, *P = RP + ld, *V = P + ld, *S = V + ld, *T = S + ld, *tmp = w.tmp;
   double *sc = w.small;
   const int nblk = red_blocks(n);
   WB_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * n, c->stream));
@@ -1412,7 +1706,7 @@ static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_
   WB_CUDA(cudaMemsetAsync(w.d_st, 0, sizeof(KspState), c->stream));
   WB_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 16, c->stream));
   WB_TRY(wb_pc_apply_dev(pc, d_b, R));
-  WB_TRY(multi_dot(w, R, R, 1, sc + 7, nullptr));
+  WB_TRY(multi_dot(w, R, R, ld, 1, sc + 7, nullptr));
   k_bcgs_begin<<<1, 1, 0, c->stream>>>(sc, w.d_st, w.d_done, o->rtol, o->atol);
   WB_LAUNCH(c);
   WB_CUDA(cudaMemcpyAsync(RP, R, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
@@ -1420,21 +1714,21 @@ static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_
   int enq = 0;
   while (w.h_st->reason == 0) {
     for (int q = 0; q < g_check_every && enq < o->maxit; q++, enq++) {
-      WB_TRY(multi_dot(w, R, RP, 1, sc + 0, w.d_done));
+      WB_TRY(multi_dot(w, R, RP, ld, 1, sc + 0, w.d_done));
       k_bcgs_step<<<1, 1, 0, c->stream>>>(sc, 0, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, o->maxit);
       WB_LAUNCH(c);
       k_bcgs_pupdate<<<nblk, 256, 0, c->stream>>>(P, R, V, sc, (int)n, w.d_done);
       WB_LAUNCH(c);
       WB_TRY(wb_spmv_launch(A, P, tmp));
       WB_TRY(wb_pc_apply_dev(pc, tmp, V));
-      WB_TRY(multi_dot(w, V, RP, 1, sc + 5, w.d_done));
+      WB_TRY(multi_dot(w, V, RP, ld, 1, sc + 5, w.d_done));
       k_bcgs_step<<<1, 1, 0, c->stream>>>(sc, 1, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, o->maxit);
       WB_LAUNCH(c);
       WB_TRY(lin3(w, S, R, 1.0, nullptr, V, 1.0, sc + 9, nullptr, 0.0, nullptr, nullptr, w.d_done));
       WB_TRY(wb_spmv_launch(A, S, tmp));
       WB_TRY(wb_pc_apply_dev(pc, tmp, T));
-      WB_TRY(multi_dot(w, S, T, 1, sc + 5, w.d_done));
-      WB_TRY(multi_dot(w, T, T, 1, sc + 8, w.d_done));
+      WB_TRY(multi_dot(w, S, T, ld, 1, sc + 5, w.d_done));
+      WB_TRY(multi_dot(w, T, T, ld, 1, sc + 8, w.d_done));
       k_bcgs_step<<<1, 1, 0, c->stream>>>(sc, 2, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, o->maxit);
       WB_LAUNCH(c);
       k_bcgs_xupdate<<<nblk, 256, 0, c->stream>>>(d_x, P, S, sc, (int)n, w.d_done, 1);
@@ -1470,7 +1764,7 @@ int wb_vec_dot_host(wb_ctx *c, const double *d_a, const double *d_b, size_t n, d
   }
   KspWork &w = *wp;
   double *sc = w.small;
-  WB_TRY(multi_dot(w, d_a, d_b, 1, sc, nullptr));
+  WB_TRY(multi_dot(w, d_a, d_b, w.ld, 1, sc, nullptr));
   WB_CUDA(cudaMemcpyAsync(c->h_red, sc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   WB_CUDA(cudaStreamSynchronize(c->stream));
   *out = c->h_red[0];
