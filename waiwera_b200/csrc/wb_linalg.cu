@@ -270,8 +270,8 @@ struct wb_pc {
   int32_t *d_blk_rows = nullptr;  // global row of each block-local row
   double *d_stream = nullptr;     // level-ordered factor stream (see "sub-domain resident ILU(0) solve")
   size_t stream_words = 0;
-  int2 *d_repack = nullptr;       // (block index into d_val, word offset into d_stream) of every factor block
-  int stage_words = 0, nstage = 0, solve_threads = 128;  // TMA ring geometry (nstage 0: read the stream from global)
+  int4 *d_repack = nullptr;       // (block index into d_val, word offset into d_stream, plane stride, 0) of every factor block
+  int stage_words = 0, nstage = 0, desc_words = 0, solve_threads = 128;  // TMA ring geometry (nstage 0: read the stream from global)
 };
 
 template <int BS>
@@ -462,15 +462,17 @@ template <class T> static int upload(T **p, const std::vector<T> &v) {
 // One CTA per block-Jacobi sub-domain.  The sub-domain's part of the solution lives in shared
 // memory for both sweeps, so the only HBM traffic is ONE streaming read of the factors plus r in
 // and z out.  The factors are stored as a level-ordered stream: for every dependency level of the
-// forward sweep, then of the backward sweep, one contiguous 16-byte-aligned record
-//     [n, nk, bwd, 0 : int32]  [row(n) : int32, padded to 16 B]  [col(nk*n) : int32, padded]
-//     [L or U blocks (nk*n, ELL: entry k of row r at k*n+r) : bs*bs doubles]  [inverted diagonal blocks (n), bwd only]
-// so a whole level is ONE TMA bulk copy (cp.async.bulk, mbarrier-completed) into a shared-memory
-// ring `nstage` levels deep: the copy of level l+nstage is in flight while level l is applied,
-// which takes the HBM latency off the level-to-level dependency chain.  Rows inside a level are
-// independent; levels are separated by __syncthreads.  Per row the blocks are applied in ascending
-// column order, i.e. the arithmetic of the sequential MatSolve_SeqBAIJ_N_NaturalOrdering
-// restricted to the sub-domain.
+// forward sweep, then of the backward sweep, one contiguous 16-byte-aligned record of n rows with
+// nk off-diagonal blocks each (ELL, padded with zero blocks that point at a zero slot of the vector):
+//     index planes   int4[NI][n]      (local row, col_0, col_1, col_2), (col_3 .. col_6), ...
+//     value planes   double[PW]-wide planes [ (nk + bwd) * bs*bs/PW ][n]   L or U blocks, then the
+//                    inverted diagonal block (backward sweep only); PW = 2 for even bs*bs
+// Thread r of a level reads element r of every plane: conflict-free shared-memory accesses.  A whole
+// level is ONE TMA bulk copy (cp.async.bulk, mbarrier-completed) into a shared-memory ring `nstage`
+// levels deep: the copy of level l+nstage is in flight while level l is applied, which takes the HBM
+// latency off the level-to-level dependency chain.  Rows inside a level are independent; levels are
+// separated by __syncthreads.  Per row the blocks are applied in ascending column order, i.e. the
+// arithmetic of the sequential MatSolve_SeqBAIJ_N_NaturalOrdering restricted to the sub-domain.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -498,51 +500,67 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
-__host__ __device__ __forceinline__ int ilu_pad_i32(int n) { return (n + 3) / 4 * 2; }  // int32 count -> 8-byte words, 16 B aligned
-__host__ __device__ __forceinline__ int ilu_pad_f64(int n) { return (n + 1) & ~1; }
+__host__ __device__ __forceinline__ int ilu_ni(int nk) { return (nk + 4) / 4; }  // int4 index planes per row
+template <int BS> struct IluPlane {
+  static constexpr int B2 = BS * BS;
+  static constexpr int PW = (B2 % 2 == 0) ? 2 : 1;  // doubles per plane element
+  static constexpr int NP = B2 / PW;                // planes per block
+};
+static inline int ilu_pw(int bs) { return (bs * bs) % 2 == 0 ? 2 : 1; }
 
 // apply one level record (in shared or global memory) to the sub-domain vector zs
 template <int BS>
-__device__ __forceinline__ void ilu_level(const double *lv, double *zs) {
-  constexpr int B2 = BS * BS;
-  const int4 hd = *reinterpret_cast<const int4 *>(lv);
-  const int n = hd.x, nk = hd.y;
-  const bool bwd = hd.z != 0;
-  const int *rows = reinterpret_cast<const int *>(lv + 2);
-  const int *cols = reinterpret_cast<const int *>(lv + 2 + ilu_pad_i32(n));
-  const double *vals = lv + 2 + ilu_pad_i32(n) + ilu_pad_i32(nk * n);
-  const double *dinv = vals + ilu_pad_f64(nk * n * B2);
+__device__ __forceinline__ void ilu_level(const double *lv, int n, int nk, bool bwd, double *zs) {
+  constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
+  const int4 *idx = reinterpret_cast<const int4 *>(lv);
+  const double *vals = lv + 2 * ilu_ni(nk) * n;
   for (int rr = threadIdx.x; rr < n; rr += blockDim.x) {
-    const int li = rows[rr];
+    const int4 i0 = idx[rr];
+    const int li = i0.x;
     double sv[BS];
 #pragma unroll
     for (int i = 0; i < BS; i++) sv[i] = zs[li * BS + i];
-    for (int k = 0; k < nk; k++) {
-      const int e = k * n + rr;
-      const int col = cols[e];
-      if (col >= 0) {
-        double v[B2];
-        if (BS == 2) {
-          const double2 p = *reinterpret_cast<const double2 *>(vals + (size_t)e * 4);
-          const double2 q = *reinterpret_cast<const double2 *>(vals + (size_t)e * 4 + 2);
-          v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
+    auto apply = [&](int col, int k) {
+      double v[B2];
+      const double *pl = vals + ((size_t)k * NPL * n + rr) * PW;
+#pragma unroll
+      for (int q = 0; q < NPL; q++) {
+        if (PW == 2) {
+          const double2 t = *reinterpret_cast<const double2 *>(pl + (size_t)q * n * 2);
+          v[2 * q] = t.x; v[2 * q + 1] = t.y;
         } else {
-#pragma unroll
-          for (int q = 0; q < B2; q++) v[q] = vals[(size_t)e * B2 + q];
-        }
-#pragma unroll
-        for (int j = 0; j < BS; j++) {
-          const double xj = zs[col * BS + j];
-#pragma unroll
-          for (int i = 0; i < BS; i++) sv[i] -= v[j * BS + i] * xj;
+          v[q] = pl[(size_t)q * n];
         }
       }
+#pragma unroll
+      for (int j = 0; j < BS; j++) {
+        const double xj = zs[col * BS + j];
+#pragma unroll
+        for (int i = 0; i < BS; i++) sv[i] -= v[j * BS + i] * xj;
+      }
+    };
+    if (nk > 0) apply(i0.y, 0);
+    if (nk > 1) apply(i0.z, 1);
+    if (nk > 2) apply(i0.w, 2);
+    for (int k = 3; k < nk; k++) {
+      const int c = reinterpret_cast<const int *>(&idx[(size_t)((k + 1) >> 2) * n + rr])[(k + 1) & 3];
+      apply(c, k);
     }
     if (!bwd) {
 #pragma unroll
       for (int i = 0; i < BS; i++) zs[li * BS + i] = sv[i];
     } else {
-      const double *di = dinv + (size_t)rr * B2;
+      double di[B2];
+      const double *pl = vals + ((size_t)nk * NPL * n + rr) * PW;
+#pragma unroll
+      for (int q = 0; q < NPL; q++) {
+        if (PW == 2) {
+          const double2 t = *reinterpret_cast<const double2 *>(pl + (size_t)q * n * 2);
+          di[2 * q] = t.x; di[2 * q + 1] = t.y;
+        } else {
+          di[q] = pl[(size_t)q * n];
+        }
+      }
       double t[BS];
 #pragma unroll
       for (int i = 0; i < BS; i++) {
@@ -562,16 +580,18 @@ struct IluSolveArgs {
   const int32_t *blk_rows;
   const double *stream, *r;
   double *z;
-  int stage_words, nstage;
+  int stage_words, nstage, desc_words;
   const int *done;
 };
 
+#define ILU_ROWS_PER_THREAD 8
 template <int BS, bool TMA>
 __global__ void __launch_bounds__(256) k_ilu0_block_solve(const IluSolveArgs a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-  double *ring = reinterpret_cast<double *>(smem_raw + 128);
+  int4 *desc = reinterpret_cast<int4 *>(smem_raw + 128);  // (word offset, bytes, n, nk | bwd << 16) of every level
+  double *ring = reinterpret_cast<double *>(smem_raw + 128) + a.desc_words;
   double *zs = ring + (size_t)a.nstage * a.stage_words;
   const int4 d = a.blk[blockIdx.x];
   const int row0 = d.x, nrows = d.y, lev0 = d.z, nl = d.w;
@@ -581,57 +601,89 @@ __global__ void __launch_bounds__(256) k_ilu0_block_solve(const IluSolveArgs a) 
       for (int st = 0; st < a.nstage; st++) mbar_init(&bars[st], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int l = tid; l < nl; l += blockDim.x) desc[l] = a.lev[lev0 + l];
     __syncthreads();
     if (tid == 0) {
       const int npre = nl < a.nstage ? nl : a.nstage;
       for (int l = 0; l < npre; l++) {
-        const int4 L = a.lev[lev0 + l];
-        mbar_expect_tx(&bars[l], (uint32_t)L.y);
-        tma_load_1d(ring + (size_t)l * a.stage_words, a.stream + L.x, (uint32_t)L.y, &bars[l]);
+        mbar_expect_tx(&bars[l], (uint32_t)desc[l].y);
+        tma_load_1d(ring + (size_t)l * a.stage_words, a.stream + desc[l].x, (uint32_t)desc[l].y, &bars[l]);
       }
     }
   }
-  // right-hand side of the sub-domain -> shared memory (overwritten in place by the sweeps)
-  for (int li = tid; li < nrows; li += blockDim.x) {
-    const int grow = a.blk_rows[row0 + li];
+  // right-hand side of the sub-domain -> shared memory (overwritten in place by the sweeps); the global row of
+  // each local row stays in registers for the final store when the sub-domain is small enough.  Slot `nrows` of
+  // the vector is the zero that padding blocks multiply.
+  int grow[ILU_ROWS_PER_THREAD];
+  const bool rows_in_regs = nrows <= ILU_ROWS_PER_THREAD * (int)blockDim.x;
+  if (tid < BS) zs[nrows * BS + tid] = 0.0;
+  for (int base = 0; base < nrows; base += ILU_ROWS_PER_THREAD * blockDim.x) {
 #pragma unroll
-    for (int i = 0; i < BS; i++) zs[li * BS + i] = a.r[(size_t)grow * BS + i];
+    for (int u = 0; u < ILU_ROWS_PER_THREAD; u++) {
+      const int li = base + u * blockDim.x + tid;
+      grow[u] = li < nrows ? a.blk_rows[row0 + li] : -1;
+    }
+    double rv[ILU_ROWS_PER_THREAD][BS];
+#pragma unroll
+    for (int u = 0; u < ILU_ROWS_PER_THREAD; u++)
+#pragma unroll
+      for (int i = 0; i < BS; i++) rv[u][i] = grow[u] >= 0 ? a.r[(size_t)grow[u] * BS + i] : 0.0;
+#pragma unroll
+    for (int u = 0; u < ILU_ROWS_PER_THREAD; u++) {
+      const int li = base + u * blockDim.x + tid;
+      if (li < nrows) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) zs[li * BS + i] = rv[u][i];
+      }
+    }
   }
   __syncthreads();
-  for (int l = 0; l < nl; l++) {
-    if (TMA) {
-      const int st = l % a.nstage;
-      int4 Lnext = make_int4(0, 0, 0, 0);
-      const bool refill = tid == 0 && l + a.nstage < nl;
-      if (refill) Lnext = a.lev[lev0 + l + a.nstage];  // in flight while this level is applied
-      mbar_wait(&bars[st], (uint32_t)((l / a.nstage) & 1));
-      ilu_level<BS>(ring + (size_t)st * a.stage_words, zs);
+  if (TMA) {
+    int st = 0;
+    uint32_t parity = 0;
+    for (int l = 0; l < nl; l++) {
+      const int4 L = desc[l];
+      mbar_wait(&bars[st], parity);
+      ilu_level<BS>(ring + (size_t)st * a.stage_words, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs);
       __syncthreads();  // level l applied by all threads: its ring slot is free and zs is consistent
-      if (refill) {
-        mbar_expect_tx(&bars[st], (uint32_t)Lnext.y);
-        tma_load_1d(ring + (size_t)st * a.stage_words, a.stream + Lnext.x, (uint32_t)Lnext.y, &bars[st]);
+      if (tid == 0 && l + a.nstage < nl) {
+        const int4 Ln = desc[l + a.nstage];
+        mbar_expect_tx(&bars[st], (uint32_t)Ln.y);
+        tma_load_1d(ring + (size_t)st * a.stage_words, a.stream + Ln.x, (uint32_t)Ln.y, &bars[st]);
       }
-    } else {
+      if (++st == a.nstage) {
+        st = 0;
+        parity ^= 1u;
+      }
+    }
+  } else {
+    for (int l = 0; l < nl; l++) {
       const int4 L = a.lev[lev0 + l];
-      ilu_level<BS>(a.stream + L.x, zs);
+      ilu_level<BS>(a.stream + L.x, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs);
       __syncthreads();
     }
   }
-  for (int li = tid; li < nrows; li += blockDim.x) {
-    const int grow = a.blk_rows[row0 + li];
+  for (int base = 0; base < nrows; base += ILU_ROWS_PER_THREAD * blockDim.x) {
 #pragma unroll
-    for (int i = 0; i < BS; i++) a.z[(size_t)grow * BS + i] = zs[li * BS + i];
+    for (int u = 0; u < ILU_ROWS_PER_THREAD; u++) {
+      const int li = base + u * blockDim.x + tid;
+      if (li < nrows) {
+        const int g = rows_in_regs ? grow[u] : a.blk_rows[row0 + li];
+#pragma unroll
+        for (int i = 0; i < BS; i++) a.z[(size_t)g * BS + i] = zs[li * BS + i];
+      }
+    }
   }
 }
 
-// numeric part: scatter the factor blocks into the level stream
-__global__ void k_ilu_repack(const double *__restrict__ fac, const int2 *__restrict__ map, int nmap, int b2,
+// numeric part: scatter the factor blocks into the value planes of the level stream
+__global__ void k_ilu_repack(const double *__restrict__ fac, const int4 *__restrict__ map, int nmap, int b2, int pw,
                              double *__restrict__ stream) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nmap * b2) {
     const int e = i / b2, q = i - e * b2;
-    const int2 m = map[e];
-    stream[(size_t)m.y + q] = fac[(size_t)m.x * b2 + q];
+    const int4 m = map[e];
+    stream[(size_t)m.y + (size_t)(q / pw) * m.z * pw + (q % pw)] = fac[(size_t)m.x * b2 + q];
   }
 }
 
@@ -670,11 +722,11 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
   }
   std::vector<int4> blk(nblk), lev;
   std::vector<double> stream;  // 8-byte words
-  std::vector<int2> repack;
+  std::vector<int4> repack;
   std::vector<std::vector<int32_t>> rows_of_level;
   stream.reserve((size_t)pc->nnzb * b2 + (size_t)pc->nnzb / 2 + 4 * (size_t)nb);
   repack.reserve(pc->nnzb);
-  int max_level_words = 0, max_level_rows = 0;
+  int max_level_words = 0, max_level_rows = 0, max_levels = 0;
   for (int b = 0; b < nblk; b++) {
     const int r0 = bcount[b], nr = bcount[b + 1] - bcount[b];
     const int lev0 = (int)lev.size();
@@ -694,30 +746,27 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
         for (int row : rows)
           nk = std::max(nk, pass == 0 ? diag[row] - rowptr[row] : rowptr[row + 1] - diag[row] - 1);
         const size_t w0 = stream.size();
-        const int w_rows = ilu_pad_i32(n), w_cols = ilu_pad_i32(nk * n), w_vals = ilu_pad_f64(nk * n * b2),
-                  w_dinv = pass == 1 ? ilu_pad_f64(n * b2) : 0;
-        const int words = 2 + w_rows + w_cols + w_vals + w_dinv;
+        const int ni = ilu_ni(nk), pw = ilu_pw(pc->bs), npl = b2 / pw;
+        const int w_idx = 2 * ni * n, w_vals = (nk + pass) * b2 * n;
+        const int words = (w_idx + w_vals + 1) & ~1;
         WB_CHECK(w0 + words < ((size_t)1 << 31), "wb_pc_setup: factor stream too large for 32-bit word offsets");
         stream.resize(w0 + words, 0.0);
-        int32_t *hd = reinterpret_cast<int32_t *>(&stream[w0]);
-        hd[0] = n; hd[1] = nk; hd[2] = pass; hd[3] = 0;
-        int32_t *prow = reinterpret_cast<int32_t *>(&stream[w0 + 2]);
-        int32_t *pcol = reinterpret_cast<int32_t *>(&stream[w0 + 2 + w_rows]);
-        for (int q = 0; q < nk * n; q++) pcol[q] = -1;
-        const size_t wv = w0 + 2 + w_rows + w_cols, wd = wv + w_vals;
+        int32_t *pidx = reinterpret_cast<int32_t *>(&stream[w0]);
+        for (int q = 0; q < 4 * ni * n; q++) pidx[q] = nr;  // padding blocks multiply the zero slot `nrows`
+        const size_t wv = w0 + w_idx;
         for (int q = 0; q < n; q++) {
           const int row = rows[q];
-          prow[q] = local[row];
+          pidx[4 * q] = local[row];
           const int k0 = pass == 0 ? rowptr[row] : diag[row] + 1, k1 = pass == 0 ? diag[row] : rowptr[row + 1];
           for (int k = k0; k < k1; k++) {
-            const int e = (k - k0) * n + q;
-            pcol[e] = local[colidx[k]];
-            repack.push_back(make_int2(k, (int)(wv + (size_t)e * b2)));
+            const int kk = k - k0, slot = kk + 1;
+            pidx[4 * ((size_t)(slot >> 2) * n + q) + (slot & 3)] = local[colidx[k]];
+            repack.push_back(make_int4(k, (int)(wv + ((size_t)kk * npl * n + q) * pw), n, 0));
           }
-          if (pass == 1) repack.push_back(make_int2(diag[row], (int)(wd + (size_t)q * b2)));
+          if (pass == 1) repack.push_back(make_int4(diag[row], (int)(wv + ((size_t)nk * npl * n + q) * pw), n, 0));
         }
         int4 L;
-        L.x = (int)w0; L.y = words * 8; L.z = n; L.w = 0;
+        L.x = (int)w0; L.y = words * 8; L.z = n; L.w = nk | (pass << 16);
         lev.push_back(L);
         max_level_words = std::max(max_level_words, words);
         max_level_rows = std::max(max_level_rows, n);
@@ -728,6 +777,7 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
     blk[b].y = nr;
     blk[b].z = lev0;
     blk[b].w = (int)lev.size() - lev0;
+    max_levels = std::max(max_levels, blk[b].w);
   }
   pc->nblk = nblk;
   pc->max_block_rows = maxrows;
@@ -742,11 +792,12 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
   // the mbarrier transaction count (< 2^20 bytes); otherwise the stream is read from global memory
   pc->solve_threads = max_level_rows > 128 ? 256 : 128;
   pc->stage_words = max_level_words;
-  const size_t zs_bytes = (size_t)maxrows * pc->bs * sizeof(double), stage_bytes = (size_t)max_level_words * 8;
+  pc->desc_words = 2 * max_levels;
+  const size_t zs_bytes = (size_t)(maxrows + 1) * pc->bs * sizeof(double), stage_bytes = (size_t)max_level_words * 8;
   pc->nstage = 0;
   if (stage_bytes < (1u << 20)) {
     for (int ns = 4; ns >= 2; ns--) {
-      const size_t need = 128 + ns * stage_bytes + zs_bytes;
+      const size_t need = 128 + (size_t)pc->desc_words * 8 + ns * stage_bytes + zs_bytes;
       if (need <= (ns == 2 ? 200u * 1024 : 72u * 1024)) {
         pc->nstage = ns;
         break;
@@ -820,7 +871,7 @@ static int pc_numeric(wb_pc *pc) {
     WB_LAUNCH(c);
     if (pc->blocked) {
       k_ilu_repack<<<wb_grid((size_t)pc->nrepack * bs2, 256), 256, 0, c->stream>>>(pc->d_val, pc->d_repack, pc->nrepack,
-                                                                                  bs2, pc->d_stream);
+                                                                                  bs2, ilu_pw(pc->bs), pc->d_stream);
       WB_LAUNCH(c);
     }
   }
@@ -957,8 +1008,11 @@ int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z, const int *done) 
     return 0;
   }
   if (pc->blocked) {
-    const size_t smem = 128 + (size_t)pc->nstage * pc->stage_words * 8 + (size_t)pc->max_block_rows * pc->bs * sizeof(double);
-    IluSolveArgs a = {pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_stream, d_r, d_z, pc->stage_words, pc->nstage, done};
+    const int desc_words = pc->nstage > 0 ? pc->desc_words : 0;
+    const size_t smem = 128 + (size_t)desc_words * 8 + (size_t)pc->nstage * pc->stage_words * 8 +
+                        (size_t)(pc->max_block_rows + 1) * pc->bs * sizeof(double);
+    IluSolveArgs a = {pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_stream, d_r, d_z, pc->stage_words, pc->nstage,
+                      desc_words, done};
 #define BSOLVE(BS)                                                                                           \
   do {                                                                                                       \
     if (pc->nstage > 0) {                                                                                    \
@@ -1035,12 +1089,12 @@ extern "C" int wb_pc_apply(wb_pc *pc, const double *r, double *z) {
 // 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
 __device__ __forceinline__ double4 ld256(const double *p) {
   double4 r;
-  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ double4 ld256_stream(const double *p) {  // evict-first: the Krylov basis is read once per pass
   double4 r;
-  asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  asm("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void st256(double *p, const double4 &v) {
@@ -1075,7 +1129,7 @@ __device__ __forceinline__ bool last_block(unsigned *counter) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(counter, 1u);
-    s_last = (t == gridDim.x - 1);
+    s_last = (t == gridDim.x * gridDim.y - 1);
     if (s_last) *counter = 0u;
   }
   __syncthreads();
@@ -1160,6 +1214,11 @@ struct MdotArgs {
 template <int NVT, bool VEC>
 __global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
   if (a.done && *a.done) return;
+  // blockIdx.y selects a group of NVT (<= 8) basis vectors: every CTA streams its slice of w (L2-resident after
+  // the first group) against 8 vectors with all 8 loads of an entry in flight before the first use
+  const int jbase = blockIdx.y * NVT;
+  const int nv = min(NVT, a.nv - jbase);
+  const double *V = a.V + (size_t)jbase * a.ldv;
   double acc[NVT];
 #pragma unroll
   for (int j = 0; j < NVT; j++) acc[j] = 0.0;
@@ -1167,46 +1226,48 @@ __global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
     const int n4 = a.n >> 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
       const double4 wi = ld256(a.w + 4 * (size_t)i);
+      double4 v[NVT];
 #pragma unroll
-      for (int j = 0; j < NVT; j++) {
-        if (j < a.nv) {
-          const double4 v = ld256_stream(a.V + (size_t)j * a.ldv + 4 * (size_t)i);
-          acc[j] += wi.x * v.x;
-          acc[j] += wi.y * v.y;
-          acc[j] += wi.z * v.z;
-          acc[j] += wi.w * v.w;
-        }
+      for (int g = 0; g < NVT; g++) {
+        // vectors past nv re-read the last one (same cache line, no extra traffic); their sums are dropped
+        const int j = g < nv ? g : nv - 1;
+        v[g] = ld256_stream(V + (size_t)j * a.ldv + 4 * (size_t)i);
+      }
+#pragma unroll
+      for (int g = 0; g < NVT; g++) {
+        acc[g] += wi.x * v[g].x;
+        acc[g] += wi.y * v[g].y;
+        acc[g] += wi.z * v[g].z;
+        acc[g] += wi.w * v[g].w;
       }
     }
     if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {  // tail
       const int i = (n4 << 2) + threadIdx.x;
 #pragma unroll
       for (int j = 0; j < NVT; j++)
-        if (j < a.nv) acc[j] += a.w[i] * a.V[(size_t)j * a.ldv + i];
+        if (j < nv) acc[j] += a.w[i] * V[(size_t)j * a.ldv + i];
     }
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
       const double wi = a.w[i];
 #pragma unroll
       for (int j = 0; j < NVT; j++)
-        if (j < a.nv) acc[j] += wi * a.V[(size_t)j * a.ldv + i];
+        if (j < nv) acc[j] += wi * V[(size_t)j * a.ldv + i];
     }
   }
   __shared__ double sh[8][NVT];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < NVT; j++) {
-    if (j < a.nv) {
-      const double v = warp_sum(acc[j]);
-      if (lane == 0) sh[wid][j] = v;
-    }
+    const double v = warp_sum(acc[j]);
+    if (lane == 0) sh[wid][j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < a.nv) {
+  if (threadIdx.x < nv) {
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < 8; q++) s += sh[q][threadIdx.x];
-    a.part[(size_t)threadIdx.x * RED_BLOCKS + blockIdx.x] = s;
+    a.part[(size_t)(jbase + threadIdx.x) * RED_BLOCKS + blockIdx.x] = s;
   }
   if (last_block(a.counter)) {
     for (int j = wid; j < a.nv; j += 8) {
@@ -1235,24 +1296,32 @@ struct MaxpyArgs {
   GmresUpd upd;
 };
 template <int NVT, bool VEC>
-__global__ void __launch_bounds__(256) k_maxpy_all(const MaxpyArgs a) {
+__global__ void __launch_bounds__(256, 2) k_maxpy_all(const MaxpyArgs a) {
   if (a.done && *a.done) return;
-  double cf[NVT];
-#pragma unroll
-  for (int j = 0; j < NVT; j++) cf[j] = j < a.nv ? a.sign * a.coef[j] : 0.0;
+  __shared__ double cf[KRY_MAXV];
+  if (threadIdx.x < KRY_MAXV) cf[threadIdx.x] = threadIdx.x < a.nv ? a.sign * a.coef[threadIdx.x] : 0.0;
+  __syncthreads();
   double nrm = 0.0;
   if (VEC) {
     const int n4 = a.n >> 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
       double4 wi = ld256(a.w + 4 * (size_t)i);
+      constexpr int G = (NVT % 8 == 0) ? 8 : (NVT < 4 ? NVT : 4);
 #pragma unroll
-      for (int j = 0; j < NVT; j++) {
-        if (j < a.nv) {
-          const double4 v = ld256_stream(a.V + (size_t)j * a.ldv + 4 * (size_t)i);
-          wi.x += cf[j] * v.x;
-          wi.y += cf[j] * v.y;
-          wi.z += cf[j] * v.z;
-          wi.w += cf[j] * v.w;
+      for (int j0 = 0; j0 < NVT; j0 += G) {
+        double4 v[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          const int j = (j0 + g) < a.nv ? (j0 + g) : a.nv - 1;  // cf is zero past nv
+          v[g] = ld256_stream(a.V + (size_t)j * a.ldv + 4 * (size_t)i);
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          const double cj = cf[j0 + g];
+          wi.x += cj * v[g].x;
+          wi.y += cj * v[g].y;
+          wi.z += cj * v[g].z;
+          wi.w += cj * v[g].w;
         }
       }
       st256(a.w + 4 * (size_t)i, wi);
@@ -1264,7 +1333,7 @@ __global__ void __launch_bounds__(256) k_maxpy_all(const MaxpyArgs a) {
     if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {  // tail
       const int i = (n4 << 2) + threadIdx.x;
       double wi = a.w[i];
-      for (int j = 0; j < a.nv; j++) wi += a.sign * a.coef[j] * a.V[(size_t)j * a.ldv + i];
+      for (int j = 0; j < a.nv; j++) wi += cf[j] * a.V[(size_t)j * a.ldv + i];
       a.w[i] = wi;
       nrm += wi * wi;
     }
@@ -1418,8 +1487,10 @@ static int red_blocks(size_t n) { return (int)std::min<size_t>(RED_BLOCKS, (n / 
 
 static bool aligned32(const void *p) { return ((uintptr_t)p & 31) == 0; }
 template <int NVT> static void launch_mdot(const MdotArgs &a, int nblk, cudaStream_t s) {
-  if (aligned32(a.w) && aligned32(a.V) && (a.ldv & 3) == 0) k_mdot_all<NVT, true><<<nblk, 256, 0, s>>>(a);
-  else k_mdot_all<NVT, false><<<nblk, 256, 0, s>>>(a);
+  const int ngroup = (a.nv + NVT - 1) / NVT;
+  dim3 grid(std::max(nblk / ngroup, 2 * WB_NUM_SMS), ngroup);
+  if (aligned32(a.w) && aligned32(a.V) && (a.ldv & 3) == 0) k_mdot_all<NVT, true><<<grid, 256, 0, s>>>(a);
+  else k_mdot_all<NVT, false><<<grid, 256, 0, s>>>(a);
 }
 template <int NVT> static void launch_maxpy(const MaxpyArgs &a, int nblk, cudaStream_t s) {
   if (aligned32(a.w) && aligned32(a.V) && (a.ldv & 3) == 0) k_maxpy_all<NVT, true><<<nblk, 256, 0, s>>>(a);
@@ -1437,13 +1508,7 @@ static int multi_dot(KspWork &w, const double *d_w, const double *V, size_t ldv,
     if (nv <= 1) launch_mdot<1>(a, nblk, c->stream);
     else if (nv <= 2) launch_mdot<2>(a, nblk, c->stream);
     else if (nv <= 4) launch_mdot<4>(a, nblk, c->stream);
-    else if (nv <= 8) launch_mdot<8>(a, nblk, c->stream);
-    else if (nv <= 12) launch_mdot<12>(a, nblk, c->stream);
-    else if (nv <= 16) launch_mdot<16>(a, nblk, c->stream);
-    else if (nv <= 20) launch_mdot<20>(a, nblk, c->stream);
-    else if (nv <= 24) launch_mdot<24>(a, nblk, c->stream);
-    else if (nv <= 28) launch_mdot<28>(a, nblk, c->stream);
-    else launch_mdot<32>(a, nblk, c->stream);
+    else launch_mdot<8>(a, nblk, c->stream);
     WB_LAUNCH(c);
   }
   WB_CUDA(cudaGetLastError());
