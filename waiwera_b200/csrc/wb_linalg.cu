@@ -271,7 +271,8 @@ struct wb_pc {
   double *d_stream = nullptr;     // level-ordered factor stream (see "sub-domain resident ILU(0) solve")
   size_t stream_words = 0;
   int4 *d_repack = nullptr;       // (block index into d_val, word offset into d_stream, plane stride, 0) of every factor block
-  int stage_words = 0, nstage = 0, desc_words = 0, solve_threads = 128;  // TMA ring geometry (nstage 0: read the stream from global)
+  int stage_words = 0, nstage = 0, desc_words = 0, solve_threads = 128;
+  long long *d_trace = nullptr;  // debug timeline of the sub-domain solve (wb_debug_pc_trace)  // TMA ring geometry (nstage 0: read the stream from global)
 };
 
 template <int BS>
@@ -508,60 +509,85 @@ template <int BS> struct IluPlane {
 };
 static inline int ilu_pw(int bs) { return (bs * bs) % 2 == 0 ? 2 : 1; }
 
-// apply one level record (in shared or global memory) to the sub-domain vector zs
+// one block of a plane-layout record: planes q of entry k, row rr
 template <int BS>
-__device__ __forceinline__ void ilu_level(const double *lv, int n, int nk, bool bwd, double *zs) {
-  constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
+__device__ __forceinline__ void ilu_load_block(const double *vals, int n, int k, int rr, double *v) {
+  constexpr int PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
+  const double *pl = vals + ((size_t)k * NPL * n + rr) * PW;
+#pragma unroll
+  for (int q = 0; q < NPL; q++) {
+    if (PW == 2) {
+      const double2 t = *reinterpret_cast<const double2 *>(pl + (size_t)q * n * 2);
+      v[2 * q] = t.x; v[2 * q + 1] = t.y;
+    } else {
+      v[q] = pl[(size_t)q * n];
+    }
+  }
+}
+
+// apply one level record (in shared or global memory) to the sub-domain vector zs.  Records are padded on
+// the host to nk = 3, 7, 11, ... (index planes are full); the common nk == 3 case (7-point stencils) is
+// branch-free with every load issued before the first use, so a level costs one shared-memory round trip
+// plus the dependent FMA chain.
+template <int BS>
+__device__ __forceinline__ void ilu_level(const double *lv, int n, int nk, bool bwd, double *zs, int nthr) {
+  constexpr int B2 = BS * BS;
   const int4 *idx = reinterpret_cast<const int4 *>(lv);
   const double *vals = lv + 2 * ilu_ni(nk) * n;
-  for (int rr = threadIdx.x; rr < n; rr += blockDim.x) {
+  for (int rr = threadIdx.x; rr < n; rr += nthr) {
     const int4 i0 = idx[rr];
     const int li = i0.x;
     double sv[BS];
+    if (nk == 3) {
+      double v[3][B2], x[3][BS], di[B2];
+      const int col[3] = {i0.y, i0.z, i0.w};
+#pragma unroll
+      for (int k = 0; k < 3; k++) ilu_load_block<BS>(vals, n, k, rr, v[k]);
+      if (bwd) ilu_load_block<BS>(vals, n, 3, rr, di);
+#pragma unroll
+      for (int i = 0; i < BS; i++) sv[i] = zs[li * BS + i];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < BS; j++) x[k][j] = zs[col[k] * BS + j];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < BS; j++)
+#pragma unroll
+          for (int i = 0; i < BS; i++) sv[i] -= v[k][j * BS + i] * x[k][j];
+      if (bwd) {
+        double t[BS];
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < BS; j++) acc += di[j * BS + i] * sv[j];
+          t[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < BS; i++) sv[i] = t[i];
+      }
+#pragma unroll
+      for (int i = 0; i < BS; i++) zs[li * BS + i] = sv[i];
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < BS; i++) sv[i] = zs[li * BS + i];
-    auto apply = [&](int col, int k) {
+    for (int k = 0; k < nk; k++) {
+      const int col = reinterpret_cast<const int *>(&idx[(size_t)((k + 1) >> 2) * n + rr])[(k + 1) & 3];
       double v[B2];
-      const double *pl = vals + ((size_t)k * NPL * n + rr) * PW;
-#pragma unroll
-      for (int q = 0; q < NPL; q++) {
-        if (PW == 2) {
-          const double2 t = *reinterpret_cast<const double2 *>(pl + (size_t)q * n * 2);
-          v[2 * q] = t.x; v[2 * q + 1] = t.y;
-        } else {
-          v[q] = pl[(size_t)q * n];
-        }
-      }
+      ilu_load_block<BS>(vals, n, k, rr, v);
 #pragma unroll
       for (int j = 0; j < BS; j++) {
         const double xj = zs[col * BS + j];
 #pragma unroll
         for (int i = 0; i < BS; i++) sv[i] -= v[j * BS + i] * xj;
       }
-    };
-    if (nk > 0) apply(i0.y, 0);
-    if (nk > 1) apply(i0.z, 1);
-    if (nk > 2) apply(i0.w, 2);
-    for (int k = 3; k < nk; k++) {
-      const int c = reinterpret_cast<const int *>(&idx[(size_t)((k + 1) >> 2) * n + rr])[(k + 1) & 3];
-      apply(c, k);
     }
-    if (!bwd) {
-#pragma unroll
-      for (int i = 0; i < BS; i++) zs[li * BS + i] = sv[i];
-    } else {
-      double di[B2];
-      const double *pl = vals + ((size_t)nk * NPL * n + rr) * PW;
-#pragma unroll
-      for (int q = 0; q < NPL; q++) {
-        if (PW == 2) {
-          const double2 t = *reinterpret_cast<const double2 *>(pl + (size_t)q * n * 2);
-          di[2 * q] = t.x; di[2 * q + 1] = t.y;
-        } else {
-          di[q] = pl[(size_t)q * n];
-        }
-      }
-      double t[BS];
+    if (bwd) {
+      double di[B2], t[BS];
+      ilu_load_block<BS>(vals, n, nk, rr, di);
 #pragma unroll
       for (int i = 0; i < BS; i++) {
         double acc = 0.0;
@@ -570,8 +596,10 @@ __device__ __forceinline__ void ilu_level(const double *lv, int n, int nk, bool 
         t[i] = acc;
       }
 #pragma unroll
-      for (int i = 0; i < BS; i++) zs[li * BS + i] = t[i];
+      for (int i = 0; i < BS; i++) sv[i] = t[i];
     }
+#pragma unroll
+    for (int i = 0; i < BS; i++) zs[li * BS + i] = sv[i];
   }
 }
 
@@ -582,45 +610,82 @@ struct IluSolveArgs {
   double *z;
   int stage_words, nstage, desc_words;
   const int *done;
+  long long *trace;  // debug: per CTA (start ns, end ns, SM id, 0) when non-null
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 #define ILU_ROWS_PER_THREAD 8
+#define ILU_MAX_STAGES 8
+// TMA variant: blockDim.x = consumer threads + one producer warp.  The producer warp's lane 0 refills ring slot
+// st with level l+nstage as soon as the consumers have released it (empty[st] mbarrier), so issuing the bulk
+// copies never sits on the consumers' level-to-level critical path; consumers synchronise among themselves on
+// named barrier 1.
 template <int BS, bool TMA>
-__global__ void __launch_bounds__(256) k_ilu0_block_solve(const IluSolveArgs a) {
+__global__ void __launch_bounds__(288) k_ilu0_block_solve(const IluSolveArgs a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);       // [ILU_MAX_STAGES]
+  uint64_t *empty = full + ILU_MAX_STAGES;                        // [ILU_MAX_STAGES]
   int4 *desc = reinterpret_cast<int4 *>(smem_raw + 128);  // (word offset, bytes, n, nk | bwd << 16) of every level
   double *ring = reinterpret_cast<double *>(smem_raw + 128) + a.desc_words;
   double *zs = ring + (size_t)a.nstage * a.stage_words;
   const int4 d = a.blk[blockIdx.x];
   const int row0 = d.x, nrows = d.y, lev0 = d.z, nl = d.w;
   const int tid = threadIdx.x;
+  const int ncons = TMA ? (int)blockDim.x - 32 : (int)blockDim.x;
+  if (a.trace && tid == 0) {
+    long long t;
+    unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    a.trace[4 * blockIdx.x] = t;
+    a.trace[4 * blockIdx.x + 2] = sm;
+  }
   if (TMA) {
     if (tid == 0) {
-      for (int st = 0; st < a.nstage; st++) mbar_init(&bars[st], 1);
+      for (int st = 0; st < a.nstage; st++) {
+        mbar_init(&full[st], 1);
+        mbar_init(&empty[st], 1);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int l = tid; l < nl; l += blockDim.x) desc[l] = a.lev[lev0 + l];
     __syncthreads();
-    if (tid == 0) {
-      const int npre = nl < a.nstage ? nl : a.nstage;
-      for (int l = 0; l < npre; l++) {
-        mbar_expect_tx(&bars[l], (uint32_t)desc[l].y);
-        tma_load_1d(ring + (size_t)l * a.stage_words, a.stream + desc[l].x, (uint32_t)desc[l].y, &bars[l]);
+    if (tid >= ncons) {
+      // ---- producer warp
+      if (tid == ncons) {
+        int st = 0;
+        uint32_t parity = 0;
+        for (int l = 0; l < nl; l++) {
+          if (l >= a.nstage) mbar_wait(&empty[st], parity ^ 1u);  // slot released by the consumers of level l-nstage
+          const int4 L = desc[l];
+          mbar_expect_tx(&full[st], (uint32_t)L.y);
+          tma_load_1d(ring + (size_t)st * a.stage_words, a.stream + L.x, (uint32_t)L.y, &full[st]);
+          if (++st == a.nstage) {
+            st = 0;
+            parity ^= 1u;
+          }
+        }
       }
+      return;
     }
   }
-  // right-hand side of the sub-domain -> shared memory (overwritten in place by the sweeps); the global row of
-  // each local row stays in registers for the final store when the sub-domain is small enough.  Slot `nrows` of
-  // the vector is the zero that padding blocks multiply.
+  // ---- consumers.  Right-hand side of the sub-domain -> shared memory (overwritten in place by the sweeps); the
+  // global row of each local row stays in registers for the final store when the sub-domain is small enough.
+  // Slot `nrows` of the vector is the zero that padding blocks multiply.
   int grow[ILU_ROWS_PER_THREAD];
-  const bool rows_in_regs = nrows <= ILU_ROWS_PER_THREAD * (int)blockDim.x;
+  const bool rows_in_regs = nrows <= ILU_ROWS_PER_THREAD * ncons;
   if (tid < BS) zs[nrows * BS + tid] = 0.0;
-  for (int base = 0; base < nrows; base += ILU_ROWS_PER_THREAD * blockDim.x) {
+  for (int base = 0; base < nrows; base += ILU_ROWS_PER_THREAD * ncons) {
 #pragma unroll
     for (int u = 0; u < ILU_ROWS_PER_THREAD; u++) {
-      const int li = base + u * blockDim.x + tid;
+      const int li = base + u * ncons + tid;
       grow[u] = li < nrows ? a.blk_rows[row0 + li] : -1;
     }
     double rv[ILU_ROWS_PER_THREAD][BS];
@@ -630,27 +695,23 @@ __global__ void __launch_bounds__(256) k_ilu0_block_solve(const IluSolveArgs a) 
       for (int i = 0; i < BS; i++) rv[u][i] = grow[u] >= 0 ? a.r[(size_t)grow[u] * BS + i] : 0.0;
 #pragma unroll
     for (int u = 0; u < ILU_ROWS_PER_THREAD; u++) {
-      const int li = base + u * blockDim.x + tid;
+      const int li = base + u * ncons + tid;
       if (li < nrows) {
 #pragma unroll
         for (int i = 0; i < BS; i++) zs[li * BS + i] = rv[u][i];
       }
     }
   }
-  __syncthreads();
+  bar_sync_named(1, ncons);
   if (TMA) {
     int st = 0;
     uint32_t parity = 0;
     for (int l = 0; l < nl; l++) {
       const int4 L = desc[l];
-      mbar_wait(&bars[st], parity);
-      ilu_level<BS>(ring + (size_t)st * a.stage_words, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs);
-      __syncthreads();  // level l applied by all threads: its ring slot is free and zs is consistent
-      if (tid == 0 && l + a.nstage < nl) {
-        const int4 Ln = desc[l + a.nstage];
-        mbar_expect_tx(&bars[st], (uint32_t)Ln.y);
-        tma_load_1d(ring + (size_t)st * a.stage_words, a.stream + Ln.x, (uint32_t)Ln.y, &bars[st]);
-      }
+      mbar_wait(&full[st], parity);
+      ilu_level<BS>(ring + (size_t)st * a.stage_words, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs, ncons);
+      bar_sync_named(1, ncons);  // level l applied by all consumers: zs is consistent, the ring slot is free
+      if (tid == 0) mbar_arrive(&empty[st]);
       if (++st == a.nstage) {
         st = 0;
         parity ^= 1u;
@@ -659,20 +720,25 @@ __global__ void __launch_bounds__(256) k_ilu0_block_solve(const IluSolveArgs a) 
   } else {
     for (int l = 0; l < nl; l++) {
       const int4 L = a.lev[lev0 + l];
-      ilu_level<BS>(a.stream + L.x, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs);
-      __syncthreads();
+      ilu_level<BS>(a.stream + L.x, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs, ncons);
+      bar_sync_named(1, ncons);
     }
   }
-  for (int base = 0; base < nrows; base += ILU_ROWS_PER_THREAD * blockDim.x) {
+  for (int base = 0; base < nrows; base += ILU_ROWS_PER_THREAD * ncons) {
 #pragma unroll
     for (int u = 0; u < ILU_ROWS_PER_THREAD; u++) {
-      const int li = base + u * blockDim.x + tid;
+      const int li = base + u * ncons + tid;
       if (li < nrows) {
         const int g = rows_in_regs ? grow[u] : a.blk_rows[row0 + li];
 #pragma unroll
         for (int i = 0; i < BS; i++) a.z[(size_t)g * BS + i] = zs[li * BS + i];
       }
     }
+  }
+  if (a.trace && tid == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[4 * blockIdx.x + 1] = t;
   }
 }
 
@@ -745,6 +811,7 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
         int nk = 0;
         for (int row : rows)
           nk = std::max(nk, pass == 0 ? diag[row] - rowptr[row] : rowptr[row + 1] - diag[row] - 1);
+        nk = nk <= 3 ? 3 : 3 + (nk - 3 + 3) / 4 * 4;  // full index planes: 3, 7, 11, ... (padding blocks are zero)
         const size_t w0 = stream.size();
         const int ni = ilu_ni(nk), pw = ilu_pw(pc->bs), npl = b2 / pw;
         const int w_idx = 2 * ni * n, w_vals = (nk + pass) * b2 * n;
@@ -788,7 +855,7 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
   WB_TRY(upload(&pc->d_blk_rows, blk_rows));
   WB_TRY(upload(&pc->d_stream, stream));
   WB_TRY(upload(&pc->d_repack, repack));
-  // ring geometry: as many stages (<= 4) as keep >= 3 CTAs per SM when possible; a level record must fit
+  // ring geometry: 3 stages when that keeps >= 4 CTAs per SM (else 2); a level record must fit
   // the mbarrier transaction count (< 2^20 bytes); otherwise the stream is read from global memory
   pc->solve_threads = max_level_rows > 128 ? 256 : 128;
   pc->stage_words = max_level_words;
@@ -796,9 +863,9 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
   const size_t zs_bytes = (size_t)(maxrows + 1) * pc->bs * sizeof(double), stage_bytes = (size_t)max_level_words * 8;
   pc->nstage = 0;
   if (stage_bytes < (1u << 20)) {
-    for (int ns = 4; ns >= 2; ns--) {
+    for (int ns = 3; ns >= 2; ns--) {
       const size_t need = 128 + (size_t)pc->desc_words * 8 + ns * stage_bytes + zs_bytes;
-      if (need <= (ns == 2 ? 200u * 1024 : 72u * 1024)) {
+      if (need <= (ns == 2 ? 200u * 1024 : 55u * 1024)) {
         pc->nstage = ns;
         break;
       }
@@ -1012,12 +1079,12 @@ int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z, const int *done) 
     const size_t smem = 128 + (size_t)desc_words * 8 + (size_t)pc->nstage * pc->stage_words * 8 +
                         (size_t)(pc->max_block_rows + 1) * pc->bs * sizeof(double);
     IluSolveArgs a = {pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_stream, d_r, d_z, pc->stage_words, pc->nstage,
-                      desc_words, done};
+                      desc_words, done, pc->d_trace};
 #define BSOLVE(BS)                                                                                           \
   do {                                                                                                       \
     if (pc->nstage > 0) {                                                                                    \
       cudaFuncSetAttribute(k_ilu0_block_solve<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      k_ilu0_block_solve<BS, true><<<pc->nblk, pc->solve_threads, smem, c->stream>>>(a);                     \
+      k_ilu0_block_solve<BS, true><<<pc->nblk, pc->solve_threads + 32, smem, c->stream>>>(a);                \
     } else {                                                                                                 \
       cudaFuncSetAttribute(k_ilu0_block_solve<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       k_ilu0_block_solve<BS, false><<<pc->nblk, pc->solve_threads, smem, c->stream>>>(a);                    \
@@ -1061,6 +1128,23 @@ int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z, const int *done) 
   }
   WB_CUDA(cudaGetLastError());
   return 0;
+}
+
+// debug / tuning aid (not part of the public header): one PC apply with a per-CTA timeline of the sub-domain
+// solve; out[4*b] = start ns, end ns, SM id of sub-domain b.  Also lets the tuner override the ring depth.
+extern "C" int wb_debug_pc_trace(wb_pc *pc, const double *d_r, double *d_z, long long *out, int nstage_override) {
+  wb_ctx *c = pc->A->ctx;
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CHECK(pc->blocked, "wb_debug_pc_trace: not a sub-domain resident solve");
+  if (nstage_override >= 0) pc->nstage = nstage_override;
+  WB_CUDA(cudaMalloc(&pc->d_trace, sizeof(long long) * (4 * pc->nblk + 128)));
+  WB_CUDA(cudaMemset(pc->d_trace, 0, sizeof(long long) * (4 * pc->nblk + 128)));
+  int rc = wb_pc_apply_dev(pc, d_r, d_z, nullptr);
+  cudaStreamSynchronize(c->stream);
+  if (out) cudaMemcpy(out, pc->d_trace, sizeof(long long) * (4 * pc->nblk + 128), cudaMemcpyDeviceToHost);
+  cudaFree(pc->d_trace);
+  pc->d_trace = nullptr;
+  return rc;
 }
 
 extern "C" int wb_pc_apply(wb_pc *pc, const double *r, double *z) {
