@@ -1,0 +1,119 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): the partitioned path through the C ABI with the
+NCCL halo -- residual, SpMV, Krylov solve and a Newton solve on 2 ranks -- against the single-GPU path on the same
+problem.  One process per GPU, rendezvous on 127.0.0.1."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DIMS = (12, 10, 16)
+DT = 1.0e6
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def problem():
+    from waiwera_b200 import mesh as wmesh
+    gm = wmesh.structured(*DIMS, dx=10.0, seed=wmesh.SEED)
+    primary, region = wmesh.hydrostatic_state(gm, seed=wmesh.SEED)
+    y = np.ascontiguousarray(wmesh.scale_primaries(primary, region)).reshape(-1)
+    return gm, y, region
+
+
+def worker(rank, world, port, out):
+    import torch.distributed as dist
+    from waiwera_b200 import flow, mesh as wmesh
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        gm, gy, gregion = problem()
+        owner = wmesh.box_owner(gm, wmesh.default_parts(world))
+        m = wmesh.partition(gm, owner, rank, world)
+        nat = m.natural[:m.nowned]
+        y = np.ascontiguousarray(gy.reshape(-1, 2)[nat].reshape(-1))
+        region = np.ascontiguousarray(gregion[nat])
+        sim = flow.FlowSimulation(flow.make_params(), m, device=rank)
+        uid = torch.from_numpy(flow.FlowSimulation.unique_id()).cuda() if rank == 0 else torch.zeros(128, dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        sim.comm_init(rank, world, uid.cpu().numpy())
+        assert sim.fluid_init(y, region) == 0
+        err, L0 = sim.lhs(y)
+        assert err == 0
+        y1 = y * (1.0 + 1e-5)
+        err, lhs, rhs, r = sim.residual(y1, L0, DT)
+        assert err == 0
+        mv, ml = sim.max_scaled(r, L0, 1.0)
+        assert sim.jacobian(y1, L0, DT) == 0
+        J = sim.jacobian_mat()
+        x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * 2).reshape(-1, 2)[nat].reshape(-1)
+        ax = np.zeros_like(x)
+        J.mult(x, ax)
+        y2 = y.copy()
+        res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
+                                                            ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, dict(nat=nat, r=r, ax=ax, y2=y2, mv=mv, ml=ml, reason=res.reason,
+                                              its=res.iterations, lits=res.linear_iterations))
+        if rank == 0:
+            out.put(gathered)
+        sim.destroy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_path_matches_single_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d CUDA devices" % world)
+    import torch.multiprocessing as mp
+    from waiwera_b200 import flow
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = out.get(timeout=600)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    # single-GPU reference on the whole mesh
+    gm, gy, gregion = problem()
+    sim = flow.FlowSimulation(flow.make_params(), gm, device=0)
+    assert sim.fluid_init(gy, gregion) == 0
+    err, L0 = sim.lhs(gy)
+    y1 = gy * (1.0 + 1e-5)
+    err, lhs, rhs, r = sim.residual(y1, L0, DT)
+    mv, ml = sim.max_scaled(r, L0, 1.0)
+    assert sim.jacobian(y1, L0, DT) == 0
+    J = sim.jacobian_mat()
+    x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * 2)
+    ax = np.zeros_like(x)
+    J.mult(x, ax)
+    y2 = gy.copy()
+    res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
+                                                        ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))
+    gr, gax, gy2 = np.zeros_like(r).reshape(-1, 2), np.zeros_like(ax).reshape(-1, 2), np.zeros_like(y2).reshape(-1, 2)
+    for g in gathered:
+        gr[g["nat"]] = g["r"].reshape(-1, 2)
+        gax[g["nat"]] = g["ax"].reshape(-1, 2)
+        gy2[g["nat"]] = g["y2"].reshape(-1, 2)
+    # residual: same faces, same summation order -> bit exact; SpMV: local column order differs -> rounding
+    assert np.array_equal(gr.reshape(-1), r)
+    assert np.abs(gax.reshape(-1) - ax).max() <= 1e-13 * np.abs(ax).max()
+    assert all(abs(g["mv"] - mv) <= 1e-14 * abs(mv) for g in gathered)
+    assert all(g["reason"] == res.reason and g["its"] == res.iterations for g in gathered)
+    assert np.abs(gy2.reshape(-1) - y2).max() <= 1e-8 * np.abs(y2).max()
+    sim.destroy()
