@@ -40,6 +40,8 @@ extern "C" {
 /* equation of state (src/eos_setup.F90) */
 #define WB_EOS_WE 0 /* water + energy, 2 primaries        (src/eos_we.F90)  */
 #define WB_EOS_W 1  /* isothermal water, 1 primary        (src/eos_w.F90)   */
+#define WB_EOS_WCE 2 /* water + CO2 + energy, 3 primaries (src/eos_wge.F90, src/eos_wce.F90,
+                        src/ncg_co2_thermodynamics.F90) */
 
 /* relative permeability curves (src/relative_permeability.F90:197-558) */
 #define WB_RP_FULLY_MOBILE 0
@@ -86,6 +88,9 @@ typedef struct {
   int thermo;      /* WB_THERMO_* */
   int extrapolate; /* thermodynamics.extrapolate */
   double pressure_scale, temperature_scale; /* eos.primary.scale.* (<=0: defaults 1e6, 1e2) */
+  double partial_pressure_scale;            /* eos.primary.scale.partial_pressure for eos_wce; <= 0: adaptive
+                                               scaling by the cell's total pressure, the reference default
+                                               (src/eos_wge.F90:96-100, 639-674) */
   double eos_w_temperature;                 /* eos.temperature for eos_w */
   wb_relperm relperm;
   wb_cappress cappress;

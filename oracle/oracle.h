@@ -140,6 +140,7 @@ typedef struct {
   int thermo;             /* WO_THERMO_* */
   int extrapolate;
   double pressure_scale, temperature_scale; /* eos.primary.scale.* */
+  double partial_pressure_scale;            /* eos_wge: <= 0 adaptive Pg/P scaling (the reference default, eos_wge.F90:96-100) */
   double eos_w_temperature;                 /* eos_w fixed temperature */
   wo_relperm relperm;
   wo_cappress cappress;
@@ -163,6 +164,12 @@ int wo_eos_transition(wo_eos *e, const double *old_primary, double *primary,
                       const double *old_fluid, double *fluid, int *transition);
 int wo_eos_check_primary_variables(const wo_eos *e, const double *fluid, double *primary, int *changed);
 double wo_eos_conductivity(const double *rock, const double *fluid, int nc);
+
+/* ---- CO2 non-condensible gas (src/ncg_co2_thermodynamics.F90, src/ncg_thermodynamics.F90) ---- */
+void wo_co2_properties(double partial_pressure, double temperature, double props[2]); /* density, enthalpy */
+double wo_co2_henrys_constant(double temperature);
+double wo_co2_energy_solution(double temperature, double henrys_constant);
+int wo_co2_viscosity(double partial_pressure, double temperature, double *viscosity);
 
 /* ---- local cell / face objects (src/cell.F90:114, src/face.F90:443) ---- */
 void wo_cell_balance(const double *rock, const double *fluid, int nc, int nphase, int np, double *balance);

@@ -39,7 +39,7 @@ class Cappress(C.Structure):
 class Params(C.Structure):
     _fields_ = [("eos", C.c_int), ("thermo", C.c_int), ("extrapolate", C.c_int),
                 ("pressure_scale", C.c_double), ("temperature_scale", C.c_double),
-                ("eos_w_temperature", C.c_double),
+                ("partial_pressure_scale", C.c_double), ("eos_w_temperature", C.c_double),
                 ("relperm", Relperm), ("cappress", Cappress), ("gravity", C.c_double * 3)]
 
 
@@ -113,6 +113,10 @@ def lib():
         "wo_eos_transition": (i, [vp, c_dp, c_dp, c_dp, c_dp, C.POINTER(i)]),
         "wo_eos_check_primary_variables": (i, [vp, c_dp, c_dp, C.POINTER(i)]),
         "wo_eos_conductivity": (d, [c_dp, c_dp, i]),
+        "wo_co2_properties": (None, [d, d, c_dp]),
+        "wo_co2_henrys_constant": (d, [d]),
+        "wo_co2_energy_solution": (d, [d, d]),
+        "wo_co2_viscosity": (i, [d, d, c_dp]),
         "wo_cell_balance": (None, [c_dp, c_dp, i, i, i, c_dp]),
         "wo_face_flux": (None, [c_dp, c_dp, c_dp, c_dp, c_dp, i, i, i, i, i, c_dp]),
         "wo_face_calculate_distances": (None, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
@@ -228,10 +232,11 @@ def make_cappress(kind="zero", **kw):
 
 
 def make_params(eos=EOS_WE, thermo=THERMO_IAPWS, relperm=None, cappress=None, gravity=(0.0, 0.0, -9.8),
-                extrapolate=0, eos_w_temperature=20.0):
+                extrapolate=0, eos_w_temperature=20.0, partial_pressure_scale=0.0):
     p = Params()
     p.eos, p.thermo, p.extrapolate = eos, thermo, extrapolate
     p.pressure_scale, p.temperature_scale = 1.0e6, 1.0e2
+    p.partial_pressure_scale = partial_pressure_scale  # <= 0: adaptive Pg/P (the reference default)
     p.eos_w_temperature = eos_w_temperature
     p.relperm = relperm if relperm is not None else make_relperm("linear")
     p.cappress = cappress if cappress is not None else make_cappress("zero")

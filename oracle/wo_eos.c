@@ -1,7 +1,8 @@
 /*
- * wo_eos.c -- oracle (TEST INFRASTRUCTURE): equations of state (we, w) and
+ * wo_eos.c -- oracle (TEST INFRASTRUCTURE): equations of state (we, w, wce) and
  * the local cell / face objects.  Restated from src/eos.F90:186-257,
- * src/eos_we.F90:149-526, src/eos_w.F90, src/fluid.F90:197-370,
+ * src/eos_we.F90:149-526, src/eos_w.F90, src/eos_wge.F90:40-705, src/eos_wce.F90,
+ * src/ncg_thermodynamics.F90:145-340, src/ncg_co2_thermodynamics.F90:14-292, src/fluid.F90:197-370,
  * src/rock.F90:142, src/cell.F90:114-142, src/face.F90:230-515.
  *
  * Fluid record layout (src/fluid.F90:232-267), nc components, nph phases:
@@ -22,6 +23,7 @@ struct wo_eos {
   wo_thermo *thermo;
   int np, nc, nphase, nmobile, isothermal;
   double primary_scale[WO_MAX_NP][5]; /* [var][region 1..4] */
+  int adaptive_pp_scale;              /* eos_wge: partial pressure scaled by the cell's total pressure */
 };
 
 enum { F_P = 0, F_T = 1, F_REGION = 2, F_OLD_REGION = 3, F_PHASES = 4, F_PERMFAC = 5, F_PARTIAL = 6 };
@@ -54,6 +56,16 @@ wo_eos *wo_eos_create(const wo_params *prm) {
       e->np = 1; e->nc = 1; e->nphase = 1; e->nmobile = 1; e->isothermal = 1;
       e->primary_scale[0][1] = ps; e->primary_scale[0][2] = ps;
       break;
+    case WO_EOS_WCE: { /* eos_wge.F90:40-131 + eos_wce.F90:23-53 */
+      e->np = 3; e->nc = 2; e->nphase = 2; e->nmobile = 2; e->isothermal = 0;
+      double pps = prm->partial_pressure_scale;
+      e->adaptive_pp_scale = !(pps > 0.0);
+      if (e->adaptive_pp_scale) pps = 0.0;
+      e->primary_scale[0][1] = ps; e->primary_scale[1][1] = ts; e->primary_scale[2][1] = pps;
+      e->primary_scale[0][2] = ps; e->primary_scale[1][2] = ts; e->primary_scale[2][2] = pps;
+      e->primary_scale[0][4] = ps; e->primary_scale[1][4] = 1.0; e->primary_scale[2][4] = pps;
+      break;
+    }
     default:
       wo_thermo_destroy(e->thermo);
       free(e);
@@ -73,12 +85,90 @@ int wo_eos_num_phases(const wo_eos *e) { return e->nphase; }
 int wo_eos_fluid_dof(const wo_eos *e) { return bulk_dof(e->nc) + e->nphase * phase_dof(e->nc); }
 wo_thermo *wo_eos_thermo(wo_eos *e) { return e->thermo; }
 
-/* eos.F90:186-210 */
+/* eos.F90:186-210 ; adaptive: eos_wge.F90:639-674 */
 void wo_eos_scale(const wo_eos *e, const double *primary, int region, double *scaled) {
+  if (e->adaptive_pp_scale) {
+    for (int i = 0; i < 2; i++) scaled[i] = primary[i] / e->primary_scale[i][region];
+    scaled[2] = primary[2] / primary[0];
+    return;
+  }
   for (int i = 0; i < e->np; i++) scaled[i] = primary[i] / e->primary_scale[i][region];
 }
 void wo_eos_unscale(const wo_eos *e, const double *scaled, int region, double *primary) {
+  if (e->adaptive_pp_scale) {
+    for (int i = 0; i < 2; i++) primary[i] = scaled[i] * e->primary_scale[i][region];
+    primary[2] = scaled[2] * primary[0];
+    return;
+  }
   for (int i = 0; i < e->np; i++) primary[i] = scaled[i] * e->primary_scale[i][region];
+}
+
+/* ---- CO2 (src/ncg_co2_thermodynamics.F90) and the NCG base class (src/ncg_thermodynamics.F90) ---- */
+static const double co2_molecular_weight = 44.01;     /* ncg_co2_thermodynamics.F90:14 */
+static const double water_molecular_weight = 18.01528; /* thermodynamics.F90:38 */
+static const double gas_constant = 8.3144598;          /* thermodynamics.F90:39 */
+static const double henry_data[6] = {0.783666, 1.96025, 8.20574, -7.40674, 2.18380, -0.220999};
+static const double co2_tscale = 100.0;
+/* viscosity_data(5,6), column-major: pressures (MPa), then 5 polynomial coefficients per pressure (:22-30) */
+static const double co2_visc_p[5] = {0.0, 10.0, 15.0, 20.0, 30.0};
+static const double co2_visc_c[5][5] = {
+    {1.3578, 3.9189, 9.6607, 13.1566, 14.7968},
+    {4.9227e-3, -35.984e-3, -135.479e-3, -179.352e-3, -160.731e-3},
+    {-2.9661e-6, 0.25825e-3, 0.90087e-3, 1.12474e-3, 0.850257e-3},
+    {2.8529e-9, -7.1178e-7, -2.4727e-6, -2.98864e-6, -1.99076e-6},
+    {-2.1829e-12, 6.9578e-10, 2.4156e-9, 2.85911e-9, 1.73423e-9}};
+
+/* utils.F90:224-241 (Horner) */
+static double polynomial(const double *a, int n, double x) {
+  double p = a[n - 1];
+  for (int i = n - 2; i >= 0; i--) p = a[i] + x * p;
+  return p;
+}
+
+/* ncg_co2_thermodynamics.F90:84-111 */
+void wo_co2_properties(double partial_pressure, double temperature, double props[2]) {
+  double tk = temperature + WO_TC_K;
+  double pp = partial_pressure * 1.0e-6;
+  double tc = pow(0.01 * tk, 3.3333333333);
+  double hci = 1.667 + 0.001542 * tk - 0.7948 * log10(tk) - 41.35 / tk;
+  props[1] = 1.e6 * (hci - 0.3571 * pp * (1.0 + 0.07576 * pp) / tc);
+  double vc = 0.00018882 * tk - pp * (0.0824 + 0.01249 * pp) / tc;
+  props[0] = pp / vc;
+}
+
+/* ncg_co2_thermodynamics.F90:115-135 */
+double wo_co2_henrys_constant(double temperature) {
+  return 1.e8 * polynomial(henry_data, 6, temperature / co2_tscale);
+}
+
+/* henrys_derivative (:172-197) with polynomial_derivative (utils.F90:291-310: da(i) = i*a(i+1)), then
+   energy_solution (ncg_thermodynamics.F90:196-223, 176-192) */
+double wo_co2_energy_solution(double temperature, double henrys_constant) {
+  double da[5];
+  for (int i = 0; i < 5; i++) da[i] = (double)(i + 1) * henry_data[i + 1];
+  double henrys_derivative = 1.e8 * polynomial(da, 5, temperature / co2_tscale) / (henrys_constant * co2_tscale);
+  double tk = temperature + WO_TC_K;
+  return -1.e3 * gas_constant * tk * tk * henrys_derivative / co2_molecular_weight;
+}
+
+/* ncg_co2_thermodynamics.F90:237-263: coefficients interpolated linearly in pressure (MPa), polynomial in T */
+int wo_co2_viscosity(double partial_pressure, double temperature, double *viscosity) {
+  if (!(partial_pressure <= 300.e5)) return 1;
+  double vals[25], coefs[5];
+  for (int i = 0; i < 5; i++)
+    for (int d = 0; d < 5; d++) vals[d + 5 * i] = co2_visc_c[d][i];
+  wo_table tbl;
+  wo_table_init(&tbl, co2_visc_p, vals, 5, 5);
+  wo_table_interpolate(&tbl, partial_pressure / 1.e6, coefs);
+  wo_table_destroy(&tbl);
+  *viscosity = 1.e-5 * polynomial(coefs, 5, temperature);
+  return 0;
+}
+
+/* ncg_thermodynamics.F90:145-157 */
+static double co2_mole_to_mass_fraction(double xmole) {
+  double w = xmole * co2_molecular_weight;
+  return w / (w + (1.0 - xmole) * water_molecular_weight);
 }
 
 /* eos.F90:214-236 */
@@ -107,6 +197,26 @@ int wo_eos_bulk_properties(wo_eos *e, const double *primary, double *fluid) {
   }
   fluid[F_P] = primary[0];
   int region = nint_(fluid[F_REGION]);
+  if (e->prm.eos == WO_EOS_WCE) { /* eos_wge.F90:350-389 */
+    fluid[F_PARTIAL] = fluid[F_P] - primary[2];
+    fluid[F_PARTIAL + 1] = primary[2];
+    if (region == 4) err = wo_saturation_temperature(e->thermo, fluid[F_PARTIAL], &fluid[F_T]);
+    else fluid[F_T] = primary[1];
+    if (err == 0) {
+      fluid[F_PERMFAC] = 1.0;
+      err = eos_phase_composition(e, fluid);
+      if (err == 0) { /* phase_saturations: eos_wge.F90:393-417 */
+        double *l = phase_ptr(fluid, nc, 0), *v = phase_ptr(fluid, nc, 1);
+        switch (region) {
+          case 1: l[PH_SAT] = 1.0; v[PH_SAT] = 0.0; break;
+          case 2: l[PH_SAT] = 0.0; v[PH_SAT] = 1.0; break;
+          case 4: l[PH_SAT] = 1.0 - primary[1]; v[PH_SAT] = primary[1]; break;
+          default: break;
+        }
+      }
+    }
+    return err;
+  }
   if (region == 4) err = wo_saturation_temperature(e->thermo, fluid[F_P], &fluid[F_T]);
   else fluid[F_T] = primary[1];
   if (err == 0) {
@@ -153,6 +263,63 @@ int wo_eos_phase_properties(wo_eos *e, const double *primary, const double *rock
   double sl = phase_ptr(fluid, nc, 0)[PH_SAT];
   double relperm[2], cap[2];
   wo_relperm_values(&e->prm.relperm, sl, relperm);
+  if (e->prm.eos == WO_EOS_WCE) { /* eos_wge.F90:421-543 */
+    double gas_properties[2];
+    wo_co2_properties(fluid[F_PARTIAL + 1], fluid[F_T], gas_properties);
+    for (int p = 0; p < e->nphase; p++) {
+      double *ph = phase_ptr(fluid, nc, p);
+      if (phases & (1 << p)) {
+        double water_pressure, capillary_pressure, henrys_constant, energy_solution;
+        if (p == 0) {
+          water_pressure = fluid[F_P];
+          capillary_pressure = wo_cappress_value(&e->prm.cappress, sl, fluid[F_T]);
+          henrys_constant = wo_co2_henrys_constant(fluid[F_T]);
+          energy_solution = wo_co2_energy_solution(fluid[F_T], henrys_constant);
+        } else {
+          water_pressure = fluid[F_PARTIAL];
+          capillary_pressure = 0.0;
+          henrys_constant = 0.0;
+          energy_solution = 0.0;
+        }
+        double param[2] = {water_pressure, fluid[F_T]};
+        err = wo_region_properties(e->thermo, p + 1, param, properties);
+        if (err) break;
+        /* effective_properties: no free gas density in the liquid phase (ncg_thermodynamics.F90:315-340) */
+        double gas_density = (p == 0) ? 0.0 : gas_properties[0], gas_enthalpy = gas_properties[1];
+        double water_density = properties[0], water_internal_energy = properties[1];
+        /* mass_fraction: ncg_thermodynamics.F90:279-311 */
+        double xg;
+        if (p == 0) {
+          xg = co2_mole_to_mass_fraction(fluid[F_PARTIAL + 1] / henrys_constant);
+        } else {
+          double total_density = gas_density + water_density;
+          xg = (total_density < 1.e-30) ? 0.0 : gas_density / total_density;
+        }
+        double water_viscosity = wo_region_viscosity(e->thermo, p + 1, fluid[F_T], fluid[F_P], water_density);
+        /* mixture_viscosity: ncg_co2_thermodynamics.F90:267-292 */
+        if (p == 0) {
+          ph[PH_MU] = water_viscosity;
+        } else {
+          double gas_viscosity;
+          err = wo_co2_viscosity(fluid[F_PARTIAL + 1], fluid[F_T], &gas_viscosity);
+          if (err) break;
+          ph[PH_MU] = water_viscosity * (1.0 - xg) + gas_viscosity * xg;
+        }
+        ph[PH_RHO] = water_density + gas_density;
+        ph[PH_X] = 1.0 - xg;
+        ph[PH_X + 1] = xg;
+        ph[PH_KR] = relperm[p];
+        ph[PH_PC] = capillary_pressure;
+        double water_enthalpy = water_internal_energy + water_pressure / water_density;
+        ph[PH_H] = water_enthalpy * (1.0 - xg) + (gas_enthalpy + energy_solution) * xg;
+        ph[PH_U] = ph[PH_H] - fluid[F_P] / ph[PH_RHO];
+      } else {
+        ph[PH_RHO] = 0.0; ph[PH_U] = 0.0; ph[PH_H] = 0.0; ph[PH_KR] = 0.0;
+        ph[PH_PC] = 0.0; ph[PH_MU] = 0.0; ph[PH_X] = 0.0; ph[PH_X + 1] = 0.0;
+      }
+    }
+    return err;
+  }
   cap[0] = wo_cappress_value(&e->prm.cappress, sl, fluid[F_T]);
   cap[1] = 0.0;
   for (int p = 0; p < e->nphase; p++) {
@@ -195,6 +362,91 @@ typedef struct {
 static void pv_interp(const satline_ctx *c, int np, double x, double *y) {
   double xi = (x - 0.0) / (1.0 - 0.0);
   for (int i = 0; i < np; i++) y[i] = (1.0 - xi) * c->v0[i] + xi * c->v1[i];
+}
+
+/* eos_wge.F90:678-701 */
+static double wge_saturation_difference(double x, void *ctx) {
+  satline_ctx *c = (satline_ctx *)ctx;
+  double var[WO_MAX_NP], Ps = 0.0;
+  pv_interp(c, 3, x, var);
+  wo_saturation_pressure(c->thermo, var[1], &Ps);
+  return var[0] - var[2] - Ps;
+}
+
+/* eos_wge.F90:149-227 */
+static int wge_transition_to_single_phase(wo_eos *e, const double *old_primary, const double *old_fluid,
+                                          int new_region, double *primary, double *fluid, int *transition) {
+  const double small = 1.e-6;
+  int err = 0;
+  *transition = 0;
+  double saturation_bound = (new_region == 1) ? 0.0 : 1.0;
+  double pressure_factor = (new_region == 1) ? 1.0 + small : 1.0 - small;
+  primary[2] = fmax(0.0, fmin(primary[2], primary[0]));
+  double xs[2] = {0.0, 1.0}, vals[2 * WO_MAX_NP];
+  for (int i = 0; i < 3; i++) {
+    vals[i] = old_primary[i];
+    vals[3 + i] = primary[i];
+  }
+  wo_table tbl;
+  wo_table_init(&tbl, xs, vals, 2, 3);
+  tbl.index = 1;
+  double xi = 0.0;
+  err = wo_table_find_component_at_index(&tbl, saturation_bound, 2, &xi);
+  if (err == 0) {
+    double ip[WO_MAX_NP];
+    wo_table_interpolate(&tbl, xi, ip);
+    double interpolated_water_pressure = ip[0] - ip[2];
+    primary[0] = pressure_factor * interpolated_water_pressure + ip[2];
+    primary[2] = ip[2];
+    err = wo_saturation_temperature(e->thermo, interpolated_water_pressure, &primary[1]);
+    if (err == 0) {
+      fluid[F_REGION] = (double)new_region;
+      *transition = 1;
+    }
+  } else {
+    double old_ps;
+    err = wo_saturation_pressure(e->thermo, old_fluid[F_T], &old_ps);
+    if (err == 0) {
+      primary[0] = pressure_factor * old_ps + primary[2];
+      primary[1] = old_fluid[F_T];
+      fluid[F_REGION] = (double)new_region;
+      *transition = 1;
+    }
+  }
+  wo_table_destroy(&tbl);
+  return err;
+}
+
+/* eos_wge.F90:231-285 */
+static int wge_transition_to_two_phase(wo_eos *e, double saturation_pressure, const double *old_primary,
+                                       const double *old_fluid, double *primary, double *fluid, int *transition) {
+  const double small = 1.e-6;
+  primary[2] = fmax(0.0, fmin(primary[2], primary[0]));
+  satline_ctx c;
+  c.thermo = e->thermo;
+  for (int i = 0; i < 3; i++) {
+    c.v0[i] = old_primary[i];
+    c.v1[i] = primary[i];
+  }
+  wo_root_finder rf;
+  wo_root_finder_init(&rf);
+  wo_root_finder_find(&rf, wge_saturation_difference, &c);
+  if (rf.err == 0) {
+    double xs[2] = {0.0, 1.0}, vals[6] = {c.v0[0], c.v0[1], c.v0[2], c.v1[0], c.v1[1], c.v1[2]}, ip[3];
+    wo_table tbl;
+    wo_table_init(&tbl, xs, vals, 2, 3);
+    wo_table_interpolate(&tbl, rf.root, ip);
+    wo_table_destroy(&tbl);
+    primary[0] = ip[0];
+    primary[2] = ip[2];
+  } else {
+    primary[0] = saturation_pressure + primary[2];
+  }
+  int old_region = nint_(old_fluid[F_REGION]);
+  primary[1] = (old_region == 1) ? small : 1.0 - small;
+  fluid[F_REGION] = 4.0;
+  *transition = 1;
+  return 0;
 }
 
 /* eos_we.F90:530-553 */
@@ -295,6 +547,22 @@ int wo_eos_transition(wo_eos *e, const double *old_primary, double *primary, con
   *transition = 0;
   if (e->prm.eos == WO_EOS_W) return 0;
   int old_region = nint_(old_fluid[F_REGION]);
+  if (e->prm.eos == WO_EOS_WCE) { /* eos_wge.F90:289-346 */
+    if (old_region == 4) {
+      double sv = primary[1];
+      if (sv < 0.0) err = wge_transition_to_single_phase(e, old_primary, old_fluid, 1, primary, fluid, transition);
+      else if (sv > 1.0) err = wge_transition_to_single_phase(e, old_primary, old_fluid, 2, primary, fluid, transition);
+    } else {
+      double ps;
+      err = wo_saturation_pressure(e->thermo, primary[1], &ps);
+      if (err == 0) {
+        double water_pressure = primary[0] - primary[2];
+        if ((old_region == 1 && water_pressure < ps) || (old_region == 2 && water_pressure > ps))
+          err = wge_transition_to_two_phase(e, ps, old_primary, old_fluid, primary, fluid, transition);
+      }
+    }
+    return err;
+  }
   if (old_region == 4) {
     double sv = primary[1];
     if (sv < 0.0) err = we_transition_to_single_phase(e, old_primary, old_fluid, 1, primary, fluid, transition);
@@ -313,6 +581,26 @@ int wo_eos_transition(wo_eos *e, const double *old_primary, double *primary, con
 /* eos_we.F90:486-526 ; eos_w.F90 check_primary_variables */
 int wo_eos_check_primary_variables(const wo_eos *e, const double *fluid, double *primary, int *changed) {
   *changed = 0;
+  if (e->prm.eos == WO_EOS_WCE) { /* eos_wge.F90:573-635: clamps the gas partial pressure */
+    const double small = 1.e-6;
+    if (!(primary[0] > 0.0)) return 1;
+    double max_pp = (1.0 - small) * primary[0];
+    if (primary[2] > max_pp) {
+      primary[2] = max_pp;
+      *changed = 1;
+    } else if (primary[2] < 0.0) {
+      primary[2] = 0.0;
+      *changed = 1;
+    }
+    double pw = primary[0] - primary[2];
+    if (pw > 100.e6) return 1;
+    if (nint_(fluid[F_REGION]) == 4) {
+      if (primary[1] < -1.0 || primary[1] > 2.0) return 1;
+    } else {
+      if (primary[1] < 0.0 || primary[1] > 800.0) return 1;
+    }
+    return 0;
+  }
   double p = primary[0];
   if (p < 0.0 || p > 100.e6) return 1;
   if (e->prm.eos == WO_EOS_W) return 0;

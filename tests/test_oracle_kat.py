@@ -466,3 +466,159 @@ def test_cappress_curves(wo):
     tab = wo.make_cappress("table", pressure=[(0, -5.e5), (0.4, -1.e5), (0.7, 0)])
     for sl, ex in [(0., -5.e5), (0.3, -2.e5), (0.7, 0.), (0.9, 0.)]:
         assert abs(L.wo_cappress_value(C.byref(tab), sl, t) - ex) <= 1e-9 * max(abs(ex), 1)
+
+
+# ---- test/unit/src/ncg_co2_thermodynamics_test.F90 (AUTOUGH2 values; tolerances 1e-9 / 1e-8) ----
+
+def test_co2_henrys_constant(wo):
+    """ncg_co2_thermodynamics_test.F90:47-135 (zero-salt cases)"""
+    for t, ex in [(20., 1.44811504032e+08), (100., 5.50571700000e+08), (240., 5.21847810624e+08),
+                  (300., 3.71913900000e+08), (350., 2.23454746875e+08)]:
+        assert rel(wo.lib().wo_co2_henrys_constant(t), ex) < 1e-12
+
+
+def test_co2_energy_solution(wo):
+    """ncg_co2_thermodynamics_test.F90:139-257 (zero-salt cases)"""
+    L = wo.lib()
+    for t, ex in [(20., -495750.87299689), (100., -180685.98723494), (240., 242741.64505202),
+                  (300., 407409.27618764)]:
+        assert rel(L.wo_co2_energy_solution(t, L.wo_co2_henrys_constant(t)), ex) < 1e-12
+
+
+def test_co2_viscosity(wo):
+    """ncg_co2_thermodynamics_test.F90:261-309 (tol 1e-8)"""
+    pc = [0.1e6, 1.e6, 5.e6, 10.e6, 20.e6, 30.e6]
+    ts = [20., 100., 200., 300., 350.]
+    expected = np.array([
+        1.47350850e-5, 1.63927474e-5, 2.37601356e-5, 3.29693708e-5, 9.99600434e-5, 1.19066342e-4,
+        1.82742115e-5, 1.86681905e-5, 2.04192081e-5, 2.26079800e-5, 3.76607100e-5, 5.40893300e-5,
+        2.24530737e-5, 2.26583470e-5, 2.35706728e-5, 2.47110800e-5, 2.94125600e-5, 3.50956800e-5,
+        2.62857731e-5, 2.64270283e-5, 2.70548291e-5, 2.78395800e-5, 3.04311100e-5, 3.39737300e-5,
+        2.80772517e-5, 2.81462344e-5, 2.84528241e-5, 2.88360612e-5, 2.93062944e-5, 3.36788644e-5]).reshape(5, 6)
+    v = C.c_double()
+    for ip_, p in enumerate(pc):
+        for it, t in enumerate(ts):
+            assert wo.lib().wo_co2_viscosity(p, t, C.byref(v)) == 0
+            assert abs(v.value - expected[it, ip_]) < 1e-8 * max(1.0, abs(expected[it, ip_]))
+            assert rel(v.value, expected[it, ip_]) < 1e-7
+    assert wo.lib().wo_co2_viscosity(301.e5, 100., C.byref(v)) == 1
+
+
+def test_co2_properties(wo):
+    """ncg_co2_thermodynamics_test.F90:313-362 (tol 1e-9): (Pc, T) -> enthalpy, density"""
+    data = np.array([
+        0.0, 20.0, 17140.18077231938, 0.0,
+        100000.0, 20.0, 16142.247883091828, 1.8142044368713437,
+        0.0, 100.0, 87450.99131436742, 0.0,
+        100000.0, 100.0, 87004.524163092, 1.4213754811567743,
+        4000000.0, 100.0, 64355.3813832885, 62.608990505735434,
+        9000000.0, 100.0, 20379.357776952613, 184.7959892299282,
+        0.0, 240.0, 223594.37705727902, 0.0,
+        100000.0, 240.0, 223439.99865083068, 1.0324489144812645,
+        4000000.0, 240.0, 215608.4290498441, 42.27375154306431,
+        9000000.0, 240.0, 200402.49860929986, 100.70459422220841,
+        0.0, 300.0, 286380.4950504236, 0.0,
+        100000.0, 300.0, 286273.71092985675, 0.9242369906584087,
+        4000000.0, 300.0, 280856.58497462136, 37.5055455044134,
+        9000000.0, 300.0, 270338.58607276645, 87.3627658128452]).reshape(14, 4)
+    props = np.zeros(2)
+    for pc, t, h, d in data:
+        wo.lib().wo_co2_properties(pc, t, wo.dp(props))
+        assert rel(props[1], h) < 1e-12
+        assert abs(props[0] - d) <= 1e-12 * max(d, 1.0)
+
+
+# ---- test/unit/src/eos_wge_test.F90:53-279 (eos wce is the concrete CO2 child, src/eos_wce.F90) ----
+
+def test_eos_wge_transitions(wo):
+    """all 14 cases of test_eos_wge_transition (transition_compare tolerance 1e-6)"""
+    prm = wo.make_params(eos=wo.EOS_WCE, thermo=wo.THERMO_IAPWS)
+    L = wo.lib()
+    e = L.wo_eos_create(C.byref(prm))
+    assert L.wo_eos_num_primary(e) == 3 and L.wo_eos_fluid_dof(e) == 26
+    small = 1e-6
+    t41, t42 = 299.27215502281706, 212.38453531849041
+    cases = [
+        (1, 0., [1.e5, 20., 0.], [1.e5, 20., 0.], [1.e5, 20., 0.], 1, False),
+        (1, 0., [1.e5, 20., 0.2e5], [1.e5, 20., 0.2e5], [1.e5, 20., 0.2e5], 1, False),
+        (1, 0., [20.e5, 210., 0.], [15.e5, 200., 0.], [16.647121334271149e5, small, 0.], 4, True),
+        (1, 0., [21.e5, 210., 1.e5], [17.e5, 200., 2.e5], [18.31769706741692e5, small, 1.6705757331457702e5], 4, True),
+        (2, 0., [1.e5, 120., 0.], [1.e5, 120., 0.], [1.e5, 120., 0.], 2, False),
+        (2, 0., [1.e5, 120., 0.2e5], [1.e5, 120., 0.2e5], [1.e5, 120., 0.2e5], 2, False),
+        (2, 0., [84.0e5, 302., 0.], [86.e5, t41, 0.], [85.621455812056474e5, 1. - small, 0.], 4, True),
+        (2, 0., [86.0e5, 302., 2.e5], [87.e5, t41, 1.e5], [86.810727906028237e5, 1. - small, 1.1892720939717567e5], 4, True),
+        (4, 0., [1.e5, 0.5, 0.], [1.e5, 0.5, 0.], [1.e5, 0.5, 0.], 4, False),
+        (4, 0., [1.e5, 0.5, 0.2e5], [1.e5, 0.5, 0.2e5], [1.e5, 0.5, 0.2e5], 4, False),
+        (4, t41, [85.e5, 0.1, 0.], [86.e5, -0.01, 0.], [85.909176818181816e5, 300.02645326107097, 0.], 1, True),
+        (4, t41, [88.e5, 0.1, 3.e5], [87.5e5, -0.01, 1.5e5], [87.545540454545449e5, 300.02645326107097, 1.6363636363636365e5], 1, True),
+        (4, t42, [20.e5, 0.9, 0.], [20.1e5, 1.02, 0.], [20.08331325e5, 212.59487472987195, 0.], 2, True),
+        (4, t42, [22.e5, 0.9, 2.e5], [24.1e5, 1.02, 4.e5], [23.749979916666667e5, 212.59487472987195, 3.6666666666666663e5], 2, True),
+    ]
+    for old_region, old_t, old_p, prim, exp_p, exp_region, exp_tr in cases:
+        old_fluid, fluid = np.zeros(26), np.zeros(26)
+        old_fluid[2] = fluid[2] = float(old_region)
+        old_fluid[1] = old_t
+        op, p = np.array(old_p), np.array(prim)
+        tr = C.c_int()
+        err = L.wo_eos_transition(e, wo.dp(op), wo.dp(p), wo.dp(old_fluid), wo.dp(fluid), C.byref(tr))
+        assert err == 0
+        assert bool(tr.value) == exp_tr, (old_p, prim)
+        assert int(round(fluid[2])) == exp_region
+        for a, b in zip(p, exp_p):
+            assert abs(a - b) <= 1e-6 * max(abs(b), 1.0), (old_p, prim, p, exp_p)
+    L.wo_eos_destroy(e)
+
+
+def test_eos_wce_scaling_and_consistency(wo):
+    """adaptive partial-pressure scaling round trip (eos_wge.F90:639-674), check_primary_variables clamping
+    (:573-635) and internal consistency of a two-phase wce record: pure-water limit equals eos_we, mass
+    fractions sum to 1, u = h - P/rho, liquid density carries no free gas (effective_properties)"""
+    L = wo.lib()
+    prm = wo.make_params(eos=wo.EOS_WCE, thermo=wo.THERMO_IAPWS)
+    e = L.wo_eos_create(C.byref(prm))
+    prim = np.array([30.e5, 0.3, 4.e5])
+    y, back = np.zeros(3), np.zeros(3)
+    L.wo_eos_scale(e, wo.dp(prim), 4, wo.dp(y))
+    assert np.allclose(y, [3.0, 0.3, 4.e5 / 30.e5], rtol=1e-15)
+    L.wo_eos_unscale(e, wo.dp(y), 4, wo.dp(back))
+    assert np.allclose(back, prim, rtol=1e-15)
+    fluid = np.zeros(26)
+    fluid[2] = 4.0
+    ch = C.c_int()
+    p2 = np.array([30.e5, 0.3, 31.e5])
+    assert L.wo_eos_check_primary_variables(e, wo.dp(fluid), wo.dp(p2), C.byref(ch)) == 0
+    assert ch.value == 1 and p2[2] == (1. - 1e-6) * 30.e5
+    p3 = np.array([30.e5, 0.3, -5.])
+    assert L.wo_eos_check_primary_variables(e, wo.dp(fluid), wo.dp(p3), C.byref(ch)) == 0 and p3[2] == 0.0 and ch.value == 1
+    assert L.wo_eos_check_primary_variables(e, wo.dp(fluid), wo.dp(np.array([30.e5, 2.5, 1.e5])), C.byref(ch)) == 1
+    rock = np.zeros(8)
+    assert L.wo_eos_bulk_properties(e, wo.dp(prim), wo.dp(fluid)) == 0
+    assert L.wo_eos_phase_properties(e, wo.dp(prim), wo.dp(rock), wo.dp(fluid)) == 0
+    assert fluid[6] == 26.e5 and fluid[7] == 4.e5
+    liq, vap = fluid[8:17], fluid[17:26]
+    for ph in (liq, vap):
+        assert abs(ph[7] + ph[8] - 1.0) < 1e-15
+        assert rel(ph[6], ph[5] - fluid[0] / ph[0]) < 1e-14
+    props = np.zeros(2)
+    L.wo_co2_properties(4.e5, fluid[1], wo.dp(props))
+    th = L.wo_thermo_create(0, 0)
+    wp = np.zeros(2)
+    L.wo_region_properties(th, 1, wo.dp(np.array([30.e5, fluid[1]])), wo.dp(wp))
+    assert liq[0] == wp[0]                      # liquid: water density only
+    L.wo_region_properties(th, 2, wo.dp(np.array([26.e5, fluid[1]])), wo.dp(wp))
+    assert rel(vap[0], wp[0] + props[0]) < 1e-15 and rel(vap[8], props[0] / (wp[0] + props[0])) < 1e-14
+    # pure-water limit: Pg = 0 reproduces eos_we
+    prm_we = wo.make_params(eos=wo.EOS_WE, thermo=wo.THERMO_IAPWS)
+    ewe = L.wo_eos_create(C.byref(prm_we))
+    f3, f2 = np.zeros(26), np.zeros(23)
+    f3[2] = f2[2] = 4.0
+    assert L.wo_eos_bulk_properties(e, wo.dp(np.array([30.e5, 0.3, 0.0])), wo.dp(f3)) == 0
+    assert L.wo_eos_phase_properties(e, wo.dp(np.array([30.e5, 0.3, 0.0])), wo.dp(rock), wo.dp(f3)) == 0
+    assert L.wo_eos_bulk_properties(ewe, wo.dp(np.array([30.e5, 0.3])), wo.dp(f2)) == 0
+    assert L.wo_eos_phase_properties(ewe, wo.dp(np.array([30.e5, 0.3])), wo.dp(rock), wo.dp(f2)) == 0
+    assert f3[1] == f2[1]
+    for k in range(7):  # density .. internal energy of both phases
+        assert rel(f3[8 + k], f2[7 + k]) < 1e-13 and rel(f3[17 + k], f2[15 + k]) < 1e-13
+    L.wo_eos_destroy(e)
+    L.wo_eos_destroy(ewe)
+    L.wo_thermo_destroy(th)

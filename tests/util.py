@@ -11,10 +11,11 @@ SEED = 20240917
 def wb_params_from_oracle(wo, flow, prm):
     """wb_params with the same contents as the oracle's wo_params (independent struct definitions,
     identical field layout)."""
-    return flow.make_params(eos={wo.EOS_WE: flow.EOS_WE, wo.EOS_W: flow.EOS_W}[prm.eos], thermo=prm.thermo,
-                            relperm=prm.relperm, cappress=prm.cappress,
+    return flow.make_params(eos={wo.EOS_WE: flow.EOS_WE, wo.EOS_W: flow.EOS_W, wo.EOS_WCE: flow.EOS_WCE}[prm.eos],
+                            thermo=prm.thermo, relperm=prm.relperm, cappress=prm.cappress,
                             gravity=tuple(prm.gravity), extrapolate=prm.extrapolate,
-                            eos_w_temperature=prm.eos_w_temperature)
+                            eos_w_temperature=prm.eos_w_temperature,
+                            partial_pressure_scale=prm.partial_pressure_scale)
 
 
 def psat_fn(wo, thermo):

@@ -30,7 +30,7 @@ class Cappress(C.Structure):
 class Params(C.Structure):
     _fields_ = [("eos", C.c_int), ("thermo", C.c_int), ("extrapolate", C.c_int),
                 ("pressure_scale", C.c_double), ("temperature_scale", C.c_double),
-                ("eos_w_temperature", C.c_double),
+                ("partial_pressure_scale", C.c_double), ("eos_w_temperature", C.c_double),
                 ("relperm", Relperm), ("cappress", Cappress), ("gravity", C.c_double * 3)]
 
 

@@ -8,6 +8,7 @@
 // Block storage is PETSc BAIJ: bs x bs blocks, column-major inside a block.
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 #include "wb_common.cuh"
 
@@ -34,54 +35,115 @@ struct SpmvArgs {
   const int *done;  // nullable: device-side "solver finished" flag
 };
 
-template <int BS>
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
+__device__ __forceinline__ double4 ld256(const double *p) {
+  double4 r;
+  asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double4 ld256_stream(const double *p) {  // evict-first: the Krylov basis is read once per pass
+  double4 r;
+  asm("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256(double *p, const double4 &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
+// R block rows per 8-lane group, processed level by level (all row pointers, then all column indices and
+// value blocks, then all x gathers): the three dependent global-memory round trips of a row are shared by R
+// rows, which multiplies the bytes in flight per warp by R at the same occupancy.
+template <int BS, int R>
 __global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
   if (a.done && *a.done) return;
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = gt >> 3, lane = gt & 7;
+  constexpr int B2 = BS * BS;
+  const int lane = threadIdx.x & 7;
+  const int group = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int gstride = gridDim.x * 32;
   const double s = a.scale ? *a.scale : 1.0;
-  double acc[BS];
+  int e0[R], e1[R];
 #pragma unroll
-  for (int i = 0; i < BS; i++) acc[i] = 0.0;
-  if (row < a.nb) {
-    const int e1 = a.rowptr[row + 1];
-    for (int e = a.rowptr[row] + lane; e < e1; e += 8) {
-      const int col = a.colidx[e];
-      const bool own = col < a.nb;
-      const double *xp = own ? a.x + (size_t)col * BS : a.xg + (size_t)(col - a.nb) * BS;
-      const double sc = own ? s : 1.0;  // ghost entries arrive already scaled by their owner
-      double xb[BS], v[BS * BS];
+  for (int r = 0; r < R; r++) {
+    const int row = group + r * gstride;
+    e0[r] = 0; e1[r] = 0;
+    if (row < a.nb) {
+      e0[r] = a.rowptr[row] + lane;
+      e1[r] = a.rowptr[row + 1];
+    }
+  }
+  double acc[R][BS];
+#pragma unroll
+  for (int r = 0; r < R; r++)
+#pragma unroll
+    for (int i = 0; i < BS; i++) acc[r][i] = 0.0;
+  bool more = false;
+#pragma unroll
+  for (int r = 0; r < R; r++) more = more || (e0[r] < e1[r]);
+  while (more) {
+    int col[R];
+    double v[R][B2], xb[R][BS];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const bool on = e0[r] < e1[r];
+      col[r] = on ? a.colidx[e0[r]] : -1;
       if (BS == 2) {
-        const double2 x2 = *reinterpret_cast<const double2 *>(xp);
-        xb[0] = x2.x * sc; xb[1] = x2.y * sc;
-        const double2 p = __ldcs(reinterpret_cast<const double2 *>(a.val + (size_t)e * 4));
-        const double2 q = __ldcs(reinterpret_cast<const double2 *>(a.val + (size_t)e * 4) + 1);
-        v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
+        double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
+        if (on) {
+          // two 128-bit evict-first loads per 2x2 block (one 256-bit load measured slower here: 87 vs 71 us)
+          p = __ldcs(reinterpret_cast<const double2 *>(a.val + (size_t)e0[r] * 4));
+          q = __ldcs(reinterpret_cast<const double2 *>(a.val + (size_t)e0[r] * 4) + 1);
+        }
+        v[r][0] = p.x; v[r][1] = p.y; v[r][2] = q.x; v[r][3] = q.y;
       } else {
 #pragma unroll
-        for (int j = 0; j < BS; j++) xb[j] = xp[j] * sc;
-#pragma unroll
-        for (int q = 0; q < BS * BS; q++) v[q] = __ldcs(a.val + (size_t)e * BS * BS + q);
+        for (int q = 0; q < B2; q++) v[r][q] = on ? __ldcs(a.val + (size_t)e0[r] * B2 + q) : 0.0;
       }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const bool own = col[r] < a.nb;
+      const double sc = own ? s : 1.0;  // ghost entries arrive already scaled by their owner
+#pragma unroll
+      for (int j = 0; j < BS; j++) xb[r][j] = 0.0;
+      if (col[r] >= 0) {
+        const double *xp = own ? a.x + (size_t)col[r] * BS : a.xg + (size_t)(col[r] - a.nb) * BS;
+        if (BS == 2) {
+          const double2 x2 = *reinterpret_cast<const double2 *>(xp);
+          xb[r][0] = x2.x * sc; xb[r][1] = x2.y * sc;
+        } else {
+#pragma unroll
+          for (int j = 0; j < BS; j++) xb[r][j] = xp[j] * sc;
+        }
+      }
+    }
+    more = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
 #pragma unroll
       for (int j = 0; j < BS; j++)
 #pragma unroll
-        for (int i = 0; i < BS; i++) acc[i] += v[j * BS + i] * xb[j];
+        for (int i = 0; i < BS; i++) acc[r][i] += v[r][j * BS + i] * xb[r][j];
+      e0[r] += 8;
+      more = more || (e0[r] < e1[r]);
     }
   }
 #pragma unroll
-  for (int off = 4; off > 0; off >>= 1)
+  for (int r = 0; r < R; r++) {
 #pragma unroll
-    for (int i = 0; i < BS; i++) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], off, 8);
-  if (row < a.nb && lane == 0) {
-    if (BS == 2) *reinterpret_cast<double2 *>(a.y + (size_t)row * 2) = make_double2(acc[0], acc[1]);
-    else {
+    for (int off = 4; off > 0; off >>= 1)
 #pragma unroll
-      for (int i = 0; i < BS; i++) a.y[(size_t)row * BS + i] = acc[i];
-    }
-    if (a.xn) {
+      for (int i = 0; i < BS; i++) acc[r][i] += __shfl_down_sync(0xffffffffu, acc[r][i], off, 8);
+    const int row = group + r * gstride;
+    if (row < a.nb && lane == 0) {
+      if (BS == 2) *reinterpret_cast<double2 *>(a.y + (size_t)row * 2) = make_double2(acc[r][0], acc[r][1]);
+      else {
 #pragma unroll
-      for (int i = 0; i < BS; i++) a.xn[(size_t)row * BS + i] = a.x[(size_t)row * BS + i] * s;
+        for (int i = 0; i < BS; i++) a.y[(size_t)row * BS + i] = acc[r][i];
+      }
+      if (a.xn) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) a.xn[(size_t)row * BS + i] = a.x[(size_t)row * BS + i] * s;
+      }
     }
   }
 }
@@ -99,13 +161,27 @@ int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d
     xg = A->d_xloc;  // ghost columns without a communicator: zeros
   }
   SpmvArgs a = {A->d_rowptr, A->d_colidx, A->d_val, d_x, xg, d_scale, d_xn, d_y, A->nb, done};
-  const int grid = wb_grid((size_t)A->nb * 8, 256);
+  static int rows_per_group = 0;  // tuning knob (WB_SPMV_ROWS = 1, 2, 4); measured 70.9 / 70.6 / 97 us at 1 M cells
+  if (!rows_per_group) {
+    const char *e = getenv("WB_SPMV_ROWS");
+    rows_per_group = e ? atoi(e) : 2;
+    if (rows_per_group != 1 && rows_per_group != 2 && rows_per_group != 4) rows_per_group = 2;
+  }
+  const int R = rows_per_group;
+  const int grid = std::max(1, wb_grid((size_t)A->nb, 32 * R));
+#define SPMV(BS)                                                                       \
+  do {                                                                                 \
+    if (R == 1) k_bsr_spmv<BS, 1><<<grid, 256, 0, c->stream>>>(a);                     \
+    else if (R == 2) k_bsr_spmv<BS, 2><<<grid, 256, 0, c->stream>>>(a);                \
+    else k_bsr_spmv<BS, 4><<<grid, 256, 0, c->stream>>>(a);                            \
+  } while (0)
   switch (A->bs) {
-    case 1: k_bsr_spmv<1><<<grid, 256, 0, c->stream>>>(a); break;
-    case 2: k_bsr_spmv<2><<<grid, 256, 0, c->stream>>>(a); break;
-    case 3: k_bsr_spmv<3><<<grid, 256, 0, c->stream>>>(a); break;
+    case 1: SPMV(1); break;
+    case 2: SPMV(2); break;
+    case 3: SPMV(3); break;
     default: WB_CHECK(false, "wb_mat_mult: block size %d not supported", A->bs);
   }
+#undef SPMV
   WB_LAUNCH(c);
   WB_CUDA(cudaGetLastError());
   return 0;
@@ -1169,21 +1245,6 @@ extern "C" int wb_pc_apply(wb_pc *pc, const double *r, double *z) {
 #define RED_BLOCKS (4 * WB_NUM_SMS)
 #define KRY_MAXV 32  // vectors per fused multi-dot / multi-axpy launch (>= restart + 1 is not needed: one cycle
                      // of GMRES(30) dots against at most 30 vectors; longer restarts go in chunks)
-
-// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
-__device__ __forceinline__ double4 ld256(const double *p) {
-  double4 r;
-  asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ double4 ld256_stream(const double *p) {  // evict-first: the Krylov basis is read once per pass
-  double4 r;
-  asm("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void st256(double *p, const double4 &v) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

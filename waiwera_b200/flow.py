@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import Params, Relperm, Cappress, KspOpts, NewtonOpts, NewtonResult, check
 
 THERMO_IAPWS, THERMO_IFC67 = 0, 1
-EOS_WE, EOS_W = 0, 1
+EOS_WE, EOS_W, EOS_WCE = 0, 1, 2
 RP_FULLY_MOBILE, RP_LINEAR, RP_PICKENS, RP_COREY, RP_GRANT, RP_VAN_GENUCHTEN, RP_TABLE = range(7)
 CP_ZERO, CP_LINEAR, CP_VAN_GENUCHTEN, CP_TABLE = range(4)
 PC_NONE, PC_PBJACOBI, PC_BJACOBI_ILU0 = 0, 1, 2
@@ -36,11 +36,12 @@ def ptr(a, dtype=None):
 
 
 def make_params(eos=EOS_WE, thermo=THERMO_IAPWS, relperm=None, cappress=None, gravity=(0.0, 0.0, -9.8),
-                extrapolate=0, eos_w_temperature=20.0):
+                extrapolate=0, eos_w_temperature=20.0, partial_pressure_scale=0.0):
     """wb_params from any object with the same fields (e.g. the oracle's ctypes structs in the tests)."""
     p = Params()
     p.eos, p.thermo, p.extrapolate = eos, thermo, extrapolate
     p.pressure_scale, p.temperature_scale = 1.0e6, 1.0e2
+    p.partial_pressure_scale = partial_pressure_scale  # <= 0: adaptive (reference default)
     p.eos_w_temperature = eos_w_temperature
     if relperm is None:
         p.relperm.type = RP_LINEAR
