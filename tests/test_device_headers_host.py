@@ -38,6 +38,10 @@ def hc(wo):
     L.hc_we_fluid.argtypes = [C.c_void_p, dp, i, dp]
     L.hc_we_flux.argtypes = [C.c_void_p, dp, dp, dp, dp, i, dp, i, dp, dp]
     L.hc_we_transition.argtypes = [C.c_void_p, dp, dp, i, d, ip, ip]
+    L.hc_wce_fluid.argtypes = [C.c_void_p, dp, i, dp]
+    L.hc_wce_flux.argtypes = [C.c_void_p, dp, dp, dp, dp, i, dp, i, dp, dp]
+    L.hc_wce_transition.argtypes = [C.c_void_p, dp, dp, i, d, ip, ip, ip]
+    L.hc_wce_scale.argtypes = [C.c_void_p, dp, i, dp, dp]
     return L
 
 
@@ -253,6 +257,166 @@ def test_we_transitions_match_oracle(wo, hc, thermo):
                 assert np.array_equal(p_ref, p_got), (trial, p_ref, p_got)
                 ntrans += tr.value
         assert ntrans > 50
+    finally:
+        wo.lib().wo_eos_destroy(eos)
+        wo.lib().wo_thermo_destroy(th)
+
+
+# ---------------------------------------------------------------- eos_wce (water + CO2 + energy)
+
+def wce_cell(wo, thermo, rng, region):
+    """random valid (P, T | Sv, Pg) for eos_wce: the water partial pressure P - Pg plays the role of the eos_we pressure"""
+    pw = we_cell(wo, thermo, rng, region)
+    pg = rng.choice([0.0, rng.uniform(1e3, 5e5), rng.uniform(1e5, 3e6)])
+    return np.array([pw[0] + pg, pw[1], pg])
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_wce_fluid_record_matches_oracle(wo, hc, thermo):
+    """a5: all 26 fields of the wce fluid record, device header vs oracle, bit for bit"""
+    rng = np.random.default_rng(SEED + 13)
+    rock = np.array([1e-13, 1e-13, 1e-14, 2.5, 1.5, 0.1, 2200.0, 1000.0])
+    n_ok = 0
+    for rp, cp in curve_cases(wo)[:4]:
+        prm = wo.make_params(eos=wo.EOS_WCE, thermo=thermo, relperm=rp, cappress=cp)
+        eos = wo.lib().wo_eos_create(C.byref(prm))
+        try:
+            for region in (1, 2, 4):
+                for _ in range(40):
+                    primary = wce_cell(wo, thermo, rng, region)
+                    ref = np.zeros(26)
+                    ref[2] = region
+                    e0 = wo.lib().wo_eos_bulk_properties(eos, wo.dp(primary), wo.dp(ref))
+                    if e0 == 0:
+                        e0 = wo.lib().wo_eos_phase_properties(eos, wo.dp(primary), wo.dp(rock), wo.dp(ref))
+                    got = np.zeros(26)
+                    e1 = hc.hc_wce_fluid(C.byref(prm), wo.dp(primary), region, wo.dp(got))
+                    assert e0 == e1
+                    if e0 == 0:
+                        n_ok += 1
+                        # pow / log10 come from the same libm on both sides here: bit-identical
+                        assert np.array_equal(ref, got), (region, primary, ref - got)
+        finally:
+            wo.lib().wo_eos_destroy(eos)
+    assert n_ok > 300
+
+
+@pytest.mark.parametrize("fixed_scale", [0.0, 1.0e6])
+def test_wce_scaling_matches_oracle(wo, hc, fixed_scale):
+    """adaptive (reference default) and fixed partial-pressure scaling, eos_wge.F90:96-110, 639-674"""
+    rng = np.random.default_rng(SEED + 14)
+    prm = wo.make_params(eos=wo.EOS_WCE, partial_pressure_scale=fixed_scale)
+    eos = wo.lib().wo_eos_create(C.byref(prm))
+    try:
+        for region in (1, 2, 4):
+            for _ in range(20):
+                primary = wce_cell(wo, 0, rng, region)
+                y0, y1, back = np.zeros(3), np.zeros(3), np.zeros(3)
+                wo.lib().wo_eos_scale(eos, wo.dp(primary), region, wo.dp(y0))
+                hc.hc_wce_scale(C.byref(prm), wo.dp(primary), region, wo.dp(y1), wo.dp(back))
+                assert np.array_equal(y0, y1)
+                ref_back = np.zeros(3)
+                wo.lib().wo_eos_unscale(eos, wo.dp(y0), region, wo.dp(ref_back))
+                assert np.array_equal(back, ref_back)
+    finally:
+        wo.lib().wo_eos_destroy(eos)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_wce_flux_and_balance_match_oracle(wo, hc, thermo):
+    """a8-a10 with two components: component + energy fluxes, phase fluxes and the 3 balances"""
+    rng = np.random.default_rng(SEED + 15)
+    rp, cp = curve_cases(wo)[3]
+    prm = wo.make_params(eos=wo.EOS_WCE, thermo=thermo, relperm=rp, cappress=cp)
+    eos = wo.lib().wo_eos_create(C.byref(prm))
+    n_ok = 0
+    try:
+        for trial in range(300):
+            r1, r2 = rng.choice([1, 2, 4], 2)
+            p1, p2 = wce_cell(wo, thermo, rng, r1), wce_cell(wo, thermo, rng, r2)
+            if trial % 3 == 0:
+                r2 = r1
+                p2 = p1 * (1 + rng.uniform(-1e-4, 1e-4, 3))
+            rock1 = np.array([1e-13, 2e-13, 1e-14, 2.5, 1.5, 0.1, 2200.0, 1000.0]) * rng.uniform(0.5, 1.5, 8)
+            rock2 = np.array([1e-13, 2e-13, 1e-14, 2.5, 1.5, 0.1, 2200.0, 1000.0]) * rng.uniform(0.5, 1.5, 8)
+            d1, d2 = rng.uniform(1, 20, 2)
+            g = np.zeros(12)
+            g[0], g[1], g[2], g[3] = rng.uniform(1, 100), d1, d2, d1 + d2
+            g[7] = rng.choice([0.0, -9.8, 9.8, 3.3])
+            g[11] = float(rng.integers(1, 4))
+            if trial % 10 == 1:
+                g[2], g[3] = 0.0, d1
+            f1, f2 = np.zeros(26), np.zeros(26)
+            f1[2], f2[2] = r1, r2
+            ok = True
+            for pr, fl, rk in ((p1, f1, rock1), (p2, f2, rock2)):
+                e = wo.lib().wo_eos_bulk_properties(eos, wo.dp(pr), wo.dp(fl))
+                if e == 0:
+                    e = wo.lib().wo_eos_phase_properties(eos, wo.dp(pr), wo.dp(rk), wo.dp(fl))
+                ok = ok and e == 0
+            if not ok:
+                continue
+            n_ok += 1
+            ref = np.zeros(5)
+            wo.lib().wo_face_flux(wo.dp(g), wo.dp(rock1), wo.dp(rock2), wo.dp(f1), wo.dp(f2), 2, 3, 2, 2, 0, wo.dp(ref))
+            bref = np.zeros(3)
+            wo.lib().wo_cell_balance(wo.dp(rock1), wo.dp(f1), 2, 2, 3, wo.dp(bref))
+            got, bgot = np.zeros(5), np.zeros(3)
+            assert hc.hc_wce_flux(C.byref(prm), wo.dp(g), wo.dp(rock1), wo.dp(rock2), wo.dp(p1), int(r1), wo.dp(p2), int(r2),
+                                  wo.dp(got), wo.dp(bgot)) == 0
+            assert np.array_equal(ref, got), (trial, ref, got)
+            assert np.array_equal(bref, bgot)
+        assert n_ok > 200
+    finally:
+        wo.lib().wo_eos_destroy(eos)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_wce_transitions_match_oracle(wo, hc, thermo):
+    """a15 for eos_wge: transitions + the Pg-clamping check_primary_variables"""
+    rng = np.random.default_rng(SEED + 16)
+    prm = wo.make_params(eos=wo.EOS_WCE, thermo=thermo)
+    eos = wo.lib().wo_eos_create(C.byref(prm))
+    th = wo.lib().wo_thermo_create(thermo, 0)
+    ntrans = nchanged = 0
+    try:
+        for trial in range(500):
+            old_region = int(rng.choice([1, 2, 4]))
+            oldp = wce_cell(wo, thermo, rng, old_region)
+            dpg = rng.uniform(-1.2, 0.5) * oldp[2] + rng.choice([0.0, rng.uniform(-2e4, 2e4)])
+            if old_region == 4:
+                newp = oldp + np.array([rng.uniform(-2e5, 2e5), rng.uniform(-1.2, 1.2), dpg])
+                if trial % 7 == 0:
+                    newp[1] = oldp[1]
+                    oldp[1] = newp[1] = rng.choice([-0.2, 1.3])
+            else:
+                ps = C.c_double()
+                wo.lib().wo_saturation_pressure(th, oldp[1], C.byref(ps))
+                pg = max(oldp[2] + dpg, -1e4)
+                newp = np.array([ps.value * rng.uniform(0.7, 1.3) + max(pg, 0.0), oldp[1] + rng.uniform(-5, 5), pg])
+            if trial % 11 == 0:
+                newp[2] = newp[0] * 1.01  # partial pressure above the total pressure: clamped
+            old_fluid = np.zeros(26)
+            old_fluid[2] = old_region
+            assert wo.lib().wo_eos_bulk_properties(eos, wo.dp(oldp), wo.dp(old_fluid)) == 0
+            fluid = old_fluid.copy()
+            p_ref = newp.copy()
+            tr, ch = C.c_int(), C.c_int()
+            e0 = wo.lib().wo_eos_transition(eos, wo.dp(oldp), wo.dp(p_ref), wo.dp(old_fluid), wo.dp(fluid), C.byref(tr))
+            if e0 == 0:
+                e0 = wo.lib().wo_eos_check_primary_variables(eos, wo.dp(fluid), wo.dp(p_ref), C.byref(ch))
+            p_got = newp.copy()
+            reg, tr1, ch1 = C.c_int(old_region), C.c_int(), C.c_int()
+            e1 = hc.hc_wce_transition(C.byref(prm), wo.dp(oldp), wo.dp(p_got), old_region, old_fluid[1], C.byref(reg),
+                                      C.byref(tr1), C.byref(ch1))
+            assert (e0 != 0) == (e1 != 0), (trial, e0, e1)
+            if e0 == 0:
+                assert tr.value == tr1.value and ch.value == ch1.value
+                assert int(round(fluid[2])) == reg.value
+                assert np.array_equal(p_ref, p_got), (trial, p_ref, p_got)
+                ntrans += tr.value
+                nchanged += ch.value
+        assert ntrans > 50 and nchanged > 10
     finally:
         wo.lib().wo_eos_destroy(eos)
         wo.lib().wo_thermo_destroy(th)

@@ -39,6 +39,17 @@ def make_problem(wo, dims=(8, 7, 6), thermo=0, two_phase_layers=0, top_boundary=
     return m, y, region, prm
 
 
+def make_problem_wce(wo, dims=(8, 7, 6), thermo=0, two_phase_layers=0, relperm=None, cappress=None, seed=SEED,
+                     dx=10.0, partial_pressure_scale=0.0):
+    """eos_wce (water + CO2 + energy, 3 primaries, BAIJ bs=3): mesh + scaled state + oracle params"""
+    m = wmesh.structured(*dims, dx=dx, seed=seed)
+    primary, region = wmesh.wce_state(m, seed=seed, two_phase_layers=two_phase_layers, thermo_psat=psat_fn(wo, thermo))
+    y = np.ascontiguousarray(wmesh.scale_primaries(primary, region, partial_pressure_scale=partial_pressure_scale)).reshape(-1)
+    prm = wo.make_params(eos=wo.EOS_WCE, thermo=thermo, relperm=relperm, cappress=cappress,
+                         partial_pressure_scale=partial_pressure_scale)
+    return m, y, region, prm
+
+
 def boundary_values(m):
     """Dirichlet values of the top boundary ghost cells: 1 bar, 15 degC liquid"""
     nb = len(m.boundary["ghost_cells"])

@@ -18,6 +18,7 @@ struct WbEosParams {
   int eos, np, nc, nphase;
   WbThermo thermo;
   double scale[WB_MAX_NP][5];  // primary_scale(var, region 1..4), src/eos_we.F90:104-109
+  int adaptive_pp;             // eos_wce: gas partial pressure scaled by the cell's total pressure
   double eos_w_temperature;
   wb_relperm relperm;
   wb_cappress cappress;
@@ -40,6 +41,14 @@ inline int wb_eos_params_make(const wb_params &prm, WbEosParams &e) {
   } else if (prm.eos == WB_EOS_W) {  // src/eos_w.F90:67-96
     e.np = 1; e.nc = 1; e.nphase = 1;
     e.scale[0][1] = ps; e.scale[0][2] = ps;
+  } else if (prm.eos == WB_EOS_WCE) {  // src/eos_wge.F90:40-131, src/eos_wce.F90:23-53
+    e.np = 3; e.nc = 2; e.nphase = 2;
+    double pps = prm.partial_pressure_scale;
+    e.adaptive_pp = !(pps > 0.0);
+    if (e.adaptive_pp) pps = 0.0;
+    e.scale[0][1] = ps; e.scale[1][1] = ts; e.scale[2][1] = pps;
+    e.scale[0][2] = ps; e.scale[1][2] = ts; e.scale[2][2] = pps;
+    e.scale[0][4] = ps; e.scale[1][4] = 1.0; e.scale[2][4] = pps;
   } else {
     return 1;
   }
@@ -49,6 +58,7 @@ inline int wb_eos_params_make(const wb_params &prm, WbEosParams &e) {
 template <int EOS> struct WbEosTraits;
 template <> struct WbEosTraits<WB_EOS_WE> { static constexpr int NP = 2, NC = 1, NPH = 2; };
 template <> struct WbEosTraits<WB_EOS_W> { static constexpr int NP = 1, NC = 1, NPH = 1; };
+template <> struct WbEosTraits<WB_EOS_WCE> { static constexpr int NP = 3, NC = 2, NPH = 2; };
 
 // ---------------------------------------------------------------- curves
 
@@ -180,15 +190,94 @@ template <int NC, int NPH> struct WbStateLayout {
 
 WB_HD int wb_nint(double x) { return (int)(x < 0 ? x - 0.5 : x + 0.5); }
 
-// eos%unscale (src/eos.F90:200-210)
+// eos%unscale (src/eos.F90:200-210; adaptive partial pressure: src/eos_wge.F90:659-674)
 template <int NP> WB_HD void wb_unscale(const WbEosParams &e, const double *y, int region, double *primary) {
 #pragma unroll
   for (int i = 0; i < NP; i++) primary[i] = y[i] * e.scale[i][region];
+  if (NP == 3 && e.adaptive_pp) primary[NP - 1] = y[NP - 1] * primary[0];
 }
-// eos%scale (src/eos.F90:186-196)
+// eos%scale (src/eos.F90:186-196; adaptive: src/eos_wge.F90:639-655)
 template <int NP> WB_HD void wb_scale(const WbEosParams &e, const double *primary, int region, double *y) {
 #pragma unroll
   for (int i = 0; i < NP; i++) y[i] = primary[i] / e.scale[i][region];
+  if (NP == 3 && e.adaptive_pp) y[NP - 1] = primary[NP - 1] / primary[0];
+}
+
+// ---------------------------------------------------------------- CO2 (non-condensible gas)
+// src/ncg_co2_thermodynamics.F90:14-292, src/ncg_thermodynamics.F90:145-340
+
+#define WB_CO2_MW 44.01          // ncg_co2_thermodynamics.F90:14
+#define WB_WATER_MW 18.01528     // thermodynamics.F90:38
+#define WB_GAS_CONSTANT 8.3144598  // thermodynamics.F90:39
+
+// utils.F90:224-241 (Horner), coefficients a[0..n-1]
+template <int N> WB_HD double wb_polynomial(const double *a, double x) {
+  double p = a[N - 1];
+#pragma unroll
+  for (int i = N - 2; i >= 0; i--) p = a[i] + x * p;
+  return p;
+}
+
+// density and enthalpy of CO2 at (partial pressure, temperature): ncg_co2_thermodynamics.F90:84-111
+WB_HD void wb_co2_properties(double partial_pressure, double temperature, double &density, double &enthalpy) {
+  const double tk = temperature + 273.15;
+  const double pp = partial_pressure * 1.0e-6;
+  const double tc = pow(0.01 * tk, 3.3333333333);
+  const double hci = 1.667 + 0.001542 * tk - 0.7948 * log10(tk) - 41.35 / tk;
+  enthalpy = 1.e6 * (hci - 0.3571 * pp * (1.0 + 0.07576 * pp) / tc);
+  const double vc = 0.00018882 * tk - pp * (0.0824 + 0.01249 * pp) / tc;
+  density = pp / vc;
+}
+
+// Henry's constant (:115-135) and the energy of solution from its temperature derivative
+// (:172-197 with polynomial_derivative utils.F90:291-310; ncg_thermodynamics.F90:176-223)
+WB_HD double wb_co2_henrys_constant(double temperature) {
+  const double a[6] = {0.783666, 1.96025, 8.20574, -7.40674, 2.18380, -0.220999};
+  return 1.e8 * wb_polynomial<6>(a, temperature / 100.0);
+}
+WB_HD double wb_co2_energy_solution(double temperature, double henrys_constant) {
+  const double a[6] = {0.783666, 1.96025, 8.20574, -7.40674, 2.18380, -0.220999};
+  double da[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) da[i] = (double)(i + 1) * a[i + 1];
+  const double henrys_derivative = 1.e8 * wb_polynomial<5>(da, temperature / 100.0) / (henrys_constant * 100.0);
+  const double tk = temperature + 273.15;
+  return -1.e3 * WB_GAS_CONSTANT * tk * tk * henrys_derivative / WB_CO2_MW;
+}
+
+// viscosity: coefficients interpolated linearly in pressure (MPa) on the table of :22-30 (end clamping of
+// interpolation.F90:202-306, 494-510), polynomial in temperature (:237-263)
+WB_HD int wb_co2_viscosity(double partial_pressure, double temperature, double &viscosity) {
+  if (!(partial_pressure <= 300.e5)) return 1;
+  const double xp[5] = {0.0, 10.0, 15.0, 20.0, 30.0};
+  const double c[5][5] = {{1.3578, 3.9189, 9.6607, 13.1566, 14.7968},
+                          {4.9227e-3, -35.984e-3, -135.479e-3, -179.352e-3, -160.731e-3},
+                          {-2.9661e-6, 0.25825e-3, 0.90087e-3, 1.12474e-3, 0.850257e-3},
+                          {2.8529e-9, -7.1178e-7, -2.4727e-6, -2.98864e-6, -1.99076e-6},
+                          {-2.1829e-12, 6.9578e-10, 2.4156e-9, 2.85911e-9, 1.73423e-9}};
+  const double x = partial_pressure / 1.e6;
+  double coefs[5];
+  if (x <= xp[0]) {
+#pragma unroll
+    for (int d = 0; d < 5; d++) coefs[d] = c[d][0];
+  } else if (x >= xp[4]) {
+#pragma unroll
+    for (int d = 0; d < 5; d++) coefs[d] = c[d][4];
+  } else {
+    int i = 0;
+    while (i + 2 < 5 && x >= xp[i + 1]) i++;
+    const double xi = (x - xp[i]) / (xp[i + 1] - xp[i]);
+#pragma unroll
+    for (int d = 0; d < 5; d++) coefs[d] = (1.0 - xi) * c[d][i] + xi * c[d][i + 1];
+  }
+  viscosity = 1.e-5 * wb_polynomial<5>(coefs, temperature);
+  return 0;
+}
+
+// ncg_thermodynamics.F90:145-157
+WB_HD double wb_co2_mole_to_mass_fraction(double xmole) {
+  const double w = xmole * WB_CO2_MW;
+  return w / (w + (1.0 - xmole) * WB_WATER_MW);
 }
 
 // bulk_properties + phase_saturations + phase_properties for one cell:
@@ -220,6 +309,78 @@ WB_HD int wb_eos_properties(const WbEosParams &e, const double *primary,
     fl.ph[0].pc = 0.0;
     fl.ph[0].X[0] = 1.0;
     fl.ph[0].mu = wb_region_viscosity(th, p, fl.T, fl.P, rho);
+    return 0;
+  } else if (EOS == WB_EOS_WCE) {
+    // bulk_properties src/eos_wge.F90:350-389, phase_saturations :393-417, phase_properties :421-543
+    constexpr int NPH = WbEosTraits<EOS>::NPH, XG = WbEosTraits<EOS>::NC - 1;
+    fl.P = primary[0];
+    const int region = fl.region;
+    const double pg = primary[WbEosTraits<EOS>::NP - 1];
+    fl.pp[0] = fl.P - pg;
+    fl.pp[XG] = pg;
+    if (region == 4) err = wb_saturation_temperature(th, fl.pp[0], fl.T);
+    else fl.T = primary[1];
+    if (err) return err;
+    const int phases = wb_phase_composition(th, region, fl.P, fl.T);
+    if (phases <= 0) return 1;
+    fl.phases = phases;
+    double sl = fl.ph[0].sat, sv = fl.ph[1].sat;
+    if (region == 1) { sl = 1.0; sv = 0.0; }
+    else if (region == 2) { sl = 0.0; sv = 1.0; }
+    else if (region == 4) { sl = 1.0 - primary[1]; sv = primary[1]; }
+    fl.ph[0].sat = sl;
+    fl.ph[1].sat = sv;
+    double kr[2];
+    wb_relperm_values(e.relperm, sl, kr[0], kr[1]);
+    double gas_density_free, gas_enthalpy;
+    wb_co2_properties(pg, fl.T, gas_density_free, gas_enthalpy);
+#pragma unroll
+    for (int p = 0; p < NPH; p++) {
+      if (phases & (1 << p)) {
+        double water_pressure, capillary_pressure, henrys_constant = 0.0, energy_solution = 0.0;
+        if (p == 0) {
+          water_pressure = fl.P;
+          capillary_pressure = wb_cappress_value(e.cappress, sl, fl.T);
+          henrys_constant = wb_co2_henrys_constant(fl.T);
+          energy_solution = wb_co2_energy_solution(fl.T, henrys_constant);
+        } else {
+          water_pressure = fl.pp[0];
+          capillary_pressure = 0.0;
+        }
+        double water_density, water_u;
+        err = wb_region_properties(th, p + 1, water_pressure, fl.T, water_density, water_u);
+        if (err) return err;
+        // effective_properties: no free gas density in the liquid phase (ncg_thermodynamics.F90:315-340)
+        const double gas_density = (p == 0) ? 0.0 : gas_density_free;
+        // mass_fraction: ncg_thermodynamics.F90:279-311
+        double xg;
+        if (p == 0) {
+          xg = wb_co2_mole_to_mass_fraction(pg / henrys_constant);
+        } else {
+          const double total_density = gas_density + water_density;
+          xg = (total_density < 1.e-30) ? 0.0 : gas_density / total_density;
+        }
+        const double water_viscosity = wb_region_viscosity(th, p + 1, fl.T, fl.P, water_density);
+        if (p == 0) {
+          fl.ph[p].mu = water_viscosity;  // mixture_viscosity: ncg_co2_thermodynamics.F90:267-292
+        } else {
+          double gas_viscosity;
+          if (wb_co2_viscosity(pg, fl.T, gas_viscosity)) return 1;
+          fl.ph[p].mu = water_viscosity * (1.0 - xg) + gas_viscosity * xg;
+        }
+        fl.ph[p].rho = water_density + gas_density;
+        fl.ph[p].X[0] = 1.0 - xg;
+        fl.ph[p].X[XG] = xg;
+        fl.ph[p].kr = kr[p];
+        fl.ph[p].pc = capillary_pressure;
+        const double water_enthalpy = water_u + water_pressure / water_density;
+        fl.ph[p].h = water_enthalpy * (1.0 - xg) + (gas_enthalpy + energy_solution) * xg;
+        fl.ph[p].u = fl.ph[p].h - fl.P / fl.ph[p].rho;
+      } else {
+        fl.ph[p].rho = 0.0; fl.ph[p].u = 0.0; fl.ph[p].h = 0.0; fl.ph[p].kr = 0.0;
+        fl.ph[p].pc = 0.0; fl.ph[p].mu = 0.0; fl.ph[p].X[0] = 0.0; fl.ph[p].X[XG] = 0.0;
+      }
+    }
     return 0;
   } else {
     constexpr int NPH = WbEosTraits<EOS>::NPH;
@@ -382,6 +543,8 @@ WB_HD void wb_face_flux(const WbFaceGeom &g, const WbCellState<NC, NPH> &s1, con
 // (src/root_finder.F90:127-248 with the defaults of :76-79; src/eos_we.F90:530-553)
 struct WbSatLine {
   double p0, t0, p1, t1;
+  double g0, g1;  // gas partial pressure at both ends (eos_wge: f = P - Pg - Psat(T), src/eos_wge.F90:678-701)
+  bool gas;
 };
 WB_HD double wb_satline_f(const WbThermo &th, const WbSatLine &c, double x) {
   const double xi = (x - 0.0) / (1.0 - 0.0);
@@ -389,6 +552,10 @@ WB_HD double wb_satline_f(const WbThermo &th, const WbSatLine &c, double x) {
   const double T = (1.0 - xi) * c.t0 + xi * c.t1;
   double Ps = 0.0;
   wb_saturation_pressure(th, T, Ps);
+  if (c.gas) {
+    const double Pg = (1.0 - xi) * c.g0 + xi * c.g1;
+    return P - Pg - Ps;
+  }
   return P - Ps;
 }
 
@@ -507,7 +674,7 @@ WB_HD int wb_we_transition(const WbThermo &th, const double *old_primary, double
     if (err == 0) {
       if ((old_region == 1 && primary[0] < ps) || (old_region == 2 && primary[0] > ps)) {
         // transition_to_two_phase: src/eos_we.F90:220-268
-        WbSatLine c = {old_primary[0], old_primary[1], primary[0], primary[1]};
+        WbSatLine c = {old_primary[0], old_primary[1], primary[0], primary[1], 0.0, 0.0, false};
         double root;
         if (wb_brent_satline(th, c, root) == 0) {
           double pint;
@@ -540,6 +707,107 @@ WB_HD int wb_we_check_primary(const double *primary, int region) {
   } else {
     const double t = primary[1];
     if (t < 0.0 || t > 800.0) return 1;
+  }
+  return 0;
+}
+
+
+// 2-point table on x = [0, 1]: interpolate(xi) = find + interpolate_at_index, clamped outside [0, 1]
+// (src/interpolation.F90:202-306, 388-403)
+WB_HD double wb_interp01(double v0, double v1, double xi) {
+  if (xi <= 0.0) return v0;
+  if (xi >= 1.0) return v1;
+  const double w = (xi - 0.0) / (1.0 - 0.0);
+  return (1.0 - w) * v0 + w * v1;
+}
+
+// eos_wge%transition: src/eos_wge.F90:149-346.  primary = (P, T | Sv, Pg) unscaled, in/out.
+WB_HD int wb_wge_transition(const WbThermo &th, const double *old_primary, double *primary, int old_region,
+                            double old_T, int &region, bool &transition) {
+  const double small = 1.e-6;
+  int err = 0;
+  transition = false;
+  if (old_region == 4) {
+    const double sv = primary[1];
+    int new_region = 0;
+    if (sv < 0.0) new_region = 1;
+    else if (sv > 1.0) new_region = 2;
+    if (new_region) {
+      // transition_to_single_phase: :149-227
+      const double bound = (new_region == 1) ? 0.0 : 1.0;
+      const double pfac = (new_region == 1) ? 1.0 + small : 1.0 - small;
+      primary[2] = fmax(0.0, fmin(primary[2], primary[0]));
+      const double v1 = old_primary[1], v2 = primary[1];
+      const double vmax = fmax(fabs(v1), fabs(v2));
+      if (fabs(v2 - v1) >= 1.e-8 * vmax) {
+        const double vs1 = v1 / vmax, vs2 = v2 / vmax, ys = bound / vmax;
+        const double xq = (ys - vs1) / (vs2 - vs1);
+        const double xi = (1.0 - xq) * 0.0 + xq * 1.0;
+        const double pint = wb_interp01(old_primary[0], primary[0], xi);
+        const double gint = wb_interp01(old_primary[2], primary[2], xi);
+        const double water_pressure = pint - gint;
+        primary[0] = pfac * water_pressure + gint;
+        primary[2] = gint;
+        err = wb_saturation_temperature(th, water_pressure, primary[1]);
+        if (err == 0) {
+          region = new_region;
+          transition = true;
+        }
+      } else {
+        double old_ps;
+        err = wb_saturation_pressure(th, old_T, old_ps);
+        if (err == 0) {
+          primary[0] = pfac * old_ps + primary[2];
+          primary[1] = old_T;
+          region = new_region;
+          transition = true;
+        }
+      }
+    }
+  } else {
+    double ps;
+    err = wb_saturation_pressure(th, primary[1], ps);
+    if (err == 0) {
+      const double water_pressure = primary[0] - primary[2];
+      if ((old_region == 1 && water_pressure < ps) || (old_region == 2 && water_pressure > ps)) {
+        // transition_to_two_phase: :231-285
+        primary[2] = fmax(0.0, fmin(primary[2], primary[0]));
+        WbSatLine c = {old_primary[0], old_primary[1], primary[0], primary[1], old_primary[2], primary[2], true};
+        double root;
+        if (wb_brent_satline(th, c, root) == 0) {
+          primary[0] = wb_interp01(c.p0, c.p1, root);
+          primary[2] = wb_interp01(c.g0, c.g1, root);
+        } else {
+          primary[0] = ps + primary[2];
+        }
+        primary[1] = (old_region == 1) ? small : 1.0 - small;
+        region = 4;
+        transition = true;
+      }
+    }
+  }
+  return err;
+}
+
+// eos_wge%check_primary_variables: src/eos_wge.F90:573-635 (clamps the gas partial pressure; `changed` set)
+WB_HD int wb_wge_check_primary(double *primary, int region, bool &changed) {
+  const double small = 1.e-6;
+  changed = false;
+  if (!(primary[0] > 0.0)) return 1;
+  const double max_pp = (1.0 - small) * primary[0];
+  if (primary[2] > max_pp) {
+    primary[2] = max_pp;
+    changed = true;
+  } else if (primary[2] < 0.0) {
+    primary[2] = 0.0;
+    changed = true;
+  }
+  const double pw = primary[0] - primary[2];
+  if (pw > 100.e6) return 1;
+  if (region == 4) {
+    if (primary[1] < -1.0 || primary[1] > 2.0) return 1;
+  } else {
+    if (primary[1] < 0.0 || primary[1] > 800.0) return 1;
   }
   return 0;
 }

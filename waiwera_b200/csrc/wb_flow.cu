@@ -21,13 +21,18 @@ __device__ __forceinline__ void load_state(const double *__restrict__ st, size_t
   s.phases = (int)p[3 * ncell];
 #pragma unroll
   for (int q = 0; q < NPH; q++) {
-    const double *pp = p + (size_t)(4 + q * 5) * ncell;
+    const double *pp = p + (size_t)(4 + q * (5 + (NC > 1 ? NC : 0))) * ncell;
     s.rho[q] = pp[0];
     s.sat[q] = pp[ncell];
     s.pc[q] = pp[2 * ncell];
     s.mob[q] = pp[3 * ncell];
     s.h[q] = pp[4 * ncell];
-    s.X[q][0] = (s.phases & (1 << q)) ? 1.0 : 0.0;  // single component
+    if (NC == 1) {
+      s.X[q][0] = (s.phases & (1 << q)) ? 1.0 : 0.0;  // single component
+    } else {
+#pragma unroll
+      for (int k = 0; k < NC; k++) s.X[q][k] = pp[(size_t)(5 + k) * ncell];
+    }
   }
 }
 
@@ -41,12 +46,16 @@ __device__ __forceinline__ void store_state(double *__restrict__ st, size_t ncel
   p[3 * ncell] = (double)s.phases;
 #pragma unroll
   for (int q = 0; q < NPH; q++) {
-    double *pp = p + (size_t)(4 + q * 5) * ncell;
+    double *pp = p + (size_t)(4 + q * (5 + (NC > 1 ? NC : 0))) * ncell;
     pp[0] = s.rho[q];
     pp[ncell] = s.sat[q];
     pp[2 * ncell] = s.pc[q];
     pp[3 * ncell] = s.mob[q];
     pp[4 * ncell] = s.h[q];
+    if (NC > 1) {
+#pragma unroll
+      for (int k = 0; k < NC; k++) pp[(size_t)(5 + k) * ncell] = s.X[q][k];
+    }
   }
 }
 
@@ -447,13 +456,20 @@ __global__ void k_transitions(const __grid_constant__ WbEosParams e, const Trans
     wb_unscale<NP>(e, yo, oreg, old_primary);
     int new_region = region;
     bool transition = false;
-    int err = wb_we_transition(e.thermo, old_primary, primary, oreg, a.T_iter[c], new_region, transition);
-    if (err == 0) err = wb_we_check_primary(primary, new_region);
+    int err;
+    bool changed = false;
+    if (EOS == WB_EOS_WCE) {
+      err = wb_wge_transition(e.thermo, old_primary, primary, oreg, a.T_iter[c], new_region, transition);
+      if (err == 0) err = wb_wge_check_primary(primary, new_region, changed);  // may clamp Pg (eos_wge.F90:594-606)
+    } else {
+      err = wb_we_transition(e.thermo, old_primary, primary, oreg, a.T_iter[c], new_region, transition);
+      if (err == 0) err = wb_we_check_primary(primary, new_region);
+    }
     if (err) {
       atomicMax(&a.flags[0], 1);
       return;
     }
-    if (transition) {
+    if (transition || changed) {  // changed_y: flow_simulation.F90:2521-2545
       a.region[c] = new_region;
       wb_scale<NP>(e, primary, new_region, yn);
 #pragma unroll
@@ -558,10 +574,11 @@ __global__ void k_unpack_yr(const double *__restrict__ in, int c0, int n, int np
 
 // ================================================================ host side
 
-#define DISPATCH_EOS(ctx, CALL)                         \
-  do {                                                  \
-    if ((ctx)->prm.eos == WB_EOS_WE) { CALL(WB_EOS_WE); } \
-    else { CALL(WB_EOS_W); }                            \
+#define DISPATCH_EOS(ctx, CALL)                                  \
+  do {                                                           \
+    if ((ctx)->prm.eos == WB_EOS_WE) { CALL(WB_EOS_WE); }        \
+    else if ((ctx)->prm.eos == WB_EOS_WCE) { CALL(WB_EOS_WCE); } \
+    else { CALL(WB_EOS_W); }                                     \
   } while (0)
 
 template <class T> static int dev_alloc(T **p, size_t n) {

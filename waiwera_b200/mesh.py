@@ -229,13 +229,26 @@ def hydrostatic_state(mesh, seed=SEED, two_phase_layers=0, thermo_psat=None):
     return primary, region
 
 
-def scale_primaries(primary, region, pressure_scale=1e6, temperature_scale=1e2):
-    """eos%scale for eos_we / eos_w (src/eos.F90:186-196, src/eos_we.F90:104-109, src/eos_w.F90: pressure only)."""
+def scale_primaries(primary, region, pressure_scale=1e6, temperature_scale=1e2, partial_pressure_scale=0.0):
+    """eos%scale for eos_we / eos_w / eos_wce (src/eos.F90:186-196, src/eos_we.F90:104-109, src/eos_w.F90: pressure
+    only; third primary of eos_wce: gas partial pressure, adaptive Pg/P scaling unless a fixed scale is given,
+    src/eos_wge.F90:96-110, 639-655)."""
     y = np.array(primary, float, copy=True)
+    if y.shape[1] > 2:
+        y[:, 2] = y[:, 2] / (partial_pressure_scale if partial_pressure_scale > 0 else y[:, 0])
     y[:, 0] /= pressure_scale
     if y.shape[1] > 1:
         y[:, 1] = np.where(region == 4, y[:, 1], y[:, 1] / temperature_scale)
     return y
+
+
+def wce_state(mesh, seed=SEED, two_phase_layers=0, thermo_psat=None, pco2=(1.0e4, 5.0e5)):
+    """SURVEY 8(d) config 4 state for eos_wce: the eos_we hydrostatic state for the water partial pressure plus a
+    CO2 partial pressure U(pco2) per cell; P = P_water + P_CO2.  Returns unscaled primaries [n,3], regions [n]."""
+    primary, region = hydrostatic_state(mesh, seed=seed, two_phase_layers=two_phase_layers, thermo_psat=thermo_psat)
+    rng = np.random.default_rng(seed + 2)
+    pg = rng.uniform(pco2[0], pco2[1], len(primary))
+    return np.stack([primary[:, 0] + pg, primary[:, 1], pg], 1), region
 
 
 def cube_blocks(mesh, size):
