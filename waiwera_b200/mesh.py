@@ -43,6 +43,9 @@ class Mesh:
     send_idx: np.ndarray = None
     recv_ptr: np.ndarray = None
     recv_idx: np.ndarray = None
+    # MINC (add_minc): number of matrix levels and number of fracture (original) cells of the serial mesh
+    minc_levels: int = 0
+    minc_base: int = 0
 
     @property
     def nface(self):
@@ -255,6 +258,127 @@ def cube_blocks(mesh, size):
     """block-Jacobi sub-domain of every owned cell: size^3 boxes of the structured grid (numbered per rank)"""
     nx, ny, nz = mesh.dims
     idx = mesh.natural[:mesh.nowned]
+    i, j, k = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+    bx, by = -(-nx // size), -(-ny // size)
+    key = (i // size) + bx * ((j // size) + by * (k // size))
+    _, inv = np.unique(key, return_inverse=True)
+    return inv.astype(np.int32)
+
+
+# ---------------------------------------------------------------- MINC (dual porosity)
+
+def minc_geometry(volumes, spacing, fracture_connection_distance=0.0):
+    """MINC 'nested cube' geometry (src/minc.F90:393-544): volumes = (fracture, matrix level 1, ...) fractions summing
+    to 1 (normalised if not), spacing = fracture spacing per set of planes (1-3 values).  Returns
+    (volume fractions, connection_area[num_levels], connection_distance[num_levels + 1])."""
+    vol = np.asarray(volumes, float)
+    vol = vol / vol.sum()
+    sp = np.atleast_1d(np.asarray(spacing, float))
+    nlev = len(vol) - 1
+
+    def proximity(d):  # :393-411
+        fout = 1.0 - 2.0 * d / sp
+        return 1.0 if (fout < 0).any() else 1.0 - np.prod(fout)
+
+    def proximity_derivative(d):  # :415-433
+        fout = 1.0 - 2.0 * d / sp
+        if (fout < 0).any():
+            return 0.0
+        excl = np.array([np.prod(np.delete(fout, i)) for i in range(len(fout))])
+        return 2.0 * np.sum(excl / sp)
+
+    def inner_connection_distance(x):  # :437-460 (Pruess 1983)
+        u = sp - 2.0 * x
+        if len(u) == 1:
+            return u[0] / 6.0
+        if len(u) == 2:
+            return 0.25 * np.prod(u) / np.sum(u)
+        pair = sum(u[i] * u[(i + 1) % 3] for i in range(3))
+        return 0.3 * np.prod(u) / pair
+
+    vmatrix = 1.0 - vol[0]
+    volsum = np.cumsum(vol[1:]) / vmatrix
+    dist = np.zeros(nlev + 1)
+    area = np.zeros(nlev)
+    x = 0.0
+    dist[0] = fracture_connection_distance
+    area[0] = vmatrix * proximity_derivative(x)
+    xr = vol[1] / area[0]
+    for i in range(nlev - 1):  # :495-517: bracket, then root of proximity(x) - volsum(i) (Brent, tolerance 1e-8)
+        xl = x
+        while proximity(xr) - volsum[i] < 0.0:
+            xr *= 2.0
+        lo, hi = xl, xr
+        for _ in range(200):  # bisection to machine precision: same root as the reference's Brent to its 1e-8 tolerance
+            mid = 0.5 * (lo + hi)
+            if proximity(mid) - volsum[i] < 0.0:
+                lo = mid
+            else:
+                hi = mid
+        x = 0.5 * (lo + hi)
+        dist[i + 1] = 0.5 * (x - xl)
+        area[i + 1] = vmatrix * proximity_derivative(x)
+    dist[nlev] = inner_connection_distance(x)
+    return vol, area, dist
+
+
+def add_minc(mesh, volumes=(0.1, 0.9), spacing=(50.0, 50.0, 50.0), matrix_permeability_factor=1.0):
+    """MINC mesh on top of a serial structured mesh (all cells in the MINC zone), in the reference's numbering
+    (src/mesh.F90:2286-2380): original cells keep their index and become the fracture cells, then all level-1
+    matrix cells (in cell order), then all level-2 cells, ...; one new flux face per MINC cell with support
+    (level m-1 cell, level m cell), appended after the original faces.  Geometry per src/mesh.F90:3120-3160:
+    fracture volume = V*volume(1), level-m volume = V*volume(m+1), face area = V*connection_area(m), distance =
+    connection_distance(m:m+1), normal = 0, gravity_normal = 0, permeability_direction = 1."""
+    assert mesh.nranks == 1 and not mesh.boundary, "add_minc works on a serial mesh without boundary ghosts"
+    vol, area, dist = minc_geometry(volumes, spacing)
+    nlev = len(vol) - 1
+    n = mesh.ninterior
+    V = mesh.cell_geom[:n, 3].copy()
+    cg = [mesh.cell_geom[:n].copy()]
+    cg[0][:, 3] = V * vol[0]
+    rock = [mesh.rock[:n].copy()]
+    fcs, fgs = [mesh.face_cells], [mesh.face_geom]
+    for m in range(1, nlev + 1):
+        g = mesh.cell_geom[:n].copy()
+        g[:, 3] = V * vol[m]
+        cg.append(g)
+        r = mesh.rock[:n].copy()
+        r[:, 0:3] *= matrix_permeability_factor
+        rock.append(r)
+        fg = np.zeros((n, 12))
+        fg[:, 0] = V * area[m - 1]
+        fg[:, 1] = dist[m - 1]
+        fg[:, 2] = dist[m]
+        fg[:, 3] = dist[m - 1] + dist[m]
+        fg[:, 8:11] = mesh.cell_geom[:n, :3]
+        fg[:, 11] = 1.0
+        inner = np.arange(n, dtype=np.int64) + (m - 1) * n
+        fcs.append(np.stack([inner, inner + n], 1).astype(np.int32))
+        fgs.append(fg)
+    ntot = n * (nlev + 1)
+    natural = np.arange(ntot, dtype=np.int64)
+    out = Mesh(ncell=ntot, ninterior=ntot, nowned=ntot, face_cells=np.ascontiguousarray(np.concatenate(fcs).astype(np.int32)),
+               face_geom=np.ascontiguousarray(np.concatenate(fgs)), cell_geom=np.ascontiguousarray(np.concatenate(cg)),
+               rock=np.ascontiguousarray(np.concatenate(rock)), dims=mesh.dims, natural=natural, ncell_global=ntot,
+               minc_levels=nlev, minc_base=n)
+    return out
+
+
+def minc_owner(mesh, parts):
+    """owner rank of every cell of a MINC mesh: a matrix cell stays with its fracture cell (src/mesh.F90:2201-2282)"""
+    n = mesh.minc_base
+    base = Mesh(ncell=n, ninterior=n, nowned=n, face_cells=None, face_geom=None, cell_geom=None, rock=None,
+                dims=mesh.dims, natural=np.arange(n, dtype=np.int64))
+    own = box_owner(base, parts)
+    return np.tile(own, mesh.minc_levels + 1)
+
+
+def minc_cube_blocks(mesh, size):
+    """block-Jacobi sub-domains of a (possibly partitioned) MINC mesh: size^3 boxes of fracture cells, every
+    matrix cell in the sub-domain of its fracture cell"""
+    nx, ny, nz = mesh.dims
+    n = nx * ny * nz
+    idx = mesh.natural[:mesh.nowned] % n
     i, j, k = idx % nx, (idx // nx) % ny, idx // (nx * ny)
     bx, by = -(-nx // size), -(-ny // size)
     key = (i // size) + bx * ((j // size) + by * (k // size))
