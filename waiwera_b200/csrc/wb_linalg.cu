@@ -41,7 +41,7 @@ __device__ __forceinline__ double4 ld256(const double *p) {
   asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
 }
-__device__ __forceinline__ double4 ld256_stream(const double *p) {  // evict-first: the Krylov basis is read once per pass
+__device__ __forceinline__ double4 ld256_stream(const double *p) {  // evict-first variant (single-use streams)
   double4 r;
   asm("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const bool on = e0[r] < e1[r];
-      col[r] = on ? a.colidx[e0[r]] : -1;
+      col[r] = on ? __ldcs(a.colidx + e0[r]) : -1;  // evict-first like the values: single-use stream
       if (BS == 2) {
         double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
         if (on) {
@@ -557,11 +557,16 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// bulk copy global -> shared, completing on an mbarrier; L2 evict-first: the factor stream is read once per
+// apply and must not displace the Krylov basis from L2
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
@@ -1369,14 +1374,18 @@ __global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
   for (int j = 0; j < NVT; j++) acc[j] = 0.0;
   if (VEC) {
     const int n4 = a.n >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    // Traversal from the END of the vectors: the multi-axpy that ran just before (previous iteration) went
+    // front to back, so the tail of every basis vector is what the 126 MB L2 still holds; the two passes
+    // zig-zag and each one starts on the other's most recently used lines.  The basis is loaded with the
+    // default L2 policy, the matrix and factor streams are evict-first.
+    for (int i = n4 - 1 - (int)(blockIdx.x * blockDim.x + threadIdx.x); i >= 0; i -= (int)(gridDim.x * blockDim.x)) {
       const double4 wi = ld256(a.w + 4 * (size_t)i);
       double4 v[NVT];
 #pragma unroll
       for (int g = 0; g < NVT; g++) {
         // vectors past nv re-read the last one (same cache line, no extra traffic); their sums are dropped
         const int j = g < nv ? g : nv - 1;
-        v[g] = ld256_stream(V + (size_t)j * a.ldv + 4 * (size_t)i);
+        v[g] = ld256(V + (size_t)j * a.ldv + 4 * (size_t)i);
       }
 #pragma unroll
       for (int g = 0; g < NVT; g++) {
@@ -1458,7 +1467,7 @@ __global__ void __launch_bounds__(256, 2) k_maxpy_all(const MaxpyArgs a) {
 #pragma unroll
         for (int g = 0; g < G; g++) {
           const int j = (j0 + g) < a.nv ? (j0 + g) : a.nv - 1;  // cf is zero past nv
-          v[g] = ld256_stream(a.V + (size_t)j * a.ldv + 4 * (size_t)i);
+          v[g] = ld256(a.V + (size_t)j * a.ldv + 4 * (size_t)i);
         }
 #pragma unroll
         for (int g = 0; g < G; g++) {
