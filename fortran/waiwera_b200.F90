@@ -71,7 +71,7 @@ module waiwera_b200
 
   public :: wb_last_error, wb_version, wb_create, wb_destroy, wb_num_primary, wb_fluid_dof, wb_set_mesh, &
        wb_jacobian_pattern, wb_jacobian_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
-       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
+       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
        wb_mat_set_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
@@ -195,6 +195,15 @@ module waiwera_b200
        type(c_ptr), value :: ghost_cells, interior_cells, primary, region
        integer(c_int) :: ierr
      end function wb_set_boundaries
+
+     ! source_network%assemble_cell_inflows for fixed-rate sources (src/source.F90:375-480)
+     function wb_set_sources(ctx, n, cell, component, rate, enthalpy) bind(C, name="wb_set_sources") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: n
+       type(c_ptr), value :: cell, component, rate, enthalpy
+       integer(c_int) :: ierr
+     end function wb_set_sources
 
      function wb_get_fluid(ctx, fluid) bind(C, name="wb_get_fluid") result(ierr)
        import :: c_int, c_ptr

@@ -151,6 +151,14 @@ int wb_set_boundary(wb_ctx *ctx, int ghost_cell, int interior_cell, const double
 /* the same for n boundary cells at once: primary[n*np], region[n] */
 int wb_set_boundaries(wb_ctx *ctx, int n, const int32_t *ghost_cells, const int32_t *interior_cells,
                       const double *primary, const int32_t *region);
+/* Fixed-rate sources / sinks (source%update_flow src/source.F90:375-480 and
+   source_network%assemble_cell_inflows src/source_network.F90:296-355, called from cell_inflows
+   src/flow_simulation.F90:1468-1473): rhs_i += flow / V_i.  cell: local owned cell; component: 1-based
+   mass component, np = heat, 0 = all mass components (production only); rate > 0 injects `rate` of that
+   component with specific enthalpy `enthalpy`, rate < 0 produces by mobility-weighted phase flow
+   fractions (src/fluid.F90:374-456).  n = 0 removes all sources. */
+int wb_set_sources(wb_ctx *ctx, int n, const int32_t *cell, const int32_t *component, const double *rate,
+                   const double *enthalpy);
 /* current fluid records of all local cells, reference AoS layout [ncell*fluid_dof] */
 int wb_get_fluid(wb_ctx *ctx, double *fluid);
 int wb_get_regions(wb_ctx *ctx, int32_t *region);

@@ -204,6 +204,10 @@ double *wo_flow_flux(wo_flow *f);           /* nface * (np+nmobile) */
 int wo_flow_fluid_init(wo_flow *f, const double *y, const int32_t *region);
 /* Dirichlet boundary ghost cell (mesh.F90:1185-1202): rock copied from interior cell, fluid from unscaled primary */
 int wo_flow_set_boundary(wo_flow *f, int ghost_cell, int interior_cell, const double *primary, int region);
+/* fixed-rate sources / sinks (src/source.F90:375-480): local owned cell, component (1-based; 0 = all mass
+   components for production; np = heat), rate (< 0 production), injection enthalpy */
+void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *component, const double *rate,
+                         const double *enthalpy);
 /* pre_eval: update mask from perturbed block columns (NULL/0 => unperturbed) + fluid_properties */
 int wo_flow_pre_eval(wo_flow *f, const double *y, const int32_t *perturbed, int nperturbed);
 int wo_flow_cell_balances(wo_flow *f, double *lhs);

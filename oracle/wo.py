@@ -129,6 +129,7 @@ def lib():
         "wo_flow_flux": (c_dp, [vp]),
         "wo_flow_fluid_init": (i, [vp, c_dp, c_ip]),
         "wo_flow_set_boundary": (i, [vp, i, i, c_dp, i]),
+        "wo_flow_set_sources": (None, [vp, i, c_ip, c_ip, c_dp, c_dp]),
         "wo_flow_pre_eval": (i, [vp, c_dp, c_ip, i]),
         "wo_flow_cell_balances": (i, [vp, c_dp]),
         "wo_flow_cell_inflows": (i, [vp, c_dp]),
@@ -289,6 +290,13 @@ class Flow:
         r = np.zeros(self.ncell, np.int32)
         self.L.wo_flow_get_regions(self.h, ip(r))
         return r
+
+    def set_sources(self, cells, components, rates, enthalpies):
+        c = np.ascontiguousarray(cells, np.int32)
+        k = np.ascontiguousarray(components, np.int32)
+        r = np.ascontiguousarray(rates, np.float64)
+        h = np.ascontiguousarray(enthalpies, np.float64)
+        self.L.wo_flow_set_sources(self.h, len(c), ip(c), ip(k), dp(r), dp(h))
 
     def residual(self, y, lhs_last, dt, perturbed=None):
         lhs, rhs, r = np.zeros(self.n), np.zeros(self.n), np.zeros(self.n)

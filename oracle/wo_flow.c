@@ -27,6 +27,10 @@ struct wo_flow {
   double *update;   /* ncell: +1 / -1 */
   double *rock;     /* private copy so boundary ghost rock can be set */
   int unperturbed;
+  /* fixed-rate sources / sinks (src/source.F90:375-480), in input order */
+  int nsrc;
+  int32_t *src_cell, *src_component;
+  double *src_rate, *src_enthalpy;
 };
 
 static inline int nint_(double x) { return (int)lround(x); }
@@ -62,8 +66,75 @@ wo_flow *wo_flow_create(const wo_params *prm, const wo_mesh *mesh) {
   return f;
 }
 
+/* Fixed-rate sources: cell (local owned index), component (1-based; 0 = all mass components, production
+   only; np = heat), rate (kg/s or W; < 0 production), injection enthalpy (J/kg). */
+void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *component, const double *rate,
+                         const double *enthalpy) {
+  free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
+  f->nsrc = n;
+  f->src_cell = (int32_t *)malloc((n + 1) * sizeof(int32_t));
+  f->src_component = (int32_t *)malloc((n + 1) * sizeof(int32_t));
+  f->src_rate = (double *)malloc((n + 1) * sizeof(double));
+  f->src_enthalpy = (double *)malloc((n + 1) * sizeof(double));
+  memcpy(f->src_cell, cell, n * sizeof(int32_t));
+  memcpy(f->src_component, component, n * sizeof(int32_t));
+  memcpy(f->src_rate, rate, n * sizeof(double));
+  memcpy(f->src_enthalpy, enthalpy, n * sizeof(double));
+}
+
+/* source%update_flow: src/source.F90:457-480 with update_injection_mass_flow :385-399,
+   update_production_mass_flow :403-438 (fluid%phase_flow_fractions / component_flow_fractions /
+   specific_enthalpy src/fluid.F90:374-456) and update_energy_flow :442-453 */
+static void source_flow(const wo_flow *f, int s, double *flow) {
+  int np = f->np, nc = f->nc;
+  int component = f->src_component[s];
+  double rate = f->src_rate[s], enthalpy = 0.0;
+  for (int k = 0; k < np; k++) flow[k] = 0.0;
+  if (rate > 0.0) {
+    if (component > 0) {
+      enthalpy = f->src_enthalpy[s];
+      flow[component - 1] = rate;
+    }
+  } else {
+    const double *fl = f->current_fluid + (size_t)f->src_cell[s] * f->dof;
+    int phases = nint_(fl[4]);
+    double frac[2] = {0.0, 0.0};
+    if (component < np) {
+      double sum = 0.0;
+      for (int p = 0; p < f->nphase; p++) {
+        const double *ph = fl + (7 + nc - 1) + p * (8 + nc - 1);
+        if (phases & (1 << p)) frac[p] = ph[3] * ph[0] / ph[1]; /* mobility kr*rho/mu */
+        sum += frac[p];
+      }
+      for (int p = 0; p < f->nphase; p++) frac[p] = frac[p] / sum;
+      if (!f->isothermal) {
+        for (int p = 0; p < f->nphase; p++) {
+          const double *ph = fl + (7 + nc - 1) + p * (8 + nc - 1);
+          if (phases & (1 << p)) enthalpy = enthalpy + frac[p] * ph[5];
+        }
+      }
+    }
+    if (component <= 0) {
+      double cf[WO_MAX_NC], csum = 0.0;
+      for (int c = 0; c < nc; c++) {
+        cf[c] = 0.0;
+        for (int p = 0; p < f->nphase; p++) {
+          const double *ph = fl + (7 + nc - 1) + p * (8 + nc - 1);
+          if (phases & (1 << p)) cf[c] = cf[c] + frac[p] * ph[7 + c];
+        }
+        csum += cf[c];
+      }
+      for (int c = 0; c < nc; c++) flow[c] = rate * (cf[c] / csum);
+    } else {
+      flow[component - 1] = rate;
+    }
+  }
+  if (!f->isothermal && component < np) flow[np - 1] = flow[np - 1] + enthalpy * rate;
+}
+
 void wo_flow_destroy(wo_flow *f) {
   if (!f) return;
+  free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
   wo_eos_destroy(f->eos);
   free(f->fluid);
   free(f->current_fluid);
@@ -162,7 +233,8 @@ int wo_flow_cell_balances(wo_flow *f, double *lhs) {
   return 0;
 }
 
-/* cell_inflows: flow_simulation.F90:1334-1485 (no sources) */
+/* cell_inflows: flow_simulation.F90:1334-1485, then the source terms (:1468-1473,
+   source_network.F90:296-355: inflow = inflow + flow / volume, in source order) */
 int wo_flow_cell_inflows(wo_flow *f, double *rhs) {
   const wo_mesh *m = &f->mesh;
   int np = f->np, nf = f->nflux;
@@ -192,6 +264,15 @@ int wo_flow_cell_inflows(wo_flow *f, double *rhs) {
         double *inflow = rhs + (size_t)c * np;
         for (int k = 0; k < np; k++) inflow[k] = inflow[k] + flux_sign[i] * flow[k] / vol;
       }
+    }
+  }
+  for (int s = 0; s < f->nsrc; s++) {
+    int c = f->src_cell[s];
+    if (c >= 0 && c < m->nowned) {
+      double vol = m->cell_geom[4 * (size_t)c + 3];
+      double *inflow = rhs + (size_t)c * np;
+      source_flow(f, s, flow);
+      for (int k = 0; k < np; k++) inflow[k] = inflow[k] + flow[k] / vol;
     }
   }
   return 0;

@@ -71,6 +71,7 @@ SIGNATURES = {
     "wb_fluid_init": (i, [vp, vp, vp]),
     "wb_set_boundary": (i, [vp, i, i, vp, i]),
     "wb_set_boundaries": (i, [vp, i, vp, vp, vp, vp]),
+    "wb_set_sources": (i, [vp, i, vp, vp, vp, vp]),
     "wb_get_fluid": (i, [vp, vp]),
     "wb_get_regions": (i, [vp, vp]),
     "wb_pre_iteration": (i, [vp]),

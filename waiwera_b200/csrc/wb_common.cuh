@@ -130,6 +130,10 @@ struct wb_ctx {
   double *d_yloc = nullptr;      // [ninterior*np] primaries incl. partition ghosts
   double *d_balances = nullptr;  // [nowned*np] lhs of the last unperturbed evaluation
   int eval_variant = 0;          // state slot of the last wb_pre_eval (0 unperturbed, 1 perturbed scratch)
+  // fixed-rate sources / sinks, sorted by cell
+  int nsrc = 0;
+  int32_t *d_src_head = nullptr, *d_src_cell = nullptr, *d_src_comp = nullptr;
+  double *d_src_rate = nullptr, *d_src_enth = nullptr;
   int *d_flags = nullptr;        // [8] device flags (error, changed_y, changed_search, ...)
   int *h_flags = nullptr;        // pinned mirror
 

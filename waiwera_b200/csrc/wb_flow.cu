@@ -223,6 +223,80 @@ __global__ void k_boundary(const __grid_constant__ WbEosParams e, const Boundary
     store_state(a.state + (size_t)slot * WbStateLayout<NC, NPH>::NF * nc, nc, c, s);
 }
 
+// ---------------------------------------------------------------- sources / sinks
+
+// fixed-rate sources sorted by cell (stable: input order inside a cell); head[c] = first source of owned cell c or -1
+struct WbSources {
+  const int32_t *head, *cell, *comp;
+  const double *rate, *enth;
+  int n;
+};
+
+// adds the inflow of every source of cell i, in source order (src/source_network.F90:296-355: inflow += flow / V);
+// source%update_flow src/source.F90:457-480: injection :385-399, production by mobility-weighted phase flow
+// fractions :403-438 (src/fluid.F90:374-456), energy :442-453
+template <int NP, int NC, int NPH>
+__device__ __forceinline__ void source_terms(const WbSources &S, int i, const WbCellState<NC, NPH> &s, double vol,
+                                             double *acc) {
+  if (!S.head) return;
+  int k = S.head[i];
+  if (k < 0) return;
+  for (; k < S.n && S.cell[k] == i; k++) {
+    const int component = S.comp[k];
+    const double rate = S.rate[k];
+    double flow[NP], enthalpy = 0.0;
+#pragma unroll
+    for (int q = 0; q < NP; q++) flow[q] = 0.0;
+    if (rate > 0.0) {
+      if (component > 0) {
+        enthalpy = S.enth[k];
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+          if (q == component - 1) flow[q] = rate;
+      }
+    } else {
+      double frac[NPH];
+#pragma unroll
+      for (int p = 0; p < NPH; p++) frac[p] = 0.0;
+      if (component < NP) {
+        double sum = 0.0;
+#pragma unroll
+        for (int p = 0; p < NPH; p++) {
+          if (s.phases & (1 << p)) frac[p] = s.mob[p];
+          sum += frac[p];
+        }
+#pragma unroll
+        for (int p = 0; p < NPH; p++) frac[p] = frac[p] / sum;
+        if (NP != NC) {
+#pragma unroll
+          for (int p = 0; p < NPH; p++)
+            if (s.phases & (1 << p)) enthalpy = enthalpy + frac[p] * s.h[p];
+        }
+      }
+      if (component <= 0) {
+        double cf[NC], csum = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          cf[c] = 0.0;
+#pragma unroll
+          for (int p = 0; p < NPH; p++)
+            if (s.phases & (1 << p)) cf[c] = cf[c] + frac[p] * s.X[p][c];
+          csum += cf[c];
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) flow[c] = rate * (cf[c] / csum);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+          if (q == component - 1) flow[q] = rate;
+      }
+    }
+    if (NP != NC && component < NP) flow[NP - 1] = flow[NP - 1] + enthalpy * rate;
+#pragma unroll
+    for (int q = 0; q < NP; q++) acc[q] = acc[q] + flow[q] / vol;
+  }
+}
+
 // ---------------------------------------------------------------- K3: inflows + BE residual
 
 struct ResidualArgs {
@@ -235,6 +309,7 @@ struct ResidualArgs {
   double *lhs, *rhs, *r;   // any may be null; AoS [nowned*np]
   double dt;
   int ncell, nowned, nface;
+  WbSources src;
 };
 
 // inflow term of one face seen from cell i (src/flow_simulation.F90:1445-1455):
@@ -276,6 +351,7 @@ __global__ void __launch_bounds__(128) k_residual(const ResidualArgs a) {
 #pragma unroll
     for (int k = 0; k < NP; k++) acc[k] = acc[k] + term[k];
   }
+  source_terms<NP, NC, NPH>(a.src, i, si, vol, acc);
 #pragma unroll
   for (int k = 0; k < NP; k++) {
     const double L = a.Lvar[(size_t)k * a.nowned + i];
@@ -301,6 +377,7 @@ struct JacArgs {
   double *val;  // BAIJ blocks, column-major bs x bs
   double dt;
   int ncell, ninterior, nowned, nface;
+  WbSources src;
 };
 
 // Thread per owned cell (= block row).  Row i of the FD-coloured Jacobian only ever sees one
@@ -343,6 +420,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const JacArgs a) {
         for (int k = 0; k < NP; k++) acc[k] = acc[k] + t[m][k];
       }
     }
+    source_terms<NP, NC, NPH>(a.src, i, s0, vol, acc);
 #pragma unroll
     for (int k = 0; k < NP; k++) F0[k] = (L0[k] + (-1.0) * Ll[k]) + (-a.dt) * acc[k];
   }
@@ -368,6 +446,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const JacArgs a) {
           for (int k = 0; k < NP; k++) acc[k] = acc[k] + term[k];
         }
       }
+      source_terms<NP, NC, NPH>(a.src, i, sv, vol, acc);
       const double vscale = 1.0 / a.dx[(size_t)v * a.ninterior + i];
 #pragma unroll
       for (int k = 0; k < NP; k++) {
@@ -406,6 +485,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const JacArgs a) {
               for (int k = 0; k < NP; k++) acc[k] = acc[k] + (q == m ? term[k] : t[q][k]);
             }
           }
+          source_terms<NP, NC, NPH>(a.src, i, s0, vol, acc);
           const double vscale = 1.0 / a.dx[(size_t)v * a.ninterior + o];
 #pragma unroll
           for (int k = 0; k < NP; k++) {
@@ -580,6 +660,11 @@ __global__ void k_unpack_yr(const double *__restrict__ in, int c0, int n, int np
     else if ((ctx)->prm.eos == WB_EOS_WCE) { CALL(WB_EOS_WCE); } \
     else { CALL(WB_EOS_W); }                                     \
   } while (0)
+
+static WbSources wb_sources_args(const wb_ctx *c) {
+  WbSources S = {c->nsrc > 0 ? c->d_src_head : nullptr, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth, c->nsrc};
+  return S;
+}
 
 template <class T> static int dev_alloc(T **p, size_t n) {
   WB_CUDA(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
@@ -842,11 +927,48 @@ static int launch_residual(wb_ctx *c, int slot, const double *d_lhs_last, double
   a.face = c->d_face; a.vol = c->d_vol; a.cf_ptr = c->d_cf_ptr; a.cf_face = c->d_cf_face; a.cf_other = c->d_cf_other;
   a.lhs_last = d_lhs_last; a.lhs = d_lhs; a.rhs = d_rhs; a.r = d_r; a.dt = dt;
   a.ncell = c->ncell; a.nowned = c->nowned; a.nface = c->nface;
+  a.src = wb_sources_args(c);
 #define CALL(E) k_residual<E><<<wb_grid(c->nowned, 128), 128, 0, c->stream>>>(a)
   DISPATCH_EOS(c, CALL);
 #undef CALL
   WB_LAUNCH(c);
   WB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- sources ---------------------------------------------------------------------------------
+// (source_network%assemble_cell_inflows, src/flow_simulation.F90:1468-1473)
+extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32_t *component, const double *rate,
+                              const double *enthalpy) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CHECK(c->ncell > 0, "wb_set_sources: no mesh");
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  void *old[] = {c->d_src_head, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth};
+  for (void *p : old) cudaFree(p);
+  c->d_src_head = c->d_src_cell = c->d_src_comp = nullptr;
+  c->d_src_rate = c->d_src_enth = nullptr;
+  c->nsrc = 0;
+  if (n <= 0) return 0;
+  std::vector<int> order(n);
+  for (int k = 0; k < n; k++) {
+    WB_CHECK(cell[k] >= 0 && cell[k] < c->nowned, "wb_set_sources: source %d is not in an owned cell", k);
+    WB_CHECK(component[k] >= 0 && component[k] <= c->np, "wb_set_sources: source %d: bad component %d", k, component[k]);
+    order[k] = k;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cell[x] < cell[y]; });
+  std::vector<int32_t> head(c->nowned, -1), sc(n), sk(n);
+  std::vector<double> sr(n), se(n);
+  for (int k = 0; k < n; k++) {
+    const int o = order[k];
+    sc[k] = cell[o]; sk[k] = component[o]; sr[k] = rate[o]; se[k] = enthalpy[o];
+    if (head[sc[k]] < 0) head[sc[k]] = k;
+  }
+  WB_TRY(dev_upload(&c->d_src_head, head));
+  WB_TRY(dev_upload(&c->d_src_cell, sc));
+  WB_TRY(dev_upload(&c->d_src_comp, sk));
+  WB_TRY(dev_upload(&c->d_src_rate, sr));
+  WB_TRY(dev_upload(&c->d_src_enth, se));
+  c->nsrc = n;
   return 0;
 }
 
@@ -1151,6 +1273,7 @@ int wb_jacobian_be_dev(wb_ctx *c, const double *d_y, const double *d_lhs_last, d
   a.lhs_last = d_lhs_last; a.cf_ptr = c->d_cf_ptr; a.cf_face = c->d_cf_face; a.cf_other = c->d_cf_other;
   a.cf_bpos = c->d_cf_bpos; a.diagpos = c->d_diagpos; a.val = c->J.d_val; a.dt = dt;
   a.ncell = c->ncell; a.ninterior = c->ninterior; a.nowned = c->nowned; a.nface = c->nface;
+  a.src = wb_sources_args(c);
   const int grid = wb_grid(c->nowned, 128);
   if (c->maxdeg <= 6) {
 #define CALL(E) k_jacobian<E, 6><<<grid, 128, 0, c->stream>>>(a)

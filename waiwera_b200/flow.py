@@ -194,6 +194,14 @@ class FlowSimulation:
         rg = np.ascontiguousarray(region, np.int32)
         return check(self.L.wb_set_boundaries(self.h, len(g), ptr(g), ptr(ic), ptr(pr), ptr(rg)), "wb_set_boundaries")
 
+    def set_sources(self, cells, components, rates, enthalpies):
+        """fixed-rate sources / sinks (source.F90:375-480); see wb_set_sources"""
+        c = np.ascontiguousarray(cells, np.int32)
+        k = np.ascontiguousarray(components, np.int32)
+        r = np.ascontiguousarray(rates, np.float64)
+        h = np.ascontiguousarray(enthalpies, np.float64)
+        return check(self.L.wb_set_sources(self.h, len(c), ptr(c), ptr(k), ptr(r), ptr(h)), "wb_set_sources")
+
     def fluid(self):
         out = np.zeros((self.ncell, self.dof))
         check(self.L.wb_get_fluid(self.h, ptr(out)), "wb_get_fluid")

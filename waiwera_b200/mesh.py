@@ -384,3 +384,50 @@ def minc_cube_blocks(mesh, size):
     key = (i // size) + bx * ((j // size) + by * (k // size))
     _, inv = np.unique(key, return_inverse=True)
     return inv.astype(np.int32)
+
+
+# ---------------------------------------------------------------- 1-D radial meshes (config 1)
+
+def radial_1d(nr, dr, thickness, outer_boundary=True):
+    """1-D radial mesh as the reference builds it from a 2-D (r, z) gmsh strip with "radial": true
+    (src/mesh.F90:340-432): cell volume = dr*thickness*2*pi*r_centroid and face area = thickness*2*pi*r_face
+    (Pappus), horizontal connections only (gravity_normal = 0).  With outer_boundary a Dirichlet ghost cell
+    sits beyond the last cell (distance (d1, 0), src/mesh.F90:583-664).  Cell i spans [i*dr, (i+1)*dr]."""
+    i = np.arange(nr)
+    rc = (i + 0.5) * dr
+    cell_geom = np.zeros((nr + (1 if outer_boundary else 0), 4))
+    cell_geom[:nr, 0] = rc
+    cell_geom[:nr, 1] = -0.5 * thickness
+    cell_geom[:nr, 3] = dr * thickness * 2.0 * np.pi * rc
+    rf = (i[:-1] + 1.0) * dr
+    fg = np.zeros((nr - 1, 12))
+    fg[:, 0] = thickness * 2.0 * np.pi * rf
+    fg[:, 1] = 0.5 * dr
+    fg[:, 2] = 0.5 * dr
+    fg[:, 3] = dr
+    fg[:, 4] = 1.0
+    fg[:, 8] = rf
+    fg[:, 9] = -0.5 * thickness
+    fg[:, 11] = 1.0
+    fc = np.stack([i[:-1], i[:-1] + 1], 1)
+    boundary = {}
+    if outer_boundary:
+        rb = nr * dr
+        bg = np.zeros((1, 12))
+        bg[0, 0] = thickness * 2.0 * np.pi * rb
+        bg[0, 1] = 0.5 * dr
+        bg[0, 2] = 0.0
+        bg[0, 3] = 0.5 * dr
+        bg[0, 4] = 1.0
+        bg[0, 8] = rb
+        bg[0, 9] = -0.5 * thickness
+        bg[0, 11] = 1.0
+        fg = np.concatenate([fg, bg])
+        fc = np.concatenate([fc, [[nr - 1, nr]]])
+        cell_geom[nr, 0] = rb
+        cell_geom[nr, 1] = -0.5 * thickness
+        boundary = {"ghost_cells": np.array([nr], np.int32), "interior_cells": np.array([nr - 1], np.int32)}
+    rock = default_rock(len(cell_geom), None, heterogeneous=False)
+    return Mesh(ncell=len(cell_geom), ninterior=nr, nowned=nr, face_cells=np.ascontiguousarray(fc.astype(np.int32)),
+                face_geom=np.ascontiguousarray(fg), cell_geom=np.ascontiguousarray(cell_geom), rock=rock,
+                dims=(nr, 1, 1), natural=np.arange(nr, dtype=np.int64), boundary=boundary, ncell_global=nr)
