@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-its", type=int, default=30)
     ap.add_argument("--spmv-launches", type=int, default=50)
+    ap.add_argument("--no-p2p", action="store_true", help="N > 1: keep NCCL for the per-iteration exchanges (halo, dots, norm)")
     ap.add_argument("--ksp-maxit", type=int, default=10000,
                     help="cap on Krylov iterations (profiling runs only: a capped solve is not a bench value)")
     return ap.parse_args()
@@ -229,10 +230,18 @@ def run_b200(args):
     else:
         m, y, region = gm, gy, gregion
     sim = flow.FlowSimulation(flow.make_params(eos=flow.EOS_WE, thermo=flow.THERMO_IAPWS), m, device=local)
+    p2p = False
     if world > 1:
         uid = torch.from_numpy(flow.FlowSimulation.unique_id()).cuda() if rank == 0 else torch.zeros(128, dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         sim.comm_init(rank, world, uid.cpu().numpy())
+        if not args.no_p2p:
+            try:
+                p2p = sim.p2p_setup(dist, torch.device("cuda", local))
+            except Exception as e:  # CUDA IPC not available on this box: NCCL carries the exchanges
+                if rank == 0:
+                    sys.stderr.write("bench.py: NVLink P2P path unavailable (%s); using NCCL\n" % e)
+                p2p = False
     assert sim.fluid_init(y, region) == 0
     err, L0 = sim.lhs(y)
     assert err == 0
@@ -348,7 +357,7 @@ def run_b200(args):
     out = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(dims), "parallelism": "domain decomposition %s, halo of x inside SpMV" % (wmesh.default_parts(world),),
+           "config": {"workload": workload_name(dims), "parallelism": "domain decomposition %s, halo of x inside SpMV%s" % (wmesh.default_parts(world), "" if world == 1 else (", per-iteration exchanges over NVLink P2P (CUDA IPC)" if p2p else ", NCCL exchanges")),
                       "pc": args.pc, "pc_subdomains": ("cubes of %d^3 cells" % args.pc_cube) if args.pc_cube > 0 else ("%d contiguous ranges per GPU" % args.pc_blocks),
                       "ksp": args.ksp,
                       "l2": "working set (Jacobian 222 MB + Krylov basis 496 MB) exceeds the 126 MB L2; no explicit flush",

@@ -71,6 +71,7 @@ module waiwera_b200
 
   public :: wb_last_error, wb_version, wb_create, wb_destroy, wb_num_primary, wb_fluid_dof, wb_set_mesh, &
        wb_jacobian_pattern, wb_jacobian_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
+       wb_comm_p2p_blob_size, wb_comm_p2p_export, wb_comm_p2p_open, wb_comm_p2p_enabled, wb_comm_p2p_disable, &
        wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
@@ -163,6 +164,36 @@ module waiwera_b200
        type(c_ptr), value :: neigh_rank, send_ptr, send_idx, recv_ptr, recv_idx
        integer(c_int) :: ierr
      end function wb_set_halo
+
+     ! NVLink peer-to-peer exchange: export a blob, MPI_Allgather the blobs, open them
+     function wb_comm_p2p_blob_size() bind(C, name="wb_comm_p2p_blob_size") result(n)
+       import :: c_int
+       integer(c_int) :: n
+     end function wb_comm_p2p_blob_size
+
+     function wb_comm_p2p_export(ctx, blob) bind(C, name="wb_comm_p2p_export") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, blob
+       integer(c_int) :: ierr
+     end function wb_comm_p2p_export
+
+     function wb_comm_p2p_open(ctx, blobs) bind(C, name="wb_comm_p2p_open") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, blobs
+       integer(c_int) :: ierr
+     end function wb_comm_p2p_open
+
+     function wb_comm_p2p_enabled(ctx) bind(C, name="wb_comm_p2p_enabled") result(on)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int) :: on
+     end function wb_comm_p2p_enabled
+
+     function wb_comm_p2p_disable(ctx) bind(C, name="wb_comm_p2p_disable") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int) :: ierr
+     end function wb_comm_p2p_disable
 
      function wb_set_global_offset(ctx, first_cell, ncell_global) bind(C, name="wb_set_global_offset") result(ierr)
        import :: c_int, c_int64_t, c_ptr

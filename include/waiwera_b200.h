@@ -138,6 +138,17 @@ int wb_comm_init(wb_ctx *ctx, int rank, int nranks, const void *id128);
    (local indices in [nowned,ninterior)) to receive, CSR style. */
 int wb_set_halo(wb_ctx *ctx, int nneigh, const int32_t *neigh_rank, const int32_t *send_ptr,
                 const int32_t *send_idx, const int32_t *recv_ptr, const int32_t *recv_idx);
+/* NVLink / NVSwitch peer-to-peer exchange for the three per-iteration exchanges of GMRES (ghost entries of x inside
+   the SpMV, Gram-Schmidt coefficients, norm): peers write into CUDA-IPC-mapped buffers and publish sequence
+   numbers, so none of them is a separate collective launch (replaces VecScatter + MPI_Allreduce inside
+   KSPSolve_GMRES for the context's Jacobian).  Call after wb_comm_init + wb_set_halo: every rank exports a blob of
+   wb_comm_p2p_blob_size() bytes, the host all-gathers them in rank order (torch.distributed / MPI), every rank
+   opens the gathered array.  NCCL stays in use for everything else; on failure the context keeps using NCCL. */
+int wb_comm_p2p_blob_size(void);
+int wb_comm_p2p_export(wb_ctx *ctx, void *blob);
+int wb_comm_p2p_open(wb_ctx *ctx, const void *blobs);
+int wb_comm_p2p_enabled(const wb_ctx *ctx);
+int wb_comm_p2p_disable(wb_ctx *ctx);
 /* global offset of this rank's first owned cell (VecGetOwnershipRange / bs) */
 int wb_set_global_offset(wb_ctx *ctx, int64_t first_cell, int64_t ncell_global);
 

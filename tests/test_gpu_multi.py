@@ -30,7 +30,7 @@ def problem():
     return gm, y, region
 
 
-def worker(rank, world, port, out):
+def worker(rank, world, port, out, p2p):
     import torch.distributed as dist
     from waiwera_b200 import flow, mesh as wmesh
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -48,6 +48,8 @@ def worker(rank, world, port, out):
         uid = torch.from_numpy(flow.FlowSimulation.unique_id()).cuda() if rank == 0 else torch.zeros(128, dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         sim.comm_init(rank, world, uid.cpu().numpy())
+        if p2p:
+            assert sim.p2p_setup(dist, torch.device("cuda", rank))
         assert sim.fluid_init(y, region) == 0
         err, L0 = sim.lhs(y)
         assert err == 0
@@ -73,8 +75,9 @@ def worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("world", [2, 4])
-def test_partitioned_path_matches_single_gpu(world):
+def test_partitioned_path_matches_single_gpu(world, p2p):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d CUDA devices" % world)
     import torch.multiprocessing as mp
@@ -82,7 +85,7 @@ def test_partitioned_path_matches_single_gpu(world):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, out, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     gathered = out.get(timeout=600)

@@ -67,6 +67,11 @@ SIGNATURES = {
     "wb_comm_unique_id": (i, [vp]),
     "wb_comm_init": (i, [vp, i, i, vp]),
     "wb_set_halo": (i, [vp, i, vp, vp, vp, vp, vp]),
+    "wb_comm_p2p_blob_size": (i, []),
+    "wb_comm_p2p_export": (i, [vp, vp]),
+    "wb_comm_p2p_open": (i, [vp, vp]),
+    "wb_comm_p2p_enabled": (i, [vp]),
+    "wb_comm_p2p_disable": (i, [vp]),
     "wb_set_global_offset": (i, [vp, i64, i64]),
     "wb_fluid_init": (i, [vp, vp, vp]),
     "wb_set_boundary": (i, [vp, i, i, vp, i]),

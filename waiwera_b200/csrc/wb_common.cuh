@@ -83,6 +83,38 @@ struct WbHalo {
   bool recv_contiguous = false;  // ghost cell k of the receive list is local cell nowned + k
 };
 
+// ---- NVLink peer-to-peer exchange (one process per GPU, CUDA IPC mapped buffers) -------------------
+// Every rank owns one comm region with the SAME layout; peers write into it directly over NVLink / NVSwitch
+// and publish a sequence number afterwards, the owner spins on the sequence number (system-scope acquire).
+// Used for the three per-iteration exchanges of GMRES -- ghost entries of x, the Gram-Schmidt
+// coefficients, the norm -- so that none of them is a separate collective launch.
+#define WB_P2P_MAX_RANKS 8
+#define WB_P2P_MAXV 32
+#define WB_P2P_SLOT_A 4096   // byte offsets inside the region
+#define WB_P2P_SLOT_B (WB_P2P_SLOT_A + WB_P2P_MAX_RANKS * WB_P2P_MAXV * 8)
+#define WB_P2P_GHOST (WB_P2P_SLOT_B + 1024)
+struct WbP2PDev {  // by-value kernel argument
+  int on, rank, nranks;
+  unsigned char *region[WB_P2P_MAX_RANKS];  // region[r] = rank r's region as mapped in this process (region[rank] local)
+  int *err;                                 // device flag: set when a spin wait times out
+};
+struct WbP2P {
+  bool on = false;
+  void *local = nullptr;
+  size_t bytes = 0;
+  WbP2PDev dev = {};
+  int seq_halo = 0, seq_a = 0, seq_b = 0;
+  std::vector<int> recv_off;          // [nranks] cell offset in MY ghost area of the data rank r sends (or -1)
+  std::vector<int> peer_off;          // [nneigh] cell offset in neighbour n's ghost area where my data goes
+  int32_t *d_send_nb = nullptr;       // [nsend] neighbour slot of every send entry
+  int32_t *d_nb_rank = nullptr;       // [nneigh]
+  int32_t *d_nb_off = nullptr;        // [nneigh] = peer_off
+  int32_t *d_nb_start = nullptr;      // [nneigh] = send_ptr
+  unsigned *d_counter = nullptr;
+};
+// flags live in the first 4 KB of the region: one 64-byte line per (kind, sender rank)
+__host__ __device__ inline size_t wb_p2p_flag_off(int kind, int sender) { return (size_t)(kind * WB_P2P_MAX_RANKS + sender) * 64; }
+
 struct wb_mat {
   wb_ctx *ctx = nullptr;
   int nb = 0, ncolb = 0, bs = 0, nnzb = 0;
@@ -148,6 +180,7 @@ struct wb_ctx {
   int rank = 0, nranks = 1;
   int64_t first_cell = 0, ncell_global = 0;
   WbHalo halo;
+  WbP2P p2p;
 
   // instrumentation
   std::map<std::string, WbTimer> timers;
@@ -194,6 +227,8 @@ int wb_halo_exchange(wb_ctx *ctx, double *vec, int width);  // vec[(ninterior)*w
 // SpMV halo: owned[idx]*scale -> neighbours; ghost[(cell-nowned)*width+k] <- neighbours
 int wb_halo_exchange_ghost(wb_ctx *ctx, const double *owned, int width, const double *scale, double *ghost);
 int wb_allreduce_sum(wb_ctx *ctx, double *dbuf, int n);     // in-stream, device buffer
+// P2P halo push of owned[idx]*scale into the neighbours' ghost areas; returns the sequence number consumers wait for
+int wb_p2p_halo_push(wb_ctx *ctx, const double *owned, int width, const double *scale, const int *done, int *seq);
 int wb_allreduce_max_int(wb_ctx *ctx, int *dbuf, int n);
 int wb_reduce_flags(wb_ctx *ctx, int nflags);               // device flags -> host (max over ranks)
 

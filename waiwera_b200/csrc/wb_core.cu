@@ -1,5 +1,6 @@
 // wb_core.cu -- context life cycle, error reporting, pointer staging, timers,
 // NCCL communicator and halo exchange.
+#include <algorithm>
 #include <dlfcn.h>
 #include <stdarg.h>
 
@@ -229,6 +230,13 @@ extern "C" int wb_destroy(wb_ctx *c) {
   cudaFree(c->halo.d_recv_idx);
   cudaFree(c->halo.d_sendbuf);
   cudaFree(c->halo.d_recvbuf);
+  if (c->p2p.local) {
+    for (int r = 0; r < c->nranks; r++)
+      if (r != c->rank && c->p2p.dev.region[r]) cudaIpcCloseMemHandle(c->p2p.dev.region[r]);
+    cudaFree(c->p2p.local);
+    cudaFree(c->p2p.d_send_nb); cudaFree(c->p2p.d_nb_rank); cudaFree(c->p2p.d_nb_off); cudaFree(c->p2p.d_nb_start);
+    cudaFree(c->p2p.d_counter);
+  }
   if (c->comm && wb_nccl()) wb_nccl()->CommDestroy(c->comm);
   cudaFree(c->d_flags);
   cudaFreeHost(c->h_flags);
@@ -398,6 +406,149 @@ int wb_halo_exchange_ghost(wb_ctx *c, const double *owned, int width, const doub
                                                                                       width, c->nowned, h.d_recvbuf);
     WB_LAUNCH(c);
   }
+  return 0;
+}
+
+// ================================================================ NVLink peer-to-peer exchange
+
+struct WbP2PBlob {
+  cudaIpcMemHandle_t handle;
+  int recv_off[WB_P2P_MAX_RANKS];
+  int ghost_cells;
+  int pad;
+};
+
+extern "C" int wb_comm_p2p_blob_size(void) { return (int)sizeof(WbP2PBlob); }
+
+// after wb_comm_init + wb_set_halo: allocate this rank's comm region and describe it for the peers
+extern "C" int wb_comm_p2p_export(wb_ctx *c, void *blob) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CHECK(c->nranks > 1 && c->nranks <= WB_P2P_MAX_RANKS, "wb_comm_p2p_export: needs 2..%d ranks", WB_P2P_MAX_RANKS);
+  WbP2P &p = c->p2p;
+  WbHalo &h = c->halo;
+  WB_CHECK(h.recv_contiguous || h.nrecv == 0, "wb_comm_p2p_export: ghost cells must be numbered in receive order");
+  const int nghost = c->ninterior - c->nowned;
+  p.bytes = WB_P2P_GHOST + (size_t)(nghost + 1) * h.maxwidth * sizeof(double);
+  WB_CUDA(cudaMalloc(&p.local, p.bytes));
+  WB_CUDA(cudaMemset(p.local, 0, p.bytes));
+  WbP2PBlob b;
+  memset(&b, 0, sizeof(b));
+  WB_CUDA(cudaIpcGetMemHandle(&b.handle, p.local));
+  p.recv_off.assign(c->nranks, -1);
+  for (int n = 0; n < h.nneigh; n++) p.recv_off[h.rank[n]] = h.recv_ptr[n];
+  for (int r = 0; r < WB_P2P_MAX_RANKS; r++) b.recv_off[r] = r < c->nranks ? p.recv_off[r] : -1;
+  b.ghost_cells = nghost;
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+// blobs: nranks blobs in rank order (all-gathered by the host).  Maps every peer's region and turns the P2P path on.
+extern "C" int wb_comm_p2p_open(wb_ctx *c, const void *blobs) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WbP2P &p = c->p2p;
+  WbHalo &h = c->halo;
+  WB_CHECK(p.local, "wb_comm_p2p_open: call wb_comm_p2p_export first");
+  const WbP2PBlob *B = (const WbP2PBlob *)blobs;
+  memset(&p.dev, 0, sizeof(p.dev));
+  for (int r = 0; r < c->nranks; r++) {
+    if (r == c->rank) {
+      p.dev.region[r] = (unsigned char *)p.local;
+    } else {
+      void *ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, B[r].handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        wb_set_error("wb_comm_p2p_open: cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        return -1;
+      }
+      p.dev.region[r] = (unsigned char *)ptr;
+    }
+  }
+  p.dev.rank = c->rank;
+  p.dev.nranks = c->nranks;
+  p.dev.err = c->d_flags + 5;
+  // where my data lands in each neighbour's ghost area
+  p.peer_off.assign(h.nneigh, 0);
+  std::vector<int32_t> send_nb(std::max(h.nsend, 1), 0), nb_rank(std::max(h.nneigh, 1), 0), nb_off(std::max(h.nneigh, 1), 0),
+      nb_start(std::max(h.nneigh, 1), 0);
+  for (int n = 0; n < h.nneigh; n++) {
+    const int off = B[h.rank[n]].recv_off[c->rank];
+    WB_CHECK(off >= 0, "wb_comm_p2p_open: rank %d does not expect data from rank %d", h.rank[n], c->rank);
+    p.peer_off[n] = off;
+    nb_rank[n] = h.rank[n];
+    nb_off[n] = off;
+    nb_start[n] = h.send_ptr[n];
+    for (int k = h.send_ptr[n]; k < h.send_ptr[n + 1]; k++) send_nb[k] = n;
+  }
+  WB_CUDA(cudaMalloc(&p.d_send_nb, sizeof(int32_t) * send_nb.size()));
+  WB_CUDA(cudaMalloc(&p.d_nb_rank, sizeof(int32_t) * nb_rank.size()));
+  WB_CUDA(cudaMalloc(&p.d_nb_off, sizeof(int32_t) * nb_off.size()));
+  WB_CUDA(cudaMalloc(&p.d_nb_start, sizeof(int32_t) * nb_start.size()));
+  WB_CUDA(cudaMalloc(&p.d_counter, sizeof(unsigned)));
+  WB_CUDA(cudaMemset(p.d_counter, 0, sizeof(unsigned)));
+  WB_CUDA(cudaMemcpy(p.d_send_nb, send_nb.data(), sizeof(int32_t) * send_nb.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMemcpy(p.d_nb_rank, nb_rank.data(), sizeof(int32_t) * nb_rank.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMemcpy(p.d_nb_off, nb_off.data(), sizeof(int32_t) * nb_off.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMemcpy(p.d_nb_start, nb_start.data(), sizeof(int32_t) * nb_start.size(), cudaMemcpyHostToDevice));
+  p.dev.on = 1;
+  p.on = true;
+  return 0;
+}
+
+extern "C" int wb_comm_p2p_enabled(const wb_ctx *c) { return c->p2p.on ? 1 : 0; }
+extern "C" int wb_comm_p2p_disable(wb_ctx *c) {
+  c->p2p.on = false;
+  c->p2p.dev.on = 0;
+  return 0;
+}
+
+__device__ __forceinline__ void p2p_store_release_sys(int *p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ghost entries: every send entry goes straight into its neighbour's ghost area over NVLink; the last CTA to
+// finish publishes the sequence number to every neighbour (after a system-scope fence)
+__global__ void k_p2p_halo_push(const double *__restrict__ vec, const int32_t *__restrict__ idx,
+                                const int32_t *__restrict__ send_nb, const int32_t *__restrict__ nb_rank,
+                                const int32_t *__restrict__ nb_off, const int32_t *__restrict__ nb_start, int nsend,
+                                int nneigh, int width, const double *scale, WbP2PDev P, int seq, unsigned *counter,
+                                const int *done) {
+  if (done && *done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nsend * width) {
+    const int e = i / width, k = i - e * width;
+    const int n = send_nb[e];
+    double *ghost = reinterpret_cast<double *>(P.region[nb_rank[n]] + WB_P2P_GHOST);
+    ghost[(size_t)(nb_off[n] + (e - nb_start[n])) * width + k] = vec[(size_t)idx[e] * width + k] * (scale ? *scale : 1.0);
+  }
+  __shared__ bool s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < nneigh) {
+    __threadfence_system();
+    int *flag = reinterpret_cast<int *>(P.region[nb_rank[threadIdx.x]] + wb_p2p_flag_off(0, P.rank));
+    p2p_store_release_sys(flag, seq);
+  }
+}
+
+int wb_p2p_halo_push(wb_ctx *c, const double *owned, int width, const double *scale, const int *done, int *seq) {
+  WbP2P &p = c->p2p;
+  WbHalo &h = c->halo;
+  p.seq_halo++;
+  *seq = p.seq_halo;
+  if (h.nneigh == 0) return 0;
+  WB_CHECK(h.nneigh <= 256, "too many halo neighbours");
+  const int grid = std::max(1, wb_grid((size_t)h.nsend * width, 256));
+  k_p2p_halo_push<<<grid, 256, 0, c->stream>>>(owned, h.d_send_idx, p.d_send_nb, p.d_nb_rank, p.d_nb_off, p.d_nb_start,
+                                              h.nsend, h.nneigh, width, scale, p.dev, p.seq_halo, p.d_counter, done);
+  WB_LAUNCH(c);
+  WB_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -12,6 +12,31 @@
 
 #include "wb_common.cuh"
 
+// ================================================================ NVLink P2P helpers
+
+__device__ __forceinline__ int p2p_ld_acquire_sys(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_st_release_sys(int *p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until the peer's sequence number reaches `seq`; bounded (~2 s) so that a lost peer raises an error flag
+// instead of hanging the GPU
+__device__ __forceinline__ void p2p_wait(const int *flag, int seq, int *err) {
+  const long long t0 = clock64();
+  while (p2p_ld_acquire_sys(flag) < seq) {
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(err, 1);
+      break;
+    }
+  }
+}
+__device__ __forceinline__ const int *p2p_my_flag(const WbP2PDev &P, int kind, int sender) {
+  return reinterpret_cast<const int *>(P.region[P.rank] + wb_p2p_flag_off(kind, sender));
+}
+
 // ================================================================ SpMV (K5)
 
 // Eight lanes per block row: lane l takes blocks rowptr[i]+l, +8, ...  Consecutive rows are
@@ -33,6 +58,11 @@ struct SpmvArgs {
   double *y;
   int nb;
   const int *done;  // nullable: device-side "solver finished" flag
+  // P2P halo: ghost entries are pushed by the neighbours; wait (lazily, on the first ghost column) for their
+  // sequence numbers.  hseq == 0: no waiting (NCCL path or no ghosts)
+  WbP2PDev P;
+  int hseq, nwait;
+  const int32_t *nb_rank;
 };
 
 // 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
@@ -76,7 +106,7 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
   for (int r = 0; r < R; r++)
 #pragma unroll
     for (int i = 0; i < BS; i++) acc[r][i] = 0.0;
-  bool more = false;
+  bool more = false, waited = (a.hseq == 0);
 #pragma unroll
   for (int r = 0; r < R; r++) more = more || (e0[r] < e1[r]);
   while (more) {
@@ -106,8 +136,15 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
 #pragma unroll
       for (int j = 0; j < BS; j++) xb[r][j] = 0.0;
       if (col[r] >= 0) {
+        if (!own && !waited) {  // rows without ghost columns never wait: interior work overlaps the exchange
+          for (int n = 0; n < a.nwait; n++) p2p_wait(p2p_my_flag(a.P, 0, a.nb_rank[n]), a.hseq, a.P.err);
+          waited = true;
+        }
         const double *xp = own ? a.x + (size_t)col[r] * BS : a.xg + (size_t)(col[r] - a.nb) * BS;
-        if (BS == 2) {
+        if (!own) {
+#pragma unroll
+          for (int j = 0; j < BS; j++) xb[r][j] = __ldcg(xp + j) * sc;  // written by a peer GPU: read at L2
+        } else if (BS == 2) {
           const double2 x2 = *reinterpret_cast<const double2 *>(xp);
           xb[r][0] = x2.x * sc; xb[r][1] = x2.y * sc;
         } else {
@@ -154,13 +191,21 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
 int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d_xn, double *d_y, const int *done) {
   wb_ctx *c = A->ctx;
   const double *xg = nullptr;
+  int hseq = 0;
   if (A->ncolb > A->nb && c->nranks > 1) {
-    WB_TRY(wb_halo_exchange_ghost(c, d_x, A->bs, d_scale, A->d_xloc));
-    xg = A->d_xloc;
+    if (c->p2p.on && A == &c->J) {
+      // neighbours write their entries straight into this GPU's ghost area over NVLink
+      WB_TRY(wb_p2p_halo_push(c, d_x, A->bs, d_scale, done, &hseq));
+      xg = reinterpret_cast<const double *>(c->p2p.dev.region[c->rank] + WB_P2P_GHOST);
+    } else {
+      WB_TRY(wb_halo_exchange_ghost(c, d_x, A->bs, d_scale, A->d_xloc));
+      xg = A->d_xloc;
+    }
   } else if (A->ncolb > A->nb) {
     xg = A->d_xloc;  // ghost columns without a communicator: zeros
   }
-  SpmvArgs a = {A->d_rowptr, A->d_colidx, A->d_val, d_x, xg, d_scale, d_xn, d_y, A->nb, done};
+  SpmvArgs a = {A->d_rowptr, A->d_colidx, A->d_val, d_x, xg, d_scale, d_xn, d_y, A->nb, done,
+                c->p2p.dev, hseq, hseq ? c->halo.nneigh : 0, c->p2p.d_nb_rank};
   static int rows_per_group = 0;  // tuning knob (WB_SPMV_ROWS = 1, 2, 4); measured 70.9 / 70.6 / 97 us at 1 M cells
   if (!rows_per_group) {
     const char *e = getenv("WB_SPMV_ROWS");
@@ -1346,6 +1391,19 @@ __device__ void gmres_update(const GmresUpd &u) {
   }
 }
 __global__ void k_gmres_update(const GmresUpd u) { gmres_update(u); }
+// multi-GPU: |w|^2 = sum over ranks of slot B (fixed rank order, identical on every rank), then the update
+__global__ void k_gmres_update_p2p(const GmresUpd u, const WbP2PDev P, int seq) {
+  if (*u.done) return;
+  if (threadIdx.x < P.nranks) p2p_wait(p2p_my_flag(P, 2, threadIdx.x), seq, P.err);
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    const double *slot = reinterpret_cast<const double *>(P.region[P.rank] + WB_P2P_SLOT_B);
+    double s = 0.0;
+    for (int r = 0; r < P.nranks; r++) s += __ldcg(&slot[r]);
+    u.scal[0] = s;
+    gmres_update(u);
+  }
+}
 
 // Krylov kernels all take the solver's device-side `done` flag and return at once when it is
 // set, so the host can enqueue a whole restart cycle between convergence checks.
@@ -1360,6 +1418,8 @@ struct MdotArgs {
   double *part, *out;
   unsigned *counter;
   const int *done;
+  WbP2PDev P;  // seq > 0: the local sums are published to every rank's slot A instead of `out`
+  int seq;
 };
 template <int NVT, bool VEC>
 __global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
@@ -1428,7 +1488,20 @@ __global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
       double s = 0.0;
       for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&a.part[(size_t)j * RED_BLOCKS + b]);
       s = warp_sum(s);
-      if (lane == 0) a.out[j] = s;
+      if (a.seq > 0) {
+        // all-gather over NVLink: lane r writes this rank's partial into rank r's slot
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (lane < a.P.nranks)
+          reinterpret_cast<double *>(a.P.region[lane] + WB_P2P_SLOT_A)[a.P.rank * WB_P2P_MAXV + j] = s;
+      } else if (lane == 0) {
+        a.out[j] = s;
+      }
+    }
+    if (a.seq > 0) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < a.P.nranks)
+        p2p_st_release_sys(reinterpret_cast<int *>(a.P.region[threadIdx.x] + wb_p2p_flag_off(1, a.P.rank)), a.seq);
     }
   }
 }
@@ -1448,12 +1521,30 @@ struct MaxpyArgs {
   const int *done;
   int with_upd;
   GmresUpd upd;
+  WbP2PDev P;
+  int seq_coef;      // > 0: coefficients = sum over ranks of slot A (waits for every rank's sequence number)
+  double *coef_out;  // reduced coefficients for the Hessenberg update (written by CTA 0)
+  int seq_norm;      // > 0: the local |w|^2 is published to every rank's slot B instead of `out`
 };
 template <int NVT, bool VEC>
 __global__ void __launch_bounds__(256, 2) k_maxpy_all(const MaxpyArgs a) {
   if (a.done && *a.done) return;
   __shared__ double cf[KRY_MAXV];
-  if (threadIdx.x < KRY_MAXV) cf[threadIdx.x] = threadIdx.x < a.nv ? a.sign * a.coef[threadIdx.x] : 0.0;
+  if (a.seq_coef > 0) {
+    if (threadIdx.x < a.P.nranks) p2p_wait(p2p_my_flag(a.P, 1, threadIdx.x), a.seq_coef, a.P.err);
+    __syncthreads();
+    if (threadIdx.x < KRY_MAXV) {
+      double sum = 0.0;
+      if (threadIdx.x < a.nv) {
+        const double *slot = reinterpret_cast<const double *>(a.P.region[a.P.rank] + WB_P2P_SLOT_A);
+        for (int r = 0; r < a.P.nranks; r++) sum += __ldcg(&slot[r * WB_P2P_MAXV + threadIdx.x]);  // fixed rank order
+        if (blockIdx.x == 0 && a.coef_out) a.coef_out[threadIdx.x] = sum;
+      }
+      cf[threadIdx.x] = a.sign * sum;
+    }
+  } else if (threadIdx.x < KRY_MAXV) {
+    cf[threadIdx.x] = threadIdx.x < a.nv ? a.sign * a.coef[threadIdx.x] : 0.0;
+  }
   __syncthreads();
   double nrm = 0.0;
   if (VEC) {
@@ -1509,7 +1600,15 @@ __global__ void __launch_bounds__(256, 2) k_maxpy_all(const MaxpyArgs a) {
       double t = 0.0;
       for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += __ldcg(&a.part[b]);
       t = warp_sum(t);
-      if (threadIdx.x == 0) {
+      if (a.seq_norm > 0) {
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (threadIdx.x < a.P.nranks)
+          reinterpret_cast<double *>(a.P.region[threadIdx.x] + WB_P2P_SLOT_B)[a.P.rank] = t;
+        __threadfence_system();
+        __syncwarp();
+        if (threadIdx.x < a.P.nranks)
+          p2p_st_release_sys(reinterpret_cast<int *>(a.P.region[threadIdx.x] + wb_p2p_flag_off(2, a.P.rank)), a.seq_norm);
+      } else if (threadIdx.x == 0) {
         a.out[0] = t;
         if (a.with_upd) gmres_update(a.upd);
       }
@@ -1652,13 +1751,22 @@ template <int NVT> static void launch_maxpy(const MaxpyArgs &a, int nblk, cudaSt
 }
 
 // dots[j] = w . V_j for j in [0, nd), summed over ranks.  V_j = V + j*ldv (16-byte aligned vectors).
+// With p2p_seq (multi-GPU, NVLink path, nd <= WB_P2P_MAXV) the per-rank sums are all-gathered into every rank's
+// slot A by the kernel itself and *p2p_seq is the sequence number the consumer (multi_axpy) waits for; no
+// collective is launched and d_out is not written here.
 static int multi_dot(KspWork &w, const double *d_w, const double *V, size_t ldv, int nd, double *d_out,
-                     const int *done) {
+                     const int *done, int *p2p_seq = nullptr) {
   wb_ctx *c = w.ctx;
   const int nblk = red_blocks(w.n);
+  const bool p2p = p2p_seq && c->p2p.on && nd <= WB_P2P_MAXV;
+  if (p2p_seq) *p2p_seq = 0;
   for (int j0 = 0; j0 < nd; j0 += KRY_MAXV) {
     const int nv = std::min(KRY_MAXV, nd - j0);
-    MdotArgs a = {d_w, V + (size_t)j0 * ldv, ldv, (int)w.n, nv, w.part, d_out + j0, w.d_counter, done};
+    MdotArgs a = {d_w, V + (size_t)j0 * ldv, ldv, (int)w.n, nv, w.part, d_out + j0, w.d_counter, done, c->p2p.dev, 0};
+    if (p2p) {
+      a.seq = ++c->p2p.seq_a;
+      *p2p_seq = a.seq;
+    }
     if (nv <= 1) launch_mdot<1>(a, nblk, c->stream);
     else if (nv <= 2) launch_mdot<2>(a, nblk, c->stream);
     else if (nv <= 4) launch_mdot<4>(a, nblk, c->stream);
@@ -1666,17 +1774,20 @@ static int multi_dot(KspWork &w, const double *d_w, const double *V, size_t ldv,
     WB_LAUNCH(c);
   }
   WB_CUDA(cudaGetLastError());
-  WB_TRY(wb_allreduce_sum(c, d_out, nd));
+  if (!p2p) WB_TRY(wb_allreduce_sum(c, d_out, nd));
   return 0;
 }
 
 // w += sign * sum_j coef[j] V_j ; if d_nrm2: also |w|^2 (summed over ranks); if upd (and one rank): the
-// Arnoldi-step update runs in the same launch
+// Arnoldi-step update runs in the same launch.  coef_seq > 0: the coefficients are the rank sums of slot A
+// published by multi_dot (NVLink path); d_coef then receives the reduced values for the Hessenberg update.
 static int multi_axpy(KspWork &w, double *d_w, const double *V, size_t ldv, int nd, const double *d_coef, double sign,
-                      double *d_nrm2, const int *done, const GmresUpd *upd) {
+                      double *d_nrm2, const int *done, const GmresUpd *upd, int coef_seq = 0) {
   wb_ctx *c = w.ctx;
   const int nblk = red_blocks(w.n);
   const bool fuse_upd = upd && c->nranks <= 1;
+  const bool p2p_norm = coef_seq > 0 && d_nrm2 && upd;
+  int seq_norm = 0;
   for (int j0 = 0; j0 < nd; j0 += KRY_MAXV) {
     const int nv = std::min(KRY_MAXV, nd - j0);
     const bool last = j0 + nv >= nd;
@@ -1687,6 +1798,12 @@ static int multi_axpy(KspWork &w, double *d_w, const double *V, size_t ldv, int 
     a.out = d_nrm2; a.counter = w.d_counter; a.done = done;
     a.with_upd = (last && fuse_upd) ? 1 : 0;
     if (a.with_upd) a.upd = *upd;
+    a.P = c->p2p.dev;
+    if (coef_seq > 0) {
+      a.seq_coef = coef_seq;
+      a.coef_out = const_cast<double *>(d_coef);
+      if (p2p_norm && last) a.seq_norm = seq_norm = ++c->p2p.seq_b;
+    }
     if (nv <= 1) launch_maxpy<1>(a, nblk, c->stream);
     else if (nv <= 2) launch_maxpy<2>(a, nblk, c->stream);
     else if (nv <= 4) launch_maxpy<4>(a, nblk, c->stream);
@@ -1700,6 +1817,11 @@ static int multi_axpy(KspWork &w, double *d_w, const double *V, size_t ldv, int 
     WB_LAUNCH(c);
   }
   WB_CUDA(cudaGetLastError());
+  if (seq_norm > 0) {
+    k_gmres_update_p2p<<<1, 32, 0, c->stream>>>(*upd, c->p2p.dev, seq_norm);
+    WB_LAUNCH(c);
+    return 0;
+  }
   if (d_nrm2) WB_TRY(wb_allreduce_sum(c, d_nrm2, 1));
   if (upd && !fuse_upd) {
     k_gmres_update<<<1, 1, 0, c->stream>>>(*upd);
@@ -1728,7 +1850,12 @@ static int lin3(KspWork &w, double *z, const double *x, double a, const double *
 static int fetch_state(KspWork &w) {
   wb_ctx *c = w.ctx;
   WB_CUDA(cudaMemcpyAsync(w.h_st, w.d_st, sizeof(KspState), cudaMemcpyDeviceToHost, c->stream));
+  if (c->p2p.on) WB_CUDA(cudaMemcpyAsync(c->h_flags + 5, c->d_flags + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   WB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->p2p.on && c->h_flags[5]) {
+    wb_set_error("NVLink peer exchange timed out waiting for a peer's sequence number (a rank is missing or out of step)");
+    return -4;
+  }
   return 0;
 }
 
@@ -1786,8 +1913,9 @@ static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
         // V_it = wbuf * (1/|wbuf|) stored by the SpMV that also forms tmp = A V_it
         WB_TRY(wb_spmv_fused(A, wbuf, scal + 1, w.V + (size_t)it * ld, tmp, w.d_done));
         WB_TRY(wb_pc_apply_dev(pc, tmp, wbuf, w.d_done));
-        WB_TRY(multi_dot(w, wbuf, w.V, ld, it + 1, hcol, w.d_done));
-        WB_TRY(multi_axpy(w, wbuf, w.V, ld, it + 1, hcol, -1.0, scal, w.d_done, &upd));
+        int coef_seq = 0;
+        WB_TRY(multi_dot(w, wbuf, w.V, ld, it + 1, hcol, w.d_done, &coef_seq));
+        WB_TRY(multi_axpy(w, wbuf, w.V, ld, it + 1, hcol, -1.0, scal, w.d_done, &upd, coef_seq));
       }
       WB_TRY(fetch_state(w));
       if (w.h_st->reason != 0) stop = true;

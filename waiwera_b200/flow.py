@@ -166,6 +166,25 @@ class FlowSimulation:
             check(self.L.wb_set_halo(self.h, len(m.neigh_rank), ptr(m.neigh_rank), ptr(m.send_ptr), ptr(m.send_idx),
                                      ptr(m.recv_ptr), ptr(m.recv_idx)), "wb_set_halo")
 
+    # NVLink peer-to-peer path: export -> all-gather by the caller -> open
+    def p2p_export(self):
+        blob = np.zeros(self.L.wb_comm_p2p_blob_size(), np.uint8)
+        check(self.L.wb_comm_p2p_export(self.h, ptr(blob)), "wb_comm_p2p_export")
+        return blob
+
+    def p2p_open(self, blobs):
+        b = np.ascontiguousarray(blobs, np.uint8)
+        check(self.L.wb_comm_p2p_open(self.h, ptr(b)), "wb_comm_p2p_open")
+        return bool(self.L.wb_comm_p2p_enabled(self.h))
+
+    def p2p_setup(self, dist, device):
+        """convenience for torch.distributed hosts: all-gather the blobs and open them"""
+        import torch
+        mine = torch.from_numpy(self.p2p_export()).to(device)
+        parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, mine)
+        return self.p2p_open(torch.cat(parts).cpu().numpy())
+
     @staticmethod
     def unique_id():
         uid = np.zeros(128, np.uint8)
