@@ -24,6 +24,7 @@ module waiwera_b200
   integer(c_int), parameter, public :: WB_CP_ZERO = 0, WB_CP_LINEAR = 1, WB_CP_VAN_GENUCHTEN = 2, WB_CP_TABLE = 3
   integer(c_int), parameter, public :: WB_PC_NONE = 0, WB_PC_PBJACOBI = 1, WB_PC_BJACOBI_ILU0 = 2
   integer(c_int), parameter, public :: WB_KSP_GMRES = 0, WB_KSP_BCGS = 1
+  integer(c_int), parameter, public :: WB_METHOD_BEULER = 0, WB_METHOD_BDF2 = 1, WB_METHOD_DIRECTSS = 2
   integer(c_int), parameter, public :: WB_MAX_TABLE = 16
 
   type, bind(C), public :: wb_relperm
@@ -72,7 +73,7 @@ module waiwera_b200
   public :: wb_last_error, wb_version, wb_create, wb_destroy, wb_num_primary, wb_fluid_dof, wb_set_mesh, &
        wb_jacobian_pattern, wb_jacobian_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
        wb_comm_p2p_blob_size, wb_comm_p2p_export, wb_comm_p2p_open, wb_comm_p2p_enabled, wb_comm_p2p_disable, &
-       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
+       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
        wb_mat_set_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
@@ -235,6 +236,16 @@ module waiwera_b200
        type(c_ptr), value :: cell, component, rate, enthalpy
        integer(c_int) :: ierr
      end function wb_set_sources
+
+     ! context%residual selection (src/timestepper.F90:345-452): BE / BDF2 / direct steady state
+     function wb_set_method(ctx, method, dt_last, lhs_last2) bind(C, name="wb_set_method") result(ierr)
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: method
+       real(c_double), value :: dt_last
+       type(c_ptr), value :: lhs_last2
+       integer(c_int) :: ierr
+     end function wb_set_method
 
      function wb_get_fluid(ctx, fluid) bind(C, name="wb_get_fluid") result(ierr)
        import :: c_int, c_ptr

@@ -179,6 +179,17 @@ int wb_pre_iteration(wb_ctx *ctx);
 int wb_pre_timestep(wb_ctx *ctx);
 int wb_pre_retry_timestep(wb_ctx *ctx);
 
+/* time-stepping method (context%residual, src/timestepper.F90:2223-2245): selects the residual that
+   wb_residual_be, wb_jacobian_be(_colored) and wb_newton_solve_be evaluate from then on:
+     WB_METHOD_BEULER   backwards_Euler_residual (:345-374)  r = L - L_last - dt R            (default)
+     WB_METHOD_BDF2     BDF2_residual (:378-427)  r = (1+2q) L - (q+1)^2 L_last + q^2 L_last2 - dt (q+1) R,
+                        q = dt / dt_last; lhs_last2 = L two steps back (host or device, nowned*np)
+     WB_METHOD_DIRECTSS direct_ss_residual (:431-452)  r = R  (dt and lhs_last arguments are ignored) */
+#define WB_METHOD_BEULER 0
+#define WB_METHOD_BDF2 1
+#define WB_METHOD_DIRECTSS 2
+int wb_set_method(wb_ctx *ctx, int method, double dt_last, const double *lhs_last2);
+
 /* ---- function evaluation (ode_type lhs / rhs, SNES_residual) ----------- */
 /* pre_eval (src/flow_simulation.F90:2126): fluid_properties for y.  perturbed /
    nperturbed are the block columns MatFDColoring perturbed (src/dm_utils.F90:1544);

@@ -130,6 +130,7 @@ def lib():
         "wo_flow_fluid_init": (i, [vp, c_dp, c_ip]),
         "wo_flow_set_boundary": (i, [vp, i, i, c_dp, i]),
         "wo_flow_set_sources": (None, [vp, i, c_ip, c_ip, c_dp, c_dp]),
+        "wo_flow_set_method": (None, [vp, i, d, c_dp]),
         "wo_flow_pre_eval": (i, [vp, c_dp, c_ip, i]),
         "wo_flow_cell_balances": (i, [vp, c_dp]),
         "wo_flow_cell_inflows": (i, [vp, c_dp]),
@@ -290,6 +291,9 @@ class Flow:
         r = np.zeros(self.ncell, np.int32)
         self.L.wo_flow_get_regions(self.h, ip(r))
         return r
+
+    def set_method(self, method, dt_last=0.0, lhs_last2=None):
+        self.L.wo_flow_set_method(self.h, method, dt_last, dp(lhs_last2))
 
     def set_sources(self, cells, components, rates, enthalpies):
         c = np.ascontiguousarray(cells, np.int32)

@@ -27,6 +27,10 @@ struct wo_flow {
   double *update;   /* ncell: +1 / -1 */
   double *rock;     /* private copy so boundary ghost rock can be set */
   int unperturbed;
+  /* time-stepping method: 0 backward Euler, 1 BDF2, 2 direct steady state (timestepper.F90:345-452) */
+  int method;
+  double dt_last;
+  double *lhs_last2;
   /* fixed-rate sources / sinks (src/source.F90:375-480), in input order */
   int nsrc;
   int32_t *src_cell, *src_component;
@@ -64,6 +68,16 @@ wo_flow *wo_flow_create(const wo_params *prm, const wo_mesh *mesh) {
   f->mesh.rock = f->rock;
   f->unperturbed = 1;
   return f;
+}
+
+void wo_flow_set_method(wo_flow *f, int method, double dt_last, const double *lhs_last2) {
+  size_t n = (size_t)f->mesh.nowned * f->np;
+  f->method = method;
+  f->dt_last = dt_last;
+  if (method == 1) {
+    if (!f->lhs_last2) f->lhs_last2 = (double *)malloc(n * sizeof(double));
+    memcpy(f->lhs_last2, lhs_last2, n * sizeof(double));
+  }
 }
 
 /* Fixed-rate sources: cell (local owned index), component (1-based; 0 = all mass components, production
@@ -135,6 +149,7 @@ static void source_flow(const wo_flow *f, int s, double *flow) {
 void wo_flow_destroy(wo_flow *f) {
   if (!f) return;
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
+  free(f->lhs_last2);
   wo_eos_destroy(f->eos);
   free(f->fluid);
   free(f->current_fluid);
@@ -331,8 +346,27 @@ int wo_residual_be(wo_flow *f, const double *y, const double *lhs_last, double d
   size_t n = (size_t)f->mesh.nowned * f->np;
   int err = wo_flow_pre_eval(f, y, perturbed, nperturbed);
   if (err) return err;
+  if (f->method == 2) { /* direct_ss_residual: timestepper.F90:431-452 */
+    err = wo_flow_cell_balances(f, lhs);
+    if (err) return err;
+    err = wo_flow_cell_inflows(f, rhs);
+    if (err) return err;
+    for (size_t i = 0; i < n; i++) r[i] = rhs[i]; /* VecCopy */
+    return 0;
+  }
   err = wo_flow_cell_balances(f, lhs);
   if (err) return err;
+  if (f->method == 1) { /* BDF2_residual: timestepper.F90:378-427 */
+    double q = dt / f->dt_last, q1 = q + 1.0;
+    for (size_t i = 0; i < n; i++) r[i] = lhs[i];                            /* VecCopy */
+    for (size_t i = 0; i < n; i++) r[i] = r[i] * (1.0 + 2.0 * q);            /* VecScale */
+    for (size_t i = 0; i < n; i++) r[i] = r[i] + (-q1 * q1) * lhs_last[i];   /* VecAXPY */
+    for (size_t i = 0; i < n; i++) r[i] = r[i] + (q * q) * f->lhs_last2[i];  /* VecAXPY */
+    err = wo_flow_cell_inflows(f, rhs);
+    if (err) return err;
+    for (size_t i = 0; i < n; i++) r[i] = r[i] + (-dt * q1) * rhs[i];        /* VecAXPY */
+    return 0;
+  }
   for (size_t i = 0; i < n; i++) r[i] = lhs[i];                 /* VecCopy */
   for (size_t i = 0; i < n; i++) r[i] = r[i] + (-1.0) * lhs_last[i]; /* VecAXPY */
   err = wo_flow_cell_inflows(f, rhs);

@@ -162,6 +162,10 @@ struct wb_ctx {
   double *d_yloc = nullptr;      // [ninterior*np] primaries incl. partition ghosts
   double *d_balances = nullptr;  // [nowned*np] lhs of the last unperturbed evaluation
   int eval_variant = 0;          // state slot of the last wb_pre_eval (0 unperturbed, 1 perturbed scratch)
+  // time-stepping method whose residual wb_residual_be / wb_jacobian_be / wb_newton_solve_be evaluate
+  int method = 0;
+  double dt_last = 0.0;
+  double *d_lhs_last2 = nullptr;  // BDF2: lhs two steps back
   // fixed-rate sources / sinks, sorted by cell
   int nsrc = 0;
   int32_t *d_src_head = nullptr, *d_src_cell = nullptr, *d_src_comp = nullptr;

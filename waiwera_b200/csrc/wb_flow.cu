@@ -223,6 +223,29 @@ __global__ void k_boundary(const __grid_constant__ WbEosParams e, const Boundary
     store_state(a.state + (size_t)slot * WbStateLayout<NC, NPH>::NF * nc, nc, c, s);
 }
 
+// ---------------------------------------------------------------- time-stepping residual forms
+
+// residual of the method timestepper.F90 selects (context%residual):
+//   backward Euler  (:345-374)  r = L - L_last - dt R                        [VecCopy, VecAXPY, VecAXPY]
+//   BDF2            (:378-427)  r = (1+2q) L - (q+1)^2 L_last + q^2 L_last2 - dt (q+1) R,  q = dt / dt_last
+//                                                                            [VecCopy, VecScale, 3 x VecAXPY]
+//   direct steady state (:431-452)  r = R
+// evaluated entry by entry in the reference's operation order
+struct WbResForm {
+  int method;               // WB_METHOD_*
+  double a0, a1, a2, cR;    // scale of L (BDF2 only), of L_last, of L_last2, of R
+  const double *l1, *l2;    // L_last, L_last2 (AoS [nowned*np])
+};
+__device__ __forceinline__ double wb_form_residual(const WbResForm &f, double L, double R, size_t idx) {
+  if (f.method == WB_METHOD_DIRECTSS) return R;
+  double r = L;
+  if (f.method == WB_METHOD_BDF2) r = r * f.a0;
+  r = r + f.a1 * f.l1[idx];
+  if (f.method == WB_METHOD_BDF2) r = r + f.a2 * f.l2[idx];
+  r = r + f.cR * R;
+  return r;
+}
+
 // ---------------------------------------------------------------- sources / sinks
 
 // fixed-rate sources sorted by cell (stable: input order inside a cell); head[c] = first source of owned cell c or -1
@@ -305,7 +328,7 @@ struct ResidualArgs {
   const double *face;   // SoA [6][nface]
   const double *vol;
   const int32_t *cf_ptr, *cf_face, *cf_other;
-  const double *lhs_last;  // may be null (then r is not formed)
+  WbResForm form;          // r is formed when r != null
   double *lhs, *rhs, *r;   // any may be null; AoS [nowned*np]
   double dt;
   int ncell, nowned, nface;
@@ -357,12 +380,7 @@ __global__ void __launch_bounds__(128) k_residual(const ResidualArgs a) {
     const double L = a.Lvar[(size_t)k * a.nowned + i];
     if (a.lhs) a.lhs[(size_t)i * NP + k] = L;
     if (a.rhs) a.rhs[(size_t)i * NP + k] = acc[k];
-    if (a.r) {
-      // timestepper.F90:363-370: r = L; r += -1*L_last; r += -dt*R
-      double r = L + (-1.0) * a.lhs_last[(size_t)i * NP + k];
-      r = r + (-a.dt) * acc[k];
-      a.r[(size_t)i * NP + k] = r;
-    }
+    if (a.r) a.r[(size_t)i * NP + k] = wb_form_residual(a.form, L, acc[k], (size_t)i * NP + k);
   }
 }
 
@@ -372,7 +390,8 @@ struct JacArgs {
   const double *state;  // [(np+1)][nf][ncell]
   const double *Lvar;   // [(np+1)][np][nowned]
   const double *dx;     // [np][ninterior]
-  const double *face, *vol, *lhs_last;
+  const double *face, *vol;
+  WbResForm form;
   const int32_t *cf_ptr, *cf_face, *cf_other, *cf_bpos, *diagpos;
   double *val;  // BAIJ blocks, column-major bs x bs
   double dt;
@@ -399,12 +418,9 @@ __global__ void __launch_bounds__(128) k_jacobian(const JacArgs a) {
   load_state(a.state, nc, i, s0);
 
   double t[MAXDEG][NP];  // base inflow terms, face order
-  double L0[NP], Ll[NP], F0[NP];
+  double L0[NP], F0[NP];
 #pragma unroll
-  for (int k = 0; k < NP; k++) {
-    L0[k] = a.Lvar[(size_t)k * a.nowned + i];
-    Ll[k] = a.lhs_last[(size_t)i * NP + k];
-  }
+  for (int k = 0; k < NP; k++) L0[k] = a.Lvar[(size_t)k * a.nowned + i];
   {
     double acc[NP];
 #pragma unroll
@@ -422,7 +438,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const JacArgs a) {
     }
     source_terms<NP, NC, NPH>(a.src, i, s0, vol, acc);
 #pragma unroll
-    for (int k = 0; k < NP; k++) F0[k] = (L0[k] + (-1.0) * Ll[k]) + (-a.dt) * acc[k];
+    for (int k = 0; k < NP; k++) F0[k] = wb_form_residual(a.form, L0[k], acc[k], (size_t)i * NP + k);
   }
 
   // diagonal block: own variable v perturbed
@@ -451,7 +467,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const JacArgs a) {
 #pragma unroll
       for (int k = 0; k < NP; k++) {
         const double Lv = a.Lvar[((size_t)(v + 1) * NP + k) * a.nowned + i];
-        const double Fp = (Lv + (-1.0) * Ll[k]) + (-a.dt) * acc[k];
+        const double Fp = wb_form_residual(a.form, Lv, acc[k], (size_t)i * NP + k);
         blk[v * NP + k] = (Fp + (-1.0) * F0[k]) * vscale;
       }
     }
@@ -489,7 +505,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const JacArgs a) {
           const double vscale = 1.0 / a.dx[(size_t)v * a.ninterior + o];
 #pragma unroll
           for (int k = 0; k < NP; k++) {
-            const double Fp = (L0[k] + (-1.0) * Ll[k]) + (-a.dt) * acc[k];
+            const double Fp = wb_form_residual(a.form, L0[k], acc[k], (size_t)i * NP + k);
             blk[v * NP + k] = (Fp + (-1.0) * F0[k]) * vscale;
           }
         }
@@ -660,6 +676,21 @@ __global__ void k_unpack_yr(const double *__restrict__ in, int c0, int n, int np
     else if ((ctx)->prm.eos == WB_EOS_WCE) { CALL(WB_EOS_WCE); } \
     else { CALL(WB_EOS_W); }                                     \
   } while (0)
+
+// residual form of the context's time-stepping method for step size dt
+static WbResForm wb_res_form(const wb_ctx *c, const double *d_lhs_last, double dt) {
+  WbResForm f;
+  f.method = c->method;
+  f.l1 = d_lhs_last;
+  f.l2 = c->d_lhs_last2;
+  if (c->method == WB_METHOD_BDF2) {
+    const double q = dt / c->dt_last, q1 = q + 1.0;
+    f.a0 = 1.0 + 2.0 * q; f.a1 = -q1 * q1; f.a2 = q * q; f.cR = -dt * q1;
+  } else {
+    f.a0 = 1.0; f.a1 = -1.0; f.a2 = 0.0; f.cR = -dt;
+  }
+  return f;
+}
 
 static WbSources wb_sources_args(const wb_ctx *c) {
   WbSources S = {c->nsrc > 0 ? c->d_src_head : nullptr, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth, c->nsrc};
@@ -925,7 +956,8 @@ static int launch_residual(wb_ctx *c, int slot, const double *d_lhs_last, double
   a.state = c->d_state + (size_t)slot * c->nf * c->ncell;
   a.Lvar = c->d_Lvar + (size_t)slot * c->np * c->nowned;
   a.face = c->d_face; a.vol = c->d_vol; a.cf_ptr = c->d_cf_ptr; a.cf_face = c->d_cf_face; a.cf_other = c->d_cf_other;
-  a.lhs_last = d_lhs_last; a.lhs = d_lhs; a.rhs = d_rhs; a.r = d_r; a.dt = dt;
+  a.form = wb_res_form(c, d_lhs_last, dt);
+  a.lhs = d_lhs; a.rhs = d_rhs; a.r = (d_lhs_last || c->method == WB_METHOD_DIRECTSS) ? d_r : nullptr; a.dt = dt;
   a.ncell = c->ncell; a.nowned = c->nowned; a.nface = c->nface;
   a.src = wb_sources_args(c);
 #define CALL(E) k_residual<E><<<wb_grid(c->nowned, 128), 128, 0, c->stream>>>(a)
@@ -933,6 +965,23 @@ static int launch_residual(wb_ctx *c, int slot, const double *d_lhs_last, double
 #undef CALL
   WB_LAUNCH(c);
   WB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- time-stepping method ----------------------------------------------------------------------
+extern "C" int wb_set_method(wb_ctx *c, int method, double dt_last, const double *lhs_last2) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CHECK(method == WB_METHOD_BEULER || method == WB_METHOD_BDF2 || method == WB_METHOD_DIRECTSS,
+           "wb_set_method: unknown method %d", method);
+  if (method == WB_METHOD_BDF2) {
+    WB_CHECK(c->ncell > 0 && lhs_last2 && dt_last > 0.0, "wb_set_method: BDF2 needs a mesh, dt_last > 0 and lhs_last2");
+    const size_t n = (size_t)c->nowned * c->np;
+    if (!c->d_lhs_last2) WB_CUDA(cudaMalloc(&c->d_lhs_last2, sizeof(double) * n));
+    WB_CUDA(cudaMemcpyAsync(c->d_lhs_last2, lhs_last2, sizeof(double) * n, cudaMemcpyDefault, c->stream));
+    WB_CUDA(cudaStreamSynchronize(c->stream));
+    c->dt_last = dt_last;
+  }
+  c->method = method;
   return 0;
 }
 
@@ -1270,7 +1319,8 @@ int wb_jacobian_be_dev(wb_ctx *c, const double *d_y, const double *d_lhs_last, d
   }
   JacArgs a;
   a.state = c->d_state; a.Lvar = c->d_Lvar; a.dx = c->d_dx; a.face = c->d_face; a.vol = c->d_vol;
-  a.lhs_last = d_lhs_last; a.cf_ptr = c->d_cf_ptr; a.cf_face = c->d_cf_face; a.cf_other = c->d_cf_other;
+  a.form = wb_res_form(c, d_lhs_last, dt);
+  a.cf_ptr = c->d_cf_ptr; a.cf_face = c->d_cf_face; a.cf_other = c->d_cf_other;
   a.cf_bpos = c->d_cf_bpos; a.diagpos = c->d_diagpos; a.val = c->J.d_val; a.dt = dt;
   a.ncell = c->ncell; a.ninterior = c->ninterior; a.nowned = c->nowned; a.nface = c->nface;
   a.src = wb_sources_args(c);

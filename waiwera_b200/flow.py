@@ -19,6 +19,7 @@ RP_FULLY_MOBILE, RP_LINEAR, RP_PICKENS, RP_COREY, RP_GRANT, RP_VAN_GENUCHTEN, RP
 CP_ZERO, CP_LINEAR, CP_VAN_GENUCHTEN, CP_TABLE = range(4)
 PC_NONE, PC_PBJACOBI, PC_BJACOBI_ILU0 = 0, 1, 2
 KSP_GMRES, KSP_BCGS = 0, 1
+METHOD_BEULER, METHOD_BDF2, METHOD_DIRECTSS = 0, 1, 2
 
 
 def ptr(a, dtype=None):
@@ -212,6 +213,10 @@ class FlowSimulation:
         pr = np.ascontiguousarray(primary, np.float64)
         rg = np.ascontiguousarray(region, np.int32)
         return check(self.L.wb_set_boundaries(self.h, len(g), ptr(g), ptr(ic), ptr(pr), ptr(rg)), "wb_set_boundaries")
+
+    def set_method(self, method, dt_last=0.0, lhs_last2=None):
+        """time-stepping residual form (timestepper.F90:345-452): METHOD_BEULER / METHOD_BDF2 / METHOD_DIRECTSS"""
+        return check(self.L.wb_set_method(self.h, method, dt_last, ptr(lhs_last2)), "wb_set_method")
 
     def set_sources(self, cells, components, rates, enthalpies):
         """fixed-rate sources / sinks (source.F90:375-480); see wb_set_sources"""
