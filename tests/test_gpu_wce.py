@@ -154,3 +154,53 @@ def test_wce_newton_step_matches_oracle(wo, flow, ksp):
     assert res0.reason == res1.reason and res0.iterations == res1.iterations, (res0.reason, res1.reason, res0.iterations, res1.iterations)
     assert relerr(y1, y0) < 1e-6
     sim.destroy()
+
+
+def test_full_size_wce_properties(wo, flow):
+    """BASELINE config 4 size (100x100x50 = 500 k cells, eos_wce, BAIJ bs = 3, 3.46 M blocks): size-independent
+    properties -- closed box => the inflows conserve water, CO2 and energy (sum_i V_i R_i = 0 to rounding), the
+    evaluation is deterministic, the Jacobian SpMV is linear, per-cell balances agree with the oracle on a sample,
+    and one Newton step with BiCGStab + ILU(0) sub-domains reduces the residual."""
+    m, y, region, prm = make_problem_wce(wo, dims=(100, 100, 50), two_phase_layers=10)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    e, L = sim.lhs(y)
+    assert e == 0
+    dt = 1.0e5
+    e, lhs, rhs, r = sim.residual(y, L, dt)
+    assert e == 0
+    vol = m.cell_geom[:m.nowned, 3]
+    for k in range(3):
+        tot = np.sum(vol * rhs[k::3])
+        assert abs(tot) <= 1e-9 * np.sum(vol * np.abs(rhs[k::3]))
+    assert np.array_equal(sim.residual(y, L, dt)[3], r)
+    eos = wo.lib().wo_eos_create(C.byref(prm))
+    for c in range(0, m.nowned, 50021):
+        fl = np.zeros(26)
+        fl[2] = region[c]
+        pr = np.zeros(3)
+        wo.lib().wo_eos_unscale(eos, wo.dp(y[3 * c:3 * c + 3].copy()), int(region[c]), wo.dp(pr))
+        assert wo.lib().wo_eos_bulk_properties(eos, wo.dp(pr), wo.dp(fl)) == 0
+        assert wo.lib().wo_eos_phase_properties(eos, wo.dp(pr), wo.dp(m.rock[c].copy()), wo.dp(fl)) == 0
+        bal = np.zeros(3)
+        wo.lib().wo_cell_balance(wo.dp(m.rock[c].copy()), wo.dp(fl), 2, 2, 3, wo.dp(bal))
+        assert np.allclose(bal, L[3 * c:3 * c + 3], rtol=1e-12, atol=0)
+    wo.lib().wo_eos_destroy(eos)
+    assert sim.jacobian(y, L, dt) == 0
+    nb, bs, rowptr, colidx = sim.jacobian_pattern()
+    assert bs == 3 and len(colidx) == 3460000
+    J = sim.jacobian_mat()
+    rng = np.random.default_rng(SEED)
+    x1, x2 = rng.uniform(-1, 1, nb * 3), rng.uniform(-1, 1, nb * 3)
+    a1, a2, a12 = np.zeros(nb * 3), np.zeros(nb * 3), np.zeros(nb * 3)
+    J.mult(x1, a1)
+    J.mult(x2, a2)
+    J.mult(1.5 * x1 - 0.25 * x2, a12)
+    assert relerr(a12, 1.5 * a1 - 0.25 * a2) < 1e-13
+    from waiwera_b200 import mesh as wmesh
+    sim.set_pc_blocks(wmesh.cube_blocks(m, 10))
+    y1 = y.copy()
+    res = sim.newton_solve(y1, L, dt, flow.newton_opts(max_iterations=2, pc_type=flow.PC_BJACOBI_ILU0,
+                                                       ksp=flow.ksp_opts(type=flow.KSP_BCGS)))
+    assert res.iterations >= 1 and res.reason in (3, 4, -5)
+    assert res.max_residual[1] < 0.5 * res.max_residual[0]
+    sim.destroy()

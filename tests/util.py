@@ -22,6 +22,8 @@ def psat_fn(wo, thermo):
     th = wo.lib().wo_thermo_create(thermo, 0)
 
     def f(t):
+        if np.ndim(t) > 0:
+            return np.array([f(v) for v in np.asarray(t).reshape(-1)])
         p = C.c_double()
         assert wo.lib().wo_saturation_pressure(th, float(t), C.byref(p)) == 0
         return p.value

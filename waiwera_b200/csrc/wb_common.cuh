@@ -123,7 +123,13 @@ struct wb_mat {
   double *d_xloc = nullptr;  // (ncolb-nb)*bs: ghost entries of x (multi-GPU), filled by the halo exchange
   std::vector<int32_t> h_rowptr, h_colidx;
   bool owns = true;
+  // TMA-staged SpMV: first block of every tile of WB_SPMV_TILE rows (+ end), stage capacity in blocks
+  int32_t *d_tile_e0 = nullptr;
+  int ntiles = 0, tile_cap = 0;
 };
+#define WB_SPMV_TILE 128
+#define WB_PAD_BYTES 256  // slack after rowptr / colidx / val so that 16-byte-rounded bulk copies stay inside the allocation
+int wb_mat_build_tiles(wb_mat *A);  // after h_rowptr is known
 
 struct wb_ctx {
   int device = 0;

@@ -200,6 +200,8 @@ static void free_mat(wb_mat &m) {
     cudaFree(m.d_val);
   }
   cudaFree(m.d_xloc);
+  cudaFree(m.d_tile_e0);
+  m.d_tile_e0 = nullptr;
   m.d_rowptr = m.d_colidx = nullptr;
   m.d_val = m.d_xloc = nullptr;
 }

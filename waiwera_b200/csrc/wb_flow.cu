@@ -848,10 +848,15 @@ extern "C" int wb_set_mesh(wb_ctx *c, int ncell, int ninterior, int nowned, int 
   WB_TRY(dev_upload(&c->d_cf_other, c->h_cf_other));
   WB_TRY(dev_upload(&c->d_cf_bpos, bpos));
   WB_TRY(dev_upload(&c->d_diagpos, diagpos));
-  WB_TRY(dev_upload(&J.d_rowptr, J.h_rowptr));
-  WB_TRY(dev_upload(&J.d_colidx, J.h_colidx));
-  WB_TRY(dev_alloc(&J.d_val, (size_t)J.nnzb * np * np));
-  WB_CUDA(cudaMemset(J.d_val, 0, (size_t)J.nnzb * np * np * sizeof(double)));
+  // (padded: the TMA-staged SpMV rounds its bulk copies to 16 bytes)
+  WB_CUDA(cudaMalloc(&J.d_rowptr, sizeof(int32_t) * J.h_rowptr.size() + WB_PAD_BYTES));
+  WB_CUDA(cudaMalloc(&J.d_colidx, sizeof(int32_t) * std::max<size_t>(J.h_colidx.size(), 1) + WB_PAD_BYTES));
+  WB_CUDA(cudaMemset(J.d_colidx, 0, sizeof(int32_t) * std::max<size_t>(J.h_colidx.size(), 1) + WB_PAD_BYTES));
+  WB_CUDA(cudaMemcpy(J.d_rowptr, J.h_rowptr.data(), sizeof(int32_t) * J.h_rowptr.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMemcpy(J.d_colidx, J.h_colidx.data(), sizeof(int32_t) * J.h_colidx.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(cudaMalloc(&J.d_val, (size_t)J.nnzb * np * np * sizeof(double) + WB_PAD_BYTES));
+  WB_CUDA(cudaMemset(J.d_val, 0, (size_t)J.nnzb * np * np * sizeof(double) + WB_PAD_BYTES));
+  WB_TRY(wb_mat_build_tiles(&J));
   WB_TRY(dev_alloc(&J.d_xloc, (size_t)(ninterior - nowned + 1) * np));  // ghost entries of x for the SpMV
   WB_CUDA(cudaMemset(J.d_xloc, 0, (size_t)(ninterior - nowned + 1) * np * sizeof(double)));
 

@@ -185,6 +185,9 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
   }
 }
 
+static bool wb_spmv_tma_enabled(const wb_mat *A);
+static int wb_spmv_tma_launch(wb_mat *A, const SpmvArgs &a);
+
 // y = A (x*scale) with device pointers; x holds the nb*bs owned entries.  With ghost columns
 // (multi-GPU) the ghost entries are gathered straight into the matrix's ghost buffer by the halo
 // exchange (MatMult_MPIBAIJ's VecScatter); the owned part is never copied.
@@ -206,6 +209,7 @@ int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d
   }
   SpmvArgs a = {A->d_rowptr, A->d_colidx, A->d_val, d_x, xg, d_scale, d_xn, d_y, A->nb, done,
                 c->p2p.dev, hseq, hseq ? c->halo.nneigh : 0, c->p2p.d_nb_rank};
+  if (wb_spmv_tma_enabled(A)) return wb_spmv_tma_launch(A, a);
   static int rows_per_group = 0;  // tuning knob (WB_SPMV_ROWS = 1, 2, 4); measured 70.9 / 70.6 / 97 us at 1 M cells
   if (!rows_per_group) {
     const char *e = getenv("WB_SPMV_ROWS");
@@ -247,15 +251,16 @@ extern "C" int wb_mat_create(wb_ctx *c, int nb, int ncolb, int bs, int nnzb, con
   A->h_colidx.resize(nnzb);
   WB_CUDA(cudaMemcpy(A->h_rowptr.data(), rowptr, sizeof(int32_t) * (nb + 1), cudaMemcpyDefault));
   WB_CUDA(cudaMemcpy(A->h_colidx.data(), colidx, sizeof(int32_t) * nnzb, cudaMemcpyDefault));
-  WB_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int32_t) * (nb + 1)));
-  WB_CUDA(cudaMalloc(&A->d_colidx, sizeof(int32_t) * std::max(nnzb, 1)));
-  WB_CUDA(cudaMalloc(&A->d_val, sizeof(double) * std::max<size_t>((size_t)nnzb * bs * bs, 1)));
+  WB_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int32_t) * (nb + 1) + WB_PAD_BYTES));
+  WB_CUDA(cudaMalloc(&A->d_colidx, sizeof(int32_t) * std::max(nnzb, 1) + WB_PAD_BYTES));
+  WB_CUDA(cudaMalloc(&A->d_val, sizeof(double) * std::max<size_t>((size_t)nnzb * bs * bs, 1) + WB_PAD_BYTES));
   WB_CUDA(cudaMalloc(&A->d_xloc, sizeof(double) * (size_t)(ncolb - nb + 1) * bs));
   WB_CUDA(cudaMemset(A->d_xloc, 0, sizeof(double) * (size_t)(ncolb - nb + 1) * bs));
   WB_CUDA(cudaMemcpy(A->d_rowptr, A->h_rowptr.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice));
   WB_CUDA(cudaMemcpy(A->d_colidx, A->h_colidx.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice));
   if (vals) WB_CUDA(cudaMemcpy(A->d_val, vals, sizeof(double) * (size_t)nnzb * bs * bs, cudaMemcpyDefault));
   else WB_CUDA(cudaMemset(A->d_val, 0, sizeof(double) * (size_t)nnzb * bs * bs));
+  WB_TRY(wb_mat_build_tiles(A));
   *out = A;
   return 0;
 }
@@ -275,6 +280,7 @@ extern "C" int wb_mat_destroy(wb_mat *A) {
   cudaFree(A->d_colidx);
   cudaFree(A->d_val);
   cudaFree(A->d_xloc);
+  cudaFree(A->d_tile_e0);
   delete A;
   return 0;
 }
@@ -1287,6 +1293,249 @@ extern "C" int wb_pc_apply(wb_pc *pc, const double *r, double *z) {
     WB_TRY(wb_pc_apply_dev(pc, dr, dz, nullptr));
   }
   return st.finish();
+}
+
+// ================================================================ SpMV (K5), TMA-staged
+// Persistent CTAs (2 per SM) walk tiles of WB_SPMV_TILE block rows.  A dedicated producer warp brings each
+// tile's three contiguous spans -- row pointers, column indices, value blocks -- into a shared-memory ring
+// with cp.async.bulk (TMA, mbarrier-completed, L2 evict-first), NSTAGE tiles ahead, so the only global
+// round trip left on the consumers' path is the gather of x (L2 resident): the rowptr -> colidx -> x
+// dependency chain of the plain kernel becomes shared -> shared -> L2.  Consumers use the same 8-lanes-per-row
+// scheme and fixed-order shuffle fold as k_bsr_spmv (identical arithmetic), four rows per lane group in flight;
+// each consumer warp releases a ring slot with one mbarrier arrive, no CTA-wide barrier.
+#define SPMV_TMA_STAGES 3
+struct SpmvTmaArgs {
+  SpmvArgs a;
+  const int32_t *tile_e0;  // [ntiles + 1]
+  int ntiles, cap;         // cap: stage capacity in blocks
+};
+
+template <int BS, int SPMV_TMA_CONSUMERS>
+__global__ void __launch_bounds__(SPMV_TMA_CONSUMERS + 32) k_bsr_spmv_tma(const SpmvTmaArgs t) {
+  const SpmvArgs &a = t.a;
+  if (a.done && *a.done) return;
+  constexpr int B2 = BS * BS, TR = WB_SPMV_TILE, NG = SPMV_TMA_CONSUMERS / 8, R = TR / NG;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+  uint64_t *empty = full + SPMV_TMA_STAGES;
+  // stage layout: [rowptr slice: (TR+4) ints][colidx: cap+8 ints][values: (cap+2)*B2 doubles], 16-byte aligned parts
+  const int rp_bytes = (TR + 4) * 4, ci_bytes = ((t.cap + 8) * 4 + 15) & ~15, va_bytes = (t.cap + 4) * B2 * 8;
+  const int stage_bytes = (rp_bytes + ci_bytes + va_bytes + 127) & ~127;
+  unsigned char *stages = smem_raw + 128;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < SPMV_TMA_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], SPMV_TMA_CONSUMERS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= SPMV_TMA_CONSUMERS) {
+    // ---- producer warp
+    if (tid == SPMV_TMA_CONSUMERS) {
+      int st = 0;
+      uint32_t parity = 0;
+      int k = 0;
+      for (int tile = blockIdx.x; tile < t.ntiles; tile += gridDim.x, k++) {
+        if (k >= SPMV_TMA_STAGES) mbar_wait(&empty[st], parity ^ 1u);
+        const int r0 = tile * TR;
+        const int nr = min(TR, a.nb - r0);
+        const int e0 = t.tile_e0[tile], e1 = t.tile_e0[tile + 1];
+        const int ec = e0 & ~3, ev = e0 & ~1;  // 16-byte aligned starts of the index / value spans
+        const uint32_t b_rp = (uint32_t)(((nr + 1) * 4 + 15) & ~15);
+        const uint32_t b_ci = (uint32_t)(((e1 - ec) * 4 + 15) & ~15);
+        const uint32_t b_va = (uint32_t)((((size_t)(e1 - ev) * B2 * 8) + 15) & ~(size_t)15);
+        unsigned char *sp = stages + (size_t)st * stage_bytes;
+        mbar_expect_tx(&full[st], b_rp + b_ci + b_va);
+        tma_load_1d(sp, a.rowptr + r0, b_rp, &full[st]);
+        if (b_ci) tma_load_1d(sp + rp_bytes, a.colidx + ec, b_ci, &full[st]);
+        if (b_va) tma_load_1d(sp + rp_bytes + ci_bytes, a.val + (size_t)ev * B2, b_va, &full[st]);
+        if (++st == SPMV_TMA_STAGES) {
+          st = 0;
+          parity ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+  // ---- consumers
+  const int lane = tid & 7, grp = tid >> 3;  // NG lane groups, R rows each per tile
+  const double s = a.scale ? *a.scale : 1.0;
+  bool waited = (a.hseq == 0);
+  int st = 0;
+  uint32_t parity = 0;
+  for (int tile = blockIdx.x; tile < t.ntiles; tile += gridDim.x) {
+    const int r0 = tile * TR;
+    const unsigned char *sp = stages + (size_t)st * stage_bytes;
+    const int *rp = reinterpret_cast<const int *>(sp);
+    const int *sci = reinterpret_cast<const int *>(sp + rp_bytes);
+    const double *sva = reinterpret_cast<const double *>(sp + rp_bytes + ci_bytes);
+    mbar_wait(&full[st], parity);
+    const int e_base = rp[0];
+    const int ec = e_base & ~3, ev = e_base & ~1;
+    int e0[R], e1[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int rl = grp + r * NG;
+      e0[r] = 0; e1[r] = 0;
+      if (r0 + rl < a.nb) {
+        e0[r] = rp[rl] + lane;
+        e1[r] = rp[rl + 1];
+      }
+    }
+    double acc[R][BS];
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+      for (int i = 0; i < BS; i++) acc[r][i] = 0.0;
+    bool more = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) more = more || (e0[r] < e1[r]);
+    while (more) {
+      int col[R];
+      double xb[R][BS];
+#pragma unroll
+      for (int r = 0; r < R; r++) col[r] = (e0[r] < e1[r]) ? sci[e0[r] - ec] : -1;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const bool own = col[r] < a.nb;
+        const double sc = own ? s : 1.0;
+#pragma unroll
+        for (int j = 0; j < BS; j++) xb[r][j] = 0.0;
+        if (col[r] >= 0) {
+          if (!own && !waited) {
+            for (int n = 0; n < a.nwait; n++) p2p_wait(p2p_my_flag(a.P, 0, a.nb_rank[n]), a.hseq, a.P.err);
+            waited = true;
+          }
+          const double *xp = own ? a.x + (size_t)col[r] * BS : a.xg + (size_t)(col[r] - a.nb) * BS;
+          if (!own) {
+#pragma unroll
+            for (int j = 0; j < BS; j++) xb[r][j] = __ldcg(xp + j) * sc;
+          } else if (BS == 2) {
+            const double2 x2 = *reinterpret_cast<const double2 *>(xp);
+            xb[r][0] = x2.x * sc; xb[r][1] = x2.y * sc;
+          } else {
+#pragma unroll
+            for (int j = 0; j < BS; j++) xb[r][j] = xp[j] * sc;
+          }
+        }
+      }
+      more = false;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (col[r] >= 0) {
+          const double *vp = sva + (size_t)(e0[r] - ev) * B2;
+          double v[B2];
+          if (BS == 2) {
+            const double2 p = *reinterpret_cast<const double2 *>(vp);
+            const double2 q = *reinterpret_cast<const double2 *>(vp + 2);
+            v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
+          } else {
+#pragma unroll
+            for (int q = 0; q < B2; q++) v[q] = vp[q];
+          }
+#pragma unroll
+          for (int j = 0; j < BS; j++)
+#pragma unroll
+            for (int i = 0; i < BS; i++) acc[r][i] += v[j * BS + i] * xb[r][j];
+        }
+        e0[r] += 8;
+        more = more || (e0[r] < e1[r]);
+      }
+    }
+    // this warp is done with the ring slot
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    if (++st == SPMV_TMA_STAGES) {
+      st = 0;
+      parity ^= 1u;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+      for (int off = 4; off > 0; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < BS; i++) acc[r][i] += __shfl_down_sync(0xffffffffu, acc[r][i], off, 8);
+      const int row = r0 + grp + r * NG;
+      if (row < a.nb && lane == 0) {
+        if (BS == 2) *reinterpret_cast<double2 *>(a.y + (size_t)row * 2) = make_double2(acc[r][0], acc[r][1]);
+        else {
+#pragma unroll
+          for (int i = 0; i < BS; i++) a.y[(size_t)row * BS + i] = acc[r][i];
+        }
+        if (a.xn) {
+#pragma unroll
+          for (int i = 0; i < BS; i++) a.xn[(size_t)row * BS + i] = a.x[(size_t)row * BS + i] * s;
+        }
+      }
+    }
+  }
+}
+
+int wb_mat_build_tiles(wb_mat *A) {
+  cudaFree(A->d_tile_e0);
+  A->d_tile_e0 = nullptr;
+  A->ntiles = (A->nb + WB_SPMV_TILE - 1) / WB_SPMV_TILE;
+  std::vector<int32_t> e0(A->ntiles + 1, 0);
+  int cap = 0;
+  for (int t = 0; t < A->ntiles; t++) {
+    const int r0 = t * WB_SPMV_TILE, r1 = std::min(A->nb, r0 + WB_SPMV_TILE);
+    e0[t] = A->h_rowptr[r0];
+    cap = std::max(cap, A->h_rowptr[r1] - A->h_rowptr[r0]);
+  }
+  e0[A->ntiles] = A->nb > 0 ? A->h_rowptr[A->nb] : 0;
+  A->tile_cap = cap;
+  WB_CUDA(cudaMalloc(&A->d_tile_e0, sizeof(int32_t) * e0.size()));
+  WB_CUDA(cudaMemcpy(A->d_tile_e0, e0.data(), sizeof(int32_t) * e0.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static size_t spmv_tma_smem(const wb_mat *A) {
+  const int b2 = A->bs * A->bs;
+  const size_t rp = (WB_SPMV_TILE + 4) * 4, ci = (((size_t)A->tile_cap + 8) * 4 + 15) & ~(size_t)15,
+               va = ((size_t)A->tile_cap + 4) * b2 * 8;
+  const size_t stage = (rp + ci + va + 127) & ~(size_t)127;
+  return 128 + SPMV_TMA_STAGES * stage;
+}
+
+static int spmv_tma_mode() {
+  static int mode = -1;  // WB_SPMV_TMA = 0 plain kernel, 1 TMA ring with 256 consumer threads, 2 with 512
+  if (mode < 0) {
+    const char *e = getenv("WB_SPMV_TMA");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+static bool wb_spmv_tma_enabled(const wb_mat *A) {
+  return spmv_tma_mode() != 0 && A->d_tile_e0 && A->ntiles > 0 && spmv_tma_smem(A) <= 110 * 1024;
+}
+
+static int wb_spmv_tma_launch(wb_mat *A, const SpmvArgs &a) {
+  wb_ctx *c = A->ctx;
+  SpmvTmaArgs t = {a, A->d_tile_e0, A->ntiles, A->tile_cap};
+  const size_t smem = spmv_tma_smem(A);
+  const int grid = std::min(A->ntiles, 2 * WB_NUM_SMS);
+#define SPMV_TMA(BS)                                                                                         \
+  do {                                                                                                       \
+    if (spmv_tma_mode() == 2) {                                                                              \
+      cudaFuncSetAttribute(k_bsr_spmv_tma<BS, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      k_bsr_spmv_tma<BS, 512><<<grid, 512 + 32, smem, c->stream>>>(t);                                       \
+    } else {                                                                                                 \
+      cudaFuncSetAttribute(k_bsr_spmv_tma<BS, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      k_bsr_spmv_tma<BS, 256><<<grid, 256 + 32, smem, c->stream>>>(t);                                       \
+    }                                                                                                        \
+  } while (0)
+  switch (A->bs) {
+    case 1: SPMV_TMA(1); break;
+    case 2: SPMV_TMA(2); break;
+    case 3: SPMV_TMA(3); break;
+    default: WB_CHECK(false, "wb_mat_mult: block size %d not supported", A->bs);
+  }
+#undef SPMV_TMA
+  WB_LAUNCH(c);
+  WB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ================================================================ vector kernels (K7)
