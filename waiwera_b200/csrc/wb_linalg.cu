@@ -836,18 +836,28 @@ __global__ void __launch_bounds__(288) k_ilu0_block_solve(const IluSolveArgs a) 
   }
   bar_sync_named(1, ncons);
   if (TMA) {
+    // Only ONE thread observes the arrival of a level's record: lane 0 of the last consumer warp (the warp with
+    // the fewest rows -- none at all in most levels) waits for level l+1 while the others apply level l; the
+    // consumer barrier that ends level l then orders the waiter's acquire before everybody's reads of level l+1,
+    // which takes the ~100-cycle mbarrier round trip off the level-to-level critical path.
     int st = 0;
     uint32_t parity = 0;
+    const bool waiter = tid == ncons - 32;
+    if (nl > 0) mbar_wait(&full[0], 0);  // level 0: everybody
     for (int l = 0; l < nl; l++) {
       const int4 L = desc[l];
-      mbar_wait(&full[st], parity);
       ilu_level<BS>(ring + (size_t)st * a.stage_words, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs, ncons);
+      int stn = st + 1;
+      uint32_t parn = parity;
+      if (stn == a.nstage) {
+        stn = 0;
+        parn ^= 1u;
+      }
+      if (waiter && l + 1 < nl) mbar_wait(&full[stn], parn);
       bar_sync_named(1, ncons);  // level l applied by all consumers: zs is consistent, the ring slot is free
       if (tid == 0) mbar_arrive(&empty[st]);
-      if (++st == a.nstage) {
-        st = 0;
-        parity ^= 1u;
-      }
+      st = stn;
+      parity = parn;
     }
   } else {
     for (int l = 0; l < nl; l++) {
