@@ -22,15 +22,41 @@ def _free_port():
     return p
 
 
-def problem():
+def problem(kind="we"):
+    """we: structured eos_we; wce: eos_wce (3 primaries, halo width 4); minc: eos_we on a MINC mesh with two matrix
+    levels (irregular rows, matrix cells owned by their fracture cell's rank)"""
     from waiwera_b200 import mesh as wmesh
     gm = wmesh.structured(*DIMS, dx=10.0, seed=wmesh.SEED)
-    primary, region = wmesh.hydrostatic_state(gm, seed=wmesh.SEED)
+    if kind == "wce":
+        primary, region = wmesh.wce_state(gm, seed=wmesh.SEED)
+    else:
+        primary, region = wmesh.hydrostatic_state(gm, seed=wmesh.SEED)
+    if kind == "minc":
+        n = gm.ninterior
+        gm = wmesh.add_minc(gm, volumes=(0.1, 0.3, 0.6), spacing=(50., 50., 50.), matrix_permeability_factor=0.01)
+        rng = np.random.default_rng(11)
+        prims = [primary]
+        for _ in range(2):
+            pm = primary.copy()
+            pm[:, 0] *= 1.0 + 1e-3 * rng.uniform(-1, 1, n)
+            prims.append(pm)
+        primary, region = np.concatenate(prims), np.concatenate([region] * 3)
     y = np.ascontiguousarray(wmesh.scale_primaries(primary, region)).reshape(-1)
     return gm, y, region
 
 
-def worker(rank, world, port, out, p2p):
+def params_for(kind):
+    from waiwera_b200 import flow
+    return flow.make_params(eos=flow.EOS_WCE if kind == "wce" else flow.EOS_WE)
+
+
+def owner_for(kind, gm, world):
+    from waiwera_b200 import mesh as wmesh
+    parts = wmesh.default_parts(world)
+    return wmesh.minc_owner(gm, parts) if kind == "minc" else wmesh.box_owner(gm, parts)
+
+
+def worker(rank, world, port, out, p2p, kind="we"):
     import torch.distributed as dist
     from waiwera_b200 import flow, mesh as wmesh
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -38,13 +64,14 @@ def worker(rank, world, port, out, p2p):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        gm, gy, gregion = problem()
-        owner = wmesh.box_owner(gm, wmesh.default_parts(world))
+        gm, gy, gregion = problem(kind)
+        npv = 3 if kind == "wce" else 2
+        owner = owner_for(kind, gm, world)
         m = wmesh.partition(gm, owner, rank, world)
         nat = m.natural[:m.nowned]
-        y = np.ascontiguousarray(gy.reshape(-1, 2)[nat].reshape(-1))
+        y = np.ascontiguousarray(gy.reshape(-1, npv)[nat].reshape(-1))
         region = np.ascontiguousarray(gregion[nat])
-        sim = flow.FlowSimulation(flow.make_params(), m, device=rank)
+        sim = flow.FlowSimulation(params_for(kind), m, device=rank)
         uid = torch.from_numpy(flow.FlowSimulation.unique_id()).cuda() if rank == 0 else torch.zeros(128, dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         sim.comm_init(rank, world, uid.cpu().numpy())
@@ -59,7 +86,7 @@ def worker(rank, world, port, out, p2p):
         mv, ml = sim.max_scaled(r, L0, 1.0)
         assert sim.jacobian(y1, L0, DT) == 0
         J = sim.jacobian_mat()
-        x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * 2).reshape(-1, 2)[nat].reshape(-1)
+        x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * npv).reshape(-1, npv)[nat].reshape(-1)
         ax = np.zeros_like(x)
         J.mult(x, ax)
         y2 = y.copy()
@@ -75,9 +102,9 @@ def worker(rank, world, port, out, p2p):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, True])
-@pytest.mark.parametrize("world", [2, 4])
-def test_partitioned_path_matches_single_gpu(world, p2p):
+@pytest.mark.parametrize("world,p2p,kind", [(2, False, "we"), (2, True, "we"), (4, False, "we"), (4, True, "we"),
+                                            (2, True, "wce"), (2, True, "minc")])
+def test_partitioned_path_matches_single_gpu(world, p2p, kind):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d CUDA devices" % world)
     import torch.multiprocessing as mp
@@ -85,7 +112,7 @@ def test_partitioned_path_matches_single_gpu(world, p2p):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=worker, args=(r, world, port, out, p2p)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, out, p2p, kind)) for r in range(world)]
     for p in procs:
         p.start()
     gathered = out.get(timeout=600)
@@ -93,8 +120,9 @@ def test_partitioned_path_matches_single_gpu(world, p2p):
         p.join(120)
         assert p.exitcode == 0
     # single-GPU reference on the whole mesh
-    gm, gy, gregion = problem()
-    sim = flow.FlowSimulation(flow.make_params(), gm, device=0)
+    gm, gy, gregion = problem(kind)
+    npv = 3 if kind == "wce" else 2
+    sim = flow.FlowSimulation(params_for(kind), gm, device=0)
     assert sim.fluid_init(gy, gregion) == 0
     err, L0 = sim.lhs(gy)
     y1 = gy * (1.0 + 1e-5)
@@ -102,17 +130,17 @@ def test_partitioned_path_matches_single_gpu(world, p2p):
     mv, ml = sim.max_scaled(r, L0, 1.0)
     assert sim.jacobian(y1, L0, DT) == 0
     J = sim.jacobian_mat()
-    x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * 2)
+    x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * npv)
     ax = np.zeros_like(x)
     J.mult(x, ax)
     y2 = gy.copy()
     res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
                                                         ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))
-    gr, gax, gy2 = np.zeros_like(r).reshape(-1, 2), np.zeros_like(ax).reshape(-1, 2), np.zeros_like(y2).reshape(-1, 2)
+    gr, gax, gy2 = np.zeros_like(r).reshape(-1, npv), np.zeros_like(ax).reshape(-1, npv), np.zeros_like(y2).reshape(-1, npv)
     for g in gathered:
-        gr[g["nat"]] = g["r"].reshape(-1, 2)
-        gax[g["nat"]] = g["ax"].reshape(-1, 2)
-        gy2[g["nat"]] = g["y2"].reshape(-1, 2)
+        gr[g["nat"]] = g["r"].reshape(-1, npv)
+        gax[g["nat"]] = g["ax"].reshape(-1, npv)
+        gy2[g["nat"]] = g["y2"].reshape(-1, npv)
     # residual: same faces, same summation order -> bit exact; SpMV: local column order differs -> rounding
     assert np.array_equal(gr.reshape(-1), r)
     assert np.abs(gax.reshape(-1) - ax).max() <= 1e-13 * np.abs(ax).max()

@@ -22,12 +22,12 @@ __device__ __forceinline__ int p2p_ld_acquire_sys(const int *p) {
 __device__ __forceinline__ void p2p_st_release_sys(int *p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// spin until the peer's sequence number reaches `seq`; bounded (~2 s) so that a lost peer raises an error flag
+// spin until the peer's sequence number reaches `seq`; bounded (~15 s) so that a lost peer raises an error flag
 // instead of hanging the GPU
 __device__ __forceinline__ void p2p_wait(const int *flag, int seq, int *err) {
   const long long t0 = clock64();
   while (p2p_ld_acquire_sys(flag) < seq) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > 30000000000LL) {
       atomicExch(err, 1);
       break;
     }
