@@ -98,6 +98,13 @@ struct WbP2PDev {  // by-value kernel argument
   unsigned char *region[WB_P2P_MAX_RANKS];  // region[r] = rank r's region as mapped in this process (region[rank] local)
   int *err;                                 // device flag: set when a spin wait times out
 };
+struct WbHaloPush {  // what a kernel needs to push this rank's boundary entries to its neighbours
+  const int32_t *idx;       // [nsend] local owned cell of every send entry
+  const int32_t *dst_rank;  // [nsend] destination rank
+  const int32_t *dst_off;   // [nsend] cell offset in the destination's ghost area
+  const int32_t *nb_rank;   // [nneigh]
+  int nsend, nneigh, width, seq;
+};
 struct WbP2P {
   bool on = false;
   void *local = nullptr;
@@ -110,6 +117,7 @@ struct WbP2P {
   int32_t *d_nb_rank = nullptr;       // [nneigh]
   int32_t *d_nb_off = nullptr;        // [nneigh] = peer_off
   int32_t *d_nb_start = nullptr;      // [nneigh] = send_ptr
+  int32_t *d_dst_rank = nullptr, *d_dst_off = nullptr;  // [nsend] destination of every send entry
   unsigned *d_counter = nullptr;
 };
 // flags live in the first 4 KB of the region: one 64-byte line per (kind, sender rank)
@@ -239,12 +247,15 @@ int wb_halo_exchange_ghost(wb_ctx *ctx, const double *owned, int width, const do
 int wb_allreduce_sum(wb_ctx *ctx, double *dbuf, int n);     // in-stream, device buffer
 // P2P halo push of owned[idx]*scale into the neighbours' ghost areas; returns the sequence number consumers wait for
 int wb_p2p_halo_push(wb_ctx *ctx, const double *owned, int width, const double *scale, const int *done, int *seq);
+// arguments for a push fused into another kernel; takes the next halo sequence number
+WbHaloPush wb_p2p_halo_push_args(wb_ctx *ctx, int width);
 int wb_allreduce_max_int(wb_ctx *ctx, int *dbuf, int n);
 int wb_reduce_flags(wb_ctx *ctx, int nflags);               // device flags -> host (max over ranks)
 
 int wb_spmv_launch(wb_mat *A, const double *d_x, double *d_y);  // device pointers, handles halo
 // y = A (x*scale); optionally stores the scaled owned entries to xn; skipped when *done
-int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d_xn, double *d_y, const int *done);
+int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d_xn, double *d_y, const int *done,
+                  int prepushed_halo_seq = 0);
 
 // device-pointer cores shared between the translation units (no staging, no flag check)
 int wb_pre_eval_dev(wb_ctx *c, const double *d_y, bool unperturbed);

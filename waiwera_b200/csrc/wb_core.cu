@@ -239,6 +239,7 @@ extern "C" int wb_destroy(wb_ctx *c) {
     cudaFree(c->p2p.local);
     cudaFree(c->p2p.d_send_nb); cudaFree(c->p2p.d_nb_rank); cudaFree(c->p2p.d_nb_off); cudaFree(c->p2p.d_nb_start);
     cudaFree(c->p2p.d_counter);
+    cudaFree(c->p2p.d_dst_rank); cudaFree(c->p2p.d_dst_off);
   }
   if (c->comm && wb_nccl()) wb_nccl()->CommDestroy(c->comm);
   cudaFree(c->d_flags);
@@ -487,6 +488,18 @@ extern "C" int wb_comm_p2p_open(wb_ctx *c, const void *blobs) {
   WB_CUDA(cudaMalloc(&p.d_nb_rank, sizeof(int32_t) * nb_rank.size()));
   WB_CUDA(cudaMalloc(&p.d_nb_off, sizeof(int32_t) * nb_off.size()));
   WB_CUDA(cudaMalloc(&p.d_nb_start, sizeof(int32_t) * nb_start.size()));
+  {
+    std::vector<int32_t> dr(send_nb.size(), 0), doff(send_nb.size(), 0);
+    for (int n = 0; n < h.nneigh; n++)
+      for (int k = h.send_ptr[n]; k < h.send_ptr[n + 1]; k++) {
+        dr[k] = h.rank[n];
+        doff[k] = nb_off[n] + (k - h.send_ptr[n]);
+      }
+    WB_CUDA(cudaMalloc(&p.d_dst_rank, sizeof(int32_t) * dr.size()));
+    WB_CUDA(cudaMalloc(&p.d_dst_off, sizeof(int32_t) * doff.size()));
+    WB_CUDA(cudaMemcpy(p.d_dst_rank, dr.data(), sizeof(int32_t) * dr.size(), cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(p.d_dst_off, doff.data(), sizeof(int32_t) * doff.size(), cudaMemcpyHostToDevice));
+  }
   WB_CUDA(cudaMalloc(&p.d_counter, sizeof(unsigned)));
   WB_CUDA(cudaMemset(p.d_counter, 0, sizeof(unsigned)));
   WB_CUDA(cudaMemcpy(p.d_send_nb, send_nb.data(), sizeof(int32_t) * send_nb.size(), cudaMemcpyHostToDevice));
@@ -553,6 +566,13 @@ int wb_p2p_halo_push(wb_ctx *c, const double *owned, int width, const double *sc
   WB_LAUNCH(c);
   WB_CUDA(cudaGetLastError());
   return 0;
+}
+
+WbHaloPush wb_p2p_halo_push_args(wb_ctx *c, int width) {
+  WbP2P &p = c->p2p;
+  WbHalo &h = c->halo;
+  WbHaloPush a = {h.d_send_idx, p.d_dst_rank, p.d_dst_off, p.d_nb_rank, h.nsend, h.nneigh, width, ++p.seq_halo};
+  return a;
 }
 
 int wb_allreduce_sum(wb_ctx *c, double *dbuf, int n) {

@@ -191,14 +191,17 @@ static int wb_spmv_tma_launch(wb_mat *A, const SpmvArgs &a);
 // y = A (x*scale) with device pointers; x holds the nb*bs owned entries.  With ghost columns
 // (multi-GPU) the ghost entries are gathered straight into the matrix's ghost buffer by the halo
 // exchange (MatMult_MPIBAIJ's VecScatter); the owned part is never copied.
-int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d_xn, double *d_y, const int *done) {
+int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d_xn, double *d_y, const int *done,
+                  int prepushed_halo_seq) {
   wb_ctx *c = A->ctx;
   const double *xg = nullptr;
   int hseq = 0;
   if (A->ncolb > A->nb && c->nranks > 1) {
     if (c->p2p.on && A == &c->J) {
-      // neighbours write their entries straight into this GPU's ghost area over NVLink
-      WB_TRY(wb_p2p_halo_push(c, d_x, A->bs, d_scale, done, &hseq));
+      // neighbours write their entries straight into this GPU's ghost area over NVLink (already done by the
+      // tail of the previous multi-axpy when prepushed_halo_seq is set)
+      if (prepushed_halo_seq > 0) hseq = prepushed_halo_seq;
+      else WB_TRY(wb_p2p_halo_push(c, d_x, A->bs, d_scale, done, &hseq));
       xg = reinterpret_cast<const double *>(c->p2p.dev.region[c->rank] + WB_P2P_GHOST);
     } else {
       WB_TRY(wb_halo_exchange_ghost(c, d_x, A->bs, d_scale, A->d_xloc));
@@ -1784,6 +1787,9 @@ struct MaxpyArgs {
   int seq_coef;      // > 0: coefficients = sum over ranks of slot A (waits for every rank's sequence number)
   double *coef_out;  // reduced coefficients for the Hessenberg update (written by CTA 0)
   int seq_norm;      // > 0: the local |w|^2 is published to every rank's slot B instead of `out`
+  int fuse_tail;     // with seq_norm: the last CTA also waits for every rank's norm, runs the Hessenberg update and
+                     // pushes the (scaled) boundary entries of w to the neighbours for the next SpMV
+  WbHaloPush push;
 };
 template <int NVT, bool VEC>
 __global__ void __launch_bounds__(256, 2) k_maxpy_all(const MaxpyArgs a) {
@@ -1855,22 +1861,75 @@ __global__ void __launch_bounds__(256, 2) k_maxpy_all(const MaxpyArgs a) {
   const double s = block_sum(nrm);
   if (threadIdx.x == 0) a.part[blockIdx.x] = s;
   if (last_block(a.counter)) {
+    __shared__ double s_t;
     if (threadIdx.x < 32) {
       double t = 0.0;
       for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) t += __ldcg(&a.part[b]);
       t = warp_sum(t);
-      if (a.seq_norm > 0) {
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (threadIdx.x < a.P.nranks)
-          reinterpret_cast<double *>(a.P.region[threadIdx.x] + WB_P2P_SLOT_B)[a.P.rank] = t;
-        __threadfence_system();
-        __syncwarp();
-        if (threadIdx.x < a.P.nranks)
-          p2p_st_release_sys(reinterpret_cast<int *>(a.P.region[threadIdx.x] + wb_p2p_flag_off(2, a.P.rank)), a.seq_norm);
-      } else if (threadIdx.x == 0) {
-        a.out[0] = t;
-        if (a.with_upd) gmres_update(a.upd);
+      if (threadIdx.x == 0) s_t = t;
+    }
+    __syncthreads();
+    if (a.seq_norm > 0) {
+      if (threadIdx.x < a.P.nranks)
+        reinterpret_cast<double *>(a.P.region[threadIdx.x] + WB_P2P_SLOT_B)[a.P.rank] = s_t;
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < a.P.nranks)
+        p2p_st_release_sys(reinterpret_cast<int *>(a.P.region[threadIdx.x] + wb_p2p_flag_off(2, a.P.rank)), a.seq_norm);
+      if (a.fuse_tail) {
+        // |w|^2 over all ranks (fixed rank order), Hessenberg / convergence update, then the halo of the next SpMV
+        if (threadIdx.x < a.P.nranks) p2p_wait(p2p_my_flag(a.P, 2, threadIdx.x), a.seq_norm, a.P.err);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          const double *slot = reinterpret_cast<const double *>(a.P.region[a.P.rank] + WB_P2P_SLOT_B);
+          double sum = 0.0;
+          for (int r = 0; r < a.P.nranks; r++) sum += __ldcg(&slot[r]);
+          a.upd.scal[0] = sum;
+          gmres_update(a.upd);
+          __threadfence();
+        }
+        __syncthreads();
+        if (!*reinterpret_cast<volatile int *>(a.upd.done)) {
+          const double scale = *reinterpret_cast<volatile double *>(a.upd.scal + 1);
+          const WbHaloPush &h = a.push;
+          // one CTA pushes the whole boundary: 8 entries per thread in flight (index loads, then the gathers of
+          // w at L2, then the peer stores) so the push costs a few L2 round trips, not one per entry
+          constexpr int U = 8, WMAX = WB_MAX_NP;
+          for (int e0 = threadIdx.x; e0 < h.nsend; e0 += U * blockDim.x) {
+            int src[U], dr[U], doff[U];
+            double v[U][WMAX];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              const int e = e0 + u * blockDim.x;
+              src[u] = e < h.nsend ? h.idx[e] : -1;
+              dr[u] = e < h.nsend ? h.dst_rank[e] : 0;
+              doff[u] = e < h.nsend ? h.dst_off[e] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+              for (int k = 0; k < WMAX; k++)
+                v[u][k] = (src[u] >= 0 && k < h.width) ? __ldcg(&a.w[(size_t)src[u] * h.width + k]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              if (src[u] >= 0) {
+                double *ghost = reinterpret_cast<double *>(a.P.region[dr[u]] + WB_P2P_GHOST) + (size_t)doff[u] * h.width;
+#pragma unroll
+                for (int k = 0; k < WMAX; k++)
+                  if (k < h.width) ghost[k] = v[u][k] * scale;
+              }
+            }
+          }
+          __threadfence_system();
+          __syncthreads();
+          if (threadIdx.x < h.nneigh)
+            p2p_st_release_sys(reinterpret_cast<int *>(a.P.region[h.nb_rank[threadIdx.x]] + wb_p2p_flag_off(0, a.P.rank)),
+                               h.seq);
+        }
       }
+    } else if (threadIdx.x == 0) {
+      a.out[0] = s_t;
+      if (a.with_upd) gmres_update(a.upd);
     }
   }
 }
@@ -2041,7 +2100,8 @@ static int multi_dot(KspWork &w, const double *d_w, const double *V, size_t ldv,
 // Arnoldi-step update runs in the same launch.  coef_seq > 0: the coefficients are the rank sums of slot A
 // published by multi_dot (NVLink path); d_coef then receives the reduced values for the Hessenberg update.
 static int multi_axpy(KspWork &w, double *d_w, const double *V, size_t ldv, int nd, const double *d_coef, double sign,
-                      double *d_nrm2, const int *done, const GmresUpd *upd, int coef_seq = 0) {
+                      double *d_nrm2, const int *done, const GmresUpd *upd, int coef_seq = 0,
+                      int *pushed_halo_seq = nullptr, int halo_width = 0) {
   wb_ctx *c = w.ctx;
   const int nblk = red_blocks(w.n);
   const bool fuse_upd = upd && c->nranks <= 1;
@@ -2061,7 +2121,23 @@ static int multi_axpy(KspWork &w, double *d_w, const double *V, size_t ldv, int 
     if (coef_seq > 0) {
       a.seq_coef = coef_seq;
       a.coef_out = const_cast<double *>(d_coef);
-      if (p2p_norm && last) a.seq_norm = seq_norm = ++c->p2p.seq_b;
+      if (p2p_norm && last) {
+        a.seq_norm = seq_norm = ++c->p2p.seq_b;
+        // Optional (WB_P2P_FUSE_MAX = largest boundary, in cells, to fuse; default 0 = off): one CTA pushing the
+        // boundary costs what the two saved launches cost -- measured 244.7 vs 244.2 ms per step on 8 GPUs, and
+        // slower on 2 GPUs (10 000-cell faces) -- so the dedicated multi-CTA push kernel stays the default.
+        static int fuse_max = -1;
+        if (fuse_max < 0) {
+          const char *e = getenv("WB_P2P_FUSE_MAX");
+          fuse_max = e ? atoi(e) : 0;
+        }
+        if (pushed_halo_seq && c->halo.nneigh > 0 && c->halo.nneigh <= 256 && c->halo.nsend <= fuse_max) {
+          a.fuse_tail = 1;
+          a.upd = *upd;
+          a.push = wb_p2p_halo_push_args(c, halo_width);
+          *pushed_halo_seq = a.push.seq;
+        }
+      }
     }
     if (nv <= 1) launch_maxpy<1>(a, nblk, c->stream);
     else if (nv <= 2) launch_maxpy<2>(a, nblk, c->stream);
@@ -2077,6 +2153,7 @@ static int multi_axpy(KspWork &w, double *d_w, const double *V, size_t ldv, int 
   }
   WB_CUDA(cudaGetLastError());
   if (seq_norm > 0) {
+    if (pushed_halo_seq && *pushed_halo_seq > 0) return 0;  // update + halo push ran in the multi-axpy's last CTA
     k_gmres_update_p2p<<<1, 32, 0, c->stream>>>(*upd, c->p2p.dev, seq_norm);
     WB_LAUNCH(c);
     return 0;
@@ -2163,18 +2240,23 @@ static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
       WB_TRY(fetch_state(w));
       if (w.h_st->reason != 0) break;
     }
-    int it = 0;
+    int it = 0, halo_seq = 0;
     bool stop = false;
     while (it < m && !stop) {
       const int chunk = first ? std::min(g_check_every, m - it) : m - it;
       for (int q = 0; q < chunk; q++, it++) {
         // the kernels below are no-ops once the device-side done flag is up
         // V_it = wbuf * (1/|wbuf|) stored by the SpMV that also forms tmp = A V_it
-        WB_TRY(wb_spmv_fused(A, wbuf, scal + 1, w.V + (size_t)it * ld, tmp, w.d_done));
+        WB_TRY(wb_spmv_fused(A, wbuf, scal + 1, w.V + (size_t)it * ld, tmp, w.d_done, halo_seq));
+        halo_seq = 0;
         WB_TRY(wb_pc_apply_dev(pc, tmp, wbuf, w.d_done));
         int coef_seq = 0;
         WB_TRY(multi_dot(w, wbuf, w.V, ld, it + 1, hcol, w.d_done, &coef_seq));
-        WB_TRY(multi_axpy(w, wbuf, w.V, ld, it + 1, hcol, -1.0, scal, w.d_done, &upd, coef_seq));
+        // multi-GPU NVLink path: the last CTA of the multi-axpy also reduces the norm, updates the Hessenberg
+        // matrix and pushes the halo of the next SpMV (which is on wbuf again unless the cycle ends here)
+        const bool next_is_wbuf = it + 1 < m && A == &c->J;
+        WB_TRY(multi_axpy(w, wbuf, w.V, ld, it + 1, hcol, -1.0, scal, w.d_done, &upd, coef_seq,
+                          next_is_wbuf ? &halo_seq : nullptr, A->bs));
       }
       WB_TRY(fetch_state(w));
       if (w.h_st->reason != 0) stop = true;
