@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -14,6 +15,9 @@
 #include "wb_eos.cuh"
 
 void wb_set_error(const char *fmt, ...);
+// guards the per-context work-space registries (std::map keyed by context): contexts may live on different
+// host threads (one per GPU); a context itself is not re-entrant
+std::mutex &wb_registry_mutex();
 
 // NCCL is bound at run time (dlopen of libnccl.so.2 on the first communicator call) so that the
 // library shares whichever NCCL the host process already carries (PyTorch's bundled one, or the

@@ -9,6 +9,11 @@
 static thread_local char g_err[1024] = "";
 bool g_wb_timers_enabled = true;
 
+std::mutex &wb_registry_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 void wb_set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

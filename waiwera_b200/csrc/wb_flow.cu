@@ -716,8 +716,13 @@ struct MeshDev {  // extra device arrays private to this file
   double *d_w = nullptr, *d_F = nullptr;  // coloured-FD work vectors
 };
 static std::map<wb_ctx *, MeshDev> g_meshdev;
+static MeshDev &meshdev(wb_ctx *c) {
+  std::lock_guard<std::mutex> lk(wb_registry_mutex());
+  return g_meshdev[c];  // node addresses of a std::map are stable
+}
 
 void wb_flow_release(wb_ctx *c) {
+  std::lock_guard<std::mutex> lk(wb_registry_mutex());
   auto it = g_meshdev.find(c);
   if (it == g_meshdev.end()) return;
   MeshDev &md = it->second;
@@ -727,7 +732,7 @@ void wb_flow_release(wb_ctx *c) {
 }
 
 static int recompute_face_perm(wb_ctx *c) {
-  MeshDev &md = g_meshdev[c];
+  MeshDev &md = meshdev(c);
   if (c->nface == 0) return 0;
   k_face_perm<<<wb_grid(c->nface, 256), 256, 0, c->stream>>>(c->d_face_cells, md.d_perm, md.d_permdir, c->d_face,
                                                            c->nface, c->ncell);
@@ -743,7 +748,7 @@ extern "C" int wb_set_mesh(wb_ctx *c, int ncell, int ninterior, int nowned, int 
   WB_CUDA(cudaSetDevice(c->device));
   wb_newton_invalidate_pc(c);
   wb_free_mesh(c);
-  MeshDev &md = g_meshdev[c];
+  MeshDev &md = meshdev(c);
   cudaFree(md.d_perm); cudaFree(md.d_permdir); cudaFree(md.d_bprimary); cudaFree(md.d_old_region);
   cudaFree(md.d_yr); cudaFree(md.d_w); cudaFree(md.d_F);
   md = MeshDev();
@@ -926,7 +931,7 @@ static int load_y(wb_ctx *c, const double *d_y) {
     WB_CUDA(cudaMemcpyAsync(c->d_yloc, d_y, sizeof(double) * (size_t)c->nowned * np, cudaMemcpyDeviceToDevice,
                             c->stream));
   if (c->nranks > 1 && c->halo.nneigh > 0) {
-    MeshDev &md = g_meshdev[c];
+    MeshDev &md = meshdev(c);
     k_pack_yr<<<wb_grid(c->nowned, 256), 256, 0, c->stream>>>(c->d_yloc, c->d_region, c->nowned, np, md.d_yr);
     WB_LAUNCH(c);
     WB_TRY(wb_halo_exchange(c, md.d_yr, np + 1));
@@ -1054,7 +1059,7 @@ extern "C" int wb_set_boundaries(wb_ctx *c, int n, const int32_t *ghost_cells, c
                                  const double *primary, const int32_t *region) {
   WB_CUDA(cudaSetDevice(c->device));
   if (n == 0) return 0;
-  MeshDev &md = g_meshdev[c];
+  MeshDev &md = meshdev(c);
   const int ncell = c->ncell;
   // rock copied from the interior cell (src/mesh.F90:1189-1193)
   for (int i = 0; i < n; i++) {
@@ -1104,7 +1109,7 @@ extern "C" int wb_set_boundary(wb_ctx *c, int ghost_cell, int interior_cell, con
 
 extern "C" int wb_get_fluid(wb_ctx *c, double *fluid) {
   WB_CUDA(cudaSetDevice(c->device));
-  MeshDev &md = g_meshdev[c];
+  MeshDev &md = meshdev(c);
   int rc = 0;
   WbStage st(c);
   RecordArgs a;
@@ -1431,7 +1436,7 @@ extern "C" int wb_jacobian_be_colored(wb_ctx *c, const double *y, const double *
                                       double fd_err, double fd_umin, double *vals_out, int *ncolors) {
   WB_CUDA(cudaSetDevice(c->device));
   WB_CHECK(c->nranks == 1, "wb_jacobian_be_colored: single-GPU parity path only");
-  MeshDev &md = g_meshdev[c];
+  MeshDev &md = meshdev(c);
   const int nb = c->nowned, np = c->np;
   const size_t n = (size_t)nb * np;
   if (c->h_color.empty()) color_pattern(c);
@@ -1480,7 +1485,7 @@ extern "C" int wb_jacobian_be_colored(wb_ctx *c, const double *y, const double *
 
 int wb_fluid_transitions_dev(wb_ctx *c, const double *d_y_old, double *d_search, double *d_y) {
   WbScopedTimer tm(c, "fluid_trans");
-  MeshDev &md = g_meshdev[c];
+  MeshDev &md = meshdev(c);
   TransArgs a;
   a.y_old = d_y_old; a.y = d_y; a.search = d_search; a.region = c->d_region; a.old_region = md.d_old_region;
   a.region_iter = c->d_region_iter; a.T_iter = c->d_T_iter; a.flags = c->d_flags; a.nowned = c->nowned;

@@ -1673,6 +1673,16 @@ __global__ void k_gmres_update_p2p(const GmresUpd u, const WbP2PDev P, int seq) 
 // out[j] = w . V_j, j < nv <= NVT, in ONE pass over w and the nv basis vectors (VecMDot): every thread
 // keeps nv partial sums; 32-byte vector loads; partials are folded warp -> CTA -> last CTA in a fixed
 // order, so the result does not depend on scheduling.
+// single-GPU fused BiCGStab (defined with the BiCGStab kernels below)
+struct BcgsEpi {
+  double *sc;
+  KspState *st;
+  int *done;
+  double rtol, atol, dtol;
+  int maxit;
+};
+__device__ void bcgs_epilogue(const BcgsEpi &e, int which);
+
 struct MdotArgs {
   const double *w, *V;
   size_t ldv;
@@ -1682,6 +1692,8 @@ struct MdotArgs {
   const int *done;
   WbP2PDev P;  // seq > 0: the local sums are published to every rank's slot A instead of `out`
   int seq;
+  int epi;      // single-GPU fused BiCGStab: scalar recurrence to run in the last CTA after the sums (0 = none)
+  BcgsEpi be;
 };
 template <int NVT, bool VEC>
 __global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
@@ -1764,6 +1776,9 @@ __global__ void __launch_bounds__(256) k_mdot_all(const MdotArgs a) {
       __syncthreads();
       if (threadIdx.x < a.P.nranks)
         p2p_st_release_sys(reinterpret_cast<int *>(a.P.region[threadIdx.x] + wb_p2p_flag_off(1, a.P.rank)), a.seq);
+    } else if (a.epi) {
+      __syncthreads();
+      if (threadIdx.x == 0) bcgs_epilogue(a.be, a.epi);
     }
   }
 }
@@ -2026,7 +2041,12 @@ static void free_work(KspWork &w) {
 }
 
 static int ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
-  KspWork &w = g_work[c];
+  KspWork *wq;
+  {
+    std::lock_guard<std::mutex> lk(wb_registry_mutex());
+    wq = &g_work[c];  // node addresses of a std::map are stable
+  }
+  KspWork &w = *wq;
   if (w.n != n || w.m < m) {
     free_work(w);
     w = KspWork();
@@ -2048,6 +2068,7 @@ static int ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
 }
 
 void wb_linalg_release(wb_ctx *c) {
+  std::lock_guard<std::mutex> lk(wb_registry_mutex());
   auto it = g_work.find(c);
   if (it == g_work.end()) return;
   free_work(it->second);
@@ -2073,14 +2094,18 @@ template <int NVT> static void launch_maxpy(const MaxpyArgs &a, int nblk, cudaSt
 // slot A by the kernel itself and *p2p_seq is the sequence number the consumer (multi_axpy) waits for; no
 // collective is launched and d_out is not written here.
 static int multi_dot(KspWork &w, const double *d_w, const double *V, size_t ldv, int nd, double *d_out,
-                     const int *done, int *p2p_seq = nullptr) {
+                     const int *done, int *p2p_seq = nullptr, int epi = 0, const BcgsEpi *be = nullptr) {
   wb_ctx *c = w.ctx;
   const int nblk = red_blocks(w.n);
   const bool p2p = p2p_seq && c->p2p.on && nd <= WB_P2P_MAXV;
   if (p2p_seq) *p2p_seq = 0;
   for (int j0 = 0; j0 < nd; j0 += KRY_MAXV) {
     const int nv = std::min(KRY_MAXV, nd - j0);
-    MdotArgs a = {d_w, V + (size_t)j0 * ldv, ldv, (int)w.n, nv, w.part, d_out + j0, w.d_counter, done, c->p2p.dev, 0};
+    MdotArgs a = {d_w, V + (size_t)j0 * ldv, ldv, (int)w.n, nv, w.part, d_out + j0, w.d_counter, done, c->p2p.dev, 0, 0, {}};
+    if (epi && be && j0 + nv >= nd) {
+      a.epi = epi;
+      a.be = *be;
+    }
     if (p2p) {
       a.seq = ++c->p2p.seq_a;
       *p2p_seq = a.seq;
@@ -2281,8 +2306,8 @@ static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
 
 // scalar recurrences of KSPSolve_BCGS on the device.  sc: 0 rho, 1 rhoold, 2 alpha, 3 omegaold,
 // 4 beta, 5 d1, 6 omega, 7 dp2, 8 d2, 9 -alpha, 10 -omega, 11 beta*omegaold (negated)
-__global__ void k_bcgs_step(double *sc, int phase, KspState *st, int *done, double rtol, double atol, double dtol,
-                            int maxit) {
+__device__ void bcgs_step(double *sc, int phase, KspState *st, int *done, double rtol, double atol, double dtol,
+                          int maxit) {
   if (*done) return;
   if (phase == 0) {  // after rho = (R, RP)
     if (sc[0] == 0.0) {
@@ -2331,7 +2356,12 @@ __global__ void k_bcgs_step(double *sc, int phase, KspState *st, int *done, doub
   }
 }
 
-__global__ void k_bcgs_begin(double *sc, KspState *st, int *done, double rtol, double atol) {
+__global__ void k_bcgs_step(double *sc, int phase, KspState *st, int *done, double rtol, double atol, double dtol,
+                            int maxit) {
+  bcgs_step(sc, phase, st, done, rtol, atol, dtol, maxit);
+}
+
+__device__ void bcgs_begin(double *sc, KspState *st, int *done, double rtol, double atol) {
   const double dp = sqrt(sc[7]);
   st->res = dp;
   st->rnorm0 = dp;
@@ -2349,6 +2379,73 @@ __global__ void k_bcgs_begin(double *sc, KspState *st, int *done, double rtol, d
   sc[1] = 1.0;
   sc[2] = 1.0;
   sc[3] = 1.0;
+}
+__global__ void k_bcgs_begin(double *sc, KspState *st, int *done, double rtol, double atol) {
+  bcgs_begin(sc, st, done, rtol, atol);
+}
+
+// ---- single-GPU fused BiCGStab: the scalar recurrences run in the last CTA of the reduction that feeds them
+// epilogues: 4 = after (R,R) of the start vector: begin + first rho/beta; 1 = after (V,RP): alpha;
+// 2 = after (T,S),(T,T) in sc[12..13]: omega
+__device__ void bcgs_epilogue(const BcgsEpi &e, int which) {
+  double *sc = e.sc;
+  if (which == 4) {
+    bcgs_begin(sc, e.st, e.done, e.rtol, e.atol);
+    sc[0] = sc[7];  // RP = R: rho = (R,RP) = |R|^2
+    bcgs_step(sc, 0, e.st, e.done, e.rtol, e.atol, e.dtol, e.maxit);
+  } else if (which == 1) {
+    bcgs_step(sc, 1, e.st, e.done, e.rtol, e.atol, e.dtol, e.maxit);
+  } else if (which == 2) {
+    sc[5] = sc[12];
+    sc[8] = sc[13];
+    bcgs_step(sc, 2, e.st, e.done, e.rtol, e.atol, e.dtol, e.maxit);
+  }
+}
+
+// X += alpha P + omega S (VecAXPBYPCZ), R = S - omega T (VecWAXPY), |R|^2 and the next rho = (R,RP) in one pass;
+// the last CTA then runs the convergence test of this iteration and the beta of the next one
+__global__ void __launch_bounds__(256) k_bcgs_update(double *__restrict__ x, double *__restrict__ R,
+                                                     const double *__restrict__ P, const double *__restrict__ S,
+                                                     const double *__restrict__ T, const double *__restrict__ RP, int n,
+                                                     double *__restrict__ part, unsigned *counter, const BcgsEpi e) {
+  const int d = *e.done;
+  if (d == 1) return;
+  const double alpha = e.sc[2], omega = (d == 2) ? 0.0 : e.sc[6], momega = (d == 2) ? 0.0 : e.sc[10];
+  double rr = 0.0, rrp = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    x[i] += alpha * P[i] + omega * S[i];
+    const double r = S[i] + momega * T[i];
+    R[i] = r;
+    rr += r * r;
+    rrp += r * RP[i];
+  }
+  const double s1 = block_sum(rr);
+  const double s2 = block_sum(rrp);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = s1;
+    part[RED_BLOCKS + blockIdx.x] = s2;
+  }
+  if (last_block(counter)) {
+    if (threadIdx.x < 64) {
+      const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      double t = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&part[(size_t)j * RED_BLOCKS + b]);
+      t = warp_sum(t);
+      if (lane == 0) e.sc[j == 0 ? 7 : 14] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (d == 2) {  // omega undefined ((T,T) = 0): x += alpha P was the whole update; converged (KSPSolve_BCGS)
+        *e.done = 1;
+      } else {
+        bcgs_step(e.sc, 3, e.st, e.done, e.rtol, e.atol, e.dtol, e.maxit);
+        if (!*e.done) {
+          e.sc[0] = e.sc[14];  // rho of the next iteration
+          bcgs_step(e.sc, 0, e.st, e.done, e.rtol, e.atol, e.dtol, e.maxit);
+        }
+      }
+    }
+  }
 }
 
 // x += alpha*P + omega*S with device scalars
@@ -2375,9 +2472,63 @@ __global__ void __launch_bounds__(256) k_bcgs_pupdate(double *__restrict__ P, co
     P[i] = R[i] + beta * (P[i] - omegaold * V[i]);
 }
 
+// single GPU: nine launches per iteration -- P update, SpMV, PC, (V,RP)+alpha, S, SpMV, PC, (T,S),(T,T)+omega,
+// X/R update + |R| + next rho + convergence test -- every scalar recurrence in the last CTA of the reduction that
+// feeds it (the arithmetic of each recurrence is the k_bcgs_step code of the multi-GPU path)
+static int bcgs_dev_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b, double *d_x, int *its,
+                          int *reason, double *rnorm) {
+  wb_ctx *c = A->ctx;
+  const size_t n = (size_t)A->nb * A->bs;
+  KspWork *wp;
+  WB_TRY(ensure_work(c, n, 30, &wp));
+  KspWork &w = *wp;
+  const size_t ld = w.ld;
+  double *R = w.V, *RP = R + ld, *P = RP + ld, *V = P + ld, *S = V + ld, *T = S + ld, *tmp = w.tmp;
+  double *sc = w.small;
+  const int nblk = std::min<int>(RED_BLOCKS, (int)((n + 255) / 256));
+  const BcgsEpi be = {sc, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, o->maxit};
+  WB_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * n, c->stream));
+  WB_CUDA(cudaMemsetAsync(P, 0, sizeof(double) * n, c->stream));
+  WB_CUDA(cudaMemsetAsync(V, 0, sizeof(double) * n, c->stream));
+  WB_CUDA(cudaMemsetAsync(w.d_done, 0, sizeof(int), c->stream));
+  WB_CUDA(cudaMemsetAsync(w.d_st, 0, sizeof(KspState), c->stream));
+  WB_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 16, c->stream));
+  WB_TRY(wb_pc_apply_dev(pc, d_b, R));
+  WB_TRY(multi_dot(w, R, R, ld, 1, sc + 7, nullptr, nullptr, 4, &be));
+  WB_CUDA(cudaMemcpyAsync(RP, R, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+  WB_TRY(fetch_state(w));
+  int enq = 0;
+  while (w.h_st->reason == 0) {
+    for (int q = 0; q < g_check_every && enq < o->maxit; q++, enq++) {
+      k_bcgs_pupdate<<<nblk, 256, 0, c->stream>>>(P, R, V, sc, (int)n, w.d_done);
+      WB_LAUNCH(c);
+      WB_TRY(wb_spmv_fused(A, P, nullptr, nullptr, tmp, w.d_done));
+      WB_TRY(wb_pc_apply_dev(pc, tmp, V, w.d_done));
+      WB_TRY(multi_dot(w, V, RP, ld, 1, sc + 5, w.d_done, nullptr, 1, &be));
+      WB_TRY(lin3(w, S, R, 1.0, nullptr, V, 1.0, sc + 9, nullptr, 0.0, nullptr, nullptr, w.d_done));
+      WB_TRY(wb_spmv_fused(A, S, nullptr, nullptr, tmp, w.d_done));
+      WB_TRY(wb_pc_apply_dev(pc, tmp, T, w.d_done));
+      WB_TRY(multi_dot(w, T, S, ld, 2, sc + 12, w.d_done, nullptr, 2, &be));  // S, T adjacent: (T,S), (T,T) in one pass
+      k_bcgs_update<<<nblk, 256, 0, c->stream>>>(d_x, R, P, S, T, RP, (int)n, w.part, w.d_counter, be);
+      WB_LAUNCH(c);
+    }
+    WB_CUDA(cudaGetLastError());
+    WB_TRY(fetch_state(w));
+    if (enq >= o->maxit && w.h_st->reason == 0) {
+      w.h_st->reason = -3;
+      break;
+    }
+  }
+  *its = w.h_st->its;
+  *reason = w.h_st->reason;
+  *rnorm = w.h_st->res;
+  return 0;
+}
+
 static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b, double *d_x, int *its,
                     int *reason, double *rnorm) {
   wb_ctx *c = A->ctx;
+  if (c->nranks <= 1) return bcgs_dev_fused(A, pc, o, d_b, d_x, its, reason, rnorm);
   const size_t n = (size_t)A->nb * A->bs;
   KspWork *wp;
   WB_TRY(ensure_work(c, n, 30, &wp));
@@ -2446,9 +2597,14 @@ static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_
 int wb_vec_dot_host(wb_ctx *c, const double *d_a, const double *d_b, size_t n, double *out) {
   KspWork *wp;
   {
-    auto it = g_work.find(c);
-    if (it == g_work.end() || it->second.n != n) WB_TRY(ensure_work(c, n, 30, &wp));
-    else wp = &it->second;
+    bool have = false;
+    {
+      std::lock_guard<std::mutex> lk(wb_registry_mutex());
+      auto it = g_work.find(c);
+      have = it != g_work.end() && it->second.n == n;
+      if (have) wp = &it->second;
+    }
+    if (!have) WB_TRY(ensure_work(c, n, 30, &wp));
   }
   KspWork &w = *wp;
   double *sc = w.small;

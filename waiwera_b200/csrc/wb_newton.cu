@@ -28,6 +28,7 @@ struct NewtonWork {
 static std::map<wb_ctx *, NewtonWork> g_newton;
 
 void wb_newton_release(wb_ctx *c) {
+  std::lock_guard<std::mutex> lk(wb_registry_mutex());
   auto it = g_newton.find(c);
   if (it == g_newton.end()) return;
   NewtonWork &w = it->second;
@@ -37,7 +38,12 @@ void wb_newton_release(wb_ctx *c) {
 }
 
 static int ensure(wb_ctx *c, size_t n, NewtonWork **out) {
-  NewtonWork &w = g_newton[c];
+  NewtonWork *wq;
+  {
+    std::lock_guard<std::mutex> lk(wb_registry_mutex());
+    wq = &g_newton[c];
+  }
+  NewtonWork &w = *wq;
   if (w.n != n) {
     if (w.pc) wb_pc_destroy(w.pc);
     cudaFree(w.F);
@@ -55,6 +61,7 @@ static int ensure(wb_ctx *c, size_t n, NewtonWork **out) {
 
 // the PC's pattern belongs to the mesh: drop it when the mesh changes
 void wb_newton_invalidate_pc(wb_ctx *c) {
+  std::lock_guard<std::mutex> lk(wb_registry_mutex());
   auto it = g_newton.find(c);
   if (it == g_newton.end()) return;
   if (it->second.pc) wb_pc_destroy(it->second.pc);
