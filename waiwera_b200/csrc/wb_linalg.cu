@@ -83,8 +83,8 @@ __device__ __forceinline__ void st256(double *p, const double4 &v) {
 // R block rows per 8-lane group, processed level by level (all row pointers, then all column indices and
 // value blocks, then all x gathers): the three dependent global-memory round trips of a row are shared by R
 // rows, which multiplies the bytes in flight per warp by R at the same occupancy.
-template <int BS, int R>
-__global__ void __launch_bounds__(256) k_bsr_spmv(const SpmvArgs a) {
+template <int BS, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_bsr_spmv(const SpmvArgs a) {
   if (a.done && *a.done) return;
   constexpr int B2 = BS * BS;
   const int lane = threadIdx.x & 7;
@@ -213,19 +213,24 @@ int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d
   SpmvArgs a = {A->d_rowptr, A->d_colidx, A->d_val, d_x, xg, d_scale, d_xn, d_y, A->nb, done,
                 c->p2p.dev, hseq, hseq ? c->halo.nneigh : 0, c->p2p.d_nb_rank};
   if (wb_spmv_tma_enabled(A)) return wb_spmv_tma_launch(A, a);
-  static int rows_per_group = 0;  // tuning knob (WB_SPMV_ROWS = 1, 2, 4); measured 70.9 / 70.6 / 97 us at 1 M cells
+  // tuning knob (WB_SPMV_ROWS = 1, 2, 4).  R = 1 needs 32 registers => 8 CTAs / SM (full occupancy) and is the
+  // fastest: 68.5 us vs 75.9 (R = 2, 54 registers) vs 97 (R = 4) at 1 M cells on the same box
+  static int rows_per_group = 0;
   if (!rows_per_group) {
     const char *e = getenv("WB_SPMV_ROWS");
-    rows_per_group = e ? atoi(e) : 2;
-    if (rows_per_group != 1 && rows_per_group != 2 && rows_per_group != 4) rows_per_group = 2;
+    rows_per_group = e ? atoi(e) : 1;
+    if (rows_per_group != 1 && rows_per_group != 2 && rows_per_group != 4 && rows_per_group != 11 && rows_per_group != 12)
+      rows_per_group = 1;
   }
-  const int R = rows_per_group;
-  const int grid = std::max(1, wb_grid((size_t)A->nb, 32 * R));
+  const int R = rows_per_group;  // 11 / 12: R = 1 / 2 with the register count capped for 8 / 6 CTAs per SM
+  const int grid = std::max(1, wb_grid((size_t)A->nb, 32 * (R > 10 ? R - 10 : R)));
 #define SPMV(BS)                                                                       \
   do {                                                                                 \
-    if (R == 1) k_bsr_spmv<BS, 1><<<grid, 256, 0, c->stream>>>(a);                     \
-    else if (R == 2) k_bsr_spmv<BS, 2><<<grid, 256, 0, c->stream>>>(a);                \
-    else k_bsr_spmv<BS, 4><<<grid, 256, 0, c->stream>>>(a);                            \
+    if (R == 1) k_bsr_spmv<BS, 1, 1><<<grid, 256, 0, c->stream>>>(a);                  \
+    else if (R == 11) k_bsr_spmv<BS, 1, 8><<<grid, 256, 0, c->stream>>>(a);            \
+    else if (R == 2) k_bsr_spmv<BS, 2, 1><<<grid, 256, 0, c->stream>>>(a);             \
+    else if (R == 12) k_bsr_spmv<BS, 2, 6><<<grid, 256, 0, c->stream>>>(a);            \
+    else k_bsr_spmv<BS, 4, 1><<<grid, 256, 0, c->stream>>>(a);                         \
   } while (0)
   switch (A->bs) {
     case 1: SPMV(1); break;
