@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
     python bench.py --steps 1 --warmup 1 --ksp-maxit $MAXIT --no-cpu-baseline --spmv-launches 5 > gpurun_out/${TAG}_launches_bench.log 2>&1
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on \
-    -k 'regex:k_bsr_spmv|k_ilu0_block_solve|k_mdot_all|k_maxpy_all|k_jacobian|k_residual|k_eos|k_ilu0_factor' -s 40 -c 26 \
+    -k 'regex:k_bsr_spmv|k_ilu0_block_solve|k_mdot_all|k_maxpy_all|k_jacobian|k_residual|k_eos|k_ilu0_factor' -s 40 -c 14 \
     -f -o gpurun_out/${TAG}_full python bench.py --steps 1 --warmup 1 --ksp-maxit 40 --no-cpu-baseline --spmv-launches 5 > gpurun_out/${TAG}_full_bench.log 2>&1
 echo "full capture rc=$?"
 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
