@@ -221,6 +221,19 @@ int wo_flow_fluid_transitions(wo_flow *f, const double *y_old, double *search, d
                               int *changed_search, int *changed_y);
 void wo_flow_get_regions(wo_flow *f, int32_t *region);
 
+/* ---- passive tracers: auxiliary linear problem (wo_tracer.c; src/tracer.F90, src/flow_simulation.F90:1489-1959,
+   src/timestepper.F90:458-581) ---- */
+typedef struct {
+  int phase;          /* 1-based phase index (tracer%phase_index) */
+  double diffusion;   /* diffusion coefficient (m2/s) */
+  double decay;       /* decay constant (1/s) */
+  double activation;  /* activation energy (J/mol) */
+} wo_tracer;
+void wo_flow_set_tracers(wo_flow *f, int nt, const wo_tracer *tracers);
+/* source%tracer_injection_rate, rate[nsources*nt] in the order of wo_flow_set_sources */
+void wo_flow_set_tracer_injection(wo_flow *f, const double *rate);
+double wo_tracer_decay(const wo_tracer *t, double temperature);
+
 /* BE residual r = L(y) - L_last - dt*R(y)  (src/timestepper.F90:345-374), includes pre_eval */
 int wo_residual_be(wo_flow *f, const double *y, const double *lhs_last, double dt,
                    const int32_t *perturbed, int nperturbed, double *lhs, double *rhs, double *r);
@@ -246,6 +259,16 @@ int wo_bsr_coloring(const wo_bsr *A, int32_t *color);
 int wo_fd_jacobian(wo_flow *f, const double *y, const double *lhs_last, double dt,
                    const double *F0, const int32_t *color, int ncolor,
                    double fd_err, double fd_umin, wo_bsr *J);
+
+/* tracer system (bs = nt): rows = owned cells, then boundary ghost cells (identity rows after pre_solve) */
+wo_bsr *wo_tracer_pattern(const wo_mesh *mesh, int nt);
+void wo_tracer_cell_balances(wo_flow *f, double *Al);
+void wo_tracer_cell_inflows(wo_flow *f, wo_bsr *Ar, double *br);
+void wo_tracer_pre_solve(wo_flow *f, wo_bsr *A, double *b, const double *x_prev);
+/* method 0 backward Euler, 1 BDF2, 2 direct steady state, then aux_pre_solve */
+void wo_tracer_setup_linear(wo_flow *f, int method, double dt, double dt_last, const double *al_last,
+                            const double *x_last, const double *al_last2, const double *x_last2, wo_bsr *A,
+                            double *b, double *al);
 
 typedef struct wo_pc wo_pc;
 #define WO_PC_NONE 0

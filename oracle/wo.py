@@ -53,6 +53,10 @@ class Bsr(C.Structure):
                 ("rowptr", c_ip), ("colidx", c_ip), ("val", c_dp)]
 
 
+class Tracer(C.Structure):
+    _fields_ = [("phase", C.c_int), ("diffusion", C.c_double), ("decay", C.c_double), ("activation", C.c_double)]
+
+
 class KspOpts(C.Structure):
     _fields_ = [("type", C.c_int), ("restart", C.c_int), ("maxit", C.c_int),
                 ("rtol", C.c_double), ("atol", C.c_double), ("dtol", C.c_double)]
@@ -140,6 +144,14 @@ def lib():
         "wo_flow_fluid_transitions": (i, [vp, c_dp, c_dp, c_dp, C.POINTER(i), C.POINTER(i)]),
         "wo_flow_get_regions": (None, [vp, c_ip]),
         "wo_residual_be": (i, [vp, c_dp, c_dp, d, c_ip, i, c_dp, c_dp, c_dp]),
+        "wo_flow_set_tracers": (None, [vp, i, C.POINTER(Tracer)]),
+        "wo_flow_set_tracer_injection": (None, [vp, c_dp]),
+        "wo_tracer_decay": (d, [C.POINTER(Tracer), d]),
+        "wo_tracer_pattern": (C.POINTER(Bsr), [C.POINTER(Mesh), i]),
+        "wo_tracer_cell_balances": (None, [vp, c_dp]),
+        "wo_tracer_cell_inflows": (None, [vp, C.POINTER(Bsr), c_dp]),
+        "wo_tracer_pre_solve": (None, [vp, C.POINTER(Bsr), c_dp, c_dp]),
+        "wo_tracer_setup_linear": (None, [vp, i, d, d, c_dp, c_dp, c_dp, c_dp, C.POINTER(Bsr), c_dp, c_dp]),
         "wo_vec_max_pointwise_abs_scale": (None, [c_dp, c_dp, d, i, c_dp, C.POINTER(i)]),
         "wo_bsr_from_mesh": (C.POINTER(Bsr), [C.POINTER(Mesh), i]),
         "wo_bsr_destroy": (None, [C.POINTER(Bsr)]),
@@ -318,6 +330,39 @@ class Flow:
 
     def bsr(self):
         return self.L.wo_bsr_from_mesh(C.byref(self.mesh), self.np)
+
+    # ---- passive tracers (auxiliary linear problem) ----
+    def set_tracers(self, phases, diffusion=None, decay=None, activation=None):
+        nt = len(phases)
+        arr = (Tracer * nt)()
+        for k in range(nt):
+            arr[k].phase = int(phases[k])
+            arr[k].diffusion = 0.0 if diffusion is None else float(diffusion[k])
+            arr[k].decay = 0.0 if decay is None else float(decay[k])
+            arr[k].activation = 0.0 if activation is None else float(activation[k])
+        self.nt = nt
+        self.L.wo_flow_set_tracers(self.h, nt, arr)
+        self.ntrows = self.nowned + (self.ncell - self.ninterior)
+
+    def set_tracer_injection(self, rates):
+        r = np.ascontiguousarray(rates, np.float64)
+        self.L.wo_flow_set_tracer_injection(self.h, dp(r))
+
+    def tracer_pattern(self):
+        return self.L.wo_tracer_pattern(C.byref(self.mesh), self.nt)
+
+    def tracer_balances(self):
+        al = np.zeros(self.ntrows * self.nt)
+        self.L.wo_tracer_cell_balances(self.h, dp(al))
+        return al
+
+    def tracer_setup_linear(self, A, dt, al_last, x_last, method=0, dt_last=0.0, al_last2=None, x_last2=None):
+        """setup_linear + aux_pre_solve for the state of the last unperturbed evaluation; returns b, Al."""
+        n = self.ntrows * self.nt
+        b, al = np.zeros(n), np.zeros(n)
+        self.L.wo_tracer_setup_linear(self.h, method, dt, dt_last, dp(al_last), dp(x_last), dp(al_last2), dp(x_last2),
+                                      A, dp(b), dp(al))
+        return b, al
 
 
 def bsr_arrays(A):

@@ -11,31 +11,11 @@
  * The reference loops visit owned cells in local index order; the face loop
  * visits flux faces in flux_face order (here: face index order).
  */
-#include "oracle.h"
+#include "wo_flow_priv.h"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
-struct wo_flow {
-  wo_params prm;
-  wo_mesh mesh;
-  wo_eos *eos;
-  int np, nc, nphase, nmobile, dof, nflux, isothermal;
-  double *fluid, *current_fluid, *last_iteration_fluid, *last_timestep_fluid;
-  double *balances; /* nowned*np: last unperturbed lhs */
-  double *flux;     /* nface*nflux */
-  double *update;   /* ncell: +1 / -1 */
-  double *rock;     /* private copy so boundary ghost rock can be set */
-  int unperturbed;
-  /* time-stepping method: 0 backward Euler, 1 BDF2, 2 direct steady state (timestepper.F90:345-452) */
-  int method;
-  double dt_last;
-  double *lhs_last2;
-  /* fixed-rate sources / sinks (src/source.F90:375-480), in input order */
-  int nsrc;
-  int32_t *src_cell, *src_component;
-  double *src_rate, *src_enthalpy;
-};
 
 static inline int nint_(double x) { return (int)lround(x); }
 
@@ -96,6 +76,20 @@ void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *
   memcpy(f->src_enthalpy, enthalpy, n * sizeof(double));
 }
 
+/* fluid%phase_flow_fractions (src/fluid.F90:394-411) of the current fluid in the cell of source s */
+void wo_flow_source_phase_fractions(const wo_flow *f, int s, double *frac) {
+  const double *fl = f->current_fluid + (size_t)f->src_cell[s] * f->dof;
+  int phases = nint_(fl[4]);
+  double sum = 0.0;
+  for (int p = 0; p < f->nphase; p++) {
+    const double *ph = fl + (7 + f->nc - 1) + p * (8 + f->nc - 1);
+    frac[p] = 0.0;
+    if (phases & (1 << p)) frac[p] = ph[3] * ph[0] / ph[1];
+    sum += frac[p];
+  }
+  for (int p = 0; p < f->nphase; p++) frac[p] = frac[p] / sum;
+}
+
 /* source%update_flow: src/source.F90:457-480 with update_injection_mass_flow :385-399,
    update_production_mass_flow :403-438 (fluid%phase_flow_fractions / component_flow_fractions /
    specific_enthalpy src/fluid.F90:374-456) and update_energy_flow :442-453 */
@@ -150,6 +144,8 @@ void wo_flow_destroy(wo_flow *f) {
   if (!f) return;
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
   free(f->lhs_last2);
+  free(f->tracers);
+  free(f->tracer_injection);
   wo_eos_destroy(f->eos);
   free(f->fluid);
   free(f->current_fluid);

@@ -1,0 +1,38 @@
+/*
+ * wo_flow_priv.h -- oracle (TEST INFRASTRUCTURE): the flow-simulation object shared by
+ * wo_flow.c and wo_tracer.c (the fields of flow_simulation_type this path uses,
+ * src/flow_simulation.F90:43-130).
+ */
+#ifndef WO_FLOW_PRIV_H
+#define WO_FLOW_PRIV_H
+#include "oracle.h"
+
+struct wo_flow {
+  wo_params prm;
+  wo_mesh mesh;
+  wo_eos *eos;
+  int np, nc, nphase, nmobile, dof, nflux, isothermal;
+  double *fluid, *current_fluid, *last_iteration_fluid, *last_timestep_fluid;
+  double *balances; /* nowned*np: last unperturbed lhs */
+  double *flux;     /* nface*nflux */
+  double *update;   /* ncell: +1 / -1 */
+  double *rock;     /* private copy so boundary ghost rock can be set */
+  int unperturbed;
+  /* time-stepping method: 0 backward Euler, 1 BDF2, 2 direct steady state (timestepper.F90:345-452) */
+  int method;
+  double dt_last;
+  double *lhs_last2;
+  /* fixed-rate sources / sinks (src/source.F90:375-480), in input order */
+  int nsrc;
+  int32_t *src_cell, *src_component;
+  double *src_rate, *src_enthalpy;
+  /* passive tracers (src/tracer.F90:25-41): auxiliary linear problem, wo_tracer.c */
+  int nt;
+  wo_tracer *tracers;
+  double *tracer_injection; /* nsrc*nt: source%tracer_injection_rate */
+};
+
+/* source%fluid%phase_flow_fractions (src/fluid.F90:374-398) of the current fluid of source s's cell */
+void wo_flow_source_phase_fractions(const wo_flow *f, int s, double *frac);
+
+#endif

@@ -37,6 +37,63 @@ def runs(path, lo, hi, minlen):
     return out
 
 
+def listing_tables(path):
+    """ELEMENT TABLE blocks of an AUTOUGH2 listing: [(time_s, {name: [P, T, Sv, Sl, tracer]})] and the
+    GENERATION TABLE rows [(time_s, rate, enthalpy, tracer_flow)]"""
+    import re
+    lines = open(path).read().splitlines()
+    elems, gens, t = [], [], None
+    i = 0
+    while i < len(lines):
+        m = re.search(r"OUTPUT AFTER\s+\d+ TIME STEPS\s+([0-9.E+-]+) SECONDS", lines[i])
+        if m:
+            t = float(m.group(1))
+        if "ELEMENT TABLE" in lines[i]:
+            i += 4
+            rows = []
+            while i < len(lines) and lines[i].strip() and not lines[i].startswith(" EEEE"):
+                f = lines[i].split()
+                if len(f) >= 9:
+                    rows.append([float(v) for v in f[-7:-2]])
+                i += 1
+            elems.append((t, rows))
+        if "GENERATION TABLE" in lines[i]:
+            i += 4
+            while i < len(lines) and lines[i].strip() and not lines[i].startswith(" GGGG"):
+                f = lines[i].split()
+                gens.append((t, float(f[-7]), float(f[-6]), float(f[-5])))
+                i += 1
+        i += 1
+    return elems, gens
+
+
+def tracer_oned():
+    """test/benchmark/tracer/oned: AUTOUGH2 listings of the 1-D liquid tracer problems (test_tracer_1d.py compares
+    pressure and tracer mass fraction at the last output with tolerance 1e-3 and the tracer production history)"""
+    base = "/root/reference/test/benchmark/tracer/oned/run"
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/tracer/oned/run/"
+                            "oned_{single,two}_phase.listing (AUTOUGH2), columns P, T, Sv, Sl, tracer mass fraction; "
+                            "the last row of every table is the Dirichlet boundary block"}
+    for case in ("single", "two"):
+        elems, gens = listing_tables(os.path.join(base, "oned_%s_phase.listing" % case))
+        # initial state of the transient run = the Waiwera output file the benchmark ships (final state of the
+        # *_ss.json run; PETSc HDF5 viewer, contiguous f64 found by a byte scan): pressure and, in the two-phase
+        # case, vapour saturation of the 10 cells (the single-phase file holds the uniform 3 MPa / 20 degC state)
+        h5 = os.path.join(base, "oned_%s_phase_ss.h5" % case)
+        init = {"pressure": [float(v) for v in runs(h5, 1e4, 1e7, 10)[0][:10]]}
+        if case == "two":
+            init["vapour_saturation"] = [float(v) for v in runs(h5, 1e-3, 1.0, 10)[0][:10]]
+            init["temperature"] = [float(v) for v in runs(h5, 10, 200, 10)[0][:10]]
+        else:
+            init["temperature"] = [float(v) for v in runs(h5, 10, 200, 10)[0][:10]]
+        doc[case] = {"times": [t for t, _ in elems], "tables": [rows for _, rows in elems],
+                     "source": [list(g) for g in gens], "initial": init}
+    out = os.path.join(os.path.dirname(OUT), "tracer_oned.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -62,3 +119,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    tracer_oned()

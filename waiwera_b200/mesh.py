@@ -132,6 +132,37 @@ def structured(nx, ny, nz, dx=10.0, dy=None, dz=None, gravity=(0.0, 0.0, -9.8), 
                 dims=(nx, ny, nz), natural=idx.copy(), boundary=boundary, ncell_global=n)
 
 
+def add_boundary(mesh, cells, normal, distance, area, direction, gravity=(0.0, 0.0, -9.8)):
+    """Dirichlet boundary ghost cells on the outward faces (unit `normal`) of the given interior cells of a serial
+    mesh (src/mesh.F90:583-664, 1069-1264): the ghost is cell 2 of the new face, distances (distance, 0),
+    distance12 = distance, volume 0, rock copied from the interior cell; `direction` = permeability direction 1..3."""
+    assert mesh.nranks == 1 and mesh.nowned == mesh.ninterior
+    cells = np.asarray(cells, np.int64)
+    nb = len(cells)
+    normal = np.asarray(normal, float)
+    ghosts = mesh.ncell + np.arange(nb)
+    fg = np.zeros((nb, 12))
+    fg[:, 0] = area
+    fg[:, 1] = distance
+    fg[:, 2] = 0.0
+    fg[:, 3] = distance
+    fg[:, 4:7] = normal
+    fg[:, 7] = float(np.dot(np.asarray(gravity, float), normal))
+    fg[:, 8:11] = mesh.cell_geom[cells, :3] + distance * normal
+    fg[:, 11] = direction
+    gg = np.zeros((nb, 4))
+    gg[:, :3] = fg[:, 8:11]
+    old = mesh.boundary if mesh.boundary else {"ghost_cells": np.zeros(0, np.int32), "interior_cells": np.zeros(0, np.int32)}
+    boundary = {"ghost_cells": np.concatenate([old["ghost_cells"], ghosts]).astype(np.int32),
+                "interior_cells": np.concatenate([old["interior_cells"], cells]).astype(np.int32)}
+    return Mesh(ncell=mesh.ncell + nb, ninterior=mesh.ninterior, nowned=mesh.nowned,
+                face_cells=np.ascontiguousarray(np.vstack([mesh.face_cells, np.stack([cells, ghosts], 1)]), dtype=np.int32),
+                face_geom=np.ascontiguousarray(np.vstack([mesh.face_geom, fg])),
+                cell_geom=np.ascontiguousarray(np.vstack([mesh.cell_geom, gg])),
+                rock=np.ascontiguousarray(np.vstack([mesh.rock, mesh.rock[cells]])),
+                dims=mesh.dims, natural=mesh.natural, boundary=boundary, ncell_global=mesh.ncell_global)
+
+
 def box_owner(mesh, parts):
     """owner rank of each interior cell for a px*py*pz box decomposition (rank = a + px*(b + py*c))."""
     nx, ny, nz = mesh.dims
