@@ -25,6 +25,7 @@ module waiwera_b200
   integer(c_int), parameter, public :: WB_PC_NONE = 0, WB_PC_PBJACOBI = 1, WB_PC_BJACOBI_ILU0 = 2
   integer(c_int), parameter, public :: WB_KSP_GMRES = 0, WB_KSP_BCGS = 1
   integer(c_int), parameter, public :: WB_METHOD_BEULER = 0, WB_METHOD_BDF2 = 1, WB_METHOD_DIRECTSS = 2
+  integer(c_int), parameter, public :: WB_MAX_TRACERS = 3
   integer(c_int), parameter, public :: WB_MAX_TABLE = 16
 
   type, bind(C), public :: wb_relperm
@@ -76,8 +77,9 @@ module waiwera_b200
        wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
-       wb_mat_set_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
+       wb_mat_set_values, wb_mat_get_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
        wb_pc_destroy, wb_ksp_solve, wb_ksp_set_check_every, wb_set_pc_blocks, wb_newton_solve_be, wb_timer_get, &
+       wb_set_tracers, wb_set_tracer_injection, wb_tracer_cell_balances, wb_tracer_setup_linear, wb_tracer_solve, &
        wb_timer_reset, wb_timers_enable, wb_launch_count, wb_stream
 
   interface
@@ -365,6 +367,12 @@ module waiwera_b200
        integer(c_int) :: ierr
      end function wb_mat_set_values
 
+     function wb_mat_get_values(mat, vals) bind(C, name="wb_mat_get_values") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: mat, vals
+       integer(c_int) :: ierr
+     end function wb_mat_get_values
+
      function wb_mat_destroy(mat) bind(C, name="wb_mat_destroy") result(ierr)
        import :: c_int, c_ptr
        type(c_ptr), value :: mat
@@ -432,6 +440,53 @@ module waiwera_b200
        type(c_ptr), value :: ctx, block_of_row
        integer(c_int) :: ierr
      end function wb_set_pc_blocks
+
+     ! setup_tracers (src/tracer.F90:64-150): phase(nt) 1-based phase index; diffusion / decay / activation may be c_null_ptr
+     function wb_set_tracers(ctx, nt, phase, diffusion, decay, activation) bind(C, name="wb_set_tracers") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: nt
+       type(c_ptr), value :: phase, diffusion, decay, activation
+       integer(c_int) :: ierr
+     end function wb_set_tracers
+
+     ! source%tracer_injection_rate for every source of wb_set_sources: rate(nt, nsources)
+     function wb_set_tracer_injection(ctx, rate) bind(C, name="wb_set_tracer_injection") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, rate
+       integer(c_int) :: ierr
+     end function wb_set_tracer_injection
+
+     ! aux_lhs (src/flow_simulation.F90:1489-1556)
+     function wb_tracer_cell_balances(ctx, al) bind(C, name="wb_tracer_cell_balances") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, al
+       integer(c_int) :: ierr
+     end function wb_tracer_cell_balances
+
+     ! method%setup_linear (src/timestepper.F90:458-581) + aux_pre_solve (src/flow_simulation.F90:1837-1959)
+     function wb_tracer_setup_linear(ctx, dt, al_last, x_last, al_last2, x_last2, x_boundary, al, b, mat) &
+          bind(C, name="wb_tracer_setup_linear") result(ierr)
+       import :: c_int, c_double, c_ptr
+       type(c_ptr), value :: ctx
+       real(c_double), value :: dt
+       type(c_ptr), value :: al_last, x_last, al_last2, x_last2, x_boundary, al, b
+       type(c_ptr), intent(out) :: mat
+       integer(c_int) :: ierr
+     end function wb_tracer_setup_linear
+
+     ! the auxiliary step of timestepper_step (src/timestepper.F90:2347-2353): setup_linear, aux_pre_solve, KSPSolve
+     function wb_tracer_solve(ctx, ksp, pc_type, pc_nblocks, dt, al_last, x_last, al_last2, x_last2, x_boundary, al, x, &
+          its, reason) bind(C, name="wb_tracer_solve") result(ierr)
+       import :: c_int, c_double, c_ptr, wb_ksp_opts
+       type(c_ptr), value :: ctx
+       type(wb_ksp_opts), intent(in) :: ksp
+       integer(c_int), value :: pc_type, pc_nblocks
+       real(c_double), value :: dt
+       type(c_ptr), value :: al_last, x_last, al_last2, x_last2, x_boundary, al, x
+       integer(c_int), intent(out) :: its, reason
+       integer(c_int) :: ierr
+     end function wb_tracer_solve
 
      ! SNESSolve as configured by timestepper.F90:1552-1641, one backward-Euler step
      function wb_newton_solve_be(ctx, opts, dt, lhs_last, y, res) bind(C, name="wb_newton_solve_be") result(ierr)

@@ -232,6 +232,8 @@ typedef struct wb_pc wb_pc;
 int wb_mat_create(wb_ctx *ctx, int nb, int ncolb, int bs, int nnzb, const int32_t *rowptr,
                   const int32_t *colidx, const double *vals, wb_mat **out);
 int wb_mat_set_values(wb_mat *A, const double *vals);
+/* MatSeqBAIJGetArray: copies the nnzb*bs*bs block values to vals (host or device) */
+int wb_mat_get_values(wb_mat *A, double *vals);
 int wb_mat_destroy(wb_mat *A);
 /* the context's own Jacobian as a wb_mat (borrowed; do not destroy) */
 int wb_jacobian_mat(wb_ctx *ctx, wb_mat **out);
@@ -284,6 +286,41 @@ int wb_set_pc_blocks(wb_ctx *ctx, const int32_t *block_of_row);
 /* one backward-Euler step solve: y in/out (scaled primaries of owned cells) */
 int wb_newton_solve_be(wb_ctx *ctx, const wb_newton_opts *opts, double dt, const double *lhs_last, double *y,
                        wb_newton_result *res);
+
+/* ---- passive tracers: the auxiliary linear problem ------------------
+   After a converged Newton solve the reference assembles and solves one LINEAR system for the tracer
+   mass fractions (src/timestepper.F90:2347-2353): method%setup_linear (:458-581) builds
+   A = Al - dt Ar, b = Al_last x_last + dt br from aux_lhs (src/flow_simulation.F90:1489-1556) and aux_rhs
+   (:1560-1833: upstream advection with the stored phase fluxes, diffusion, production, injection, Arrhenius
+   decay), aux_pre_solve (:1837-1959) pins absent phases and Dirichlet cells, KSPSolve solves it.  Here A_aux
+   lives on the Jacobian's block pattern with bs = nt (tracers do not couple: diagonal blocks); rows of
+   Dirichlet ghost cells are eliminated into b.  All calls use the fluid state of the last UNPERTURBED
+   evaluation (wb_pre_eval / wb_residual_be with nperturbed = 0, or the end of wb_newton_solve_be), as the
+   reference does.  The time-stepping method is the one set with wb_set_method. */
+#define WB_MAX_TRACERS 3
+/* setup_tracers (src/tracer.F90:64-150): phase[nt] 1-based phase index, diffusion[nt] (m2/s),
+   decay[nt] constant (1/s), activation[nt] energy (J/mol); any of the last three may be NULL (zeros).
+   nt = 0 removes the tracers. */
+int wb_set_tracers(wb_ctx *ctx, int nt, const int32_t *phase, const double *diffusion, const double *decay,
+                   const double *activation);
+/* source%tracer_injection_rate (src/source.F90): rate[nsources*nt] (kg/s) in the order of the last
+   wb_set_sources; NULL removes them.  Only injecting sources (rate > 0) use it. */
+int wb_set_tracer_injection(wb_ctx *ctx, const double *rate);
+/* aux_lhs (src/flow_simulation.F90:1489-1556): al[nowned*nt] = porosity * saturation * density of the tracer's phase */
+int wb_tracer_cell_balances(wb_ctx *ctx, double *al);
+/* setup_linear + aux_pre_solve.  al_last / x_last: balance coefficients and mass fractions at the last step
+   (nowned*nt); al_last2 / x_last2: two steps back (BDF2 only, else NULL); x_boundary[(ncell-ninterior)*nt]:
+   mass fractions of the Dirichlet ghost cells (NULL if there are none).  Outputs: al (new coefficients, may be
+   NULL), b (right-hand side, nowned*nt, may be NULL) and A (borrowed wb_mat, bs = nt, valid until the tracers or
+   the mesh change; may be NULL). */
+int wb_tracer_setup_linear(wb_ctx *ctx, double dt, const double *al_last, const double *x_last,
+                           const double *al_last2, const double *x_last2, const double *x_boundary, double *al,
+                           double *b, wb_mat **A);
+/* the whole auxiliary step: setup_linear, aux_pre_solve, PCSetUp, KSPSolve (zero initial guess).
+   x (out): new mass fractions, nowned*nt. */
+int wb_tracer_solve(wb_ctx *ctx, const wb_ksp_opts *ksp, int pc_type, int pc_nblocks, double dt,
+                    const double *al_last, const double *x_last, const double *al_last2, const double *x_last2,
+                    const double *x_boundary, double *al, double *x, int *its, int *reason);
 
 /* ---- instrumentation (PetscLogEvent equivalents, src/profiling.F90:42-65) -- */
 /* accumulated device time (ms) and call count of a named phase:

@@ -146,3 +146,140 @@ void hc_wce_scale(const wb_params *prm, const double *primary, int region, doubl
   wb_unscale<3>(e, y, region, back);
 }
 }
+
+// ---------------------------------------------------------------- tracer row assembly (wb_tracer.cuh)
+#include <vector>
+
+#include "../../waiwera_b200/csrc/wb_tracer.cuh"
+
+// Runs wb_tracer_row -- the body of k_tracer_assemble -- over all owned rows on the host.  The harness builds
+// what wb_set_mesh / k_eos / k_face_perm hold on the device: SoA cell states from unscaled primaries, SoA faces
+// with the harmonic permeability, the cell -> face lists in ascending face order and the block positions in
+// the given BSR pattern (rowptr / colidx over owned cells, sorted columns).
+template <int EOS, int NT>
+static int tracer_assemble_host(const wb_params *prm, int ncell, int nowned, int nface, const int32_t *face_cells,
+                                const double *face12, const double *cell4, const double *rock8,
+                                const double *primary, const int32_t *region, const int32_t *phase,
+                                const double *diffusion, const double *decay, const double *activation, int nsrc,
+                                const int32_t *src_cell, const int32_t *src_comp, const double *src_rate,
+                                const double *inj, int method, double dt, double dt_last, const double *al_last,
+                                const double *x_last, const double *al_last2, const double *x_last2,
+                                const double *xb, const int32_t *rowptr, const int32_t *colidx, double *val,
+                                double *b, double *al) {
+  constexpr int NP = WbEosTraits<EOS>::NP, NC = WbEosTraits<EOS>::NC, NPH = WbEosTraits<EOS>::NPH;
+  constexpr int NF = WbStateLayout<NC, NPH>::NF;
+  WbEosParams e;
+  if (wb_eos_params_make(*prm, e)) return -1;
+  std::vector<double> state((size_t)NF * ncell), rockp((size_t)5 * ncell), vol(ncell), face((size_t)6 * nface);
+  for (int c = 0; c < ncell; c++) {
+    const double *rk = rock8 + 8 * (size_t)c;
+    WbFluid<NC, NPH> fl = {};
+    fl.region = region[c];
+    if (wb_eos_properties<EOS>(e, primary + (size_t)c * NP, fl)) return 1;
+    WbCellState<NC, NPH> s;
+    wb_state_from_fluid(fl, rk[WB_R_WET], rk[WB_R_DRY], s);
+    store_state(state.data(), (size_t)ncell, c, s);
+    rockp[c] = rk[WB_R_POR];
+    vol[c] = cell4[4 * (size_t)c + 3];
+  }
+  for (int f = 0; f < nface; f++) {
+    const double *g = face12 + 12 * (size_t)f;
+    const int c1 = face_cells[2 * f], c2 = face_cells[2 * f + 1];
+    const int d = (int)(g[11] + 0.5) - 1;
+    face[f] = g[0];
+    face[(size_t)nface + f] = g[1];
+    face[(size_t)2 * nface + f] = g[2];
+    face[(size_t)3 * nface + f] = g[3];
+    face[(size_t)4 * nface + f] = g[7];
+    face[(size_t)5 * nface + f] = wb_harmonic(g[1], g[2], g[3], rock8[8 * (size_t)c1 + d] * 1.0, rock8[8 * (size_t)c2 + d] * 1.0);
+  }
+  std::vector<int32_t> cf_ptr(nowned + 1, 0), cf_face, cf_other, cf_bpos, diagpos(nowned);
+  for (int f = 0; f < nface; f++)
+    for (int s = 0; s < 2; s++)
+      if (face_cells[2 * f + s] < nowned) cf_ptr[face_cells[2 * f + s] + 1]++;
+  for (int i = 0; i < nowned; i++) cf_ptr[i + 1] += cf_ptr[i];
+  cf_face.resize(cf_ptr[nowned]); cf_other.resize(cf_ptr[nowned]); cf_bpos.resize(cf_ptr[nowned]);
+  std::vector<int32_t> fill(cf_ptr.begin(), cf_ptr.end() - 1);
+  auto find = [&](int row, int col) {
+    for (int k = rowptr[row]; k < rowptr[row + 1]; k++)
+      if (colidx[k] == col) return k;
+    return -1;
+  };
+  for (int f = 0; f < nface; f++)
+    for (int s = 0; s < 2; s++) {
+      const int c = face_cells[2 * f + s], o = face_cells[2 * f + 1 - s];
+      if (c >= nowned) continue;
+      const int e = fill[c]++;
+      cf_face[e] = 2 * f + s;
+      cf_other[e] = o;
+      cf_bpos[e] = o < nowned ? find(c, o) : -1;
+    }
+  for (int i = 0; i < nowned; i++) diagpos[i] = find(i, i);
+  // sources sorted by cell (stable), as wb_set_sources keeps them
+  std::vector<int> order(nsrc);
+  for (int k = 0; k < nsrc; k++) order[k] = k;
+  for (int a = 1; a < nsrc; a++) {
+    const int v = order[a];
+    int q = a - 1;
+    while (q >= 0 && src_cell[order[q]] > src_cell[v]) { order[q + 1] = order[q]; q--; }
+    order[q + 1] = v;
+  }
+  std::vector<int32_t> head(nowned, -1), sc(nsrc + 1), sk(nsrc + 1);
+  std::vector<double> sr(nsrc + 1), sinj((size_t)nsrc * NT + 1);
+  for (int k = 0; k < nsrc; k++) {
+    sc[k] = src_cell[order[k]]; sk[k] = src_comp[order[k]]; sr[k] = src_rate[order[k]];
+    for (int t = 0; t < NT; t++) sinj[(size_t)k * NT + t] = inj ? inj[(size_t)order[k] * NT + t] : 0.0;
+    if (head[sc[k]] < 0) head[sc[k]] = k;
+  }
+  TracerArgs a = {};
+  a.state = state.data(); a.face = face.data(); a.vol = vol.data(); a.rockp = rockp.data();
+  a.cf_ptr = cf_ptr.data(); a.cf_face = cf_face.data(); a.cf_other = cf_other.data(); a.cf_bpos = cf_bpos.data();
+  a.diagpos = diagpos.data(); a.rowptr = rowptr;
+  a.src.head = nsrc ? head.data() : nullptr; a.src.cell = sc.data(); a.src.comp = sk.data(); a.src.rate = sr.data();
+  a.src.enth = nullptr; a.src.n = nsrc;
+  a.inj = inj ? sinj.data() : nullptr;
+  for (int t = 0; t < NT; t++) {
+    a.trc.phase[t] = phase[t] - 1; a.trc.diffusion[t] = diffusion[t]; a.trc.decay[t] = decay[t];
+    a.trc.activation[t] = activation[t];
+  }
+  a.method = method;
+  if (method == WB_METHOD_BDF2) {
+    const double r = dt / dt_last, r1 = r + 1.0;
+    a.sA = -dt * r1; a.sD = 1.0 + 2.0 * r; a.s0 = r1 * r1; a.s2 = -r * r; a.sb = dt * r1;
+  } else if (method == WB_METHOD_DIRECTSS) {
+    a.sA = 1.0; a.sD = 0.0;
+  } else {
+    a.sA = -dt; a.sD = 1.0; a.s0 = 1.0; a.sb = dt;
+  }
+  a.al_last = al_last; a.x_last = x_last; a.al_last2 = al_last2; a.x_last2 = x_last2; a.xb = xb;
+  a.val = val; a.b = b; a.al = al;
+  a.ncell = ncell; a.ninterior = nowned; a.nowned = nowned; a.nface = nface;
+  for (int i = 0; i < nowned; i++) wb_tracer_row<EOS, NT>(a, i);
+  return 0;
+}
+
+extern "C" int hc_tracer_assemble(const wb_params *prm, int nt, int ncell, int nowned, int nface,
+                                  const int32_t *face_cells, const double *face12, const double *cell4,
+                                  const double *rock8, const double *primary, const int32_t *region,
+                                  const int32_t *phase, const double *diffusion, const double *decay,
+                                  const double *activation, int nsrc, const int32_t *src_cell,
+                                  const int32_t *src_comp, const double *src_rate, const double *inj, int method,
+                                  double dt, double dt_last, const double *al_last, const double *x_last,
+                                  const double *al_last2, const double *x_last2, const double *xb,
+                                  const int32_t *rowptr, const int32_t *colidx, double *val, double *b, double *al) {
+#define HC_TRACER(E, T)                                                                                              \
+  return tracer_assemble_host<E, T>(prm, ncell, nowned, nface, face_cells, face12, cell4, rock8, primary, region,    \
+                                    phase, diffusion, decay, activation, nsrc, src_cell, src_comp, src_rate, inj,    \
+                                    method, dt, dt_last, al_last, x_last, al_last2, x_last2, xb, rowptr, colidx, val, \
+                                    b, al)
+  if (prm->eos == WB_EOS_WE) {
+    if (nt == 1) HC_TRACER(WB_EOS_WE, 1);
+    if (nt == 2) HC_TRACER(WB_EOS_WE, 2);
+    if (nt == 3) HC_TRACER(WB_EOS_WE, 3);
+  } else if (prm->eos == WB_EOS_WCE) {
+    if (nt == 1) HC_TRACER(WB_EOS_WCE, 1);
+    if (nt == 2) HC_TRACER(WB_EOS_WCE, 2);
+  }
+#undef HC_TRACER
+  return -2;
+}

@@ -22,7 +22,7 @@ SEED = 20240917
 @pytest.fixture(scope="module")
 def hc(wo):
     deps = [SRC] + [os.path.join(HERE, "..", "waiwera_b200", "csrc", f)
-                    for f in ("wb_eos.cuh", "wb_thermo.cuh", "wb_iapws_gen.cuh")]
+                    for f in ("wb_eos.cuh", "wb_thermo.cuh", "wb_iapws_gen.cuh", "wb_state.cuh", "wb_tracer.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-o", LIB, SRC])
     L = C.CDLL(LIB)
@@ -42,6 +42,8 @@ def hc(wo):
     L.hc_wce_flux.argtypes = [C.c_void_p, dp, dp, dp, dp, i, dp, i, dp, dp]
     L.hc_wce_transition.argtypes = [C.c_void_p, dp, dp, i, d, ip, ip, ip]
     L.hc_wce_scale.argtypes = [C.c_void_p, dp, i, dp, dp]
+    L.hc_tracer_assemble.argtypes = [C.c_void_p, i, i, i, i, ip, dp, dp, dp, dp, ip, ip, dp, dp, dp, i, ip, ip, dp, dp, i,
+                                     d, d, dp, dp, dp, dp, dp, ip, ip, dp, dp, dp]
     return L
 
 

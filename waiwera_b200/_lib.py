@@ -93,6 +93,7 @@ SIGNATURES = {
     "wb_fluid_transitions": (i, [vp, vp, vp, vp, C.POINTER(i), C.POINTER(i)]),
     "wb_mat_create": (i, [vp, i, i, i, i, vp, vp, vp, C.POINTER(vp)]),
     "wb_mat_set_values": (i, [vp, vp]),
+    "wb_mat_get_values": (i, [vp, vp]),
     "wb_mat_destroy": (i, [vp]),
     "wb_jacobian_mat": (i, [vp, C.POINTER(vp)]),
     "wb_mat_mult": (i, [vp, vp, vp]),
@@ -104,6 +105,11 @@ SIGNATURES = {
     "wb_ksp_set_check_every": (i, [i]),
     "wb_set_pc_blocks": (i, [vp, vp]),
     "wb_newton_solve_be": (i, [vp, C.POINTER(NewtonOpts), d, vp, vp, C.POINTER(NewtonResult)]),
+    "wb_set_tracers": (i, [vp, i, vp, vp, vp, vp]),
+    "wb_set_tracer_injection": (i, [vp, vp]),
+    "wb_tracer_cell_balances": (i, [vp, vp]),
+    "wb_tracer_setup_linear": (i, [vp, d, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    "wb_tracer_solve": (i, [vp, C.POINTER(KspOpts), i, i, d, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i), C.POINTER(i)]),
     "wb_timer_get": (i, [vp, C.c_char_p, C.POINTER(d), C.POINTER(i64)]),
     "wb_timer_reset": (i, [vp]),
     "wb_timers_enable": (i, [i]),

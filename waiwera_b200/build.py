@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwaiwera_b200.so")
-SOURCES = ["wb_core.cu", "wb_flow.cu", "wb_linalg.cu", "wb_newton.cu"]
-HEADERS = ["wb_common.cuh", "wb_eos.cuh", "wb_thermo.cuh", "wb_iapws_gen.cuh"]
+SOURCES = ["wb_core.cu", "wb_flow.cu", "wb_tracer.cu", "wb_linalg.cu", "wb_newton.cu"]
+HEADERS = ["wb_common.cuh", "wb_state.cuh", "wb_tracer.cuh", "wb_eos.cuh", "wb_thermo.cuh", "wb_iapws_gen.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
         # the physics translation unit is compiled without FMA contraction so that every evaluation of
         # F (residual kernel, Jacobian kernel, colouring loop) rounds identically, and identically to the
         # reference arithmetic order; the bandwidth-bound linear algebra keeps FMA
-        extra = ["-fmad=false"] if src == "wb_flow.cu" else []
+        extra = ["-fmad=false"] if src in ("wb_flow.cu", "wb_tracer.cu") else []
         cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:

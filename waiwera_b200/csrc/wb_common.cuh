@@ -13,6 +13,7 @@
 
 #include "../../include/waiwera_b200.h"
 #include "wb_eos.cuh"
+#include "wb_state.cuh"
 
 void wb_set_error(const char *fmt, ...);
 // guards the per-context work-space registries (std::map keyed by context): contexts may live on different
@@ -188,6 +189,17 @@ struct wb_ctx {
   int nsrc = 0;
   int32_t *d_src_head = nullptr, *d_src_cell = nullptr, *d_src_comp = nullptr;
   double *d_src_rate = nullptr, *d_src_enth = nullptr;
+  std::vector<int> h_src_order;  // sorted position -> input position
+  // passive tracers: auxiliary linear problem (wb_tracer.cu)
+  int nt = 0;
+  int trc_phase[WB_MAX_TRACERS] = {0, 0, 0};  // 1-based phase index
+  double trc_diffusion[WB_MAX_TRACERS] = {0, 0, 0}, trc_decay[WB_MAX_TRACERS] = {0, 0, 0},
+         trc_activation[WB_MAX_TRACERS] = {0, 0, 0};
+  double *d_trc_inj = nullptr;  // [nsrc*nt] injection rates in sorted source order
+  wb_mat *A_aux = nullptr;      // BAIJ bs = nt on the Jacobian's block pattern
+  double *d_trc_b = nullptr, *d_trc_x = nullptr, *d_trc_al = nullptr;  // [nowned*nt] work vectors
+  wb_pc *trc_pc = nullptr;      // preconditioner of A_aux (symbolic part kept between steps)
+  int trc_pc_type = -1, trc_pc_nblocks = 0;
   int *d_flags = nullptr;        // [8] device flags (error, changed_y, changed_search, ...)
   int *h_flags = nullptr;        // pinned mirror
 
@@ -279,3 +291,5 @@ extern "C" int wb_pc_refactor(wb_pc *pc);
 void wb_linalg_release(wb_ctx *c);
 void wb_flow_release(wb_ctx *c);
 void wb_newton_release(wb_ctx *c);
+void wb_tracer_release(wb_ctx *c);
+WbSources wb_sources_args(const wb_ctx *c);

@@ -212,6 +212,8 @@ static void free_mat(wb_mat &m) {
 }
 
 void wb_free_mesh(wb_ctx *c) {
+  wb_tracer_release(c);  // A_aux borrows the Jacobian's pattern
+  c->nt = 0;
   void *ptrs[] = {c->d_face_cells, c->d_face, c->d_vol, c->d_rockp, c->d_cf_ptr, c->d_cf_face, c->d_cf_other,
                   c->d_cf_bpos, c->d_diagpos, c->d_region, c->d_region_iter, c->d_region_step, c->d_T_iter,
                   c->d_T_step, c->d_sat_step, c->d_state, c->d_Lvar, c->d_dx, c->d_yloc, c->d_balances};
@@ -233,6 +235,7 @@ extern "C" int wb_destroy(wb_ctx *c) {
   wb_free_mesh(c);
   for (void *p : c->stage) cudaFree(p);
   cudaFree(c->d_lhs_last2);
+  cudaFree(c->d_trc_inj);
   cudaFree(c->d_src_head); cudaFree(c->d_src_cell); cudaFree(c->d_src_comp); cudaFree(c->d_src_rate); cudaFree(c->d_src_enth);
   cudaFree(c->halo.d_send_idx);
   cudaFree(c->halo.d_recv_idx);

@@ -5,71 +5,10 @@
 #include <algorithm>
 
 #include "wb_common.cuh"
+#include "wb_state.cuh"
 
 void wb_free_mesh(wb_ctx *c);
 void wb_newton_invalidate_pc(wb_ctx *c);
-
-// ---------------------------------------------------------------- state SoA
-
-template <int NC, int NPH>
-__device__ __forceinline__ void load_state(const double *__restrict__ st, size_t ncell, int c,
-                                           WbCellState<NC, NPH> &s) {
-  const double *p = st + c;
-  s.P = p[0];
-  s.T = p[ncell];
-  s.cond = p[2 * ncell];
-  s.phases = (int)p[3 * ncell];
-#pragma unroll
-  for (int q = 0; q < NPH; q++) {
-    const double *pp = p + (size_t)(4 + q * (5 + (NC > 1 ? NC : 0))) * ncell;
-    s.rho[q] = pp[0];
-    s.sat[q] = pp[ncell];
-    s.pc[q] = pp[2 * ncell];
-    s.mob[q] = pp[3 * ncell];
-    s.h[q] = pp[4 * ncell];
-    if (NC == 1) {
-      s.X[q][0] = (s.phases & (1 << q)) ? 1.0 : 0.0;  // single component
-    } else {
-#pragma unroll
-      for (int k = 0; k < NC; k++) s.X[q][k] = pp[(size_t)(5 + k) * ncell];
-    }
-  }
-}
-
-template <int NC, int NPH>
-__device__ __forceinline__ void store_state(double *__restrict__ st, size_t ncell, int c,
-                                            const WbCellState<NC, NPH> &s) {
-  double *p = st + c;
-  p[0] = s.P;
-  p[ncell] = s.T;
-  p[2 * ncell] = s.cond;
-  p[3 * ncell] = (double)s.phases;
-#pragma unroll
-  for (int q = 0; q < NPH; q++) {
-    double *pp = p + (size_t)(4 + q * (5 + (NC > 1 ? NC : 0))) * ncell;
-    pp[0] = s.rho[q];
-    pp[ncell] = s.sat[q];
-    pp[2 * ncell] = s.pc[q];
-    pp[3 * ncell] = s.mob[q];
-    pp[4 * ncell] = s.h[q];
-    if (NC > 1) {
-#pragma unroll
-      for (int k = 0; k < NC; k++) pp[(size_t)(5 + k) * ncell] = s.X[q][k];
-    }
-  }
-}
-
-__device__ __forceinline__ WbFaceGeom load_face(const double *__restrict__ face, size_t nface, int f) {
-  WbFaceGeom g;
-  const double *p = face + f;
-  g.area = p[0];
-  g.d1 = p[nface];
-  g.d2 = p[2 * nface];
-  g.d12 = p[3 * nface];
-  g.gravn = p[4 * nface];
-  g.k = p[5 * nface];
-  return g;
-}
 
 // MATMFFD_DS step (PETSc MatFDColoringApply, doc/user/setup_time.rst:434-452)
 __device__ __forceinline__ double fd_step(double yj, double err, double umin) {
@@ -247,13 +186,6 @@ __device__ __forceinline__ double wb_form_residual(const WbResForm &f, double L,
 }
 
 // ---------------------------------------------------------------- sources / sinks
-
-// fixed-rate sources sorted by cell (stable: input order inside a cell); head[c] = first source of owned cell c or -1
-struct WbSources {
-  const int32_t *head, *cell, *comp;
-  const double *rate, *enth;
-  int n;
-};
 
 // adds the inflow of every source of cell i, in source order (src/source_network.F90:296-355: inflow += flow / V);
 // source%update_flow src/source.F90:457-480: injection :385-399, production by mobility-weighted phase flow
@@ -692,7 +624,7 @@ static WbResForm wb_res_form(const wb_ctx *c, const double *d_lhs_last, double d
   return f;
 }
 
-static WbSources wb_sources_args(const wb_ctx *c) {
+WbSources wb_sources_args(const wb_ctx *c) {
   WbSources S = {c->nsrc > 0 ? c->d_src_head : nullptr, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth, c->nsrc};
   return S;
 }
@@ -1007,6 +939,9 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   c->d_src_head = c->d_src_cell = c->d_src_comp = nullptr;
   c->d_src_rate = c->d_src_enth = nullptr;
   c->nsrc = 0;
+  c->h_src_order.clear();
+  cudaFree(c->d_trc_inj);  // tracer injection rates belong to the old source list
+  c->d_trc_inj = nullptr;
   if (n <= 0) return 0;
   std::vector<int> order(n);
   for (int k = 0; k < n; k++) {
@@ -1028,6 +963,7 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   WB_TRY(dev_upload(&c->d_src_rate, sr));
   WB_TRY(dev_upload(&c->d_src_enth, se));
   c->nsrc = n;
+  c->h_src_order = order;
   return 0;
 }
 

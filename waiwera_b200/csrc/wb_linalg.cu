@@ -281,6 +281,14 @@ extern "C" int wb_mat_set_values(wb_mat *A, const double *vals) {
   return 0;
 }
 
+extern "C" int wb_mat_get_values(wb_mat *A, double *vals) {
+  WB_CUDA(cudaSetDevice(A->ctx->device));
+  WB_CUDA(cudaMemcpyAsync(vals, A->d_val, sizeof(double) * (size_t)A->nnzb * A->bs * A->bs, cudaMemcpyDefault,
+                          A->ctx->stream));
+  WB_CUDA(cudaStreamSynchronize(A->ctx->stream));
+  return 0;
+}
+
 extern "C" int wb_mat_destroy(wb_mat *A) {
   if (!A || !A->owns || A == &A->ctx->J) return 0;
   cudaSetDevice(A->ctx->device);
@@ -2031,6 +2039,7 @@ __global__ void k_gmres_solve_y(const double *H, const double *rs, double *yv, i
 struct KspWork {
   wb_ctx *ctx = nullptr;
   size_t n = 0, ld = 0;  // ld: n rounded up to 32 doubles so every basis vector is 256-byte aligned
+  size_t cap = 0;        // allocated leading dimension: systems of different size (Jacobian, tracers) share the work space
   int m = 0;
   double *V = nullptr, *tmp = nullptr, *wbuf = nullptr, *small = nullptr, *part = nullptr;
   KspState *d_st = nullptr, *h_st = nullptr;
@@ -2052,13 +2061,20 @@ static int ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
     wq = &g_work[c];  // node addresses of a std::map are stable
   }
   KspWork &w = *wq;
-  if (w.n != n || w.m < m) {
+  const size_t ld = (n + 31) / 32 * 32;
+  if (ld <= w.cap && m <= w.m) {
+    w.n = n; w.ld = ld;
+    w.wbuf = w.tmp + 2 * w.ld;
+  } else {
+    const int mcap = std::max(m, w.m);
+    const size_t cap = std::max(ld, w.cap);
     free_work(w);
     w = KspWork();
-    w.ctx = c; w.n = n; w.m = m;
-    w.ld = (n + 31) / 32 * 32;
-    WB_CUDA(cudaMalloc(&w.V, sizeof(double) * w.ld * (m + 1)));
-    WB_CUDA(cudaMalloc(&w.tmp, sizeof(double) * w.ld * 3));
+    w.ctx = c; w.n = n; w.m = mcap; w.cap = cap;
+    w.ld = ld;
+    m = mcap;
+    WB_CUDA(cudaMalloc(&w.V, sizeof(double) * cap * (m + 1)));
+    WB_CUDA(cudaMalloc(&w.tmp, sizeof(double) * cap * 3));
     w.wbuf = w.tmp + 2 * w.ld;
     WB_CUDA(cudaMalloc(&w.small, sizeof(double) * ((size_t)(m + 1) * m + 6 * (m + 2) + 16)));
     WB_CUDA(cudaMalloc(&w.part, sizeof(double) * RED_BLOCKS * KRY_MAXV));

@@ -96,6 +96,11 @@ class Mat:
     def set_values(self, vals):
         check(self.L.wb_mat_set_values(self.h, ptr(vals)), "wb_mat_set_values")
 
+    def get_values(self, nnzb):
+        vals = np.zeros(nnzb * self.bs * self.bs)
+        check(self.L.wb_mat_get_values(self.h, ptr(vals)), "wb_mat_get_values")
+        return vals
+
     def mult(self, x, y):
         check(self.L.wb_mat_mult(self.h, ptr(x), ptr(y)), "wb_mat_mult")
         return y
@@ -306,6 +311,48 @@ class FlowSimulation:
         h = C.c_void_p()
         check(self.L.wb_jacobian_mat(self.h, C.byref(h)))
         return Mat(self, h, self.nowned, self.np, owned=False)
+
+    # ---- passive tracers: the auxiliary linear problem (flow_simulation.F90:1489-1959, timestepper.F90:458-581)
+    def set_tracers(self, phases, diffusion=None, decay=None, activation=None):
+        """setup_tracers (tracer.F90:64-150); phases are 1-based phase indices"""
+        ph = np.ascontiguousarray(phases, np.int32)
+        arr = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (diffusion, decay, activation)]
+        self.nt = len(ph)
+        return check(self.L.wb_set_tracers(self.h, len(ph), ptr(ph), ptr(arr[0]), ptr(arr[1]), ptr(arr[2])),
+                     "wb_set_tracers")
+
+    def set_tracer_injection(self, rates):
+        r = None if rates is None else np.ascontiguousarray(rates, np.float64)
+        return check(self.L.wb_set_tracer_injection(self.h, ptr(r)), "wb_set_tracer_injection")
+
+    def tracer_balances(self):
+        """aux_lhs: porosity * saturation * density of each tracer's phase, [nowned*nt]"""
+        al = np.zeros(self.nowned * self.nt)
+        check(self.L.wb_tracer_cell_balances(self.h, ptr(al)), "wb_tracer_cell_balances")
+        return al
+
+    def tracer_setup_linear(self, dt, al_last, x_last, x_boundary=None, al_last2=None, x_last2=None):
+        """setup_linear + aux_pre_solve; returns (A, b, Al) with A a borrowed Mat (bs = nt)"""
+        n = self.nowned * self.nt
+        al, b = np.zeros(n), np.zeros(n)
+        h = C.c_void_p()
+        xb = None if x_boundary is None else np.ascontiguousarray(x_boundary, np.float64)
+        check(self.L.wb_tracer_setup_linear(self.h, dt, ptr(al_last), ptr(x_last), ptr(al_last2), ptr(x_last2), ptr(xb),
+                                            ptr(al), ptr(b), C.byref(h)), "wb_tracer_setup_linear")
+        return Mat(self, h, self.nowned, self.nt, owned=False), b, al
+
+    def tracer_solve(self, dt, al_last, x_last, x_boundary=None, al_last2=None, x_last2=None, opts=None,
+                     pc_type=PC_BJACOBI_ILU0, pc_nblocks=1):
+        """the auxiliary step of timestepper_step (timestepper.F90:2347-2353); returns (x, Al, reason, iterations)"""
+        n = self.nowned * self.nt
+        al, x = np.zeros(n), np.zeros(n)
+        o = opts if opts is not None else ksp_opts()
+        its, reason = C.c_int(), C.c_int()
+        xb = None if x_boundary is None else np.ascontiguousarray(x_boundary, np.float64)
+        check(self.L.wb_tracer_solve(self.h, C.byref(o), pc_type, pc_nblocks, dt, ptr(al_last), ptr(x_last),
+                                     ptr(al_last2), ptr(x_last2), ptr(xb), ptr(al), ptr(x), C.byref(its),
+                                     C.byref(reason)), "wb_tracer_solve")
+        return x, al, reason.value, its.value
 
     # ---- transitions
     def fluid_transitions(self, y_old, search, y):
