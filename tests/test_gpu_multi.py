@@ -56,6 +56,23 @@ def owner_for(kind, gm, world):
     return wmesh.minc_owner(gm, parts) if kind == "minc" else wmesh.box_owner(gm, parts)
 
 
+NT = 2
+
+
+def tracer_step(sim, flow, gm, y, nat):
+    """one auxiliary tracer solve (liquid tracer with diffusion, decaying liquid tracer) at the state y: the
+    partitioned system (ghost columns through the halo inside the SpMV) must give the single-GPU solution"""
+    err, _ = sim.lhs(y)                    # unperturbed evaluation: the state the tracer system is built from
+    assert err == 0
+    assert sim.set_tracers([1, 1], diffusion=[1.0e-6, 0.0], decay=[0.0, 1.0e-7]) == 0
+    x0 = np.random.default_rng(5).uniform(0.0, 0.01, gm.ninterior * NT).reshape(-1, NT)[nat].reshape(-1)
+    al = sim.tracer_balances()
+    x, _, reason, its = sim.tracer_solve(DT, al, np.ascontiguousarray(x0), opts=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-12),
+                                         pc_type=flow.PC_PBJACOBI)
+    assert reason > 0
+    return x
+
+
 def worker(rank, world, port, out, p2p, kind="we"):
     import torch.distributed as dist
     from waiwera_b200 import flow, mesh as wmesh
@@ -92,9 +109,10 @@ def worker(rank, world, port, out, p2p, kind="we"):
         y2 = y.copy()
         res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
                                                             ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))
+        xt = tracer_step(sim, flow, gm, y1, nat)
         gathered = [None] * world
         dist.all_gather_object(gathered, dict(nat=nat, r=r, ax=ax, y2=y2, mv=mv, ml=ml, reason=res.reason,
-                                              its=res.iterations, lits=res.linear_iterations))
+                                              its=res.iterations, lits=res.linear_iterations, xt=xt))
         if rank == 0:
             out.put(gathered)
         sim.destroy()
@@ -136,6 +154,11 @@ def test_partitioned_path_matches_single_gpu(world, p2p, kind):
     y2 = gy.copy()
     res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
                                                         ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))
+    xt = tracer_step(sim, flow, gm, y1, np.arange(gm.ninterior))
+    gxt = np.zeros_like(xt).reshape(-1, NT)
+    for g in gathered:
+        gxt[g["nat"]] = g["xt"].reshape(-1, NT)
+    assert np.abs(gxt.reshape(-1) - xt).max() <= 1e-9 * np.abs(xt).max()
     gr, gax, gy2 = np.zeros_like(r).reshape(-1, npv), np.zeros_like(ax).reshape(-1, npv), np.zeros_like(y2).reshape(-1, npv)
     for g in gathered:
         gr[g["nat"]] = g["r"].reshape(-1, npv)
