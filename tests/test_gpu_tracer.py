@@ -122,3 +122,44 @@ def test_tracers_can_be_removed_and_reset(wo):
     with pytest.raises(Exception):
         sim.tracer_balances()
     sim.destroy()
+
+
+def test_full_size_tracer_properties(wo):
+    """BASELINE config 2 size (100^3 cells, eos_we, top 20 layers two-phase): size-independent properties of the
+    tracer step.  Closed box, no sources, no decay => the liquid tracer's mass sum_i V_i Al_i x_i is conserved by
+    A x = b (advective and diffusive entries cancel in the volume-weighted column sums); the vapour tracer is
+    pinned to zero where there is no vapour; x >= 0 (upstream weighting makes A an M-matrix); the solve is
+    deterministic.  Prints the device times of the assembly kernel and of the solve."""
+    import json
+    from waiwera_b200 import flow
+    from util import make_problem
+    m, y, region, prm = make_problem(wo, dims=(100, 100, 100), two_phase_layers=20)
+    sim = gpu_flow(wo, flow, m, prm, y, region)
+    err, _ = sim.lhs(y)
+    assert err == 0
+    assert sim.set_tracers([1, 2], diffusion=[1.0e-6, 1.0e-5]) == 0
+    n, nt = m.nowned, 2
+    rng = np.random.default_rng(7)
+    x0 = rng.uniform(0.0, 0.01, (n, nt))
+    two_phase = region[:n] == 4
+    x0[~two_phase, 1] = 0.0                      # no vapour: no vapour tracer
+    x0 = np.ascontiguousarray(x0.reshape(-1))
+    al0 = sim.tracer_balances()
+    from waiwera_b200 import mesh as wmesh
+    sim.set_pc_blocks(wmesh.cube_blocks(m, 10))  # block Jacobi over 10^3-cell cubes, ILU(0) inside (as bench.py)
+    dt = 1.0e6
+    x, al, reason, its = sim.tracer_solve(dt, al0, x0, opts=flow.ksp_opts(type=flow.KSP_BCGS, rtol=1e-12))
+    assert reason > 0
+    xa, x0a, ala, al0a = x.reshape(n, nt), x0.reshape(n, nt), al.reshape(n, nt), al0.reshape(n, nt)
+    vol = m.cell_geom[:n, 3]
+    mass0, mass1 = np.sum(vol * al0a[:, 0] * x0a[:, 0]), np.sum(vol * ala[:, 0] * xa[:, 0])
+    assert abs(mass1 - mass0) <= 1e-9 * mass0, (mass0, mass1)
+    assert np.array_equal(ala, al0a)             # same state: same balance coefficients
+    assert (xa[~two_phase, 1] == 0.0).all()
+    assert xa.min() >= -1e-12                    # M-matrix (upstream weighting), b >= 0 => x >= 0
+    x2, _, reason2, its2 = sim.tracer_solve(dt, al0, x0, opts=flow.ksp_opts(type=flow.KSP_BCGS, rtol=1e-12))
+    assert its2 == its and np.array_equal(x2, x)
+    t_setup, t_solve = sim.timer("tracer_setup"), sim.timer("tracer_solve")
+    print("TRACER_FULL_SIZE " + json.dumps(dict(cells=n, tracers=nt, ksp_iterations=its, setup_ms=t_setup[0] / max(t_setup[1], 1),
+                                                solve_ms=t_solve[0] / max(t_solve[1], 1))))
+    sim.destroy()
