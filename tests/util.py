@@ -81,3 +81,75 @@ def gpu_flow(wo, flow, m, prm, y, region, device=0):
 def relerr(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+class OracleSim:
+    """The oracle behind the method names of flow.FlowSimulation that the time-stepping helpers use, so that one
+    driver runs the reference benchmarks through the oracle and through the CUDA path."""
+
+    def __init__(self, wo, f, opts):
+        self.wo, self.f, self.L, self.opts = wo, f, wo.lib(), opts
+        self.J = f.bsr()
+        self.color = np.zeros(self.J.contents.nb, np.int32)
+        self.ncolor = self.L.wo_bsr_coloring(self.J, wo.ip(self.color))
+
+    def lhs(self, y):
+        return self.f.lhs(y)
+
+    def pre_timestep(self):
+        self.L.wo_flow_pre_timestep(self.f.h)
+
+    def pre_retry_timestep(self):
+        self.L.wo_flow_pre_retry_timestep(self.f.h)
+
+    def newton_solve(self, y, L0, dt, opts=None):
+        res = self.wo.NewtonResult()
+        self.L.wo_newton_solve_be(self.f.h, self.J, self.wo.ip(self.color), self.ncolor, None, C.byref(self.opts), dt,
+                                  self.wo.dp(L0), self.wo.dp(y), C.byref(res))
+        return res
+
+    def residual(self, y, L0, dt):
+        return self.f.residual(y, L0, dt)
+
+    def fluid(self):
+        return self.f.fluid()
+
+    def regions(self):
+        return self.f.regions()
+
+    def destroy(self):
+        self.L.wo_bsr_destroy(self.J)
+
+
+def run_adaptive(sim, y, dt0, t_stop, opts=None, max_steps=500, reduction=0.2, amplification=2.0, its_min=5,
+                 its_max=8, max_tries=20):
+    """timestepper_step with the "iteration" step-size adaptor (src/timestepper.F90:863-1476, 2330-2375): a step that
+    does not converge is retried with the step size times `reduction` after pre_retry_timestep; a step that converged
+    in fewer than its_min Newton iterations is followed by one `amplification` times larger (more than its_max:
+    reduced).  y is advanced in place; returns (time, steps, total Newton iterations, retries)."""
+    t, dt, nsteps, nits, nretry = 0.0, dt0, 0, 0, 0
+    while t < t_stop * (1.0 - 1e-14) and nsteps < max_steps:
+        dt = min(dt, t_stop - t)
+        err, L0 = sim.lhs(y)
+        assert err == 0
+        sim.pre_timestep()
+        y0 = y.copy()
+        for attempt in range(max_tries):
+            res = sim.newton_solve(y, L0, dt, opts)
+            if res.reason > 0:
+                break
+            nretry += 1
+            dt *= reduction
+            y[:] = y0
+            sim.pre_retry_timestep()
+        assert res.reason > 0, (t, dt, res.reason)
+        t += dt
+        nsteps += 1
+        nits += res.iterations
+        if res.iterations < its_min:
+            dt *= amplification
+        elif res.iterations > its_max:
+            dt *= reduction
+    err, L0 = sim.lhs(y)        # unperturbed evaluation: fluid records of the final state
+    assert err == 0
+    return t, nsteps, nits, nretry

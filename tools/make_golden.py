@@ -94,6 +94,70 @@ def tracer_oned():
     print("wrote", out)
 
 
+def listing_generic(path):
+    """every ELEMENT / GENERATION table of an AUTOUGH2 listing as rows of floats (the numeric tail of each line)"""
+    import re
+    lines = open(path).read().splitlines()
+    out, t, i = [], None, 0
+    num = re.compile(r"^[-+]?\d\.\d+E[-+]\d+$")
+    while i < len(lines):
+        m = re.search(r"OUTPUT AFTER\s+\d+ TIME STEPS\s+([0-9.E+-]+) SECONDS", lines[i])
+        if m:
+            t = float(m.group(1))
+        for kind in ("ELEMENT TABLE", "GENERATION TABLE"):
+            if kind in lines[i]:
+                i += 4
+                rows = []
+                while i < len(lines) and lines[i].strip() and lines[i][1:5] not in ("EEEE", "GGGG"):
+                    vals = [float(v) for v in lines[i].split() if num.match(v)]
+                    if vals:
+                        rows.append(vals)
+                    i += 1
+                out.append((kind[0], t, rows))
+        i += 1
+    return out
+
+
+def co2_one_cell():
+    """test/benchmark/ncg/co2_one_cell (O'Sullivan et al. 1985, fig. 5): AUTOUGH2 history of the single cell --
+    test_co2_one_cell.py compares pressure, temperature, vapour saturation and the production enthalpy at 1e-3"""
+    path = "/root/reference/test/benchmark/ncg/co2_one_cell/run/co2_one_cell.listing"
+    el = [(t, r[0]) for k, t, r in listing_generic(path) if k == "E"]
+    ge = [(t, r[0]) for k, t, r in listing_generic(path) if k == "G"]
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/ncg/co2_one_cell/run/"
+                            "co2_one_cell.listing (AUTOUGH2)",
+           "times": [t for t, _ in el],
+           "columns": ["pressure", "temperature", "gas_saturation", "co2_partial_pressure", "co2_mass_fraction"],
+           "element": [r[:5] for _, r in el],
+           "source_times": [t for t, _ in ge], "source_enthalpy": [r[1] for _, r in ge]}
+    out = os.path.join(os.path.dirname(OUT), "co2_one_cell.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
+def co2_column():
+    """test/benchmark/ncg/co2_column (O'Sullivan et al. 1985, figs 10-11): AUTOUGH2 steady state of the 30-layer
+    column for 0 / 0.1 / 1 / 5 % CO2 in the injected fluid -- test_co2_column.py compares pressure, temperature,
+    vapour saturation and total CO2 mass fraction of the last output at 1e-3"""
+    base = "/root/reference/test/benchmark/ncg/co2_column/run"
+    doc = {"_generated_by": "tools/make_golden.py: last ELEMENT table of test/benchmark/ncg/co2_column/run/"
+                            "co2_column_{0,0.1,1,5}.listing (AUTOUGH2), atmosphere block dropped",
+           "columns": ["pressure", "temperature", "gas_saturation", "co2_partial_pressure", "co2_mass_fraction"]}
+    for case in ("0", "0.1", "1", "5"):
+        tabs = [(t, r) for k, t, r in listing_generic(os.path.join(base, "co2_column_%s.listing" % case)) if k == "E"]
+        t, rows = tabs[-1]
+        assert len(rows) == 31
+        src = json.load(open(os.path.join(base, "co2_column_%s.json" % case)))
+        doc[case] = {"time": t, "element": [r[:5] for r in rows[1:]],
+                     "initial_pressure": [p[0] for p in src["initial"]["primary"]],
+                     "sources": [[s_.get("component", 1), s_["rate"], s_.get("enthalpy", 0.0)] for s_ in src["source"]]}
+    out = os.path.join(os.path.dirname(OUT), "co2_column.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -120,3 +184,5 @@ def main():
 if __name__ == "__main__":
     main()
     tracer_oned()
+    co2_one_cell()
+    co2_column()
