@@ -158,6 +158,37 @@ def co2_column():
     print("wrote", out)
 
 
+def minc_column():
+    """test/benchmark/minc/column: AUTOUGH2 listings of the 11-layer production column, single porosity and MINC
+    (2 matrix levels in layers 3-8) -- test_minc_column.py compares P, T, Sv of the last output (2.5e-2), their
+    history in the production cell (2e-2) and the production enthalpy history (1e-2)"""
+    base = "/root/reference/test/benchmark/minc/column/run"
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/minc/column/run/"
+                            "minc_column_{single,minc}.listing (AUTOUGH2); atmosphere block dropped; MINC blocks "
+                            "reordered level by level as Waiwera numbers them (test_minc_column.py:57-67)",
+           "columns": ["pressure", "temperature", "vapour_saturation"]}
+    for case in ("single", "minc"):
+        tabs = listing_generic(os.path.join(base, "minc_column_%s.listing" % case))
+        el = [(t, r) for k, t, r in tabs if k == "E"]
+        ge = [(t, r) for k, t, r in tabs if k == "G"]
+        tables = []
+        for t, rows in el:
+            rows = [r[:3] for r in rows[1:]]
+            frac, minc = rows[:11], rows[11:]
+            nlev = 2 if case == "minc" else 0
+            for l in range(nlev):
+                frac = frac + minc[l::nlev]
+            tables.append(frac)
+        src = json.load(open(os.path.join(base, "minc_column_%s.json" % case)))
+        doc[case] = {"times": [t for t, _ in el], "tables": tables,
+                     "production_enthalpy": [r[1][1] for _, r in ge], "source_times": [t for t, _ in ge],
+                     "initial_primary": src["initial"]["primary"], "initial_region": src["initial"]["region"]}
+    out = os.path.join(os.path.dirname(OUT), "minc_column.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -186,3 +217,4 @@ if __name__ == "__main__":
     tracer_oned()
     co2_one_cell()
     co2_column()
+    minc_column()

@@ -353,51 +353,62 @@ def minc_geometry(volumes, spacing, fracture_connection_distance=0.0):
     return vol, area, dist
 
 
-def add_minc(mesh, volumes=(0.1, 0.9), spacing=(50.0, 50.0, 50.0), matrix_permeability_factor=1.0):
-    """MINC mesh on top of a serial structured mesh (all cells in the MINC zone), in the reference's numbering
-    (src/mesh.F90:2286-2380): original cells keep their index and become the fracture cells, then all level-1
-    matrix cells (in cell order), then all level-2 cells, ...; one new flux face per MINC cell with support
-    (level m-1 cell, level m cell), appended after the original faces.  Geometry per src/mesh.F90:3120-3160:
-    fracture volume = V*volume(1), level-m volume = V*volume(m+1), face area = V*connection_area(m), distance =
-    connection_distance(m:m+1), normal = 0, gravity_normal = 0, permeability_direction = 1."""
+def add_minc(mesh, volumes=(0.1, 0.9), spacing=(50.0, 50.0, 50.0), matrix_permeability_factor=1.0, cells=None,
+             matrix_rock=None):
+    """MINC mesh on top of a serial mesh, in the reference's numbering (src/mesh.F90:2286-2380): original cells keep
+    their index and become the fracture cells, then all level-1 matrix cells (in cell order), then all level-2
+    cells, ...; one new flux face per MINC cell with support (level m-1 cell, level m cell), appended after the
+    original faces.  Geometry per src/mesh.F90:3120-3160: fracture volume = V*volume(1), level-m volume =
+    V*volume(m+1), face area = V*connection_area(m), distance = connection_distance(m:m+1), normal = 0,
+    gravity_normal = 0, permeability_direction = 1.
+    cells: the MINC zone (default: every cell; the partition helpers minc_owner / minc_cube_blocks need that);
+    matrix_rock: 8-double rock record of the matrix cells (default: the fracture cell's rock with its permeability
+    times matrix_permeability_factor)."""
     assert mesh.nranks == 1 and not mesh.boundary, "add_minc works on a serial mesh without boundary ghosts"
     vol, area, dist = minc_geometry(volumes, spacing)
     nlev = len(vol) - 1
     n = mesh.ninterior
-    V = mesh.cell_geom[:n, 3].copy()
+    zone = np.arange(n, dtype=np.int64) if cells is None else np.asarray(cells, np.int64)
+    nz = len(zone)
+    V = mesh.cell_geom[zone, 3].copy()
     cg = [mesh.cell_geom[:n].copy()]
-    cg[0][:, 3] = V * vol[0]
+    cg[0][zone, 3] = V * vol[0]
     rock = [mesh.rock[:n].copy()]
     fcs, fgs = [mesh.face_cells], [mesh.face_geom]
     for m in range(1, nlev + 1):
-        g = mesh.cell_geom[:n].copy()
+        g = mesh.cell_geom[zone].copy()
         g[:, 3] = V * vol[m]
         cg.append(g)
-        r = mesh.rock[:n].copy()
-        r[:, 0:3] *= matrix_permeability_factor
+        r = mesh.rock[zone].copy()
+        if matrix_rock is not None:
+            r[:] = np.asarray(matrix_rock, float)
+        else:
+            r[:, 0:3] *= matrix_permeability_factor
         rock.append(r)
-        fg = np.zeros((n, 12))
+        fg = np.zeros((nz, 12))
         fg[:, 0] = V * area[m - 1]
         fg[:, 1] = dist[m - 1]
         fg[:, 2] = dist[m]
         fg[:, 3] = dist[m - 1] + dist[m]
-        fg[:, 8:11] = mesh.cell_geom[:n, :3]
+        fg[:, 8:11] = mesh.cell_geom[zone, :3]
         fg[:, 11] = 1.0
-        inner = np.arange(n, dtype=np.int64) + (m - 1) * n
-        fcs.append(np.stack([inner, inner + n], 1).astype(np.int32))
+        inner = zone if m == 1 else n + (m - 2) * nz + np.arange(nz, dtype=np.int64)
+        outer = n + (m - 1) * nz + np.arange(nz, dtype=np.int64)
+        fcs.append(np.stack([inner, outer], 1).astype(np.int32))
         fgs.append(fg)
-    ntot = n * (nlev + 1)
+    ntot = n + nz * nlev
     natural = np.arange(ntot, dtype=np.int64)
     out = Mesh(ncell=ntot, ninterior=ntot, nowned=ntot, face_cells=np.ascontiguousarray(np.concatenate(fcs).astype(np.int32)),
                face_geom=np.ascontiguousarray(np.concatenate(fgs)), cell_geom=np.ascontiguousarray(np.concatenate(cg)),
                rock=np.ascontiguousarray(np.concatenate(rock)), dims=mesh.dims, natural=natural, ncell_global=ntot,
-               minc_levels=nlev, minc_base=n)
+               minc_levels=nlev, minc_base=n if cells is None else -n)
     return out
 
 
 def minc_owner(mesh, parts):
     """owner rank of every cell of a MINC mesh: a matrix cell stays with its fracture cell (src/mesh.F90:2201-2282)"""
     n = mesh.minc_base
+    assert n > 0, "minc_owner needs a MINC zone covering every cell"
     base = Mesh(ncell=n, ninterior=n, nowned=n, face_cells=None, face_geom=None, cell_geom=None, rock=None,
                 dims=mesh.dims, natural=np.arange(n, dtype=np.int64))
     own = box_owner(base, parts)
@@ -407,6 +418,7 @@ def minc_owner(mesh, parts):
 def minc_cube_blocks(mesh, size):
     """block-Jacobi sub-domains of a (possibly partitioned) MINC mesh: size^3 boxes of fracture cells, every
     matrix cell in the sub-domain of its fracture cell"""
+    assert mesh.minc_base > 0, "minc_cube_blocks needs a MINC zone covering every cell"
     nx, ny, nz = mesh.dims
     n = nx * ny * nz
     idx = mesh.natural[:mesh.nowned] % n
