@@ -1,0 +1,111 @@
+"""SURVEY.md section 8 row f-2 (mesh / input ingest): waiwera_b200.ingest reads the reference's own benchmark inputs
+(JSON + binary gmsh meshes, copied unmodified as small fixtures under tests/golden/inputs/) into the array contract.
+Checked against the hand-built meshes the benchmark tests use (same volumes, areas, distances, gravity normals,
+boundary ghosts, rock records, sources) and end to end: the CO2 column benchmark run FROM THE INPUT FILE through the
+oracle reproduces the AUTOUGH2 listing."""
+import os
+
+import numpy as np
+
+from waiwera_b200 import ingest
+from waiwera_b200 import mesh as wmesh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+INP = os.path.join(HERE, "golden", "inputs")
+
+
+def same_geometry(a, b, skip_direction=False):
+    assert (a.ncell, a.ninterior, a.nowned, a.nface) == (b.ncell, b.ninterior, b.nowned, b.nface)
+    assert np.array_equal(a.face_cells, b.face_cells)
+    assert np.allclose(a.cell_geom[:, 3], b.cell_geom[:, 3], rtol=1e-14, atol=0)
+    for col in (0, 1, 2, 3, 7):              # area, distances, distance12, gravity normal
+        assert np.allclose(a.face_geom[:, col], b.face_geom[:, col], rtol=1e-13, atol=1e-13), col
+    if not skip_direction:
+        assert np.array_equal(a.face_geom[:, 11], b.face_geom[:, 11])
+    assert np.array_equal(a.boundary["ghost_cells"], b.boundary["ghost_cells"])
+    assert np.array_equal(a.boundary["interior_cells"], b.boundary["interior_cells"])
+
+
+def test_gmsh_ascii_hexahedra_match_structured_mesh(tmp_path):
+    """a 3 x 2 x 2 box of hexahedra written as ASCII MSH 2.2: 3-D cell / face geometry against mesh.structured"""
+    nx, ny, nz, d = 3, 2, 2, 10.0
+    nid = lambda i, j, k: 1 + i + (nx + 1) * (j + (ny + 1) * k)
+    lines = ["$MeshFormat", "2.2 0 8", "$EndMeshFormat", "$Nodes", str((nx + 1) * (ny + 1) * (nz + 1))]
+    for k in range(nz + 1):
+        for j in range(ny + 1):
+            for i in range(nx + 1):
+                lines.append("%d %g %g %g" % (nid(i, j, k), i * d, j * d, -k * d))
+    lines += ["$EndNodes", "$Elements", str(nx * ny * nz)]
+    e = 1
+    for k in range(nz):                      # cell index i + nx (j + ny k), k = 0 on top, as mesh.structured
+        for j in range(ny):
+            for i in range(nx):
+                n = [nid(i, j, k + 1), nid(i + 1, j, k + 1), nid(i + 1, j + 1, k + 1), nid(i, j + 1, k + 1),
+                     nid(i, j, k), nid(i + 1, j, k), nid(i + 1, j + 1, k), nid(i, j + 1, k)]
+                lines.append("%d 5 2 0 1 %s" % (e, " ".join(map(str, n))))
+                e += 1
+    lines += ["$EndElements", ""]
+    path = tmp_path / "box.msh"
+    path.write_text("\n".join(lines))
+    nodes, elems = ingest.read_gmsh(str(path))
+    m, exterior = ingest.build_mesh(nodes, elems)
+    ref = wmesh.structured(nx, ny, nz, dx=d, heterogeneous=False)
+    assert m.dim == 3 and m.ncell == ref.ncell and m.nface == ref.nface
+    assert np.allclose(m.cell_geom, ref.cell_geom, rtol=1e-13, atol=1e-12)
+    key = lambda fc: fc[:, 0].astype(np.int64) * ref.ncell + fc[:, 1]
+    o1, o2 = np.argsort(key(m.face_cells)), np.argsort(key(ref.face_cells))
+    assert np.array_equal(m.face_cells[o1], ref.face_cells[o2])
+    assert np.allclose(m.face_geom[o1], ref.face_geom[o2], rtol=1e-13, atol=1e-12)
+    assert len(exterior) == 2 * (nx * ny + ny * nz + nx * nz)
+
+
+def test_tracer_oned_input():
+    import test_tracer_oned as T
+    p = ingest.load(os.path.join(INP, "oned_single_phase.json"))
+    ref, y, region = T.problem("single")
+    same_geometry(p.mesh, ref)
+    assert np.array_equal(p.mesh.rock, ref.rock)
+    assert p.primary is None                                  # "initial": {"filename": ...}: HDF5 restart
+    assert p.boundary_primary.tolist() == [T.CASES["single"]["primary"]] and p.boundary_region.tolist() == [1]
+    assert p.boundary_tracer.tolist() == [[T.X_BOUNDARY]] and len(p.tracers) == 1
+    assert p.source_cells.tolist() == [9] and p.source_components.tolist() == [0]
+    assert p.source_rates.tolist() == [T.CASES["single"]["rate"]]
+
+
+def test_mis_problem1_radial_input():
+    import test_config1_radial as T
+    p = ingest.load(os.path.join(INP, "problem1.json"))
+    ref, y, region = T.problem()
+    same_geometry(p.mesh, ref)
+    assert np.allclose(p.mesh.rock[:, [0, 3, 4, 5, 6, 7]], ref.rock[:, [0, 3, 4, 5, 6, 7]])
+    assert np.array_equal(p.y, y) and np.array_equal(p.region, region)
+    assert p.source_cells.tolist() == [0] and p.source_components.tolist() == [1]
+    assert p.source_rates.tolist() == [10.0] and abs(p.source_enthalpies[0] - 678052.7777224329) < 1e-6
+    assert p.time["step"]["size"][:len(T.STEP_SIZES)] == T.STEP_SIZES and p.time["stop"] == T.T_STOP
+
+
+def test_co2_column_from_input_file(wo):
+    """geometry against the hand-built column, then the whole benchmark from the ingested problem"""
+    import test_co2_column as T
+    from util import OracleSim, run_adaptive
+    p = ingest.load(os.path.join(INP, "co2_column_1.json"), mod=wo)
+    ref, y, region, src = T.problem("1")
+    same_geometry(p.mesh, ref, skip_direction=True)              # vertical axis is y in the 2-D mesh file: direction 2
+    assert set(p.mesh.face_geom[:, 11]) == {2.0}
+    assert np.array_equal(p.mesh.rock[:, 1], ref.rock[:, 2]) and np.array_equal(p.mesh.rock[:, 3:], ref.rock[:, 3:])
+    assert np.array_equal(p.y, y) and np.array_equal(p.region, region)
+    assert [list(s) for s in zip(p.source_components, p.source_rates, p.source_enthalpies)] == [list(s) for s in src]
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for g, ic, pr, rg in zip(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region):
+        assert f.set_boundary(int(g), int(ic), pr, int(rg)) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    assert f.fluid_init(p.y, p.region) == 0
+    sim = OracleSim(wo, f, T.newton_opts(wo))
+    yy = p.y.copy()
+    st = p.time["step"]
+    run_adaptive(sim, yy, st["size"], p.time["stop"], max_steps=st["maximum"]["number"], reduction=st["adapt"]["reduction"],
+                 amplification=st["adapt"]["amplification"], its_min=st["adapt"]["minimum"], its_max=st["adapt"]["maximum"])
+    T.check_steady_state("1", T.fields(f.fluid()))
+    sim.destroy()

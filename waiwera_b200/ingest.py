@@ -1,0 +1,391 @@
+"""Reads a Waiwera input (JSON + gmsh mesh) into the array contract of the C ABI (SURVEY.md section 8 row f-2,
+Appendix A): cell and face geometry as src/mesh.F90:438-664 computes it (finite-volume centroids and areas, 2-D
+meshes with a thickness or as solids of revolution, normal distances with the non-orthogonality correction,
+gravity normal, permeability direction), Dirichlet boundary ghost cells from the "boundaries" face specifications
+(src/mesh.F90:1631-1813, 583-664), rock records from the rock types (src/rock_setup.F90), initial primaries /
+regions, fixed-rate sources, tracers and the EOS / curve parameters.
+
+Setup-time host code (numpy), nothing here is on the hot path.  Not covered: ExodusII meshes (need netCDF / HDF5,
+not in this image), HDF5 initial conditions (pass the arrays), source controls / networks, MINC (use
+mesh.add_minc on the result).  Cell order = element order of the mesh file (DMPlex numbering of a serial mesh);
+faces are ordered by (cell 1, cell 2), which is not DMPlex's face numbering -- only the rounding of the inflow
+sums depends on it."""
+import json
+import os
+import struct
+
+import numpy as np
+
+from . import mesh as wmesh
+
+# gmsh element type -> (dimension, number of nodes)
+_GMSH = {1: (1, 2), 2: (2, 3), 3: (2, 4), 4: (3, 4), 5: (3, 8), 6: (3, 6), 7: (3, 5), 15: (0, 1)}
+# local faces of the 3-D elements (gmsh node ordering)
+_FACES3 = {4: [(0, 2, 1), (0, 1, 3), (0, 3, 2), (1, 2, 3)],
+           5: [(0, 3, 2, 1), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7)],
+           6: [(0, 2, 1), (3, 4, 5), (0, 1, 4, 3), (1, 2, 5, 4), (2, 0, 3, 5)],
+           7: [(0, 3, 2, 1), (0, 1, 4), (1, 2, 4), (2, 3, 4), (3, 0, 4)]}
+
+
+def read_gmsh(path):
+    """gmsh MSH 2.2 file, ASCII or binary -> (nodes [n,3], list of (element type, node indices 0-based))"""
+    data = open(path, "rb").read()
+    pos = data.index(b"$MeshFormat") + len(b"$MeshFormat")
+    end = data.index(b"\n", pos + 1)
+    version, ftype, dsize = data[pos:end].split()
+    assert version.startswith(b"2"), "only gmsh format 2.x is supported"
+    binary = int(ftype) == 1
+    pos = end + 1
+    endian = "<"
+    if binary:
+        if struct.unpack("<i", data[pos:pos + 4])[0] != 1:
+            endian = ">"
+        pos += 4
+    pos = data.index(b"$Nodes", pos) + len(b"$Nodes")
+    end = data.index(b"\n", pos + 1)
+    nn = int(data[pos:end])
+    pos = end + 1
+    ids, xyz = np.zeros(nn, np.int64), np.zeros((nn, 3))
+    if binary:
+        rec = np.dtype([("id", endian + "i4"), ("x", endian + "f8", 3)])
+        a = np.frombuffer(data, rec, nn, pos)
+        ids, xyz = a["id"].astype(np.int64), a["x"].copy()
+        pos += nn * rec.itemsize
+    else:
+        for k in range(nn):
+            end = data.index(b"\n", pos)
+            f = data[pos:end].split()
+            ids[k], xyz[k] = int(f[0]), [float(v) for v in f[1:4]]
+            pos = end + 1
+    index = {int(i): k for k, i in enumerate(ids)}
+    pos = data.index(b"$Elements", pos) + len(b"$Elements")
+    end = data.index(b"\n", pos + 1)
+    ne = int(data[pos:end])
+    pos = end + 1
+    elems = []
+    if binary:
+        done = 0
+        while done < ne:
+            etype, nfollow, ntags = struct.unpack(endian + "3i", data[pos:pos + 12])
+            pos += 12
+            nnode = _GMSH[etype][1]
+            for _ in range(nfollow):
+                vals = struct.unpack(endian + "%di" % (1 + ntags + nnode), data[pos:pos + 4 * (1 + ntags + nnode)])
+                pos += 4 * (1 + ntags + nnode)
+                elems.append((etype, [index[v] for v in vals[1 + ntags:]]))
+            done += nfollow
+    else:
+        for _ in range(ne):
+            end = data.index(b"\n", pos)
+            f = [int(v) for v in data[pos:end].split()]
+            pos = end + 1
+            etype, ntags = f[1], f[2]
+            elems.append((etype, [index[v] for v in f[3 + ntags:3 + ntags + _GMSH[etype][1]]]))
+    return xyz, elems
+
+
+def _polygon_geometry(p):
+    """area-weighted centroid and area of a planar polygon in 2-D (DMPlexComputeGeometryFVM for a 2-D cell)"""
+    x, y = p[:, 0], p[:, 1]
+    x1, y1 = np.roll(x, -1), np.roll(y, -1)
+    cr = x * y1 - x1 * y
+    a = 0.5 * cr.sum()
+    cx, cy = ((x + x1) * cr).sum() / (6.0 * a), ((y + y1) * cr).sum() / (6.0 * a)
+    return np.array([cx, cy]), abs(a)
+
+
+def _face3_geometry(p):
+    """centroid, area, unit normal of a (nearly) planar polygon in 3-D: fan of triangles about the vertex mean"""
+    c0 = p.mean(0)
+    an, cen = np.zeros(3), np.zeros(3)
+    atot = 0.0
+    for k in range(len(p)):
+        a, b = p[k], p[(k + 1) % len(p)]
+        n = 0.5 * np.cross(a - c0, b - c0)
+        an += n
+        ar = np.linalg.norm(n)
+        cen += ar * (c0 + a + b) / 3.0
+        atot += ar
+    area = np.linalg.norm(an)
+    return cen / atot, area, an / area
+
+
+def _cell3_geometry(nodes, faces):
+    """centroid and volume of a polyhedron from its faces: pyramids over the face triangles about the vertex mean"""
+    pts = np.unique(np.concatenate(faces))
+    c0 = nodes[pts].mean(0)
+    vol, cen = 0.0, np.zeros(3)
+    for f in faces:
+        p = nodes[list(f)]
+        fc = p.mean(0)
+        for k in range(len(p)):
+            a, b = p[k], p[(k + 1) % len(p)]
+            v = abs(np.dot(np.cross(a - c0, b - c0), fc - c0)) / 6.0
+            vol += v
+            cen += v * (c0 + a + b + fc) / 4.0
+    return cen / vol, vol
+
+
+def build_mesh(nodes, elems, thickness=1.0, radial=False, gravity=None, permeability_angle=0.0):
+    """Mesh (waiwera_b200.mesh.Mesh) of the top-dimensional elements.  Returns (mesh, exterior) where exterior is a
+    list of (cell, face centroid, area, outward unit normal, distance) of the boundary faces, for boundary ghosts."""
+    dim = max(_GMSH[t][0] for t, _ in elems)
+    cells = [(t, n) for t, n in elems if _GMSH[t][0] == dim]
+    nc = len(cells)
+    g = np.zeros(3)
+    if gravity is None:
+        if dim == 3:
+            g[2] = -9.8                                    # default_gravity_3D; 2-D default: none
+    elif np.ndim(gravity) == 0:
+        g[dim - 1] = -float(gravity)
+    else:
+        g[:len(gravity)] = gravity
+    cell_geom = np.zeros((nc, 4))
+    facemap = {}                                           # sorted node tuple -> [(cell, ordered nodes)]
+    for c, (t, n) in enumerate(cells):
+        if dim == 2:
+            cen, area = _polygon_geometry(nodes[n, :2])
+            cell_geom[c, :2] = cen
+            # modify_cell_geometry (src/mesh.F90:369-395): thickness, or Pappus for a solid of revolution
+            cell_geom[c, 3] = area * (2.0 * np.pi * cen[0] if radial else thickness)
+            local = [(n[k], n[(k + 1) % len(n)]) for k in range(len(n))]
+        else:
+            local = [tuple(n[i] for i in f) for f in _FACES3[t]]
+            cell_geom[c, :3], cell_geom[c, 3] = _cell3_geometry(nodes, local)
+        for f in local:
+            facemap.setdefault(tuple(sorted(f)), []).append((c, f))
+    interior, exterior = [], []
+    for key, owners in facemap.items():
+        c1, f = owners[0]
+        if dim == 2:
+            a, b = nodes[f[0], :2], nodes[f[1], :2]
+            cen = np.zeros(3)
+            cen[:2] = 0.5 * (a + b)
+            length = np.linalg.norm(b - a)
+            nrm = np.zeros(3)
+            nrm[:2] = np.array([b[1] - a[1], -(b[0] - a[0])]) / length
+            # modify_face_geometry (src/mesh.F90:399-432)
+            area = length * (2.0 * np.pi * cen[0] if radial else thickness)
+        else:
+            cen, area, nrm = _face3_geometry(nodes[list(f)])
+        if np.dot(cen - cell_geom[c1, :3], nrm) < 0.0:
+            nrm = -nrm                                     # outward from the first owner
+        if len(owners) == 2:
+            c2 = owners[1][0]
+            if c2 < c1:
+                c1, c2, nrm = c2, c1, -nrm
+            interior.append((c1, c2, cen, area, nrm))
+        else:
+            exterior.append((c1, cen, area, nrm, float(np.dot(cen - cell_geom[c1, :3], nrm))))
+    interior.sort(key=lambda r: (r[0], r[1]))
+    nf = len(interior)
+    fc, fg = np.zeros((nf, 2), np.int32), np.zeros((nf, 12))
+    for k, (c1, c2, cen, area, nrm) in enumerate(interior):
+        fc[k] = (c1, c2)
+        # face%calculate_distances (src/face.F90:230-250)
+        d1 = np.dot(cen - cell_geom[c1, :3], nrm)
+        d2 = np.dot(cell_geom[c2, :3] - cen, nrm)
+        d12 = np.dot(cell_geom[c2, :3] - cell_geom[c1, :3], nrm)
+        corr = d12 / (d1 + d2)
+        fg[k, 0], fg[k, 1], fg[k, 2], fg[k, 3] = area, d1 * corr, d2 * corr, d12
+        fg[k, 4:7], fg[k, 7], fg[k, 8:11] = nrm, np.dot(g, nrm), cen
+        fg[k, 11] = permeability_direction(nrm, dim, permeability_angle)
+    m = wmesh.Mesh(ncell=nc, ninterior=nc, nowned=nc, face_cells=np.ascontiguousarray(fc), face_geom=np.ascontiguousarray(fg),
+                   cell_geom=np.ascontiguousarray(cell_geom), rock=wmesh.default_rock(nc, None, heterogeneous=False),
+                   dims=(nc, 1, 1), natural=np.arange(nc, dtype=np.int64), ncell_global=nc)
+    m.gravity = g
+    m.dim = dim
+    m.permeability_angle = permeability_angle
+    return m, exterior
+
+
+def permeability_direction(normal, dim, angle=0.0):
+    """face%calculate_permeability_direction (src/face.F90:210-226): axis of the (rotated) permeability tensor
+    closest to the face normal, 1-based"""
+    n = np.array(normal[:3], float)
+    if angle != 0.0:
+        c, s = np.cos(angle), np.sin(angle)
+        n[:2] = np.array([[c, s], [-s, c]]) @ n[:2]
+    return int(np.argmax(np.abs(n))) + 1
+
+
+def add_boundary_faces(m, exterior, specs):
+    """Dirichlet ghost cells for the "boundaries" of the input: every spec {"faces": {"cells": [...], "normal":
+    [...]}} (or a list of those) selects, per listed cell, the exterior face whose outward normal is closest to the
+    given one (dm_cell_normal_face, src/mesh.F90:1772-1800).  Returns (mesh, boundary index of every ghost cell)."""
+    by_cell = {}
+    for e in exterior:
+        by_cell.setdefault(e[0], []).append(e)
+    cells, owner, rows = [], [], []
+    for ib, spec in enumerate(specs):
+        faces = spec.get("faces", {})
+        for fs in (faces if isinstance(faces, list) else [faces]):
+            nrm = np.zeros(3)
+            given = fs.get("normal", [0.0, 0.0, 1.0])
+            nrm[:len(given)] = given
+            for c in fs.get("cells", []):
+                cand = by_cell.get(c, [])
+                assert cand, "cell %d has no exterior face" % c
+                e = max(cand, key=lambda r: float(np.dot(r[3], nrm)))
+                cells.append(c)
+                owner.append(ib)
+                rows.append(e)
+    n0 = m.ncell
+    nb = len(cells)
+    fg = np.zeros((nb, 12))
+    gg = np.zeros((nb, 4))
+    for k, (c, cen, area, nrm, dist) in enumerate(rows):
+        # mesh_boundary_face_geometry (src/mesh.F90:583-664): distances (d1, 0), ghost volume 0 at the face centroid
+        fg[k, 0], fg[k, 1], fg[k, 2], fg[k, 3] = area, dist, 0.0, dist
+        fg[k, 4:7], fg[k, 7], fg[k, 8:11] = nrm, np.dot(m.gravity, nrm), cen
+        fg[k, 11] = permeability_direction(nrm, m.dim, m.permeability_angle)
+        gg[k, :3] = cen
+    ghosts = n0 + np.arange(nb)
+    out = wmesh.Mesh(ncell=n0 + nb, ninterior=m.ninterior, nowned=m.nowned,
+                     face_cells=np.ascontiguousarray(np.vstack([m.face_cells, np.stack([cells, ghosts], 1)]).astype(np.int32)) if nb else m.face_cells,
+                     face_geom=np.ascontiguousarray(np.vstack([m.face_geom, fg])),
+                     cell_geom=np.ascontiguousarray(np.vstack([m.cell_geom, gg])),
+                     rock=np.ascontiguousarray(np.vstack([m.rock, m.rock[cells]])) if nb else m.rock,
+                     dims=m.dims, natural=m.natural, ncell_global=m.ncell_global,
+                     boundary={"ghost_cells": ghosts.astype(np.int32), "interior_cells": np.array(cells, np.int32)} if nb else {})
+    out.gravity, out.dim, out.permeability_angle = m.gravity, m.dim, m.permeability_angle
+    return out, np.array(owner, np.int32)
+
+
+def _zone_cells(zone, m):
+    """cells of a box zone {"x": [lo, hi], "y": ..., "z": ...}, or all cells for {"type": "box"} without limits"""
+    sel = np.ones(m.ninterior, bool)
+    for k, ax in enumerate("xyz"):
+        if ax in zone:
+            lo, hi = zone[ax]
+            sel &= (m.cell_geom[:m.ninterior, k] >= lo) & (m.cell_geom[:m.ninterior, k] <= hi)
+    return np.nonzero(sel)[0]
+
+
+def rock_records(spec, m, zones=None):
+    """8-double rock records from the "rock" value of the input (src/rock_setup.F90:236-465; defaults src/rock.F90:69-76)"""
+    n = m.ninterior
+    rock = np.zeros((n, 8))
+    rock[:, 0:3], rock[:, 3:5], rock[:, 5], rock[:, 6], rock[:, 7] = 1e-13, 2.5, 0.1, 2200.0, 1000.0
+    for rt in (spec or {}).get("types", []):
+        idx = list(rt.get("cells", []))
+        zs = rt.get("zones", [])
+        for z in ([zs] if isinstance(zs, str) else zs):
+            idx += _zone_cells((zones or {}).get(z, {}), m).tolist()
+        idx = np.array(sorted(set(idx)), np.int64)
+        if len(idx) == 0:
+            continue
+        if "permeability" in rt:
+            k = np.atleast_1d(np.array(rt["permeability"], float))
+            rock[idx, 0:len(k)] = k
+            if len(k) == 1:
+                rock[idx, 0:3] = k[0]
+        for key, col in (("wet_conductivity", 3), ("dry_conductivity", 4), ("porosity", 5), ("density", 6), ("specific_heat", 7)):
+            if rt.get(key) is not None:
+                rock[idx, col] = rt[key]
+        if rt.get("dry_conductivity") is None and rt.get("wet_conductivity") is not None:
+            rock[idx, 4] = rt["wet_conductivity"]          # dry defaults to wet (src/rock_setup.F90)
+    return rock
+
+
+_EOS = {"we": ("EOS_WE", 2), "w": ("EOS_W", 1), "wce": ("EOS_WCE", 3)}
+
+
+def make_params(mod, doc, gravity):
+    """wb_params / wo_params (mod = waiwera_b200.flow or oracle.wo) from the eos / thermodynamics / rock curves"""
+    eos = doc.get("eos", "we")
+    name = eos if isinstance(eos, str) else eos.get("name", "we")
+    assert name in _EOS, "eos %r is not built" % name
+    thermo = doc.get("thermodynamics", "iapws")
+    thermo = thermo if isinstance(thermo, str) else thermo.get("name", "iapws")
+    rock = doc.get("rock") or {}
+    rp = rock.get("relative_permeability") or {"type": "linear"}
+    kw = {k: v for k, v in rp.items() if k != "type"}
+    if rp.get("type", "linear") == "linear":
+        kw = {"liquid": tuple(rp.get("liquid", (0.0, 1.0))), "vapour": tuple(rp.get("vapour", (0.0, 1.0)))}
+    relperm = mod.make_relperm(rp.get("type", "linear").replace(" ", "_"), **kw)
+    cp = rock.get("capillary_pressure") or {"type": "zero"}
+    ckw = {k: v for k, v in cp.items() if k != "type"}
+    if "saturation_limits" in ckw:
+        ckw["saturation_limits"] = tuple(ckw["saturation_limits"])
+    cappress = mod.make_cappress(cp.get("type", "zero").replace(" ", "_"), **ckw)
+    kwargs = dict(eos=getattr(mod, _EOS[name][0]), thermo=mod.THERMO_IFC67 if thermo.lower() == "ifc67" else mod.THERMO_IAPWS,
+                  relperm=relperm, cappress=cappress, gravity=tuple(gravity))
+    if name == "w" and not isinstance(eos, str) and "temperature" in eos:
+        kwargs["eos_w_temperature"] = eos["temperature"]
+    return mod.make_params(**kwargs), _EOS[name][1]
+
+
+class Problem:
+    """what load() returns: mesh, initial state, boundary values, sources, tracers, time stepping"""
+
+
+def load(path, mod=None, mesh_path=None):
+    """Reads <path> (Waiwera JSON input) and the gmsh mesh it names.  mod: waiwera_b200.flow or oracle.wo, for the
+    parameter struct (None: no params)."""
+    doc = json.load(open(path))
+    mspec = doc["mesh"] if isinstance(doc["mesh"], dict) else {"filename": doc["mesh"]}
+    mfile = mesh_path or os.path.join(os.path.dirname(path), mspec["filename"])
+    assert not mfile.endswith(".exo"), "ExodusII meshes need netCDF, which this image lacks"
+    nodes, elems = read_gmsh(mfile)
+    m, exterior = build_mesh(nodes, elems, thickness=mspec.get("thickness", 1.0), radial=bool(mspec.get("radial", False)),
+                             gravity=doc.get("gravity"), permeability_angle=np.deg2rad(mspec.get("permeability_angle", 0.0)))
+    rock = rock_records(doc.get("rock"), m, mspec.get("zones"))
+    m.rock[:] = rock
+    bspecs = doc.get("boundaries") or []
+    m, bowner = add_boundary_faces(m, exterior, bspecs)
+    p = Problem()
+    p.doc, p.mesh = doc, m
+    if mod is not None:
+        p.params, p.np = make_params(mod, doc, m.gravity)
+    else:
+        eos = doc.get("eos", "we")
+        p.params, p.np = None, _EOS[eos if isinstance(eos, str) else eos.get("name", "we")][1]
+    n = m.ninterior
+    init = doc.get("initial") or {}
+    if "primary" in init:
+        prim = np.array(init["primary"], float)
+        p.primary = np.tile(prim, (n, 1)) if prim.ndim == 1 else prim.reshape(n, -1)
+        reg = np.array(init.get("region", 1))
+        p.region = (np.full(n, int(reg)) if reg.ndim == 0 else reg).astype(np.int32)
+        p.y = np.ascontiguousarray(wmesh.scale_primaries(p.primary, p.region)).reshape(-1)
+    else:
+        p.primary = p.region = p.y = None                  # "filename": HDF5 restart, pass the arrays
+    tr = doc.get("tracer")
+    p.tracers = [] if tr is None else ([tr] if isinstance(tr, dict) else list(tr))
+    nt = len(p.tracers)
+    p.boundary_primary = np.array([bspecs[i]["primary"] for i in bowner], float).reshape(len(bowner), -1)
+    p.boundary_region = np.array([bspecs[i].get("region", 1) for i in bowner], np.int32)
+    p.boundary_tracer = np.array([np.broadcast_to(np.atleast_1d(bspecs[i].get("tracer", 0.0)), (max(nt, 1),)) for i in bowner],
+                                 float).reshape(len(bowner), max(nt, 1))
+    p.initial_tracer = np.broadcast_to(np.atleast_1d(init.get("tracer", 0.0)), (max(nt, 1),)).astype(float)
+    src = doc.get("source") or []
+    for s in src:
+        unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer"}
+        assert not unsupported, "source controls are not built: %s" % sorted(unsupported)
+    src = [s for s in src if s.get("rate", 0.0) != 0.0]
+    p.source_cells = np.array([s["cell"] for s in src], np.int32)
+    p.source_rates = np.array([s["rate"] for s in src], float)
+    # get_components (src/source_setup.F90:2052-2083; doc/user/setup_sources.rst): injection uses "component"
+    # (default water = 1); production uses "production_component", which defaults to energy if "component" is
+    # energy and to 0 (all mass components) otherwise
+    names = {"water": 1, "energy": p.np, "co2": 2, "air": 2, "ncg": 2}
+
+    def comp(v):
+        return names[v.lower()] if isinstance(v, str) else int(v)
+
+    def component(s):
+        inj = comp(s.get("component", 1))
+        if s["rate"] > 0:
+            return inj
+        if "production_component" in s:
+            return comp(s["production_component"])
+        return inj if (inj == p.np and p.np > 1 and name_of_eos != "w") else 0
+    eos_doc = doc.get("eos", "we")
+    name_of_eos = eos_doc if isinstance(eos_doc, str) else eos_doc.get("name", "we")
+    p.source_components = np.array([component(s) for s in src], np.int32)
+    p.source_enthalpies = np.array([s.get("enthalpy", 83.9e3) for s in src], float)
+    p.source_tracer = np.array([np.broadcast_to(np.atleast_1d(s.get("tracer", 0.0)), (max(nt, 1),)) for s in src],
+                               float).reshape(len(src), max(nt, 1))
+    p.time = doc.get("time", {})
+    return p
