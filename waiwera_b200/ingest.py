@@ -292,7 +292,8 @@ _EOS = {"we": ("EOS_WE", 2), "w": ("EOS_W", 1), "wce": ("EOS_WCE", 3)}
 
 
 def make_params(mod, doc, gravity):
-    """wb_params / wo_params (mod = waiwera_b200.flow or oracle.wo) from the eos / thermodynamics / rock curves"""
+    """wb_params from the eos / thermodynamics / rock curves.  mod: the module whose make_params / make_relperm /
+    make_cappress build the struct (waiwera_b200.flow; the parity tests pass their checker's module, same layout)"""
     eos = doc.get("eos", "we")
     name = eos if isinstance(eos, str) else eos.get("name", "we")
     assert name in _EOS, "eos %r is not built" % name
@@ -321,8 +322,8 @@ class Problem:
 
 
 def load(path, mod=None, mesh_path=None):
-    """Reads <path> (Waiwera JSON input) and the gmsh mesh it names.  mod: waiwera_b200.flow or oracle.wo, for the
-    parameter struct (None: no params)."""
+    """Reads <path> (Waiwera JSON input) and the gmsh mesh it names.  mod: waiwera_b200.flow (see make_params),
+    None: no parameter struct."""
     doc = json.load(open(path))
     mspec = doc["mesh"] if isinstance(doc["mesh"], dict) else {"filename": doc["mesh"]}
     mfile = mesh_path or os.path.join(os.path.dirname(path), mspec["filename"])
