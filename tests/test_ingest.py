@@ -109,3 +109,50 @@ def test_co2_column_from_input_file(wo):
                  amplification=st["adapt"]["amplification"], its_min=st["adapt"]["minimum"], its_max=st["adapt"]["maximum"])
     T.check_steady_state("1", T.fields(f.fluid()))
     sim.destroy()
+
+
+def test_product_curve_builders_fill_the_documented_layout(wo):
+    """flow.make_relperm / make_cappress (the product's own builders) against the checker's structs, every curve type"""
+    from waiwera_b200 import flow
+    rp = [("fully_mobile", {}), ("linear", dict(liquid=(0.1, 0.9), vapour=(0.2, 0.8))), ("pickens", dict(power=2.5)),
+          ("corey", dict(slr=0.25, ssr=0.1)), ("grant", dict(slr=0.2, ssr=0.5)),
+          ("van_genuchten", dict(slr=0.1, sls=0.95)), ("van_genuchten", dict(slr=0.1, sls=0.95, ssr=0.2)),
+          ("table", dict(liquid=[(0, 0), (0.5, 0.3), (1, 1)], vapour=[(0, 0), (1, 1)]))]
+    for kind, kw in rp:
+        a, b = flow.make_relperm(kind, **kw), wo.make_relperm(kind, **kw)
+        assert bytes(a) == bytes(b), kind
+    lam = {"lambda": 0.5}
+    assert bytes(flow.make_relperm("van Genuchten", **lam)) == bytes(wo.make_relperm("van_genuchten", lambda_=0.5))
+    cp = [("zero", {}), ("linear", dict(saturation_limits=(0.1, 0.8), pressure=2e4)),
+          ("van_genuchten", dict(P0=1e4, slr=0.1, sls=0.99)), ("van_genuchten", dict(P0=1e4, Pmax=1e6)),
+          ("table", dict(pressure=[(0, -1e5), (1, 0)]))]
+    for kind, kw in cp:
+        assert bytes(flow.make_cappress(kind, **kw)) == bytes(wo.make_cappress(kind, **kw)), kind
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_co2_column_from_input_file_on_gpu():
+    """the product path alone: ingest -> FlowSimulation -> adaptive backward Euler to the steady state, checked
+    against the AUTOUGH2 listing"""
+    import test_co2_column as T
+    from util import run_adaptive
+    from waiwera_b200 import flow
+    p = ingest.load(os.path.join(INP, "co2_column_1.json"), mod=flow)
+    m = p.mesh
+    sim = flow.FlowSimulation(p.params, m)
+    assert sim.set_boundaries(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region) == 0
+    assert sim.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies) == 0
+    assert sim.fluid_init(p.y, p.region) == 0
+    st = p.time["step"]
+    o = flow.newton_opts(max_iterations=st["solver"]["nonlinear"]["maximum"]["iterations"], min_iterations=1, rel_tol=1e-5,
+                         pc_type=flow.PC_BJACOBI_ILU0, ksp=flow.ksp_opts(type=flow.KSP_BCGS))
+    y = p.y.copy()
+    t, nsteps, nits, nretry = run_adaptive(sim, y, st["size"], p.time["stop"], opts=o, max_steps=st["maximum"]["number"],
+                                           reduction=st["adapt"]["reduction"], amplification=st["adapt"]["amplification"],
+                                           its_min=st["adapt"]["minimum"], its_max=st["adapt"]["maximum"])
+    assert t >= p.time["stop"] * (1 - 1e-12)
+    T.check_steady_state("1", T.fields(sim.fluid()))
+    sim.destroy()

@@ -36,6 +36,73 @@ def ptr(a, dtype=None):
     return a.data_ptr()
 
 
+def make_relperm(kind="linear", **kw):
+    """wb_relperm from the "relative_permeability" value of the input (src/relative_permeability.F90:197-558;
+    parameter layout: include/waiwera_b200.h).  kind: "fully_mobile", "linear", "pickens", "corey", "grant",
+    "van_genuchten", "table"; keyword names are the input's ("liquid", "vapour", "power", "slr", "ssr", "lambda",
+    "sls", "sum_unity")."""
+    kind = kind.lower().replace(" ", "_")
+    r = Relperm()
+    if kind in ("fully_mobile", "fully mobile"):
+        r.type = RP_FULLY_MOBILE
+    elif kind == "linear":
+        r.type = RP_LINEAR
+        liq, vap = kw.get("liquid", (0.0, 1.0)), kw.get("vapour", (0.0, 1.0))
+        r.p[0], r.p[1], r.p[2], r.p[3] = liq[0], liq[1], vap[0], vap[1]
+    elif kind == "pickens":
+        r.type = RP_PICKENS
+        r.p[0] = kw.get("power", 1.0)
+    elif kind in ("corey", "grant"):
+        r.type = RP_COREY if kind == "corey" else RP_GRANT
+        r.p[0], r.p[1] = kw.get("slr", 0.3), kw.get("ssr", 0.05 if kind == "corey" else 0.6)
+    elif kind == "van_genuchten":
+        r.type = RP_VAN_GENUCHTEN
+        r.p[0] = kw.get("lambda", kw.get("lambda_", 0.45))
+        r.p[1], r.p[2] = kw.get("slr", 1e-3), kw.get("sls", 1.0)
+        r.p[3] = 0.0 if "ssr" in kw else 1.0        # without ssr the vapour curve is 1 - krl (sum_unity)
+        r.p[4] = kw.get("ssr", 0.0)
+    elif kind == "table":
+        r.type = RP_TABLE
+        liq, vap = kw["liquid"], kw["vapour"]
+        assert len(liq) <= _lib.WB_MAX_TABLE and len(vap) <= _lib.WB_MAX_TABLE
+        r.nl, r.nv = len(liq), len(vap)
+        for k, (x, y) in enumerate(liq):
+            r.lx[k], r.ly[k] = x, y
+        for k, (x, y) in enumerate(vap):
+            r.vx[k], r.vy[k] = x, y
+    else:
+        raise ValueError("relative permeability type %r" % kind)
+    return r
+
+
+def make_cappress(kind="zero", **kw):
+    """wb_cappress from the "capillary_pressure" value of the input (src/capillary_pressure.F90:159-358)"""
+    kind = kind.lower().replace(" ", "_")
+    c = Cappress()
+    if kind == "zero":
+        c.type = CP_ZERO
+    elif kind == "linear":
+        c.type = CP_LINEAR
+        lim = kw.get("saturation_limits", (0.0, 1.0))
+        c.p[0], c.p[1], c.p[2] = lim[0], lim[1], kw.get("pressure", 0.125e5)
+    elif kind == "van_genuchten":
+        c.type = CP_VAN_GENUCHTEN
+        c.p[0], c.p[1] = kw.get("P0", 0.125e5), kw.get("lambda", kw.get("lambda_", 0.45))
+        c.p[2], c.p[3] = kw.get("slr", 1e-3), kw.get("sls", 1.0)
+        c.p[4] = kw.get("Pmax", 0.0)
+        c.p[5] = 1.0 if "Pmax" in kw else 0.0
+    elif kind == "table":
+        c.type = CP_TABLE
+        pts = kw["pressure"]
+        assert len(pts) <= _lib.WB_MAX_TABLE
+        c.n = len(pts)
+        for k, (x, y) in enumerate(pts):
+            c.x[k], c.y[k] = x, y
+    else:
+        raise ValueError("capillary pressure type %r" % kind)
+    return c
+
+
 def make_params(eos=EOS_WE, thermo=THERMO_IAPWS, relperm=None, cappress=None, gravity=(0.0, 0.0, -9.8),
                 extrapolate=0, eos_w_temperature=20.0, partial_pressure_scale=0.0):
     """wb_params from any object with the same fields (e.g. the oracle's ctypes structs in the tests)."""
