@@ -111,6 +111,10 @@ class OracleSim:
     def residual(self, y, L0, dt):
         return self.f.residual(y, L0, dt)
 
+    def set_sources(self, cells, components, rates, enthalpies):
+        self.f.set_sources(cells, components, rates, enthalpies)
+        return 0
+
     def fluid(self):
         return self.f.fluid()
 
@@ -153,3 +157,57 @@ def run_adaptive(sim, y, dt0, t_stop, opts=None, max_steps=500, reduction=0.2, a
     err, L0 = sim.lhs(y)        # unperturbed evaluation: fluid records of the final state
     assert err == 0
     return t, nsteps, nits, nretry
+
+
+def we_fields(fluid, n):
+    """P, T, vapour saturation of the first n cells from eos_we fluid records (23 doubles)"""
+    fl = np.asarray(fluid)[:n]
+    return np.stack([fl[:, 0], fl[:, 1], fl[:, 7 + 8 + 2]], 1)
+
+
+def we_production_enthalpy(fl):
+    """enthalpy of the fluid a producing source takes from an eos_we cell (src/fluid.F90:417-436)"""
+    phases = int(round(fl[4]))
+    mob = [(fl[7 + 8 * p + 3] * fl[7 + 8 * p] / fl[7 + 8 * p + 1]) if phases & (1 << p) else 0.0 for p in range(2)]
+    return (mob[0] * fl[7 + 5] + mob[1] * fl[7 + 8 + 5]) / (mob[0] + mob[1])
+
+
+def run_input(problem, sim, opts=None):
+    """Runs an ingested input (waiwera_b200.ingest.Problem, eos_we) through `sim` (flow.FlowSimulation or OracleSim,
+    mesh / boundaries / fluid_init already done) with the time stepping of its "time" value: a list of step sizes
+    (the last one repeats), or one size with the "iteration" adaptor, maximum size / number, stop time; table sources
+    are averaged over each step.  Returns [(time, P/T/Sv of the interior cells, production enthalpy)]."""
+    from waiwera_b200 import ingest
+    p = problem
+    st = p.time["step"]
+    sizes = st["size"] if isinstance(st["size"], list) else [st["size"]]
+    adapt = st.get("adapt", {}).get("on", False)
+    dt_max = (st.get("maximum") or {}).get("size") or np.inf
+    nmax = (st.get("maximum") or {}).get("number") or 10 ** 9
+    stop = p.time.get("stop")
+    stop = np.inf if stop is None else stop
+    ad = st.get("adapt", {})
+    n = p.mesh.ninterior
+    y = p.y.copy()
+    t, k, dt = 0.0, 0, sizes[0]
+    hist = []
+    prod = int(p.source_cells[0]) if len(p.source_cells) else 0
+    while t < stop * (1 - 1e-12) and k < nmax:
+        if not adapt:
+            dt = sizes[min(k, len(sizes) - 1)]
+        dt = min(dt, stop - t, dt_max)
+        if p.source_tables:
+            assert sim.set_sources(p.source_cells, p.source_components, ingest.rates_at(p, t, t + dt), p.source_enthalpies) == 0
+        t1, _, its, _ = run_adaptive(sim, y, dt, dt, opts=opts, max_steps=1, reduction=ad.get("reduction", 0.2),
+                                     amplification=1.0, its_min=0, its_max=10 ** 9)
+        t += t1
+        k += 1
+        fl = sim.fluid()
+        hist.append((t, we_fields(fl, n), we_production_enthalpy(np.asarray(fl)[prod])))
+        dt = t1
+        if adapt:
+            if its < ad.get("minimum", 5):
+                dt = dt * ad.get("amplification", 2.0)
+            elif its > ad.get("maximum", 8):
+                dt = dt * ad.get("reduction", 0.2)
+    return hist, y

@@ -189,6 +189,47 @@ def minc_column():
     print("wrote", out)
 
 
+def mis_problems():
+    """test/benchmark/model_intercomparison_study problems 2a-c, 4, 5a-b: AUTOUGH2 listings.  Kept: P, T, Sv of all
+    cells at ~12 evenly spaced output times, the full history of a few cells (production cell first) and the
+    production enthalpy history; inputs (JSON + gmsh) copied unmodified to tests/golden/inputs/ for the ingest"""
+    import shutil
+    base = "/root/reference/test/benchmark/model_intercomparison_study"
+    inputs = os.path.join(os.path.dirname(OUT), "inputs")
+    os.makedirs(inputs, exist_ok=True)
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/"
+                            "model_intercomparison_study/problem{2,4,5}/run/*.listing (AUTOUGH2); boundary / atmosphere "
+                            "blocks dropped", "columns": ["pressure", "temperature", "vapour_saturation"]}
+    for prob, cases in (("problem2", ["problem2a", "problem2b", "problem2c"]), ("problem4", ["problem4"]),
+                        ("problem5", ["problem5a", "problem5b"])):
+        run = os.path.join(base, prob, "run")
+        for fn in os.listdir(run):
+            if fn.endswith(".msh"):
+                shutil.copyfile(os.path.join(run, fn), os.path.join(inputs, fn))
+        for case in cases:
+            shutil.copyfile(os.path.join(run, case + ".json"), os.path.join(inputs, case + ".json"))
+            inp = json.load(open(os.path.join(run, case + ".json")))
+            tabs = listing_generic(os.path.join(run, case + ".listing"))
+            el = [(t, r) for k, t, r in tabs if k == "E"]
+            ge = [(t, r) for k, t, r in tabs if k == "G"]
+            # number of interior cells from the initial conditions / rock types of the input
+            ncell = max(max(rt.get("cells", [0]) or [0]) for rt in inp["rock"]["types"]) + 1
+            nrow = len(el[-1][1])
+            first = nrow - ncell if prob == "problem4" else 0      # atmosphere block first (problem 4), boundary blocks last
+            rows = lambda r: [x[:3] for x in r[first:first + ncell]]
+            sel = sorted(set(np.linspace(1, len(el) - 1, 12).round().astype(int).tolist()))
+            prod = inp["source"][0]["cell"]
+            hist_cells = sorted(set([prod, 0, ncell // 2, ncell - 1]), key=lambda c: (c != prod, c))
+            doc[case] = {"ncell": ncell, "times": [t for t, _ in el], "table_index": sel,
+                         "tables": [rows(el[i][1]) for i in sel], "history_cells": hist_cells,
+                         "history": [[rows(r)[c] for c in hist_cells] for _, r in el],
+                         "source_times": [t for t, _ in ge], "production_enthalpy": [r[0][1] for _, r in ge]}
+    out = os.path.join(os.path.dirname(OUT), "mis_problems.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -218,3 +259,4 @@ if __name__ == "__main__":
     co2_one_cell()
     co2_column()
     minc_column()
+    mis_problems()

@@ -355,16 +355,29 @@ def load(path, mod=None, mesh_path=None):
     tr = doc.get("tracer")
     p.tracers = [] if tr is None else ([tr] if isinstance(tr, dict) else list(tr))
     nt = len(p.tracers)
-    p.boundary_primary = np.array([bspecs[i]["primary"] for i in bowner], float).reshape(len(bowner), -1)
+    p.boundary_primary = np.array([bspecs[i]["primary"] for i in bowner], float).reshape(len(bowner), p.np)
     p.boundary_region = np.array([bspecs[i].get("region", 1) for i in bowner], np.int32)
     p.boundary_tracer = np.array([np.broadcast_to(np.atleast_1d(bspecs[i].get("tracer", 0.0)), (max(nt, 1),)) for i in bowner],
                                  float).reshape(len(bowner), max(nt, 1))
     p.initial_tracer = np.broadcast_to(np.atleast_1d(init.get("tracer", 0.0)), (max(nt, 1),)).astype(float)
     src = doc.get("source") or []
     for s in src:
-        unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer"}
+        unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer",
+                                "interpolation", "averaging"}
         assert not unsupported, "source controls are not built: %s" % sorted(unsupported)
-    src = [s for s in src if s.get("rate", 0.0) != 0.0]
+    # a rank-2 "rate" is a table source control (src/source_control.F90: table of (time, rate)); kept as a table
+    # that rates_at() evaluates over each time step, "step" or "linear" interpolation, "endpoint" averaging
+    p.source_tables = {}
+    kept = []
+    for s in src:
+        if isinstance(s.get("rate"), list):
+            assert s.get("averaging", "endpoint") == "endpoint", "only endpoint averaging of rate tables is built"
+            p.source_tables[len(kept)] = (np.array(s["rate"], float), s.get("interpolation", "linear"))
+            s = dict(s, rate=0.0)
+            kept.append(s)
+        elif s.get("rate", 0.0) != 0.0:
+            kept.append(s)
+    src = kept
     p.source_cells = np.array([s["cell"] for s in src], np.int32)
     p.source_rates = np.array([s["rate"] for s in src], float)
     # get_components (src/source_setup.F90:2052-2083; doc/user/setup_sources.rst): injection uses "component"
@@ -377,7 +390,7 @@ def load(path, mod=None, mesh_path=None):
 
     def component(s):
         inj = comp(s.get("component", 1))
-        if s["rate"] > 0:
+        if s["rate"] >= 0:
             return inj
         if "production_component" in s:
             return comp(s["production_component"])
@@ -390,3 +403,18 @@ def load(path, mod=None, mesh_path=None):
                                float).reshape(len(src), max(nt, 1))
     p.time = doc.get("time", {})
     return p
+
+
+def rates_at(p, t0, t1):
+    """source rates for the time step [t0, t1]: fixed rates, and table sources averaged over the step with the
+    reference's default "endpoint" averaging -- the mean of the interpolated values at both ends of the interval
+    (src/interpolation.F90:585-602)"""
+    r = p.source_rates.copy()
+
+    def value(tab, interp, t):
+        if interp == "step":
+            return tab[max(np.searchsorted(tab[:, 0], t, side="right") - 1, 0), 1]
+        return np.interp(t, tab[:, 0], tab[:, 1])
+    for k, (tab, interp) in p.source_tables.items():
+        r[k] = 0.5 * (value(tab, interp, t0) + value(tab, interp, t1))
+    return r
