@@ -74,7 +74,7 @@ module waiwera_b200
   public :: wb_last_error, wb_version, wb_create, wb_destroy, wb_num_primary, wb_fluid_dof, wb_set_mesh, &
        wb_jacobian_pattern, wb_jacobian_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
        wb_comm_p2p_blob_size, wb_comm_p2p_export, wb_comm_p2p_open, wb_comm_p2p_enabled, wb_comm_p2p_disable, &
-       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
+       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_source_controls, wb_get_source_rates, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
        wb_mat_set_values, wb_mat_get_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
@@ -238,6 +238,23 @@ module waiwera_b200
        type(c_ptr), value :: cell, component, rate, enthalpy
        integer(c_int) :: ierr
      end function wb_set_sources
+
+     ! source controls re-evaluated at every function evaluation: deliverability (src/source_control.F90:322-507),
+     ! direction (:596-620), total limiter (src/source_network_node.F90:245-315); direction / limit may be c_null_ptr
+     function wb_set_source_controls(ctx, n, source, productivity, reference_pressure, direction, limit) &
+          bind(C, name="wb_set_source_controls") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: n
+       type(c_ptr), value :: source, productivity, reference_pressure, direction, limit
+       integer(c_int) :: ierr
+     end function wb_set_source_controls
+
+     function wb_get_source_rates(ctx, rate) bind(C, name="wb_get_source_rates") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, rate
+       integer(c_int) :: ierr
+     end function wb_get_source_rates
 
      ! context%residual selection (src/timestepper.F90:345-452): BE / BDF2 / direct steady state
      function wb_set_method(ctx, method, dt_last, lhs_last2) bind(C, name="wb_set_method") result(ierr)

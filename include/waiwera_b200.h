@@ -170,6 +170,21 @@ int wb_set_boundaries(wb_ctx *ctx, int n, const int32_t *ghost_cells, const int3
    fractions (src/fluid.F90:374-456).  n = 0 removes all sources. */
 int wb_set_sources(wb_ctx *ctx, int n, const int32_t *cell, const int32_t *component, const double *rate,
                    const double *enthalpy);
+/* Source controls for n of the sources of the last wb_set_sources (source[k]: index into those arrays), re-evaluated
+   from the fluid state of the source's cell at EVERY function evaluation -- the reference's source_network%update
+   inside cell_inflows (src/flow_simulation.F90:1468-1473, src/source_network.F90:90-292) -- so that the
+   finite-difference Jacobian carries their pressure / mobility dependence:
+     deliverability  rate = -productivity * sum_p mobility_p * (P - reference_pressure) over the phases present
+                     (deliverability_source_control_flow_rate, src/source_control.F90:359-403; productivity <= 0:
+                     the fixed rate of wb_set_sources is kept)
+     direction       0 both, 1 production only, 2 injection only (direction_source_control_iterator, :596-620)
+     limit           "total" flow limiter: |rate| scaled down to limit (src/source_network_node.F90:245-315; <= 0: none)
+   direction and limit may be NULL.  n = 0 removes all controls; wb_set_sources also removes them. */
+int wb_set_source_controls(wb_ctx *ctx, int n, const int32_t *source, const double *productivity,
+                           const double *reference_pressure, const int32_t *direction, const double *limit);
+/* rate of every source (order of wb_set_sources) for the state of the last unperturbed evaluation: the
+   "rate" source output field */
+int wb_get_source_rates(wb_ctx *ctx, double *rate);
 /* current fluid records of all local cells, reference AoS layout [ncell*fluid_dof] */
 int wb_get_fluid(wb_ctx *ctx, double *fluid);
 int wb_get_regions(wb_ctx *ctx, int32_t *region);

@@ -210,6 +210,13 @@ void wo_flow_set_method(wo_flow *f, int method, double dt_last, const double *lh
    components for production; np = heat), rate (< 0 production), injection enthalpy */
 void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *component, const double *rate,
                          const double *enthalpy);
+/* source controls for n of those sources (source: index into the wo_flow_set_sources arrays): deliverability
+   (src/source_control.F90:322-507; pi <= 0: none), direction (0 both, 1 production, 2 injection; :596-620), total-flow
+   limiter (limit <= 0: none; src/source_network_node.F90:245-315); re-evaluated at every function evaluation */
+void wo_flow_set_source_controls(wo_flow *f, int n, const int32_t *source, const double *pi, const double *pref,
+                                 const int32_t *direction, const double *limit);
+/* rate of every source at the last unperturbed evaluation */
+void wo_flow_get_source_rates(const wo_flow *f, double *rate);
 /* pre_eval: update mask from perturbed block columns (NULL/0 => unperturbed) + fluid_properties */
 int wo_flow_pre_eval(wo_flow *f, const double *y, const int32_t *perturbed, int nperturbed);
 int wo_flow_cell_balances(wo_flow *f, double *lhs);

@@ -135,6 +135,8 @@ def lib():
         "wo_flow_set_boundary": (i, [vp, i, i, c_dp, i]),
         "wo_flow_set_sources": (None, [vp, i, c_ip, c_ip, c_dp, c_dp]),
         "wo_flow_set_method": (None, [vp, i, d, c_dp]),
+        "wo_flow_set_source_controls": (None, [vp, i, c_ip, c_dp, c_dp, c_ip, c_dp]),
+        "wo_flow_get_source_rates": (None, [vp, c_dp]),
         "wo_flow_pre_eval": (i, [vp, c_dp, c_ip, i]),
         "wo_flow_cell_balances": (i, [vp, c_dp]),
         "wo_flow_cell_inflows": (i, [vp, c_dp]),
@@ -313,6 +315,19 @@ class Flow:
         r = np.ascontiguousarray(rates, np.float64)
         h = np.ascontiguousarray(enthalpies, np.float64)
         self.L.wo_flow_set_sources(self.h, len(c), ip(c), ip(k), dp(r), dp(h))
+
+    def set_source_controls(self, sources, productivity, reference_pressure, direction=None, limit=None):
+        s = np.ascontiguousarray(sources, np.int32)
+        pi = np.ascontiguousarray(productivity, np.float64)
+        pr = np.ascontiguousarray(reference_pressure, np.float64)
+        dr = None if direction is None else np.ascontiguousarray(direction, np.int32)
+        lm = None if limit is None else np.ascontiguousarray(limit, np.float64)
+        self.L.wo_flow_set_source_controls(self.h, len(s), ip(s), dp(pi), dp(pr), ip(dr), dp(lm))
+
+    def source_rates(self, n):
+        r = np.zeros(n)
+        self.L.wo_flow_get_source_rates(self.h, dp(r))
+        return r
 
     def residual(self, y, lhs_last, dt, perturbed=None):
         lhs, rhs, r = np.zeros(self.n), np.zeros(self.n), np.zeros(self.n)

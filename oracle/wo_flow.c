@@ -65,6 +65,10 @@ void wo_flow_set_method(wo_flow *f, int method, double dt_last, const double *lh
 void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *component, const double *rate,
                          const double *enthalpy) {
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
+  free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
+  f->src_ctrl = f->src_direction = NULL;
+  f->src_pi = f->src_pref = f->src_limit = NULL;
+  f->src_rate_eval = (double *)calloc(n + 1, sizeof(double));
   f->nsrc = n;
   f->src_cell = (int32_t *)malloc((n + 1) * sizeof(int32_t));
   f->src_component = (int32_t *)malloc((n + 1) * sizeof(int32_t));
@@ -74,6 +78,62 @@ void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *
   memcpy(f->src_component, component, n * sizeof(int32_t));
   memcpy(f->src_rate, rate, n * sizeof(double));
   memcpy(f->src_enthalpy, enthalpy, n * sizeof(double));
+  memcpy(f->src_rate_eval, rate, n * sizeof(double));
+}
+
+/* Source controls for n of the sources of the last wo_flow_set_sources (source: index into those arrays):
+   deliverability with productivity index pi and reference pressure pref (pi <= 0: no deliverability control),
+   flow direction (0 both, 1 production only, 2 injection only), total-flow limiter (limit <= 0: none). */
+void wo_flow_set_source_controls(wo_flow *f, int n, const int32_t *source, const double *pi, const double *pref,
+                                 const int32_t *direction, const double *limit) {
+  int ns = f->nsrc;
+  free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit);
+  f->src_ctrl = (int32_t *)calloc(ns + 1, sizeof(int32_t));
+  f->src_direction = (int32_t *)calloc(ns + 1, sizeof(int32_t));
+  f->src_pi = (double *)calloc(ns + 1, sizeof(double));
+  f->src_pref = (double *)calloc(ns + 1, sizeof(double));
+  f->src_limit = (double *)calloc(ns + 1, sizeof(double));
+  for (int k = 0; k < n; k++) {
+    int s = source[k];
+    f->src_ctrl[s] = pi[k] > 0.0;
+    f->src_pi[s] = pi[k];
+    f->src_pref[s] = pref[k];
+    f->src_direction[s] = direction ? direction[k] : 0;
+    f->src_limit[s] = limit ? limit[k] : 0.0;
+  }
+}
+
+void wo_flow_get_source_rates(const wo_flow *f, double *rate) { memcpy(rate, f->src_rate_eval, f->nsrc * sizeof(double)); }
+
+/* source_network%update for one source (src/source_network.F90:90-292): source controls, then network controls.
+   deliverability_source_control_flow_rate (src/source_control.F90:359-403, constant productivity and reference
+   pressure), direction_source_control_iterator (:596-620), limit_rate with a "total" limiter
+   (src/source_network_node.F90:245-315) */
+double wo_flow_source_rate(const wo_flow *f, int s) {
+  double rate = f->src_rate[s];
+  if (!f->src_ctrl) return rate;
+  const double *fl = f->current_fluid + (size_t)f->src_cell[s] * f->dof;
+  if (f->src_ctrl[s]) {
+    int phases = nint_(fl[4]);
+    double effective_productivity = f->src_pi[s] * fl[5]; /* permeability_factor */
+    double pressure_difference = fl[0] - f->src_pref[s];
+    rate = 0.0;
+    for (int p = 0; p < f->nphase; p++) {
+      const double *ph = fl + (7 + f->nc - 1) + p * (8 + f->nc - 1);
+      if (phases & (1 << p)) rate = rate - effective_productivity * (ph[3] * ph[0] / ph[1]) * pressure_difference;
+    }
+  }
+  if (f->src_direction[s] == 1 && !(rate < 0.0)) rate = 0.0;
+  if (f->src_direction[s] == 2 && !(rate > 0.0)) rate = 0.0;
+  if (f->src_limit[s] > 0.0) {
+    const double small = 1.e-6;
+    double abs_rate = fabs(rate), scale = 1.0;
+    if (abs_rate > f->src_limit[s]) {
+      if (abs_rate > small) scale = fmin(scale, f->src_limit[s] / abs_rate);
+      rate = rate * scale;
+    }
+  }
+  return rate;
 }
 
 /* fluid%phase_flow_fractions (src/fluid.F90:394-411) of the current fluid in the cell of source s */
@@ -96,7 +156,8 @@ void wo_flow_source_phase_fractions(const wo_flow *f, int s, double *frac) {
 static void source_flow(const wo_flow *f, int s, double *flow) {
   int np = f->np, nc = f->nc;
   int component = f->src_component[s];
-  double rate = f->src_rate[s], enthalpy = 0.0;
+  double rate = wo_flow_source_rate(f, s), enthalpy = 0.0;
+  if (f->unperturbed) f->src_rate_eval[s] = rate;
   for (int k = 0; k < np; k++) flow[k] = 0.0;
   if (rate > 0.0) {
     if (component > 0) {
@@ -143,6 +204,7 @@ static void source_flow(const wo_flow *f, int s, double *flow) {
 void wo_flow_destroy(wo_flow *f) {
   if (!f) return;
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
+  free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
   free(f->lhs_last2);
   free(f->tracers);
   free(f->tracer_injection);

@@ -26,6 +26,11 @@ struct wo_flow {
   int nsrc;
   int32_t *src_cell, *src_component;
   double *src_rate, *src_enthalpy;
+  /* source controls (src/source_control.F90): deliverability (:322-507), direction (:596-620), total limiter
+     (src/source_network_node.F90:245-315); all NULL when no control is set */
+  int32_t *src_ctrl, *src_direction;   /* per source: 1 = on deliverability; 0 both / 1 production / 2 injection */
+  double *src_pi, *src_pref, *src_limit; /* productivity index, reference pressure, total rate limit (<= 0: none) */
+  double *src_rate_eval;               /* rate every source had at the last unperturbed evaluation */
   /* passive tracers (src/tracer.F90:25-41): auxiliary linear problem, wo_tracer.c */
   int nt;
   wo_tracer *tracers;
@@ -34,5 +39,7 @@ struct wo_flow {
 
 /* source%fluid%phase_flow_fractions (src/fluid.F90:374-398) of the current fluid of source s's cell */
 void wo_flow_source_phase_fractions(const wo_flow *f, int s, double *frac);
+/* rate of source s after its controls, evaluated from the current fluid of its cell */
+double wo_flow_source_rate(const wo_flow *f, int s);
 
 #endif

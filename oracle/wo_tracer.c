@@ -191,12 +191,13 @@ void wo_tracer_cell_inflows(wo_flow *f, wo_bsr *Ar, double *br) {
     int c = f->src_cell[s];
     if (c < 0 || c >= m->nowned) continue;
     double volume = m->cell_geom[4 * (size_t)c + 3];
+    double rate = wo_flow_source_rate(f, s);
     if (f->src_component[s] < np) {
-      if (f->src_rate[s] < 0.0) {
+      if (rate < 0.0) {
         double frac[WO_MAX_NP];
         wo_flow_source_phase_fractions(f, s, frac);
         for (int it = 0; it < nt; it++) {
-          double q = frac[f->tracers[it].phase - 1] * f->src_rate[s] / volume;
+          double q = frac[f->tracers[it].phase - 1] * rate / volume;
           add_value(Ar, c, c, it, q);
         }
       } else if (f->tracer_injection) {

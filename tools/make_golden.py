@@ -230,6 +230,31 @@ def mis_problems():
     print("wrote", out)
 
 
+def deliverability():
+    """test/benchmark/source/deliverability: AUTOUGH2 listings of the 10-cell production problems on deliverability
+    (delv: fixed productivity index; delt: with a total-flow limiter; delg_flow: productivity index from the initial
+    rate) -- test_deliverability.py compares P, T, Sv of the last output (5e-3), their history in the production cell
+    and the generation rate / enthalpy history (1e-2)"""
+    base = "/root/reference/test/benchmark/source/deliverability/run"
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/source/deliverability/"
+                            "run/deliv_{delv,delt,delg_flow}.listing (AUTOUGH2); boundary block dropped",
+           "columns": ["pressure", "temperature", "vapour_saturation"]}
+    for case in ("delv", "delt", "delg_flow"):
+        tabs = listing_generic(os.path.join(base, "deliv_%s.listing" % case))
+        el = [(t, r) for k, t, r in tabs if k == "E"]
+        ge = [(t, r) for k, t, r in tabs if k == "G"]
+        src = json.load(open(os.path.join(base, "deliv_%s.json" % case)))
+        doc[case] = {"times": [t for t, _ in el], "tables": [[x[:3] for x in r[:10]] for _, r in el],
+                     "source_times": [t for t, _ in ge], "rate": [r[0][0] for _, r in ge],
+                     "enthalpy": [r[0][1] for _, r in ge], "step_sizes": src["time"]["step"]["size"],
+                     "stop": src["time"]["stop"], "source": src["source"], "boundary": src["boundaries"][0]["primary"],
+                     "initial": src["initial"]["primary"]}
+    out = os.path.join(os.path.dirname(OUT), "deliverability.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -260,3 +285,4 @@ if __name__ == "__main__":
     co2_column()
     minc_column()
     mis_problems()
+    deliverability()

@@ -78,6 +78,8 @@ SIGNATURES = {
     "wb_set_boundaries": (i, [vp, i, vp, vp, vp, vp]),
     "wb_set_sources": (i, [vp, i, vp, vp, vp, vp]),
     "wb_set_method": (i, [vp, i, d, vp]),
+    "wb_set_source_controls": (i, [vp, i, vp, vp, vp, vp, vp]),
+    "wb_get_source_rates": (i, [vp, vp]),
     "wb_get_fluid": (i, [vp, vp]),
     "wb_get_regions": (i, [vp, vp]),
     "wb_pre_iteration": (i, [vp]),

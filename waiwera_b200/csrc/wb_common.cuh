@@ -190,6 +190,8 @@ struct wb_ctx {
   int32_t *d_src_head = nullptr, *d_src_cell = nullptr, *d_src_comp = nullptr;
   double *d_src_rate = nullptr, *d_src_enth = nullptr;
   std::vector<int> h_src_order;  // sorted position -> input position
+  int32_t *d_src_ctrl = nullptr;  // source controls, sorted like the sources (null: none)
+  double *d_src_pi = nullptr, *d_src_pref = nullptr, *d_src_limit = nullptr;
   // passive tracers: auxiliary linear problem (wb_tracer.cu)
   int nt = 0;
   int trc_phase[WB_MAX_TRACERS] = {0, 0, 0};  // 1-based phase index

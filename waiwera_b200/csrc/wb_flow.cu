@@ -198,7 +198,7 @@ __device__ __forceinline__ void source_terms(const WbSources &S, int i, const Wb
   if (k < 0) return;
   for (; k < S.n && S.cell[k] == i; k++) {
     const int component = S.comp[k];
-    const double rate = S.rate[k];
+    const double rate = wb_source_rate(S, k, s);
     double flow[NP], enthalpy = 0.0;
 #pragma unroll
     for (int q = 0; q < NP; q++) flow[q] = 0.0;
@@ -625,7 +625,8 @@ static WbResForm wb_res_form(const wb_ctx *c, const double *d_lhs_last, double d
 }
 
 WbSources wb_sources_args(const wb_ctx *c) {
-  WbSources S = {c->nsrc > 0 ? c->d_src_head : nullptr, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth, c->nsrc};
+  WbSources S = {c->nsrc > 0 ? c->d_src_head : nullptr, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth, c->nsrc,
+                 c->d_src_ctrl, c->d_src_pi, c->d_src_pref, c->d_src_limit};
   return S;
 }
 
@@ -940,6 +941,9 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   c->d_src_rate = c->d_src_enth = nullptr;
   c->nsrc = 0;
   c->h_src_order.clear();
+  cudaFree(c->d_src_ctrl); cudaFree(c->d_src_pi); cudaFree(c->d_src_pref); cudaFree(c->d_src_limit);
+  c->d_src_ctrl = nullptr;
+  c->d_src_pi = c->d_src_pref = c->d_src_limit = nullptr;
   cudaFree(c->d_trc_inj);  // tracer injection rates belong to the old source list
   c->d_trc_inj = nullptr;
   if (n <= 0) return 0;
@@ -965,6 +969,69 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   c->nsrc = n;
   c->h_src_order = order;
   return 0;
+}
+
+// ---- source controls -----------------------------------------------------------------------------
+extern "C" int wb_set_source_controls(wb_ctx *c, int n, const int32_t *source, const double *productivity,
+                                      const double *reference_pressure, const int32_t *direction, const double *limit) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_src_ctrl); cudaFree(c->d_src_pi); cudaFree(c->d_src_pref); cudaFree(c->d_src_limit);
+  c->d_src_ctrl = nullptr;
+  c->d_src_pi = c->d_src_pref = c->d_src_limit = nullptr;
+  if (n <= 0) return 0;
+  WB_CHECK(c->nsrc > 0, "wb_set_source_controls: no sources");
+  const int ns = c->nsrc;
+  std::vector<int> pos(ns);  // input position -> sorted position
+  for (int k = 0; k < ns; k++) pos[c->h_src_order[k]] = k;
+  std::vector<int32_t> ctrl(ns, 0);
+  std::vector<double> pi(ns, 0.0), pref(ns, 0.0), lim(ns, 0.0);
+  for (int k = 0; k < n; k++) {
+    WB_CHECK(source[k] >= 0 && source[k] < ns, "wb_set_source_controls: source index %d out of range", source[k]);
+    const int d = direction ? direction[k] : 0;
+    WB_CHECK(d >= 0 && d <= 2, "wb_set_source_controls: direction %d", d);
+    const int q = pos[source[k]];
+    ctrl[q] = (productivity[k] > 0.0 ? 1 : 0) | (d << 1);
+    pi[q] = productivity[k];
+    pref[q] = reference_pressure[k];
+    lim[q] = limit ? limit[k] : 0.0;
+  }
+  WB_TRY(dev_upload(&c->d_src_ctrl, ctrl));
+  WB_TRY(dev_upload(&c->d_src_pi, pi));
+  WB_TRY(dev_upload(&c->d_src_pref, pref));
+  WB_TRY(dev_upload(&c->d_src_limit, lim));
+  return 0;
+}
+
+template <int EOS>
+__global__ void k_source_rates(const WbSources S, const double *state, int ncell, const int32_t *order, double *out) {
+  constexpr int NC = WbEosTraits<EOS>::NC, NPH = WbEosTraits<EOS>::NPH;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S.n) return;
+  WbCellState<NC, NPH> s;
+  load_state(state, (size_t)ncell, S.cell[k], s);
+  out[order[k]] = wb_source_rate(S, k, s);
+}
+
+extern "C" int wb_get_source_rates(wb_ctx *c, double *rate) {
+  WB_CUDA(cudaSetDevice(c->device));
+  if (c->nsrc == 0) return 0;
+  int rc = 0;
+  WbStage st(c);
+  double *d_out = st.out(rate, (size_t)c->nsrc, &rc);
+  if (rc) return rc;
+  int32_t *d_order = nullptr;
+  std::vector<int32_t> order(c->h_src_order.begin(), c->h_src_order.end());
+  WB_TRY(dev_upload(&d_order, order));
+  const WbSources S = wb_sources_args(c);
+#define CALL(E) k_source_rates<E><<<wb_grid(c->nsrc, 128), 128, 0, c->stream>>>(S, c->d_state, c->ncell, d_order, d_out)
+  DISPATCH_EOS(c, CALL);
+#undef CALL
+  WB_LAUNCH(c);
+  WB_CUDA(cudaGetLastError());
+  rc = st.finish();
+  cudaFree(d_order);
+  return rc;
 }
 
 // error flag of the property kernels, reduced over ranks (mpi_broadcast_error_flag)

@@ -74,5 +74,42 @@ struct WbSources {
   const int32_t *head, *cell, *comp;
   const double *rate, *enth;
   int n;
+  // source controls (null: none), sorted like the sources: ctrl bit 0 = on deliverability, bits 1-2 = direction
+  // (0 both, 1 production, 2 injection); productivity index, reference pressure, total-flow limit (<= 0: none)
+  const int32_t *ctrl;
+  const double *pi, *pref, *limit;
 };
+
+// source_network%update for one source (src/source_network.F90:90-292): its rate after the source controls
+// (deliverability_source_control_flow_rate src/source_control.F90:359-403 with constant productivity and reference
+// pressure and permeability factor 1; direction_source_control_iterator :596-620) and the network controls
+// ("total" limiter, src/source_network_node.F90:245-315), evaluated from the state of the source's cell -- at
+// every function evaluation, perturbed ones included, so that the finite-difference Jacobian sees it
+template <int NC, int NPH>
+WB_HD double wb_source_rate(const WbSources &S, int k, const WbCellState<NC, NPH> &s) {
+  double rate = S.rate[k];
+  if (!S.ctrl) return rate;
+  const int ctrl = S.ctrl[k];
+  if (ctrl & 1) {
+    const double effective_productivity = S.pi[k] * 1.0;
+    const double pressure_difference = s.P - S.pref[k];
+    rate = 0.0;
+#pragma unroll
+    for (int p = 0; p < NPH; p++)
+      if (s.phases & (1 << p)) rate = rate - effective_productivity * s.mob[p] * pressure_difference;
+  }
+  const int direction = (ctrl >> 1) & 3;
+  if (direction == 1 && !(rate < 0.0)) rate = 0.0;
+  if (direction == 2 && !(rate > 0.0)) rate = 0.0;
+  const double limit = S.limit[k];
+  if (limit > 0.0) {
+    const double abs_rate = fabs(rate);
+    if (abs_rate > limit) {
+      double scale = 1.0;
+      if (abs_rate > 1.e-6) scale = fmin(scale, limit / abs_rate);
+      rate = rate * scale;
+    }
+  }
+  return rate;
+}
 

@@ -296,7 +296,23 @@ class FlowSimulation:
         k = np.ascontiguousarray(components, np.int32)
         r = np.ascontiguousarray(rates, np.float64)
         h = np.ascontiguousarray(enthalpies, np.float64)
+        self.nsrc = len(c)
         return check(self.L.wb_set_sources(self.h, len(c), ptr(c), ptr(k), ptr(r), ptr(h)), "wb_set_sources")
+
+    def set_source_controls(self, sources, productivity, reference_pressure, direction=None, limit=None):
+        """deliverability / direction / total-limiter controls of some of the sources; see wb_set_source_controls"""
+        s = np.ascontiguousarray(sources, np.int32)
+        pi = np.ascontiguousarray(productivity, np.float64)
+        pr = np.ascontiguousarray(reference_pressure, np.float64)
+        dr = None if direction is None else np.ascontiguousarray(direction, np.int32)
+        lm = None if limit is None else np.ascontiguousarray(limit, np.float64)
+        return check(self.L.wb_set_source_controls(self.h, len(s), ptr(s), ptr(pi), ptr(pr), ptr(dr), ptr(lm)),
+                     "wb_set_source_controls")
+
+    def source_rates(self):
+        r = np.zeros(self.nsrc)
+        check(self.L.wb_get_source_rates(self.h, ptr(r)), "wb_get_source_rates")
+        return r
 
     def fluid(self):
         out = np.zeros((self.ncell, self.dof))
