@@ -162,7 +162,9 @@ static int tracer_assemble_host(const wb_params *prm, int ncell, int nowned, int
                                 const double *primary, const int32_t *region, const int32_t *phase,
                                 const double *diffusion, const double *decay, const double *activation, int nsrc,
                                 const int32_t *src_cell, const int32_t *src_comp, const double *src_rate,
-                                const double *inj, int method, double dt, double dt_last, const double *al_last,
+                                const int32_t *src_ctrl, const double *src_pi, const double *src_pref,
+                                const double *src_limit, const double *inj, int method, double dt, double dt_last,
+                                const double *al_last,
                                 const double *x_last, const double *al_last2, const double *x_last2,
                                 const double *xb, const int32_t *rowptr, const int32_t *colidx, double *val,
                                 double *b, double *al) {
@@ -224,10 +226,13 @@ static int tracer_assemble_host(const wb_params *prm, int ncell, int nowned, int
     while (q >= 0 && src_cell[order[q]] > src_cell[v]) { order[q + 1] = order[q]; q--; }
     order[q + 1] = v;
   }
-  std::vector<int32_t> head(nowned, -1), sc(nsrc + 1), sk(nsrc + 1);
-  std::vector<double> sr(nsrc + 1), sinj((size_t)nsrc * NT + 1);
+  std::vector<int32_t> head(nowned, -1), sc(nsrc + 1), sk(nsrc + 1), sctrl(nsrc + 1);
+  std::vector<double> sr(nsrc + 1), sinj((size_t)nsrc * NT + 1), spi(nsrc + 1), spref(nsrc + 1), slim(nsrc + 1);
   for (int k = 0; k < nsrc; k++) {
     sc[k] = src_cell[order[k]]; sk[k] = src_comp[order[k]]; sr[k] = src_rate[order[k]];
+    if (src_ctrl) {
+      sctrl[k] = src_ctrl[order[k]]; spi[k] = src_pi[order[k]]; spref[k] = src_pref[order[k]]; slim[k] = src_limit[order[k]];
+    }
     for (int t = 0; t < NT; t++) sinj[(size_t)k * NT + t] = inj ? inj[(size_t)order[k] * NT + t] : 0.0;
     if (head[sc[k]] < 0) head[sc[k]] = k;
   }
@@ -237,6 +242,7 @@ static int tracer_assemble_host(const wb_params *prm, int ncell, int nowned, int
   a.diagpos = diagpos.data(); a.rowptr = rowptr;
   a.src.head = nsrc ? head.data() : nullptr; a.src.cell = sc.data(); a.src.comp = sk.data(); a.src.rate = sr.data();
   a.src.enth = nullptr; a.src.n = nsrc;
+  a.src.ctrl = src_ctrl ? sctrl.data() : nullptr; a.src.pi = spi.data(); a.src.pref = spref.data(); a.src.limit = slim.data();
   a.inj = inj ? sinj.data() : nullptr;
   for (int t = 0; t < NT; t++) {
     a.trc.phase[t] = phase[t] - 1; a.trc.diffusion[t] = diffusion[t]; a.trc.decay[t] = decay[t];
@@ -263,13 +269,16 @@ extern "C" int hc_tracer_assemble(const wb_params *prm, int nt, int ncell, int n
                                   const double *rock8, const double *primary, const int32_t *region,
                                   const int32_t *phase, const double *diffusion, const double *decay,
                                   const double *activation, int nsrc, const int32_t *src_cell,
-                                  const int32_t *src_comp, const double *src_rate, const double *inj, int method,
+                                  const int32_t *src_comp, const double *src_rate, const int32_t *src_ctrl,
+                                  const double *src_pi, const double *src_pref, const double *src_limit,
+                                  const double *inj, int method,
                                   double dt, double dt_last, const double *al_last, const double *x_last,
                                   const double *al_last2, const double *x_last2, const double *xb,
                                   const int32_t *rowptr, const int32_t *colidx, double *val, double *b, double *al) {
 #define HC_TRACER(E, T)                                                                                              \
   return tracer_assemble_host<E, T>(prm, ncell, nowned, nface, face_cells, face12, cell4, rock8, primary, region,    \
-                                    phase, diffusion, decay, activation, nsrc, src_cell, src_comp, src_rate, inj,    \
+                                    phase, diffusion, decay, activation, nsrc, src_cell, src_comp, src_rate, src_ctrl, \
+                                    src_pi, src_pref, src_limit, inj,                                               \
                                     method, dt, dt_last, al_last, x_last, al_last2, x_last2, xb, rowptr, colidx, val, \
                                     b, al)
   if (prm->eos == WB_EOS_WE) {

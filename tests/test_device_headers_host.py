@@ -42,7 +42,7 @@ def hc(wo):
     L.hc_wce_flux.argtypes = [C.c_void_p, dp, dp, dp, dp, i, dp, i, dp, dp]
     L.hc_wce_transition.argtypes = [C.c_void_p, dp, dp, i, d, ip, ip, ip]
     L.hc_wce_scale.argtypes = [C.c_void_p, dp, i, dp, dp]
-    L.hc_tracer_assemble.argtypes = [C.c_void_p, i, i, i, i, ip, dp, dp, dp, dp, ip, ip, dp, dp, dp, i, ip, ip, dp, dp, i,
+    L.hc_tracer_assemble.argtypes = [C.c_void_p, i, i, i, i, ip, dp, dp, dp, dp, ip, ip, dp, dp, dp, i, ip, ip, dp, ip, dp, dp, dp, dp, i,
                                      d, d, dp, dp, dp, dp, dp, ip, ip, dp, dp, dp]
     return L
 

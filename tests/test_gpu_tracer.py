@@ -18,6 +18,8 @@ def gpu_case(wo, flow, eos, nt):
     y, region = tracer_case.last["y"], tracer_case.last["region"]
     sim = gpu_flow(wo, flow, m, prm, y, region)
     assert sim.set_sources(src["cells"], src["comps"], src["rates"], np.zeros(len(src["cells"]))) == 0
+    c = src["ctrl"]
+    assert sim.set_source_controls(c["sources"], c["pi"], c["pref"], c["direction"], c["limit"]) == 0
     assert sim.set_tracers(t["phases"], t["diffusion"], t["decay"], t["activation"]) == 0
     assert sim.set_tracer_injection(src["inj"]) == 0
     err, L0 = sim.lhs(y)

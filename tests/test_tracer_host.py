@@ -39,6 +39,10 @@ def tracer_case(wo, eos="we", nt=3, seed=SEED):
     f.set_tracers(t["phases"], t["diffusion"], t["decay"], t["activation"])
     inj = rng.uniform(0.0, 1.0e-4, (len(cells), nt))
     f.set_tracer_injection(inj)
+    # source controls: the first producer on deliverability (production only), the second with a total limiter
+    ctrl = dict(sources=np.array([0, 1], np.int32), pi=np.array([2.0e-12, 0.0]), pref=np.array([2.0e5, 0.0]),
+                direction=np.array([1, 0], np.int32), limit=np.array([0.0, 0.15]))
+    f.set_source_controls(ctrl["sources"], ctrl["pi"], ctrl["pref"], ctrl["direction"], ctrl["limit"])
     assert f.fluid_init(y, region) == 0
     err, L0 = f.lhs(y)
     assert err == 0
@@ -55,7 +59,7 @@ def tracer_case(wo, eos="we", nt=3, seed=SEED):
         wo.lib().wo_eos_unscale(f.eos, wo.dp(y[c * f.np:(c + 1) * f.np].copy()), int(region[c]), wo.dp(primary[c]))
     prim_all = np.vstack([primary[:m.nowned], bprim]) if nb else primary[:m.nowned]
     reg_all = np.concatenate([region[:m.nowned], breg]).astype(np.int32)
-    src = dict(cells=cells, comps=comps, rates=rates, inj=inj)
+    src = dict(cells=cells, comps=comps, rates=rates, inj=inj, ctrl=ctrl)
     tracer_case.last = dict(y=y, region=region)   # scaled state, for the GPU tests that rebuild the same problem
     return m, f, prm, t, src, x_last, x_last2, al_last, al_last2, np.ascontiguousarray(prim_all), reg_all
 
@@ -73,13 +77,18 @@ def host_assemble(wo, hc, m, f, prm, t, src, method, dt, dt_last, al_last, x_las
     arr = lambda a: np.ascontiguousarray(a, np.float64)
     a0, x0 = arr(al_last.reshape(-1, nt)[:n].reshape(-1)), arr(x_last.reshape(-1, nt)[:n].reshape(-1))
     a2, x2 = arr(al_last2.reshape(-1, nt)[:n].reshape(-1)), arr(x_last2.reshape(-1, nt)[:n].reshape(-1))
+    ns, c = len(src["cells"]), src["ctrl"]
+    cw, cpi, cpref, clim = np.zeros(ns, np.int32), np.zeros(ns), np.zeros(ns), np.zeros(ns)
+    for k, sidx in enumerate(c["sources"]):      # control word as wb_set_source_controls packs it
+        cw[sidx] = (1 if c["pi"][k] > 0 else 0) | (int(c["direction"][k]) << 1)
+        cpi[sidx], cpref[sidx], clim[sidx] = c["pi"][k], c["pref"][k], c["limit"][k]
     rc = hc.hc_tracer_assemble(
         C.byref(prm), nt, m.ncell, n, m.nface, wo.ip(np.ascontiguousarray(m.face_cells.reshape(-1))),
         wo.dp(arr(m.face_geom.reshape(-1))), wo.dp(arr(m.cell_geom.reshape(-1))), wo.dp(arr(f.L and np.ctypeslib.as_array(
             C.cast(f.mesh.rock, C.POINTER(C.c_double)), shape=(m.ncell * 8,)).copy())),
         wo.dp(prim_all.reshape(-1)), wo.ip(reg_all), wo.ip(np.array(t["phases"], np.int32)), wo.dp(arr(t["diffusion"])),
         wo.dp(arr(t["decay"])), wo.dp(arr(t["activation"])), len(src["cells"]), wo.ip(src["cells"]), wo.ip(src["comps"]),
-        wo.dp(src["rates"]), wo.dp(arr(src["inj"].reshape(-1))), method, dt, dt_last, wo.dp(a0), wo.dp(x0), wo.dp(a2),
+        wo.dp(src["rates"]), wo.ip(cw), wo.dp(cpi), wo.dp(cpref), wo.dp(clim), wo.dp(arr(src["inj"].reshape(-1))), method, dt, dt_last, wo.dp(a0), wo.dp(x0), wo.dp(a2),
         wo.dp(x2), wo.dp(xb), wo.ip(rowptr), wo.ip(colidx), wo.dp(val), wo.dp(b), wo.dp(al))
     assert rc == 0
     return rowptr, colidx, val.reshape(-1, nt * nt), b, al
