@@ -622,3 +622,134 @@ def test_eos_wce_scaling_and_consistency(wo):
     L.wo_eos_destroy(e)
     L.wo_eos_destroy(ewe)
     L.wo_thermo_destroy(th)
+
+
+def test_fluid_sums(wo):
+    """test/unit/src/fluid_test.F90:115-243: fluid%component_density / energy (through cell%balance with porosity 1),
+    phase_mobilities, phase_flow_fractions, component_flow_fractions and specific_enthalpy (through a producing source
+    of all mass components at -1 kg/s in a unit-volume cell: inflow = -(component flow fractions, enthalpy))"""
+    L = wo.lib()
+    rec = np.array([2.7e5, 130., 4., 4., 3., 1., 0., 0.,
+                    935., 0., 0.8, 0., 0., 0., 5.461e5, 0.7, 0.3,
+                    1.5, 0., 0.2, 0., 0., 0., 2.540e6, 0.4, 0.6])
+    rock = np.array([1e-13, 1e-13, 1e-13, 2.5, 2.5, 1.0, 0.0, 0.0])      # porosity 1: balance = fluid sums
+    bal = np.zeros(3)
+    L.wo_cell_balance(wo.dp(rock), wo.dp(rec), 2, 2, 3, wo.dp(bal))
+    assert np.allclose(bal[:2], [523.72, 224.58], rtol=1e-12)            # fluid_test.F90:125
+    assert np.isclose(bal[2], 4.092448e8, rtol=1e-12)                    # :160
+    # :197-230 (same record with viscosities, relative permeabilities and enthalpies)
+    rec2 = np.array([2.7e5, 130., 4., 4., 3., 1., 0., 0.,
+                     935., 1.e-6, 0.8, 0.7, 0., 83.9e3, 5.461e5, 0.7, 0.3,
+                     1.5, 2.e-7, 0.2, 0.3, 0., 800.e3, 2.540e6, 0.4, 0.6])
+    from waiwera_b200 import mesh as wmesh
+    m = wmesh.structured(2, 1, 1, dx=1.0, gravity=(0.0, 0.0, 0.0), heterogeneous=False)
+    f = wo.Flow(wo.make_params(eos=wo.EOS_WCE, gravity=(0.0, 0.0, 0.0)), m.ncell, m.ninterior, m.nowned,
+                m.face_cells.reshape(-1), m.face_geom.reshape(-1), m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    f.set_sources([0], [0], [-1.0], [0.0])
+    f.current_fluid()[:] = rec2                      # both cells: no flux between them, stored fluxes are zero
+    rhs = np.zeros(6)
+    assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+    assert np.allclose(-rhs[:2], [0.6989722116, 0.3010277884], rtol=1e-9)    # component flow fractions
+    assert np.isclose(-rhs[2], 86353.3307955843, rtol=1e-12)                 # specific enthalpy
+    mob = np.array([935. * 0.7 / 1.e-6, 1.5 * 0.3 / 2.e-7])
+    assert np.allclose(mob, [654500000., 2250000.]) and np.allclose(mob / mob.sum(), [0.9965740388, 0.0034259612])
+    assert (rhs[3:] == 0.0).all()
+
+
+# ---- test/unit/src/root_finder_test.F90:48-294 (Brent; the saturation-line search of the phase transitions) ----
+class _RootFinder(C.Structure):
+    _fields_ = [("interval", C.c_double * 2), ("root_tolerance", C.c_double), ("function_tolerance", C.c_double),
+                ("root", C.c_double), ("max_iterations", C.c_int), ("iterations", C.c_int), ("err", C.c_int)]
+
+
+_ROOT_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+
+
+def _find_root(wo, fn, interval=None):
+    L = wo.lib()
+    r = _RootFinder()
+    L.wo_root_finder_init.argtypes = [C.POINTER(_RootFinder)]
+    L.wo_root_finder_find.argtypes = [C.POINTER(_RootFinder), _ROOT_FN, C.c_void_p]
+    L.wo_root_finder_init.restype = L.wo_root_finder_find.restype = None
+    L.wo_root_finder_init(C.byref(r))
+    if interval is not None:
+        r.interval[0], r.interval[1] = interval
+    cb = _ROOT_FN(lambda x, ctx: fn(x))
+    L.wo_root_finder_find(C.byref(r), cb, None)
+    return r
+
+
+def test_root_finder(wo):
+    import math
+    r = _find_root(wo, lambda x: 0.5 - x)                                        # :48-91 linear
+    assert r.err == 0 and abs(r.root - 0.5) <= r.root_tolerance and r.iterations <= 2
+    assert _find_root(wo, lambda x: 0.5 - x, (0.75, 1.0)).err != 0                # interval not bracketed
+    r = _find_root(wo, lambda x: (x - 0.75) ** 2 - 0.5)                          # :95-131 quadratic
+    assert r.err == 0 and abs(r.root - (0.75 - math.sqrt(0.5))) <= r.root_tolerance and r.iterations <= 7
+    r = _find_root(wo, lambda x: math.cos(x) - x ** 3, (0.0, 4.0))               # :135-174 Zhang
+    assert r.err == 0 and abs(r.root - 0.8654740331015734) <= r.root_tolerance and r.iterations <= 12
+
+    def invquad(x):                                                              # :178-222 inverse quadratic
+        xs = x - 2.0 / 3.0
+        return -math.sqrt(abs(xs)) if xs > 0 else math.sqrt(abs(xs))
+    r = _find_root(wo, invquad, (-10.0, 10.0))
+    assert r.err == 0 and abs(r.root - 2.0 / 3.0) <= r.root_tolerance and r.iterations <= 18
+    # :226-294 saturation line intersection (IAPWS): from (20 bar, 210 degC) to (23 bar, 220 degC)
+    th = wo.lib().wo_thermo_create(wo.THERMO_IAPWS, 0)
+
+    def satdiff(x):
+        P, T = 20.e5 + x * 3.e5, 210.0 + x * 10.0
+        ps = C.c_double()
+        wo.lib().wo_saturation_pressure(th, T, C.byref(ps))
+        return ps.value - P
+    r = _find_root(wo, satdiff)
+    assert r.err == 0 and r.iterations <= 6
+    assert abs((210.0 + r.root * 10.0) - 218.61315743282924) <= 10.0 * r.root_tolerance
+    wo.lib().wo_thermo_destroy(th)
+
+
+# ---- test/unit/src/interpolation_test.F90:73-296 (tables of the curves, rate tables of the sources) ----
+DATA5_X, DATA5_Y = [0., 2.1, 3.7, 6.3, 8.9], [1., 2.0, 0.5, -1.1, -0.1]
+
+
+class _Table(C.Structure):
+    _fields_ = [("n", C.c_int), ("dim", C.c_int), ("index", C.c_int), ("x", C.POINTER(C.c_double)),
+                ("val", C.POINTER(C.c_double))]
+
+
+def test_interpolation_table(wo):
+    L = wo.lib()
+    t = _Table()
+    x, v = np.array(DATA5_X), np.array(DATA5_Y)
+    L.wo_table_init.argtypes = [C.POINTER(_Table), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int]
+    L.wo_table_interpolate.argtypes = [C.POINTER(_Table), C.c_double, C.POINTER(C.c_double)]
+    L.wo_table_destroy.argtypes = [C.POINTER(_Table)]
+    L.wo_table_init.restype = L.wo_table_interpolate.restype = L.wo_table_destroy.restype = None
+    L.wo_table_init(C.byref(t), wo.dp(x), wo.dp(v), 5, 1)
+    for xq, expect, index in [(-0.5, 1.0, 0), (0.0, 1.0, 0), (1.0, 1.4761904761904763, 1), (4.5, 0.007692307692307665, 3),
+                              (3.6, 0.59375, 2), (6.3, -1.1, 4), (10.0, -0.1, 5)]:      # :88-109
+        y = C.c_double()
+        L.wo_table_interpolate(C.byref(t), xq, C.byref(y))
+        assert abs(y.value - expect) <= 1e-9 * max(abs(expect), 1.0), (xq, y.value)
+        assert t.index == index, (xq, t.index)
+    L.wo_table_destroy(C.byref(t))
+
+
+def test_rate_table_averaging():
+    """waiwera_b200.ingest.rates_at: the reference's default endpoint averaging of linear and step tables
+    (interpolation_test.F90:223-296)"""
+    from waiwera_b200 import ingest
+
+    class P:
+        pass
+    tab = np.stack([DATA5_X, DATA5_Y], 1)
+    for interp, cases in (("linear", [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.0238095238095237), ((0.1, 2.0), 1.5),
+                                      ((0.1, 3.0), 1.1019345238095237), ((3.1, 7.0), 0.11586538461538454),
+                                      ((8.0, 12.0), -0.27307692307692316), ((1.0, 1.0), 1.4761904761904763)]),
+                          ("step", [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.0), ((0.1, 2.0), 1.0), ((0.1, 3.0), 1.5),
+                                    ((3.1, 7.0), 0.45), ((8.0, 12.0), -0.6), ((1.0, 1.0), 1.0)])):
+        p = P()
+        p.source_rates = np.zeros(1)
+        p.source_tables = {0: (tab, interp)}
+        for (t0, t1), expect in cases:
+            assert abs(ingest.rates_at(p, t0, t1)[0] - expect) <= 1e-9, (interp, t0, t1)
