@@ -18,7 +18,7 @@ module waiwera_b200
   private
 
   integer(c_int), parameter, public :: WB_THERMO_IAPWS = 0, WB_THERMO_IFC67 = 1
-  integer(c_int), parameter, public :: WB_EOS_WE = 0, WB_EOS_W = 1, WB_EOS_WCE = 2
+  integer(c_int), parameter, public :: WB_EOS_WE = 0, WB_EOS_W = 1, WB_EOS_WCE = 2, WB_EOS_WAE = 3
   integer(c_int), parameter, public :: WB_RP_FULLY_MOBILE = 0, WB_RP_LINEAR = 1, WB_RP_PICKENS = 2, &
        WB_RP_COREY = 3, WB_RP_GRANT = 4, WB_RP_VAN_GENUCHTEN = 5, WB_RP_TABLE = 6
   integer(c_int), parameter, public :: WB_CP_ZERO = 0, WB_CP_LINEAR = 1, WB_CP_VAN_GENUCHTEN = 2, WB_CP_TABLE = 3

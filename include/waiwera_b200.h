@@ -57,6 +57,9 @@ extern "C" {
 #define WB_CP_VAN_GENUCHTEN 2
 #define WB_CP_TABLE 3
 
+#define WB_EOS_WAE 3 /* water + air + energy: eos_wge with the air NCG (src/eos_wae.F90,
+                        src/ncg_air_thermodynamics.F90); 3 primaries, same kernels as WB_EOS_WCE */
+
 #define WB_MAX_TABLE 16
 #define WB_MAX_NP 3
 

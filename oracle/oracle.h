@@ -130,6 +130,7 @@ double wo_cappress_value(const wo_cappress *cp, double sl, double t);
 #define WO_EOS_WE 0
 #define WO_EOS_W 1
 #define WO_EOS_WCE 2
+#define WO_EOS_WAE 3 /* water + air + energy: eos_wge with the air NCG (src/eos_wae.F90, src/ncg_air_thermodynamics.F90) */
 #define WO_EOS_WAE 3
 
 #define WO_MAX_NP 3  /* max primaries */
@@ -170,6 +171,12 @@ void wo_co2_properties(double partial_pressure, double temperature, double props
 double wo_co2_henrys_constant(double temperature);
 double wo_co2_energy_solution(double temperature, double henrys_constant);
 int wo_co2_viscosity(double partial_pressure, double temperature, double *viscosity);
+
+/* ---- air non-condensible gas (src/ncg_air_thermodynamics.F90) ---- */
+void wo_air_properties(double partial_pressure, double temperature, double props[2]); /* density, enthalpy */
+double wo_air_henrys_constant(double temperature, double constituent[2]);
+double wo_air_energy_solution(double temperature, const double constituent_henrys_constant[2]);
+double wo_air_mixture_viscosity(double water_viscosity, double temperature, double xg, int phase);
 
 /* ---- local cell / face objects (src/cell.F90:114, src/face.F90:443) ---- */
 void wo_cell_balance(const double *rock, const double *fluid, int nc, int nphase, int np, double *balance);

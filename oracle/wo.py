@@ -121,6 +121,10 @@ def lib():
         "wo_co2_henrys_constant": (d, [d]),
         "wo_co2_energy_solution": (d, [d, d]),
         "wo_co2_viscosity": (i, [d, d, c_dp]),
+        "wo_air_properties": (None, [d, d, c_dp]),
+        "wo_air_henrys_constant": (d, [d, c_dp]),
+        "wo_air_energy_solution": (d, [d, c_dp]),
+        "wo_air_mixture_viscosity": (d, [d, d, d, i]),
         "wo_cell_balance": (None, [c_dp, c_dp, i, i, i, c_dp]),
         "wo_face_flux": (None, [c_dp, c_dp, c_dp, c_dp, c_dp, i, i, i, i, i, c_dp]),
         "wo_face_calculate_distances": (None, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
@@ -207,7 +211,7 @@ def make_relperm(kind="linear", **kw):
         r.p[0], r.p[1] = kw.get("slr", 0.3), kw.get("ssr", 0.05 if kind == "corey" else 0.6)
     elif kind == "van_genuchten":
         r.type = RP_VAN_GENUCHTEN
-        r.p[0], r.p[1], r.p[2] = kw.get("lambda_", 0.45), kw.get("slr", 1e-3), kw.get("sls", 1.0)
+        r.p[0], r.p[1], r.p[2] = kw.get("lambda", kw.get("lambda_", 0.45)), kw.get("slr", 1e-3), kw.get("sls", 1.0)
         r.p[3] = 0.0 if "ssr" in kw else 1.0
         r.p[4] = kw.get("ssr", 0.0)
     elif kind == "table":
@@ -233,7 +237,7 @@ def make_cappress(kind="zero", **kw):
         c.p[0], c.p[1], c.p[2] = lim[0], lim[1], kw.get("pressure", 0.125e5)
     elif kind == "van_genuchten":
         c.type = CP_VAN_GENUCHTEN
-        c.p[0], c.p[1], c.p[2], c.p[3] = kw.get("P0", 0.125e5), kw.get("lambda_", 0.45), kw.get("slr", 1e-3), kw.get("sls", 1.0)
+        c.p[0], c.p[1], c.p[2], c.p[3] = kw.get("P0", 0.125e5), kw.get("lambda", kw.get("lambda_", 0.45)), kw.get("slr", 1e-3), kw.get("sls", 1.0)
         c.p[4] = kw.get("Pmax", 0.0)
         c.p[5] = 1.0 if "Pmax" in kw else 0.0
     elif kind == "table":

@@ -24,6 +24,7 @@ struct wo_eos {
   int np, nc, nphase, nmobile, isothermal;
   double primary_scale[WO_MAX_NP][5]; /* [var][region 1..4] */
   int adaptive_pp_scale;              /* eos_wge: partial pressure scaled by the cell's total pressure */
+  int gas;                            /* eos_wge: 0 CO2 (eos_wce), 1 air (eos_wae) */
 };
 
 enum { F_P = 0, F_T = 1, F_REGION = 2, F_OLD_REGION = 3, F_PHASES = 4, F_PERMFAC = 5, F_PARTIAL = 6 };
@@ -41,10 +42,14 @@ static inline int nint_(double x) { return (int)lround(x); }
 wo_eos *wo_eos_create(const wo_params *prm) {
   wo_eos *e = (wo_eos *)calloc(1, sizeof(wo_eos));
   e->prm = *prm;
+  if (prm->eos == WO_EOS_WAE) { /* eos_wae.F90:27-64: eos_wge with the air NCG */
+    e->gas = 1;
+    e->prm.eos = WO_EOS_WCE;
+  }
   e->thermo = wo_thermo_create(prm->thermo, prm->extrapolate);
   double ps = prm->pressure_scale > 0 ? prm->pressure_scale : 1.e6;      /* eos_we.F90:75-76 */
   double ts = prm->temperature_scale > 0 ? prm->temperature_scale : 1.e2;
-  switch (prm->eos) {
+  switch (e->prm.eos) {
     case WO_EOS_WE: /* eos_we.F90:78-109 */
       e->np = 2; e->nc = 1; e->nphase = 2; e->nmobile = 2; e->isothermal = 0;
       e->primary_scale[0][1] = ps; e->primary_scale[1][1] = ts;
@@ -171,6 +176,87 @@ static double co2_mole_to_mass_fraction(double xmole) {
   return w / (w + (1.0 - xmole) * water_molecular_weight);
 }
 
+/* ---- air (src/ncg_air_thermodynamics.F90) ---- */
+static const double air_molecular_weight = 28.96;                           /* :14 */
+static const double air_enthalpy_data[4] = {1.20740, 9.24502, 0.115984, -5.63568e-4};
+static const double air_constituent_weight[2] = {0.79, 0.21};
+static const double air_henry_p0[2] = {1.01325e5, 1.e5};
+/* henry_data(2,7): coefficient k of constituent c at [c][k] */
+static const double air_henry_data[2][7] = {
+    {0.513726, 1.58603, -5.9378e-1, -6.98282e-1, 5.10330e-1, -1.21388e-1, 1.00041e-2},
+    {0.26234, 0.610628, 7.00732e-1, -0.139299e1, 7.13850e-1, -1.54216e-1, 1.23190e-2}};
+static const double air_tscale = 100.0;
+static const double air_fair = 97.0, air_fwat = 363.0, air_cair = 3.617, air_cwat = 2.655;
+
+/* ncg_air_properties (:97-121): ideal gas with deviation factor 1, enthalpy relative to the triple point */
+void wo_air_properties(double partial_pressure, double temperature, double props[2]) {
+  const double ttriple = 0.01;                                              /* thermodynamics.F90 */
+  double tk = temperature + WO_TC_K;
+  double enthalpy_shift = polynomial(air_enthalpy_data, 4, (ttriple + WO_TC_K) / air_tscale); /* ncg_air_init :84-86 */
+  props[0] = partial_pressure * air_molecular_weight / (1.e3 * gas_constant * 1.0 * tk);
+  props[1] = 1.e4 * (polynomial(air_enthalpy_data, 4, tk / air_tscale) - enthalpy_shift);
+}
+
+/* ncg_air_henrys_constant (:125-143): weighted sum over N2 and O2 */
+double wo_air_henrys_constant(double temperature, double constituent[2]) {
+  double hc = 0.0;
+  for (int c = 0; c < 2; c++) {
+    constituent[c] = 1.e5 * air_henry_p0[c] * polynomial(air_henry_data[c], 7, temperature / air_tscale);
+    hc += air_constituent_weight[c] * constituent[c];
+  }
+  return hc;
+}
+
+/* ncg_air_henrys_derivative (:176-198) then ncg_energy_solution (ncg_thermodynamics.F90:187-231) */
+double wo_air_energy_solution(double temperature, const double constituent_henrys_constant[2]) {
+  double henrys_derivative = 0.0;
+  for (int c = 0; c < 2; c++) {
+    double da[6];
+    for (int i = 0; i < 6; i++) da[i] = (double)(i + 1) * air_henry_data[c][i + 1];
+    double dhinv = 1.e5 * polynomial(da, 6, temperature / air_tscale);
+    double d = air_henry_p0[c] * dhinv / (constituent_henrys_constant[c] * air_tscale);
+    henrys_derivative += air_constituent_weight[c] * d;
+  }
+  double tk = temperature + WO_TC_K;
+  return -1.e3 * gas_constant * tk * tk * henrys_derivative / air_molecular_weight;
+}
+
+static double air_mass_to_mole_fraction(double xg) { /* ncg_thermodynamics.F90:171-183 */
+  double w = xg / air_molecular_weight;
+  return w / (w + (1.0 - xg) / water_molecular_weight);
+}
+static double air_mole_to_mass_fraction(double xmole) { /* :155-167 */
+  double w = xmole * air_molecular_weight;
+  return w / (w + (1.0 - xmole) * water_molecular_weight);
+}
+static double covis(double trd, double c, double ome, double rm, double f) {
+  return 266.93e-7 * sqrt(rm * trd * f) / (c * c * ome * trd);
+}
+
+/* ncg_air_mixture_viscosity (:256-312); phase 1-based */
+double wo_air_mixture_viscosity(double water_viscosity, double temperature, double xg, int phase) {
+  if (phase == 1) return water_viscosity;
+  double rm1 = air_molecular_weight, rm2 = water_molecular_weight;
+  double fmix = sqrt(air_fair * air_fwat), cmix = 0.5 * (air_cair + air_cwat);
+  double x1 = air_mass_to_mole_fraction(xg), x2 = 1.0 - x1;
+  double tk = temperature + WO_TC_K;
+  double trd1 = tk / air_fair, trd3 = tk / fmix;
+  double ome1 = (1.188 - 0.051 * trd1) / trd1;
+  double ome3 = (1.48 - 0.412 * log(trd3)) / trd3;
+  double ard = 1.095 / trd3;
+  double rm3 = 2.0 * rm1 * rm2 / (rm1 + rm2);
+  double vis1 = covis(trd1, air_cair, ome1, rm1, air_fair);
+  double vis2 = 10.0 * water_viscosity;
+  double vis3 = covis(trd3, cmix, ome3, rm3, fmix);
+  double z1 = x1 * x1 / vis1 + 2.0 * x2 * x1 / vis3 + x2 * x2 / vis2;
+  double g = x1 * x1 * rm1 / rm2;
+  double h = x2 * x2 * rm2 / rm1;
+  double e = (2.0 * x1 * x2 * rm1 * rm2 / (rm3 * rm3)) * vis3 / (vis1 * vis2);
+  double z2 = 0.6 * ard * (g / vis1 + e + h / vis2);
+  double z3 = 0.6 * ard * (g + e * (vis1 + vis2) - 2.0 * x1 * x2 + h);
+  return 0.1 * (1.0 + z3) / (z1 + z2);
+}
+
 /* eos.F90:214-236 */
 static int eos_phase_composition(wo_eos *e, double *fluid) {
   int region = nint_(fluid[F_REGION]);
@@ -264,8 +350,9 @@ int wo_eos_phase_properties(wo_eos *e, const double *primary, const double *rock
   double relperm[2], cap[2];
   wo_relperm_values(&e->prm.relperm, sl, relperm);
   if (e->prm.eos == WO_EOS_WCE) { /* eos_wge.F90:421-543 */
-    double gas_properties[2];
-    wo_co2_properties(fluid[F_PARTIAL + 1], fluid[F_T], gas_properties);
+    double gas_properties[2], constituent_henrys[2];
+    if (e->gas == 1) wo_air_properties(fluid[F_PARTIAL + 1], fluid[F_T], gas_properties);
+    else wo_co2_properties(fluid[F_PARTIAL + 1], fluid[F_T], gas_properties);
     for (int p = 0; p < e->nphase; p++) {
       double *ph = phase_ptr(fluid, nc, p);
       if (phases & (1 << p)) {
@@ -273,8 +360,13 @@ int wo_eos_phase_properties(wo_eos *e, const double *primary, const double *rock
         if (p == 0) {
           water_pressure = fluid[F_P];
           capillary_pressure = wo_cappress_value(&e->prm.cappress, sl, fluid[F_T]);
-          henrys_constant = wo_co2_henrys_constant(fluid[F_T]);
-          energy_solution = wo_co2_energy_solution(fluid[F_T], henrys_constant);
+          if (e->gas == 1) {
+            henrys_constant = wo_air_henrys_constant(fluid[F_T], constituent_henrys);
+            energy_solution = wo_air_energy_solution(fluid[F_T], constituent_henrys);
+          } else {
+            henrys_constant = wo_co2_henrys_constant(fluid[F_T]);
+            energy_solution = wo_co2_energy_solution(fluid[F_T], henrys_constant);
+          }
         } else {
           water_pressure = fluid[F_PARTIAL];
           capillary_pressure = 0.0;
@@ -290,14 +382,17 @@ int wo_eos_phase_properties(wo_eos *e, const double *primary, const double *rock
         /* mass_fraction: ncg_thermodynamics.F90:279-311 */
         double xg;
         if (p == 0) {
-          xg = co2_mole_to_mass_fraction(fluid[F_PARTIAL + 1] / henrys_constant);
+          double xmole = fluid[F_PARTIAL + 1] / henrys_constant;
+          xg = (e->gas == 1) ? air_mole_to_mass_fraction(xmole) : co2_mole_to_mass_fraction(xmole);
         } else {
           double total_density = gas_density + water_density;
           xg = (total_density < 1.e-30) ? 0.0 : gas_density / total_density;
         }
         double water_viscosity = wo_region_viscosity(e->thermo, p + 1, fluid[F_T], fluid[F_P], water_density);
-        /* mixture_viscosity: ncg_co2_thermodynamics.F90:267-292 */
-        if (p == 0) {
+        /* mixture_viscosity: ncg_co2_thermodynamics.F90:267-292 / ncg_air_thermodynamics.F90:256-312 */
+        if (e->gas == 1) {
+          ph[PH_MU] = wo_air_mixture_viscosity(water_viscosity, fluid[F_T], xg, p + 1);
+        } else if (p == 0) {
           ph[PH_MU] = water_viscosity;
         } else {
           double gas_viscosity;

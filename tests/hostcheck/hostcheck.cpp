@@ -285,7 +285,7 @@ extern "C" int hc_tracer_assemble(const wb_params *prm, int nt, int ncell, int n
     if (nt == 1) HC_TRACER(WB_EOS_WE, 1);
     if (nt == 2) HC_TRACER(WB_EOS_WE, 2);
     if (nt == 3) HC_TRACER(WB_EOS_WE, 3);
-  } else if (prm->eos == WB_EOS_WCE) {
+  } else if (prm->eos == WB_EOS_WCE || prm->eos == WB_EOS_WAE) {
     if (nt == 1) HC_TRACER(WB_EOS_WCE, 1);
     if (nt == 2) HC_TRACER(WB_EOS_WCE, 2);
   }

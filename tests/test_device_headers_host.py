@@ -273,14 +273,15 @@ def wce_cell(wo, thermo, rng, region):
     return np.array([pw[0] + pg, pw[1], pg])
 
 
+@pytest.mark.parametrize("gas", ["co2", "air"])
 @pytest.mark.parametrize("thermo", [0, 1])
-def test_wce_fluid_record_matches_oracle(wo, hc, thermo):
-    """a5: all 26 fields of the wce fluid record, device header vs oracle, bit for bit"""
+def test_wce_fluid_record_matches_oracle(wo, hc, thermo, gas):
+    """a5: all 26 fields of the eos_wge fluid record (CO2: eos_wce, air: eos_wae), device header vs oracle, bit for bit"""
     rng = np.random.default_rng(SEED + 13)
     rock = np.array([1e-13, 1e-13, 1e-14, 2.5, 1.5, 0.1, 2200.0, 1000.0])
     n_ok = 0
     for rp, cp in curve_cases(wo)[:4]:
-        prm = wo.make_params(eos=wo.EOS_WCE, thermo=thermo, relperm=rp, cappress=cp)
+        prm = wo.make_params(eos=wo.EOS_WCE if gas == "co2" else wo.EOS_WAE, thermo=thermo, relperm=rp, cappress=cp)
         eos = wo.lib().wo_eos_create(C.byref(prm))
         try:
             for region in (1, 2, 4):

@@ -11,7 +11,7 @@ SEED = 20240917
 def wb_params_from_oracle(wo, flow, prm):
     """wb_params with the same contents as the oracle's wo_params (independent struct definitions,
     identical field layout)."""
-    return flow.make_params(eos={wo.EOS_WE: flow.EOS_WE, wo.EOS_W: flow.EOS_W, wo.EOS_WCE: flow.EOS_WCE}[prm.eos],
+    return flow.make_params(eos={wo.EOS_WE: flow.EOS_WE, wo.EOS_W: flow.EOS_W, wo.EOS_WCE: flow.EOS_WCE, wo.EOS_WAE: flow.EOS_WAE}[prm.eos],
                             thermo=prm.thermo, relperm=prm.relperm, cappress=prm.cappress,
                             gravity=tuple(prm.gravity), extrapolate=prm.extrapolate,
                             eos_w_temperature=prm.eos_w_temperature,
@@ -172,7 +172,14 @@ def we_production_enthalpy(fl):
     return (mob[0] * fl[7 + 5] + mob[1] * fl[7 + 8 + 5]) / (mob[0] + mob[1])
 
 
-def run_input(problem, sim, opts=None):
+def wge_fields(fluid, n):
+    """P, T, vapour saturation, gas mass fraction in the vapour and in the liquid, gas partial pressure of the first n
+    cells from eos_wge (wce / wae) fluid records (26 doubles)"""
+    fl = np.asarray(fluid)[:n]
+    return np.stack([fl[:, 0], fl[:, 1], fl[:, 17 + 2], fl[:, 17 + 8], fl[:, 8 + 8], fl[:, 7]], 1)
+
+
+def run_input(problem, sim, opts=None, fields=None):
     """Runs an ingested input (waiwera_b200.ingest.Problem, eos_we) through `sim` (flow.FlowSimulation or OracleSim,
     mesh / boundaries / fluid_init already done) with the time stepping of its "time" value: a list of step sizes
     (the last one repeats), or one size with the "iteration" adaptor, maximum size / number, stop time; table sources
@@ -203,7 +210,10 @@ def run_input(problem, sim, opts=None):
         t += t1
         k += 1
         fl = sim.fluid()
-        hist.append((t, we_fields(fl, n), we_production_enthalpy(np.asarray(fl)[prod])))
+        if fields is None:
+            hist.append((t, we_fields(fl, n), we_production_enthalpy(np.asarray(fl)[prod])))
+        else:
+            hist.append((t, fields(fl, n), 0.0))
         dt = t1
         if adapt:
             if its < ad.get("minimum", 5):

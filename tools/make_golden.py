@@ -255,6 +255,29 @@ def deliverability():
     print("wrote", out)
 
 
+def wae_benchmarks():
+    """test/benchmark/ncg/{infiltration,heat_pipe} (eos wae: water, air, energy): AUTOUGH2 ELEMENT tables --
+    test_infiltration.py compares the liquid saturation profiles (1e-4), test_heat_pipe.py P, T, Sv and the air
+    mass fractions of the last output (5e-3); inputs copied unmodified to tests/golden/inputs/"""
+    import shutil
+    base = "/root/reference/test/benchmark/ncg"
+    inputs = os.path.join(os.path.dirname(OUT), "inputs")
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT tables of test/benchmark/ncg/{infiltration,heat_pipe}/run/"
+                            "*.listing (AUTOUGH2); boundary blocks dropped",
+           "columns": ["pressure", "temperature", "gas_saturation", "air_gas_mass_fraction", "air_liquid_mass_fraction",
+                       "air_partial_pressure"]}
+    for case, ncell in (("infiltration", 40), ("heat_pipe", 120)):
+        run = os.path.join(base, case, "run")
+        shutil.copyfile(os.path.join(run, "g%s.msh" % case), os.path.join(inputs, "g%s.msh" % case))
+        shutil.copyfile(os.path.join(run, case + ".json"), os.path.join(inputs, case + ".json"))
+        el = [(t, r) for k, t, r in listing_generic(os.path.join(run, case + ".listing")) if k == "E"]
+        doc[case] = {"times": [t for t, _ in el], "tables": [[x[:6] for x in r[:ncell]] for _, r in el]}
+    out = os.path.join(os.path.dirname(OUT), "wae_benchmarks.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -286,3 +309,4 @@ if __name__ == "__main__":
     minc_column()
     mis_problems()
     deliverability()
+    wae_benchmarks()

@@ -19,6 +19,7 @@ struct WbEosParams {
   WbThermo thermo;
   double scale[WB_MAX_NP][5];  // primary_scale(var, region 1..4), src/eos_we.F90:104-109
   int adaptive_pp;             // eos_wce: gas partial pressure scaled by the cell's total pressure
+  int gas;                     // eos_wge family: 0 CO2 (eos_wce), 1 air (eos_wae)
   double eos_w_temperature;
   wb_relperm relperm;
   wb_cappress cappress;
@@ -27,21 +28,25 @@ struct WbEosParams {
 inline int wb_eos_params_make(const wb_params &prm, WbEosParams &e) {
   e = WbEosParams();
   e.eos = prm.eos;
+  if (prm.eos == WB_EOS_WAE) {  // src/eos_wae.F90:27-64: eos_wge with the air NCG; same kernels as eos_wce
+    e.eos = WB_EOS_WCE;
+    e.gas = 1;
+  }
   e.thermo = wb_thermo_make(prm.thermo, prm.extrapolate);
   e.eos_w_temperature = prm.eos_w_temperature;
   e.relperm = prm.relperm;
   e.cappress = prm.cappress;
   const double ps = prm.pressure_scale > 0 ? prm.pressure_scale : 1.e6;  // src/eos_we.F90:75-76
   const double ts = prm.temperature_scale > 0 ? prm.temperature_scale : 1.e2;
-  if (prm.eos == WB_EOS_WE) {  // src/eos_we.F90:78-109
+  if (e.eos == WB_EOS_WE) {  // src/eos_we.F90:78-109
     e.np = 2; e.nc = 1; e.nphase = 2;
     e.scale[0][1] = ps; e.scale[1][1] = ts;
     e.scale[0][2] = ps; e.scale[1][2] = ts;
     e.scale[0][4] = ps; e.scale[1][4] = 1.0;
-  } else if (prm.eos == WB_EOS_W) {  // src/eos_w.F90:67-96
+  } else if (e.eos == WB_EOS_W) {  // src/eos_w.F90:67-96
     e.np = 1; e.nc = 1; e.nphase = 1;
     e.scale[0][1] = ps; e.scale[0][2] = ps;
-  } else if (prm.eos == WB_EOS_WCE) {  // src/eos_wge.F90:40-131, src/eos_wce.F90:23-53
+  } else if (e.eos == WB_EOS_WCE) {  // src/eos_wge.F90:40-131, src/eos_wce.F90:23-53
     e.np = 3; e.nc = 2; e.nphase = 2;
     double pps = prm.partial_pressure_scale;
     e.adaptive_pp = !(pps > 0.0);
@@ -280,6 +285,76 @@ WB_HD double wb_co2_mole_to_mass_fraction(double xmole) {
   return w / (w + (1.0 - xmole) * WB_WATER_MW);
 }
 
+// ---------------------------------------------------------------- air (non-condensible gas of eos_wae)
+// src/ncg_air_thermodynamics.F90
+
+#define WB_AIR_MW 28.96  // :14
+
+// ncg_air_properties (:97-121): ideal gas (deviation factor 1), enthalpy relative to the triple point of water
+WB_HD void wb_air_properties(double partial_pressure, double temperature, double &density, double &enthalpy) {
+  const double a[4] = {1.20740, 9.24502, 0.115984, -5.63568e-4};
+  const double tk = temperature + 273.15;
+  const double enthalpy_shift = wb_polynomial<4>(a, (0.01 + 273.15) / 100.0);  // ncg_air_init :84-86
+  density = partial_pressure * WB_AIR_MW / (1.e3 * WB_GAS_CONSTANT * 1.0 * tk);
+  enthalpy = 1.e4 * (wb_polynomial<4>(a, tk / 100.0) - enthalpy_shift);
+}
+
+// Henry's constant of the two constituents (N2, O2) and their weighted sum (:125-143); energy of solution from the
+// temperature derivatives (:176-198, ncg_thermodynamics.F90:187-231)
+WB_HD void wb_air_henry(double temperature, double &henrys_constant, double &energy_solution) {
+  const double w[2] = {0.79, 0.21}, p0[2] = {1.01325e5, 1.e5};
+  const double a[2][7] = {{0.513726, 1.58603, -5.9378e-1, -6.98282e-1, 5.10330e-1, -1.21388e-1, 1.00041e-2},
+                          {0.26234, 0.610628, 7.00732e-1, -0.139299e1, 7.13850e-1, -1.54216e-1, 1.23190e-2}};
+  double hc = 0.0, henrys_derivative = 0.0;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const double chc = 1.e5 * p0[c] * wb_polynomial<7>(a[c], temperature / 100.0);
+    hc += w[c] * chc;
+    double da[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) da[i] = (double)(i + 1) * a[c][i + 1];
+    const double dhinv = 1.e5 * wb_polynomial<6>(da, temperature / 100.0);
+    const double d = p0[c] * dhinv / (chc * 100.0);
+    henrys_derivative += w[c] * d;
+  }
+  henrys_constant = hc;
+  const double tk = temperature + 273.15;
+  energy_solution = -1.e3 * WB_GAS_CONSTANT * tk * tk * henrys_derivative / WB_AIR_MW;
+}
+
+WB_HD double wb_air_mole_to_mass_fraction(double xmole) {  // ncg_thermodynamics.F90:155-167
+  const double w = xmole * WB_AIR_MW;
+  return w / (w + (1.0 - xmole) * WB_WATER_MW);
+}
+
+WB_HD double wb_air_covis(double trd, double c, double ome, double rm, double f) {
+  return 266.93e-7 * sqrt(rm * trd * f) / (c * c * ome * trd);
+}
+// ncg_air_mixture_viscosity (:256-312) for the vapour phase
+WB_HD double wb_air_vapour_viscosity(double water_viscosity, double temperature, double xg) {
+  const double fair = 97.0, fwat = 363.0, cair = 3.617, cwat = 2.655;
+  const double rm1 = WB_AIR_MW, rm2 = WB_WATER_MW;
+  const double fmix = sqrt(fair * fwat), cmix = 0.5 * (cair + cwat);
+  const double wm = xg / WB_AIR_MW;  // mass_to_mole_fraction, ncg_thermodynamics.F90:171-183
+  const double x1 = wm / (wm + (1.0 - xg) / WB_WATER_MW), x2 = 1.0 - x1;
+  const double tk = temperature + 273.15;
+  const double trd1 = tk / fair, trd3 = tk / fmix;
+  const double ome1 = (1.188 - 0.051 * trd1) / trd1;
+  const double ome3 = (1.48 - 0.412 * log(trd3)) / trd3;
+  const double ard = 1.095 / trd3;
+  const double rm3 = 2.0 * rm1 * rm2 / (rm1 + rm2);
+  const double vis1 = wb_air_covis(trd1, cair, ome1, rm1, fair);
+  const double vis2 = 10.0 * water_viscosity;
+  const double vis3 = wb_air_covis(trd3, cmix, ome3, rm3, fmix);
+  const double z1 = x1 * x1 / vis1 + 2.0 * x2 * x1 / vis3 + x2 * x2 / vis2;
+  const double g = x1 * x1 * rm1 / rm2;
+  const double h = x2 * x2 * rm2 / rm1;
+  const double ee = (2.0 * x1 * x2 * rm1 * rm2 / (rm3 * rm3)) * vis3 / (vis1 * vis2);
+  const double z2 = 0.6 * ard * (g / vis1 + ee + h / vis2);
+  const double z3 = 0.6 * ard * (g + ee * (vis1 + vis2) - 2.0 * x1 * x2 + h);
+  return 0.1 * (1.0 + z3) / (z1 + z2);
+}
+
 // bulk_properties + phase_saturations + phase_properties for one cell:
 // eos_we: src/eos_we.F90:327-390, 394-458; eos_w: src/eos_w.F90.
 // `fl.region` must be set on entry.  Returns the reference's err (0 / 1).
@@ -333,7 +408,9 @@ WB_HD int wb_eos_properties(const WbEosParams &e, const double *primary,
     double kr[2];
     wb_relperm_values(e.relperm, sl, kr[0], kr[1]);
     double gas_density_free, gas_enthalpy;
-    wb_co2_properties(pg, fl.T, gas_density_free, gas_enthalpy);
+    const bool air = e.gas == 1;
+    if (air) wb_air_properties(pg, fl.T, gas_density_free, gas_enthalpy);
+    else wb_co2_properties(pg, fl.T, gas_density_free, gas_enthalpy);
 #pragma unroll
     for (int p = 0; p < NPH; p++) {
       if (phases & (1 << p)) {
@@ -341,8 +418,12 @@ WB_HD int wb_eos_properties(const WbEosParams &e, const double *primary,
         if (p == 0) {
           water_pressure = fl.P;
           capillary_pressure = wb_cappress_value(e.cappress, sl, fl.T);
-          henrys_constant = wb_co2_henrys_constant(fl.T);
-          energy_solution = wb_co2_energy_solution(fl.T, henrys_constant);
+          if (air) {
+            wb_air_henry(fl.T, henrys_constant, energy_solution);
+          } else {
+            henrys_constant = wb_co2_henrys_constant(fl.T);
+            energy_solution = wb_co2_energy_solution(fl.T, henrys_constant);
+          }
         } else {
           water_pressure = fl.pp[0];
           capillary_pressure = 0.0;
@@ -355,14 +436,16 @@ WB_HD int wb_eos_properties(const WbEosParams &e, const double *primary,
         // mass_fraction: ncg_thermodynamics.F90:279-311
         double xg;
         if (p == 0) {
-          xg = wb_co2_mole_to_mass_fraction(pg / henrys_constant);
+          xg = air ? wb_air_mole_to_mass_fraction(pg / henrys_constant) : wb_co2_mole_to_mass_fraction(pg / henrys_constant);
         } else {
           const double total_density = gas_density + water_density;
           xg = (total_density < 1.e-30) ? 0.0 : gas_density / total_density;
         }
         const double water_viscosity = wb_region_viscosity(th, p + 1, fl.T, fl.P, water_density);
         if (p == 0) {
-          fl.ph[p].mu = water_viscosity;  // mixture_viscosity: ncg_co2_thermodynamics.F90:267-292
+          fl.ph[p].mu = water_viscosity;  // mixture_viscosity: ncg_co2_thermodynamics.F90:267-292, ncg_air :256-312
+        } else if (air) {
+          fl.ph[p].mu = wb_air_vapour_viscosity(water_viscosity, fl.T, xg);
         } else {
           double gas_viscosity;
           if (wb_co2_viscosity(pg, fl.T, gas_viscosity)) return 1;

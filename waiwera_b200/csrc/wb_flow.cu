@@ -604,8 +604,8 @@ __global__ void k_unpack_yr(const double *__restrict__ in, int c0, int n, int np
 
 #define DISPATCH_EOS(ctx, CALL)                                  \
   do {                                                           \
-    if ((ctx)->prm.eos == WB_EOS_WE) { CALL(WB_EOS_WE); }        \
-    else if ((ctx)->prm.eos == WB_EOS_WCE) { CALL(WB_EOS_WCE); } \
+    if ((ctx)->eos.eos == WB_EOS_WE) { CALL(WB_EOS_WE); }        \
+    else if ((ctx)->eos.eos == WB_EOS_WCE) { CALL(WB_EOS_WCE); } \
     else { CALL(WB_EOS_W); }                                     \
   } while (0)
 

@@ -99,9 +99,9 @@ extern "C" int wb_set_tracer_injection(wb_ctx *c, const double *rate) {
 #define DISPATCH_EOS_NT(ctx, CALL)                                               \
   do {                                                                           \
     const int nt_ = (ctx)->nt;                                                   \
-    if ((ctx)->prm.eos == WB_EOS_WE) {                                           \
+    if ((ctx)->eos.eos == WB_EOS_WE) {                                           \
       if (nt_ == 1) { CALL(WB_EOS_WE, 1); } else if (nt_ == 2) { CALL(WB_EOS_WE, 2); } else { CALL(WB_EOS_WE, 3); }    \
-    } else if ((ctx)->prm.eos == WB_EOS_WCE) {                                   \
+    } else if ((ctx)->eos.eos == WB_EOS_WCE) {                                   \
       if (nt_ == 1) { CALL(WB_EOS_WCE, 1); } else if (nt_ == 2) { CALL(WB_EOS_WCE, 2); } else { CALL(WB_EOS_WCE, 3); } \
     } else {                                                                     \
       if (nt_ == 1) { CALL(WB_EOS_W, 1); } else if (nt_ == 2) { CALL(WB_EOS_W, 2); } else { CALL(WB_EOS_W, 3); }       \

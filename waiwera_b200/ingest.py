@@ -288,7 +288,7 @@ def rock_records(spec, m, zones=None):
     return rock
 
 
-_EOS = {"we": ("EOS_WE", 2), "w": ("EOS_W", 1), "wce": ("EOS_WCE", 3)}
+_EOS = {"we": ("EOS_WE", 2), "w": ("EOS_W", 1), "wce": ("EOS_WCE", 3), "wae": ("EOS_WAE", 3)}
 
 
 def make_params(mod, doc, gravity):
@@ -304,12 +304,12 @@ def make_params(mod, doc, gravity):
     kw = {k: v for k, v in rp.items() if k != "type"}
     if rp.get("type", "linear") == "linear":
         kw = {"liquid": tuple(rp.get("liquid", (0.0, 1.0))), "vapour": tuple(rp.get("vapour", (0.0, 1.0)))}
-    relperm = mod.make_relperm(rp.get("type", "linear").replace(" ", "_"), **kw)
+    relperm = mod.make_relperm(rp.get("type", "linear").lower().replace(" ", "_"), **kw)
     cp = rock.get("capillary_pressure") or {"type": "zero"}
     ckw = {k: v for k, v in cp.items() if k != "type"}
     if "saturation_limits" in ckw:
         ckw["saturation_limits"] = tuple(ckw["saturation_limits"])
-    cappress = mod.make_cappress(cp.get("type", "zero").replace(" ", "_"), **ckw)
+    cappress = mod.make_cappress(cp.get("type", "zero").lower().replace(" ", "_"), **ckw)
     kwargs = dict(eos=getattr(mod, _EOS[name][0]), thermo=mod.THERMO_IFC67 if thermo.lower() == "ifc67" else mod.THERMO_IAPWS,
                   relperm=relperm, cappress=cappress, gravity=tuple(gravity))
     if name == "w" and not isinstance(eos, str) and "temperature" in eos:
