@@ -736,45 +736,27 @@ def test_interpolation_table(wo):
 
 
 def test_rate_table_averaging():
-    """waiwera_b200.ingest.rates_at: the reference's default endpoint averaging of linear and step tables
-    (interpolation_test.F90:223-296)"""
+    """waiwera_b200.ingest.rates_at: endpoint and integral averaging of linear and step tables
+    (interpolation_test.F90:223-373)"""
     from waiwera_b200 import ingest
 
     class P:
         pass
     tab = np.stack([DATA5_X, DATA5_Y], 1)
-    for interp, cases in (("linear", [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.0238095238095237), ((0.1, 2.0), 1.5),
-                                      ((0.1, 3.0), 1.1019345238095237), ((3.1, 7.0), 0.11586538461538454),
-                                      ((8.0, 12.0), -0.27307692307692316), ((1.0, 1.0), 1.4761904761904763)]),
-                          ("step", [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.0), ((0.1, 2.0), 1.0), ((0.1, 3.0), 1.5),
-                                    ((3.1, 7.0), 0.45), ((8.0, 12.0), -0.6), ((1.0, 1.0), 1.0)])):
+    cases = {
+        ("linear", "endpoint"): [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.0238095238095237), ((0.1, 2.0), 1.5),
+                                 ((0.1, 3.0), 1.1019345238095237), ((3.1, 7.0), 0.11586538461538454),
+                                 ((8.0, 12.0), -0.27307692307692316), ((1.0, 1.0), 1.4761904761904763)],
+        ("step", "endpoint"): [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.0), ((0.1, 2.0), 1.0), ((0.1, 3.0), 1.5),
+                               ((3.1, 7.0), 0.45), ((8.0, 12.0), -0.6), ((1.0, 1.0), 1.0)],
+        ("linear", "integrate"): [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.003968253968254), ((0.1, 2.0), 1.5),
+                                  ((0.1, 3.0), 1.5406660509031198), ((3.1, 7.0), -0.2530818540433925),
+                                  ((8.0, 12.0), -0.1389423076923077), ((9.0, 12.0), -0.1), ((1.0, 1.0), 1.4761904761904763)],
+        ("step", "integrate"): [((-0.5, -0.1), 1.0), ((-0.5, 0.1), 1.0), ((0.1, 2.0), 1.0), ((0.1, 3.0), 3.8 / 2.9),
+                                ((3.1, 7.0), 1.73 / 3.9), ((8.0, 12.0), -0.325), ((1.0, 1.0), 1.0)]}
+    for (interp, averaging), rows in cases.items():
         p = P()
         p.source_rates = np.zeros(1)
-        p.source_tables = {0: (tab, interp)}
-        for (t0, t1), expect in cases:
-            assert abs(ingest.rates_at(p, t0, t1)[0] - expect) <= 1e-9, (interp, t0, t1)
-
-
-# ---- test/unit/src/ncg_air_thermodynamics_test.F90 (air NCG of eos_wae) ----
-def test_air_thermodynamics(wo):
-    L = wo.lib()
-    props = np.zeros(2)
-    for t, h in [(20., 19766.68740112), (100., 99758.4176379), (240., 243111.52506676), (300., 305841.67918959),
-                 (350., 358701.73310281)]:                                           # :62-94 enthalpy at 1 bar
-        L.wo_air_properties(1.e5, t, wo.dp(props))
-        assert abs(props[1] - h) <= 1e-7 * abs(h), (t, props[1])
-    assert abs(props[0] - 1.e5 * 28.96 / (1.e3 * 8.3144598 * 623.15)) < 1e-12     # ideal gas density
-    chc = np.zeros(2)
-    for t, hc in [(20., 7.26786761e+09), (100., 1.12393541e+10), (240., 3.95721621e+09), (300., 1.90169063e+09),
-                  (350., 6.10714550e+08)]:                                           # :117-184 Henry's constant
-        got = L.wo_air_henrys_constant(t, wo.dp(chc))
-        assert abs(got - hc) <= 1e-7 * hc, (t, got)
-    for t, hs in [(20., -.40693012e6), (100., 53825.89), (240., 850547.65), (300., 1378067.69), (350., 4498309.62)]:
-        L.wo_air_henrys_constant(t, wo.dp(chc))                                      # :207-311 energy of solution
-        got = L.wo_air_energy_solution(t, wo.dp(chc))
-        assert abs(got - hs) <= 1e-7 * abs(hs), (t, got)
-    for t, xg, muw, mu in [(240., 0.1, 0.171595480e-4, 1.81800535828e-05), (120., 0.5, 0.128139659e-4, 0.178797007e-4),
-                           (20., 0.8, 8.73278989112e-6, 1.67537163543e-5)]:          # :337-359 vapour mixture viscosity
-        got = L.wo_air_mixture_viscosity(muw, t, xg, 2)
-        assert abs(got - mu) <= 1e-5 * mu, (t, got)
-    assert L.wo_air_mixture_viscosity(1.0e-4, 50.0, 0.3, 1) == 1.0e-4               # liquid: water viscosity
+        p.source_tables = {0: (tab, interp, averaging)}
+        for (t0, t1), expect in rows:
+            assert abs(ingest.rates_at(p, t0, t1)[0] - expect) <= 1e-9, (interp, averaging, t0, t1)

@@ -278,6 +278,30 @@ def wae_benchmarks():
     print("wrote", out)
 
 
+def tracer_doublet():
+    """test/benchmark/tracer/doublet: AUTOUGH2 listing of the injection / production doublet with a tracer pulse
+    (100-cell row, producer on deliverability with a total-flow limiter, tracer diffusion) -- test_doublet.py compares
+    the tracer mass fraction at every output (1e-3, absolute 1e-6) and the tracer production rate history (1e-3);
+    also the steady state the Waiwera output file doublet_ss.h5 holds (P, T), the run's initial condition"""
+    base = "/root/reference/test/benchmark/tracer/doublet/run"
+    tabs = listing_generic(os.path.join(base, "doublet.listing"))
+    el = [(t, r) for k, t, r in tabs if k == "E"]
+    ge = [(t, r) for k, t, r in tabs if k == "G"]
+    h5 = os.path.join(base, "doublet_ss.h5")
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/tracer/doublet/run/"
+                            "doublet.listing (AUTOUGH2); doublet_ss.h5 by byte scan",
+           "times": [t for t, _ in el], "pressure": [[x[0] for x in r[:100]] for _, r in el],
+           "tracer": [[x[4] for x in r[:100]] for _, r in el],
+           "source_times": [t for t, _ in ge], "production_rate": [r[1][0] for _, r in ge],
+           "tracer_production": [r[1][2] for _, r in ge],
+           "steady_pressure": [float(v) for v in runs(h5, 1e5, 1e8, 100)[0][:100]],
+           "steady_temperature": [float(v) for v in runs(h5, 10, 400, 100)[1][:100]]}
+    out = os.path.join(os.path.dirname(OUT), "tracer_doublet.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -310,3 +334,4 @@ if __name__ == "__main__":
     mis_problems()
     deliverability()
     wae_benchmarks()
+    tracer_doublet()

@@ -363,21 +363,46 @@ def load(path, mod=None, mesh_path=None):
     src = doc.get("source") or []
     for s in src:
         unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer",
-                                "interpolation", "averaging"}
+                                "interpolation", "averaging", "deliverability", "direction", "limiter"}
         assert not unsupported, "source controls are not built: %s" % sorted(unsupported)
+        dl, lm = s.get("deliverability"), s.get("limiter")
+        assert dl is None or all(np.ndim(dl.get(k, 0.0)) == 0 for k in ("pressure", "productivity")), \
+            "table-valued deliverability parameters are not built"
+        assert lm is None or lm.get("type", "total") == "total", "only the total-flow limiter is built"
     # a rank-2 "rate" is a table source control (src/source_control.F90: table of (time, rate)); kept as a table
     # that rates_at() evaluates over each time step, "step" or "linear" interpolation, "endpoint" averaging
     p.source_tables = {}
     kept = []
     for s in src:
         if isinstance(s.get("rate"), list):
-            assert s.get("averaging", "endpoint") == "endpoint", "only endpoint averaging of rate tables is built"
-            p.source_tables[len(kept)] = (np.array(s["rate"], float), s.get("interpolation", "linear"))
+            p.source_tables[len(kept)] = (np.array(s["rate"], float), s.get("interpolation", "linear"),
+                                          s.get("averaging", "integrate"))
             s = dict(s, rate=0.0)
             kept.append(s)
-        elif s.get("rate", 0.0) != 0.0:
+        elif s.get("rate", 0.0) != 0.0 or "deliverability" in s:
             kept.append(s)
     src = kept
+    # source controls (see wb_set_source_controls): deliverability (productivity None: to be calculated from the
+    # initial rate, src/source_control.F90:407-468), direction, total-flow limiter
+    p.source_controls = []
+    for k, s in enumerate(src):
+        if "deliverability" in s or "limiter" in s or "direction" in s:
+            dl = s.get("deliverability") or {}
+            p.source_controls.append(dict(
+                source=k, deliverability="deliverability" in s, productivity=dl.get("productivity"),
+                reference_pressure=dl.get("pressure", 1.0e5),
+                direction={"both": 0, "production": 1, "injection": 2}[s.get("direction", "both")],
+                limit=(s.get("limiter") or {}).get("limit", 0.0)))
+        if "deliverability" in s and "rate" not in s:
+            s["rate"] = -1.0          # placeholder: producing, the control sets the rate
+    # tracer injection rates: numbers or (time, rate) tables per source
+    p.source_tracer_tables = {}
+    for k, s in enumerate(src):
+        tr_ = s.get("tracer")
+        if isinstance(tr_, list) and tr_ and isinstance(tr_[0], list):
+            p.source_tracer_tables[k] = (np.array(tr_, float), s.get("interpolation", "linear"), s.get("averaging", "integrate"))
+            s["tracer"] = 0.0
+
     p.source_cells = np.array([s["cell"] for s in src], np.int32)
     p.source_rates = np.array([s["rate"] for s in src], float)
     # get_components (src/source_setup.F90:2052-2083; doc/user/setup_sources.rst): injection uses "component"
@@ -405,16 +430,42 @@ def load(path, mod=None, mesh_path=None):
     return p
 
 
-def rates_at(p, t0, t1):
-    """source rates for the time step [t0, t1]: fixed rates, and table sources averaged over the step with the
-    reference's default "endpoint" averaging -- the mean of the interpolated values at both ends of the interval
-    (src/interpolation.F90:585-602)"""
-    r = p.source_rates.copy()
+def _table_value(tab, interp, t):
+    """table%interpolate: linear, or step (right-continuous at the data points); constant beyond both ends"""
+    if interp == "step":
+        return tab[max(np.searchsorted(tab[:, 0], t, side="right") - 1, 0), 1]
+    return np.interp(t, tab[:, 0], tab[:, 1])
 
-    def value(tab, interp, t):
+
+def _table_average(tab, interp, t0, t1, averaging="integrate"):
+    """table%average over [t0, t1] (src/interpolation.F90:565-680): "integrate" (the default of the JSON input,
+    default_averaging_str) integrates the interpolant exactly over the interval, "endpoint" is the mean of the
+    values at both ends"""
+    if averaging == "endpoint":
+        return 0.5 * (_table_value(tab, interp, t0) + _table_value(tab, interp, t1))
+    if t1 - t0 < 1.e-15:
+        return _table_value(tab, interp, t0)
+    xs = np.concatenate([[t0], tab[(tab[:, 0] > t0) & (tab[:, 0] < t1), 0], [t1]])
+    total = 0.0
+    for a, b in zip(xs[:-1], xs[1:]):
         if interp == "step":
-            return tab[max(np.searchsorted(tab[:, 0], t, side="right") - 1, 0), 1]
-        return np.interp(t, tab[:, 0], tab[:, 1])
-    for k, (tab, interp) in p.source_tables.items():
-        r[k] = 0.5 * (value(tab, interp, t0) + value(tab, interp, t1))
+            total += _table_value(tab, interp, a) * (b - a)
+        else:
+            total += 0.5 * (_table_value(tab, interp, a) + _table_value(tab, interp, b)) * (b - a)
+    return total / (t1 - t0)
+
+
+def tracer_rates_at(p, t0, t1):
+    """tracer injection rates [nsources, ntracers] for the time step [t0, t1] (a table applies to every tracer)"""
+    r = p.source_tracer.copy()
+    for k, (tab, interp, averaging) in p.source_tracer_tables.items():
+        r[k, :] = _table_average(tab, interp, t0, t1, averaging)
+    return r
+
+
+def rates_at(p, t0, t1):
+    """source rates for the time step [t0, t1]: fixed rates, and table sources averaged over the step"""
+    r = p.source_rates.copy()
+    for k, (tab, interp, averaging) in p.source_tables.items():
+        r[k] = _table_average(tab, interp, t0, t1, averaging)
     return r
