@@ -302,6 +302,25 @@ def tracer_doublet():
     print("wrote", out)
 
 
+def minc_doublet():
+    """test/benchmark/minc/doublet_1d: AUTOUGH2 final states of the 10-cell injection / production doublet, single
+    porosity and MINC with one matrix level at fracture spacings 50 / 100 / 200 m -- test_minc_1d.py compares P, T, Sv
+    of the last output at 2e-3"""
+    base = "/root/reference/test/benchmark/minc/doublet_1d/run"
+    doc = {"_generated_by": "tools/make_golden.py: last ELEMENT table of test/benchmark/minc/doublet_1d/run/"
+                            "minc_1d_{single,50,100,200}.listing (AUTOUGH2): 10 fracture blocks, then 10 matrix blocks",
+           "columns": ["pressure", "temperature", "vapour_saturation"]}
+    for case in ("single", "50", "100", "200"):
+        el = [(t, r) for k, t, r in listing_generic(os.path.join(base, "minc_1d_%s.listing" % case)) if k == "E"]
+        src = json.load(open(os.path.join(base, "minc_1d_%s.json" % case)))
+        doc[case] = {"time": el[-1][0], "element": [x[:3] for x in el[-1][1]], "stop": src["time"]["stop"],
+                     "step": src["time"]["step"]}
+    out = os.path.join(os.path.dirname(OUT), "minc_doublet.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -335,3 +354,4 @@ if __name__ == "__main__":
     deliverability()
     wae_benchmarks()
     tracer_doublet()
+    minc_doublet()
