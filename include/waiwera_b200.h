@@ -343,7 +343,7 @@ int wb_tracer_solve(wb_ctx *ctx, const wb_ksp_opts *ksp, int pc_type, int pc_nbl
 /* ---- instrumentation (PetscLogEvent equivalents, src/profiling.F90:42-65) -- */
 /* accumulated device time (ms) and call count of a named phase:
    "fluid_props", "cell_balances", "cell_inflows", "jacobian", "pc_setup", "ksp_solve", "mat_mult",
-   "pc_apply", "fluid_trans" */
+   "pc_apply", "fluid_trans", "tracer_setup", "tracer_solve" */
 int wb_timer_get(wb_ctx *ctx, const char *name, double *ms, int64_t *count);
 int wb_timer_reset(wb_ctx *ctx);
 /* phase timers synchronise the stream at every phase end; switch them off for throughput runs */
