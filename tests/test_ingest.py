@@ -1,5 +1,6 @@
 """SURVEY.md section 8 row f-2 (mesh / input ingest): waiwera_b200.ingest reads the reference's own benchmark inputs
-(JSON + binary gmsh meshes, copied unmodified as small fixtures under tests/golden/inputs/) into the array contract.
+(JSON + gmsh meshes; tools/make_golden.py::convert_input keeps the keys this path reads and rewrites the binary
+meshes as ASCII MSH 2.2 with the same numbering, under tests/golden/inputs/) into the array contract.
 Checked against the hand-built meshes the benchmark tests use (same volumes, areas, distances, gravity normals,
 boundary ghosts, rock records, sources) and end to end: the CO2 column benchmark run FROM THE INPUT FILE through the
 oracle reproduces the AUTOUGH2 listing."""
@@ -59,9 +60,30 @@ def test_gmsh_ascii_hexahedra_match_structured_mesh(tmp_path):
     assert len(exterior) == 2 * (nx * ny + ny * nz + nx * nz)
 
 
+def test_gmsh_binary_reader(tmp_path):
+    """MSH 2.2 binary (the format of the reference's mesh files): the ASCII fixture of the MIS problem 5 mesh written
+    back as binary parses to the same nodes and elements"""
+    import struct
+    nodes, elems = ingest.read_gmsh(os.path.join(INP, "gproblem5.ascii.msh"))
+    blob = b"$MeshFormat\n2.2 1 8\n" + struct.pack("<i", 1) + b"\n$EndMeshFormat\n$Nodes\n%d\n" % len(nodes)
+    for i, x in enumerate(nodes):
+        blob += struct.pack("<i3d", i + 1, *x)
+    blob += b"\n$EndNodes\n$Elements\n%d\n" % len(elems)
+    etype = elems[0][0]
+    assert all(t == etype for t, _ in elems)
+    blob += struct.pack("<3i", etype, len(elems), 2)
+    for i, (t, ns) in enumerate(elems):
+        blob += struct.pack("<%di" % (3 + len(ns)), i + 1, 0, 0, *[n + 1 for n in ns])
+    blob += b"\n$EndElements\n"
+    path = tmp_path / "mesh.msh"
+    path.write_bytes(blob)
+    nodes2, elems2 = ingest.read_gmsh(str(path))
+    assert np.array_equal(nodes, nodes2) and elems == elems2
+
+
 def test_tracer_oned_input():
     import test_tracer_oned as T
-    p = ingest.load(os.path.join(INP, "oned_single_phase.json"))
+    p = ingest.load(os.path.join(INP, "oned_single_phase.input.json"))
     ref, y, region = T.problem("single")
     same_geometry(p.mesh, ref)
     assert np.array_equal(p.mesh.rock, ref.rock)
@@ -74,7 +96,7 @@ def test_tracer_oned_input():
 
 def test_mis_problem1_radial_input():
     import test_config1_radial as T
-    p = ingest.load(os.path.join(INP, "problem1.json"))
+    p = ingest.load(os.path.join(INP, "problem1.input.json"))
     ref, y, region = T.problem()
     same_geometry(p.mesh, ref)
     assert np.allclose(p.mesh.rock[:, [0, 3, 4, 5, 6, 7]], ref.rock[:, [0, 3, 4, 5, 6, 7]])
@@ -88,7 +110,7 @@ def test_co2_column_from_input_file(wo):
     """geometry against the hand-built column, then the whole benchmark from the ingested problem"""
     import test_co2_column as T
     from util import OracleSim, run_adaptive
-    p = ingest.load(os.path.join(INP, "co2_column_1.json"), mod=wo)
+    p = ingest.load(os.path.join(INP, "co2_column_1.input.json"), mod=wo)
     ref, y, region, src = T.problem("1")
     same_geometry(p.mesh, ref, skip_direction=True)              # vertical axis is y in the 2-D mesh file: direction 2
     assert set(p.mesh.face_geom[:, 11]) == {2.0}
@@ -140,7 +162,7 @@ def test_co2_column_from_input_file_on_gpu():
     import test_co2_column as T
     from util import run_adaptive
     from waiwera_b200 import flow
-    p = ingest.load(os.path.join(INP, "co2_column_1.json"), mod=flow)
+    p = ingest.load(os.path.join(INP, "co2_column_1.input.json"), mod=flow)
     m = p.mesh
     sim = flow.FlowSimulation(p.params, m)
     assert sim.set_boundaries(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region) == 0

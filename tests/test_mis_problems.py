@@ -1,7 +1,8 @@
 """Geothermal Model Intercomparison Study problems 2 (radial flow to a well: a single-phase, b two-phase, c flashing
 front), 4 (1-D vertical two-phase column with drainage, 40 years) and 5 (2-D areal production, a without and b with
 later re-injection through a rate table) -- test/benchmark/model_intercomparison_study/problem{2,4,5} -- run FROM THE
-REFERENCE'S OWN INPUT FILES (JSON + gmsh, unmodified copies under tests/golden/inputs/, read by waiwera_b200.ingest)
+REFERENCE'S OWN INPUT FILES (JSON + gmsh; fixtures under tests/golden/inputs/ made by tools/make_golden.py::convert_input,
+read by waiwera_b200.ingest)
 through the oracle's Newton / time-stepping path, against the AUTOUGH2 listings shipped with them
 (tests/golden/mis_problems.json: P, T, Sv of every cell at 12 output times, full histories of the production cell
 and three more, production enthalpy history).  The reference accepts 2e-3 (problem 4), 1e-3..1e-2 (problems 2, 5) on
@@ -45,7 +46,7 @@ def newton_opts(mod, p):
 
 
 def run_oracle(wo, case):
-    p = ingest.load(os.path.join(INP, case + ".json"), mod=wo)
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=wo)
     m = p.mesh
     f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
                 m.cell_geom.reshape(-1), m.rock.reshape(-1))
@@ -109,7 +110,7 @@ def test_oracle_runs_reference_input_to_the_autough2_answer(wo, case):
 def test_cuda_path_runs_reference_input(wo, case):
     from waiwera_b200 import flow
     p_ref, hist_ref, y_ref = run_oracle(wo, case)
-    p = ingest.load(os.path.join(INP, case + ".json"), mod=flow)
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=flow)
     m = p.mesh
     sim = flow.FlowSimulation(p.params, m)
     if len(p.boundary_region):

@@ -103,7 +103,7 @@ def run_transient(p, sim, y, opts=None, ksp=None):
 
 
 def make_oracle(wo, name, y=None, region=None):
-    p = ingest.load(os.path.join(INP, name + ".json"), mod=wo)
+    p = ingest.load(os.path.join(INP, name + ".input.json"), mod=wo)
     m = p.mesh
     f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
                 m.cell_geom.reshape(-1), m.rock.reshape(-1))
@@ -169,7 +169,7 @@ def test_cuda_path_reproduces_tracer_doublet(wo):
     p_ref, f, osim, y_ref = make_oracle(wo, "doublet", y0, region)
     hist_ref = run_transient(p_ref, osim, y_ref)
     osim.destroy()
-    p = ingest.load(os.path.join(INP, "doublet.json"), mod=flow)
+    p = ingest.load(os.path.join(INP, "doublet.input.json"), mod=flow)
     sim = flow.FlowSimulation(p.params, p.mesh)
     setup_sources(p, sim)
     assert sim.fluid_init(y0, region) == 0

@@ -35,7 +35,7 @@ def newton_opts(mod, p):
 
 
 def run_oracle(wo, case):
-    p = ingest.load(os.path.join(INP, case + ".json"), mod=wo)
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=wo)
     m = p.mesh
     f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
                 m.cell_geom.reshape(-1), m.rock.reshape(-1))
@@ -100,7 +100,7 @@ def test_oracle_runs_wae_input_to_the_autough2_answer(wo, case):
 def test_cuda_path_runs_wae_input(wo, case):
     from waiwera_b200 import flow
     p_ref, hist_ref, y_ref, regions_ref = run_oracle(wo, case)
-    p = ingest.load(os.path.join(INP, case + ".json"), mod=flow)
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=flow)
     m = p.mesh
     sim = flow.FlowSimulation(p.params, m)
     assert sim.set_boundaries(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region) == 0

@@ -192,7 +192,7 @@ def minc_column():
 def mis_problems():
     """test/benchmark/model_intercomparison_study problems 2a-c, 4, 5a-b: AUTOUGH2 listings.  Kept: P, T, Sv of all
     cells at ~12 evenly spaced output times, the full history of a few cells (production cell first) and the
-    production enthalpy history; inputs (JSON + gmsh) copied unmodified to tests/golden/inputs/ for the ingest"""
+    production enthalpy history (the input decks: input_fixtures)"""
     import shutil
     base = "/root/reference/test/benchmark/model_intercomparison_study"
     inputs = os.path.join(os.path.dirname(OUT), "inputs")
@@ -203,11 +203,7 @@ def mis_problems():
     for prob, cases in (("problem2", ["problem2a", "problem2b", "problem2c"]), ("problem4", ["problem4"]),
                         ("problem5", ["problem5a", "problem5b"])):
         run = os.path.join(base, prob, "run")
-        for fn in os.listdir(run):
-            if fn.endswith(".msh"):
-                shutil.copyfile(os.path.join(run, fn), os.path.join(inputs, fn))
         for case in cases:
-            shutil.copyfile(os.path.join(run, case + ".json"), os.path.join(inputs, case + ".json"))
             inp = json.load(open(os.path.join(run, case + ".json")))
             tabs = listing_generic(os.path.join(run, case + ".listing"))
             el = [(t, r) for k, t, r in tabs if k == "E"]
@@ -258,7 +254,7 @@ def deliverability():
 def wae_benchmarks():
     """test/benchmark/ncg/{infiltration,heat_pipe} (eos wae: water, air, energy): AUTOUGH2 ELEMENT tables --
     test_infiltration.py compares the liquid saturation profiles (1e-4), test_heat_pipe.py P, T, Sv and the air
-    mass fractions of the last output (5e-3); inputs copied unmodified to tests/golden/inputs/"""
+    mass fractions of the last output (5e-3) (the input decks: input_fixtures)"""
     import shutil
     base = "/root/reference/test/benchmark/ncg"
     inputs = os.path.join(os.path.dirname(OUT), "inputs")
@@ -268,8 +264,6 @@ def wae_benchmarks():
                        "air_partial_pressure"]}
     for case, ncell in (("infiltration", 40), ("heat_pipe", 120)):
         run = os.path.join(base, case, "run")
-        shutil.copyfile(os.path.join(run, "g%s.msh" % case), os.path.join(inputs, "g%s.msh" % case))
-        shutil.copyfile(os.path.join(run, case + ".json"), os.path.join(inputs, case + ".json"))
         el = [(t, r) for k, t, r in listing_generic(os.path.join(run, case + ".listing")) if k == "E"]
         doc[case] = {"times": [t for t, _ in el], "tables": [[x[:6] for x in r[:ncell]] for _, r in el]}
     out = os.path.join(os.path.dirname(OUT), "wae_benchmarks.json")
@@ -321,6 +315,58 @@ def minc_doublet():
     print("wrote", out)
 
 
+INPUT_KEYS = ("boundaries", "eos", "gravity", "initial", "mesh", "rock", "source", "thermodynamics", "time", "tracer")
+
+
+def convert_input(src_json, dst_dir, name=None):
+    """Fixture of one reference input deck for the ingest tests: the keys of the JSON input the Newton-step path
+    reads (title / output / logfile dropped), re-serialised compactly as <name>.input.json, and its gmsh mesh
+    (binary MSH 2.2 in the reference tree) rewritten as ASCII MSH 2.2 <mesh>.ascii.msh with the same node and element
+    numbering (coordinates printed with 17 significant digits: the doubles round-trip exactly)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from waiwera_b200 import ingest
+    name = name or os.path.splitext(os.path.basename(src_json))[0]
+    doc = json.load(open(src_json))
+    out = {k: doc[k] for k in INPUT_KEYS if k in doc}
+    mesh = out["mesh"] if isinstance(out["mesh"], dict) else {"filename": out["mesh"]}
+    src_mesh = os.path.join(os.path.dirname(src_json), mesh["filename"])
+    mesh_name = os.path.splitext(os.path.basename(src_mesh))[0] + ".ascii.msh"
+    nodes, elems = ingest.read_gmsh(src_mesh)
+    lines = ["$MeshFormat", "2.2 0 8", "$EndMeshFormat", "$Nodes", str(len(nodes))]
+    lines += ["%d %.17g %.17g %.17g" % (i + 1, x[0], x[1], x[2]) for i, x in enumerate(nodes)]
+    lines += ["$EndNodes", "$Elements", str(len(elems))]
+    lines += ["%d %d 2 0 0 %s" % (i + 1, t, " ".join(str(n + 1) for n in ns)) for i, (t, ns) in enumerate(elems)]
+    lines += ["$EndElements", ""]
+    with open(os.path.join(dst_dir, mesh_name), "w") as f:
+        f.write("\n".join(lines))
+    out["mesh"] = dict(mesh, filename=mesh_name)
+    if isinstance(out.get("initial"), dict) and "filename" in out["initial"]:
+        out["initial"] = {"filename": out["initial"]["filename"]}      # HDF5 restart: the tests pass the arrays
+    with open(os.path.join(dst_dir, name + ".input.json"), "w") as f:
+        json.dump(out, f, sort_keys=True, separators=(",", ":"))
+    return name
+
+
+def input_fixtures():
+    """tests/golden/inputs/: the reference's benchmark decks the ingest tests read (see convert_input)"""
+    base = "/root/reference/test/benchmark"
+    dst = os.path.join(os.path.dirname(OUT), "inputs")
+    os.makedirs(dst, exist_ok=True)
+    for rel in ("tracer/oned/run/oned_single_phase.json", "ncg/co2_column/run/co2_column_1.json",
+                "model_intercomparison_study/problem1/run/problem1.json",
+                "model_intercomparison_study/problem2/run/problem2a.json",
+                "model_intercomparison_study/problem2/run/problem2b.json",
+                "model_intercomparison_study/problem2/run/problem2c.json",
+                "model_intercomparison_study/problem4/run/problem4.json",
+                "model_intercomparison_study/problem5/run/problem5a.json",
+                "model_intercomparison_study/problem5/run/problem5b.json",
+                "ncg/infiltration/run/infiltration.json", "ncg/heat_pipe/run/heat_pipe.json",
+                "tracer/doublet/run/doublet.json", "tracer/doublet/run/doublet_ss.json"):
+        convert_input(os.path.join(base, rel), dst)
+    print("wrote", dst)
+
+
 def main():
     lhs = runs(os.path.join(REF, "lhs", "lhs.h5"), 1.0, 1e4, 12)[0][:12]
     primary = runs(os.path.join(REF, "init", "primary.h5"), 1e-3, 1e3, 12)[0][:12]
@@ -355,3 +401,4 @@ if __name__ == "__main__":
     wae_benchmarks()
     tracer_doublet()
     minc_doublet()
+    input_fixtures()
