@@ -760,3 +760,67 @@ def test_rate_table_averaging():
         p.source_tables = {0: (tab, interp, averaging)}
         for (t0, t1), expect in rows:
             assert abs(ingest.rates_at(p, t0, t1)[0] - expect) <= 1e-9, (interp, averaging, t0, t1)
+
+
+def test_source_update_flow(wo):
+    """test/unit/src/source_test.F90:53-194: source%update_flow for injection of either mass component or heat and
+    for production of all components / one component / heat, from the two-phase two-component fluid record of the
+    test; checked through cell_inflows on a unit-volume cell (inflow = flow / volume)"""
+    from waiwera_b200 import mesh as wmesh
+    rec = np.array([2.7e5, 130., 4., 4., 3., 1., 0., 0.,
+                    935., 1.e-6, 0.8, 0.7, 0., 83.9e3, 5.461e5, 0.7, 0.3,
+                    1.5, 2.e-7, 0.2, 0.3, 0., 800.e3, 2.540e6, 0.4, 0.6])
+    m = wmesh.structured(2, 1, 1, dx=1.0, gravity=(0.0, 0.0, 0.0), heterogeneous=False)
+    f = wo.Flow(wo.make_params(eos=wo.EOS_WCE, gravity=(0.0, 0.0, 0.0)), m.ncell, m.ninterior, m.nowned,
+                m.face_cells.reshape(-1), m.face_geom.reshape(-1), m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    cases = [("inject 1", 10., 200.e3, 1, [10., 0., 2.e6]),
+             ("inject 2", 5., 200.e3, 2, [0., 5., 1.e6]),
+             ("inject heat", 1000., 0., 3, [0., 0., 1000.]),
+             ("produce all", -5., 0., 0, [-3.4948610582, -1.5051389418, -431766.653977922]),
+             ("produce 1", -5., 0., 1, [-5., 0., -431766.653977922]),
+             ("produce heat", -5000., 0., 3, [0., 0., -5000.]),
+             ("no flow 1", 0., 100.e3, 1, [0., 0., 0.])]
+    for tag, rate, enthalpy, component, flow in cases:
+        f.set_sources([0], [component], [rate], [enthalpy])
+        f.current_fluid()[:] = rec
+        rhs = np.zeros(6)
+        assert wo.lib().wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+        assert np.allclose(rhs[:3], flow, rtol=1e-9, atol=1e-12), (tag, rhs[:3])
+
+
+def test_source_control_deliverability(wo):
+    """test/unit/src/source_control_test.F90:226-610 (test_source_controls_pressure_reference.json), the controls this
+    build has: source 1 (deliverability, production only) -12.8728519749 kg/s, source 2 (the same behind a 10 kg/s
+    total limiter) -10, source 4 (productivity index calculated from an initial rate of -11) -11, source 6
+    (deliverability, injection only: no flow) 0 -- in a two-phase cell at 50 bar, Sv = 0.8, kr = saturations"""
+    from waiwera_b200 import mesh as wmesh
+    L = wo.lib()
+    th = L.wo_thermo_create(wo.THERMO_IAPWS, 0)
+    P, sv = 50.e5, 0.8
+    T = C.c_double()
+    assert L.wo_saturation_temperature(th, P, C.byref(T)) == 0
+    rec = np.zeros(26)
+    rec[0], rec[1], rec[2], rec[3], rec[5] = P, T.value, 4.0, 4.0, 1.0
+    rec[4] = L.wo_phase_composition(th, 4, P, T.value)
+    for p, (sat, X) in enumerate([(1.0 - sv, [0.75, 0.25]), (sv, [0.9, 0.1])]):
+        props = np.zeros(2)
+        assert L.wo_region_properties(th, p + 1, wo.dp(np.array([P, T.value])), wo.dp(props)) == 0
+        ph = rec[8 + 9 * p: 8 + 9 * (p + 1)]
+        ph[0], ph[6] = props
+        ph[1] = L.wo_region_viscosity(th, p + 1, T.value, P, props[0])
+        ph[2] = ph[3] = sat
+        ph[5] = props[1] + P / props[0]
+        ph[7:9] = X
+    L.wo_thermo_destroy(th)
+    m = wmesh.structured(2, 1, 1, dx=1.0, gravity=(0.0, 0.0, 0.0), heterogeneous=False)
+    f = wo.Flow(wo.make_params(eos=wo.EOS_WCE, gravity=(0.0, 0.0, 0.0)), m.ncell, m.ninterior, m.nowned,
+                m.face_cells.reshape(-1), m.face_geom.reshape(-1), m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    f.set_sources([0, 0, 0, 0], [0, 0, 0, 0], [-1.0, -1.0, -11.0, -1.0], [0.0] * 4)
+    f.current_fluid()[:] = rec
+    mob = sum(rec[8 + 9 * p + 3] * rec[8 + 9 * p] / rec[8 + 9 * p + 1] for p in range(2))
+    pi4 = 11.0 / (mob * (P - 2.0e5) * 1.0)                       # calculate_PI_from_rate :407-468
+    f.set_source_controls([0, 1, 2, 3], [1e-12, 1e-12, pi4, 1e-12], [2.0e5] * 4, [1, 0, 0, 2], [0.0, 10.0, 0.0, 0.0])
+    rhs = np.zeros(6)
+    assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+    rates = f.source_rates(4)
+    assert np.allclose(rates, [-12.8728519749, -10.0, -11.0, 0.0], rtol=1e-9, atol=1e-12), rates
