@@ -178,3 +178,27 @@ def test_co2_column_from_input_file_on_gpu():
     assert t >= p.time["stop"] * (1 - 1e-12)
     T.check_steady_state("1", T.fields(sim.fluid()))
     sim.destroy()
+
+
+def test_reference_mesh_geometry_kats():
+    """test/unit/src/mesh_test.F90:257-470 on the reference's mesh/2D.msh (the same file as the MIS problem 5 mesh,
+    12 x 8 cells of 25 m): 2-D Cartesian geometry with thickness 100 m -- every cell volume 62 500 m3, every face area
+    2 500 m2 -- and radial geometry (Pappus): cell volume pi (r2^2 - r1^2) dy, face area 2 pi r l"""
+    nodes, elems = ingest.read_gmsh(os.path.join(INP, "gproblem5.ascii.msh"))
+    m, ext = ingest.build_mesh(nodes, elems, thickness=100.0)
+    assert m.ncell == 96
+    assert np.abs(m.cell_geom[:, 3] - 62500.0).max() <= 1e-6
+    assert np.abs(m.face_geom[:, 0] - 2500.0).max() <= 1e-6 and all(abs(e[2] - 2500.0) <= 1e-6 for e in ext)
+    mr, extr = ingest.build_mesh(nodes, elems, radial=True)
+    dr, dy = 300.0 / 12, 200.0 / 8
+    r = mr.cell_geom[:, 0]
+    assert np.abs(mr.cell_geom[:, 3] - np.pi * ((r + 0.5 * dr) ** 2 - (r - 0.5 * dr) ** 2) * dy).max() <= 1e-6
+    for k in range(mr.nface):
+        g = mr.face_geom[k]
+        length = dr if abs(g[5]) > 1e-6 else dy            # face with a vertical normal spans dr, else dy
+        assert abs(g[0] - 2.0 * np.pi * g[8] * length) <= 1e-6
+    # sanity of every face (mesh_geometry_sanity_check): positive distances that add up, unit normals
+    for mm in (m, mr):
+        g = mm.face_geom
+        assert (g[:, 1] > 0).all() and (g[:, 2] > 0).all() and np.allclose(g[:, 1] + g[:, 2], g[:, 3])
+        assert np.allclose(np.linalg.norm(g[:, 4:7], axis=1), 1.0)
