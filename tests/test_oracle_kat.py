@@ -824,3 +824,38 @@ def test_source_control_deliverability(wo):
     assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
     rates = f.source_rates(4)
     assert np.allclose(rates, [-12.8728519749, -10.0, -11.0, 0.0], rtol=1e-9, atol=1e-12), rates
+
+
+def test_eos_scaling(wo):
+    """test/unit/src/eos_test.F90:94-200: eos%scale / eos%unscale of every EOS of this build with default, user and
+    adaptive (partial pressure / pressure) scales"""
+    L = wo.lib()
+    cases = [
+        (wo.EOS_W, {}, [([3.e5], 1, [0.3]), ([4.e5], 2, [0.4])]),
+        (wo.EOS_W, dict(pressure_scale=1.e5), [([3.e5], 1, [3.0])]),
+        (wo.EOS_WE, {}, [([1.e5, 20.], 1, [0.1, 0.2]), ([0.9e5, 100.], 2, [0.09, 1.]), ([13.e5, 0.4], 4, [1.3, 0.4])]),
+        (wo.EOS_WE, dict(pressure_scale=1.e7, temperature_scale=200.),
+         [([1.e5, 20.], 1, [0.01, 0.1]), ([0.9e5, 100.], 2, [0.009, 0.5]), ([13.e5, 0.4], 4, [0.13, 0.4])]),
+        (wo.EOS_WCE, {}, [([15.e5, 40., 3.e5], 1, [1.5, 0.4, 0.2]), ([0.8e5, 110., 0.6e5], 2, [0.08, 1.1, 0.75]),
+                          ([20.e5, 0.4, 10.e5], 4, [2.0, 0.4, 0.5]), ([100.e5, 0.5, 50.e5], 4, [10., 0.5, 0.5])]),
+        (wo.EOS_WCE, dict(pressure_scale=1.e7, temperature_scale=200., partial_pressure_scale=1.e5),
+         [([15.e5, 40., 2.e5], 1, [0.15, 0.2, 2.]), ([0.7e5, 110., 0.6e5], 2, [0.007, 0.55, 0.6]),
+          ([13.e5, 0.4, 10.e5], 4, [0.13, 0.4, 10.0])]),
+        (wo.EOS_WAE, dict(pressure_scale=1.e7, temperature_scale=200., partial_pressure_scale=1.e5),
+         [([15.e5, 40., 2.e5], 1, [0.15, 0.2, 2.]), ([0.7e5, 110., 0.6e5], 2, [0.007, 0.55, 0.6]),
+          ([13.e5, 0.4, 10.e5], 4, [0.13, 0.4, 10.0])])]
+    for eos_id, scales, rows in cases:
+        prm = wo.make_params(eos=eos_id)
+        for k, v in scales.items():
+            setattr(prm, k, v)
+        eos = L.wo_eos_create(C.byref(prm))
+        try:
+            for primary, region, expect in rows:
+                pr = np.array(primary)
+                y, back = np.zeros(len(pr)), np.zeros(len(pr))
+                L.wo_eos_scale(eos, wo.dp(pr), region, wo.dp(y))
+                assert np.allclose(y, expect, rtol=1e-12), (eos_id, scales, primary, y)
+                L.wo_eos_unscale(eos, wo.dp(y), region, wo.dp(back))
+                assert np.allclose(back, pr, rtol=1e-12)
+        finally:
+            L.wo_eos_destroy(eos)

@@ -314,7 +314,18 @@ def make_params(mod, doc, gravity):
                   relperm=relperm, cappress=cappress, gravity=tuple(gravity))
     if name == "w" and not isinstance(eos, str) and "temperature" in eos:
         kwargs["eos_w_temperature"] = eos["temperature"]
-    return mod.make_params(**kwargs), _EOS[name][1]
+    prm = mod.make_params(**kwargs)
+    # eos.primary.scale (src/eos_we.F90:75-109, src/eos_wge.F90:96-110): pressure, temperature, partial_pressure
+    # (a number, or "pressure" for the adaptive Pg / P scaling, the default)
+    scale = ({} if isinstance(eos, str) else eos.get("primary", {}).get("scale", {})) or {}
+    if "pressure" in scale:
+        prm.pressure_scale = float(scale["pressure"])
+    if "temperature" in scale:
+        prm.temperature_scale = float(scale["temperature"])
+    pp = scale.get("partial_pressure", scale.get("air_partial_pressure", scale.get("CO2_partial_pressure")))
+    if pp is not None:
+        prm.partial_pressure_scale = 0.0 if isinstance(pp, str) else float(pp)
+    return prm, _EOS[name][1]
 
 
 class Problem:
