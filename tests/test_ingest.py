@@ -202,3 +202,25 @@ def test_reference_mesh_geometry_kats():
         g = mm.face_geom
         assert (g[:, 1] > 0).all() and (g[:, 2] > 0).all() and np.allclose(g[:, 1] + g[:, 2], g[:, 3])
         assert np.allclose(np.linalg.norm(g[:, 4:7], axis=1), 1.0)
+
+
+def test_hybrid_3d_mesh():
+    """the reference's 3-D hybrid mesh (6 prisms + 4 hexahedra, test/unit/data/mesh/hybrid10.msh, used by its
+    flow_simulation and initial-condition unit tests): the cells fill the 0.75 x 1 x 0.25 box, every cell is closed
+    (outward area vectors sum to zero) and the face distances are consistent"""
+    nodes, elems = ingest.read_gmsh(os.path.join(INP, "hybrid10.ascii.msh"))
+    m, ext = ingest.build_mesh(nodes, elems)
+    assert (m.dim, m.ncell, m.nface, len(ext)) == (3, 10, 12, 30)
+    assert abs(m.cell_geom[:, 3].sum() - 0.75 * 1.0 * 0.25) < 1e-14
+    acc = np.zeros((m.ncell, 3))
+    for k, (c1, c2) in enumerate(m.face_cells):
+        a = m.face_geom[k, 0] * m.face_geom[k, 4:7]
+        acc[c1] += a
+        acc[c2] -= a
+    for c, cen, area, nrm, d in ext:
+        acc[c] += area * nrm
+        assert d > 0
+    assert np.abs(acc).max() < 1e-15
+    g = m.face_geom
+    assert (g[:, 1] > 0).all() and (g[:, 2] > 0).all() and np.allclose(g[:, 1] + g[:, 2], g[:, 3], atol=1e-15)
+    assert m.gravity.tolist() == [0.0, 0.0, -9.8] and set(g[:, 11]) <= {1.0, 2.0, 3.0}

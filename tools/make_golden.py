@@ -364,6 +364,17 @@ def input_fixtures():
                 "ncg/infiltration/run/infiltration.json", "ncg/heat_pipe/run/heat_pipe.json",
                 "tracer/doublet/run/doublet.json", "tracer/doublet/run/doublet_ss.json"):
         convert_input(os.path.join(base, rel), dst)
+    # mesh only: the reference's 3-D hybrid mesh (hexahedra + prisms) of its flow_simulation / initial unit tests
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from waiwera_b200 import ingest
+    nodes, elems = ingest.read_gmsh("/root/reference/test/unit/data/mesh/hybrid10.msh")
+    lines = ["$MeshFormat", "2.2 0 8", "$EndMeshFormat", "$Nodes", str(len(nodes))]
+    lines += ["%d %.17g %.17g %.17g" % (i + 1, x[0], x[1], x[2]) for i, x in enumerate(nodes)]
+    lines += ["$EndNodes", "$Elements", str(len(elems))]
+    lines += ["%d %d 2 0 0 %s" % (i + 1, t, " ".join(str(n + 1) for n in ns)) for i, (t, ns) in enumerate(elems)]
+    with open(os.path.join(dst, "hybrid10.ascii.msh"), "w") as f:
+        f.write("\n".join(lines + ["$EndElements", ""]))
     print("wrote", dst)
 
 
