@@ -229,13 +229,13 @@ def mis_problems():
 def deliverability():
     """test/benchmark/source/deliverability: AUTOUGH2 listings of the 10-cell production problems on deliverability
     (delv: fixed productivity index; delt: with a total-flow limiter; delg_flow: productivity index from the initial
-    rate) -- test_deliverability.py compares P, T, Sv of the last output (5e-3), their history in the production cell
+    rate; delg_pi_table: productivity index from a table in time) -- test_deliverability.py compares P, T, Sv of the last output (5e-3), their history in the production cell
     and the generation rate / enthalpy history (1e-2)"""
     base = "/root/reference/test/benchmark/source/deliverability/run"
     doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/source/deliverability/"
-                            "run/deliv_{delv,delt,delg_flow}.listing (AUTOUGH2); boundary block dropped",
+                            "run/deliv_{delv,delt,delg_flow,delg_pi_table}.listing (AUTOUGH2); boundary block dropped",
            "columns": ["pressure", "temperature", "vapour_saturation"]}
-    for case in ("delv", "delt", "delg_flow"):
+    for case in ("delv", "delt", "delg_flow", "delg_pi_table"):
         tabs = listing_generic(os.path.join(base, "deliv_%s.listing" % case))
         el = [(t, r) for k, t, r in tabs if k == "E"]
         ge = [(t, r) for k, t, r in tabs if k == "G"]
