@@ -3,30 +3,43 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+  python bench.py --config 4 | --config 5 ...              # the other measured configurations of BASELINE.json
 
-A step is ONE Newton iteration of a backward-Euler time step on the 100x100x100 (1 M cell) eos_we /
-IAPWS mesh of BASELINE.json configs[1]: residual evaluation, FD Jacobian assembly (BAIJ bs=2,
-6.94 M blocks), PC set-up (block-Jacobi / ILU(0)), GMRES(30) solve to rtol 1e-5, update, phase
-transitions and the convergence norm -- exactly what SNES newtonls does per iteration with the
-callbacks timestepper.F90 registers.  Every step restarts from the same initial state, so all steps do
-identical work.  Prints one JSON line (rank 0).
+A step is ONE Newton iteration of a backward-Euler time step: residual evaluation, FD Jacobian assembly (BAIJ),
+PC set-up (block-Jacobi / ILU(0)), Krylov solve to rtol 1e-5, update, phase transitions, the residual at the new
+iterate and the convergence norm -- what SNES newtonls does per iteration with the callbacks timestepper.F90
+registers.  Every step restarts from the same initial state, so all steps do identical work.
+
+  --config 2 (default, the headline): 100x100x100 (1 M cells) eos_we / IAPWS, BAIJ bs = 2, 6.94 M blocks; N > 1 splits
+             the same mesh over N GPUs (strong scaling, BASELINE configs[1] and [2])
+  --config 4: 100x100x50 (500 k cells) eos_wce with a band of cells straddling the saturation line, bs = 3,
+             3.46 M blocks, 1 GPU (configs[3])
+  --config 5: MINC dual porosity, eos_wce, 250 k cells (125 k fracture + 125 k matrix) PER GPU: 2 M cells on 8 GPUs
+             (weak scaling, configs[4]); rows of 2 and 8 blocks
+
+Prints one JSON line (rank 0).
 """
-import argparse
-import ctypes as C
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (oracle, OpenMP) must use all host cores, and the
+# OpenMP runtime reads the variable when it is first loaded -- so set it before anything imports numpy / torch.
+_NCORES = os.cpu_count() or 1
+if "--impl" in sys.argv and "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ["OMP_NUM_THREADS"] = str(_NCORES)
+
+import argparse  # noqa: E402
+import ctypes as C  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DT = 1.0e6
-DIMS = (100, 100, 100)
 METRIC = "newton_steps_per_sec"
 UNIT = "Newton steps/s"
 
@@ -37,14 +50,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dims", type=int, nargs=3, default=list(DIMS))
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5])
+    ap.add_argument("--dims", type=int, nargs=3, default=None, help="override the mesh dimensions of the configuration")
+    ap.add_argument("--dt", type=float, default=None)
     ap.add_argument("--pc", default="ilu0", choices=["ilu0", "pbjacobi", "none"])
     ap.add_argument("--pc-blocks", type=int, default=1, help="block-Jacobi sub-domains per GPU (contiguous row ranges)")
     ap.add_argument("--pc-cube", type=int, default=10,
                     help="block-Jacobi sub-domains = cubes of this many cells per side (0: use --pc-blocks)")
     ap.add_argument("--ksp", default="gmres", choices=["gmres", "bcgs"])
+    ap.add_argument("--restart", type=int, default=30, help="GMRES restart (timestepper.F90:1776-1778)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-sample-its", type=int, default=30)
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget for the timed steps")
     ap.add_argument("--spmv-launches", type=int, default=50)
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: keep NCCL for the per-iteration exchanges (halo, dots, norm)")
     ap.add_argument("--ksp-maxit", type=int, default=10000,
@@ -52,18 +70,68 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(dims):
-    return "eos_we IAPWS %dx%dx%d structured (%d cells), BAIJ bs=2, BE dt=1e6 s, Krylov+bjacobi/ILU(0) rtol 1e-5" % (
-        dims[0], dims[1], dims[2], dims[0] * dims[1] * dims[2])
+# ------------------------------------------------------------------ problems
 
+class Problem:
+    """global mesh + scaled initial state of one configuration (setup-time numpy; nothing here touches oracle/)"""
 
-def build_problem(dims):
-    """synthetic config 2: hydrostatic single-phase liquid + noise, heterogeneous rock, closed box"""
-    from waiwera_b200 import mesh as wmesh
-    m = wmesh.structured(*dims, dx=10.0, seed=wmesh.SEED)
-    primary, region = wmesh.hydrostatic_state(m, seed=wmesh.SEED)
-    y = np.ascontiguousarray(wmesh.scale_primaries(primary, region)).reshape(-1)
-    return m, y, region
+    def __init__(self, cfg, world, dims=None, dt=None):
+        from waiwera_b200 import flow, mesh as wmesh
+        self.cfg, self.world = cfg, world
+        if cfg == 2:
+            self.dims = tuple(dims or (100, 100, 100))
+            self.eos, self.eos_name, self.npv = flow.EOS_WE, "eos_we", 2
+            self.dt = dt or 1.0e6
+            self.mesh = wmesh.structured(*self.dims, dx=10.0, seed=wmesh.SEED)
+            primary, self.region = wmesh.hydrostatic_state(self.mesh, seed=wmesh.SEED)
+            self.scaling = "strong"
+            self.parts = wmesh.default_parts(world)
+            self.owner = wmesh.box_owner(self.mesh, self.parts) if world > 1 else None
+            self.minc = False
+        elif cfg == 4:
+            self.dims = tuple(dims or (100, 100, 50))
+            self.eos, self.eos_name, self.npv = flow.EOS_WCE, "eos_wce", 3
+            self.dt = dt or 1.0e5
+            self.mesh = wmesh.structured(*self.dims, dx=10.0, seed=wmesh.SEED)
+            nz = self.dims[2]
+            primary, self.region = wmesh.wce_band_state(self.mesh, seed=wmesh.SEED, band=(2 * nz // 5, 3 * nz // 5))
+            self.scaling = "strong"
+            self.parts = wmesh.default_parts(world)
+            self.owner = wmesh.box_owner(self.mesh, self.parts) if world > 1 else None
+            self.minc = False
+        else:
+            # weak scaling: one 50^3 box of fracture cells (+ one MINC level) per GPU
+            self.parts = wmesh.default_parts(world)
+            per = dims or (50, 50, 50)
+            self.dims = tuple(per[k] * self.parts[k] for k in range(3))
+            self.eos, self.eos_name, self.npv = flow.EOS_WCE, "eos_wce", 3
+            self.dt = dt or 1.0e5
+            base = wmesh.structured(*self.dims, dx=10.0, seed=wmesh.SEED)
+            n = base.ninterior
+            self.mesh = wmesh.add_minc(base, volumes=(0.1, 0.9), spacing=(50.0, 50.0, 50.0), matrix_permeability_factor=0.01)
+            pf, rf = wmesh.wce_state(base, seed=wmesh.SEED)
+            rng = np.random.default_rng(wmesh.SEED + 9)
+            pm = pf.copy()
+            pm[:, 0] *= 1.0 + 1e-3 * rng.uniform(-1, 1, n)   # matrix slightly out of equilibrium with the fractures
+            primary, self.region = np.concatenate([pf, pm]), np.concatenate([rf, rf])
+            self.scaling = "weak"
+            self.owner = wmesh.minc_owner(self.mesh, self.parts) if world > 1 else None
+            self.minc = True
+        self.y = np.ascontiguousarray(wmesh.scale_primaries(primary, self.region)).reshape(-1)
+        self.region = np.ascontiguousarray(self.region, np.int32)
+
+    def blocks(self, m, cube):
+        from waiwera_b200 import mesh as wmesh
+        return wmesh.minc_cube_blocks(m, cube) if self.minc else wmesh.cube_blocks(m, cube)
+
+    def name(self, args):
+        d = self.dims
+        ncell = self.mesh.ninterior
+        what = {2: "%s IAPWS %dx%dx%d structured (%d cells)" % (self.eos_name, d[0], d[1], d[2], ncell),
+                4: "%s IAPWS %dx%dx%d structured (%d cells), band of cells on the saturation line" % (self.eos_name, d[0], d[1], d[2], ncell),
+                5: "%s IAPWS MINC dual porosity, %dx%dx%d fracture cells + 1 matrix level (%d cells)" % (self.eos_name, d[0], d[1], d[2], ncell)}[self.cfg]
+        return "config %d: %s, BAIJ bs=%d, BE dt=%g s, %s%s + bjacobi/ILU(0) rtol 1e-5" % (
+            self.cfg, what, self.npv, self.dt, args.ksp.upper(), "(%d)" % args.restart if args.ksp == "gmres" else "")
 
 
 # ------------------------------------------------------------------ clocks sampler
@@ -108,96 +176,145 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------ CPU arm (oracle = port of the reference algorithm)
 
-def cpu_newton_sample(dims, pc_blocks, sample_its, total_its_hint=None, pc_cube=0, ksp="gmres"):
-    """Times the reference algorithm (oracle port: FD-coloured Jacobian, ILU(0), GMRES(30)) on the host cores.
-    cpu_baseline leg (sample_its small): a bounded sample of the same workload -- the full mesh, one residual, one
-    FD Jacobian, one PC set-up and `sample_its` Krylov iterations; the Newton-step time is that with the Krylov
-    part extrapolated linearly to the iteration count `total_its_hint` of the full solve.
-    --impl reference leg (sample_its = the solver's own limit, no hint): the whole Newton step, Krylov solve run to
-    its rtol on the CPU, nothing extrapolated."""
-    from oracle import wo
-    wo.build()
-    L = wo.lib()
-    ncores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(ncores))
-    m, y, region = build_problem(dims)
-    prm = wo.make_params(eos=wo.EOS_WE, thermo=wo.THERMO_IAPWS)
-    f = wo.Flow(prm, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
-                m.cell_geom.reshape(-1), m.rock.reshape(-1))
-    assert f.fluid_init(y, region) == 0
-    t0 = time.perf_counter()
-    e, L0 = f.lhs(y)
-    e, lhs, rhs, F0 = f.residual(y, L0, DT)
-    t_res = time.perf_counter() - t0
-    A = f.bsr()
-    nb = A.contents.nb
-    color = np.zeros(nb, np.int32)
-    nc = L.wo_bsr_coloring(A, wo.ip(color))
-    t0 = time.perf_counter()
-    assert L.wo_fd_jacobian(f.h, wo.dp(y), wo.dp(L0), DT, wo.dp(F0), wo.ip(color), nc, 1e-8, 1e-2, A) == 0
-    t_jac = time.perf_counter() - t0
-    nblk = max(pc_blocks, 1)
-    bor = None if nblk == 1 else ((np.arange(nb, dtype=np.int64) * nblk) // nb).astype(np.int32)
-    if pc_cube > 0:
-        from waiwera_b200 import mesh as wmesh
-        bor = wmesh.cube_blocks(m, pc_cube)
-    t0 = time.perf_counter()
-    pc = L.wo_pc_create(A, wo.PC_BJACOBI_ILU0, wo.ip(bor))
-    t_pc = time.perf_counter() - t0
-    o = wo.KspOpts()
-    o.type, o.restart, o.maxit = (wo.KSP_GMRES if ksp == "gmres" else wo.KSP_BCGS), 30, sample_its
-    o.rtol, o.atol, o.dtol = 1e-5, 1e-50, 1e5
-    x = np.zeros(nb * 2)
-    its, rn = C.c_int(), C.c_double()
-    t0 = time.perf_counter()
-    L.wo_ksp_solve(A, pc, C.byref(o), wo.dp(F0), wo.dp(x), C.byref(its), C.byref(rn))
-    t_ksp = time.perf_counter() - t0
-    # SpMV rate of the CPU path
-    xx, yy = np.ones(nb * 2), np.zeros(nb * 2)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        L.wo_bsr_spmv(A, wo.dp(xx), wo.dp(yy))
-    t_spmv = (time.perf_counter() - t0) / 5
-    nnzb = A.contents.nnzb
-    spmv_bytes = nnzb * (4 * 8 + 4) + (nb + 1) * 4 + 2 * nb * 2 * 8
-    L.wo_pc_destroy(pc)
-    L.wo_bsr_destroy(A)
-    per_it = t_ksp / max(its.value, 1)
-    total_its = total_its_hint if total_its_hint else its.value
-    t_step = t_res + t_jac + t_pc + per_it * total_its
-    how = ("Krylov part extrapolated to %d iterations" % total_its) if total_its != its.value else \
-        "whole Krylov solve run on the CPU (nothing extrapolated)"
-    return {"value": 1.0 / t_step, "unit": UNIT, "cores": ncores, "kind": "port",
+class CpuArm:
+    """The reference algorithm (oracle port: OpenMP owner-computes residual, FD-coloured Jacobian, block-Jacobi
+    ILU(0), GMRES / BiCGStab) on all host cores, set up once; `step` times one whole Newton step."""
+
+    def __init__(self, prob, args):
+        from oracle import wo
+        wo.build()
+        self.wo, self.L = wo, wo.lib()
+        self.cores = self.L.wo_set_num_threads(_NCORES)
+        self.prob, self.args = prob, args
+        m = prob.mesh
+        eos = {2: wo.EOS_WE, 4: wo.EOS_WCE, 5: wo.EOS_WCE}[prob.cfg]
+        prm = wo.make_params(eos=eos, thermo=wo.THERMO_IAPWS)
+        self.f = wo.Flow(prm, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                         m.cell_geom.reshape(-1), m.rock.reshape(-1))
+        assert self.f.fluid_init(prob.y, prob.region) == 0
+        e, self.L0 = self.f.lhs(prob.y)
+        assert e == 0
+        self.A = self.f.bsr()
+        self.nb, self.bs = self.A.contents.nb, self.A.contents.bs
+        self.color = np.zeros(self.nb, np.int32)
+        self.ncolor = self.L.wo_bsr_coloring(self.A, wo.ip(self.color))
+        nblk = max(args.pc_blocks, 1)
+        self.bor = None if nblk == 1 else ((np.arange(self.nb, dtype=np.int64) * nblk) // self.nb).astype(np.int32)
+        if args.pc_cube > 0:
+            self.bor = prob.blocks(m, args.pc_cube)
+
+    def residual(self, y):
+        e, lhs, rhs, r = self.f.residual(y, self.L0, self.prob.dt)
+        assert e == 0
+        return r
+
+    def step(self, maxit):
+        """one Newton iteration from the initial state; returns the phase times"""
+        wo, L, p = self.wo, self.L, self.prob
+        y = p.y
+        t = {}
+        t0 = time.perf_counter()
+        F0 = self.residual(y)
+        t["residual"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        assert L.wo_fd_jacobian(self.f.h, wo.dp(y), wo.dp(self.L0), p.dt, wo.dp(F0), wo.ip(self.color), self.ncolor,
+                                1e-8, 1e-2, self.A) == 0
+        t["jacobian"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        pc = L.wo_pc_create(self.A, wo.PC_BJACOBI_ILU0, wo.ip(self.bor))
+        t["pc_setup"] = time.perf_counter() - t0
+        o = wo.KspOpts()
+        o.type, o.restart, o.maxit = (wo.KSP_GMRES if self.args.ksp == "gmres" else wo.KSP_BCGS), self.args.restart, maxit
+        o.rtol, o.atol, o.dtol = 1e-5, 1e-50, 1e5
+        x = np.zeros(self.nb * self.bs)
+        its, rn = C.c_int(), C.c_double()
+        t0 = time.perf_counter()
+        reason = L.wo_ksp_solve(self.A, pc, C.byref(o), wo.dp(F0), wo.dp(x), C.byref(its), C.byref(rn))
+        t["ksp"] = time.perf_counter() - t0
+        L.wo_pc_destroy(pc)
+        t0 = time.perf_counter()
+        ynew = y - x
+        self.residual(ynew)           # the line search's function evaluation at the new iterate
+        t["residual_new"] = time.perf_counter() - t0
+        self.f.lhs(y)                 # back to the initial state for the next step (not part of a step: untimed)
+        t["its"], t["ksp_reason"] = its.value, reason
+        return t
+
+    def spmv_gbs(self):
+        wo, L = self.wo, self.L
+        xx, yy = np.ones(self.nb * self.bs), np.zeros(self.nb * self.bs)
+        L.wo_bsr_spmv(self.A, wo.dp(xx), wo.dp(yy))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            L.wo_bsr_spmv(self.A, wo.dp(xx), wo.dp(yy))
+        t = (time.perf_counter() - t0) / 5
+        nnzb, bs = self.A.contents.nnzb, self.bs
+        return (nnzb * (bs * bs * 8 + 4) + (self.nb + 1) * 4 + 2 * self.nb * bs * 8) / t / 1e9
+
+
+def cpu_baseline_sample(prob, args, total_its):
+    """cpu_baseline leg of the B200 arm: a bounded sample of the same workload -- the full mesh, one residual, one
+    FD-coloured Jacobian, one PC set-up, `cpu_sample_its` Krylov iterations and the residual at the new iterate; the
+    Newton-step time is that with the Krylov part extrapolated linearly to the iteration count of the full solve."""
+    arm = CpuArm(prob, args)
+    t = arm.step(args.cpu_sample_its)
+    per_it = t["ksp"] / max(t["its"], 1)
+    t_step = t["residual"] + t["jacobian"] + t["pc_setup"] + per_it * total_its + t["residual_new"]
+    d = prob.dims
+    return {"value": 1.0 / t_step, "unit": UNIT, "cores": arm.cores, "kind": "port",
             "sample": "full %dx%dx%d mesh: 1 residual (%.2fs) + 1 FD-coloured Jacobian, %d colours (%.2fs) + ILU(0) factor "
-                      "(%.2fs) + %d %s iterations (%.3fs each); %s; "
-                      "oracle port of the reference algorithm (not the PETSc binary), OpenMP over sub-domains / SpMV / dots"
-                      % (dims[0], dims[1], dims[2], t_res, nc, t_jac, t_pc, its.value, ksp.upper(), per_it, how),
-            "s_per_step": t_step, "spmv_gbs": spmv_bytes / t_spmv / 1e9, "ksp_iterations": total_its}
+                      "(%.2fs) + %d %s iterations (%.3fs each), Krylov part extrapolated to %d iterations; oracle port of "
+                      "the reference algorithm (not the PETSc binary), gcc -O3 -march=native, OpenMP on %d threads "
+                      "(owner-computes cell chunks, sub-domains, SpMV rows, dots)"
+                      % (d[0], d[1], d[2], t["residual"], arm.ncolor, t["jacobian"], t["pc_setup"], t["its"], args.ksp.upper(),
+                         per_it, total_its, arm.cores),
+            "s_per_step": t_step, "spmv_gbs": arm.spmv_gbs(), "ksp_iterations": total_its}
 
 
 def run_reference(args):
     """The reference's CPU algorithm for the same Newton step on all host cores (oracle port: the reference itself is
-    Fortran + PETSc and cannot be built in this image).  Every step is the WHOLE step -- residual, FD-coloured
-    Jacobian, ILU(0) factor and the Krylov solve run to rtol 1e-5 -- about 45 s at 1 M cells on 16 cores, so at most
-    two steps are timed whatever --steps says; the best one is reported."""
+    Fortran + PETSc and cannot be built in this image).  Every timed step is the WHOLE step -- residual, FD-coloured
+    Jacobian, ILU(0) factor, the Krylov solve run to rtol 1e-5 and the residual at the new iterate, nothing
+    extrapolated.  A step takes tens of seconds, so after one warm-up step as many steps as fit into --cpu-budget-s
+    (at least 2, at most --steps) are timed and their MEAN is reported; `steps` says how many."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    dims = tuple(args.dims)
-    t0 = time.perf_counter()
+    t_all = time.perf_counter()
+    prob = Problem(args.config, 1 if args.config != 5 else args.gpus, args.dims, args.dt)
+    arm = CpuArm(prob, args)
     samples = []
-    nrep = max(1, min(args.steps, 2))
-    for _ in range(nrep):
-        samples.append(cpu_newton_sample(dims, args.pc_blocks, args.ksp_maxit, None, args.pc_cube, args.ksp))
-    best = max(samples, key=lambda s: s["value"])
-    out = {"metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": nrep,
-           "warmup": 0, "ms_per_step": 1e3 * best["s_per_step"], "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-           "config": {"workload": workload_name(dims), "timing": "host wall clock around whole Newton steps (see cpu_baseline.sample)",
-                      "ksp": args.ksp, "pc": args.pc, "ksp_iterations_per_step": best["ksp_iterations"]},
-           "cpu_baseline": best,
-           "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "wall_s": time.perf_counter() - t0}
+    if args.warmup > 0:
+        arm.step(min(args.ksp_maxit, 30))       # warm-up: page in the arrays, spin up the thread team
+    t_budget = time.perf_counter()
+    while len(samples) < max(2, args.steps):
+        t0 = time.perf_counter()
+        t = arm.step(args.ksp_maxit)
+        t["step"] = t["residual"] + t["jacobian"] + t["pc_setup"] + t["ksp"] + t["residual_new"]
+        samples.append(t)
+        if len(samples) >= 2 and time.perf_counter() - t_budget + (time.perf_counter() - t0) > args.cpu_budget_s:
+            break
+    s_step = float(np.mean([s["step"] for s in samples]))
+    d = prob.dims
+    mean = {k: float(np.mean([s[k] for s in samples])) for k in ("residual", "jacobian", "pc_setup", "ksp", "residual_new")}
+    its = int(round(np.mean([s["its"] for s in samples])))
+    base = {"value": 1.0 / s_step, "unit": UNIT, "cores": arm.cores, "kind": "port",
+            "sample": "%d whole Newton steps on the full %dx%dx%d mesh (mean): residual %.2fs + FD-coloured Jacobian, %d colours, "
+                      "%.2fs + ILU(0) factor %.2fs + %d %s iterations run to rtol (%.2fs) + residual at the new iterate %.2fs; "
+                      "oracle port of the reference algorithm (not the PETSc binary), gcc -O3 -march=native, OpenMP on %d threads"
+                      % (len(samples), d[0], d[1], d[2], mean["residual"], arm.ncolor, mean["jacobian"], mean["pc_setup"], its,
+                         args.ksp.upper(), mean["ksp"], mean["residual_new"], arm.cores),
+            "s_per_step": s_step, "spmv_gbs": arm.spmv_gbs(), "ksp_iterations": its,
+            "step_s": [round(s["step"], 3) for s in samples]}
+    out = {"metric": METRIC, "value": 1.0 / s_step, "unit": UNIT, "n_gpus": args.gpus, "steps": len(samples),
+           "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": 1e3 * s_step, "higher_is_better": True,
+           "scaling": prob.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "config": {"workload": prob.name(args), "timing": "host wall clock around whole Newton steps, mean of `steps` (see cpu_baseline.sample)",
+                      "ksp": args.ksp, "pc": args.pc, "ksp_iterations_per_step": its,
+                      "ksp_reason": int(samples[-1]["ksp_reason"]), "omp_threads": arm.cores},
+           "cpu_baseline": base,
+           "e2e": {"value": 1.0 / s_step, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.perf_counter() - t_all}
     print(json.dumps(out))
 
 
@@ -217,17 +334,17 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
-    dims = tuple(args.dims)
-    gm, gy, gregion = build_problem(dims)
+    prob = Problem(args.config, world, args.dims, args.dt)
+    gm, gy, gregion, npv, dt = prob.mesh, prob.y, prob.region, prob.npv, prob.dt
     if world > 1:
-        owner = wmesh.box_owner(gm, wmesh.default_parts(world))
-        m = wmesh.partition(gm, owner, rank, world)
+        m = wmesh.partition(gm, prob.owner, rank, world)
         nat = m.natural[:m.nowned]
-        y = np.ascontiguousarray(gy.reshape(-1, 2)[nat].reshape(-1))
+        y = np.ascontiguousarray(gy.reshape(-1, npv)[nat].reshape(-1))
         region = np.ascontiguousarray(gregion[nat])
     else:
         m, y, region = gm, gy, gregion
-    sim = flow.FlowSimulation(flow.make_params(eos=flow.EOS_WE, thermo=flow.THERMO_IAPWS), m, device=local)
+        nat = None
+    sim = flow.FlowSimulation(flow.make_params(eos=prob.eos, thermo=flow.THERMO_IAPWS), m, device=local)
     p2p = False
     if world > 1:
         uid = torch.from_numpy(flow.FlowSimulation.unique_id()).cuda() if rank == 0 else torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -244,10 +361,11 @@ def run_b200(args):
     err, L0 = sim.lhs(y)
     assert err == 0
     if args.pc_cube > 0 and args.pc == "ilu0":
-        sim.set_pc_blocks(wmesh.cube_blocks(m, args.pc_cube))
+        sim.set_pc_blocks(prob.blocks(m, args.pc_cube))
     pc_type = {"ilu0": flow.PC_BJACOBI_ILU0, "pbjacobi": flow.PC_PBJACOBI, "none": flow.PC_NONE}[args.pc]
     ksp_type = {"gmres": flow.KSP_GMRES, "bcgs": flow.KSP_BCGS}[args.ksp]
-    opts = flow.newton_opts(max_iterations=1, pc_type=pc_type, pc_nblocks=args.pc_blocks, ksp=flow.ksp_opts(type=ksp_type, maxit=args.ksp_maxit))
+    opts = flow.newton_opts(max_iterations=1, pc_type=pc_type, pc_nblocks=args.pc_blocks,
+                            ksp=flow.ksp_opts(type=ksp_type, maxit=args.ksp_maxit, restart=args.restart))
     n = sim.n
     stream = torch.cuda.ExternalStream(sim.stream())
     y0_d = torch.from_numpy(y).cuda()
@@ -261,11 +379,11 @@ def run_b200(args):
     def step_device():
         with torch.cuda.stream(stream):
             y_d.copy_(y0_d, non_blocking=True)
-        return sim.newton_solve(y_d, L0_d, DT, opts)
+        return sim.newton_solve(y_d, L0_d, dt, opts)
 
     def step_host():
         y_h.copy_(y0_h)
-        return sim.newton_solve(y_h.numpy(), L0_h.numpy(), DT, opts)
+        return sim.newton_solve(y_h.numpy(), L0_h.numpy(), dt, opts)
 
     def barrier():
         torch.cuda.synchronize()
@@ -304,7 +422,7 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     ksp_its = int(res.linear_iterations)
 
-    # ---- phase breakdown + SpMV roofline (timers on: device events around each phase / kernel)
+    # ---- phase breakdown (timers on: device events around each phase; every rank runs it, rank 0 reports its own)
     L.wb_timers_enable(1)
     L.wb_timer_reset(sim.h)
     step_device()
@@ -312,62 +430,115 @@ def run_b200(args):
     for nm in ("fluid_props", "cell_inflows", "jacobian", "pc_setup", "ksp_solve", "fluid_trans"):
         t, cnt = sim.timer(nm)
         phases[nm] = {"ms": round(t, 4), "calls": cnt}
+    ksp_breakdown = sim.ksp_breakdown() if hasattr(sim, "ksp_breakdown") else None
+    L.wb_timers_enable(0)
+
+    # ---- parity against the CPU oracle at this state (outside every timed region): residual vector, max-scaled norm
+    # and its argmax (timestepper.F90:1898-1951, dm_utils.F90:644-685), and the TRUE residual after the step
+    y_fin = y_d.cpu().numpy()
+    e, _, _, r0 = sim.residual(y, L0, dt)
+    assert e == 0
+    mv0, ml0 = sim.max_scaled(r0, L0, 1.0)
+    e, _, _, r1 = sim.residual(y_fin, L0, dt)
+    mv1, ml1 = sim.max_scaled(r1, L0, 1.0) if e == 0 else (float("nan"), -1)
+    sim.lhs(y)
+    parity = None
+    if not args.no_parity:
+        if world > 1:
+            parts = [None] * world
+            dist.gather_object(dict(nat=nat, r=r0), parts if rank == 0 else None, dst=0)
+            if rank == 0:
+                r_glob = np.zeros(gm.ninterior * npv)
+                for p in parts:
+                    r_glob.reshape(-1, npv)[p["nat"]] = p["r"].reshape(-1, npv)
+        else:
+            r_glob = r0
+        if rank == 0:
+            arm = CpuArm(prob, args)
+            r_cpu = arm.residual(gy)
+            from oracle import wo
+            mv_cpu, ml_cpu = wo.max_scaled(r_cpu, arm.L0, 1.0)
+            rel = float(np.linalg.norm(r_glob - r_cpu) / np.linalg.norm(r_cpu))
+            # the GPU argmax is a global index in rank-contiguous numbering; map the oracle's (natural) one the same way
+            if world > 1:
+                order = np.concatenate([p["nat"] for p in parts])
+                inv = np.empty_like(order)
+                inv[order] = np.arange(len(order))
+                ml_cpu_g = int(inv[ml_cpu // npv] * npv + ml_cpu % npv)
+            else:
+                ml_cpu_g = int(ml_cpu)
+            parity = {"residual_relerr": rel, "residual_norm2": float(np.linalg.norm(r_glob)),
+                      "residual_norm2_relerr": float(abs(np.linalg.norm(r_glob) - np.linalg.norm(r_cpu)) / np.linalg.norm(r_cpu)),
+                      "max_scaled": mv0, "max_scaled_rel": float(abs(mv0 - mv_cpu) / abs(mv_cpu)),
+                      "argmax": int(ml0), "argmax_equal": bool(int(ml0) == ml_cpu_g),
+                      "oracle": "CPU port evaluated on the same state outside the timed region", "tolerance": 1e-10}
+            del arm
+
+    # ---- SpMV roofline (the north-star kernel, K5): CUDA events on the context's stream around each launch
     roofline = None
     if world == 1:
         J = sim.jacobian_mat()
         x_d = torch.randn(n, dtype=torch.float64, device="cuda")
         z_d = torch.empty_like(x_d)
         torch.cuda.synchronize()
+        L.wb_timers_enable(1)
         for _ in range(5):
             J.mult(x_d, z_d)
         L.wb_timer_reset(sim.h)
         for _ in range(args.spmv_launches):
             J.mult(x_d, z_d)
         t, cnt = sim.timer("mat_mult")
+        L.wb_timers_enable(0)
         nb, bs, rowptr, colidx = sim.jacobian_pattern()
         nnzb = len(colidx)
         abytes = nnzb * (bs * bs * 8 + 4) + (nb + 1) * 4 + 2 * nb * bs * 8
-        peaks = {}
         pk_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         which = "fallback 6650 GB/s (B200_PROFILING.md)"
         peak = 6650.0
         if os.path.exists(pk_file):
-            peaks = json.load(open(pk_file))
-            peak = float(peaks.get("hbm_gbs", peak))
+            peak = float(json.load(open(pk_file)).get("hbm_gbs", peak))
             which = "MEASURED_PEAKS.json hbm_gbs"
         achieved = abytes / (t / cnt * 1e-3) / 1e9
         traffic = None
         tf = os.path.join(ROOT, "profiles", "spmv_traffic.json")
         if os.path.exists(tf):
             try:
-                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tf)).get("config%d" % args.config, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"kernel": "k_bsr_spmv<2> (GMRES block SpMV, K5)", "bound": "hbm", "achieved": round(achieved, 1),
-                    "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                    "algorithmic_bytes": abytes, "us_per_launch": round(1e3 * t / cnt, 2), "launches_timed": cnt,
-                    "peak_source": which, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
+        roofline = {"kernel": "BAIJ block SpMV bs=%d (K5, wb_mat_mult on the Jacobian)" % bs, "bound": "hbm",
+                    "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": traffic, "algorithmic_bytes": abytes, "us_per_launch": round(1e3 * t / cnt, 2),
+                    "launches_timed": cnt, "peak_source": which, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    ncell_global = gm.ninterior
     out = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": prob.scaling,
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(dims), "parallelism": "domain decomposition %s, halo of x inside SpMV%s" % (wmesh.default_parts(world), "" if world == 1 else (", per-iteration exchanges over NVLink P2P (CUDA IPC)" if p2p else ", NCCL exchanges")),
+           "config": {"workload": prob.name(args), "cells": int(ncell_global), "cells_per_gpu": int(m.nowned),
+                      "parallelism": "domain decomposition %s, halo of x inside SpMV%s" % (prob.parts, "" if world == 1 else (", per-iteration exchanges over NVLink P2P (CUDA IPC)" if p2p else ", NCCL exchanges")),
                       "pc": args.pc, "pc_subdomains": ("cubes of %d^3 cells" % args.pc_cube) if args.pc_cube > 0 else ("%d contiguous ranges per GPU" % args.pc_blocks),
-                      "ksp": args.ksp,
-                      "l2": "working set (Jacobian 222 MB + Krylov basis 496 MB) exceeds the 126 MB L2; no explicit flush",
-                      "ksp_iterations_per_step": ksp_its, "newton_reason": int(res.reason),
-                      "max_scaled_residual": [res.max_residual[0], res.max_residual[1]]},
+                      "ksp": args.ksp, "restart": args.restart,
+                      "l2": "working set (Jacobian + factors + Krylov basis) exceeds the 126 MB L2 at 1 GPU; no explicit flush",
+                      "ksp_iterations_per_step": ksp_its, "ksp_reason": int(res.lin_reason[0]), "ksp_rnorm": res.lin_rnorm[0],
+                      "us_per_ksp_iteration": round(1e3 * phases["ksp_solve"]["ms"] / max(ksp_its, 1), 2),
+                      "newton_reason": int(res.reason),
+                      "max_scaled_residual": [res.max_residual[0], res.max_residual[1]],
+                      "post_step_max_scaled_residual": mv1,
+                      "cell_updates_per_s": ncell_global * args.steps / (ms * 1e-3)},
            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8,
                    "d2h_bytes_per_step": n * 8 + C.sizeof(flow.NewtonResult), "ms_per_step": ms_e2e / args.steps},
-           "gpu_launches": int(launches), "clocks": clocks, "phases_ms": phases}
+           "gpu_launches": int(launches), "clocks": clocks, "phases_ms": phases, "parity": parity}
+    if ksp_breakdown:
+        out["ksp_breakdown_us_per_iteration"] = ksp_breakdown
     if roofline:
         out["roofline"] = roofline
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_newton_sample(dims, args.pc_blocks, args.cpu_sample_its, ksp_its, args.pc_cube, args.ksp)
+        out["cpu_baseline"] = cpu_baseline_sample(prob, args, ksp_its)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

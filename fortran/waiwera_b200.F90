@@ -69,10 +69,12 @@ module waiwera_b200
      integer(c_int) :: reason, iterations, linear_iterations
      real(c_double) :: max_residual(32)
      integer(c_int) :: lin_its(32)
+     integer(c_int) :: lin_reason(32)
+     real(c_double) :: lin_rnorm(32)
   end type wb_newton_result
 
   public :: wb_last_error, wb_version, wb_create, wb_destroy, wb_num_primary, wb_fluid_dof, wb_set_mesh, &
-       wb_jacobian_pattern, wb_jacobian_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
+       wb_jacobian_pattern, wb_jacobian_get, wb_cell_faces_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
        wb_comm_p2p_blob_size, wb_comm_p2p_export, wb_comm_p2p_open, wb_comm_p2p_enabled, wb_comm_p2p_disable, &
        wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_source_controls, wb_get_source_rates, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
@@ -144,6 +146,14 @@ module waiwera_b200
        type(c_ptr), value :: ctx, rowptr, colidx, vals
        integer(c_int) :: ierr
      end function wb_jacobian_get
+
+     ! cell -> face gather lists (order of the face loop's scatter, src/flow_simulation.F90:1410-1458)
+     function wb_cell_faces_get(ctx, ncf, cf_ptr, cf_face, cf_other) bind(C, name="wb_cell_faces_get") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, cf_ptr, cf_face, cf_other
+       integer(c_int), intent(out) :: ncf
+       integer(c_int) :: ierr
+     end function wb_cell_faces_get
 
      function wb_comm_unique_id(id128) bind(C, name="wb_comm_unique_id") result(ierr)
        import :: c_int, c_ptr

@@ -130,6 +130,11 @@ int wb_jacobian_pattern(wb_ctx *ctx, int *nb, int *bs, int *nnzb, const int32_t 
                         double **vals);
 /* copy pattern / values to host arrays (any may be NULL) */
 int wb_jacobian_get(wb_ctx *ctx, int32_t *rowptr, int32_t *colidx, double *vals);
+/* The cell -> face gather lists the residual / Jacobian kernels walk (the order in which the reference's face loop
+   scatters into a cell, src/flow_simulation.F90:1410-1458): for owned cell i, entries cf_ptr[i] .. cf_ptr[i+1]-1 in
+   ascending face order; cf_face = 2*face + side (0: the cell is cell 1 of the face), cf_other = the cell on the other
+   side.  *ncf receives the number of entries; the arrays (host, any may be NULL) receive nowned+1 / ncf / ncf values. */
+int wb_cell_faces_get(wb_ctx *ctx, int *ncf, int32_t *cf_ptr, int32_t *cf_face, int32_t *cf_other);
 
 /* ---- multi-GPU -------------------------------------------------------- */
 /* NCCL communicator over the ranks of the partition (replaces PetscSF /
@@ -296,6 +301,8 @@ typedef struct {
   int reason, iterations, linear_iterations;
   double max_residual[32];
   int lin_its[32];
+  int lin_reason[32];    /* KSPConvergedReason of the linear solve of every Newton iteration */
+  double lin_rnorm[32];  /* its final (preconditioned) residual norm */
 } wb_newton_result;
 /* sub-domain of every owned row for the block-Jacobi preconditioner the Newton solve sets up
    (arbitrary index sets as with PCASMSetLocalSubdomains at overlap 0; NULL restores the default

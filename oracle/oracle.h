@@ -200,6 +200,10 @@ typedef struct {
   const double *rock;          /* 8*ncell */
 } wo_mesh;
 
+/* OpenMP threads used by the oracle's loops (0: leave the runtime's choice); returns the thread count in effect.
+   Every result is bit-identical for every thread count (see wo_flow.c). */
+int wo_set_num_threads(int n);
+
 typedef struct wo_flow wo_flow;
 wo_flow *wo_flow_create(const wo_params *prm, const wo_mesh *mesh);
 void wo_flow_destroy(wo_flow *f);
@@ -314,6 +318,8 @@ typedef struct {
   int reason, iterations, linear_iterations;
   double max_residual[32];
   int lin_its[32];
+  int lin_reason[32];
+  double lin_rnorm[32];
 } wo_newton_result;
 int wo_newton_solve_be(wo_flow *f, wo_bsr *J, const int32_t *color, int ncolor,
                        const int32_t *block_of_row,

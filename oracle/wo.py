@@ -71,14 +71,43 @@ class NewtonOpts(C.Structure):
 
 class NewtonResult(C.Structure):
     _fields_ = [("reason", C.c_int), ("iterations", C.c_int), ("linear_iterations", C.c_int),
-                ("max_residual", C.c_double * 32), ("lin_its", C.c_int * 32)]
+                ("max_residual", C.c_double * 32), ("lin_its", C.c_int * 32),
+                ("lin_reason", C.c_int * 32), ("lin_rnorm", C.c_double * 32)]
+
+
+def _cpu_key():
+    """identifies the host CPU (model + ISA flags): the library is built -march=native, and the build directory
+    travels from the build container to the GPU box, whose CPU may differ"""
+    import hashlib
+    model, flags = "", ""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name") and not model:
+                    model = line.split(":", 1)[1].strip()
+                elif line.startswith("flags") and not flags:
+                    flags = " ".join(sorted(line.split(":", 1)[1].split()))
+                if model and flags:
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1((model + "|" + flags).encode()).hexdigest()
 
 
 def build(force=False):
-    """Compile the oracle with gcc (oracle/Makefile)."""
-    if force:
+    """Compile the oracle with gcc (oracle/Makefile); rebuilt from scratch when the host CPU is not the one the
+    existing library was built for."""
+    stamp = os.path.join(_HERE, "_build", "cpu.stamp")
+    key = _cpu_key()
+    try:
+        same = open(stamp).read().strip() == key
+    except OSError:
+        same = False
+    if force or not same:
         subprocess.check_call(["make", "-C", _HERE, "clean"], stdout=subprocess.DEVNULL)
     subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+    with open(stamp, "w") as fh:
+        fh.write(key + "\n")
     return _LIB
 
 
@@ -89,11 +118,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB):
-        build()
+    build()  # no-op when up to date; rebuilds on a different host CPU
     L = C.CDLL(_LIB)
     vp, i, d = C.c_void_p, C.c_int, C.c_double
     sig = {
+        "wo_set_num_threads": (i, [i]),
         "wo_powertable_eval": (None, [c_ip, i, d, c_ip, i, c_dp]),
         "wo_thermo_create": (vp, [i, i]),
         "wo_thermo_destroy": (None, [vp]),

@@ -15,6 +15,121 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Host parallelism (OpenMP): the cell loops are split into contiguous chunks of owned cells, one per thread, and
+   every thread visits the faces that touch its chunk in ascending face order and adds only to its own cells --
+   "owner computes", the way the reference's MPI ranks each loop over their local faces and own cells
+   (flow_simulation.F90:1291-1316, 1410-1458).  Per cell the additions happen in the same order as in the serial
+   face loop, so the results are bit-identical for every thread count. */
+/* problems smaller than this many cells run serially (thread start-up costs more than the loop) */
+#define WO_PAR_MIN 20000
+static int wo_nthreads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int wo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+  return wo_nthreads();
+}
+
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+  const size_t chunk = (size_t)1 << 22;
+  if (bytes < 2 * chunk) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const long nchunk = (long)((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static)
+  for (long k = 0; k < nchunk; k++) {
+    size_t o = (size_t)k * chunk, len = bytes - o < chunk ? bytes - o : chunk;
+    memcpy((char *)dst + o, (const char *)src + o, len);
+  }
+}
+
+/* The EOS object carries mutable scratch (the IAPWS power tables, powertable.F90:261-278), as the reference's does:
+   every thread evaluates with its own instance, the way every MPI rank of the reference owns one. */
+static void eos_pool_build(wo_flow *f) {
+  int T = wo_nthreads();
+  if (f->eos_nthr >= T) return;
+  f->eos_thr = (wo_eos **)realloc(f->eos_thr, T * sizeof(wo_eos *));
+  for (int t = f->eos_nthr; t < T; t++) f->eos_thr[t] = t == 0 ? f->eos : wo_eos_create(&f->prm);
+  f->eos_nthr = T;
+}
+static inline wo_eos *thread_eos(const wo_flow *f) {
+#ifdef _OPENMP
+  int t = omp_get_thread_num();
+  return t < f->eos_nthr ? f->eos_thr[t] : f->eos;
+#else
+  return f->eos;
+#endif
+}
+
+/* face lists of the thread chunks (built on first use for the current thread count) */
+static void face_plan_free(wo_flow *f) {
+  if (f->plan_faces) {
+    for (int t = 0; t < f->plan_nthr; t++) free(f->plan_faces[t]);
+  }
+  free(f->plan_faces);
+  free(f->plan_nfaces);
+  free(f->plan_c0);
+  f->plan_faces = NULL;
+  f->plan_nfaces = NULL;
+  f->plan_c0 = NULL;
+  f->plan_nthr = 0;
+}
+
+static void face_plan_build(wo_flow *f) {
+  const wo_mesh *m = &f->mesh;
+  int T = m->nowned >= WO_PAR_MIN ? wo_nthreads() : 1;
+  if (f->plan_nthr == T) return;
+  face_plan_free(f);
+  f->plan_nthr = T;
+  f->plan_c0 = (int *)malloc((T + 1) * sizeof(int));
+  for (int t = 0; t <= T; t++) f->plan_c0[t] = (int)(((long long)m->nowned * t) / T);
+  f->plan_nfaces = (int *)calloc(T, sizeof(int));
+  f->plan_faces = (int32_t **)calloc(T, sizeof(int32_t *));
+  /* chunk of an owned cell: chunks are equal-sized up to rounding, found by division + correction */
+#define CHUNK_OF(c, out)                                          \
+  do {                                                            \
+    int t_ = (int)(((long long)(c)*T) / (m->nowned > 0 ? m->nowned : 1)); \
+    if (t_ >= T) t_ = T - 1;                                      \
+    while (t_ > 0 && (c) < f->plan_c0[t_]) t_--;                  \
+    while (t_ < T - 1 && (c) >= f->plan_c0[t_ + 1]) t_++;         \
+    (out) = t_;                                                   \
+  } while (0)
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1)
+      for (int t = 0; t < T; t++) {
+        f->plan_faces[t] = (int32_t *)malloc((f->plan_nfaces[t] + 1) * sizeof(int32_t));
+        f->plan_nfaces[t] = 0;
+      }
+    for (int iface = 0; iface < m->nface; iface++) {
+      const int32_t *cells = m->face_cells + 2 * (size_t)iface;
+      int t0 = -1, t1 = -1;
+      if (cells[0] < m->nowned) CHUNK_OF(cells[0], t0);
+      if (cells[1] < m->nowned) CHUNK_OF(cells[1], t1);
+      if (t0 < 0 && t1 < 0) t0 = 0; /* no owned cell: evaluated (and stored) once, added nowhere */
+      if (t0 >= 0) {
+        if (pass == 1) f->plan_faces[t0][f->plan_nfaces[t0]] = iface;
+        f->plan_nfaces[t0]++;
+      }
+      if (t1 >= 0 && t1 != t0) {
+        if (pass == 1) f->plan_faces[t1][f->plan_nfaces[t1]] = iface;
+        f->plan_nfaces[t1]++;
+      }
+    }
+  }
+#undef CHUNK_OF
+}
 
 
 static inline int nint_(double x) { return (int)lround(x); }
@@ -206,6 +321,9 @@ void wo_flow_destroy(wo_flow *f) {
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
   free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
   free(f->lhs_last2);
+  face_plan_free(f);
+  for (int t = 1; t < f->eos_nthr; t++) wo_eos_destroy(f->eos_thr[t]);
+  free(f->eos_thr);
   free(f->tracers);
   free(f->tracer_injection);
   wo_eos_destroy(f->eos);
@@ -260,26 +378,42 @@ int wo_flow_fluid_init(wo_flow *f, const double *y, const int32_t *region) {
 /* identify_update_cells: flow_simulation.F90:1102-1137 */
 static void identify_update_cells(wo_flow *f, const int32_t *perturbed, int nperturbed) {
   f->unperturbed = (nperturbed == 0);
+  const int ncell = f->mesh.ncell;
+  double *update = f->update;
   if (f->unperturbed) {
-    for (int c = 0; c < f->mesh.ncell; c++) f->update[c] = 1.0;
+#pragma omp parallel for schedule(static) if (ncell >= WO_PAR_MIN)
+    for (int c = 0; c < ncell; c++) update[c] = 1.0;
   } else {
-    for (int c = 0; c < f->mesh.ncell; c++) f->update[c] = -1.0;
-    for (int k = 0; k < nperturbed; k++) f->update[perturbed[k]] = 1.0;
+#pragma omp parallel for schedule(static) if (ncell >= WO_PAR_MIN)
+    for (int c = 0; c < ncell; c++) update[c] = -1.0;
+#pragma omp parallel for schedule(static) if (nperturbed >= WO_PAR_MIN)
+    for (int k = 0; k < nperturbed; k++) update[perturbed[k]] = 1.0;
   }
 }
 
 /* fluid_properties: flow_simulation.F90:2291-2415 */
 static int fluid_properties(wo_flow *f, const double *y) {
-  int err = 0;
-  double primary[WO_MAX_NP];
-  memcpy(f->current_fluid, f->fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double)); /* :2331 */
+  int err = 0, first_bad = f->mesh.nowned;
+  eos_pool_build(f);
+  par_memcpy(f->current_fluid, f->fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double)); /* :2331 */
+  /* the serial loop stops at the first cell in error; here every cell is evaluated and the error of the
+     lowest-numbered failing cell is returned (the evaluation is abandoned by the caller either way) */
+#pragma omp parallel for schedule(static) if (f->mesh.nowned >= WO_PAR_MIN)
   for (int c = 0; c < f->mesh.nowned; c++) {
     if (f->update[c] > 0) {
+      double primary[WO_MAX_NP];
+      wo_eos *eos = thread_eos(f);
       double *fl = f->current_fluid + (size_t)c * f->dof;
-      wo_eos_unscale(f->eos, y + (size_t)c * f->np, nint_(fl[2]), primary);
-      err = wo_eos_bulk_properties(f->eos, primary, fl);
-      if (err == 0) err = wo_eos_phase_properties(f->eos, primary, f->rock + (size_t)c * 8, fl);
-      if (err) break;
+      wo_eos_unscale(eos, y + (size_t)c * f->np, nint_(fl[2]), primary);
+      int e = wo_eos_bulk_properties(eos, primary, fl);
+      if (e == 0) e = wo_eos_phase_properties(eos, primary, f->rock + (size_t)c * 8, fl);
+      if (e) {
+#pragma omp critical(wo_fluid_err)
+        if (c < first_bad) {
+          first_bad = c;
+          err = e;
+        }
+      }
     }
   }
   return err;
@@ -289,20 +423,21 @@ static int fluid_properties(wo_flow *f, const double *y) {
 int wo_flow_pre_eval(wo_flow *f, const double *y, const int32_t *perturbed, int nperturbed) {
   identify_update_cells(f, perturbed, nperturbed);
   int err = fluid_properties(f, y);
-  if (f->unperturbed) memcpy(f->fluid, f->current_fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double));
+  if (f->unperturbed) par_memcpy(f->fluid, f->current_fluid, (size_t)f->mesh.ncell * f->dof * sizeof(double));
   return err;
 }
 
 /* cell_balances: flow_simulation.F90:1242-1330 */
 int wo_flow_cell_balances(wo_flow *f, double *lhs) {
   size_t n = (size_t)f->mesh.nowned * f->np;
-  memcpy(lhs, f->balances, n * sizeof(double)); /* :1273 */
+  par_memcpy(lhs, f->balances, n * sizeof(double)); /* :1273 */
+#pragma omp parallel for schedule(static) if (f->mesh.nowned >= WO_PAR_MIN)
   for (int c = 0; c < f->mesh.nowned; c++) {
     if (f->update[c] > 0)
       wo_cell_balance(f->rock + (size_t)c * 8, f->current_fluid + (size_t)c * f->dof, f->nc, f->nphase, f->np,
                       lhs + (size_t)c * f->np);
   }
-  if (f->unperturbed) memcpy(f->balances, lhs, n * sizeof(double));
+  if (f->unperturbed) par_memcpy(f->balances, lhs, n * sizeof(double));
   return 0;
 }
 
@@ -312,30 +447,42 @@ int wo_flow_cell_inflows(wo_flow *f, double *rhs) {
   const wo_mesh *m = &f->mesh;
   int np = f->np, nf = f->nflux;
   const double flux_sign[2] = {-1.0, 1.0};
-  double face_flux[WO_MAX_NP + 3], flow[WO_MAX_NP];
-  for (size_t i = 0; i < (size_t)m->nowned * np; i++) rhs[i] = 0.0;
-  for (int iface = 0; iface < m->nface; iface++) {
-    const int32_t *cells = m->face_cells + 2 * (size_t)iface;
-    const double *g = m->face_geom + 12 * (size_t)iface;
-    int update_flux = 0;
-    for (int i = 0; i < 2; i++)
-      if (cells[i] < m->ninterior) update_flux = update_flux || (f->update[cells[i]] > 0);
-    double *stored = f->flux + (size_t)iface * nf;
-    if (update_flux) {
-      wo_face_flux(g, f->rock + 8 * (size_t)cells[0], f->rock + 8 * (size_t)cells[1],
-                   f->current_fluid + (size_t)cells[0] * f->dof, f->current_fluid + (size_t)cells[1] * f->dof,
-                   f->nc, np, f->nphase, f->nmobile, f->isothermal, face_flux);
-      if (f->unperturbed) memcpy(stored, face_flux, nf * sizeof(double));
-    } else {
-      memcpy(face_flux, stored, nf * sizeof(double));
-    }
-    for (int k = 0; k < np; k++) flow[k] = face_flux[k] * g[0];
-    for (int i = 0; i < 2; i++) {
-      int c = cells[i];
-      if (c < m->nowned) { /* ghost_cell(c) < 0 and c < end_interior_cell */
-        double vol = m->cell_geom[4 * (size_t)c + 3];
-        double *inflow = rhs + (size_t)c * np;
-        for (int k = 0; k < np; k++) inflow[k] = inflow[k] + flux_sign[i] * flow[k] / vol;
+  double flow[WO_MAX_NP];
+  face_plan_build(f);
+  const int T = f->plan_nthr;
+#pragma omp parallel for schedule(static, 1) if (T > 1)
+  for (int t = 0; t < T; t++) {
+    const int c0 = f->plan_c0[t], c1 = f->plan_c0[t + 1];
+    double face_flux[WO_MAX_NP + 3], fl[WO_MAX_NP];
+    for (size_t i = (size_t)c0 * np; i < (size_t)c1 * np; i++) rhs[i] = 0.0;
+    for (int q = 0; q < f->plan_nfaces[t]; q++) {
+      const int iface = f->plan_faces[t][q];
+      const int32_t *cells = m->face_cells + 2 * (size_t)iface;
+      const double *g = m->face_geom + 12 * (size_t)iface;
+      int update_flux = 0;
+      for (int i = 0; i < 2; i++)
+        if (cells[i] < m->ninterior) update_flux = update_flux || (f->update[cells[i]] > 0);
+      double *stored = f->flux + (size_t)iface * nf;
+      if (update_flux) {
+        wo_face_flux(g, f->rock + 8 * (size_t)cells[0], f->rock + 8 * (size_t)cells[1],
+                     f->current_fluid + (size_t)cells[0] * f->dof, f->current_fluid + (size_t)cells[1] * f->dof,
+                     f->nc, np, f->nphase, f->nmobile, f->isothermal, face_flux);
+        /* a face shared by two chunks is evaluated by both (as by two ranks in the reference); the chunk of its
+           first owned cell keeps the stored copy */
+        const int writer_cell = cells[0] < m->nowned ? cells[0] : cells[1];
+        const int mine = (writer_cell >= c0 && writer_cell < c1) || (writer_cell >= m->nowned && t == 0);
+        if (f->unperturbed && mine) memcpy(stored, face_flux, nf * sizeof(double));
+      } else {
+        memcpy(face_flux, stored, nf * sizeof(double));
+      }
+      for (int k = 0; k < np; k++) fl[k] = face_flux[k] * g[0];
+      for (int i = 0; i < 2; i++) {
+        int c = cells[i];
+        if (c >= c0 && c < c1) { /* ghost_cell(c) < 0 and c < end_interior_cell, and the cell is this chunk's */
+          double vol = m->cell_geom[4 * (size_t)c + 3];
+          double *inflow = rhs + (size_t)c * np;
+          for (int k = 0; k < np; k++) inflow[k] = inflow[k] + flux_sign[i] * fl[k] / vol;
+        }
       }
     }
   }
@@ -366,35 +513,49 @@ void wo_flow_pre_retry_timestep(wo_flow *f) { /* :2093-2104 */
    is the last visited cell's; changed_search is sticky. */
 int wo_flow_fluid_transitions(wo_flow *f, const double *y_old, double *search, double *y, int *changed_search,
                               int *changed_y) {
-  int err = 0, np = f->np;
-  *changed_search = 0;
-  *changed_y = 0;
-  double primary[WO_MAX_NP], old_primary[WO_MAX_NP];
-  for (int c = 0; c < f->mesh.nowned; c++) {
+  int err = 0, np = f->np, first_bad = f->mesh.nowned;
+  int any_search = 0, last_changed = 0;
+  const int nowned = f->mesh.nowned;
+  eos_pool_build(f);
+  /* cells are independent; changed_y ends up as the value of the last cell visited, changed_search as the OR over
+     all cells, exactly as in the serial loop (which stops at the first cell in error: here the error of the
+     lowest-numbered failing cell is returned and the caller abandons the step) */
+#pragma omp parallel for schedule(static) reduction(| : any_search) if (nowned >= WO_PAR_MIN)
+  for (int c = 0; c < nowned; c++) {
+    double primary[WO_MAX_NP], old_primary[WO_MAX_NP];
     double *fl = f->fluid + (size_t)c * f->dof;
     const double *ofl = f->last_iteration_fluid + (size_t)c * f->dof;
     double *yc = y + (size_t)c * np;
     const double *yo = y_old + (size_t)c * np;
     double *sc = search + (size_t)c * np;
-    int transition = 0;
-    wo_eos_unscale(f->eos, yc, nint_(fl[2]), primary);
-    wo_eos_unscale(f->eos, yo, nint_(ofl[2]), old_primary);
+    int transition = 0, changed = 0;
+    wo_eos *eos = thread_eos(f);
+    wo_eos_unscale(eos, yc, nint_(fl[2]), primary);
+    wo_eos_unscale(eos, yo, nint_(ofl[2]), old_primary);
     fl[3] = fl[2]; /* old_region = region :2502 */
-    err = wo_eos_transition(f->eos, old_primary, primary, ofl, fl, &transition);
-    if (err == 0) {
-      err = wo_eos_check_primary_variables(f->eos, fl, primary, changed_y);
-      if (err == 0) {
-        if (transition) *changed_y = 1;
-      } else
-        break;
-      if (*changed_y) {
-        *changed_search = 1;
-        wo_eos_scale(f->eos, primary, nint_(fl[2]), yc);
-        for (int k = 0; k < np; k++) sc[k] = yo[k] - yc[k];
+    int e = wo_eos_transition(eos, old_primary, primary, ofl, fl, &transition);
+    if (e == 0) {
+      e = wo_eos_check_primary_variables(eos, fl, primary, &changed);
+      if (e == 0) {
+        if (transition) changed = 1;
+        if (changed) {
+          any_search = 1;
+          wo_eos_scale(eos, primary, nint_(fl[2]), yc);
+          for (int k = 0; k < np; k++) sc[k] = yo[k] - yc[k];
+        }
       }
-    } else
-      break;
+    }
+    if (c == nowned - 1) last_changed = changed;
+    if (e) {
+#pragma omp critical(wo_trans_err)
+      if (c < first_bad) {
+        first_bad = c;
+        err = e;
+      }
+    }
   }
+  *changed_search = any_search;
+  *changed_y = last_changed;
   return err;
 }
 
@@ -409,26 +570,34 @@ int wo_residual_be(wo_flow *f, const double *y, const double *lhs_last, double d
     if (err) return err;
     err = wo_flow_cell_inflows(f, rhs);
     if (err) return err;
-    for (size_t i = 0; i < n; i++) r[i] = rhs[i]; /* VecCopy */
+    par_memcpy(r, rhs, n * sizeof(double)); /* VecCopy */
     return 0;
   }
   err = wo_flow_cell_balances(f, lhs);
   if (err) return err;
   if (f->method == 1) { /* BDF2_residual: timestepper.F90:378-427 */
     double q = dt / f->dt_last, q1 = q + 1.0;
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
     for (size_t i = 0; i < n; i++) r[i] = lhs[i];                            /* VecCopy */
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
     for (size_t i = 0; i < n; i++) r[i] = r[i] * (1.0 + 2.0 * q);            /* VecScale */
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
     for (size_t i = 0; i < n; i++) r[i] = r[i] + (-q1 * q1) * lhs_last[i];   /* VecAXPY */
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
     for (size_t i = 0; i < n; i++) r[i] = r[i] + (q * q) * f->lhs_last2[i];  /* VecAXPY */
     err = wo_flow_cell_inflows(f, rhs);
     if (err) return err;
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
     for (size_t i = 0; i < n; i++) r[i] = r[i] + (-dt * q1) * rhs[i];        /* VecAXPY */
     return 0;
   }
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
   for (size_t i = 0; i < n; i++) r[i] = lhs[i];                 /* VecCopy */
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
   for (size_t i = 0; i < n; i++) r[i] = r[i] + (-1.0) * lhs_last[i]; /* VecAXPY */
   err = wo_flow_cell_inflows(f, rhs);
   if (err) return err;
+#pragma omp parallel for schedule(static) if (n >= WO_PAR_MIN)
   for (size_t i = 0; i < n; i++) r[i] = r[i] + (-dt) * rhs[i];   /* VecAXPY */
   return 0;
 }

@@ -18,6 +18,12 @@ struct wo_flow {
   double *update;   /* ncell: +1 / -1 */
   double *rock;     /* private copy so boundary ghost rock can be set */
   int unperturbed;
+  /* OpenMP owner-computes plan of the face loop: cell chunk bounds and per-chunk face lists (wo_flow.c) */
+  int eos_nthr;      /* per-thread EOS instances (the EOS carries mutable power-table scratch) */
+  wo_eos **eos_thr;
+  int plan_nthr;
+  int *plan_c0, *plan_nfaces;
+  int32_t **plan_faces;
   /* time-stepping method: 0 backward Euler, 1 BDF2, 2 direct steady state (timestepper.F90:345-452) */
   int method;
   double dt_last;

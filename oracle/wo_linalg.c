@@ -160,7 +160,10 @@ int wo_fd_jacobian(wo_flow *f, const double *y, const double *lhs_last, double d
       }
       err = wo_residual_be(f, w3, lhs_last, dt, cols, ncols, lhs, rhs, w2);
       if (err) break;
+#pragma omp parallel for schedule(static) if (n >= 20000)
       for (size_t q = 0; q < n; q++) w2[q] = w2[q] + (-1.0) * F0[q];
+      /* columns of one colour touch disjoint rows: independent */
+#pragma omp parallel for schedule(static) if (ncols >= 1000)
       for (int l = 0; l < ncols; l++) {
         int c = cols[l];
         size_t col = (size_t)i + (size_t)bs * c;

@@ -97,12 +97,15 @@ int wo_newton_solve_be(wo_flow *f, wo_bsr *J, const int32_t *color, int ncolor, 
     int kreason = wo_ksp_solve(J, pc, &o->ksp, F, Y, &lits, &lres);
     wo_pc_destroy(pc);
     res->lin_its[it < 32 ? it : 31] = lits;
+    res->lin_reason[it < 32 ? it : 31] = kreason;
+    res->lin_rnorm[it < 32 ? it : 31] = lres;
     res->linear_iterations += lits;
     if (kreason < 0) {
       reason = SNES_DIVERGED_LINEAR_SOLVE;
       break;
     }
     /* shell line search: timestepper.F90:673-735, lambda = 1 */
+#pragma omp parallel for schedule(static) if (n >= 20000)
     for (size_t i = 0; i < n; i++) W[i] = -1.0 * Y[i] + y[i]; /* VecWAXPY(w,-lambda,y,x) */
     int changed_search = 0, changed_w = 0;
     err = wo_flow_fluid_transitions(f, y, Y, W, &changed_search, &changed_w);
@@ -113,12 +116,11 @@ int wo_newton_solve_be(wo_flow *f, wo_bsr *J, const int32_t *color, int ncolor, 
     if (changed_search && !changed_w)
       for (size_t i = 0; i < n; i++) W[i] = -1.0 * Y[i] + y[i];
     memcpy(y, W, n * sizeof(double));
-    if (it < o->max_iterations - 1) {
-      err = wo_residual_be(f, y, lhs_last, dt, NULL, 0, lhs, rhs, F);
-      if (err) {
-        reason = SNES_DIVERGED_LINE_SEARCH; /* line search failed: function domain */
-        break;
-      }
+    /* the line search evaluates F at the new iterate in every iteration, the last one included */
+    err = wo_residual_be(f, y, lhs_last, dt, NULL, 0, lhs, rhs, F);
+    if (err) {
+      reason = SNES_DIVERGED_LINE_SEARCH; /* line search failed: function domain */
+      break;
     }
     fnorm = norm2(F, n);
     xnorm = norm2(y, n);

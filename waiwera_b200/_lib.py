@@ -49,7 +49,8 @@ class NewtonOpts(C.Structure):
 
 class NewtonResult(C.Structure):
     _fields_ = [("reason", C.c_int), ("iterations", C.c_int), ("linear_iterations", C.c_int),
-                ("max_residual", C.c_double * 32), ("lin_its", C.c_int * 32)]
+                ("max_residual", C.c_double * 32), ("lin_its", C.c_int * 32),
+                ("lin_reason", C.c_int * 32), ("lin_rnorm", C.c_double * 32)]
 
 
 # every symbol include/waiwera_b200.h declares: name -> (restype, argtypes)
@@ -106,6 +107,7 @@ SIGNATURES = {
     "wb_ksp_solve": (i, [vp, vp, C.POINTER(KspOpts), vp, vp, C.POINTER(i), C.POINTER(i), C.POINTER(d)]),
     "wb_ksp_set_check_every": (i, [i]),
     "wb_set_pc_blocks": (i, [vp, vp]),
+    "wb_cell_faces_get": (i, [vp, C.POINTER(i), vp, vp, vp]),
     "wb_newton_solve_be": (i, [vp, C.POINTER(NewtonOpts), d, vp, vp, C.POINTER(NewtonResult)]),
     "wb_set_tracers": (i, [vp, i, vp, vp, vp, vp]),
     "wb_set_tracer_injection": (i, [vp, vp]),

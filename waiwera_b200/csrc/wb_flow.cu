@@ -842,6 +842,15 @@ extern "C" int wb_jacobian_pattern(wb_ctx *c, int *nb, int *bs, int *nnzb, const
   return 0;
 }
 
+extern "C" int wb_cell_faces_get(wb_ctx *c, int *ncf, int32_t *cf_ptr, int32_t *cf_face, int32_t *cf_other) {
+  WB_CHECK(c->ncell > 0, "wb_cell_faces_get: no mesh");
+  if (ncf) *ncf = c->ncf;
+  if (cf_ptr) memcpy(cf_ptr, c->h_cf_ptr.data(), sizeof(int32_t) * (c->nowned + 1));
+  if (cf_face) memcpy(cf_face, c->h_cf_face.data(), sizeof(int32_t) * c->ncf);
+  if (cf_other) memcpy(cf_other, c->h_cf_other.data(), sizeof(int32_t) * c->ncf);
+  return 0;
+}
+
 extern "C" int wb_jacobian_get(wb_ctx *c, int32_t *rowptr, int32_t *colidx, double *vals) {
   WB_CUDA(cudaSetDevice(c->device));
   WB_CUDA(cudaStreamSynchronize(c->stream));

@@ -186,6 +186,8 @@ extern "C" int wb_newton_solve_be(wb_ctx *c, const wb_newton_opts *o, double dt,
     double lres = 0.0;
     WB_TRY(wb_ksp_solve_dev(J, w.pc, &o->ksp, w.F, w.Y, &lits, &kreason, &lres));
     res->lin_its[it < 32 ? it : 31] = lits;
+    res->lin_reason[it < 32 ? it : 31] = kreason;
+    res->lin_rnorm[it < 32 ? it : 31] = lres;
     res->linear_iterations += lits;
     if (kreason < 0) {
       reason = SNES_DIVERGED_LINEAR_SOLVE;
@@ -201,13 +203,13 @@ extern "C" int wb_newton_solve_be(wb_ctx *c, const wb_newton_opts *o, double dt,
     }
     if (c->h_flags[1] && !c->h_flags[2]) WB_TRY(wb_vec_axpby_dev(c, w.W, -1.0, w.Y, 1.0, d_y, n));
     WB_CUDA(cudaMemcpyAsync(d_y, w.W, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    if (it < o->max_iterations - 1) {
-      WB_TRY(wb_residual_be_dev(c, d_y, d_ll, dt, true, nullptr, nullptr, w.F));
-      WB_TRY(flags_err(c, &err));
-      if (err) {
-        reason = SNES_DIVERGED_LINE_SEARCH;
-        break;
-      }
+    // the line search evaluates F at the new iterate in every iteration, the last one included
+    // (SNESLineSearchApply -> SNESComputeFunction): the norms below are those of the new state
+    WB_TRY(wb_residual_be_dev(c, d_y, d_ll, dt, true, nullptr, nullptr, w.F));
+    WB_TRY(flags_err(c, &err));
+    if (err) {
+      reason = SNES_DIVERGED_LINE_SEARCH;
+      break;
     }
     WB_TRY(norm2(c, w.F, n, &fnorm));
     WB_TRY(norm2(c, d_y, n, &xnorm));

@@ -374,6 +374,14 @@ class FlowSimulation:
         check(self.L.wb_jacobian_get(self.h, ptr(rowptr), ptr(colidx), None), "wb_jacobian_get")
         return nb.value, bs.value, rowptr, colidx
 
+    def cell_faces(self):
+        """cell -> face gather lists (wb_cell_faces_get): cf_ptr, cf_face (2*face + side), cf_other"""
+        ncf = C.c_int()
+        check(self.L.wb_cell_faces_get(self.h, C.byref(ncf), None, None, None), "wb_cell_faces_get")
+        p, f, o = np.zeros(self.nowned + 1, np.int32), np.zeros(ncf.value, np.int32), np.zeros(ncf.value, np.int32)
+        check(self.L.wb_cell_faces_get(self.h, C.byref(ncf), ptr(p), ptr(f), ptr(o)), "wb_cell_faces_get")
+        return p, f, o
+
     def jacobian_values(self):
         nb, bs, rowptr, colidx = self.jacobian_pattern()
         vals = np.zeros((len(colidx), bs * bs))

@@ -233,7 +233,7 @@ def partition(mesh, owner, rank, nranks):
                 rank=rank, nranks=nranks, first_cell=first, ncell_global=n,
                 neigh_rank=np.asarray(neigh, np.int32), send_ptr=np.asarray(send_ptr, np.int32),
                 send_idx=np.asarray(send_idx, np.int32), recv_ptr=np.asarray(recv_ptr, np.int32),
-                recv_idx=np.asarray(recv_idx, np.int32))
+                recv_idx=np.asarray(recv_idx, np.int32), minc_levels=mesh.minc_levels, minc_base=mesh.minc_base)
 
 
 def hydrostatic_state(mesh, seed=SEED, two_phase_layers=0, thermo_psat=None):
@@ -283,6 +283,66 @@ def wce_state(mesh, seed=SEED, two_phase_layers=0, thermo_psat=None, pco2=(1.0e4
     rng = np.random.default_rng(seed + 2)
     pg = rng.uniform(pco2[0], pco2[1], len(primary))
     return np.stack([primary[:, 0] + pg, primary[:, 1], pg], 1), region
+
+
+# IAPWS-IF97 saturation line (region 4 basic equation, the published closed form): used only to GENERATE
+# synthetic initial states near the saturation line (config 4); the EOS kernels carry their own implementation.
+_IF97_N = (0.11670521452767e4, -0.72421316703206e6, -0.17073846940092e2, 0.12020824702470e5, -0.32325550322333e7,
+           0.14915108613530e2, -0.48232657361591e4, 0.40511340542057e6, -0.23855557567849, 0.65017534844798e3)
+
+
+def if97_saturation_pressure(t_celsius):
+    """saturation pressure (Pa) at temperature (degC), 0..373.9 degC"""
+    n = _IF97_N
+    T = np.asarray(t_celsius, float) + 273.15
+    th = T + n[8] / (T - n[9])
+    A = th * th + n[0] * th + n[1]
+    B = n[2] * th * th + n[3] * th + n[4]
+    Cc = n[5] * th * th + n[6] * th + n[7]
+    return (2.0 * Cc / (-B + np.sqrt(B * B - 4.0 * A * Cc))) ** 4 * 1.0e6
+
+
+def if97_saturation_temperature(p_pa):
+    """saturation temperature (degC) at pressure (Pa)"""
+    n = _IF97_N
+    beta = (np.asarray(p_pa, float) * 1.0e-6) ** 0.25
+    E = beta * beta + n[2] * beta + n[5]
+    F = n[0] * beta * beta + n[3] * beta + n[6]
+    G = n[1] * beta * beta + n[4] * beta + n[7]
+    D = 2.0 * G / (-F - np.sqrt(F * F - 4.0 * E * G))
+    return 0.5 * (n[9] + D - np.sqrt((n[9] + D) ** 2 - 4.0 * (n[8] + n[9] * D))) - 273.15
+
+
+def wce_band_state(mesh, seed=SEED, band=(20, 30), pco2=(1.0e4, 5.0e5)):
+    """SURVEY 8(d) config 4 state for eos_wce: hydrostatic liquid with a CO2 partial pressure U(pco2) per cell, and a
+    band of layers straddling the saturation line (T within +-2 degC of T_sat(P - P_CO2)): in the band, cells are
+    alternately single-phase liquid just below the saturation temperature (T = T_sat - U(0, 2), region 1) and
+    two-phase with a little vapour (P = P_sat(T) + P_CO2, S_v = U(0.01, 0.1), region 4, T = T_sat + U(0, 2) of the
+    hydrostatic water pressure), so that the first Newton updates push cells across the line in both directions.
+    Returns unscaled primaries [n,3] = (P, T or S_v, P_CO2) and regions [n]."""
+    primary, region = hydrostatic_state(mesh, seed=seed)
+    n = len(primary)
+    rng = np.random.default_rng(seed + 2)
+    pg = rng.uniform(pco2[0], pco2[1], n)
+    nx, ny, nz = mesh.dims
+    nat = mesh.natural[:n] % (nx * ny * nz)
+    k = nat // (nx * ny)
+    inb = (k >= band[0]) & (k < band[1])
+    pw = primary[:, 0].copy()                     # hydrostatic water pressure
+    tsat = if97_saturation_temperature(pw)
+    du = rng.uniform(0.0, 2.0, n)
+    sv = rng.uniform(0.01, 0.1, n)
+    two = inb & (((nat % nx) + (nat // nx) % ny + k) % 2 == 1)
+    liq = inb & ~two
+    P = pw + pg
+    second = primary[:, 1].copy()
+    second[liq] = tsat[liq] - du[liq]
+    t2 = tsat[two] + du[two]
+    P[two] = if97_saturation_pressure(t2) + pg[two]
+    second[two] = sv[two]
+    region = region.copy()
+    region[two] = 4
+    return np.stack([P, second, pg], 1), region
 
 
 def cube_blocks(mesh, size):
