@@ -194,6 +194,7 @@ class CpuArm:
         assert self.f.fluid_init(prob.y, prob.region) == 0
         e, self.L0 = self.f.lhs(prob.y)
         assert e == 0
+        self.L.wo_flow_pre_timestep(self.f.h)   # every step starts from this state (regions restored by pre_retry_timestep)
         self.A = self.f.bsr()
         self.nb, self.bs = self.A.contents.nb, self.A.contents.bs
         self.color = np.zeros(self.nb, np.int32)
@@ -213,10 +214,12 @@ class CpuArm:
         wo, L, p = self.wo, self.L, self.prob
         y = p.y
         t = {}
+        L.wo_flow_pre_retry_timestep(self.f.h)   # regions of the initial state (a step's transitions change them)
         t0 = time.perf_counter()
         F0 = self.residual(y)
         t["residual"] = time.perf_counter() - t0
         t0 = time.perf_counter()
+        L.wo_flow_pre_iteration(self.f.h)
         assert L.wo_fd_jacobian(self.f.h, wo.dp(y), wo.dp(self.L0), p.dt, wo.dp(F0), wo.ip(self.color), self.ncolor,
                                 1e-8, 1e-2, self.A) == 0
         t["jacobian"] = time.perf_counter() - t0
@@ -233,10 +236,13 @@ class CpuArm:
         t["ksp"] = time.perf_counter() - t0
         L.wo_pc_destroy(pc)
         t0 = time.perf_counter()
-        ynew = y - x
-        self.residual(ynew)           # the line search's function evaluation at the new iterate
+        ynew = y - x                  # shell line search, lambda = 1, with the post-check (fluid_transitions)
+        cs, cy = C.c_int(), C.c_int()
+        et = L.wo_flow_fluid_transitions(self.f.h, wo.dp(y), wo.dp(x), wo.dp(ynew), C.byref(cs), C.byref(cy))
+        if et == 0:
+            self.f.residual(ynew, self.L0, p.dt)   # the line search's function evaluation at the new iterate
         t["residual_new"] = time.perf_counter() - t0
-        self.f.lhs(y)                 # back to the initial state for the next step (not part of a step: untimed)
+        t["transitions_err"] = et
         t["its"], t["ksp_reason"] = its.value, reason
         return t
 
@@ -360,6 +366,7 @@ def run_b200(args):
     assert sim.fluid_init(y, region) == 0
     err, L0 = sim.lhs(y)
     assert err == 0
+    sim.pre_timestep()   # every step starts from this state: pre_retry_timestep restores the regions a step's transitions changed
     if args.pc_cube > 0 and args.pc == "ilu0":
         sim.set_pc_blocks(prob.blocks(m, args.pc_cube))
     pc_type = {"ilu0": flow.PC_BJACOBI_ILU0, "pbjacobi": flow.PC_PBJACOBI, "none": flow.PC_NONE}[args.pc]
@@ -377,11 +384,13 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     def step_device():
+        sim.pre_retry_timestep()
         with torch.cuda.stream(stream):
             y_d.copy_(y0_d, non_blocking=True)
         return sim.newton_solve(y_d, L0_d, dt, opts)
 
     def step_host():
+        sim.pre_retry_timestep()
         y_h.copy_(y0_h)
         return sim.newton_solve(y_h.numpy(), L0_h.numpy(), dt, opts)
 
@@ -430,18 +439,20 @@ def run_b200(args):
     for nm in ("fluid_props", "cell_inflows", "jacobian", "pc_setup", "ksp_solve", "fluid_trans"):
         t, cnt = sim.timer(nm)
         phases[nm] = {"ms": round(t, 4), "calls": cnt}
-    ksp_breakdown = sim.ksp_breakdown() if hasattr(sim, "ksp_breakdown") else None
+    ksp_breakdown_ctas = sim.ksp_breakdown_ctas()
+    ksp_breakdown = sim.ksp_breakdown()
     L.wb_timers_enable(0)
 
     # ---- parity against the CPU oracle at this state (outside every timed region): residual vector, max-scaled norm
     # and its argmax (timestepper.F90:1898-1951, dm_utils.F90:644-685), and the TRUE residual after the step
     y_fin = y_d.cpu().numpy()
+    e, _, _, r1 = sim.residual(y_fin, L0, dt)          # regions as the step left them
+    mv1, ml1 = sim.max_scaled(r1, L0, 1.0) if e == 0 else (float("nan"), -1)
+    regions_changed = int((sim.regions()[:m.nowned] != region).sum())
+    sim.pre_retry_timestep()
     e, _, _, r0 = sim.residual(y, L0, dt)
     assert e == 0
     mv0, ml0 = sim.max_scaled(r0, L0, 1.0)
-    e, _, _, r1 = sim.residual(y_fin, L0, dt)
-    mv1, ml1 = sim.max_scaled(r1, L0, 1.0) if e == 0 else (float("nan"), -1)
-    sim.lhs(y)
     parity = None
     if not args.no_parity:
         if world > 1:
@@ -528,13 +539,14 @@ def run_b200(args):
                       "us_per_ksp_iteration": round(1e3 * phases["ksp_solve"]["ms"] / max(ksp_its, 1), 2),
                       "newton_reason": int(res.reason),
                       "max_scaled_residual": [res.max_residual[0], res.max_residual[1]],
-                      "post_step_max_scaled_residual": mv1,
+                      "post_step_max_scaled_residual": mv1, "cells_changing_region_in_the_step": regions_changed,
                       "cell_updates_per_s": ncell_global * args.steps / (ms * 1e-3)},
            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8,
                    "d2h_bytes_per_step": n * 8 + C.sizeof(flow.NewtonResult), "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": int(launches), "clocks": clocks, "phases_ms": phases, "parity": parity}
     if ksp_breakdown:
         out["ksp_breakdown_us_per_iteration"] = ksp_breakdown
+        out["ksp_breakdown_min_mean_max_over_ctas"] = ksp_breakdown_ctas
     if roofline:
         out["roofline"] = roofline
     if world == 1 and not args.no_cpu_baseline:

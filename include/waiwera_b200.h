@@ -288,6 +288,10 @@ int wb_ksp_solve(wb_mat *A, wb_pc *pc, const wb_ksp_opts *opts, const double *b,
 /* Krylov iterations enqueued between host-side convergence checks (the kernels skip their
    work once the device-side flag says converged, so results do not depend on it); default 4 */
 int wb_ksp_set_check_every(int k);
+/* GMRES with block-Jacobi / ILU(0) sub-domains normally runs as one persistent kernel for the whole solve
+   (sub-domain-resident: SpMV, PC apply and Gram-Schmidt of a sub-domain stay on one SM; restart <= 31); 0 selects the
+   launch-per-operation solver instead (also: environment WB_FUSED=0).  Takes effect at the next PC set-up. */
+int wb_ksp_set_fused(int on);
 
 /* ---- Newton (SNESSolve as configured by timestepper.F90:1552-1641) ------ */
 typedef struct {
@@ -355,6 +359,12 @@ int wb_timer_get(wb_ctx *ctx, const char *name, double *ms, int64_t *count);
 int wb_timer_reset(wb_ctx *ctx);
 /* phase timers synchronise the stream at every phase end; switch them off for throughput runs */
 int wb_timers_enable(int on);
+/* The GMRES solve with block-Jacobi / ILU(0) sub-domains runs as ONE persistent kernel (the whole KSPSolve: no
+   per-operation launches to time).  Its CTA 0 accumulates the device time it spends in each phase of the Krylov
+   iterations; ns7 receives nanoseconds since the last reset: [0] SpMV + PC apply, [1] Gram-Schmidt dots, [2] grid /
+   NVLink reduction of the dots, [3] multi-AXPY + norm + halo push, [4] reduction of the norm + Hessenberg update,
+   [5] everything else (cycle starts, solution update), and [6] the number of iterations counted. */
+int wb_ksp_fused_profile(wb_ctx *ctx, double *ns7, int reset);
 /* number of kernels launched by this context since creation */
 int64_t wb_launch_count(const wb_ctx *ctx);
 /* stream the context launches on (cudaStream_t) */

@@ -12,6 +12,11 @@ pytestmark = pytest.mark.gpu
 
 DIMS = (12, 10, 16)
 DT = 1.0e6
+DT_KSP = 1.0e3
+
+
+def relerr_(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
 def _free_port():
@@ -106,13 +111,28 @@ def worker(rank, world, port, out, p2p, kind="we"):
         x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * npv).reshape(-1, npv)[nat].reshape(-1)
         ax = np.zeros_like(x)
         J.mult(x, ax)
+        # the benchmark's solver configuration: GMRES + block Jacobi over ILU(0) cube sub-domains (with the NVLink
+        # path: the persistent kernel, halo / dots / norm exchanged inside it)
+        # (the Newton system of a short time step, DT_KSP: converges in tens of iterations, so iteration counts are
+        # comparable between partitions; at DT restarted GMRES stagnates and the count moves with rounding)
+        err, _, _, rk = sim.residual(y1, L0, DT_KSP)
+        assert err == 0 and sim.jacobian(y1, L0, DT_KSP) == 0
+        bor = wmesh.minc_cube_blocks(m, 4) if kind == "minc" else wmesh.cube_blocks(m, 4)
+        pck = flow.PC(J, flow.PC_BJACOBI_ILU0, 1, bor)
+        xk = np.zeros_like(x)
+        kreason, kits, _ = flow.ksp_solve(J, pck, rk, xk, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10))
+        xk2 = np.zeros_like(x)
+        k2 = flow.ksp_solve(J, pck, rk, xk2, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10, restart=7))
+        pck.destroy()
+        assert sim.jacobian(y1, L0, DT) == 0
         y2 = y.copy()
         res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
                                                             ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))
         xt = tracer_step(sim, flow, gm, y1, nat)
         gathered = [None] * world
         dist.all_gather_object(gathered, dict(nat=nat, r=r, ax=ax, y2=y2, mv=mv, ml=ml, reason=res.reason,
-                                              its=res.iterations, lits=res.linear_iterations, xt=xt))
+                                              its=res.iterations, lits=res.linear_iterations, xt=xt, xk=xk,
+                                              kreason=kreason, kits=kits, xk2=xk2, k2=k2[:2]))
         if rank == 0:
             out.put(gathered)
         sim.destroy()
@@ -151,6 +171,28 @@ def test_partitioned_path_matches_single_gpu(world, p2p, kind):
     x = np.random.default_rng(3).uniform(-1, 1, gm.ninterior * npv)
     ax = np.zeros_like(x)
     J.mult(x, ax)
+    # the same sub-domains on one GPU: cubes cut at the partition boundaries
+    from waiwera_b200 import mesh as wmesh
+    owner = owner_for(kind, gm, world)
+    cube = wmesh.minc_cube_blocks(gm, 4) if kind == "minc" else wmesh.cube_blocks(gm, 4)
+    _, bor = np.unique(owner.astype(np.int64) * (cube.max() + 1) + cube, return_inverse=True)
+    err, _, _, rk = sim.residual(y1, L0, DT_KSP)
+    assert err == 0 and sim.jacobian(y1, L0, DT_KSP) == 0
+    pck = flow.PC(J, flow.PC_BJACOBI_ILU0, 1, bor.astype(np.int32))
+    xk = np.zeros_like(x)
+    kreason, kits, _ = flow.ksp_solve(J, pck, rk, xk, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10))
+    xk2 = np.zeros_like(x)
+    k2 = flow.ksp_solve(J, pck, rk, xk2, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10, restart=7))
+    pck.destroy()
+    assert kits < 200, kits
+    assert sim.jacobian(y1, L0, DT) == 0
+    gxk, gxk2 = np.zeros_like(xk).reshape(-1, npv), np.zeros_like(xk).reshape(-1, npv)
+    for g in gathered:
+        gxk[g["nat"]] = g["xk"].reshape(-1, npv)
+        gxk2[g["nat"]] = g["xk2"].reshape(-1, npv)
+        assert g["kreason"] == kreason > 0 and abs(g["kits"] - kits) <= 3, (g["kreason"], g["kits"], kreason, kits)
+        assert g["k2"][0] == k2[0] > 0 and abs(g["k2"][1] - k2[1]) <= 6, (g["k2"], k2[:2])
+    assert relerr_(gxk.reshape(-1), xk) < 1e-7 and relerr_(gxk2.reshape(-1), xk2) < 1e-7
     y2 = gy.copy()
     res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
                                                         ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))

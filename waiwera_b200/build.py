@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwaiwera_b200.so")
-SOURCES = ["wb_core.cu", "wb_flow.cu", "wb_tracer.cu", "wb_linalg.cu", "wb_newton.cu"]
-HEADERS = ["wb_common.cuh", "wb_state.cuh", "wb_tracer.cuh", "wb_eos.cuh", "wb_thermo.cuh", "wb_iapws_gen.cuh"]
+SOURCES = ["wb_core.cu", "wb_flow.cu", "wb_tracer.cu", "wb_linalg.cu", "wb_fused.cu", "wb_newton.cu"]
+HEADERS = ["wb_common.cuh", "wb_linalg.cuh", "wb_state.cuh", "wb_tracer.cuh", "wb_eos.cuh", "wb_thermo.cuh", "wb_iapws_gen.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -97,7 +97,12 @@ struct WbHalo {
 #define WB_P2P_MAXV 32
 #define WB_P2P_SLOT_A 4096   // byte offsets inside the region
 #define WB_P2P_SLOT_B (WB_P2P_SLOT_A + WB_P2P_MAX_RANKS * WB_P2P_MAXV * 8)
-#define WB_P2P_GHOST (WB_P2P_SLOT_B + 1024)
+// the persistent (fused) GMRES kernel keeps its own, double-buffered slots and flag kinds 3..5 (wb_fused.cu)
+// Its data travels in the "LL" format (as NCCL's low-latency protocol): every double is one 16-byte store of two words
+// (low half | sequence << 32, high half | sequence << 32), so data and flag arrive together and no fence is needed.
+#define WB_P2P_SLOT_FA (WB_P2P_SLOT_B + 1024)                                   // [2][ranks][MAXV] x 16 bytes
+#define WB_P2P_SLOT_FB (WB_P2P_SLOT_FA + 2 * WB_P2P_MAX_RANKS * WB_P2P_MAXV * 16)  // [2][ranks] x 16 bytes
+#define WB_P2P_GHOST (WB_P2P_SLOT_FB + 1024)
 struct WbP2PDev {  // by-value kernel argument
   int on, rank, nranks;
   unsigned char *region[WB_P2P_MAX_RANKS];  // region[r] = rank r's region as mapped in this process (region[rank] local)
@@ -124,6 +129,10 @@ struct WbP2P {
   int32_t *d_nb_start = nullptr;      // [nneigh] = send_ptr
   int32_t *d_dst_rank = nullptr, *d_dst_off = nullptr;  // [nsend] destination of every send entry
   unsigned *d_counter = nullptr;
+  // fused kernel: two LL ghost buffers (16 bytes per double) behind the plain ghost area
+  size_t ll_off = 0, ll_stride = 0;   // byte offset of the first buffer in the region, bytes between the two
+  std::vector<size_t> peer_ll_off, peer_ll_stride;  // [nranks] the same for every rank's region
+  int *d_fseq = nullptr;              // [4] sequence numbers of the fused kernel's exchanges (halo, dots, norm), device resident
 };
 // flags live in the first 4 KB of the region: one 64-byte line per (kind, sender rank)
 __host__ __device__ inline size_t wb_p2p_flag_off(int kind, int sender) { return (size_t)(kind * WB_P2P_MAX_RANKS + sender) * 64; }

@@ -249,6 +249,7 @@ extern "C" int wb_destroy(wb_ctx *c) {
     cudaFree(c->p2p.d_send_nb); cudaFree(c->p2p.d_nb_rank); cudaFree(c->p2p.d_nb_off); cudaFree(c->p2p.d_nb_start);
     cudaFree(c->p2p.d_counter);
     cudaFree(c->p2p.d_dst_rank); cudaFree(c->p2p.d_dst_off);
+    cudaFree(c->p2p.d_fseq);
   }
   if (c->comm && wb_nccl()) wb_nccl()->CommDestroy(c->comm);
   cudaFree(c->d_flags);
@@ -429,6 +430,7 @@ struct WbP2PBlob {
   int recv_off[WB_P2P_MAX_RANKS];
   int ghost_cells;
   int pad;
+  unsigned long long ll_off, ll_stride;
 };
 
 extern "C" int wb_comm_p2p_blob_size(void) { return (int)sizeof(WbP2PBlob); }
@@ -441,7 +443,9 @@ extern "C" int wb_comm_p2p_export(wb_ctx *c, void *blob) {
   WbHalo &h = c->halo;
   WB_CHECK(h.recv_contiguous || h.nrecv == 0, "wb_comm_p2p_export: ghost cells must be numbered in receive order");
   const int nghost = c->ninterior - c->nowned;
-  p.bytes = WB_P2P_GHOST + (size_t)(nghost + 1) * h.maxwidth * sizeof(double);
+  p.ll_off = WB_P2P_GHOST + ((((size_t)(nghost + 1) * h.maxwidth * sizeof(double)) + 255) & ~(size_t)255);
+  p.ll_stride = (((size_t)(nghost + 1) * h.maxwidth * 16) + 255) & ~(size_t)255;
+  p.bytes = p.ll_off + 2 * p.ll_stride;
   WB_CUDA(cudaMalloc(&p.local, p.bytes));
   WB_CUDA(cudaMemset(p.local, 0, p.bytes));
   WbP2PBlob b;
@@ -451,6 +455,8 @@ extern "C" int wb_comm_p2p_export(wb_ctx *c, void *blob) {
   for (int n = 0; n < h.nneigh; n++) p.recv_off[h.rank[n]] = h.recv_ptr[n];
   for (int r = 0; r < WB_P2P_MAX_RANKS; r++) b.recv_off[r] = r < c->nranks ? p.recv_off[r] : -1;
   b.ghost_cells = nghost;
+  b.ll_off = p.ll_off;
+  b.ll_stride = p.ll_stride;
   memcpy(blob, &b, sizeof(b));
   return 0;
 }
@@ -476,6 +482,12 @@ extern "C" int wb_comm_p2p_open(wb_ctx *c, const void *blobs) {
       }
       p.dev.region[r] = (unsigned char *)ptr;
     }
+  }
+  p.peer_ll_off.assign(c->nranks, 0);
+  p.peer_ll_stride.assign(c->nranks, 0);
+  for (int r = 0; r < c->nranks; r++) {
+    p.peer_ll_off[r] = (size_t)B[r].ll_off;
+    p.peer_ll_stride[r] = (size_t)B[r].ll_stride;
   }
   p.dev.rank = c->rank;
   p.dev.nranks = c->nranks;
@@ -511,6 +523,8 @@ extern "C" int wb_comm_p2p_open(wb_ctx *c, const void *blobs) {
   }
   WB_CUDA(cudaMalloc(&p.d_counter, sizeof(unsigned)));
   WB_CUDA(cudaMemset(p.d_counter, 0, sizeof(unsigned)));
+  WB_CUDA(cudaMalloc(&p.d_fseq, 4 * sizeof(int)));
+  WB_CUDA(cudaMemset(p.d_fseq, 0, 4 * sizeof(int)));
   WB_CUDA(cudaMemcpy(p.d_send_nb, send_nb.data(), sizeof(int32_t) * send_nb.size(), cudaMemcpyHostToDevice));
   WB_CUDA(cudaMemcpy(p.d_nb_rank, nb_rank.data(), sizeof(int32_t) * nb_rank.size(), cudaMemcpyHostToDevice));
   WB_CUDA(cudaMemcpy(p.d_nb_off, nb_off.data(), sizeof(int32_t) * nb_off.size(), cudaMemcpyHostToDevice));

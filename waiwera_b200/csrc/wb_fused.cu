@@ -1,0 +1,1265 @@
+// wb_fused.cu -- sub-domain-resident persistent GMRES: KSPSolve_GMRES (restarted, classical Gram-Schmidt, left
+// preconditioning with block-Jacobi / ILU(0)) as ONE cooperative kernel for the whole solve.
+//
+// Stands in for the same PETSc library code as wb_linalg.cu (KSPSolve_GMRES, MatMult_SeqBAIJ / MatMult_MPIBAIJ,
+// MatSolve_SeqBAIJ_N_NaturalOrdering, VecMDot / VecMAXPY / VecNorm; call site src/timestepper.F90:1645-1836) with
+// the same arithmetic per operation; what changes is where the data lives between the operations.
+//
+// One CTA per SM owns a fixed, contiguous set of block-Jacobi sub-domains.  The solver works in the sub-domain-major
+// ordering (a symmetric permutation of the system: rows of a sub-domain contiguous, ascending natural order inside
+// it -- the ordering the ILU(0) factors were computed in), so every vector segment a CTA touches is one contiguous
+// span.  Per Krylov iteration a CTA runs, for each of its sub-domains,
+//     SpMV rows (sliced-ELL copy of the BAIJ matrix, thread per row, operand gathered through L2)  ->  shared memory
+//     ILU(0) forward / backward sweeps in shared memory (level records streamed by TMA bulk copies into a byte ring)
+// then the Gram-Schmidt dots of its rows against the basis, a grid-wide reduction, the multi-AXPY + norm of its rows,
+// and a second grid-wide reduction whose last CTA runs the Givens / convergence update.  The only grid-wide
+// synchronisations of an iteration are those two reductions; kernel boundaries, the matrix-vector product's trip
+// through HBM, the separate normalisation and the PC's read of its right-hand side are gone.
+//
+// Multi-GPU (one process per GPU, NVLink P2P over CUDA-IPC-mapped regions): boundary entries of the new Krylov vector
+// are stored straight into the neighbours' ghost buffers by the CTA that owns them, UNSCALED, as soon as the
+// multi-AXPY has produced them (the normalisation factor is a global scalar every rank applies itself), so the halo
+// travels while the norm is being reduced; the two reductions are all-gathers of the per-GPU sums into every rank's
+// slot, summed in rank order.  No collective launch, no host involvement until the solve is over.
+#include <algorithm>
+#include <math.h>
+#include <stdlib.h>
+
+#include "wb_linalg.cuh"
+
+#define FZ_NBAR 32   // mbarriers per group and direction: at most FZ_NBAR - 1 level records in flight
+#define FZ_MAXG 4    // sub-domain groups per CTA
+#define FZ_SLICE 32  // rows per sliced-ELL slice (one warp)
+#define FZ_CH 8      // blocks of a row in flight per SpMV round
+#define FZ_SPIN_LIMIT 20000000000LL  // cycles (~10 s): a lost CTA / peer raises the abort flag instead of hanging the GPU
+
+struct WbFusedPlan {
+  int ncta = 0, ng = 1, gt = 512, nc = 512;  // CTAs, groups per CTA, threads per group, consumer threads
+  int lt = 32, off_gm = 0, off_prof = 0;     // threads of a group in the level sweeps; offsets of the GMRES state, timers
+  int sd_cap = 0, slice_cap = 0, rec_cap = 0;
+  int zs_words = 0, ring_bytes = 0;
+  size_t smem = 0;
+  int off_red = 0, off_misc = 0, off_sd = 0, off_slice = 0, off_rec = 0, off_zs = 0, off_ring = 0;
+  int nslots = 0, nslices = 0;  // sliced-ELL entries (slice, k, lane), slices
+  int4 *d_cta = nullptr, *d_sd = nullptr, *d_slice = nullptr, *d_recA = nullptr, *d_recB = nullptr;
+  int32_t *d_rec_ptr = nullptr, *d_sidx = nullptr, *d_ssrc = nullptr;
+  double *d_sval = nullptr;
+  std::vector<int32_t> h_invperm;  // original row -> row in sub-domain-major order
+  std::vector<int4> h_cta;
+  // multi-GPU: boundary rows each CTA pushes (built on first use, when the halo plan and the peer map exist)
+  bool push_built = false;
+  int32_t *d_push_ptr = nullptr, *d_push_row = nullptr, *d_push_rank = nullptr, *d_push_off = nullptr;
+};
+
+// ================================================================ host: symbolic plan
+
+template <class T> static int up(T **p, const std::vector<T> &v) {
+  WB_CUDA(cudaMalloc((void **)p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) WB_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void wb_fused_free(wb_pc *pc) {
+  WbFusedPlan *f = pc->fused;
+  if (!f) return;
+  void *ptrs[] = {f->d_cta, f->d_sd, f->d_slice, f->d_recA, f->d_recB, f->d_rec_ptr, f->d_sidx, f->d_ssrc, f->d_sval,
+                  f->d_push_ptr, f->d_push_row, f->d_push_rank, f->d_push_off};
+  for (void *p : ptrs) cudaFree(p);
+  delete f;
+  pc->fused = nullptr;
+}
+
+static int g_fused_mode = -1;  // WB_FUSED = 0 turns the persistent kernel off (launch-per-operation GMRES of wb_linalg.cu)
+static int fused_mode() {
+  if (g_fused_mode < 0) {
+    const char *e = getenv("WB_FUSED");
+    g_fused_mode = e ? atoi(e) : 1;
+  }
+  return g_fused_mode;
+}
+extern "C" int wb_ksp_set_fused(int on) {
+  g_fused_mode = on ? 1 : 0;
+  return 0;
+}
+
+int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
+  (void)blk_of;
+  wb_mat *A = pc->A;
+  wb_ctx *c = A->ctx;
+  if (!fused_mode()) return 0;
+  const int nb = pc->nb, bs = pc->bs, b2 = bs * bs, nsd = pc->nblk;
+  if (nsd < 1 || nb < 1) return 0;
+  cudaDeviceProp prop;
+  WB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  const int nsm = prop.multiProcessorCount;
+  const size_t smem_max = prop.sharedMemPerBlockOptin;
+  WbFusedPlan *f = new WbFusedPlan();
+  f->ncta = std::min(nsd, nsm);
+  // contiguous runs of sub-domains per CTA, balanced by rows
+  std::vector<int> first_sd(f->ncta + 1, 0);
+  {
+    int sd = 0;
+    long long acc = 0;
+    for (int ct = 0; ct < f->ncta; ct++) {
+      first_sd[ct] = sd;
+      const long long target = (long long)nb * (ct + 1) / f->ncta;
+      const int left_ctas = f->ncta - ct - 1;
+      // at least one sub-domain, and leave at least one for every remaining CTA
+      do {
+        acc += pc->h_blk[sd].y;
+        sd++;
+      } while (sd < nsd - left_ctas && acc + pc->h_blk[sd].y / 2 <= target);
+    }
+    first_sd[f->ncta] = nsd;
+    if (sd != nsd) {  // the tail went to nobody: cannot happen with the loop above, but never launch a wrong plan
+      delete f;
+      return 0;
+    }
+  }
+  int spc = 0;
+  for (int ct = 0; ct < f->ncta; ct++) spc = std::max(spc, first_sd[ct + 1] - first_sd[ct]);
+  f->sd_cap = spc;
+  // 12 consumer warps + the producer warp = 13 warps: at most 4 per SM sub-partition, 128 registers per thread
+  // (bs = 3: 6 + 1 warps, 2 per sub-partition, 255 registers: its 3x3 blocks need them)
+  f->nc = bs >= 3 ? 192 : 384;
+  // permutation
+  f->h_invperm.assign(nb, 0);
+  for (int p = 0; p < nb; p++) f->h_invperm[pc->h_blk_rows[p]] = p;
+  // ---- sliced-ELL copy of the matrix in the sub-domain-major ordering
+  std::vector<int4> sdtab(nsd), slices;
+  std::vector<int32_t> sidx, ssrc;
+  size_t val_words = 0;
+  f->h_cta.assign(f->ncta, make_int4(0, 0, 0, 0));
+  int slice_cap = 0;
+  const int pw = (b2 % 2 == 0) ? 2 : 1;
+  (void)pw;
+  for (int ct = 0; ct < f->ncta; ct++) {
+    const int cta_slice0 = (int)slices.size();
+    for (int sd = first_sd[ct]; sd < first_sd[ct + 1]; sd++) {
+      const int row0 = pc->h_blk[sd].x, nr = pc->h_blk[sd].y;
+      const int ns = (nr + FZ_SLICE - 1) / FZ_SLICE;
+      sdtab[sd] = make_int4(row0, nr, (int)slices.size() - cta_slice0, ns);
+      for (int s = 0; s < ns; s++) {
+        const int r0 = row0 + s * FZ_SLICE, n = std::min(FZ_SLICE, row0 + nr - r0);
+        int nk = 0;
+        for (int l = 0; l < n; l++) {
+          const int orow = pc->h_blk_rows[r0 + l];
+          nk = std::max(nk, A->h_rowptr[orow + 1] - A->h_rowptr[orow]);
+        }
+        if (val_words + (size_t)nk * b2 * FZ_SLICE >= ((size_t)1 << 31)) {
+          delete f;
+          return 0;  // 32-bit offsets
+        }
+        slices.push_back(make_int4(r0, n | (nk << 8), (int)sidx.size(), (int)val_words));
+        const size_t base = sidx.size();
+        sidx.resize(base + (size_t)nk * FZ_SLICE);
+        ssrc.resize(base + (size_t)nk * FZ_SLICE);
+        for (int k = 0; k < nk; k++)
+          for (int l = 0; l < FZ_SLICE; l++) {
+            int col = r0 + std::min(l, n - 1), src = -1;  // padding: a zero block times the row's own entry
+            if (l < n) {
+              const int orow = pc->h_blk_rows[r0 + l];
+              const int e = A->h_rowptr[orow] + k;
+              if (e < A->h_rowptr[orow + 1]) {
+                const int oc = A->h_colidx[e];
+                col = oc < nb ? f->h_invperm[oc] : oc;  // ghost columns keep their index (>= nb)
+                src = e;
+              }
+            }
+            sidx[base + (size_t)k * FZ_SLICE + l] = col;
+            ssrc[base + (size_t)k * FZ_SLICE + l] = src;
+          }
+        val_words += (size_t)nk * b2 * FZ_SLICE;
+      }
+    }
+    slice_cap = std::max(slice_cap, (int)slices.size() - cta_slice0);
+    f->h_cta[ct] = make_int4(first_sd[ct], first_sd[ct + 1] - first_sd[ct], cta_slice0, 0);
+  }
+  f->slice_cap = slice_cap;
+  f->nslots = (int)sidx.size();
+  f->nslices = (int)slices.size();
+  // ---- groups, ring plans.  Try 4, 2, 1 groups per CTA until the byte ring holds at least three of the largest
+  // level records (deep enough to hide the HBM latency behind the level-to-level dependency chain)
+  int max_rec_bytes = 0, max_rows = 0, max_level_rows = 1;
+  for (const int4 &L : pc->h_lev) {
+    max_rec_bytes = std::max(max_rec_bytes, L.y);
+    max_level_rows = std::max(max_level_rows, L.z);
+  }
+  for (int sd = 0; sd < nsd; sd++) max_rows = std::max(max_rows, pc->h_blk[sd].y);
+  f->zs_words = ((max_rows + 1) * bs + 1) & ~1;
+  bool ok = false;
+  std::vector<int32_t> rec_ptr;
+  std::vector<int4> recA, recB;
+  for (int ng = std::min(bs >= 3 ? 2 : FZ_MAXG, spc >= 4 ? 4 : (spc >= 2 ? 2 : 1)); ng >= 1 && !ok; ng >>= 1) {
+    f->ng = ng;
+    f->gt = f->nc / ng;
+    f->lt = std::min(f->gt, (max_level_rows + 31) / 32 * 32);
+    // records per group and iteration
+    int rec_cap = 0;
+    for (int ct = 0; ct < f->ncta; ct++)
+      for (int g = 0; g < ng; g++) {
+        int cnt = 0;
+        for (int sd = first_sd[ct] + g; sd < first_sd[ct + 1]; sd += ng) cnt += pc->h_blk[sd].w;
+        rec_cap = std::max(rec_cap, cnt);
+      }
+    f->rec_cap = rec_cap;
+    size_t off = 2 * FZ_MAXG * FZ_NBAR * sizeof(uint64_t);  // full + empty mbarriers
+    f->off_red = (int)off;
+    off += (size_t)std::max(f->nc / 32, WB_P2P_MAX_RANKS) * KRY_MAXV * sizeof(double);  // warp partials / rank sums
+    f->off_misc = (int)off;
+    off += 512;  // coefficients (KRY_MAXV doubles), flags, phase timers, solver state
+    f->off_prof = (int)off;
+    off += 16 * sizeof(unsigned long long);
+    f->off_gm = (int)off;
+    off += (size_t)(4 * KRY_MAXV + 8 + (KRY_MAXV + 1) * KRY_MAXV) * sizeof(double);  // column, rotations, rs, H
+    f->off_sd = (int)off;
+    off += (size_t)f->sd_cap * 2 * sizeof(int4);
+    f->off_slice = (int)off;
+    off += (size_t)f->slice_cap * sizeof(int4);
+    f->off_rec = (int)off;
+    off += (size_t)ng * rec_cap * 2 * sizeof(int4);
+    off = (off + 127) & ~(size_t)127;
+    f->off_zs = (int)off;
+    off += (size_t)ng * f->zs_words * sizeof(double);
+    off = (off + 127) & ~(size_t)127;
+    f->off_ring = (int)off;
+    if (off + (size_t)ng * 2 * max_rec_bytes + 1024 > smem_max) continue;
+    f->ring_bytes = (int)(((smem_max - 1024 - off) / ng) & ~(size_t)127);
+    f->ring_bytes = std::min(f->ring_bytes, 1 << 20);
+    f->smem = off + (size_t)ng * f->ring_bytes;
+    // ring placement of every group's records (one period = one Krylov iteration; the period restarts at offset 0)
+    rec_ptr.assign((size_t)f->ncta * ng + 1, 0);
+    recA.clear();
+    recB.clear();
+    for (int ct = 0; ct < f->ncta; ct++)
+      for (int g = 0; g < ng; g++) {
+        const size_t r0 = recA.size();
+        std::vector<int> roff, rbytes;
+        int pos = 0;
+        for (int sd = first_sd[ct] + g, slot = g; sd < first_sd[ct + 1]; sd += ng, slot += ng) {
+          const int lev0 = pc->h_blk[sd].z, nl = pc->h_blk[sd].w;
+          for (int l = 0; l < nl; l++) {
+            const int4 L = pc->h_lev[lev0 + l];
+            const int bytes = (L.y + 15) & ~15;
+            if (pos + bytes > f->ring_bytes) pos = 0;
+            roff.push_back(pos);
+            rbytes.push_back(bytes);
+            recA.push_back(make_int4(L.x, L.y, pos, 0));
+            recB.push_back(make_int4(L.z, L.w, slot, (l == 0 ? 1 : 0) | (l == nl - 1 ? 2 : 0)));
+            pos += bytes;
+          }
+        }
+        const int P = (int)roff.size();
+        for (int i = 0; i < P; i++) {
+          // the most recent earlier record (cyclically) whose space overlaps record i must have been consumed
+          int lag = P;
+          for (int d = 1; d < P; d++) {
+            const int j = ((i - d) % P + P) % P;
+            if (roff[j] < roff[i] + rbytes[i] && roff[i] < roff[j] + rbytes[j]) {
+              lag = d;
+              break;
+            }
+          }
+          recA[r0 + i].w = std::max(1, std::min(lag, FZ_NBAR - 1));
+        }
+        rec_ptr[(size_t)ct * ng + g + 1] = (int32_t)recA.size();
+      }
+    ok = true;
+  }
+  if (getenv("WB_FUSED_VERBOSE"))
+    fprintf(stderr, "[wb_fused] %s: %d sub-domains (max %d rows) on %d CTAs (max %d each), %d group(s) x %d threads, level records <= %d bytes, "
+                    "ring %d bytes per group, %d records per group and iteration, shared memory %zu of %zu bytes\n",
+            ok ? "plan" : "NOT USABLE (level records do not fit the ring)", nsd, max_rows, f->ncta, spc, f->ng, f->gt, max_rec_bytes,
+            f->ring_bytes, f->rec_cap, f->smem, smem_max);
+  if (!ok) {
+    delete f;
+    return 0;
+  }
+  WB_TRY(up(&f->d_cta, f->h_cta));
+  WB_TRY(up(&f->d_sd, sdtab));
+  WB_TRY(up(&f->d_slice, slices));
+  WB_TRY(up(&f->d_recA, recA));
+  WB_TRY(up(&f->d_recB, recB));
+  WB_TRY(up(&f->d_rec_ptr, rec_ptr));
+  WB_TRY(up(&f->d_sidx, sidx));
+  WB_TRY(up(&f->d_ssrc, ssrc));
+  WB_CUDA(cudaMalloc(&f->d_sval, std::max<size_t>(val_words, 1) * sizeof(double) + WB_PAD_BYTES));
+  pc->fused = f;
+  return 0;
+}
+
+// numeric part: BAIJ values -> plane layout of the slices (zero blocks where a row is shorter than its slice)
+template <int BS>
+__global__ void k_sell_fill(const double *__restrict__ val, const int4 *__restrict__ slices, int nslices,
+                            const int32_t *__restrict__ ssrc, double *__restrict__ sval) {
+  constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int4 S = slices[s];
+  const int nk = S.y >> 8;
+  for (int k = 0; k < nk; k++) {
+    const int src = ssrc[S.z + k * FZ_SLICE + lane];
+    double v[B2];
+#pragma unroll
+    for (int q = 0; q < B2; q++) v[q] = src >= 0 ? __ldcs(val + (size_t)src * B2 + q) : 0.0;
+    double *dst = sval + (size_t)S.w + (size_t)k * B2 * FZ_SLICE;
+#pragma unroll
+    for (int q = 0; q < NPL; q++)
+#pragma unroll
+      for (int w = 0; w < PW; w++) dst[((size_t)q * FZ_SLICE + lane) * PW + w] = v[q * PW + w];
+  }
+}
+
+int wb_fused_refresh(wb_pc *pc) {
+  WbFusedPlan *f = pc->fused;
+  if (!f || f->nslices == 0) return 0;
+  wb_mat *A = pc->A;
+  wb_ctx *c = A->ctx;
+  const int grid = wb_grid((size_t)f->nslices * 32, 256);
+  switch (pc->bs) {
+    case 1: k_sell_fill<1><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_sval); break;
+    case 2: k_sell_fill<2><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_sval); break;
+    default: k_sell_fill<3><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_sval); break;
+  }
+  WB_LAUNCH(c);
+  WB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================ device: the persistent kernel
+
+struct FusedArgs {
+  // plan
+  const int4 *cta, *sd, *blk, *slice, *recA, *recB;
+  const int32_t *rec_ptr, *sidx, *perm;
+  const double *sval, *stream;
+  int ng, gt, nc, lt, sd_cap, slice_cap, rec_cap, zs_words, ring_bytes;
+  int off_red, off_misc, off_gm, off_prof, off_sd, off_slice, off_rec, off_zs, off_ring;
+  int nb, ncta;
+  size_t ld;
+  // vectors: b / xout in the caller's ordering, everything else in the sub-domain-major ordering
+  const double *b;
+  double *xout, *V, *wa, *wb, *xp, *part;
+  int *bar;  // [0] arrivals, [1] release generation, [2] abort
+  GmresUpd upd;
+  double *yv;
+  // multi-GPU
+  WbP2PDev P;
+  int nneigh;
+  const int32_t *nb_rank;
+  unsigned long long ll_off[WB_P2P_MAX_RANKS], ll_stride[WB_P2P_MAX_RANKS];  // LL ghost buffers of every rank
+  const int32_t *push_ptr, *push_row, *push_rank, *push_off;
+  int *fseq;
+  unsigned long long *prof;
+};
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking phase test (try_wait may suspend the thread for a while: the producer polls several barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// consumer-side wait for a level record: bounded, so that a broken ring plan raises the abort flag instead of hanging
+__device__ __forceinline__ void fz_mbar_wait(uint64_t *bar, uint32_t parity, int *abort_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 1023u) == 0) {
+      if (clock64() - t0 > FZ_SPIN_LIMIT) atomicExch(abort_flag, 1);
+      if (__ldcg(abort_flag)) return;
+    }
+  }
+}
+__device__ __forceinline__ int fz_ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fz_st_release(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long fz_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- LL transport of one double: a 16-byte store of (low half | seq << 32, high half | seq << 32); the reader
+// polls until both words carry the sequence number it expects -- data and flag travel together, no fence
+__device__ __forceinline__ void ll_store(void *slot, double v, int seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), sq = (unsigned long long)(unsigned)seq << 32;
+  const unsigned long long w0 = (b & 0xffffffffull) | sq, w1 = (b >> 32) | sq;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_load_wait(const void *slot, int seq, int *err) {
+  unsigned long long w0, w1;
+  const unsigned sq = (unsigned)seq;
+  long long t0 = 0;
+  unsigned n = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    if ((unsigned)(w0 >> 32) == sq && (unsigned)(w1 >> 32) == sq) break;
+    if ((++n & 1023u) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > FZ_SPIN_LIMIT) {
+        atomicExch(err, 1);
+        break;
+      }
+    }
+  }
+  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+
+#define FZ_BAR_ALL 15  // named barrier of all consumer threads; groups use 1 + g
+
+struct FzGrid {
+  int *bar;  // [0] arrivals (monotonic), [2] abort
+  int ncta, gen;
+};
+// Grid-wide synchronisation of the co-resident CTAs on a monotonic arrival counter: every CTA adds 1 (release) and
+// polls (acquire) until all have arrived.  There is no "last CTA" section and no second flag: what follows a
+// reduction is computed redundantly, in the same order, by every CTA from the partials all of them can now read.
+__device__ __forceinline__ void fz_grid_sync(FzGrid &G, int tid, int nc) {
+  bar_sync_named(FZ_BAR_ALL, nc);  // the CTA's writes happen before thread 0's release (cumulativity)
+  if (tid == 0) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(&G.bar[0]) : "memory");
+    const int target = (G.gen + 1) * G.ncta;
+    const long long t0 = clock64();
+    unsigned n = 0;
+    while (fz_ld_acquire(&G.bar[0]) < target) {
+      if ((++n & 255u) == 0) {
+        if (clock64() - t0 > FZ_SPIN_LIMIT) atomicExch(&G.bar[2], 1);
+        if (__ldcg(&G.bar[2])) break;
+      }
+    }
+  }
+  bar_sync_named(FZ_BAR_ALL, nc);
+  G.gen++;
+}
+
+// every CTA: sums of all CTAs' partials part[cta][j], j < nv, in a fixed order -> s_vals[j] (shared).  Thread (j, sub)
+// sums every (nc / 32)-th CTA's partial in ascending CTA order with the loads issued ahead of the adds, then thread j
+// folds the sub-sums in order.
+__device__ __forceinline__ void fz_fold_parts(const double *part, int ncta, int nv, double *s_vals, double *s_tmp,
+                                              int tid, int nc) {
+  const int j = tid & 31, sub = tid >> 5, nsub = nc >> 5;
+  if (j < nv) {
+    double s = 0.0;
+    for (int c0 = sub; c0 < ncta; c0 += 8 * nsub) {
+      double t[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int ct = c0 + k * nsub;
+        t[k] = ct < ncta ? __ldcg(&part[(size_t)ct * KRY_MAXV + j]) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (c0 + k * nsub < ncta) s += t[k];
+    }
+    s_tmp[sub * KRY_MAXV + j] = s;
+  }
+  bar_sync_named(FZ_BAR_ALL, nc);
+  if (tid < nv) {
+    double s = 0.0;
+    for (int q = 0; q < nsub; q++) s += s_tmp[q * KRY_MAXV + tid];
+    s_vals[tid] = s;
+  }
+  bar_sync_named(FZ_BAR_ALL, nc);
+}
+
+// multi-GPU: all-gather of this GPU's nv sums (s_vals, identical in every CTA) over NVLink in the LL format -- CTA 0
+// stores them into every rank's slot (buffer seq & 1), every CTA of every GPU polls its own GPU's slots -- then the
+// sum over ranks in rank order (bit-identical everywhere) -> s_vals
+__device__ __forceinline__ void fz_allgather_sum(const FusedArgs &a, int seq, int nv, double *s_vals, double *s_tmp,
+                                                 size_t slot_off, int per_rank, int cta, int tid, int nc) {
+  const WbP2PDev &P = a.P;
+  const size_t buf = (size_t)(seq & 1) * WB_P2P_MAX_RANKS * per_rank * 16;
+  if (cta == 0) {
+    for (int idx = tid; idx < P.nranks * nv; idx += nc) {
+      const int r = idx / nv, j = idx - r * nv;
+      ll_store(P.region[r] + slot_off + buf + (size_t)(P.rank * per_rank + j) * 16, s_vals[j], seq);
+    }
+  }
+  for (int idx = tid; idx < P.nranks * nv; idx += nc) {
+    const int r = idx / nv, j = idx - r * nv;
+    s_tmp[r * KRY_MAXV + j] = ll_load_wait(P.region[P.rank] + slot_off + buf + (size_t)(r * per_rank + j) * 16, seq, P.err);
+  }
+  bar_sync_named(FZ_BAR_ALL, nc);
+  if (tid < nv) {
+    double s = 0.0;
+    for (int r = 0; r < P.nranks; r++) s += s_tmp[r * KRY_MAXV + tid];
+    s_vals[tid] = s;
+  }
+  bar_sync_named(FZ_BAR_ALL, nc);
+}
+
+// The small GMRES state (Hessenberg matrix in its rotated form, Givens rotations, right-hand side of the least-squares
+// problem, convergence state) lives in the shared memory of EVERY CTA and is updated redundantly by each of them from
+// the same reduced numbers with the same instructions: no broadcast, no serial section behind a grid barrier.
+struct FzState {
+  double res, rnorm0, scal1;
+  int its, it_inner, reason, done;
+};
+// Arnoldi column `it` complete: s_h[0..it] = dots, nrm2 = |w|^2.  One thread; the arithmetic of gmres_update
+// (wb_linalg.cuh: KSPGMRESUpdateHessenberg + KSPConvergedDefault) on the CTA's copy of the state.
+__device__ __forceinline__ void fz_gmres_update(const GmresUpd &u, FzState *st, double nrm2, double *s_h, double *s_H,
+                                                double *s_cs, double *s_sn, double *s_rs) {
+  const int it = st->it_inner, m = u.m;
+  const double tt = sqrt(nrm2);
+  s_h[it + 1] = tt;
+  const bool happy = (tt < 1.e-30 * fmax(st->res, 1e-300)) || tt == 0.0;
+  st->scal1 = happy ? 1.0 : 1.0 / tt;
+  double *Hc = s_H + (size_t)(m + 1) * it;
+  for (int j = 0; j <= it + 1; j++) Hc[j] = s_h[j];
+  for (int j = 0; j < it; j++) {
+    const double t1 = Hc[j], t2 = Hc[j + 1];
+    Hc[j] = s_cs[j] * t1 + s_sn[j] * t2;
+    Hc[j + 1] = -s_sn[j] * t1 + s_cs[j] * t2;
+  }
+  const double hh = Hc[it], hp = Hc[it + 1];
+  const double den = sqrt(hh * hh + hp * hp);
+  if (den == 0.0) {
+    st->reason = -5;  // KSP_DIVERGED_BREAKDOWN
+    st->done = 1;
+    return;
+  }
+  s_cs[it] = hh / den;
+  s_sn[it] = hp / den;
+  s_rs[it + 1] = -s_sn[it] * s_rs[it];
+  s_rs[it] = s_cs[it] * s_rs[it];
+  Hc[it] = s_cs[it] * hh + s_sn[it] * hp;
+  Hc[it + 1] = 0.0;
+  const double res = fabs(s_rs[it + 1]);
+  st->res = res;
+  st->it_inner = it + 1;
+  st->its += 1;
+  int reason = 0;
+  const double ttol = fmax(u.rtol * st->rnorm0, u.atol);
+  if (res != res) reason = -9;
+  else if (res <= ttol) reason = (res < u.atol) ? 3 : 2;
+  else if (res >= u.dtol * st->rnorm0) reason = -4;
+  if (!reason && happy) reason = 5;
+  if (!reason && st->its >= u.maxit) reason = -3;
+  if (reason) {
+    st->reason = reason;
+    st->done = 1;
+  }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const FusedArgs a) {
+  constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, nc = a.nc, ng = a.ng, gt = a.gt;
+  const int cta = blockIdx.x;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  double *s_red = reinterpret_cast<double *>(smem + a.off_red);       // [warps][KRY_MAXV]
+  double *s_cf = reinterpret_cast<double *>(smem + a.off_misc);       // [KRY_MAXV + 2]
+  double *s_h = reinterpret_cast<double *>(smem + a.off_gm);          // [KRY_MAXV + 2] dots / Hessenberg column
+  double *s_cs = s_h + KRY_MAXV + 2, *s_sn = s_cs + KRY_MAXV, *s_rs = s_sn + KRY_MAXV;  // rs: [KRY_MAXV + 1]
+  double *s_H = s_rs + KRY_MAXV + 2;                                  // [(m + 1) * m]
+  FzState *s_st = reinterpret_cast<FzState *>(smem + a.off_misc + 448);
+  volatile int *s_stop = reinterpret_cast<volatile int *>(smem + a.off_misc + 324);
+  int *s_nrec = reinterpret_cast<int *>(smem + a.off_misc + 328);     // [FZ_MAXG]
+  volatile int *s_consumed = reinterpret_cast<volatile int *>(smem + a.off_misc + 432);  // [FZ_MAXG] level records consumed
+  int4 *s_sd = reinterpret_cast<int4 *>(smem + a.off_sd);             // [sd_cap][2]
+  int4 *s_slice = reinterpret_cast<int4 *>(smem + a.off_slice);
+  int4 *s_rec = reinterpret_cast<int4 *>(smem + a.off_rec);           // [ng][rec_cap][2]
+  const int4 C = a.cta[cta];
+  const int sd0 = C.x, nsd = C.y, slice0 = C.z;
+
+  // ---- set-up: barriers, tables -> shared memory
+  if (tid == 0) {
+    for (int i = 0; i < FZ_MAXG * FZ_NBAR; i++) {
+      mbar_init(&full[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *s_stop = 0;
+    for (int i = 0; i < FZ_MAXG; i++) s_consumed[i] = 0;
+  }
+  int nslice_cta = 0;
+  for (int s = tid; s < nsd; s += blockDim.x) {
+    s_sd[2 * s] = a.sd[sd0 + s];
+    s_sd[2 * s + 1] = a.blk[sd0 + s];
+  }
+  {
+    const int4 last = a.sd[sd0 + nsd - 1];
+    nslice_cta = last.z + last.w;
+  }
+  for (int s = tid; s < nslice_cta; s += blockDim.x) s_slice[s] = a.slice[slice0 + s];
+  for (int g = 0; g < ng; g++) {
+    const int r0 = a.rec_ptr[cta * ng + g], r1 = a.rec_ptr[cta * ng + g + 1];
+    if (tid == 0) s_nrec[g] = r1 - r0;
+    for (int r = tid; r < r1 - r0; r += blockDim.x) {
+      s_rec[((size_t)g * a.rec_cap + r) * 2] = a.recA[r0 + r];
+      s_rec[((size_t)g * a.rec_cap + r) * 2 + 1] = a.recB[r0 + r];
+    }
+  }
+  __syncthreads();
+
+  // ================================================================ producer warp: feeds the rings of all groups.
+  // Every LANE owns every (32 / ng)-th record of one group: it waits until the record whose ring space its next record
+  // takes has been consumed, issues the bulk copy, and moves on -- 32 records are being issued at any time, so the
+  // per-record issue cost (a few hundred cycles of dependent instructions in one thread) is off the consumers'
+  // critical path.  The lanes run ahead of the consumers across phases and iterations until the stop flag is raised.
+  if (tid >= nc) {
+    const int pl = tid - nc, g = pl % ng, per = 32 / ng;
+    const int P = s_nrec[g];
+    if (P > 0) {
+      const int4 *rec = s_rec + (size_t)g * a.rec_cap * 2;
+      uint64_t *fullg = full + g * FZ_NBAR;
+      unsigned char *ring = smem + a.off_ring + (size_t)g * a.ring_bytes;
+      long long q = pl / ng, qlast = -1;
+      int pos = (int)(q % P);
+      while (true) {
+        const int4 A = rec[2 * pos];
+        bool stopped = false;
+        if (q >= A.w) {
+          // the record whose space this one takes must have been consumed.  The consumers publish a monotonic count
+          // (a lane may be asking about a record far ahead of the consumers: mbarrier phase parities would alias)
+          const int need = (int)(q - A.w) + 1;
+          while (s_consumed[g] < need) {
+            if (*s_stop) {
+              stopped = true;
+              break;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // their reads before this bulk write
+        }
+        if (stopped || *s_stop) break;
+        uint64_t *fb = &fullg[q % FZ_NBAR];
+        mbar_expect_tx(fb, (uint32_t)A.y);
+        tma_load_1d(ring + A.z, a.stream + A.x, (uint32_t)A.y, fb);
+        qlast = q;
+        q += per;
+        pos = (int)((pos + per) % P);
+      }
+      // the copy this lane issued last must have landed before the CTA's shared memory goes away (its earlier ones
+      // were consumed: the lane waited for a later record's space)
+      if (qlast >= 0) mbar_wait(&fullg[qlast % FZ_NBAR], (uint32_t)((qlast / FZ_NBAR) & 1));
+    }
+    return;
+  }
+
+  // ================================================================ consumers
+  const int g = tid / gt, gtid = tid - g * gt;
+  const int gwarp = gtid >> 5, gwarps = gt >> 5, lane = tid & 31;
+  const int warp = tid >> 5, nwarps = nc >> 5;
+  double *zs = reinterpret_cast<double *>(smem + a.off_zs) + (size_t)g * a.zs_words;
+  const unsigned char *ring = smem + a.off_ring + (size_t)g * a.ring_bytes;
+  const int4 *rec = s_rec + (size_t)g * a.rec_cap * 2;
+  uint64_t *fullg = full + g * FZ_NBAR;
+  const int nrec = s_nrec[g];
+  const int lt = a.lt;  // threads of the group that take part in the level sweeps (the widest level, rounded to warps)
+  const bool waiter = gtid == lt - 32;
+  // rows [R0, R1) and elements [e0, e1) of this CTA; vector body [eb, ee) is 16-byte aligned
+  const int R0 = s_sd[0].x, R1 = s_sd[2 * (nsd - 1)].x + s_sd[2 * (nsd - 1)].y;
+  const int e0 = R0 * BS, e1 = R1 * BS;
+  const int eb = (e0 + 1) & ~1, ee = e1 & ~1;
+  const bool multi = a.P.on != 0 && a.P.nranks > 1;
+  FzGrid G = {a.bar, a.ncta, 0};
+  double *partA = a.part, *partB = a.part + (size_t)WB_NUM_SMS * 2 * KRY_MAXV;  // dots / norm partials: two buffers
+  int hseq = 0, aseq = 0, bseq = 0;
+  if (multi) {
+    hseq = __ldcg(&a.fseq[0]);
+    aseq = __ldcg(&a.fseq[1]);
+    bseq = __ldcg(&a.fseq[2]);
+  }
+  const GmresUpd &u = a.upd;
+  const int m = u.m;
+  int slot = 0, ri = 0, nconsumed = 0;  // mbarrier slot of the group's next level record, its position in the record list
+  uint32_t phase = 0;
+  // phase timers of CTA 0 (thread 0), kept in shared memory
+  unsigned long long *s_prof = reinterpret_cast<unsigned long long *>(smem + a.off_prof);  // [16]; [8] = previous stamp
+  const bool profiler = (tid == 0);  // every CTA keeps its own phase times (CTA 0's are the ones the ABI reports)
+  if (profiler) {
+    for (int k = 0; k < 16; k++) s_prof[k] = 0;
+    s_prof[8] = fz_now();
+  }
+#define FZ_STAMP(k)                  \
+  do {                               \
+    if (profiler) {                  \
+      const unsigned long long t_ = fz_now(); \
+      s_prof[k] += t_ - s_prof[8];   \
+      s_prof[8] = t_;                \
+    }                                \
+  } while (0)
+
+  // x = 0 on the rows of this CTA
+  for (int e = e0 + tid; e < e1; e += nc) a.xp[e] = 0.0;
+
+  // ---- SpMV + ILU(0) of the CTA's sub-domains.  mode 0: t = b; 1: t = A (xop * s), V_it = xop * s;
+  // 2: t = b - A xop.  Result w_dst = M^-1 t on the CTA's rows.
+  auto sp_phase = [&](int mode, const double *xop, double s, double *vstore, double *w_dst) {
+    // ghost entries: this GPU's LL buffer (hseq & 1); every entry carries the sequence number of its push, so a
+    // gather simply polls the entry it needs -- rows without ghost columns never wait
+    const unsigned char *xg = multi ? a.P.region[a.P.rank] + a.ll_off[a.P.rank] + (size_t)(hseq & 1) * a.ll_stride[a.P.rank]
+                                    : nullptr;
+    for (int sl = g; sl < nsd; sl += ng) {
+      const int4 sA = s_sd[2 * sl], sB = s_sd[2 * sl + 1];
+      const int row0 = sA.x, nr = sA.y, nl = sB.w;
+      if (gtid < BS) zs[nr * BS + gtid] = 0.0;  // the slot padding blocks of the level records multiply
+      if (mode == 0) {
+        for (int li = gtid; li < nr; li += gt) {
+          const size_t ob = (size_t)a.perm[row0 + li] * BS;
+#pragma unroll
+          for (int i = 0; i < BS; i++) zs[li * BS + i] = a.b[ob + i];
+        }
+      } else {
+        for (int si = gwarp; si < sA.w; si += gwarps) {
+          const int4 S = s_slice[sA.z + si];
+          const int n = S.y & 255, nk = S.y >> 8;
+          const int32_t *ip = a.sidx + S.z + lane;
+          const double *vp = a.sval + (size_t)S.w + (size_t)lane * PW;
+          double acc[BS];
+#pragma unroll
+          for (int i = 0; i < BS; i++) acc[i] = 0.0;
+          // up to FZ_CH blocks of the row in flight at once (index and value loads first, then the gathers of the
+          // operand in two halves): a 7-point row is one round trip to HBM plus one to L2
+          for (int k0 = 0; k0 < nk; k0 += FZ_CH) {
+            int col[FZ_CH];
+            double v[FZ_CH][B2];
+#pragma unroll
+            for (int uu = 0; uu < FZ_CH; uu++) {
+              const int k = min(k0 + uu, nk - 1);  // past the end: re-read the last block, its x is zeroed
+              col[uu] = __ldcs(ip + k * FZ_SLICE);
+              const double *bp = vp + (size_t)k * B2 * FZ_SLICE;
+#pragma unroll
+              for (int qq = 0; qq < NPL; qq++) {
+                if (PW == 2) {
+                  const double2 t = __ldcs(reinterpret_cast<const double2 *>(bp + (size_t)qq * FZ_SLICE * 2));
+                  v[uu][2 * qq] = t.x;
+                  v[uu][2 * qq + 1] = t.y;
+                } else {
+                  v[uu][qq] = __ldcs(bp + (size_t)qq * FZ_SLICE);
+                }
+              }
+            }
+#pragma unroll
+            for (int h0 = 0; h0 < FZ_CH; h0 += FZ_CH / 2) {
+              double x[FZ_CH / 2][BS];
+#pragma unroll
+              for (int uh = 0; uh < FZ_CH / 2; uh++) {
+                const int uu = h0 + uh;
+                const bool on = k0 + uu < nk;
+                const bool own = col[uu] < a.nb;
+                if (on && !own) {
+                  const unsigned char *gp = xg + (size_t)(col[uu] - a.nb) * BS * 16;
+#pragma unroll
+                  for (int j = 0; j < BS; j++) x[uh][j] = ll_load_wait(gp + j * 16, hseq, a.P.err) * s;
+                } else {
+                  const double *xp_ = xop + (size_t)col[uu] * BS;
+                  if (BS == 2) {
+                    const double2 t = on ? __ldcg(reinterpret_cast<const double2 *>(xp_)) : make_double2(0.0, 0.0);
+                    x[uh][0] = t.x * s;
+                    x[uh][1] = t.y * s;
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < BS; j++) x[uh][j] = on ? __ldcg(xp_ + j) * s : 0.0;
+                  }
+                }
+              }
+#pragma unroll
+              for (int uh = 0; uh < FZ_CH / 2; uh++)
+#pragma unroll
+                for (int j = 0; j < BS; j++)
+#pragma unroll
+                  for (int i = 0; i < BS; i++) acc[i] += v[h0 + uh][j * BS + i] * x[uh][j];
+            }
+          }
+          if (lane < n) {
+            const int row = S.x + lane, li = row - row0;
+            if (mode == 1) {
+#pragma unroll
+              for (int i = 0; i < BS; i++) {
+                vstore[(size_t)row * BS + i] = __ldcg(xop + (size_t)row * BS + i) * s;
+                zs[li * BS + i] = acc[i];
+              }
+            } else {
+              const size_t ob = (size_t)a.perm[row] * BS;
+#pragma unroll
+              for (int i = 0; i < BS; i++) zs[li * BS + i] = a.b[ob + i] - acc[i];
+            }
+          }
+        }
+      }
+      bar_sync_named(1 + g, gt);
+      if (profiler) s_prof[7] += fz_now() - s_prof[8];  // SpMV share of the phase (group 0)
+      // forward and backward sweeps, level by level, by the first `lt` threads of the group only (a level never has
+      // more rows; the other warps would just burn issue slots walking the loop).  One thread looks out for the next
+      // record while the others apply the current one; the level barrier then publishes its acquire to everybody.
+      if (gtid < lt && nl > 0) {
+        long long tc0 = 0, tc1 = 0, tc2 = 0;
+        if (profiler) tc0 = clock64();
+        fz_mbar_wait(&fullg[slot], phase, &a.bar[2]);
+        if (profiler) {
+          tc1 = clock64();
+          s_prof[9] += tc1 - tc0;  // cycles waiting for the first level record
+        }
+        for (int l = 0; l < nl; l++) {
+          if (profiler) tc0 = clock64();
+          const int4 A = rec[2 * ri], B = rec[2 * ri + 1];
+          ilu_level<BS>(reinterpret_cast<const double *>(ring + A.z), B.x, B.y & 0xffff, (B.y >> 16) != 0, zs, lt, gtid);
+          const int slot_n = slot + 1 == FZ_NBAR ? 0 : slot + 1;
+          const uint32_t phase_n = slot + 1 == FZ_NBAR ? phase ^ 1u : phase;
+          if (waiter && l + 1 < nl) fz_mbar_wait(&fullg[slot_n], phase_n, &a.bar[2]);
+          if (profiler) tc1 = clock64();
+          bar_sync_named(8 + g, lt);
+          if (profiler) {
+            tc2 = clock64();
+            s_prof[10] += tc1 - tc0;  // cycles in thread 0's own part of a level
+            s_prof[11] += tc2 - tc1;  // cycles at the level barrier (the other warps' rows, the waiter's look-out)
+          }
+          nconsumed++;
+          if (gtid == 0) s_consumed[g] = nconsumed;  // the ring space of this record may be reused
+          slot = slot_n;
+          phase = phase_n;
+          if (++ri == nrec) ri = 0;
+        }
+      }
+      bar_sync_named(1 + g, gt);
+      for (int li = gtid; li < nr; li += gt) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) w_dst[(size_t)(row0 + li) * BS + i] = zs[li * BS + i];
+      }
+      bar_sync_named(1 + g, gt);
+    }
+  };
+
+  // ---- dots of w (this CTA's rows) against nv vectors V_j = V + j * ldv -> part[cta][j]
+  auto dots = [&](const double *w, const double *V, size_t ldv, int nv, double *part) {
+    for (int j0 = 0; j0 < nv; j0 += 8) {
+      const int nvc = min(8, nv - j0);
+      double acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] = 0.0;
+      for (int i = (eb >> 1) + tid; i < (ee >> 1); i += 2 * nc) {
+        // two entries per thread in flight: 2 x 8 vector loads before the first use
+        const int i2 = i + nc < (ee >> 1) ? i + nc : i;
+        const double2 wi = __ldcg(reinterpret_cast<const double2 *>(w + 2 * (size_t)i));
+        double2 wj = __ldcg(reinterpret_cast<const double2 *>(w + 2 * (size_t)i2));
+        if (i2 == i) wj = make_double2(0.0, 0.0);
+        double2 v[8], v2[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int j = j0 + (k < nvc ? k : nvc - 1);  // past nvc: re-read the last vector, sums dropped
+          v[k] = *reinterpret_cast<const double2 *>(V + (size_t)j * ldv + 2 * (size_t)i);
+          v2[k] = *reinterpret_cast<const double2 *>(V + (size_t)j * ldv + 2 * (size_t)i2);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          acc[k] += wi.x * v[k].x;
+          acc[k] += wi.y * v[k].y;
+          acc[k] += wj.x * v2[k].x;
+          acc[k] += wj.y * v2[k].y;
+        }
+      }
+      if (tid == 0) {  // unaligned head / tail element
+        if (eb > e0)
+          for (int k = 0; k < nvc; k++) acc[k] += w[e0] * V[(size_t)(j0 + k) * ldv + e0];
+        if (ee < e1 && ee >= eb)
+          for (int k = 0; k < nvc; k++) acc[k] += w[e1 - 1] * V[(size_t)(j0 + k) * ldv + e1 - 1];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const double sres = warp_sum(acc[k]);
+        if (lane == 0 && k < nvc) s_red[warp * KRY_MAXV + j0 + k] = sres;
+      }
+    }
+    bar_sync_named(FZ_BAR_ALL, nc);
+    if (tid < nv) {
+      double sres = 0.0;
+      for (int wq = 0; wq < nwarps; wq++) sres += s_red[wq * KRY_MAXV + tid];
+      part[(size_t)cta * KRY_MAXV + tid] = sres;
+    }
+  };
+
+  // ---- w += sum_j s_cf[j] V_j on this CTA's rows (sequential in j per entry, as VecMAXPY); with `norm` the CTA's
+  // part of |w|^2 -> part[cta][0]
+  auto maxpy = [&](double *w, const double *V, size_t ldv, int nv, double *part) {
+    double nrm = 0.0;
+    for (int i = (eb >> 1) + tid; i < (ee >> 1); i += 2 * nc) {
+      const int i2 = i + nc;
+      const bool two = i2 < (ee >> 1);
+      const int ib = two ? i2 : i;
+      double2 wi = __ldcg(reinterpret_cast<const double2 *>(w + 2 * (size_t)i));
+      double2 wj = __ldcg(reinterpret_cast<const double2 *>(w + 2 * (size_t)ib));
+      for (int j0 = 0; j0 < nv; j0 += 8) {
+        const int nvc = min(8, nv - j0);
+        double2 v[8], v2[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int j = j0 + (k < nvc ? k : nvc - 1);
+          v[k] = *reinterpret_cast<const double2 *>(V + (size_t)j * ldv + 2 * (size_t)i);
+          v2[k] = *reinterpret_cast<const double2 *>(V + (size_t)j * ldv + 2 * (size_t)ib);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const double cj = k < nvc ? s_cf[j0 + k] : 0.0;
+          wi.x += cj * v[k].x;
+          wi.y += cj * v[k].y;
+          wj.x += cj * v2[k].x;
+          wj.y += cj * v2[k].y;
+        }
+      }
+      *reinterpret_cast<double2 *>(w + 2 * (size_t)i) = wi;
+      nrm += wi.x * wi.x;
+      nrm += wi.y * wi.y;
+      if (two) {
+        *reinterpret_cast<double2 *>(w + 2 * (size_t)i2) = wj;
+        nrm += wj.x * wj.x;
+        nrm += wj.y * wj.y;
+      }
+    }
+    if (tid == 0) {
+      if (eb > e0) {
+        double wi = w[e0];
+        for (int j = 0; j < nv; j++) wi += s_cf[j] * V[(size_t)j * ldv + e0];
+        w[e0] = wi;
+        nrm += wi * wi;
+      }
+      if (ee < e1 && ee >= eb) {
+        double wi = w[e1 - 1];
+        for (int j = 0; j < nv; j++) wi += s_cf[j] * V[(size_t)j * ldv + e1 - 1];
+        w[e1 - 1] = wi;
+        nrm += wi * wi;
+      }
+    }
+    if (part) {
+      const double sres = warp_sum(nrm);
+      if (lane == 0) s_red[warp * KRY_MAXV] = sres;
+      bar_sync_named(FZ_BAR_ALL, nc);
+      if (tid == 0) {
+        double t = 0.0;
+        for (int wq = 0; wq < nwarps; wq++) t += s_red[wq * KRY_MAXV];
+        part[(size_t)cta * KRY_MAXV] = t;
+      }
+    }
+  };
+
+  // ---- multi-GPU: the boundary rows of this CTA -> the neighbours' ghost buffers (buffer (hseq + 1) & 1), unscaled
+  auto push = [&](const double *w) {
+    if (!multi || a.nneigh == 0) return;
+    bar_sync_named(FZ_BAR_ALL, nc);  // the rows were written by other threads of this CTA
+    const int p0 = a.push_ptr[cta], p1 = a.push_ptr[cta + 1];
+    for (int e = p0 + tid; e < p1; e += nc) {
+      const int row = a.push_row[e], r = a.push_rank[e];
+      unsigned char *ghost = a.P.region[r] + a.ll_off[r] + (size_t)((hseq + 1) & 1) * a.ll_stride[r] +
+                             (size_t)a.push_off[e] * BS * 16;
+#pragma unroll
+      for (int i = 0; i < BS; i++) ll_store(ghost + i * 16, w[(size_t)row * BS + i], hseq + 1);
+    }
+  };
+  double *w_old = a.wa, *w_new = a.wb;
+  bool first = true, done = false;
+  if (tid == 0) {
+    s_st->res = 0.0; s_st->rnorm0 = 0.0; s_st->scal1 = 1.0;
+    s_st->its = 0; s_st->it_inner = 0; s_st->reason = 0; s_st->done = 0;
+  }
+  FZ_STAMP(5);
+  while (true) {
+    // ================================ start of a restart cycle: w = M^-1 (b - A x), res = |w|
+    sp_phase(first ? 0 : 2, a.xp, 1.0, nullptr, w_new);
+    FZ_STAMP(0);
+    bar_sync_named(FZ_BAR_ALL, nc);
+    push(w_new);
+    dots(w_new, w_new, 0, 1, partB);
+    FZ_STAMP(1);
+    fz_grid_sync(G, tid, nc);
+    fz_fold_parts(partB, a.ncta, 1, s_h, s_red, tid, nc);
+    if (multi) fz_allgather_sum(a, bseq + 1, 1, s_h, s_red, WB_P2P_SLOT_FB, 1, cta, tid, nc);
+    if (tid == 0) {  // k_gmres_begin
+      const double res = sqrt(s_h[0]);
+      s_st->res = res;
+      s_st->it_inner = 0;
+      if (first) {
+        s_st->rnorm0 = res;
+        s_st->its = 0;
+        s_st->reason = 0;
+        int reason = 0;
+        const double ttol = fmax(u.rtol * res, u.atol);
+        if (res != res) reason = -9;
+        else if (res <= ttol) reason = (res < u.atol) ? 3 : 2;
+        if (!reason && res == 0.0) reason = 3;
+        if (reason) {
+          s_st->reason = reason;
+          s_st->done = 1;
+        }
+      }
+      s_st->scal1 = res > 0.0 ? 1.0 / res : 1.0;
+      s_rs[0] = res;
+    }
+    bar_sync_named(FZ_BAR_ALL, nc);
+    bseq++;
+    hseq++;
+    FZ_STAMP(2);
+    if (__ldcg(&a.bar[2])) break;
+    done = s_st->done != 0;
+    if (done) break;
+    {
+      double *t = w_old;
+      w_old = w_new;
+      w_new = t;
+    }
+    // ================================ Arnoldi iterations of the cycle
+    int it = 0;
+    while (true) {
+      sp_phase(1, w_old, s_st->scal1, a.V + (size_t)it * a.ld, w_new);
+      FZ_STAMP(0);
+      bar_sync_named(FZ_BAR_ALL, nc);
+      dots(w_new, a.V, a.ld, it + 1, partA);
+      FZ_STAMP(1);
+      fz_grid_sync(G, tid, nc);
+      fz_fold_parts(partA, a.ncta, it + 1, s_h, s_red, tid, nc);
+      if (multi) fz_allgather_sum(a, aseq + 1, it + 1, s_h, s_red, WB_P2P_SLOT_FA, WB_P2P_MAXV, cta, tid, nc);
+      aseq++;
+      FZ_STAMP(2);
+      if (__ldcg(&a.bar[2])) break;
+      if (tid <= it) s_cf[tid] = -s_h[tid];
+      bar_sync_named(FZ_BAR_ALL, nc);
+      maxpy(w_new, a.V, a.ld, it + 1, partB);
+      push(w_new);
+      FZ_STAMP(3);
+      fz_grid_sync(G, tid, nc);
+      fz_fold_parts(partB, a.ncta, 1, s_cf, s_red, tid, nc);
+      if (multi) fz_allgather_sum(a, bseq + 1, 1, s_cf, s_red, WB_P2P_SLOT_FB, 1, cta, tid, nc);
+      if (tid == 0) {
+        fz_gmres_update(u, s_st, s_cf[0], s_h, s_H, s_cs, s_sn, s_rs);
+        // end of the cycle (restart length reached or finished): back substitution y = H^-1 rs (k_gmres_solve_y)
+        const int itn = s_st->it_inner;
+        if (s_st->done || itn >= m) {
+          for (int k = itn - 1; k >= 0; k--) {
+            double sy = s_rs[k];
+            for (int j = k + 1; j < itn; j++) sy -= s_H[(size_t)(m + 1) * j + k] * s_cf[j];
+            s_cf[k] = sy / s_H[(size_t)(m + 1) * k + k];
+          }
+        }
+      }
+      bar_sync_named(FZ_BAR_ALL, nc);
+      bseq++;
+      hseq++;
+      FZ_STAMP(4);
+      if (profiler) s_prof[6]++;
+      if (__ldcg(&a.bar[2])) break;
+      {
+        double *t = w_old;
+        w_old = w_new;
+        w_new = t;
+      }
+      it = s_st->it_inner;
+      done = s_st->done != 0;
+      if (done || it >= m) break;
+    }
+    if (__ldcg(&a.bar[2])) break;
+    // ================================ x += sum_j y_j V_j over the columns built in this cycle (y is in s_cf)
+    if (it > 0) maxpy(a.xp, a.V, a.ld, it, nullptr);
+    if (done) break;
+    // another cycle follows: its residual needs everybody's x (the neighbours' on the boundary)
+    push(a.xp);
+    fz_grid_sync(G, tid, nc);
+    hseq++;
+    first = false;
+    FZ_STAMP(5);
+    if (__ldcg(&a.bar[2])) break;
+  }
+  // ---- the solution in the caller's ordering; the solver state for the host; stop the producer
+  bar_sync_named(FZ_BAR_ALL, nc);
+  for (int r = R0 + tid; r < R1; r += nc) {
+    const size_t ob = (size_t)a.perm[r] * BS;
+#pragma unroll
+    for (int i = 0; i < BS; i++) a.xout[ob + i] = a.xp[(size_t)r * BS + i];
+  }
+  if (tid == 0) *s_stop = 1;
+  if (cta == 0 && tid == 0) {
+    KspState *st = u.st;
+    st->res = s_st->res;
+    st->rnorm0 = s_st->rnorm0;
+    st->its = s_st->its;
+    st->reason = s_st->reason;
+    st->it_inner = s_st->it_inner;
+    *u.done = s_st->done;
+    if (multi) {
+      a.fseq[0] = hseq;
+      a.fseq[1] = aseq;
+      a.fseq[2] = bseq;
+    }
+  }
+  FZ_STAMP(5);
+  if (profiler)
+    for (int k = 0; k < 16; k++) a.prof[(size_t)cta * 16 + k] += s_prof[k];
+#undef FZ_STAMP
+}
+
+// ================================================================ host: the solve
+
+bool wb_fused_usable(const wb_mat *A, const wb_pc *pc, const wb_ksp_opts *o) {
+  if (!pc || !pc->fused || !pc->blocked || pc->type != WB_PC_BJACOBI_ILU0 || !fused_mode()) return false;
+  if (o->type != WB_KSP_GMRES) return false;
+  const int m = o->restart > 0 ? o->restart : 30;
+  if (m + 1 > KRY_MAXV) return false;
+  const wb_ctx *c = A->ctx;
+  if (c->nranks > 1) return c->p2p.on && A == &c->J && c->nranks <= WB_P2P_MAX_RANKS;
+  return A->ncolb == A->nb;
+}
+
+// boundary rows of every CTA and where they go in the neighbours' ghost buffers
+static int build_push_lists(wb_ctx *c, wb_pc *pc) {
+  WbFusedPlan *f = pc->fused;
+  if (f->push_built) return 0;
+  const WbHalo &h = c->halo;
+  const WbP2P &p = c->p2p;
+  std::vector<int32_t> idx(std::max(h.nsend, 1));
+  if (h.nsend > 0) WB_CUDA(cudaMemcpy(idx.data(), h.d_send_idx, sizeof(int32_t) * h.nsend, cudaMemcpyDeviceToHost));
+  struct E { int row, rank, off; };
+  std::vector<std::vector<E>> per(f->ncta);
+  // CTA of a row in the sub-domain-major ordering
+  std::vector<int> row_end(f->ncta);
+  for (int ct = 0; ct < f->ncta; ct++) {
+    const int4 C = f->h_cta[ct];
+    const int4 last = pc->h_blk[C.x + C.y - 1];
+    row_end[ct] = last.x + last.y;
+  }
+  for (int n = 0; n < h.nneigh; n++)
+    for (int k = h.send_ptr[n]; k < h.send_ptr[n + 1]; k++) {
+      const int row = f->h_invperm[idx[k]];
+      const int ct = (int)(std::upper_bound(row_end.begin(), row_end.end(), row) - row_end.begin());
+      WB_CHECK(ct < f->ncta, "fused GMRES: boundary row outside every CTA");
+      per[ct].push_back({row, h.rank[n], p.peer_off[n] + (k - h.send_ptr[n])});
+    }
+  std::vector<int32_t> ptr(f->ncta + 1, 0), row, rank, off;
+  for (int ct = 0; ct < f->ncta; ct++) {
+    for (const E &e : per[ct]) {
+      row.push_back(e.row);
+      rank.push_back(e.rank);
+      off.push_back(e.off);
+    }
+    ptr[ct + 1] = (int32_t)row.size();
+  }
+  WB_TRY(up(&f->d_push_ptr, ptr));
+  WB_TRY(up(&f->d_push_row, row));
+  WB_TRY(up(&f->d_push_rank, rank));
+  WB_TRY(up(&f->d_push_off, off));
+  f->push_built = true;
+  return 0;
+}
+
+int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b, double *d_x, int *its, int *reason,
+                   double *rnorm) {
+  wb_ctx *c = A->ctx;
+  WbFusedPlan *f = pc->fused;
+  const size_t n = (size_t)A->nb * A->bs;
+  const int m = o->restart > 0 ? o->restart : 30;
+  KspWork *wp;
+  WB_TRY(wb_ensure_work(c, n, m, &wp));
+  KspWork &w = *wp;
+  double *hcol = w.small, *H = hcol + (m + 2), *cs = H + (size_t)(m + 1) * m, *sn = cs + (m + 1), *rs = sn + (m + 1),
+         *yv = rs + (m + 2), *scal = yv + (m + 1);
+  const bool multi = c->nranks > 1;
+  if (multi) WB_TRY(build_push_lists(c, pc));
+  WB_TRY(wb_fused_refresh(pc));  // the operator of this solve is the matrix as it is now
+  WB_CUDA(cudaMemsetAsync(w.d_done, 0, sizeof(int), c->stream));
+  WB_CUDA(cudaMemsetAsync(w.d_st, 0, sizeof(KspState), c->stream));
+  WB_CUDA(cudaMemsetAsync(w.d_bar, 0, 8 * sizeof(int), c->stream));
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.cta = f->d_cta; a.sd = f->d_sd; a.blk = pc->d_blk; a.slice = f->d_slice; a.recA = f->d_recA; a.recB = f->d_recB;
+  a.rec_ptr = f->d_rec_ptr; a.sidx = f->d_sidx; a.perm = pc->d_blk_rows; a.sval = f->d_sval; a.stream = pc->d_stream;
+  a.ng = f->ng; a.gt = f->gt; a.nc = f->nc; a.lt = f->lt; a.off_gm = f->off_gm; a.off_prof = f->off_prof; a.sd_cap = f->sd_cap; a.slice_cap = f->slice_cap; a.rec_cap = f->rec_cap;
+  a.zs_words = f->zs_words; a.ring_bytes = f->ring_bytes;
+  a.off_red = f->off_red; a.off_misc = f->off_misc; a.off_sd = f->off_sd; a.off_slice = f->off_slice;
+  a.off_rec = f->off_rec; a.off_zs = f->off_zs; a.off_ring = f->off_ring;
+  a.nb = A->nb; a.ncta = f->ncta; a.ld = w.ld;
+  a.b = d_b; a.xout = d_x; a.V = w.V; a.wa = w.tmp; a.wb = w.tmp + w.ld; a.xp = w.tmp + 2 * w.ld; a.part = w.part;
+  a.bar = w.d_bar;
+  a.upd = {hcol, H, cs, sn, rs, scal, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, m, o->maxit};
+  a.yv = yv;
+  a.prof = w.d_prof;
+  if (multi) {
+    a.P = c->p2p.dev;
+    a.nneigh = c->halo.nneigh;
+    a.nb_rank = c->p2p.d_nb_rank;
+    for (int r = 0; r < WB_P2P_MAX_RANKS; r++) {
+      a.ll_off[r] = r < c->nranks ? c->p2p.peer_ll_off[r] : 0;
+      a.ll_stride[r] = r < c->nranks ? c->p2p.peer_ll_stride[r] : 0;
+    }
+    a.push_ptr = f->d_push_ptr; a.push_row = f->d_push_row; a.push_rank = f->d_push_rank; a.push_off = f->d_push_off;
+    a.fseq = c->p2p.d_fseq;
+  }
+  const int threads = f->nc + 32;  // consumers + the producer warp
+  void *args[] = {&a};
+  cudaError_t e;
+  switch (A->bs) {
+    case 1:
+      WB_CUDA(cudaFuncSetAttribute(k_gmres_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
+      e = cudaLaunchCooperativeKernel((void *)k_gmres_fused<1>, dim3(f->ncta), dim3(threads), args, f->smem, c->stream);
+      break;
+    case 2:
+      WB_CUDA(cudaFuncSetAttribute(k_gmres_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
+      e = cudaLaunchCooperativeKernel((void *)k_gmres_fused<2>, dim3(f->ncta), dim3(threads), args, f->smem, c->stream);
+      break;
+    default:
+      WB_CUDA(cudaFuncSetAttribute(k_gmres_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
+      e = cudaLaunchCooperativeKernel((void *)k_gmres_fused<3>, dim3(f->ncta), dim3(threads), args, f->smem, c->stream);
+      break;
+  }
+  WB_CHECK(e == cudaSuccess, "fused GMRES: cooperative launch failed: %s", cudaGetErrorString(e));
+  WB_LAUNCH(c);
+  WB_TRY(wb_fetch_state(w));
+  int h_abort = 0;
+  WB_CUDA(cudaMemcpy(&h_abort, w.d_bar + 2, sizeof(int), cudaMemcpyDeviceToHost));
+  WB_CHECK(!h_abort, "fused GMRES: grid barrier timed out (a CTA or a peer GPU is missing)");
+  *its = w.h_st->its;
+  *reason = w.h_st->reason;
+  *rnorm = w.h_st->res;
+  return 0;
+}
+
+// per-phase device time of CTA 0 accumulated over the fused solves of this context since the last reset
+// (nanoseconds): SpMV + PC, dots, dots barrier, multi-AXPY + norm, norm barrier, other; iterations
+extern "C" int wb_ksp_fused_profile(wb_ctx *c, double *ns7, int reset) {
+  KspWork *wp = wb_find_work(c);
+  for (int k = 0; k < 7; k++) ns7[k] = 0.0;
+  if (!wp) return 0;
+  WB_CUDA(cudaSetDevice(c->device));
+  unsigned long long h[16];
+  WB_CUDA(cudaMemcpy(h, wp->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 7; k++) ns7[k] = (double)h[k];
+  if (reset) WB_CUDA(cudaMemset(wp->d_prof, 0, WB_PROF_WORDS * sizeof(unsigned long long)));
+  return 0;
+}
+
+// tuning aid (not part of the public header): the counters of every CTA, out[cta * 16 + k] (k < 8 as above; 9..11:
+// SM cycles of thread 0 waiting for the first level record, in its own part of the levels, at the level barriers);
+// returns the CTA count
+extern "C" int wb_debug_fused_profile_all(wb_ctx *c, double *out, int max_ctas) {
+  KspWork *wp = wb_find_work(c);
+  if (!wp) return 0;
+  WB_CUDA(cudaSetDevice(c->device));
+  std::vector<unsigned long long> h(WB_PROF_WORDS);
+  WB_CUDA(cudaMemcpy(h.data(), wp->d_prof, WB_PROF_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  const int n = std::min(max_ctas, WB_PROF_WORDS / 16);
+  for (int k = 0; k < n * 16; k++) out[k] = (double)h[k];
+  return n;
+}

@@ -10,32 +10,8 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "wb_common.cuh"
+#include "wb_linalg.cuh"
 
-// ================================================================ NVLink P2P helpers
-
-__device__ __forceinline__ int p2p_ld_acquire_sys(const int *p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void p2p_st_release_sys(int *p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// spin until the peer's sequence number reaches `seq`; bounded (~15 s) so that a lost peer raises an error flag
-// instead of hanging the GPU
-__device__ __forceinline__ void p2p_wait(const int *flag, int seq, int *err) {
-  const long long t0 = clock64();
-  while (p2p_ld_acquire_sys(flag) < seq) {
-    if (clock64() - t0 > 30000000000LL) {
-      atomicExch(err, 1);
-      break;
-    }
-  }
-}
-__device__ __forceinline__ const int *p2p_my_flag(const WbP2PDev &P, int kind, int sender) {
-  return reinterpret_cast<const int *>(P.region[P.rank] + wb_p2p_flag_off(kind, sender));
-}
 
 // ================================================================ SpMV (K5)
 
@@ -65,20 +41,6 @@ struct SpmvArgs {
   const int32_t *nb_rank;
 };
 
-// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256); pointers must be 32-byte aligned
-__device__ __forceinline__ double4 ld256(const double *p) {
-  double4 r;
-  asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ double4 ld256_stream(const double *p) {  // evict-first variant (single-use streams)
-  double4 r;
-  asm("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void st256(double *p, const double4 &v) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
-}
 
 // R block rows per 8-lane group, processed level by level (all row pointers, then all column indices and
 // value blocks, then all x gathers): the three dependent global-memory round trips of a row are shared by R
@@ -392,31 +354,6 @@ template <int BS> __device__ __forceinline__ void blk_mulsub(const double *a, co
 
 // ================================================================ preconditioners (K6)
 
-struct wb_pc {
-  wb_mat *A = nullptr;
-  int type = 0, nb = 0, bs = 0, nblocks = 1;
-  double *d_dinv = nullptr;  // pbjacobi: inverted diagonal blocks
-  // block-Jacobi ILU(0): factor pattern = matrix pattern restricted to each sub-domain
-  int nnzb = 0, nsched_f = 0, nsched_b = 0, nlev_f = 0, nlev_b = 0;
-  int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_diag = nullptr, *d_src = nullptr;
-  int32_t *d_sched_f = nullptr, *d_sched_b = nullptr;  // rows in level order, warp-aligned levels, -1 padded
-  double *d_val = nullptr;
-  int *d_flag = nullptr;    // per-row completion epoch
-  int *d_ticket = nullptr;  // CTA ticket counter
-  int epoch = 0;
-  // sub-domain resident solve (one CTA per block-Jacobi sub-domain, solution kept in shared memory):
-  // level-ordered ELL streams of the L and U factors
-  bool blocked = false;
-  int nblk = 0, max_block_rows = 0, nrepack = 0;
-  int4 *d_blk = nullptr;          // per block: row0, nrows, lev0 (forward levels first, then backward), number of levels
-  int4 *d_lev = nullptr;          // per level: word offset into d_stream, bytes, rows, unused
-  int32_t *d_blk_rows = nullptr;  // global row of each block-local row
-  double *d_stream = nullptr;     // level-ordered factor stream (see "sub-domain resident ILU(0) solve")
-  size_t stream_words = 0;
-  int4 *d_repack = nullptr;       // (block index into d_val, word offset into d_stream, plane stride, 0) of every factor block
-  int stage_words = 0, nstage = 0, desc_words = 0, solve_threads = 128;
-  long long *d_trace = nullptr;  // debug timeline of the sub-domain solve (wb_debug_pc_trace)  // TMA ring geometry (nstage 0: read the stream from global)
-};
 
 template <int BS>
 __global__ void k_pbjacobi_setup(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
@@ -596,160 +533,8 @@ __global__ void __launch_bounds__(128) k_ilu0_solve(const int32_t *__restrict__ 
 }
 
 
-template <class T> static int upload(T **p, const std::vector<T> &v) {
-  WB_CUDA(cudaMalloc((void **)p, std::max<size_t>(v.size(), 1) * sizeof(T)));
-  if (!v.empty()) WB_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return 0;
-}
 
-// ---- sub-domain resident ILU(0) solve ---------------------------------------------------
-// One CTA per block-Jacobi sub-domain.  The sub-domain's part of the solution lives in shared
-// memory for both sweeps, so the only HBM traffic is ONE streaming read of the factors plus r in
-// and z out.  The factors are stored as a level-ordered stream: for every dependency level of the
-// forward sweep, then of the backward sweep, one contiguous 16-byte-aligned record of n rows with
-// nk off-diagonal blocks each (ELL, padded with zero blocks that point at a zero slot of the vector):
-//     index planes   int4[NI][n]      (local row, col_0, col_1, col_2), (col_3 .. col_6), ...
-//     value planes   double[PW]-wide planes [ (nk + bwd) * bs*bs/PW ][n]   L or U blocks, then the
-//                    inverted diagonal block (backward sweep only); PW = 2 for even bs*bs
-// Thread r of a level reads element r of every plane: conflict-free shared-memory accesses.  A whole
-// level is ONE TMA bulk copy (cp.async.bulk, mbarrier-completed) into a shared-memory ring `nstage`
-// levels deep: the copy of level l+nstage is in flight while level l is applied, which takes the HBM
-// latency off the level-to-level dependency chain.  Rows inside a level are independent; levels are
-// separated by __syncthreads.  Per row the blocks are applied in ascending column order, i.e. the
-// arithmetic of the sequential MatSolve_SeqBAIJ_N_NaturalOrdering restricted to the sub-domain.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// bulk copy global -> shared, completing on an mbarrier; L2 evict-first: the factor stream is read once per
-// apply and must not displace the Krylov basis from L2
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 
-__host__ __device__ __forceinline__ int ilu_ni(int nk) { return (nk + 4) / 4; }  // int4 index planes per row
-template <int BS> struct IluPlane {
-  static constexpr int B2 = BS * BS;
-  static constexpr int PW = (B2 % 2 == 0) ? 2 : 1;  // doubles per plane element
-  static constexpr int NP = B2 / PW;                // planes per block
-};
-static inline int ilu_pw(int bs) { return (bs * bs) % 2 == 0 ? 2 : 1; }
-
-// one block of a plane-layout record: planes q of entry k, row rr
-template <int BS>
-__device__ __forceinline__ void ilu_load_block(const double *vals, int n, int k, int rr, double *v) {
-  constexpr int PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
-  const double *pl = vals + ((size_t)k * NPL * n + rr) * PW;
-#pragma unroll
-  for (int q = 0; q < NPL; q++) {
-    if (PW == 2) {
-      const double2 t = *reinterpret_cast<const double2 *>(pl + (size_t)q * n * 2);
-      v[2 * q] = t.x; v[2 * q + 1] = t.y;
-    } else {
-      v[q] = pl[(size_t)q * n];
-    }
-  }
-}
-
-// apply one level record (in shared or global memory) to the sub-domain vector zs.  Records are padded on
-// the host to nk = 3, 7, 11, ... (index planes are full); the common nk == 3 case (7-point stencils) is
-// branch-free with every load issued before the first use, so a level costs one shared-memory round trip
-// plus the dependent FMA chain.
-template <int BS>
-__device__ __forceinline__ void ilu_level(const double *lv, int n, int nk, bool bwd, double *zs, int nthr) {
-  constexpr int B2 = BS * BS;
-  const int4 *idx = reinterpret_cast<const int4 *>(lv);
-  const double *vals = lv + 2 * ilu_ni(nk) * n;
-  for (int rr = threadIdx.x; rr < n; rr += nthr) {
-    const int4 i0 = idx[rr];
-    const int li = i0.x;
-    double sv[BS];
-    if (nk == 3) {
-      double v[3][B2], x[3][BS], di[B2];
-      const int col[3] = {i0.y, i0.z, i0.w};
-#pragma unroll
-      for (int k = 0; k < 3; k++) ilu_load_block<BS>(vals, n, k, rr, v[k]);
-      if (bwd) ilu_load_block<BS>(vals, n, 3, rr, di);
-#pragma unroll
-      for (int i = 0; i < BS; i++) sv[i] = zs[li * BS + i];
-#pragma unroll
-      for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int j = 0; j < BS; j++) x[k][j] = zs[col[k] * BS + j];
-#pragma unroll
-      for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int j = 0; j < BS; j++)
-#pragma unroll
-          for (int i = 0; i < BS; i++) sv[i] -= v[k][j * BS + i] * x[k][j];
-      if (bwd) {
-        double t[BS];
-#pragma unroll
-        for (int i = 0; i < BS; i++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < BS; j++) acc += di[j * BS + i] * sv[j];
-          t[i] = acc;
-        }
-#pragma unroll
-        for (int i = 0; i < BS; i++) sv[i] = t[i];
-      }
-#pragma unroll
-      for (int i = 0; i < BS; i++) zs[li * BS + i] = sv[i];
-      continue;
-    }
-#pragma unroll
-    for (int i = 0; i < BS; i++) sv[i] = zs[li * BS + i];
-    for (int k = 0; k < nk; k++) {
-      const int col = reinterpret_cast<const int *>(&idx[(size_t)((k + 1) >> 2) * n + rr])[(k + 1) & 3];
-      double v[B2];
-      ilu_load_block<BS>(vals, n, k, rr, v);
-#pragma unroll
-      for (int j = 0; j < BS; j++) {
-        const double xj = zs[col * BS + j];
-#pragma unroll
-        for (int i = 0; i < BS; i++) sv[i] -= v[j * BS + i] * xj;
-      }
-    }
-    if (bwd) {
-      double di[B2], t[BS];
-      ilu_load_block<BS>(vals, n, nk, rr, di);
-#pragma unroll
-      for (int i = 0; i < BS; i++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < BS; j++) acc += di[j * BS + i] * sv[j];
-        t[i] = acc;
-      }
-#pragma unroll
-      for (int i = 0; i < BS; i++) sv[i] = t[i];
-    }
-#pragma unroll
-    for (int i = 0; i < BS; i++) zs[li * BS + i] = sv[i];
-  }
-}
 
 struct IluSolveArgs {
   const int4 *blk, *lev;
@@ -761,12 +546,6 @@ struct IluSolveArgs {
   long long *trace;  // debug: per CTA (start ns, end ns, SM id, 0) when non-null
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 #define ILU_ROWS_PER_THREAD 8
 #define ILU_MAX_STAGES 8
@@ -862,7 +641,7 @@ __global__ void __launch_bounds__(288) k_ilu0_block_solve(const IluSolveArgs a) 
     if (nl > 0) mbar_wait(&full[0], 0);  // level 0: everybody
     for (int l = 0; l < nl; l++) {
       const int4 L = desc[l];
-      ilu_level<BS>(ring + (size_t)st * a.stage_words, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs, ncons);
+      ilu_level<BS>(ring + (size_t)st * a.stage_words, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs, ncons, tid);
       int stn = st + 1;
       uint32_t parn = parity;
       if (stn == a.nstage) {
@@ -878,7 +657,7 @@ __global__ void __launch_bounds__(288) k_ilu0_block_solve(const IluSolveArgs a) 
   } else {
     for (int l = 0; l < nl; l++) {
       const int4 L = a.lev[lev0 + l];
-      ilu_level<BS>(a.stream + L.x, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs, ncons);
+      ilu_level<BS>(a.stream + L.x, L.z, L.w & 0xffff, (L.w >> 16) != 0, zs, ncons, tid);
       bar_sync_named(1, ncons);
     }
   }
@@ -901,13 +680,13 @@ __global__ void __launch_bounds__(288) k_ilu0_block_solve(const IluSolveArgs a) 
 }
 
 // numeric part: scatter the factor blocks into the value planes of the level stream
-__global__ void k_ilu_repack(const double *__restrict__ fac, const int4 *__restrict__ map, int nmap, int b2, int pw,
+__global__ void k_ilu_repack(const double *__restrict__ fac, const int4 *__restrict__ map, int nmap, int b2,
                              double *__restrict__ stream) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nmap * b2) {
     const int e = i / b2, q = i - e * b2;
-    const int4 m = map[e];
-    stream[(size_t)m.y + (size_t)(q / pw) * m.z * pw + (q % pw)] = fac[(size_t)m.x * b2 + q];
+    const int4 m = map[e];  // (factor block, word offset of its copy in the level stream)
+    stream[(size_t)m.y + q] = fac[(size_t)m.x * b2 + q];
   }
 }
 
@@ -969,26 +748,26 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
         int nk = 0;
         for (int row : rows)
           nk = std::max(nk, pass == 0 ? diag[row] - rowptr[row] : rowptr[row + 1] - diag[row] - 1);
-        nk = nk <= 3 ? 3 : 3 + (nk - 3 + 3) / 4 * 4;  // full index planes: 3, 7, 11, ... (padding blocks are zero)
+        nk = std::max(nk, 3);  // at least the branch-free 7-point case; index planes are full, padding blocks are zero
         const size_t w0 = stream.size();
-        const int ni = ilu_ni(nk), pw = ilu_pw(pc->bs), npl = b2 / pw;
-        const int w_idx = 2 * ni * n, w_vals = (nk + pass) * b2 * n;
-        const int words = (w_idx + w_vals + 1) & ~1;
+        const int ni4 = ilu_ni4(nk), stride = ilu_row_stride(pc->bs, nk, pass);
+        const int words = n * stride / 8;  // stride is a multiple of 16 bytes
         WB_CHECK(w0 + words < ((size_t)1 << 31), "wb_pc_setup: factor stream too large for 32-bit word offsets");
         stream.resize(w0 + words, 0.0);
-        int32_t *pidx = reinterpret_cast<int32_t *>(&stream[w0]);
-        for (int q = 0; q < 4 * ni * n; q++) pidx[q] = nr;  // padding blocks multiply the zero slot `nrows`
-        const size_t wv = w0 + w_idx;
+        const int zero_slot = nr * pc->bs * 8;  // byte offset of the zero entry behind the sub-domain vector
         for (int q = 0; q < n; q++) {
           const int row = rows[q];
-          pidx[4 * q] = local[row];
+          int32_t *pidx = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(&stream[w0]) + (size_t)q * stride);
+          for (int e = 0; e < 4 * ni4; e++) pidx[e] = zero_slot;  // padding blocks multiply the zero slot
+          pidx[0] = local[row] * pc->bs * 8;
+          const size_t wblk = w0 + ((size_t)q * stride + (size_t)ni4 * 16) / 8;  // first block of the row (words)
           const int k0 = pass == 0 ? rowptr[row] : diag[row] + 1, k1 = pass == 0 ? diag[row] : rowptr[row + 1];
           for (int k = k0; k < k1; k++) {
-            const int kk = k - k0, slot = kk + 1;
-            pidx[4 * ((size_t)(slot >> 2) * n + q) + (slot & 3)] = local[colidx[k]];
-            repack.push_back(make_int4(k, (int)(wv + ((size_t)kk * npl * n + q) * pw), n, 0));
+            const int kk = k - k0;
+            pidx[kk + 1] = local[colidx[k]] * pc->bs * 8;
+            repack.push_back(make_int4(k, (int)(wblk + (size_t)kk * b2), 0, 0));
           }
-          if (pass == 1) repack.push_back(make_int4(diag[row], (int)(wv + ((size_t)nk * npl * n + q) * pw), n, 0));
+          if (pass == 1) repack.push_back(make_int4(diag[row], (int)(wblk + (size_t)nk * b2), 0, 0));
         }
         int4 L;
         L.x = (int)w0; L.y = words * 8; L.z = n; L.w = nk | (pass << 16);
@@ -1005,6 +784,9 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
     max_levels = std::max(max_levels, blk[b].w);
   }
   pc->nblk = nblk;
+  pc->h_blk = blk;
+  pc->h_lev = lev;
+  pc->h_blk_rows = blk_rows;
   pc->max_block_rows = maxrows;
   pc->nrepack = (int)repack.size();
   pc->stream_words = stream.size();
@@ -1096,7 +878,7 @@ static int pc_numeric(wb_pc *pc) {
     WB_LAUNCH(c);
     if (pc->blocked) {
       k_ilu_repack<<<wb_grid((size_t)pc->nrepack * bs2, 256), 256, 0, c->stream>>>(pc->d_val, pc->d_repack, pc->nrepack,
-                                                                                  bs2, ilu_pw(pc->bs), pc->d_stream);
+                                                                                  bs2, pc->d_stream);
       WB_LAUNCH(c);
     }
   }
@@ -1112,6 +894,7 @@ extern "C" int wb_pc_destroy(wb_pc *pc) {
                   pc->d_val, pc->d_flag, pc->d_ticket, pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_stream,
                   pc->d_repack};
   for (void *p : ptrs) cudaFree(p);
+  wb_fused_free(pc);
   delete pc;
   return 0;
 }
@@ -1177,6 +960,7 @@ extern "C" int wb_pc_setup(wb_mat *A, int type, int nblocks, const int32_t *bloc
     if (nblk_used > 1 && (size_t)maxrows * A->bs * sizeof(double) <= 160 * 1024) {
       WB_TRY(build_block_streams(pc, blk, rowptr, colidx, diag));
       pc->blocked = true;
+      WB_TRY(wb_fused_build(pc, blk));  // leaves pc->fused null when the sub-domains do not fit the resident kernel
     }
   }
   int rc;
@@ -1566,16 +1350,6 @@ static int wb_spmv_tma_launch(wb_mat *A, const SpmvArgs &a) {
 
 // ================================================================ vector kernels (K7)
 
-// Persistent-style grid for the streaming vector kernels: 4 CTAs of 256 threads per SM.
-#define RED_BLOCKS (4 * WB_NUM_SMS)
-#define KRY_MAXV 32  // vectors per fused multi-dot / multi-axpy launch (>= restart + 1 is not needed: one cycle
-                     // of GMRES(30) dots against at most 30 vectors; longer restarts go in chunks)
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-  return v;
-}
 
 __device__ __forceinline__ double block_sum(double v) {
   __shared__ double sh[32];
@@ -1607,64 +1381,6 @@ __device__ __forceinline__ bool last_block(unsigned *counter) {
   return s_last;
 }
 
-struct KspState {
-  double res, rnorm0;
-  int its, reason, it_inner, pad;
-};
-
-// Arnoldi column `it_inner` is complete (hcol = dots, scal[0] = |w|^2): update the Givens QR and the
-// convergence state (KSPGMRESUpdateHessenberg + KSPConvergedDefault).  One thread.
-struct GmresUpd {
-  double *hcol, *H, *cs, *sn, *rs, *scal;
-  KspState *st;
-  int *done;
-  double rtol, atol, dtol;
-  int m, maxit;
-};
-__device__ void gmres_update(const GmresUpd &u) {
-  if (*u.done) return;
-  KspState *st = u.st;
-  const int it = st->it_inner, m = u.m;
-  const double tt = sqrt(u.scal[0]);
-  u.hcol[it + 1] = tt;
-  const bool happy = (tt < 1.e-30 * fmax(st->res, 1e-300)) || tt == 0.0;
-  u.scal[1] = happy ? 1.0 : 1.0 / tt;
-  double *Hc = u.H + (size_t)(m + 1) * it;
-  for (int j = 0; j <= it + 1; j++) Hc[j] = u.hcol[j];
-  for (int j = 0; j < it; j++) {
-    const double t1 = Hc[j], t2 = Hc[j + 1];
-    Hc[j] = u.cs[j] * t1 + u.sn[j] * t2;
-    Hc[j + 1] = -u.sn[j] * t1 + u.cs[j] * t2;
-  }
-  const double hh = Hc[it], hp = Hc[it + 1];
-  const double den = sqrt(hh * hh + hp * hp);
-  if (den == 0.0) {
-    st->reason = -5;  // KSP_DIVERGED_BREAKDOWN
-    *u.done = 1;
-    return;
-  }
-  u.cs[it] = hh / den;
-  u.sn[it] = hp / den;
-  u.rs[it + 1] = -u.sn[it] * u.rs[it];
-  u.rs[it] = u.cs[it] * u.rs[it];
-  Hc[it] = u.cs[it] * hh + u.sn[it] * hp;
-  Hc[it + 1] = 0.0;
-  const double res = fabs(u.rs[it + 1]);
-  st->res = res;
-  st->it_inner = it + 1;
-  st->its += 1;
-  int reason = 0;
-  const double ttol = fmax(u.rtol * st->rnorm0, u.atol);
-  if (res != res) reason = -9;
-  else if (res <= ttol) reason = (res < u.atol) ? 3 : 2;
-  else if (res >= u.dtol * st->rnorm0) reason = -4;
-  if (!reason && happy) reason = 5;
-  if (!reason && st->its >= u.maxit) reason = -3;
-  if (reason) {
-    st->reason = reason;
-    *u.done = 1;
-  }
-}
 __global__ void k_gmres_update(const GmresUpd u) { gmres_update(u); }
 // multi-GPU: |w|^2 = sum over ranks of slot B (fixed rank order, identical on every rank), then the update
 __global__ void k_gmres_update_p2p(const GmresUpd u, const WbP2PDev P, int seq) {
@@ -2036,25 +1752,17 @@ __global__ void k_gmres_solve_y(const double *H, const double *rs, double *yv, i
   for (int k = it; k < m; k++) yv[k] = 0.0;
 }
 
-struct KspWork {
-  wb_ctx *ctx = nullptr;
-  size_t n = 0, ld = 0;  // ld: n rounded up to 32 doubles so every basis vector is 256-byte aligned
-  size_t cap = 0;        // allocated leading dimension: systems of different size (Jacobian, tracers) share the work space
-  int m = 0;
-  double *V = nullptr, *tmp = nullptr, *wbuf = nullptr, *small = nullptr, *part = nullptr;
-  KspState *d_st = nullptr, *h_st = nullptr;
-  int *d_done = nullptr;
-  unsigned *d_counter = nullptr;
-};
 static std::map<wb_ctx *, KspWork> g_work;
 
 static void free_work(KspWork &w) {
   cudaFree(w.V); cudaFree(w.tmp); cudaFree(w.small); cudaFree(w.part); cudaFree(w.d_st); cudaFree(w.d_done);
   cudaFree(w.d_counter);
+  cudaFree(w.d_bar);
+  cudaFree(w.d_prof);
   if (w.h_st) cudaFreeHost(w.h_st);
 }
 
-static int ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
+int wb_ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
   KspWork *wq;
   {
     std::lock_guard<std::mutex> lk(wb_registry_mutex());
@@ -2083,9 +1791,19 @@ static int ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
     WB_CUDA(cudaMalloc(&w.d_done, sizeof(int)));
     WB_CUDA(cudaMalloc(&w.d_counter, sizeof(unsigned)));
     WB_CUDA(cudaMemset(w.d_counter, 0, sizeof(unsigned)));
+    WB_CUDA(cudaMalloc(&w.d_bar, 8 * sizeof(int)));
+    WB_CUDA(cudaMemset(w.d_bar, 0, 8 * sizeof(int)));
+    WB_CUDA(cudaMalloc(&w.d_prof, WB_PROF_WORDS * sizeof(unsigned long long)));
+    WB_CUDA(cudaMemset(w.d_prof, 0, WB_PROF_WORDS * sizeof(unsigned long long)));
   }
   *out = &w;
   return 0;
+}
+
+KspWork *wb_find_work(wb_ctx *c) {
+  std::lock_guard<std::mutex> lk(wb_registry_mutex());
+  auto it = g_work.find(c);
+  return it == g_work.end() ? nullptr : &it->second;
 }
 
 void wb_linalg_release(wb_ctx *c) {
@@ -2229,7 +1947,7 @@ static int lin3(KspWork &w, double *z, const double *x, double a, const double *
 }
 
 
-static int fetch_state(KspWork &w) {
+int wb_fetch_state(KspWork &w) {
   wb_ctx *c = w.ctx;
   WB_CUDA(cudaMemcpyAsync(w.h_st, w.d_st, sizeof(KspState), cudaMemcpyDeviceToHost, c->stream));
   if (c->p2p.on) WB_CUDA(cudaMemcpyAsync(c->h_flags + 5, c->d_flags + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -2259,7 +1977,7 @@ static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
   const size_t n = (size_t)A->nb * A->bs;
   const int m = o->restart > 0 ? o->restart : 30;
   KspWork *wp;
-  WB_TRY(ensure_work(c, n, m, &wp));
+  WB_TRY(wb_ensure_work(c, n, m, &wp));
   KspWork &w = *wp;
   const size_t ld = w.ld;
   double *hcol = w.small, *H = hcol + (m + 2), *cs = H + (size_t)(m + 1) * m, *sn = cs + (m + 1),
@@ -2283,7 +2001,7 @@ static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
     k_gmres_begin<<<1, 1, 0, c->stream>>>(rs, scal, w.d_st, w.d_done, first ? 1 : 0, o->rtol, o->atol, o->dtol);
     WB_LAUNCH(c);
     if (first) {
-      WB_TRY(fetch_state(w));
+      WB_TRY(wb_fetch_state(w));
       if (w.h_st->reason != 0) break;
     }
     int it = 0, halo_seq = 0;
@@ -2304,7 +2022,7 @@ static int gmres_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
         WB_TRY(multi_axpy(w, wbuf, w.V, ld, it + 1, hcol, -1.0, scal, w.d_done, &upd, coef_seq,
                           next_is_wbuf ? &halo_seq : nullptr, A->bs));
       }
-      WB_TRY(fetch_state(w));
+      WB_TRY(wb_fetch_state(w));
       if (w.h_st->reason != 0) stop = true;
     }
     first = false;
@@ -2501,7 +2219,7 @@ static int bcgs_dev_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const doub
   wb_ctx *c = A->ctx;
   const size_t n = (size_t)A->nb * A->bs;
   KspWork *wp;
-  WB_TRY(ensure_work(c, n, 30, &wp));
+  WB_TRY(wb_ensure_work(c, n, 30, &wp));
   KspWork &w = *wp;
   const size_t ld = w.ld;
   double *R = w.V, *RP = R + ld, *P = RP + ld, *V = P + ld, *S = V + ld, *T = S + ld, *tmp = w.tmp;
@@ -2517,7 +2235,7 @@ static int bcgs_dev_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const doub
   WB_TRY(wb_pc_apply_dev(pc, d_b, R));
   WB_TRY(multi_dot(w, R, R, ld, 1, sc + 7, nullptr, nullptr, 4, &be));
   WB_CUDA(cudaMemcpyAsync(RP, R, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-  WB_TRY(fetch_state(w));
+  WB_TRY(wb_fetch_state(w));
   int enq = 0;
   while (w.h_st->reason == 0) {
     for (int q = 0; q < g_check_every && enq < o->maxit; q++, enq++) {
@@ -2534,7 +2252,7 @@ static int bcgs_dev_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const doub
       WB_LAUNCH(c);
     }
     WB_CUDA(cudaGetLastError());
-    WB_TRY(fetch_state(w));
+    WB_TRY(wb_fetch_state(w));
     if (enq >= o->maxit && w.h_st->reason == 0) {
       w.h_st->reason = -3;
       break;
@@ -2552,7 +2270,7 @@ static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_
   if (c->nranks <= 1) return bcgs_dev_fused(A, pc, o, d_b, d_x, its, reason, rnorm);
   const size_t n = (size_t)A->nb * A->bs;
   KspWork *wp;
-  WB_TRY(ensure_work(c, n, 30, &wp));
+  WB_TRY(wb_ensure_work(c, n, 30, &wp));
   KspWork &w = *wp;
   // carve the BCGS vectors out of the Krylov basis storage
   const size_t ld = w.ld;
@@ -2570,7 +2288,7 @@ static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_
   k_bcgs_begin<<<1, 1, 0, c->stream>>>(sc, w.d_st, w.d_done, o->rtol, o->atol);
   WB_LAUNCH(c);
   WB_CUDA(cudaMemcpyAsync(RP, R, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-  WB_TRY(fetch_state(w));
+  WB_TRY(wb_fetch_state(w));
   int enq = 0;
   while (w.h_st->reason == 0) {
     for (int q = 0; q < g_check_every && enq < o->maxit; q++, enq++) {
@@ -2602,7 +2320,7 @@ static int bcgs_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_
       WB_LAUNCH(c);
     }
     WB_CUDA(cudaGetLastError());
-    WB_TRY(fetch_state(w));
+    WB_TRY(wb_fetch_state(w));
     if (enq >= o->maxit && w.h_st->reason == 0) {
       w.h_st->reason = -3;
       break;
@@ -2625,7 +2343,7 @@ int wb_vec_dot_host(wb_ctx *c, const double *d_a, const double *d_b, size_t n, d
       have = it != g_work.end() && it->second.n == n;
       if (have) wp = &it->second;
     }
-    if (!have) WB_TRY(ensure_work(c, n, 30, &wp));
+    if (!have) WB_TRY(wb_ensure_work(c, n, 30, &wp));
   }
   KspWork &w = *wp;
   double *sc = w.small;
@@ -2649,6 +2367,7 @@ int wb_ksp_solve_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d
                      int *reason, double *rnorm) {
   WbScopedTimer tm(A->ctx, "ksp_solve");
   if (o->type == WB_KSP_BCGS) return bcgs_dev(A, pc, o, d_b, d_x, its, reason, rnorm);
+  if (wb_fused_usable(A, pc, o)) return wb_gmres_fused(A, pc, o, d_b, d_x, its, reason, rnorm);
   return gmres_dev(A, pc, o, d_b, d_x, its, reason, rnorm);
 }
 

@@ -469,6 +469,44 @@ class FlowSimulation:
         self.L.wb_timer_get(self.h, name.encode(), C.byref(ms), C.byref(cnt))
         return ms.value, cnt.value
 
+    def ksp_breakdown(self, reset=True):
+        """device time per Krylov iteration of the persistent GMRES kernel's phases (microseconds, CTA 0), or None
+        when no fused solve ran since the last reset (wb_ksp_fused_profile)"""
+        ns = (C.c_double * 7)()
+        check(self.L.wb_ksp_fused_profile(self.h, ns, 1 if reset else 0), "wb_ksp_fused_profile")
+        its = ns[6]
+        if its <= 0:
+            return None
+        names = ("spmv_pc", "dots", "dots_reduce", "maxpy_norm_push", "norm_reduce_update", "other")
+        out = {k: round(ns[i] * 1e-3 / its, 3) for i, k in enumerate(names)}
+        out["iterations"] = int(its)
+        return out
+
+    def ksp_breakdown_ctas(self):
+        """tuning aid: min / mean / max over the CTAs of the persistent kernel's phase times per iteration (us);
+        call before ksp_breakdown(reset=True)"""
+        L = self.L
+        if not hasattr(L, "wb_debug_fused_profile_all"):
+            return None
+        L.wb_debug_fused_profile_all.restype = C.c_int
+        L.wb_debug_fused_profile_all.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        buf = (C.c_double * (16 * 256))()
+        n = L.wb_debug_fused_profile_all(self.h, buf, 256)
+        a = np.array(buf[:16 * n]).reshape(n, 16)
+        a = a[a[:, 6] > 0]
+        if len(a) == 0:
+            return None
+        per = a[:, :6] * 1e-3 / a[:, 6:7]
+        names = ("spmv_pc", "dots", "dots_reduce", "maxpy_norm_push", "norm_reduce_update", "other")
+        out = {k: [round(float(per[:, i].min()), 2), round(float(per[:, i].mean()), 2), round(float(per[:, i].max()), 2)]
+               for i, k in enumerate(names)}
+        sp = a[:, 7] * 1e-3 / a[:, 6]
+        out["spmv_share_of_spmv_pc"] = [round(float(sp.min()), 2), round(float(sp.mean()), 2), round(float(sp.max()), 2)]
+        for k, nm in ((9, "level_first_wait_cycles"), (10, "level_own_cycles"), (11, "level_barrier_cycles")):
+            v = a[:, k] / a[:, 6]
+            out[nm] = [round(float(v.min())), round(float(v.mean())), round(float(v.max()))]
+        return out
+
     def launches(self):
         return self.L.wb_launch_count(self.h)
 
