@@ -42,8 +42,8 @@ struct WbFusedPlan {
   int off_red = 0, off_misc = 0, off_sd = 0, off_slice = 0, off_rec = 0, off_zs = 0, off_ring = 0;
   int nslots = 0, nslices = 0;  // sliced-ELL entries (slice, k, lane), slices
   int4 *d_cta = nullptr, *d_sd = nullptr, *d_slice = nullptr, *d_recA = nullptr, *d_recB = nullptr;
-  int32_t *d_rec_ptr = nullptr, *d_sidx = nullptr, *d_ssrc = nullptr;
-  double *d_sval = nullptr;
+  int32_t *d_rec_ptr = nullptr, *d_ssrc = nullptr, *d_slot0 = nullptr;
+  unsigned char *d_sell = nullptr;  // slices: [nk][32] column indices, then [nk][planes][32] values; one bulk copy each
   std::vector<int32_t> h_invperm;  // original row -> row in sub-domain-major order
   std::vector<int4> h_cta;
   // multi-GPU: boundary rows each CTA pushes (built on first use, when the halo plan and the peer map exist)
@@ -62,7 +62,7 @@ template <class T> static int up(T **p, const std::vector<T> &v) {
 void wb_fused_free(wb_pc *pc) {
   WbFusedPlan *f = pc->fused;
   if (!f) return;
-  void *ptrs[] = {f->d_cta, f->d_sd, f->d_slice, f->d_recA, f->d_recB, f->d_rec_ptr, f->d_sidx, f->d_ssrc, f->d_sval,
+  void *ptrs[] = {f->d_cta, f->d_sd, f->d_slice, f->d_recA, f->d_recB, f->d_rec_ptr, f->d_ssrc, f->d_slot0, f->d_sell,
                   f->d_push_ptr, f->d_push_row, f->d_push_rank, f->d_push_off};
   for (void *p : ptrs) cudaFree(p);
   delete f;
@@ -94,7 +94,7 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
   const int nsm = prop.multiProcessorCount;
   const size_t smem_max = prop.sharedMemPerBlockOptin;
   WbFusedPlan *f = new WbFusedPlan();
-  f->ncta = std::min(nsd, nsm);
+  f->ncta = std::min(std::min(nsd, nsm), WB_NUM_SMS);
   // contiguous runs of sub-domains per CTA, balanced by rows
   std::vector<int> first_sd(f->ncta + 1, 0);
   {
@@ -127,33 +127,36 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
   for (int p = 0; p < nb; p++) f->h_invperm[pc->h_blk_rows[p]] = p;
   // ---- sliced-ELL copy of the matrix in the sub-domain-major ordering
   std::vector<int4> sdtab(nsd), slices;
-  std::vector<int32_t> sidx, ssrc;
-  size_t val_words = 0;
+  std::vector<int32_t> ssrc, slot0;
+  std::vector<unsigned char> sell;
   f->h_cta.assign(f->ncta, make_int4(0, 0, 0, 0));
-  int slice_cap = 0;
-  const int pw = (b2 % 2 == 0) ? 2 : 1;
-  (void)pw;
+  int max_slice_bytes = 0;
   for (int ct = 0; ct < f->ncta; ct++) {
-    const int cta_slice0 = (int)slices.size();
     for (int sd = first_sd[ct]; sd < first_sd[ct + 1]; sd++) {
       const int row0 = pc->h_blk[sd].x, nr = pc->h_blk[sd].y;
       const int ns = (nr + FZ_SLICE - 1) / FZ_SLICE;
-      sdtab[sd] = make_int4(row0, nr, (int)slices.size() - cta_slice0, ns);
-      for (int s = 0; s < ns; s++) {
-        const int r0 = row0 + s * FZ_SLICE, n = std::min(FZ_SLICE, row0 + nr - r0);
+      sdtab[sd] = make_int4(row0, nr, (int)slices.size(), ns);
+      for (int sidx_ = 0; sidx_ < ns; sidx_++) {
+        const int r0 = row0 + sidx_ * FZ_SLICE, n = std::min(FZ_SLICE, row0 + nr - r0);
         int nk = 0;
         for (int l = 0; l < n; l++) {
           const int orow = pc->h_blk_rows[r0 + l];
           nk = std::max(nk, A->h_rowptr[orow + 1] - A->h_rowptr[orow]);
         }
-        if (val_words + (size_t)nk * b2 * FZ_SLICE >= ((size_t)1 << 31)) {
+        nk = std::max(nk, 1);
+        const size_t bytes = (size_t)nk * (FZ_SLICE * 4 + (size_t)b2 * FZ_SLICE * 8);
+        const size_t base = sell.size();
+        if (base + bytes >= ((size_t)1 << 35) || nk > 255) {
           delete f;
-          return 0;  // 32-bit offsets
+          return 0;  // offsets are kept in 16-byte units in 32 bits
         }
-        slices.push_back(make_int4(r0, n | (nk << 8), (int)sidx.size(), (int)val_words));
-        const size_t base = sidx.size();
-        sidx.resize(base + (size_t)nk * FZ_SLICE);
-        ssrc.resize(base + (size_t)nk * FZ_SLICE);
+        slices.push_back(make_int4(r0, n | (nk << 8), (int)(base / 16), (int)bytes));
+        max_slice_bytes = std::max(max_slice_bytes, (int)bytes);
+        sell.resize(base + bytes, 0);
+        int32_t *ip = reinterpret_cast<int32_t *>(sell.data() + base);
+        const size_t sbase = ssrc.size();
+        slot0.push_back((int32_t)sbase);
+        ssrc.resize(sbase + (size_t)nk * FZ_SLICE);
         for (int k = 0; k < nk; k++)
           for (int l = 0; l < FZ_SLICE; l++) {
             int col = r0 + std::min(l, n - 1), src = -1;  // padding: a zero block times the row's own entry
@@ -166,17 +169,14 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
                 src = e;
               }
             }
-            sidx[base + (size_t)k * FZ_SLICE + l] = col;
-            ssrc[base + (size_t)k * FZ_SLICE + l] = src;
+            ip[(size_t)k * FZ_SLICE + l] = col;
+            ssrc[sbase + (size_t)k * FZ_SLICE + l] = src;
           }
-        val_words += (size_t)nk * b2 * FZ_SLICE;
       }
     }
-    slice_cap = std::max(slice_cap, (int)slices.size() - cta_slice0);
-    f->h_cta[ct] = make_int4(first_sd[ct], first_sd[ct + 1] - first_sd[ct], cta_slice0, 0);
+    f->h_cta[ct] = make_int4(first_sd[ct], first_sd[ct + 1] - first_sd[ct], 0, 0);
   }
-  f->slice_cap = slice_cap;
-  f->nslots = (int)sidx.size();
+  f->nslots = (int)ssrc.size();
   f->nslices = (int)slices.size();
   // ---- groups, ring plans.  Try 4, 2, 1 groups per CTA until the byte ring holds at least three of the largest
   // level records (deep enough to hide the HBM latency behind the level-to-level dependency chain)
@@ -185,6 +185,7 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
     max_rec_bytes = std::max(max_rec_bytes, L.y);
     max_level_rows = std::max(max_level_rows, L.z);
   }
+  max_rec_bytes = std::max(max_rec_bytes, max_slice_bytes);
   for (int sd = 0; sd < nsd; sd++) max_rows = std::max(max_rows, pc->h_blk[sd].y);
   f->zs_words = ((max_rows + 1) * bs + 1) & ~1;
   bool ok = false;
@@ -199,7 +200,7 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
     for (int ct = 0; ct < f->ncta; ct++)
       for (int g = 0; g < ng; g++) {
         int cnt = 0;
-        for (int sd = first_sd[ct] + g; sd < first_sd[ct + 1]; sd += ng) cnt += pc->h_blk[sd].w;
+        for (int sd = first_sd[ct] + g; sd < first_sd[ct + 1]; sd += ng) cnt += pc->h_blk[sd].w + sdtab[sd].w;
         rec_cap = std::max(rec_cap, cnt);
       }
     f->rec_cap = rec_cap;
@@ -214,10 +215,9 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
     off += (size_t)(4 * KRY_MAXV + 8 + (KRY_MAXV + 1) * KRY_MAXV) * sizeof(double);  // column, rotations, rs, H
     f->off_sd = (int)off;
     off += (size_t)f->sd_cap * 2 * sizeof(int4);
-    f->off_slice = (int)off;
-    off += (size_t)f->slice_cap * sizeof(int4);
+    f->off_slice = (int)off;  // (unused: the slice descriptors travel in the record tables)
     f->off_rec = (int)off;
-    off += (size_t)ng * rec_cap * 2 * sizeof(int4);
+    off += (size_t)ng * (rec_cap + 1) * 2 * sizeof(int4);  // + 1: the level loop reads one descriptor ahead
     off = (off + 127) & ~(size_t)127;
     f->off_zs = (int)off;
     off += (size_t)ng * f->zs_words * sizeof(double);
@@ -238,6 +238,17 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
         int pos = 0;
         for (int sd = first_sd[ct] + g, slot = g; sd < first_sd[ct + 1]; sd += ng, slot += ng) {
           const int lev0 = pc->h_blk[sd].z, nl = pc->h_blk[sd].w;
+          // the sub-domain's matrix slices (SpMV), then its level records (ILU sweeps), in the order they are consumed
+          for (int sl = 0; sl < sdtab[sd].w; sl++) {
+            const int4 S = slices[sdtab[sd].z + sl];
+            const int bytes = (S.w + 15) & ~15;
+            if (pos + bytes > f->ring_bytes) pos = 0;
+            roff.push_back(pos);
+            rbytes.push_back(bytes);
+            recA.push_back(make_int4(S.z, S.w, pos, 0));
+            recB.push_back(make_int4(S.x, S.y, slot, 4));
+            pos += bytes;
+          }
           for (int l = 0; l < nl; l++) {
             const int4 L = pc->h_lev[lev0 + l];
             const int bytes = (L.y + 15) & ~15;
@@ -281,9 +292,10 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
   WB_TRY(up(&f->d_recA, recA));
   WB_TRY(up(&f->d_recB, recB));
   WB_TRY(up(&f->d_rec_ptr, rec_ptr));
-  WB_TRY(up(&f->d_sidx, sidx));
   WB_TRY(up(&f->d_ssrc, ssrc));
-  WB_CUDA(cudaMalloc(&f->d_sval, std::max<size_t>(val_words, 1) * sizeof(double) + WB_PAD_BYTES));
+  WB_TRY(up(&f->d_slot0, slot0));
+  WB_CUDA(cudaMalloc(&f->d_sell, sell.size() + WB_PAD_BYTES));
+  WB_CUDA(cudaMemcpy(f->d_sell, sell.data(), sell.size(), cudaMemcpyHostToDevice));
   pc->fused = f;
   return 0;
 }
@@ -291,18 +303,21 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
 // numeric part: BAIJ values -> plane layout of the slices (zero blocks where a row is shorter than its slice)
 template <int BS>
 __global__ void k_sell_fill(const double *__restrict__ val, const int4 *__restrict__ slices, int nslices,
-                            const int32_t *__restrict__ ssrc, double *__restrict__ sval) {
+                            const int32_t *__restrict__ ssrc, const int32_t *__restrict__ slot0,
+                            unsigned char *__restrict__ sell) {
   constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (s >= nslices) return;
   const int4 S = slices[s];
   const int nk = S.y >> 8;
+  double *vals = reinterpret_cast<double *>(sell + (size_t)S.z * 16 + (size_t)nk * FZ_SLICE * 4);
+  const int32_t *src_ = ssrc + slot0[s];
   for (int k = 0; k < nk; k++) {
-    const int src = ssrc[S.z + k * FZ_SLICE + lane];
+    const int src = src_[k * FZ_SLICE + lane];
     double v[B2];
 #pragma unroll
     for (int q = 0; q < B2; q++) v[q] = src >= 0 ? __ldcs(val + (size_t)src * B2 + q) : 0.0;
-    double *dst = sval + (size_t)S.w + (size_t)k * B2 * FZ_SLICE;
+    double *dst = vals + (size_t)k * B2 * FZ_SLICE;
 #pragma unroll
     for (int q = 0; q < NPL; q++)
 #pragma unroll
@@ -317,9 +332,9 @@ int wb_fused_refresh(wb_pc *pc) {
   wb_ctx *c = A->ctx;
   const int grid = wb_grid((size_t)f->nslices * 32, 256);
   switch (pc->bs) {
-    case 1: k_sell_fill<1><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_sval); break;
-    case 2: k_sell_fill<2><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_sval); break;
-    default: k_sell_fill<3><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_sval); break;
+    case 1: k_sell_fill<1><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_slot0, f->d_sell); break;
+    case 2: k_sell_fill<2><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_slot0, f->d_sell); break;
+    default: k_sell_fill<3><<<grid, 256, 0, c->stream>>>(A->d_val, f->d_slice, f->nslices, f->d_ssrc, f->d_slot0, f->d_sell); break;
   }
   WB_LAUNCH(c);
   WB_CUDA(cudaGetLastError());
@@ -331,15 +346,17 @@ int wb_fused_refresh(wb_pc *pc) {
 struct FusedArgs {
   // plan
   const int4 *cta, *sd, *blk, *slice, *recA, *recB;
-  const int32_t *rec_ptr, *sidx, *perm;
-  const double *sval, *stream;
+  const int32_t *rec_ptr, *perm;
+  const unsigned char *sell;
+  const double *stream;
   int ng, gt, nc, lt, sd_cap, slice_cap, rec_cap, zs_words, ring_bytes;
   int off_red, off_misc, off_gm, off_prof, off_sd, off_slice, off_rec, off_zs, off_ring;
   int nb, ncta;
   size_t ld;
   // vectors: b / xout in the caller's ordering, everything else in the sub-domain-major ordering
   const double *b;
-  double *xout, *V, *wa, *wb, *xp, *part;
+  double *xout, *V, *wa, *wb, *xp;
+  unsigned char *llpart;  // LL partials and totals of the grid-wide reductions (zeroed before every solve)
   int *bar;  // [0] arrivals, [1] release generation, [2] abort
   GmresUpd upd;
   double *yv;
@@ -432,85 +449,88 @@ __device__ __forceinline__ double ll_load_wait(const void *slot, int seq, int *e
   return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
 
+// the same inside one GPU (partials and totals of the grid-wide reductions live in this GPU's memory): L2 is the point
+// of coherence, so GPU-scope relaxed accesses are enough (plain cache-global loads are weak: a polling loop may never
+// observe the store)
+__device__ __forceinline__ void ll_store_gpu(void *slot, double v, int seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), sq = (unsigned long long)(unsigned)seq << 32;
+  const unsigned long long w0 = (b & 0xffffffffull) | sq, w1 = (b >> 32) | sq;
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_load_wait_gpu(const void *slot, int seq, int *err) {
+  unsigned long long w0, w1;
+  const unsigned sq = (unsigned)seq;
+  long long t0 = 0;
+  unsigned n = 0;
+  while (true) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    if ((unsigned)(w0 >> 32) == sq && (unsigned)(w1 >> 32) == sq) break;
+    if ((++n & 1023u) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > FZ_SPIN_LIMIT) {
+        atomicExch(err, 1);
+        break;
+      }
+    }
+  }
+  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+
 #define FZ_BAR_ALL 15  // named barrier of all consumer threads; groups use 1 + g
 
-struct FzGrid {
-  int *bar;  // [0] arrivals (monotonic), [2] abort
-  int ncta, gen;
+// ---- grid-wide (and machine-wide) reductions without atomics or barriers --------------------------------------
+// Every CTA contributes nv local sums; afterwards every CTA holds the nv global sums, bit-identical everywhere.
+//   1. each CTA stores its partials in LL format (value and sequence number in one 16-byte word pair) into
+//      part[kind][j][cta];
+//   2. value j has an owner CTA (j mod #CTAs): it polls the partials of all CTAs, sums them in a fixed order and
+//      publishes the total -- single GPU: into tot[kind][j]; multi-GPU: straight into every rank's NVLink slot;
+//   3. every CTA polls the totals (multi-GPU: the slots of all ranks, summed in rank order).
+// The flag travels with the data, so nothing waits for a fence or an atomic round trip: the latency is two
+// store-to-poll hops inside the GPU (plus one NVLink flight).  `release` (used where the reduction also has to act as a
+// grid barrier for the vector rows written before it) makes the CTA's earlier global writes visible first.
+struct FzRed {
+  unsigned char *part, *tot;  // [2][KRY_MAXV][WB_NUM_SMS] and [2][KRY_MAXV] LL words
+  int ncta;
 };
-// Grid-wide synchronisation of the co-resident CTAs on a monotonic arrival counter: every CTA adds 1 (release) and
-// polls (acquire) until all have arrived.  There is no "last CTA" section and no second flag: what follows a
-// reduction is computed redundantly, in the same order, by every CTA from the partials all of them can now read.
-__device__ __forceinline__ void fz_grid_sync(FzGrid &G, int tid, int nc) {
-  bar_sync_named(FZ_BAR_ALL, nc);  // the CTA's writes happen before thread 0's release (cumulativity)
-  if (tid == 0) {
-    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(&G.bar[0]) : "memory");
-    const int target = (G.gen + 1) * G.ncta;
-    const long long t0 = clock64();
-    unsigned n = 0;
-    while (fz_ld_acquire(&G.bar[0]) < target) {
-      if ((++n & 255u) == 0) {
-        if (clock64() - t0 > FZ_SPIN_LIMIT) atomicExch(&G.bar[2], 1);
-        if (__ldcg(&G.bar[2])) break;
+__device__ __forceinline__ void fz_reduce_ll(const FusedArgs &a, const FzRed &R, int kind, int seq, int nv, double *s_vals,
+                                             double *s_tmp, bool release, bool multi, int mseq, size_t slot_off,
+                                             int per_rank, int cta, int tid, int nc) {
+  const int lane = tid & 31;
+  if (release) __threadfence();
+  bar_sync_named(FZ_BAR_ALL, nc);  // s_vals complete; with `release`: every thread's earlier writes are visible
+  if (tid < nv) ll_store_gpu(R.part + ((size_t)(kind * KRY_MAXV + tid) * WB_NUM_SMS + cta) * 16, s_vals[tid], seq);
+  const size_t buf = multi ? (size_t)(mseq & 1) * WB_P2P_MAX_RANKS * per_rank * 16 : 0;
+  for (int j = cta; j < nv; j += R.ncta) {  // owner duty
+    if (tid < R.ncta)
+      s_tmp[tid] = ll_load_wait_gpu(R.part + ((size_t)(kind * KRY_MAXV + j) * WB_NUM_SMS + tid) * 16, seq, &a.bar[2]);
+    bar_sync_named(FZ_BAR_ALL, nc);
+    if (tid < 32) {
+      double t = 0.0;
+      for (int c = lane; c < R.ncta; c += 32) t += s_tmp[c];  // fixed order: lane strides, then the shuffle tree
+      t = warp_sum(t);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (!multi) {
+        if (lane == 0) ll_store_gpu(R.tot + (size_t)(kind * KRY_MAXV + j) * 16, t, seq);
+      } else if (lane < a.P.nranks) {
+        ll_store(a.P.region[lane] + slot_off + buf + (size_t)(a.P.rank * per_rank + j) * 16, t, mseq);
       }
     }
+    bar_sync_named(FZ_BAR_ALL, nc);
   }
-  bar_sync_named(FZ_BAR_ALL, nc);
-  G.gen++;
-}
-
-// every CTA: sums of all CTAs' partials part[cta][j], j < nv, in a fixed order -> s_vals[j] (shared).  Thread (j, sub)
-// sums every (nc / 32)-th CTA's partial in ascending CTA order with the loads issued ahead of the adds, then thread j
-// folds the sub-sums in order.
-__device__ __forceinline__ void fz_fold_parts(const double *part, int ncta, int nv, double *s_vals, double *s_tmp,
-                                              int tid, int nc) {
-  const int j = tid & 31, sub = tid >> 5, nsub = nc >> 5;
-  if (j < nv) {
-    double s = 0.0;
-    for (int c0 = sub; c0 < ncta; c0 += 8 * nsub) {
-      double t[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int ct = c0 + k * nsub;
-        t[k] = ct < ncta ? __ldcg(&part[(size_t)ct * KRY_MAXV + j]) : 0.0;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        if (c0 + k * nsub < ncta) s += t[k];
-    }
-    s_tmp[sub * KRY_MAXV + j] = s;
-  }
-  bar_sync_named(FZ_BAR_ALL, nc);
-  if (tid < nv) {
-    double s = 0.0;
-    for (int q = 0; q < nsub; q++) s += s_tmp[q * KRY_MAXV + tid];
-    s_vals[tid] = s;
-  }
-  bar_sync_named(FZ_BAR_ALL, nc);
-}
-
-// multi-GPU: all-gather of this GPU's nv sums (s_vals, identical in every CTA) over NVLink in the LL format -- CTA 0
-// stores them into every rank's slot (buffer seq & 1), every CTA of every GPU polls its own GPU's slots -- then the
-// sum over ranks in rank order (bit-identical everywhere) -> s_vals
-__device__ __forceinline__ void fz_allgather_sum(const FusedArgs &a, int seq, int nv, double *s_vals, double *s_tmp,
-                                                 size_t slot_off, int per_rank, int cta, int tid, int nc) {
-  const WbP2PDev &P = a.P;
-  const size_t buf = (size_t)(seq & 1) * WB_P2P_MAX_RANKS * per_rank * 16;
-  if (cta == 0) {
+  if (!multi) {
+    if (tid < nv) s_vals[tid] = ll_load_wait_gpu(R.tot + (size_t)(kind * KRY_MAXV + tid) * 16, seq, &a.bar[2]);
+  } else {
+    const WbP2PDev &P = a.P;
     for (int idx = tid; idx < P.nranks * nv; idx += nc) {
       const int r = idx / nv, j = idx - r * nv;
-      ll_store(P.region[r] + slot_off + buf + (size_t)(P.rank * per_rank + j) * 16, s_vals[j], seq);
+      s_tmp[r * KRY_MAXV + j] = ll_load_wait(P.region[P.rank] + slot_off + buf + (size_t)(r * per_rank + j) * 16, mseq, P.err);
     }
-  }
-  for (int idx = tid; idx < P.nranks * nv; idx += nc) {
-    const int r = idx / nv, j = idx - r * nv;
-    s_tmp[r * KRY_MAXV + j] = ll_load_wait(P.region[P.rank] + slot_off + buf + (size_t)(r * per_rank + j) * 16, seq, P.err);
-  }
-  bar_sync_named(FZ_BAR_ALL, nc);
-  if (tid < nv) {
-    double s = 0.0;
-    for (int r = 0; r < P.nranks; r++) s += s_tmp[r * KRY_MAXV + tid];
-    s_vals[tid] = s;
+    bar_sync_named(FZ_BAR_ALL, nc);
+    if (tid < nv) {
+      double t = 0.0;
+      for (int r = 0; r < P.nranks; r++) t += s_tmp[r * KRY_MAXV + tid];
+      s_vals[tid] = t;
+    }
   }
   bar_sync_named(FZ_BAR_ALL, nc);
 }
@@ -585,10 +605,9 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   int *s_nrec = reinterpret_cast<int *>(smem + a.off_misc + 328);     // [FZ_MAXG]
   volatile int *s_consumed = reinterpret_cast<volatile int *>(smem + a.off_misc + 432);  // [FZ_MAXG] level records consumed
   int4 *s_sd = reinterpret_cast<int4 *>(smem + a.off_sd);             // [sd_cap][2]
-  int4 *s_slice = reinterpret_cast<int4 *>(smem + a.off_slice);
   int4 *s_rec = reinterpret_cast<int4 *>(smem + a.off_rec);           // [ng][rec_cap][2]
   const int4 C = a.cta[cta];
-  const int sd0 = C.x, nsd = C.y, slice0 = C.z;
+  const int sd0 = C.x, nsd = C.y;
 
   // ---- set-up: barriers, tables -> shared memory
   if (tid == 0) {
@@ -599,22 +618,16 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
     *s_stop = 0;
     for (int i = 0; i < FZ_MAXG; i++) s_consumed[i] = 0;
   }
-  int nslice_cta = 0;
   for (int s = tid; s < nsd; s += blockDim.x) {
     s_sd[2 * s] = a.sd[sd0 + s];
     s_sd[2 * s + 1] = a.blk[sd0 + s];
   }
-  {
-    const int4 last = a.sd[sd0 + nsd - 1];
-    nslice_cta = last.z + last.w;
-  }
-  for (int s = tid; s < nslice_cta; s += blockDim.x) s_slice[s] = a.slice[slice0 + s];
   for (int g = 0; g < ng; g++) {
     const int r0 = a.rec_ptr[cta * ng + g], r1 = a.rec_ptr[cta * ng + g + 1];
     if (tid == 0) s_nrec[g] = r1 - r0;
     for (int r = tid; r < r1 - r0; r += blockDim.x) {
-      s_rec[((size_t)g * a.rec_cap + r) * 2] = a.recA[r0 + r];
-      s_rec[((size_t)g * a.rec_cap + r) * 2 + 1] = a.recB[r0 + r];
+      s_rec[((size_t)g * (a.rec_cap + 1) + r) * 2] = a.recA[r0 + r];
+      s_rec[((size_t)g * (a.rec_cap + 1) + r) * 2 + 1] = a.recB[r0 + r];
     }
   }
   __syncthreads();
@@ -628,13 +641,14 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
     const int pl = tid - nc, g = pl % ng, per = 32 / ng;
     const int P = s_nrec[g];
     if (P > 0) {
-      const int4 *rec = s_rec + (size_t)g * a.rec_cap * 2;
+      const int4 *rec = s_rec + (size_t)g * (a.rec_cap + 1) * 2;
       uint64_t *fullg = full + g * FZ_NBAR;
       unsigned char *ring = smem + a.off_ring + (size_t)g * a.ring_bytes;
       long long q = pl / ng, qlast = -1;
       int pos = (int)(q % P);
       while (true) {
         const int4 A = rec[2 * pos];
+        const bool is_slice = (rec[2 * pos + 1].w & 4) != 0;
         bool stopped = false;
         if (q >= A.w) {
           // the record whose space this one takes must have been consumed.  The consumers publish a monotonic count
@@ -651,7 +665,8 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
         if (stopped || *s_stop) break;
         uint64_t *fb = &fullg[q % FZ_NBAR];
         mbar_expect_tx(fb, (uint32_t)A.y);
-        tma_load_1d(ring + A.z, a.stream + A.x, (uint32_t)A.y, fb);
+        tma_load_1d(ring + A.z, is_slice ? static_cast<const void *>(a.sell + (size_t)A.x * 16)
+                                         : static_cast<const void *>(a.stream + A.x), (uint32_t)A.y, fb);
         qlast = q;
         q += per;
         pos = (int)((pos + per) % P);
@@ -669,18 +684,20 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   const int warp = tid >> 5, nwarps = nc >> 5;
   double *zs = reinterpret_cast<double *>(smem + a.off_zs) + (size_t)g * a.zs_words;
   const unsigned char *ring = smem + a.off_ring + (size_t)g * a.ring_bytes;
-  const int4 *rec = s_rec + (size_t)g * a.rec_cap * 2;
+  const int4 *rec = s_rec + (size_t)g * (a.rec_cap + 1) * 2;
   uint64_t *fullg = full + g * FZ_NBAR;
   const int nrec = s_nrec[g];
-  const int lt = a.lt;  // threads of the group that take part in the level sweeps (the widest level, rounded to warps)
-  const bool waiter = gtid == lt - 32;
+  // threads of the group that take part in the level sweeps: the widest level rounded to warps, plus (when the group
+  // has a warp to spare) one warp whose first lane only looks out for the next record
+  const int lt = a.lt, ltw = lt + 32 <= gt ? lt + 32 : lt;
+  const bool waiter = gtid == ltw - 32;
   // rows [R0, R1) and elements [e0, e1) of this CTA; vector body [eb, ee) is 16-byte aligned
   const int R0 = s_sd[0].x, R1 = s_sd[2 * (nsd - 1)].x + s_sd[2 * (nsd - 1)].y;
   const int e0 = R0 * BS, e1 = R1 * BS;
   const int eb = (e0 + 1) & ~1, ee = e1 & ~1;
   const bool multi = a.P.on != 0 && a.P.nranks > 1;
-  FzGrid G = {a.bar, a.ncta, 0};
-  double *partA = a.part, *partB = a.part + (size_t)WB_NUM_SMS * 2 * KRY_MAXV;  // dots / norm partials: two buffers
+  const FzRed R = {a.llpart, a.llpart + (size_t)2 * KRY_MAXV * WB_NUM_SMS * 16, a.ncta};
+  int rseqA = 0, rseqB = 0;  // sequence numbers of the dots (kind 0) and norm / barrier (kind 1) reductions
   int hseq = 0, aseq = 0, bseq = 0;
   if (multi) {
     hseq = __ldcg(&a.fseq[0]);
@@ -689,8 +706,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   }
   const GmresUpd &u = a.upd;
   const int m = u.m;
-  int slot = 0, ri = 0, nconsumed = 0;  // mbarrier slot of the group's next level record, its position in the record list
-  uint32_t phase = 0;
+  int qrec = 0, ri = 0;  // records this group has consumed (slot = qrec % FZ_NBAR, parity = (qrec / FZ_NBAR) & 1), position in its list
   // phase timers of CTA 0 (thread 0), kept in shared memory
   unsigned long long *s_prof = reinterpret_cast<unsigned long long *>(smem + a.off_prof);  // [16]; [8] = previous stamp
   const bool profiler = (tid == 0);  // every CTA keeps its own phase times (CTA 0's are the ones the ABI reports)
@@ -719,126 +735,122 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
                                     : nullptr;
     for (int sl = g; sl < nsd; sl += ng) {
       const int4 sA = s_sd[2 * sl], sB = s_sd[2 * sl + 1];
-      const int row0 = sA.x, nr = sA.y, nl = sB.w;
+      const int row0 = sA.x, nr = sA.y, ns = sA.w, nl = sB.w;
       if (gtid < BS) zs[nr * BS + gtid] = 0.0;  // the slot padding blocks of the level records multiply
-      if (mode == 0) {
-        for (int li = gtid; li < nr; li += gt) {
-          const size_t ob = (size_t)a.perm[row0 + li] * BS;
+      // ---- SpMV: the sub-domain's matrix slices arrive through the ring (records qrec .. qrec + ns - 1, one warp
+      // each, `gwarps` of them per round); the operand is gathered through L2
+      for (int s0 = 0; s0 < ns; s0 += gwarps) {
+        const int si = s0 + gwarp;
+        if (si < ns) {
+          const int qi = qrec + si;
+          const int4 A = rec[2 * (ri + si)], B = rec[2 * (ri + si) + 1];
+          fz_mbar_wait(&fullg[qi & (FZ_NBAR - 1)], (uint32_t)((qi / FZ_NBAR) & 1), &a.bar[2]);
+          const int n = B.y & 255, nk = B.y >> 8, srow0 = B.x;
+          const int row = srow0 + lane, li = row - row0;
+          if (mode == 0) {
+            if (lane < n) {
+              const size_t ob = (size_t)a.perm[row] * BS;
 #pragma unroll
-          for (int i = 0; i < BS; i++) zs[li * BS + i] = a.b[ob + i];
-        }
-      } else {
-        for (int si = gwarp; si < sA.w; si += gwarps) {
-          const int4 S = s_slice[sA.z + si];
-          const int n = S.y & 255, nk = S.y >> 8;
-          const int32_t *ip = a.sidx + S.z + lane;
-          const double *vp = a.sval + (size_t)S.w + (size_t)lane * PW;
-          double acc[BS];
-#pragma unroll
-          for (int i = 0; i < BS; i++) acc[i] = 0.0;
-          // up to FZ_CH blocks of the row in flight at once (index and value loads first, then the gathers of the
-          // operand in two halves): a 7-point row is one round trip to HBM plus one to L2
-          for (int k0 = 0; k0 < nk; k0 += FZ_CH) {
-            int col[FZ_CH];
-            double v[FZ_CH][B2];
-#pragma unroll
-            for (int uu = 0; uu < FZ_CH; uu++) {
-              const int k = min(k0 + uu, nk - 1);  // past the end: re-read the last block, its x is zeroed
-              col[uu] = __ldcs(ip + k * FZ_SLICE);
-              const double *bp = vp + (size_t)k * B2 * FZ_SLICE;
-#pragma unroll
-              for (int qq = 0; qq < NPL; qq++) {
-                if (PW == 2) {
-                  const double2 t = __ldcs(reinterpret_cast<const double2 *>(bp + (size_t)qq * FZ_SLICE * 2));
-                  v[uu][2 * qq] = t.x;
-                  v[uu][2 * qq + 1] = t.y;
-                } else {
-                  v[uu][qq] = __ldcs(bp + (size_t)qq * FZ_SLICE);
-                }
-              }
+              for (int i = 0; i < BS; i++) zs[li * BS + i] = a.b[ob + i];
             }
+          } else {
+            const int32_t *ip = reinterpret_cast<const int32_t *>(ring + A.z) + lane;
+            const double *vp = reinterpret_cast<const double *>(ring + A.z + (size_t)nk * FZ_SLICE * 4) + (size_t)lane * PW;
+            double acc[BS];
 #pragma unroll
-            for (int h0 = 0; h0 < FZ_CH; h0 += FZ_CH / 2) {
-              double x[FZ_CH / 2][BS];
+            for (int i = 0; i < BS; i++) acc[i] = 0.0;
+            // FZ_CH blocks of the row at a time: their operand entries are gathered together (one L2 round trip)
+            for (int k0 = 0; k0 < nk; k0 += FZ_CH) {
+              int col[FZ_CH];
+              double x[FZ_CH][BS];
 #pragma unroll
-              for (int uh = 0; uh < FZ_CH / 2; uh++) {
-                const int uu = h0 + uh;
+              for (int uu = 0; uu < FZ_CH; uu++) col[uu] = ip[min(k0 + uu, nk - 1) * FZ_SLICE];
+#pragma unroll
+              for (int uu = 0; uu < FZ_CH; uu++) {
                 const bool on = k0 + uu < nk;
                 const bool own = col[uu] < a.nb;
                 if (on && !own) {
                   const unsigned char *gp = xg + (size_t)(col[uu] - a.nb) * BS * 16;
 #pragma unroll
-                  for (int j = 0; j < BS; j++) x[uh][j] = ll_load_wait(gp + j * 16, hseq, a.P.err) * s;
+                  for (int j = 0; j < BS; j++) x[uu][j] = ll_load_wait(gp + j * 16, hseq, a.P.err) * s;
                 } else {
                   const double *xp_ = xop + (size_t)col[uu] * BS;
                   if (BS == 2) {
                     const double2 t = on ? __ldcg(reinterpret_cast<const double2 *>(xp_)) : make_double2(0.0, 0.0);
-                    x[uh][0] = t.x * s;
-                    x[uh][1] = t.y * s;
+                    x[uu][0] = t.x * s;
+                    x[uu][1] = t.y * s;
                   } else {
 #pragma unroll
-                    for (int j = 0; j < BS; j++) x[uh][j] = on ? __ldcg(xp_ + j) * s : 0.0;
+                    for (int j = 0; j < BS; j++) x[uu][j] = on ? __ldcg(xp_ + j) * s : 0.0;
                   }
                 }
               }
 #pragma unroll
-              for (int uh = 0; uh < FZ_CH / 2; uh++)
+              for (int uu = 0; uu < FZ_CH; uu++) {
+                const int k = min(k0 + uu, nk - 1);  // past the end: the last block again, its x is zero
+                const double *bp = vp + (size_t)k * B2 * FZ_SLICE;
+                double v[B2];
+#pragma unroll
+                for (int qq = 0; qq < NPL; qq++) {
+                  if (PW == 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(bp + (size_t)qq * FZ_SLICE * 2);
+                    v[2 * qq] = t.x;
+                    v[2 * qq + 1] = t.y;
+                  } else {
+                    v[qq] = bp[(size_t)qq * FZ_SLICE];
+                  }
+                }
 #pragma unroll
                 for (int j = 0; j < BS; j++)
 #pragma unroll
-                  for (int i = 0; i < BS; i++) acc[i] += v[h0 + uh][j * BS + i] * x[uh][j];
-            }
-          }
-          if (lane < n) {
-            const int row = S.x + lane, li = row - row0;
-            if (mode == 1) {
-#pragma unroll
-              for (int i = 0; i < BS; i++) {
-                vstore[(size_t)row * BS + i] = __ldcg(xop + (size_t)row * BS + i) * s;
-                zs[li * BS + i] = acc[i];
+                  for (int i = 0; i < BS; i++) acc[i] += v[j * BS + i] * x[uu][j];
               }
-            } else {
-              const size_t ob = (size_t)a.perm[row] * BS;
+            }
+            if (lane < n) {
+              if (mode == 1) {
 #pragma unroll
-              for (int i = 0; i < BS; i++) zs[li * BS + i] = a.b[ob + i] - acc[i];
+                for (int i = 0; i < BS; i++) {
+                  vstore[(size_t)row * BS + i] = __ldcg(xop + (size_t)row * BS + i) * s;
+                  zs[li * BS + i] = acc[i];
+                }
+              } else {
+                const size_t ob = (size_t)a.perm[row] * BS;
+#pragma unroll
+                for (int i = 0; i < BS; i++) zs[li * BS + i] = a.b[ob + i] - acc[i];
+              }
             }
           }
         }
+        bar_sync_named(1 + g, gt);
+        if (gtid == 0) s_consumed[g] = qrec + min(s0 + gwarps, ns);  // the ring space of these slices may be reused
       }
-      bar_sync_named(1 + g, gt);
+      qrec += ns;
+      ri += ns;
       if (profiler) s_prof[7] += fz_now() - s_prof[8];  // SpMV share of the phase (group 0)
-      // forward and backward sweeps, level by level, by the first `lt` threads of the group only (a level never has
-      // more rows; the other warps would just burn issue slots walking the loop).  One thread looks out for the next
-      // record while the others apply the current one; the level barrier then publishes its acquire to everybody.
-      if (gtid < lt && nl > 0) {
-        long long tc0 = 0, tc1 = 0, tc2 = 0;
-        if (profiler) tc0 = clock64();
-        fz_mbar_wait(&fullg[slot], phase, &a.bar[2]);
-        if (profiler) {
-          tc1 = clock64();
-          s_prof[9] += tc1 - tc0;  // cycles waiting for the first level record
-        }
+      // ---- forward and backward sweeps, level by level, by the first `lt` threads of the group only (a level never
+      // has more rows; the other warps would just burn issue slots walking the loop).  One thread looks out for the
+      // next record while the others apply the current one; the level barrier then publishes its acquire to everybody.
+      if (gtid < ltw && nl > 0) {
+        int qi = qrec, rl = ri;
+        fz_mbar_wait(&fullg[qi & (FZ_NBAR - 1)], (uint32_t)((qi / FZ_NBAR) & 1), &a.bar[2]);
+        int4 A = rec[2 * rl], B = rec[2 * rl + 1];
         for (int l = 0; l < nl; l++) {
-          if (profiler) tc0 = clock64();
-          const int4 A = rec[2 * ri], B = rec[2 * ri + 1];
-          ilu_level<BS>(reinterpret_cast<const double *>(ring + A.z), B.x, B.y & 0xffff, (B.y >> 16) != 0, zs, lt, gtid);
-          const int slot_n = slot + 1 == FZ_NBAR ? 0 : slot + 1;
-          const uint32_t phase_n = slot + 1 == FZ_NBAR ? phase ^ 1u : phase;
-          if (waiter && l + 1 < nl) fz_mbar_wait(&fullg[slot_n], phase_n, &a.bar[2]);
-          if (profiler) tc1 = clock64();
-          bar_sync_named(8 + g, lt);
-          if (profiler) {
-            tc2 = clock64();
-            s_prof[10] += tc1 - tc0;  // cycles in thread 0's own part of a level
-            s_prof[11] += tc2 - tc1;  // cycles at the level barrier (the other warps' rows, the waiter's look-out)
-          }
-          nconsumed++;
-          if (gtid == 0) s_consumed[g] = nconsumed;  // the ring space of this record may be reused
-          slot = slot_n;
-          phase = phase_n;
-          if (++ri == nrec) ri = 0;
+          const int4 An = rec[2 * (rl + 1)], Bn = rec[2 * (rl + 1) + 1];  // next record's descriptor (table is padded)
+          if (gtid < lt)
+            ilu_level<BS>(reinterpret_cast<const double *>(ring + A.z), B.x, B.y & 0xffff, (B.y >> 16) != 0, zs, lt, gtid);
+          if (waiter && l + 1 < nl)
+            fz_mbar_wait(&fullg[(qi + 1) & (FZ_NBAR - 1)], (uint32_t)(((qi + 1) / FZ_NBAR) & 1), &a.bar[2]);
+          bar_sync_named(8 + g, ltw);
+          qi++;
+          rl++;
+          A = An;
+          B = Bn;
+          if (gtid == 0) s_consumed[g] = qi;  // the ring space of this record may be reused
         }
       }
+      qrec += nl;
+      ri += nl;
+      if (ri >= nrec) ri = 0;  // a group's record list covers whole sub-domains: it ends exactly here
       bar_sync_named(1 + g, gt);
       for (int li = gtid; li < nr; li += gt) {
 #pragma unroll
@@ -849,7 +861,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   };
 
   // ---- dots of w (this CTA's rows) against nv vectors V_j = V + j * ldv -> part[cta][j]
-  auto dots = [&](const double *w, const double *V, size_t ldv, int nv, double *part) {
+  auto dots = [&](const double *w, const double *V, size_t ldv, int nv, double *s_out) {
     for (int j0 = 0; j0 < nv; j0 += 8) {
       const int nvc = min(8, nv - j0);
       double acc[8];
@@ -892,13 +904,13 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
     if (tid < nv) {
       double sres = 0.0;
       for (int wq = 0; wq < nwarps; wq++) sres += s_red[wq * KRY_MAXV + tid];
-      part[(size_t)cta * KRY_MAXV + tid] = sres;
+      s_out[tid] = sres;
     }
   };
 
   // ---- w += sum_j s_cf[j] V_j on this CTA's rows (sequential in j per entry, as VecMAXPY); with `norm` the CTA's
   // part of |w|^2 -> part[cta][0]
-  auto maxpy = [&](double *w, const double *V, size_t ldv, int nv, double *part) {
+  auto maxpy = [&](double *w, const double *V, size_t ldv, int nv, double *s_out) {
     double nrm = 0.0;
     for (int i = (eb >> 1) + tid; i < (ee >> 1); i += 2 * nc) {
       const int i2 = i + nc;
@@ -947,14 +959,14 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
         nrm += wi * wi;
       }
     }
-    if (part) {
+    if (s_out) {
       const double sres = warp_sum(nrm);
       if (lane == 0) s_red[warp * KRY_MAXV] = sres;
       bar_sync_named(FZ_BAR_ALL, nc);
       if (tid == 0) {
         double t = 0.0;
         for (int wq = 0; wq < nwarps; wq++) t += s_red[wq * KRY_MAXV];
-        part[(size_t)cta * KRY_MAXV] = t;
+        s_out[0] = t;
       }
     }
   };
@@ -985,11 +997,9 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
     FZ_STAMP(0);
     bar_sync_named(FZ_BAR_ALL, nc);
     push(w_new);
-    dots(w_new, w_new, 0, 1, partB);
+    dots(w_new, w_new, 0, 1, s_h);
     FZ_STAMP(1);
-    fz_grid_sync(G, tid, nc);
-    fz_fold_parts(partB, a.ncta, 1, s_h, s_red, tid, nc);
-    if (multi) fz_allgather_sum(a, bseq + 1, 1, s_h, s_red, WB_P2P_SLOT_FB, 1, cta, tid, nc);
+    fz_reduce_ll(a, R, 1, ++rseqB, 1, s_h, s_red, true, multi, bseq + 1, WB_P2P_SLOT_FB, 1, cta, tid, nc);
     if (tid == 0) {  // k_gmres_begin
       const double res = sqrt(s_h[0]);
       s_st->res = res;
@@ -1029,22 +1039,18 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       sp_phase(1, w_old, s_st->scal1, a.V + (size_t)it * a.ld, w_new);
       FZ_STAMP(0);
       bar_sync_named(FZ_BAR_ALL, nc);
-      dots(w_new, a.V, a.ld, it + 1, partA);
+      dots(w_new, a.V, a.ld, it + 1, s_h);
       FZ_STAMP(1);
-      fz_grid_sync(G, tid, nc);
-      fz_fold_parts(partA, a.ncta, it + 1, s_h, s_red, tid, nc);
-      if (multi) fz_allgather_sum(a, aseq + 1, it + 1, s_h, s_red, WB_P2P_SLOT_FA, WB_P2P_MAXV, cta, tid, nc);
+      fz_reduce_ll(a, R, 0, ++rseqA, it + 1, s_h, s_red, false, multi, aseq + 1, WB_P2P_SLOT_FA, WB_P2P_MAXV, cta, tid, nc);
       aseq++;
       FZ_STAMP(2);
       if (__ldcg(&a.bar[2])) break;
       if (tid <= it) s_cf[tid] = -s_h[tid];
       bar_sync_named(FZ_BAR_ALL, nc);
-      maxpy(w_new, a.V, a.ld, it + 1, partB);
+      maxpy(w_new, a.V, a.ld, it + 1, s_cf);
       push(w_new);
       FZ_STAMP(3);
-      fz_grid_sync(G, tid, nc);
-      fz_fold_parts(partB, a.ncta, 1, s_cf, s_red, tid, nc);
-      if (multi) fz_allgather_sum(a, bseq + 1, 1, s_cf, s_red, WB_P2P_SLOT_FB, 1, cta, tid, nc);
+      fz_reduce_ll(a, R, 1, ++rseqB, 1, s_cf, s_red, true, multi, bseq + 1, WB_P2P_SLOT_FB, 1, cta, tid, nc);
       if (tid == 0) {
         fz_gmres_update(u, s_st, s_cf[0], s_h, s_H, s_cs, s_sn, s_rs);
         // end of the cycle (restart length reached or finished): back substitution y = H^-1 rs (k_gmres_solve_y)
@@ -1078,7 +1084,9 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
     if (done) break;
     // another cycle follows: its residual needs everybody's x (the neighbours' on the boundary)
     push(a.xp);
-    fz_grid_sync(G, tid, nc);
+    if (tid == 0) s_cf[0] = 0.0;
+    fz_reduce_ll(a, R, 1, ++rseqB, 1, s_cf, s_red, true, multi, bseq + 1, WB_P2P_SLOT_FB, 1, cta, tid, nc);  // barrier only
+    bseq++;
     hseq++;
     first = false;
     FZ_STAMP(5);
@@ -1181,17 +1189,18 @@ int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b
   WB_TRY(wb_fused_refresh(pc));  // the operator of this solve is the matrix as it is now
   WB_CUDA(cudaMemsetAsync(w.d_done, 0, sizeof(int), c->stream));
   WB_CUDA(cudaMemsetAsync(w.d_st, 0, sizeof(KspState), c->stream));
-  WB_CUDA(cudaMemsetAsync(w.d_bar, 0, 8 * sizeof(int), c->stream));
+  WB_CUDA(cudaMemsetAsync(w.d_bar, 0, 64 * sizeof(int), c->stream));
+  WB_CUDA(cudaMemsetAsync(w.d_ll, 0, WB_LL_BYTES, c->stream));
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   a.cta = f->d_cta; a.sd = f->d_sd; a.blk = pc->d_blk; a.slice = f->d_slice; a.recA = f->d_recA; a.recB = f->d_recB;
-  a.rec_ptr = f->d_rec_ptr; a.sidx = f->d_sidx; a.perm = pc->d_blk_rows; a.sval = f->d_sval; a.stream = pc->d_stream;
+  a.rec_ptr = f->d_rec_ptr; a.perm = pc->d_blk_rows; a.sell = f->d_sell; a.stream = pc->d_stream;
   a.ng = f->ng; a.gt = f->gt; a.nc = f->nc; a.lt = f->lt; a.off_gm = f->off_gm; a.off_prof = f->off_prof; a.sd_cap = f->sd_cap; a.slice_cap = f->slice_cap; a.rec_cap = f->rec_cap;
   a.zs_words = f->zs_words; a.ring_bytes = f->ring_bytes;
   a.off_red = f->off_red; a.off_misc = f->off_misc; a.off_sd = f->off_sd; a.off_slice = f->off_slice;
   a.off_rec = f->off_rec; a.off_zs = f->off_zs; a.off_ring = f->off_ring;
   a.nb = A->nb; a.ncta = f->ncta; a.ld = w.ld;
-  a.b = d_b; a.xout = d_x; a.V = w.V; a.wa = w.tmp; a.wb = w.tmp + w.ld; a.xp = w.tmp + 2 * w.ld; a.part = w.part;
+  a.b = d_b; a.xout = d_x; a.V = w.V; a.wa = w.tmp; a.wb = w.tmp + w.ld; a.xp = w.tmp + 2 * w.ld; a.llpart = w.d_ll;
   a.bar = w.d_bar;
   a.upd = {hcol, H, cs, sn, rs, scal, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, m, o->maxit};
   a.yv = yv;

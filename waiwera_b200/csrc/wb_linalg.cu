@@ -743,37 +743,52 @@ static int build_block_streams(wb_pc *pc, const std::vector<int32_t> &blk_of, co
       else
         for (int q = nr - 1; q >= 0; q--) rows_of_level[lv[blk_rows[r0 + q]]].push_back(blk_rows[r0 + q]);
       for (int l = 0; l < nl; l++) {
-        const std::vector<int32_t> &rows = rows_of_level[l];
-        const int n = (int)rows.size();
-        int nk = 0;
-        for (int row : rows)
-          nk = std::max(nk, pass == 0 ? diag[row] - rowptr[row] : rowptr[row + 1] - diag[row] - 1);
-        nk = std::max(nk, 3);  // at least the branch-free 7-point case; index planes are full, padding blocks are zero
-        const size_t w0 = stream.size();
-        const int ni4 = ilu_ni4(nk), stride = ilu_row_stride(pc->bs, nk, pass);
-        const int words = n * stride / 8;  // stride is a multiple of 16 bytes
-        WB_CHECK(w0 + words < ((size_t)1 << 31), "wb_pc_setup: factor stream too large for 32-bit word offsets");
-        stream.resize(w0 + words, 0.0);
-        const int zero_slot = nr * pc->bs * 8;  // byte offset of the zero entry behind the sub-domain vector
-        for (int q = 0; q < n; q++) {
-          const int row = rows[q];
-          int32_t *pidx = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(&stream[w0]) + (size_t)q * stride);
-          for (int e = 0; e < 4 * ni4; e++) pidx[e] = zero_slot;  // padding blocks multiply the zero slot
-          pidx[0] = local[row] * pc->bs * 8;
-          const size_t wblk = w0 + ((size_t)q * stride + (size_t)ni4 * 16) / 8;  // first block of the row (words)
-          const int k0 = pass == 0 ? rowptr[row] : diag[row] + 1, k1 = pass == 0 ? diag[row] : rowptr[row + 1];
-          for (int k = k0; k < k1; k++) {
-            const int kk = k - k0;
-            pidx[kk + 1] = local[colidx[k]] * pc->bs * 8;
-            repack.push_back(make_int4(k, (int)(wblk + (size_t)kk * b2), 0, 0));
+        // A level becomes one or more records: rows with no off-diagonal block in this sweep (e.g. all MINC matrix
+        // cells in the backward sweep) go into records of their own without padding blocks, rows with 1..3 blocks
+        // share the branch-free 3-block form, wider rows keep their exact width; a record is cut at ~16 KB so that
+        // it streams through the shared-memory rings (rows of a level are independent: the cut is free).
+        std::vector<int32_t> rows = rows_of_level[l];
+        auto width = [&](int row) { return pass == 0 ? diag[row] - rowptr[row] : rowptr[row + 1] - diag[row] - 1; };
+        auto cls = [&](int row) {
+          const int w = width(row);
+          return w == 0 ? 0 : (w <= 3 ? 3 : w);
+        };
+        std::stable_sort(rows.begin(), rows.end(), [&](int a_, int b_) { return cls(a_) < cls(b_); });
+        size_t r_begin = 0;
+        while (r_begin < rows.size()) {
+          const int nk = cls(rows[r_begin]);
+          const int stride = ilu_row_stride(pc->bs, nk, pass), ni4 = ilu_ni4(nk);
+          const size_t max_rows = std::max<size_t>(32, 16384 / stride);
+          size_t r_end = r_begin;
+          while (r_end < rows.size() && cls(rows[r_end]) == nk && r_end - r_begin < max_rows) r_end++;
+          const int n = (int)(r_end - r_begin);
+          const size_t w0 = stream.size();
+          const int words = n * stride / 8;  // stride is a multiple of 16 bytes
+          WB_CHECK(w0 + words < ((size_t)1 << 31), "wb_pc_setup: factor stream too large for 32-bit word offsets");
+          stream.resize(w0 + words, 0.0);
+          const int zero_slot = nr * pc->bs * 8;  // byte offset of the zero entry behind the sub-domain vector
+          for (int q = 0; q < n; q++) {
+            const int row = rows[r_begin + q];
+            int32_t *pidx =
+                reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(&stream[w0]) + (size_t)q * stride);
+            for (int e = 0; e < 4 * ni4; e++) pidx[e] = zero_slot;  // padding blocks multiply the zero slot
+            pidx[0] = local[row] * pc->bs * 8;
+            const size_t wblk = w0 + ((size_t)q * stride + (size_t)ni4 * 16) / 8;  // first block of the row (words)
+            const int k0 = pass == 0 ? rowptr[row] : diag[row] + 1, k1 = pass == 0 ? diag[row] : rowptr[row + 1];
+            for (int k = k0; k < k1; k++) {
+              const int kk = k - k0;
+              pidx[kk + 1] = local[colidx[k]] * pc->bs * 8;
+              repack.push_back(make_int4(k, (int)(wblk + (size_t)kk * b2), 0, 0));
+            }
+            if (pass == 1) repack.push_back(make_int4(diag[row], (int)(wblk + (size_t)nk * b2), 0, 0));
           }
-          if (pass == 1) repack.push_back(make_int4(diag[row], (int)(wblk + (size_t)nk * b2), 0, 0));
+          int4 L;
+          L.x = (int)w0; L.y = words * 8; L.z = n; L.w = nk | (pass << 16);
+          lev.push_back(L);
+          max_level_words = std::max(max_level_words, words);
+          max_level_rows = std::max(max_level_rows, n);
+          r_begin = r_end;
         }
-        int4 L;
-        L.x = (int)w0; L.y = words * 8; L.z = n; L.w = nk | (pass << 16);
-        lev.push_back(L);
-        max_level_words = std::max(max_level_words, words);
-        max_level_rows = std::max(max_level_rows, n);
       }
     }
     WB_CHECK((int)lev.size() - lev0 < (1 << 30), "wb_pc_setup: sub-domain with too many levels");
@@ -1758,6 +1773,7 @@ static void free_work(KspWork &w) {
   cudaFree(w.V); cudaFree(w.tmp); cudaFree(w.small); cudaFree(w.part); cudaFree(w.d_st); cudaFree(w.d_done);
   cudaFree(w.d_counter);
   cudaFree(w.d_bar);
+  cudaFree(w.d_ll);
   cudaFree(w.d_prof);
   if (w.h_st) cudaFreeHost(w.h_st);
 }
@@ -1791,8 +1807,10 @@ int wb_ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
     WB_CUDA(cudaMalloc(&w.d_done, sizeof(int)));
     WB_CUDA(cudaMalloc(&w.d_counter, sizeof(unsigned)));
     WB_CUDA(cudaMemset(w.d_counter, 0, sizeof(unsigned)));
-    WB_CUDA(cudaMalloc(&w.d_bar, 8 * sizeof(int)));
-    WB_CUDA(cudaMemset(w.d_bar, 0, 8 * sizeof(int)));
+    WB_CUDA(cudaMalloc(&w.d_bar, 64 * sizeof(int)));
+    WB_CUDA(cudaMemset(w.d_bar, 0, 64 * sizeof(int)));
+    WB_CUDA(cudaMalloc(&w.d_ll, WB_LL_BYTES));
+    WB_CUDA(cudaMemset(w.d_ll, 0, WB_LL_BYTES));
     WB_CUDA(cudaMalloc(&w.d_prof, WB_PROF_WORDS * sizeof(unsigned long long)));
     WB_CUDA(cudaMemset(w.d_prof, 0, WB_PROF_WORDS * sizeof(unsigned long long)));
   }

@@ -179,8 +179,8 @@ template <int BS> __device__ __forceinline__ void ilu_ld_vec(const unsigned char
 
 // apply one level record (in shared or global memory) to the sub-domain vector zs.  The common nk == 3 case
 // (7-point stencils) is branch-free with every load issued before the first use, so a level costs one shared-memory
-// round trip plus the dependent FMA chain.  Per row the blocks are applied in ascending column order: the
-// arithmetic of the sequential MatSolve_SeqBAIJ_N_NaturalOrdering restricted to the sub-domain.
+// round trip plus a short dependent FMA chain.  Per row the products are those of the sequential
+// MatSolve_SeqBAIJ_N_NaturalOrdering restricted to the sub-domain.
 template <int BS>
 __device__ __forceinline__ void ilu_level(const double *lv, int n, int nk, bool bwd, double *zs, int nthr, int tid) {
   constexpr int B2 = BS * BS;
@@ -201,12 +201,22 @@ __device__ __forceinline__ void ilu_level(const double *lv, int n, int nk, bool 
       ilu_ld_vec<BS>(zb, i0.y, x[0]);
       ilu_ld_vec<BS>(zb, i0.z, x[1]);
       ilu_ld_vec<BS>(zb, i0.w, x[2]);
+      // three independent block products, then (s - p0) - (p1 + p2): the FP64 dependency chain of the level is
+      // bs + 2 operations deep instead of 3 bs (the sweep is a chain of dependent levels run by a few warps, so its
+      // time is this latency, not throughput).  Same products as the sequential MatSolve loop, the sum associated
+      // differently: results agree to rounding.
+      double pr[3][BS];
 #pragma unroll
       for (int k = 0; k < 3; k++)
 #pragma unroll
-        for (int j = 0; j < BS; j++)
+        for (int i = 0; i < BS; i++) {
+          double acc = v[k][i] * x[k][0];
 #pragma unroll
-          for (int i = 0; i < BS; i++) sv[i] -= v[k][j * BS + i] * x[k][j];
+          for (int j = 1; j < BS; j++) acc += v[k][j * BS + i] * x[k][j];
+          pr[k][i] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < BS; i++) sv[i] = (sv[i] - pr[0][i]) - (pr[1][i] + pr[2][i]);
       if (bwd) {
         double t[BS];
 #pragma unroll
@@ -332,6 +342,7 @@ static __device__ void gmres_update(const GmresUpd &u) {
 }
 
 #define WB_PROF_WORDS (16 * 256)
+#define WB_LL_BYTES ((2 * KRY_MAXV * WB_NUM_SMS + 2 * KRY_MAXV) * 16)
 struct KspWork {
   wb_ctx *ctx = nullptr;
   size_t n = 0, ld = 0;  // ld: n rounded up to 32 doubles so every basis vector is 256-byte aligned
@@ -341,7 +352,8 @@ struct KspWork {
   KspState *d_st = nullptr, *h_st = nullptr;
   int *d_done = nullptr;
   unsigned *d_counter = nullptr;
-  int *d_bar = nullptr;                  // fused kernel: grid-barrier counter, release generation, abort flag
+  int *d_bar = nullptr;                  // fused kernel: abort flag ([2])
+  unsigned char *d_ll = nullptr;         // fused kernel: LL partials / totals of its grid-wide reductions
   unsigned long long *d_prof = nullptr;  // fused kernel: per-phase nanoseconds (+ iteration count) of every CTA, [cta][8]
 };
 
