@@ -290,7 +290,9 @@ int wb_ksp_solve(wb_mat *A, wb_pc *pc, const wb_ksp_opts *opts, const double *b,
 int wb_ksp_set_check_every(int k);
 /* GMRES with block-Jacobi / ILU(0) sub-domains normally runs as one persistent kernel for the whole solve
    (sub-domain-resident: SpMV, PC apply and Gram-Schmidt of a sub-domain stay on one SM; restart <= 31); 0 selects the
-   launch-per-operation solver instead (also: environment WB_FUSED=0).  Takes effect at the next PC set-up. */
+   launch-per-operation solver instead, 2 uses the persistent kernel wherever it can run (1, the default, leaves 3x3
+   block systems with many sub-domains per SM to the launch-per-operation kernels); also: environment WB_FUSED.
+   Takes effect at the next PC set-up. */
 int wb_ksp_set_fused(int on);
 
 /* ---- Newton (SNESSolve as configured by timestepper.F90:1552-1641) ------ */

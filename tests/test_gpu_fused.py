@@ -43,7 +43,7 @@ def solve_three_ways(wo, flow, sim, M, A, bor, b, restart, maxit, rtol):
     wo.lib().wo_pc_destroy(pc_ref)
     res = [(reason0, its0.value, rn0.value, x0)]
     opts = flow.ksp_opts(type=0, restart=restart, maxit=maxit, rtol=rtol)
-    for fused in (0, 1):
+    for fused in (0, 2):   # 2: the persistent kernel wherever it can run (1 = automatic choice)
         L.wb_ksp_set_fused(fused)
         pc = flow.PC(M, 2, 1, bor)
         x = np.full(n, 7.0)          # the solvers start from zero whatever the buffer holds

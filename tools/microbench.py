@@ -64,7 +64,7 @@ def main():
     for label, pct, bor, reps in pcs:
         if label.startswith("ilu0_cube"):
             # the persistent kernel (one launch per solve) against the launch-per-operation solver
-            for fused in (1, 0):
+            for fused in (2, 0):
                 L.wb_ksp_set_fused(fused)
                 pcf = flow.PC(J, pct, 1, bor)
                 o = flow.ksp_opts(type=flow.KSP_GMRES, maxit=20000, rtol=1e-5)

@@ -145,6 +145,9 @@ struct wb_mat {
   double *d_xloc = nullptr;  // (ncolb-nb)*bs: ghost entries of x (multi-GPU), filled by the halo exchange
   std::vector<int32_t> h_rowptr, h_colidx;
   bool owns = true;
+  uint64_t version = 1;          // bumped whenever the values change (the sliced-ELL copy follows it)
+  bool external_vals = false;    // the value array was handed out (wb_jacobian_pattern): assume it changes between calls
+  struct WbSell *sell = nullptr; // sliced-ELL copy for the stand-alone SpMV (wb_linalg.cu), built on first use
   // TMA-staged SpMV: first block of every tile of WB_SPMV_TILE rows (+ end), stage capacity in blocks
   int32_t *d_tile_e0 = nullptr;
   int ntiles = 0, tile_cap = 0;
@@ -152,6 +155,7 @@ struct wb_mat {
 #define WB_SPMV_TILE 128
 #define WB_PAD_BYTES 256  // slack after rowptr / colidx / val so that 16-byte-rounded bulk copies stay inside the allocation
 int wb_mat_build_tiles(wb_mat *A);  // after h_rowptr is known
+void wb_sell_free(wb_mat *A);       // drops the sliced-ELL copy (wb_linalg.cu)
 
 struct wb_ctx {
   int device = 0;

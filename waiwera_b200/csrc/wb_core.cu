@@ -206,6 +206,7 @@ static void free_mat(wb_mat &m) {
   }
   cudaFree(m.d_xloc);
   cudaFree(m.d_tile_e0);
+  wb_sell_free(&m);
   m.d_tile_e0 = nullptr;
   m.d_rowptr = m.d_colidx = nullptr;
   m.d_val = m.d_xloc = nullptr;

@@ -838,7 +838,10 @@ extern "C" int wb_jacobian_pattern(wb_ctx *c, int *nb, int *bs, int *nnzb, const
   if (nnzb) *nnzb = c->J.nnzb;
   if (rowptr) *rowptr = c->J.d_rowptr;
   if (colidx) *colidx = c->J.d_colidx;
-  if (vals) *vals = c->J.d_val;
+  if (vals) {
+    *vals = c->J.d_val;
+    c->J.external_vals = true;  // the caller may write values behind our back from now on
+  }
   return 0;
 }
 
@@ -1344,6 +1347,7 @@ int wb_jacobian_be_dev(wb_ctx *c, const double *d_y, const double *d_lhs_last, d
   a.form = wb_res_form(c, d_lhs_last, dt);
   a.cf_ptr = c->d_cf_ptr; a.cf_face = c->d_cf_face; a.cf_other = c->d_cf_other;
   a.cf_bpos = c->d_cf_bpos; a.diagpos = c->d_diagpos; a.val = c->J.d_val; a.dt = dt;
+  c->J.version++;
   a.ncell = c->ncell; a.ninterior = c->ninterior; a.nowned = c->nowned; a.nface = c->nface;
   a.src = wb_sources_args(c);
   const int grid = wb_grid(c->nowned, 128);
@@ -1467,6 +1471,7 @@ extern "C" int wb_jacobian_be_colored(wb_ctx *c, const double *y, const double *
     if (rc) return rc;
     WB_TRY(wb_residual_be_dev(c, dy, dl, dt, true, nullptr, nullptr, d_F0));
     WB_CUDA(cudaMemsetAsync(c->J.d_val, 0, sizeof(double) * (size_t)c->J.nnzb * np * np, c->stream));
+    c->J.version++;
     for (int k = 0; k < c->ncolor; k++)
       for (int var = 0; var < np; var++) {
         k_perturb_color<<<wb_grid(nb, 256), 256, 0, c->stream>>>(dy, d_color, k, var, nb, np, fd_err, fd_umin,

@@ -29,7 +29,7 @@
 
 #define FZ_NBAR 32   // mbarriers per group and direction: at most FZ_NBAR - 1 level records in flight
 #define FZ_MAXG 4    // sub-domain groups per CTA
-#define FZ_SLICE 32  // rows per sliced-ELL slice (one warp)
+#define FZ_SLICE WB_SELL_SLICE  // rows per sliced-ELL slice (one warp)
 #define FZ_CH 8      // blocks of a row in flight per SpMV round
 #define FZ_SPIN_LIMIT 20000000000LL  // cycles (~10 s): a lost CTA / peer raises the abort flag instead of hanging the GPU
 
@@ -78,7 +78,7 @@ static int fused_mode() {
   return g_fused_mode;
 }
 extern "C" int wb_ksp_set_fused(int on) {
-  g_fused_mode = on ? 1 : 0;
+  g_fused_mode = on < 0 ? 0 : on;  // 0 off, 1 automatic, 2 wherever it is usable
   return 0;
 }
 
@@ -298,31 +298,6 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
   WB_CUDA(cudaMemcpy(f->d_sell, sell.data(), sell.size(), cudaMemcpyHostToDevice));
   pc->fused = f;
   return 0;
-}
-
-// numeric part: BAIJ values -> plane layout of the slices (zero blocks where a row is shorter than its slice)
-template <int BS>
-__global__ void k_sell_fill(const double *__restrict__ val, const int4 *__restrict__ slices, int nslices,
-                            const int32_t *__restrict__ ssrc, const int32_t *__restrict__ slot0,
-                            unsigned char *__restrict__ sell) {
-  constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (s >= nslices) return;
-  const int4 S = slices[s];
-  const int nk = S.y >> 8;
-  double *vals = reinterpret_cast<double *>(sell + (size_t)S.z * 16 + (size_t)nk * FZ_SLICE * 4);
-  const int32_t *src_ = ssrc + slot0[s];
-  for (int k = 0; k < nk; k++) {
-    const int src = src_[k * FZ_SLICE + lane];
-    double v[B2];
-#pragma unroll
-    for (int q = 0; q < B2; q++) v[q] = src >= 0 ? __ldcs(val + (size_t)src * B2 + q) : 0.0;
-    double *dst = vals + (size_t)k * B2 * FZ_SLICE;
-#pragma unroll
-    for (int q = 0; q < NPL; q++)
-#pragma unroll
-      for (int w = 0; w < PW; w++) dst[((size_t)q * FZ_SLICE + lane) * PW + w] = v[q * PW + w];
-  }
 }
 
 int wb_fused_refresh(wb_pc *pc) {
@@ -1127,6 +1102,10 @@ bool wb_fused_usable(const wb_mat *A, const wb_pc *pc, const wb_ksp_opts *o) {
   if (o->type != WB_KSP_GMRES) return false;
   const int m = o->restart > 0 ? o->restart : 30;
   if (m + 1 > KRY_MAXV) return false;
+  // 3x3 blocks leave the persistent kernel with 6 consumer warps per SM: with several sub-domains per CTA (the
+  // bandwidth-bound regime) the launch-per-operation kernels stream faster (measured on config 4: 294 vs 274 us per
+  // iteration); with one or two sub-domains per CTA (latency-bound) the persistent kernel wins (config 5: 145 vs 177)
+  if (fused_mode() == 1 && pc->bs >= 3 && pc->fused->sd_cap > 2) return false;  // WB_FUSED=2 forces it
   const wb_ctx *c = A->ctx;
   if (c->nranks > 1) return c->p2p.on && A == &c->J && c->nranks <= WB_P2P_MAX_RANKS;
   return A->ncolb == A->nb;

@@ -147,6 +147,204 @@ __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(const SpmvArgs a) {
   }
 }
 
+// ================================================================ SpMV (K5), sliced-ELL
+// One warp per slice of 32 rows, thread per row: all of a row's blocks (up to 8 per round) are requested before the
+// first use -- column indices and value planes with streaming loads (read once), then the operand entries through
+// L2 -- so a 7-point row costs one round trip to HBM and one to L2, with no row pointer to chase first.  Same fused
+// Krylov form as k_bsr_spmv (operand x * scale, normalised copy of the row's own entries), same arithmetic per row
+// except that the block products are summed in column order by one thread instead of by eight lanes and a shuffle tree.
+struct SellArgs {
+  const int4 *slice;
+  const unsigned char *data;
+  const double *x, *xg, *scale;
+  double *xn, *y;
+  int nslices, nb;
+  const int *done;
+};
+template <int BS, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k_sell_spmv(const SellArgs a) {
+  if (a.done && *a.done) return;
+  constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP, CH = BS >= 3 ? 4 : 8;
+  const int lane = threadIdx.x & 31;
+  const int s0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const double s = a.scale ? *a.scale : 1.0;
+  for (int sl = s0; sl < a.nslices; sl += gridDim.x * (blockDim.x >> 5)) {
+    const int4 S = a.slice[sl];
+    const int n = S.y & 255, nk = S.y >> 8;
+    const unsigned char *base = a.data + (size_t)S.z * 16;
+    const int32_t *ip = reinterpret_cast<const int32_t *>(base) + lane;
+    const double *vp = reinterpret_cast<const double *>(base + (size_t)nk * WB_SELL_SLICE * 4) + (size_t)lane * PW;
+    double acc[BS];
+#pragma unroll
+    for (int i = 0; i < BS; i++) acc[i] = 0.0;
+    for (int k0 = 0; k0 < nk; k0 += CH) {
+      int col[CH];
+      double v[CH][B2];
+#pragma unroll
+      for (int u = 0; u < CH; u++) {
+        const int k = min(k0 + u, nk - 1);  // past the end: the last block again, its x is zero
+        col[u] = __ldcs(ip + k * WB_SELL_SLICE);
+        const double *bp = vp + (size_t)k * B2 * WB_SELL_SLICE;
+#pragma unroll
+        for (int q = 0; q < NPL; q++) {
+          if (PW == 2) {
+            const double2 t = __ldcs(reinterpret_cast<const double2 *>(bp + (size_t)q * WB_SELL_SLICE * 2));
+            v[u][2 * q] = t.x;
+            v[u][2 * q + 1] = t.y;
+          } else {
+            v[u][q] = __ldcs(bp + (size_t)q * WB_SELL_SLICE);
+          }
+        }
+      }
+#pragma unroll
+      for (int h0 = 0; h0 < CH; h0 += CH / 2) {
+        double x[CH / 2][BS];
+#pragma unroll
+        for (int uh = 0; uh < CH / 2; uh++) {
+          const int u = h0 + uh;
+          const bool on = k0 + u < nk, own = col[u] < a.nb;
+          const double sc = own ? s : 1.0;  // ghost entries arrive already scaled by their owner
+          const double *xp = own ? a.x + (size_t)col[u] * BS : a.xg + (size_t)(col[u] - a.nb) * BS;
+          if (BS == 2 && own) {
+            const double2 t = on ? *reinterpret_cast<const double2 *>(xp) : make_double2(0.0, 0.0);
+            x[uh][0] = t.x * sc;
+            x[uh][1] = t.y * sc;
+          } else {
+#pragma unroll
+            for (int j = 0; j < BS; j++) x[uh][j] = on ? (own ? xp[j] : __ldcg(xp + j)) * sc : 0.0;
+          }
+        }
+#pragma unroll
+        for (int uh = 0; uh < CH / 2; uh++)
+#pragma unroll
+          for (int j = 0; j < BS; j++)
+#pragma unroll
+            for (int i = 0; i < BS; i++) acc[i] += v[h0 + uh][j * BS + i] * x[uh][j];
+      }
+    }
+    if (lane < n) {
+      const size_t row = (size_t)S.x + lane;
+      if (BS == 2) *reinterpret_cast<double2 *>(a.y + row * 2) = make_double2(acc[0], acc[1]);
+      else {
+#pragma unroll
+        for (int i = 0; i < BS; i++) a.y[row * BS + i] = acc[i];
+      }
+      if (a.xn) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) a.xn[row * BS + i] = a.x[row * BS + i] * s;
+      }
+    }
+  }
+}
+
+void wb_sell_free(wb_mat *A) {
+  WbSell *S = A->sell;
+  if (!S) return;
+  cudaFree(S->d_slice); cudaFree(S->d_ssrc); cudaFree(S->d_slot0); cudaFree(S->d_data);
+  delete S;
+  A->sell = nullptr;
+}
+
+static int sell_mode() {
+  static int mode = -1;  // WB_SPMV_SELL = 0: keep the BAIJ kernel
+  if (mode < 0) {
+    const char *e = getenv("WB_SPMV_SELL");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
+
+// symbolic part (once per pattern): slices of 32 consecutive rows in the matrix's own ordering
+static int sell_build(wb_mat *A) {
+  const int nb = A->nb, b2 = A->bs * A->bs;
+  WbSell *S = new WbSell();
+  std::vector<int4> slices;
+  std::vector<int32_t> ssrc, slot0;
+  std::vector<unsigned char> data;
+  for (int r0 = 0; r0 < nb; r0 += WB_SELL_SLICE) {
+    const int n = std::min(WB_SELL_SLICE, nb - r0);
+    int nk = 1;
+    for (int l = 0; l < n; l++) nk = std::max(nk, A->h_rowptr[r0 + l + 1] - A->h_rowptr[r0 + l]);
+    const size_t bytes = (size_t)nk * (WB_SELL_SLICE * 4 + (size_t)b2 * WB_SELL_SLICE * 8), base = data.size();
+    if (base + bytes >= ((size_t)1 << 35) || nk > 255) {
+      delete S;
+      return 1;
+    }
+    slices.push_back(make_int4(r0, n | (nk << 8), (int)(base / 16), (int)bytes));
+    data.resize(base + bytes, 0);
+    int32_t *ip = reinterpret_cast<int32_t *>(data.data() + base);
+    const size_t sbase = ssrc.size();
+    slot0.push_back((int32_t)sbase);
+    ssrc.resize(sbase + (size_t)nk * WB_SELL_SLICE);
+    for (int k = 0; k < nk; k++)
+      for (int l = 0; l < WB_SELL_SLICE; l++) {
+        const int row = r0 + std::min(l, n - 1);
+        int col = row < A->ncolb ? row : 0, src = -1;  // padding: a zero block times the row's own entry
+        if (l < n) {
+          const int e = A->h_rowptr[row] + k;
+          if (e < A->h_rowptr[row + 1]) {
+            col = A->h_colidx[e];
+            src = e;
+          }
+        }
+        ip[(size_t)k * WB_SELL_SLICE + l] = col;
+        ssrc[sbase + (size_t)k * WB_SELL_SLICE + l] = src;
+      }
+  }
+  S->nslices = (int)slices.size();
+  WB_TRY(upload(&S->d_slice, slices));
+  WB_TRY(upload(&S->d_ssrc, ssrc));
+  WB_TRY(upload(&S->d_slot0, slot0));
+  WB_CUDA(cudaMalloc(&S->d_data, data.size() + WB_PAD_BYTES));
+  WB_CUDA(cudaMemcpy(S->d_data, data.data(), data.size(), cudaMemcpyHostToDevice));
+  A->sell = S;
+  return 0;
+}
+
+int wb_sell_spmv(wb_mat *A, const double *d_x, const double *xg, const double *d_scale, double *d_xn, double *d_y,
+                 const int *done) {
+  wb_ctx *c = A->ctx;
+  if (!sell_mode() || A->nb < 1024 || A->h_rowptr.empty()) return 1;  // tiny systems: not worth a second copy
+  if (A->ncolb > A->nb && !xg) return 1;
+  if (!A->sell) {
+    const int rc = sell_build(A);
+    if (rc) return rc;
+  }
+  WbSell *S = A->sell;
+  if (S->version != A->version || A->external_vals) {  // numeric part: the values as they are now
+    const int grid = wb_grid((size_t)S->nslices * 32, 256);
+    switch (A->bs) {
+      case 1: k_sell_fill<1><<<grid, 256, 0, c->stream>>>(A->d_val, S->d_slice, S->nslices, S->d_ssrc, S->d_slot0, S->d_data); break;
+      case 2: k_sell_fill<2><<<grid, 256, 0, c->stream>>>(A->d_val, S->d_slice, S->nslices, S->d_ssrc, S->d_slot0, S->d_data); break;
+      default: k_sell_fill<3><<<grid, 256, 0, c->stream>>>(A->d_val, S->d_slice, S->nslices, S->d_ssrc, S->d_slot0, S->d_data); break;
+    }
+    WB_LAUNCH(c);
+    S->version = A->version;
+  }
+  SellArgs a = {S->d_slice, S->d_data, d_x, xg, d_scale, d_xn, d_y, S->nslices, A->nb, done};
+  static int cta_threads = 0;  // tuning knob WB_SELL_CTA = 128 | 256 (threads per CTA; 512 threads per SM either way)
+  if (!cta_threads) {
+    const char *e = getenv("WB_SELL_CTA");
+    cta_threads = e ? atoi(e) : 128;
+    if (cta_threads != 128 && cta_threads != 256) cta_threads = 128;
+  }
+  const int grid = wb_grid((size_t)S->nslices, cta_threads / 32);  // one slice per warp
+#define SELL(BS)                                                            \
+  do {                                                                      \
+    if (cta_threads == 128) k_sell_spmv<BS, 128><<<grid, 128, 0, c->stream>>>(a); \
+    else k_sell_spmv<BS, 256><<<grid, 256, 0, c->stream>>>(a);              \
+  } while (0)
+  switch (A->bs) {
+    case 1: SELL(1); break;
+    case 2: SELL(2); break;
+    default: SELL(3); break;
+  }
+#undef SELL
+  WB_LAUNCH(c);
+  WB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static bool wb_spmv_tma_enabled(const wb_mat *A);
 static int wb_spmv_tma_launch(wb_mat *A, const SpmvArgs &a);
 
@@ -175,6 +373,10 @@ int wb_spmv_fused(wb_mat *A, const double *d_x, const double *d_scale, double *d
   SpmvArgs a = {A->d_rowptr, A->d_colidx, A->d_val, d_x, xg, d_scale, d_xn, d_y, A->nb, done,
                 c->p2p.dev, hseq, hseq ? c->halo.nneigh : 0, c->p2p.d_nb_rank};
   if (wb_spmv_tma_enabled(A)) return wb_spmv_tma_launch(A, a);
+  if (hseq == 0) {
+    const int rc = wb_sell_spmv(A, d_x, xg, d_scale, d_xn, d_y, done);
+    if (rc <= 0) return rc;  // done (0) or failed (< 0); 1: not available for this matrix
+  }
   // tuning knob (WB_SPMV_ROWS = 1, 2, 4).  R = 1 needs 32 registers => 8 CTAs / SM (full occupancy) and is the
   // fastest: 68.5 us vs 75.9 (R = 2, 54 registers) vs 97 (R = 4) at 1 M cells on the same box
   static int rows_per_group = 0;
@@ -237,6 +439,7 @@ extern "C" int wb_mat_create(wb_ctx *c, int nb, int ncolb, int bs, int nnzb, con
 
 extern "C" int wb_mat_set_values(wb_mat *A, const double *vals) {
   WB_CUDA(cudaSetDevice(A->ctx->device));
+  A->version++;
   WB_CUDA(cudaMemcpyAsync(A->d_val, vals, sizeof(double) * (size_t)A->nnzb * A->bs * A->bs, cudaMemcpyDefault,
                           A->ctx->stream));
   WB_CUDA(cudaStreamSynchronize(A->ctx->stream));
@@ -259,6 +462,7 @@ extern "C" int wb_mat_destroy(wb_mat *A) {
   cudaFree(A->d_val);
   cudaFree(A->d_xloc);
   cudaFree(A->d_tile_e0);
+  wb_sell_free(A);
   delete A;
   return 0;
 }

@@ -357,6 +357,52 @@ struct KspWork {
   unsigned long long *d_prof = nullptr;  // fused kernel: per-phase nanoseconds (+ iteration count) of every CTA, [cta][8]
 };
 
+// ---- sliced-ELL copy of a BAIJ matrix (slices of 32 rows, one warp each, thread per row) --------------------------
+// Per slice one contiguous chunk: [nk][32] int32 column indices, then [nk][planes][32] value planes (double2 planes for
+// even bs*bs): lane l of a warp reads element l of every plane -- fully coalesced from HBM, conflict-free from shared
+// memory -- with arithmetic offsets: no row pointers, no dependent load before the column indices.  Rows shorter than
+// the slice's widest are padded with zero blocks.  Used by the stand-alone SpMV (natural ordering) and, in the
+// sub-domain-major ordering, by the persistent GMRES kernel (one bulk copy per slice).
+#define WB_SELL_SLICE 32
+// numeric part: BAIJ values -> plane layout of the slices (zero blocks where a row is shorter than its slice)
+template <int BS>
+__global__ void k_sell_fill(const double *__restrict__ val, const int4 *__restrict__ slices, int nslices,
+                            const int32_t *__restrict__ ssrc, const int32_t *__restrict__ slot0,
+                            unsigned char *__restrict__ sell) {
+  constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int4 S = slices[s];
+  const int nk = S.y >> 8;
+  double *vals = reinterpret_cast<double *>(sell + (size_t)S.z * 16 + (size_t)nk * WB_SELL_SLICE * 4);
+  const int32_t *src_ = ssrc + slot0[s];
+  for (int k = 0; k < nk; k++) {
+    const int src = src_[k * WB_SELL_SLICE + lane];
+    double v[B2];
+#pragma unroll
+    for (int q = 0; q < B2; q++) v[q] = src >= 0 ? __ldcs(val + (size_t)src * B2 + q) : 0.0;
+    double *dst = vals + (size_t)k * B2 * WB_SELL_SLICE;
+#pragma unroll
+    for (int q = 0; q < NPL; q++)
+#pragma unroll
+      for (int w = 0; w < PW; w++) dst[((size_t)q * WB_SELL_SLICE + lane) * PW + w] = v[q * PW + w];
+  }
+}
+
+
+struct WbSell {
+  int nslices = 0;
+  int4 *d_slice = nullptr;  // (first row, rows | nk << 8, byte offset / 16, bytes)
+  int32_t *d_ssrc = nullptr, *d_slot0 = nullptr;
+  unsigned char *d_data = nullptr;
+  uint64_t version = ~0ull;  // value version of the matrix the copy holds
+};
+// y = A (x * scale) through the sliced-ELL copy (built on first use, refreshed when the values changed); returns 1 if
+// the matrix cannot use it (fall back to the BAIJ kernel)
+int wb_sell_spmv(wb_mat *A, const double *d_x, const double *xg, const double *d_scale, double *d_xn, double *d_y,
+                 const int *done);
+void wb_sell_free(wb_mat *A);
+
 // Krylov work space of a context (created on first use, shared by all its systems)
 int wb_ensure_work(wb_ctx *c, size_t n, int m, KspWork **out);
 KspWork *wb_find_work(wb_ctx *c);  // null if the context has not solved anything yet

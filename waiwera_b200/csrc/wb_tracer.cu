@@ -35,6 +35,7 @@ void wb_tracer_release(wb_ctx *c) {
     cudaFree(c->A_aux->d_val);
     cudaFree(c->A_aux->d_xloc);
     cudaFree(c->A_aux->d_tile_e0);
+    wb_sell_free(c->A_aux);
     delete c->A_aux;
   }
   c->A_aux = nullptr;
@@ -135,6 +136,7 @@ static int tracer_assemble_dev(wb_ctx *c, bool assemble, double dt, const double
   a.al_last = d_al_last; a.x_last = d_x_last; a.al_last2 = d_al_last2; a.x_last2 = d_x_last2;
   a.xb = d_xb;
   a.val = assemble ? c->A_aux->d_val : nullptr;
+  if (assemble) c->A_aux->version++;
   a.b = d_b; a.al = d_al;
   a.ncell = c->ncell; a.ninterior = c->ninterior; a.nowned = c->nowned; a.nface = c->nface;
   const int grid = wb_grid(c->nowned, 128);
