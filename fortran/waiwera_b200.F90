@@ -76,7 +76,7 @@ module waiwera_b200
   public :: wb_last_error, wb_version, wb_create, wb_destroy, wb_num_primary, wb_fluid_dof, wb_set_mesh, &
        wb_jacobian_pattern, wb_jacobian_get, wb_cell_faces_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
        wb_comm_p2p_blob_size, wb_comm_p2p_export, wb_comm_p2p_open, wb_comm_p2p_enabled, wb_comm_p2p_disable, &
-       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_source_controls, wb_get_source_rates, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
+       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_source_components, wb_set_source_controls, wb_get_source_rates, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
        wb_mat_set_values, wb_mat_get_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
@@ -251,6 +251,15 @@ module waiwera_b200
 
      ! source controls re-evaluated at every function evaluation: deliverability (src/source_control.F90:322-507),
      ! direction (:596-620), total limiter (src/source_network_node.F90:245-315); direction / limit may be c_null_ptr
+     ! injection / production component of every source (get_components, src/source_setup.F90:2052-2083)
+     function wb_set_source_components(ctx, n, injection_component, production_component) &
+          bind(C, name="wb_set_source_components") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, injection_component, production_component
+       integer(c_int), value :: n
+       integer(c_int) :: ierr
+     end function wb_set_source_components
+
      function wb_set_source_controls(ctx, n, source, productivity, reference_pressure, direction, limit) &
           bind(C, name="wb_set_source_controls") result(ierr)
        import :: c_int, c_ptr

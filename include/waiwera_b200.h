@@ -14,6 +14,10 @@
  *   Jacobian       BAIJ: rowptr/colidx + bs*bs column-major blocks
  *                                                   (src/ode.F90:266-287)
  *
+ * Set-up arrays that are index lists or per-source / per-boundary parameters (wb_set_boundaries, wb_set_sources,
+ * wb_set_source_components, wb_set_source_controls, wb_set_halo, wb_set_pc_blocks) are read on the HOST: device
+ * pointers are rejected there.
+ *
  * Return value of every function: 0 ok; >0 recoverable physics / domain
  * error (the reference's `err` argument, already reduced over all GPUs of the
  * communicator -- src/mpi_utils.F90:46); <0 fatal (CUDA/NCCL/usage), message
@@ -178,6 +182,13 @@ int wb_set_boundaries(wb_ctx *ctx, int n, const int32_t *ghost_cells, const int3
    fractions (src/fluid.F90:374-456).  n = 0 removes all sources. */
 int wb_set_sources(wb_ctx *ctx, int n, const int32_t *cell, const int32_t *component, const double *rate,
                    const double *enthalpy);
+/* Injection and production component of every source of the last wb_set_sources (n = their number), as
+   get_components reads them from the input (src/source_setup.F90:2052-2083): the reference picks one or the other from
+   the sign of the CURRENT rate at every update (src/source.F90:372-380, 469-476), which matters for sources whose rate
+   changes sign (rate tables, deliverability with direction "both").  Without this call the `component` of
+   wb_set_sources applies to both signs.  injection_component: 1..np; production_component: 0..np (0 = all mass
+   components by flow fraction). */
+int wb_set_source_components(wb_ctx *ctx, int n, const int32_t *injection_component, const int32_t *production_component);
 /* Source controls for n of the sources of the last wb_set_sources (source[k]: index into those arrays), re-evaluated
    from the fluid state of the source's cell at EVERY function evaluation -- the reference's source_network%update
    inside cell_inflows (src/flow_simulation.F90:1468-1473, src/source_network.F90:90-292) -- so that the

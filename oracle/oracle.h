@@ -221,6 +221,8 @@ void wo_flow_set_method(wo_flow *f, int method, double dt_last, const double *lh
    components for production; np = heat), rate (< 0 production), injection enthalpy */
 void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *component, const double *rate,
                          const double *enthalpy);
+/* injection / production component of every source; which applies follows the sign of the current rate */
+void wo_flow_set_source_components(wo_flow *f, int n, const int32_t *injection, const int32_t *production);
 /* source controls for n of those sources (source: index into the wo_flow_set_sources arrays): deliverability
    (src/source_control.F90:322-507; pi <= 0: none), direction (0 both, 1 production, 2 injection; :596-620), total-flow
    limiter (limit <= 0: none; src/source_network_node.F90:245-315); re-evaluated at every function evaluation */

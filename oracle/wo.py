@@ -167,6 +167,7 @@ def lib():
         "wo_flow_fluid_init": (i, [vp, c_dp, c_ip]),
         "wo_flow_set_boundary": (i, [vp, i, i, c_dp, i]),
         "wo_flow_set_sources": (None, [vp, i, c_ip, c_ip, c_dp, c_dp]),
+        "wo_flow_set_source_components": (None, [vp, i, c_ip, c_ip]),
         "wo_flow_set_method": (None, [vp, i, d, c_dp]),
         "wo_flow_set_source_controls": (None, [vp, i, c_ip, c_dp, c_dp, c_ip, c_dp]),
         "wo_flow_get_source_rates": (None, [vp, c_dp]),
@@ -241,8 +242,8 @@ def make_relperm(kind="linear", **kw):
     elif kind == "van_genuchten":
         r.type = RP_VAN_GENUCHTEN
         r.p[0], r.p[1], r.p[2] = kw.get("lambda", kw.get("lambda_", 0.45)), kw.get("slr", 1e-3), kw.get("sls", 1.0)
-        r.p[3] = 0.0 if "ssr" in kw else 1.0
-        r.p[4] = kw.get("ssr", 0.0)
+        r.p[3] = 1.0 if kw.get("sum_unity", True) else 0.0
+        r.p[4] = kw.get("ssr", 0.6)
     elif kind == "table":
         r.type = RP_TABLE
         liq, vap = kw["liquid"], kw["vapour"]
@@ -348,6 +349,11 @@ class Flow:
         r = np.ascontiguousarray(rates, np.float64)
         h = np.ascontiguousarray(enthalpies, np.float64)
         self.L.wo_flow_set_sources(self.h, len(c), ip(c), ip(k), dp(r), dp(h))
+
+    def set_source_components(self, injection_components, production_components):
+        a = np.ascontiguousarray(injection_components, np.int32)
+        b = np.ascontiguousarray(production_components, np.int32)
+        self.L.wo_flow_set_source_components(self.h, len(a), ip(a), ip(b))
 
     def set_source_controls(self, sources, productivity, reference_pressure, direction=None, limit=None):
         s = np.ascontiguousarray(sources, np.int32)

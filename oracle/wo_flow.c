@@ -179,7 +179,7 @@ void wo_flow_set_method(wo_flow *f, int method, double dt_last, const double *lh
    only; np = heat), rate (kg/s or W; < 0 production), injection enthalpy (J/kg). */
 void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *component, const double *rate,
                          const double *enthalpy) {
-  free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
+  free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy); free(f->src_pcomponent);
   free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
   f->src_ctrl = f->src_direction = NULL;
   f->src_pi = f->src_pref = f->src_limit = NULL;
@@ -191,9 +191,23 @@ void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *
   f->src_enthalpy = (double *)malloc((n + 1) * sizeof(double));
   memcpy(f->src_cell, cell, n * sizeof(int32_t));
   memcpy(f->src_component, component, n * sizeof(int32_t));
+  f->src_pcomponent = (int32_t *)malloc((n + 1) * sizeof(int32_t));
+  memcpy(f->src_pcomponent, component, n * sizeof(int32_t));
   memcpy(f->src_rate, rate, n * sizeof(double));
   memcpy(f->src_enthalpy, enthalpy, n * sizeof(double));
   memcpy(f->src_rate_eval, rate, n * sizeof(double));
+}
+
+/* injection / production component of every source (get_components, src/source_setup.F90:2052-2083); source%update_flow
+   picks by the sign of the current rate (src/source.F90:372-380, 469-476) */
+void wo_flow_set_source_components(wo_flow *f, int n, const int32_t *injection, const int32_t *production) {
+  for (int k = 0; k < n && k < f->nsrc; k++) {
+    f->src_component[k] = injection[k];
+    f->src_pcomponent[k] = production[k];
+  }
+}
+int wo_flow_source_component(const wo_flow *f, int s, double rate) {
+  return rate > 0.0 ? f->src_component[s] : f->src_pcomponent[s];
 }
 
 /* Source controls for n of the sources of the last wo_flow_set_sources (source: index into those arrays):
@@ -270,8 +284,8 @@ void wo_flow_source_phase_fractions(const wo_flow *f, int s, double *frac) {
    specific_enthalpy src/fluid.F90:374-456) and update_energy_flow :442-453 */
 static void source_flow(const wo_flow *f, int s, double *flow) {
   int np = f->np, nc = f->nc;
-  int component = f->src_component[s];
   double rate = wo_flow_source_rate(f, s), enthalpy = 0.0;
+  int component = wo_flow_source_component(f, s, rate);
   if (f->unperturbed) f->src_rate_eval[s] = rate;
   for (int k = 0; k < np; k++) flow[k] = 0.0;
   if (rate > 0.0) {
@@ -318,7 +332,7 @@ static void source_flow(const wo_flow *f, int s, double *flow) {
 
 void wo_flow_destroy(wo_flow *f) {
   if (!f) return;
-  free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy);
+  free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy); free(f->src_pcomponent);
   free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
   free(f->lhs_last2);
   face_plan_free(f);

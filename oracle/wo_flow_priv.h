@@ -31,6 +31,7 @@ struct wo_flow {
   /* fixed-rate sources / sinks (src/source.F90:375-480), in input order */
   int nsrc;
   int32_t *src_cell, *src_component;
+  int32_t *src_pcomponent; /* production component (src_component is the injection component) */
   double *src_rate, *src_enthalpy;
   /* source controls (src/source_control.F90): deliverability (:322-507), direction (:596-620), total limiter
      (src/source_network_node.F90:245-315); all NULL when no control is set */
@@ -47,5 +48,7 @@ struct wo_flow {
 void wo_flow_source_phase_fractions(const wo_flow *f, int s, double *frac);
 /* rate of source s after its controls, evaluated from the current fluid of its cell */
 double wo_flow_source_rate(const wo_flow *f, int s);
+/* injection or production component of source s for a rate of this sign */
+int wo_flow_source_component(const wo_flow *f, int s, double rate);
 
 #endif

@@ -192,7 +192,7 @@ void wo_tracer_cell_inflows(wo_flow *f, wo_bsr *Ar, double *br) {
     if (c < 0 || c >= m->nowned) continue;
     double volume = m->cell_geom[4 * (size_t)c + 3];
     double rate = wo_flow_source_rate(f, s);
-    if (f->src_component[s] < np) {
+    if (wo_flow_source_component(f, s, rate) < np) {
       if (rate < 0.0) {
         double frac[WO_MAX_NP];
         wo_flow_source_phase_fractions(f, s, frac);

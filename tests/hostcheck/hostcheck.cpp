@@ -229,7 +229,8 @@ static int tracer_assemble_host(const wb_params *prm, int ncell, int nowned, int
   std::vector<int32_t> head(nowned, -1), sc(nsrc + 1), sk(nsrc + 1), sctrl(nsrc + 1);
   std::vector<double> sr(nsrc + 1), sinj((size_t)nsrc * NT + 1), spi(nsrc + 1), spref(nsrc + 1), slim(nsrc + 1);
   for (int k = 0; k < nsrc; k++) {
-    sc[k] = src_cell[order[k]]; sk[k] = src_comp[order[k]]; sr[k] = src_rate[order[k]];
+    sc[k] = src_cell[order[k]]; sk[k] = src_comp[order[k]] | (src_comp[order[k]] << 8);  // as wb_set_sources packs it
+    sr[k] = src_rate[order[k]];
     if (src_ctrl) {
       sctrl[k] = src_ctrl[order[k]]; spi[k] = src_pi[order[k]]; spref[k] = src_pref[order[k]]; slim[k] = src_limit[order[k]];
     }

@@ -109,7 +109,7 @@ def curve_cases(wo):
         (wo.make_relperm("pickens", power=2.5), wo.make_cappress("zero")),
         (wo.make_relperm("fully_mobile"), wo.make_cappress("zero")),
         (wo.make_relperm("van_genuchten", lambda_=0.45, slr=0.1, sls=0.95), wo.make_cappress("zero")),
-        (wo.make_relperm("van_genuchten", lambda_=0.5, slr=0.1, sls=1.0, ssr=0.1), wo.make_cappress("zero")),
+        (wo.make_relperm("van_genuchten", lambda_=0.5, slr=0.1, sls=1.0, ssr=0.1, sum_unity=False), wo.make_cappress("zero")),
         (wo.make_relperm("table", liquid=[(0, 0), (0.3, 0.1), (0.8, 0.7), (1, 1)], vapour=[(0, 0), (0.5, 0.6), (1, 1)]),
          wo.make_cappress("table", pressure=[(0, -1e5), (0.4, -2e4), (1.0, 0.0)])),
     ]

@@ -138,7 +138,7 @@ def test_product_curve_builders_fill_the_documented_layout(wo):
     from waiwera_b200 import flow
     rp = [("fully_mobile", {}), ("linear", dict(liquid=(0.1, 0.9), vapour=(0.2, 0.8))), ("pickens", dict(power=2.5)),
           ("corey", dict(slr=0.25, ssr=0.1)), ("grant", dict(slr=0.2, ssr=0.5)),
-          ("van_genuchten", dict(slr=0.1, sls=0.95)), ("van_genuchten", dict(slr=0.1, sls=0.95, ssr=0.2)),
+          ("van_genuchten", dict(slr=0.1, sls=0.95)), ("van_genuchten", dict(slr=0.1, sls=0.95, ssr=0.2, sum_unity=False)), ("van_genuchten", dict(slr=0.1, sls=0.95, sum_unity=False)),
           ("table", dict(liquid=[(0, 0), (0.5, 0.3), (1, 1)], vapour=[(0, 0), (1, 1)]))]
     for kind, kw in rp:
         a, b = flow.make_relperm(kind, **kw), wo.make_relperm(kind, **kw)
@@ -224,3 +224,74 @@ def test_hybrid_3d_mesh():
     g = m.face_geom
     assert (g[:, 1] > 0).all() and (g[:, 2] > 0).all() and np.allclose(g[:, 1] + g[:, 2], g[:, 3], atol=1e-15)
     assert m.gravity.tolist() == [0.0, 0.0, -9.8] and set(g[:, 11]) <= {1.0, 2.0, 3.0}
+
+
+def _modified_input(tmp_path, name, edit):
+    """a fixture input with `edit(doc)` applied, written next to a copy of its mesh"""
+    import json
+    import shutil
+    doc = json.load(open(os.path.join(INP, name)))
+    edit(doc)
+    mesh_name = doc["mesh"]["filename"] if isinstance(doc["mesh"], dict) else doc["mesh"]
+    shutil.copy(os.path.join(INP, mesh_name), tmp_path / mesh_name)
+    path = tmp_path / name
+    path.write_text(json.dumps(doc))
+    return str(path)
+
+
+def test_primary_scale_of_the_input_is_used_for_the_initial_state(wo, tmp_path):
+    """eos.primary.scale (src/eos_we.F90:75-109, src/eos_wge.F90:96-110): the initial primaries are scaled with the
+    same scales the parameter block carries to the engine, not with the defaults"""
+    def edit(doc):
+        doc["eos"] = {"name": "wce", "primary": {"scale": {"pressure": 2.0e5, "temperature": 50.0, "partial_pressure": 1.0e5}}}
+    p = ingest.load(_modified_input(tmp_path, "co2_column_1.input.json", edit), wo)
+    assert (p.params.pressure_scale, p.params.temperature_scale, p.params.partial_pressure_scale) == (2.0e5, 50.0, 1.0e5)
+    y = p.y.reshape(-1, 3)
+    single = p.region != 4
+    assert np.allclose(y[:, 0], p.primary[:, 0] / 2.0e5, rtol=1e-15)
+    assert np.allclose(y[single, 1], p.primary[single, 1] / 50.0, rtol=1e-15)
+    assert np.allclose(y[:, 2], p.primary[:, 2] / 1.0e5, rtol=1e-15)
+    # and the engine's own unscale gives the primaries back
+    eos = wo.lib().wo_eos_create(p.params)
+    back = np.zeros(3)
+    for c in (0, len(y) - 1):
+        wo.lib().wo_eos_unscale(eos, wo.dp(np.ascontiguousarray(y[c])), int(p.region[c]), wo.dp(back))
+        assert np.allclose(back, p.primary[c], rtol=1e-14)
+    wo.lib().wo_eos_destroy(eos)
+
+
+def test_source_component_follows_the_sign_of_the_rate(wo, tmp_path):
+    """a rate table that changes sign on a two-component EOS: injection uses "component", production the production
+    component (default: all mass components by flow fraction) -- chosen from the CURRENT rate (src/source.F90:372-380,
+    469-476), through ingest.components_at and through the engine's own choice (wo_flow_set_source_components)"""
+    def edit(doc):
+        doc["source"] = [{"cell": 0, "component": "co2", "enthalpy": 1.0e5,
+                          "rate": [[0.0, 1.0e-3], [1.0e6, 1.0e-3], [1.0e6 + 1.0, -2.0e-3], [1.0e9, -2.0e-3]]}]
+    p = ingest.load(_modified_input(tmp_path, "co2_column_1.input.json", edit), wo)
+    assert p.source_injection_components.tolist() == [2] and p.source_production_components.tolist() == [0]
+    r_in, r_out = ingest.rates_at(p, 0.0, 1.0e5), ingest.rates_at(p, 2.0e6, 3.0e6)
+    assert r_in[0] > 0 > r_out[0]
+    assert ingest.components_at(p, r_in).tolist() == [2] and ingest.components_at(p, r_out).tolist() == [0]
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for g, ic, pr, rg in zip(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region):
+        assert f.set_boundary(int(g), int(ic), pr, int(rg)) == 0
+    assert f.fluid_init(p.y, p.region) == 0
+    e, L0 = f.lhs(p.y)
+    vol = m.cell_geom[0, 3]
+    out = {}
+    for tag, rates in (("in", r_in), ("out", r_out)):
+        f.set_sources(p.source_cells, [2], rates, p.source_enthalpies)      # one component for both signs ...
+        f.set_source_components(p.source_injection_components, p.source_production_components)   # ... then both
+        f.lhs(p.y)
+        rhs = np.zeros(f.n)
+        assert wo.lib().wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+        f.set_sources(p.source_cells, [2], 0.0 * rates, p.source_enthalpies)
+        base = np.zeros(f.n)
+        assert wo.lib().wo_flow_cell_inflows(f.h, wo.dp(base)) == 0
+        out[tag] = (rhs - base)[:3] * vol
+    # injection: CO2 only (+ its enthalpy); production: both mass components leave (single-phase liquid: mostly water)
+    assert abs(out["in"][0]) < 1e-12 * r_in[0] and abs(out["in"][1] - r_in[0]) < 1e-9 * r_in[0] and out["in"][2] > 0
+    assert out["out"][0] < 0 and out["out"][1] <= 0 and abs(out["out"][0] + out["out"][1] - r_out[0]) < 1e-9 * abs(r_out[0])
+    assert out["out"][0] < 10 * out["out"][1]

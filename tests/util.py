@@ -115,6 +115,10 @@ class OracleSim:
         self.f.set_sources(cells, components, rates, enthalpies)
         return 0
 
+    def set_source_components(self, injection, production):
+        self.f.set_source_components(injection, production)
+        return 0
+
     def fluid(self):
         return self.f.fluid()
 
@@ -204,7 +208,9 @@ def run_input(problem, sim, opts=None, fields=None):
             dt = sizes[min(k, len(sizes) - 1)]
         dt = min(dt, stop - t, dt_max)
         if p.source_tables:
-            assert sim.set_sources(p.source_cells, p.source_components, ingest.rates_at(p, t, t + dt), p.source_enthalpies) == 0
+            rates = ingest.rates_at(p, t, t + dt)
+            assert sim.set_sources(p.source_cells, ingest.components_at(p, rates), rates, p.source_enthalpies) == 0
+            sim.set_source_components(p.source_injection_components, p.source_production_components)
         t1, _, its, _ = run_adaptive(sim, y, dt, dt, opts=opts, max_steps=1, reduction=ad.get("reduction", 0.2),
                                      amplification=1.0, its_min=0, its_max=10 ** 9)
         t += t1

@@ -79,6 +79,7 @@ SIGNATURES = {
     "wb_set_boundaries": (i, [vp, i, vp, vp, vp, vp]),
     "wb_set_sources": (i, [vp, i, vp, vp, vp, vp]),
     "wb_set_method": (i, [vp, i, d, vp]),
+    "wb_set_source_components": (i, [vp, i, vp, vp]),
     "wb_set_source_controls": (i, [vp, i, vp, vp, vp, vp, vp]),
     "wb_get_source_rates": (i, [vp, vp]),
     "wb_get_fluid": (i, [vp, vp]),

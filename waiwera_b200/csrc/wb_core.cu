@@ -184,15 +184,23 @@ extern "C" int wb_create(const wb_params *prm, int device, wb_ctx **out) {
   c->nph = c->eos.nphase;
   c->dof = 7 + c->nc - 1 + c->nph * (8 + c->nc - 1);  // src/fluid.F90:223-226
   c->nf = 4 + c->nph * (5 + (c->nc > 1 ? c->nc : 0));
-  WB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  WB_CUDA(cudaEventCreate(&c->ev0));
-  WB_CUDA(cudaEventCreate(&c->ev1));
-  WB_CUDA(cudaMalloc(&c->d_flags, 8 * sizeof(int)));
-  WB_CUDA(cudaMemset(c->d_flags, 0, 8 * sizeof(int)));
-  WB_CUDA(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
+  // from here on a failure releases what was created (wb_destroy copes with the partly built context)
+  cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev0);
+  if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev1);
+  if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_flags, 8 * sizeof(int));
+  if (e2 == cudaSuccess) e2 = cudaMemset(c->d_flags, 0, 8 * sizeof(int));
+  if (e2 == cudaSuccess) e2 = cudaMallocHost(&c->h_flags, 8 * sizeof(int));
   c->red_cap = 64 * 1024;
-  WB_CUDA(cudaMalloc(&c->d_red, c->red_cap * sizeof(double)));
-  WB_CUDA(cudaMallocHost(&c->h_red, 4096 * sizeof(double)));
+  if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_red, c->red_cap * sizeof(double));
+  if (e2 == cudaSuccess) e2 = cudaMallocHost(&c->h_red, 4096 * sizeof(double));
+  if (e2 != cudaSuccess) {
+    wb_set_error("wb_create: %s", cudaGetErrorString(e2));
+    cudaGetLastError();
+    c->J.ctx = c;
+    wb_destroy(c);
+    return -1;
+  }
   c->J.ctx = c;
   *out = c;
   return 0;

@@ -197,8 +197,8 @@ __device__ __forceinline__ void source_terms(const WbSources &S, int i, const Wb
   int k = S.head[i];
   if (k < 0) return;
   for (; k < S.n && S.cell[k] == i; k++) {
-    const int component = S.comp[k];
     const double rate = wb_source_rate(S, k, s);
+    const int component = wb_source_component(S.comp[k], rate);
     double flow[NP], enthalpy = 0.0;
 #pragma unroll
     for (int q = 0; q < NP; q++) flow[q] = 0.0;
@@ -946,6 +946,9 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
                               const double *enthalpy) {
   WB_CUDA(cudaSetDevice(c->device));
   WB_CHECK(c->ncell > 0, "wb_set_sources: no mesh");
+  WB_CHECK(n <= 0 || (!wb_is_device_ptr(cell) && !wb_is_device_ptr(component) && !wb_is_device_ptr(rate) &&
+                      !wb_is_device_ptr(enthalpy)),
+           "wb_set_sources: source arrays are read on the host (set-up data): pass host arrays");
   WB_CUDA(cudaStreamSynchronize(c->stream));
   void *old[] = {c->d_src_head, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth};
   for (void *p : old) cudaFree(p);
@@ -970,7 +973,7 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   std::vector<double> sr(n), se(n);
   for (int k = 0; k < n; k++) {
     const int o = order[k];
-    sc[k] = cell[o]; sk[k] = component[o]; sr[k] = rate[o]; se[k] = enthalpy[o];
+    sc[k] = cell[o]; sk[k] = component[o] | (component[o] << 8); sr[k] = rate[o]; se[k] = enthalpy[o];
     if (head[sc[k]] < 0) head[sc[k]] = k;
   }
   WB_TRY(dev_upload(&c->d_src_head, head));
@@ -980,6 +983,26 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   WB_TRY(dev_upload(&c->d_src_enth, se));
   c->nsrc = n;
   c->h_src_order = order;
+  return 0;
+}
+
+// injection and production component of every source of the last wb_set_sources (get_components,
+// src/source_setup.F90:2052-2083): which one applies is decided from the sign of the rate at every evaluation
+extern "C" int wb_set_source_components(wb_ctx *c, int n, const int32_t *injection_component,
+                                        const int32_t *production_component) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CHECK(n == c->nsrc && n > 0, "wb_set_source_components: %d components for %d sources", n, c->nsrc);
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<int32_t> sk(n);
+  for (int k = 0; k < n; k++) {
+    const int o = c->h_src_order[k];
+    WB_CHECK(injection_component[o] >= 1 && injection_component[o] <= c->np,
+             "wb_set_source_components: source %d: bad injection component %d", o, injection_component[o]);
+    WB_CHECK(production_component[o] >= 0 && production_component[o] <= c->np,
+             "wb_set_source_components: source %d: bad production component %d", o, production_component[o]);
+    sk[k] = injection_component[o] | (production_component[o] << 8);
+  }
+  WB_CUDA(cudaMemcpy(c->d_src_comp, sk.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -993,6 +1016,9 @@ extern "C" int wb_set_source_controls(wb_ctx *c, int n, const int32_t *source, c
   c->d_src_pi = c->d_src_pref = c->d_src_limit = nullptr;
   if (n <= 0) return 0;
   WB_CHECK(c->nsrc > 0, "wb_set_source_controls: no sources");
+  WB_CHECK(!wb_is_device_ptr(source) && !wb_is_device_ptr(productivity) && !wb_is_device_ptr(reference_pressure) &&
+               !wb_is_device_ptr(direction) && !wb_is_device_ptr(limit),
+           "wb_set_source_controls: control arrays are read on the host (set-up data): pass host arrays");
   const int ns = c->nsrc;
   std::vector<int> pos(ns);  // input position -> sorted position
   for (int k = 0; k < ns; k++) pos[c->h_src_order[k]] = k;
@@ -1074,6 +1100,8 @@ extern "C" int wb_set_boundaries(wb_ctx *c, int n, const int32_t *ghost_cells, c
                                  const double *primary, const int32_t *region) {
   WB_CUDA(cudaSetDevice(c->device));
   if (n == 0) return 0;
+  WB_CHECK(!wb_is_device_ptr(ghost_cells) && !wb_is_device_ptr(interior_cells),
+           "wb_set_boundaries: ghost_cells / interior_cells are read on the host (set-up data): pass host arrays");
   MeshDev &md = meshdev(c);
   const int ncell = c->ncell;
   // rock copied from the interior cell (src/mesh.F90:1189-1193)

@@ -70,6 +70,11 @@ WB_HD WbFaceGeom load_face(const double *face, size_t nface, int f) {
 }
 
 // fixed-rate sources sorted by cell (stable: input order inside a cell); head[c] = first source of owned cell c or -1
+// component word of a source: injection component | production component << 8 (source%update_flow picks by the
+// sign of the current rate, src/source.F90:372-380, 469-476)
+WB_HD int wb_source_component(int word, double rate) {
+  return rate > 0.0 ? (word & 0xff) : (word >> 8);
+}
 struct WbSources {
   const int32_t *head, *cell, *comp;
   const double *rate, *enth;

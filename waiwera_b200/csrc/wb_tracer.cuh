@@ -125,8 +125,8 @@ WB_HD void wb_tracer_row(const TracerArgs &a, int i) {
     int k = a.src.head[i];
     if (k >= 0) {
       for (; k < a.src.n && a.src.cell[k] == i; k++) {
-        if (a.src.comp[k] < NP) {
-          const double rate = wb_source_rate(a.src, k, si);
+        const double rate = wb_source_rate(a.src, k, si);
+        if (wb_source_component(a.src.comp[k], rate) < NP) {
           if (rate < 0.0) {
             // fluid%phase_flow_fractions (src/fluid.F90:394-411)
             double frac[NPH], sum = 0.0;

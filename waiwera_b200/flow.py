@@ -59,8 +59,10 @@ def make_relperm(kind="linear", **kw):
         r.type = RP_VAN_GENUCHTEN
         r.p[0] = kw.get("lambda", kw.get("lambda_", 0.45))
         r.p[1], r.p[2] = kw.get("slr", 1e-3), kw.get("sls", 1.0)
-        r.p[3] = 0.0 if "ssr" in kw else 1.0        # without ssr the vapour curve is 1 - krl (sum_unity)
-        r.p[4] = kw.get("ssr", 0.0)
+        # "sum_unity" (default true): vapour curve 1 - krl; otherwise the ssr curve, ssr default 0.6
+        # (src/relative_permeability.F90:436-455)
+        r.p[3] = 1.0 if kw.get("sum_unity", True) else 0.0
+        r.p[4] = kw.get("ssr", 0.6)
     elif kind == "table":
         r.type = RP_TABLE
         liq, vap = kw["liquid"], kw["vapour"]
@@ -298,6 +300,12 @@ class FlowSimulation:
         h = np.ascontiguousarray(enthalpies, np.float64)
         self.nsrc = len(c)
         return check(self.L.wb_set_sources(self.h, len(c), ptr(c), ptr(k), ptr(r), ptr(h)), "wb_set_sources")
+
+    def set_source_components(self, injection_components, production_components):
+        """injection / production component of every source, chosen by the sign of the rate at every evaluation"""
+        a = np.ascontiguousarray(injection_components, np.int32)
+        b = np.ascontiguousarray(production_components, np.int32)
+        return check(self.L.wb_set_source_components(self.h, len(a), ptr(a), ptr(b)), "wb_set_source_components")
 
     def set_source_controls(self, sources, productivity, reference_pressure, direction=None, limit=None):
         """deliverability / direction / total-limiter controls of some of the sources; see wb_set_source_controls"""

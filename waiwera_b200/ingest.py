@@ -360,7 +360,14 @@ def load(path, mod=None, mesh_path=None):
         p.primary = np.tile(prim, (n, 1)) if prim.ndim == 1 else prim.reshape(n, -1)
         reg = np.array(init.get("region", 1))
         p.region = (np.full(n, int(reg)) if reg.ndim == 0 else reg).astype(np.int32)
-        p.y = np.ascontiguousarray(wmesh.scale_primaries(p.primary, p.region)).reshape(-1)
+        # scaled with the SAME scales the parameters carry (eos.primary.scale of the input, else the defaults)
+        sc = dict(pressure_scale=1e6, temperature_scale=1e2, partial_pressure_scale=0.0)
+        if p.params is not None:
+            sc = dict(pressure_scale=p.params.pressure_scale if p.params.pressure_scale > 0 else 1e6,
+                      temperature_scale=p.params.temperature_scale if p.params.temperature_scale > 0 else 1e2,
+                      partial_pressure_scale=max(p.params.partial_pressure_scale, 0.0))
+        p.primary_scales = sc
+        p.y = np.ascontiguousarray(wmesh.scale_primaries(p.primary, p.region, **sc)).reshape(-1)
     else:
         p.primary = p.region = p.y = None                  # "filename": HDF5 restart, pass the arrays
     tr = doc.get("tracer")
@@ -424,16 +431,22 @@ def load(path, mod=None, mesh_path=None):
     def comp(v):
         return names[v.lower()] if isinstance(v, str) else int(v)
 
-    def component(s):
+    def components(s):
         inj = comp(s.get("component", 1))
-        if s["rate"] >= 0:
-            return inj
         if "production_component" in s:
-            return comp(s["production_component"])
-        return inj if (inj == p.np and p.np > 1 and name_of_eos != "w") else 0
+            prod = comp(s["production_component"])
+        else:
+            prod = inj if (inj == p.np and p.np > 1 and name_of_eos != "w") else 0
+        return inj, prod
     eos_doc = doc.get("eos", "we")
     name_of_eos = eos_doc if isinstance(eos_doc, str) else eos_doc.get("name", "we")
-    p.source_components = np.array([component(s) for s in src], np.int32)
+    both = [components(s) for s in src]
+    # the reference picks the injection or the production component from the sign of the CURRENT rate at every update
+    # (src/source.F90:372-380, 469-476): both travel to the engine (wb_set_source_components); source_components is the
+    # choice for the initial rate, for callers that only have fixed-sign sources
+    p.source_injection_components = np.array([b[0] for b in both], np.int32)
+    p.source_production_components = np.array([b[1] for b in both], np.int32)
+    p.source_components = np.array([b[0] if s["rate"] >= 0 else b[1] for s, b in zip(src, both)], np.int32)
     p.source_enthalpies = np.array([s.get("enthalpy", 83.9e3) for s in src], float)
     p.source_tracer = np.array([np.broadcast_to(np.atleast_1d(s.get("tracer", 0.0)), (max(nt, 1),)) for s in src],
                                float).reshape(len(src), max(nt, 1))
@@ -472,6 +485,12 @@ def tracer_rates_at(p, t0, t1):
     for k, (tab, interp, averaging) in p.source_tracer_tables.items():
         r[k, :] = _table_average(tab, interp, t0, t1, averaging)
     return r
+
+
+def components_at(p, rates):
+    """component of every source for rates of these signs (source%update_flow, src/source.F90:372-380, 469-476)"""
+    r = np.asarray(rates, float)
+    return np.where(r > 0, p.source_injection_components, p.source_production_components).astype(np.int32)
 
 
 def rates_at(p, t0, t1):
