@@ -46,6 +46,23 @@ const WbNccl *wb_nccl();  // nullptr (with wb_last_error set) if libnccl cannot 
     }                                                                                      \
   } while (0)
 
+// Synchronous copy that is complete when it returns.  cudaMemcpy from PAGEABLE host memory returns once the data sits
+// in the driver's staging buffer -- the DMA to the device may still be in flight -- and every kernel of this library
+// runs on a non-blocking stream, which is not ordered behind the legacy stream the copy uses: a kernel launched right
+// after a set-up upload could read the destination before the data landed.
+static inline cudaError_t wb_memcpy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpy(dst, src, bytes, kind);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+  return e;
+}
+
+// cudaMemset of device memory is asynchronous with respect to the host and runs on the legacy stream: the same hazard
+static inline cudaError_t wb_memset_sync(void *dst, int value, size_t bytes) {
+  cudaError_t e = cudaMemset(dst, value, bytes);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+  return e;
+}
+
 #define WB_NCCL(call)                                                                      \
   do {                                                                                     \
     ncclResult_t r_ = (call);                                                              \

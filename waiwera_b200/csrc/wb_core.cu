@@ -189,7 +189,7 @@ extern "C" int wb_create(const wb_params *prm, int device, wb_ctx **out) {
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev0);
   if (e2 == cudaSuccess) e2 = cudaEventCreate(&c->ev1);
   if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_flags, 8 * sizeof(int));
-  if (e2 == cudaSuccess) e2 = cudaMemset(c->d_flags, 0, 8 * sizeof(int));
+  if (e2 == cudaSuccess) e2 = wb_memset_sync(c->d_flags, 0, 8 * sizeof(int));
   if (e2 == cudaSuccess) e2 = cudaMallocHost(&c->h_flags, 8 * sizeof(int));
   c->red_cap = 64 * 1024;
   if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_red, c->red_cap * sizeof(double));
@@ -322,8 +322,8 @@ extern "C" int wb_set_halo(wb_ctx *c, int nneigh, const int32_t *neigh_rank, con
   h.maxwidth = WB_MAX_NP + 1;
   WB_CUDA(cudaMalloc(&h.d_send_idx, sizeof(int32_t) * (h.nsend + 1)));
   WB_CUDA(cudaMalloc(&h.d_recv_idx, sizeof(int32_t) * (h.nrecv + 1)));
-  WB_CUDA(cudaMemcpy(h.d_send_idx, send_idx, sizeof(int32_t) * h.nsend, cudaMemcpyHostToDevice));
-  WB_CUDA(cudaMemcpy(h.d_recv_idx, recv_idx, sizeof(int32_t) * h.nrecv, cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(h.d_send_idx, send_idx, sizeof(int32_t) * h.nsend, cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(h.d_recv_idx, recv_idx, sizeof(int32_t) * h.nrecv, cudaMemcpyHostToDevice));
   // ghost cells are numbered owner by owner in the order they arrive: then the receive buffer is the ghost
   // part of the vector itself and the SpMV halo needs no unpack kernel
   h.recv_contiguous = true;
@@ -456,7 +456,7 @@ extern "C" int wb_comm_p2p_export(wb_ctx *c, void *blob) {
   p.ll_stride = (((size_t)(nghost + 1) * h.maxwidth * 16) + 255) & ~(size_t)255;
   p.bytes = p.ll_off + 2 * p.ll_stride;
   WB_CUDA(cudaMalloc(&p.local, p.bytes));
-  WB_CUDA(cudaMemset(p.local, 0, p.bytes));
+  WB_CUDA(wb_memset_sync(p.local, 0, p.bytes));
   WbP2PBlob b;
   memset(&b, 0, sizeof(b));
   WB_CUDA(cudaIpcGetMemHandle(&b.handle, p.local));
@@ -527,17 +527,17 @@ extern "C" int wb_comm_p2p_open(wb_ctx *c, const void *blobs) {
       }
     WB_CUDA(cudaMalloc(&p.d_dst_rank, sizeof(int32_t) * dr.size()));
     WB_CUDA(cudaMalloc(&p.d_dst_off, sizeof(int32_t) * doff.size()));
-    WB_CUDA(cudaMemcpy(p.d_dst_rank, dr.data(), sizeof(int32_t) * dr.size(), cudaMemcpyHostToDevice));
-    WB_CUDA(cudaMemcpy(p.d_dst_off, doff.data(), sizeof(int32_t) * doff.size(), cudaMemcpyHostToDevice));
+    WB_CUDA(wb_memcpy_sync(p.d_dst_rank, dr.data(), sizeof(int32_t) * dr.size(), cudaMemcpyHostToDevice));
+    WB_CUDA(wb_memcpy_sync(p.d_dst_off, doff.data(), sizeof(int32_t) * doff.size(), cudaMemcpyHostToDevice));
   }
   WB_CUDA(cudaMalloc(&p.d_counter, sizeof(unsigned)));
-  WB_CUDA(cudaMemset(p.d_counter, 0, sizeof(unsigned)));
+  WB_CUDA(wb_memset_sync(p.d_counter, 0, sizeof(unsigned)));
   WB_CUDA(cudaMalloc(&p.d_fseq, 4 * sizeof(int)));
-  WB_CUDA(cudaMemset(p.d_fseq, 0, 4 * sizeof(int)));
-  WB_CUDA(cudaMemcpy(p.d_send_nb, send_nb.data(), sizeof(int32_t) * send_nb.size(), cudaMemcpyHostToDevice));
-  WB_CUDA(cudaMemcpy(p.d_nb_rank, nb_rank.data(), sizeof(int32_t) * nb_rank.size(), cudaMemcpyHostToDevice));
-  WB_CUDA(cudaMemcpy(p.d_nb_off, nb_off.data(), sizeof(int32_t) * nb_off.size(), cudaMemcpyHostToDevice));
-  WB_CUDA(cudaMemcpy(p.d_nb_start, nb_start.data(), sizeof(int32_t) * nb_start.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memset_sync(p.d_fseq, 0, 4 * sizeof(int)));
+  WB_CUDA(wb_memcpy_sync(p.d_send_nb, send_nb.data(), sizeof(int32_t) * send_nb.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(p.d_nb_rank, nb_rank.data(), sizeof(int32_t) * nb_rank.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(p.d_nb_off, nb_off.data(), sizeof(int32_t) * nb_off.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(p.d_nb_start, nb_start.data(), sizeof(int32_t) * nb_start.size(), cudaMemcpyHostToDevice));
   p.dev.on = 1;
   p.on = true;
   return 0;

@@ -55,7 +55,7 @@ struct WbFusedPlan {
 
 template <class T> static int up(T **p, const std::vector<T> &v) {
   WB_CUDA(cudaMalloc((void **)p, std::max<size_t>(v.size(), 1) * sizeof(T)));
-  if (!v.empty()) WB_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (!v.empty()) WB_CUDA(wb_memcpy_sync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -295,7 +295,7 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
   WB_TRY(up(&f->d_ssrc, ssrc));
   WB_TRY(up(&f->d_slot0, slot0));
   WB_CUDA(cudaMalloc(&f->d_sell, sell.size() + WB_PAD_BYTES));
-  WB_CUDA(cudaMemcpy(f->d_sell, sell.data(), sell.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(f->d_sell, sell.data(), sell.size(), cudaMemcpyHostToDevice));
   pc->fused = f;
   return 0;
 }
@@ -471,8 +471,8 @@ __device__ __forceinline__ void fz_reduce_ll(const FusedArgs &a, const FzRed &R,
                                              double *s_tmp, bool release, bool multi, int mseq, size_t slot_off,
                                              int per_rank, int cta, int tid, int nc) {
   const int lane = tid & 31;
-  if (release) __threadfence();
-  bar_sync_named(FZ_BAR_ALL, nc);  // s_vals complete; with `release`: every thread's earlier writes are visible
+  if (release) __threadfence();    // every thread's earlier global writes (its rows of the vector) become visible first
+  bar_sync_named(FZ_BAR_ALL, nc);  // s_vals complete
   if (tid < nv) ll_store_gpu(R.part + ((size_t)(kind * KRY_MAXV + tid) * WB_NUM_SMS + cta) * 16, s_vals[tid], seq);
   const size_t buf = multi ? (size_t)(mseq & 1) * WB_P2P_MAX_RANKS * per_rank * 16 : 0;
   for (int j = cta; j < nv; j += R.ncta) {  // owner duty
@@ -1118,7 +1118,7 @@ static int build_push_lists(wb_ctx *c, wb_pc *pc) {
   const WbHalo &h = c->halo;
   const WbP2P &p = c->p2p;
   std::vector<int32_t> idx(std::max(h.nsend, 1));
-  if (h.nsend > 0) WB_CUDA(cudaMemcpy(idx.data(), h.d_send_idx, sizeof(int32_t) * h.nsend, cudaMemcpyDeviceToHost));
+  if (h.nsend > 0) WB_CUDA(wb_memcpy_sync(idx.data(), h.d_send_idx, sizeof(int32_t) * h.nsend, cudaMemcpyDeviceToHost));
   struct E { int row, rank, off; };
   std::vector<std::vector<E>> per(f->ncta);
   // CTA of a row in the sub-domain-major ordering
@@ -1216,7 +1216,7 @@ int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b
   WB_LAUNCH(c);
   WB_TRY(wb_fetch_state(w));
   int h_abort = 0;
-  WB_CUDA(cudaMemcpy(&h_abort, w.d_bar + 2, sizeof(int), cudaMemcpyDeviceToHost));
+  WB_CUDA(wb_memcpy_sync(&h_abort, w.d_bar + 2, sizeof(int), cudaMemcpyDeviceToHost));
   WB_CHECK(!h_abort, "fused GMRES: grid barrier timed out (a CTA or a peer GPU is missing)");
   *its = w.h_st->its;
   *reason = w.h_st->reason;
@@ -1232,9 +1232,9 @@ extern "C" int wb_ksp_fused_profile(wb_ctx *c, double *ns7, int reset) {
   if (!wp) return 0;
   WB_CUDA(cudaSetDevice(c->device));
   unsigned long long h[16];
-  WB_CUDA(cudaMemcpy(h, wp->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+  WB_CUDA(wb_memcpy_sync(h, wp->d_prof, sizeof(h), cudaMemcpyDeviceToHost));
   for (int k = 0; k < 7; k++) ns7[k] = (double)h[k];
-  if (reset) WB_CUDA(cudaMemset(wp->d_prof, 0, WB_PROF_WORDS * sizeof(unsigned long long)));
+  if (reset) WB_CUDA(wb_memset_sync(wp->d_prof, 0, WB_PROF_WORDS * sizeof(unsigned long long)));
   return 0;
 }
 
@@ -1246,7 +1246,7 @@ extern "C" int wb_debug_fused_profile_all(wb_ctx *c, double *out, int max_ctas) 
   if (!wp) return 0;
   WB_CUDA(cudaSetDevice(c->device));
   std::vector<unsigned long long> h(WB_PROF_WORDS);
-  WB_CUDA(cudaMemcpy(h.data(), wp->d_prof, WB_PROF_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  WB_CUDA(wb_memcpy_sync(h.data(), wp->d_prof, WB_PROF_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   const int n = std::min(max_ctas, WB_PROF_WORDS / 16);
   for (int k = 0; k < n * 16; k++) out[k] = (double)h[k];
   return n;

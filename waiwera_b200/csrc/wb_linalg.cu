@@ -296,7 +296,7 @@ static int sell_build(wb_mat *A) {
   WB_TRY(upload(&S->d_ssrc, ssrc));
   WB_TRY(upload(&S->d_slot0, slot0));
   WB_CUDA(cudaMalloc(&S->d_data, data.size() + WB_PAD_BYTES));
-  WB_CUDA(cudaMemcpy(S->d_data, data.data(), data.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(S->d_data, data.data(), data.size(), cudaMemcpyHostToDevice));
   A->sell = S;
   return 0;
 }
@@ -421,17 +421,17 @@ extern "C" int wb_mat_create(wb_ctx *c, int nb, int ncolb, int bs, int nnzb, con
   A->ctx = c; A->nb = nb; A->ncolb = ncolb; A->bs = bs; A->nnzb = nnzb; A->owns = true;
   A->h_rowptr.resize(nb + 1);
   A->h_colidx.resize(nnzb);
-  WB_CUDA(cudaMemcpy(A->h_rowptr.data(), rowptr, sizeof(int32_t) * (nb + 1), cudaMemcpyDefault));
-  WB_CUDA(cudaMemcpy(A->h_colidx.data(), colidx, sizeof(int32_t) * nnzb, cudaMemcpyDefault));
+  WB_CUDA(wb_memcpy_sync(A->h_rowptr.data(), rowptr, sizeof(int32_t) * (nb + 1), cudaMemcpyDefault));
+  WB_CUDA(wb_memcpy_sync(A->h_colidx.data(), colidx, sizeof(int32_t) * nnzb, cudaMemcpyDefault));
   WB_CUDA(cudaMalloc(&A->d_rowptr, sizeof(int32_t) * (nb + 1) + WB_PAD_BYTES));
   WB_CUDA(cudaMalloc(&A->d_colidx, sizeof(int32_t) * std::max(nnzb, 1) + WB_PAD_BYTES));
   WB_CUDA(cudaMalloc(&A->d_val, sizeof(double) * std::max<size_t>((size_t)nnzb * bs * bs, 1) + WB_PAD_BYTES));
   WB_CUDA(cudaMalloc(&A->d_xloc, sizeof(double) * (size_t)(ncolb - nb + 1) * bs));
-  WB_CUDA(cudaMemset(A->d_xloc, 0, sizeof(double) * (size_t)(ncolb - nb + 1) * bs));
-  WB_CUDA(cudaMemcpy(A->d_rowptr, A->h_rowptr.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice));
-  WB_CUDA(cudaMemcpy(A->d_colidx, A->h_colidx.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice));
-  if (vals) WB_CUDA(cudaMemcpy(A->d_val, vals, sizeof(double) * (size_t)nnzb * bs * bs, cudaMemcpyDefault));
-  else WB_CUDA(cudaMemset(A->d_val, 0, sizeof(double) * (size_t)nnzb * bs * bs));
+  WB_CUDA(wb_memset_sync(A->d_xloc, 0, sizeof(double) * (size_t)(ncolb - nb + 1) * bs));
+  WB_CUDA(wb_memcpy_sync(A->d_rowptr, A->h_rowptr.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(A->d_colidx, A->h_colidx.data(), sizeof(int32_t) * nnzb, cudaMemcpyHostToDevice));
+  if (vals) WB_CUDA(wb_memcpy_sync(A->d_val, vals, sizeof(double) * (size_t)nnzb * bs * bs, cudaMemcpyDefault));
+  else WB_CUDA(wb_memset_sync(A->d_val, 0, sizeof(double) * (size_t)nnzb * bs * bs));
   WB_TRY(wb_mat_build_tiles(A));
   *out = A;
   return 0;
@@ -1164,7 +1164,7 @@ extern "C" int wb_pc_setup(wb_mat *A, int type, int nblocks, const int32_t *bloc
     WB_TRY(upload(&pc->d_sched_b, sb));
     WB_CUDA(cudaMalloc(&pc->d_val, sizeof(double) * (size_t)pc->nnzb * bs2));
     WB_CUDA(cudaMalloc(&pc->d_flag, sizeof(int) * nb));
-    WB_CUDA(cudaMemset(pc->d_flag, 0, sizeof(int) * nb));
+    WB_CUDA(wb_memset_sync(pc->d_flag, 0, sizeof(int) * nb));
     WB_CUDA(cudaMalloc(&pc->d_ticket, sizeof(int)));
     // sub-domains small enough for one CTA's shared memory use the resident solve
     int nblk_used = 0, maxrows = 0;
@@ -1299,10 +1299,10 @@ extern "C" int wb_debug_pc_trace(wb_pc *pc, const double *d_r, double *d_z, long
   WB_CHECK(pc->blocked, "wb_debug_pc_trace: not a sub-domain resident solve");
   if (nstage_override >= 0) pc->nstage = nstage_override;
   WB_CUDA(cudaMalloc(&pc->d_trace, sizeof(long long) * (4 * pc->nblk + 128)));
-  WB_CUDA(cudaMemset(pc->d_trace, 0, sizeof(long long) * (4 * pc->nblk + 128)));
+  WB_CUDA(wb_memset_sync(pc->d_trace, 0, sizeof(long long) * (4 * pc->nblk + 128)));
   int rc = wb_pc_apply_dev(pc, d_r, d_z, nullptr);
   cudaStreamSynchronize(c->stream);
-  if (out) cudaMemcpy(out, pc->d_trace, sizeof(long long) * (4 * pc->nblk + 128), cudaMemcpyDeviceToHost);
+  if (out) wb_memcpy_sync(out, pc->d_trace, sizeof(long long) * (4 * pc->nblk + 128), cudaMemcpyDeviceToHost);
   cudaFree(pc->d_trace);
   pc->d_trace = nullptr;
   return rc;
@@ -1516,7 +1516,7 @@ int wb_mat_build_tiles(wb_mat *A) {
   e0[A->ntiles] = A->nb > 0 ? A->h_rowptr[A->nb] : 0;
   A->tile_cap = cap;
   WB_CUDA(cudaMalloc(&A->d_tile_e0, sizeof(int32_t) * e0.size()));
-  WB_CUDA(cudaMemcpy(A->d_tile_e0, e0.data(), sizeof(int32_t) * e0.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(A->d_tile_e0, e0.data(), sizeof(int32_t) * e0.size(), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -2010,13 +2010,13 @@ int wb_ensure_work(wb_ctx *c, size_t n, int m, KspWork **out) {
     WB_CUDA(cudaMallocHost(&w.h_st, sizeof(KspState)));
     WB_CUDA(cudaMalloc(&w.d_done, sizeof(int)));
     WB_CUDA(cudaMalloc(&w.d_counter, sizeof(unsigned)));
-    WB_CUDA(cudaMemset(w.d_counter, 0, sizeof(unsigned)));
+    WB_CUDA(wb_memset_sync(w.d_counter, 0, sizeof(unsigned)));
     WB_CUDA(cudaMalloc(&w.d_bar, 64 * sizeof(int)));
-    WB_CUDA(cudaMemset(w.d_bar, 0, 64 * sizeof(int)));
+    WB_CUDA(wb_memset_sync(w.d_bar, 0, 64 * sizeof(int)));
     WB_CUDA(cudaMalloc(&w.d_ll, WB_LL_BYTES));
-    WB_CUDA(cudaMemset(w.d_ll, 0, WB_LL_BYTES));
+    WB_CUDA(wb_memset_sync(w.d_ll, 0, WB_LL_BYTES));
     WB_CUDA(cudaMalloc(&w.d_prof, WB_PROF_WORDS * sizeof(unsigned long long)));
-    WB_CUDA(cudaMemset(w.d_prof, 0, WB_PROF_WORDS * sizeof(unsigned long long)));
+    WB_CUDA(wb_memset_sync(w.d_prof, 0, WB_PROF_WORDS * sizeof(unsigned long long)));
   }
   *out = &w;
   return 0;

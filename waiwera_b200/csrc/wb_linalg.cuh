@@ -77,7 +77,7 @@ struct wb_pc {
 
 template <class T> static int upload(T **p, const std::vector<T> &v) {
   WB_CUDA(cudaMalloc((void **)p, std::max<size_t>(v.size(), 1) * sizeof(T)));
-  if (!v.empty()) WB_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (!v.empty()) WB_CUDA(wb_memcpy_sync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   return 0;
 }
 

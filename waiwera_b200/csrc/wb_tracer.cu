@@ -70,9 +70,9 @@ extern "C" int wb_set_tracers(wb_ctx *c, int nt, const int32_t *phase, const dou
   c->A_aux = A;
   const size_t nv = (size_t)J.nnzb * nt * nt;
   WB_CUDA(cudaMalloc(&A->d_val, sizeof(double) * std::max<size_t>(nv, 1) + WB_PAD_BYTES));
-  WB_CUDA(cudaMemset(A->d_val, 0, sizeof(double) * std::max<size_t>(nv, 1) + WB_PAD_BYTES));
+  WB_CUDA(wb_memset_sync(A->d_val, 0, sizeof(double) * std::max<size_t>(nv, 1) + WB_PAD_BYTES));
   WB_CUDA(cudaMalloc(&A->d_xloc, sizeof(double) * (size_t)(J.ncolb - J.nb + 1) * nt));
-  WB_CUDA(cudaMemset(A->d_xloc, 0, sizeof(double) * (size_t)(J.ncolb - J.nb + 1) * nt));
+  WB_CUDA(wb_memset_sync(A->d_xloc, 0, sizeof(double) * (size_t)(J.ncolb - J.nb + 1) * nt));
   WB_TRY(wb_mat_build_tiles(A));
   const size_t n = (size_t)c->nowned * nt;
   WB_CUDA(cudaMalloc(&c->d_trc_b, sizeof(double) * std::max<size_t>(n, 1)));
@@ -89,11 +89,11 @@ extern "C" int wb_set_tracer_injection(wb_ctx *c, const double *rate) {
   if (!rate || c->nsrc == 0 || c->nt == 0) return 0;
   const int nt = c->nt;
   std::vector<double> host((size_t)c->nsrc * nt), sorted((size_t)c->nsrc * nt);
-  WB_CUDA(cudaMemcpy(host.data(), rate, sizeof(double) * host.size(), cudaMemcpyDefault));
+  WB_CUDA(wb_memcpy_sync(host.data(), rate, sizeof(double) * host.size(), cudaMemcpyDefault));
   for (int k = 0; k < c->nsrc; k++)
     for (int t = 0; t < nt; t++) sorted[(size_t)k * nt + t] = host[(size_t)c->h_src_order[k] * nt + t];
   WB_CUDA(cudaMalloc(&c->d_trc_inj, sizeof(double) * sorted.size()));
-  WB_CUDA(cudaMemcpy(c->d_trc_inj, sorted.data(), sizeof(double) * sorted.size(), cudaMemcpyHostToDevice));
+  WB_CUDA(wb_memcpy_sync(c->d_trc_inj, sorted.data(), sizeof(double) * sorted.size(), cudaMemcpyHostToDevice));
   return 0;
 }
 
