@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5])
     ap.add_argument("--dims", type=int, nargs=3, default=None, help="override the mesh dimensions of the configuration")
     ap.add_argument("--dt", type=float, default=None)
-    ap.add_argument("--pc", default="ilu0", choices=["ilu0", "pbjacobi", "none"])
+    ap.add_argument("--pc", default="ilu0", choices=["ilu0", "asm", "pbjacobi", "none"],
+                    help="ilu0: block Jacobi + ILU(0) on the --pc-cube sub-domains; asm: PCASM (restricted, overlap 1) + ILU(0) on the same sub-domains")
     ap.add_argument("--pc-blocks", type=int, default=1, help="block-Jacobi sub-domains per GPU (contiguous row ranges)")
     ap.add_argument("--pc-cube", type=int, default=10,
                     help="block-Jacobi sub-domains = cubes of this many cells per side (0: use --pc-blocks)")
@@ -100,8 +101,9 @@ class Problem:
             self.owner = wmesh.box_owner(self.mesh, self.parts) if world > 1 else None
             self.minc = False
         else:
-            # weak scaling: one 50^3 box of fracture cells (+ one MINC level) per GPU
-            self.parts = wmesh.default_parts(world)
+            # weak scaling: one 50^3 box of fracture cells (+ one MINC level) per GPU, boxes side by side in x and y so
+            # that every N has the same depth (the same hydrostatic column, the same kind of Newton system)
+            self.parts = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (4, 2, 1)}.get(world) or wmesh.default_parts(world)
             per = dims or (50, 50, 50)
             self.dims = tuple(per[k] * self.parts[k] for k in range(3))
             self.eos, self.eos_name, self.npv = flow.EOS_WCE, "eos_wce", 3
@@ -130,8 +132,9 @@ class Problem:
         what = {2: "%s IAPWS %dx%dx%d structured (%d cells)" % (self.eos_name, d[0], d[1], d[2], ncell),
                 4: "%s IAPWS %dx%dx%d structured (%d cells), band of cells on the saturation line" % (self.eos_name, d[0], d[1], d[2], ncell),
                 5: "%s IAPWS MINC dual porosity, %dx%dx%d fracture cells + 1 matrix level (%d cells)" % (self.eos_name, d[0], d[1], d[2], ncell)}[self.cfg]
-        return "config %d: %s, BAIJ bs=%d, BE dt=%g s, %s%s + bjacobi/ILU(0) rtol 1e-5" % (
-            self.cfg, what, self.npv, self.dt, args.ksp.upper(), "(%d)" % args.restart if args.ksp == "gmres" else "")
+        pc = {"ilu0": "bjacobi/ILU(0)", "asm": "ASM(overlap 1)/ILU(0)"}.get(getattr(args, "pc", "ilu0"), getattr(args, "pc", "ilu0"))
+        return "config %d: %s, BAIJ bs=%d, BE dt=%g s, %s%s + %s rtol 1e-5" % (
+            self.cfg, what, self.npv, self.dt, args.ksp.upper(), "(%d)" % args.restart if args.ksp == "gmres" else "", pc)
 
 
 # ------------------------------------------------------------------ clocks sampler
@@ -224,7 +227,7 @@ class CpuArm:
                                 1e-8, 1e-2, self.A) == 0
         t["jacobian"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        pc = L.wo_pc_create(self.A, wo.PC_BJACOBI_ILU0, wo.ip(self.bor))
+        pc = L.wo_pc_create(self.A, wo.PC_ASM_ILU0 if self.args.pc == "asm" else wo.PC_BJACOBI_ILU0, wo.ip(self.bor))
         t["pc_setup"] = time.perf_counter() - t0
         o = wo.KspOpts()
         o.type, o.restart, o.maxit = (wo.KSP_GMRES if self.args.ksp == "gmres" else wo.KSP_BCGS), self.args.restart, maxit
@@ -367,9 +370,9 @@ def run_b200(args):
     err, L0 = sim.lhs(y)
     assert err == 0
     sim.pre_timestep()   # every step starts from this state: pre_retry_timestep restores the regions a step's transitions changed
-    if args.pc_cube > 0 and args.pc == "ilu0":
+    if args.pc_cube > 0 and args.pc in ("ilu0", "asm"):
         sim.set_pc_blocks(prob.blocks(m, args.pc_cube))
-    pc_type = {"ilu0": flow.PC_BJACOBI_ILU0, "pbjacobi": flow.PC_PBJACOBI, "none": flow.PC_NONE}[args.pc]
+    pc_type = {"ilu0": flow.PC_BJACOBI_ILU0, "asm": flow.PC_ASM_ILU0, "pbjacobi": flow.PC_PBJACOBI, "none": flow.PC_NONE}[args.pc]
     ksp_type = {"gmres": flow.KSP_GMRES, "bcgs": flow.KSP_BCGS}[args.ksp]
     opts = flow.newton_opts(max_iterations=1, pc_type=pc_type, pc_nblocks=args.pc_blocks,
                             ksp=flow.ksp_opts(type=ksp_type, maxit=args.ksp_maxit, restart=args.restart))

@@ -22,7 +22,8 @@ module waiwera_b200
   integer(c_int), parameter, public :: WB_RP_FULLY_MOBILE = 0, WB_RP_LINEAR = 1, WB_RP_PICKENS = 2, &
        WB_RP_COREY = 3, WB_RP_GRANT = 4, WB_RP_VAN_GENUCHTEN = 5, WB_RP_TABLE = 6
   integer(c_int), parameter, public :: WB_CP_ZERO = 0, WB_CP_LINEAR = 1, WB_CP_VAN_GENUCHTEN = 2, WB_CP_TABLE = 3
-  integer(c_int), parameter, public :: WB_PC_NONE = 0, WB_PC_PBJACOBI = 1, WB_PC_BJACOBI_ILU0 = 2
+  integer(c_int), parameter, public :: WB_PC_NONE = 0, WB_PC_PBJACOBI = 1, WB_PC_BJACOBI_ILU0 = 2, &
+       WB_PC_ASM_ILU0 = 3
   integer(c_int), parameter, public :: WB_KSP_GMRES = 0, WB_KSP_BCGS = 1
   integer(c_int), parameter, public :: WB_METHOD_BEULER = 0, WB_METHOD_BDF2 = 1, WB_METHOD_DIRECTSS = 2
   integer(c_int), parameter, public :: WB_MAX_TRACERS = 3

@@ -277,6 +277,8 @@ int wb_mat_mult(wb_mat *A, const double *x, double *y);
 #define WB_PC_NONE 0
 #define WB_PC_PBJACOBI 1 /* point-block Jacobi */
 #define WB_PC_BJACOBI_ILU0 2 /* block Jacobi, ILU(0) natural ordering on each block */
+#define WB_PC_ASM_ILU0 3     /* PCASM (restricted, overlap 1) on the same sub-domains, ILU(0) on each extended sub-domain;
+                                the overlap stays inside the rank (rows of other ranks are not fetched) */
 /* PCSetUp.  nblocks: number of block-Jacobi sub-domains on this GPU (PETSc
    -pc_bjacobi_local_blocks; 1 = one ILU(0) over all owned rows, the PETSc default).
    block_of_row[nb] (host, may be NULL => contiguous equal split) assigns rows to blocks. */

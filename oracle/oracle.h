@@ -294,6 +294,8 @@ typedef struct wo_pc wo_pc;
 #define WO_PC_NONE 0
 #define WO_PC_PBJACOBI 1
 #define WO_PC_BJACOBI_ILU0 2   /* nblocks sub-domains, ILU(0) each (1 block = global ILU(0)) */
+#define WO_PC_ASM_ILU0 3       /* restricted additive Schwarz (PCASM default, PC_ASM_RESTRICT), overlap 1, ILU(0) on each
+                                  extended sub-domain */
 wo_pc *wo_pc_create(const wo_bsr *A, int type, const int32_t *block_of_row /* may be NULL */);
 void wo_pc_apply(const wo_pc *pc, const double *r, double *z);
 void wo_pc_destroy(wo_pc *pc);

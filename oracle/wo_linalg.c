@@ -252,7 +252,96 @@ struct wo_pc {
      (one MPI rank per block in the reference); per row the arithmetic is the sequential one. */
   int nblocks;
   int32_t *blk_ptr, *blk_rows;
+  /* additive Schwarz: the extended sub-domain matrices side by side (one block-diagonal matrix `ext`), the block-Jacobi
+     ILU(0) of it, and the maps between the two numberings */
+  wo_bsr *ext;
+  wo_pc *inner;
+  int32_t *ext_row; /* [ext->nb] global row of each extended row */
+  int32_t *own_pos; /* [nb] extended row that holds the owned copy of a global row */
+  double *ext_r, *ext_z;
 };
+
+/* PCASM with overlap 1 (PCSetUp_ASM: MatIncreaseOverlap by one layer of matrix neighbours, MatCreateSubMatrices on the
+   sorted index sets, sub-KSP preonly + ILU(0); PCApply_ASM with PC_ASM_RESTRICT: the residual is restricted to the
+   extended sub-domain, only the rows the sub-domain owns are written back). */
+static int asm_build(wo_pc *pc, const wo_bsr *A, const int32_t *block_of_row) {
+  int nb = A->nb, bs2 = A->bs * A->bs;
+  int nblk = 1;
+  if (block_of_row)
+    for (int i = 0; i < nb; i++)
+      if (block_of_row[i] + 1 > nblk) nblk = block_of_row[i] + 1;
+  /* rows of the extended sub-domains, ascending inside each: a row belongs to E_b when it or one of its matrix
+     neighbours is owned by b (symmetric pattern: the blocks that reach row i through one matrix entry are the blocks
+     of the columns of row i) */
+  int32_t *start = (int32_t *)calloc(nblk + 1, sizeof(int32_t));
+  int32_t *cnt = (int32_t *)malloc(nblk * sizeof(int32_t));
+  int32_t *seen = (int32_t *)malloc(nblk * sizeof(int32_t));
+  for (int pass = 0; pass < 2; pass++) {
+    for (int b = 0; b < nblk; b++) seen[b] = -1;
+    for (int i = 0; i < nb; i++)
+      for (int k = A->rowptr[i]; k < A->rowptr[i + 1]; k++) {
+        int b = block_of_row ? block_of_row[A->colidx[k]] : 0;
+        if (seen[b] == i) continue;
+        seen[b] = i;
+        if (pass == 0) start[b + 1]++;
+        else pc->ext_row[cnt[b]++] = i;
+      }
+    if (pass == 0) {
+      for (int b = 0; b < nblk; b++) start[b + 1] += start[b];
+      for (int b = 0; b < nblk; b++) cnt[b] = start[b];
+      pc->ext_row = (int32_t *)malloc((size_t)start[nblk] * sizeof(int32_t));
+    }
+  }
+  int ne = start[nblk];
+  wo_bsr *E = (wo_bsr *)calloc(1, sizeof(wo_bsr));
+  E->nb = ne;
+  E->bs = A->bs;
+  E->rowptr = (int32_t *)malloc((size_t)(ne + 1) * sizeof(int32_t));
+  pc->own_pos = (int32_t *)malloc((size_t)nb * sizeof(int32_t));
+  int32_t *blk_ext = (int32_t *)malloc((size_t)ne * sizeof(int32_t));
+  int32_t *loc = (int32_t *)malloc((size_t)nb * sizeof(int32_t)); /* global row -> extended row of the current block */
+  for (int i = 0; i < nb; i++) loc[i] = -1;
+  for (int pass = 0; pass < 2; pass++) {
+    int q = 0;
+    for (int b = 0; b < nblk; b++) {
+      for (int e = start[b]; e < start[b + 1]; e++) loc[pc->ext_row[e]] = e;
+      for (int e = start[b]; e < start[b + 1]; e++) {
+        int i = pc->ext_row[e];
+        if (pass == 0) {
+          E->rowptr[e] = q;
+          blk_ext[e] = b;
+          if ((block_of_row ? block_of_row[i] : 0) == b) pc->own_pos[i] = e;
+        }
+        for (int k = A->rowptr[i]; k < A->rowptr[i + 1]; k++) {
+          int le = loc[A->colidx[k]];
+          if (le < 0) continue;
+          if (pass == 1) {
+            E->colidx[q] = le;
+            memcpy(E->val + (size_t)q * bs2, A->val + (size_t)k * bs2, bs2 * sizeof(double));
+          }
+          q++;
+        }
+      }
+      for (int e = start[b]; e < start[b + 1]; e++) loc[pc->ext_row[e]] = -1;
+    }
+    if (pass == 0) {
+      E->rowptr[ne] = q;
+      E->nnzb = q;
+      E->colidx = (int32_t *)malloc((size_t)q * sizeof(int32_t));
+      E->val = (double *)malloc((size_t)q * bs2 * sizeof(double));
+    }
+  }
+  pc->ext = E;
+  pc->inner = wo_pc_create(E, WO_PC_BJACOBI_ILU0, blk_ext);
+  pc->ext_r = (double *)malloc((size_t)ne * A->bs * sizeof(double));
+  pc->ext_z = (double *)malloc((size_t)ne * A->bs * sizeof(double));
+  free(cnt);
+  free(seen);
+  free(start);
+  free(blk_ext);
+  free(loc);
+  return pc->inner ? 0 : 1;
+}
 
 wo_pc *wo_pc_create(const wo_bsr *A, int type, const int32_t *block_of_row) {
   int nb = A->nb, bs = A->bs, bs2 = bs * bs;
@@ -269,6 +358,13 @@ wo_pc *wo_pc_create(const wo_bsr *A, int type, const int32_t *block_of_row) {
         wo_pc_destroy(pc);
         return NULL;
       }
+    }
+    return pc;
+  }
+  if (type == WO_PC_ASM_ILU0) {
+    if (asm_build(pc, A, block_of_row)) {
+      wo_pc_destroy(pc);
+      return NULL;
     }
     return pc;
   }
@@ -369,6 +465,17 @@ void wo_pc_apply(const wo_pc *pc, const double *r, double *z) {
     }
     return;
   }
+  if (pc->type == WO_PC_ASM_ILU0) {
+    int ne = pc->ext->nb;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < ne; e++)
+      for (int ii = 0; ii < bs; ii++) pc->ext_r[(size_t)e * bs + ii] = r[(size_t)pc->ext_row[e] * bs + ii];
+    wo_pc_apply(pc->inner, pc->ext_r, pc->ext_z);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nb; i++)
+      for (int ii = 0; ii < bs; ii++) z[(size_t)i * bs + ii] = pc->ext_z[(size_t)pc->own_pos[i] * bs + ii];
+    return;
+  }
   /* MatSolve_SeqBAIJ_N_NaturalOrdering: forward (unit L), backward with inverted diagonal,
      one sub-domain per host thread */
 #pragma omp parallel for schedule(dynamic, 1)
@@ -414,6 +521,12 @@ void wo_pc_destroy(wo_pc *pc) {
   free(pc->val);
   free(pc->blk_ptr);
   free(pc->blk_rows);
+  if (pc->inner) wo_pc_destroy(pc->inner);
+  if (pc->ext) wo_bsr_destroy(pc->ext);
+  free(pc->ext_row);
+  free(pc->own_pos);
+  free(pc->ext_r);
+  free(pc->ext_z);
   free(pc);
 }
 

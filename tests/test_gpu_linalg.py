@@ -220,3 +220,48 @@ def test_full_size_spmv_properties(wo, flow):
     M.destroy()
     wo.lib().wo_bsr_destroy(A)
     sim.destroy()
+
+
+@pytest.mark.parametrize("bs,dims,box", [(2, (9, 8, 7), (3, 4, 4)), (3, (6, 5, 7), (3, 3, 4)), (1, (10, 3, 4), (5, 3, 2)),
+                                         (2, (24, 20, 20), (10, 10, 10))])
+def test_asm_overlap1_matches_oracle(wo, flow, bs, dims, box):
+    """PCASM (restricted, overlap 1) + ILU(0) on box sub-domains: PC apply, refactor, and a GMRES(30) solve against
+    the oracle (whose ASM is pinned to the definition in test_oracle_linalg_independent.py); fewer iterations than
+    block Jacobi on the same sub-domains"""
+    import ctypes as C
+    from test_gpu_fused import box_blocks
+    m, A, rowptr, colidx, val = random_bsr(wo, dims, bs, SEED + 31 + bs, diag_boost=3.0)
+    _, y0, region, prm = make_problem(wo, dims=dims)
+    sim = gpu_flow(wo, flow, m, prm, y0, region)
+    nb = m.nowned
+    M = flow.Mat.create(sim, nb, nb, bs, rowptr, colidx, val)
+    bor = box_blocks(dims, box)
+    pc_ref = wo.lib().wo_pc_create(A, wo.PC_ASM_ILU0, wo.ip(bor))
+    pc = flow.PC(M, flow.PC_ASM_ILU0, 1, bor)
+    rng = np.random.default_rng(SEED)
+    r = rng.uniform(-1, 1, nb * bs)
+    z0, z1 = np.zeros(nb * bs), np.zeros(nb * bs)
+    wo.lib().wo_pc_apply(pc_ref, wo.dp(r), wo.dp(z0))
+    pc.apply(r, z1)
+    assert relerr(z1, z0) < 1e-12
+    o = wo.KspOpts()
+    o.type, o.restart, o.maxit, o.rtol, o.atol, o.dtol = 0, 30, 10000, 1e-8, 1e-50, 1e5
+    x0, x1 = np.zeros(nb * bs), np.zeros(nb * bs)
+    its0, rn0 = C.c_int(), C.c_double()
+    reason0 = wo.lib().wo_ksp_solve(A, pc_ref, C.byref(o), wo.dp(r), wo.dp(x0), C.byref(its0), C.byref(rn0))
+    reason, its, rn = flow.ksp_solve(M, pc, r, x1, flow.ksp_opts(type=0, restart=30, maxit=10000, rtol=1e-8))
+    assert reason == reason0 > 0 and abs(its - its0.value) <= 1 and relerr(x1, x0) < 1e-6
+    pcb = flow.PC(M, flow.PC_BJACOBI_ILU0, 1, bor)
+    xb = np.zeros(nb * bs)
+    _, its_bj, _ = flow.ksp_solve(M, pcb, r, xb, flow.ksp_opts(type=0, restart=30, maxit=10000, rtol=1e-8))
+    assert its <= its_bj
+    pcb.destroy()
+    M.set_values(val * 1.5)
+    assert pc.refactor() == 0
+    pc.apply(r, z1)
+    assert relerr(z1, z0 / 1.5) < 1e-12
+    wo.lib().wo_pc_destroy(pc_ref)
+    pc.destroy()
+    M.destroy()
+    wo.lib().wo_bsr_destroy(A)
+    sim.destroy()

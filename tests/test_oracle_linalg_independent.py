@@ -143,3 +143,46 @@ def test_krylov_matches_scipy(wo, ksp):
     assert 0.3 * count[0] <= its.value <= 3 * max(count[0], 1), (its.value, count[0])
     wo.lib().wo_pc_destroy(pc)
     wo.lib().wo_bsr_destroy(A)
+
+
+@pytest.mark.parametrize("bs,box", [(2, (2, 3, 3)), (1, (4, 3, 1)), (3, (2, 2, 2))])
+def test_asm_overlap1_matches_definition(wo, bs, box):
+    """restricted additive Schwarz with overlap 1 from its definition: for every sub-domain, the dense ILU(0) of the
+    matrix restricted to the sub-domain plus one layer of matrix neighbours (rows in ascending order), applied to the
+    restricted residual; only the owned rows are kept"""
+    dims = (4, 3, 3)
+    A, S, keep = random_system(wo, dims, bs, SEED + 40 + bs)
+    nb = A.contents.nb
+    idx = np.arange(nb)
+    i, j, k = idx % dims[0], (idx // dims[0]) % dims[1], idx // (dims[0] * dims[1])
+    key = (i // box[0]) + 10 * (j // box[1]) + 100 * (k // box[2])
+    bor = np.unique(key, return_inverse=True)[1].astype(np.int32)
+    B = S.tobsr(blocksize=(bs, bs))
+    r = np.random.default_rng(5).uniform(-1, 1, nb * bs)
+    ref = np.zeros_like(r)
+    for b in range(bor.max() + 1):
+        own = np.flatnonzero(bor == b)
+        ext = sorted(set(own) | {int(B.indices[q]) for row in own for q in range(B.indptr[row], B.indptr[row + 1])})
+        assert len(ext) > len(own)
+        dof = np.concatenate([np.arange(e * bs, (e + 1) * bs) for e in ext])
+        Sb = sp.csr_matrix(S.toarray()[np.ix_(dof, dof)])
+        L, U, _ = dense_block_ilu0(Sb, bs)
+        zb = np.linalg.solve(U, np.linalg.solve(L, r[dof]))
+        for pos, e in enumerate(ext):
+            if bor[e] == b:
+                ref[e * bs:(e + 1) * bs] = zb[pos * bs:(pos + 1) * bs]
+    pc = wo.lib().wo_pc_create(A, wo.PC_ASM_ILU0, wo.ip(bor))
+    assert pc
+    z = np.zeros_like(r)
+    wo.lib().wo_pc_apply(pc, wo.dp(r), wo.dp(z))
+    assert np.abs(z - ref).max() <= 1e-11 * np.abs(ref).max()
+    # one sub-domain: the extension adds nothing, ASM == global ILU(0)
+    pc1 = wo.lib().wo_pc_create(A, wo.PC_ASM_ILU0, None)
+    pc2 = wo.lib().wo_pc_create(A, wo.PC_BJACOBI_ILU0, None)
+    z1, z2 = np.zeros_like(r), np.zeros_like(r)
+    wo.lib().wo_pc_apply(pc1, wo.dp(r), wo.dp(z1))
+    wo.lib().wo_pc_apply(pc2, wo.dp(r), wo.dp(z2))
+    assert np.array_equal(z1, z2)
+    for p in (pc, pc1, pc2):
+        wo.lib().wo_pc_destroy(p)
+    wo.lib().wo_bsr_destroy(A)

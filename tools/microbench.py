@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--global-ilu", action="store_true")
     ap.add_argument("--restarts", type=int, nargs="*", default=[])
     ap.add_argument("--skip-pcs", action="store_true")
+    ap.add_argument("--fused-only", action="store_true", help="only the full GMRES(30) solve with the persistent kernel")
+    ap.add_argument("--asm", action="store_true", help="PCASM (restricted, overlap 1) + ILU(0) on the same sub-domains")
     a = ap.parse_args()
     import torch
     import bench
@@ -59,12 +61,14 @@ def main():
         pcs += [("pbjacobi", flow.PC_PBJACOBI, None, 30), ("none", flow.PC_NONE, None, 30)]
     if a.global_ilu:
         pcs.append(("ilu0_global", flow.PC_BJACOBI_ILU0, None, 5))
+    if a.asm:
+        pcs.append(("asm1_ilu0_cube%d" % a.cube, flow.PC_ASM_ILU0, prob.blocks(m, a.cube), 30))
     b = torch.from_numpy(F0).cuda()
     sol = torch.empty_like(b)
     for label, pct, bor, reps in pcs:
         if label.startswith("ilu0_cube"):
             # the persistent kernel (one launch per solve) against the launch-per-operation solver
-            for fused in (2, 0):
+            for fused in ((2,) if a.fused_only else (2, 0)):
                 L.wb_ksp_set_fused(fused)
                 pcf = flow.PC(J, pct, 1, bor)
                 o = flow.ksp_opts(type=flow.KSP_GMRES, maxit=20000, rtol=1e-5)
@@ -78,6 +82,8 @@ def main():
                     "breakdown_ctas_min_mean_max": sim.ksp_breakdown_ctas(), "breakdown_us": sim.ksp_breakdown()}
                 pcf.destroy()
             L.wb_ksp_set_fused(1)
+            if a.fused_only:
+                continue
         pc = flow.PC(J, pct, 1, bor)
         t, c = timed("pc_apply", lambda: pc.apply(x, z), reps)
         out["pc_apply_%s_us" % label] = 1e3 * t / c
@@ -94,6 +100,15 @@ def main():
             reason, its, rn = flow.ksp_solve(J, pc, b, sol, o)
             t, c = sim.timer("ksp_solve")
             out["%s_%s_us_per_it" % ("gmres" if ksp == flow.KSP_GMRES else "bcgs", label)] = 1e3 * t / max(its, 1)
+        if label.startswith("asm1"):
+            # full solves to rtol 1e-5 (launch-per-operation solver; the persistent kernel has no overlap support)
+            for ksp, nm in ((flow.KSP_GMRES, "gmres30"), (flow.KSP_BCGS, "bcgs")):
+                o = flow.ksp_opts(type=ksp, maxit=20000, rtol=1e-5)
+                flow.ksp_solve(J, pc, b, sol, o)
+                L.wb_timer_reset(sim.h)
+                reason, its, rn = flow.ksp_solve(J, pc, b, sol, o)
+                t, c = sim.timer("ksp_solve")
+                out["%s_full_%s" % (nm, label)] = {"its": its, "reason": reason, "rnorm": rn, "ms": t, "us_per_it": 1e3 * t / max(its, 1)}
         if label.startswith("ilu0_cube"):
             for rs in a.restarts:
                 o = flow.ksp_opts(type=flow.KSP_GMRES, restart=rs, maxit=20000, rtol=1e-5)

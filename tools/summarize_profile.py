@@ -4,6 +4,9 @@ into the small text summaries committed under profiles/:
     python tools/summarize_profile.py <tag>
 -> profiles/<tag>_launch_shares.txt   per-kernel launch count, total / average device time, share of the run
 -> profiles/<tag>_ncu_metrics.csv     selected `ncu --set full` metrics of the captured kernels (first 2 per kernel)
+-> profiles/<tag>_<part>_ncu_metrics.csv   the same for the other captures of the call (<tag>_fused, <tag>_k4);
+   a capture may come back as the raw page already exported on the GPU box (<tag>_<part>_raw.csv) when the
+   .ncu-rep is too large to travel
 """
 import collections
 import csv
@@ -20,7 +23,15 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
            "smsp__inst_executed.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
            "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
-           "smsp__average_warp_latency_issue_stalled_barrier.ratio"]
+           "smsp__average_warp_latency_issue_stalled_barrier.ratio",
+           "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
+           "smsp__average_warp_latency_issue_stalled_membar.ratio",
+           "smsp__average_warp_latency_issue_stalled_wait.ratio",
+           "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio",
+           "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warps_eligible.avg.per_cycle_active",
+           "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers",
+           "launch__occupancy_limit_shared_mem", "sm__maximum_warps_per_active_cycle_pct"]
 
 
 def launches(tag):
@@ -50,15 +61,19 @@ def launches(tag):
     print("wrote", out)
 
 
-def full(tag):
-    rep = os.path.join(ROOT, "gpurun_out", tag + "_full.ncu-rep")
-    if not os.path.exists(rep):
+def full(tag, part="full"):
+    rep = os.path.join(ROOT, "gpurun_out", "%s_%s.ncu-rep" % (tag, part))
+    pre = os.path.join(ROOT, "gpurun_out", "%s_%s_raw.csv" % (tag, part))
+    if os.path.exists(pre):
+        raw = open(pre).read()
+    elif os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = list(csv.reader([l for l in raw.splitlines() if not l.startswith("==")]))
     hdr, units = rows[0], rows[1]
     cols = [hdr.index("Kernel Name")] + [hdr.index(m) for m in METRICS if m in hdr]
-    out = os.path.join(ROOT, "profiles", tag + "_ncu_metrics.csv")
+    out = os.path.join(ROOT, "profiles", tag + ("_ncu_metrics.csv" if part == "full" else "_%s_ncu_metrics.csv" % part))
     seen = {}
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
@@ -75,4 +90,5 @@ def full(tag):
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     launches(sys.argv[1])
-    full(sys.argv[1])
+    for part in ("full", "fused", "k4"):
+        full(sys.argv[1], part)

@@ -343,6 +343,7 @@ struct FusedArgs {
   const int32_t *push_ptr, *push_row, *push_rank, *push_off;
   int *fseq;
   unsigned long long *prof;
+  int jitter;  // test aid (WB_FUSED_JITTER = 2^k ns): random per-thread delays at every phase boundary
 };
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
@@ -691,6 +692,10 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   }
 #define FZ_STAMP(k)                  \
   do {                               \
+    if (a.jitter) {                  \
+      const unsigned h_ = ((unsigned)clock() + tid * 40503u + cta * 9973u) * 2654435761u; \
+      __nanosleep((h_ >> 12) & (unsigned)(a.jitter - 1)); \
+    }                                \
     if (profiler) {                  \
       const unsigned long long t_ = fz_now(); \
       s_prof[k] += t_ - s_prof[8];   \
@@ -1184,6 +1189,14 @@ int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b
   a.upd = {hcol, H, cs, sn, rs, scal, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, m, o->maxit};
   a.yv = yv;
   a.prof = w.d_prof;
+  {
+    static int jitter = -1;
+    if (jitter < 0) {
+      const char *e = getenv("WB_FUSED_JITTER");
+      jitter = e ? atoi(e) : 0;
+    }
+    a.jitter = jitter;
+  }
   if (multi) {
     a.P = c->p2p.dev;
     a.nneigh = c->halo.nneigh;

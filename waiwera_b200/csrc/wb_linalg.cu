@@ -1069,10 +1069,37 @@ static void level_schedule(int nb, const std::vector<int32_t> &rowptr, const std
 }
 
 
+// additive Schwarz: rows of the residual -> the extended numbering; owned rows of the sub-domain solutions -> z
+__global__ void k_asm_gather(const double *__restrict__ r, const int32_t *__restrict__ ext_row, int ne, int bs,
+                             double *__restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)ne * bs) return;
+  const int e = (int)(i / bs), k = (int)(i - (size_t)e * bs);
+  out[i] = r[(size_t)ext_row[e] * bs + k];
+}
+__global__ void k_asm_scatter(const double *__restrict__ ze, const int32_t *__restrict__ own, int nb, int bs,
+                              double *__restrict__ z) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)nb * bs) return;
+  const int row = (int)(i / bs), k = (int)(i - (size_t)row * bs);
+  z[i] = ze[(size_t)own[row] * bs + k];
+}
+
+static bool g_skip_fused_plan = false;  // set while the inner PC of an additive Schwarz PC is built
+
 static int pc_numeric(wb_pc *pc) {
   wb_mat *A = pc->A;
   wb_ctx *c = A->ctx;
   const int nb = pc->nb;
+  if (pc->type == WB_PC_ASM_ILU0) {
+    wb_mat *E = pc->asm_mat;
+    const int bs2 = pc->bs * pc->bs;
+    k_gather_vals<<<wb_grid((size_t)E->nnzb * bs2, 256), 256, 0, c->stream>>>(A->d_val, pc->d_asm_src, E->nnzb, bs2,
+                                                                             E->d_val);
+    WB_LAUNCH(c);
+    E->version++;
+    return pc_numeric(pc->asm_inner);
+  }
   if (pc->type == WB_PC_PBJACOBI) {
     const int grid = wb_grid(nb, 128);
     switch (pc->bs) {
@@ -1111,8 +1138,10 @@ extern "C" int wb_pc_destroy(wb_pc *pc) {
   cudaStreamSynchronize(pc->A->ctx->stream);
   void *ptrs[] = {pc->d_dinv, pc->d_rowptr, pc->d_colidx, pc->d_diag, pc->d_src, pc->d_sched_f, pc->d_sched_b,
                   pc->d_val, pc->d_flag, pc->d_ticket, pc->d_blk, pc->d_lev, pc->d_blk_rows, pc->d_stream,
-                  pc->d_repack};
+                  pc->d_repack, pc->d_asm_src, pc->d_asm_row, pc->d_asm_own, pc->d_asm_r, pc->d_asm_z};
   for (void *p : ptrs) cudaFree(p);
+  if (pc->asm_inner) wb_pc_destroy(pc->asm_inner);
+  if (pc->asm_mat) wb_mat_destroy(pc->asm_mat);
   wb_fused_free(pc);
   delete pc;
   return 0;
@@ -1122,12 +1151,76 @@ extern "C" int wb_pc_destroy(wb_pc *pc) {
 extern "C" int wb_pc_setup(wb_mat *A, int type, int nblocks, const int32_t *block_of_row, wb_pc **out) {
   wb_ctx *c = A->ctx;
   WB_CUDA(cudaSetDevice(c->device));
-  WB_CHECK(type >= WB_PC_NONE && type <= WB_PC_BJACOBI_ILU0, "wb_pc_setup: unknown type %d", type);
+  WB_CHECK(type >= WB_PC_NONE && type <= WB_PC_ASM_ILU0, "wb_pc_setup: unknown type %d", type);
   wb_pc *pc = new wb_pc();
   pc->A = A; pc->type = type; pc->nb = A->nb; pc->bs = A->bs; pc->nblocks = std::max(nblocks, 1);
   const int nb = A->nb, bs2 = A->bs * A->bs;
   if (type == WB_PC_PBJACOBI) {
     WB_CUDA(cudaMalloc(&pc->d_dinv, sizeof(double) * (size_t)nb * bs2));
+  } else if (type == WB_PC_ASM_ILU0) {
+    // PCSetUp_ASM with overlap 1: every sub-domain grows by the columns of its rows (MatIncreaseOverlap), rows in
+    // ascending order (sorted index sets); the sub-matrices A[E_b, E_b] are laid side by side and factored as the
+    // block-Jacobi ILU(0) of that block-diagonal matrix, so the sub-domain resident solve is reused unchanged.
+    std::vector<int32_t> blk(nb, 0);
+    if (block_of_row) blk.assign(block_of_row, block_of_row + nb);
+    else if (pc->nblocks > 1)
+      for (int i = 0; i < nb; i++) blk[i] = (int)(((int64_t)i * pc->nblocks) / nb);
+    int nblk = 0;
+    for (int i = 0; i < nb; i++) nblk = std::max(nblk, blk[i] + 1);
+    std::vector<std::vector<int32_t>> ext(nblk);
+    for (int i = 0; i < nb; i++) {
+      std::vector<int32_t> &e = ext[blk[i]];
+      for (int k = A->h_rowptr[i]; k < A->h_rowptr[i + 1]; k++)
+        if (A->h_colidx[k] < nb) e.push_back(A->h_colidx[k]);  // ghost columns: rows of another rank, not fetched
+      e.push_back(i);
+    }
+    std::vector<int32_t> ext_row, ext_blk, own(nb, -1), rowptr(1, 0), colidx, src, loc(nb, -1);
+    for (int b = 0; b < nblk; b++) {
+      std::vector<int32_t> &e = ext[b];
+      std::sort(e.begin(), e.end());
+      e.erase(std::unique(e.begin(), e.end()), e.end());
+      const int e0 = (int)ext_row.size();
+      for (size_t q = 0; q < e.size(); q++) loc[e[q]] = e0 + (int)q;
+      for (size_t q = 0; q < e.size(); q++) {
+        const int i = e[q];
+        ext_row.push_back(i);
+        ext_blk.push_back(b);
+        if (blk[i] == b) own[i] = e0 + (int)q;
+        for (int k = A->h_rowptr[i]; k < A->h_rowptr[i + 1]; k++) {
+          const int col = A->h_colidx[k];
+          if (col < nb && loc[col] >= 0) {
+            colidx.push_back(loc[col]);
+            src.push_back(k);
+          }
+        }
+        rowptr.push_back((int32_t)colidx.size());
+      }
+      for (int32_t i : e) loc[i] = -1;
+      std::vector<int32_t>().swap(e);
+    }
+    pc->asm_ne = (int)ext_row.size();
+    int rc = wb_mat_create(c, pc->asm_ne, pc->asm_ne, A->bs, (int)colidx.size(), rowptr.data(), colidx.data(), nullptr,
+                           &pc->asm_mat);
+    if (rc == 0) rc = upload(&pc->d_asm_src, src);
+    if (rc == 0) rc = upload(&pc->d_asm_row, ext_row);
+    if (rc == 0) rc = upload(&pc->d_asm_own, own);
+    if (rc == 0 && cudaMalloc(&pc->d_asm_r, sizeof(double) * (size_t)pc->asm_ne * A->bs) != cudaSuccess) rc = 1;
+    if (rc == 0 && cudaMalloc(&pc->d_asm_z, sizeof(double) * (size_t)pc->asm_ne * A->bs) != cudaSuccess) rc = 1;
+    if (rc == 0) {
+      const int bs2v = A->bs * A->bs;
+      k_gather_vals<<<wb_grid((size_t)colidx.size() * bs2v, 256), 256, 0, c->stream>>>(A->d_val, pc->d_asm_src,
+                                                                                      (int)colidx.size(), bs2v,
+                                                                                      pc->asm_mat->d_val);
+      g_skip_fused_plan = true;
+      rc = wb_pc_setup(pc->asm_mat, WB_PC_BJACOBI_ILU0, nblk, ext_blk.data(), &pc->asm_inner);
+      g_skip_fused_plan = false;
+    }
+    if (rc) {
+      wb_pc_destroy(pc);
+      return rc ? rc : 1;
+    }
+    *out = pc;
+    return 0;
   } else if (type == WB_PC_BJACOBI_ILU0) {
     std::vector<int32_t> blk(nb, 0);
     if (block_of_row) blk.assign(block_of_row, block_of_row + nb);
@@ -1179,7 +1272,8 @@ extern "C" int wb_pc_setup(wb_mat *A, int type, int nblocks, const int32_t *bloc
     if (nblk_used > 1 && (size_t)maxrows * A->bs * sizeof(double) <= 160 * 1024) {
       WB_TRY(build_block_streams(pc, blk, rowptr, colidx, diag));
       pc->blocked = true;
-      WB_TRY(wb_fused_build(pc, blk));  // leaves pc->fused null when the sub-domains do not fit the resident kernel
+      if (!g_skip_fused_plan)
+        WB_TRY(wb_fused_build(pc, blk));  // leaves pc->fused null when the sub-domains do not fit the resident kernel
     }
   }
   int rc;
@@ -1222,6 +1316,16 @@ int wb_pc_apply_dev(wb_pc *pc, const double *d_r, double *d_z, const int *done) 
   if (pc->type == WB_PC_NONE) {
     if (d_r != d_z)
       WB_CUDA(cudaMemcpyAsync(d_z, d_r, sizeof(double) * (size_t)nb * pc->bs, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+  }
+  if (pc->type == WB_PC_ASM_ILU0) {
+    const size_t ne = (size_t)pc->asm_ne * pc->bs, n = (size_t)nb * pc->bs;
+    k_asm_gather<<<wb_grid(ne, 256), 256, 0, c->stream>>>(d_r, pc->d_asm_row, pc->asm_ne, pc->bs, pc->d_asm_r);
+    WB_LAUNCH(c);
+    WB_TRY(wb_pc_apply_dev(pc->asm_inner, pc->d_asm_r, pc->d_asm_z, done));
+    k_asm_scatter<<<wb_grid(n, 256), 256, 0, c->stream>>>(pc->d_asm_z, pc->d_asm_own, nb, pc->bs, d_z);
+    WB_LAUNCH(c);
+    WB_CUDA(cudaGetLastError());
     return 0;
   }
   if (pc->type == WB_PC_PBJACOBI) {

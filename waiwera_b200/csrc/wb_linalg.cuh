@@ -70,6 +70,13 @@ struct wb_pc {
   int stage_words = 0, nstage = 0, desc_words = 0, solve_threads = 128;
   long long *d_trace = nullptr;  // debug timeline of the sub-domain solve (wb_debug_pc_trace)
   struct WbFusedPlan *fused = nullptr;
+  // restricted additive Schwarz, overlap 1 (WB_PC_ASM_ILU0): the matrices of the extended sub-domains side by side as
+  // one block-diagonal matrix, its block-Jacobi ILU(0), and the maps between the two row numberings
+  wb_mat *asm_mat = nullptr;
+  wb_pc *asm_inner = nullptr;
+  int asm_ne = 0;
+  int32_t *d_asm_src = nullptr, *d_asm_row = nullptr, *d_asm_own = nullptr;
+  double *d_asm_r = nullptr, *d_asm_z = nullptr;
   // host copies of the sub-domain tables (symbolic), kept for the fused plan
   std::vector<int4> h_blk, h_lev;
   std::vector<int32_t> h_blk_rows;  // sub-domain-resident persistent GMRES (wb_fused.cu); null: not available

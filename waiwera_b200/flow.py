@@ -17,7 +17,7 @@ THERMO_IAPWS, THERMO_IFC67 = 0, 1
 EOS_WE, EOS_W, EOS_WCE, EOS_WAE = 0, 1, 2, 3
 RP_FULLY_MOBILE, RP_LINEAR, RP_PICKENS, RP_COREY, RP_GRANT, RP_VAN_GENUCHTEN, RP_TABLE = range(7)
 CP_ZERO, CP_LINEAR, CP_VAN_GENUCHTEN, CP_TABLE = range(4)
-PC_NONE, PC_PBJACOBI, PC_BJACOBI_ILU0 = 0, 1, 2
+PC_NONE, PC_PBJACOBI, PC_BJACOBI_ILU0, PC_ASM_ILU0 = 0, 1, 2, 3
 KSP_GMRES, KSP_BCGS = 0, 1
 METHOD_BEULER, METHOD_BDF2, METHOD_DIRECTSS = 0, 1, 2
 
