@@ -81,7 +81,7 @@ module waiwera_b200
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
        wb_mat_set_values, wb_mat_get_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
-       wb_pc_destroy, wb_ksp_solve, wb_ksp_set_check_every, wb_ksp_set_fused, wb_set_pc_blocks, wb_newton_solve_be, wb_timer_get, &
+       wb_pc_destroy, wb_ksp_solve, wb_ksp_set_check_every, wb_ksp_set_fused, wb_ksp_set_fused_norm, wb_set_pc_blocks, wb_newton_solve_be, wb_timer_get, &
        wb_set_tracers, wb_set_tracer_injection, wb_tracer_cell_balances, wb_tracer_setup_linear, wb_tracer_solve, &
        wb_timer_reset, wb_timers_enable, wb_ksp_fused_profile, wb_launch_count, wb_stream
 
@@ -551,6 +551,13 @@ module waiwera_b200
        integer(c_int), value :: on
        integer(c_int) :: ierr
      end function wb_ksp_set_fused
+
+     ! 0: VecNorm as a second reduction; 1: norm from the dot-product pass on multi-GPU solves; 2: always
+     function wb_ksp_set_fused_norm(mode) bind(C, name="wb_ksp_set_fused_norm") result(ierr)
+       import :: c_int
+       integer(c_int), value :: mode
+       integer(c_int) :: ierr
+     end function wb_ksp_set_fused_norm
 
      ! per-phase device time of the persistent GMRES kernel (nanoseconds, 7 values)
      function wb_ksp_fused_profile(ctx, ns7, reset) bind(C, name="wb_ksp_fused_profile") result(ierr)

@@ -307,6 +307,17 @@ int wb_ksp_set_check_every(int k);
    block systems with many sub-domains per SM to the launch-per-operation kernels); also: environment WB_FUSED.
    Takes effect at the next PC set-up. */
 int wb_ksp_set_fused(int on);
+/* Norm of the new Krylov vector inside the persistent kernel.  PETSc's GMRES (classical Gram-Schmidt, no refinement)
+   takes VecNorm of the orthogonalised vector: a second all-reduce per iteration.  Mode 0 does exactly that.  Mode 2
+   takes the norm from the first reduction instead, |w|^2 - sum_j h_j^2 with |w|^2 accumulated on the dot-product pass
+   (the "Pythagorean" form used by low-synchronisation GMRES variants), and falls back to the explicit norm whenever
+   the difference is below 1e-4 |w|^2 or the estimated loss of orthogonality of the basis (eps times the square of the
+   residual reduction inside the restart cycle) would change it by more than 1e-6; what is left of the second reduction is a barrier inside each GPU.  The value
+   differs from VecNorm's by rounding times |w|^2 / |w'|^2 and by the loss of orthogonality of the basis, so iteration
+   counts can move by a few in thousands; converged solutions agree to the solver tolerance.  Mode 1 (default) uses
+   mode 2 only when the solve spans several GPUs, where it removes an NVLink all-gather from every iteration.
+   Environment: WB_FUSED_NORM. */
+int wb_ksp_set_fused_norm(int mode);
 
 /* ---- Newton (SNESSolve as configured by timestepper.F90:1552-1641) ------ */
 typedef struct {

@@ -30,8 +30,9 @@ def box_blocks(dims, box):
     return inv.astype(np.int32)
 
 
-def solve_three_ways(wo, flow, sim, M, A, bor, b, restart, maxit, rtol):
-    """oracle, launch-per-operation GPU solver, persistent kernel"""
+def solve_three_ways(wo, flow, sim, M, A, bor, b, restart, maxit, rtol, norm_mode=0):
+    """oracle, launch-per-operation GPU solver, persistent kernel (norm_mode 0: VecNorm as a second reduction, the
+    reference's arithmetic; 2: the norm from the dot-product pass)"""
     L = flow._lib.lib()
     n = len(b)
     pc_ref = wo.lib().wo_pc_create(A, 2, wo.ip(bor))
@@ -43,6 +44,7 @@ def solve_three_ways(wo, flow, sim, M, A, bor, b, restart, maxit, rtol):
     wo.lib().wo_pc_destroy(pc_ref)
     res = [(reason0, its0.value, rn0.value, x0)]
     opts = flow.ksp_opts(type=0, restart=restart, maxit=maxit, rtol=rtol)
+    L.wb_ksp_set_fused_norm(norm_mode)
     for fused in (0, 2):   # 2: the persistent kernel wherever it can run (1 = automatic choice)
         L.wb_ksp_set_fused(fused)
         pc = flow.PC(M, 2, 1, bor)
@@ -52,6 +54,7 @@ def solve_three_ways(wo, flow, sim, M, A, bor, b, restart, maxit, rtol):
         res.append((reason, its, rn, x, sim.launches() - launches))
         pc.destroy()
     L.wb_ksp_set_fused(1)
+    L.wb_ksp_set_fused_norm(1)
     return res
 
 
@@ -68,8 +71,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("norm_mode", [0, 2])
 @pytest.mark.parametrize("case", CASES)
-def test_fused_gmres_matches_oracle_and_unfused(wo, flow, case):
+def test_fused_gmres_matches_oracle_and_unfused(wo, flow, case, norm_mode):
     dims, bs = case["dims"], case["bs"]
     m, A, rowptr, colidx, val = random_bsr(wo, dims, bs, SEED + 21, diag_boost=3.0)
     _, y0, region, prm = make_problem(wo, dims=dims)
@@ -78,7 +82,8 @@ def test_fused_gmres_matches_oracle_and_unfused(wo, flow, case):
     M = flow.Mat.create(sim, nb, nb, bs, rowptr, colidx, val)
     bor = box_blocks(dims, case["box"])
     b = np.random.default_rng(SEED + 5).uniform(-1, 1, nb * bs)
-    ref, unfused, fused = solve_three_ways(wo, flow, sim, M, A, bor, b, case["restart"], case["maxit"], case["rtol"])
+    ref, unfused, fused = solve_three_ways(wo, flow, sim, M, A, bor, b, case["restart"], case["maxit"], case["rtol"],
+                                           norm_mode)
     assert fused[4] <= 3, "the persistent path is one solver launch (+ the matrix refresh)"
     assert unfused[4] > 3 * max(unfused[1], 1)
     assert ref[0] == unfused[0] == fused[0]

@@ -26,4 +26,14 @@ PY
 for cfg in $2; do
   if [ "$cfg" = "2" ]; then run c2 --no-cpu-baseline; fi
   if [ "$cfg" = "5" ]; then run c5 --config 5 --no-cpu-baseline; fi
+  if [ "$cfg" = "tests" ]; then
+    timeout -k 10 900 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2s_multi_tests_n$N.log 2>&1; echo "rc=$?" >> gpurun_out/r2s_multi_tests_n$N.log
+    tail -3 gpurun_out/r2s_multi_tests_n$N.log
+  fi
+  if [ "$cfg" = "ref" ]; then
+    # the CPU arm launched the way the driver launches it at N > 1: rank 0 alone runs, on all host threads
+    timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/r2s_ref_n$N.json 2> gpurun_out/r2s_ref_n$N.err
+    grep -a '^{' gpurun_out/r2s_ref_n$N.json | tail -1 | cut -c1-300
+  fi
 done

@@ -116,6 +116,7 @@ SIGNATURES = {
     "wb_tracer_setup_linear": (i, [vp, d, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "wb_tracer_solve": (i, [vp, C.POINTER(KspOpts), i, i, d, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i), C.POINTER(i)]),
     "wb_ksp_set_fused": (i, [i]),
+    "wb_ksp_set_fused_norm": (i, [i]),
     "wb_ksp_fused_profile": (i, [vp, C.POINTER(d), i]),
     "wb_timer_get": (i, [vp, C.c_char_p, C.POINTER(d), C.POINTER(i64)]),
     "wb_timer_reset": (i, [vp]),

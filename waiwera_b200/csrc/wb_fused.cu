@@ -31,6 +31,8 @@
 #define FZ_MAXG 4    // sub-domain groups per CTA
 #define FZ_SLICE WB_SELL_SLICE  // rows per sliced-ELL slice (one warp)
 #define FZ_CH 8      // blocks of a row in flight per SpMV round
+#define FZ_PYTH_ORTH 1e-6  // largest estimated relative error of that norm^2 from the basis' loss of orthogonality
+#define FZ_PYTH_MIN 1e-4  // smallest |w'|^2 / |w|^2 for which the norm is taken from the dots (see k_gmres_fused)
 #define FZ_SPIN_LIMIT 20000000000LL  // cycles (~10 s): a lost CTA / peer raises the abort flag instead of hanging the GPU
 
 struct WbFusedPlan {
@@ -77,6 +79,15 @@ static int fused_mode() {
   }
   return g_fused_mode;
 }
+// Norm of the new Krylov vector in the persistent kernel: 0 = always a second reduction (VecNorm, the reference's
+// arithmetic); 1 (default) = from the dots (|w|^2 - sum h_j^2) when the solve spans several GPUs, where it replaces an
+// NVLink all-gather by a barrier inside each GPU; 2 = always.  WB_FUSED_NORM overrides the default.
+static int g_fused_norm = -1;
+extern "C" int wb_ksp_set_fused_norm(int mode) {
+  g_fused_norm = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return 0;
+}
+
 extern "C" int wb_ksp_set_fused(int on) {
   g_fused_mode = on < 0 ? 0 : on;  // 0 off, 1 automatic, 2 wherever it is usable
   return 0;
@@ -343,6 +354,7 @@ struct FusedArgs {
   const int32_t *push_ptr, *push_row, *push_rank, *push_off;
   int *fseq;
   unsigned long long *prof;
+  int pyth;    // norm of the new Krylov vector from |w|^2 - sum h_j^2 (one machine-wide reduction per iteration)
   int jitter;  // test aid (WB_FUSED_JITTER = 2^k ns): random per-thread delays at every phase boundary
 };
 
@@ -576,6 +588,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   double *s_h = reinterpret_cast<double *>(smem + a.off_gm);          // [KRY_MAXV + 2] dots / Hessenberg column
   double *s_cs = s_h + KRY_MAXV + 2, *s_sn = s_cs + KRY_MAXV, *s_rs = s_sn + KRY_MAXV;  // rs: [KRY_MAXV + 1]
   double *s_H = s_rs + KRY_MAXV + 2;                                  // [(m + 1) * m]
+  double *s_pn = reinterpret_cast<double *>(smem + a.off_misc + 280);  // [3] norm^2 from the dots, "use it" flag, cycle-start residual
   FzState *s_st = reinterpret_cast<FzState *>(smem + a.off_misc + 448);
   volatile int *s_stop = reinterpret_cast<volatile int *>(smem + a.off_misc + 324);
   int *s_nrec = reinterpret_cast<int *>(smem + a.off_misc + 328);     // [FZ_MAXG]
@@ -685,6 +698,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   int qrec = 0, ri = 0;  // records this group has consumed (slot = qrec % FZ_NBAR, parity = (qrec / FZ_NBAR) & 1), position in its list
   // phase timers of CTA 0 (thread 0), kept in shared memory
   unsigned long long *s_prof = reinterpret_cast<unsigned long long *>(smem + a.off_prof);  // [16]; [8] = previous stamp
+  const bool pyth = a.pyth != 0;
   const bool profiler = (tid == 0);  // every CTA keeps its own phase times (CTA 0's are the ones the ABI reports)
   if (profiler) {
     for (int k = 0; k < 16; k++) s_prof[k] = 0;
@@ -841,7 +855,8 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
   };
 
   // ---- dots of w (this CTA's rows) against nv vectors V_j = V + j * ldv -> part[cta][j]
-  auto dots = [&](const double *w, const double *V, size_t ldv, int nv, double *s_out) {
+  auto dots = [&](const double *w, const double *V, size_t ldv, int nv, double *s_out, bool with_ww) {
+    double accw = 0.0;  // with_ww: w . w on the same pass, stored as sum number nv
     for (int j0 = 0; j0 < nv; j0 += 8) {
       const int nvc = min(8, nv - j0);
       double acc[8];
@@ -867,12 +882,22 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
           acc[k] += wj.x * v2[k].x;
           acc[k] += wj.y * v2[k].y;
         }
+        if (with_ww && j0 == 0) {
+          accw += wi.x * wi.x;
+          accw += wi.y * wi.y;
+          accw += wj.x * wj.x;
+          accw += wj.y * wj.y;
+        }
       }
       if (tid == 0) {  // unaligned head / tail element
-        if (eb > e0)
+        if (eb > e0) {
           for (int k = 0; k < nvc; k++) acc[k] += w[e0] * V[(size_t)(j0 + k) * ldv + e0];
-        if (ee < e1 && ee >= eb)
+          if (with_ww && j0 == 0) accw += w[e0] * w[e0];
+        }
+        if (ee < e1 && ee >= eb) {
           for (int k = 0; k < nvc; k++) acc[k] += w[e1 - 1] * V[(size_t)(j0 + k) * ldv + e1 - 1];
+          if (with_ww && j0 == 0) accw += w[e1 - 1] * w[e1 - 1];
+        }
       }
 #pragma unroll
       for (int k = 0; k < 8; k++) {
@@ -880,8 +905,12 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
         if (lane == 0 && k < nvc) s_red[warp * KRY_MAXV + j0 + k] = sres;
       }
     }
+    if (with_ww) {
+      const double sres = warp_sum(accw);
+      if (lane == 0) s_red[warp * KRY_MAXV + nv] = sres;
+    }
     bar_sync_named(FZ_BAR_ALL, nc);
-    if (tid < nv) {
+    if (tid < nv + (with_ww ? 1 : 0)) {
       double sres = 0.0;
       for (int wq = 0; wq < nwarps; wq++) sres += s_red[wq * KRY_MAXV + tid];
       s_out[tid] = sres;
@@ -977,7 +1006,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
     FZ_STAMP(0);
     bar_sync_named(FZ_BAR_ALL, nc);
     push(w_new);
-    dots(w_new, w_new, 0, 1, s_h);
+    dots(w_new, w_new, 0, 1, s_h, false);
     FZ_STAMP(1);
     fz_reduce_ll(a, R, 1, ++rseqB, 1, s_h, s_red, true, multi, bseq + 1, WB_P2P_SLOT_FB, 1, cta, tid, nc);
     if (tid == 0) {  // k_gmres_begin
@@ -1000,6 +1029,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       }
       s_st->scal1 = res > 0.0 ? 1.0 / res : 1.0;
       s_rs[0] = res;
+      s_pn[2] = res;  // residual norm at the start of this restart cycle
     }
     bar_sync_named(FZ_BAR_ALL, nc);
     bseq++;
@@ -1019,20 +1049,44 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       sp_phase(1, w_old, s_st->scal1, a.V + (size_t)it * a.ld, w_new);
       FZ_STAMP(0);
       bar_sync_named(FZ_BAR_ALL, nc);
-      dots(w_new, a.V, a.ld, it + 1, s_h);
+      dots(w_new, a.V, a.ld, it + 1, s_h, pyth);
       FZ_STAMP(1);
-      fz_reduce_ll(a, R, 0, ++rseqA, it + 1, s_h, s_red, false, multi, aseq + 1, WB_P2P_SLOT_FA, WB_P2P_MAXV, cta, tid, nc);
+      fz_reduce_ll(a, R, 0, ++rseqA, it + 1 + (pyth ? 1 : 0), s_h, s_red, false, multi, aseq + 1, WB_P2P_SLOT_FA, WB_P2P_MAXV, cta,
+                   tid, nc);
       aseq++;
       FZ_STAMP(2);
       if (__ldcg(&a.bar[2])) break;
       if (tid <= it) s_cf[tid] = -s_h[tid];
+      if (pyth && tid == 0) {
+        // |w - sum h_j v_j|^2 = |w|^2 - sum h_j^2 for an orthonormal basis.  Every CTA of every rank evaluates this from
+        // the same reduced numbers with the same instructions, so all take the same branch.  When the difference
+        // cancels below FZ_PYTH_MIN of |w|^2, or the estimated loss of orthogonality of the basis would change it by
+        // more than FZ_PYTH_ORTH, the norm is measured explicitly instead (second reduction, as VecNorm).
+        const double ww = s_h[it + 1];
+        double sh = 0.0;
+        for (int j = 0; j <= it; j++) sh += s_h[j] * s_h[j];
+        const double n2 = ww - sh;
+        // the identity needs an orthonormal basis: classical Gram-Schmidt loses orthogonality like
+        // eps * (residual at the start of the cycle / residual now)^2, which enters n2 as that times |w|^2
+        const double red = s_pn[2] / fmax(s_st->res, 1e-300);
+        s_pn[0] = n2;
+        s_pn[1] = (n2 > FZ_PYTH_MIN * ww && 2.3e-16 * red * red * ww < FZ_PYTH_ORTH * n2) ? 1.0 : 0.0;
+      }
       bar_sync_named(FZ_BAR_ALL, nc);
-      maxpy(w_new, a.V, a.ld, it + 1, s_cf);
+      const bool fast = pyth && s_pn[1] != 0.0;
+      maxpy(w_new, a.V, a.ld, it + 1, fast ? nullptr : s_cf);
       push(w_new);
       FZ_STAMP(3);
-      fz_reduce_ll(a, R, 1, ++rseqB, 1, s_cf, s_red, true, multi, bseq + 1, WB_P2P_SLOT_FB, 1, cta, tid, nc);
+      if (fast) {
+        // no number to exchange: a barrier of this GPU's CTAs orders the rows of w before the next product reads them;
+        // the neighbours' rows arrive through the flagged halo entries
+        fz_reduce_ll(a, R, 1, ++rseqB, 1, s_cf, s_red, true, false, 0, 0, 1, cta, tid, nc);
+      } else {
+        fz_reduce_ll(a, R, 1, ++rseqB, 1, s_cf, s_red, true, multi, bseq + 1, WB_P2P_SLOT_FB, 1, cta, tid, nc);
+        bseq++;
+      }
       if (tid == 0) {
-        fz_gmres_update(u, s_st, s_cf[0], s_h, s_H, s_cs, s_sn, s_rs);
+        fz_gmres_update(u, s_st, fast ? s_pn[0] : s_cf[0], s_h, s_H, s_cs, s_sn, s_rs);
         // end of the cycle (restart length reached or finished): back substitution y = H^-1 rs (k_gmres_solve_y)
         const int itn = s_st->it_inner;
         if (s_st->done || itn >= m) {
@@ -1044,7 +1098,6 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
         }
       }
       bar_sync_named(FZ_BAR_ALL, nc);
-      bseq++;
       hseq++;
       FZ_STAMP(4);
       if (profiler) s_prof[6]++;
@@ -1189,6 +1242,11 @@ int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b
   a.upd = {hcol, H, cs, sn, rs, scal, w.d_st, w.d_done, o->rtol, o->atol, o->dtol, m, o->maxit};
   a.yv = yv;
   a.prof = w.d_prof;
+  if (g_fused_norm < 0) {
+    const char *e = getenv("WB_FUSED_NORM");
+    g_fused_norm = e ? atoi(e) : 1;
+  }
+  a.pyth = (g_fused_norm == 2 || (g_fused_norm == 1 && multi)) ? 1 : 0;
   {
     static int jitter = -1;
     if (jitter < 0) {
