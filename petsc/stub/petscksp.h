@@ -31,6 +31,7 @@ int MPI_Comm_rank(MPI_Comm, int *);
 int MPI_Comm_size(MPI_Comm, int *);
 int MPI_Bcast(void *, int, MPI_Datatype, int, MPI_Comm);
 int MPI_Alltoall(const void *, int, MPI_Datatype, void *, int, MPI_Datatype, MPI_Comm);
+int MPI_Allgather(const void *, int, MPI_Datatype, void *, int, MPI_Datatype, MPI_Comm);
 int MPI_Alltoallv(const void *, const int *, const int *, MPI_Datatype, void *, const int *, const int *, MPI_Datatype, MPI_Comm);
 
 typedef struct _p_PetscObject *PetscObject;

@@ -32,6 +32,7 @@ typedef struct {
   PetscInt nb, ncolb, bs, nnzb;
   PetscInt local_blocks; /* -pc_wb_local_blocks: block-Jacobi sub-domains per GPU (PETSc -pc_bjacobi_local_blocks) */
   PetscInt cube;         /* -pc_wb_subdomain_rows: rows per sub-domain (contiguous ranges), 0 = use local_blocks */
+  PetscInt overlap;      /* -pc_wb_overlap: 0 block Jacobi, 1 restricted additive Schwarz (PCASM default) on the same sub-domains */
   int32_t *rowptr, *colidx;
   double *vals;
 } WbPC;
@@ -112,6 +113,22 @@ static PetscErrorCode WbHaloFromGarray(Mat P, WbPC *w, const PetscInt *garray, P
   }
   PetscCall(WbCheck(wb_set_halo(w->ctx, (int)nneigh, neigh, send_ptr, send_idx, recv_ptr, recv_idx), "wb_set_halo"));
   PetscCall(WbCheck(wb_set_global_offset(w->ctx, ranges[rank] / bs, ranges[size] / bs), "wb_set_global_offset"));
+  { /* NVLink peer memory for the per-iteration exchanges (halo entries, Gram-Schmidt sums): every rank exports its
+       CUDA-IPC blob, all ranks open all of them; on failure (no peer access, ranks on different nodes) the context
+       stays on NCCL and the launch-per-operation solver */
+    int blob = wb_comm_p2p_blob_size();
+    unsigned char *mine, *all;
+    PetscCall(PetscMalloc2(blob, &mine, (size_t)blob * size, &all));
+    if (wb_comm_p2p_export(w->ctx, mine) == 0) {
+      PetscCallMPI(MPI_Allgather(mine, blob, MPI_BYTE, all, blob, MPI_BYTE, comm));
+      if (wb_comm_p2p_open(w->ctx, all) != 0) PetscCall(WbCheck(wb_comm_p2p_disable(w->ctx), "wb_comm_p2p_disable"));
+    } else {
+      PetscCall(PetscMemzero(mine, blob)); /* keep the collective matched: an all-zero blob makes every rank fall back */
+      PetscCallMPI(MPI_Allgather(mine, blob, MPI_BYTE, all, blob, MPI_BYTE, comm));
+      PetscCall(WbCheck(wb_comm_p2p_disable(w->ctx), "wb_comm_p2p_disable"));
+    }
+    PetscCall(PetscFree2(mine, all));
+  }
   PetscCall(PetscFree5(neigh, send_ptr, send_idx, recv_ptr, recv_idx));
   PetscCall(PetscFree2(want, give));
   PetscCall(PetscFree4(rcount, scount, rdisp, sdisp));
@@ -188,7 +205,7 @@ static PetscErrorCode PCSetUp_WB(PC pc) {
       for (i = 0; i < w->nb; i++) block_of_row[i] = (int32_t)(i / w->cube);
       nblocks = (w->nb + w->cube - 1) / w->cube;
     }
-    PetscCall(WbCheck(wb_pc_setup(w->A, WB_PC_BJACOBI_ILU0, (int)nblocks, block_of_row, &w->pc), "wb_pc_setup"));
+    PetscCall(WbCheck(wb_pc_setup(w->A, w->overlap > 0 ? WB_PC_ASM_ILU0 : WB_PC_BJACOBI_ILU0, (int)nblocks, block_of_row, &w->pc), "wb_pc_setup"));
     PetscCall(PetscFree(block_of_row));
   } else {
     int rc;
@@ -221,6 +238,8 @@ static PetscErrorCode PCSetFromOptions_WB(PC pc, PetscOptionItems *items) {
   PetscCall(PetscOptionsInt("-pc_wb_local_blocks", "block-Jacobi sub-domains per GPU", "PCBJacobiSetLocalBlocks", w->local_blocks,
                             &w->local_blocks, NULL));
   PetscCall(PetscOptionsInt("-pc_wb_subdomain_rows", "rows per sub-domain (0: use -pc_wb_local_blocks)", "", w->cube, &w->cube, NULL));
+  PetscCall(PetscOptionsInt("-pc_wb_overlap", "0: block Jacobi; 1: restricted additive Schwarz, overlap 1", "PCASMSetOverlap", w->overlap,
+                            &w->overlap, NULL));
   PetscOptionsHeadEnd();
   PetscFunctionReturn(PETSC_SUCCESS);
 }
