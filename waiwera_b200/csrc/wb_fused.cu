@@ -242,6 +242,7 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
     rec_ptr.assign((size_t)f->ncta * ng + 1, 0);
     recA.clear();
     recB.clear();
+    bool lag_ok = true;
     for (int ct = 0; ct < f->ncta; ct++)
       for (int g = 0; g < ng; g++) {
         const size_t r0 = recA.size();
@@ -283,9 +284,13 @@ int wb_fused_build(wb_pc *pc, const std::vector<int32_t> &blk_of) {
             }
           }
           recA[r0 + i].w = std::max(1, std::min(lag, FZ_NBAR - 1));
+          // the sweep threads ask for record i + 1 before they release record i, so no record may take the space of its
+          // predecessor: a ring of three largest records guarantees that, a smaller one is checked record by record
+          if (P >= 3 && lag < 2) lag_ok = false;
         }
         rec_ptr[(size_t)ct * ng + g + 1] = (int32_t)recA.size();
       }
+    if (!lag_ok) continue;  // fewer groups per CTA = larger rings
     ok = true;
   }
   if (getenv("WB_FUSED_VERBOSE"))
@@ -386,13 +391,24 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 // consumer-side wait for a level record: bounded, so that a broken ring plan raises the abort flag instead of hanging
-__device__ __forceinline__ void fz_mbar_wait(uint64_t *bar, uint32_t parity, int *abort_flag) {
+// (abort_flag = &bar[2]; the first record wait that times out leaves a note for the host's error message in bar[8..11]:
+// which wait, CTA, thread, the record number it waited for)
+__device__ __noinline__ void fz_note_timeout(int *abort_flag, int code, int q) {
+  int *d = abort_flag + 6;
+  if (atomicCAS(d, 0, code) == 0) {
+    d[1] = blockIdx.x;
+    d[2] = threadIdx.x;
+    d[3] = q;
+  }
+  atomicExch(abort_flag, 1);
+}
+__device__ __forceinline__ void fz_mbar_wait(uint64_t *bar, uint32_t parity, int *abort_flag, int q = -1) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   unsigned n = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++n & 1023u) == 0) {
-      if (clock64() - t0 > FZ_SPIN_LIMIT) atomicExch(abort_flag, 1);
+      if (clock64() - t0 > FZ_SPIN_LIMIT) fz_note_timeout(abort_flag, 1, q);
       if (__ldcg(abort_flag)) return;
     }
   }
@@ -738,7 +754,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
         if (si < ns) {
           const int qi = qrec + si;
           const int4 A = rec[2 * (ri + si)], B = rec[2 * (ri + si) + 1];
-          fz_mbar_wait(&fullg[qi & (FZ_NBAR - 1)], (uint32_t)((qi / FZ_NBAR) & 1), &a.bar[2]);
+          fz_mbar_wait(&fullg[qi & (FZ_NBAR - 1)], (uint32_t)((qi / FZ_NBAR) & 1), &a.bar[2], qi);
           const int n = B.y & 255, nk = B.y >> 8, srow0 = B.x;
           const int row = srow0 + lane, li = row - row0;
           if (mode == 0) {
@@ -826,14 +842,14 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       // next record while the others apply the current one; the level barrier then publishes its acquire to everybody.
       if (gtid < ltw && nl > 0) {
         int qi = qrec, rl = ri;
-        fz_mbar_wait(&fullg[qi & (FZ_NBAR - 1)], (uint32_t)((qi / FZ_NBAR) & 1), &a.bar[2]);
+        fz_mbar_wait(&fullg[qi & (FZ_NBAR - 1)], (uint32_t)((qi / FZ_NBAR) & 1), &a.bar[2], qi);
         int4 A = rec[2 * rl], B = rec[2 * rl + 1];
         for (int l = 0; l < nl; l++) {
           const int4 An = rec[2 * (rl + 1)], Bn = rec[2 * (rl + 1) + 1];  // next record's descriptor (table is padded)
           if (gtid < lt)
             ilu_level<BS>(reinterpret_cast<const double *>(ring + A.z), B.x, B.y & 0xffff, (B.y >> 16) != 0, zs, lt, gtid);
           if (waiter && l + 1 < nl)
-            fz_mbar_wait(&fullg[(qi + 1) & (FZ_NBAR - 1)], (uint32_t)(((qi + 1) / FZ_NBAR) & 1), &a.bar[2]);
+            fz_mbar_wait(&fullg[(qi + 1) & (FZ_NBAR - 1)], (uint32_t)(((qi + 1) / FZ_NBAR) & 1), &a.bar[2], qi + 1);
           bar_sync_named(8 + g, ltw);
           qi++;
           rl++;
@@ -1286,9 +1302,12 @@ int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b
   WB_CHECK(e == cudaSuccess, "fused GMRES: cooperative launch failed: %s", cudaGetErrorString(e));
   WB_LAUNCH(c);
   WB_TRY(wb_fetch_state(w));
-  int h_abort = 0;
-  WB_CUDA(wb_memcpy_sync(&h_abort, w.d_bar + 2, sizeof(int), cudaMemcpyDeviceToHost));
-  WB_CHECK(!h_abort, "fused GMRES: grid barrier timed out (a CTA or a peer GPU is missing)");
+  int h_bar[16] = {0};
+  WB_CUDA(wb_memcpy_sync(h_bar, w.d_bar, sizeof(h_bar), cudaMemcpyDeviceToHost));
+  WB_CHECK(!h_bar[2],
+           "fused GMRES: a wait timed out (a CTA or a peer GPU is missing) [%s, CTA %d, thread %d, record %d; %d groups, "
+           "%d records per group]",
+           h_bar[8] == 1 ? "waiting for a record's bulk copy" : "in a reduction", h_bar[9], h_bar[10], h_bar[11], f->ng, f->rec_cap);
   *its = w.h_st->its;
   *reason = w.h_st->reason;
   *rnorm = w.h_st->res;
