@@ -145,9 +145,19 @@ def test_full_size_krylov_solve_matches_oracle(wo, flow):
     its0, rn0 = C.c_int(), C.c_double()
     reason0 = L.wo_ksp_solve(arm.A, pc0, C.byref(o), wo.dp(r0), wo.dp(xc), C.byref(its0), C.byref(rn0))
     assert reason == reason0 == 2             # KSP_CONVERGED_RTOL
-    # restarted GMRES stagnates on this system (~2 100 iterations): the count moves with the rounding of the dot
-    # products (the oracle itself gives 2 093 .. 2 235 for different thread counts); band +-10 %
-    assert abs(its - its0.value) <= 0.10 * its0.value, (its, its0.value)
+    # restarted GMRES stagnates on this system (~2 100 iterations): the count moves with the summation order of the dot
+    # products (the oracle alone gives 2 009 .. 2 235 depending on its thread count, the GPU 2 231 every time); band +-25 %
+    assert abs(its - its0.value) <= 0.25 * its0.value, (its, its0.value)
+    # where rounding has not yet been amplified the two solvers walk the same path: after two restart cycles (60
+    # iterations) the residual norms agree to 1e-6 and the iterates to 1e-5 of their size
+    x60, c60 = np.zeros(sim.n), np.zeros(sim.n)
+    reason60, its60, rn60 = flow.ksp_solve(J, pc, r, x60, flow.ksp_opts(type=flow.KSP_GMRES, restart=30, maxit=60))
+    o.maxit = 60
+    i60, r60 = C.c_int(), C.c_double()
+    reason60o = L.wo_ksp_solve(arm.A, pc0, C.byref(o), wo.dp(r0), wo.dp(c60), C.byref(i60), C.byref(r60))
+    assert reason60 == reason60o == -3 and its60 == i60.value == 60
+    assert abs(rn60 - r60.value) <= 1e-6 * r60.value
+    assert relerr(x60, c60) < 1e-5
     # both iterates satisfy the stopping criterion of the other side's operator: |M^-1 (b - A x)| <= rtol |M^-1 b|
     t, zb, zr = np.zeros(sim.n), np.zeros(sim.n), np.zeros(sim.n)
     L.wo_pc_apply(pc0, wo.dp(r0), wo.dp(zb))
