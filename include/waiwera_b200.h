@@ -204,6 +204,21 @@ int wb_set_source_controls(wb_ctx *ctx, int n, const int32_t *source, const doub
 /* rate of every source (order of wb_set_sources) for the state of the last unperturbed evaluation: the
    "rate" source output field */
 int wb_get_source_rates(wb_ctx *ctx, double *rate);
+/* Separators and limiters on the separated flows (src/separator.F90; source input "separator": {"pressure": p | [p1, p2]},
+   "limiter": {"type": "water" | "steam", "limit": ..., "separator_pressure": ...} or {"total": ..., "water": ...,
+   "steam": ...}, src/source_setup.F90:2255-2330, 3117-3276).  A producing source with a separator flashes its flow
+   (mass rate and the flowing enthalpy of its cell's fluid, src/source_network.F90:197-216) through nstage[k] <= 2 stages
+   at pressure[2 k], pressure[2 k + 1] (separator_separate, :212-260); limit_water / limit_steam (<= 0: none) limit the
+   separated rates exactly as the total limiter limits the whole flow: one scale, the smallest over the limited flow types
+   (source_network_node_limit_rate, src/source_network_node.F90:245-315).  Evaluated at every function evaluation like the
+   other controls.  Call after wb_set_sources / wb_set_source_controls; n = 0 removes the separators. */
+int wb_set_source_separators(wb_ctx *ctx, int n, const int32_t *source, const int32_t *nstage, const double *pressure,
+                             const double *limit_water, const double *limit_steam);
+/* separator_stage_init (src/separator.F90:108-136): reference water and steam enthalpies of a stage at `pressure` */
+int wb_separator_stage(wb_ctx *ctx, double pressure, double *ref_water_enthalpy, double *ref_steam_enthalpy);
+/* the separated-flow source output fields [nsources][5]: water_rate, water_enthalpy, steam_rate, steam_enthalpy,
+   steam_fraction (src/source_network_node.F90:95-112), state of the last unperturbed evaluation */
+int wb_get_source_separated(wb_ctx *ctx, double *out5);
 /* current fluid records of all local cells, reference AoS layout [ncell*fluid_dof] */
 int wb_get_fluid(wb_ctx *ctx, double *fluid);
 int wb_get_regions(wb_ctx *ctx, int32_t *region);

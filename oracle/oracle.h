@@ -230,6 +230,12 @@ void wo_flow_set_source_controls(wo_flow *f, int n, const int32_t *source, const
                                  const int32_t *direction, const double *limit);
 /* rate of every source at the last unperturbed evaluation */
 void wo_flow_get_source_rates(const wo_flow *f, double *rate);
+/* separators (src/separator.F90) and limiters on the separated water / steam flows (src/source_network_node.F90:245-315) */
+int wo_separator_stage(wo_thermo *th, double pressure, double *ref_water_enthalpy, double *ref_steam_enthalpy);
+void wo_separate(int nstage, const double *stage_h, double rate, double enthalpy, double out[5]);
+int wo_flow_set_source_separators(wo_flow *f, int n, const int32_t *source, const int32_t *nstage, const double *pressure,
+                                  const double *limit_water, const double *limit_steam);
+void wo_flow_source_separated(const wo_flow *f, int s, double rate, double out[5]);
 /* pre_eval: update mask from perturbed block columns (NULL/0 => unperturbed) + fluid_properties */
 int wo_flow_pre_eval(wo_flow *f, const double *y, const int32_t *perturbed, int nperturbed);
 int wo_flow_cell_balances(wo_flow *f, double *lhs);

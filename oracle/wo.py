@@ -171,6 +171,10 @@ def lib():
         "wo_flow_set_method": (None, [vp, i, d, c_dp]),
         "wo_flow_set_source_controls": (None, [vp, i, c_ip, c_dp, c_dp, c_ip, c_dp]),
         "wo_flow_get_source_rates": (None, [vp, c_dp]),
+        "wo_separator_stage": (i, [vp, d, c_dp, c_dp]),
+        "wo_separate": (None, [i, c_dp, d, d, c_dp]),
+        "wo_flow_set_source_separators": (i, [vp, i, c_ip, c_ip, c_dp, c_dp, c_dp]),
+        "wo_flow_source_separated": (None, [vp, i, d, c_dp]),
         "wo_flow_pre_eval": (i, [vp, c_dp, c_ip, i]),
         "wo_flow_cell_balances": (i, [vp, c_dp]),
         "wo_flow_cell_inflows": (i, [vp, c_dp]),
@@ -362,6 +366,23 @@ class Flow:
         dr = None if direction is None else np.ascontiguousarray(direction, np.int32)
         lm = None if limit is None else np.ascontiguousarray(limit, np.float64)
         self.L.wo_flow_set_source_controls(self.h, len(s), ip(s), dp(pi), dp(pr), ip(dr), dp(lm))
+
+    def set_source_separators(self, sources, pressures, limit_water=None, limit_steam=None):
+        """pressures: per source a list of 0, 1 or 2 separator stage pressures"""
+        s = np.ascontiguousarray(sources, np.int32)
+        ns = np.array([len(p) for p in pressures], np.int32)
+        pr = np.zeros(2 * len(s))
+        for k, p in enumerate(pressures):
+            pr[2 * k:2 * k + len(p)] = p
+        lw = None if limit_water is None else np.ascontiguousarray(limit_water, np.float64)
+        ls = None if limit_steam is None else np.ascontiguousarray(limit_steam, np.float64)
+        return self.L.wo_flow_set_source_separators(self.h, len(s), ip(s), ip(ns), dp(pr), dp(lw), dp(ls))
+
+    def source_separated(self, s, rate):
+        """water rate, water enthalpy, steam rate, steam enthalpy, steam fraction of source s at the given rate"""
+        out = np.zeros(5)
+        self.L.wo_flow_source_separated(self.h, int(s), float(rate), dp(out))
+        return out
 
     def source_rates(self, n):
         r = np.zeros(n)

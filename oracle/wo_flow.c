@@ -181,6 +181,9 @@ void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *
                          const double *enthalpy) {
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy); free(f->src_pcomponent);
   free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
+  free(f->src_sep_n); free(f->src_sep_h); free(f->src_limit_water); free(f->src_limit_steam);
+  f->src_sep_n = NULL;
+  f->src_sep_h = f->src_limit_water = f->src_limit_steam = NULL;
   f->src_ctrl = f->src_direction = NULL;
   f->src_pi = f->src_pref = f->src_limit = NULL;
   f->src_rate_eval = (double *)calloc(n + 1, sizeof(double));
@@ -234,6 +237,112 @@ void wo_flow_set_source_controls(wo_flow *f, int n, const int32_t *source, const
 
 void wo_flow_get_source_rates(const wo_flow *f, double *rate) { memcpy(rate, f->src_rate_eval, f->nsrc * sizeof(double)); }
 
+/* separator_stage_init (src/separator.F90:108-136): reference water and steam enthalpies u + P / rho on the saturation
+   line at the stage's pressure */
+int wo_separator_stage(wo_thermo *th, double pressure, double *ref_water_enthalpy, double *ref_steam_enthalpy) {
+  double saturation_temperature, params[2], water_props[2], steam_props[2];
+  int err = wo_saturation_temperature(th, pressure, &saturation_temperature);
+  if (err) return err;
+  params[0] = pressure;
+  params[1] = saturation_temperature;
+  err = wo_region_properties(th, 1, params, water_props);
+  if (err) return err;
+  err = wo_region_properties(th, 2, params, steam_props);
+  if (err) return err;
+  *ref_water_enthalpy = water_props[1] + pressure / water_props[0];
+  *ref_steam_enthalpy = steam_props[1] + pressure / steam_props[0];
+  return 0;
+}
+
+/* separator_separate (src/separator.F90:212-260) over stages of separator_stage_separate (:140-166); stage_h holds
+   (reference water enthalpy, reference steam enthalpy) per stage; out = water rate, water enthalpy, steam rate, steam
+   enthalpy, steam fraction */
+void wo_separate(int nstage, const double *stage_h, double rate, double enthalpy, double out[5]) {
+  const double tol = 1.e-9;
+  double q = rate, h = enthalpy, total_steam_mass_rate = 0.0, total_steam_energy_rate = 0.0;
+  for (int i = 0; i < nstage; i++) {
+    double ref_water_enthalpy = stage_h[2 * i], ref_steam_enthalpy = stage_h[2 * i + 1];
+    double steam_fraction, water_enthalpy, steam_enthalpy;
+    if (h <= ref_water_enthalpy) {
+      steam_fraction = 0.0;
+      water_enthalpy = h;
+      steam_enthalpy = 0.0;
+    } else if (h <= ref_steam_enthalpy) {
+      steam_fraction = (h - ref_water_enthalpy) / (ref_steam_enthalpy - ref_water_enthalpy);
+      water_enthalpy = ref_water_enthalpy;
+      steam_enthalpy = ref_steam_enthalpy;
+    } else {
+      steam_fraction = 1.0;
+      water_enthalpy = 0.0;
+      steam_enthalpy = h;
+    }
+    double water_rate = (1.0 - steam_fraction) * q, steam_rate = steam_fraction * q;
+    total_steam_mass_rate = total_steam_mass_rate + steam_rate;
+    total_steam_energy_rate = total_steam_energy_rate + steam_rate * steam_enthalpy;
+    q = water_rate;
+    h = water_enthalpy;
+  }
+  out[0] = q;
+  out[1] = h;
+  out[2] = total_steam_mass_rate;
+  out[3] = fabs(total_steam_mass_rate) > tol ? total_steam_energy_rate / total_steam_mass_rate : 0.0;
+  out[4] = fabs(rate) > tol ? total_steam_mass_rate / rate : 0.0;
+}
+
+/* Separators and separated-flow limiters of n sources (after wo_flow_set_source_controls): nstage[k] <= 2 separator stages
+   at pressure[2 k], pressure[2 k + 1]; limits on the separated water and steam mass rates (<= 0: none).  Source input
+   "separator": {"pressure": ...} / "limiter": {"type": "water" | "steam", "limit": ..., "separator_pressure": ...} or
+   {"total": ..., "water": ..., "steam": ...} (src/source_setup.F90:2255-2330, 3117-3276). */
+int wo_flow_set_source_separators(wo_flow *f, int n, const int32_t *source, const int32_t *nstage, const double *pressure,
+                                  const double *limit_water, const double *limit_steam) {
+  int ns = f->nsrc;
+  free(f->src_sep_n); free(f->src_sep_h); free(f->src_limit_water); free(f->src_limit_steam);
+  f->src_sep_n = (int32_t *)calloc(ns + 1, sizeof(int32_t));
+  f->src_sep_h = (double *)calloc(4 * (size_t)ns + 4, sizeof(double));
+  f->src_limit_water = (double *)calloc(ns + 1, sizeof(double));
+  f->src_limit_steam = (double *)calloc(ns + 1, sizeof(double));
+  if (!f->src_ctrl) wo_flow_set_source_controls(f, 0, NULL, NULL, NULL, NULL, NULL);
+  for (int k = 0; k < n; k++) {
+    int s = source[k];
+    if (nstage[k] < 0 || nstage[k] > 2) return 1;
+    f->src_sep_n[s] = nstage[k];
+    for (int i = 0; i < nstage[k]; i++) {
+      int err = wo_separator_stage(wo_eos_thermo(f->eos), pressure[2 * k + i], &f->src_sep_h[4 * s + 2 * i], &f->src_sep_h[4 * s + 2 * i + 1]);
+      if (err) return err;
+    }
+    f->src_limit_water[s] = limit_water ? limit_water[k] : 0.0;
+    f->src_limit_steam[s] = limit_steam ? limit_steam[k] : 0.0;
+  }
+  return 0;
+}
+
+/* enthalpy of the fluid a producing source takes from its cell: fluid%specific_enthalpy(fluid%phase_flow_fractions())
+   (src/fluid.F90:394-436), what source_separator_iterator (src/source_network.F90:197-216) gives the separator */
+static double source_fluid_enthalpy(const wo_flow *f, int s) {
+  const double *fl = f->current_fluid + (size_t)f->src_cell[s] * f->dof;
+  int phases = nint_(fl[4]);
+  double frac[2] = {0.0, 0.0}, sum = 0.0, h = 0.0;
+  for (int p = 0; p < f->nphase; p++) {
+    const double *ph = fl + (7 + f->nc - 1) + p * (8 + f->nc - 1);
+    if (phases & (1 << p)) frac[p] = ph[3] * ph[0] / ph[1];
+    sum += frac[p];
+  }
+  for (int p = 0; p < f->nphase; p++) {
+    const double *ph = fl + (7 + f->nc - 1) + p * (8 + f->nc - 1);
+    frac[p] = frac[p] / sum;
+    if (phases & (1 << p)) h = h + frac[p] * ph[5];
+  }
+  return h;
+}
+
+/* separated flows of source s at the given rate (source_network_node_get_separated_flows, src/source_network_node.F90:
+   116-131): zero unless the source produces and has a separator */
+void wo_flow_source_separated(const wo_flow *f, int s, double rate, double out[5]) {
+  for (int i = 0; i < 5; i++) out[i] = 0.0;
+  if (f->src_sep_n && f->src_sep_n[s] > 0 && rate < 0.0)
+    wo_separate(f->src_sep_n[s], f->src_sep_h + 4 * s, rate, source_fluid_enthalpy(f, s), out);
+}
+
 /* source_network%update for one source (src/source_network.F90:90-292): source controls, then network controls.
    deliverability_source_control_flow_rate (src/source_control.F90:359-403, constant productivity and reference
    pressure), direction_source_control_iterator (:596-620), limit_rate with a "total" limiter
@@ -254,13 +363,24 @@ double wo_flow_source_rate(const wo_flow *f, int s) {
   }
   if (f->src_direction[s] == 1 && !(rate < 0.0)) rate = 0.0;
   if (f->src_direction[s] == 2 && !(rate > 0.0)) rate = 0.0;
-  if (f->src_limit[s] > 0.0) {
+  /* limiter: source_network_node_limit_rate (src/source_network_node.F90:245-315) over the limited flow types (total,
+     separated water, separated steam): the smallest scale that brings every rate over its limit back to it */
+  {
     const double small = 1.e-6;
-    double abs_rate = fabs(rate), scale = 1.0;
-    if (abs_rate > f->src_limit[s]) {
-      if (abs_rate > small) scale = fmin(scale, f->src_limit[s] / abs_rate);
-      rate = rate * scale;
+    double scale = 1.0, sep[5];
+    int over = 0;
+    int has_sep_limit = f->src_sep_n && (f->src_limit_water[s] > 0.0 || f->src_limit_steam[s] > 0.0);
+    if (has_sep_limit) wo_flow_source_separated(f, s, rate, sep);
+    for (int type = 0; type < 3; type++) {
+      double limit = type == 0 ? f->src_limit[s] : (has_sep_limit ? (type == 1 ? f->src_limit_water[s] : f->src_limit_steam[s]) : 0.0);
+      if (!(limit > 0.0)) continue;
+      double abs_rate = fabs(type == 0 ? rate : (type == 1 ? sep[0] : sep[2]));
+      if (abs_rate > limit) {
+        over = 1;
+        if (abs_rate > small) scale = fmin(scale, limit / abs_rate);
+      }
     }
+    if (over) rate = rate * scale;
   }
   return rate;
 }
@@ -334,6 +454,7 @@ void wo_flow_destroy(wo_flow *f) {
   if (!f) return;
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy); free(f->src_pcomponent);
   free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
+  free(f->src_sep_n); free(f->src_sep_h); free(f->src_limit_water); free(f->src_limit_steam);
   free(f->lhs_last2);
   face_plan_free(f);
   for (int t = 1; t < f->eos_nthr; t++) wo_eos_destroy(f->eos_thr[t]);

@@ -37,6 +37,10 @@ struct wo_flow {
      (src/source_network_node.F90:245-315); all NULL when no control is set */
   int32_t *src_ctrl, *src_direction;   /* per source: 1 = on deliverability; 0 both / 1 production / 2 injection */
   double *src_pi, *src_pref, *src_limit; /* productivity index, reference pressure, total rate limit (<= 0: none) */
+  /* separators (src/separator.F90) and separated-flow limiters: stages per source (0: none), reference water and steam
+     enthalpies of up to two stages [4 per source: hw0, hs0, hw1, hs1], limits on the separated water and steam rates */
+  int32_t *src_sep_n;
+  double *src_sep_h, *src_limit_water, *src_limit_steam;
   double *src_rate_eval;               /* rate every source had at the last unperturbed evaluation */
   /* passive tracers (src/tracer.F90:25-41): auxiliary linear problem, wo_tracer.c */
   int nt;

@@ -82,6 +82,9 @@ SIGNATURES = {
     "wb_set_source_components": (i, [vp, i, vp, vp]),
     "wb_set_source_controls": (i, [vp, i, vp, vp, vp, vp, vp]),
     "wb_get_source_rates": (i, [vp, vp]),
+    "wb_set_source_separators": (i, [vp, i, vp, vp, vp, vp, vp]),
+    "wb_separator_stage": (i, [vp, d, vp, vp]),
+    "wb_get_source_separated": (i, [vp, vp]),
     "wb_get_fluid": (i, [vp, vp]),
     "wb_get_regions": (i, [vp, vp]),
     "wb_pre_iteration": (i, [vp]),

@@ -222,6 +222,8 @@ struct wb_ctx {
   std::vector<int> h_src_order;  // sorted position -> input position
   int32_t *d_src_ctrl = nullptr;  // source controls, sorted like the sources (null: none)
   double *d_src_pi = nullptr, *d_src_pref = nullptr, *d_src_limit = nullptr;
+  int32_t *d_src_sep_n = nullptr;  // separators: stages per source, reference enthalpies, separated-flow limits
+  double *d_src_sep_h = nullptr, *d_src_limit_w = nullptr, *d_src_limit_s = nullptr;
   // passive tracers: auxiliary linear problem (wb_tracer.cu)
   int nt = 0;
   int trc_phase[WB_MAX_TRACERS] = {0, 0, 0};  // 1-based phase index

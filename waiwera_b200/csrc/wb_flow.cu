@@ -748,7 +748,8 @@ static WbResForm wb_res_form(const wb_ctx *c, const double *d_lhs_last, double d
 
 WbSources wb_sources_args(const wb_ctx *c) {
   WbSources S = {c->nsrc > 0 ? c->d_src_head : nullptr, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth, c->nsrc,
-                 c->d_src_ctrl, c->d_src_pi, c->d_src_pref, c->d_src_limit};
+                 c->d_src_ctrl, c->d_src_pi, c->d_src_pref, c->d_src_limit,
+                 c->d_src_sep_n, c->d_src_sep_h, c->d_src_limit_w, c->d_src_limit_s};
   return S;
 }
 
@@ -1081,6 +1082,9 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   cudaFree(c->d_src_ctrl); cudaFree(c->d_src_pi); cudaFree(c->d_src_pref); cudaFree(c->d_src_limit);
   c->d_src_ctrl = nullptr;
   c->d_src_pi = c->d_src_pref = c->d_src_limit = nullptr;
+  cudaFree(c->d_src_sep_n); cudaFree(c->d_src_sep_h); cudaFree(c->d_src_limit_w); cudaFree(c->d_src_limit_s);
+  c->d_src_sep_n = nullptr;
+  c->d_src_sep_h = c->d_src_limit_w = c->d_src_limit_s = nullptr;
   cudaFree(c->d_trc_inj);  // tracer injection rates belong to the old source list
   c->d_trc_inj = nullptr;
   if (n <= 0) return 0;
@@ -1161,6 +1165,97 @@ extern "C" int wb_set_source_controls(wb_ctx *c, int n, const int32_t *source, c
   WB_TRY(dev_upload(&c->d_src_pref, pref));
   WB_TRY(dev_upload(&c->d_src_limit, lim));
   return 0;
+}
+
+// separator_stage_init (src/separator.F90:108-136) on the host: reference water and steam enthalpies u + P / rho on the
+// saturation line at the stage's pressure, with the context's thermodynamic formulation
+extern "C" int wb_separator_stage(wb_ctx *c, double pressure, double *ref_water_enthalpy, double *ref_steam_enthalpy) {
+  double ts = 0.0, rho = 0.0, u = 0.0;
+  int err = wb_saturation_temperature(c->eos.thermo, pressure, ts);
+  if (err) return 1;
+  if (wb_region_properties(c->eos.thermo, 1, pressure, ts, rho, u)) return 1;
+  *ref_water_enthalpy = u + pressure / rho;
+  if (wb_region_properties(c->eos.thermo, 2, pressure, ts, rho, u)) return 1;
+  *ref_steam_enthalpy = u + pressure / rho;
+  return 0;
+}
+
+extern "C" int wb_set_source_separators(wb_ctx *c, int n, const int32_t *source, const int32_t *nstage, const double *pressure,
+                                        const double *limit_water, const double *limit_steam) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_src_sep_n); cudaFree(c->d_src_sep_h); cudaFree(c->d_src_limit_w); cudaFree(c->d_src_limit_s);
+  c->d_src_sep_n = nullptr;
+  c->d_src_sep_h = c->d_src_limit_w = c->d_src_limit_s = nullptr;
+  if (n <= 0) return 0;
+  WB_CHECK(c->nsrc > 0, "wb_set_source_separators: no sources");
+  WB_CHECK(!wb_is_device_ptr(source) && !wb_is_device_ptr(nstage) && !wb_is_device_ptr(pressure) &&
+               !wb_is_device_ptr(limit_water) && !wb_is_device_ptr(limit_steam),
+           "wb_set_source_separators: the arrays are read on the host (set-up data): pass host arrays");
+  const int ns = c->nsrc;
+  if (!c->d_src_ctrl) {  // the rate evaluation looks at the separators only behind the control arrays: create empty ones
+    std::vector<int32_t> ctrl(ns, 0);
+    std::vector<double> zero(ns, 0.0);
+    WB_TRY(dev_upload(&c->d_src_ctrl, ctrl));
+    WB_TRY(dev_upload(&c->d_src_pi, zero));
+    WB_TRY(dev_upload(&c->d_src_pref, zero));
+    WB_TRY(dev_upload(&c->d_src_limit, zero));
+  }
+  std::vector<int> pos(ns);  // input position -> sorted position
+  for (int k = 0; k < ns; k++) pos[c->h_src_order[k]] = k;
+  std::vector<int32_t> sn(ns, 0);
+  std::vector<double> sh(4 * (size_t)ns, 0.0), lw(ns, 0.0), ls(ns, 0.0);
+  for (int k = 0; k < n; k++) {
+    WB_CHECK(source[k] >= 0 && source[k] < ns, "wb_set_source_separators: source index %d out of range", source[k]);
+    WB_CHECK(nstage[k] >= 0 && nstage[k] <= 2, "wb_set_source_separators: %d separator stages (at most 2)", nstage[k]);
+    const int q = pos[source[k]];
+    sn[q] = nstage[k];
+    for (int i = 0; i < nstage[k]; i++)
+      WB_CHECK(wb_separator_stage(c, pressure[2 * k + i], &sh[4 * (size_t)q + 2 * i], &sh[4 * (size_t)q + 2 * i + 1]) == 0,
+               "wb_set_source_separators: separator pressure %g outside the saturation line", pressure[2 * k + i]);
+    lw[q] = limit_water ? limit_water[k] : 0.0;
+    ls[q] = limit_steam ? limit_steam[k] : 0.0;
+  }
+  WB_TRY(dev_upload(&c->d_src_sep_n, sn));
+  WB_TRY(dev_upload(&c->d_src_sep_h, sh));
+  WB_TRY(dev_upload(&c->d_src_limit_w, lw));
+  WB_TRY(dev_upload(&c->d_src_limit_s, ls));
+  return 0;
+}
+
+template <int EOS>
+__global__ void k_source_separated(const WbSources S, const double *state, int ncell, const int32_t *order, double *out) {
+  constexpr int NC = WbEosTraits<EOS>::NC, NPH = WbEosTraits<EOS>::NPH;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S.n) return;
+  WbCellState<NC, NPH> s;
+  load_state(state, (size_t)ncell, S.cell[k], s);
+  double sep[5];
+  wb_source_separated(S, k, s, wb_source_rate(S, k, s), sep);
+  for (int i = 0; i < 5; i++) out[5 * (size_t)order[k] + i] = sep[i];
+}
+
+// the separated-flow output fields of the sources (water_rate, water_enthalpy, steam_rate, steam_enthalpy,
+// steam_fraction: src/source_network_node.F90:95-112) at the state of the last unperturbed evaluation
+extern "C" int wb_get_source_separated(wb_ctx *c, double *out5) {
+  WB_CUDA(cudaSetDevice(c->device));
+  if (c->nsrc == 0) return 0;
+  int rc = 0;
+  WbStage st(c);
+  double *d_out = st.out(out5, 5 * (size_t)c->nsrc, &rc);
+  if (rc) return rc;
+  int32_t *d_order = nullptr;
+  std::vector<int32_t> order(c->h_src_order.begin(), c->h_src_order.end());
+  WB_TRY(dev_upload(&d_order, order));
+  const WbSources S = wb_sources_args(c);
+#define CALL(E) k_source_separated<E><<<wb_grid(c->nsrc, 128), 128, 0, c->stream>>>(S, c->d_state, c->ncell, d_order, d_out)
+  DISPATCH_EOS(c, CALL);
+#undef CALL
+  WB_LAUNCH(c);
+  WB_CUDA(cudaGetLastError());
+  rc = st.finish();
+  cudaFree(d_order);
+  return rc;
 }
 
 template <int EOS>

@@ -83,7 +83,67 @@ struct WbSources {
   // (0 both, 1 production, 2 injection); productivity index, reference pressure, total-flow limit (<= 0: none)
   const int32_t *ctrl;
   const double *pi, *pref, *limit;
+  // separators and limiters on the separated flows (null: none): stages per source (0..2), reference water / steam
+  // enthalpies of the stages [4 per source], limits on the separated water and steam rates (<= 0: none)
+  const int32_t *sep_n;
+  const double *sep_h, *limit_w, *limit_s;
 };
+
+// separator_separate (src/separator.F90:212-260) over separator_stage_separate (:140-166): separated water and steam
+// mass rates of a flow of `rate` at `enthalpy` through nstage <= 2 flash stages with the reference enthalpies stage_h
+WB_HD void wb_separate(int nstage, const double *stage_h, double rate, double enthalpy, double &water_rate,
+                       double &water_enthalpy, double &steam_rate, double &steam_enthalpy) {
+  double q = rate, h = enthalpy, total_steam_mass_rate = 0.0, total_steam_energy_rate = 0.0;
+  for (int i = 0; i < nstage; i++) {
+    const double ref_water_enthalpy = stage_h[2 * i], ref_steam_enthalpy = stage_h[2 * i + 1];
+    double steam_fraction, stage_water_enthalpy, stage_steam_enthalpy;
+    if (h <= ref_water_enthalpy) {
+      steam_fraction = 0.0;
+      stage_water_enthalpy = h;
+      stage_steam_enthalpy = 0.0;
+    } else if (h <= ref_steam_enthalpy) {
+      steam_fraction = (h - ref_water_enthalpy) / (ref_steam_enthalpy - ref_water_enthalpy);
+      stage_water_enthalpy = ref_water_enthalpy;
+      stage_steam_enthalpy = ref_steam_enthalpy;
+    } else {
+      steam_fraction = 1.0;
+      stage_water_enthalpy = 0.0;
+      stage_steam_enthalpy = h;
+    }
+    const double stage_water_rate = (1.0 - steam_fraction) * q, stage_steam_rate = steam_fraction * q;
+    total_steam_mass_rate = total_steam_mass_rate + stage_steam_rate;
+    total_steam_energy_rate = total_steam_energy_rate + stage_steam_rate * stage_steam_enthalpy;
+    q = stage_water_rate;
+    h = stage_water_enthalpy;
+  }
+  water_rate = q;
+  water_enthalpy = h;
+  steam_rate = total_steam_mass_rate;
+  steam_enthalpy = fabs(total_steam_mass_rate) > 1.e-9 ? total_steam_energy_rate / total_steam_mass_rate : 0.0;
+}
+
+// separated flows of source k at the given rate (source_network_node_get_separated_flows, src/source_network_node.F90:
+// 116-131; the enthalpy is that of the fluid the source takes from its cell, src/source_network.F90:197-216): zero
+// unless the source produces and has a separator.  out: water rate, water enthalpy, steam rate, steam enthalpy, fraction
+template <int NC, int NPH>
+WB_HD void wb_source_separated(const WbSources &S, int k, const WbCellState<NC, NPH> &s, double rate, double *out) {
+  for (int i = 0; i < 5; i++) out[i] = 0.0;
+  if (!S.sep_n || S.sep_n[k] <= 0 || !(rate < 0.0)) return;
+  double frac[NPH], sum = 0.0, h = 0.0;
+#pragma unroll
+  for (int p = 0; p < NPH; p++) {
+    frac[p] = 0.0;
+    if (s.phases & (1 << p)) frac[p] = s.mob[p];
+    sum += frac[p];
+  }
+#pragma unroll
+  for (int p = 0; p < NPH; p++) {
+    frac[p] = frac[p] / sum;
+    if (s.phases & (1 << p)) h = h + frac[p] * s.h[p];
+  }
+  wb_separate(S.sep_n[k], S.sep_h + 4 * (size_t)k, rate, h, out[0], out[1], out[2], out[3]);
+  out[4] = fabs(rate) > 1.e-9 ? out[2] / rate : 0.0;
+}
 
 // source_network%update for one source (src/source_network.F90:90-292): its rate after the source controls
 // (deliverability_source_control_flow_rate src/source_control.F90:359-403 with constant productivity and reference
@@ -106,15 +166,22 @@ WB_HD double wb_source_rate(const WbSources &S, int k, const WbCellState<NC, NPH
   const int direction = (ctrl >> 1) & 3;
   if (direction == 1 && !(rate < 0.0)) rate = 0.0;
   if (direction == 2 && !(rate > 0.0)) rate = 0.0;
-  const double limit = S.limit[k];
-  if (limit > 0.0) {
-    const double abs_rate = fabs(rate);
+  // limiter (source_network_node_limit_rate, src/source_network_node.F90:245-315) over the limited flow types -- total,
+  // separated water, separated steam: the smallest scale that brings every rate over its limit back to it
+  double scale = 1.0, sep[5];
+  bool over = false;
+  const bool sep_limits = S.sep_n && (S.limit_w[k] > 0.0 || S.limit_s[k] > 0.0);
+  if (sep_limits) wb_source_separated(S, k, s, rate, sep);
+  for (int type = 0; type < 3; type++) {
+    const double limit = type == 0 ? S.limit[k] : (sep_limits ? (type == 1 ? S.limit_w[k] : S.limit_s[k]) : 0.0);
+    if (!(limit > 0.0)) continue;
+    const double abs_rate = fabs(type == 0 ? rate : (type == 1 ? sep[0] : sep[2]));
     if (abs_rate > limit) {
-      double scale = 1.0;
+      over = true;
       if (abs_rate > 1.e-6) scale = fmin(scale, limit / abs_rate);
-      rate = rate * scale;
     }
   }
+  if (over) rate = rate * scale;
   return rate;
 }
 

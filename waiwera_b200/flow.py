@@ -317,6 +317,30 @@ class FlowSimulation:
         return check(self.L.wb_set_source_controls(self.h, len(s), ptr(s), ptr(pi), ptr(pr), ptr(dr), ptr(lm)),
                      "wb_set_source_controls")
 
+    def set_source_separators(self, sources, pressures, limit_water=None, limit_steam=None):
+        """separators (per source a list of 0, 1 or 2 stage pressures) and limits on the separated water / steam rates;
+        see wb_set_source_separators"""
+        s = np.ascontiguousarray(sources, np.int32)
+        ns = np.array([len(p) for p in pressures], np.int32)
+        pr = np.zeros(2 * max(len(s), 1))
+        for k, p in enumerate(pressures):
+            pr[2 * k:2 * k + len(p)] = p
+        lw = None if limit_water is None else np.ascontiguousarray(limit_water, np.float64)
+        ls = None if limit_steam is None else np.ascontiguousarray(limit_steam, np.float64)
+        return check(self.L.wb_set_source_separators(self.h, len(s), ptr(s), ptr(ns), ptr(pr), ptr(lw), ptr(ls)),
+                     "wb_set_source_separators")
+
+    def separator_stage(self, pressure):
+        hw, hs = C.c_double(), C.c_double()
+        check(self.L.wb_separator_stage(self.h, float(pressure), C.byref(hw), C.byref(hs)), "wb_separator_stage")
+        return hw.value, hs.value
+
+    def source_separated(self):
+        """[nsources][5]: water rate, water enthalpy, steam rate, steam enthalpy, steam fraction"""
+        out = np.zeros((self.nsrc, 5))
+        check(self.L.wb_get_source_separated(self.h, ptr(out)), "wb_get_source_separated")
+        return out
+
     def source_rates(self):
         r = np.zeros(self.nsrc)
         check(self.L.wb_get_source_rates(self.h, ptr(r)), "wb_get_source_rates")

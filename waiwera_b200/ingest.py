@@ -381,12 +381,13 @@ def load(path, mod=None, mesh_path=None):
     src = doc.get("source") or []
     for s in src:
         unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer",
-                                "interpolation", "averaging", "deliverability", "direction", "limiter"}
+                                "interpolation", "averaging", "deliverability", "direction", "limiter", "separator"}
         assert not unsupported, "source controls are not built: %s" % sorted(unsupported)
         dl, lm = s.get("deliverability"), s.get("limiter")
         assert dl is None or all(np.ndim(dl.get(k, 0.0)) == 0 for k in ("pressure", "productivity")), \
             "table-valued deliverability parameters are not built"
-        assert lm is None or lm.get("type", "total") == "total", "only the total-flow limiter is built"
+        assert lm is None or all(np.ndim(lm.get(k, 0.0)) == 0 for k in ("limit", "total", "water", "steam")), \
+            "table-valued limits are not built"
     # a rank-2 "rate" is a table source control (src/source_control.F90: table of (time, rate)); kept as a table
     # that rates_at() evaluates over each time step, "step" or "linear" interpolation, "endpoint" averaging
     p.source_tables = {}
@@ -400,6 +401,36 @@ def load(path, mod=None, mesh_path=None):
         elif s.get("rate", 0.0) != 0.0 or "deliverability" in s:
             kept.append(s)
     src = kept
+
+    def separator_pressures(s):
+        """get_separator_pressure (src/source_setup.F90:2255-2330): "separator": true | {"pressure": p | [p1, p2]}, or the
+        "separator_pressure" of a water / steam limiter in the single-type syntax; [] = no separator"""
+        sep = s.get("separator")
+        if sep is not None:
+            if sep is True or (isinstance(sep, dict) and "pressure" not in sep):
+                return [0.55e6]                      # default_separator_pressure, src/separator.F90:34
+            if sep is False:
+                return []
+            return [float(v) for v in np.atleast_1d(sep["pressure"])]
+        lm = s.get("limiter")
+        if lm is not None and str(lm.get("type", "total")).lower() != "total" and "separator_pressure" in lm:
+            return [float(v) for v in np.atleast_1d(lm["separator_pressure"])]
+        return []
+
+    def limits(s):
+        """add_limiter (src/source_setup.F90:3117-3276): {"type": t, "limit": x} (one flow type, default total, default
+        limit 1) or {"total": x, "water": y, "steam": z}"""
+        lm = s.get("limiter")
+        out = {"total": 0.0, "water": 0.0, "steam": 0.0}
+        if lm is None:
+            return out
+        if "limit" in lm or "type" in lm:
+            out[str(lm.get("type", "total")).lower()] = float(lm.get("limit", 1.0))
+        else:
+            for k in out:
+                if k in lm:
+                    out[k] = float(lm[k])
+        return out
     # source controls (see wb_set_source_controls): deliverability (productivity None: to be calculated from the
     # initial rate, src/source_control.F90:407-468), direction, total-flow limiter
     p.source_controls = []
@@ -410,9 +441,17 @@ def load(path, mod=None, mesh_path=None):
                 source=k, deliverability="deliverability" in s, productivity=dl.get("productivity"),
                 reference_pressure=dl.get("pressure", 1.0e5),
                 direction={"both": 0, "production": 1, "injection": 2}[s.get("direction", "both")],
-                limit=(s.get("limiter") or {}).get("limit", 0.0)))
+                limit=limits(s)["total"]))
         if "deliverability" in s and "rate" not in s:
             s["rate"] = -1.0          # placeholder: producing, the control sets the rate
+    # separators and limits on the separated water / steam flows (see wb_set_source_separators)
+    p.source_separators = []
+    for k, s in enumerate(src):
+        pr, lm = separator_pressures(s), limits(s)
+        if pr or lm["water"] > 0.0 or lm["steam"] > 0.0:
+            assert len(pr) <= 2, "separators with more than two stages are not built"
+            assert pr or not (lm["water"] > 0.0 or lm["steam"] > 0.0), "a water / steam limiter needs a separator"
+            p.source_separators.append(dict(source=k, pressure=pr, limit_water=lm["water"], limit_steam=lm["steam"]))
     # tracer injection rates: numbers or (time, rate) tables per source
     p.source_tracer_tables = {}
     for k, s in enumerate(src):
