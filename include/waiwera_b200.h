@@ -201,6 +201,12 @@ int wb_set_source_components(wb_ctx *ctx, int n, const int32_t *injection_compon
    direction and limit may be NULL.  n = 0 removes all controls; wb_set_sources also removes them. */
 int wb_set_source_controls(wb_ctx *ctx, int n, const int32_t *source, const double *productivity,
                            const double *reference_pressure, const int32_t *direction, const double *limit);
+/* Recharge / injectivity controls (source input "recharge" / "injectivity": {"coefficient": c, "pressure": p};
+   recharge_source_control_iterator, src/source_control.F90:554-577): rate = -c (P - p) with P the pressure of the
+   source's cell, then the direction control and the limiters as for any source.  Edits the entries of these sources:
+   call after wb_set_source_controls. */
+int wb_set_source_recharge(wb_ctx *ctx, int n, const int32_t *source, const double *coefficient,
+                           const double *reference_pressure);
 /* rate of every source (order of wb_set_sources) for the state of the last unperturbed evaluation: the
    "rate" source output field */
 int wb_get_source_rates(wb_ctx *ctx, double *rate);

@@ -229,6 +229,7 @@ void wo_flow_set_source_components(wo_flow *f, int n, const int32_t *injection, 
 void wo_flow_set_source_controls(wo_flow *f, int n, const int32_t *source, const double *pi, const double *pref,
                                  const int32_t *direction, const double *limit);
 /* rate of every source at the last unperturbed evaluation */
+void wo_flow_set_source_recharge(wo_flow *f, int n, const int32_t *source, const double *coefficient, const double *pref);
 void wo_flow_get_source_rates(const wo_flow *f, double *rate);
 /* separators (src/separator.F90) and limiters on the separated water / steam flows (src/source_network_node.F90:245-315) */
 int wo_separator_stage(wo_thermo *th, double pressure, double *ref_water_enthalpy, double *ref_steam_enthalpy);

@@ -170,6 +170,7 @@ def lib():
         "wo_flow_set_source_components": (None, [vp, i, c_ip, c_ip]),
         "wo_flow_set_method": (None, [vp, i, d, c_dp]),
         "wo_flow_set_source_controls": (None, [vp, i, c_ip, c_dp, c_dp, c_ip, c_dp]),
+        "wo_flow_set_source_recharge": (None, [vp, i, c_ip, c_dp, c_dp]),
         "wo_flow_get_source_rates": (None, [vp, c_dp]),
         "wo_separator_stage": (i, [vp, d, c_dp, c_dp]),
         "wo_separate": (None, [i, c_dp, d, d, c_dp]),
@@ -366,6 +367,11 @@ class Flow:
         dr = None if direction is None else np.ascontiguousarray(direction, np.int32)
         lm = None if limit is None else np.ascontiguousarray(limit, np.float64)
         self.L.wo_flow_set_source_controls(self.h, len(s), ip(s), dp(pi), dp(pr), ip(dr), dp(lm))
+
+    def set_source_recharge(self, sources, coefficient, reference_pressure):
+        s = np.ascontiguousarray(sources, np.int32)
+        self.L.wo_flow_set_source_recharge(self.h, len(s), ip(s), dp(np.ascontiguousarray(coefficient, np.float64)),
+                                           dp(np.ascontiguousarray(reference_pressure, np.float64)))
 
     def set_source_separators(self, sources, pressures, limit_water=None, limit_steam=None):
         """pressures: per source a list of 0, 1 or 2 separator stage pressures"""

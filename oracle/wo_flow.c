@@ -235,6 +235,19 @@ void wo_flow_set_source_controls(wo_flow *f, int n, const int32_t *source, const
   }
 }
 
+/* recharge / injectivity controls (recharge_source_control_iterator, src/source_control.F90:554-577; both input keys set
+   up this control, src/source_setup.F90:2984-3092): rate = -coefficient (P - reference pressure); replaces a
+   deliverability control of the same source, keeps its direction and limiter.  After wo_flow_set_source_controls. */
+void wo_flow_set_source_recharge(wo_flow *f, int n, const int32_t *source, const double *coefficient, const double *pref) {
+  if (!f->src_ctrl) wo_flow_set_source_controls(f, 0, NULL, NULL, NULL, NULL, NULL);
+  for (int k = 0; k < n; k++) {
+    int s = source[k];
+    f->src_ctrl[s] = 2;
+    f->src_pi[s] = coefficient[k];
+    f->src_pref[s] = pref[k];
+  }
+}
+
 void wo_flow_get_source_rates(const wo_flow *f, double *rate) { memcpy(rate, f->src_rate_eval, f->nsrc * sizeof(double)); }
 
 /* separator_stage_init (src/separator.F90:108-136): reference water and steam enthalpies u + P / rho on the saturation
@@ -351,7 +364,10 @@ double wo_flow_source_rate(const wo_flow *f, int s) {
   double rate = f->src_rate[s];
   if (!f->src_ctrl) return rate;
   const double *fl = f->current_fluid + (size_t)f->src_cell[s] * f->dof;
-  if (f->src_ctrl[s]) {
+  if (f->src_ctrl[s] == 2) {
+    double pressure_difference = fl[0] - f->src_pref[s];
+    rate = -f->src_pi[s] * pressure_difference;
+  } else if (f->src_ctrl[s]) {
     int phases = nint_(fl[4]);
     double effective_productivity = f->src_pi[s] * fl[5]; /* permeability_factor */
     double pressure_difference = fl[0] - f->src_pref[s];

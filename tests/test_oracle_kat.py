@@ -826,6 +826,55 @@ def test_source_control_deliverability(wo):
     assert np.allclose(rates, [-12.8728519749, -10.0, -11.0, 0.0], rtol=1e-9, atol=1e-12), rates
 
 
+def test_source_separator_limiter_known_answers(wo):
+    """test/unit/src/source_control_test.F90:226-610 again, the sources with a separator: source 3 (deliverability behind a
+    10 bar separator and a steam limiter at 5 kg/s) -9.3081349399 kg/s with 5 kg/s of steam, source 16 (fixed -10 kg/s
+    through a 15 / 5 bar two-stage separator) 5.60996474758954 kg/s of steam, source 17 (deliverability, 10 bar
+    separator, limiter {"total": 10, "steam": 5}) -9.3081349399 / 5 -- same two-phase cell at 50 bar, Sv = 0.8"""
+    from waiwera_b200 import mesh as wmesh
+    L = wo.lib()
+    th = L.wo_thermo_create(wo.THERMO_IAPWS, 0)
+    P, sv = 50.e5, 0.8
+    T = C.c_double()
+    assert L.wo_saturation_temperature(th, P, C.byref(T)) == 0
+    rec = np.zeros(26)
+    rec[0], rec[1], rec[2], rec[3], rec[5] = P, T.value, 4.0, 4.0, 1.0
+    rec[4] = L.wo_phase_composition(th, 4, P, T.value)
+    for p, (sat, X) in enumerate([(1.0 - sv, [0.75, 0.25]), (sv, [0.9, 0.1])]):
+        props = np.zeros(2)
+        assert L.wo_region_properties(th, p + 1, wo.dp(np.array([P, T.value])), wo.dp(props)) == 0
+        ph = rec[8 + 9 * p: 8 + 9 * (p + 1)]
+        ph[0], ph[6] = props
+        ph[1] = L.wo_region_viscosity(th, p + 1, T.value, P, props[0])
+        ph[2] = ph[3] = sat
+        ph[5] = props[1] + P / props[0]
+        ph[7:9] = X
+    L.wo_thermo_destroy(th)
+    m = wmesh.structured(2, 1, 1, dx=1.0, gravity=(0.0, 0.0, 0.0), heterogeneous=False)
+    f = wo.Flow(wo.make_params(eos=wo.EOS_WCE, gravity=(0.0, 0.0, 0.0)), m.ncell, m.ninterior, m.nowned,
+                m.face_cells.reshape(-1), m.face_geom.reshape(-1), m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    f.set_sources([0, 0, 0], [0, 0, 0], [-1.0, -10.0, -1.0], [0.0] * 3)
+    f.current_fluid()[:] = rec
+    f.set_source_controls([0, 1, 2], [1e-12, 0.0, 1e-12], [2.0e5, 0.0, 2.0e5], [0, 0, 0], [0.0, 0.0, 10.0])
+    assert f.set_source_separators([0, 1, 2], [[10.e5], [15.e5, 5.e5], [10.e5]], [0.0, 0.0, 0.0], [5.0, 0.0, 5.0]) == 0
+    rhs = np.zeros(6)
+    assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+    rates = f.source_rates(3)
+    assert np.allclose(rates, [-9.3081349399, -10.0, -9.3081349399], rtol=1e-9, atol=1e-12), rates
+    steam = [f.source_separated(s, rates[s])[2] for s in range(3)]
+    assert np.allclose(steam, [-5.0, -5.60996474758954, -5.0], rtol=1e-9, atol=1e-12), steam
+    # sources 7, 8, 9, 12 of the same file: recharge 0.013 (P - 50.1 bar) both ways = +130; recharge 0.013 against
+    # 49.99 bar, production only = -13; injectivity 0.011 against 49.99 bar, injection only = 0; recharge against the
+    # cell's initial pressure = 0
+    f.set_sources([0, 0, 0, 0], [1, 1, 1, 1], [0.0] * 4, [0.0] * 4)
+    f.current_fluid()[:] = rec
+    f.set_source_controls([0, 1, 2, 3], [0.0] * 4, [0.0] * 4, [0, 1, 2, 0], [0.0] * 4)
+    f.set_source_recharge([0, 1, 2, 3], [0.013, 0.013, 0.011, 0.012], [50.1e5, 49.99e5, 49.99e5, P])
+    assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+    rates = f.source_rates(4)
+    assert np.allclose(rates, [130.0, -13.0, 0.0, 0.0], rtol=1e-9, atol=1e-9), rates
+
+
 def test_eos_scaling(wo):
     """test/unit/src/eos_test.F90:94-200: eos%scale / eos%unscale of every EOS of this build with default, user and
     adaptive (partial pressure / pressure) scales"""

@@ -76,11 +76,17 @@ CASES = [
     dict(p=[Q1, Q1, Q1, Q2], lw=[1.0, 1.0, 1.0, 2.0], ls=[0, 0, 0, 0], lt=[0, 0, 0, 0]),      # water limiters
     dict(p=[Q2, Q1, [], Q1], lw=[3.0, 0, 1.0, 1.5], ls=[0.4, 0.1, 1.0, 5.0], lt=[4.0, 3.0, 1.0, 0]),  # several types at once
     dict(p=[Q1, [], [], []], lw=[0, 0, 0, 0], ls=[0, 0, 0, 0], lt=[0, 2.0, 0, 0]),            # separator without limiter
+    # recharge controls (rate = -c (P - Pref)): producing through a separator with a steam limiter, injecting, blocked
+    # by its direction, and limited in total
+    dict(p=[Q1, [], [], []], lw=[0, 0, 0, 0], ls=[0.3, 0, 0, 0], lt=[0, 0, 0, 2.5], dir=[0, 0, 1, 0],
+         recharge=([0, 1, 2, 3], [2.0e-5, 1.0e-5, 1.0e-5, 3.0e-5], [1.0e5, 9.0e5, 9.0e5, 1.0e5])),
 ]
 
 
 def apply_case(obj, case, n):
-    obj.set_source_controls(list(range(n)), [0.0] * n, [0.0] * n, [0] * n, case["lt"])
+    obj.set_source_controls(list(range(n)), [0.0] * n, [0.0] * n, case.get("dir", [0] * n), case["lt"])
+    if "recharge" in case:
+        obj.set_source_recharge(*case["recharge"])
     r = obj.set_source_separators(list(range(n)), case["p"], case["lw"], case["ls"])
     assert r in (0, None)
 
@@ -95,6 +101,17 @@ def test_oracle_separated_limiters(wo, case):
     assert np.array_equal(base, rates)
     apply_case(f, case, n)
     got, _ = evaluate(f, y, n)
+    if "recharge" in case:           # the rate before the limiters: -c (P - Pref), then the direction control
+        fl = f.fluid()
+        cells = [int(np.flatnonzero(region == 4)[0]), int(np.flatnonzero(region == 1)[0])]
+        cells = [cells[0], cells[1], cells[0], cells[0]]
+        rates = list(rates)
+        for s, c, pr in zip(*case["recharge"]):
+            rates[s] = -c * (fl[cells[s]][0] - pr)
+            d = case["dir"][s]
+            if (d == 1 and not rates[s] < 0) or (d == 2 and not rates[s] > 0):
+                rates[s] = 0.0
+        assert rates[0] < 0 and rates[1] > 0 and rates[2] == 0.0
     for s in range(n):
         sep0 = f.source_separated(s, rates[s])
         has_sep = len(case["p"][s]) > 0 and rates[s] < 0

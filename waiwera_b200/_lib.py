@@ -81,6 +81,7 @@ SIGNATURES = {
     "wb_set_method": (i, [vp, i, d, vp]),
     "wb_set_source_components": (i, [vp, i, vp, vp]),
     "wb_set_source_controls": (i, [vp, i, vp, vp, vp, vp, vp]),
+    "wb_set_source_recharge": (i, [vp, i, vp, vp, vp]),
     "wb_get_source_rates": (i, [vp, vp]),
     "wb_set_source_separators": (i, [vp, i, vp, vp, vp, vp, vp]),
     "wb_separator_stage": (i, [vp, d, vp, vp]),

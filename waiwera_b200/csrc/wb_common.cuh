@@ -222,6 +222,8 @@ struct wb_ctx {
   std::vector<int> h_src_order;  // sorted position -> input position
   int32_t *d_src_ctrl = nullptr;  // source controls, sorted like the sources (null: none)
   double *d_src_pi = nullptr, *d_src_pref = nullptr, *d_src_limit = nullptr;
+  std::vector<int32_t> h_src_ctrl;  // host copies of the control arrays (sorted source order): setters edit and re-upload
+  std::vector<double> h_src_pi, h_src_pref, h_src_limit;
   int32_t *d_src_sep_n = nullptr;  // separators: stages per source, reference enthalpies, separated-flow limits
   double *d_src_sep_h = nullptr, *d_src_limit_w = nullptr, *d_src_limit_s = nullptr;
   // passive tracers: auxiliary linear problem (wb_tracer.cu)

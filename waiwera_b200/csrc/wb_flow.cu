@@ -1082,6 +1082,7 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   cudaFree(c->d_src_ctrl); cudaFree(c->d_src_pi); cudaFree(c->d_src_pref); cudaFree(c->d_src_limit);
   c->d_src_ctrl = nullptr;
   c->d_src_pi = c->d_src_pref = c->d_src_limit = nullptr;
+  c->h_src_ctrl.clear(); c->h_src_pi.clear(); c->h_src_pref.clear(); c->h_src_limit.clear();
   cudaFree(c->d_src_sep_n); cudaFree(c->d_src_sep_h); cudaFree(c->d_src_limit_w); cudaFree(c->d_src_limit_s);
   c->d_src_sep_n = nullptr;
   c->d_src_sep_h = c->d_src_limit_w = c->d_src_limit_s = nullptr;
@@ -1133,14 +1134,31 @@ extern "C" int wb_set_source_components(wb_ctx *c, int n, const int32_t *injecti
 }
 
 // ---- source controls -----------------------------------------------------------------------------
+static int upload_source_controls(wb_ctx *c) {
+  cudaFree(c->d_src_ctrl); cudaFree(c->d_src_pi); cudaFree(c->d_src_pref); cudaFree(c->d_src_limit);
+  c->d_src_ctrl = nullptr;
+  c->d_src_pi = c->d_src_pref = c->d_src_limit = nullptr;
+  if (c->h_src_ctrl.empty()) return 0;
+  WB_TRY(dev_upload(&c->d_src_ctrl, c->h_src_ctrl));
+  WB_TRY(dev_upload(&c->d_src_pi, c->h_src_pi));
+  WB_TRY(dev_upload(&c->d_src_pref, c->h_src_pref));
+  WB_TRY(dev_upload(&c->d_src_limit, c->h_src_limit));
+  return 0;
+}
+static void ensure_source_controls(wb_ctx *c) {
+  if ((int)c->h_src_ctrl.size() == c->nsrc) return;
+  c->h_src_ctrl.assign(c->nsrc, 0);
+  c->h_src_pi.assign(c->nsrc, 0.0);
+  c->h_src_pref.assign(c->nsrc, 0.0);
+  c->h_src_limit.assign(c->nsrc, 0.0);
+}
+
 extern "C" int wb_set_source_controls(wb_ctx *c, int n, const int32_t *source, const double *productivity,
                                       const double *reference_pressure, const int32_t *direction, const double *limit) {
   WB_CUDA(cudaSetDevice(c->device));
   WB_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(c->d_src_ctrl); cudaFree(c->d_src_pi); cudaFree(c->d_src_pref); cudaFree(c->d_src_limit);
-  c->d_src_ctrl = nullptr;
-  c->d_src_pi = c->d_src_pref = c->d_src_limit = nullptr;
-  if (n <= 0) return 0;
+  c->h_src_ctrl.clear(); c->h_src_pi.clear(); c->h_src_pref.clear(); c->h_src_limit.clear();
+  if (n <= 0) return upload_source_controls(c);
   WB_CHECK(c->nsrc > 0, "wb_set_source_controls: no sources");
   WB_CHECK(!wb_is_device_ptr(source) && !wb_is_device_ptr(productivity) && !wb_is_device_ptr(reference_pressure) &&
                !wb_is_device_ptr(direction) && !wb_is_device_ptr(limit),
@@ -1148,23 +1166,44 @@ extern "C" int wb_set_source_controls(wb_ctx *c, int n, const int32_t *source, c
   const int ns = c->nsrc;
   std::vector<int> pos(ns);  // input position -> sorted position
   for (int k = 0; k < ns; k++) pos[c->h_src_order[k]] = k;
-  std::vector<int32_t> ctrl(ns, 0);
-  std::vector<double> pi(ns, 0.0), pref(ns, 0.0), lim(ns, 0.0);
+  ensure_source_controls(c);
   for (int k = 0; k < n; k++) {
     WB_CHECK(source[k] >= 0 && source[k] < ns, "wb_set_source_controls: source index %d out of range", source[k]);
     const int d = direction ? direction[k] : 0;
     WB_CHECK(d >= 0 && d <= 2, "wb_set_source_controls: direction %d", d);
     const int q = pos[source[k]];
-    ctrl[q] = (productivity[k] > 0.0 ? 1 : 0) | (d << 1);
-    pi[q] = productivity[k];
-    pref[q] = reference_pressure[k];
-    lim[q] = limit ? limit[k] : 0.0;
+    c->h_src_ctrl[q] = (productivity[k] > 0.0 ? 1 : 0) | (d << 1);
+    c->h_src_pi[q] = productivity[k];
+    c->h_src_pref[q] = reference_pressure[k];
+    c->h_src_limit[q] = limit ? limit[k] : 0.0;
   }
-  WB_TRY(dev_upload(&c->d_src_ctrl, ctrl));
-  WB_TRY(dev_upload(&c->d_src_pi, pi));
-  WB_TRY(dev_upload(&c->d_src_pref, pref));
-  WB_TRY(dev_upload(&c->d_src_limit, lim));
-  return 0;
+  return upload_source_controls(c);
+}
+
+// recharge / injectivity controls (recharge_source_control_iterator, src/source_control.F90:554-577; both input keys set
+// up the same control, src/source_setup.F90:2984-3092): rate = -coefficient (P - reference pressure) of the source's
+// cell, before the direction control and the limiters.  Edits the entries of these sources in the control arrays:
+// call after wb_set_source_controls (which starts from scratch).
+extern "C" int wb_set_source_recharge(wb_ctx *c, int n, const int32_t *source, const double *coefficient,
+                                      const double *reference_pressure) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  if (n <= 0) return 0;
+  WB_CHECK(c->nsrc > 0, "wb_set_source_recharge: no sources");
+  WB_CHECK(!wb_is_device_ptr(source) && !wb_is_device_ptr(coefficient) && !wb_is_device_ptr(reference_pressure),
+           "wb_set_source_recharge: the arrays are read on the host (set-up data): pass host arrays");
+  const int ns = c->nsrc;
+  std::vector<int> pos(ns);
+  for (int k = 0; k < ns; k++) pos[c->h_src_order[k]] = k;
+  ensure_source_controls(c);
+  for (int k = 0; k < n; k++) {
+    WB_CHECK(source[k] >= 0 && source[k] < ns, "wb_set_source_recharge: source index %d out of range", source[k]);
+    const int q = pos[source[k]];
+    c->h_src_ctrl[q] = (c->h_src_ctrl[q] & 6) | 8;  // keeps the direction, replaces deliverability
+    c->h_src_pi[q] = coefficient[k];
+    c->h_src_pref[q] = reference_pressure[k];
+  }
+  return upload_source_controls(c);
 }
 
 // separator_stage_init (src/separator.F90:108-136) on the host: reference water and steam enthalpies u + P / rho on the
@@ -1194,12 +1233,8 @@ extern "C" int wb_set_source_separators(wb_ctx *c, int n, const int32_t *source,
            "wb_set_source_separators: the arrays are read on the host (set-up data): pass host arrays");
   const int ns = c->nsrc;
   if (!c->d_src_ctrl) {  // the rate evaluation looks at the separators only behind the control arrays: create empty ones
-    std::vector<int32_t> ctrl(ns, 0);
-    std::vector<double> zero(ns, 0.0);
-    WB_TRY(dev_upload(&c->d_src_ctrl, ctrl));
-    WB_TRY(dev_upload(&c->d_src_pi, zero));
-    WB_TRY(dev_upload(&c->d_src_pref, zero));
-    WB_TRY(dev_upload(&c->d_src_limit, zero));
+    ensure_source_controls(c);
+    WB_TRY(upload_source_controls(c));
   }
   std::vector<int> pos(ns);  // input position -> sorted position
   for (int k = 0; k < ns; k++) pos[c->h_src_order[k]] = k;

@@ -80,7 +80,8 @@ struct WbSources {
   const double *rate, *enth;
   int n;
   // source controls (null: none), sorted like the sources: ctrl bit 0 = on deliverability, bits 1-2 = direction
-  // (0 both, 1 production, 2 injection); productivity index, reference pressure, total-flow limit (<= 0: none)
+  // (0 both, 1 production, 2 injection), bit 3 = recharge / injectivity (pi = its coefficient); productivity index,
+  // reference pressure, total-flow limit (<= 0: none)
   const int32_t *ctrl;
   const double *pi, *pref, *limit;
   // separators and limiters on the separated flows (null: none): stages per source (0..2), reference water / steam
@@ -162,6 +163,10 @@ WB_HD double wb_source_rate(const WbSources &S, int k, const WbCellState<NC, NPH
 #pragma unroll
     for (int p = 0; p < NPH; p++)
       if (s.phases & (1 << p)) rate = rate - effective_productivity * s.mob[p] * pressure_difference;
+  }
+  if (ctrl & 8) {  // recharge / injectivity (recharge_source_control_iterator, src/source_control.F90:554-577)
+    const double pressure_difference = s.P - S.pref[k];
+    rate = -S.pi[k] * pressure_difference;
   }
   const int direction = (ctrl >> 1) & 3;
   if (direction == 1 && !(rate < 0.0)) rate = 0.0;

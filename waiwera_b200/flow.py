@@ -317,6 +317,13 @@ class FlowSimulation:
         return check(self.L.wb_set_source_controls(self.h, len(s), ptr(s), ptr(pi), ptr(pr), ptr(dr), ptr(lm)),
                      "wb_set_source_controls")
 
+    def set_source_recharge(self, sources, coefficient, reference_pressure):
+        """recharge / injectivity controls: rate = -coefficient (P - reference pressure); see wb_set_source_recharge"""
+        s = np.ascontiguousarray(sources, np.int32)
+        cf = np.ascontiguousarray(coefficient, np.float64)
+        pr = np.ascontiguousarray(reference_pressure, np.float64)
+        return check(self.L.wb_set_source_recharge(self.h, len(s), ptr(s), ptr(cf), ptr(pr)), "wb_set_source_recharge")
+
     def set_source_separators(self, sources, pressures, limit_water=None, limit_steam=None):
         """separators (per source a list of 0, 1 or 2 stage pressures) and limits on the separated water / steam rates;
         see wb_set_source_separators"""

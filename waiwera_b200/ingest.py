@@ -381,7 +381,8 @@ def load(path, mod=None, mesh_path=None):
     src = doc.get("source") or []
     for s in src:
         unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer",
-                                "interpolation", "averaging", "deliverability", "direction", "limiter", "separator"}
+                                "interpolation", "averaging", "deliverability", "direction", "limiter", "separator",
+                                "recharge", "injectivity"}
         assert not unsupported, "source controls are not built: %s" % sorted(unsupported)
         dl, lm = s.get("deliverability"), s.get("limiter")
         assert dl is None or all(np.ndim(dl.get(k, 0.0)) == 0 for k in ("pressure", "productivity")), \
@@ -398,7 +399,7 @@ def load(path, mod=None, mesh_path=None):
                                           s.get("averaging", "integrate"))
             s = dict(s, rate=0.0)
             kept.append(s)
-        elif s.get("rate", 0.0) != 0.0 or "deliverability" in s:
+        elif s.get("rate", 0.0) != 0.0 or "deliverability" in s or "recharge" in s or "injectivity" in s:
             kept.append(s)
     src = kept
 
@@ -435,15 +436,28 @@ def load(path, mod=None, mesh_path=None):
     # initial rate, src/source_control.F90:407-468), direction, total-flow limiter
     p.source_controls = []
     for k, s in enumerate(src):
-        if "deliverability" in s or "limiter" in s or "direction" in s:
+        if "deliverability" in s or "limiter" in s or "direction" in s or "recharge" in s or "injectivity" in s:
             dl = s.get("deliverability") or {}
             p.source_controls.append(dict(
                 source=k, deliverability="deliverability" in s, productivity=dl.get("productivity"),
                 reference_pressure=dl.get("pressure", 1.0e5),
-                direction={"both": 0, "production": 1, "injection": 2}[s.get("direction", "both")],
+                direction={"both": 0, "production": 1, "out": 1, "injection": 2, "in": 2}[str(s.get("direction", "both")).lower()],
                 limit=limits(s)["total"]))
         if "deliverability" in s and "rate" not in s:
             s["rate"] = -1.0          # placeholder: producing, the control sets the rate
+    # recharge / injectivity controls (see wb_set_source_recharge; src/source_setup.F90:2925-3092): coefficient (default
+    # 1e-2, src/source_control.F90:37), reference pressure (a number, or None = "initial": the pressure of the cell
+    # at the start of the run)
+    p.source_recharge = []
+    for k, s in enumerate(src):
+        rc = s.get("recharge", s.get("injectivity"))
+        if rc is not None:
+            assert np.ndim(rc.get("coefficient", 0.0)) == 0 and not isinstance(rc.get("pressure"), (list, dict)), \
+                "table-valued recharge parameters are not built"
+            pr = rc.get("pressure", "initial")
+            p.source_recharge.append(dict(source=k, coefficient=float(rc.get("coefficient", 1.0e-2)),
+                                          reference_pressure=None if isinstance(pr, str) else float(pr)))
+            s.setdefault("rate", 0.0)
     # separators and limits on the separated water / steam flows (see wb_set_source_separators)
     p.source_separators = []
     for k, s in enumerate(src):
