@@ -875,6 +875,66 @@ def test_source_separator_limiter_known_answers(wo):
     assert np.allclose(rates, [130.0, -13.0, 0.0, 0.0], rtol=1e-9, atol=1e-9), rates
 
 
+def test_source_control_tables_known_answers(wo):
+    """the sources of the same reference file whose control parameters are tables in time, evaluated over the test's
+    interval [30, 120] s by ingest.controls_at (table averaging pinned by interpolation_test.F90): source 5 (productivity
+    index table, endpoint averaging) -10.1910078135, source 10 (reference pressure table, step, endpoint: 1.8 bar)
+    -12.9264888581701, sources 14 / 15 (rate factor tables, step / linear) 0.75 and 0.375 of -12.8728519749"""
+    import json
+    import os
+    import shutil
+    import tempfile
+    from waiwera_b200 import ingest, mesh as wmesh
+    inp = os.path.join(os.path.dirname(__file__), "golden", "inputs")
+    doc = json.load(open(os.path.join(inp, "problem2a.input.json")))
+    cell = doc["source"][0]["cell"]
+    doc["source"] = [
+        {"cell": cell, "direction": "out", "deliverability": {"productivity": {"time": [[0.0, 1e-12], [60.0, 9e-13], [90.0, 7e-13], [180.0, 5e-13]]}, "pressure": 200000.0}, "averaging": "endpoint"},
+        {"cell": cell, "deliverability": {"productivity": 1e-12, "pressure": {"time": [[0.0, 200000.0], [60.0, 190000.0], [90.0, 160000.0], [180.0, 150000.0]]}}, "interpolation": "step", "averaging": "endpoint"},
+        {"cell": cell, "direction": "production", "deliverability": {"productivity": 1e-12, "pressure": 200000.0}, "factor": {"time": [[0.0, 1.0], [30.0, 0.75], [120.0, 0.0]], "interpolation": "step"}},
+        {"cell": cell, "direction": "production", "deliverability": {"productivity": 1e-12, "pressure": 200000.0}, "factor": [[0.0, 1.0], [30.0, 0.75], [120.0, 0.0]]},
+    ]
+    with tempfile.TemporaryDirectory() as d:
+        for fn in os.listdir(inp):
+            if fn.endswith(".msh"):
+                shutil.copy(os.path.join(inp, fn), d)
+        path = os.path.join(d, "in.json")
+        json.dump(doc, open(path, "w"))
+        p = ingest.load(path)
+    ctrl, _ = ingest.controls_at(p, 30.0, 120.0)
+    assert abs(ctrl[1]["reference_pressure"] - 1.8e5) < 1e-6          # asserted by the reference test itself
+    L = wo.lib()
+    th = L.wo_thermo_create(wo.THERMO_IAPWS, 0)
+    P, sv = 50.e5, 0.8
+    T = C.c_double()
+    assert L.wo_saturation_temperature(th, P, C.byref(T)) == 0
+    rec = np.zeros(26)
+    rec[0], rec[1], rec[2], rec[3], rec[5] = P, T.value, 4.0, 4.0, 1.0
+    rec[4] = L.wo_phase_composition(th, 4, P, T.value)
+    for q, (sat, X) in enumerate([(1.0 - sv, [0.75, 0.25]), (sv, [0.9, 0.1])]):
+        props = np.zeros(2)
+        assert L.wo_region_properties(th, q + 1, wo.dp(np.array([P, T.value])), wo.dp(props)) == 0
+        ph = rec[8 + 9 * q: 8 + 9 * (q + 1)]
+        ph[0], ph[6] = props
+        ph[1] = L.wo_region_viscosity(th, q + 1, T.value, P, props[0])
+        ph[2] = ph[3] = sat
+        ph[5] = props[1] + P / props[0]
+        ph[7:9] = X
+    L.wo_thermo_destroy(th)
+    m = wmesh.structured(2, 1, 1, dx=1.0, gravity=(0.0, 0.0, 0.0), heterogeneous=False)
+    f = wo.Flow(wo.make_params(eos=wo.EOS_WCE, gravity=(0.0, 0.0, 0.0)), m.ncell, m.ninterior, m.nowned,
+                m.face_cells.reshape(-1), m.face_geom.reshape(-1), m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    f.set_sources([0] * 4, [0] * 4, [-1.0] * 4, [0.0] * 4)
+    f.current_fluid()[:] = rec
+    f.set_source_controls([c["source"] for c in ctrl], [c["productivity"] for c in ctrl], [c["reference_pressure"] for c in ctrl],
+                          [c["direction"] for c in ctrl], [c["limit"] for c in ctrl])
+    rhs = np.zeros(6)
+    assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+    rates = f.source_rates(4)
+    expect = [-10.1910078135, -12.9264888581701, -12.8728519749 * 0.75, -12.8728519749 * 0.375]
+    assert np.allclose(rates, expect, rtol=1e-9, atol=1e-12), rates
+
+
 def test_eos_scaling(wo):
     """test/unit/src/eos_test.F90:94-200: eos%scale / eos%unscale of every EOS of this build with default, user and
     adaptive (partial pressure / pressure) scales"""

@@ -382,13 +382,24 @@ def load(path, mod=None, mesh_path=None):
     for s in src:
         unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer",
                                 "interpolation", "averaging", "deliverability", "direction", "limiter", "separator",
-                                "recharge", "injectivity"}
+                                "recharge", "injectivity", "factor"}
         assert not unsupported, "source controls are not built: %s" % sorted(unsupported)
-        dl, lm = s.get("deliverability"), s.get("limiter")
-        assert dl is None or all(np.ndim(dl.get(k, 0.0)) == 0 for k in ("pressure", "productivity")), \
-            "table-valued deliverability parameters are not built"
-        assert lm is None or all(np.ndim(lm.get(k, 0.0)) == 0 for k in ("limit", "total", "water", "steam")), \
-            "table-valued limits are not built"
+        dl = s.get("deliverability")
+        assert dl is None or "threshold" not in dl, "deliverability thresholds are not built"
+        assert dl is None or not (isinstance(dl.get("pressure"), dict) and "enthalpy" in dl["pressure"]), \
+            "reference pressures tabulated against enthalpy are not built"
+
+    def as_table(v, s, sub=None):
+        """a control parameter given as a table in time: [[t, v], ...] or {"time": [[t, v], ...]} (a sub-object may carry
+        its own "interpolation" / "averaging", else the source's: src/source_setup.F90); None for a plain number"""
+        own = sub if isinstance(sub, dict) else {}
+        if isinstance(v, dict) and "time" in v:
+            own = dict(own, **{k: v[k] for k in ("interpolation", "averaging") if k in v})
+            v = v["time"]
+        if isinstance(v, list) and v and isinstance(v[0], list):
+            return (np.array(v, float), own.get("interpolation", s.get("interpolation", "linear")),
+                    own.get("averaging", s.get("averaging", "integrate")))
+        return None
     # a rank-2 "rate" is a table source control (src/source_control.F90: table of (time, rate)); kept as a table
     # that rates_at() evaluates over each time step, "step" or "linear" interpolation, "endpoint" averaging
     p.source_tables = {}
@@ -434,10 +445,33 @@ def load(path, mod=None, mesh_path=None):
         return out
     # source controls (see wb_set_source_controls): deliverability (productivity None: to be calculated from the
     # initial rate, src/source_control.F90:407-468), direction, total-flow limiter
+    # parameters given as tables in time are kept in p.source_control_tables[(source, key)] and evaluated over each
+    # time step by controls_at(); key: "productivity", "reference_pressure", "limit", "limit_water", "limit_steam",
+    # "factor" (rate_factor_source_control: the rate after the other controls times the factor)
     p.source_controls = []
+    p.source_control_tables = {}
     for k, s in enumerate(src):
+        if "factor" in s:
+            tab = as_table(s["factor"], s, s["factor"])
+            if tab is not None:
+                p.source_control_tables[(k, "factor")] = tab
+            else:
+                p.source_control_tables[(k, "factor")] = (np.array([[0.0, float(s["factor"])]]), "step", "integrate")
         if "deliverability" in s or "limiter" in s or "direction" in s or "recharge" in s or "injectivity" in s:
-            dl = s.get("deliverability") or {}
+            dl = dict(s.get("deliverability") or {})
+            for key, name in (("productivity", "productivity"), ("pressure", "reference_pressure")):
+                tab = as_table(dl.get(key), s, dl)
+                if tab is not None:
+                    p.source_control_tables[(k, name)] = tab
+                    dl[key] = float(tab[0][0, 1])
+            lm = s.get("limiter") or {}
+            for key, name in (("limit", "limit"), ("total", "limit"), ("water", "limit_water"), ("steam", "limit_steam")):
+                tab = as_table(lm.get(key), s, lm)
+                if tab is not None:
+                    if key == "limit":
+                        name = {"total": "limit", "water": "limit_water", "steam": "limit_steam"}[str(lm.get("type", "total")).lower()]
+                    p.source_control_tables[(k, name)] = tab
+                    lm[key] = float(tab[0][0, 1])
             p.source_controls.append(dict(
                 source=k, deliverability="deliverability" in s, productivity=dl.get("productivity"),
                 reference_pressure=dl.get("pressure", 1.0e5),
@@ -547,8 +581,37 @@ def components_at(p, rates):
 
 
 def rates_at(p, t0, t1):
-    """source rates for the time step [t0, t1]: fixed rates, and table sources averaged over the step"""
+    """source rates for the time step [t0, t1]: fixed rates, and table sources averaged over the step; a "factor"
+    control of a fixed-rate source scales its rate (sources on deliverability: see controls_at)"""
     r = p.source_rates.copy()
     for k, (tab, interp, averaging) in p.source_tables.items():
         r[k] = _table_average(tab, interp, t0, t1, averaging)
+    on_deliv = {c["source"] for c in getattr(p, "source_controls", []) if c["deliverability"]}
+    for (k, key), (tab, interp, averaging) in getattr(p, "source_control_tables", {}).items():
+        if key == "factor" and k not in on_deliv:
+            r[k] = r[k] * _table_average(tab, interp, t0, t1, averaging)
     return r
+
+
+def controls_at(p, t0, t1):
+    """the source controls and separator limits for the time step [t0, t1]: copies of p.source_controls /
+    p.source_separators with every table-valued parameter replaced by its average over the step (table_object_control
+    update, src/control.F90 with interpolation_table%average), and the "factor" of a source on deliverability folded
+    into its productivity index (the deliverability rate is linear in it).  Pass them to wb_set_source_controls /
+    wb_set_source_separators before the step."""
+    tabs = getattr(p, "source_control_tables", {})
+    avg = lambda k, key: _table_average(*tabs[(k, key)][:2], t0, t1, tabs[(k, key)][2])
+    ctrl = [dict(c) for c in p.source_controls]
+    for c in ctrl:
+        k = c["source"]
+        for key in ("productivity", "reference_pressure", "limit"):
+            if (k, key) in tabs:
+                c[key] = avg(k, key)
+        if (k, "factor") in tabs and c["deliverability"] and c["productivity"] is not None:
+            c["productivity"] = c["productivity"] * avg(k, "factor")
+    seps = [dict(q) for q in getattr(p, "source_separators", [])]
+    for q in seps:
+        for key in ("limit_water", "limit_steam"):
+            if (q["source"], key) in tabs:
+                q[key] = avg(q["source"], key)
+    return ctrl, seps
