@@ -30,20 +30,20 @@ def box_blocks(dims, box):
     return inv.astype(np.int32)
 
 
-def solve_three_ways(wo, flow, sim, M, A, bor, b, restart, maxit, rtol, norm_mode=0):
+def solve_three_ways(wo, flow, sim, M, A, bor, b, restart, maxit, rtol, norm_mode=0, ksp=0):
     """oracle, launch-per-operation GPU solver, persistent kernel (norm_mode 0: VecNorm as a second reduction, the
-    reference's arithmetic; 2: the norm from the dot-product pass)"""
+    reference's arithmetic; 2: the norm from the dot-product pass; ksp 0: GMRES, 1: BiCGStab)"""
     L = flow._lib.lib()
     n = len(b)
     pc_ref = wo.lib().wo_pc_create(A, 2, wo.ip(bor))
     o = wo.KspOpts()
-    o.type, o.restart, o.maxit, o.rtol, o.atol, o.dtol = 0, restart, maxit, rtol, 1e-50, 1e5
+    o.type, o.restart, o.maxit, o.rtol, o.atol, o.dtol = ksp, restart, maxit, rtol, 1e-50, 1e5
     x0 = np.zeros(n)
     its0, rn0 = C.c_int(), C.c_double()
     reason0 = wo.lib().wo_ksp_solve(A, pc_ref, C.byref(o), wo.dp(b), wo.dp(x0), C.byref(its0), C.byref(rn0))
     wo.lib().wo_pc_destroy(pc_ref)
     res = [(reason0, its0.value, rn0.value, x0)]
-    opts = flow.ksp_opts(type=0, restart=restart, maxit=maxit, rtol=rtol)
+    opts = flow.ksp_opts(type=ksp, restart=restart, maxit=maxit, rtol=rtol)
     L.wb_ksp_set_fused_norm(norm_mode)
     for fused in (0, 2):   # 2: the persistent kernel wherever it can run (1 = automatic choice)
         L.wb_ksp_set_fused(fused)
@@ -98,6 +98,64 @@ def test_fused_gmres_matches_oracle_and_unfused(wo, flow, case, norm_mode):
         M.mult(fused[3], ax)
         assert relerr(ax, b) < 1e-5
         assert abs(fused[2] - ref[2]) <= 1e-6 * abs(ref[2]) + 1e-3 * case["rtol"] * np.linalg.norm(b)
+    M.destroy()
+    wo.lib().wo_bsr_destroy(A)
+    sim.destroy()
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[2], CASES[3], CASES[5], CASES[6], CASES[7],
+                                  dict(dims=(10, 9, 7), bs=2, box=(4, 4, 3), restart=30, maxit=7, rtol=1e-12)])
+def test_fused_bcgs_matches_oracle_and_unfused(wo, flow, case):
+    """KSPSolve_BCGS in the persistent kernel against the oracle's BiCGStab and the launch-per-operation GPU BiCGStab"""
+    dims, bs = case["dims"], case["bs"]
+    m, A, rowptr, colidx, val = random_bsr(wo, dims, bs, SEED + 23, diag_boost=3.0)
+    _, y0, region, prm = make_problem(wo, dims=dims)
+    sim = gpu_flow(wo, flow, m, prm, y0, region)
+    nb = m.nowned
+    M = flow.Mat.create(sim, nb, nb, bs, rowptr, colidx, val)
+    bor = box_blocks(dims, case["box"])
+    b = np.random.default_rng(SEED + 6).uniform(-1, 1, nb * bs)
+    ref, unfused, fused = solve_three_ways(wo, flow, sim, M, A, bor, b, 30, case["maxit"], case["rtol"], 0, ksp=1)
+    assert fused[4] <= 3 and unfused[4] > 3 * max(unfused[1], 1)
+    assert ref[0] == unfused[0] == fused[0], (ref[:3], unfused[:3], fused[:3])
+    # BiCGStab's iteration count moves with the summation order of its dot products (three implementations, three
+    # orders: e.g. 71 / 66 / 72): a band; a solve cut off by the iteration limit runs the same number of iterations
+    tol_its = 0 if case["maxit"] < 100 else max(2, int(0.15 * ref[1]))
+    assert abs(fused[1] - ref[1]) <= tol_its and abs(fused[1] - unfused[1]) <= tol_its, (ref[1], unfused[1], fused[1])
+    lim = 1e-6 if case["maxit"] > 100 else 1e-8
+    assert relerr(fused[3], unfused[3]) < lim and relerr(fused[3], ref[3]) < lim
+    if case["maxit"] > 100:
+        ax = np.zeros(nb * bs)
+        M.mult(fused[3], ax)
+        assert relerr(ax, b) < 1e-5
+    M.destroy()
+    wo.lib().wo_bsr_destroy(A)
+    sim.destroy()
+
+
+def test_fused_bcgs_zero_rhs_and_repeat(wo, flow):
+    dims, bs = (8, 8, 6), 2
+    m, A, rowptr, colidx, val = random_bsr(wo, dims, bs, SEED + 24, diag_boost=3.0)
+    _, y0, region, prm = make_problem(wo, dims=dims)
+    sim = gpu_flow(wo, flow, m, prm, y0, region)
+    nb = m.nowned
+    M = flow.Mat.create(sim, nb, nb, bs, rowptr, colidx, val)
+    bor = box_blocks(dims, (4, 4, 3))
+    pc = flow.PC(M, 2, 1, bor)
+    x = np.ones(nb * bs)
+    launches = sim.launches()
+    reason, its, rn = flow.ksp_solve(M, pc, np.zeros(nb * bs), x, flow.ksp_opts(type=1))
+    assert sim.launches() - launches <= 3
+    assert reason > 0 and its == 0 and not x.any()
+    b = np.random.default_rng(3).uniform(-1, 1, nb * bs)
+    xs = []
+    for _ in range(3):
+        x = np.zeros(nb * bs)
+        r = flow.ksp_solve(M, pc, b, x, flow.ksp_opts(type=1, rtol=1e-10))
+        xs.append((r, x))
+    assert xs[0][0] == xs[1][0] == xs[2][0] and xs[0][0][0] > 0
+    assert np.array_equal(xs[0][1], xs[1][1]) and np.array_equal(xs[0][1], xs[2][1])
+    pc.destroy()
     M.destroy()
     wo.lib().wo_bsr_destroy(A)
     sim.destroy()

@@ -123,6 +123,8 @@ def worker(rank, world, port, out, p2p, kind="we"):
         kreason, kits, _ = flow.ksp_solve(J, pck, rk, xk, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10))
         xk2 = np.zeros_like(x)
         k2 = flow.ksp_solve(J, pck, rk, xk2, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10, restart=7))
+        xk3 = np.zeros_like(x)   # the reference's default Krylov method, also inside the persistent kernel
+        k3 = flow.ksp_solve(J, pck, rk, xk3, flow.ksp_opts(type=flow.KSP_BCGS, rtol=1e-10))
         pck.destroy()
         assert sim.jacobian(y1, L0, DT) == 0
         y2 = y.copy()
@@ -132,7 +134,7 @@ def worker(rank, world, port, out, p2p, kind="we"):
         gathered = [None] * world
         dist.all_gather_object(gathered, dict(nat=nat, r=r, ax=ax, y2=y2, mv=mv, ml=ml, reason=res.reason,
                                               its=res.iterations, lits=res.linear_iterations, xt=xt, xk=xk,
-                                              kreason=kreason, kits=kits, xk2=xk2, k2=k2[:2]))
+                                              kreason=kreason, kits=kits, xk2=xk2, k2=k2[:2], xk3=xk3, k3=k3[:2]))
         if rank == 0:
             out.put(gathered)
         sim.destroy()
@@ -183,16 +185,21 @@ def test_partitioned_path_matches_single_gpu(world, p2p, kind):
     kreason, kits, _ = flow.ksp_solve(J, pck, rk, xk, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10))
     xk2 = np.zeros_like(x)
     k2 = flow.ksp_solve(J, pck, rk, xk2, flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10, restart=7))
+    xk3 = np.zeros_like(x)
+    k3 = flow.ksp_solve(J, pck, rk, xk3, flow.ksp_opts(type=flow.KSP_BCGS, rtol=1e-10))
     pck.destroy()
     assert kits < 200, kits
     assert sim.jacobian(y1, L0, DT) == 0
-    gxk, gxk2 = np.zeros_like(xk).reshape(-1, npv), np.zeros_like(xk).reshape(-1, npv)
+    gxk, gxk2, gxk3 = np.zeros_like(xk).reshape(-1, npv), np.zeros_like(xk).reshape(-1, npv), np.zeros_like(xk).reshape(-1, npv)
     for g in gathered:
         gxk[g["nat"]] = g["xk"].reshape(-1, npv)
         gxk2[g["nat"]] = g["xk2"].reshape(-1, npv)
+        gxk3[g["nat"]] = g["xk3"].reshape(-1, npv)
+        assert g["k3"][0] == k3[0] > 0 and abs(g["k3"][1] - k3[1]) <= 3, (g["k3"], k3[:2])
         assert g["kreason"] == kreason > 0 and abs(g["kits"] - kits) <= 3, (g["kreason"], g["kits"], kreason, kits)
         assert g["k2"][0] == k2[0] > 0 and abs(g["k2"][1] - k2[1]) <= 6, (g["k2"], k2[:2])
     assert relerr_(gxk.reshape(-1), xk) < 1e-7 and relerr_(gxk2.reshape(-1), xk2) < 1e-7
+    assert relerr_(gxk3.reshape(-1), xk3) < 1e-7
     y2 = gy.copy()
     res = sim.newton_solve(y2, L0, DT, flow.newton_opts(max_iterations=4, pc_type=flow.PC_PBJACOBI,
                                                         ksp=flow.ksp_opts(type=flow.KSP_GMRES, rtol=1e-10)))

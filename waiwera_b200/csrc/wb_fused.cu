@@ -592,7 +592,8 @@ __device__ __forceinline__ void fz_gmres_update(const GmresUpd &u, FzState *st, 
   }
 }
 
-template <int BS>
+// BCGS = 1: the same resident machinery running KSPSolve_BCGS instead of KSPSolve_GMRES (main loop at the end)
+template <int BS, int BCGS = 0>
 __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const FusedArgs a) {
   constexpr int B2 = BS * BS, PW = IluPlane<BS>::PW, NPL = IluPlane<BS>::NP;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
               if (mode == 1) {
 #pragma unroll
                 for (int i = 0; i < BS; i++) {
-                  vstore[(size_t)row * BS + i] = __ldcg(xop + (size_t)row * BS + i) * s;
+                  if (!BCGS) vstore[(size_t)row * BS + i] = __ldcg(xop + (size_t)row * BS + i) * s;
                   zs[li * BS + i] = acc[i];
                 }
               } else {
@@ -1009,6 +1010,173 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       for (int i = 0; i < BS; i++) ll_store(ghost + i * 16, w[(size_t)row * BS + i], hseq + 1);
     }
   };
+  if (BCGS) {
+    // ================================================================ KSPSolve_BCGS (left preconditioning, x0 = 0,
+    // convergence on the preconditioned residual norm): R, RP, P, V, S, T live in the first six columns of the basis
+    // storage, every CTA updates its own rows; the scalars are replicated like the GMRES state.  Per iteration: two
+    // products, three reductions of numbers ((V,RP); (T,S),(T,T); (R,RP),(R,R)) and two barriers that only order the
+    // new operand rows inside the GPU (the neighbours' rows on other GPUs arrive as flagged halo entries).
+    double *vR = a.V, *vRP = a.V + a.ld, *vP = a.V + 2 * a.ld, *vV = a.V + 3 * a.ld, *vS = a.V + 4 * a.ld,
+           *vT = a.V + 5 * a.ld;
+    double *sc = s_cs;  // [0] rho_old, [1] alpha, [2] omega_old, [3] beta, [4] omega, [5] rho, [6] flag: T . T == 0
+    auto reduce_numbers = [&](int nv, bool release) {
+      fz_reduce_ll(a, R, 0, ++rseqA, nv, s_h, s_red, release, multi, aseq + 1, WB_P2P_SLOT_FA, WB_P2P_MAXV, cta, tid, nc);
+      aseq++;
+    };
+    auto barrier_gpu = [&]() {  // rows written by this GPU's CTAs become visible to each other
+      if (tid == 0) s_cf[0] = 0.0;
+      fz_reduce_ll(a, R, 1, ++rseqB, 1, s_cf, s_red, true, false, 0, 0, 1, cta, tid, nc);
+    };
+    if (tid == 0) {
+      s_st->res = 0.0; s_st->rnorm0 = 0.0; s_st->scal1 = 1.0;
+      s_st->its = 0; s_st->it_inner = 0; s_st->reason = 0; s_st->done = 0;
+      sc[0] = 1.0; sc[1] = 1.0; sc[2] = 1.0; sc[6] = 0.0;
+    }
+    FZ_STAMP(5);
+    sp_phase(0, a.xp, 1.0, nullptr, vR);  // R = M^-1 b
+    FZ_STAMP(0);
+    bar_sync_named(FZ_BAR_ALL, nc);
+    for (int e = e0 + tid; e < e1; e += nc) {
+      vRP[e] = __ldcg(vR + e);
+      vP[e] = 0.0;
+      vV[e] = 0.0;
+    }
+    dots(vR, vR, 0, 1, s_h, false);  // (R, R) = (R, RP)
+    FZ_STAMP(1);
+    reduce_numbers(1, false);
+    if (tid == 0) {
+      const double dp = sqrt(s_h[0]);
+      s_h[1] = s_h[0];
+      s_st->res = dp;
+      s_st->rnorm0 = dp;
+      int reason = 0;
+      const double ttol = fmax(u.rtol * dp, u.atol);
+      if (dp != dp) reason = -9;
+      else if (dp <= ttol) reason = (dp < u.atol) ? 3 : 2;
+      if (!reason && dp == 0.0) reason = 3;
+      if (reason) {
+        s_st->reason = reason;
+        s_st->done = 1;
+      }
+    }
+    bar_sync_named(FZ_BAR_ALL, nc);
+    FZ_STAMP(2);
+    while (!__ldcg(&a.bar[2]) && !s_st->done) {
+      // ---- rho = (R, RP) (in s_h[0] from the last reduction), beta, P = R + beta (P - omega_old V)
+      if (tid == 0) {
+        const double rho = s_h[0];
+        sc[5] = rho;
+        if (rho == 0.0) {
+          s_st->reason = -5;  // KSP_DIVERGED_BREAKDOWN
+          s_st->done = 1;
+        }
+        sc[3] = (rho / sc[0]) * (sc[1] / sc[2]);
+      }
+      bar_sync_named(FZ_BAR_ALL, nc);
+      if (s_st->done) break;
+      {
+        const double beta = sc[3], omegaold = sc[2];
+        for (int e = e0 + tid; e < e1; e += nc)
+          vP[e] = __dadd_rn(__ldcg(vR + e), __dmul_rn(beta, __dsub_rn(__ldcg(vP + e), __dmul_rn(omegaold, __ldcg(vV + e)))));
+      }
+      push(vP);
+      FZ_STAMP(3);
+      barrier_gpu();
+      hseq++;
+      FZ_STAMP(4);
+      if (__ldcg(&a.bar[2])) break;
+      // ---- V = M^-1 A P, alpha = rho / (V, RP)
+      sp_phase(1, vP, 1.0, nullptr, vV);
+      FZ_STAMP(0);
+      bar_sync_named(FZ_BAR_ALL, nc);
+      dots(vV, vRP, 0, 1, s_h, false);
+      FZ_STAMP(1);
+      reduce_numbers(1, false);
+      FZ_STAMP(2);
+      if (__ldcg(&a.bar[2])) break;
+      if (tid == 0) {
+        const double d1 = s_h[0];
+        if (d1 == 0.0) {
+          s_st->reason = -5;
+          s_st->done = 1;
+        }
+        sc[1] = sc[5] / d1;
+      }
+      bar_sync_named(FZ_BAR_ALL, nc);
+      if (s_st->done) break;
+      // ---- S = R - alpha V, T = M^-1 A S
+      {
+        const double alpha = sc[1];
+        for (int e = e0 + tid; e < e1; e += nc) vS[e] = __dsub_rn(__ldcg(vR + e), __dmul_rn(alpha, __ldcg(vV + e)));
+      }
+      push(vS);
+      FZ_STAMP(3);
+      barrier_gpu();
+      hseq++;
+      FZ_STAMP(4);
+      if (__ldcg(&a.bar[2])) break;
+      sp_phase(1, vS, 1.0, nullptr, vT);
+      FZ_STAMP(0);
+      bar_sync_named(FZ_BAR_ALL, nc);
+      dots(vT, vS, 0, 1, s_h, true);  // (T, S), (T, T)
+      FZ_STAMP(1);
+      reduce_numbers(2, false);
+      FZ_STAMP(2);
+      if (__ldcg(&a.bar[2])) break;
+      if (tid == 0) {
+        const double d1 = s_h[0], d2 = s_h[1];
+        sc[6] = d2 == 0.0 ? 1.0 : 0.0;
+        sc[4] = d2 == 0.0 ? 0.0 : d1 / d2;
+      }
+      bar_sync_named(FZ_BAR_ALL, nc);
+      // ---- x += alpha P + omega S, R = S - omega T   (T . T == 0: x += alpha P and the solve ends, KSP_CONVERGED_ATOL)
+      {
+        const double alpha = sc[1], omega = sc[4];
+        const bool t0 = sc[6] != 0.0;
+        for (int e = e0 + tid; e < e1; e += nc) {
+          const double pe = __ldcg(vP + e), se = __ldcg(vS + e), xe = a.xp[e];
+          if (t0) {
+            a.xp[e] = __dadd_rn(xe, __dmul_rn(alpha, pe));
+          } else {
+            a.xp[e] = __dadd_rn(xe, __dadd_rn(__dmul_rn(alpha, pe), __dmul_rn(omega, se)));
+            vR[e] = __dsub_rn(se, __dmul_rn(omega, __ldcg(vT + e)));
+          }
+        }
+      }
+      FZ_STAMP(3);
+      bar_sync_named(FZ_BAR_ALL, nc);
+      dots(vR, vRP, 0, 1, s_h, true);  // (R, RP), (R, R)
+      FZ_STAMP(1);
+      reduce_numbers(2, false);
+      FZ_STAMP(2);
+      if (__ldcg(&a.bar[2])) break;
+      if (tid == 0) {
+        s_st->its += 1;
+        if (sc[6] != 0.0) {
+          s_st->res = 0.0;
+          s_st->reason = 3;
+          s_st->done = 1;
+        } else {
+          const double dp = sqrt(s_h[1]);
+          s_st->res = dp;
+          sc[0] = sc[5];
+          sc[2] = sc[4];
+          int reason = 0;
+          const double ttol = fmax(u.rtol * s_st->rnorm0, u.atol);
+          if (dp != dp) reason = -9;
+          else if (dp <= ttol) reason = (dp < u.atol) ? 3 : 2;
+          else if (dp >= u.dtol * s_st->rnorm0) reason = -4;
+          if (!reason && s_st->its >= u.maxit) reason = -3;
+          if (reason) {
+            s_st->reason = reason;
+            s_st->done = 1;
+          }
+        }
+      }
+      bar_sync_named(FZ_BAR_ALL, nc);
+      if (profiler) s_prof[6]++;
+    }
+  } else {
   double *w_old = a.wa, *w_new = a.wb;
   bool first = true, done = false;
   if (tid == 0) {
@@ -1141,6 +1309,7 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
     FZ_STAMP(5);
     if (__ldcg(&a.bar[2])) break;
   }
+  }
   // ---- the solution in the caller's ordering; the solver state for the host; stop the producer
   bar_sync_named(FZ_BAR_ALL, nc);
   for (int r = R0 + tid; r < R1; r += nc) {
@@ -1173,9 +1342,17 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
 
 bool wb_fused_usable(const wb_mat *A, const wb_pc *pc, const wb_ksp_opts *o) {
   if (!pc || !pc->fused || !pc->blocked || pc->type != WB_PC_BJACOBI_ILU0 || !fused_mode()) return false;
-  if (o->type != WB_KSP_GMRES) return false;
+  if (o->type != WB_KSP_GMRES && o->type != WB_KSP_BCGS) return false;
+  if (o->type == WB_KSP_BCGS) {
+    static int on = -1;  // WB_FUSED_BCGS=0: BiCGStab stays with the launch-per-operation kernels
+    if (on < 0) {
+      const char *e = getenv("WB_FUSED_BCGS");
+      on = e ? atoi(e) : 1;
+    }
+    if (!on) return false;
+  }
   const int m = o->restart > 0 ? o->restart : 30;
-  if (m + 1 > KRY_MAXV) return false;
+  if (o->type == WB_KSP_GMRES && m + 1 > KRY_MAXV) return false;
   // 3x3 blocks leave the persistent kernel with 6 consumer warps per SM: with several sub-domains per CTA (the
   // bandwidth-bound regime) the launch-per-operation kernels stream faster (measured on config 4: 294 vs 274 us per
   // iteration); with one or two sub-domains per CTA (latency-bound) the persistent kernel wins (config 5: 145 vs 177)
@@ -1231,7 +1408,8 @@ int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b
   wb_ctx *c = A->ctx;
   WbFusedPlan *f = pc->fused;
   const size_t n = (size_t)A->nb * A->bs;
-  const int m = o->restart > 0 ? o->restart : 30;
+  const bool bcgs = o->type == WB_KSP_BCGS;
+  const int m = bcgs ? 30 : (o->restart > 0 ? o->restart : 30);  // BiCGStab keeps its six vectors in the basis storage
   KspWork *wp;
   WB_TRY(wb_ensure_work(c, n, m, &wp));
   KspWork &w = *wp;
@@ -1285,20 +1463,21 @@ int wb_gmres_fused(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b
   const int threads = f->nc + 32;  // consumers + the producer warp
   void *args[] = {&a};
   cudaError_t e;
-  switch (A->bs) {
-    case 1:
-      WB_CUDA(cudaFuncSetAttribute(k_gmres_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
-      e = cudaLaunchCooperativeKernel((void *)k_gmres_fused<1>, dim3(f->ncta), dim3(threads), args, f->smem, c->stream);
-      break;
-    case 2:
-      WB_CUDA(cudaFuncSetAttribute(k_gmres_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
-      e = cudaLaunchCooperativeKernel((void *)k_gmres_fused<2>, dim3(f->ncta), dim3(threads), args, f->smem, c->stream);
-      break;
-    default:
-      WB_CUDA(cudaFuncSetAttribute(k_gmres_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
-      e = cudaLaunchCooperativeKernel((void *)k_gmres_fused<3>, dim3(f->ncta), dim3(threads), args, f->smem, c->stream);
-      break;
+#define FZ_LAUNCH(BS_, BC_)                                                                                          \
+  do {                                                                                                             \
+    WB_CUDA(cudaFuncSetAttribute(k_gmres_fused<BS_, BC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem)); \
+    e = cudaLaunchCooperativeKernel((void *)k_gmres_fused<BS_, BC_>, dim3(f->ncta), dim3(threads), args, f->smem,  \
+                                    c->stream);                                                                    \
+  } while (0)
+  switch (A->bs * 2 + (bcgs ? 1 : 0)) {
+    case 2: FZ_LAUNCH(1, 0); break;
+    case 3: FZ_LAUNCH(1, 1); break;
+    case 4: FZ_LAUNCH(2, 0); break;
+    case 5: FZ_LAUNCH(2, 1); break;
+    case 6: FZ_LAUNCH(3, 0); break;
+    default: FZ_LAUNCH(3, 1); break;
   }
+#undef FZ_LAUNCH
   WB_CHECK(e == cudaSuccess, "fused GMRES: cooperative launch failed: %s", cudaGetErrorString(e));
   WB_LAUNCH(c);
   WB_TRY(wb_fetch_state(w));

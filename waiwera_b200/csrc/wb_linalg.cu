@@ -2692,8 +2692,9 @@ int wb_vec_axpby_dev(wb_ctx *c, double *z, double a, const double *x, double b, 
 int wb_ksp_solve_dev(wb_mat *A, wb_pc *pc, const wb_ksp_opts *o, const double *d_b, double *d_x, int *its,
                      int *reason, double *rnorm) {
   WbScopedTimer tm(A->ctx, "ksp_solve");
-  if (o->type == WB_KSP_BCGS) return bcgs_dev(A, pc, o, d_b, d_x, its, reason, rnorm);
+  // the persistent kernel runs GMRES and BiCGStab over block-Jacobi / ILU(0) sub-domains (wb_fused.cu)
   if (wb_fused_usable(A, pc, o)) return wb_gmres_fused(A, pc, o, d_b, d_x, its, reason, rnorm);
+  if (o->type == WB_KSP_BCGS) return bcgs_dev(A, pc, o, d_b, d_x, its, reason, rnorm);
   return gmres_dev(A, pc, o, d_b, d_x, its, reason, rnorm);
 }
 
