@@ -1076,8 +1076,16 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       if (s_st->done) break;
       {
         const double beta = sc[3], omegaold = sc[2];
-        for (int e = e0 + tid; e < e1; e += nc)
-          vP[e] = __dadd_rn(__ldcg(vR + e), __dmul_rn(beta, __dsub_rn(__ldcg(vP + e), __dmul_rn(omegaold, __ldcg(vV + e)))));
+        auto fp = [&](double r, double p_, double v) { return __dadd_rn(r, __dmul_rn(beta, __dsub_rn(p_, __dmul_rn(omegaold, v)))); };
+        for (int i = (eb >> 1) + tid; i < (ee >> 1); i += nc) {  // 16-byte body of the CTA's rows, two entries per thread
+          const double2 r = __ldcg(reinterpret_cast<const double2 *>(vR) + i), p_ = __ldcg(reinterpret_cast<const double2 *>(vP) + i),
+                        v = __ldcg(reinterpret_cast<const double2 *>(vV) + i);
+          reinterpret_cast<double2 *>(vP)[i] = make_double2(fp(r.x, p_.x, v.x), fp(r.y, p_.y, v.y));
+        }
+        if (tid == 0) {  // unaligned head / tail element
+          if (eb > e0) vP[e0] = fp(__ldcg(vR + e0), __ldcg(vP + e0), __ldcg(vV + e0));
+          if (ee < e1 && ee >= eb) vP[e1 - 1] = fp(__ldcg(vR + e1 - 1), __ldcg(vP + e1 - 1), __ldcg(vV + e1 - 1));
+        }
       }
       push(vP);
       FZ_STAMP(3);
@@ -1107,7 +1115,15 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       // ---- S = R - alpha V, T = M^-1 A S
       {
         const double alpha = sc[1];
-        for (int e = e0 + tid; e < e1; e += nc) vS[e] = __dsub_rn(__ldcg(vR + e), __dmul_rn(alpha, __ldcg(vV + e)));
+        auto fs = [&](double r, double v) { return __dsub_rn(r, __dmul_rn(alpha, v)); };
+        for (int i = (eb >> 1) + tid; i < (ee >> 1); i += nc) {
+          const double2 r = __ldcg(reinterpret_cast<const double2 *>(vR) + i), v = __ldcg(reinterpret_cast<const double2 *>(vV) + i);
+          reinterpret_cast<double2 *>(vS)[i] = make_double2(fs(r.x, v.x), fs(r.y, v.y));
+        }
+        if (tid == 0) {
+          if (eb > e0) vS[e0] = fs(__ldcg(vR + e0), __ldcg(vV + e0));
+          if (ee < e1 && ee >= eb) vS[e1 - 1] = fs(__ldcg(vR + e1 - 1), __ldcg(vV + e1 - 1));
+        }
       }
       push(vS);
       FZ_STAMP(3);
@@ -1133,13 +1149,28 @@ __global__ void __launch_bounds__(BS >= 3 ? 224 : 416, 1) k_gmres_fused(const Fu
       {
         const double alpha = sc[1], omega = sc[4];
         const bool t0 = sc[6] != 0.0;
-        for (int e = e0 + tid; e < e1; e += nc) {
-          const double pe = __ldcg(vP + e), se = __ldcg(vS + e), xe = a.xp[e];
-          if (t0) {
-            a.xp[e] = __dadd_rn(xe, __dmul_rn(alpha, pe));
-          } else {
-            a.xp[e] = __dadd_rn(xe, __dadd_rn(__dmul_rn(alpha, pe), __dmul_rn(omega, se)));
-            vR[e] = __dsub_rn(se, __dmul_rn(omega, __ldcg(vT + e)));
+        auto fx = [&](double xe, double pe, double se) {
+          return t0 ? __dadd_rn(xe, __dmul_rn(alpha, pe)) : __dadd_rn(xe, __dadd_rn(__dmul_rn(alpha, pe), __dmul_rn(omega, se)));
+        };
+        auto fr = [&](double se, double te) { return __dsub_rn(se, __dmul_rn(omega, te)); };
+        for (int i = (eb >> 1) + tid; i < (ee >> 1); i += nc) {
+          const double2 pe = __ldcg(reinterpret_cast<const double2 *>(vP) + i), se = __ldcg(reinterpret_cast<const double2 *>(vS) + i),
+                        xe = __ldcg(reinterpret_cast<const double2 *>(a.xp) + i);
+          reinterpret_cast<double2 *>(a.xp)[i] = make_double2(fx(xe.x, pe.x, se.x), fx(xe.y, pe.y, se.y));
+          if (!t0) {
+            const double2 te = __ldcg(reinterpret_cast<const double2 *>(vT) + i);
+            reinterpret_cast<double2 *>(vR)[i] = make_double2(fr(se.x, te.x), fr(se.y, te.y));
+          }
+        }
+        if (tid == 0) {
+          if (eb > e0) {
+            a.xp[e0] = fx(__ldcg(a.xp + e0), __ldcg(vP + e0), __ldcg(vS + e0));
+            if (!t0) vR[e0] = fr(__ldcg(vS + e0), __ldcg(vT + e0));
+          }
+          if (ee < e1 && ee >= eb) {
+            const int q = e1 - 1;
+            a.xp[q] = fx(__ldcg(a.xp + q), __ldcg(vP + q), __ldcg(vS + q));
+            if (!t0) vR[q] = fr(__ldcg(vS + q), __ldcg(vT + q));
           }
         }
       }
