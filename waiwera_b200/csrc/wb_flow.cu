@@ -1158,7 +1158,10 @@ extern "C" int wb_set_source_controls(wb_ctx *c, int n, const int32_t *source, c
   WB_CUDA(cudaSetDevice(c->device));
   WB_CUDA(cudaStreamSynchronize(c->stream));
   c->h_src_ctrl.clear(); c->h_src_pi.clear(); c->h_src_pref.clear(); c->h_src_limit.clear();
-  if (n <= 0) return upload_source_controls(c);
+  if (n <= 0) {
+    if (c->d_src_sep_n) ensure_source_controls(c);  // separators stay in force: they are evaluated behind these arrays
+    return upload_source_controls(c);
+  }
   WB_CHECK(c->nsrc > 0, "wb_set_source_controls: no sources");
   WB_CHECK(!wb_is_device_ptr(source) && !wb_is_device_ptr(productivity) && !wb_is_device_ptr(reference_pressure) &&
                !wb_is_device_ptr(direction) && !wb_is_device_ptr(limit),
