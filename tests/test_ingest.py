@@ -295,3 +295,64 @@ def test_source_component_follows_the_sign_of_the_rate(wo, tmp_path):
     assert abs(out["in"][0]) < 1e-12 * r_in[0] and abs(out["in"][1] - r_in[0]) < 1e-9 * r_in[0] and out["in"][2] > 0
     assert out["out"][0] < 0 and out["out"][1] <= 0 and abs(out["out"][0] + out["out"][1] - r_out[0]) < 1e-9 * abs(r_out[0])
     assert out["out"][0] < 10 * out["out"][1]
+
+
+def _write_exodus_grid(path, xs, ys, zs):
+    """a one-block HEX8 ExodusII file (netCDF classic) of a tensor grid, nodes x-fastest then y then z, elements
+    x-fastest: the layout of the reference's test/unit/data/mesh/7x7grid.exo"""
+    from scipy.io import netcdf_file
+    nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    order = lambda A: A.transpose(2, 1, 0).reshape(-1)
+    node = lambda i, j, k: i + (nx + 1) * (j + (ny + 1) * k)
+    con = [[node(i, j, k), node(i + 1, j, k), node(i + 1, j + 1, k), node(i, j + 1, k),
+            node(i, j, k + 1), node(i + 1, j, k + 1), node(i + 1, j + 1, k + 1), node(i, j + 1, k + 1)]
+           for k in range(nz) for j in range(ny) for i in range(nx)]
+    f = netcdf_file(path, "w")
+    f.createDimension("num_dim", 3)
+    f.createDimension("num_nodes", (nx + 1) * (ny + 1) * (nz + 1))
+    f.createDimension("num_elem", len(con))
+    f.createDimension("num_el_blk", 1)
+    f.createDimension("num_el_in_blk1", len(con))
+    f.createDimension("num_nod_per_el1", 8)
+    for name, A in (("coordx", X), ("coordy", Y), ("coordz", Z)):
+        v = f.createVariable(name, "d", ("num_nodes",))
+        v[:] = order(A)
+    c = f.createVariable("connect1", "i", ("num_el_in_blk1", "num_nod_per_el1"))
+    c[:] = np.array(con, np.int32) + 1
+    c.elem_type = "HEX"
+    f.close()
+
+
+def test_exodus_mesh_and_zones_known_answers(tmp_path):
+    """ExodusII (netCDF classic) meshes are read directly; zones: the known answers of test/unit/src/zone_test.F90:320-489
+    on the reference's 7 x 7 grid (box zones 14 / 49 / 9 cells; combined zones 14, 7, 3, 21, 19, 2, 2, 49)"""
+    xs = [0.0, 1000.0, 1500.0, 2000.0, 2500.0, 3000.0, 3500.0, 4500.0]
+    path = str(tmp_path / "grid7.exo")
+    _write_exodus_grid(path, xs, xs, [300.0, 500.0])
+    xyz, elems = ingest.read_mesh(path)
+    assert xyz.shape == (128, 3) and len(elems) == 49 and all(t == 5 for t, _ in elems)
+    ref = "/root/reference/test/unit/data/mesh/7x7grid.exo"
+    if os.path.exists(ref):      # this container only: the synthetic file is the reference's file
+        rxyz, relems = ingest.read_exodus(ref)
+        assert np.array_equal(rxyz, xyz) and relems == elems
+    m, _ = ingest.build_mesh(xyz, elems)
+    assert m.ninterior == 49
+    assert np.allclose(m.cell_geom[0], [500.0, 500.0, 400.0, 1000.0 * 1000.0 * 200.0])
+    zones = {"xzone": {"x": [2000, 3000]}, "all": {"type": "box"}, "xyzone": {"x": [0, 2000], "y": [2500, 4500]},
+             "zone1": {"x": [2000, 3000]}, "zone2": {"x": [3500, 4500]}, "zone3": {"x": [2500, 4500], "y": [0, 1000]},
+             "zone_plus": {"+": ["zone1", "zone2"]}, "zone_minus": {"+": "zone_plus", "-": "zone3"},
+             "zone_times": {"+": "zone_plus", "*": "zone3"}, "zone_times2": {"*": ["zone_plus", "zone3"]},
+             "all2": {"-": None}, "cells": [3, 1, 2], "cells2": {"cells": [1, 2, 3]}, "cells3": {"type": "array", "cells": [2]}}
+    expect = {"xzone": 14, "all": 49, "xyzone": 9, "zone1": 14, "zone2": 7, "zone3": 3, "zone_plus": 21, "zone_minus": 19,
+              "zone_times": 2, "zone_times2": 2, "all2": 49, "cells": 3, "cells2": 3, "cells3": 1}
+    for z, n in expect.items():
+        assert len(ingest._zone_cells(z, m, zones)) == n, z
+    assert list(ingest._zone_cells("cells", m, zones)) == [1, 2, 3]
+    # rock types assigned through zones (rock_setup.F90): later types overwrite earlier ones on shared cells
+    rock = ingest.rock_records({"types": [{"porosity": 0.2, "zones": "zone_plus"}, {"porosity": 0.3, "zones": ["zone3"], "cells": [0]}]},
+                               m, zones)
+    por = rock[:, 5]
+    assert (por == 0.2).sum() == 19 and (por == 0.3).sum() == 4 and (por == 0.1).sum() == 49 - 23
+    with pytest.raises(ValueError):
+        ingest.read_exodus(__file__)

@@ -84,6 +84,50 @@ def read_gmsh(path):
     return xyz, elems
 
 
+# ExodusII element names -> the gmsh type codes build_mesh works with (the node orderings of these element types
+# are the same in both formats)
+_EXO = {"HEX": 5, "HEX8": 5, "WEDGE": 6, "WEDGE6": 6, "TETRA": 4, "TETRA4": 4, "TET4": 4, "PYRAMID": 7, "PYRAMID5": 7,
+        "QUAD": 3, "QUAD4": 3, "SHELL": 3, "SHELL4": 3, "TRI": 2, "TRI3": 2, "TRIANGLE": 2}
+
+
+def read_exodus(path):
+    """ExodusII mesh in the netCDF classic format (what the reference's test and benchmark meshes use) -> (nodes [n,3],
+    list of (gmsh element type, node indices 0-based)), element blocks in file order as DMPlexCreateExodus numbers the
+    cells.  Read with scipy's pure-Python netCDF-3 reader; netCDF-4 (HDF5-based) files cannot be read in this image."""
+    from scipy.io import netcdf_file
+    try:
+        f = netcdf_file(path, "r", mmap=False)
+    except TypeError as e:
+        raise ValueError("%s: not a netCDF classic file (HDF5-based ExodusII files need a netCDF-4 library)" % path) from e
+    v = f.variables
+    nn = f.dimensions["num_nodes"]
+    xyz = np.zeros((nn, 3))
+    if "coord" in v:
+        c = np.array(v["coord"][:], float)
+        xyz[:, :c.shape[0]] = c.T
+    else:
+        for k, name in enumerate(("coordx", "coordy", "coordz")):
+            if name in v:
+                xyz[:, k] = np.array(v[name][:], float)
+    elems = []
+    for b in range(1, f.dimensions.get("num_el_blk", 0) + 1):
+        con = v["connect%d" % b]
+        et = con.elem_type
+        et = (et.decode() if isinstance(et, bytes) else str(et)).strip().upper()
+        assert et in _EXO, "ExodusII element type %r is not supported" % et
+        for row in np.array(con[:], np.int64) - 1:
+            elems.append((_EXO[et], [int(i) for i in row]))
+    f.close()
+    return xyz, elems
+
+
+def read_mesh(path):
+    """mesh file by extension: gmsh MSH 2.2 (.msh) or ExodusII (.exo / .e / .ex2)"""
+    if path.lower().endswith((".exo", ".e", ".ex2", ".exii")):
+        return read_exodus(path)
+    return read_gmsh(path)
+
+
 def _polygon_geometry(p):
     """area-weighted centroid and area of a planar polygon in 2-D (DMPlexComputeGeometryFVM for a 2-D cell)"""
     x, y = p[:, 0], p[:, 1]
@@ -252,14 +296,64 @@ def add_boundary_faces(m, exterior, specs):
     return out, np.array(owner, np.int32)
 
 
-def _zone_cells(zone, m):
-    """cells of a box zone {"x": [lo, hi], "y": ..., "z": ...}, or all cells for {"type": "box"} without limits"""
-    sel = np.ones(m.ninterior, bool)
-    for k, ax in enumerate("xyz"):
-        if ax in zone:
-            lo, hi = zone[ax]
-            sel &= (m.cell_geom[:m.ninterior, k] >= lo) & (m.cell_geom[:m.ninterior, k] <= hi)
-    return np.nonzero(sel)[0]
+def _zone_type(spec):
+    """get_zone_type (src/zone.F90:91-163): an array is a cell list; an object says its "type" (array / box / combine) or
+    shows it by its keys: "cells"; "x" "y" "z" "r"; "+" "-" "*" """
+    if isinstance(spec, list):
+        return "array"
+    if isinstance(spec, dict):
+        t = str(spec.get("type", "")).lower()
+        if t in ("array", "box", "combine"):
+            return t
+        if "cells" in spec:
+            return "array"
+        if any(k in spec for k in ("x", "y", "z", "r")):
+            return "box"
+        if any(k in spec for k in ("+", "-", "*")):
+            return "combine"
+    return None
+
+
+def _zone_cells(zone, m, zones=None, _seen=()):
+    """interior cells of a zone (src/zone.F90): cell list; box in the cell-centroid coordinates, limits inclusive, a
+    missing axis unbounded ("r" is the first coordinate of a radial mesh); combination: the union of the "+" zones (all
+    cells if there are none), intersected with every "*" zone, without the "-" zones.  `zone`: a name in `zones` or a
+    zone value."""
+    zones = zones or {}
+    if isinstance(zone, str):
+        assert zone in zones, "unknown zone %r" % zone
+        assert zone not in _seen, "zone %r depends on itself" % zone
+        return _zone_cells(zones[zone], m, zones, _seen + (zone,))
+    n = m.ninterior
+    kind = _zone_type(zone)
+    if kind == "array":
+        cells = zone if isinstance(zone, list) else zone.get("cells", [])
+        return np.array(sorted(set(int(c) for c in cells)), np.int64)
+    if kind == "box":
+        sel = np.ones(n, bool)
+        for ax, k in (("x", 0), ("r", 0), ("y", 1), ("z", 2)):
+            if ax in zone:
+                lo, hi = zone[ax]
+                sel &= (m.cell_geom[:n, k] >= lo) & (m.cell_geom[:n, k] <= hi)
+        return np.nonzero(sel)[0]
+    if kind == "combine":
+        def names(key):
+            v = zone.get(key)
+            return [] if v is None else ([v] if isinstance(v, str) else list(v))
+        sel = np.zeros(n, bool)
+        if names("+"):
+            for z in names("+"):
+                sel[_zone_cells(z, m, zones, _seen)] = True
+        else:
+            sel[:] = True
+        for z in names("*"):
+            keep = np.zeros(n, bool)
+            keep[_zone_cells(z, m, zones, _seen)] = True
+            sel &= keep
+        for z in names("-"):
+            sel[_zone_cells(z, m, zones, _seen)] = False
+        return np.nonzero(sel)[0]
+    raise ValueError("unrecognised zone %r" % (zone,))
 
 
 def rock_records(spec, m, zones=None):
@@ -271,7 +365,7 @@ def rock_records(spec, m, zones=None):
         idx = list(rt.get("cells", []))
         zs = rt.get("zones", [])
         for z in ([zs] if isinstance(zs, str) else zs):
-            idx += _zone_cells((zones or {}).get(z, {}), m).tolist()
+            idx += _zone_cells(z, m, zones).tolist()
         idx = np.array(sorted(set(idx)), np.int64)
         if len(idx) == 0:
             continue
@@ -338,8 +432,7 @@ def load(path, mod=None, mesh_path=None):
     doc = json.load(open(path))
     mspec = doc["mesh"] if isinstance(doc["mesh"], dict) else {"filename": doc["mesh"]}
     mfile = mesh_path or os.path.join(os.path.dirname(path), mspec["filename"])
-    assert not mfile.endswith(".exo"), "ExodusII meshes need netCDF, which this image lacks"
-    nodes, elems = read_gmsh(mfile)
+    nodes, elems = read_mesh(mfile)
     m, exterior = build_mesh(nodes, elems, thickness=mspec.get("thickness", 1.0), radial=bool(mspec.get("radial", False)),
                              gravity=doc.get("gravity"), permeability_angle=np.deg2rad(mspec.get("permeability_angle", 0.0)))
     rock = rock_records(doc.get("rock"), m, mspec.get("zones"))
