@@ -251,6 +251,28 @@ def deliverability():
     print("wrote", out)
 
 
+def recharge():
+    """test/benchmark/source/recharge: AUTOUGH2 listing of the 10-cell outflow problem with a recharge source
+    (rate = -coefficient (P - reference pressure), production only) -- tests/test_recharge.py"""
+    base = "/root/reference/test/benchmark/source/recharge/run"
+    tabs = listing_generic(os.path.join(base, "recharge_outflow.listing"))
+    el = [(t, r) for k, t, r in tabs if k == "E"]
+    ge = [(t, r) for k, t, r in tabs if k == "G"]
+    src = json.load(open(os.path.join(base, "recharge_outflow.json")))
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/source/recharge/run/"
+                            "recharge_outflow.listing (AUTOUGH2)",
+           "columns": ["pressure", "temperature", "vapour_saturation"],
+           "outflow": {"times": [t for t, _ in el], "tables": [[x[:3] for x in r[:10]] for _, r in el],
+                       "source_times": [t for t, _ in ge], "rate": [r[0][0] for _, r in ge],
+                       "enthalpy": [r[0][1] for _, r in ge], "step_sizes": src["time"]["step"]["size"],
+                       "stop": src["time"]["stop"], "source": src["source"], "initial": src["initial"]["primary"],
+                       "rock": src["rock"]["types"][0]}}
+    out = os.path.join(os.path.dirname(OUT), "recharge.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 def wae_benchmarks():
     """test/benchmark/ncg/{infiltration,heat_pipe} (eos wae: water, air, energy): AUTOUGH2 ELEMENT tables --
     test_infiltration.py compares the liquid saturation profiles (1e-4), test_heat_pipe.py P, T, Sv and the air
@@ -409,6 +431,7 @@ if __name__ == "__main__":
     minc_column()
     mis_problems()
     deliverability()
+    recharge()
     wae_benchmarks()
     tracer_doublet()
     minc_doublet()
