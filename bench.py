@@ -137,6 +137,30 @@ class Problem:
             self.cfg, what, self.npv, self.dt, args.ksp.upper(), "(%d)" % args.restart if args.ksp == "gmres" else "", pc)
 
 
+def solver_bytes_per_iteration(nb, bs, rowptr, colidx, block_of_row, restart, ksp):
+    """Algorithmic bytes one Krylov iteration of the persistent solver kernel moves: the matrix
+    once per product (blocks + 4-byte column indices), the ILU(0) factors of the sub-domains once per preconditioner
+    apply (the blocks of the matrix pattern with both ends in one sub-domain), and the vector passes.  GMRES(m), column
+    k of a cycle (k = 1..m, mean (m + 1) / 2): gathered operand + stored basis vector + stored product, dots against k
+    vectors + the product, multi-AXPY over k vectors + product read and written = (2 k + 6) vectors.  BiCGStab: two
+    products and applies, and 22 vector reads / writes (P, S, x, R updates and five dot products)."""
+    rowptr = np.asarray(rowptr, np.int64)
+    colidx = np.asarray(colidx, np.int64)
+    nnzb = len(colidx)
+    rows = np.repeat(np.arange(nb, dtype=np.int64), np.diff(rowptr))
+    own = colidx < nb
+    if block_of_row is None:
+        nnzf = int(own.sum())
+    else:
+        b = np.asarray(block_of_row, np.int64)
+        nnzf = int((own & (b[rows] == b[np.minimum(colidx, nb - 1)])).sum())
+    blk = bs * bs * 8 + 4
+    vec = nb * bs * 8
+    if ksp == "bcgs":
+        return 2 * (nnzb + nnzf) * blk + 22 * vec
+    return (nnzb + nnzf) * blk + (restart + 1 + 6) * vec
+
+
 # ------------------------------------------------------------------ clocks sampler
 
 class ClockSampler(threading.Thread):
@@ -525,6 +549,23 @@ def run_b200(args):
                     "traffic": traffic, "algorithmic_bytes": abytes, "us_per_launch": round(1e3 * t / cnt, 2),
                     "launches_timed": cnt, "peak_source": which, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
 
+    # ---- the dominant kernel of the step: the persistent solver kernel (one launch = one KSPSolve, 99 % of the step).
+    # achieved = algorithmic bytes per iteration x iterations / the device time of the solve inside the timed steps
+    roofline_solver = None
+    if world == 1 and roofline and ksp_breakdown and args.pc == "ilu0":
+        try:
+            bor_ = prob.blocks(m, args.pc_cube) if args.pc_cube > 0 else None
+            per_it = solver_bytes_per_iteration(nb, bs, rowptr, colidx, bor_, args.restart, args.ksp)
+            t_solve = phases["ksp_solve"]["ms"] * 1e-3
+            ach = per_it * max(ksp_its, 1) / t_solve / 1e9
+            roofline_solver = {"kernel": "k_gmres_fused (persistent %s: the whole KSPSolve, the dominant kernel of the step)" % args.ksp.upper(),
+                               "bound": "hbm", "achieved": round(ach, 1), "peak": roofline["peak"], "unit": "GB/s",
+                               "frac": round(ach / roofline["peak"], 4), "algorithmic_bytes_per_iteration": int(per_it),
+                               "iterations_per_launch": int(ksp_its), "ms_per_launch": round(phases["ksp_solve"]["ms"], 3),
+                               "traffic_per_iteration": 1.111e9 if (args.config == 2 and args.ksp == "gmres") else None,
+                               "traffic_source": "profiles/r2f_fused_ncu_metrics.csv (ncu --set full: 95.85 GB read + 4.16 GB written over 90 iterations)"}
+        except Exception as e:          # never let the extra line break the bench
+            roofline_solver = {"error": str(e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -552,6 +593,8 @@ def run_b200(args):
         out["ksp_breakdown_min_mean_max_over_ctas"] = ksp_breakdown_ctas
     if roofline:
         out["roofline"] = roofline
+    if roofline_solver:
+        out["roofline_solver"] = roofline_solver
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(prob, args, ksp_its)
     print(json.dumps(out))

@@ -58,3 +58,32 @@ def test_strong_scaling_problems_split_evenly(cfg, dims):
         assert p.scaling == "strong" and p.mesh.ninterior == dims[0] * dims[1] * dims[2]
         counts = np.bincount(p.owner, minlength=world)
         assert counts.sum() == p.mesh.ninterior and counts.max() - counts.min() <= counts.max() // 2
+
+
+def test_solver_bytes_per_iteration():
+    """the algorithmic byte count behind bench.py's `roofline_solver`: config 2's pattern at a small size against a
+    count by hand, and the full-size formula against the figure DESIGN.md quotes (1.09 GB per GMRES(30) iteration)"""
+    nx = 4
+    m = wmesh.structured(nx, nx, nx)
+    nb = m.ninterior
+    rows = [[i] for i in range(nb)]
+    for c1, c2 in m.face_cells:
+        if c1 < nb and c2 < nb:
+            rows[c1].append(int(c2))
+            rows[c2].append(int(c1))
+    rowptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+    colidx = np.concatenate([sorted(r) for r in rows])
+    nnzb = len(colidx)
+    assert nnzb == nb + 2 * 3 * nx * nx * (nx - 1)
+    bor = wmesh.cube_blocks(m, 2)
+    # couplings cut by 2^3 cubes: the faces between cubes, one plane per direction in a 4^3 mesh
+    nnzf = nnzb - 2 * 3 * nx * nx
+    got = bench.solver_bytes_per_iteration(nb, 2, rowptr, colidx, bor, 30, "gmres")
+    assert got == (nnzb + nnzf) * 36 + 37 * nb * 16
+    assert bench.solver_bytes_per_iteration(nb, 2, rowptr, colidx, None, 30, "gmres") == 2 * nnzb * 36 + 37 * nb * 16
+    assert bench.solver_bytes_per_iteration(nb, 3, rowptr, colidx, bor, 30, "bcgs") == 2 * (nnzb + nnzf) * 76 + 22 * nb * 24
+    # full size: 100^3 cells, 10^3 cubes
+    N = 100
+    nnz = N ** 3 + 6 * N * N * (N - 1)
+    nnf = nnz - 2 * 3 * N * N * 9
+    assert abs(((nnz + nnf) * 36 + 37 * N ** 3 * 16) / 1e9 - 1.072) < 0.001   # DESIGN.md: 1.07-1.09 GB, ncu: 1.11 GB
