@@ -267,7 +267,7 @@ PETSC_EXTERN PetscErrorCode PCCreate_WB(PC pc) {
   PetscFunctionReturn(PETSC_SUCCESS);
 }
 
-/* ---- KSP: the whole Krylov solve on the device (GMRES: one persistent kernel; -ksp_wb_type bcgs: BiCGStab) ---- */
+/* ---- KSP: the whole Krylov solve on the device, one persistent kernel (GMRES; -ksp_wb_bcgs: BiCGStab) ---- */
 typedef struct {
   PetscInt type, restart;
 } WbKSP;
