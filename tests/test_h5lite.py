@@ -1,0 +1,157 @@
+"""Waiwera's HDF5 output / restart files without an HDF5 library (none in this image):
+waiwera_b200/h5lite.py parses and writes the file format itself, waiwera_b200/output.py lays out the reference's
+datasets.  The READER is pinned by two files the reference's own stack wrote (tests/golden/h5/, copied by
+tools/make_golden.py::h5_fixtures): the golden cell balances of flow_simulation_test.F90 and a Waiwera output file with
+chunked time-sequence datasets.  The WRITER is checked through the reader and structure by structure against what the
+library wrote into those files; it cannot be checked against libhdf5 itself here."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from waiwera_b200 import h5lite, output
+from waiwera_b200 import mesh as wmesh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+H5 = os.path.join(HERE, "golden", "h5")
+
+
+def test_reader_on_files_written_by_the_reference_stack():
+    h = h5lite.H5File(os.path.join(H5, "lhs.h5"))
+    assert h.groups() == ["cell_fields", "fields"]
+    assert h.datasets() == ["cell_fields/lhs_Primary", "cell_index", "fields/lhs"]
+    ref = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
+    assert np.array_equal(h["fields/lhs"], np.array(ref["lhs"]["values"]))    # 12 x 99.82512244887545
+    assert np.array_equal(h["cell_fields/lhs_Primary"], h["fields/lhs"])
+    ci = h["cell_index"]
+    assert ci.dtype == np.int32 and ci.shape == (12, 1) and sorted(ci.reshape(-1)) == list(range(12))
+    # a Waiwera output file: chunked [time, cell] datasets, int32 index sets, source fields
+    h = h5lite.H5File(os.path.join(H5, "oned_two_phase_ss.h5"))
+    assert "cell_fields/fluid_pressure" in h and h.shape("cell_fields/fluid_pressure") == (1, 10)
+    assert h["time"].reshape(-1).tolist() == [1.0e15]
+    assert h["source_fields/source_natural_cell_index"].dtype == np.int32
+    g = json.load(open(os.path.join(HERE, "golden", "tracer_oned.json")))["two"]["initial"]
+    assert np.array_equal(h["cell_fields/fluid_pressure"][0], g["pressure"])
+    assert np.array_equal(h["cell_fields/fluid_temperature"][0], g["temperature"])
+    assert np.array_equal(h["cell_fields/fluid_vapour_saturation"][0], g["vapour_saturation"])
+    assert np.allclose(h["cell_fields/cell_geometry_volume"], 10.0)
+    with pytest.raises(h5lite.H5Error):
+        h5lite.H5File(__file__)
+
+
+def test_restart_from_a_waiwera_output_file():
+    """initial.filename (src/initial.F90:421-507): primaries and regions of the last time in natural cell order"""
+    prim, region, t = output.read_restart(os.path.join(H5, "oned_two_phase_ss.h5"), "we")
+    g = json.load(open(os.path.join(HERE, "golden", "tracer_oned.json")))["two"]["initial"]
+    assert t == 1.0e15 and (region == 4).all()
+    assert np.array_equal(prim[:, 0], g["pressure"]) and np.array_equal(prim[:, 1], g["vapour_saturation"])
+    with pytest.raises(IndexError):
+        output.read_restart(os.path.join(H5, "oned_two_phase_ss.h5"), "we", index=3)
+    with pytest.raises(KeyError):
+        output.read_restart(os.path.join(H5, "oned_two_phase_ss.h5"), "wce")       # no CO2 partial pressure in the file
+
+
+def _messages_of(h, path):
+    ent = h.root_entry
+    for p in path.split("/"):
+        msgs = h._messages(ent["header"])
+        if ent.get("cache") == 1:
+            bt, hp = ent["btree"], ent["heap"]
+        else:
+            d = [m for t, m in msgs if t == 0x11][0]
+            bt, hp = int.from_bytes(d[:8], "little"), int.from_bytes(d[8:16], "little")
+        ent = [e for e in h._group_entries(bt, hp) if e["name"] == p][0]
+    return dict((t, bytes(m)) for t, m in h._messages(ent["header"]))
+
+
+def test_writer_round_trip_and_structures(tmp_path):
+    rng = np.random.default_rng(1)
+    data = {"time": rng.uniform(size=(5, 1)), "cell_index": np.arange(7, dtype=np.int32).reshape(7, 1),
+            "cell_fields/fluid_pressure": rng.uniform(size=(5, 7)), "cell_fields/fluid_region": np.ones((5, 7)),
+            "source_fields/source_rate": rng.uniform(size=(5, 2)), "deep/er/group/x": np.arange(3.0),
+            "empty": np.zeros((0, 4)), "i64": np.arange(4, dtype=np.int64), "f32": np.arange(4, dtype=np.float32)}
+    for k in range(40):                                   # more entries than one symbol node holds
+        data["many/f%02d" % k] = np.full(3, float(k))
+    path = str(tmp_path / "t.h5")
+    h5lite.write(path, data)
+    h = h5lite.H5File(path)
+    assert h.datasets() == sorted(data) and h.groups() == ["cell_fields", "deep", "deep/er", "deep/er/group", "many", "source_fields"]
+    for k, v in data.items():
+        a = h[k]
+        assert a.shape == v.shape and a.dtype == v.dtype and np.array_equal(a, v), k
+    raw = open(path, "rb").read()
+    lib = h5lite.H5File(os.path.join(H5, "oned_two_phase_ss.h5"))
+    # superblock: the same versions, offset / length sizes and B-tree ranks as the library's file; end-of-file address
+    assert raw[:24] == lib.buf[:24]
+    assert int.from_bytes(raw[40:48], "little") == len(raw)
+    # messages of a float64 and an int32 dataset: dataspace, datatype and fill value byte for byte as the library
+    # writes them (the layout differs by design: contiguous here, chunked there)
+    mine, theirs = _messages_of(h, "cell_fields/fluid_region"), _messages_of(lib, "cell_fields/cell_geometry_volume")
+    assert mine[0x03] == theirs[0x03] and mine[0x05] == theirs[0x05]
+    assert _messages_of(h, "cell_index")[0x03] == _messages_of(lib, "cell_index")[0x03]
+    space = _messages_of(h, "cell_index")[0x01]           # version 1, rank 2, no maximum sizes, then the sizes
+    assert space[:24] == b"\x01\x02\x00" + bytes(5) + (7).to_bytes(8, "little") + (1).to_bytes(8, "little")
+    # every structure is 8-byte aligned and carries its signature; node sizes follow the superblock's ranks
+    for sig, size in ((b"TREE", 24 + 33 * 8 + 32 * 8), (b"SNOD", 8 + 8 * 40)):
+        pos = raw.find(sig)
+        n = 0
+        while pos >= 0:
+            assert pos % 8 == 0
+            n += 1
+            pos = raw.find(sig, pos + size)
+        assert n >= 6
+    assert raw.count(b"HEAP") == 7                        # one local heap per group (root + 6)
+
+
+def test_output_file_and_restart_round_trip(wo, tmp_path):
+    """write_output in the reference's layout from fluid records, read_restart gives back the primaries (also with a
+    storage order that is not the natural one, as in a parallel run)"""
+    from util import make_problem_wce, oracle_flow
+    m, y, region, prm = make_problem_wce(wo, dims=(4, 3, 5), two_phase_layers=2)
+    f = oracle_flow(wo, m, prm, y, region)
+    fl = f.fluid()
+    n = m.ninterior
+    order = np.random.default_rng(4).permutation(n).astype(np.int32)
+    path = str(tmp_path / "out.h5")
+    output.write_output(path, m, "wce", [0.0, 1.0e6], [fl, fl], source_cells=[3, 5],
+                        source_history=[[[0, -1.0, 2.0e5], [1, 2.0, 1.0e5]]] * 2, cell_index=order)
+    h = h5lite.H5File(path)
+    assert set(h.datasets()) >= {"time", "cell_index", "cell_fields/cell_geometry_centroid", "cell_fields/cell_geometry_volume",
+                                 "cell_fields/fluid_pressure", "cell_fields/fluid_temperature", "cell_fields/fluid_region",
+                                 "cell_fields/fluid_CO2_partial_pressure", "cell_fields/fluid_vapour_saturation",
+                                 "source_index", "source_fields/source_rate", "source_fields/source_natural_cell_index"}
+    assert h.shape("cell_fields/fluid_pressure") == (2, n) and h["source_fields/source_rate"].tolist() == [[-1.0, 2.0]] * 2
+    prim, reg, t = output.read_restart(path, "wce", index=-1)
+    assert t == 1.0e6 and np.array_equal(reg, region[:n])
+    fl = np.asarray(fl)[:n]
+    assert np.array_equal(prim[:, 0], fl[:, 0]) and np.array_equal(prim[:, 2], fl[:, 7])
+    two = reg == 4
+    assert two.any() and np.array_equal(prim[two, 1], fl[two, 8 + 9 + 2]) and np.array_equal(prim[~two, 1], fl[~two, 1])
+    # the restart state is the state the run started from
+    back = wmesh.scale_primaries(prim, reg).reshape(-1)
+    assert np.allclose(back, y[:3 * n], rtol=1e-12, atol=1e-14)
+
+
+def test_reader_on_every_hdf5_file_of_the_reference():
+    import glob
+    files = sorted(glob.glob("/root/reference/**/*.h5", recursive=True))
+    if not files:
+        pytest.skip("the reference tree is not here")
+    for f in files:
+        h = h5lite.H5File(f)
+        for d in h.datasets():
+            assert h[d].shape == h.shape(d)
+    assert len(files) >= 10
+
+
+def test_ingest_restarts_from_the_file_the_input_names():
+    """the tracer doublet input starts from "initial": {"filename": "doublet_ss.h5"}: ingest reads the Waiwera output
+    file itself; the state equals the golden steady state (tests/golden/tracer_doublet.json, the same file read by a
+    byte scan in round 1)"""
+    from waiwera_b200 import ingest
+    p = ingest.load(os.path.join(HERE, "golden", "inputs", "doublet.input.json"))
+    g = json.load(open(os.path.join(HERE, "golden", "tracer_doublet.json")))
+    assert p.primary.shape == (100, 2) and (p.region == 1).all() and p.restart_time == 1.0e15
+    assert np.array_equal(p.primary[:, 0], g["steady_pressure"]) and np.array_equal(p.primary[:, 1], g["steady_temperature"])
+    assert np.allclose(p.y.reshape(-1, 2), p.primary / [1e6, 1e2])

@@ -273,6 +273,23 @@ def recharge():
     print("wrote", out)
 
 
+def h5_fixtures():
+    """two small HDF5 files written by the reference's own stack (PETSc HDF5 viewer), kept as binary fixtures for the
+    reader of waiwera_b200/h5lite.py: test/unit/data/flow_simulation/lhs/lhs.h5 (11 KB: the golden cell balances, a
+    time-independent Vec) and test/benchmark/tracer/oned/run/oned_two_phase_ss.h5 (42 KB: a Waiwera output file with
+    chunked time-sequence datasets, the restart file of the tracer benchmark)"""
+    import shutil
+    dst = os.path.join(os.path.dirname(OUT), "h5")
+    os.makedirs(dst, exist_ok=True)
+    for src in ("/root/reference/test/unit/data/flow_simulation/lhs/lhs.h5",
+                "/root/reference/test/benchmark/tracer/oned/run/oned_two_phase_ss.h5"):
+        shutil.copy(src, os.path.join(dst, os.path.basename(src)))
+        print("copied", src)
+    # the restart file the tracer doublet input names ("initial": {"filename": "doublet_ss.h5"}), next to that input
+    shutil.copy("/root/reference/test/benchmark/tracer/doublet/run/doublet_ss.h5",
+                os.path.join(os.path.dirname(OUT), "inputs", "doublet_ss.h5"))
+
+
 def wae_benchmarks():
     """test/benchmark/ncg/{infiltration,heat_pipe} (eos wae: water, air, energy): AUTOUGH2 ELEMENT tables --
     test_infiltration.py compares the liquid saturation profiles (1e-4), test_heat_pipe.py P, T, Sv and the air
@@ -432,6 +449,7 @@ if __name__ == "__main__":
     mis_problems()
     deliverability()
     recharge()
+    h5_fixtures()
     wae_benchmarks()
     tracer_doublet()
     minc_doublet()

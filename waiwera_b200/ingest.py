@@ -461,8 +461,25 @@ def load(path, mod=None, mesh_path=None):
                       partial_pressure_scale=max(p.params.partial_pressure_scale, 0.0))
         p.primary_scales = sc
         p.y = np.ascontiguousarray(wmesh.scale_primaries(p.primary, p.region, **sc)).reshape(-1)
+    elif "filename" in init and os.path.exists(os.path.join(os.path.dirname(path), init["filename"])):
+        # restart from a Waiwera HDF5 output file (src/initial.F90:421-507): the fields of the time index "index"
+        # (default -1: the last one, src/initial.F90:776; negative: from the end), read without an HDF5 library
+        # (waiwera_b200/h5lite.py)
+        from . import output
+        eos_ = doc.get("eos", "we")
+        eos_ = eos_ if isinstance(eos_, str) else eos_.get("name", "we")
+        p.primary, p.region, p.restart_time = output.read_restart(os.path.join(os.path.dirname(path), init["filename"]), eos_,
+                                                                  int(init.get("index", -1)))
+        assert len(p.region) == n, "restart file holds %d cells, the mesh %d" % (len(p.region), n)
+        sc = dict(pressure_scale=1e6, temperature_scale=1e2, partial_pressure_scale=0.0)
+        if p.params is not None:
+            sc = dict(pressure_scale=p.params.pressure_scale if p.params.pressure_scale > 0 else 1e6,
+                      temperature_scale=p.params.temperature_scale if p.params.temperature_scale > 0 else 1e2,
+                      partial_pressure_scale=max(p.params.partial_pressure_scale, 0.0))
+        p.primary_scales = sc
+        p.y = np.ascontiguousarray(wmesh.scale_primaries(p.primary, p.region, **sc)).reshape(-1)
     else:
-        p.primary = p.region = p.y = None                  # "filename": HDF5 restart, pass the arrays
+        p.primary = p.region = p.y = None                  # restart file not at hand: pass the arrays
     tr = doc.get("tracer")
     p.tracers = [] if tr is None else ([tr] if isinstance(tr, dict) else list(tr))
     nt = len(p.tracers)
