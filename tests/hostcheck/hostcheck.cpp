@@ -293,3 +293,50 @@ extern "C" int hc_tracer_assemble(const wb_params *prm, int nt, int ncell, int n
 #undef HC_TRACER
   return -2;
 }
+
+
+// wb_source_rate / wb_source_separated (wb_state.cuh: deliverability, recharge, direction, total / water / steam
+// limiters, separators) for ONE source in a cell of the given primaries: what k_residual / k_jacobian evaluate per
+// source.  out: rate, then water rate, water enthalpy, steam rate, steam enthalpy, steam fraction at that rate.
+template <int EOS>
+static int source_rate_host(const wb_params *prm, const double *primary, int region, const double *rock8, int ctrl, double pi,
+                            double pref, double limit, double rate, int sep_n, const double *sep_h, double limit_w,
+                            double limit_s, double *out) {
+  constexpr int NC = WbEosTraits<EOS>::NC, NPH = WbEosTraits<EOS>::NPH;
+  WbEosParams e;
+  if (wb_eos_params_make(*prm, e)) return -1;
+  WbFluid<NC, NPH> fl = {};
+  fl.region = region;
+  if (wb_eos_properties<EOS>(e, primary, fl)) return 1;
+  WbCellState<NC, NPH> s;
+  wb_state_from_fluid(fl, rock8[WB_R_WET], rock8[WB_R_DRY], s);
+  int32_t c_ctrl = ctrl, c_sep = sep_n, c_cell = 0, c_comp = 0, c_head = 0;
+  double c_enth = 0.0;
+  WbSources S = {};
+  S.head = &c_head; S.cell = &c_cell; S.comp = &c_comp; S.rate = &rate; S.enth = &c_enth; S.n = 1;
+  S.ctrl = &c_ctrl; S.pi = &pi; S.pref = &pref; S.limit = &limit;
+  S.sep_n = sep_h ? &c_sep : nullptr; S.sep_h = sep_h; S.limit_w = &limit_w; S.limit_s = &limit_s;
+  out[0] = wb_source_rate(S, 0, s);
+  wb_source_separated(S, 0, s, out[0], out + 1);
+  return 0;
+}
+extern "C" int hc_source_rate(const wb_params *prm, const double *primary, int region, const double *rock8, int ctrl,
+                              double pi, double pref, double limit, double rate, int sep_n, const double *sep_h,
+                              double limit_w, double limit_s, double *out) {
+  if (prm->eos == WB_EOS_WE)
+    return source_rate_host<WB_EOS_WE>(prm, primary, region, rock8, ctrl, pi, pref, limit, rate, sep_n, sep_h, limit_w, limit_s, out);
+  if (prm->eos == WB_EOS_WCE || prm->eos == WB_EOS_WAE)
+    return source_rate_host<WB_EOS_WCE>(prm, primary, region, rock8, ctrl, pi, pref, limit, rate, sep_n, sep_h, limit_w, limit_s, out);
+  return -2;
+}
+// separator_stage_init with the device thermodynamics (what wb_separator_stage runs on the host side of the library)
+extern "C" int hc_separator_stage(int thermo, double pressure, double *hw, double *hs) {
+  WbThermo th = wb_thermo_make(thermo, 0);
+  double ts = 0.0, rho = 0.0, u = 0.0;
+  if (wb_saturation_temperature(th, pressure, ts)) return 1;
+  if (wb_region_properties(th, 1, pressure, ts, rho, u)) return 1;
+  *hw = u + pressure / rho;
+  if (wb_region_properties(th, 2, pressure, ts, rho, u)) return 1;
+  *hs = u + pressure / rho;
+  return 0;
+}

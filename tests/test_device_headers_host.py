@@ -44,6 +44,8 @@ def hc(wo):
     L.hc_wce_scale.argtypes = [C.c_void_p, dp, i, dp, dp]
     L.hc_tracer_assemble.argtypes = [C.c_void_p, i, i, i, i, ip, dp, dp, dp, dp, ip, ip, dp, dp, dp, i, ip, ip, dp, ip, dp, dp, dp, dp, i,
                                      d, d, dp, dp, dp, dp, dp, ip, ip, dp, dp, dp]
+    L.hc_source_rate.argtypes = [C.c_void_p, dp, i, dp, i, d, d, d, d, i, dp, d, d, dp]
+    L.hc_separator_stage.argtypes = [i, d, dp, dp]
     return L
 
 
@@ -423,3 +425,75 @@ def test_wce_transitions_match_oracle(wo, hc, thermo):
     finally:
         wo.lib().wo_eos_destroy(eos)
         wo.lib().wo_thermo_destroy(th)
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_source_controls_match_oracle(wo, hc, thermo):
+    """wb_source_rate / wb_source_separated of wb_state.cuh (deliverability, recharge / injectivity, direction, total /
+    water / steam limiters, one- and two-stage separators) against the oracle's source_network update, source by source
+    on two-phase, liquid and vapour cells; the separator stage enthalpies bit for bit (the reference's known answers for
+    them are in tests/test_separator.py)"""
+    from waiwera_b200 import flow, mesh as wmesh
+    L = wo.lib()
+    for pr in (1.0e5, 5.5e5, 10.0e5, 14.5e5):
+        a, b = C.c_double(), C.c_double()
+        th = L.wo_thermo_create(thermo, 0)
+        assert L.wo_separator_stage(th, pr, C.byref(a), C.byref(b)) == 0
+        L.wo_thermo_destroy(th)
+        ha, hb = C.c_double(), C.c_double()
+        assert hc.hc_separator_stage(thermo, pr, C.byref(ha), C.byref(hb)) == 0
+        assert (ha.value, hb.value) == (a.value, b.value)
+    m = wmesh.structured(3, 1, 1, dx=10.0, heterogeneous=False)
+    cells = [([30.0e5, 0.4], 4), ([30.0e5, 150.0], 1), ([1.0e5, 150.0], 2)]          # two-phase, liquid, vapour
+    primary = np.array([c[0] for c in cells])
+    region = np.array([c[1] for c in cells], np.int32)
+    prm_o = wo.make_params(eos=wo.EOS_WE, thermo=thermo)
+    prm_h = flow.make_params(eos=flow.EOS_WE, thermo=thermo)
+    y = np.ascontiguousarray(wmesh.scale_primaries(primary, region)).reshape(-1)
+    f = wo.Flow(prm_o, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    assert f.fluid_init(y, region) == 0
+    rng = np.random.default_rng(SEED + 9)
+    sep1, sep2 = [2.0e5], [8.0e5, 1.5e5]
+    cases = []
+    for cell in range(3):
+        for kind in ("fixed", "deliv", "recharge"):
+            for direction in (0, 1, 2):
+                for seps in ([], sep1, sep2):
+                    cases.append(dict(cell=cell, kind=kind, direction=direction, seps=seps,
+                                      rate=float(rng.choice([-6.0, -0.5, 4.0])), pi=float(rng.uniform(1e-13, 1e-11)),
+                                      coef=float(rng.uniform(1e-7, 1e-5)), pref=float(rng.choice([0.5e5, 20.0e5, 45.0e5])),
+                                      limit=float(rng.choice([0.0, 0.3, 50.0])), lw=float(rng.choice([0.0, 0.2, 50.0])),
+                                      ls=float(rng.choice([0.0, 0.05, 50.0]))))
+    n = len(cases)
+    f.set_sources([c["cell"] for c in cases], [0] * n, [c["rate"] for c in cases], [0.0] * n)
+    f.set_source_controls(list(range(n)), [c["pi"] if c["kind"] == "deliv" else 0.0 for c in cases], [c["pref"] for c in cases],
+                          [c["direction"] for c in cases], [c["limit"] for c in cases])
+    rc = [k for k, c in enumerate(cases) if c["kind"] == "recharge"]
+    f.set_source_recharge(rc, [cases[k]["coef"] for k in rc], [cases[k]["pref"] for k in rc])
+    assert f.set_source_separators(list(range(n)), [c["seps"] for c in cases], [c["lw"] for c in cases], [c["ls"] for c in cases]) == 0
+    e, L0 = f.lhs(y)
+    assert e == 0 and f.residual(y, L0, 1.0e3)[0] == 0
+    ref = f.source_rates(n)
+    nonzero = limited = separated = 0
+    for k, c in enumerate(cases):
+        ctrl = (1 if c["kind"] == "deliv" else 0) | (c["direction"] << 1) | (8 if c["kind"] == "recharge" else 0)
+        sh = np.zeros(4)
+        for q, pr in enumerate(c["seps"]):
+            a, b = C.c_double(), C.c_double()
+            assert hc.hc_separator_stage(thermo, pr, C.byref(a), C.byref(b)) == 0
+            sh[2 * q], sh[2 * q + 1] = a.value, b.value
+        out = np.zeros(6)
+        pi = c["coef"] if c["kind"] == "recharge" else (c["pi"] if c["kind"] == "deliv" else 0.0)
+        r = hc.hc_source_rate(C.addressof(prm_h), wo.dp(np.ascontiguousarray(primary[c["cell"]])), int(region[c["cell"]]),
+                              wo.dp(np.ascontiguousarray(m.rock[c["cell"]])), ctrl, pi, c["pref"], c["limit"], c["rate"],
+                              len(c["seps"]), wo.dp(sh), c["lw"], c["ls"], wo.dp(out))
+        assert r == 0
+        assert close(out[0], ref[k], 1e-14) or (out[0] == 0.0 and ref[k] == 0.0), (c, out[0], ref[k])
+        sep = f.source_separated(k, ref[k])
+        assert np.allclose(out[1:], sep, rtol=1e-13, atol=0.0), (c, out[1:], sep)
+        nonzero += ref[k] != 0.0
+        separated += sep[2] != 0.0
+        base = c["rate"] if c["kind"] == "fixed" else None
+        limited += base is not None and ref[k] != 0.0 and abs(ref[k]) < abs(base) * (1 - 1e-12)
+    assert nonzero > n // 3 and separated > 10 and limited > 5
