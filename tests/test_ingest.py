@@ -356,3 +356,37 @@ def test_exodus_mesh_and_zones_known_answers(tmp_path):
     assert (por == 0.2).sum() == 19 and (por == 0.3).sum() == 4 and (por == 0.1).sum() == 49 - 23
     with pytest.raises(ValueError):
         ingest.read_exodus(__file__)
+
+
+def test_mulgraph_geometry(tmp_path):
+    """MULgraph geometry files (the `g*.dat` the reference's benchmark meshes are generated from): a square column
+    beside a triangular one, two layers -> hexahedra and wedges numbered layer by layer from the top; and the mesh
+    fixture of MIS problem 6 (made from test/benchmark/model_intercomparison_study/problem6/run/gproblem6.dat)"""
+    path = str(tmp_path / "gtest.dat")
+    with open(path, "w") as f:
+        f.write("GENER01  1.00e+25  1.00e-06                                0.00\nVERTICES\n"
+                "  a      0.00      0.00\n  b    100.00      0.00\n  c    100.00     50.00\n  d      0.00     50.00\n"
+                "  e    160.00     25.00\n\nGRID\n"
+                "  a0 4\n  a\n  d\n  c\n  b\n"           # clockwise: the reader turns it round
+                "  b0 3\n  b\n  e\n  c\n\nCONNECTIONS\n  a0  b0\n\nLAYERS\n"
+                " 0     10.00     10.00\n 1     -5.00      2.50\n 2    -25.00    -15.00\n\n")
+    xyz, elems = ingest.read_mesh(path)
+    assert xyz.shape == (15, 3) and [t for t, _ in elems] == [5, 6, 5, 6]
+    m, ext = ingest.build_mesh(xyz, elems)
+    assert m.ninterior == 4
+    assert np.allclose(m.cell_geom[:4, 3], [100 * 50 * 15.0, 0.5 * 50 * 60 * 15.0, 100 * 50 * 20.0, 0.5 * 50 * 60 * 20.0])
+    assert np.allclose(m.cell_geom[0, :3], [50.0, 25.0, 2.5]) and np.allclose(m.cell_geom[3, :3], [120.0, 25.0, -15.0])
+    # faces: a0-b0 in each layer (area 50 x thickness) and the two vertical ones (areas of the columns)
+    fc = m.face_cells.reshape(-1, 2)
+    fg = m.face_geom.reshape(len(fc), -1)
+    interior = [(tuple(sorted(c)), a) for c, a in zip(fc.tolist(), fg[:, 0]) if max(c) < 4]
+    assert sorted(interior) == [((0, 1), 750.0), ((0, 2), 5000.0), ((1, 3), 1500.0), ((2, 3), 1000.0)]
+    # problem 6: 25 columns x 5 layers, thicknesses 300 x 4 + 600, columns in the order of the file
+    xyz, elems = ingest.read_gmsh(os.path.join(INP, "gproblem6.ascii.msh"))
+    m, _ = ingest.build_mesh(xyz, elems)
+    assert m.ninterior == 125
+    assert np.allclose(m.cell_geom[0], [500.0, 400.0, -150.0, 2.4e8]) and np.allclose(m.cell_geom[124, 2:], [-1500.0, 9.6e8 * 0.5])
+    ref = "/root/reference/test/benchmark/model_intercomparison_study/problem6/run/gproblem6.dat"
+    if os.path.exists(ref):      # this container only
+        rxyz, relems = ingest.read_mulgraph(ref)
+        assert np.array_equal(rxyz, xyz) and relems == elems

@@ -1,8 +1,10 @@
 """Geothermal Model Intercomparison Study problems 2 (radial flow to a well: a single-phase, b two-phase, c flashing
-front), 4 (1-D vertical two-phase column with drainage, 40 years) and 5 (2-D areal production, a without and b with
-later re-injection through a rate table) -- test/benchmark/model_intercomparison_study/problem{2,4,5} -- run FROM THE
-REFERENCE'S OWN INPUT FILES (JSON + gmsh; fixtures under tests/golden/inputs/ made by tools/make_golden.py::convert_input,
-read by waiwera_b200.ingest)
+front), 4 (1-D vertical two-phase column with drainage, 40 years), 5 (2-D areal production, a without and b with
+later re-injection through a rate table) and 6 (3-D 5 x 5 x 5 field with two rock types, atmosphere / side / bottom
+boundaries and a stepped production rate, adaptive steps) -- test/benchmark/model_intercomparison_study/problem{2,4,5,6}
+-- run FROM THE REFERENCE'S OWN INPUT FILES (JSON + gmsh; fixtures under tests/golden/inputs/ made by
+tools/make_golden.py::convert_input, read by waiwera_b200.ingest; problem 6's mesh is rebuilt from its MULgraph geometry
+file, the shipped ExodusII file being HDF5-based)
 through the oracle's Newton / time-stepping path, against the AUTOUGH2 listings shipped with them
 (tests/golden/mis_problems.json: P, T, Sv of every cell at 12 output times, full histories of the production cell
 and three more, production enthalpy history).  The reference accepts 2e-3 (problem 4), 1e-3..1e-2 (problems 2, 5) on
@@ -19,15 +21,20 @@ from waiwera_b200 import ingest
 HERE = os.path.dirname(os.path.abspath(__file__))
 INP = os.path.join(HERE, "golden", "inputs")
 GOLD = json.load(open(os.path.join(HERE, "golden", "mis_problems.json")))
-CASES = ["problem2a", "problem2b", "problem2c", "problem4", "problem5a", "problem5b"]
+CASES = ["problem2a", "problem2b", "problem2c", "problem4", "problem5a", "problem5b", "problem6"]
 # relative L2 error accepted over tables / histories: pressure, temperature, vapour saturation, production enthalpy.
 # Measured with the oracle: 2a, 2b, 5a, 5b agree with the listings to their printed digits (P, T 1e-6..9e-6, Sv
 # <= 6e-5; the reference accepts 1e-4 / 1e-3); problem 4 to 3e-4 / 9e-5 / 1e-3 (2e-3); in 2c AUTOUGH2 left the prescribed
 # step list after t = 5828 s (its own step cuts at the flashing front), until then the runs agree to the printed digits,
-# afterwards to 2e-3 / 9e-4 / 1e-2 (the reference accepts 1e-2).
+# afterwards to 2e-3 / 9e-4 / 1e-2 (the reference accepts 1e-2).  Problem 6: the reference compares only the production
+# enthalpy history with AUTOUGH2 (2e-2; here 6e-3) and the well's P / Sv with digitised curves (1.5e-2 .. 7.5e-2); here
+# the production cell's pressure follows the listing to 2e-5 until it boils, the top layer drifts to 1.3e-2 below it
+# (from the first step on and uniformly over the layer: the atmosphere connection, where AUTOUGH2's interface density
+# differs), and the adaptive step sequences part after the cell dries out (141 steps against 145).
 TIGHT = (5e-5, 5e-5, 3e-4, 5e-5)
 TOL = {"problem2a": TIGHT, "problem2b": TIGHT, "problem2c": (3e-3, 1e-3, 1.5e-2, 3e-3),
-       "problem4": (2e-3, 2e-3, 2e-3, 2e-3), "problem5a": TIGHT, "problem5b": TIGHT}
+       "problem4": (2e-3, 2e-3, 2e-3, 2e-3), "problem5a": TIGHT, "problem5b": TIGHT,
+       "problem6": (4e-3, 6e-3, 2e-2, 1e-2)}
 
 
 def newton_opts(mod, p):

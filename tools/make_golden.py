@@ -190,7 +190,7 @@ def minc_column():
 
 
 def mis_problems():
-    """test/benchmark/model_intercomparison_study problems 2a-c, 4, 5a-b: AUTOUGH2 listings.  Kept: P, T, Sv of all
+    """test/benchmark/model_intercomparison_study problems 2a-c, 4, 5a-b, 6: AUTOUGH2 listings.  Kept: P, T, Sv of all
     cells at ~12 evenly spaced output times, the full history of a few cells (production cell first) and the
     production enthalpy history (the input decks: input_fixtures)"""
     import shutil
@@ -198,10 +198,10 @@ def mis_problems():
     inputs = os.path.join(os.path.dirname(OUT), "inputs")
     os.makedirs(inputs, exist_ok=True)
     doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/"
-                            "model_intercomparison_study/problem{2,4,5}/run/*.listing (AUTOUGH2); boundary / atmosphere "
+                            "model_intercomparison_study/problem{2,4,5,6}/run/*.listing (AUTOUGH2); boundary / atmosphere "
                             "blocks dropped", "columns": ["pressure", "temperature", "vapour_saturation"]}
     for prob, cases in (("problem2", ["problem2a", "problem2b", "problem2c"]), ("problem4", ["problem4"]),
-                        ("problem5", ["problem5a", "problem5b"])):
+                        ("problem5", ["problem5a", "problem5b"]), ("problem6", ["problem6"])):
         run = os.path.join(base, prob, "run")
         for case in cases:
             inp = json.load(open(os.path.join(run, case + ".json")))
@@ -211,7 +211,8 @@ def mis_problems():
             # number of interior cells from the initial conditions / rock types of the input
             ncell = max(max(rt.get("cells", [0]) or [0]) for rt in inp["rock"]["types"]) + 1
             nrow = len(el[-1][1])
-            first = nrow - ncell if prob == "problem4" else 0      # atmosphere block first (problem 4), boundary blocks last
+            # atmosphere blocks first (problem 4: one; problem 6: one per column), other boundary blocks last
+            first = nrow - ncell if prob == "problem4" else 25 if prob == "problem6" else 0
             rows = lambda r: [x[:3] for x in r[first:first + ncell]]
             sel = sorted(set(np.linspace(1, len(el) - 1, 12).round().astype(int).tolist()))
             prod = inp["source"][0]["cell"]
@@ -357,6 +358,16 @@ def minc_doublet():
 INPUT_KEYS = ("boundaries", "eos", "gravity", "initial", "mesh", "rock", "source", "thermodynamics", "time", "tracer")
 
 
+def write_ascii_msh(path, nodes, elems):
+    lines = ["$MeshFormat", "2.2 0 8", "$EndMeshFormat", "$Nodes", str(len(nodes))]
+    lines += ["%d %.17g %.17g %.17g" % (i + 1, x[0], x[1], x[2]) for i, x in enumerate(nodes)]
+    lines += ["$EndNodes", "$Elements", str(len(elems))]
+    lines += ["%d %d 2 0 0 %s" % (i + 1, t, " ".join(str(n + 1) for n in ns)) for i, (t, ns) in enumerate(elems)]
+    lines += ["$EndElements", ""]
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
 def convert_input(src_json, dst_dir, name=None):
     """Fixture of one reference input deck for the ingest tests: the keys of the JSON input the Newton-step path
     reads (title / output / logfile dropped), re-serialised compactly as <name>.input.json, and its gmsh mesh
@@ -371,14 +382,12 @@ def convert_input(src_json, dst_dir, name=None):
     mesh = out["mesh"] if isinstance(out["mesh"], dict) else {"filename": out["mesh"]}
     src_mesh = os.path.join(os.path.dirname(src_json), mesh["filename"])
     mesh_name = os.path.splitext(os.path.basename(src_mesh))[0] + ".ascii.msh"
-    nodes, elems = ingest.read_gmsh(src_mesh)
-    lines = ["$MeshFormat", "2.2 0 8", "$EndMeshFormat", "$Nodes", str(len(nodes))]
-    lines += ["%d %.17g %.17g %.17g" % (i + 1, x[0], x[1], x[2]) for i, x in enumerate(nodes)]
-    lines += ["$EndNodes", "$Elements", str(len(elems))]
-    lines += ["%d %d 2 0 0 %s" % (i + 1, t, " ".join(str(n + 1) for n in ns)) for i, (t, ns) in enumerate(elems)]
-    lines += ["$EndElements", ""]
-    with open(os.path.join(dst_dir, mesh_name), "w") as f:
-        f.write("\n".join(lines))
+    try:
+        nodes, elems = ingest.read_mesh(src_mesh)
+    except ValueError:
+        # HDF5-based ExodusII: rebuild the mesh from the MULgraph geometry file it was generated from (same stem)
+        nodes, elems = ingest.read_mulgraph(os.path.splitext(src_mesh)[0] + ".dat")
+    write_ascii_msh(os.path.join(dst_dir, mesh_name), nodes, elems)
     out["mesh"] = dict(mesh, filename=mesh_name)
     if isinstance(out.get("initial"), dict) and "filename" in out["initial"]:
         out["initial"] = {"filename": out["initial"]["filename"]}      # HDF5 restart: the tests pass the arrays
@@ -400,6 +409,7 @@ def input_fixtures():
                 "model_intercomparison_study/problem4/run/problem4.json",
                 "model_intercomparison_study/problem5/run/problem5a.json",
                 "model_intercomparison_study/problem5/run/problem5b.json",
+                "model_intercomparison_study/problem6/run/problem6.json",
                 "ncg/infiltration/run/infiltration.json", "ncg/heat_pipe/run/heat_pipe.json",
                 "tracer/doublet/run/doublet.json", "tracer/doublet/run/doublet_ss.json"):
         convert_input(os.path.join(base, rel), dst)
@@ -408,12 +418,7 @@ def input_fixtures():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from waiwera_b200 import ingest
     nodes, elems = ingest.read_gmsh("/root/reference/test/unit/data/mesh/hybrid10.msh")
-    lines = ["$MeshFormat", "2.2 0 8", "$EndMeshFormat", "$Nodes", str(len(nodes))]
-    lines += ["%d %.17g %.17g %.17g" % (i + 1, x[0], x[1], x[2]) for i, x in enumerate(nodes)]
-    lines += ["$EndNodes", "$Elements", str(len(elems))]
-    lines += ["%d %d 2 0 0 %s" % (i + 1, t, " ".join(str(n + 1) for n in ns)) for i, (t, ns) in enumerate(elems)]
-    with open(os.path.join(dst, "hybrid10.ascii.msh"), "w") as f:
-        f.write("\n".join(lines + ["$EndElements", ""]))
+    write_ascii_msh(os.path.join(dst, "hybrid10.ascii.msh"), nodes, elems)
     print("wrote", dst)
 
 

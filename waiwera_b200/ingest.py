@@ -121,10 +121,56 @@ def read_exodus(path):
     return xyz, elems
 
 
+def read_mulgraph(path):
+    """MULgraph geometry file (the fixed-format `g*.dat` files of TOUGH2 / PyTOUGH that the reference's benchmark meshes
+    are generated from: VERTICES name x y; GRID columns `name centre-flag nnodes` + their vertex names; LAYERS name
+    bottom centre) -> (nodes [n,3], elements) of the layered mesh: one prism (hexahedron for 4-sided, wedge for 3-sided
+    columns) per column and layer, cells ordered layer by layer from the top, columns in file order -- the numbering of
+    the meshes the reference ships next to these files.  Surfaces that cut columns (SURFACE section) are not read."""
+    lines = open(path).read().split("\n")
+    sec = {}
+    cur = None
+    for ln in lines[1:]:
+        key = ln.strip()
+        if key in ("VERTICES", "GRID", "CONNECTIONS", "LAYERS", "SURFACE", "SURFA", "WELLS"):
+            cur = key
+            sec[cur] = []
+        elif cur is not None and ln.strip():
+            sec[cur].append(ln)
+    assert not sec.get("SURFACE") and not sec.get("SURFA"), "MULgraph surfaces are not supported"
+    vert = {}
+    for ln in sec["VERTICES"]:
+        vert[ln[:3]] = (float(ln[3:13]), float(ln[13:23]))
+    cols = []
+    it = iter(sec["GRID"])
+    for ln in it:
+        nn = int(ln[4:6])
+        cols.append([next(it)[:3] for _ in range(nn)])
+    layers = [(float(ln[3:13]), float(ln[13:23])) for ln in sec["LAYERS"]]     # (bottom, centre); the first is the surface
+    tops = [layers[0][0]] + [b for b, _ in layers[1:-1]]
+    bottoms = [b for b, _ in layers[1:]]
+    levels = [layers[0][0]] + bottoms
+    names = sorted(vert)
+    index = {(nme, k): i for i, (k, nme) in enumerate((k, nme) for k in range(len(levels)) for nme in names)}
+    nodes = np.array([[vert[nme][0], vert[nme][1], levels[k]] for k in range(len(levels)) for nme in names])
+    elems = []
+    for k in range(len(bottoms)):                      # layer k: top = level k, bottom = level k + 1
+        for col in cols:
+            poly = np.array([vert[v] for v in col])
+            area2 = np.sum(poly[:, 0] * np.roll(poly[:, 1], -1) - np.roll(poly[:, 0], -1) * poly[:, 1])
+            ring = col if area2 > 0 else col[::-1]     # counter-clockwise seen from above
+            assert len(ring) in (3, 4), "columns with %d sides are not supported" % len(ring)
+            elems.append((5 if len(ring) == 4 else 6, [index[(v, k + 1)] for v in ring] + [index[(v, k)] for v in ring]))
+    return nodes, elems
+
+
 def read_mesh(path):
-    """mesh file by extension: gmsh MSH 2.2 (.msh) or ExodusII (.exo / .e / .ex2)"""
-    if path.lower().endswith((".exo", ".e", ".ex2", ".exii")):
+    """mesh file by extension: gmsh MSH 2.2 (.msh), ExodusII (.exo / .e / .ex2) or MULgraph geometry (.dat)"""
+    low = path.lower()
+    if low.endswith((".exo", ".e", ".ex2", ".exii")):
         return read_exodus(path)
+    if low.endswith(".dat"):
+        return read_mulgraph(path)
     return read_gmsh(path)
 
 
