@@ -361,7 +361,8 @@ def test_exodus_mesh_and_zones_known_answers(tmp_path):
 def test_mulgraph_geometry(tmp_path):
     """MULgraph geometry files (the `g*.dat` the reference's benchmark meshes are generated from): a square column
     beside a triangular one, two layers -> hexahedra and wedges numbered layer by layer from the top; and the mesh
-    fixture of MIS problem 6 (made from test/benchmark/model_intercomparison_study/problem6/run/gproblem6.dat)"""
+    fixture of MIS problem 6 (the ExodusII mesh that was generated from
+    test/benchmark/model_intercomparison_study/problem6/run/gproblem6.dat)"""
     path = str(tmp_path / "gtest.dat")
     with open(path, "w") as f:
         f.write("GENER01  1.00e+25  1.00e-06                                0.00\nVERTICES\n"
@@ -387,6 +388,8 @@ def test_mulgraph_geometry(tmp_path):
     assert m.ninterior == 125
     assert np.allclose(m.cell_geom[0], [500.0, 400.0, -150.0, 2.4e8]) and np.allclose(m.cell_geom[124, 2:], [-1500.0, 9.6e8 * 0.5])
     ref = "/root/reference/test/benchmark/model_intercomparison_study/problem6/run/gproblem6.dat"
-    if os.path.exists(ref):      # this container only
-        rxyz, relems = ingest.read_mulgraph(ref)
-        assert np.array_equal(rxyz, xyz) and relems == elems
+    if os.path.exists(ref):      # this container only: same cells and connections as the mesh file made from it
+        g, _ = ingest.build_mesh(*ingest.read_mulgraph(ref))
+        assert np.array_equal(g.cell_geom, m.cell_geom)
+        pairs = lambda q: sorted(map(tuple, np.sort(q.face_cells.reshape(-1, 2), 1).tolist()))
+        assert pairs(g) == pairs(m)

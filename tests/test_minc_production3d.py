@@ -1,0 +1,112 @@
+"""The reference's 3-D MINC production benchmark (test/benchmark/minc/production3d: minc_3d_{base,refined}.json,
+test_minc_3d.py) run FROM ITS OWN INPUT FILES: a 5 x 5 x 5 field (refined: 540 cells, hexahedra and wedges; meshes read
+from the ExodusII / HDF5 files the reference ships, fixtures by tools/make_golden.py), two-phase reservoir under a cap
+rock with an atmosphere boundary, MINC (3 sets of fracture planes, 2 matrix levels) in the box zone around the well,
+rock types by name for fracture and matrix, bottom mass / heat inflow, and a well on deliverability whose productivity
+index is stepped up in time (step interpolation, endpoint averaging; its steam limiter has no separator and therefore
+never acts, source_network_node.F90:116-156), adaptive time steps over 4 years.  Golden output: the AUTOUGH2 listings
+shipped with the benchmark (tests/golden/minc_production3d.json); the reference accepts 1e-2 on P, T, Sv of the last
+output, on their history in the observation cell and on the well's rate and enthalpy history."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from test_mis_problems import newton_opts
+from util import OracleSim, run_input
+from waiwera_b200 import ingest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+INP = os.path.join(HERE, "golden", "inputs")
+GOLD = json.load(open(os.path.join(HERE, "golden", "minc_production3d.json")))
+
+
+def run_oracle(wo, case):
+    p = ingest.load(os.path.join(INP, "minc_3d_%s.input.json" % case), mod=wo)
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for k in range(len(p.boundary_region)):
+        assert f.set_boundary(int(m.boundary["ghost_cells"][k]), int(m.boundary["interior_cells"][k]),
+                              p.boundary_primary[k], int(p.boundary_region[k])) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    assert f.fluid_init(p.y, p.region) == 0
+    sim = OracleSim(wo, f, newton_opts(wo, p))
+    well = len(p.source_cells) - 1
+    rates = []
+    hist, y = run_input(p, sim, controls=True, well=well, on_step=lambda t, s: rates.append(s.source_rates(well + 1)[well]))
+    sim.destroy()
+    return p, hist, y, np.array(rates)
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("case", ["base", "refined"])
+def test_ingest_builds_the_minc_mesh(case):
+    g = GOLD[case]
+    p = ingest.load(os.path.join(INP, "minc_3d_%s.input.json" % case))
+    m = p.mesh
+    assert m.minc_cells == g["ncell"] and len(m.minc_zone) == g["nminc"] and m.minc_levels == 2
+    assert m.ninterior == g["ncell"] + 2 * g["nminc"] == len(g["final"])
+    # fracture 10 %, matrix 30 % + 60 % of the original cell; fracture / matrix rock types by name
+    v = m.cell_geom[:, 3]
+    z = m.minc_zone
+    n, nz = m.minc_cells, len(z)
+    assert np.allclose(v[n:n + nz], 3.0 * v[z]) and np.allclose(v[n + nz:n + 2 * nz], 6.0 * v[z])
+    assert np.allclose(m.rock[z, 5], 0.7) and np.allclose(m.rock[n:n + 2 * nz, 0:3], 1e-18)
+    # a matrix cell starts from the state of its fracture cell
+    assert np.array_equal(p.primary[n:n + nz], p.primary[z]) and np.array_equal(p.region[n + nz:], p.region[z])
+
+
+def errors(case, hist, rates):
+    """relative L2 errors against the listing: [P, T, Sv] of the last output, of the observation cell's history, well
+    enthalpy and rate histories"""
+    g = GOLD[case]
+    t = np.array([h[0] for h in hist])
+    f = np.array([h[1] for h in hist])
+    assert abs(t[-1] - g["times"][-1]) < 1.0
+    final = np.array(g["final"])
+    err = [rel(f[-1][:, c], final[:, c]) for c in range(3)]
+    gt = np.array(g["times"])
+    obs = g["obs_cell"]
+    herr = [rel(np.interp(gt, t, f[:, obs, c]), np.array(g["history"])[:, c]) for c in range(3)]
+    eh = rel(np.interp(g["source_times"], t, [h[2] for h in hist]), g["source_enthalpy"])
+    er = rel(np.interp(g["source_times"], t, rates), g["source_rate"])
+    return err, herr, eh, er
+
+
+@pytest.mark.parametrize("case", ["base", "refined"])
+def test_oracle_runs_reference_input_to_the_autough2_answer(wo, case):
+    p, hist, y, rates = run_oracle(wo, case)
+    err, herr, eh, er = errors(case, hist, rates)
+    # measured: P 1.6e-4, T 1.3e-5, Sv 3e-3 at the last output; 5e-5 / 1.3e-5 / 2e-4 in the observation cell; well
+    # enthalpy 1.2e-4, rate 4e-4 (the reference accepts 1e-2 on all of them); the same 80 steps as AUTOUGH2
+    assert all(e < tl for e, tl in zip(err, (5e-4, 5e-5, 6e-3))), (case, "last output", err)
+    assert all(e < tl for e, tl in zip(herr, (2e-4, 5e-5, 6e-4))), (case, "history", herr)
+    assert eh < 5e-4 and er < 1.5e-3, (case, "well enthalpy / rate", eh, er)
+    assert len(hist) == len(GOLD[case]["times"])
+
+
+@pytest.mark.gpu
+def test_cuda_path_runs_reference_input(wo):
+    """the base case through the CUDA path, to the reference's own acceptance tolerance (1e-2) and against the oracle run"""
+    from waiwera_b200 import flow
+    p_ref, hist_ref, y_ref, rates_ref = run_oracle(wo, "base")
+    p = ingest.load(os.path.join(INP, "minc_3d_base.input.json"), mod=flow)
+    m = p.mesh
+    sim = flow.FlowSimulation(p.params, m)
+    assert sim.set_boundaries(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region) == 0
+    assert sim.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies) == 0
+    assert sim.fluid_init(p.y, p.region) == 0
+    well = len(p.source_cells) - 1
+    rates = []
+    hist, y = run_input(p, sim, opts=newton_opts(flow, p), controls=True, well=well,
+                        on_step=lambda t, s: rates.append(s.source_rates()[well]))
+    err, herr, eh, er = errors("base", hist, np.array(rates))
+    assert all(e < 1e-2 for e in err + herr) and eh < 1e-2 and er < 1e-2, (err, herr, eh, er)
+    assert len(hist) == len(hist_ref)
+    assert np.abs(y - y_ref).max() / np.abs(y_ref).max() < 1e-3
+    sim.destroy()

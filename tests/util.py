@@ -119,6 +119,13 @@ class OracleSim:
         self.f.set_source_components(injection, production)
         return 0
 
+    def set_source_controls(self, sources, pi, pref, direction, limit):
+        self.f.set_source_controls(sources, pi, pref, direction, limit)
+        return 0
+
+    def source_rates(self, n):
+        return self.f.source_rates(n)
+
     def fluid(self):
         return self.f.fluid()
 
@@ -183,11 +190,13 @@ def wge_fields(fluid, n):
     return np.stack([fl[:, 0], fl[:, 1], fl[:, 17 + 2], fl[:, 17 + 8], fl[:, 8 + 8], fl[:, 7]], 1)
 
 
-def run_input(problem, sim, opts=None, fields=None):
+def run_input(problem, sim, opts=None, fields=None, controls=False, well=0, on_step=None):
     """Runs an ingested input (waiwera_b200.ingest.Problem, eos_we) through `sim` (flow.FlowSimulation or OracleSim,
     mesh / boundaries / fluid_init already done) with the time stepping of its "time" value: a list of step sizes
     (the last one repeats), or one size with the "iteration" adaptor, maximum size / number, stop time; table sources
-    are averaged over each step.  Returns [(time, P/T/Sv of the interior cells, production enthalpy)]."""
+    are averaged over each step; with `controls` the source controls of the input (ingest.controls_at: tables in time
+    averaged over the step) are set before every step.  Returns [(time, P/T/Sv of the interior cells, production
+    enthalpy of source `well`)]; on_step(time, sim) is called after every step."""
     from waiwera_b200 import ingest
     p = problem
     st = p.time["step"]
@@ -202,7 +211,7 @@ def run_input(problem, sim, opts=None, fields=None):
     y = p.y.copy()
     t, k, dt = 0.0, 0, sizes[0]
     hist = []
-    prod = int(p.source_cells[0]) if len(p.source_cells) else 0
+    prod = int(p.source_cells[well]) if len(p.source_cells) else 0
     while t < stop * (1 - 1e-12) and k < nmax:
         if not adapt:
             dt = sizes[min(k, len(sizes) - 1)]
@@ -211,6 +220,13 @@ def run_input(problem, sim, opts=None, fields=None):
             rates = ingest.rates_at(p, t, t + dt)
             assert sim.set_sources(p.source_cells, ingest.components_at(p, rates), rates, p.source_enthalpies) == 0
             sim.set_source_components(p.source_injection_components, p.source_production_components)
+        if controls and p.source_controls:
+            ctrl, _ = ingest.controls_at(p, t, t + dt)
+            assert all(c["productivity"] is not None for c in ctrl)
+            r = sim.set_source_controls([c["source"] for c in ctrl], [c["productivity"] if c["deliverability"] else 0.0 for c in ctrl],
+                                        [c["reference_pressure"] or 0.0 for c in ctrl], [c["direction"] for c in ctrl],
+                                        [c["limit"] for c in ctrl])
+            assert not r
         t1, _, its, _ = run_adaptive(sim, y, dt, dt, opts=opts, max_steps=1, reduction=ad.get("reduction", 0.2),
                                      amplification=1.0, its_min=0, its_max=10 ** 9)
         t += t1
@@ -220,6 +236,8 @@ def run_input(problem, sim, opts=None, fields=None):
             hist.append((t, we_fields(fl, n), we_production_enthalpy(np.asarray(fl)[prod])))
         else:
             hist.append((t, fields(fl, n), 0.0))
+        if on_step is not None:
+            on_step(t, sim)
         dt = t1
         if adapt:
             if its < ad.get("minimum", 5):

@@ -283,7 +283,10 @@ def h5_fixtures():
     dst = os.path.join(os.path.dirname(OUT), "h5")
     os.makedirs(dst, exist_ok=True)
     for src in ("/root/reference/test/unit/data/flow_simulation/lhs/lhs.h5",
-                "/root/reference/test/benchmark/tracer/oned/run/oned_two_phase_ss.h5"):
+                "/root/reference/test/benchmark/tracer/oned/run/oned_two_phase_ss.h5",
+                # an ExodusII mesh in the netCDF-4 container (HDF5 with version-2 object headers, links in a fractal
+                # heap, attributes, a chunked dataset): the hexahedra + wedges mesh of the 3-D MINC benchmark (76 KB)
+                "/root/reference/test/benchmark/minc/production3d/run/gminc_3d_refined.exo"):
         shutil.copy(src, os.path.join(dst, os.path.basename(src)))
         print("copied", src)
     # the restart file the tracer doublet input names ("initial": {"filename": "doublet_ss.h5"}), next to that input
@@ -355,6 +358,47 @@ def minc_doublet():
     print("wrote", out)
 
 
+def minc_production3d():
+    """test/benchmark/minc/production3d (3-D MINC production: well on deliverability with a productivity index
+    stepped in time, base and refined (hexahedra + wedges) meshes): AUTOUGH2 listings.  Kept, in Waiwera's cell order
+    (original cells, then the matrix cells level by level -- test_minc_3d.py::minc_level_map): P, T, Sv of every cell at
+    the last output; their history in the cell that contains (10, 10, -1000); rate and enthalpy history of the well."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from waiwera_b200 import ingest
+    base = "/root/reference/test/benchmark/minc/production3d/run"
+    doc = {"_generated_by": "tools/make_golden.py: ELEMENT / GENERATION tables of test/benchmark/minc/production3d/run/"
+                            "minc_3d_{base,refined}.listing (AUTOUGH2); atmosphere blocks dropped, matrix blocks reordered by level",
+           "columns": ["pressure", "temperature", "vapour_saturation"]}
+    for case in ("base", "refined"):
+        inp = json.load(open(os.path.join(base, "minc_3d_%s.json" % case)))
+        nodes, elems = ingest.read_exodus(os.path.join(base, inp["mesh"]["filename"]))
+        ncell = len(elems)
+        natm = len(inp["boundaries"])
+        nlev = len(inp["mesh"]["minc"]["geometry"]["matrix"]["volume"])
+        tabs = listing_generic(os.path.join(base, "minc_3d_%s.listing" % case))
+        el = [(t, r) for k, t, r in tabs if k == "E"]
+        ge = [(t, r) for k, t, r in tabs if k == "G"]
+        nrow = len(el[-1][1])
+        nmatrix = nrow - natm - ncell
+        order = list(range(natm, natm + ncell))
+        for l in range(nlev):
+            order += list(range(natm + ncell + l, natm + ncell + nmatrix, nlev))
+        pts = np.array(nodes)
+        obs = [c for c, (_, ns) in enumerate(elems)
+               if np.all(pts[ns].min(0) <= [10.0, 10.0, -1000.0]) and np.all(pts[ns].max(0) >= [10.0, 10.0, -1000.0])]
+        assert len(obs) == 1
+        doc[case] = {"ncell": ncell, "nminc": nmatrix // nlev, "times": [t for t, _ in el],
+                     "final": [el[-1][1][i][:3] for i in order], "obs_cell": obs[0],
+                     "history": [r[natm + obs[0]][:3] for _, r in el],
+                     "source_times": [t for t, _ in ge], "source_rate": [r[-1][0] for _, r in ge],
+                     "source_enthalpy": [r[-1][1] for _, r in ge]}
+    out = os.path.join(os.path.dirname(OUT), "minc_production3d.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 INPUT_KEYS = ("boundaries", "eos", "gravity", "initial", "mesh", "rock", "source", "thermodynamics", "time", "tracer")
 
 
@@ -411,7 +455,8 @@ def input_fixtures():
                 "model_intercomparison_study/problem5/run/problem5b.json",
                 "model_intercomparison_study/problem6/run/problem6.json",
                 "ncg/infiltration/run/infiltration.json", "ncg/heat_pipe/run/heat_pipe.json",
-                "tracer/doublet/run/doublet.json", "tracer/doublet/run/doublet_ss.json"):
+                "tracer/doublet/run/doublet.json", "tracer/doublet/run/doublet_ss.json",
+                "minc/production3d/run/minc_3d_base.json", "minc/production3d/run/minc_3d_refined.json"):
         convert_input(os.path.join(base, rel), dst)
     # mesh only: the reference's 3-D hybrid mesh (hexahedra + prisms) of its flow_simulation / initial unit tests
     import sys
@@ -457,5 +502,6 @@ if __name__ == "__main__":
     h5_fixtures()
     wae_benchmarks()
     tracer_doublet()
+    minc_production3d()
     minc_doublet()
     input_fixtures()

@@ -6,9 +6,13 @@ which is what PETSc's HDF5 viewer writes with the library's default "earliest" f
     superblock version 0; "old-style" groups (symbol-table message -> B-tree version 1 of group nodes + SNOD symbol
     nodes + local heap); object headers version 1 incl. continuation blocks; dataspace messages version 1 / 2;
     fixed-point and IEEE floating-point datatypes, fixed-length strings; data layout message version 3 (compact,
-    contiguous, chunked with a version-1 B-tree of chunks) and versions 1 / 2; no filters (PETSc writes none).
+    contiguous, chunked with a version-1 B-tree of chunks) and versions 1 / 2;
+    and, read only, what netCDF-4 adds to that (the reference's benchmark meshes are ExodusII files in that container):
+    object headers version 2 ("OHDR" / "OCHK"), "new-style" groups (link messages in the header, or in a fractal heap
+    with direct blocks under one indirect block, indexed by a version-2 B-tree of depth <= 1), attribute messages
+    versions 1-3 (in the header or in a fractal heap), filter pipelines with deflate / shuffle / fletcher32.
 
-Reading: H5File(path) -> .datasets() (paths), [path] -> numpy array, .groups().  Writing: write(path, {"a/b": array})
+Reading: H5File(path) -> .datasets() (paths), [path] -> numpy array, .groups(), .attrs(path).  Writing: write(path, {"a/b": array})
 lays down the same structures with contiguous datasets.  The reader is checked against the reference's own files
 (tools/make_golden.py reads them with it; tests/test_h5lite.py); the writer against the reader and against structural
 checks -- it cannot be checked against libhdf5 here, which DESIGN.md states.
@@ -55,6 +59,7 @@ class H5File:
         pos += 4 * 8                              # base, free-space info, end of file, driver info
         self.root_entry = self._symbol_entry(pos)
         self._objects = {}
+        self._headers = {}
         self._walk("", self.root_entry["header"], self.root_entry)
 
     # ---- primitives
@@ -71,6 +76,8 @@ class H5File:
         """(type, payload bytes) of an object header version 1, following continuation blocks"""
         b = self.buf
         addr += self.base
+        if b[addr:addr + 4] == b"OHDR":
+            return self._messages_v2(addr)
         if b[addr] != 1:
             raise H5Error("object header version %d is not supported" % b[addr])
         nmsg = self._u(addr + 2, 2)
@@ -87,6 +94,199 @@ class H5File:
                 if mtype == 0x10:
                     blocks.append((self.base + int.from_bytes(data[:8], "little"), int.from_bytes(data[8:16], "little")))
                 out.append((mtype, data))
+        return out
+
+    def _messages_v2(self, addr):
+        """(type, payload bytes) of an object header version 2 ("OHDR", with "OCHK" continuation chunks)"""
+        b = self.buf
+        if b[addr + 4] != 2:
+            raise H5Error("object header version %d is not supported" % b[addr + 4])
+        flags = b[addr + 5]
+        pos = addr + 6 + (16 if flags & 0x20 else 0) + (4 if flags & 0x10 else 0)
+        nsz = 1 << (flags & 3)
+        size = self._u(pos, nsz)
+        blocks = [(pos + nsz, size)]
+        mhdr = 6 if flags & 0x04 else 4
+        out = []
+        while blocks:
+            pos, left = blocks.pop(0)
+            end = pos + left
+            while pos + mhdr <= end:
+                mtype, msize = b[pos], self._u(pos + 1, 2)
+                data = b[pos + mhdr:pos + mhdr + msize]
+                pos += mhdr + msize
+                if mtype == 0x10:
+                    caddr, clen = self.base + int.from_bytes(data[:8], "little"), int.from_bytes(data[8:16], "little")
+                    if b[caddr:caddr + 4] != b"OCHK":
+                        raise H5Error("bad object header continuation chunk")
+                    blocks.append((caddr + 4, clen - 8))          # signature in front, checksum behind
+                elif mtype != 0:
+                    out.append((mtype, data))
+        return out
+
+    # ---- version-2 groups: link messages in the header, or in a fractal heap ("dense" storage)
+    def _link(self, d):
+        """(name, object header address or None for soft / external links, bytes used) of a link message"""
+        flags = d[1]
+        pos = 2
+        ltype = 0
+        if flags & 0x08:
+            ltype = d[pos]
+            pos += 1
+        if flags & 0x04:
+            pos += 8
+        if flags & 0x10:
+            pos += 1
+        nsz = 1 << (flags & 3)
+        nlen = int.from_bytes(d[pos:pos + nsz], "little")
+        pos += nsz
+        name = bytes(d[pos:pos + nlen]).decode()
+        pos += nlen
+        if ltype == 0:
+            return name, int.from_bytes(d[pos:pos + 8], "little"), pos + 8
+        vlen = int.from_bytes(d[pos:pos + 2], "little")
+        return name, None, pos + 2 + vlen
+
+    def _fractal_heap(self, addr):
+        """header fields and the direct blocks [(heap offset, file address, size)] of a fractal heap"""
+        b = self.buf
+        h = self.base + addr
+        if b[h:h + 4] != b"FRHP" or b[h + 4] != 0:
+            raise H5Error("bad fractal heap header")
+        if self._u(h + 7, 2):
+            raise H5Error("filtered fractal heaps are not supported")
+        hflags = b[h + 9]
+        max_man = self._u(h + 10, 4)
+        pos = h + 14 + 12 * 8                          # next huge id ... number of tiny objects
+        width = self._u(pos, 2)
+        start, max_direct = self._u(pos + 2, 8), self._u(pos + 10, 8)
+        max_bits = self._u(pos + 18, 2)
+        root, nrows = self._u(pos + 22, 8), self._u(pos + 30, 2)
+        offb = (max_bits + 7) // 8
+        info = {"off_bytes": offb, "len_bytes": (min(max_direct, max_man).bit_length() - 1) // 8 + 1,
+                "block_header": 5 + 8 + offb + (4 if hflags & 2 else 0)}
+        blocks = []
+        if root != UNDEF:
+            if nrows == 0:
+                blocks.append((0, self.base + root, start))
+            else:
+                r = self.base + root
+                if b[r:r + 4] != b"FHIB":
+                    raise H5Error("bad fractal heap indirect block")
+                pos = r + 5 + 8 + offb
+                off = 0
+                for row in range(nrows):
+                    size = start if row < 2 else start << (row - 1)
+                    if size > max_direct:
+                        raise H5Error("fractal heaps with nested indirect blocks are not supported")
+                    for _ in range(width):
+                        child = self._u(pos, 8)
+                        pos += 8
+                        if child != UNDEF:
+                            blocks.append((off, self.base + child, size))
+                        off += size
+        info["blocks"] = blocks
+        return info
+
+    def _heap_objects(self, heap_addr, btree_addr, id_offset):
+        """the managed objects of a fractal heap that a version-2 B-tree's records point at (heap id at id_offset of each record)"""
+        b = self.buf
+        heap = self._fractal_heap(heap_addr)
+        t = self.base + btree_addr
+        if b[t:t + 4] != b"BTHD":
+            raise H5Error("bad version-2 B-tree header")
+        node_size, rec_size, depth = self._u(t + 6, 4), self._u(t + 10, 2), self._u(t + 12, 2)
+        root, nroot = self._u(t + 16, 8), self._u(t + 24, 2)
+        max_leaf = (node_size - 10) // rec_size
+        nsz = (max_leaf.bit_length() + 7) // 8
+        records = []
+
+        def node(addr, nrec, level):
+            n = self.base + addr
+            if b[n:n + 4] != (b"BTIN" if level else b"BTLF"):
+                raise H5Error("bad version-2 B-tree node")
+            recs = [b[n + 6 + k * rec_size:n + 6 + (k + 1) * rec_size] for k in range(nrec)]
+            if level == 0:
+                records.extend(recs)
+                return
+            if level > 1:
+                raise H5Error("version-2 B-trees deeper than 1 are not supported")
+            pos = n + 6 + nrec * rec_size
+            for k in range(nrec + 1):
+                node(self._u(pos, 8), self._u(pos + 8, nsz), level - 1)
+                pos += 8 + nsz
+                if k < nrec:
+                    records.append(recs[k])
+
+        if root != UNDEF and nroot:
+            node(root, nroot, depth)
+        out = []
+        for rec in records:
+            hid = rec[id_offset:]
+            if (hid[0] >> 4) & 3 != 0:
+                raise H5Error("huge / tiny fractal heap objects are not supported")
+            off = int.from_bytes(hid[1:1 + heap["off_bytes"]], "little")
+            ln = int.from_bytes(hid[1 + heap["off_bytes"]:1 + heap["off_bytes"] + heap["len_bytes"]], "little")
+            for boff, baddr, bsize in heap["blocks"]:
+                if boff <= off < boff + bsize:
+                    out.append(b[baddr + off - boff:baddr + off - boff + ln])
+                    break
+            else:
+                raise H5Error("fractal heap object outside the direct blocks")
+        return out
+
+    def _links(self, msgs):
+        """[(name, header address)] of a version-2 group"""
+        out = []
+        for t, d in msgs:
+            if t == 0x06:
+                out.append(self._link(d)[:2])
+            elif t == 0x02:
+                flags = d[1]
+                pos = 2 + (8 if flags & 1 else 0)
+                heap, btree = int.from_bytes(d[pos:pos + 8], "little"), int.from_bytes(d[pos + 8:pos + 16], "little")
+                if heap != UNDEF:
+                    out += [self._link(o)[:2] for o in self._heap_objects(heap, btree, 4)]
+        return sorted((n, a) for n, a in out if a is not None)
+
+    def _attributes(self, msgs):
+        """{name: value} of the attributes with a plain datatype (numbers, fixed-length strings); others -> None"""
+        raw = [d for t, d in msgs if t == 0x0C]
+        for t, d in msgs:
+            if t == 0x15:
+                flags = d[1]
+                pos = 2 + (2 if flags & 1 else 0)
+                heap, btree = int.from_bytes(d[pos:pos + 8], "little"), int.from_bytes(d[pos + 8:pos + 16], "little")
+                if heap != UNDEF:
+                    raw += self._heap_objects(heap, btree, 0)
+        out = {}
+        for d in raw:
+            ver = d[0]
+            nlen, tlen, slen = (int.from_bytes(d[2 + 2 * i:4 + 2 * i], "little") for i in range(3))
+            pos = 9 if ver == 3 else 8
+            pad = (lambda n: (n + 7) & ~7) if ver == 1 else (lambda n: n)
+            name = bytes(d[pos:pos + nlen]).split(b"\0")[0].decode()
+            pos += pad(nlen)
+            td = d[pos:pos + tlen]
+            pos += pad(tlen)
+            sd = d[pos:pos + slen]
+            pos += pad(slen)
+            try:
+                dt = self._dtype(td)
+            except H5Error:
+                out[name] = None
+                continue
+            rank = sd[1]
+            off = 8 if sd[0] == 1 else 4
+            shape = [int.from_bytes(sd[off + 8 * i:off + 8 * i + 8], "little") for i in range(rank)]
+            if sd[0] == 2 and sd[3] == 2:                 # null dataspace
+                out[name] = np.zeros(0, dt)
+                continue
+            n = int(np.prod(shape)) if shape else 1
+            v = np.frombuffer(bytes(d[pos:pos + n * dt.itemsize]), dt, n).reshape(shape)
+            if dt.kind == "S":
+                v = v.reshape(-1)[0].split(b"\0")[0].decode() if n == 1 else [x.split(b"\0")[0].decode() for x in v.reshape(-1)]
+            out[name] = v
         return out
 
     def _heap_name(self, heap_addr, off):
@@ -132,12 +332,18 @@ class H5File:
             self._objects[prefix or "/"] = ("group", None)
             for e in self._group_entries(btree, heap):
                 self._walk((prefix + "/" + e["name"]).lstrip("/") if prefix else e["name"], e["header"], e)
+        elif 0x02 in types or (0x06 in types and 0x08 not in types):
+            self._objects[prefix or "/"] = ("group", None)
+            for name, child in self._links(msgs):
+                self._walk(prefix + "/" + name if prefix else name, child)
         elif 0x08 in types:
             self._objects[prefix] = ("dataset", self._dataset(msgs))
+        self._headers[prefix or "/"] = header
 
     # ---- datasets
     def _dataset(self, msgs):
         shape = maxshape = dtype = layout = None
+        filters = []
         for t, d in msgs:
             if t == 0x01:
                 ver, rank, flags = d[0], d[1], d[2]
@@ -147,18 +353,9 @@ class H5File:
                     off += 8 * rank
                     maxshape = [int.from_bytes(d[off + 8 * i:off + 8 * i + 8], "little") for i in range(rank)]
             elif t == 0x03:
-                cls, bits0, size = d[0] & 15, d[1], int.from_bytes(d[4:8], "little")
-                order = ">" if bits0 & 1 else "<"
-                if cls == 0:
-                    dtype = np.dtype("%s%s%d" % (order, "i" if bits0 & 8 else "u", size))
-                elif cls == 1:
-                    dtype = np.dtype("%sf%d" % (order, size))
-                elif cls == 3:
-                    dtype = np.dtype("S%d" % size)
-                else:
-                    raise H5Error("datatype class %d is not supported" % cls)
+                dtype = self._dtype(d)
             elif t == 0x0B:
-                raise H5Error("filtered (compressed) datasets are not supported")
+                filters = self._filters(d)
             elif t == 0x08:
                 ver = d[0]
                 if ver == 3:
@@ -195,7 +392,62 @@ class H5File:
                     raise H5Error("data layout message version %d is not supported" % ver)
         if shape is None or dtype is None or layout is None:
             raise H5Error("dataset without dataspace, datatype or layout")
-        return _Dataset(shape, dtype, layout, maxshape)
+        ds = _Dataset(shape, dtype, layout, maxshape)
+        ds.filters = filters
+        return ds
+
+    @staticmethod
+    def _dtype(d):
+        cls, bits0, size = d[0] & 15, d[1], int.from_bytes(d[4:8], "little")
+        order = ">" if bits0 & 1 else "<"
+        if cls == 0:
+            return np.dtype("%s%s%d" % (order, "i" if bits0 & 8 else "u", size))
+        if cls == 1:
+            return np.dtype("%sf%d" % (order, size))
+        if cls == 3:
+            return np.dtype("S%d" % size)
+        raise H5Error("datatype class %d is not supported" % cls)
+
+    @staticmethod
+    def _filters(d):
+        """[(filter id, client data)] of a filter pipeline message (versions 1 and 2)"""
+        ver, n = d[0], d[1]
+        pos = 8 if ver == 1 else 2
+        out = []
+        for _ in range(n):
+            fid = int.from_bytes(d[pos:pos + 2], "little")
+            pos += 2
+            nlen = 0
+            if ver == 1 or fid >= 256:
+                nlen = int.from_bytes(d[pos:pos + 2], "little")
+                pos += 2
+            ncd = int.from_bytes(d[pos + 2:pos + 4], "little")
+            pos += 4 + ((nlen + 7) & ~7 if ver == 1 else nlen)
+            cd = [int.from_bytes(d[pos + 4 * i:pos + 4 * i + 4], "little") for i in range(ncd)]
+            pos += 4 * ncd + (4 if ver == 1 and ncd % 2 else 0)
+            if fid not in (1, 2, 3):
+                raise H5Error("filter %d is not supported (deflate, shuffle and fletcher32 are)" % fid)
+            out.append((fid, cd))
+        return out
+
+    @staticmethod
+    def _unfilter(raw, filters, mask, itemsize):
+        """undo the filter pipeline on one chunk (filters are applied in order on write: undone in reverse)"""
+        import zlib
+        for k in range(len(filters) - 1, -1, -1):
+            fid, cd = filters[k]
+            if mask >> k & 1:
+                continue
+            if fid == 3:
+                raw = raw[:-4]
+            elif fid == 1:
+                raw = zlib.decompress(raw)
+            elif fid == 2:
+                size = cd[0] if cd else itemsize
+                n = len(raw) // size
+                body = np.frombuffer(raw, np.uint8, n * size).reshape(size, n).T.tobytes()
+                raw = body + raw[n * size:]
+        return raw
 
     def _chunks(self, addr, rank):
         """(offsets, address, bytes) of every chunk under a version-1 chunk B-tree node"""
@@ -215,9 +467,7 @@ class H5File:
             if level > 0:
                 out += self._chunks(child, rank)
             else:
-                if mask:
-                    raise H5Error("filtered chunks are not supported")
-                out.append((offs, child, nbytes))
+                out.append((offs, child, nbytes, mask))
         return out
 
     def __getitem__(self, path):
@@ -237,8 +487,12 @@ class H5File:
         if bt == UNDEF or n == 0:
             return out
         cshape = cdims[:rank]
-        for offs, addr, nbytes in self._chunks(bt, rank):
-            chunk = np.frombuffer(self.buf, ds.dtype, int(np.prod(cshape)), self.base + addr).reshape(cshape)
+        for offs, addr, nbytes, mask in self._chunks(bt, rank):
+            if ds.filters:
+                raw = self._unfilter(self.buf[self.base + addr:self.base + addr + nbytes], ds.filters, mask, ds.dtype.itemsize)
+                chunk = np.frombuffer(raw, ds.dtype, int(np.prod(cshape))).reshape(cshape)
+            else:
+                chunk = np.frombuffer(self.buf, ds.dtype, int(np.prod(cshape)), self.base + addr).reshape(cshape)
             sl_out = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, cshape, ds.shape))
             sl_in = tuple(slice(0, s.stop - s.start) for s in sl_out)
             out[sl_out] = chunk[sl_in]
@@ -249,6 +503,10 @@ class H5File:
 
     def groups(self):
         return sorted(k for k, (kind, _) in self._objects.items() if kind == "group" and k != "/")
+
+    def attrs(self, path):
+        """attributes of a dataset or group ("/" for the root)"""
+        return self._attributes(self._messages(self._headers[path.strip("/") or "/"]))
 
     def shape(self, path):
         return self._objects[path.strip("/")][1].shape

@@ -5,9 +5,10 @@ gravity normal, permeability direction), Dirichlet boundary ghost cells from the
 (src/mesh.F90:1631-1813, 583-664), rock records from the rock types (src/rock_setup.F90), initial primaries /
 regions, fixed-rate sources, tracers and the EOS / curve parameters.
 
-Setup-time host code (numpy), nothing here is on the hot path.  Not covered: ExodusII meshes (need netCDF / HDF5,
-not in this image), HDF5 initial conditions (pass the arrays), source controls / networks, MINC (use
-mesh.add_minc on the result).  Cell order = element order of the mesh file (DMPlex numbering of a serial mesh);
+Setup-time host code (numpy), nothing here is on the hot path.  Also read: ExodusII meshes (netCDF classic, and
+netCDF-4 through h5lite) and MULgraph geometry files, zones, MINC ("mesh.minc"), source controls (deliverability,
+recharge, limiters, separators, tables in time), restarts from HDF5 output files.  Not covered: source networks.
+Cell order = element order of the mesh file (DMPlex numbering of a serial mesh);
 faces are ordered by (cell 1, cell 2), which is not DMPlex's face numbering -- only the rounding of the inflow
 sums depends on it."""
 import json
@@ -86,38 +87,53 @@ def read_gmsh(path):
 
 # ExodusII element names -> the gmsh type codes build_mesh works with (the node orderings of these element types
 # are the same in both formats)
-_EXO = {"HEX": 5, "HEX8": 5, "WEDGE": 6, "WEDGE6": 6, "TETRA": 4, "TETRA4": 4, "TET4": 4, "PYRAMID": 7, "PYRAMID5": 7,
+_EXO = {"HEX": 5, "HEX8": 5, "HEXAHEDRON": 5, "WEDGE": 6, "WEDGE6": 6, "TETRA": 4, "TETRA4": 4, "TET4": 4, "PYRAMID": 7, "PYRAMID5": 7,
         "QUAD": 3, "QUAD4": 3, "SHELL": 3, "SHELL4": 3, "TRI": 2, "TRI3": 2, "TRIANGLE": 2}
 
 
 def read_exodus(path):
-    """ExodusII mesh in the netCDF classic format (what the reference's test and benchmark meshes use) -> (nodes [n,3],
-    list of (gmsh element type, node indices 0-based)), element blocks in file order as DMPlexCreateExodus numbers the
-    cells.  Read with scipy's pure-Python netCDF-3 reader; netCDF-4 (HDF5-based) files cannot be read in this image."""
-    from scipy.io import netcdf_file
-    try:
+    """ExodusII mesh -> (nodes [n,3], list of (gmsh element type, node indices 0-based)), element blocks in the order
+    DMPlexCreateExodus numbers the cells (file order, wedge blocks last).  Both containers the reference's meshes come in are read without a netCDF
+    library: the netCDF classic format (its unit-test meshes) with scipy's pure-Python reader, netCDF-4 (= HDF5: its
+    benchmark meshes) with h5lite."""
+    with open(path, "rb") as fh:
+        magic = fh.read(8)
+    if magic == b"\x89HDF\r\n\x1a\n":
+        from . import h5lite
+        h = h5lite.H5File(path)
+        var = lambda name: h[name] if name in h else None
+        attr = lambda name, a: h.attrs(name).get(a)
+        nblk = h.shape("num_el_blk")[0] if "num_el_blk" in h else 0
+        nn = h.shape("num_nodes")[0]
+    elif magic[:3] == b"CDF":
+        from scipy.io import netcdf_file
         f = netcdf_file(path, "r", mmap=False)
-    except TypeError as e:
-        raise ValueError("%s: not a netCDF classic file (HDF5-based ExodusII files need a netCDF-4 library)" % path) from e
-    v = f.variables
-    nn = f.dimensions["num_nodes"]
+        var = lambda name: np.array(f.variables[name][:]) if name in f.variables else None
+        attr = lambda name, a: getattr(f.variables[name], a)
+        nblk = f.dimensions.get("num_el_blk", 0)
+        nn = f.dimensions["num_nodes"]
+    else:
+        raise ValueError("%s: neither a netCDF classic nor an HDF5-based ExodusII file" % path)
     xyz = np.zeros((nn, 3))
-    if "coord" in v:
-        c = np.array(v["coord"][:], float)
-        xyz[:, :c.shape[0]] = c.T
+    c = var("coord")
+    if c is not None:
+        xyz[:, :c.shape[0]] = np.asarray(c, float).T
     else:
         for k, name in enumerate(("coordx", "coordy", "coordz")):
-            if name in v:
-                xyz[:, k] = np.array(v[name][:], float)
-    elems = []
-    for b in range(1, f.dimensions.get("num_el_blk", 0) + 1):
-        con = v["connect%d" % b]
-        et = con.elem_type
+            c = var(name)
+            if c is not None:
+                xyz[:, k] = np.asarray(c, float)
+    blocks = []
+    for b in range(1, nblk + 1):
+        et = attr("connect%d" % b, "elem_type")
         et = (et.decode() if isinstance(et, bytes) else str(et)).strip().upper()
         assert et in _EXO, "ExodusII element type %r is not supported" % et
-        for row in np.array(con[:], np.int64) - 1:
-            elems.append((_EXO[et], [int(i) for i in row]))
-    f.close()
+        blocks.append((_EXO[et], np.asarray(var("connect%d" % b), np.int64) - 1))
+    # DMPlex numbers the prism (wedge) blocks of a hybrid mesh after all the others, each group in file order: the cell
+    # indices of the reference's minc_3d_refined deck (wedge block first in the file, top-layer hexahedra 0..92, wedges
+    # 465..479) only fit this order
+    blocks = [b for b in blocks if b[0] != 6] + [b for b in blocks if b[0] == 6]
+    elems = [(t, [int(i) for i in row]) for t, con in blocks for row in con]
     return xyz, elems
 
 
@@ -339,6 +355,9 @@ def add_boundary_faces(m, exterior, specs):
                      dims=m.dims, natural=m.natural, ncell_global=m.ncell_global,
                      boundary={"ghost_cells": ghosts.astype(np.int32), "interior_cells": np.array(cells, np.int32)} if nb else {})
     out.gravity, out.dim, out.permeability_angle = m.gravity, m.dim, m.permeability_angle
+    out.minc_levels, out.minc_base = m.minc_levels, m.minc_base
+    if hasattr(m, "minc_zone"):
+        out.minc_zone, out.minc_cells = m.minc_zone, m.minc_cells
     return out, np.array(owner, np.int32)
 
 
@@ -428,6 +447,93 @@ def rock_records(spec, m, zones=None):
     return rock
 
 
+def apply_minc(m, minc, rock_spec, zones=None):
+    """"mesh.minc" of the input (src/minc.F90:73-190 geometry and zones, src/mesh.F90:3186-3375 rock properties) on a
+    mesh without boundary ghosts -> the MINC mesh of mesh.add_minc.  The MINC zone is the union of the "zones" and of the
+    cells of the rock "types" of every entry of "rock"; in it the fracture cells take the properties the "fracture"
+    rock type gives (the others stay), the matrix cells those of the "matrix" rock type, porosity by default the one
+    that keeps the void fraction of the original cell.  One MINC geometry per mesh is built (the reference allows a
+    list of zones with different geometries)."""
+    mlist = [minc] if isinstance(minc, dict) else list(minc)
+    if len(mlist) != 1:
+        raise NotImplementedError("several MINC geometries in one mesh are not built")
+    spec = mlist[0]
+    geom = spec.get("geometry", {})
+    fr, mx = geom.get("fracture", {}), geom.get("matrix", {})
+    mvol = mx.get("volume")
+    if "volume" in fr:
+        fvol = float(fr["volume"])
+        mvol = [1.0 - fvol] if mvol is None else list(np.atleast_1d(mvol).astype(float))
+    else:
+        mvol = [0.9] if mvol is None else list(np.atleast_1d(mvol).astype(float))
+        fvol = 1.0 - sum(mvol)
+    volumes = np.array([fvol] + mvol)
+    volumes = volumes / volumes.sum()
+    planes = int(fr.get("planes", 1))
+    sp = np.atleast_1d(np.asarray(fr.get("spacing", 50.0), float))
+    spacing = np.full(planes, sp[0])
+    spacing[:min(len(sp), planes)] = sp[:planes]
+    types = {rt.get("name"): rt for rt in (rock_spec or {}).get("types", [])}
+
+    def cells_of_type(name):
+        assert name in types, "unrecognised rock type %r" % name
+        rt = types[name]
+        idx = list(rt.get("cells", []))
+        zs = rt.get("zones", [])
+        for z in ([zs] if isinstance(zs, str) else zs):
+            idx += _zone_cells(z, m, zones).tolist()
+        return idx
+
+    def properties(entry, which):
+        """the 8 rock properties of the named rock type, -1 where it does not give one"""
+        assert which in entry and "type" in entry[which], "mesh.minc.rock: %s.type not found" % which
+        name = entry[which]["type"]
+        assert name in types, "unrecognised rock type %r" % name
+        rt = types[name]
+        out = np.full(8, -1.0)
+        if rt.get("permeability") is not None:
+            k = np.atleast_1d(np.asarray(rt["permeability"], float))
+            out[0:3] = k[0] if len(k) == 1 else -1.0
+            if len(k) > 1:
+                out[0:len(k)] = k
+        for key, col in (("wet_conductivity", 3), ("dry_conductivity", 4), ("porosity", 5), ("density", 6), ("specific_heat", 7)):
+            if rt.get(key) is not None:
+                out[col] = rt[key]
+        return out
+
+    n = m.ninterior
+    entry_of = np.full(n, -1)
+    rocks = spec.get("rock", [])
+    rocks = [rocks] if isinstance(rocks, dict) else list(rocks)
+    for k, entry in enumerate(rocks):
+        zs = entry.get("zones", [])
+        for z in ([zs] if isinstance(zs, str) else zs):
+            entry_of[_zone_cells(z, m, zones)] = k
+        ts = entry.get("types", [])
+        for t in ([ts] if isinstance(ts, str) else ts):
+            entry_of[np.array(cells_of_type(t), np.int64)] = k
+    zone = np.nonzero(entry_of >= 0)[0]
+    orig = m.rock[:n].copy()
+    matrix = orig[zone].copy()
+    for k, entry in enumerate(rocks):
+        sel = zone[entry_of[zone] == k]
+        if len(sel) == 0:
+            continue
+        fp, mp = properties(entry, "fracture"), properties(entry, "matrix")
+        fpor = np.where(fp[5] < 0, orig[sel, 5], fp[5])
+        mpor = (orig[sel, 5] - fpor * volumes[0]) / (1.0 - volumes[0]) if mp[5] < 0 else np.full(len(sel), mp[5])
+        rows = np.nonzero(entry_of[zone] == k)[0]
+        matrix[rows] = np.where(mp > 0, mp, orig[sel])
+        matrix[rows, 5] = mpor
+        m.rock[sel] = np.where(fp > 0, fp, orig[sel])
+        m.rock[sel, 5] = fpor
+    out = wmesh.add_minc(m, volumes=volumes, spacing=spacing, cells=zone, matrix_rock=matrix,
+                         fracture_connection_distance=float(fr.get("connection", 0.0)))
+    out.gravity, out.dim, out.permeability_angle = m.gravity, m.dim, m.permeability_angle
+    out.minc_zone, out.minc_cells = zone, n
+    return out
+
+
 _EOS = {"we": ("EOS_WE", 2), "w": ("EOS_W", 1), "wce": ("EOS_WCE", 3), "wae": ("EOS_WAE", 3)}
 
 
@@ -483,6 +589,8 @@ def load(path, mod=None, mesh_path=None):
                              gravity=doc.get("gravity"), permeability_angle=np.deg2rad(mspec.get("permeability_angle", 0.0)))
     rock = rock_records(doc.get("rock"), m, mspec.get("zones"))
     m.rock[:] = rock
+    if mspec.get("minc"):
+        m = apply_minc(m, mspec["minc"], doc.get("rock"), mspec.get("zones"))
     bspecs = doc.get("boundaries") or []
     m, bowner = add_boundary_faces(m, exterior, bspecs)
     p = Problem()
@@ -496,8 +604,14 @@ def load(path, mod=None, mesh_path=None):
     init = doc.get("initial") or {}
     if "primary" in init:
         prim = np.array(init["primary"], float)
-        p.primary = np.tile(prim, (n, 1)) if prim.ndim == 1 else prim.reshape(n, -1)
         reg = np.array(init.get("region", 1))
+        n0 = getattr(m, "minc_cells", n)
+        if n0 < n and not init.get("minc", False) and prim.ndim == 2:
+            # values for the original cells only: a matrix cell starts from its fracture cell (src/initial.F90:976-1060)
+            parents = np.concatenate([np.arange(n0)] + [m.minc_zone] * m.minc_levels)
+            prim = prim.reshape(n0, -1)[parents]
+            reg = reg if reg.ndim == 0 else reg[parents]
+        p.primary = np.tile(prim, (n, 1)) if prim.ndim == 1 else prim.reshape(n, -1)
         p.region = (np.full(n, int(reg)) if reg.ndim == 0 else reg).astype(np.int32)
         # scaled with the SAME scales the parameters carry (eos.primary.scale of the input, else the defaults)
         sc = dict(pressure_scale=1e6, temperature_scale=1e2, partial_pressure_scale=0.0)
@@ -652,9 +766,10 @@ def load(path, mod=None, mesh_path=None):
     p.source_separators = []
     for k, s in enumerate(src):
         pr, lm = separator_pressures(s), limits(s)
-        if pr or lm["water"] > 0.0 or lm["steam"] > 0.0:
+        if pr:
+            # without a separator the separated flows are zero and a water / steam limit never acts
+            # (source_network_node.F90:116-156, separator pressures: source_setup.F90:2255-2328)
             assert len(pr) <= 2, "separators with more than two stages are not built"
-            assert pr or not (lm["water"] > 0.0 or lm["steam"] > 0.0), "a water / steam limiter needs a separator"
             p.source_separators.append(dict(source=k, pressure=pr, limit_water=lm["water"], limit_steam=lm["steam"]))
     # tracer injection rates: numbers or (time, rate) tables per source
     p.source_tracer_tables = {}

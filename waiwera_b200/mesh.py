@@ -414,7 +414,7 @@ def minc_geometry(volumes, spacing, fracture_connection_distance=0.0):
 
 
 def add_minc(mesh, volumes=(0.1, 0.9), spacing=(50.0, 50.0, 50.0), matrix_permeability_factor=1.0, cells=None,
-             matrix_rock=None):
+             matrix_rock=None, fracture_connection_distance=0.0):
     """MINC mesh on top of a serial mesh, in the reference's numbering (src/mesh.F90:2286-2380): original cells keep
     their index and become the fracture cells, then all level-1 matrix cells (in cell order), then all level-2
     cells, ...; one new flux face per MINC cell with support (level m-1 cell, level m cell), appended after the
@@ -422,10 +422,10 @@ def add_minc(mesh, volumes=(0.1, 0.9), spacing=(50.0, 50.0, 50.0), matrix_permea
     V*volume(m+1), face area = V*connection_area(m), distance = connection_distance(m:m+1), normal = 0,
     gravity_normal = 0, permeability_direction = 1.
     cells: the MINC zone (default: every cell; the partition helpers minc_owner / minc_cube_blocks need that);
-    matrix_rock: 8-double rock record of the matrix cells (default: the fracture cell's rock with its permeability
-    times matrix_permeability_factor)."""
+    matrix_rock: 8-double rock record of the matrix cells, or one per zone cell [len(cells), 8] (default: the
+    fracture cell's rock with its permeability times matrix_permeability_factor)."""
     assert mesh.nranks == 1 and not mesh.boundary, "add_minc works on a serial mesh without boundary ghosts"
-    vol, area, dist = minc_geometry(volumes, spacing)
+    vol, area, dist = minc_geometry(volumes, spacing, fracture_connection_distance)
     nlev = len(vol) - 1
     n = mesh.ninterior
     zone = np.arange(n, dtype=np.int64) if cells is None else np.asarray(cells, np.int64)
