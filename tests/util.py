@@ -123,6 +123,13 @@ class OracleSim:
         self.f.set_source_controls(sources, pi, pref, direction, limit)
         return 0
 
+    def set_source_recharge(self, *a):
+        self.f.set_source_recharge(*a)
+        return 0
+
+    def set_source_separators(self, *a):
+        return self.f.set_source_separators(*a)
+
     def source_rates(self, n):
         return self.f.source_rates(n)
 
@@ -190,6 +197,41 @@ def wge_fields(fluid, n):
     return np.stack([fl[:, 0], fl[:, 1], fl[:, 17 + 2], fl[:, 17 + 8], fl[:, 8 + 8], fl[:, 7]], 1)
 
 
+def apply_input_controls(p, sim, t0, t1):
+    """the source controls of an ingested input for the step [t0, t1] (ingest.controls_at: tables in time averaged over
+    the step): deliverability / direction / total limiter, recharge, separators with water / steam limits.  First call:
+    a productivity index to be calculated from the given rate is taken from the fluid state sim holds
+    (calculate_PI_from_rate, src/source_control.F90:407-468; eos we), a recharge reference pressure "initial" from the
+    cell's pressure."""
+    from waiwera_b200 import ingest
+    fl = None
+    for c in p.source_controls:
+        if c["deliverability"] and c["productivity"] is None:
+            fl = np.asarray(sim.fluid()) if fl is None else fl
+            f0 = fl[int(p.source_cells[c["source"]])]
+            phases = int(round(f0[4]))
+            mob = sum((f0[7 + 8 * q + 3] * f0[7 + 8 * q] / f0[7 + 8 * q + 1]) for q in range(2) if phases & (1 << q))
+            c["productivity"] = abs(p.source_rates[c["source"]]) / (mob * (f0[0] - c["reference_pressure"]) * f0[5])
+    for c in getattr(p, "source_recharge", []):
+        if c["reference_pressure"] is None:
+            fl = np.asarray(sim.fluid()) if fl is None else fl
+            c["reference_pressure"] = float(fl[int(p.source_cells[c["source"]])][0])
+    ctrl, seps = ingest.controls_at(p, t0, t1)
+    if ctrl:
+        r = sim.set_source_controls([c["source"] for c in ctrl], [c["productivity"] if c["deliverability"] else 0.0 for c in ctrl],
+                                    [c["reference_pressure"] or 0.0 for c in ctrl], [c["direction"] for c in ctrl],
+                                    [c["limit"] for c in ctrl])
+        assert not r
+    rc = getattr(p, "source_recharge", [])
+    if rc:
+        r = sim.set_source_recharge([c["source"] for c in rc], [c["coefficient"] for c in rc], [c["reference_pressure"] for c in rc])
+        assert not r
+    if seps:
+        r = sim.set_source_separators([q["source"] for q in seps], [q["pressure"] for q in seps],
+                                      [q["limit_water"] for q in seps], [q["limit_steam"] for q in seps])
+        assert not r
+
+
 def run_input(problem, sim, opts=None, fields=None, controls=False, well=0, on_step=None):
     """Runs an ingested input (waiwera_b200.ingest.Problem, eos_we) through `sim` (flow.FlowSimulation or OracleSim,
     mesh / boundaries / fluid_init already done) with the time stepping of its "time" value: a list of step sizes
@@ -220,13 +262,8 @@ def run_input(problem, sim, opts=None, fields=None, controls=False, well=0, on_s
             rates = ingest.rates_at(p, t, t + dt)
             assert sim.set_sources(p.source_cells, ingest.components_at(p, rates), rates, p.source_enthalpies) == 0
             sim.set_source_components(p.source_injection_components, p.source_production_components)
-        if controls and p.source_controls:
-            ctrl, _ = ingest.controls_at(p, t, t + dt)
-            assert all(c["productivity"] is not None for c in ctrl)
-            r = sim.set_source_controls([c["source"] for c in ctrl], [c["productivity"] if c["deliverability"] else 0.0 for c in ctrl],
-                                        [c["reference_pressure"] or 0.0 for c in ctrl], [c["direction"] for c in ctrl],
-                                        [c["limit"] for c in ctrl])
-            assert not r
+        if controls:
+            apply_input_controls(p, sim, t, t + dt)
         t1, _, its, _ = run_adaptive(sim, y, dt, dt, opts=opts, max_steps=1, reduction=ad.get("reduction", 0.2),
                                      amplification=1.0, its_min=0, its_max=10 ** 9)
         t += t1

@@ -399,6 +399,61 @@ def minc_production3d():
     print("wrote", out)
 
 
+FROM_INPUT = ["source/deliverability/run/deliv_delv.json", "source/deliverability/run/deliv_delt.json",
+              "source/deliverability/run/deliv_delw.json", "source/deliverability/run/deliv_delg_flow.json",
+              "source/deliverability/run/deliv_delg_limit.json", "source/deliverability/run/deliv_delg_pi_table.json",
+              "source/recharge/run/recharge_outflow.json",
+              "minc/column/run/minc_column_single.json", "minc/column/run/minc_column_minc.json",
+              "minc/doublet_1d/run/minc_1d_single.json", "minc/doublet_1d/run/minc_1d_50.json",
+              "minc/doublet_1d/run/minc_1d_100.json", "minc/doublet_1d/run/minc_1d_200.json"]
+
+
+def benchmarks_from_input():
+    """the reference's remaining single-well benchmark decks, for runs from their own input files
+    (tests/test_benchmarks_from_input.py): per deck the AUTOUGH2 listing's output times, P / T / Sv of every cell at the
+    last output in Waiwera's cell order (atmosphere blocks dropped, MINC matrix blocks reordered level by level), their
+    history in the first source's cell, and the rate / enthalpy history of every source"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from waiwera_b200 import ingest
+    base = "/root/reference/test/benchmark"
+    doc = {"_generated_by": "tools/make_golden.py::benchmarks_from_input from the *.listing files next to " + ", ".join(FROM_INPUT),
+           "columns": ["pressure", "temperature", "vapour_saturation"]}
+    for rel in FROM_INPUT:
+        path = os.path.join(base, rel)
+        name = os.path.splitext(os.path.basename(rel))[0]
+        p = ingest.load(path)
+        m = p.mesh
+        ncell = getattr(m, "minc_cells", m.ninterior)
+        nlev = m.minc_levels
+        nmatrix = m.ninterior - ncell
+        tabs = listing_generic(os.path.splitext(path)[0] + ".listing")
+        el = [(t, r) for k, t, r in tabs if k == "E"]
+        ge = [(t, r) for k, t, r in tabs if k == "G"]
+        nrow = len(el[-1][1])
+        # atmosphere blocks (boundaries on top faces) come first in the listing, other boundary blocks last
+        inp = json.load(open(path))
+        tops = [b for b in inp.get("boundaries") or [] if b["faces"]["normal"][-1] > 0.5 and len(b["faces"]["normal"]) == 3]
+        natm = sum(len(b["faces"]["cells"]) for b in tops)
+        nlast = sum(len(b["faces"]["cells"]) for b in inp.get("boundaries") or []) - natm
+        assert nrow == natm + ncell + nmatrix + nlast and not (nmatrix and nlast), (name, nrow, natm, ncell, nmatrix, nlast)
+        order = list(range(natm, natm + ncell))
+        for l in range(nlev):
+            order += list(range(natm + ncell + l, natm + ncell + nmatrix, nlev))
+        cell = int(p.source_cells[0])
+        nsrc = len(p.source_cells)
+        assert all(len(r) == nsrc for _, r in ge), name
+        doc[name] = {"ncell": ncell, "ninterior": m.ninterior, "times": [t for t, _ in el],
+                     "final": [el[-1][1][i][:3] for i in order], "history_cell": cell,
+                     "history": [r[natm + cell][:3] for _, r in el],
+                     "source_times": [t for t, _ in ge], "rate": [[q[0] for q in r] for _, r in ge],
+                     "enthalpy": [[q[1] for q in r] for _, r in ge]}
+    out = os.path.join(os.path.dirname(OUT), "benchmarks_from_input.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print("wrote", out)
+
+
 INPUT_KEYS = ("boundaries", "eos", "gravity", "initial", "mesh", "rock", "source", "thermodynamics", "time", "tracer")
 
 
@@ -456,7 +511,7 @@ def input_fixtures():
                 "model_intercomparison_study/problem6/run/problem6.json",
                 "ncg/infiltration/run/infiltration.json", "ncg/heat_pipe/run/heat_pipe.json",
                 "tracer/doublet/run/doublet.json", "tracer/doublet/run/doublet_ss.json",
-                "minc/production3d/run/minc_3d_base.json", "minc/production3d/run/minc_3d_refined.json"):
+                "minc/production3d/run/minc_3d_base.json", "minc/production3d/run/minc_3d_refined.json") + tuple(FROM_INPUT):
         convert_input(os.path.join(base, rel), dst)
     # mesh only: the reference's 3-D hybrid mesh (hexahedra + prisms) of its flow_simulation / initial unit tests
     import sys
@@ -503,5 +558,6 @@ if __name__ == "__main__":
     wae_benchmarks()
     tracer_doublet()
     minc_production3d()
+    benchmarks_from_input()
     minc_doublet()
     input_fixtures()
