@@ -125,6 +125,10 @@ def test_output_file_and_restart_round_trip(wo, tmp_path):
     prim, reg, t = output.read_restart(path, "wce", index=-1)
     assert t == 1.0e6 and np.array_equal(reg, region[:n])
     fl = np.asarray(fl)[:n]
+    # cell_index is "natural to global" (src/dm_utils.F90:974-1037): position i of the file holds natural cell order[i],
+    # and cell_index[order[i]] = i
+    assert np.array_equal(h["cell_fields/fluid_pressure"][1], fl[order, 0])
+    assert np.array_equal(h["cell_index"].reshape(-1)[order], np.arange(n))
     assert np.array_equal(prim[:, 0], fl[:, 0]) and np.array_equal(prim[:, 2], fl[:, 7])
     two = reg == 4
     assert two.any() and np.array_equal(prim[two, 1], fl[two, 8 + 9 + 2]) and np.array_equal(prim[~two, 1], fl[~two, 1])

@@ -4,6 +4,7 @@ meshes as ASCII MSH 2.2 with the same numbering, under tests/golden/inputs/) int
 Checked against the hand-built meshes the benchmark tests use (same volumes, areas, distances, gravity normals,
 boundary ghosts, rock records, sources) and end to end: the CO2 column benchmark run FROM THE INPUT FILE through the
 oracle reproduces the AUTOUGH2 listing."""
+import json
 import os
 
 import numpy as np
@@ -393,3 +394,212 @@ def test_mulgraph_geometry(tmp_path):
         assert np.array_equal(g.cell_geom, m.cell_geom)
         pairs = lambda q: sorted(map(tuple, np.sort(q.face_cells.reshape(-1, 2), 1).tolist()))
         assert pairs(g) == pairs(m)
+
+
+def _load_doc(tmp_path, doc, mesh="grid7.exo"):
+    """ingest.load of a JSON value whose mesh is the reference's 7 x 7 grid (written as ExodusII) or its hybrid10 mesh"""
+    import shutil
+    if mesh == "grid7.exo":
+        xs = [0.0, 1000.0, 1500.0, 2000.0, 2500.0, 3000.0, 3500.0, 4500.0]
+        _write_exodus_grid(str(tmp_path / mesh), xs, xs, [300.0, 500.0])
+    else:
+        shutil.copy(os.path.join(INP, mesh), str(tmp_path / mesh))
+    doc = dict(doc)
+    doc["mesh"] = dict(doc.get("mesh", {}), filename=mesh)
+    path = str(tmp_path / "in.json")
+    json.dump(doc, open(path, "w"))
+    return ingest.load(path)
+
+
+MINC_DM_CASES = [
+    # test/unit/src/mesh_test.F90:752-820: (name, mesh, "mesh" value, rock, cells in all, cells per MINC level)
+    ("all", "grid7.exo", {"zones": {"all": {"-": None}}, "minc": {"rock": {"zones": ["all"]}, "geometry": {"fracture": {"volume": 0.1}}}},
+     None, 98, [49, 49]),
+    ("partial", "grid7.exo", {"zones": {"left": {"x": [0, 1500]}}, "minc": {"rock": {"zones": ["left"]}, "geometry": {"matrix": {"volume": 0.9}}}},
+     None, 63, [14, 14]),
+    ("two-zone", "grid7.exo", {"zones": {"left": {"x": [0, 1500]}, "right": {"-": "left"}},
+                               "minc": [{"rock": {"zones": ["left"]}, "geometry": {"fracture": {"volume": 0.1}}},
+                                        {"rock": {"zones": ["right"]}, "geometry": {"fracture": {"volume": 0.1}, "matrix": {"volume": [0.3, 0.6]}}}]},
+     None, 133, [49, 49, 35]),
+    ("two-zone partial", "grid7.exo", {"zones": {"left": {"x": [0, 1500]}, "right corner": {"x": [2500, 4500], "y": [3000, 4500]}},
+                                       "minc": [{"rock": {"zones": ["right corner"]}, "geometry": {"fracture": {"volume": 0.1}}},
+                                                {"rock": {"zones": ["left"]}, "geometry": {"matrix": {"volume": [0.3, 0.6]}}}]},
+     None, 83, [20, 20, 14]),
+    ("two sub-zone", "grid7.exo", {"zones": {"left": {"x": [0, 1500]}, "right": {"-": "left"}},
+                                   "minc": {"rock": [{"zones": ["left"]}, {"zones": ["right"]}], "geometry": {"fracture": {"volume": 0.1}}}},
+     None, 98, [49, 49]),
+    ("rocktype", "grid7.exo", {"zones": {"left": {"x": [0, 1500]}, "right": {"-": "left"}},
+                               "minc": [{"rock": {"types": ["rock1"]}, "geometry": {"fracture": {"volume": 0.1}}},
+                                        {"rock": {"types": ["rock2"]}, "geometry": {"fracture": {"volume": 0.1}, "matrix": {"volume": [0.3, 0.6]}}}]},
+     {"types": [{"name": "rock1", "zones": "left"}, {"name": "rock2", "zones": ["right"]}]}, 133, [49, 49, 35]),
+    ("hybrid all", "hybrid10.ascii.msh", {"zones": {"all": {"-": None}}, "minc": {"rock": {"zones": ["all"]}, "geometry": {"fracture": {"volume": 0.1}}}},
+     None, 20, [10, 10]),
+    ("hybrid partial", "hybrid10.ascii.msh", {"zones": {"left": {"x": [0, 0.5]}}, "minc": {"rock": {"zones": ["left"]}, "geometry": {"matrix": {"volume": 0.9}}}},
+     None, 16, [6, 6]),
+]
+
+
+@pytest.mark.parametrize("case", MINC_DM_CASES, ids=[c[0] for c in MINC_DM_CASES])
+def test_minc_mesh_known_answers(tmp_path, case):
+    """setup_minc_dm (test/unit/src/mesh_test.F90:739-1028): numbers of cells in all and per MINC level for one zone, part
+    of the mesh, two zones with different numbers of levels, zones given through rock types, the hybrid mesh; and the
+    sanity checks of that test (volumes add up to the original cells', one face per matrix cell to the level inside)"""
+    name, mesh, mspec, rock, ncells, per_level = case
+    doc = {"mesh": mspec}
+    if rock:
+        doc["rock"] = rock
+    p = _load_doc(tmp_path, doc, mesh)
+    m = p.mesh
+    assert m.ninterior == ncells
+    n0 = m.minc_cells
+    lev = m.minc_level
+    assert [int((lev == k).sum()) for k in range(1, len(per_level))] == per_level[1:]
+    assert len(m.minc_zone) == per_level[0] if len(per_level) == 2 or per_level[0] != n0 else True
+    single = _load_doc(tmp_path, {"mesh": {k: v for k, v in mspec.items() if k != "minc"}}, mesh).mesh
+    total = np.zeros(n0)
+    np.add.at(total, m.minc_parent, m.cell_geom[:m.ninterior, 3])
+    assert np.allclose(total, single.cell_geom[:n0, 3], rtol=1e-13)
+    fc = m.face_cells.reshape(-1, 2)[single.nface:]
+    assert len(fc) == m.ninterior - n0
+    assert np.array_equal(m.minc_parent[fc[:, 0]], m.minc_parent[fc[:, 1]]) and np.array_equal(lev[fc[:, 1]], lev[fc[:, 0]] + 1)
+
+
+def test_minc_cell_order_known_answers(tmp_path):
+    """MINC cell numbering (test/unit/src/mesh_test.F90:1505-1612): level-1 cells of all zones in natural order after the
+    original cells, then the level-2 cells; unchanged by boundary faces"""
+    bdy = [{"faces": {"cells": [0, 1, 2, 3, 4, 5], "normal": [0, -1, 0]}, "primary": [1e5, 20.0]}]
+    sw = [0, 1, 2, 3, 4, 7, 8, 9, 10, 11]
+    ne = [26, 27, 33, 34, 40, 41, 47, 48]
+    for mspec, boundaries, expect in [
+        ({"zones": {"all": {"-": None}}, "minc": {"rock": {"zones": ["all"]}, "geometry": {"fracture": {"volume": 0.1}}}},
+         None, {1: dict(zip(range(49), range(49, 98)))}),
+        ({"zones": {"sw": {"x": [0, 3000], "y": [0, 1500]}}, "minc": {"rock": {"zones": ["sw"]}, "geometry": {"fracture": {"volume": 0.1}}}},
+         bdy, {1: dict(zip(sw, range(49, 59)))}),
+        ({"zones": {"sws": {"x": [0, 3000], "y": [0, 1000]}, "swn": {"x": [0, 3000], "y": [1000, 1500]}},
+          "minc": {"rock": [{"zones": ["swn"]}, {"zones": ["sws"]}], "geometry": {"fracture": {"volume": 0.1}}}},
+         bdy, {1: dict(zip(sw, range(49, 59)))}),
+        ({"zones": {"sw": {"x": [0, 3000], "y": [0, 1500]}, "ne": {"x": [3000, 4500], "y": [2000, 4500]}},
+          "minc": [{"rock": {"zones": ["sw"]}, "geometry": {"fracture": {"volume": 0.1}}},
+                   {"rock": {"zones": ["ne"]}, "geometry": {"matrix": {"volume": [0.3, 0.6]}}}]},
+         bdy, {1: dict(zip(sw + ne, range(49, 67))), 2: dict(zip(ne, range(67, 75)))}),
+    ]:
+        doc = {"mesh": mspec}
+        if boundaries:
+            doc["boundaries"] = boundaries
+        m = _load_doc(tmp_path, doc).mesh
+        for level, cells in expect.items():
+            got = {int(m.minc_parent[c]): c for c in range(m.ninterior) if m.minc_level[c] == level}
+            assert got == cells, (level, got)
+        if boundaries:
+            assert list(m.boundary["ghost_cells"]) == list(range(m.ninterior, m.ninterior + 6))
+
+
+def test_rock_assignment_known_answers(tmp_path):
+    """rock types by cells and by zones (test/unit/src/mesh_test.F90:1032-1205): cells per rock type on the 7 x 7 grid
+    and on the hybrid mesh"""
+    for mesh, mspec, types, expect in [
+        ("grid7.exo", {}, [{"name": "rock1", "porosity": 0.1, "cells": list(range(21))}, {"name": "rock2", "porosity": 0.2, "cells": list(range(21, 49))}], [21, 28]),
+        ("grid7.exo", {"zones": {"left_zone": {"x": [0, 3000]}, "right_zone": {"-": "left_zone"}}},
+         [{"name": "rock1", "porosity": 0.1, "zones": ["left_zone"]}, {"name": "rock2", "porosity": 0.2, "zones": ["right_zone"]}], [35, 14]),
+        ("grid7.exo", {"zones": {"zone4": {"-": "zone3"}, "zone3": {"+": "zone1", "-": "zone2"}, "zone1": {"x": [0, 3000]},
+                                 "zone2": {"x": [1500, 2500], "y": [1500, 2500]}}},
+         [{"name": "rock1", "porosity": 0.1, "zones": ["zone3"]}, {"name": "rock2", "porosity": 0.2, "zones": ["zone4"]}], [31, 18]),
+        ("hybrid10.ascii.msh", {}, [{"name": "rock1", "porosity": 0.1, "cells": [0, 3, 5, 7]}, {"name": "rock2", "porosity": 0.2, "cells": [1, 2, 4, 6, 8, 9]}], [4, 6]),
+        ("hybrid10.ascii.msh", {"zones": {"left_zone": {"x": [0, 0.5]}, "right_zone": {"-": "left_zone"}}},
+         [{"name": "rock1", "porosity": 0.1, "zones": ["left_zone"]}, {"name": "rock2", "porosity": 0.2, "zones": ["right_zone"]}], [6, 4]),
+    ]:
+        m = _load_doc(tmp_path, {"mesh": mspec, "rock": {"types": types}}, mesh).mesh
+        por = m.rock[:m.ninterior, 5]
+        assert [int(np.isclose(por, 0.1).sum()), int(np.isclose(por, 0.2).sum())] == expect
+
+
+def test_minc_rock_known_answers(tmp_path):
+    """fracture and matrix porosities (test/unit/src/mesh_test.F90:1209-1395): given by the rock types, or for the matrix
+    the value that keeps the void fraction of the original rock: (0.1 - 0.6 * 0.1) / 0.9 = 2/45, (0.1 - 0.7 * 0.1) / 0.9 = 1/30"""
+    geometry = {"fracture": {"volume": 0.1, "planes": 3, "spacing": 100}, "matrix": {"volume": 0.9}}
+    orig = {"name": "original", "porosity": 0.1, "zones": "all"}
+    both = {"zones": "all", "fracture": {"type": "fracture"}, "matrix": {"type": "matrix"}}
+    for mspec, types, nlev, expect in [
+        ({"zones": {"all": {"-": None}}, "minc": {"rock": both, "geometry": geometry}},
+         [orig, {"name": "fracture", "porosity": 0.6}, {"name": "matrix", "porosity": 0.02}], 1, {"all": (0.6, 0.02, 49)}),
+        ({"zones": {"all": {"-": None}}, "minc": {"rock": both, "geometry": dict(geometry, matrix={"volume": [0.3, 0.6]})}},
+         [orig, {"name": "fracture", "porosity": 0.6}, {"name": "matrix"}], 2, {"all": (0.6, 2.0 / 45.0, 49)}),
+        ({"zones": {"all": {"-": None}, "S": {"y": [0, 1500]}, "N": {"-": "S"}},
+          "minc": {"rock": [{"zones": "S", "fracture": {"type": "fractureS"}, "matrix": {"type": "matrixS"}},
+                            {"zones": "N", "fracture": {"type": "fractureN"}, "matrix": {"type": "matrixN"}}], "geometry": geometry}},
+         [orig, {"name": "fractureS", "porosity": 0.6}, {"name": "matrixS", "porosity": 0.02}, {"name": "fractureN", "porosity": 0.7},
+          {"name": "matrixN"}], 1, {"S": (0.6, 0.02, 14), "N": (0.7, 1.0 / 30.0, 35)}),
+    ]:
+        m = _load_doc(tmp_path, {"mesh": mspec, "rock": {"types": types}}).mesh
+        assert m.minc_levels == nlev and m.ninterior == 49 * (1 + nlev)
+        por = m.rock[:m.ninterior, 5]
+        for zone, (fpor, mpor, count) in expect.items():
+            cells = ingest._zone_cells(zone, _load_doc(tmp_path, {"mesh": {"zones": mspec["zones"]}}).mesh, mspec["zones"])
+            assert len(cells) == count
+            inz = np.isin(m.minc_parent, cells)
+            assert np.allclose(por[inz & (m.minc_level == 0)], fpor, rtol=1e-14)
+            assert np.allclose(por[inz & (m.minc_level > 0)], mpor, rtol=1e-14)
+
+
+def test_face_permeability_direction_override(tmp_path):
+    """"mesh.faces" (test/unit/src/mesh_test.F90:474-546): the face between cells 16 and 23 of the 7 x 7 grid, at
+    (1750, 2000, 400), faces y and would use permeability 2; the input sets direction 1 (3 for a second face)"""
+    plain = _load_doc(tmp_path, {"mesh": {}}).mesh
+    m = _load_doc(tmp_path, {"mesh": {"faces": [{"cells": [16, 23], "permeability_direction": 1},
+                                                {"cells": [24, 23], "permeability_direction": 3},
+                                                {"cells": [0, 48]}, {"cells": [5]}]}}).mesh
+    fc = np.sort(m.face_cells.reshape(-1, 2), 1)
+    f = np.nonzero((fc == [16, 23]).all(1))[0]
+    assert len(f) == 1 and np.allclose(m.face_geom[f[0], 8:11], [1750.0, 2000.0, 400.0])
+    assert plain.face_geom[f[0], 11] == 2.0 and m.face_geom[f[0], 11] == 1.0
+    g = np.nonzero((fc == [23, 24]).all(1))[0][0]
+    assert plain.face_geom[g, 11] == 1.0 and m.face_geom[g, 11] == 3.0
+    rest = np.ones(len(fc), bool)
+    rest[[f[0], g]] = False
+    assert np.array_equal(m.face_geom[rest], plain.face_geom[rest])
+
+
+INITIAL = os.path.join(HERE, "golden", "initial")
+_MINC3 = {"zones": {"all": {"-": None}}, "minc": {"rock": {"zones": ["all"]}, "geometry": {"fracture": {"volume": 0.1}, "matrix": {"volume": [0.3, 0.6]}}}}
+_MINC2 = {"zones": {"all": {"-": None}}, "minc": {"rock": {"zones": ["all"]}, "geometry": {"fracture": {"volume": 0.1}, "matrix": {"volume": 0.9}}}}
+_BDY = [{"faces": {"cells": [0], "normal": [0, 1, 0]}, "primary": [1e5, 20.0]}]
+_COL10 = [[588530.0, 21.25], [1565590.0, 23.75], [2542650.0, 26.25], [3519710.0, 28.75], [4496770.0, 31.25],
+          [5473830.0, 33.75], [6450890.0, 36.25], [7427950.0, 38.75], [8405010.0, 41.25], [9382070.0, 43.75]]
+INITIAL_CASES = [
+    # test/unit/src/initial_test.F90:86-206: (name, mesh file, "mesh" value, boundaries, "initial" value)
+    ("single porosity", "col100.exo", {}, None, {"filename": "fluid.h5"}),
+    ("single porosity minimal", "col100.exo", {}, None, {"filename": "fluid_minimal.h5"}),
+    ("MINC", "col100.exo", _MINC3, None, {"filename": "fluid.h5", "minc": False}),
+    ("MINC minimal false", "col100.exo", _MINC3, None, {"filename": "fluid_minimal.h5", "minc": False}),
+    ("MINC minimal true", "col100.exo", _MINC3, None, {"filename": "fluid_minimal_minc.h5", "minc": True}),
+    ("single porosity minimal boundary", "col100.exo", {}, _BDY, {"filename": "fluid_minimal.h5", "index": -1}),
+    ("JSON initial", "col10.exo", {}, None, {"primary": _COL10, "region": 1}),
+    ("JSON initial boundary", "col10.exo", {}, _BDY, {"primary": _COL10, "region": 1}),
+    ("MINC initial JSON false", "col10.exo", _MINC3, None, {"primary": _COL10, "minc": False}),
+    ("MINC initial boundary JSON false", "col10.exo", _MINC3, _BDY, {"primary": _COL10, "minc": False}),
+    ("MINC initial JSON true", "col10.exo", _MINC2, None, {"primary": _COL10 + _COL10, "minc": True}),
+]
+
+
+@pytest.mark.parametrize("case", INITIAL_CASES, ids=[c[0] for c in INITIAL_CASES])
+def test_initial_conditions_known_answers(tmp_path, case):
+    """setup_initial (test/unit/src/initial_test.F90:77-338) on the reference's column meshes and HDF5 restart files
+    (full output, minimal fields, MINC), from JSON arrays, with MINC meshes whose matrix cells are or are not in the
+    initial data, with a boundary: every cell has P = 1e5 + 997 * 9.8 * depth, T = 20 + 0.025 * depth, region 1"""
+    import shutil
+    name, mesh, mspec, boundaries, initial = case
+    for fn in os.listdir(INITIAL):
+        shutil.copy(os.path.join(INITIAL, fn), str(tmp_path / fn))
+    doc = {"mesh": dict(mspec, filename=mesh), "eos": {"name": "we"}, "initial": initial}
+    if boundaries:
+        doc["boundaries"] = boundaries
+    path = str(tmp_path / "in.json")
+    json.dump(doc, open(path, "w"))
+    p = ingest.load(path)
+    m = p.mesh
+    n = m.ninterior
+    assert n == (int(mesh[3:-4]) * (1 + getattr(m, "minc_levels", 0)))
+    z = m.cell_geom[:n, 2]
+    assert np.allclose(p.primary[:, 0], 1.0e5 + 997.0 * -9.8 * z, rtol=1e-9)
+    assert np.allclose(p.primary[:, 1], 20.0 - 25.0 / 1.0e3 * z, rtol=1e-9)
+    assert (p.region == 1).all() and len(p.region) == n

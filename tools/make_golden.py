@@ -289,6 +289,11 @@ def h5_fixtures():
                 "/root/reference/test/benchmark/minc/production3d/run/gminc_3d_refined.exo"):
         shutil.copy(src, os.path.join(dst, os.path.basename(src)))
         print("copied", src)
+    # test/unit/src/initial_test.F90: the column meshes and the restart files (full, minimal, minimal on a MINC mesh)
+    ini = os.path.join(os.path.dirname(OUT), "initial")
+    os.makedirs(ini, exist_ok=True)
+    for src in ("mesh/col100.exo", "mesh/col10.exo", "initial/fluid.h5", "initial/fluid_minimal.h5", "initial/fluid_minimal_minc.h5"):
+        shutil.copy(os.path.join("/root/reference/test/unit/data", src), os.path.join(ini, os.path.basename(src)))
     # the restart file the tracer doublet input names ("initial": {"filename": "doublet_ss.h5"}), next to that input
     shutil.copy("/root/reference/test/benchmark/tracer/doublet/run/doublet_ss.h5",
                 os.path.join(os.path.dirname(OUT), "inputs", "doublet_ss.h5"))

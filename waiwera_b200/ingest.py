@@ -357,7 +357,7 @@ def add_boundary_faces(m, exterior, specs):
     out.gravity, out.dim, out.permeability_angle = m.gravity, m.dim, m.permeability_angle
     out.minc_levels, out.minc_base = m.minc_levels, m.minc_base
     if hasattr(m, "minc_zone"):
-        out.minc_zone, out.minc_cells = m.minc_zone, m.minc_cells
+        out.minc_zone, out.minc_cells, out.minc_parent, out.minc_level = m.minc_zone, m.minc_cells, m.minc_parent, m.minc_level
     return out, np.array(owner, np.int32)
 
 
@@ -449,30 +449,11 @@ def rock_records(spec, m, zones=None):
 
 def apply_minc(m, minc, rock_spec, zones=None):
     """"mesh.minc" of the input (src/minc.F90:73-190 geometry and zones, src/mesh.F90:3186-3375 rock properties) on a
-    mesh without boundary ghosts -> the MINC mesh of mesh.add_minc.  The MINC zone is the union of the "zones" and of the
-    cells of the rock "types" of every entry of "rock"; in it the fracture cells take the properties the "fracture"
-    rock type gives (the others stay), the matrix cells those of the "matrix" rock type, porosity by default the one
-    that keeps the void fraction of the original cell.  One MINC geometry per mesh is built (the reference allows a
-    list of zones with different geometries)."""
-    mlist = [minc] if isinstance(minc, dict) else list(minc)
-    if len(mlist) != 1:
-        raise NotImplementedError("several MINC geometries in one mesh are not built")
-    spec = mlist[0]
-    geom = spec.get("geometry", {})
-    fr, mx = geom.get("fracture", {}), geom.get("matrix", {})
-    mvol = mx.get("volume")
-    if "volume" in fr:
-        fvol = float(fr["volume"])
-        mvol = [1.0 - fvol] if mvol is None else list(np.atleast_1d(mvol).astype(float))
-    else:
-        mvol = [0.9] if mvol is None else list(np.atleast_1d(mvol).astype(float))
-        fvol = 1.0 - sum(mvol)
-    volumes = np.array([fvol] + mvol)
-    volumes = volumes / volumes.sum()
-    planes = int(fr.get("planes", 1))
-    sp = np.atleast_1d(np.asarray(fr.get("spacing", 50.0), float))
-    spacing = np.full(planes, sp[0])
-    spacing[:min(len(sp), planes)] = sp[:planes]
+    mesh without boundary ghosts -> the MINC mesh of mesh.add_minc_zones.  "minc" is one entry or a list of entries with
+    their own geometries; the cells of an entry are the union of the "zones" and of the cells of the rock "types" of
+    every item of its "rock".  There the fracture cells take the properties the "fracture" rock type gives (the others
+    stay), the matrix cells those of the "matrix" rock type, porosity by default the one that keeps the void fraction of
+    the original cell."""
     types = {rt.get("name"): rt for rt in (rock_spec or {}).get("types", [])}
 
     def cells_of_type(name):
@@ -486,15 +467,18 @@ def apply_minc(m, minc, rock_spec, zones=None):
 
     def properties(entry, which):
         """the 8 rock properties of the named rock type, -1 where it does not give one"""
-        assert which in entry and "type" in entry[which], "mesh.minc.rock: %s.type not found" % which
+        out = np.full(8, -1.0)
+        if which not in entry:
+            return out
+        assert "type" in entry[which], "mesh.minc.rock: %s.type not found" % which
         name = entry[which]["type"]
         assert name in types, "unrecognised rock type %r" % name
         rt = types[name]
-        out = np.full(8, -1.0)
         if rt.get("permeability") is not None:
             k = np.atleast_1d(np.asarray(rt["permeability"], float))
-            out[0:3] = k[0] if len(k) == 1 else -1.0
-            if len(k) > 1:
+            if len(k) == 1:
+                out[0:3] = k[0]
+            else:
                 out[0:len(k)] = k
         for key, col in (("wet_conductivity", 3), ("dry_conductivity", 4), ("porosity", 5), ("density", 6), ("specific_heat", 7)):
             if rt.get(key) is not None:
@@ -502,35 +486,54 @@ def apply_minc(m, minc, rock_spec, zones=None):
         return out
 
     n = m.ninterior
-    entry_of = np.full(n, -1)
-    rocks = spec.get("rock", [])
-    rocks = [rocks] if isinstance(rocks, dict) else list(rocks)
-    for k, entry in enumerate(rocks):
-        zs = entry.get("zones", [])
-        for z in ([zs] if isinstance(zs, str) else zs):
-            entry_of[_zone_cells(z, m, zones)] = k
-        ts = entry.get("types", [])
-        for t in ([ts] if isinstance(ts, str) else ts):
-            entry_of[np.array(cells_of_type(t), np.int64)] = k
-    zone = np.nonzero(entry_of >= 0)[0]
     orig = m.rock[:n].copy()
-    matrix = orig[zone].copy()
-    for k, entry in enumerate(rocks):
-        sel = zone[entry_of[zone] == k]
-        if len(sel) == 0:
-            continue
-        fp, mp = properties(entry, "fracture"), properties(entry, "matrix")
-        fpor = np.where(fp[5] < 0, orig[sel, 5], fp[5])
-        mpor = (orig[sel, 5] - fpor * volumes[0]) / (1.0 - volumes[0]) if mp[5] < 0 else np.full(len(sel), mp[5])
-        rows = np.nonzero(entry_of[zone] == k)[0]
-        matrix[rows] = np.where(mp > 0, mp, orig[sel])
-        matrix[rows, 5] = mpor
-        m.rock[sel] = np.where(fp > 0, fp, orig[sel])
-        m.rock[sel, 5] = fpor
-    out = wmesh.add_minc(m, volumes=volumes, spacing=spacing, cells=zone, matrix_rock=matrix,
-                         fracture_connection_distance=float(fr.get("connection", 0.0)))
+    specs = []
+    for spec in ([minc] if isinstance(minc, dict) else list(minc)):
+        geom = spec.get("geometry", {})
+        fr, mx = geom.get("fracture", {}), geom.get("matrix", {})
+        mvol = mx.get("volume")
+        if "volume" in fr:
+            fvol = float(fr["volume"])
+            mvol = [1.0 - fvol] if mvol is None else list(np.atleast_1d(mvol).astype(float))
+        else:
+            mvol = [0.9] if mvol is None else list(np.atleast_1d(mvol).astype(float))
+            fvol = 1.0 - sum(mvol)
+        volumes = np.array([fvol] + mvol)
+        volumes = volumes / volumes.sum()
+        planes = int(fr.get("planes", 1))
+        sp = np.atleast_1d(np.asarray(fr.get("spacing", 50.0), float))
+        spacing = np.full(planes, sp[0])
+        spacing[:min(len(sp), planes)] = sp[:planes]
+        entry_of = np.full(n, -1)
+        rocks = spec.get("rock", [])
+        rocks = [rocks] if isinstance(rocks, dict) else list(rocks)
+        for k, entry in enumerate(rocks):
+            zs = entry.get("zones", [])
+            for z in ([zs] if isinstance(zs, str) else zs):
+                entry_of[_zone_cells(z, m, zones)] = k
+            ts = entry.get("types", [])
+            for t in ([ts] if isinstance(ts, str) else ts):
+                entry_of[np.array(cells_of_type(t), np.int64)] = k
+        zone = np.nonzero(entry_of >= 0)[0]
+        matrix = orig[zone].copy()
+        for k, entry in enumerate(rocks):
+            rows = np.nonzero(entry_of[zone] == k)[0]
+            sel = zone[rows]
+            if len(sel) == 0:
+                continue
+            fp, mp = properties(entry, "fracture"), properties(entry, "matrix")
+            fpor = np.where(fp[5] < 0, orig[sel, 5], fp[5])
+            mpor = (orig[sel, 5] - fpor * volumes[0]) / (1.0 - volumes[0]) if mp[5] < 0 else np.full(len(sel), mp[5])
+            matrix[rows] = np.where(mp > 0, mp, orig[sel])
+            matrix[rows, 5] = mpor
+            m.rock[sel] = np.where(fp > 0, fp, orig[sel])
+            m.rock[sel, 5] = fpor
+        specs.append(dict(cells=zone, volumes=volumes, spacing=spacing, matrix_rock=matrix,
+                          fracture_connection_distance=float(fr.get("connection", 0.0))))
+    out = wmesh.add_minc_zones(m, specs)
     out.gravity, out.dim, out.permeability_angle = m.gravity, m.dim, m.permeability_angle
-    out.minc_zone, out.minc_cells = zone, n
+    out.minc_cells = n
+    out.minc_zone = np.unique(np.concatenate([z["cells"] for z in specs])) if specs else np.zeros(0, np.int64)
     return out
 
 
@@ -587,6 +590,13 @@ def load(path, mod=None, mesh_path=None):
     nodes, elems = read_mesh(mfile)
     m, exterior = build_mesh(nodes, elems, thickness=mspec.get("thickness", 1.0), radial=bool(mspec.get("radial", False)),
                              gravity=doc.get("gravity"), permeability_angle=np.deg2rad(mspec.get("permeability_angle", 0.0)))
+    # "mesh.faces": permeability directions set by hand for the face between two cells (src/mesh.F90:1268-1350, 1355-1410)
+    for fs in mspec.get("faces") or []:
+        cells = sorted(int(c) for c in fs.get("cells", []))
+        if len(cells) == 2:
+            hit = np.nonzero((np.sort(m.face_cells.reshape(-1, 2), 1) == cells).all(1))[0]
+            if len(hit) == 1:
+                m.face_geom[hit[0], 11] = float(fs.get("permeability_direction", 1))
     rock = rock_records(doc.get("rock"), m, mspec.get("zones"))
     m.rock[:] = rock
     if mspec.get("minc"):
@@ -608,7 +618,7 @@ def load(path, mod=None, mesh_path=None):
         n0 = getattr(m, "minc_cells", n)
         if n0 < n and not init.get("minc", False) and prim.ndim == 2:
             # values for the original cells only: a matrix cell starts from its fracture cell (src/initial.F90:976-1060)
-            parents = np.concatenate([np.arange(n0)] + [m.minc_zone] * m.minc_levels)
+            parents = m.minc_parent
             prim = prim.reshape(n0, -1)[parents]
             reg = reg if reg.ndim == 0 else reg[parents]
         p.primary = np.tile(prim, (n, 1)) if prim.ndim == 1 else prim.reshape(n, -1)
@@ -630,6 +640,10 @@ def load(path, mod=None, mesh_path=None):
         eos_ = eos_ if isinstance(eos_, str) else eos_.get("name", "we")
         p.primary, p.region, p.restart_time = output.read_restart(os.path.join(os.path.dirname(path), init["filename"]), eos_,
                                                                   int(init.get("index", -1)))
+        n0 = getattr(m, "minc_cells", n)
+        if n0 < n and len(p.region) == n0 and not init.get("minc", False):
+            # a file of the original cells for a MINC mesh: a matrix cell starts from its fracture cell
+            p.primary, p.region = p.primary[m.minc_parent], p.region[m.minc_parent]
         assert len(p.region) == n, "restart file holds %d cells, the mesh %d" % (len(p.region), n)
         sc = dict(pressure_scale=1e6, temperature_scale=1e2, partial_pressure_scale=0.0)
         if p.params is not None:

@@ -465,6 +465,75 @@ def add_minc(mesh, volumes=(0.1, 0.9), spacing=(50.0, 50.0, 50.0), matrix_permea
     return out
 
 
+def add_minc_zones(mesh, zones):
+    """add_minc for several MINC zones with their own geometries (a list of "mesh.minc" entries): zones = [dict(cells,
+    volumes, spacing, matrix_rock=None, fracture_connection_distance=0.0)], disjoint cell sets (a cell named twice
+    belongs to the later zone).  Numbering (src/mesh.F90:2286-2380, pinned by mesh_test.F90:1505-1612): the original
+    cells, then the level-1 cells of ALL zones in natural cell order, then the level-2 cells of the zones that have a
+    second level, ...  One zone gives exactly add_minc's arrays.  The result carries minc_parent[ninterior] (fracture
+    cell of every cell, itself for the original cells) and minc_level[ninterior]."""
+    assert mesh.nranks == 1 and not mesh.boundary, "add_minc_zones works on a serial mesh without boundary ghosts"
+    n = mesh.ninterior
+    zone_of = np.full(n, -1)
+    for k, z in enumerate(zones):
+        zone_of[np.asarray(z["cells"], np.int64)] = k
+    geo = [minc_geometry(z["volumes"], z["spacing"], z.get("fracture_connection_distance", 0.0)) for z in zones]
+    nlev = [len(g[0]) - 1 for g in geo]
+    V = mesh.cell_geom[:n, 3].copy()
+    cg = [mesh.cell_geom[:n].copy()]
+    for k, g in enumerate(geo):
+        sel = zone_of == k
+        cg[0][sel, 3] = V[sel] * g[0][0]
+    rock = [mesh.rock[:n].copy()]
+    fcs, fgs = [mesh.face_cells], [mesh.face_geom]
+    parent, level = [np.arange(n, dtype=np.int64)], [np.zeros(n, np.int32)]
+    index = {0: np.arange(n, dtype=np.int64)}           # index[m][c]: cell number of level m of original cell c
+    ntot = n
+    for m in range(1, max(nlev + [0]) + 1):
+        cells = np.nonzero((zone_of >= 0) & (np.array([nlev[k] if k >= 0 else 0 for k in zone_of]) >= m))[0]
+        nz = len(cells)
+        g = mesh.cell_geom[cells].copy()
+        r = mesh.rock[cells].copy()
+        fg = np.zeros((nz, 12))
+        for k, (vol, area, dist) in enumerate(geo):
+            rows = np.nonzero(zone_of[cells] == k)[0]
+            if len(rows) == 0:
+                continue
+            c = cells[rows]
+            g[rows, 3] = V[c] * vol[m]
+            mr = zones[k].get("matrix_rock")
+            if mr is not None:
+                mr = np.asarray(mr, float)
+                if mr.ndim == 2:                          # one record per zone cell, in the order of zones[k]["cells"]
+                    pos = {int(cc): i for i, cc in enumerate(np.asarray(zones[k]["cells"], np.int64))}
+                    r[rows] = mr[[pos[int(cc)] for cc in c]]
+                else:
+                    r[rows] = mr
+            fg[rows, 0] = V[c] * area[m - 1]
+            fg[rows, 1] = dist[m - 1]
+            fg[rows, 2] = dist[m]
+            fg[rows, 3] = dist[m - 1] + dist[m]
+        fg[:, 8:11] = mesh.cell_geom[cells, :3]
+        fg[:, 11] = 1.0
+        cg.append(g)
+        rock.append(r)
+        idx = np.full(n, -1, np.int64)
+        idx[cells] = ntot + np.arange(nz)
+        index[m] = idx
+        fcs.append(np.stack([index[m - 1][cells], idx[cells]], 1).astype(np.int32))
+        fgs.append(fg)
+        parent.append(cells)
+        level.append(np.full(nz, m, np.int32))
+        ntot += nz
+    whole = len(zones) == 1 and len(np.unique(np.asarray(zones[0]["cells"]))) == n
+    out = Mesh(ncell=ntot, ninterior=ntot, nowned=ntot, face_cells=np.ascontiguousarray(np.concatenate(fcs).astype(np.int32)),
+               face_geom=np.ascontiguousarray(np.concatenate(fgs)), cell_geom=np.ascontiguousarray(np.concatenate(cg)),
+               rock=np.ascontiguousarray(np.concatenate(rock)), dims=mesh.dims, natural=np.arange(ntot, dtype=np.int64),
+               ncell_global=ntot, minc_levels=max(nlev + [0]), minc_base=n if whole else -n)
+    out.minc_parent, out.minc_level = np.concatenate(parent), np.concatenate(level)
+    return out
+
+
 def minc_owner(mesh, parts):
     """owner rank of every cell of a MINC mesh: a matrix cell stays with its fracture cell (src/mesh.F90:2201-2282)"""
     n = mesh.minc_base

@@ -3,7 +3,10 @@ h5lite.py.
 
 Layout (src/flow_simulation.F90 output routines, PETSc HDF5 viewer with an output sequence):
     time                                  [ntimes, 1]
-    cell_index                            [ncells, 1] int32: natural index of the cell stored at each position
+    cell_index                            [ncells, 1] int32: for every natural cell index the position its values are stored
+                                          at (mesh%cell_index, "natural to global": dm_get_cell_index,
+                                          src/dm_utils.F90:974-1037; pinned by the reference's 4-process restart file
+                                          fluid_minimal_minc.h5, tests/test_ingest.py::test_initial_conditions_known_answers)
     cell_fields/cell_geometry_centroid    [ncells, dim]      cell_fields/cell_geometry_volume [ncells]
     cell_fields/fluid_<field>             [ntimes, ncells]   field names as create_fluid_vector builds them
                                           (src/fluid.F90): pressure, temperature, region, <component>_partial_pressure,
@@ -57,11 +60,14 @@ def fluid_field_column(eos, name):
 def write_output(path, mesh, eos, times, fluids, source_cells=None, source_history=None, fields=None, cell_index=None):
     """times: [nt]; fluids: nt arrays [>= ninterior, dof] of fluid records (wb_get_fluid) in natural cell order;
     source_history: nt arrays [nsources, 3] of (component, rate, enthalpy); fields: fluid fields to write (default: the
-    EOS's default output fields); cell_index: storage order (default: natural)."""
+    EOS's default output fields); cell_index: storage order, the natural index of the cell stored at each position
+    (default: natural order) -- the file's cell_index dataset is its inverse."""
     n = mesh.ninterior
     fields = list(fields or REQUIRED[eos])
     order = np.arange(n, dtype=np.int32) if cell_index is None else np.asarray(cell_index, np.int32)
-    d = {"time": np.asarray(times, float).reshape(-1, 1), "cell_index": order.reshape(-1, 1),
+    position = np.zeros(n, np.int32)
+    position[order] = np.arange(n, dtype=np.int32)
+    d = {"time": np.asarray(times, float).reshape(-1, 1), "cell_index": position.reshape(-1, 1),
          "cell_fields/cell_geometry_centroid": np.asarray(mesh.cell_geom, float)[:n, :3][order],
          "cell_fields/cell_geometry_volume": np.asarray(mesh.cell_geom, float)[:n, 3][order]}
     for name in fields:
@@ -93,9 +99,7 @@ def read_restart(path, eos, index=-1):
             if key in h:
                 a = h[key]
                 v = a[k] if a.ndim == 2 and a.shape[0] == len(t) else a.reshape(-1)
-                out = np.zeros(n)
-                out[cell_index] = v          # position i of the file holds natural cell cell_index[i]
-                return out
+                return np.asarray(v, float)[cell_index]          # natural cell i is stored at position cell_index[i]
         raise KeyError("%s has no field %r (required for a restart of eos %s)" % (path, name, eos))
     f = {name: field(name) for name in REQUIRED[eos]}
     region = np.rint(f["region"]).astype(np.int32)
