@@ -603,3 +603,65 @@ def test_initial_conditions_known_answers(tmp_path, case):
     assert np.allclose(p.primary[:, 0], 1.0e5 + 997.0 * -9.8 * z, rtol=1e-9)
     assert np.allclose(p.primary[:, 1], 20.0 - 25.0 / 1.0e3 * z, rtol=1e-9)
     assert (p.region == 1).all() and len(p.region) == n
+
+
+def test_source_setup_known_answers(tmp_path):
+    """setup_source_network (test/unit/src/source_setup_test.F90:60-299, data/source/test_source.json, restated here): 24
+    sources from 22 specifications -- cell / cells (number or list) / zones / no cell; components by number or name
+    with the reference's defaults (injection 0 = water at update time; production: energy for an energy source, else
+    all mass components); default rate 0 and enthalpy 83.9 kJ/kg (0 for energy sources); tracer rates as a number, a
+    list, or by tracer name; the zone source becomes one source in each of the cells 0, 4, 8"""
+    import shutil
+    shutil.copy(os.path.join(INITIAL, "4x3_2d.exo"), str(tmp_path / "4x3_2d.exo"))
+    doc = {"mesh": {"filename": "4x3_2d.exo", "zones": {"LH": {"x": [0, 100]}}}, "eos": {"name": "wce"},
+           "tracer": [{"name": "foo"}, {"name": "bar"}],
+           "source": [
+               {"name": "mass injection 1", "cell": 0, "rate": 10, "enthalpy": 90000.0},
+               {"name": "mass injection 2", "cells": 1, "component": 2, "rate": 5, "enthalpy": 100000.0},
+               {"name": "heat injection", "cells": [2], "component": "energy", "rate": 1000},
+               {"name": "mass component production", "cell": 3, "component": "water", "rate": -2},
+               {"name": "mass component production enthalpy", "cell": 4, "component": 1, "rate": -3, "enthalpy": 200000.0},
+               {"name": "mass production", "cell": 5, "rate": -5},
+               {"name": "heat production", "cell": 6, "component": 3, "rate": -2000},
+               {"name": "no rate mass", "cell": 7, "component": 1},
+               {"name": "no rate mass enthalpy", "cell": 8, "component": "gas", "enthalpy": 1000000.0},
+               {"name": "no rate heat", "cell": 0, "component": 3},
+               {"name": "production component 1", "cell": 1, "component": "water", "production_component": 1, "enthalpy": 150000.0, "rate": 3},
+               {"name": "production component 2", "cell": 2, "component": 1, "production_component": 1},
+               {"name": "production component 3", "cell": 3, "component": "gas", "production_component": "gas", "enthalpy": 80000.0},
+               {"name": "production component 4", "cell": 4, "component": 1, "production_component": 2, "enthalpy": 90000.0},
+               {"name": "production component 5", "cell": 5, "component": 2, "production_component": "energy", "enthalpy": 500000.0},
+               {"name": "production component 6", "cell": 6, "production_component": 2, "enthalpy": 100000.0},
+               {"name": "null cell", "rate": 2.5, "enthalpy": 95000.0},
+               {"name": "tracer scalar", "cell": 1, "rate": 10.0, "enthalpy": 50000.0, "tracer": 0.001},
+               {"name": "tracer array", "cell": 2, "rate": 5, "enthalpy": 40000.0, "tracer": [0.002, 0.003]},
+               {"name": "tracer dict all", "cell": 3, "rate": 7.5, "enthalpy": 30000.0, "tracer": {"foo": 0.003, "bar": 0.005}},
+               {"name": "tracer dict partial", "cell": 4, "rate": 3.5, "enthalpy": 60000.0, "tracer": {"bar": 0.002}},
+               {"name": "zone source", "zones": ["LH"], "rate": 0.1, "enthalpy": 80000.0}]}
+    ref = "/root/reference/test/unit/data/source/test_source.json"
+    if os.path.exists(ref):      # this container only: the list above is the reference's file
+        assert json.load(open(ref))["source"] == doc["source"]
+    path = str(tmp_path / "in.json")
+    json.dump(doc, open(path, "w"))
+    p = ingest.load(path)
+    H0 = 83.9e3
+    expect = [  # natural cell, rate, injection enthalpy, injection component, production component[, tracer rates]
+        (0, 10.0, 90.e3, 0, 0, [0.0, 0.0]), (1, 5.0, 100.e3, 2, 0), (2, 1000.0, 0.0, 3, 3), (3, -2.0, H0, 1, 0), (4, -3.0, 200.e3, 1, 0),
+        (5, -5.0, H0, 0, 0), (6, -2000.0, 0.0, 3, 3), (7, 0.0, H0, 1, 0), (8, 0.0, 1000.e3, 2, 0), (0, 0.0, 0.0, 3, 3),
+        (1, 3.0, 150.e3, 1, 1), (2, 0.0, H0, 1, 1), (3, 0.0, 80.e3, 2, 2), (4, 0.0, 90.e3, 1, 2), (5, 0.0, 500.e3, 2, 3),
+        (6, 0.0, 100.e3, 0, 2), (-1, 2.5, 95.e3, 0, 0), (1, 10.0, 50.e3, 0, 0, [1.e-3, 1.e-3]), (2, 5.0, 40.e3, 0, 0, [2.e-3, 3.e-3]),
+        (3, 7.5, 30.e3, 0, 0, [3.e-3, 5.e-3]), (4, 3.5, 60.e3, 0, 0, [0.0, 2.e-3])]
+    t = p.source_specs
+    assert len(t) == 24
+    for k, e in enumerate(expect):
+        got = (t[k]["cell"], t[k]["rate"], t[k]["enthalpy"], t[k]["injection_component"], t[k]["production_component"])
+        assert got == e[:5], (k, got, e)
+        if len(e) > 5:
+            assert t[k]["tracer"] == e[5], (k, t[k]["tracer"])
+    assert [q["cell"] for q in t[21:]] == [0, 4, 8] and all(q["rate"] == 0.1 and q["enthalpy"] == 80.e3 for q in t[21:])
+    # what goes to the engine: the sources with a cell and something to do; injection component 0 acts as water
+    live = [q for q in t if q["cell"] >= 0 and q["rate"] != 0.0]
+    assert list(p.source_cells) == [q["cell"] for q in live] and np.allclose(p.source_rates, [q["rate"] for q in live])
+    assert list(p.source_injection_components) == [q["injection_component"] or 1 for q in live]
+    assert list(p.source_production_components) == [q["production_component"] for q in live]
+    assert np.allclose(p.source_tracer, [q["tracer"] for q in live])

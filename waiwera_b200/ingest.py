@@ -577,6 +577,66 @@ def make_params(mod, doc, gravity):
     return prm, _EOS[name][1]
 
 
+def _component(v, np_):
+    """component number of a name or number (get_component, src/source_setup.F90:2087-2121): mass components by the
+    EOS's names, "energy" = the last primary variable"""
+    names = {"water": 1, "energy": np_, "co2": 2, "air": 2, "ncg": 2, "gas": 2}
+    return names[v.lower()] if isinstance(v, str) else int(v)
+
+
+def _tracer_rates(v, tracers):
+    """tracer injection rates of a source: one number for all tracers, a list, or {tracer name: rate} (the others 0)"""
+    nt = max(len(tracers), 1)
+    if isinstance(v, list) and v and isinstance(v[0], list):
+        return [0.0] * nt                                  # a table in time: tracer_rates_at
+    if isinstance(v, dict):
+        names = [t.get("name") for t in tracers]
+        return [float(v.get(nm, 0.0)) for nm in names] + [0.0] * (nt - len(names))
+    return np.broadcast_to(np.atleast_1d(np.asarray(v, float)), (nt,)).tolist()
+
+
+def expand_sources(doc, m, np_, zones=None):
+    """The source list in natural source order (setup_source_network, src/source_setup.F90:240-340, 680-760): a
+    specification with "cell", with "cells" (a number or a list) or with "zones" gives one source per cell (zone cells in
+    natural order), all with the same parameters; one without any of them a source without a cell, which does nothing.
+    Returns (the specifications per source with "cell" set, sources without a cell left out; the table of all sources:
+    cell (-1: none), rate, injection enthalpy, injection / production component as the reference stores them)."""
+    eos = doc.get("eos", "we")
+    eos = eos if isinstance(eos, str) else eos.get("name", "we")
+    tr = doc.get("tracer")
+    tracers = [] if tr is None else ([tr] if isinstance(tr, dict) else list(tr))
+    out, table = [], []
+    for s in doc.get("source") or []:
+        if "cell" in s and s["cell"] is not None:
+            cells = [int(s["cell"])]
+        elif "cells" in s:
+            cells = [int(c) for c in np.atleast_1d(s["cells"])]
+        elif "zones" in s:
+            zs = s["zones"]
+            sel = set()
+            for z in ([zs] if isinstance(zs, str) else zs):
+                sel |= set(_zone_cells(z, m, zones).tolist())
+            cells = sorted(sel)
+        else:
+            cells = [-1]
+        inj = _component(s["component"], np_) if "component" in s else 0
+        if "production_component" in s:
+            prod = _component(s["production_component"], np_)
+        else:
+            prod = inj if (inj == np_ and np_ > 1 and eos != "w") else 0
+        rate = s.get("rate", 0.0)
+        h = 0.0 if (inj == np_ and np_ > 1 and eos != "w") else (s["enthalpy"] if isinstance(s.get("enthalpy"), (int, float)) else 83.9e3)
+        for c in cells:
+            table.append(dict(cell=c, rate=rate if isinstance(rate, (int, float)) else None, enthalpy=float(h),
+                              injection_component=inj, production_component=prod, tracer=_tracer_rates(s.get("tracer", 0.0), tracers),
+                              name=s.get("name")))
+            if c >= 0:
+                one = {k: v for k, v in s.items() if k not in ("cells", "zones")}
+                one["cell"] = c
+                out.append(one)
+    return out, table
+
+
 class Problem:
     """what load() returns: mesh, initial state, boundary values, sources, tracers, time stepping"""
 
@@ -662,7 +722,7 @@ def load(path, mod=None, mesh_path=None):
     p.boundary_tracer = np.array([np.broadcast_to(np.atleast_1d(bspecs[i].get("tracer", 0.0)), (max(nt, 1),)) for i in bowner],
                                  float).reshape(len(bowner), max(nt, 1))
     p.initial_tracer = np.broadcast_to(np.atleast_1d(init.get("tracer", 0.0)), (max(nt, 1),)).astype(float)
-    src = doc.get("source") or []
+    src, p.source_specs = expand_sources(doc, m, p.np, mspec.get("zones"))
     for s in src:
         unsupported = set(s) - {"cell", "rate", "component", "production_component", "enthalpy", "name", "tracer",
                                 "interpolation", "averaging", "deliverability", "direction", "limiter", "separator",
@@ -798,10 +858,8 @@ def load(path, mod=None, mesh_path=None):
     # get_components (src/source_setup.F90:2052-2083; doc/user/setup_sources.rst): injection uses "component"
     # (default water = 1); production uses "production_component", which defaults to energy if "component" is
     # energy and to 0 (all mass components) otherwise
-    names = {"water": 1, "energy": p.np, "co2": 2, "air": 2, "ncg": 2}
-
     def comp(v):
-        return names[v.lower()] if isinstance(v, str) else int(v)
+        return _component(v, p.np)
 
     def components(s):
         inj = comp(s.get("component", 1))
@@ -820,8 +878,7 @@ def load(path, mod=None, mesh_path=None):
     p.source_production_components = np.array([b[1] for b in both], np.int32)
     p.source_components = np.array([b[0] if s["rate"] >= 0 else b[1] for s, b in zip(src, both)], np.int32)
     p.source_enthalpies = np.array([s.get("enthalpy", 83.9e3) for s in src], float)
-    p.source_tracer = np.array([np.broadcast_to(np.atleast_1d(s.get("tracer", 0.0)), (max(nt, 1),)) for s in src],
-                               float).reshape(len(src), max(nt, 1))
+    p.source_tracer = np.array([_tracer_rates(s.get("tracer", 0.0), p.tracers) for s in src], float).reshape(len(src), max(nt, 1))
     p.time = doc.get("time", {})
     return p
 
