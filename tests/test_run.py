@@ -1,0 +1,88 @@
+"""waiwera_b200/run.py: a deck in, an output file out (`python -m waiwera_b200.run deck.json`) -- the few host lines
+around the Newton step that the reference keeps in timestepper.F90 / flow_simulation.F90.  On CPU the checker stands in for
+the engine (the driver only uses the method names of flow.FlowSimulation); on the GPU the command runs as a user would
+type it.  Checked against the AUTOUGH2 listings of the decks (tests/golden/benchmarks_from_input.json) through the output
+file it writes, read back with h5lite as a restart or a CREDO script would."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from test_benchmarks_from_input import GOLD, INP
+from test_mis_problems import newton_opts
+from util import OracleSim
+from waiwera_b200 import h5lite, ingest, output, run
+
+
+def check_output_file(case, path, nsteps_expected=None):
+    g = GOLD[case]
+    h = h5lite.H5File(path)
+    t = h["time"].reshape(-1)
+    assert t[0] == 0.0 and abs(t[-1] - g["times"][-1]) <= 1e-4 * g["times"][-1]
+    if nsteps_expected is not None:
+        assert len(t) == nsteps_expected + 1
+    final = np.array(g["final"])
+    n = len(final)
+    rel = lambda a, b: np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+    assert rel(h["cell_fields/fluid_pressure"][-1][:n], final[:, 0]) < 2e-4
+    assert rel(h["cell_fields/fluid_temperature"][-1][:n], final[:, 1]) < 2e-4
+    assert np.abs(h["cell_fields/fluid_vapour_saturation"][-1][:n] - final[:, 2]).max() < 2e-4
+    # source fields: rate and enthalpy histories of the listing (its first table is the state after the first step or t = 0)
+    st = np.array(g["source_times"])
+    s2 = st > 0
+    rate = h["source_fields/source_rate"]
+    assert rate.shape == (len(t), len(g["rate"][0]))
+    for k in range(rate.shape[1]):
+        assert rel(np.interp(st[s2], t[1:], rate[1:, k]), np.array(g["rate"])[s2, k]) < 1e-4
+        assert rel(np.interp(st[s2], t[1:], h["source_fields/source_enthalpy"][1:, k]), np.array(g["enthalpy"])[s2, k]) < 1e-4
+    assert np.array_equal(h["cell_index"].reshape(-1), np.arange(n))
+    # the file restarts a run
+    prim, region, time = output.read_restart(path, "we")
+    assert time == t[-1] and np.allclose(prim[:, 0], final[:, 0], rtol=1e-3)
+    return len(t) - 1
+
+
+@pytest.mark.parametrize("case", ["deliv_delg_flow", "deliv_delw", "minc_1d_100"])
+def test_driver_with_the_checker_as_engine(wo, tmp_path, case):
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=wo)
+    p.doc["output"] = {"initial": True, "frequency": 1, "final": True}
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for k in range(len(p.boundary_region)):
+        assert f.set_boundary(int(m.boundary["ghost_cells"][k]), int(m.boundary["interior_cells"][k]),
+                              p.boundary_primary[k], int(p.boundary_region[k])) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    f.set_source_components(p.source_injection_components, p.source_production_components)
+    assert f.fluid_init(p.y, p.region) == 0
+    sim = OracleSim(wo, f, newton_opts(wo, p))
+    log = []
+    times, fluids, sources, y = run.run(p, sim, log=log.append)
+    sim.destroy()
+    assert len(times) == len(fluids) == len(sources) and len(log) >= len(times) - 1
+    path = str(tmp_path / "out.h5")
+    run.write_results(p, path, times, fluids, sources)
+    check_output_file(case, path)
+    # "frequency": 0 keeps the initial and the final state only
+    p.doc["output"] = {"frequency": 0}
+    run.write_results(p, path, times, fluids, sources)
+    assert h5lite.H5File(path)["time"].reshape(-1).tolist() == [times[0], times[-1]]
+
+
+@pytest.mark.gpu
+def test_command_line_on_the_cuda_path(tmp_path):
+    """python -m waiwera_b200.run deck.json -o out.h5, as a user would type it"""
+    import shutil
+    import subprocess
+    import sys
+    case = "deliv_delg_flow"
+    for fn in (case + ".input.json", "gdeliv.ascii.msh"):
+        shutil.copy(os.path.join(INP, fn), str(tmp_path / fn))
+    out = str(tmp_path / "out.h5")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "waiwera_b200.run", str(tmp_path / (case + ".input.json")), "-o", out, "-q"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1])["output"] == out
+    check_output_file(case, out, nsteps_expected=len(GOLD[case]["times"]) - 1)

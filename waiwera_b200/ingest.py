@@ -665,6 +665,8 @@ def load(path, mod=None, mesh_path=None):
     m, bowner = add_boundary_faces(m, exterior, bspecs)
     p = Problem()
     p.doc, p.mesh = doc, m
+    eos_name = doc.get("eos", "we")
+    p.eos = eos_name if isinstance(eos_name, str) else eos_name.get("name", "we")
     if mod is not None:
         p.params, p.np = make_params(mod, doc, m.gravity)
     else:
