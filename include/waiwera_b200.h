@@ -220,6 +220,17 @@ int wb_get_source_rates(wb_ctx *ctx, double *rate);
    other controls.  Call after wb_set_sources / wb_set_source_controls; n = 0 removes the separators. */
 int wb_set_source_separators(wb_ctx *ctx, int n, const int32_t *source, const int32_t *nstage, const double *pressure,
                              const double *limit_water, const double *limit_steam);
+/* Reference pressure of sources on deliverability as a table (source input "deliverability": {"pressure": {"enthalpy":
+   [[h, P], ...]}} or {"pressure": [[P, Pref], ...]}; SRC_PRESSURE_TABLE_COORD_ENTHALPY / _PRESSURE in
+   deliverability_source_control_flow_rate, src/source_control.F90:359-403): at every function evaluation the table of
+   source[k] -- npts[k] <= WB_PRESSURE_TABLE_MAX points (x, y) at table[2 * WB_PRESSURE_TABLE_MAX * k ...], x increasing --
+   is looked up at the flowing enthalpy of the source's cell (coordinate[k] = 0: phase enthalpies weighted by the flow
+   fractions) or at its pressure (1), linearly or stepwise (step[k] != 0; null: linear), constant beyond the ends, and
+   replaces the reference pressure of wb_set_source_controls.  Call after wb_set_sources; the tables stay until the source
+   list changes; n = 0 removes them. */
+#define WB_PRESSURE_TABLE_MAX 8
+int wb_set_source_pressure_table(wb_ctx *ctx, int n, const int32_t *source, const int32_t *coordinate, const int32_t *step,
+                                 const int32_t *npts, const double *table);
 /* separator_stage_init (src/separator.F90:108-136): reference water and steam enthalpies of a stage at `pressure` */
 int wb_separator_stage(wb_ctx *ctx, double pressure, double *ref_water_enthalpy, double *ref_steam_enthalpy);
 /* the separated-flow source output fields [nsources][5]: water_rate, water_enthalpy, steam_rate, steam_enthalpy,

@@ -236,6 +236,11 @@ int wo_separator_stage(wo_thermo *th, double pressure, double *ref_water_enthalp
 void wo_separate(int nstage, const double *stage_h, double rate, double enthalpy, double out[5]);
 int wo_flow_set_source_separators(wo_flow *f, int n, const int32_t *source, const int32_t *nstage, const double *pressure,
                                   const double *limit_water, const double *limit_steam);
+/* reference pressure of sources on deliverability tabulated against the flowing enthalpy (coordinate 0) or the pressure (1)
+   of the cell: npts[k] <= WO_PTAB_MAX points (x, y) at table[2 WO_PTAB_MAX k ...] (src/source_control.F90:376-388) */
+#define WO_PTAB_MAX 8
+int wo_flow_set_source_pressure_table(wo_flow *f, int n, const int32_t *source, const int32_t *coordinate, const int32_t *step,
+                                      const int32_t *npts, const double *table);
 void wo_flow_source_separated(const wo_flow *f, int s, double rate, double out[5]);
 /* pre_eval: update mask from perturbed block columns (NULL/0 => unperturbed) + fluid_properties */
 int wo_flow_pre_eval(wo_flow *f, const double *y, const int32_t *perturbed, int nperturbed);

@@ -175,6 +175,7 @@ def lib():
         "wo_separator_stage": (i, [vp, d, c_dp, c_dp]),
         "wo_separate": (None, [i, c_dp, d, d, c_dp]),
         "wo_flow_set_source_separators": (i, [vp, i, c_ip, c_ip, c_dp, c_dp, c_dp]),
+        "wo_flow_set_source_pressure_table": (i, [vp, i, c_ip, c_ip, c_ip, c_ip, c_dp]),
         "wo_flow_source_separated": (None, [vp, i, d, c_dp]),
         "wo_flow_pre_eval": (i, [vp, c_dp, c_ip, i]),
         "wo_flow_cell_balances": (i, [vp, c_dp]),
@@ -383,6 +384,18 @@ class Flow:
         lw = None if limit_water is None else np.ascontiguousarray(limit_water, np.float64)
         ls = None if limit_steam is None else np.ascontiguousarray(limit_steam, np.float64)
         return self.L.wo_flow_set_source_separators(self.h, len(s), ip(s), ip(ns), dp(pr), dp(lw), dp(ls))
+
+    def set_source_pressure_table(self, sources, tables, coordinate=None, step=None):
+        """tables: per source a list of (x, y) points; coordinate 0 = flowing enthalpy (default), 1 = pressure"""
+        s = np.ascontiguousarray(sources, np.int32)
+        n = len(s)
+        npts = np.array([len(t) for t in tables], np.int32)
+        tab = np.zeros((max(n, 1), 16))
+        for k, t in enumerate(tables):
+            tab[k, :2 * len(t)] = np.asarray(t, float).reshape(-1)
+        co = np.zeros(n, np.int32) if coordinate is None else np.ascontiguousarray(coordinate, np.int32)
+        st = np.zeros(n, np.int32) if step is None else np.ascontiguousarray(step, np.int32)
+        return self.L.wo_flow_set_source_pressure_table(self.h, n, ip(s), ip(co), ip(st), ip(npts), dp(tab))
 
     def source_separated(self, s, rate):
         """water rate, water enthalpy, steam rate, steam enthalpy, steam fraction of source s at the given rate"""

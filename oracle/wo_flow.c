@@ -182,6 +182,9 @@ void wo_flow_set_sources(wo_flow *f, int n, const int32_t *cell, const int32_t *
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy); free(f->src_pcomponent);
   free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
   free(f->src_sep_n); free(f->src_sep_h); free(f->src_limit_water); free(f->src_limit_steam);
+  free(f->src_ptab_n); free(f->src_ptab_coord); free(f->src_ptab_step); free(f->src_ptab);
+  f->src_ptab_n = f->src_ptab_coord = f->src_ptab_step = NULL;
+  f->src_ptab = NULL;
   f->src_sep_n = NULL;
   f->src_sep_h = f->src_limit_water = f->src_limit_steam = NULL;
   f->src_ctrl = f->src_direction = NULL;
@@ -348,6 +351,40 @@ static double source_fluid_enthalpy(const wo_flow *f, int s) {
   return h;
 }
 
+/* Reference pressure tables of n sources on deliverability (after wo_flow_set_source_controls): npts[k] <= WO_PTAB_MAX
+   points (x, y) at table[2 WO_PTAB_MAX k ...], x the flowing enthalpy (coordinate[k] = 0) or the pressure (1) of the
+   source's cell, linear or step (step[k] != 0) interpolation, constant beyond the ends -- source input
+   "deliverability": {"pressure": {"enthalpy": [[h, P], ...]}} (src/source_setup.F90, src/source_control.F90:376-388). */
+int wo_flow_set_source_pressure_table(wo_flow *f, int n, const int32_t *source, const int32_t *coordinate, const int32_t *step,
+                                      const int32_t *npts, const double *table) {
+  int ns = f->nsrc;
+  free(f->src_ptab_n); free(f->src_ptab_coord); free(f->src_ptab_step); free(f->src_ptab);
+  f->src_ptab_n = (int32_t *)calloc(ns + 1, sizeof(int32_t));
+  f->src_ptab_coord = (int32_t *)calloc(ns + 1, sizeof(int32_t));
+  f->src_ptab_step = (int32_t *)calloc(ns + 1, sizeof(int32_t));
+  f->src_ptab = (double *)calloc(2 * WO_PTAB_MAX * ((size_t)ns + 1), sizeof(double));
+  for (int k = 0; k < n; k++) {
+    int s = source[k];
+    if (npts[k] < 1 || npts[k] > WO_PTAB_MAX) return 1;
+    f->src_ptab_n[s] = npts[k];
+    f->src_ptab_coord[s] = coordinate[k];
+    f->src_ptab_step[s] = step ? step[k] : 0;
+    for (int i = 0; i < 2 * npts[k]; i++) f->src_ptab[2 * WO_PTAB_MAX * (size_t)s + i] = table[2 * WO_PTAB_MAX * (size_t)k + i];
+  }
+  return 0;
+}
+
+/* interpolation_table%interpolate (src/interpolation.F90:300-420): find the interval, linear or step; constant outside */
+static double table_interpolate(const double *tab, int n, int step, double x) {
+  if (x <= tab[0]) return tab[1];
+  if (x >= tab[2 * (n - 1)]) return tab[2 * (n - 1) + 1];
+  int i = 0;
+  while (i + 2 < n && x >= tab[2 * (i + 1)]) i++;
+  if (step) return tab[2 * i + 1];
+  double xi = (x - tab[2 * i]) / (tab[2 * i + 2] - tab[2 * i]);
+  return tab[2 * i + 1] + (tab[2 * i + 3] - tab[2 * i + 1]) * xi;
+}
+
 /* separated flows of source s at the given rate (source_network_node_get_separated_flows, src/source_network_node.F90:
    116-131): zero unless the source produces and has a separator */
 void wo_flow_source_separated(const wo_flow *f, int s, double rate, double out[5]) {
@@ -370,7 +407,12 @@ double wo_flow_source_rate(const wo_flow *f, int s) {
   } else if (f->src_ctrl[s]) {
     int phases = nint_(fl[4]);
     double effective_productivity = f->src_pi[s] * fl[5]; /* permeability_factor */
-    double pressure_difference = fl[0] - f->src_pref[s];
+    double reference_pressure = f->src_pref[s];
+    if (f->src_ptab_n && f->src_ptab_n[s] > 0) {
+      double x = f->src_ptab_coord[s] ? fl[0] : source_fluid_enthalpy(f, s);
+      reference_pressure = table_interpolate(f->src_ptab + 2 * WO_PTAB_MAX * (size_t)s, f->src_ptab_n[s], f->src_ptab_step[s], x);
+    }
+    double pressure_difference = fl[0] - reference_pressure;
     rate = 0.0;
     for (int p = 0; p < f->nphase; p++) {
       const double *ph = fl + (7 + f->nc - 1) + p * (8 + f->nc - 1);
@@ -471,6 +513,7 @@ void wo_flow_destroy(wo_flow *f) {
   free(f->src_cell); free(f->src_component); free(f->src_rate); free(f->src_enthalpy); free(f->src_pcomponent);
   free(f->src_ctrl); free(f->src_direction); free(f->src_pi); free(f->src_pref); free(f->src_limit); free(f->src_rate_eval);
   free(f->src_sep_n); free(f->src_sep_h); free(f->src_limit_water); free(f->src_limit_steam);
+  free(f->src_ptab_n); free(f->src_ptab_coord); free(f->src_ptab_step); free(f->src_ptab);
   free(f->lhs_last2);
   face_plan_free(f);
   for (int t = 1; t < f->eos_nthr; t++) wo_eos_destroy(f->eos_thr[t]);

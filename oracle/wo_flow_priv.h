@@ -41,6 +41,11 @@ struct wo_flow {
      enthalpies of up to two stages [4 per source: hw0, hs0, hw1, hs1], limits on the separated water and steam rates */
   int32_t *src_sep_n;
   double *src_sep_h, *src_limit_water, *src_limit_steam;
+  /* reference pressure of a source on deliverability tabulated against the flowing enthalpy or the pressure
+     (deliverability.pressure: {"enthalpy": [[h, P], ...]} / {"pressure": ...}, src/source_control.F90:376-388): points per
+     source (0: none), coordinate (0 enthalpy, 1 pressure), step interpolation flag, WO_PTAB_MAX (x, y) pairs per source */
+  int32_t *src_ptab_n, *src_ptab_coord, *src_ptab_step;
+  double *src_ptab;
   double *src_rate_eval;               /* rate every source had at the last unperturbed evaluation */
   /* passive tracers (src/tracer.F90:25-41): auxiliary linear problem, wo_tracer.c */
   int nt;

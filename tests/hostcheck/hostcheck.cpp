@@ -329,6 +329,35 @@ extern "C" int hc_source_rate(const wb_params *prm, const double *primary, int r
     return source_rate_host<WB_EOS_WCE>(prm, primary, region, rock8, ctrl, pi, pref, limit, rate, sep_n, sep_h, limit_w, limit_s, out);
   return -2;
 }
+// wb_source_rate for one source on deliverability whose reference pressure is a table against the flowing enthalpy or
+// the pressure of its cell (WbSources::ptab_n / ptab)
+template <int EOS>
+static int source_rate_ptab_host(const wb_params *prm, const double *primary, int region, const double *rock8, int ctrl, double pi,
+                                 double pref, int word, const double *table, double *out) {
+  constexpr int NC = WbEosTraits<EOS>::NC, NPH = WbEosTraits<EOS>::NPH;
+  WbEosParams e;
+  if (wb_eos_params_make(*prm, e)) return -1;
+  WbFluid<NC, NPH> fl = {};
+  fl.region = region;
+  if (wb_eos_properties<EOS>(e, primary, fl)) return 1;
+  WbCellState<NC, NPH> s;
+  wb_state_from_fluid(fl, rock8[WB_R_WET], rock8[WB_R_DRY], s);
+  int32_t c_ctrl = ctrl, c_word = word, c_cell = 0, c_comp = 0, c_head = 0;
+  double c_enth = 0.0, rate = -1.0, limit = 0.0;
+  WbSources S = {};
+  S.head = &c_head; S.cell = &c_cell; S.comp = &c_comp; S.rate = &rate; S.enth = &c_enth; S.n = 1;
+  S.ctrl = &c_ctrl; S.pi = &pi; S.pref = &pref; S.limit = &limit;
+  S.ptab_n = &c_word; S.ptab = table;
+  out[0] = wb_source_rate(S, 0, s);
+  return 0;
+}
+extern "C" int hc_source_rate_ptab(const wb_params *prm, const double *primary, int region, const double *rock8, int ctrl,
+                                   double pi, double pref, int word, const double *table, double *out) {
+  if (prm->eos == WB_EOS_WE) return source_rate_ptab_host<WB_EOS_WE>(prm, primary, region, rock8, ctrl, pi, pref, word, table, out);
+  if (prm->eos == WB_EOS_WCE || prm->eos == WB_EOS_WAE)
+    return source_rate_ptab_host<WB_EOS_WCE>(prm, primary, region, rock8, ctrl, pi, pref, word, table, out);
+  return -2;
+}
 // separator_stage_init with the device thermodynamics (what wb_separator_stage runs on the host side of the library)
 extern "C" int hc_separator_stage(int thermo, double pressure, double *hw, double *hs) {
   WbThermo th = wb_thermo_make(thermo, 0);

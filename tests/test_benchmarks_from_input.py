@@ -1,14 +1,14 @@
 """The reference's single-well benchmark decks run FROM THEIR OWN INPUT FILES AND MESHES (JSON + ExodusII in the netCDF-4
-container; fixtures under tests/golden/inputs/ by tools/make_golden.py::convert_input): source/deliverability (delv,
-delt, delw, delg_flow, delg_limit, delg_pi_table: fixed and tabulated productivity index, productivity index from the
-initial rate, total / separated-water / separated-steam limiters), source/recharge, minc/column (single porosity and
+container; fixtures under tests/golden/inputs/ by tools/make_golden.py::convert_input): source/deliverability (all 7:
+delv, delt, delw, delg_flow, delg_limit, delg_pi_table, delg_pwb_table: fixed and tabulated productivity index,
+productivity index from the initial rate, total / separated-water / separated-steam limiters, reference pressure
+tabulated against the flowing enthalpy), source/recharge, minc/column (single porosity and
 MINC) and minc/doublet_1d (single porosity and three fracture spacings).  Everything the hand-built versions of these
 benchmarks (test_deliverability.py, test_recharge.py, test_minc_column.py, test_minc_doublet.py) set up by hand comes
 from waiwera_b200.ingest here: mesh geometry, boundary faces, zones and MINC, rock types, initial state, sources and
 their controls, time stepping.  Golden output: the AUTOUGH2 listings next to the decks
 (tests/golden/benchmarks_from_input.json); the reference accepts 5e-3 on the last output and 1e-2 on histories.
-Not run: deliv_delg_pwb_table (reference pressure tabulated against enthalpy), source/makeup and source/reinjection
-(source networks) -- SURVEY.md section 8 row f-1 "next"."""
+Not run: source/makeup and source/reinjection (source networks) -- SURVEY.md section 8 row f-1 "next"."""
 import json
 import os
 

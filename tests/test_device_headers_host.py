@@ -46,6 +46,7 @@ def hc(wo):
                                      d, d, dp, dp, dp, dp, dp, ip, ip, dp, dp, dp]
     L.hc_source_rate.argtypes = [C.c_void_p, dp, i, dp, i, d, d, d, d, i, dp, d, d, dp]
     L.hc_separator_stage.argtypes = [i, d, dp, dp]
+    L.hc_source_rate_ptab.argtypes = [C.c_void_p, dp, i, dp, i, d, d, i, dp, dp]
     return L
 
 
@@ -497,3 +498,48 @@ def test_source_controls_match_oracle(wo, hc, thermo):
         base = c["rate"] if c["kind"] == "fixed" else None
         limited += base is not None and ref[k] != 0.0 and abs(ref[k]) < abs(base) * (1 - 1e-12)
     assert nonzero > n // 3 and separated > 10 and limited > 5
+
+
+@pytest.mark.parametrize("thermo", [0, 1])
+def test_source_pressure_table_matches_oracle(wo, hc, thermo):
+    """wb_source_rate with a reference-pressure table (wb_set_source_pressure_table: against the flowing enthalpy or the
+    pressure, linear or step, inside and beyond the table) against the oracle, whose value for the reference's own case is
+    pinned in tests/test_oracle_kat.py (source 11 of source_control_test.F90: -10.3366086953508 kg/s)"""
+    from waiwera_b200 import flow, mesh as wmesh
+    m = wmesh.structured(3, 1, 1, dx=10.0, heterogeneous=False)
+    cells = [([30.0e5, 0.4], 4), ([30.0e5, 150.0], 1), ([1.0e5, 150.0], 2)]          # two-phase, liquid, vapour
+    primary = np.array([c[0] for c in cells])
+    region = np.array([c[1] for c in cells], np.int32)
+    prm_o = wo.make_params(eos=wo.EOS_WE, thermo=thermo)
+    prm_h = flow.make_params(eos=flow.EOS_WE, thermo=thermo)
+    y = np.ascontiguousarray(wmesh.scale_primaries(primary, region)).reshape(-1)
+    f = wo.Flow(prm_o, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    assert f.fluid_init(y, region) == 0
+    tables = [[[0.0, 22.0e5], [11.0e5, 20.0e5], [28.0e5, 0.5e5]],                     # the reference's test table
+              [[5.0e5, 1.0e5], [6.5e5, 2.0e5], [9.0e5, 4.0e5], [20.0e5, 8.0e5], [26.0e5, 12.0e5], [27.0e5, 13.0e5], [27.5e5, 14.0e5], [29.0e5, 25.0e5]],
+              [[15.0e5, 3.0e5]]]
+    cases = [dict(cell=cell, table=t, coord=coord, step=step, direction=direction)
+             for cell in range(3) for t in tables for coord in (0, 1) for step in (0, 1) for direction in (0, 1)]
+    n = len(cases)
+    f.set_sources([c["cell"] for c in cases], [0] * n, [-1.0] * n, [0.0] * n)
+    f.set_source_controls(list(range(n)), [2e-12] * n, [7.0e5] * n, [c["direction"] for c in cases], [0.0] * n)
+    assert f.set_source_pressure_table(list(range(n)), [c["table"] for c in cases], [c["coord"] for c in cases],
+                                       [c["step"] for c in cases]) == 0
+    e, L0 = f.lhs(y)
+    assert e == 0 and f.residual(y, L0, 1.0e3)[0] == 0
+    ref = f.source_rates(n)
+    plain = []
+    for k, c in enumerate(cases):
+        tab = np.zeros(16)
+        tab[:2 * len(c["table"])] = np.array(c["table"]).reshape(-1)
+        out = np.zeros(1)
+        word = len(c["table"]) | (256 if c["coord"] else 0) | (512 if c["step"] else 0)
+        args = (C.addressof(prm_h), wo.dp(np.ascontiguousarray(primary[c["cell"]])), int(region[c["cell"]]),
+                wo.dp(np.ascontiguousarray(m.rock[c["cell"]])), 1 | (c["direction"] << 1), 2e-12, 7.0e5)
+        assert hc.hc_source_rate_ptab(*args, word, wo.dp(tab), wo.dp(out)) == 0
+        assert close(out[0], ref[k], 1e-14) or (out[0] == 0.0 and ref[k] == 0.0), (c, out[0], ref[k])
+        base = np.zeros(1)
+        assert hc.hc_source_rate_ptab(*args, 0, wo.dp(tab), wo.dp(base)) == 0          # no table: the fixed reference pressure
+        plain.append(base[0])
+    assert len(set(np.round(ref / 1e-3).tolist())) > 12 and (np.abs(ref - np.array(plain)) > 1e-6).sum() > n // 2

@@ -824,6 +824,18 @@ def test_source_control_deliverability(wo):
     assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
     rates = f.source_rates(4)
     assert np.allclose(rates, [-12.8728519749, -10.0, -11.0, 0.0], rtol=1e-9, atol=1e-12), rates
+    # source 11: reference pressure tabulated against the flowing enthalpy (SRC_PRESSURE_TABLE_COORD_ENTHALPY)
+    # -10.3366086953508 kg/s; the same table looked up at the cell's pressure (50 bar, beyond its last point: 0.5 bar)
+    # gives 1e-12 * mobility * (50e5 - 0.5e5); with step interpolation the value at the point before the enthalpy
+    table = [[0.0, 2200000.0], [1100000.0, 2000000.0], [2800000.0, 50000.0]]
+    f.set_source_controls([0, 1, 2, 3], [1e-12] * 4, [2.0e5] * 4, [0] * 4, [0.0] * 4)
+    assert f.set_source_pressure_table([0, 1, 2], [table] * 3, coordinate=[0, 1, 0], step=[0, 0, 1]) == 0
+    assert L.wo_flow_cell_inflows(f.h, wo.dp(rhs)) == 0
+    rates = f.source_rates(4)
+    h = sum(rec[8 + 9 * p + 3] * rec[8 + 9 * p] / rec[8 + 9 * p + 1] * rec[8 + 9 * p + 5] for p in range(2)) / mob
+    assert 1100000.0 < h < 2800000.0
+    assert np.allclose(rates, [-10.3366086953508, -1e-12 * mob * (P - 0.5e5), -1e-12 * mob * (P - 2.0e6), -12.8728519749],
+                       rtol=1e-9, atol=1e-12), rates
 
 
 def test_source_separator_limiter_known_answers(wo):

@@ -130,6 +130,9 @@ class OracleSim:
     def set_source_separators(self, *a):
         return self.f.set_source_separators(*a)
 
+    def set_source_pressure_table(self, *a):
+        return self.f.set_source_pressure_table(*a)
+
     def source_rates(self, n):
         return self.f.source_rates(n)
 
@@ -229,6 +232,11 @@ def apply_input_controls(p, sim, t0, t1):
     if seps:
         r = sim.set_source_separators([q["source"] for q in seps], [q["pressure"] for q in seps],
                                       [q["limit_water"] for q in seps], [q["limit_steam"] for q in seps])
+        assert not r
+    pt = getattr(p, "source_pressure_tables", [])
+    if pt:
+        r = sim.set_source_pressure_table([q["source"] for q in pt], [q["table"] for q in pt], [q["coordinate"] for q in pt],
+                                          [q["step"] for q in pt])
         assert not r
 
 

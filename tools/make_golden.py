@@ -408,6 +408,7 @@ def minc_production3d():
 FROM_INPUT = ["source/deliverability/run/deliv_delv.json", "source/deliverability/run/deliv_delt.json",
               "source/deliverability/run/deliv_delw.json", "source/deliverability/run/deliv_delg_flow.json",
               "source/deliverability/run/deliv_delg_limit.json", "source/deliverability/run/deliv_delg_pi_table.json",
+              "source/deliverability/run/deliv_delg_pwb_table.json",
               "source/recharge/run/recharge_outflow.json",
               "minc/column/run/minc_column_single.json", "minc/column/run/minc_column_minc.json",
               "minc/doublet_1d/run/minc_1d_single.json", "minc/doublet_1d/run/minc_1d_50.json",

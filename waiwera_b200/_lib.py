@@ -84,6 +84,7 @@ SIGNATURES = {
     "wb_set_source_recharge": (i, [vp, i, vp, vp, vp]),
     "wb_get_source_rates": (i, [vp, vp]),
     "wb_set_source_separators": (i, [vp, i, vp, vp, vp, vp, vp]),
+    "wb_set_source_pressure_table": (i, [vp, i, vp, vp, vp, vp, vp]),
     "wb_separator_stage": (i, [vp, d, vp, vp]),
     "wb_get_source_separated": (i, [vp, vp]),
     "wb_get_fluid": (i, [vp, vp]),

@@ -224,6 +224,8 @@ struct wb_ctx {
   double *d_src_pi = nullptr, *d_src_pref = nullptr, *d_src_limit = nullptr;
   std::vector<int32_t> h_src_ctrl;  // host copies of the control arrays (sorted source order): setters edit and re-upload
   std::vector<double> h_src_pi, h_src_pref, h_src_limit;
+  int32_t *d_src_ptab_n = nullptr;  // reference-pressure tables of sources on deliverability (WbSources::ptab_n / ptab)
+  double *d_src_ptab = nullptr;
   int32_t *d_src_sep_n = nullptr;  // separators: stages per source, reference enthalpies, separated-flow limits
   double *d_src_sep_h = nullptr, *d_src_limit_w = nullptr, *d_src_limit_s = nullptr;
   // passive tracers: auxiliary linear problem (wb_tracer.cu)

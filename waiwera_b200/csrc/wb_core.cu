@@ -247,6 +247,7 @@ extern "C" int wb_destroy(wb_ctx *c) {
   cudaFree(c->d_trc_inj);
   cudaFree(c->d_src_ctrl); cudaFree(c->d_src_pi); cudaFree(c->d_src_pref); cudaFree(c->d_src_limit);
   cudaFree(c->d_src_sep_n); cudaFree(c->d_src_sep_h); cudaFree(c->d_src_limit_w); cudaFree(c->d_src_limit_s);
+  cudaFree(c->d_src_ptab_n); cudaFree(c->d_src_ptab);
   cudaFree(c->d_src_head); cudaFree(c->d_src_cell); cudaFree(c->d_src_comp); cudaFree(c->d_src_rate); cudaFree(c->d_src_enth);
   cudaFree(c->halo.d_send_idx);
   cudaFree(c->halo.d_recv_idx);

@@ -749,7 +749,8 @@ static WbResForm wb_res_form(const wb_ctx *c, const double *d_lhs_last, double d
 WbSources wb_sources_args(const wb_ctx *c) {
   WbSources S = {c->nsrc > 0 ? c->d_src_head : nullptr, c->d_src_cell, c->d_src_comp, c->d_src_rate, c->d_src_enth, c->nsrc,
                  c->d_src_ctrl, c->d_src_pi, c->d_src_pref, c->d_src_limit,
-                 c->d_src_sep_n, c->d_src_sep_h, c->d_src_limit_w, c->d_src_limit_s};
+                 c->d_src_sep_n, c->d_src_sep_h, c->d_src_limit_w, c->d_src_limit_s,
+                 c->d_src_ptab_n, c->d_src_ptab};
   return S;
 }
 
@@ -1086,6 +1087,9 @@ extern "C" int wb_set_sources(wb_ctx *c, int n, const int32_t *cell, const int32
   cudaFree(c->d_src_sep_n); cudaFree(c->d_src_sep_h); cudaFree(c->d_src_limit_w); cudaFree(c->d_src_limit_s);
   c->d_src_sep_n = nullptr;
   c->d_src_sep_h = c->d_src_limit_w = c->d_src_limit_s = nullptr;
+  cudaFree(c->d_src_ptab_n); cudaFree(c->d_src_ptab);
+  c->d_src_ptab_n = nullptr;
+  c->d_src_ptab = nullptr;
   cudaFree(c->d_trc_inj);  // tracer injection rates belong to the old source list
   c->d_trc_inj = nullptr;
   if (n <= 0) return 0;
@@ -1258,6 +1262,44 @@ extern "C" int wb_set_source_separators(wb_ctx *c, int n, const int32_t *source,
   WB_TRY(dev_upload(&c->d_src_sep_h, sh));
   WB_TRY(dev_upload(&c->d_src_limit_w, lw));
   WB_TRY(dev_upload(&c->d_src_limit_s, ls));
+  return 0;
+}
+
+// Reference pressure of sources on deliverability as a table against the flowing enthalpy (coordinate 0) or the pressure
+// (1) of the source's cell: "deliverability": {"pressure": {"enthalpy": [[h, P], ...]}} of the input
+// (deliverability_source_control_flow_rate, src/source_control.F90:376-388).  Like the separators the tables stay in force
+// until the source list changes; n <= 0 removes them.
+static_assert(WB_PTAB_MAX == WB_PRESSURE_TABLE_MAX, "table size of the header and of the device code");
+extern "C" int wb_set_source_pressure_table(wb_ctx *c, int n, const int32_t *source, const int32_t *coordinate,
+                                            const int32_t *step, const int32_t *npts, const double *table) {
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_src_ptab_n); cudaFree(c->d_src_ptab);
+  c->d_src_ptab_n = nullptr;
+  c->d_src_ptab = nullptr;
+  if (n <= 0) return 0;
+  WB_CHECK(c->nsrc > 0, "wb_set_source_pressure_table: no sources");
+  WB_CHECK(source && npts && table, "wb_set_source_pressure_table: null array");
+  WB_CHECK(!wb_is_device_ptr(source) && !wb_is_device_ptr(coordinate) && !wb_is_device_ptr(step) && !wb_is_device_ptr(npts) &&
+               !wb_is_device_ptr(table),
+           "wb_set_source_pressure_table: the arrays are read on the host (set-up data): pass host arrays");
+  const int ns = c->nsrc;
+  std::vector<int> pos(ns);  // input position -> sorted position
+  for (int k = 0; k < ns; k++) pos[c->h_src_order[k]] = k;
+  std::vector<int32_t> word(ns, 0);
+  std::vector<double> tab(2 * WB_PTAB_MAX * (size_t)ns, 0.0);
+  for (int k = 0; k < n; k++) {
+    WB_CHECK(source[k] >= 0 && source[k] < ns, "wb_set_source_pressure_table: source index %d out of range", source[k]);
+    WB_CHECK(npts[k] >= 1 && npts[k] <= WB_PTAB_MAX, "wb_set_source_pressure_table: %d points (1 .. %d)", npts[k], WB_PTAB_MAX);
+    const int q = pos[source[k]];
+    for (int i = 1; i < npts[k]; i++)
+      WB_CHECK(table[2 * WB_PTAB_MAX * (size_t)k + 2 * i] > table[2 * WB_PTAB_MAX * (size_t)k + 2 * i - 2],
+               "wb_set_source_pressure_table: the coordinates of source %d do not increase", source[k]);
+    word[q] = npts[k] | ((coordinate && coordinate[k]) ? 256 : 0) | ((step && step[k]) ? 512 : 0);
+    for (int i = 0; i < 2 * npts[k]; i++) tab[2 * WB_PTAB_MAX * (size_t)q + i] = table[2 * WB_PTAB_MAX * (size_t)k + i];
+  }
+  WB_TRY(dev_upload(&c->d_src_ptab_n, word));
+  WB_TRY(dev_upload(&c->d_src_ptab, tab));
   return 0;
 }
 

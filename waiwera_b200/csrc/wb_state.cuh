@@ -88,7 +88,26 @@ struct WbSources {
   // enthalpies of the stages [4 per source], limits on the separated water and steam rates (<= 0: none)
   const int32_t *sep_n;
   const double *sep_h, *limit_w, *limit_s;
+  // reference pressure of a source on deliverability as a table against the flowing enthalpy or the pressure of its cell
+  // (null: none): per source a word (bits 0-7 number of points, 0: no table; bit 8: the coordinate is the pressure;
+  // bit 9: step interpolation) and WB_PTAB_MAX (coordinate, value) pairs
+  const int32_t *ptab_n;
+  const double *ptab;
 };
+
+#define WB_PTAB_MAX 8
+
+// interpolation_table%interpolate (src/interpolation.F90): linear between the data points or the value of the point at or
+// before x (step); constant beyond both ends
+WB_HD double wb_table_interpolate(const double *tab, int n, bool step, double x) {
+  if (!(x > tab[0])) return tab[1];
+  if (!(x < tab[2 * (n - 1)])) return tab[2 * (n - 1) + 1];
+  int i = 0;
+  while (i + 2 < n && !(x < tab[2 * (i + 1)])) i++;
+  const double x0 = tab[2 * i], y0 = tab[2 * i + 1], x1 = tab[2 * i + 2], y1 = tab[2 * i + 3];
+  if (step) return y0;
+  return y0 + (y1 - y0) * ((x - x0) / (x1 - x0));
+}
 
 // separator_separate (src/separator.F90:212-260) over separator_stage_separate (:140-166): separated water and steam
 // mass rates of a flow of `rate` at `enthalpy` through nstage <= 2 flash stages with the reference enthalpies stage_h
@@ -158,7 +177,25 @@ WB_HD double wb_source_rate(const WbSources &S, int k, const WbCellState<NC, NPH
   const int ctrl = S.ctrl[k];
   if (ctrl & 1) {
     const double effective_productivity = S.pi[k] * 1.0;
-    const double pressure_difference = s.P - S.pref[k];
+    double reference_pressure = S.pref[k];
+    if (S.ptab_n && (S.ptab_n[k] & 255) > 0) {
+      // SRC_PRESSURE_TABLE_COORD_ENTHALPY / _PRESSURE (src/source_control.F90:376-388): the table is looked up at the
+      // enthalpy of the fluid the source takes (phase enthalpies weighted by the flow fractions) or at the pressure
+      const int word = S.ptab_n[k];
+      double x = s.P;
+      if (!(word & 256)) {
+        double sum = 0.0;
+        x = 0.0;
+#pragma unroll
+        for (int p = 0; p < NPH; p++)
+          if (s.phases & (1 << p)) sum += s.mob[p];
+#pragma unroll
+        for (int p = 0; p < NPH; p++)
+          if (s.phases & (1 << p)) x = x + (s.mob[p] / sum) * s.h[p];
+      }
+      reference_pressure = wb_table_interpolate(S.ptab + 2 * WB_PTAB_MAX * (size_t)k, word & 255, (word & 512) != 0, x);
+    }
+    const double pressure_difference = s.P - reference_pressure;
     rate = 0.0;
 #pragma unroll
     for (int p = 0; p < NPH; p++)

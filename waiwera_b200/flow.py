@@ -18,6 +18,7 @@ EOS_WE, EOS_W, EOS_WCE, EOS_WAE = 0, 1, 2, 3
 RP_FULLY_MOBILE, RP_LINEAR, RP_PICKENS, RP_COREY, RP_GRANT, RP_VAN_GENUCHTEN, RP_TABLE = range(7)
 CP_ZERO, CP_LINEAR, CP_VAN_GENUCHTEN, CP_TABLE = range(4)
 PC_NONE, PC_PBJACOBI, PC_BJACOBI_ILU0, PC_ASM_ILU0 = 0, 1, 2, 3
+PRESSURE_TABLE_MAX = 8          # WB_PRESSURE_TABLE_MAX
 KSP_GMRES, KSP_BCGS = 0, 1
 METHOD_BEULER, METHOD_BDF2, METHOD_DIRECTSS = 0, 1, 2
 
@@ -336,6 +337,20 @@ class FlowSimulation:
         ls = None if limit_steam is None else np.ascontiguousarray(limit_steam, np.float64)
         return check(self.L.wb_set_source_separators(self.h, len(s), ptr(s), ptr(ns), ptr(pr), ptr(lw), ptr(ls)),
                      "wb_set_source_separators")
+
+    def set_source_pressure_table(self, sources, tables, coordinate=None, step=None):
+        """reference pressure of sources on deliverability tabulated against the flowing enthalpy (coordinate 0, the
+        default) or the pressure (1) of their cells: tables[k] = [(x, y), ...]; see wb_set_source_pressure_table"""
+        s = np.ascontiguousarray(sources, np.int32)
+        n = len(s)
+        npts = np.array([len(t) for t in tables], np.int32)
+        tab = np.zeros((max(n, 1), 2 * PRESSURE_TABLE_MAX))
+        for k, t in enumerate(tables):
+            tab[k, :2 * len(t)] = np.asarray(t, np.float64).reshape(-1)
+        co = np.zeros(max(n, 1), np.int32) if coordinate is None else np.ascontiguousarray(coordinate, np.int32)
+        st = np.zeros(max(n, 1), np.int32) if step is None else np.ascontiguousarray(step, np.int32)
+        return check(self.L.wb_set_source_pressure_table(self.h, n, ptr(s), ptr(co), ptr(st), ptr(npts), ptr(tab)),
+                     "wb_set_source_pressure_table")
 
     def separator_stage(self, pressure):
         hw, hs = C.c_double(), C.c_double()

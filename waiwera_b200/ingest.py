@@ -732,8 +732,6 @@ def load(path, mod=None, mesh_path=None):
         assert not unsupported, "source controls are not built: %s" % sorted(unsupported)
         dl = s.get("deliverability")
         assert dl is None or "threshold" not in dl, "deliverability thresholds are not built"
-        assert dl is None or not (isinstance(dl.get("pressure"), dict) and "enthalpy" in dl["pressure"]), \
-            "reference pressures tabulated against enthalpy are not built"
 
     def as_table(v, s, sub=None):
         """a control parameter given as a table in time: [[t, v], ...] or {"time": [[t, v], ...]} (a sub-object may carry
@@ -796,6 +794,10 @@ def load(path, mod=None, mesh_path=None):
     # "factor" (rate_factor_source_control: the rate after the other controls times the factor)
     p.source_controls = []
     p.source_control_tables = {}
+    # reference pressures of sources on deliverability tabulated against the flowing enthalpy or the pressure
+    # (wb_set_source_pressure_table; src/source_setup.F90:2704-2717): source, coordinate (0 enthalpy, 1 pressure), points,
+    # step interpolation flag
+    p.source_pressure_tables = []
     for k, s in enumerate(src):
         if "factor" in s:
             tab = as_table(s["factor"], s, s["factor"])
@@ -805,6 +807,15 @@ def load(path, mod=None, mesh_path=None):
                 p.source_control_tables[(k, "factor")] = (np.array([[0.0, float(s["factor"])]]), "step", "integrate")
         if "deliverability" in s or "limiter" in s or "direction" in s or "recharge" in s or "injectivity" in s:
             dl = dict(s.get("deliverability") or {})
+            pr = dl.get("pressure")
+            if isinstance(pr, dict) and "time" not in pr and ("enthalpy" in pr or "pressure" in pr):
+                coord = 0 if "enthalpy" in pr else 1
+                pts = np.array(pr["enthalpy" if coord == 0 else "pressure"], float).reshape(-1, 2)
+                interp = str(pr.get("interpolation", s.get("interpolation", "linear"))).lower()
+                assert interp in ("linear", "step"), "%s interpolation of a reference pressure table is not built" % interp
+                assert len(pts) <= 8, "reference pressure tables of more than 8 points are not built"
+                p.source_pressure_tables.append(dict(source=k, coordinate=coord, table=pts.tolist(), step=int(interp == "step")))
+                dl["pressure"] = float(pts[0, 1])
             for key, name in (("productivity", "productivity"), ("pressure", "reference_pressure")):
                 tab = as_table(dl.get(key), s, dl)
                 if tab is not None:

@@ -75,6 +75,10 @@ def apply_controls(p, sim, t0, t1):
     if seps:
         assert not sim.set_source_separators([q["source"] for q in seps], [q["pressure"] for q in seps],
                                              [q["limit_water"] for q in seps], [q["limit_steam"] for q in seps])
+    pt = getattr(p, "source_pressure_tables", [])
+    if pt:
+        assert not sim.set_source_pressure_table([q["source"] for q in pt], [q["table"] for q in pt],
+                                                 [q["coordinate"] for q in pt], [q["step"] for q in pt])
 
 
 def run(p, sim, opts=None, log=None):
