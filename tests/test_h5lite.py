@@ -198,3 +198,27 @@ def test_ingest_restarts_from_the_file_the_input_names():
     assert p.primary.shape == (100, 2) and (p.region == 1).all() and p.restart_time == 1.0e15
     assert np.array_equal(p.primary[:, 0], g["steady_pressure"]) and np.array_equal(p.primary[:, 1], g["steady_temperature"])
     assert np.allclose(p.y.reshape(-1, 2), p.primary / [1e6, 1e2])
+
+
+def test_filter_pipeline_is_undone_in_reverse_order():
+    """chunks of a filtered dataset: shuffle (2) then deflate (1) then fletcher32 (3) on write -> undone back to front; a
+    filter whose bit is set in the chunk's mask was skipped on write.  (No file of the reference uses filters: this
+    checks the pipeline on bytes made here, and the parsing of both versions of the filter pipeline message.)"""
+    import struct
+    import zlib
+    data = np.arange(1000, dtype="<f8") * 1.5 - 7.0
+    raw = data.tobytes()
+    shuffled = np.frombuffer(raw, np.uint8).reshape(-1, 8).T.tobytes()
+    packed = zlib.compress(shuffled) + b"\0\0\0\0"          # + checksum bytes, which the reader drops
+    filters = [(2, [8]), (1, [6]), (3, [])]
+    assert h5lite.H5File._unfilter(packed, filters, 0, 8) == raw
+    assert h5lite.H5File._unfilter(zlib.compress(raw) + b"\0\0\0\0", filters, 1, 8) == raw           # shuffle skipped for this chunk
+    assert h5lite.H5File._unfilter(shuffled, [(2, [8]), (1, [6])], 2, 8) == raw                      # deflate skipped
+    # version 2 message: ids < 256 carry no name; version 1: name length field and padding of odd client data
+    v2 = bytes([2, 2]) + struct.pack("<HHHI", 2, 0, 1, 8) + struct.pack("<HHHI", 1, 1, 1, 6)
+    assert h5lite.H5File._filters(v2) == [(2, [8]), (1, [6])]
+    v1 = bytes([1, 2]) + b"\0" * 6 + struct.pack("<HHHH", 2, 8, 0, 1) + b"shuffle\0" + struct.pack("<II", 8, 0) \
+        + struct.pack("<HHHH", 1, 8, 1, 1) + b"deflate\0" + struct.pack("<II", 6, 0)
+    assert h5lite.H5File._filters(v1) == [(2, [8]), (1, [6])]
+    with pytest.raises(h5lite.H5Error):
+        h5lite.H5File._filters(bytes([2, 1]) + struct.pack("<HHHH", 32001, 0, 0, 0))               # a third-party filter

@@ -321,6 +321,8 @@ class H5File:
         return out
 
     def _walk(self, prefix, header, entry=None):
+        if header in self._headers.values() and prefix:
+            return                                          # a second hard link to an object already seen (or a cycle)
         msgs = self._messages(header)
         types = {t for t, _ in msgs}
         if 0x11 in types or (entry and entry.get("cache") == 1):
