@@ -323,6 +323,7 @@ class H5File:
     def _walk(self, prefix, header, entry=None):
         if header in self._headers.values() and prefix:
             return                                          # a second hard link to an object already seen (or a cycle)
+        self._headers[prefix or "/"] = header
         msgs = self._messages(header)
         types = {t for t, _ in msgs}
         if 0x11 in types or (entry and entry.get("cache") == 1):
@@ -340,7 +341,6 @@ class H5File:
                 self._walk(prefix + "/" + name if prefix else name, child)
         elif 0x08 in types:
             self._objects[prefix] = ("dataset", self._dataset(msgs))
-        self._headers[prefix or "/"] = header
 
     # ---- datasets
     def _dataset(self, msgs):
