@@ -64,6 +64,13 @@ def test_driver_with_the_checker_as_engine(wo, tmp_path, case):
     path = str(tmp_path / "out.h5")
     run.write_results(p, path, times, fluids, sources)
     check_output_file(case, path)
+    if case.startswith("minc"):          # flow_simulation_output_minc_data: level and parent of every cell
+        h = h5lite.H5File(path)
+        n0 = m.minc_cells
+        assert h["minc/level"].reshape(-1).tolist() == [0] * n0 + [1] * (m.ninterior - n0)
+        assert h["minc/parent"].reshape(-1).tolist() == list(range(n0)) + list(m.minc_zone)
+    else:
+        assert "minc/level" not in h5lite.H5File(path)
     # "frequency": 0 keeps the initial and the final state only
     p.doc["output"] = {"frequency": 0}
     run.write_results(p, path, times, fluids, sources)

@@ -11,6 +11,7 @@ Layout (src/flow_simulation.F90 output routines, PETSc HDF5 viewer with an outpu
     cell_fields/fluid_<field>             [ntimes, ncells]   field names as create_fluid_vector builds them
                                           (src/fluid.F90): pressure, temperature, region, <component>_partial_pressure,
                                           <phase>_<variable>, e.g. vapour_saturation, liquid_density
+    minc/level, minc/parent               [ncells, 1] int32 (MINC meshes): level of every cell, natural index of its original cell
     source_index                          [nsources, 1] int32
     source_fields/source_<field>          [ntimes, nsources]: natural_cell_index (int32), component, rate, enthalpy
                                           (default_output_source_fields, src/source.F90:60-62)
@@ -73,6 +74,11 @@ def write_output(path, mesh, eos, times, fluids, source_cells=None, source_histo
     for name in fields:
         col = fluid_field_column(eos, name)
         d["cell_fields/fluid_" + name] = np.array([np.asarray(fl)[:n, col][order] for fl in fluids], float).reshape(len(times), n)
+    if getattr(mesh, "minc_level", None) is not None and mesh.minc_levels > 0:
+        # flow_simulation_output_minc_data (src/flow_simulation.F90:2625-2691): MINC level and natural index of the
+        # original single-porosity cell of every cell, in storage order
+        d["minc/level"] = np.asarray(mesh.minc_level, np.int32)[:n][order].reshape(-1, 1)
+        d["minc/parent"] = np.asarray(mesh.minc_parent, np.int32)[:n][order].reshape(-1, 1)
     if source_cells is not None and len(source_cells):
         ns = len(source_cells)
         hist = np.asarray(source_history, float).reshape(len(times), ns, 3)
