@@ -93,3 +93,66 @@ def test_command_line_on_the_cuda_path(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])["output"] == out
     check_output_file(case, out, nsteps_expected=len(GOLD[case]["times"]) - 1)
+
+
+class OracleTracerEngine(OracleSim):
+    """OracleSim + the tracer calls of flow.FlowSimulation (the checker keeps the boundary ghost rows inside its tracer
+    system, the engine takes their mass fractions as a separate array)"""
+
+    def set_tracers(self, phases, diffusion=None, decay=None, activation=None):
+        self.f.set_tracers(phases, diffusion, decay, activation)
+        self.A = self.f.tracer_pattern()
+        self.nt = len(phases)
+
+    def set_tracer_injection(self, rates):
+        self.f.set_tracer_injection(rates)
+
+    def tracer_balances(self):
+        self.al_full = self.f.tracer_balances()
+        return self.al_full[:self.f.nowned * self.nt].copy()
+
+    def tracer_solve(self, dt, al, x, xb=None, opts=None):
+        import ctypes as C
+        n = self.f.nowned * self.nt
+        x_full = np.concatenate([x, xb]) if xb is not None else np.asarray(x)
+        b, al_new = self.f.tracer_setup_linear(self.A, dt, self.al_full, x_full)
+        k = self.wo.KspOpts()
+        k.type, k.restart, k.maxit, k.rtol, k.atol, k.dtol = self.wo.KSP_BCGS, 30, 10000, 1e-10, 1e-50, 1e5
+        pc = self.L.wo_pc_create(self.A, self.wo.PC_BJACOBI_ILU0, None)
+        xn = np.zeros(len(b))
+        its, rn = C.c_int(), C.c_double()
+        reason = self.L.wo_ksp_solve(self.A, pc, C.byref(k), self.wo.dp(b), self.wo.dp(xn), C.byref(its), C.byref(rn))
+        self.L.wo_pc_destroy(pc)
+        self.al_full = al_new
+        return xn[:n], al_new[:n], reason, its.value
+
+
+def test_driver_runs_a_tracer_deck(wo, tmp_path):
+    """test/benchmark/tracer/oned (oned_single_phase.json): restart from the steady-state file the deck names, ten flow
+    steps each followed by the tracer solve, Dirichlet tracer boundary -> cell_fields/tracer_tracer of the output file
+    against the AUTOUGH2 listing (the reference accepts 1e-3; the listing prints 6 digits)"""
+    gold = json.load(open(os.path.join(os.path.dirname(INP), "tracer_oned.json")))["single"]
+    p = ingest.load(os.path.join(INP, "oned_single_phase.input.json"), mod=wo)
+    m = p.mesh
+    assert p.y is not None and len(p.tracers) == 1 and p.boundary_tracer[0, 0] == 0.01
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    assert f.set_boundary(int(m.boundary["ghost_cells"][0]), int(m.boundary["interior_cells"][0]), p.boundary_primary[0],
+                          int(p.boundary_region[0])) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    assert f.fluid_init(p.y, p.region) == 0
+    sim = OracleTracerEngine(wo, f, newton_opts(wo, p))
+    tracers = []
+    times, fluids, sources, y = run.run(p, sim, tracer_history=tracers)
+    sim.destroy()
+    assert len(times) == len(tracers) == len(gold["times"]) + 1 and np.allclose(times[1:], gold["times"])
+    path = str(tmp_path / "tracer.h5")
+    p.doc["output"] = {"initial": True, "frequency": 1, "final": True}
+    run.write_results(p, path, times, fluids, sources, tracers)
+    h = h5lite.H5File(path)
+    X = h["cell_fields/tracer_tracer"]
+    assert X.shape == (len(times), 10) and np.all(X[0] == 0.0)
+    for k, rows in enumerate(gold["tables"]):
+        rows = np.array(rows)[:10]
+        assert np.abs(X[k + 1] - rows[:, 4]).max() < 2e-6
+        assert np.abs(h["cell_fields/fluid_pressure"][k + 1] - rows[:, 0]).max() / rows[:, 0].max() < 1e-3

@@ -298,6 +298,9 @@ def h5_fixtures():
     # the restart file the tracer doublet input names ("initial": {"filename": "doublet_ss.h5"}), next to that input
     shutil.copy("/root/reference/test/benchmark/tracer/doublet/run/doublet_ss.h5",
                 os.path.join(os.path.dirname(OUT), "inputs", "doublet_ss.h5"))
+    # likewise for the 1-D tracer deck (tests/test_run.py runs it as a whole: restart, flow, tracer, output file)
+    shutil.copy("/root/reference/test/benchmark/tracer/oned/run/oned_single_phase_ss.h5",
+                os.path.join(os.path.dirname(OUT), "inputs", "oned_single_phase_ss.h5"))
 
 
 def wae_benchmarks():

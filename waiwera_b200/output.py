@@ -11,6 +11,7 @@ Layout (src/flow_simulation.F90 output routines, PETSc HDF5 viewer with an outpu
     cell_fields/fluid_<field>             [ntimes, ncells]   field names as create_fluid_vector builds them
                                           (src/fluid.F90): pressure, temperature, region, <component>_partial_pressure,
                                           <phase>_<variable>, e.g. vapour_saturation, liquid_density
+    cell_fields/tracer_<name>             [ntimes, ncells] tracer mass fractions
     minc/level, minc/parent               [ncells, 1] int32 (MINC meshes): level of every cell, natural index of its original cell
     source_index                          [nsources, 1] int32
     source_fields/source_<field>          [ntimes, nsources]: natural_cell_index (int32), component, rate, enthalpy
@@ -58,7 +59,8 @@ def fluid_field_column(eos, name):
     raise KeyError("fluid field %r of eos %s" % (name, eos))
 
 
-def write_output(path, mesh, eos, times, fluids, source_cells=None, source_history=None, fields=None, cell_index=None):
+def write_output(path, mesh, eos, times, fluids, source_cells=None, source_history=None, fields=None, cell_index=None,
+                 tracer_names=None, tracer_history=None):
     """times: [nt]; fluids: nt arrays [>= ninterior, dof] of fluid records (wb_get_fluid) in natural cell order;
     source_history: nt arrays [nsources, 3] of (component, rate, enthalpy); fields: fluid fields to write (default: the
     EOS's default output fields); cell_index: storage order, the natural index of the cell stored at each position
@@ -74,6 +76,11 @@ def write_output(path, mesh, eos, times, fluids, source_cells=None, source_histo
     for name in fields:
         col = fluid_field_column(eos, name)
         d["cell_fields/fluid_" + name] = np.array([np.asarray(fl)[:n, col][order] for fl in fluids], float).reshape(len(times), n)
+    if tracer_names:
+        # tracer mass fractions: cell_fields/tracer_<name> (create_tracer_vector field names, src/tracer.F90:152-191)
+        hist = [np.asarray(x, float).reshape(-1, len(tracer_names)) for x in tracer_history]
+        for j, name in enumerate(tracer_names):
+            d["cell_fields/tracer_" + name] = np.array([x[:n, j][order] for x in hist], float).reshape(len(times), n)
     if getattr(mesh, "minc_level", None) is not None and mesh.minc_levels > 0:
         # flow_simulation_output_minc_data (src/flow_simulation.F90:2625-2691): MINC level and natural index of the
         # original single-porosity cell of every cell, in storage order

@@ -3,7 +3,8 @@
 The host side the reference keeps in timestepper.F90 / flow_simulation.F90 around the Newton step, restated as the few
 lines a caller of this library needs -- ingest.load -> flow.FlowSimulation -> backward-Euler steps with the input's step
 sizes, "iteration" step-size adaptor (src/timestepper.F90:863-1476, 2330-2375), step cuts on failed Newton solves,
-source tables and controls averaged over each step (ingest.rates_at / controls_at) -> the output file of
+source tables and controls averaged over each step (ingest.rates_at / controls_at), the tracer solve after every flow
+step (timestepper.F90:2347-2353) -> the output file of
 output.write_output (the layout CREDO's benchmark scripts and `initial.filename` restarts read).  It is not on the hot
 path and not part of the parity claims; tests/test_run.py drives it with the checker standing in for the engine on CPU
 and with the engine itself on the GPU.
@@ -81,10 +82,27 @@ def apply_controls(p, sim, t0, t1):
                                                  [q["coordinate"] for q in pt], [q["step"] for q in pt])
 
 
-def run(p, sim, opts=None, log=None):
+def setup_tracers(p, sim):
+    """the "tracer" value of the input (setup_tracers, src/tracer.F90:64-150) -> (initial mass fractions [nowned * nt],
+    mass fractions of the boundary ghost cells or None)"""
+    nt = len(p.tracers)
+    phase = {"liquid": 1, "vapour": 2}
+    sim.set_tracers([phase[str(t.get("phase", "liquid")).lower()] for t in p.tracers],
+                    diffusion=[float(t.get("diffusion", 0.0)) for t in p.tracers],
+                    decay=[float(t.get("decay", 0.0)) for t in p.tracers],
+                    activation=[float(t.get("activation", 0.0)) for t in p.tracers])
+    m = p.mesh
+    x = np.tile(np.asarray(p.initial_tracer, float)[:nt], m.nowned)
+    xb = np.ascontiguousarray(p.boundary_tracer[:, :nt], float).reshape(-1) if len(p.boundary_region) else None
+    return x, xb
+
+
+def run(p, sim, opts=None, log=None, tracer_ksp=None, tracer_history=None):
     """Advances the ingested problem p on sim from time.start to time.stop.  Returns (times, fluids, source_history, y):
     the output times (the initial state first), the fluid records [ncell, dof] at those times, per output time the
-    [nsources, 3] array of (component, rate, enthalpy), and the final scaled primaries."""
+    [nsources, 3] array of (component, rate, enthalpy), and the final scaled primaries.  With tracers in the input the
+    auxiliary linear problem is solved after every flow step (timestepper.F90:2347-2353) and the mass fractions
+    [nowned, nt] of every output time are appended to the list tracer_history."""
     tm = p.time or {}
     st = tm.get("step", {})
     size = st.get("size", 0.1)
@@ -122,6 +140,13 @@ def run(p, sim, opts=None, log=None):
     assert err == 0, "the initial state is outside the range of the thermodynamics"
     apply_controls(p, sim, t, t + min(sizes[0], dt_max))
     sim.residual(y, L0, min(sizes[0], dt_max))     # one function evaluation: the source rates of the initial state
+    nt = len(p.tracers)
+    if nt:
+        x, xb = setup_tracers(p, sim)
+        err, L0 = sim.lhs(y)
+        al = sim.tracer_balances()
+        if tracer_history is not None:
+            tracer_history.append(x.reshape(-1, nt).copy())
     record()
     k, dt = 0, sizes[0]
     while t < stop * (1.0 - 1e-12) and k < nmax:
@@ -146,6 +171,14 @@ def run(p, sim, opts=None, log=None):
                 log("step %d at t = %.6g: Newton failed (reason %d), step size cut to %.6g" % (k + 1, t, res.reason, dt))
         if res.reason <= 0:
             raise RuntimeError("time step %d at t = %g did not converge after %d tries" % (k + 1, t, tries))
+        if nt:
+            # the flow step left the fluxes and fluid of the new state behind: the tracer system is built from them
+            sim.set_tracer_injection(ingest.tracer_rates_at(p, t, t + dt))
+            x, al, reason, _ = sim.tracer_solve(dt, al, x, xb, opts=tracer_ksp)
+            if reason <= 0:
+                raise RuntimeError("the tracer solve of time step %d did not converge (reason %d)" % (k + 1, reason))
+            if tracer_history is not None:
+                tracer_history.append(np.asarray(x).reshape(-1, nt).copy())
         t += dt
         k += 1
         err, L0 = sim.lhs(y)           # fluid records and source rates of the new state
@@ -180,16 +213,18 @@ def run_file(path, output_path=None, sim=None, opts=None, log=None):
         opts = flow.newton_opts(max_iterations=(nl.get("maximum", {}) or {}).get("iterations") or 8,
                                 rel_tol=tol.get("relative") or 1e-5, abs_tol=tol.get("absolute") or 1.0,
                                 pc_type=flow.PC_BJACOBI_ILU0, ksp=flow.ksp_opts(type=flow.KSP_BCGS))
-    times, fluids, sources, y = run(p, sim, opts=opts, log=log)
+    tracers = [] if p.tracers else None
+    tk = flow.ksp_opts(type=flow.KSP_BCGS, rtol=1e-10) if p.tracers else None
+    times, fluids, sources, y = run(p, sim, opts=opts, log=log, tracer_ksp=tk, tracer_history=tracers)
     out = p.doc.get("output") or {}
     if output_path is None:
         name = out.get("filename") if isinstance(out, dict) else None
         output_path = os.path.join(os.path.dirname(os.path.abspath(path)), name or os.path.splitext(os.path.basename(path))[0] + ".h5")
-    write_results(p, output_path, times, fluids, sources)
+    write_results(p, output_path, times, fluids, sources, tracers)
     return output_path
 
 
-def write_results(p, output_path, times, fluids, sources):
+def write_results(p, output_path, times, fluids, sources, tracers=None):
     """the output file of a run: the states the input's "output" value asks for ("initial", "frequency", "final";
     src/flow_simulation.F90 output setup) in the reference's layout"""
     out = p.doc.get("output") or {}
@@ -206,7 +241,9 @@ def write_results(p, output_path, times, fluids, sources):
     idx = np.nonzero(keep)[0]
     output.write_output(output_path, m, p.eos, times[idx], [fluids[i] for i in idx],
                         source_cells=p.source_cells if len(p.source_cells) else None,
-                        source_history=[sources[i] for i in idx] if len(p.source_cells) else None)
+                        source_history=[sources[i] for i in idx] if len(p.source_cells) else None,
+                        tracer_names=[t.get("name", "tracer_%d" % k) for k, t in enumerate(p.tracers)] if tracers else None,
+                        tracer_history=[tracers[i] for i in idx] if tracers else None)
 
 
 def main(argv=None):
