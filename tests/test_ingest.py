@@ -88,7 +88,9 @@ def test_tracer_oned_input():
     ref, y, region = T.problem("single")
     same_geometry(p.mesh, ref)
     assert np.array_equal(p.mesh.rock, ref.rock)
-    assert p.primary is None                                  # "initial": {"filename": ...}: HDF5 restart
+    # "initial": {"filename": "oned_single_phase_ss.h5"}: the restart file next to the deck is read (the last index)
+    # (it holds one state, the uniform one the benchmark starts from)
+    assert p.primary.tolist() == [[3.0e6, 20.0]] * 10 and p.region.tolist() == [1] * 10 and p.restart_time == 0.0
     assert p.boundary_primary.tolist() == [T.CASES["single"]["primary"]] and p.boundary_region.tolist() == [1]
     assert p.boundary_tracer.tolist() == [[T.X_BOUNDARY]] and len(p.tracers) == 1
     assert p.source_cells.tolist() == [9] and p.source_components.tolist() == [0]
