@@ -667,3 +667,35 @@ def test_source_setup_known_answers(tmp_path):
     assert list(p.source_injection_components) == [q["injection_component"] or 1 for q in live]
     assert list(p.source_production_components) == [q["production_component"] for q in live]
     assert np.allclose(p.source_tracer, [q["tracer"] for q in live])
+
+
+_HYB_T = [43.4375, 27.8125, 74.6875, 59.0625, 22.77777778, 33.88888889, 24.16666667, 39.44444444, 50.55555556, 32.5]
+_HYB_REGION = [33, 8, 83, 58, 1, 34, 16, 51, 84, 66]
+HYBRID_CASES = [("no bdy", {}, None), ("hex bdy", {}, [{"faces": {"cells": [0, 1, 2, 3], "normal": [1, 0, 0]}, "primary": [1e5, 20.0]}]),
+                ("wedge bdy", {}, [{"faces": {"cells": [6, 9], "normal": [-1, 0, 0]}, "primary": [1e5, 20.0]}]),
+                ("MINC no bdy", _MINC3, None),
+                ("MINC bdy", _MINC3, [{"faces": {"cells": [0, 1, 2, 3], "normal": [1, 0, 0]}, "primary": [1e5, 20.0]}])]
+
+
+@pytest.mark.parametrize("case", HYBRID_CASES, ids=[c[0] for c in HYBRID_CASES])
+def test_initial_conditions_on_the_hybrid_mesh(tmp_path, case):
+    """test/unit/src/initial_test.F90:619-835: per-cell initial values on hybrid10.msh (6 wedges, then 4 hexahedra in the
+    file).  The test's expectation is a function of the cell centroid (T = 20 + 100 x y, region = 10 x + 100 y - 11), so
+    it fixes which cell each entry of the input arrays goes to: DMPlex numbers the hexahedra first, then the wedges.  The
+    boundary cases name hexahedra by 0..3 with an outward +x face and the wedges 6 and 9 with a -x face."""
+    name, mspec, boundaries = case
+    doc = {"mesh": mspec, "eos": {"name": "we"},
+           "initial": dict(primary=[[10.0e5, t] for t in _HYB_T], region=_HYB_REGION, **({"minc": False} if mspec else {}))}
+    if boundaries:
+        doc["boundaries"] = boundaries
+    p = _load_doc(tmp_path, doc, "hybrid10.ascii.msh")
+    m = p.mesh
+    n = m.ninterior
+    assert n == (30 if mspec else 10)
+    x, y = m.cell_geom[:n, 0], m.cell_geom[:n, 1]
+    assert np.allclose(p.primary[:, 0], 10.0e5) and np.allclose(p.primary[:, 1], 20.0 + 100.0 * x * y, rtol=1e-8)
+    assert p.region.tolist() == (np.rint(10 * x + 100 * y).astype(int) - 11).tolist()
+    if boundaries:          # every named cell has an exterior face in the asked direction
+        g = m.face_geom[-len(m.boundary["ghost_cells"]):]
+        want = np.array(boundaries[0]["faces"]["normal"], float)
+        assert list(m.boundary["interior_cells"]) == boundaries[0]["faces"]["cells"] and np.allclose(g[:, 4:7], want)

@@ -527,7 +527,7 @@ def input_fixtures():
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from waiwera_b200 import ingest
-    nodes, elems = ingest.read_gmsh("/root/reference/test/unit/data/mesh/hybrid10.msh")
+    nodes, elems = ingest.read_gmsh("/root/reference/test/unit/data/mesh/hybrid10.msh", dmplex_order=False)      # the file's own order
     write_ascii_msh(os.path.join(dst, "hybrid10.ascii.msh"), nodes, elems)
     print("wrote", dst)
 

@@ -28,8 +28,22 @@ _FACES3 = {4: [(0, 2, 1), (0, 1, 3), (0, 3, 2), (1, 2, 3)],
            7: [(0, 3, 2, 1), (0, 1, 4), (1, 2, 4), (2, 3, 4), (3, 0, 4)]}
 
 
-def read_gmsh(path):
-    """gmsh MSH 2.2 file, ASCII or binary -> (nodes [n,3], list of (element type, node indices 0-based))"""
+def _dmplex_cell_order(elems):
+    """DMPlex numbers the prism (wedge) cells of a hybrid mesh after all the others, each group in file order (pinned by
+    the reference's initial_test.F90:619-835 on hybrid10.msh, wedges first in the file, and by the cell indices of its
+    minc_3d_refined deck): stable reordering of the elements of the highest dimension; the others keep their places"""
+    dim = max(_GMSH[t][0] for t, _ in elems)
+    top = [k for k, (t, _) in enumerate(elems) if _GMSH[t][0] == dim]
+    new = [k for k in top if elems[k][0] != 6] + [k for k in top if elems[k][0] == 6]
+    out = list(elems)
+    for slot, k in zip(top, new):
+        out[slot] = elems[k]
+    return out
+
+
+def read_gmsh(path, dmplex_order=True):
+    """gmsh MSH 2.2 file, ASCII or binary -> (nodes [n,3], list of (element type, node indices 0-based)), cells in the
+    order DMPlex numbers them (file order, wedges last: _dmplex_cell_order) or, dmplex_order=False, in the file's own"""
     data = open(path, "rb").read()
     pos = data.index(b"$MeshFormat") + len(b"$MeshFormat")
     end = data.index(b"\n", pos + 1)
@@ -82,7 +96,7 @@ def read_gmsh(path):
             pos = end + 1
             etype, ntags = f[1], f[2]
             elems.append((etype, [index[v] for v in f[3 + ntags:3 + ntags + _GMSH[etype][1]]]))
-    return xyz, elems
+    return xyz, (_dmplex_cell_order(elems) if dmplex_order and elems else elems)
 
 
 # ExodusII element names -> the gmsh type codes build_mesh works with (the node orderings of these element types
@@ -132,9 +146,8 @@ def read_exodus(path):
     # DMPlex numbers the prism (wedge) blocks of a hybrid mesh after all the others, each group in file order: the cell
     # indices of the reference's minc_3d_refined deck (wedge block first in the file, top-layer hexahedra 0..92, wedges
     # 465..479) only fit this order
-    blocks = [b for b in blocks if b[0] != 6] + [b for b in blocks if b[0] == 6]
     elems = [(t, [int(i) for i in row]) for t, con in blocks for row in con]
-    return xyz, elems
+    return xyz, _dmplex_cell_order(elems)
 
 
 def read_mulgraph(path):
