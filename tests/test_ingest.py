@@ -699,3 +699,38 @@ def test_initial_conditions_on_the_hybrid_mesh(tmp_path, case):
         g = m.face_geom[-len(m.boundary["ghost_cells"]):]
         want = np.array(boundaries[0]["faces"]["normal"], float)
         assert list(m.boundary["interior_cells"]) == boundaries[0]["faces"]["cells"] and np.allclose(g[:, 4:7], want)
+
+
+def test_boundary_conditions_known_answers(tmp_path):
+    """set_boundary_conditions (test/unit/src/mesh_test.F90:1978-2200): no boundaries; the default primaries of the EOS
+    where a boundary gives none; given primaries in 1-D and on the 6 cells of the 7 x 7 grid; tracer mass fractions 0 by
+    default, one number for all tracers, a list"""
+    import shutil
+    for fn in ("col10.exo",):
+        shutil.copy(os.path.join(INITIAL, fn), str(tmp_path / fn))
+    top = {"faces": {"cells": [0], "normal": [0, 0, 1]}}
+    for bdy, expect in ((None, None), ([top], [1.0e5, 20.0]), ([dict(top, primary=[2.0e5, 40])], [2.0e5, 40.0])):
+        doc = {"mesh": {"filename": "col10.exo"}}
+        if bdy:
+            doc["boundaries"] = bdy
+        path = str(tmp_path / "b.json")
+        json.dump(doc, open(path, "w"))
+        p = ingest.load(path)
+        if expect is None:
+            assert len(p.boundary_region) == 0 and p.mesh.ncell == 10
+        else:
+            assert p.boundary_primary.tolist() == [expect] and p.boundary_region.tolist() == [1]
+            assert p.mesh.boundary["interior_cells"].tolist() == [0] and p.mesh.ncell == 11
+        # no "initial": the default primaries everywhere
+        assert p.primary.tolist() == [[1.0e5, 20.0]] * 10 and p.region.tolist() == [1] * 10
+    south = {"faces": {"cells": [0, 1, 2, 3, 4, 5], "normal": [0, -1, 0]}, "primary": [25.0e5, 60]}
+    for tracer, btracer, expect in ((None, None, [0.0]), ({"name": "foo"}, None, [0.0]), ({"name": "foo"}, 1.0e-6, [1.0e-6]),
+                                    ([{"name": "foo"}, {"name": "bar"}], [1.0e-6, 2.0e-6], [1.0e-6, 2.0e-6])):
+        doc = {"boundaries": [dict(south, **({"tracer": btracer} if btracer is not None else {}))]}
+        if tracer:
+            doc["tracer"] = tracer
+        p = _load_doc(tmp_path, doc)
+        assert p.boundary_primary.tolist() == [[25.0e5, 60.0]] * 6 and p.boundary_region.tolist() == [1] * 6
+        assert p.boundary_tracer.tolist() == [expect] * 6
+        assert p.mesh.boundary["interior_cells"].tolist() == [0, 1, 2, 3, 4, 5]
+        assert np.allclose(p.mesh.face_geom[-6:, 4:7], [0.0, -1.0, 0.0])

@@ -727,12 +727,25 @@ def load(path, mod=None, mesh_path=None):
                       partial_pressure_scale=max(p.params.partial_pressure_scale, 0.0))
         p.primary_scales = sc
         p.y = np.ascontiguousarray(wmesh.scale_primaries(p.primary, p.region, **sc)).reshape(-1)
-    else:
+    elif "filename" in init:
         p.primary = p.region = p.y = None                  # restart file not at hand: pass the arrays
+    else:
+        # no initial conditions: the default primaries of the EOS in region 1 everywhere (src/initial.F90:941-951)
+        p.primary = np.tile(np.array([1.0e5, 20.0, 0.0][:p.np]), (n, 1))
+        p.region = np.ones(n, np.int32)
+        sc = dict(pressure_scale=1e6, temperature_scale=1e2, partial_pressure_scale=0.0)
+        if p.params is not None:
+            sc = dict(pressure_scale=p.params.pressure_scale if p.params.pressure_scale > 0 else 1e6,
+                      temperature_scale=p.params.temperature_scale if p.params.temperature_scale > 0 else 1e2,
+                      partial_pressure_scale=max(p.params.partial_pressure_scale, 0.0))
+        p.primary_scales = sc
+        p.y = np.ascontiguousarray(wmesh.scale_primaries(p.primary, p.region, **sc)).reshape(-1)
     tr = doc.get("tracer")
     p.tracers = [] if tr is None else ([tr] if isinstance(tr, dict) else list(tr))
     nt = len(p.tracers)
-    p.boundary_primary = np.array([bspecs[i]["primary"] for i in bowner], float).reshape(len(bowner), p.np)
+    # eos%default_primary / default_region (src/eos_w.F90:80, eos_we.F90:90, eos_wge.F90:80) where the input gives none
+    default_primary = [1.0e5, 20.0, 0.0][:p.np]
+    p.boundary_primary = np.array([bspecs[i].get("primary", default_primary) for i in bowner], float).reshape(len(bowner), p.np)
     p.boundary_region = np.array([bspecs[i].get("region", 1) for i in bowner], np.int32)
     p.boundary_tracer = np.array([np.broadcast_to(np.atleast_1d(bspecs[i].get("tracer", 0.0)), (max(nt, 1),)) for i in bowner],
                                  float).reshape(len(bowner), max(nt, 1))
