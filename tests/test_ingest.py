@@ -734,3 +734,18 @@ def test_boundary_conditions_known_answers(tmp_path):
         assert p.boundary_tracer.tolist() == [expect] * 6
         assert p.mesh.boundary["interior_cells"].tolist() == [0, 1, 2, 3, 4, 5]
         assert np.allclose(p.mesh.face_geom[-6:, 4:7], [0.0, -1.0, 0.0])
+
+
+def test_mesh_init_known_answers():
+    """test/unit/src/mesh_test.F90:147-253 on the reference's block3.exo: 3 cells in 3-D, 16 faces in all (2 interior, 14
+    exterior), the interior faces of area 200 with distances (5, 10) and (10, 15) and centroids (5, 10, 50), (5, 10, 30)"""
+    xyz, elems = ingest.read_exodus(os.path.join(INITIAL, "block3.exo"))
+    m, ext = ingest.build_mesh(xyz, elems)
+    assert (m.dim, m.ninterior, m.nface, m.nface + len(ext)) == (3, 3, 2, 16)
+    fc = m.face_cells.reshape(-1, 2).tolist()
+    for pair, dist, cen in (([0, 1], [5.0, 10.0], [5.0, 10.0, 50.0]), ([1, 2], [10.0, 15.0], [5.0, 10.0, 30.0])):
+        k = fc.index(pair) if pair in fc else fc.index(pair[::-1])
+        g = m.face_geom[k]
+        d = g[1:3] if fc[k] == pair else g[1:3][::-1]
+        assert abs(g[0] - 200.0) < 1e-12 and np.allclose(d, dist, rtol=1e-14) and np.allclose(g[8:11], cen, rtol=1e-14)
+    assert np.allclose([e[2] for e in ext if abs(e[3][2]) > 0.5], 200.0)          # the top and bottom faces
