@@ -109,6 +109,11 @@ def run(p, sim, opts=None, log=None, tracer_ksp=None, tracer_history=None):
     sizes = list(size) if isinstance(size, list) else [size]
     ad = st.get("adapt", {}) or {}
     adapt = bool(ad.get("on", False))
+    method = str(st.get("method", "beuler")).lower()
+    if method != "beuler":
+        raise NotImplementedError("time.step.method %r: this driver steps with backward Euler only" % method)
+    if adapt and str(ad.get("method", "iteration")).lower() != "iteration":
+        raise NotImplementedError("time.step.adapt.method %r: only the iteration-count adaptor is built" % ad.get("method"))
     mx = st.get("maximum", {}) or {}
     dt_max = mx.get("size") or np.inf
     nmax = mx.get("number")
