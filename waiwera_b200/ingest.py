@@ -658,6 +658,12 @@ def load(path, mod=None, mesh_path=None):
     """Reads <path> (Waiwera JSON input) and the gmsh mesh it names.  mod: waiwera_b200.flow (see make_params),
     None: no parameter struct."""
     doc = json.load(open(path))
+    if doc.get("network"):
+        raise NotImplementedError("%s: source networks (\"network\": groups, reinjectors) are not built" % path)
+    eos_name = doc.get("eos", "we")
+    eos_name = eos_name if isinstance(eos_name, str) else eos_name.get("name", "we")
+    if eos_name not in _EOS:
+        raise NotImplementedError("%s: eos %r is not built (w, we, wce, wae are)" % (path, eos_name))
     mspec = doc["mesh"] if isinstance(doc["mesh"], dict) else {"filename": doc["mesh"]}
     mfile = mesh_path or os.path.join(os.path.dirname(path), mspec["filename"])
     nodes, elems = read_mesh(mfile)
