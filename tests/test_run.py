@@ -46,7 +46,7 @@ def check_output_file(case, path, nsteps_expected=None):
 @pytest.mark.parametrize("case", ["deliv_delg_flow", "deliv_delw", "minc_1d_100"])
 def test_driver_with_the_checker_as_engine(wo, tmp_path, case):
     p = ingest.load(os.path.join(INP, case + ".input.json"), mod=wo)
-    p.doc["output"] = {"initial": True, "frequency": 1, "final": True}
+    p.doc["output"] = {"initial": True, "frequency": 1, "final": True, "fields": {"fluid": ["liquid_saturation", "vapour_density"]}}
     m = p.mesh
     f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
                 m.cell_geom.reshape(-1), m.rock.reshape(-1))
@@ -64,6 +64,9 @@ def test_driver_with_the_checker_as_engine(wo, tmp_path, case):
     path = str(tmp_path / "out.h5")
     run.write_results(p, path, times, fluids, sources)
     check_output_file(case, path)
+    h = h5lite.H5File(path)          # the extra fluid fields the "output" value asks for
+    assert np.allclose(h["cell_fields/fluid_liquid_saturation"] + h["cell_fields/fluid_vapour_saturation"], 1.0, atol=1e-14)
+    assert h.shape("cell_fields/fluid_vapour_density") == h.shape("cell_fields/fluid_pressure")
     if case.startswith("minc"):          # flow_simulation_output_minc_data: level and parent of every cell
         h = h5lite.H5File(path)
         n0 = m.minc_cells

@@ -244,9 +244,13 @@ def write_results(p, output_path, times, fluids, sources, tracers=None):
         if out.get("final", True):
             keep[-1] = True
     idx = np.nonzero(keep)[0]
+    # fluid fields: the ones a restart needs plus those the input asks for ("output": {"fields": {"fluid": [...]}})
+    fields = list(output.REQUIRED[p.eos])
+    asked = (out.get("fields") or {}).get("fluid", []) if isinstance(out, dict) else []
+    fields += [f for f in ([asked] if isinstance(asked, str) else asked) if f not in fields]
     output.write_output(output_path, m, p.eos, times[idx], [fluids[i] for i in idx],
                         source_cells=p.source_cells if len(p.source_cells) else None,
-                        source_history=[sources[i] for i in idx] if len(p.source_cells) else None,
+                        source_history=[sources[i] for i in idx] if len(p.source_cells) else None, fields=fields,
                         tracer_names=[t.get("name", "tracer_%d" % k) for k, t in enumerate(p.tracers)] if tracers else None,
                         tracer_history=[tracers[i] for i in idx] if tracers else None)
 
