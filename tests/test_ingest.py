@@ -773,3 +773,22 @@ def test_every_deck_of_the_reference_loads_or_is_refused_loudly():
                             "makeup_uniform.json", "reinjection.json"}, refused
     assert all("network" in refused[k] for k in ("makeup_uniform.json", "reinjection.json"))
     assert all("is not built" in refused[k] for k in ("salt_column.json", "salt_co2_column.json", "salt_production.json"))
+
+
+def test_lenient_json(tmp_path):
+    """what Waiwera's JSON parser takes beyond the standard: "20." and ".5" as numbers, a comma before a closing bracket
+    (the reference's own test inputs have both, e.g. test/unit/data/flow_simulation/lhs/test_lhs.json); string contents
+    are left alone"""
+    path = str(tmp_path / "lenient.json")
+    open(path, "w").write('{"eos": {"name": "w", "temperature": 20.}, "a": [1., .5, 2.e5, 1.5e-3, -3.,], '
+                          '"title": "rate 20. kg/s, .5 bar, [1,]", "b": {"c": 1, },\n "d": [[0, 1.], [1., 2],], }')
+    d = ingest.load_json(path)
+    assert d == {"eos": {"name": "w", "temperature": 20.0}, "a": [1.0, 0.5, 2.0e5, 1.5e-3, -3.0],
+                 "title": "rate 20. kg/s, .5 bar, [1,]", "b": {"c": 1}, "d": [[0, 1.0], [1.0, 2]]}
+    ref = "/root/reference/test/unit/data/flow_simulation/lhs/test_lhs.json"
+    if os.path.exists(ref):
+        doc = ingest.load_json(ref)
+        assert doc["eos"] == {"name": "w", "temperature": 20.0} and doc["initial"]["primary"] == [2.0e5]
+    with pytest.raises(json.JSONDecodeError):
+        open(path, "w").write('{"a": [1, 2}')
+        ingest.load_json(path)

@@ -650,6 +650,25 @@ def expand_sources(doc, m, np_, zones=None):
     return out, table
 
 
+def load_json(path):
+    """a JSON input as Waiwera's parser (fson) accepts it: standard JSON, and also numbers written "20." or ".5" and a
+    comma before a closing bracket -- decks written for the reference contain these (its own test inputs do)"""
+    import re
+    text = open(path).read()
+    try:
+        return json.loads(text)
+    except json.JSONDecodeError:
+        pass
+    parts = re.split(r'("(?:\\.|[^"\\])*")', text)
+    for i in range(0, len(parts), 2):                         # the segments outside string literals
+        seg = parts[i]
+        seg = re.sub(r"(?<![\w.])(\d+)\.(?![\d])", r"\1.0", seg)
+        seg = re.sub(r"(?<![\w.])\.(\d)", r"0.\1", seg)
+        seg = re.sub(r",(\s*[}\]])", r"\1", seg)
+        parts[i] = seg
+    return json.loads("".join(parts))
+
+
 class Problem:
     """what load() returns: mesh, initial state, boundary values, sources, tracers, time stepping"""
 
@@ -657,7 +676,7 @@ class Problem:
 def load(path, mod=None, mesh_path=None):
     """Reads <path> (Waiwera JSON input) and the gmsh mesh it names.  mod: waiwera_b200.flow (see make_params),
     None: no parameter struct."""
-    doc = json.load(open(path))
+    doc = load_json(path)
     if doc.get("network"):
         raise NotImplementedError("%s: source networks (\"network\": groups, reinjectors) are not built" % path)
     eos_name = doc.get("eos", "we")
