@@ -792,3 +792,57 @@ def test_lenient_json(tmp_path):
     with pytest.raises(json.JSONDecodeError):
         open(path, "w").write('{"a": [1, 2}')
         ingest.load_json(path)
+
+
+def test_gravity_known_answers(tmp_path):
+    """setup_gravity (test/unit/src/flow_simulation_test.F90:162-222): none by default in 2-D, a number acts along -y in
+    2-D and -z in 3-D (default 9.8 there), a vector is taken as it is"""
+    mesh2d = json.load(open(os.path.join(INP, "problem5a.input.json")))["mesh"]["filename"]          # the reference's 2D.msh
+    for mesh, given, expect in ((mesh2d, "absent", [0.0, 0.0, 0.0]), (mesh2d, None, [0.0, 0.0, 0.0]), (mesh2d, 9.81, [0.0, -9.81, 0.0]),
+                                (mesh2d, [-9.8, 0.0], [-9.8, 0.0, 0.0]), ("block3.exo", "absent", [0.0, 0.0, -9.8]),
+                                ("block3.exo", 9.80665, [0.0, 0.0, -9.80665]), ("block3.exo", [0.0, 0.0, -9.81], [0.0, 0.0, -9.81])):
+        import shutil
+        shutil.copy(os.path.join(INITIAL if mesh.endswith(".exo") else INP, mesh), str(tmp_path / mesh))
+        doc = {"mesh": {"filename": mesh}}
+        if given != "absent":
+            doc["gravity"] = given
+        path = str(tmp_path / "g.json")
+        json.dump(doc, open(path, "w"))
+        p = ingest.load(path)
+        assert list(p.mesh.gravity) == expect, (mesh, given, p.mesh.gravity)
+        # gravity_normal of every face = gravity . normal
+        assert np.allclose(p.mesh.face_geom[:, 7], p.mesh.face_geom[:, 4:7] @ np.array(expect), atol=1e-12)
+
+
+def test_flux_face_counts_known_answers(tmp_path):
+    """setup_flux (test/unit/src/flow_simulation_test.F90:241-385): the number of faces that carry a flux -- interior
+    faces, one per boundary face named in the input, one per MINC matrix cell -- on the reference's 2-D, column, 3-D
+    (netCDF-4 ExodusII) and hybrid meshes"""
+    import shutil
+    mesh2d = json.load(open(os.path.join(INP, "problem5a.input.json")))["mesh"]["filename"]          # the reference's 2D.msh
+    rock = {"types": [{"name": "rock", "zones": "all"}]}
+    minc = lambda zone: {"rock": {"zones": zone, "fracture": {"type": "rock"}, "matrix": {"type": "rock"}}, "geometry": {"fracture": {"volume": 0.1}}}
+    cases = [
+        (mesh2d, {}, None, None, 172),
+        (mesh2d, {}, [{"faces": {"cells": [0, 12, 24, 36, 48, 60, 72, 84], "normal": [-1, 0]}}], None, 180),
+        (mesh2d, {}, [{"faces": {"cells": list(range(84, 96)), "normal": [0, 1]}}], None, 184),
+        ("col10.exo", {}, None, None, 9),
+        ("col10.exo", {}, [{"faces": {"cells": [0], "normal": [0, 0, 1]}}], None, 10),
+        ("3D.exo", {}, None, None, 75),
+        ("3D.exo", {}, [{"faces": {"cells": list(range(12)), "normal": [0, 0, 1]}}], None, 87),
+        ("3D.exo", {"zones": {"all": {"-": None}}, "minc": minc("all")}, None, rock, 75 + 36),
+        ("3D.exo", {"zones": {"all": {"-": None}, "top": {"z": [-125, 0]}}, "minc": minc("top")}, None, rock, 75 + 24),
+        ("hybrid10.ascii.msh", {}, None, None, 12),
+        ("hybrid10.ascii.msh", {}, [{"faces": {"cells": [6, 9], "normal": [0, 0, 1]}}], None, 14),
+    ]
+    for mesh, mspec, boundaries, rocks, nfaces in cases:
+        shutil.copy(os.path.join(INITIAL if mesh.endswith(".exo") else INP, mesh), str(tmp_path / mesh))
+        doc = {"mesh": dict(mspec, filename=mesh)}
+        if boundaries:
+            doc["boundaries"] = boundaries
+        if rocks:
+            doc["rock"] = rocks
+        path = str(tmp_path / "f.json")
+        json.dump(doc, open(path, "w"))
+        m = ingest.load(path).mesh
+        assert m.nface == nfaces, (mesh, mspec.keys(), boundaries is not None, m.nface, nfaces)

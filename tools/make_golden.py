@@ -292,7 +292,7 @@ def h5_fixtures():
     # test/unit/src/initial_test.F90: the column meshes and the restart files (full, minimal, minimal on a MINC mesh)
     ini = os.path.join(os.path.dirname(OUT), "initial")
     os.makedirs(ini, exist_ok=True)
-    for src in ("mesh/block3.exo", "mesh/col100.exo", "mesh/col10.exo", "initial/fluid.h5", "initial/fluid_minimal.h5", "initial/fluid_minimal_minc.h5",
+    for src in ("mesh/3D.exo", "mesh/block3.exo", "mesh/col100.exo", "mesh/col10.exo", "initial/fluid.h5", "initial/fluid_minimal.h5", "initial/fluid_minimal_minc.h5",
                 "flow_simulation/mesh/4x3_2d.exo"):          # the last one: the mesh of source_setup_test.F90
         shutil.copy(os.path.join("/root/reference/test/unit/data", src), os.path.join(ini, os.path.basename(src)))
     # the restart file the tracer doublet input names ("initial": {"filename": "doublet_ss.h5"}), next to that input
