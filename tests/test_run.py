@@ -159,3 +159,14 @@ def test_driver_runs_a_tracer_deck(wo, tmp_path):
         rows = np.array(rows)[:10]
         assert np.abs(X[k + 1] - rows[:, 4]).max() < 2e-6
         assert np.abs(h["cell_fields/fluid_pressure"][k + 1] - rows[:, 0]).max() / rows[:, 0].max() < 1e-3
+
+
+def test_info_describes_a_deck_without_a_gpu(capsys):
+    run.main([os.path.join(INP, "minc_3d_base.input.json"), "--info"])
+    d = json.loads(capsys.readouterr().out)
+    assert (d["eos"], d["dimension"], d["cells"], d["original_cells"], d["minc_levels"]) == ("we", 3, 161, 125, 2)
+    assert (d["boundary_faces"], d["sources"], d["source_controls"], d["gravity"]) == (25, 26, 1, [0.0, 0.0, -9.8])
+    assert d["faces"] == 300 + 36 + 25 and d["initial"] == "given" and d["stop"] == 126100000
+    run.main([os.path.join(INP, "deliv_delg_pwb_table.input.json"), "--info"])
+    d = json.loads(capsys.readouterr().out)
+    assert d["pressure_tables"] == 1 and d["cells"] == 10 and d["tracers"] == []

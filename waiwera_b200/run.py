@@ -255,12 +255,33 @@ def write_results(p, output_path, times, fluids, sources, tracers=None):
                         tracer_history=[tracers[i] for i in idx] if tracers else None)
 
 
+def describe(path):
+    """what ingest makes of a deck, without touching the GPU: a dictionary for `--info`"""
+    p = ingest.load(path)
+    m = p.mesh
+    n0 = getattr(m, "minc_cells", m.ninterior)
+    tm = p.time or {}
+    return {"input": os.path.abspath(path), "eos": p.eos, "dimension": int(m.dim), "cells": int(m.ninterior),
+            "original_cells": int(n0), "minc_levels": int(m.minc_levels), "faces": int(m.nface),
+            "boundary_faces": int(len(p.boundary_region)), "gravity": [float(g) for g in m.gravity],
+            "initial": "given" if p.y is not None else "restart file not found",
+            "sources": int(len(p.source_cells)), "source_controls": len(p.source_controls),
+            "separators": len(p.source_separators), "recharge": len(p.source_recharge),
+            "pressure_tables": len(p.source_pressure_tables), "rate_tables": len(p.source_tables),
+            "tracers": [t.get("name") for t in p.tracers], "stop": tm.get("stop"),
+            "step_method": (tm.get("step") or {}).get("method", "beuler")}
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("input")
     ap.add_argument("-o", "--output")
     ap.add_argument("-q", "--quiet", action="store_true")
+    ap.add_argument("--info", action="store_true", help="read the deck, print what was understood and stop (no GPU needed)")
     a = ap.parse_args(argv)
+    if a.info:
+        print(json.dumps(describe(a.input)))
+        return
     path = run_file(a.input, a.output, log=None if a.quiet else lambda s: print(s, file=sys.stderr))
     print(json.dumps({"output": path}))
 
