@@ -170,3 +170,30 @@ def test_info_describes_a_deck_without_a_gpu(capsys):
     run.main([os.path.join(INP, "deliv_delg_pwb_table.input.json"), "--info"])
     d = json.loads(capsys.readouterr().out)
     assert d["pressure_tables"] == 1 and d["cells"] == 10 and d["tracers"] == []
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD if not c.startswith("_") and c != "columns"])
+def test_driver_reproduces_every_single_well_deck(wo, case):
+    """all 14 decks of test_benchmarks_from_input.py through run.run (the driver a user gets) instead of the tests' own
+    stepping helper: same agreement with the AUTOUGH2 listings"""
+    from test_benchmarks_from_input import errors, tolerance
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=wo)
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for k in range(len(p.boundary_region)):
+        assert f.set_boundary(int(m.boundary["ghost_cells"][k]), int(m.boundary["interior_cells"][k]),
+                              p.boundary_primary[k], int(p.boundary_region[k])) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    f.set_source_components(p.source_injection_components, p.source_production_components)
+    assert f.fluid_init(p.y, p.region) == 0
+    sim = OracleSim(wo, f, newton_opts(wo, p))
+    times, fluids, sources, y = run.run(p, sim)
+    sim.destroy()
+    n = m.ninterior
+    hist = [(t, np.stack([fl[:n, 0], fl[:n, 1], fl[:n, output.fluid_field_column("we", "vapour_saturation")]], 1), 0.0)
+            for t, fl in zip(times[1:], fluids[1:])]
+    rates = np.array([s[:, 1] for s in sources[1:]])
+    err, herr, er = errors(case, hist, rates)
+    tl = tolerance(case)
+    assert all(e < tl[0] for e in err) and all(e < tl[1] for e in herr) and er < tl[2], (case, err, herr, er)
