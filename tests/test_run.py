@@ -197,3 +197,31 @@ def test_driver_reproduces_every_single_well_deck(wo, case):
     err, herr, er = errors(case, hist, rates)
     tl = tolerance(case)
     assert all(e < tl[0] for e in err) and all(e < tl[1] for e in herr) and er < tl[2], (case, err, herr, er)
+
+
+@pytest.mark.parametrize("case", ["problem2c", "problem4", "problem5b", "problem6"])
+def test_driver_reproduces_mis_problems(wo, case):
+    """MIS problems with a flashing front and step cuts (2c), drainage under gravity (4), a rate table with re-injection
+    (5b) and the 3-D field with adaptive steps (6) through run.run: the agreement of test_mis_problems.py"""
+    import test_mis_problems as T
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=wo)
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for k in range(len(p.boundary_region)):
+        assert f.set_boundary(int(m.boundary["ghost_cells"][k]), int(m.boundary["interior_cells"][k]),
+                              p.boundary_primary[k], int(p.boundary_region[k])) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    f.set_source_components(p.source_injection_components, p.source_production_components)
+    assert f.fluid_init(p.y, p.region) == 0
+    sim = OracleSim(wo, f, newton_opts(wo, p))
+    times, fluids, sources, y = run.run(p, sim)
+    sim.destroy()
+    n = m.ninterior
+    sv = output.fluid_field_column("we", "vapour_saturation")
+    cell = int(p.source_cells[0])
+    hist = [(t, np.stack([fl[:n, 0], fl[:n, 1], fl[:n, sv]], 1), run.production_enthalpy(fl[cell], 1, 2))
+            for t, fl in zip(times[1:], fluids[1:])]
+    etab, ehist, eh = T.compare(case, hist)
+    tol = T.TOL[case]
+    assert all(e < tl for e, tl in zip(etab, tol[:3])) and all(e < tl for e, tl in zip(ehist, tol[:3])) and eh < tol[3], (case, etab, ehist, eh)
