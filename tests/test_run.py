@@ -225,3 +225,24 @@ def test_driver_reproduces_mis_problems(wo, case):
     etab, ehist, eh = T.compare(case, hist)
     tol = T.TOL[case]
     assert all(e < tl for e, tl in zip(etab, tol[:3])) and all(e < tl for e, tl in zip(ehist, tol[:3])) and eh < tol[3], (case, etab, ehist, eh)
+
+
+@pytest.mark.parametrize("case", ["infiltration", "heat_pipe"])
+def test_driver_reproduces_the_air_water_benchmarks(wo, case):
+    """eos wae decks (ncg/infiltration, ncg/heat_pipe) through run.run: the agreement of test_wae_benchmarks.py"""
+    import test_wae_benchmarks as W
+    from util import wge_fields
+    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=wo)
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for k in range(len(p.boundary_region)):
+        assert f.set_boundary(int(m.boundary["ghost_cells"][k]), int(m.boundary["interior_cells"][k]),
+                              p.boundary_primary[k], int(p.boundary_region[k])) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    assert f.fluid_init(p.y, p.region) == 0
+    sim = OracleSim(wo, f, W.newton_opts(wo, p))
+    times, fluids, sources, y = run.run(p, sim)
+    regions = f.regions()[:m.ninterior].copy()
+    sim.destroy()
+    W.check(case, [(t, wge_fields(fl, m.ninterior), 0.0) for t, fl in zip(times[1:], fluids[1:])], regions)
