@@ -149,3 +149,63 @@ def test_partition_offsets_and_faces():
                 assert np.array_equal(m.natural[m.send_idx[m.send_ptr[n]:m.send_ptr[n + 1]]],
                                       o.natural[o.recv_idx[o.recv_ptr[k]:o.recv_ptr[k + 1]]])
         assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("deck,world", [("minc_3d_refined", 2), ("minc_3d_refined", 3), ("minc_3d_refined", 4), ("problem5b", 2),
+                                        ("problem6", 8)])
+def test_unstructured_meshes_partition_like_the_boxes(deck, world):
+    """an ingested deck (3-D hybrid mesh with a MINC zone and boundary faces; a 2-D areal mesh; the 125-cell 3-D field
+    on 8 ranks) split by mesh.coordinate_owner: balanced, matrix cells with their fracture cell, halo plans of
+    neighbouring ranks agree, and the function evaluation of every rank on its local mesh -- ghost values filled as the
+    halo exchange would -- gives the rows of the serial one (oracle, bit for bit apart from the order of the inflow sum)"""
+    from oracle import wo
+    from waiwera_b200 import ingest
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = ingest.load(os.path.join(here, "golden", "inputs", deck + ".input.json"), mod=wo)
+    gm = p.mesh
+    n = gm.ninterior
+    owner = wmesh.coordinate_owner(gm, world)
+    counts = np.bincount(owner, minlength=world)
+    assert counts.min() > 0 and counts.max() <= 1.35 * n / world + 3
+    if hasattr(gm, "minc_parent"):
+        assert np.array_equal(owner, owner[gm.minc_parent])
+    ms = [wmesh.partition(gm, owner, r, world) for r in range(world)]
+    assert sum(m.nowned for m in ms) == n
+    for m in ms:
+        for k, r in enumerate(m.neigh_rank):
+            o = ms[r]
+            j = list(o.neigh_rank).index(m.rank)
+            assert np.array_equal(m.natural[m.send_idx[m.send_ptr[k]:m.send_ptr[k + 1]]],
+                                  o.natural[o.recv_idx[o.recv_ptr[j]:o.recv_ptr[j + 1]]])
+    npv = p.np
+
+    def evaluate(m, y, region, boundary_rows, ghost_fluid=None):
+        f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                    m.cell_geom.reshape(-1), m.rock.reshape(-1))
+        for gl, il, row in boundary_rows:
+            assert f.set_boundary(int(gl), int(il), p.boundary_primary[row], int(p.boundary_region[row])) == 0
+        assert f.fluid_init(y, region) == 0
+        if ghost_fluid is not None:          # the fluid vector's global-to-local scatter (the halo exchange)
+            f.fluid()[m.nowned:m.ninterior] = ghost_fluid
+        err, L0 = f.lhs(y)
+        assert err == 0
+        err, lhs, rhs, r = f.residual(y, L0, 1.0e5)
+        assert err == 0
+        return lhs, rhs, f.fluid()[:m.ninterior].copy()
+
+    rows = [(gm.boundary["ghost_cells"][k], gm.boundary["interior_cells"][k], k) for k in range(len(p.boundary_region))]
+    lhs_g, rhs_g, fluid_g = evaluate(gm, p.y, p.region, rows)
+    yg = p.y.reshape(n, npv)
+    row_of_ghost = {int(g): k for k, g in enumerate(gm.boundary.get("ghost_cells", []))}
+    for m in ms:
+        y = np.ascontiguousarray(yg[m.natural]).reshape(-1)          # owned + partition ghosts, as after the halo exchange
+        region = np.ascontiguousarray(p.region[m.natural])
+        brows = []
+        if m.boundary:
+            brows = [(gl, il, row_of_ghost[int(gg)]) for gl, il, gg in
+                     zip(m.boundary["ghost_cells"], m.boundary["interior_cells"], m.boundary["global_ghost"])]
+        lhs, rhs, _ = evaluate(m, y, region, brows, ghost_fluid=fluid_g[m.natural[m.nowned:m.ninterior]])
+        own = m.natural[:m.nowned]
+        assert np.array_equal(lhs.reshape(-1, npv)[:m.nowned], lhs_g.reshape(-1, npv)[own])
+        a, b = rhs.reshape(-1, npv)[:m.nowned], rhs_g.reshape(-1, npv)[own]
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()

@@ -175,6 +175,43 @@ def box_owner(mesh, parts):
     return (a + px * (b + py * c)).astype(np.int32)
 
 
+def coordinate_owner(mesh, nranks):
+    """owner rank of each interior cell of ANY serial mesh (unstructured, from ingest): recursive coordinate bisection
+    of the cell centroids along the longest extent, sizes balanced by cell counts, ranks split as evenly as nranks allows.
+    The cells of a MINC mesh follow their fracture cell (src/mesh.F90:2201-2282: matrix cells are never separated from
+    it), and count towards its weight."""
+    n = mesh.ninterior
+    parent = getattr(mesh, "minc_parent", None)
+    if parent is None and mesh.minc_levels > 0 and mesh.minc_base > 0:
+        parent = np.tile(np.arange(mesh.minc_base), mesh.minc_levels + 1)
+    if parent is None:
+        parent = np.arange(n)
+    parent = np.asarray(parent)[:n]
+    base = np.flatnonzero(parent == np.arange(n))
+    weight = np.bincount(parent, minlength=n)[base].astype(float)
+    xyz = mesh.cell_geom[base, :3]
+    own_base = np.zeros(len(base), np.int32)
+
+    def split(idx, r0, nr):
+        if nr == 1 or len(idx) == 0:
+            own_base[idx] = r0
+            return
+        left = nr // 2
+        ext = xyz[idx].max(0) - xyz[idx].min(0)
+        ax = int(np.argmax(ext))
+        order = idx[np.lexsort((idx, xyz[idx, ax]))]
+        cw = np.cumsum(weight[order])
+        k = int(np.searchsorted(cw, cw[-1] * left / nr, side="left")) + 1
+        k = min(max(k, 1), len(order) - 1) if len(order) > 1 else len(order)
+        split(order[:k], r0, left)
+        split(order[k:], r0 + left, nr - left)
+
+    split(np.arange(len(base)), 0, int(nranks))
+    where = np.zeros(n, np.int64)
+    where[base] = np.arange(len(base))
+    return own_base[where[parent]].astype(np.int32)
+
+
 def default_parts(nranks):
     return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(nranks, (1, 1, nranks))
 
