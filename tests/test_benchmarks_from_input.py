@@ -92,26 +92,3 @@ def test_oracle_runs_reference_input_to_the_autough2_answer(wo, case):
     assert all(e < tl[0] for e in err), (case, "last output", err)
     assert all(e < tl[1] for e in herr), (case, "history", herr)
     assert er < tl[2], (case, "rates", er)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("case", ["deliv_delw", "deliv_delg_limit"])
-def test_cuda_path_runs_reference_input(wo, case):
-    """the two deliverability decks with limiters on the separated water / steam flow (not among the hand-built cases of
-    test_deliverability.py) through the CUDA path: the reference's acceptance tolerances against the listing, and the
-    oracle's run"""
-    from waiwera_b200 import flow
-    p_ref, hist_ref, y_ref, rates_ref = run_oracle(wo, case)
-    p = ingest.load(os.path.join(INP, case + ".input.json"), mod=flow)
-    m = p.mesh
-    sim = flow.FlowSimulation(p.params, m)
-    assert sim.set_boundaries(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region) == 0
-    assert sim.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies) == 0
-    assert sim.fluid_init(p.y, p.region) == 0
-    rates = []
-    hist, y = run_input(p, sim, opts=newton_opts(flow, p), controls=True, on_step=lambda t, s: rates.append(np.array(s.source_rates())))
-    err, herr, er = errors(case, hist, np.array(rates))
-    assert all(e < 5e-3 for e in err) and all(e < 1e-2 for e in herr) and er < 1e-2, (err, herr, er)
-    assert len(hist) == len(hist_ref)
-    assert np.abs(y - y_ref).max() / np.abs(y_ref).max() < 1e-4
-    sim.destroy()

@@ -88,25 +88,3 @@ def test_oracle_runs_reference_input_to_the_autough2_answer(wo, case):
     assert all(e < tl for e, tl in zip(herr, (2e-4, 5e-5, 6e-4))), (case, "history", herr)
     assert eh < 5e-4 and er < 1.5e-3, (case, "well enthalpy / rate", eh, er)
     assert len(hist) == len(GOLD[case]["times"])
-
-
-@pytest.mark.gpu
-def test_cuda_path_runs_reference_input(wo):
-    """the base case through the CUDA path, to the reference's own acceptance tolerance (1e-2) and against the oracle run"""
-    from waiwera_b200 import flow
-    p_ref, hist_ref, y_ref, rates_ref = run_oracle(wo, "base")
-    p = ingest.load(os.path.join(INP, "minc_3d_base.input.json"), mod=flow)
-    m = p.mesh
-    sim = flow.FlowSimulation(p.params, m)
-    assert sim.set_boundaries(m.boundary["ghost_cells"], m.boundary["interior_cells"], p.boundary_primary, p.boundary_region) == 0
-    assert sim.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies) == 0
-    assert sim.fluid_init(p.y, p.region) == 0
-    well = len(p.source_cells) - 1
-    rates = []
-    hist, y = run_input(p, sim, opts=newton_opts(flow, p), controls=True, well=well,
-                        on_step=lambda t, s: rates.append(s.source_rates()[well]))
-    err, herr, eh, er = errors("base", hist, np.array(rates))
-    assert all(e < 1e-2 for e in err + herr) and eh < 1e-2 and er < 1e-2, (err, herr, eh, er)
-    assert len(hist) == len(hist_ref)
-    assert np.abs(y - y_ref).max() / np.abs(y_ref).max() < 1e-3
-    sim.destroy()

@@ -80,23 +80,6 @@ def test_driver_with_the_checker_as_engine(wo, tmp_path, case):
     assert h5lite.H5File(path)["time"].reshape(-1).tolist() == [times[0], times[-1]]
 
 
-@pytest.mark.gpu
-def test_command_line_on_the_cuda_path(tmp_path):
-    """python -m waiwera_b200.run deck.json -o out.h5, as a user would type it"""
-    import shutil
-    import subprocess
-    import sys
-    case = "deliv_delg_flow"
-    for fn in (case + ".input.json", "gdeliv.ascii.msh"):
-        shutil.copy(os.path.join(INP, fn), str(tmp_path / fn))
-    out = str(tmp_path / "out.h5")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "waiwera_b200.run", str(tmp_path / (case + ".input.json")), "-o", out, "-q"],
-                       cwd=root, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
-    assert json.loads(r.stdout.strip().splitlines()[-1])["output"] == out
-    check_output_file(case, out, nsteps_expected=len(GOLD[case]["times"]) - 1)
-
 
 class OracleTracerEngine(OracleSim):
     """OracleSim + the tracer calls of flow.FlowSimulation (the checker keeps the boundary ghost rows inside its tracer
