@@ -846,3 +846,23 @@ def test_flux_face_counts_known_answers(tmp_path):
         json.dump(doc, open(path, "w"))
         m = ingest.load(path).mesh
         assert m.nface == nfaces, (mesh, mspec.keys(), boundaries is not None, m.nface, nfaces)
+
+
+def test_array_version_of_the_3d_mesh_builder_equals_the_loop(tmp_path):
+    """build_mesh for 3-D meshes runs as array operations over all cells and faces (a million cells in half a minute
+    instead of twenty): same faces in the same order and the same geometry, to rounding, as the cell-by-cell loop on the
+    reference's 3-D meshes (hexahedra + wedges, netCDF-4 and classic ExodusII, gmsh), with a rotated permeability tensor"""
+    meshes = [ingest.read_exodus(os.path.join(HERE, "golden", "h5", "gminc_3d_refined.exo")),
+              ingest.read_exodus(os.path.join(INITIAL, "3D.exo")), ingest.read_exodus(os.path.join(INITIAL, "col100.exo")),
+              ingest.read_gmsh(os.path.join(INP, "hybrid10.ascii.msh"))]
+    for nodes, elems in meshes:
+        for angle in (0.0, 0.3):
+            a, ea = ingest.build_mesh(nodes, elems, permeability_angle=angle)
+            b, eb = ingest.build_mesh(nodes, elems, permeability_angle=angle, vectorized=False)
+            assert np.array_equal(a.face_cells, b.face_cells)
+            assert np.allclose(a.cell_geom, b.cell_geom, rtol=1e-14, atol=1e-9)
+            assert np.allclose(a.face_geom, b.face_geom, rtol=1e-13, atol=1e-9) and np.array_equal(a.face_geom[:, 11], b.face_geom[:, 11])
+            assert len(ea) == len(eb)
+            for x, y in zip(ea, eb):
+                assert x[0] == y[0] and np.allclose(x[1], y[1], rtol=1e-13, atol=1e-9) and np.isclose(x[2], y[2], rtol=1e-13)
+                assert np.allclose(x[3], y[3], atol=1e-13) and np.isclose(x[4], y[4], rtol=1e-12, atol=1e-9)

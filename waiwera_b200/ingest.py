@@ -245,9 +245,116 @@ def _cell3_geometry(nodes, faces):
     return cen / vol, vol
 
 
-def build_mesh(nodes, elems, thickness=1.0, radial=False, gravity=None, permeability_angle=0.0):
+def _seq_mean(p):
+    """mean over axis 1 of [n, k, 3] with the additions in index order (what ndarray.mean does for one small polygon)"""
+    s = p[:, 0].copy()
+    for k in range(1, p.shape[1]):
+        s = s + p[:, k]
+    return s / p.shape[1]
+
+
+def _build_mesh3(nodes, cells, g, permeability_angle):
+    """the 3-D part of build_mesh with numpy array operations over all cells / faces at once (the loop version takes
+    20 minutes per million cells): the same formulas in the same order -- cell centroid and volume from pyramids over
+    the face triangles about the vertex mean, face centroid / area / normal from the triangle fan, faces matched through
+    their sorted node numbers -- and the same ordering conventions: face (c1, c2) with c1 < c2 oriented from c1, interior
+    faces sorted by (c1, c2), exterior faces in the order cells and their local faces are walked.  Returns
+    (cell_geom, face_cells, face_geom, exterior)."""
+    nodes = np.asarray(nodes, float)
+    nc = len(cells)
+    types = np.array([t for t, _ in cells])
+    cell_geom = np.zeros((nc, 4))
+    K, F, C, L, order_key = [], [], [], [], []
+    big = np.iinfo(np.int64).max
+    for t in np.unique(types):
+        idx = np.flatnonzero(types == t)
+        conn = np.array([cells[c][1] for c in idx], np.int64)
+        c0 = _seq_mean(nodes[np.sort(conn, axis=1)])               # mean over the sorted unique node numbers
+        vol, cen = np.zeros(len(idx)), np.zeros((len(idx), 3))
+        for lf, face in enumerate(_FACES3[int(t)]):
+            fn = conn[:, list(face)]
+            pts = nodes[fn]
+            fcen = _seq_mean(pts)
+            nfn = len(face)
+            for k in range(nfn):
+                a, b = pts[:, k], pts[:, (k + 1) % nfn]
+                v = np.abs((np.cross(a - c0, b - c0) * (fcen - c0)).sum(1)) / 6.0
+                vol = vol + v
+                cen = cen + v[:, None] * (c0 + a + b + fcen) / 4.0
+            key = np.full((len(idx), 4), big, np.int64)
+            key[:, :nfn] = np.sort(fn, axis=1)
+            ordered = np.full((len(idx), 4), -1, np.int64)
+            ordered[:, :nfn] = fn
+            K.append(key)
+            F.append(ordered)
+            C.append(idx)
+            L.append(np.full(len(idx), nfn))
+            order_key.append(idx * 8 + lf)                          # the order cells and local faces are walked in
+        cell_geom[idx, :3] = cen / vol[:, None]
+        cell_geom[idx, 3] = vol
+    K, F, C, L, order_key = np.concatenate(K), np.concatenate(F), np.concatenate(C), np.concatenate(L), np.concatenate(order_key)
+    walk = np.argsort(order_key, kind="stable")
+    K, F, C, L = K[walk], F[walk], C[walk], L[walk]
+    M = len(K)
+    _, inv, counts = np.unique(K, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.reshape(-1)
+    assert counts.max() <= 2, "a face with more than two cells"
+    first = np.full(len(counts), M, np.int64)
+    np.minimum.at(first, inv, np.arange(M))
+    last = np.zeros(len(counts), np.int64)
+    np.maximum.at(last, inv, np.arange(M))
+    faces = np.argsort(first, kind="stable")                        # faces in the order they are first met
+    first, last, counts = first[faces], last[faces], counts[faces]
+    c1 = C[first]
+    cen, area, nrm = np.zeros((len(first), 3)), np.zeros(len(first)), np.zeros((len(first), 3))
+    for nfn in (3, 4):
+        sel = np.flatnonzero(L[first] == nfn)
+        if len(sel) == 0:
+            continue
+        pts = nodes[F[first[sel], :nfn]]
+        p0 = _seq_mean(pts)
+        an, cc, atot = np.zeros((len(sel), 3)), np.zeros((len(sel), 3)), np.zeros(len(sel))
+        for k in range(nfn):
+            a, b = pts[:, k], pts[:, (k + 1) % nfn]
+            n = 0.5 * np.cross(a - p0, b - p0)
+            an = an + n
+            ar = np.sqrt((n * n).sum(1))
+            cc = cc + ar[:, None] * (p0 + a + b) / 3.0
+            atot = atot + ar
+        ar = np.sqrt((an * an).sum(1))
+        cen[sel], area[sel], nrm[sel] = cc / atot[:, None], ar, an / ar[:, None]
+    flip = ((cen - cell_geom[c1, :3]) * nrm).sum(1) < 0.0
+    nrm[flip] = -nrm[flip]                                          # outward from the first owner
+    inner = np.flatnonzero(counts == 2)
+    outer = np.flatnonzero(counts == 1)
+    a1, a2 = c1[inner], C[last[inner]]
+    assert (a1 < a2).all()
+    srt = np.lexsort((a2, a1))
+    inner, a1, a2 = inner[srt], a1[srt], a2[srt]
+    fcn, fnr, far = cen[inner], nrm[inner], area[inner]
+    # face%calculate_distances (src/face.F90:230-250)
+    d1 = ((fcn - cell_geom[a1, :3]) * fnr).sum(1)
+    d2 = ((cell_geom[a2, :3] - fcn) * fnr).sum(1)
+    d12 = ((cell_geom[a2, :3] - cell_geom[a1, :3]) * fnr).sum(1)
+    corr = d12 / (d1 + d2)
+    fg = np.zeros((len(inner), 12))
+    fg[:, 0], fg[:, 1], fg[:, 2], fg[:, 3] = far, d1 * corr, d2 * corr, d12
+    fg[:, 4:7], fg[:, 7], fg[:, 8:11] = fnr, fnr @ g, fcn
+    rot = fnr.copy()
+    if permeability_angle != 0.0:
+        c, s_ = np.cos(permeability_angle), np.sin(permeability_angle)
+        rot[:, :2] = fnr[:, :2] @ np.array([[c, s_], [-s_, c]]).T
+    fg[:, 11] = np.argmax(np.abs(rot), axis=1) + 1
+    fc = np.stack([a1, a2], 1).astype(np.int32)
+    dist = ((cen[outer] - cell_geom[c1[outer], :3]) * nrm[outer]).sum(1)
+    exterior = [(int(c1[k]), cen[k].copy(), float(area[k]), nrm[k].copy(), float(d)) for k, d in zip(outer, dist)]
+    return cell_geom, fc, fg, exterior
+
+
+def build_mesh(nodes, elems, thickness=1.0, radial=False, gravity=None, permeability_angle=0.0, vectorized=True):
     """Mesh (waiwera_b200.mesh.Mesh) of the top-dimensional elements.  Returns (mesh, exterior) where exterior is a
-    list of (cell, face centroid, area, outward unit normal, distance) of the boundary faces, for boundary ghosts."""
+    list of (cell, face centroid, area, outward unit normal, distance) of the boundary faces, for boundary ghosts.
+    3-D meshes go through the array version _build_mesh3 (vectorized=False: the cell-by-cell loop it was checked against)."""
     dim = max(_GMSH[t][0] for t, _ in elems)
     cells = [(t, n) for t, n in elems if _GMSH[t][0] == dim]
     nc = len(cells)
@@ -259,6 +366,13 @@ def build_mesh(nodes, elems, thickness=1.0, radial=False, gravity=None, permeabi
         g[dim - 1] = -float(gravity)
     else:
         g[:len(gravity)] = gravity
+    if dim == 3 and vectorized:
+        cell_geom, fc, fg, exterior = _build_mesh3(nodes, cells, g, permeability_angle)
+        m = wmesh.Mesh(ncell=nc, ninterior=nc, nowned=nc, face_cells=np.ascontiguousarray(fc), face_geom=np.ascontiguousarray(fg),
+                       cell_geom=np.ascontiguousarray(cell_geom), rock=wmesh.default_rock(nc, None, heterogeneous=False),
+                       dims=(nc, 1, 1), natural=np.arange(nc, dtype=np.int64), ncell_global=nc)
+        m.gravity, m.dim, m.permeability_angle = g, dim, permeability_angle
+        return m, exterior
     cell_geom = np.zeros((nc, 4))
     facemap = {}                                           # sorted node tuple -> [(cell, ordered nodes)]
     for c, (t, n) in enumerate(cells):
