@@ -1,5 +1,5 @@
-"""GPU cases written after round 2's GPU budget was spent: new host-side input paths onto kernels that
-the executed suite already covers.  They live in a file that sorts last so that an `-x` run reaches every other test
+"""GPU cases written after round 2's measurements (passed on a B200: profiles/r2z_zz_new_cases.log):
+new host-side input paths onto kernels that the rest of the suite already covers.  They live in a file that sorts last so that an `-x` run reaches every other test
 first.  The CPU halves of these tests (the same decks through the oracle) are in test_minc_production3d.py,
 test_benchmarks_from_input.py and test_run.py."""
 import json
