@@ -77,7 +77,7 @@ module waiwera_b200
   public :: wb_last_error, wb_version, wb_create, wb_destroy, wb_num_primary, wb_fluid_dof, wb_set_mesh, &
        wb_jacobian_pattern, wb_jacobian_get, wb_cell_faces_get, wb_comm_unique_id, wb_comm_init, wb_set_halo, wb_set_global_offset, &
        wb_comm_p2p_blob_size, wb_comm_p2p_export, wb_comm_p2p_open, wb_comm_p2p_enabled, wb_comm_p2p_disable, &
-       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_sources, wb_set_source_components, wb_set_source_controls, wb_set_source_recharge, wb_get_source_rates, wb_set_source_separators, wb_set_source_pressure_table, wb_separator_stage, wb_get_source_separated, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
+       wb_fluid_init, wb_set_boundary, wb_set_boundaries, wb_set_rock, wb_set_sources, wb_set_source_components, wb_set_source_controls, wb_set_source_recharge, wb_get_source_rates, wb_set_source_separators, wb_set_source_pressure_table, wb_separator_stage, wb_get_source_separated, wb_set_method, wb_get_fluid, wb_get_regions, wb_pre_iteration, &
        wb_pre_timestep, wb_pre_retry_timestep, wb_pre_eval, wb_cell_balances, wb_cell_inflows, wb_residual_be, &
        wb_max_scaled, wb_jacobian_be, wb_jacobian_be_colored, wb_fluid_transitions, wb_mat_create, &
        wb_mat_set_values, wb_mat_get_values, wb_mat_destroy, wb_jacobian_mat, wb_mat_mult, wb_pc_setup, wb_pc_refactor, wb_pc_apply, &
@@ -240,6 +240,14 @@ module waiwera_b200
        type(c_ptr), value :: ghost_cells, interior_cells, primary, region
        integer(c_int) :: ierr
      end function wb_set_boundaries
+
+     ! flow_simulation_update_rock_properties (src/flow_simulation.F90:2051-2089): rock records of the interior cells
+     function wb_set_rock(ctx, rock) bind(C, name="wb_set_rock") result(ierr)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr), value :: rock
+       integer(c_int) :: ierr
+     end function wb_set_rock
 
      ! source_network%assemble_cell_inflows for fixed-rate sources (src/source.F90:375-480)
      function wb_set_sources(ctx, n, cell, component, rate, enthalpy) bind(C, name="wb_set_sources") result(ierr)

@@ -174,6 +174,13 @@ int wb_set_boundary(wb_ctx *ctx, int ghost_cell, int interior_cell, const double
 /* the same for n boundary cells at once: primary[n*np], region[n] */
 int wb_set_boundaries(wb_ctx *ctx, int n, const int32_t *ghost_cells, const int32_t *interior_cells,
                       const double *primary, const int32_t *region);
+/* Rock records of the interior cells replaced between time steps: rock[8*ninterior] (host array), the layout of
+   wb_set_mesh.  Replaces flow_simulation_update_rock_properties (src/flow_simulation.F90:2051-2089), which
+   pre_try_timestep calls (:2040-2047, src/timestepper.F90:2333) to apply the permeability / porosity tables of
+   src/rock_control.F90:49-116 to the rock vector.  Boundary ghost cells keep the records copied at set-up
+   (src/mesh.F90:1189-1193; the reference's controls list interior cells only, src/rock_setup.F90:404-412).  The
+   per-face permeabilities are recomputed; fluid state, stored balances and the Jacobian pattern are untouched. */
+int wb_set_rock(wb_ctx *ctx, const double *rock);
 /* Fixed-rate sources / sinks (source%update_flow src/source.F90:375-480 and
    source_network%assemble_cell_inflows src/source_network.F90:296-355, called from cell_inflows
    src/flow_simulation.F90:1468-1473): rhs_i += flow / V_i.  cell: local owned cell; component: 1-based

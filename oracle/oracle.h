@@ -215,6 +215,7 @@ double *wo_flow_flux(wo_flow *f);           /* nface * (np+nmobile) */
 int wo_flow_fluid_init(wo_flow *f, const double *y, const int32_t *region);
 /* Dirichlet boundary ghost cell (mesh.F90:1185-1202): rock copied from interior cell, fluid from unscaled primary */
 int wo_flow_set_boundary(wo_flow *f, int ghost_cell, int interior_cell, const double *primary, int region);
+int wo_flow_set_rock(wo_flow *f, const double *rock);
 /* residual form of wo_residual_be: 0 backward Euler (timestepper.F90:345), 1 BDF2 (:378), 2 direct steady state (:431) */
 void wo_flow_set_method(wo_flow *f, int method, double dt_last, const double *lhs_last2);
 /* fixed-rate sources / sinks (src/source.F90:375-480): local owned cell, component (1-based; 0 = all mass

@@ -166,6 +166,7 @@ def lib():
         "wo_flow_flux": (c_dp, [vp]),
         "wo_flow_fluid_init": (i, [vp, c_dp, c_ip]),
         "wo_flow_set_boundary": (i, [vp, i, i, c_dp, i]),
+        "wo_flow_set_rock": (i, [vp, c_dp]),
         "wo_flow_set_sources": (None, [vp, i, c_ip, c_ip, c_dp, c_dp]),
         "wo_flow_set_source_components": (None, [vp, i, c_ip, c_ip]),
         "wo_flow_set_method": (None, [vp, i, d, c_dp]),
@@ -340,6 +341,10 @@ class Flow:
     def set_boundary(self, ghost, interior, primary, region):
         pr = np.ascontiguousarray(primary, np.float64)
         return self.L.wo_flow_set_boundary(self.h, ghost, interior, dp(pr), region)
+
+    def set_rock(self, rock):
+        r = np.ascontiguousarray(rock, np.float64).reshape(-1)
+        return self.L.wo_flow_set_rock(self.h, dp(r))
 
     def regions(self):
         r = np.zeros(self.ncell, np.int32)

@@ -553,6 +553,13 @@ int wo_flow_set_boundary(wo_flow *f, int ghost_cell, int interior_cell, const do
   return err;
 }
 
+/* update_rock_properties: flow_simulation.F90:2051-2089 (rock records of the interior cells replaced between time
+   steps by the table controls of rock_control.F90:49-116; boundary ghost cells keep their copies) */
+int wo_flow_set_rock(wo_flow *f, const double *rock) {
+  memcpy(f->rock, rock, (size_t)f->mesh.ninterior * 8 * sizeof(double));
+  return 0;
+}
+
 /* fluid_init: flow_simulation.F90:2171-2287 (regions supplied with the initial conditions) */
 int wo_flow_fluid_init(wo_flow *f, const double *y, const int32_t *region) {
   int err = 0;

@@ -7,9 +7,12 @@ CUDA path -- it only catches mistakes in a test's own set-up, arguments and tole
 
 Only tests that go through ingest.load(..., mod=flow) / flow.FlowSimulation and the source-control setters can run."""
 import importlib
+import inspect
 import os
+import pathlib
 import re
 import sys
+import tempfile
 import types
 
 import numpy as np
@@ -55,6 +58,9 @@ class ShimSimulation:
 
     def set_source_pressure_table(self, *a):
         return self.f.set_source_pressure_table(*a)
+
+    def set_rock(self, rock):
+        return self.f.set_rock(rock)
 
     def source_rates(self):
         return self.f.source_rates(self._n)
@@ -119,6 +125,8 @@ def main(argv):
         m = re.match(r"(\w+)\[(.*)\]$", name)
         args = [wo] + ([m.group(2)] if m else [])
         fn = getattr(importlib.import_module(mod), m.group(1) if m else name)
+        if "tmp_path" in inspect.signature(fn).parameters:
+            args.append(pathlib.Path(tempfile.mkdtemp()))
         fn(*args)
         print("ok", spec)
 

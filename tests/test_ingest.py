@@ -866,3 +866,44 @@ def test_array_version_of_the_3d_mesh_builder_equals_the_loop(tmp_path):
             for x, y in zip(ea, eb):
                 assert x[0] == y[0] and np.allclose(x[1], y[1], rtol=1e-13, atol=1e-9) and np.isclose(x[2], y[2], rtol=1e-13)
                 assert np.allclose(x[3], y[3], atol=1e-13) and np.isclose(x[4], y[4], rtol=1e-12, atol=1e-9)
+
+
+def test_rock_controls_known_answers(tmp_path):
+    """Rock permeabilities and porosities given as tables in time (test/unit/src/rock_control_test.F90:55-207 with
+    data/rock/test_rock_controls_table.json, restated here): a constant type, one with a one-column permeability table and
+    a porosity table on step interpolation, one with a three-column permeability table on linear interpolation; its
+    known answers at the start time and at t = 4500 s, to its tolerance of 1e-20 on permeabilities"""
+    import shutil
+    shutil.copy(os.path.join(INITIAL, "4x3_2d.exo"), str(tmp_path / "4x3_2d.exo"))
+    doc = {"mesh": {"filename": "4x3_2d.exo"}, "eos": {"name": "wce"},
+           "rock": {"types": [
+               {"name": "constant", "cells": [6, 7, 8], "permeability": 1e-13, "porosity": 0.1},
+               {"name": "scalar", "cells": [0, 1, 2],
+                "permeability": [[0, 10e-14], [3600, 7e-14], [7200, 4e-14], [9600, 3e-14]],
+                "porosity": [[0, 0.1], [4000, 0.05], [8000, 0.02]], "interpolation": "step"},
+               {"name": "array", "cells": [3, 4, 5],
+                "permeability": [[0, 1e-14, 2e-14, 3e-14], [4000, 7e-15, 8e-15, 9e-15], [5000, 1e-15, 2e-15, 3e-15]],
+                "porosity": 0.2}]}}
+    path = str(tmp_path / "rock_controls.json")
+    json.dump(doc, open(path, "w"))
+    p = ingest.load(path)
+    cells = {"constant": [6, 7, 8], "scalar": [0, 1, 2], "array": [3, 4, 5]}
+    expected = {0.0: {"constant": ([1e-13, 1e-13, 1e-13], 0.1), "scalar": ([1e-13, 1e-13, 1e-13], 0.1),
+                      "array": ([1e-14, 2e-14, 3e-14], 0.2)},
+                4500.0: {"constant": ([1e-13, 1e-13, 1e-13], 0.1), "scalar": ([7e-14, 7e-14, 7e-14], 0.05),
+                         "array": ([4e-15, 5e-15, 6e-15], 0.2)}}
+    assert len(p.rock_controls) == 3                       # scalar: permeability + porosity, array: permeability
+    for t, exp in expected.items():
+        rock = p.mesh.rock[:p.mesh.ninterior] if t == 0.0 else ingest.rock_at(p, t)
+        for name, (k, phi) in exp.items():
+            for c in cells[name]:
+                assert np.abs(rock[c, 0:3] - k).max() <= 1e-20, (t, name, rock[c, 0:3])
+                assert rock[c, 5] == phi, (t, name, rock[c, 5])
+        assert np.array_equal(rock[:, [3, 4, 6, 7]], np.tile([2.5, 2.5, 2200.0, 1000.0], (len(rock), 1)))
+    assert ingest.rock_at(p, 0.0) is not p.mesh.rock and np.array_equal(ingest.rock_at(p, 0.0), p.mesh.rock[:p.mesh.ninterior])
+    # beyond the tables: constant; an input without tables has nothing to update
+    late = ingest.rock_at(p, 1.0e9)
+    assert np.abs(late[0, 0:3] - 3e-14).max() <= 1e-20 and late[0, 5] == 0.02 and np.abs(late[3, 0:3] - [1e-15, 2e-15, 3e-15]).max() <= 1e-20
+    doc["rock"]["types"] = doc["rock"]["types"][:1]
+    json.dump(doc, open(path, "w"))
+    assert ingest.rock_at(ingest.load(path), 10.0) is None

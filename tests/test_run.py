@@ -229,3 +229,71 @@ def test_driver_reproduces_the_air_water_benchmarks(wo, case):
     regions = f.regions()[:m.ninterior].copy()
     sim.destroy()
     W.check(case, [(t, wge_fields(fl, m.ninterior), 0.0) for t, fl in zip(times[1:], fluids[1:])], regions)
+
+
+def _oracle_engine(wo, p):
+    m = p.mesh
+    f = wo.Flow(p.params, m.ncell, m.ninterior, m.nowned, m.face_cells.reshape(-1), m.face_geom.reshape(-1),
+                m.cell_geom.reshape(-1), m.rock.reshape(-1))
+    for k in range(len(p.boundary_region)):
+        assert f.set_boundary(int(m.boundary["ghost_cells"][k]), int(m.boundary["interior_cells"][k]),
+                              p.boundary_primary[k], int(p.boundary_region[k])) == 0
+    f.set_sources(p.source_cells, p.source_components, p.source_rates, p.source_enthalpies)
+    f.set_source_components(p.source_injection_components, p.source_production_components)
+    assert f.fluid_init(p.y, p.region) == 0
+    return OracleSim(wo, f, newton_opts(wo, p))
+
+
+def test_driver_updates_rock_tables_before_every_step(wo, tmp_path):
+    """Rock permeabilities / porosities given as tables in time (src/rock_control.F90, src/rock_setup.F90:383-463):
+    run.run sets the records of the time a step ends at before the step is tried (pre_try_timestep,
+    src/timestepper.F90:2333, src/flow_simulation.F90:2040-2089) while the balance of the last step keeps the porosity
+    it was computed with; checked against the same steps taken by hand, and against the run without tables"""
+    from rock_control_deck import write_deck
+    p = ingest.load(write_deck(tmp_path), mod=wo)
+    assert len(p.rock_controls) == 3
+    sim = _oracle_engine(wo, p)
+    times, fluids, sources, y = run.run(p, sim)
+    sim.destroy()
+    assert len(times) == 13
+    # by hand
+    sim = _oracle_engine(wo, p)
+    yh = p.y.copy()
+    sizes = p.time["step"]["size"]
+    t = 0.0
+    for k in range(12):
+        e, L0 = sim.lhs(yh)
+        assert e == 0
+        sim.pre_timestep()
+        assert sim.set_rock(ingest.rock_at(p, t + sizes[k])) == 0
+        run.apply_controls(p, sim, t, t + sizes[k])
+        assert sim.newton_solve(yh, L0, sizes[k]).reason > 0
+        t += sizes[k]
+    sim.destroy()
+    assert abs(times[-1] - t) <= 1e-9 * t and np.array_equal(y, yh)
+    # the tables matter: the same deck with the rock of the start time throughout
+    p0 = ingest.load(write_deck(tmp_path), mod=wo)
+    p0.rock_controls = []
+    sim = _oracle_engine(wo, p0)
+    _, _, _, y0 = run.run(p0, sim)
+    sim.destroy()
+    assert np.abs(y - y0).max() / np.abs(y0).max() > 1e-4
+
+
+def test_checker_set_rock_equals_a_fresh_mesh(wo):
+    """the checker's own set_rock (what the GPU test of wb_set_rock compares with): residual after replacing the rock
+    records == residual of an engine built on the new records, bit for bit"""
+    from util import make_problem, oracle_flow
+    m, y, region, prm = make_problem(wo, dims=(5, 4, 6), thermo=0, two_phase_layers=2, top_boundary=False)
+    rng = np.random.default_rng(5)
+    rock2 = m.rock.copy()
+    rock2[:, 0:3] *= 10.0 ** rng.uniform(-0.5, 0.5, (m.ncell, 3))
+    rock2[:, 5] = rng.uniform(0.05, 0.3, m.ncell)
+    a = oracle_flow(wo, m, prm, y, region)
+    _, L0 = a.lhs(y)
+    assert a.set_rock(rock2[:m.ninterior]) == 0
+    m.rock = rock2
+    b = oracle_flow(wo, m, prm, y, region)
+    ra, rb = a.residual(y * 1.00001, L0, 1.0e5), b.residual(y * 1.00001, L0, 1.0e5)
+    assert ra[0] == rb[0] == 0 and np.array_equal(ra[3], rb[3]) and np.abs(rb[3]).max() > 0
+    assert np.array_equal(a.lhs(y)[1], b.lhs(y)[1]) and not np.array_equal(a.lhs(y)[1], L0)

@@ -133,6 +133,9 @@ class OracleSim:
     def set_source_pressure_table(self, *a):
         return self.f.set_source_pressure_table(*a)
 
+    def set_rock(self, rock):
+        return self.f.set_rock(rock)
+
     def source_rates(self, n):
         return self.f.source_rates(n)
 

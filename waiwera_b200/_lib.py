@@ -77,6 +77,7 @@ SIGNATURES = {
     "wb_fluid_init": (i, [vp, vp, vp]),
     "wb_set_boundary": (i, [vp, i, i, vp, i]),
     "wb_set_boundaries": (i, [vp, i, vp, vp, vp, vp]),
+    "wb_set_rock": (i, [vp, vp]),
     "wb_set_sources": (i, [vp, i, vp, vp, vp, vp]),
     "wb_set_method": (i, [vp, i, d, vp]),
     "wb_set_source_components": (i, [vp, i, vp, vp]),

@@ -1442,6 +1442,40 @@ extern "C" int wb_set_boundaries(wb_ctx *c, int n, const int32_t *ghost_cells, c
   return check_err(c);
 }
 
+// Rock records of the interior cells replaced between time steps (time-dependent permeability / porosity,
+// flow_simulation_update_rock_properties src/flow_simulation.F90:2051-2089 with the table controls of
+// src/rock_control.F90:49-116).  Boundary ghost cells keep the records they copied at set-up (src/mesh.F90:1189-1193),
+// as they do in the reference, whose controls list interior cells only (src/rock_setup.F90:404-412).
+extern "C" int wb_set_rock(wb_ctx *c, const double *rock) {
+  WB_CHECK(c && rock, "wb_set_rock: null argument");
+  WB_CUDA(cudaSetDevice(c->device));
+  WB_CHECK(!wb_is_device_ptr(rock), "wb_set_rock: rock is read on the host (set-up data): pass a host array");
+  WB_CHECK(c->ncell > 0 && c->h_rock.size() == 8 * (size_t)c->ncell, "wb_set_rock: no mesh (wb_set_mesh comes first)");
+  MeshDev &md = meshdev(c);
+  const int ncell = c->ncell, ni = c->ninterior;
+  for (int i = 0; i < ni; i++) {
+    const double *r = rock + 8 * (size_t)i;
+    WB_CHECK(r[WB_R_POR] >= 0.0 && r[WB_R_POR] <= 1.0 && r[0] >= 0.0 && r[1] >= 0.0 && r[2] >= 0.0,
+             "wb_set_rock: cell %d: porosity %g, permeability %g %g %g", i, r[WB_R_POR], r[0], r[1], r[2]);
+  }
+  memcpy(c->h_rock.data(), rock, 8 * (size_t)ni * sizeof(double));
+  std::vector<double> rockp(5 * (size_t)ncell), perm(3 * (size_t)ncell);
+  for (int i = 0; i < ncell; i++) {
+    const double *r = &c->h_rock[8 * (size_t)i];
+    rockp[i] = r[WB_R_POR];
+    rockp[(size_t)ncell + i] = r[WB_R_RHO];
+    rockp[2 * (size_t)ncell + i] = r[WB_R_CP];
+    rockp[3 * (size_t)ncell + i] = r[WB_R_WET];
+    rockp[4 * (size_t)ncell + i] = r[WB_R_DRY];
+    for (int d = 0; d < 3; d++) perm[(size_t)d * ncell + i] = r[d];
+  }
+  WB_CUDA(cudaMemcpyAsync(c->d_rockp, rockp.data(), rockp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  WB_CUDA(cudaMemcpyAsync(md.d_perm, perm.data(), perm.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  WB_CUDA(cudaStreamSynchronize(c->stream));
+  WB_TRY(recompute_face_perm(c));
+  return 0;
+}
+
 extern "C" int wb_set_boundary(wb_ctx *c, int ghost_cell, int interior_cell, const double *primary, int region) {
   int32_t g = ghost_cell, ic = interior_cell, r = region;
   return wb_set_boundaries(c, 1, &g, &ic, primary, &r);

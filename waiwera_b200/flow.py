@@ -289,6 +289,14 @@ class FlowSimulation:
         rg = np.ascontiguousarray(region, np.int32)
         return check(self.L.wb_set_boundaries(self.h, len(g), ptr(g), ptr(ic), ptr(pr), ptr(rg)), "wb_set_boundaries")
 
+    def set_rock(self, rock):
+        """rock records [ninterior, 8] of the interior cells replaced between time steps (time-dependent permeability /
+        porosity: flow_simulation_update_rock_properties, src/flow_simulation.F90:2051-2089); boundary ghost cells keep
+        the records they copied at set-up"""
+        r = np.ascontiguousarray(rock, np.float64).reshape(-1)
+        assert r.size == 8 * self.mesh.ninterior, "set_rock: %d values for %d interior cells" % (r.size, self.mesh.ninterior)
+        return check(self.L.wb_set_rock(self.h, ptr(r)), "wb_set_rock")
+
     def set_method(self, method, dt_last=0.0, lhs_last2=None):
         """time-stepping residual form (timestepper.F90:345-452): METHOD_BEULER / METHOD_BDF2 / METHOD_DIRECTSS"""
         return check(self.L.wb_set_method(self.h, method, dt_last, ptr(lhs_last2)), "wb_set_method")

@@ -548,30 +548,86 @@ def _zone_cells(zone, m, zones=None, _seen=()):
     raise ValueError("unrecognised zone %r" % (zone,))
 
 
-def rock_records(spec, m, zones=None):
-    """8-double rock records from the "rock" value of the input (src/rock_setup.F90:236-465; defaults src/rock.F90:69-76)"""
+def _rock_type_cells(rt, m, zones):
+    idx = list(rt.get("cells", []))
+    zs = rt.get("zones", [])
+    for z in ([zs] if isinstance(zs, str) else zs):
+        idx += _zone_cells(z, m, zones).tolist()
+    return np.array(sorted(set(idx)), np.int64)
+
+
+def _rank(v):
+    return 0 if not isinstance(v, (list, tuple)) else 1 + max([_rank(x) for x in v], default=0)
+
+
+def rock_controls(spec, m, zones=None):
+    """Rock properties given as tables in time (setup_permeability_rock_control / setup_porosity_rock_control,
+    src/rock_setup.F90:383-463): a rock type whose "permeability" is an array of rank 2 (rows [t, k] or
+    [t, k1, k2(, k3)]) or whose "porosity" is an array (rows [t, phi]), with the "interpolation" of the type (linear or
+    step).  Returns a list of (column of the rock record, number of columns, cells, table, interpolation) in the order
+    of the reference's control list (per type: permeability, then porosity); rock_at applies them."""
+    out = []
+    for rt in (spec or {}).get("types", []):
+        idx = _rock_type_cells(rt, m, zones)
+        if len(idx) == 0:
+            continue
+        interp = rt.get("interpolation", "linear")
+        assert interp in ("linear", "step"), "%s interpolation of a rock property table is not built" % interp
+        if _rank(rt.get("permeability")) == 2:
+            tab = np.array(rt["permeability"], float)
+            assert 2 <= tab.shape[1] <= 4, "rock permeability table: rows are [time, k] or [time, k1, k2(, k3)]"
+            out.append((0, tab.shape[1] - 1, idx, tab, interp))
+        if _rank(rt.get("porosity")) >= 1:
+            tab = np.array(rt["porosity"], float).reshape(-1, 2)
+            out.append((5, 1, idx, tab, interp))
+    return out
+
+
+def apply_rock_controls(rock, controls, t):
+    """the update of every rock control at time t on the 8-double records `rock` (in place): table%interpolate(t),
+    a one-column permeability table sets all three directions, a wider one the leading directions
+    (permeability_table_rock_control_update / porosity_table_rock_control_update, src/rock_control.F90:49-116)"""
+    for col, ncol, idx, tab, interp in controls:
+        v = [_table_value(tab[:, [0, 1 + j]], interp, t) for j in range(ncol)]
+        if col == 0 and ncol == 1:
+            rock[idx, 0:3] = v[0]
+        else:
+            rock[idx, col:col + ncol] = v
+    return rock
+
+
+def rock_at(p, t):
+    """rock records of the interior cells at time t, for wb_set_rock before a time step is tried
+    (flow_simulation_update_rock_properties called from pre_try_timestep with the time the step ends at,
+    src/flow_simulation.F90:2040-2089, src/timestepper.F90:2333); None if the input has no rock controls"""
+    if not getattr(p, "rock_controls", None):
+        return None
+    n = p.mesh.ninterior
+    return apply_rock_controls(np.array(p.mesh.rock[:n], float), p.rock_controls, t)
+
+
+def rock_records(spec, m, zones=None, time=0.0):
+    """8-double rock records from the "rock" value of the input (src/rock_setup.F90:236-465; defaults src/rock.F90:69-76);
+    properties given as tables in time (rock_controls) take their value at `time`, the start of the run
+    (src/flow_simulation.F90:971)"""
     n = m.ninterior
     rock = np.zeros((n, 8))
     rock[:, 0:3], rock[:, 3:5], rock[:, 5], rock[:, 6], rock[:, 7] = 1e-13, 2.5, 0.1, 2200.0, 1000.0
     for rt in (spec or {}).get("types", []):
-        idx = list(rt.get("cells", []))
-        zs = rt.get("zones", [])
-        for z in ([zs] if isinstance(zs, str) else zs):
-            idx += _zone_cells(z, m, zones).tolist()
-        idx = np.array(sorted(set(idx)), np.int64)
+        idx = _rock_type_cells(rt, m, zones)
         if len(idx) == 0:
             continue
-        if "permeability" in rt:
+        if rt.get("permeability") is not None and _rank(rt["permeability"]) < 2:
             k = np.atleast_1d(np.array(rt["permeability"], float))
             rock[idx, 0:len(k)] = k
             if len(k) == 1:
                 rock[idx, 0:3] = k[0]
         for key, col in (("wet_conductivity", 3), ("dry_conductivity", 4), ("porosity", 5), ("density", 6), ("specific_heat", 7)):
-            if rt.get(key) is not None:
+            if rt.get(key) is not None and _rank(rt[key]) == 0:
                 rock[idx, col] = rt[key]
         if rt.get("dry_conductivity") is None and rt.get("wet_conductivity") is not None:
             rock[idx, 4] = rt["wet_conductivity"]          # dry defaults to wet (src/rock_setup.F90)
-    return rock
+    return apply_rock_controls(rock, rock_controls(spec, m, zones), time)
 
 
 def apply_minc(m, minc, rock_spec, zones=None):
@@ -809,14 +865,18 @@ def load(path, mod=None, mesh_path=None):
             hit = np.nonzero((np.sort(m.face_cells.reshape(-1, 2), 1) == cells).all(1))[0]
             if len(hit) == 1:
                 m.face_geom[hit[0], 11] = float(fs.get("permeability_direction", 1))
-    rock = rock_records(doc.get("rock"), m, mspec.get("zones"))
+    start_time = float((doc.get("time") or {}).get("start", 0.0) or 0.0)
+    rock = rock_records(doc.get("rock"), m, mspec.get("zones"), time=start_time)
+    rctl = rock_controls(doc.get("rock"), m, mspec.get("zones"))
     m.rock[:] = rock
+    assert not (rctl and mspec.get("minc")), "rock property tables on MINC meshes are not built"
     if mspec.get("minc"):
         m = apply_minc(m, mspec["minc"], doc.get("rock"), mspec.get("zones"))
     bspecs = doc.get("boundaries") or []
     m, bowner = add_boundary_faces(m, exterior, bspecs)
     p = Problem()
     p.doc, p.mesh = doc, m
+    p.rock_controls = rctl                                  # cells are interior cells: boundary ghosts come after them
     eos_name = doc.get("eos", "we")
     p.eos = eos_name if isinstance(eos_name, str) else eos_name.get("name", "we")
     if mod is not None:

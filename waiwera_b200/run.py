@@ -165,6 +165,9 @@ def run(p, sim, opts=None, log=None, tracer_ksp=None, tracer_history=None):
         sim.pre_timestep()
         y0 = y.copy()
         for attempt in range(tries):
+            rock = ingest.rock_at(p, t + dt)            # pre_try_timestep: rock tables at the time the step ends at; L0
+            if rock is not None:                        # stays the balance of the last step (src/timestepper.F90:2333)
+                assert sim.set_rock(rock) == 0
             apply_controls(p, sim, t, t + dt)
             res = sim.newton_solve(y, L0, dt, opts)
             if res.reason > 0:
