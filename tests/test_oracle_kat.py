@@ -326,6 +326,23 @@ def test_cell_balance(wo):
         assert rel(a, b) < 1e-8
 
 
+# ---- test/unit/src/rock_test.F90:55-135 ----
+
+def test_rock_record_layout_and_energy(wo):
+    """rock%assign (rock_test.F90:55-98): permeability(3), wet / dry conductivity, porosity, density, specific heat in
+    that order -- the 8-double record of the C ABI; rock%energy (:102-135, src/rock.F90:142): density * specific heat * T
+    = 2.717e8 J/m3 at 130 degC, seen through the energy balance of a cell with no fluid in it"""
+    from waiwera_b200 import mesh as wmesh
+    rock = wmesh.default_rock(1, None, heterogeneous=False)[0]
+    assert rock.shape == (8,) and list(rock[3:]) == [2.5, 2.5, 0.1, 2200.0, 1000.0]      # defaults src/rock.F90:69-76
+    rock = np.array([1.e-12, 1.e-13, 1.e-14, 2.5, 1.5, 0.1, 2200., 950.])
+    fluid = np.zeros(26)
+    fluid[1] = 130.0
+    bal = np.zeros(3)
+    wo.lib().wo_cell_balance(wo.dp(rock), wo.dp(fluid), 2, 2, 3, wo.dp(bal))
+    assert bal[0] == 0.0 and bal[1] == 0.0 and rel(bal[2] / (1.0 - rock[5]), 2.717e8) < 1e-15
+
+
 # ---- test/unit/src/face_test.F90:102-728 ----
 
 def test_face_distances(wo):
