@@ -20,7 +20,7 @@ def test_set_rock_matches_oracle(wo):
     """lhs, residual and FD Jacobian after wb_set_rock == the oracle after its set_rock, on a mesh with Dirichlet
     boundary ghost cells (which keep the records they copied at set-up in both); a bad record is refused"""
     from waiwera_b200 import flow
-    m, y, region, prm = make_problem(wo, dims=(6, 5, 8), thermo=1, two_phase_layers=2, top_boundary=True)
+    m, y, region, prm = make_problem(wo, dims=(6, 5, 8), thermo=0, two_phase_layers=2, top_boundary=True)     # the smoke() problem
     ref = oracle_flow(wo, m, prm, y, region)
     sim = gpu_flow(wo, flow, m, prm, y, region)
     _, L0 = ref.lhs(y)
@@ -44,7 +44,7 @@ def test_set_rock_matches_oracle(wo):
     for ii in range(2):
         np.maximum.at(rowmax[:, ii], rows, np.abs(val[:, [ii, 2 + ii]]).max(axis=1))
     scale = np.stack([rowmax[rows, 0], rowmax[rows, 1], rowmax[rows, 0], rowmax[rows, 1]], 1)
-    assert (np.abs(J - val) / np.maximum(scale, 1e-300)).max() < 1e-3
+    assert (np.abs(J - val) / np.maximum(scale, 1e-300)).max() < 1e-4      # FD noise floor, as in test_gpu_flow.py
     wo.lib().wo_bsr_destroy(A)
     # the new porosity is in the balances, and differs from the old one
     e, L1g = sim.lhs(y)
